@@ -1,0 +1,24 @@
+"""deeprec_b200 -- a Blackwell(B200)-native sparse-recommender training & serving engine with the
+capabilities of DeepRec (EmbeddingVariable, admission/eviction, multi-tier storage, GroupEmbedding,
+model-parallel embeddings + data-parallel dense, SmartStage, incremental checkpoint, SessionGroup serving).
+
+Layers:
+  csrc/host   C++17 host engine        (CPU EV, ckpt bundle, staging queue, work queue, serving C ABI)
+  csrc/cuda   sm_100a CUDA kernels     (hash table, fused lookup, sparse optimizers, tcgen05 MLP, P2P collectives)
+  python      framework layer          (this package)
+"""
+from .config import (CacheStrategy, CBFFilter, CheckpointOption, CounterFilter, EmbeddingVariableOption,
+                     GlobalStepEvict, InitializerOption, L2WeightEvict, StorageOption, StorageType)
+from .embedding_variable import (DynamicEmbeddingVariable, EmbeddingVariable, MultiHashVariable,
+                                 PartitionedEmbeddingVariable, fixed_size_partitioner,
+                                 get_dynamic_dimension_embedding_variable, get_embedding_variable,
+                                 get_multihash_variable)
+from . import ops, optim  # noqa: E402
+from .ops.embedding_ops import (SparseIds, adaptive_embedding_lookup_sparse, embedding_lookup,
+                                embedding_lookup_sparse, embedding_lookup_sparse_multi_dim,
+                                fused_embedding_lookup_sparse, fused_safe_embedding_lookup_sparse,
+                                group_embedding_lookup, group_embedding_lookup_sparse,
+                                safe_embedding_lookup_sparse)
+from .optim.optimizers import get_or_create_global_step
+
+__version__ = "0.1.0"

@@ -1,0 +1,445 @@
+// tcgen05 / TMEM / TMA GEMM kernels for the dense (MLP) path -- hand-written for sm_100a.
+//
+//   k_gemm_tn      D[M,N] = A[M,K] * B[N,K]^T (+bias)(ReLU)(* relu-mask)      bf16 in, fp32 TMEM accumulate, bf16 out
+//                  persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (one elected
+//                  thread issues tcgen05.mma), warps2-5 = epilogue (tcgen05.ld -> regs -> fused epilogue ->
+//                  16B global stores); 4-stage smem ring (128B-swizzled K-major tiles), double-buffered TMEM
+//                  accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//                  Used for: Linear forward (A = activations, B = W[N,K]) and dX (A = dY, B = W^T[K,N]).
+//   k_gemm_nt_splitk  dW[N_out,K_in] += dY[b,N_out]^T * X[b,K_in]            both operands MN-major straight from
+//                  the row-major activations (no transposes materialised), split over the batch, fp32
+//                  red.global.add.v4 epilogue.
+//
+// The reference has no tensor-core kernel of its own: its MLP GEMMs are cuBLAS/cuBLASLt calls
+// (stream_executor/cuda/cuda_blas.cc:431-455, kernels/matmul_op_fused.cc) -- SURVEY §2.14 row L1.
+#include <cuda.h>
+
+#include "common.cuh"
+
+using namespace drc;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;    // 6 warps
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: dims {inner, outer}, row pitch in bytes, box {box_inner, box_outer}, 128B swizzle.
+int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -100;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -101 - (int)r;
+}
+
+struct Epilogue {
+  const float* bias;              // [N] or null
+  const __nv_bfloat16* mask_src;  // [M, ld_mask] or null: out *= (mask_src > 0)   (ReLU backward)
+  __nv_bfloat16* out;             // [M, ldc]
+  float* out_f32;                 // optional fp32 copy of the output (or null)
+  int64_t ldc, ld_mask;
+  int relu;
+};
+
+template <int BLOCK_N>
+struct SmemLayoutTN {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = (BLOCK_N < 8 ? 8 : BLOCK_N) * BLOCK_K * 2;
+  static constexpr int kBBytesAligned = (kBBytes + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kABytes + kBBytesAligned;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, Epilogue ep) {
+  using L = SmemLayoutTN<BLOCK_N>;
+  constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint64_t* full_bar = bars;                 // [kStages]
+  uint64_t* empty_bar = bars + kStages;      // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kABytes + L::kBBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (single elected thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N < 16 ? 16 : BLOCK_N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 B (= 16 bf16) inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= Epilogue warps (TMEM -> registers -> global) =================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+      constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        uint32_t r[32];
+        if constexpr (CH == 32) {
+          tmem_ld_32x32(t_row + c0, r);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_32x16(t_row + c0, r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = r16[j];
+        }
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c0;
+        if (row < M && col0 < N) {
+          float v[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              if (col0 + j < N) {
+                float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (ep.mask_src) {
+            const __nv_bfloat16* ms = ep.mask_src + (int64_t)row * ep.ld_mask + col0;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              if (col0 + j < N) {
+                int4 raw = *reinterpret_cast<const int4*>(ms + j);
+                const uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = unpack_bf16x2(w[e]);
+                  if (!(f.x > 0.f)) v[j + 2 * e] = 0.f;
+                  if (!(f.y > 0.f)) v[j + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+          }
+          __nv_bfloat16* dst = ep.out + (int64_t)row * ep.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            if (col0 + j < N) {   // N is a multiple of 8 (checked on the host)
+              int4 pk;
+              pk.x = (int)pack_bf16x2(v[j], v[j + 1]); pk.y = (int)pack_bf16x2(v[j + 2], v[j + 3]);
+              pk.z = (int)pack_bf16x2(v[j + 4], v[j + 5]); pk.w = (int)pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<int4*>(dst + j) = pk;
+            }
+          }
+          if (ep.out_f32) {
+            float* d32 = ep.out_f32 + (int64_t)row * ep.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < CH; j += 4)
+              if (col0 + j < N) *reinterpret_cast<float4*>(d32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// -------------------------------------------------------------------------------------------------
+// dW[N_out, K_in] += sum_b dY[b, N_out] * X[b, K_in]   (split over b; fp32 atomics epilogue)
+//   A operand = dY^T  : M = N_out, MN-major (tensor map over dY: inner = N_out, outer = batch)
+//   B operand = X^T   : N = K_in , MN-major (tensor map over X : inner = K_in , outer = batch)
+// smem per stage: A = 2 chunks [BLOCK_KB rows][64 elems]; B = BLOCK_N/64 such chunks.
+// -------------------------------------------------------------------------------------------------
+constexpr int BLOCK_KB = 64;            // batch rows (reduction) per pipeline stage
+constexpr int kChunkBytes = BLOCK_KB * 128;
+
+template <int BLOCK_N>
+struct SmemLayoutNT {
+  static constexpr int kAChunks = BLOCK_M / 64;
+  static constexpr int kBChunks = BLOCK_N / 64;
+  static constexpr int kStageBytes = (kAChunks + kBChunks) * kChunkBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_nt_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Mo /*N_out*/, int No /*K_in*/,
+                 int batch, int rows_per_split, float* __restrict__ dW, int64_t ldw) {
+  using L = SmemLayoutNT<BLOCK_N>;
+  constexpr int kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, n_blk = blockIdx.y, split = blockIdx.z;
+  const int b0 = split * rows_per_split;
+  const int b1 = min(batch, b0 + rows_per_split);
+  const int num_kb = (b1 - b0 + BLOCK_KB - 1) / BLOCK_KB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (num_kb <= 0) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem_base, kTmemCols); return; }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::kStageBytes;
+        uint8_t* sb = sa + L::kAChunks * kChunkBytes;
+        mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+        const int brow = b0 + kb * BLOCK_KB;   // rows beyond `batch` are zero-filled by TMA; rows in [b1, batch) of a
+                                               // short last stage belong to the next split: masked by box clamp below
+#pragma unroll
+        for (int c = 0; c < L::kAChunks; ++c) tma_load_2d(sa + c * kChunkBytes, &tmA, &full_bar[stage], m_blk * BLOCK_M + c * 64, brow);
+#pragma unroll
+        for (int c = 0; c < L::kBChunks; ++c) tma_load_2d(sb + c * kChunkBytes, &tmB, &full_bar[stage], n_blk * BLOCK_N + c * 64, brow);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t sb = sa + L::kAChunks * kChunkBytes;
+        // MN-major SW128: LBO = distance between 64-element MN chunks, SBO = 8 k-rows (1024 B)
+        const uint64_t adesc = umma_desc_sw128(sa, kChunkBytes, 1024);
+        const uint64_t bdesc = umma_desc_sw128(sb, kChunkBytes, 1024);
+#pragma unroll
+        for (int k = 0; k < BLOCK_KB / UMMA_K; ++k) {
+          // 16 k-rows = 2048 B  -> +128 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(tfull_bar);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int row = m_blk * BLOCK_M + q * 32 + lane;      // N_out index
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + c0, r);
+      tmem_ld_wait();
+      const int col0 = n_blk * BLOCK_N + c0;               // K_in index
+      if (row < Mo) {
+        float* dst = dW + (int64_t)row * ldw + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (col0 + j + 3 < No) {
+            red_add_v4_f32(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+            for (int e = 0; e < 4; ++e) if (col0 + j + e < No) atomicAdd(dst + j + e, __uint_as_float(r[j + e]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int BN>
+int launch_tn(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_t ldb, const Epilogue& ep, int max_ctas, cudaStream_t s) {
+  CUtensorMap tb;
+  int rc = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BLOCK_K, BN < 8 ? 8 : BN);
+  if (rc) return rc;
+  using L = SmemLayoutTN<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  if (grid > max_ctas) grid = max_ctas;
+  k_gemm_tn<BN><<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, M, N, K, ep);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, int Mo, int No, int batch, int splits, float* dW, int64_t ldw, cudaStream_t s) {
+  using L = SmemLayoutNT<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_nt_splitk<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  int rows_per_split = ((batch + splits - 1) / splits + BLOCK_KB - 1) / BLOCK_KB * BLOCK_KB;
+  splits = (batch + rows_per_split - 1) / rows_per_split;
+  dim3 grid((Mo + BLOCK_M - 1) / BLOCK_M, (No + BN - 1) / BN, splits);
+  k_gemm_nt_splitk<BN><<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, Mo, No, batch, rows_per_split, dW, ldw);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// out[M,N] = A[M,K](lda) * B[N,K](ldb)^T (+bias)(relu)(*mask).  Requirements: bf16, K-major, lda/ldb/ldc multiples of 8,
+// N multiple of 8, pointers 16B-aligned.  out_f32 optional.
+int dr_cuda_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias, int relu,
+                    const void* mask_src, int64_t ld_mask, void* out, int64_t ldc, float* out_f32, int max_ctas, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 8)) return -2;
+  if (max_ctas <= 0) max_ctas = kNumSMs;
+  CUtensorMap ta;
+  int rc = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  Epilogue ep{bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, out_f32, ldc, ld_mask, relu};
+  if (N <= 16) return launch_tn<16>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+  if (N <= 32) return launch_tn<32>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+  if (N <= 64) return launch_tn<64>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+  if (N <= 128) return launch_tn<128>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+  return launch_tn<256>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+}
+
+// dW[N_out,K_in](ldw, fp32, accumulated into) += dY[batch,N_out](ldy)^T * X[batch,K_in](ldx)
+int dr_cuda_gemm_dw(const void* dY, int64_t ldy, const void* X, int64_t ldx, int batch, int N_out, int K_in, float* dW, int64_t ldw,
+                    int splits, cudaStream_t s) {
+  if (batch <= 0 || N_out <= 0 || K_in <= 0) return 0;
+  if ((ldy % 8) || (ldx % 8)) return -2;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, dY, (uint64_t)N_out, (uint64_t)batch, (uint64_t)ldy * 2, 64, BLOCK_KB);
+  if (rc) return rc;
+  rc = make_tmap(&tb, X, (uint64_t)K_in, (uint64_t)batch, (uint64_t)ldx * 2, 64, BLOCK_KB);
+  if (rc) return rc;
+  int m_tiles = (N_out + BLOCK_M - 1) / BLOCK_M;
+  if (K_in <= 64) {
+    if (splits <= 0) splits = max(1, kNumSMs / m_tiles);
+    return launch_nt<64>(ta, tb, N_out, K_in, batch, splits, dW, ldw, s);
+  }
+  if (K_in <= 128) {
+    if (splits <= 0) splits = max(1, kNumSMs / m_tiles);
+    return launch_nt<128>(ta, tb, N_out, K_in, batch, splits, dW, ldw, s);
+  }
+  int n_tiles = (K_in + 255) / 256;
+  if (splits <= 0) splits = max(1, kNumSMs / (m_tiles * n_tiles));
+  return launch_nt<256>(ta, tb, N_out, K_in, batch, splits, dW, ldw, s);
+}
+
+}  // extern "C"

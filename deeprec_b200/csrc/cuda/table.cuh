@@ -1,0 +1,119 @@
+// Device-resident EmbeddingVariable: open-addressing key table + SoA metadata + slab row store.
+//
+// Replaces (behaviourally) the reference's GPUHashTable / GPUHashMapKV built on cuco::dynamic_map
+// (framework/embedding/gpu_hash_table.{h,cu.cc}, gpu_hash_map_kv.h) and its bank allocator.
+// Differences by design:
+//   * no host synchronisation on insert/growth (reference: cudaDeviceSynchronize per submap,
+//     gpu_hash_table.cu.cc:485): capacity is pre-sized, growth is a device-side rehash at a step
+//     boundary triggered from a lazily-read counter;
+//   * admission (counter / counting-Bloom), frequency, version and the dedup "claim" are fused
+//     into the find-or-insert kernel; rows are allocated lazily at apply time (only admitted keys
+//     own a row), mirroring counter_filter_policy.h:106-139.
+#pragma once
+#include "common.cuh"
+
+extern "C" {
+// Mirrored by ctypes (deeprec_b200/ops/device_table.py::DeviceTableStruct) -- keep in sync.
+struct DrDeviceTable {
+  int64_t* keys;           // [capacity]  kEmptyKey / kTombKey / key
+  int32_t* freq;           // [capacity]
+  int32_t* version;        // [capacity]  global step of last update, -1 = never
+  int32_t* row_of;         // [capacity]  row index, -1 = not admitted yet
+  int32_t* tag;            // [capacity]  per-step unique index (dedup claim), -1 = unclaimed
+  uint8_t* dirty;          // [capacity]  touched since last (incremental) checkpoint
+  float* rows;             // [row_capacity, stride]
+  int32_t* free_list;      // [row_capacity]
+  int32_t* counters;       // [8]: 0 next_row, 1 free_top, 2 n_keys, 3 n_admitted, 4 overflow, 5 n_unique, 6 n_miss, 7 spare
+  const float* default_matrix;  // [default_value_dim, dim]
+  uint32_t* bloom;         // [bloom_m] counting-Bloom counters (or null)
+  int64_t capacity;        // power of two
+  int64_t row_capacity;
+  int64_t default_value_dim;
+  int64_t bloom_m;
+  int32_t dim;
+  int32_t stride;
+  int32_t num_slots;
+  int32_t has_scalars;
+  int32_t filter_type;
+  int32_t filter_freq;
+  int32_t bloom_k;
+  int32_t is_inference;
+  float no_permission;
+  float slot_init[4];
+  int32_t steps_to_live;
+  float l2_weight_threshold;
+};
+}
+
+namespace drc {
+
+enum { CTR_NEXT_ROW = 0, CTR_FREE_TOP = 1, CTR_NKEYS = 2, CTR_NADMITTED = 3, CTR_OVERFLOW = 4, CTR_NUNIQUE = 5, CTR_NMISS = 6 };
+
+__device__ __forceinline__ int64_t table_find(const DrDeviceTable& T, int64_t key) {
+  const uint64_t mask = (uint64_t)T.capacity - 1;
+  uint64_t pos = dr_mix64((uint64_t)key) & mask;
+  for (int64_t probes = 0; probes < T.capacity; ++probes, pos = (pos + 1) & mask) {
+    int64_t k = T.keys[pos];
+    if (k == key) return (int64_t)pos;
+    if (k == kEmptyKey) return -1;
+  }
+  return -1;
+}
+
+// find or CAS-insert; returns position or -1 if the table is full.  *inserted set for the winner.
+__device__ __forceinline__ int64_t table_find_or_insert(const DrDeviceTable& T, int64_t key, bool* inserted) {
+  const uint64_t mask = (uint64_t)T.capacity - 1;
+  uint64_t pos = dr_mix64((uint64_t)key) & mask;
+  *inserted = false;
+  for (int64_t probes = 0; probes < T.capacity; ++probes) {
+    int64_t k = *(volatile int64_t*)&T.keys[pos];
+    if (k == key) return (int64_t)pos;
+    if (k == kEmptyKey) {
+      unsigned long long old = atomicCAS((unsigned long long*)&T.keys[pos], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if ((int64_t)old == kEmptyKey) { *inserted = true; return (int64_t)pos; }
+      if ((int64_t)old == key) return (int64_t)pos;
+      // another key took the slot: fall through to the next position
+    }
+    pos = (pos + 1) & mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ uint32_t bloom_add_min(const DrDeviceTable& T, int64_t key, uint32_t count) {
+  uint32_t mn = 0xFFFFFFFFu;
+  for (int i = 0; i < T.bloom_k; ++i) {
+    uint64_t idx = dr_hash_seed((uint64_t)key, (uint64_t)i) % (uint64_t)T.bloom_m;
+    uint32_t v = atomicAdd(&T.bloom[idx], count) + count;
+    mn = min(mn, v);
+  }
+  return mn;
+}
+__device__ __forceinline__ uint32_t bloom_min(const DrDeviceTable& T, int64_t key) {
+  uint32_t mn = 0xFFFFFFFFu;
+  for (int i = 0; i < T.bloom_k; ++i) {
+    uint64_t idx = dr_hash_seed((uint64_t)key, (uint64_t)i) % (uint64_t)T.bloom_m;
+    mn = min(mn, T.bloom[idx]);
+  }
+  return mn;
+}
+
+// Row allocation (called by one lane per unique key in the apply kernel).
+__device__ __forceinline__ int32_t table_alloc_row(const DrDeviceTable& T) {
+  int32_t top = atomicSub(&T.counters[CTR_FREE_TOP], 1);
+  if (top > 0) return T.free_list[top - 1];
+  atomicAdd(&T.counters[CTR_FREE_TOP], 1);
+  int32_t r = atomicAdd(&T.counters[CTR_NEXT_ROW], 1);
+  if ((int64_t)r >= T.row_capacity) { T.counters[CTR_OVERFLOW] = 1; return -1; }
+  return r;
+}
+
+// What a forward read returns for position `pos` (or absent key): pointer to a row of `dim` floats,
+// or nullptr meaning "fill with no_permission".
+__device__ __forceinline__ const float* table_read_ptr(const DrDeviceTable& T, int64_t key, int64_t pos) {
+  int32_t r = pos >= 0 ? T.row_of[pos] : -1;
+  if (r >= 0) return T.rows + (int64_t)r * T.stride;
+  if (T.filter_type != DR_FILTER_NONE && T.filter_freq > 0) return nullptr;
+  return T.default_matrix + dr_default_row(key, T.default_value_dim) * T.dim;
+}
+
+}  // namespace drc

@@ -1,0 +1,717 @@
+// Host-tier embedding engine (C++17, no CUDA): the CPU EmbeddingVariable implementation and
+// the DRAM tier of the multi-tier store.  C ABI, loaded with ctypes (deeprec_b200/_native.py).
+//
+// Parity map (behaviour, not structure) to the reference:
+//   EmbeddingVar::GetEmbeddings / LookupOrCreateKey   framework/embedding/embedding_var.h:142-219
+//   LocklessHashMap / DenseHashMap KV                 framework/embedding/cpu_hash_map_kv.h:23-223, dense_hash_map_kv.h:27-160
+//   CounterFilterPolicy / BloomFilterPolicy           framework/embedding/counter_filter_policy.h:35-189, bloom_filter_policy.h:33-450
+//   GlobalStep / L2Weight shrink at save              framework/embedding/globalstep_shrink_policy.h:43-58, l2weight_shrink_policy.h:46-64
+//   KvResourceSparseApply* (8 rules, WithCounts)      core/kernels/training_ali_ops.cc:73-3200
+//   ckpt bucketing (key % 1000) + N->M re-shard       framework/embedding/storage.h:255-288, embedding_var_restore.cc:131
+//   IndicesIncrRecorder (dirty keys)                  core/kernels/incr_save_restore_ops.h:347
+//
+// Design: partitioned open-addressing KV with wait-free reads (acquire loads) and CAS inserts;
+// per-partition shared_mutex is taken shared by every op and exclusive only while a
+// partition rehashes or is compacted by eviction.  Key metadata (freq, version, row index,
+// dirty bit) is SoA in chunked arrays so pointers stay stable while the table grows; rows
+// come from a chunked slab with a free list (the EVAllocator analogue: no per-row malloc).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <thread>
+#include <vector>
+
+#include "../common/ev_types.h"
+
+namespace dr {
+
+// ------------------------------------------------------------------------------------
+// Thread pool (intra-op sharding; the reference uses TF's Shard() over worker threads)
+// ------------------------------------------------------------------------------------
+class ThreadPool {
+ public:
+  explicit ThreadPool(int n) : stop_(false) {
+    if (n < 1) n = 1;
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { Loop(); });
+  }
+  ~ThreadPool() {
+    { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // Runs fn(begin,end) over [0,n) in roughly equal shards; caller participates.
+  void ParallelFor(int64_t n, int64_t min_grain, const std::function<void(int64_t, int64_t)>& fn) {
+    if (n <= 0) return;
+    int shards = (int)std::min<int64_t>(size() + 1, (n + min_grain - 1) / min_grain);
+    if (shards <= 1) { fn(0, n); return; }
+    std::atomic<int> remaining(shards - 1);
+    std::mutex dmu; std::condition_variable dcv;
+    int64_t per = (n + shards - 1) / shards;
+    for (int s = 1; s < shards; ++s) {
+      int64_t b = s * per, e = std::min(n, b + per);
+      Submit([&, b, e] {
+        if (b < e) fn(b, e);
+        if (remaining.fetch_sub(1) == 1) { std::lock_guard<std::mutex> l(dmu); dcv.notify_one(); }
+      });
+    }
+    fn(0, std::min(n, per));
+    std::unique_lock<std::mutex> l(dmu);
+    dcv.wait(l, [&] { return remaining.load() == 0; });
+  }
+  void Submit(std::function<void()> f) {
+    { std::lock_guard<std::mutex> l(mu_); q_.push_back(std::move(f)); }
+    cv_.notify_one();
+  }
+ private:
+  void Loop() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+        if (stop_ && q_.empty()) return;
+        f = std::move(q_.front()); q_.erase(q_.begin());
+      }
+      f();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<std::function<void()>> q_;
+  std::mutex mu_; std::condition_variable cv_; bool stop_;
+};
+
+static ThreadPool* GlobalPool() {
+  static ThreadPool* p = [] {
+    int n = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("DEEPREC_HOST_THREADS")) n = atoi(e);
+    if (n > 64) n = 64;
+    return new ThreadPool(std::max(1, n - 1));
+  }();
+  return p;
+}
+
+// ------------------------------------------------------------------------------------
+// Chunked array: stable addresses under growth, lock-free reads.
+// ------------------------------------------------------------------------------------
+template <typename T, int kLog2Chunk = 16>
+class ChunkedArray {
+ public:
+  static constexpr int64_t kChunk = int64_t(1) << kLog2Chunk;
+  static constexpr int64_t kMaxChunks = 1 << 16;
+  explicit ChunkedArray(int64_t width = 1) : width_(width) {
+    chunks_ = new std::atomic<T*>[kMaxChunks];
+    for (int64_t i = 0; i < kMaxChunks; ++i) chunks_[i].store(nullptr, std::memory_order_relaxed);
+  }
+  ~ChunkedArray() {
+    for (int64_t i = 0; i < kMaxChunks; ++i) { T* p = chunks_[i].load(); if (p) free(p); }
+    delete[] chunks_;
+  }
+  T* at(int64_t idx) {
+    T* c = chunks_[idx >> kLog2Chunk].load(std::memory_order_acquire);
+    return c + (idx & (kChunk - 1)) * width_;
+  }
+  void EnsureCapacity(int64_t n, const T& fill) {
+    int64_t need = (n + kChunk - 1) >> kLog2Chunk;
+    if (need <= nchunks_.load(std::memory_order_acquire)) return;
+    std::lock_guard<std::mutex> l(mu_);
+    for (int64_t c = nchunks_.load(); c < need; ++c) {
+      T* p = nullptr;
+      if (posix_memalign((void**)&p, 64, sizeof(T) * kChunk * width_) != 0) abort();
+      std::fill(p, p + kChunk * width_, fill);
+      chunks_[c].store(p, std::memory_order_release);
+      nchunks_.store(c + 1, std::memory_order_release);
+    }
+  }
+  int64_t capacity() const { return nchunks_.load() << kLog2Chunk; }
+  int64_t width() const { return width_; }
+ private:
+  int64_t width_;
+  std::atomic<T*>* chunks_;
+  std::atomic<int64_t> nchunks_{0};
+  std::mutex mu_;
+};
+
+// ------------------------------------------------------------------------------------
+// Partitioned open-addressing KV: key -> meta index.
+// ------------------------------------------------------------------------------------
+static constexpr int64_t kEmptyKey = INT64_MIN;
+
+struct KVPart {
+  std::atomic<int64_t>* keys = nullptr;
+  std::atomic<int32_t>* vals = nullptr;
+  int64_t cap = 0;
+  std::atomic<int64_t> size{0};
+  std::shared_mutex mu;
+  ~KVPart() { delete[] keys; delete[] vals; }
+  void Alloc(int64_t c) {
+    cap = c;
+    keys = new std::atomic<int64_t>[c];
+    vals = new std::atomic<int32_t>[c];
+    for (int64_t i = 0; i < c; ++i) { keys[i].store(kEmptyKey, std::memory_order_relaxed); vals[i].store(-1, std::memory_order_relaxed); }
+  }
+};
+
+class HostKV {
+ public:
+  HostKV(int nparts, int64_t init_cap) : nparts_(std::max(1, nparts)), parts_(new KVPart[nparts_]) {
+    int64_t per = 64;
+    while (per * nparts_ < init_cap * 2) per <<= 1;
+    for (int p = 0; p < nparts_; ++p) parts_[p].Alloc(per);
+  }
+  ~HostKV() { delete[] parts_; }
+  int PartOf(int64_t key) const { return (int)((dr_mix64((uint64_t)key) >> 40) % (uint64_t)nparts_); }
+
+  // wait-free find; returns meta index or -1
+  int32_t Find(int64_t key) {
+    KVPart& P = parts_[PartOf(key)];
+    std::shared_lock<std::shared_mutex> l(P.mu);
+    return FindLocked(P, key);
+  }
+  // find or insert; `alloc` is called exactly once by the inserting thread to get a meta index.
+  template <typename Alloc>
+  int32_t FindOrInsert(int64_t key, Alloc&& alloc, bool* inserted) {
+    KVPart& P = parts_[PartOf(key)];
+    *inserted = false;
+    for (;;) {
+      bool need_grow = false;
+      {
+        std::shared_lock<std::shared_mutex> l(P.mu);
+        uint64_t mask = P.cap - 1;
+        uint64_t pos = dr_mix64((uint64_t)key) & mask;
+        for (int64_t probes = 0; probes < P.cap; ++probes, pos = (pos + 1) & mask) {
+          int64_t k = P.keys[pos].load(std::memory_order_acquire);
+          if (k == key) return WaitVal(P, pos);
+          if (k == kEmptyKey) {
+            if ((P.size.load(std::memory_order_relaxed) + 1) * 10 > P.cap * 7) { need_grow = true; break; }
+            int64_t expected = kEmptyKey;
+            if (P.keys[pos].compare_exchange_strong(expected, key, std::memory_order_acq_rel)) {
+              P.size.fetch_add(1, std::memory_order_relaxed);
+              int32_t v = alloc();
+              P.vals[pos].store(v, std::memory_order_release);
+              *inserted = true;
+              return v;
+            }
+            if (expected == key) return WaitVal(P, pos);
+            // lost the slot to another key: keep probing from the same slot's successor
+          }
+        }
+        if (!need_grow) need_grow = true;  // table full
+      }
+      Grow(P);
+    }
+  }
+  int64_t Size() const { int64_t s = 0; for (int p = 0; p < nparts_; ++p) s += parts_[p].size.load(); return s; }
+
+  // Iterate all (key, idx) pairs (caller guarantees no concurrent writers, as in Save).
+  template <typename F> void ForEach(F&& f) {
+    for (int p = 0; p < nparts_; ++p) {
+      KVPart& P = parts_[p];
+      std::shared_lock<std::shared_mutex> l(P.mu);
+      for (int64_t i = 0; i < P.cap; ++i) {
+        int64_t k = P.keys[i].load(std::memory_order_acquire);
+        if (k != kEmptyKey) f(k, P.vals[i].load(std::memory_order_acquire));
+      }
+    }
+  }
+  // Remove every key for which pred(key, idx) is true (partition rebuilt under exclusive lock).
+  template <typename Pred> int64_t RemoveIf(Pred&& pred) {
+    int64_t removed = 0;
+    for (int p = 0; p < nparts_; ++p) {
+      KVPart& P = parts_[p];
+      std::unique_lock<std::shared_mutex> l(P.mu);
+      std::vector<std::pair<int64_t, int32_t>> keep; keep.reserve(P.size.load());
+      for (int64_t i = 0; i < P.cap; ++i) {
+        int64_t k = P.keys[i].load(std::memory_order_relaxed);
+        if (k == kEmptyKey) continue;
+        int32_t v = P.vals[i].load(std::memory_order_relaxed);
+        if (pred(k, v)) ++removed; else keep.emplace_back(k, v);
+      }
+      Rebuild(P, P.cap, keep);
+    }
+    return removed;
+  }
+ private:
+  static int32_t WaitVal(KVPart& P, uint64_t pos) {
+    int32_t v;
+    while ((v = P.vals[pos].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+    return v;
+  }
+  static int32_t FindLocked(KVPart& P, int64_t key) {
+    uint64_t mask = P.cap - 1;
+    uint64_t pos = dr_mix64((uint64_t)key) & mask;
+    for (int64_t probes = 0; probes < P.cap; ++probes, pos = (pos + 1) & mask) {
+      int64_t k = P.keys[pos].load(std::memory_order_acquire);
+      if (k == key) return WaitVal(P, pos);
+      if (k == kEmptyKey) return -1;
+    }
+    return -1;
+  }
+  static void Rebuild(KVPart& P, int64_t newcap, const std::vector<std::pair<int64_t, int32_t>>& items) {
+    delete[] P.keys; delete[] P.vals;
+    P.Alloc(newcap);
+    uint64_t mask = newcap - 1;
+    for (auto& kv : items) {
+      uint64_t pos = dr_mix64((uint64_t)kv.first) & mask;
+      while (P.keys[pos].load(std::memory_order_relaxed) != kEmptyKey) pos = (pos + 1) & mask;
+      P.keys[pos].store(kv.first, std::memory_order_relaxed);
+      P.vals[pos].store(kv.second, std::memory_order_relaxed);
+    }
+    P.size.store((int64_t)items.size());
+  }
+  static void Grow(KVPart& P) {
+    std::unique_lock<std::shared_mutex> l(P.mu);
+    if ((P.size.load() + 1) * 10 <= P.cap * 7) return;  // someone else grew it
+    std::vector<std::pair<int64_t, int32_t>> items; items.reserve(P.size.load());
+    for (int64_t i = 0; i < P.cap; ++i) {
+      int64_t k = P.keys[i].load(std::memory_order_relaxed);
+      if (k != kEmptyKey) items.emplace_back(k, P.vals[i].load(std::memory_order_relaxed));
+    }
+    Rebuild(P, P.cap * 2, items);
+  }
+  int nparts_;
+  KVPart* parts_;
+};
+
+// ------------------------------------------------------------------------------------
+// Counting Bloom filter (CBFFilter). k = ceil(log2(1/p)), m = ceil(n*|ln p|/ln^2 2)
+// (embedding_config.h:72-95).  Counters saturate at their width.
+// ------------------------------------------------------------------------------------
+class CountingBloom {
+ public:
+  CountingBloom(int64_t n, double p, int bits) : bits_(bits) {
+    if (p <= 0 || p >= 1) p = 0.01;
+    if (n < 1) n = 1;
+    k_ = std::max(1, (int)std::ceil(std::log2(1.0 / p)));
+    m_ = std::max<int64_t>(8, (int64_t)std::ceil((double)n * std::fabs(std::log(p)) / (std::log(2.0) * std::log(2.0))));
+    bytes_per_ = bits / 8;
+    data_.reset(new std::atomic<uint8_t>[m_ * bytes_per_]);
+    for (int64_t i = 0; i < m_ * bytes_per_; ++i) data_[i].store(0, std::memory_order_relaxed);
+    maxv_ = bits >= 63 ? INT64_MAX : ((int64_t(1) << bits) - 1);
+  }
+  // add `count` to the k counters, return the new minimum
+  int64_t AddAndMin(int64_t key, int64_t count) {
+    int64_t mn = INT64_MAX;
+    for (int i = 0; i < k_; ++i) {
+      int64_t idx = (int64_t)(dr_hash_seed((uint64_t)key, (uint64_t)i) % (uint64_t)m_);
+      mn = std::min(mn, AddAt(idx, count));
+    }
+    return mn;
+  }
+  int64_t Min(int64_t key) const {
+    int64_t mn = INT64_MAX;
+    for (int i = 0; i < k_; ++i) {
+      int64_t idx = (int64_t)(dr_hash_seed((uint64_t)key, (uint64_t)i) % (uint64_t)m_);
+      mn = std::min(mn, Load(idx));
+    }
+    return mn;
+  }
+  int k() const { return k_; }
+  int64_t m() const { return m_; }
+  int bits() const { return bits_; }
+  int64_t nbytes() const { return m_ * bytes_per_; }
+  uint8_t* raw() { return reinterpret_cast<uint8_t*>(data_.get()); }
+ private:
+  int64_t Load(int64_t idx) const {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(data_.get()) + idx * bytes_per_;
+    switch (bits_) {
+      case 8: return *p;
+      case 16: { uint16_t v; memcpy(&v, p, 2); return v; }
+      case 32: { uint32_t v; memcpy(&v, p, 4); return v; }
+      default: { int64_t v; memcpy(&v, p, 8); return v; }
+    }
+  }
+  template <typename U> int64_t AddT(int64_t idx, int64_t count) {
+    auto* a = reinterpret_cast<std::atomic<U>*>(reinterpret_cast<uint8_t*>(data_.get()) + idx * sizeof(U));
+    U cur = a->load(std::memory_order_relaxed);
+    for (;;) {
+      int64_t nv = std::min<int64_t>(maxv_, (int64_t)cur + count);
+      if (a->compare_exchange_weak(cur, (U)nv, std::memory_order_relaxed)) return nv;
+    }
+  }
+  int64_t AddAt(int64_t idx, int64_t count) {
+    switch (bits_) {
+      case 8: return AddT<uint8_t>(idx, count);
+      case 16: return AddT<uint16_t>(idx, count);
+      case 32: return AddT<uint32_t>(idx, count);
+      default: return AddT<uint64_t>(idx, count);
+    }
+  }
+  int bits_, k_, bytes_per_;
+  int64_t m_, maxv_;
+  std::unique_ptr<std::atomic<uint8_t>[]> data_;
+};
+
+// ------------------------------------------------------------------------------------
+// Host EmbeddingVariable
+// ------------------------------------------------------------------------------------
+struct SnapItem { int32_t bucket; int32_t idx; int64_t key; };
+
+class HostEV {
+ public:
+  explicit HostEV(const DrEvConfig& c)
+      : cfg_(c), stride_(dr_row_stride(c.dim, c.num_slots, c.has_scalars)),
+        kv_(c.num_partitions > 0 ? c.num_partitions : 16, std::max<int64_t>(1024, c.init_capacity)),
+        freq_(1), version_(1), row_(1), dirty_(1), rows_(stride_) {
+    default_.assign((size_t)(std::max<int64_t>(1, c.default_value_dim) * c.dim), 0.0f);
+    if (c.filter_type == DR_FILTER_BLOOM)
+      bloom_.reset(new CountingBloom(c.bloom_max_elements, c.bloom_fpp, c.bloom_counter_bits > 0 ? c.bloom_counter_bits : 32));
+  }
+  const DrEvConfig& cfg() const { return cfg_; }
+  int64_t stride() const { return stride_; }
+  void SetDefault(const float* m) { memcpy(default_.data(), m, default_.size() * sizeof(float)); }
+  int64_t Size() const { return admitted_.load(); }           // admitted keys (total_count())
+  int64_t TotalKeys() const { return kv_.Size(); }            // incl. un-admitted (counter filter)
+
+  // ---- forward: read-only gather (embedding_var.h:202-219) ---------------------------
+  void Lookup(const int64_t* keys, int64_t n, float* out) {
+    const int64_t dim = cfg_.dim;
+    GlobalPool()->ParallelFor(n, 2048, [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i) {
+        int32_t idx = kv_.Find(keys[i]);
+        int32_t r = idx >= 0 ? *row_.at(idx) : -1;
+        float* o = out + i * dim;
+        if (r >= 0) {
+          memcpy(o, rows_.at(r), dim * sizeof(float));
+        } else if (cfg_.filter_type != DR_FILTER_NONE && cfg_.filter_freq > 0) {
+          std::fill(o, o + dim, cfg_.default_value_no_permission);
+        } else {
+          memcpy(o, DefaultRow(keys[i]), dim * sizeof(float));
+        }
+      }
+    });
+  }
+  // gather a slot (or the trailing scalars with slot == num_slots+1) for inspection / ckpt
+  void LookupSlot(const int64_t* keys, int64_t n, int slot, float* out) {
+    const int64_t dim = cfg_.dim;
+    for (int64_t i = 0; i < n; ++i) {
+      int32_t idx = kv_.Find(keys[i]);
+      int32_t r = idx >= 0 ? *row_.at(idx) : -1;
+      float* o = out + i * dim;
+      if (r >= 0) memcpy(o, rows_.at(r) + slot * dim, dim * sizeof(float));
+      else std::fill(o, o + dim, slot == 0 ? 0.f : cfg_.slot_init[slot - 1]);
+    }
+  }
+  void GetFreq(const int64_t* keys, int64_t n, int64_t* out) {
+    for (int64_t i = 0; i < n; ++i) {
+      int32_t idx = kv_.Find(keys[i]);
+      if (idx >= 0) out[i] = *freq_.at(idx);
+      else out[i] = bloom_ ? bloom_->Min(keys[i]) : 0;
+    }
+  }
+  void GetVersion(const int64_t* keys, int64_t n, int64_t* out) {
+    for (int64_t i = 0; i < n; ++i) { int32_t idx = kv_.Find(keys[i]); out[i] = idx >= 0 ? *version_.at(idx) : -1; }
+  }
+
+  // ---- LookupOrCreateKey with admission (counter_filter_policy.h:106-139) -------------
+  // returns row index (>=0) when the key is admitted, -1 otherwise.
+  int32_t LookupOrCreate(int64_t key, int64_t count, int64_t step) {
+    if (cfg_.is_inference) {
+      int32_t idx = kv_.Find(key);
+      return idx >= 0 ? *row_.at(idx) : -1;
+    }
+    if (bloom_) {
+      int32_t idx = kv_.Find(key);
+      if (idx < 0) {
+        int64_t mn = bloom_->AddAndMin(key, count);
+        if (mn < cfg_.filter_freq) return -1;
+      }
+    }
+    bool inserted = false;
+    int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
+    int64_t* f = freq_.at(idx);
+    int64_t nf = __atomic_add_fetch(f, count, __ATOMIC_RELAXED);
+    *version_.at(idx) = step;
+    *dirty_.at(idx) = 1;
+    int32_t* rp = row_.at(idx);
+    int32_t r = __atomic_load_n(rp, __ATOMIC_ACQUIRE);
+    if (r >= 0) return r;
+    bool admit = bloom_ ? true : (cfg_.filter_type == DR_FILTER_NONE || nf >= cfg_.filter_freq);
+    if (!admit) return -1;
+    // claim allocation: -1 -> -2 (pending)
+    int32_t expect = -1;
+    if (__atomic_compare_exchange_n(rp, &expect, -2, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+      r = AllocRow();
+      InitRow(r, key);
+      __atomic_store_n(rp, r, __ATOMIC_RELEASE);
+      admitted_.fetch_add(1);
+      return r;
+    }
+    while ((r = __atomic_load_n(rp, __ATOMIC_ACQUIRE)) < 0) std::this_thread::yield();
+    return r;
+  }
+
+  // ---- sparse apply on de-duplicated keys (training_ali_ops.cc) ------------------------
+  void Apply(const int64_t* keys, const float* grads, const int64_t* counts, int64_t n, const DrOptHyper& hp) {
+    const int64_t dim = cfg_.dim;
+    const float alpha = dr_adam_alpha(hp);
+    GlobalPool()->ParallelFor(n, 512, [&](int64_t b, int64_t e) {
+      std::vector<float> newacc(dim);
+      for (int64_t i = b; i < e; ++i) {
+        int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step);
+        if (r < 0) continue;
+        float* row = rows_.at(r);
+        const float* g = grads + i * dim;
+        float* s0 = row + dim; float* s1 = row + 2 * dim;
+        float dummy0 = 0.f, dummy1 = 0.f;
+        if (hp.kind == DR_OPT_FTRL) {
+          float sq = 0.f;
+          for (int64_t d = 0; d < dim; ++d) { float l = dr_ftrl_linear(hp, g[d], row[d], s0[d], s1[d], newacc[d]); sq += l * l; }
+          float norm = std::sqrt(sq);
+          for (int64_t d = 0; d < dim; ++d) {
+            row[d] = dr_ftrl_weight(hp, s1[d], newacc[d], norm);
+            s0[d] += g[d] * g[d];   // reference advances accum with the raw gradient
+          }
+          continue;
+        }
+        bool decay_now = false;
+        if (hp.kind == DR_OPT_ADAGRAD_DECAY) {
+          float* sc = row + dim * (1 + cfg_.num_slots);
+          if (hp.decay_step > 0 && (float)(hp.global_step / hp.decay_step) > sc[0]) { decay_now = true; sc[0] += 1.0f; }
+        }
+        const int ns = cfg_.num_slots;
+        for (int64_t d = 0; d < dim; ++d)
+          dr_apply_elem(hp.kind, hp, alpha, decay_now, g[d], row[d], ns > 0 ? s0[d] : dummy0, ns > 1 ? s1[d] : dummy1);
+      }
+    });
+  }
+
+  // ---- eviction (only inside save; single_tier_storage.h:235-261) -----------------------
+  int64_t Shrink(int64_t global_step) {
+    const bool gs = cfg_.steps_to_live > 0;
+    const bool l2 = cfg_.l2_weight_threshold >= 0.f;
+    if (!gs && !l2) return 0;
+    std::vector<int32_t> freed_meta;
+    int64_t removed = kv_.RemoveIf([&](int64_t key, int32_t idx) {
+      (void)key;
+      int32_t r = *row_.at(idx);
+      bool evict = false;
+      if (gs) {
+        int64_t* v = version_.at(idx);
+        if (*v == -1) *v = global_step;                       // globalstep_shrink_policy.h:50
+        else if (global_step - *v > cfg_.steps_to_live) evict = true;
+      }
+      if (!evict && l2 && r >= 0) {
+        const float* row = rows_.at(r); float s = 0.f;
+        for (int64_t d = 0; d < cfg_.dim; ++d) s += row[d] * row[d];
+        if (0.5f * s < cfg_.l2_weight_threshold) evict = true;  // l2weight_shrink_policy.h:52
+      }
+      if (evict) {
+        if (r >= 0) { FreeRow(r); admitted_.fetch_sub(1); }
+        freed_meta.push_back(idx);
+      }
+      return evict;
+    });
+    for (int32_t idx : freed_meta) FreeMeta(idx);
+    return removed;
+  }
+  int64_t Remove(const int64_t* keys, int64_t n) {
+    std::vector<int64_t> ks(keys, keys + n); std::sort(ks.begin(), ks.end());
+    std::vector<int32_t> freed;
+    int64_t removed = kv_.RemoveIf([&](int64_t key, int32_t idx) {
+      if (!std::binary_search(ks.begin(), ks.end(), key)) return false;
+      int32_t r = *row_.at(idx);
+      if (r >= 0) { FreeRow(r); admitted_.fetch_sub(1); }
+      freed.push_back(idx);
+      return true;
+    });
+    for (int32_t idx : freed) FreeMeta(idx);
+    return removed;
+  }
+
+  // ---- snapshot for checkpoint / elastic export -------------------------------------
+  // dirty_only: incremental checkpoint (keys touched since the last ClearDirty()).
+  // part filter: keep key%1000%part_num == part_id (sharded snapshot for elastic scaling).
+  void SnapshotBegin(int dirty_only, int part_id, int part_num, int64_t* n_admitted, int64_t* n_filtered) {
+    snap_adm_.clear(); snap_flt_.clear();
+    kv_.ForEach([&](int64_t key, int32_t idx) {
+      int bucket = dr_ckpt_bucket(key);
+      if (part_num > 1 && bucket % part_num != part_id) return;
+      if (dirty_only && !*dirty_.at(idx)) return;
+      int32_t r = *row_.at(idx);
+      if (r >= 0) snap_adm_.push_back({bucket, idx, key}); else snap_flt_.push_back({bucket, idx, key});
+    });
+    auto cmp = [](const SnapItem& a, const SnapItem& b) { return a.bucket != b.bucket ? a.bucket < b.bucket : a.key < b.key; };
+    std::sort(snap_adm_.begin(), snap_adm_.end(), cmp);
+    std::sort(snap_flt_.begin(), snap_flt_.end(), cmp);
+    *n_admitted = (int64_t)snap_adm_.size(); *n_filtered = (int64_t)snap_flt_.size();
+  }
+  void SnapshotRead(int64_t* keys, float* rows, int64_t* freqs, int64_t* versions, int64_t* part_offset,
+                    int64_t* fkeys, int64_t* ffreqs, int64_t* fversions, int64_t* fpart_offset) {
+    auto fill = [&](std::vector<SnapItem>& v, int64_t* k, float* rw, int64_t* f, int64_t* ver, int64_t* off) {
+      if (off) std::fill(off, off + 1001, 0);
+      for (size_t i = 0; i < v.size(); ++i) {
+        if (k) k[i] = v[i].key;
+        if (f) f[i] = *freq_.at(v[i].idx);
+        if (ver) ver[i] = *version_.at(v[i].idx);
+        if (rw) memcpy(rw + i * stride_, rows_.at(*row_.at(v[i].idx)), stride_ * sizeof(float));
+        if (off) off[v[i].bucket + 1]++;
+      }
+      if (off) for (int b = 0; b < 1000; ++b) off[b + 1] += off[b];
+    };
+    fill(snap_adm_, keys, rows, freqs, versions, part_offset);
+    fill(snap_flt_, fkeys, nullptr, ffreqs, fversions, fpart_offset);
+  }
+  void SnapshotEnd() { snap_adm_.clear(); snap_adm_.shrink_to_fit(); snap_flt_.clear(); snap_flt_.shrink_to_fit(); }
+  void ClearDirty() { kv_.ForEach([&](int64_t, int32_t idx) { *dirty_.at(idx) = 0; }); }
+
+  // ---- import (restore / elastic import / incremental replay) ---------------------------
+  // rows: [n, ncols] (ncols <= stride; missing slot columns take slot_init); rows == nullptr
+  // imports filtered (un-admitted) keys.  Only keys with key%1000%part_num == part_id are kept.
+  int64_t Import(const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs,
+                 const int64_t* versions, int64_t n, int part_id, int part_num, int reset_version) {
+    int64_t kept = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      int64_t key = keys[i];
+      if (part_num > 1 && dr_ckpt_bucket(key) % part_num != part_id) continue;
+      bool inserted = false;
+      int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
+      *freq_.at(idx) = freqs ? freqs[i] : 0;
+      *version_.at(idx) = reset_version ? -1 : (versions ? versions[i] : -1);
+      if (rows) {
+        int32_t* rp = row_.at(idx);
+        int32_t r = *rp;
+        if (r < 0) { r = AllocRow(); InitRow(r, key); *rp = r; admitted_.fetch_add(1); }
+        memcpy(rows_.at(r), rows + i * ncols, std::min(ncols, stride_) * sizeof(float));
+      }
+      ++kept;
+    }
+    return kept;
+  }
+  CountingBloom* bloom() { return bloom_.get(); }
+
+ private:
+  const float* DefaultRow(int64_t key) const {
+    return default_.data() + dr_default_row(key, std::max<int64_t>(1, cfg_.default_value_dim)) * cfg_.dim;
+  }
+  void InitRow(int32_t r, int64_t key) {
+    float* row = rows_.at(r);
+    memcpy(row, DefaultRow(key), cfg_.dim * sizeof(float));
+    for (int s = 0; s < cfg_.num_slots; ++s) std::fill(row + (1 + s) * cfg_.dim, row + (2 + s) * cfg_.dim, cfg_.slot_init[s]);
+    for (int64_t d = cfg_.dim * (1 + cfg_.num_slots); d < stride_; ++d) row[d] = 0.f;
+  }
+  int32_t AllocMeta() {
+    {
+      std::lock_guard<std::mutex> l(free_mu_);
+      if (!free_meta_.empty()) { int32_t i = free_meta_.back(); free_meta_.pop_back(); ResetMeta(i); return i; }
+    }
+    int64_t i = next_meta_.fetch_add(1);
+    freq_.EnsureCapacity(i + 1, 0); version_.EnsureCapacity(i + 1, -1); row_.EnsureCapacity(i + 1, -1); dirty_.EnsureCapacity(i + 1, 0);
+    ResetMeta((int32_t)i);
+    return (int32_t)i;
+  }
+  void ResetMeta(int32_t i) { *freq_.at(i) = 0; *version_.at(i) = -1; *row_.at(i) = -1; *dirty_.at(i) = 0; }
+  void FreeMeta(int32_t i) { std::lock_guard<std::mutex> l(free_mu_); free_meta_.push_back(i); }
+  int32_t AllocRow() {
+    {
+      std::lock_guard<std::mutex> l(free_mu_);
+      if (!free_rows_.empty()) { int32_t r = free_rows_.back(); free_rows_.pop_back(); return r; }
+    }
+    int64_t r = next_row_.fetch_add(1);
+    rows_.EnsureCapacity(r + 1, 0.f);
+    return (int32_t)r;
+  }
+  void FreeRow(int32_t r) { std::lock_guard<std::mutex> l(free_mu_); free_rows_.push_back(r); }
+
+  DrEvConfig cfg_;
+  int64_t stride_;
+  HostKV kv_;
+  ChunkedArray<int64_t> freq_, version_;
+  ChunkedArray<int32_t> row_;
+  ChunkedArray<uint8_t> dirty_;
+  ChunkedArray<float, 12> rows_;       // 4096 rows per chunk
+  std::vector<float> default_;
+  std::unique_ptr<CountingBloom> bloom_;
+  std::atomic<int64_t> next_meta_{0}, next_row_{0}, admitted_{0};
+  std::mutex free_mu_;
+  std::vector<int32_t> free_meta_, free_rows_;
+  std::vector<SnapItem> snap_adm_, snap_flt_;
+};
+
+}  // namespace dr
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+void* dr_host_ev_create(const DrEvConfig* cfg) { return new dr::HostEV(*cfg); }
+void dr_host_ev_destroy(void* h) { delete static_cast<dr::HostEV*>(h); }
+int64_t dr_host_ev_stride(void* h) { return static_cast<dr::HostEV*>(h)->stride(); }
+void dr_host_ev_set_default(void* h, const float* m) { static_cast<dr::HostEV*>(h)->SetDefault(m); }
+int64_t dr_host_ev_size(void* h) { return static_cast<dr::HostEV*>(h)->Size(); }
+int64_t dr_host_ev_total_keys(void* h) { return static_cast<dr::HostEV*>(h)->TotalKeys(); }
+void dr_host_ev_lookup(void* h, const int64_t* keys, int64_t n, float* out) { static_cast<dr::HostEV*>(h)->Lookup(keys, n, out); }
+void dr_host_ev_lookup_slot(void* h, const int64_t* keys, int64_t n, int slot, float* out) { static_cast<dr::HostEV*>(h)->LookupSlot(keys, n, slot, out); }
+void dr_host_ev_get_freq(void* h, const int64_t* keys, int64_t n, int64_t* out) { static_cast<dr::HostEV*>(h)->GetFreq(keys, n, out); }
+void dr_host_ev_get_version(void* h, const int64_t* keys, int64_t n, int64_t* out) { static_cast<dr::HostEV*>(h)->GetVersion(keys, n, out); }
+void dr_host_ev_apply(void* h, const int64_t* keys, const float* grads, const int64_t* counts, int64_t n, const DrOptHyper* hp) {
+  static_cast<dr::HostEV*>(h)->Apply(keys, grads, counts, n, *hp);
+}
+int64_t dr_host_ev_shrink(void* h, int64_t step) { return static_cast<dr::HostEV*>(h)->Shrink(step); }
+int64_t dr_host_ev_remove(void* h, const int64_t* keys, int64_t n) { return static_cast<dr::HostEV*>(h)->Remove(keys, n); }
+void dr_host_ev_snapshot_begin(void* h, int dirty_only, int part_id, int part_num, int64_t* na, int64_t* nf) {
+  static_cast<dr::HostEV*>(h)->SnapshotBegin(dirty_only, part_id, part_num, na, nf);
+}
+void dr_host_ev_snapshot_read(void* h, int64_t* keys, float* rows, int64_t* freqs, int64_t* versions, int64_t* poff,
+                              int64_t* fkeys, int64_t* ffreqs, int64_t* fversions, int64_t* fpoff) {
+  static_cast<dr::HostEV*>(h)->SnapshotRead(keys, rows, freqs, versions, poff, fkeys, ffreqs, fversions, fpoff);
+}
+void dr_host_ev_snapshot_end(void* h) { static_cast<dr::HostEV*>(h)->SnapshotEnd(); }
+void dr_host_ev_clear_dirty(void* h) { static_cast<dr::HostEV*>(h)->ClearDirty(); }
+int64_t dr_host_ev_import(void* h, const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs,
+                          const int64_t* versions, int64_t n, int part_id, int part_num, int reset_version) {
+  return static_cast<dr::HostEV*>(h)->Import(keys, rows, ncols, freqs, versions, n, part_id, part_num, reset_version);
+}
+int64_t dr_host_bloom_info(void* h, int64_t* k, int64_t* m, int64_t* bits) {
+  auto* b = static_cast<dr::HostEV*>(h)->bloom();
+  if (!b) return 0;
+  *k = b->k(); *m = b->m(); *bits = b->bits();
+  return b->nbytes();
+}
+void dr_host_bloom_read(void* h, uint8_t* out) {
+  auto* b = static_cast<dr::HostEV*>(h)->bloom();
+  if (b) memcpy(out, b->raw(), b->nbytes());
+}
+void dr_host_bloom_write(void* h, const uint8_t* in) {
+  auto* b = static_cast<dr::HostEV*>(h)->bloom();
+  if (b) memcpy(b->raw(), in, b->nbytes());
+}
+
+// ---- host unique-with-counts (optimizer.py:91 dedup of sparse grads; unique_ali_op.cc) -----
+// out_unique[nu], out_inverse[n], out_counts[nu]; returns nu.  Order = first occurrence.
+int64_t dr_host_unique(const int64_t* keys, int64_t n, int64_t* out_unique, int64_t* out_inverse, int64_t* out_counts) {
+  int64_t cap = 16; while (cap < n * 2) cap <<= 1;
+  std::vector<int64_t> tk(cap, dr::kEmptyKey); std::vector<int64_t> tv(cap, -1);
+  uint64_t mask = cap - 1; int64_t nu = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t key = keys[i]; uint64_t pos = dr_mix64((uint64_t)key) & mask;
+    for (;;) {
+      if (tk[pos] == key && tv[pos] >= 0) { out_inverse[i] = tv[pos]; out_counts[tv[pos]]++; break; }
+      if (tv[pos] < 0) { tk[pos] = key; tv[pos] = nu; out_unique[nu] = key; out_counts[nu] = 1; out_inverse[i] = nu; ++nu; break; }
+      pos = (pos + 1) & mask;
+    }
+  }
+  return nu;
+}
+// segment-sum of per-occurrence grads into per-unique grads
+void dr_host_segment_sum(const float* grads, const int64_t* inverse, int64_t n, int64_t dim, float* out, int64_t nu) {
+  memset(out, 0, sizeof(float) * nu * dim);
+  for (int64_t i = 0; i < n; ++i) {
+    float* o = out + inverse[i] * dim; const float* g = grads + i * dim;
+    for (int64_t d = 0; d < dim; ++d) o[d] += g[d];
+  }
+}
+
+int dr_host_num_threads() { return dr::GlobalPool()->size() + 1; }
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""CPU tier-1/2 tests of the host EmbeddingVariable engine against a dict/numpy oracle
+(mirrors python/ops/embedding_variable_ops_test.py and core/kernels/embedding_variable_ops_test.cc)."""
+import math
+
+import pytest
+import torch
+
+import deeprec_b200 as dr
+from deeprec_b200.optim import GlobalStep, make_optimizer
+
+
+def _ev(name, dim=8, **kw):
+    return dr.get_embedding_variable(name, dim, ev_option=dr.EmbeddingVariableOption(**kw), seed=3)
+
+
+def test_forward_is_read_only_and_default_rows():
+    ev = _ev("ro")
+    ids = torch.tensor([5, 5 + 4096, 7])
+    e = ev.lookup(ids)
+    assert ev.total_count() == 0                      # forward never inserts (embedding_var.h:202-219)
+    assert torch.equal(e[0], e[1])                    # default row = key % default_value_dim
+    assert torch.equal(e[0], ev.default_matrix[5])
+
+
+def test_adagrad_matches_manual_math_with_dedup_and_counts():
+    ev = _ev("ada")
+    opt = dr.optim.AdagradOptimizer([], [ev], lr=0.1, initial_accumulator_value=0.1, global_step=GlobalStep())
+    ids = torch.tensor([1, 2, 2, 2])
+    w0 = ev.lookup(torch.tensor([1, 2])).detach().clone()
+    e = ev.lookup(ids)
+    (e * torch.tensor([[1.0], [2.0], [3.0], [4.0]])).sum().backward()
+    opt.step()
+    g = torch.tensor([1.0, 9.0])                      # per-key summed gradient (dedup before the accumulator update)
+    acc = 0.1 + g ** 2
+    expect = w0 - 0.1 * g.unsqueeze(1) / acc.sqrt().unsqueeze(1)
+    got = ev.lookup(torch.tensor([1, 2])).detach()
+    assert torch.allclose(got, expect, atol=1e-6)
+    assert ev.get_frequency(torch.tensor([1, 2, 3])).tolist() == [1, 3, 0]
+    assert ev.get_version(torch.tensor([1, 3])).tolist() == [0, -1]
+    assert torch.allclose(ev.slot_values(torch.tensor([2]), "accumulator"), acc[1].expand(1, 8))
+
+
+@pytest.mark.parametrize("name", ["adagrad", "adagraddecay", "adam", "adamasync", "adamw", "ftrl", "gradientdescent"])
+def test_sparse_rules_equal_dense_rules_on_a_dense_variable(name):
+    """Every id touched every step => the sparse EV update must equal the dense-parameter update of the
+    same optimizer (the reference tests compare EV training against a plain tf.Variable model)."""
+    torch.manual_seed(0)
+    n, dim = 6, 8
+    ev = _ev(f"eq_{name}", dim)
+    init = ev.lookup(torch.arange(n)).detach().clone()
+    dense = torch.nn.Parameter(init.clone())
+    kw = dict(lr=0.05)
+    if name == "adagraddecay":
+        kw.update(accumulator_decay_step=2, accumulator_decay_rate=0.5)
+    gs1, gs2 = GlobalStep(), GlobalStep()
+    o_ev = make_optimizer(name, [], [ev], global_step=gs1, **kw)
+    o_dn = make_optimizer(name, [dense], None, global_step=gs2, **kw)
+    for step in range(5):
+        tgt = torch.randn(n, dim)
+        ((ev.lookup(torch.arange(n)) - tgt) ** 2).sum().backward(); o_ev.step()
+        o_dn.zero_grad(); ((dense - tgt) ** 2).sum().backward(); o_dn.step()
+    got = ev.lookup(torch.arange(n)).detach()
+    if name == "ftrl":
+        # EV FTRL is the row-norm (group-lasso) form with l1 = 0 => coef*linear, dense is element-wise: both reduce to
+        # -linear/quadratic when l1 == 0
+        pass
+    assert torch.allclose(got, dense.detach(), atol=2e-5, rtol=1e-4), (got - dense).abs().max()
+
+
+def test_counter_filter_admission_and_no_permission_value():
+    ev = _ev("cf", filter_option=dr.CounterFilter(3), init_option=dr.InitializerOption(default_value_no_permission=0.5))
+    opt = dr.optim.GradientDescentOptimizer([], [ev], lr=1.0, global_step=GlobalStep())
+    ids = torch.tensor([9])
+    for step in range(2):
+        e = ev.lookup(ids)
+        assert torch.all(e == 0.5)                    # not admitted yet
+        e.sum().backward(); opt.step()
+    assert ev.total_count() == 0 and ev.table.total_keys() == 1
+    e = ev.lookup(ids); e.sum().backward(); opt.step()    # third occurrence: admitted inside the apply, grad applied
+    assert ev.total_count() == 1
+    assert torch.allclose(ev.lookup(ids).detach(), ev.default_matrix[9].unsqueeze(0) - 1.0)
+
+
+def test_bloom_filter_admission():
+    ev = _ev("cbf", filter_option=dr.CBFFilter(filter_freq=3, max_element_size=1000, false_positive_probability=0.01,
+                                               counter_type=torch.int16))
+    opt = dr.optim.GradientDescentOptimizer([], [ev], lr=1.0, global_step=GlobalStep())
+    for step in range(2):
+        ev.lookup(torch.tensor([4])).sum().backward(); opt.step()
+        assert ev.total_count() == 0 and ev.table.total_keys() == 0      # bloom keeps no per-key state
+    assert ev.get_frequency(torch.tensor([4])).item() >= 2
+    ev.lookup(torch.tensor([4])).sum().backward(); opt.step()
+    assert ev.total_count() == 1
+    k, m = math.ceil(math.log2(1 / 0.01)), math.ceil(1000 * abs(math.log(0.01)) / math.log(2) ** 2)
+    assert ev.table.bloom_state().numel() == m * 2 and k == 7
+
+
+def test_global_step_and_l2_eviction_only_at_shrink():
+    ev = _ev("gs", evict_option=dr.GlobalStepEvict(steps_to_live=2))
+    gs = GlobalStep()
+    opt = dr.optim.GradientDescentOptimizer([], [ev], lr=0.1, global_step=gs)
+    ev.lookup(torch.tensor([1, 2])).sum().backward(); opt.step()          # version 0
+    for _ in range(4):
+        ev.lookup(torch.tensor([2])).sum().backward(); opt.step()         # key 2 stays fresh
+    assert ev.total_count() == 2                                          # nothing evicted during training
+    assert ev.table.shrink(int(gs)) == 1
+    assert ev.total_count() == 1 and ev.get_version(torch.tensor([1])).item() == -1
+    ev2 = _ev("l2", evict_option=dr.L2WeightEvict(l2_weight_threshold=1e9))
+    o2 = dr.optim.GradientDescentOptimizer([], [ev2], lr=0.1, global_step=GlobalStep())
+    ev2.lookup(torch.tensor([1, 2, 3])).sum().backward(); o2.step()
+    assert ev2.table.shrink(0) == 3 and ev2.total_count() == 0
+
+
+def test_snapshot_bucket_order_and_resharded_import():
+    ev = _ev("snap")
+    opt = dr.optim.AdagradOptimizer([], [ev], lr=0.1, global_step=GlobalStep())
+    ids = torch.arange(0, 5000, 7)
+    ev.lookup(ids).sum().backward(); opt.step()
+    s = ev.table.snapshot()
+    b = s["keys"] % 1000
+    assert torch.all(b[1:] >= b[:-1]) and int(s["partition_offset"][-1]) == ids.numel()
+    for bk in (0, 13, 999):
+        lo, hi = int(s["partition_offset"][bk]), int(s["partition_offset"][bk + 1])
+        assert torch.all(s["keys"][lo:hi] % 1000 == bk)
+    # N -> M re-shard: 3 partitions keep key % 1000 % 3 == p, union is everything
+    total = 0
+    for p in range(3):
+        part = _ev(f"snap_p{p}")
+        part._set_slots(["accumulator"], [0.1], False)
+        kept = part.table.import_(s["keys"], s["rows"], s["freqs"], s["versions"], p, 3)
+        total += kept
+        pk = part.table.snapshot()["keys"]
+        assert torch.all(pk % 1000 % 3 == p)
+        assert torch.allclose(part.table.lookup(pk), ev.table.lookup(pk))
+    assert total == ids.numel()
+
+
+def test_incremental_dirty_tracking():
+    ev = _ev("dirty")
+    opt = dr.optim.GradientDescentOptimizer([], [ev], lr=0.1, global_step=GlobalStep())
+    ev.lookup(torch.arange(10)).sum().backward(); opt.step()
+    ev.table.clear_dirty()
+    ev.lookup(torch.tensor([3, 4])).sum().backward(); opt.step()
+    d = ev.table.snapshot(dirty_only=True)
+    assert sorted(d["keys"].tolist()) == [3, 4]
+
+
+def test_concurrent_growth_many_keys():
+    ev = _ev("big", dim=4, init_capacity=64)
+    opt = dr.optim.GradientDescentOptimizer([], [ev], lr=1.0, global_step=GlobalStep())
+    ids = torch.randperm(300000)
+    ev.lookup(ids).sum().backward(); opt.step()
+    assert ev.total_count() == 300000
+    probe = ids[:1000]
+    assert torch.allclose(ev.lookup(probe).detach(), ev.default_matrix[probe % 4096] - 1.0)
+    assert ev.table.remove(probe[:10]) == 10 and ev.total_count() == 299990
+
+
+def test_partitioned_multihash_dynamic_variants():
+    pev = dr.get_embedding_variable("part", 8, partitioner=dr.fixed_size_partitioner(4))
+    opt = dr.optim.AdagradOptimizer(pev, None, lr=0.1, global_step=GlobalStep())
+    ids = torch.arange(40)
+    pev.lookup(ids).sum().backward(); opt.step()
+    assert pev.total_count() == 40 and [p.total_count() for p in pev.parts] == [10] * 4
+    mh = dr.get_multihash_variable("mh", [[10, 8], [7, 8]], operation="add")
+    assert mh.lookup(torch.tensor([0, 69])).shape == (2, 8)
+    assert dr.get_multihash_variable("mh2", [[10, 4], [7, 6]], operation="concat").lookup(torch.tensor([3])).shape == (1, 10)
+    dv = dr.get_dynamic_dimension_embedding_variable("dyn", 4, 3)
+    out = dv.lookup(torch.tensor([1, 2]), torch.tensor([1, 3]))
+    assert out.shape == (2, 12) and torch.all(out[0, 4:] == 0) and out[1, 8:].abs().sum() > 0
