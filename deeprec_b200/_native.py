@@ -137,8 +137,19 @@ def cuda():
                 if not os.path.exists(path):
                     path = _build.build_cuda()
                 from . import _cuda_sigs
-                _CUDA = _cuda_sigs.bind(C.CDLL(path))
+                lib = _cuda_sigs.bind(C.CDLL(path))
+                lib.dr_cuda_set_device.argtypes, lib.dr_cuda_set_device.restype = [C.c_int], C.c_int
+                if torch.cuda.is_available():
+                    lib.dr_cuda_set_device(torch.cuda.current_device())
+                _CUDA = lib
     return _CUDA
+
+
+def set_device(index: int) -> None:
+    """The kernel library links its own static cudart: its current device must follow torch's."""
+    rc = cuda().dr_cuda_set_device(int(index))
+    if rc != 0:
+        raise RuntimeError(f"dr_cuda_set_device({index}) failed: {rc}")
 
 
 def ptr(t: torch.Tensor | None):

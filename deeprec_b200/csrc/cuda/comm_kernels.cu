@@ -1,0 +1,274 @@
+// NVLink 5 / NVSwitch peer-memory layer: symmetric buffers (CUDA IPC), device-side rank barrier, and the
+// fused compute+collective kernels of the model-parallel embedding / data-parallel dense step.
+//
+//   k_mp_lookup         id dispatch + hash probe (+admission/claim) + row gather in ONE kernel: the owner of a
+//                       table loads the requesters' id columns over NVLink (coalesced 8 B/sample P2P loads),
+//                       probes its table, and stores bf16 rows straight into each requester's feature-major
+//                       activation buffer (coalesced 32 B/sample P2P stores).  Replaces SOK's selectKernel ->
+//                       NCCL all2all(counts) -> D2H + cudaStreamSynchronize -> NCCL all2all(keys) -> get_insert ->
+//                       gather -> NCCL all2all(vectors) -> reorderKernel   (SURVEY §3.4, C2/C3/S1/S2/S3).
+//   k_mp_sparse_grad    sparse-gradient return + dedup: the owner pulls each requester's gradient columns over
+//                       NVLink and reduces them into the per-unique-key buffer with vectorised L2 atomics; the
+//                       row-wise optimizer (k_apply) follows on the same stream.  Replaces gatherExKernel ->
+//                       NCCL all2all(grads) -> unique -> unsorted_segment_sum -> sparse apply (C4/K10/K7).
+//   k_allreduce_apply   dense gradient all-reduce fused with the optimizer: every rank loads all peers' gradient
+//                       shards over NVLink in a fixed order (bitwise identical sums on all ranks), applies the
+//                       update rule and writes fp32 master weights in one pass.  Replaces Horovod ncclAllReduce +
+//                       separate Apply* op (C1/K9).
+//   k_rank_barrier      flag barrier over peer memory (st.release.sys / ld.acquire.sys), epoch kept on device so a
+//                       captured CUDA graph replays it.
+#include "table.cuh"
+
+using namespace drc;
+
+extern "C" {
+struct DrPeers {
+  void* ptr[16];     // ptr[r] = this buffer as mapped in the local address space for rank r
+};
+}
+
+namespace {
+
+constexpr int kMaxRanks = 16;
+constexpr int kMaxChannels = 16;
+
+// signals layout (per rank, symmetric): uint32 flags[kMaxChannels][kMaxRanks]; epochs[kMaxChannels] lives in LOCAL memory
+__global__ void k_rank_barrier(DrPeers sig, uint32_t* __restrict__ epochs, int channel, int rank, int world) {
+  __shared__ uint32_t epoch;
+  if (threadIdx.x == 0) { epoch = epochs[channel] + 1; epochs[channel] = epoch; }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < world) {
+    __threadfence_system();
+    uint32_t* remote = reinterpret_cast<uint32_t*>(sig.ptr[r]) + channel * kMaxRanks + rank;
+    st_release_sys(remote, epoch);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(sig.ptr[rank]) + channel * kMaxRanks + r;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) { __nanosleep(20); }
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Fused dispatch + probe + gather.  Item i = ((j * W + s) * B + b): j = local table, s = requesting rank, b = sample.
+// Block = 256 threads = 256 consecutive items (same (j, s) for whole warps when B % 32 == 0).
+// -----------------------------------------------------------------------------------------------------------------
+template <int LPR>   // lanes per row = dim / 4 (float4 per lane), power of two <= 32
+__global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restrict__ tables, const int32_t* __restrict__ table_map,
+                                                   const int32_t* __restrict__ table_global,   // [nl] global table id of local table j
+                                                   int nl, int W, int64_t B, int T, DrPeers ids_peers /* int64 [T][B] */,
+                                                   DrPeers emb_peers /* bf16 [T][B][D] */, int train,
+                                                   const int64_t* __restrict__ step_ptr, int32_t* __restrict__ pos_out,
+                                                   int64_t* __restrict__ ulist, int32_t* __restrict__ nunique, int64_t ulist_cap) {
+  __shared__ int32_t s_pos[256];
+  __shared__ int64_t s_key[256];
+  const int64_t n = (int64_t)nl * W * B;
+  (void)step_ptr;
+  for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
+    // ---- phase 1: one thread per key: peer load + probe / insert / admission bookkeeping / dedup claim
+    const int64_t i = base + threadIdx.x;
+    if (i < n) {
+      const int64_t b = i % B;
+      const int s = (int)((i / B) % W);
+      const int j = (int)(i / (B * W));
+      const int tg = table_global[j];
+      const DrDeviceTable& TB = tables[table_map[j]];
+      const int64_t key = reinterpret_cast<const int64_t*>(ids_peers.ptr[s])[(int64_t)tg * B + b];
+      int64_t pos;
+      if (!train || TB.is_inference) {
+        pos = table_find(TB, key);
+      } else {
+        bool inserted = false, skip = false;
+        if (TB.filter_type == DR_FILTER_BLOOM) {
+          pos = table_find(TB, key);
+          if (pos < 0) {
+            if (bloom_add_min(TB, key, 1u) < (uint32_t)TB.filter_freq) skip = true;
+            else pos = table_find_or_insert(TB, key, &inserted);
+          }
+        } else {
+          pos = table_find_or_insert(TB, key, &inserted);
+        }
+        if (!skip && pos < 0) TB.counters[CTR_OVERFLOW] = 1;
+        if (!skip && pos >= 0) {
+          if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
+          atomicAdd(&TB.freq[pos], 1);
+          TB.dirty[pos] = 1;
+          if (atomicCAS(&TB.tag[pos], -1, -2) == -1) {
+            int u = atomicAdd(nunique, 1);
+            if (u < ulist_cap) { ulist[u] = ((int64_t)table_map[j] << 40) | pos; TB.tag[pos] = u; }
+            else { TB.tag[pos] = -1; TB.counters[CTR_OVERFLOW] = 2; }
+          }
+        }
+      }
+      s_pos[threadIdx.x] = (int32_t)pos;
+      s_key[threadIdx.x] = key;
+      pos_out[i] = (int32_t)pos;
+    }
+    __syncthreads();
+    // ---- phase 2: LPR lanes per row copy fp32 row -> bf16 into the requester's buffer over NVLink
+    constexpr int ROWS_PER_IT = 256 / LPR;
+    const int lane = threadIdx.x % LPR;
+    for (int it = 0; it < LPR; ++it) {
+      const int li = it * ROWS_PER_IT + threadIdx.x / LPR;
+      const int64_t ii = base + li;
+      if (ii < n) {
+        const int64_t b = ii % B;
+        const int s = (int)((ii / B) % W);
+        const int j = (int)(ii / (B * W));
+        const int tg = table_global[j];
+        const DrDeviceTable& TB = tables[table_map[j]];
+        const float* src = table_read_ptr(TB, s_key[li], s_pos[li]);
+        float4 v = src ? *reinterpret_cast<const float4*>(src + 4 * lane)
+                       : make_float4(TB.no_permission, TB.no_permission, TB.no_permission, TB.no_permission);
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(emb_peers.ptr[s]) + ((int64_t)tg * B + b) * (4 * LPR) + 4 * lane;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Sparse-gradient pull + dedup: gsum[tag[pos_i]] += peer_demb[s][t][b][:]
+// -----------------------------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256) k_mp_sparse_grad(const DrDeviceTable* __restrict__ tables, const int32_t* __restrict__ table_map,
+                                                        const int32_t* __restrict__ table_global, int nl, int W, int64_t B,
+                                                        DrPeers demb_peers /* bf16 [T][B][D] */, const int32_t* __restrict__ pos,
+                                                        float* __restrict__ gsum) {
+  const int lane = threadIdx.x % LPR;
+  const int64_t n = (int64_t)nl * W * B;
+  const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x / LPR;
+  for (int64_t i = gid; i < n; i += gstride) {
+    const int32_t p = pos[i];
+    if (p < 0) continue;
+    const int64_t b = i % B;
+    const int s = (int)((i / B) % W);
+    const int j = (int)(i / (B * W));
+    const int32_t u = tables[table_map[j]].tag[p];
+    if (u < 0) continue;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(demb_peers.ptr[s]) + ((int64_t)table_global[j] * B + b) * (4 * LPR) + 4 * lane;
+    uint2 raw = *reinterpret_cast<const uint2*>(src);
+    float2 a = unpack_bf16x2(raw.x), c = unpack_bf16x2(raw.y);
+    red_add_v4_f32(gsum + (int64_t)u * (4 * LPR) + 4 * lane, a.x, a.y, c.x, c.y);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Dense all-reduce (one-shot over peer memory, fixed summation order) fused with the optimizer update.
+// -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_allreduce_apply(DrPeers grad_peers, int W, float* __restrict__ w, float* __restrict__ s0,
+                                                         float* __restrict__ s1, int64_t n4 /* n / 4 */, const DrOptHyper* __restrict__ hp_dev,
+                                                         float* __restrict__ reduced_out) {
+  DrOptHyper hp = {};
+  if (hp_dev) hp = *hp_dev;
+  const float alpha = hp_dev ? dr_adam_alpha(hp) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < W; ++r) {
+      int4 raw = ld_nc_v4(reinterpret_cast<const float4*>(grad_peers.ptr[r]) + i);
+      g.x += __int_as_float(raw.x); g.y += __int_as_float(raw.y); g.z += __int_as_float(raw.z); g.w += __int_as_float(raw.w);
+    }
+    if (reduced_out) reinterpret_cast<float4*>(reduced_out)[i] = g;
+    if (w) {
+      float4 wv = reinterpret_cast<float4*>(w)[i];
+      float4 a = s0 ? reinterpret_cast<float4*>(s0)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 b = s1 ? reinterpret_cast<float4*>(s1)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      dr_apply_elem(hp.kind, hp, alpha, false, g.x, wv.x, a.x, b.x);
+      dr_apply_elem(hp.kind, hp, alpha, false, g.y, wv.y, a.y, b.y);
+      dr_apply_elem(hp.kind, hp, alpha, false, g.z, wv.z, a.z, b.z);
+      dr_apply_elem(hp.kind, hp, alpha, false, g.w, wv.w, a.w, b.w);
+      reinterpret_cast<float4*>(w)[i] = wv;
+      if (s0) reinterpret_cast<float4*>(s0)[i] = a;
+      if (s1) reinterpret_cast<float4*>(s1)[i] = b;
+    }
+  }
+}
+
+inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 8) {
+  int64_t b = (n + block - 1) / block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- device / IPC plumbing (this library links its own static cudart: make its current device explicit) ----------
+int dr_cuda_set_device(int dev) { DR_CUDA_CHECK(cudaSetDevice(dev)); return 0; }
+int dr_cuda_get_device() { int d = -1; cudaGetDevice(&d); return d; }
+
+int dr_comm_alloc(int64_t bytes, void** out) {
+  DR_CUDA_CHECK(cudaMalloc(out, (size_t)bytes));
+  DR_CUDA_CHECK(cudaMemset(*out, 0, (size_t)bytes));
+  return 0;
+}
+int dr_comm_free(void* p) { DR_CUDA_CHECK(cudaFree(p)); return 0; }
+int dr_comm_get_handle(void* p, void* handle64) {
+  cudaIpcMemHandle_t h;
+  DR_CUDA_CHECK(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+int dr_comm_open_handle(const void* handle64, void** out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  DR_CUDA_CHECK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int dr_comm_close_handle(void* p) { DR_CUDA_CHECK(cudaIpcCloseMemHandle(p)); return 0; }
+int dr_comm_can_access_peer(int dev, int peer) { int ok = 0; cudaDeviceCanAccessPeer(&ok, dev, peer); return ok; }
+
+int dr_comm_barrier(const DrPeers* sig, uint32_t* epochs, int channel, int rank, int world, cudaStream_t s) {
+  k_rank_barrier<<<1, 32, 0, s>>>(*sig, epochs, channel, rank, world);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_comm_mp_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map, const int32_t* table_global, int nl, int W, int64_t B,
+                      int T, int dim, const DrPeers* ids_peers, const DrPeers* emb_peers, int train, const int64_t* step_ptr,
+                      int32_t* pos_out, int64_t* ulist, int32_t* nunique, int64_t ulist_cap, cudaStream_t s) {
+  int64_t n = (int64_t)nl * W * B;
+  if (n == 0) return 0;
+  int grid = grid_for(n, 256, kNumSMs * 8);
+  switch (dim / 4) {
+    case 2: k_mp_lookup<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 4: k_mp_lookup<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 8: k_mp_lookup<8><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 16: k_mp_lookup<16><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 32: k_mp_lookup<32><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    default: return -3;
+  }
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_comm_mp_sparse_grad(const DrDeviceTable* tables_dev, const int32_t* table_map, const int32_t* table_global, int nl, int W, int64_t B,
+                           int dim, const DrPeers* demb_peers, const int32_t* pos, float* gsum, cudaStream_t s) {
+  int64_t n = (int64_t)nl * W * B;
+  if (n == 0) return 0;
+  int lpr = dim / 4;
+  int grid = grid_for(n * lpr, 256, kNumSMs * 16);
+  switch (lpr) {
+    case 2: k_mp_sparse_grad<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
+    case 4: k_mp_sparse_grad<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
+    case 8: k_mp_sparse_grad<8><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
+    case 16: k_mp_sparse_grad<16><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
+    case 32: k_mp_sparse_grad<32><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
+    default: return -3;
+  }
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+// n must be a multiple of 4.  w == null => pure all-reduce into reduced_out.
+int dr_comm_allreduce_apply(const DrPeers* grad_peers, int W, float* w, float* s0, float* s1, int64_t n, const DrOptHyper* hp_dev,
+                            float* reduced_out, cudaStream_t s) {
+  if (n % 4) return -2;
+  k_allreduce_apply<<<grid_for(n / 4, 256, kNumSMs * 4), 256, 0, s>>>(*grad_peers, W, w, s0, s1, n / 4, hp_dev, reduced_out);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) k_apply(const DrDeviceTable* __restrict__
         }
       }
       TB.tag[pos] = -1;   // release the per-step claim
+      TB.version[pos] = (int32_t)hp.global_step;   // UpdateVersion(value_ptr, gs) for every touched key, admitted or not
     }
     r = __shfl_sync(gmask, r, (threadIdx.x & 31) / LPR * LPR);
     bool fresh = r <= -2;

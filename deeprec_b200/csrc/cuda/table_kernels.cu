@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_lookup(const DrDeviceTable* __restrict_
                                                 int64_t uniform, int64_t n, int train, const int64_t* __restrict__ step_ptr,
                                                 int32_t* __restrict__ out_pos, int64_t* __restrict__ ulist,
                                                 int32_t* __restrict__ group_nunique, int64_t ulist_cap) {
-  const int step = step_ptr ? (int)*step_ptr : 0;
+  (void)step_ptr;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int tl = seg_of(offsets, T, i, uniform);
     const int t = table_map ? table_map[tl] : tl;      // index into the context-wide table array
@@ -55,8 +55,7 @@ __global__ void __launch_bounds__(256) k_lookup(const DrDeviceTable* __restrict_
     if (pos < 0) { TB.counters[CTR_OVERFLOW] = 1; out_pos[i] = -1; continue; }
     if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
     atomicAdd(&TB.freq[pos], 1);
-    TB.version[pos] = step;
-    TB.dirty[pos] = 1;
+    TB.dirty[pos] = 1;          // version is stamped by the apply kernel (UpdateVersion lives in the apply op)
     out_pos[i] = (int32_t)pos;
     if (ulist != nullptr) {
       bool won = atomicCAS(&TB.tag[pos], -1, -2) == -1;

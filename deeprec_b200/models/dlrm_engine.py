@@ -82,6 +82,7 @@ class DLRMEngine:
         self.rank, self.world = rank, world_size
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.lib = _native.cuda()
+        _native.set_device(self.dev.index)
         self.comm = comm                           # parallel.p2p.P2PComm or parallel.nccl_baseline.NcclComm (world_size > 1)
         self.B, self.T, self.D = cfg.batch_size, len(cfg.cardinalities), cfg.embedding_dim
         self.kind = _OPT_KIND[cfg.optimizer.lower()]
@@ -319,6 +320,9 @@ class DLRMEngine:
             main.wait_stream(self._side)
         else:
             self._embedding_forward(train)
+        if train:
+            # after the step's first rank barrier: every peer has finished reading last step's gradients
+            self.grads.zero_()
         # ---- interaction + top MLP
         self._call(lib.dr_cuda_dot_interaction_fwd, ptr(x), ldx, ptr(self.emb), B * self.D, self.D, self.T, self.D, B, ptr(self.Z), self.Zp)
         x, ldx = self.Z, self.Zp
@@ -387,7 +391,6 @@ class DLRMEngine:
 
     def _step_body(self) -> None:
         self.loss.zero_()
-        self.grads.zero_()
         self._forward(True)
         self._head(True)
         self._backward()

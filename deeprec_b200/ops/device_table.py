@@ -126,6 +126,7 @@ class DeviceTable:
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        _native.set_device(self.device.index)
         self.dim = int(cfg.dim)
         if self.dim % 4:
             raise ValueError("device EmbeddingVariable needs embedding_dim % 4 == 0")
