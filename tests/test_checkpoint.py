@@ -1,0 +1,105 @@
+"""Full / incremental checkpoint round trips, N->M re-shard, filtered keys, eviction-at-save (incr_ckpt_test.py analogue)."""
+import os
+
+import torch
+from torch import nn
+
+import deeprec_b200 as dr
+from deeprec_b200.checkpoint import IncrementalSaver, Saver, latest_checkpoint
+from deeprec_b200.optim import GlobalStep
+
+
+class Tiny(nn.Module):
+    def __init__(self, tag, **kw):
+        super().__init__()
+        self.ev = dr.get_embedding_variable(f"{tag}/emb", 8, ev_option=dr.EmbeddingVariableOption(**kw), seed=5)
+        self.fc = nn.Linear(8, 1)
+
+    def forward(self, ids):
+        return self.fc(self.ev.lookup(ids)).squeeze(-1)
+
+
+def _train(m, opt, steps, lo=0, hi=40):
+    g = torch.Generator().manual_seed(steps + lo)
+    for _ in range(steps):
+        ids = torch.randint(lo, hi, (32,), generator=g)
+        loss = (m(ids) - 1.0).pow(2).mean()
+        opt.zero_grad(); loss.backward(); opt.step()
+
+
+def test_full_roundtrip_with_slots_filter_and_optimizer_state(tmp_path):
+    m = Tiny("ck1", filter_option=dr.CounterFilter(2))
+    opt = dr.optim.AdamOptimizer(m, lr=0.01, global_step=GlobalStep())
+    _train(m, opt, 6)
+    sv = Saver(m, optimizer=opt)
+    prefix = sv.save(str(tmp_path / "model.ckpt"))
+    assert latest_checkpoint(str(tmp_path)) == prefix and os.path.exists(prefix + ".index")
+    m2 = Tiny("ck1", filter_option=dr.CounterFilter(2))
+    opt2 = dr.optim.AdamOptimizer(m2, lr=0.01, global_step=GlobalStep())
+    step = Saver(m2, optimizer=opt2).restore(prefix)
+    assert step == 6 and int(opt2.global_step) == 6 and abs(opt2.beta1_power - opt.beta1_power) < 1e-9
+    probe = torch.arange(0, 45)
+    assert torch.equal(m.ev.table.lookup(probe), m2.ev.table.lookup(probe))
+    for s in ("m", "v"):
+        assert torch.equal(m.ev.slot_values(probe, s), m2.ev.slot_values(probe, s))
+    assert torch.equal(m.ev.get_frequency(probe), m2.ev.get_frequency(probe))          # filtered keys keep their counts
+    assert torch.equal(m.ev.get_version(probe), m2.ev.get_version(probe))
+    assert m.ev.total_count() == m2.ev.total_count() and m.ev.table.total_keys() == m2.ev.table.total_keys()
+    # training continues identically
+    _train(m, opt, 3); _train(m2, opt2, 3)
+    assert torch.allclose(m.ev.table.lookup(probe), m2.ev.table.lookup(probe), atol=1e-6)
+    assert torch.allclose(m.fc.weight, m2.fc.weight, atol=1e-6)
+
+
+def test_reshard_2_to_3_partitions(tmp_path):
+    m = Tiny("ck2")
+    opt = dr.optim.AdagradOptimizer(m, lr=0.1, global_step=GlobalStep())
+    _train(m, opt, 5, 0, 3000)
+    prefix = Saver(m, optimizer=opt).save(str(tmp_path / "m.ckpt"))
+    total, probe = 0, torch.arange(0, 3000)
+    for p in range(3):
+        mp = Tiny("ck2")
+        op = dr.optim.AdagradOptimizer(mp, lr=0.1, global_step=GlobalStep())
+        Saver(mp, optimizer=op, partition_id=p, partition_num=3).restore(prefix)
+        keys = mp.ev.export()[0]
+        assert torch.all(keys % 1000 % 3 == p)
+        total += keys.numel()
+        assert torch.equal(mp.ev.table.lookup(keys), m.ev.table.lookup(keys))
+    assert total == m.ev.total_count()
+
+
+def test_eviction_happens_at_save(tmp_path):
+    m = Tiny("ck3", evict_option=dr.GlobalStepEvict(steps_to_live=2))
+    opt = dr.optim.AdagradOptimizer(m, lr=0.1, global_step=GlobalStep())
+    _train(m, opt, 1, 0, 20)
+    n0 = m.ev.total_count()
+    _train(m, opt, 5, 100, 120)
+    assert m.ev.total_count() > n0
+    Saver(m, optimizer=opt).save(str(tmp_path / "e.ckpt"))
+    keys = m.ev.export()[0]
+    assert torch.all(keys >= 100)          # everything from the first phase aged out
+
+
+def test_incremental_chain_recover(tmp_path):
+    m = Tiny("ck4")
+    opt = dr.optim.AdagradOptimizer(m, lr=0.1, global_step=GlobalStep())
+    sv = IncrementalSaver(m, optimizer=opt)
+    _train(m, opt, 4, 0, 50)
+    sv.save(str(tmp_path / "i.ckpt"))
+    _train(m, opt, 2, 40, 70)
+    p1 = sv.incremental_save(str(tmp_path / "i.ckpt"))
+    _train(m, opt, 2, 60, 90)
+    p2 = sv.incremental_save(str(tmp_path / "i.ckpt"))
+    assert p1 != p2
+    from deeprec_b200.checkpoint import BundleReader
+    r = BundleReader(p2)
+    incr_keys = r.read("ck4/emb-sparse_incr_keys")
+    assert incr_keys.numel() > 0 and int(incr_keys.min()) >= 60          # only rows touched since the previous save
+    m2 = Tiny("ck4")
+    opt2 = dr.optim.AdagradOptimizer(m2, lr=0.1, global_step=GlobalStep())
+    step = IncrementalSaver(m2, optimizer=opt2).recover_incr_checkpoints(str(tmp_path))
+    assert step == 8
+    probe = torch.arange(0, 95)
+    assert torch.equal(m.ev.table.lookup(probe), m2.ev.table.lookup(probe))
+    assert torch.equal(m.ev.slot_values(probe, "accumulator"), m2.ev.slot_values(probe, "accumulator"))
+    assert torch.allclose(m.fc.weight, m2.fc.weight)
