@@ -53,13 +53,17 @@ def bind(lib):
     _sig(lib, "dr_cuda_unique", [P, i64, P, P, i64, P, P, P, P, P, S])
     _sig(lib, "dr_cuda_segment_sum", [P, P, i64, INT, P, S])
     _sig(lib, "dr_cuda_gemm_tn", [P, i64, P, i64, INT, INT, INT, P, INT, P, i64, P, i64, P, INT, S])
+    _sig(lib, "dr_cuda_gemm_tn_ex", [P, i64, P, i64, INT, INT, INT, P, INT, P, i64, INT, P, i64, P, P, P, INT, INT, S])
+    _sig(lib, "dr_cuda_bn_fold", [P, P, INT, i64, P, P, f32, f32, P, P, P, P, P, P, INT, P, P, INT, INT, P, P, S])
+    _sig(lib, "dr_cuda_dw_fixup", [P, P, P, P, INT, INT, INT, S])
+    _sig(lib, "dr_cuda_bn_bwd_apply_v2", [P, P, i64, INT, i64, P, P, P, P, P, P, INT, P, S])
     _sig(lib, "dr_cuda_gemm_dw", [P, i64, P, i64, INT, INT, INT, P, i64, INT, S])
     _sig(lib, "dr_cuda_colstats", [P, P, i64, INT, i64, i64, P, P, S])
     _sig(lib, "dr_cuda_bn_finalize", [P, P, INT, i64, P, P, f32, f32, P, P, P, P, P, P, INT, S])
     _sig(lib, "dr_cuda_bn_apply", [P, i64, INT, i64, P, P, P, i64, S])
     _sig(lib, "dr_cuda_bn_bwd_finalize", [P, P, INT, i64, P, P, P, P, P, P, f32, S])
     _sig(lib, "dr_cuda_bn_bwd_apply", [P, P, i64, INT, i64, P, P, P, P, P, P, INT, S])
-    _sig(lib, "dr_cuda_head", [P, i64, i64, INT, P, P, P, f32, P, P, P, P, P, INT, INT, S])
+    _sig(lib, "dr_cuda_head", [P, i64, i64, INT, P, P, P, f32, P, P, P, P, P, INT, INT, P, S])
     _sig(lib, "dr_cuda_pack_weights", [P, INT, INT, P, P, INT, S])
     _sig(lib, "dr_cuda_cast_pad", [P, i64, INT, P, INT, S])
     _sig(lib, "dr_cuda_l2_flush", [P, i64, f32, S])

@@ -148,15 +148,16 @@ template <int R>   // K = 256 * R
 __global__ void __launch_bounds__(256) k_head(const __nv_bfloat16* __restrict__ h, int64_t ldh, int64_t B, const float* __restrict__ w,
                                               const float* __restrict__ bias, const float* __restrict__ labels, float inv_batch,
                                               float* __restrict__ prob, float* __restrict__ loss_sum, __nv_bfloat16* __restrict__ dh,
-                                              float* __restrict__ dw, float* __restrict__ db, int relu_mask, int train) {
+                                              float* __restrict__ dw, float* __restrict__ db, int relu_mask, int train,
+                                              float* __restrict__ dbias_h /* [K]: sum_b dh[b,:] = bias grad of the layer producing h */) {
   constexpr int K = 256 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  float wv[R][8], dwacc[R][8];
+  float wv[R][8], dwacc[R][8], dhacc[R][8];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { wv[r][j] = w[r * 256 + lane * 8 + j]; dwacc[r][j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { wv[r][j] = w[r * 256 + lane * 8 + j]; dwacc[r][j] = 0.f; dhacc[r][j] = 0.f; }
   const float b0 = bias[0];
   float dbacc = 0.f, lossacc = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < B; row += (int64_t)gridDim.x * wpb) {
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(256) k_head(const __nv_bfloat16* __restrict__ 
           float g0 = dz * wv[r][2 * e], g1 = dz * wv[r][2 * e + 1];
           if (relu_mask) { if (!(hv[r][2 * e] > 0.f)) g0 = 0.f; if (!(hv[r][2 * e + 1] > 0.f)) g1 = 0.f; }
           o[e] = pack_bf16x2(g0, g1);
+          dhacc[r][2 * e] += g0; dhacc[r][2 * e + 1] += g1;
           dwacc[r][2 * e] += dz * hv[r][2 * e]; dwacc[r][2 * e + 1] += dz * hv[r][2 * e + 1];
         }
         *reinterpret_cast<int4*>(dh + row * ldh + r * 256 + lane * 8) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
@@ -198,19 +200,20 @@ __global__ void __launch_bounds__(256) k_head(const __nv_bfloat16* __restrict__ 
     }
   }
   __shared__ float sdw[K];
+  __shared__ float sdh[K];
   __shared__ float sred[2];
-  for (int i = threadIdx.x; i < K; i += blockDim.x) sdw[i] = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { sdw[i] = 0.f; sdh[i] = 0.f; }
   if (threadIdx.x < 2) sred[threadIdx.x] = 0.f;
   __syncthreads();
   if (train) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sdw[r * 256 + lane * 8 + j], dwacc[r][j]);
+      for (int j = 0; j < 8; ++j) { atomicAdd(&sdw[r * 256 + lane * 8 + j], dwacc[r][j]); if (dbias_h) atomicAdd(&sdh[r * 256 + lane * 8 + j], dhacc[r][j]); }
   }
   if (lane == 0) { atomicAdd(&sred[0], lossacc); atomicAdd(&sred[1], dbacc); }
   __syncthreads();
-  if (train) for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+  if (train) for (int i = threadIdx.x; i < K; i += blockDim.x) { atomicAdd(&dw[i], sdw[i]); if (dbias_h) atomicAdd(&dbias_h[i], sdh[i]); }
   if (threadIdx.x == 0) { atomicAdd(loss_sum, sred[0] * inv_batch); if (train) atomicAdd(db, sred[1]); }
 }
 
@@ -248,6 +251,109 @@ __global__ void k_l2_flush(float* __restrict__ buf, int64_t n, float v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) buf[i] = v;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// BatchNorm folding (forward): finalize the batch statistics of layer l and fold y = s*a + t into layer l+1:
+//   W'[n,k] = W[n,k] * s[k]   (bf16, the tcgen05 B operand)      b'[n] = b[n] + sum_k W[n,k] * t[k]   (fp32)
+// so the normalised activation is never materialised (no extra pass over [B, N]).  One block per output row n;
+// block 0 also publishes mean/rstd/scale/shift and advances the running statistics.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bn_fold(const float* __restrict__ S1, const float* __restrict__ S2, int K, float invB,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                                                 float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean,
+                                                 float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift, int training,
+                                                 const float* __restrict__ Wn, const float* __restrict__ bn, int Kp,
+                                                 __nv_bfloat16* __restrict__ Wf, float* __restrict__ bf) {
+  const int n = blockIdx.x;
+  float part = 0.f;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float s = 0.f, t = 0.f;
+    if (k < K) {
+      float m, var;
+      if (training) { m = S1[k] * invB; var = fmaxf(S2[k] * invB - m * m, 0.f); }
+      else { m = running_mean[k]; var = running_var[k]; }
+      const float rs = rsqrtf(var + eps);
+      s = gamma[k] * rs; t = beta[k] - m * s;
+      if (n == 0) {
+        mean[k] = m; rstd[k] = rs; scale[k] = s; shift[k] = t;
+        if (training) {
+          running_mean[k] = momentum * running_mean[k] + (1.f - momentum) * m;
+          running_var[k] = momentum * running_var[k] + (1.f - momentum) * var;
+        }
+      }
+    }
+    const float w = Wn[(int64_t)n * Kp + k];
+    Wf[(int64_t)n * Kp + k] = __float2bfloat16(w * s);
+    part += w * t;
+  }
+  __shared__ float red[8];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    bf[n] = bn[n] + tot;
+  }
+}
+
+// dW[n,k] = G[n,k] * s[k] + db[n] * t[k]   (weight gradient of a layer whose input was a folded BatchNorm output)
+__global__ void __launch_bounds__(256) k_dw_fixup(float* __restrict__ dW, const float* __restrict__ db, const float* __restrict__ s,
+                                                  const float* __restrict__ t, int N, int K, int Kp) {
+  const int64_t total = (int64_t)N * Kp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Kp), k = (int)(i % Kp);
+    dW[i] = k < K ? dW[i] * s[k] + db[n] * t[k] : 0.f;
+  }
+}
+
+// BatchNorm backward apply, v2: each thread owns 8 columns (parameters live in registers) and walks the rows;
+// also reduces dbias[n] = sum_b da[b, n] so no separate pass over da is needed.
+__global__ void __launch_bounds__(256) k_bn_bwd_apply_v2(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ a, int64_t B,
+                                                         int N, int64_t ld, const float* __restrict__ scale, const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd, const float* __restrict__ c1,
+                                                         const float* __restrict__ c2, __nv_bfloat16* __restrict__ da, int relu_mask,
+                                                         float* __restrict__ dbias) {
+  const int tpr = N / 8;
+  const int rows_par = blockDim.x / tpr;
+  const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+  float sc[8], mu[8], rs[8], k1[8], k2[8], acc[8];
+  if (tr < rows_par) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = tc * 8 + j;
+      sc[j] = scale[n]; mu[j] = mean[n]; rs[j] = rstd[n]; k1[j] = c1[n]; k2[j] = c2[n]; acc[j] = 0.f;
+    }
+    for (int64_t b = (int64_t)blockIdx.x * rows_par + tr; b < B; b += (int64_t)gridDim.x * rows_par) {
+      int4 rdy = ld_nc_v4(dy + b * ld + tc * 8), ra = ld_nc_v4(a + b * ld + tc * 8);
+      const uint32_t wdy[4] = {(uint32_t)rdy.x, (uint32_t)rdy.y, (uint32_t)rdy.z, (uint32_t)rdy.w};
+      const uint32_t wa[4] = {(uint32_t)ra.x, (uint32_t)ra.y, (uint32_t)ra.z, (uint32_t)ra.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fdy = unpack_bf16x2(wdy[e]), fa = unpack_bf16x2(wa[e]);
+        float g0 = sc[2 * e] * (fdy.x - k1[2 * e] - (fa.x - mu[2 * e]) * rs[2 * e] * k2[2 * e]);
+        float g1 = sc[2 * e + 1] * (fdy.y - k1[2 * e + 1] - (fa.y - mu[2 * e + 1]) * rs[2 * e + 1] * k2[2 * e + 1]);
+        if (relu_mask) { if (!(fa.x > 0.f)) g0 = 0.f; if (!(fa.y > 0.f)) g1 = 0.f; }
+        acc[2 * e] += g0; acc[2 * e + 1] += g1;
+        o[e] = pack_bf16x2(g0, g1);
+      }
+      *reinterpret_cast<int4*>(da + b * ld + tc * 8) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+    }
+  }
+  if (dbias) {
+    extern __shared__ float sh[];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    if (tr < rows_par) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sh[tc * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&dbias[i], sh[i]);
+  }
+}
+
 inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 8) {
   int64_t b = (n + block - 1) / block;
   if (b < 1) b = 1;
@@ -262,7 +368,7 @@ extern "C" {
 int dr_cuda_colstats(const void* u, const void* v, int64_t B, int N, int64_t ldu, int64_t ldv, float* S1, float* S2, cudaStream_t s) {
   if (N % 8 || N / 8 > 256) return -2;
   int tpr = N / 8; int rows_par = 256 / tpr;
-  int grid = grid_for((B + rows_par - 1) / rows_par, 8, kNumSMs * 4);   // ~8 rows-groups per block minimum
+  int grid = grid_for((B + rows_par - 1) / rows_par, 2, kNumSMs * 4);   // >= 2 row-groups per block
   k_colstats<<<grid, 256, 2 * N * sizeof(float), s>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)v, B, N, ldu, ldv, S1, S2);
   DR_LAUNCH_CHECK();
   return 0;
@@ -299,10 +405,36 @@ int dr_cuda_bn_bwd_apply(const void* dy, const void* a, int64_t B, int N, int64_
   return 0;
 }
 
+int dr_cuda_bn_fold(const float* S1, const float* S2, int K, int64_t B, const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift, int training,
+                    const float* Wn, const float* bn, int Nn, int Kp, void* Wf, float* bf, cudaStream_t s) {
+  k_bn_fold<<<Nn, 256, 0, s>>>(S1, S2, K, 1.0f / (float)B, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift,
+                              training, Wn, bn, Kp, (__nv_bfloat16*)Wf, bf);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_cuda_dw_fixup(float* dW, const float* db, const float* scale, const float* shift, int N, int K, int Kp, cudaStream_t s) {
+  k_dw_fixup<<<grid_for((int64_t)N * Kp, 256), 256, 0, s>>>(dW, db, scale, shift, N, K, Kp);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_cuda_bn_bwd_apply_v2(const void* dy, const void* a, int64_t B, int N, int64_t ld, const float* scale, const float* mean,
+                            const float* rstd, const float* c1, const float* c2, void* da, int relu_mask, float* dbias, cudaStream_t s) {
+  if (N % 8 || N / 8 > 256) return -2;
+  int tpr = N / 8; int rows_par = 256 / tpr;
+  int grid = grid_for((B + rows_par - 1) / rows_par, 4, kNumSMs * 8);
+  k_bn_bwd_apply_v2<<<grid, 256, N * sizeof(float), s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a, B, N, ld, scale, mean, rstd, c1, c2,
+                                                        (__nv_bfloat16*)da, relu_mask, dbias);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
 int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, const float* bias, const float* labels, float inv_batch,
-                 float* prob, float* loss_sum, void* dh, float* dw, float* db, int relu_mask, int train, cudaStream_t s) {
+                 float* prob, float* loss_sum, void* dh, float* dw, float* db, int relu_mask, int train, float* dbias_h, cudaStream_t s) {
   int grid = grid_for((B + 7) / 8, 1, kNumSMs * 4);
-#define HEAD(R) k_head<R><<<grid, 256, 0, s>>>((const __nv_bfloat16*)h, ldh, B, w, bias, labels, inv_batch, prob, loss_sum, (__nv_bfloat16*)dh, dw, db, relu_mask, train)
+#define HEAD(R) k_head<R><<<grid, 256, 0, s>>>((const __nv_bfloat16*)h, ldh, B, w, bias, labels, inv_batch, prob, loss_sum, (__nv_bfloat16*)dh, dw, db, relu_mask, train, dbias_h)
   if (K == 256) HEAD(1); else if (K == 512) HEAD(2); else if (K == 1024) HEAD(4); else return -2;
 #undef HEAD
   DR_LAUNCH_CHECK();

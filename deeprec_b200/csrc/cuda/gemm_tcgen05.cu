@@ -56,11 +56,14 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
 
 struct Epilogue {
   const float* bias;              // [N] or null
-  const __nv_bfloat16* mask_src;  // [M, ld_mask] or null: out *= (mask_src > 0)   (ReLU backward)
+  const __nv_bfloat16* mask_src;  // aux tile [M, ld_mask] or null
   __nv_bfloat16* out;             // [M, ldc]
-  float* out_f32;                 // optional fp32 copy of the output (or null)
+  float* out_f32;                 // optional fp32 copy of the output (or null; v1 path only)
   int64_t ldc, ld_mask;
   int relu;
+  int aux_mode;                   // 1: out *= (aux > 0) (ReLU backward)   2: aux only feeds S2 (S2 += out * aux)
+  float* S1;                      // optional column sums over M:  S1[n] += sum_m out[m, n]
+  float* S2;                      // optional:  S2[n] += sum_m out[m,n] * (aux_mode == 2 ? aux[m,n] : out[m,n])
 };
 
 template <int BLOCK_N>
@@ -243,6 +246,240 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // -------------------------------------------------------------------------------------------------
+// k_gemm_tn_v2: same mainloop, production epilogue.
+//   * accumulator -> registers (tcgen05.ld) -> fused math -> bf16 -> 128B-swizzled smem staging -> TMA store
+//     (cp.async.bulk.tensor, full 128 B lines; M/N tails clipped by the tensor map), double-buffered per warp;
+//   * the aux tile (ReLU-backward mask, or the BatchNorm-backward partner activation) is fetched with
+//     coalesced 16 B loads (8 lanes per 128 B row segment) through the same swizzled staging layout;
+//   * optional per-column batch statistics S1 += sum(out), S2 += sum(out*out | out*aux) are reduced with a
+//     31-shuffle warp transpose-reduce and one global atomic per column per 32-row slab -- this is what
+//     removes the separate BatchNorm-statistics / bias-gradient passes over the activations.
+// -------------------------------------------------------------------------------------------------
+template <int BLOCK_N> struct StagesFor { static constexpr int value = BLOCK_N >= 256 ? 3 : 4; };
+
+template <int BLOCK_N>
+struct SmemLayoutTN2 {
+  static constexpr int kSt = StagesFor<BLOCK_N>::value;
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStoreBytes = 4 * 2 * 4096;      // 4 epilogue warps x double buffer x [32 rows][128 B]
+  static constexpr int kAuxBytes = 4 * 4096;            // 4 epilogue warps x [32 rows][128 B]
+  static constexpr int kTotal = kSt * kStageBytes + kStoreBytes + kAuxBytes + 1024 + 256;
+};
+
+// lane c ends with the sum over the warp's 32 rows of column c (v is destroyed)
+__device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float keep = upper ? v[k + off] : v[k];
+      const float send = upper ? v[k] : v[k + off];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+             int M, int N, int K, Epilogue ep) {
+  using L = SmemLayoutTN2<BLOCK_N>;
+  constexpr int kSt = L::kSt;
+  constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* store_base = smem + kSt * L::kStageBytes;
+  uint8_t* aux_base = store_base + L::kStoreBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux_base + L::kAuxBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kSt;
+  uint64_t* tfull_bar = bars + 2 * kSt;
+  uint64_t* tempty_bar = bars + 2 * kSt + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
+    for (int i = 0; i < kSt; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;
+    uint8_t* my_store = store_base + q * 2 * 4096;
+    uint8_t* my_aux = aux_base + q * 4096;
+    const uint32_t swz = (uint32_t)(lane & 7);
+    int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+        const int col0 = n_blk * BLOCK_N + c0;
+        if (col0 >= N) break;                           // warp-uniform
+        // ---- aux tile [32 rows x 64 cols] -> swizzled smem (coalesced: 8 lanes cover one 128 B row segment)
+        if (ep.mask_src) {
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3), ch = lane & 7;
+            int4 val = make_int4(0, 0, 0, 0);
+            if (row0 + r < M && col0 + ch * 8 < N) val = ld_nc_v4(ep.mask_src + (int64_t)(row0 + r) * ep.ld_mask + col0 + ch * 8);
+            *reinterpret_cast<int4*>(my_aux + r * 128 + ((ch ^ (r & 7)) << 4)) = val;
+          }
+          __syncwarp();
+        }
+        // the staging buffer we are about to fill was handed to TMA two chunks ago: wait until it has been read
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        uint8_t* stg = my_store + sbuf * 4096;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c0 + h * 32, r);
+          tmem_ld_wait();
+          const int colh = col0 + h * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (colh + j < N) {
+                float4 b = *reinterpret_cast<const float4*>(ep.bias + colh + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          float w[32];     // aux values (only materialised when needed)
+          if (ep.mask_src) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              int4 raw = *reinterpret_cast<const int4*>(my_aux + lane * 128 + (((uint32_t)(h * 4 + j4) ^ swz) << 4));
+              const uint32_t ww[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { float2 f = unpack_bf16x2(ww[e]); w[j4 * 8 + 2 * e] = f.x; w[j4 * 8 + 2 * e + 1] = f.y; }
+            }
+            if (ep.aux_mode == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (!(w[j] > 0.f)) v[j] = 0.f;
+            }
+          }
+          // ---- bf16 pack -> swizzled staging
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            int4 pk;
+            pk.x = (int)pack_bf16x2(v[j4 * 8 + 0], v[j4 * 8 + 1]); pk.y = (int)pack_bf16x2(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+            pk.z = (int)pack_bf16x2(v[j4 * 8 + 4], v[j4 * 8 + 5]); pk.w = (int)pack_bf16x2(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+            *reinterpret_cast<int4*>(stg + lane * 128 + (((uint32_t)(h * 4 + j4) ^ swz) << 4)) = pk;
+          }
+          // ---- fused column statistics (rows beyond M contribute nothing)
+          if (ep.S1) {
+            float p[32];
+            if (ep.S2) {
+              float s2[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s2[j] = row_ok ? v[j] * ((ep.aux_mode == 2) ? w[j] : v[j]) : 0.f;
+              const float t2 = warp_col_reduce(s2, lane);
+              if (colh + lane < N) atomicAdd(ep.S2 + colh + lane, t2);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) p[j] = row_ok ? v[j] : 0.f;
+            const float t1 = warp_col_reduce(p, lane);
+            if (colh + lane < N) atomicAdd(ep.S1 + colh + lane, t1);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          tma_store_2d(&tmC, stg, col0, row0);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// -------------------------------------------------------------------------------------------------
 // dW[N_out, K_in] += sum_b dY[b, N_out] * X[b, K_in]   (split over b; fp32 atomics epilogue)
 //   A operand = dY^T  : M = N_out, MN-major (tensor map over dY: inner = N_out, outer = batch)
 //   B operand = X^T   : N = K_in , MN-major (tensor map over X : inner = K_in , outer = batch)
@@ -380,6 +617,31 @@ int launch_tn(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_t
   return 0;
 }
 
+int make_tmap_c(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes) {
+  return make_tmap(m, ptr, inner, outer, pitch_bytes, 64, 32);     // 64 cols (128 B) x 32 rows, 128B swizzle
+}
+
+template <int BN>
+int launch_tn_v2(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_t ldb, const Epilogue& ep, int max_ctas, cudaStream_t s) {
+  CUtensorMap tb, tc;
+  int rc = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BLOCK_K, BN);
+  if (rc) return rc;
+  rc = make_tmap_c(&tc, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldc * 2);
+  if (rc) return rc;
+  using L = SmemLayoutTN2<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn_v2<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  if (grid > max_ctas) grid = max_ctas;
+  k_gemm_tn_v2<BN><<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, tc, M, N, K, ep);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int BN>
 int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, int Mo, int No, int batch, int splits, float* dW, int64_t ldw, cudaStream_t s) {
   using L = SmemLayoutNT<BN>;
@@ -400,17 +662,37 @@ int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, int Mo, int No, int 
 
 extern "C" {
 
+int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias, int relu,
+                       const void* mask_src, int64_t ld_mask, int aux_mode, void* out, int64_t ldc, float* out_f32, float* S1, float* S2,
+                       int max_ctas, int force_v1, cudaStream_t s);
+
 // out[M,N] = A[M,K](lda) * B[N,K](ldb)^T (+bias)(relu)(*mask).  Requirements: bf16, K-major, lda/ldb/ldc multiples of 8,
 // N multiple of 8, pointers 16B-aligned.  out_f32 optional.
 int dr_cuda_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias, int relu,
                     const void* mask_src, int64_t ld_mask, void* out, int64_t ldc, float* out_f32, int max_ctas, cudaStream_t s) {
+  return dr_cuda_gemm_tn_ex(A, lda, B, ldb, M, N, K, bias, relu, mask_src, ld_mask, mask_src ? 1 : 0, out, ldc, out_f32, nullptr, nullptr,
+                            max_ctas, 0, s);
+}
+
+// Extended entry: aux_mode 1 = ReLU-backward mask, 2 = statistics partner; S1/S2 = fused column statistics (v2 epilogue,
+// N >= 64 and no fp32 copy).  force_v1 selects the direct-store epilogue (kept for A/B measurements).
+int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias, int relu,
+                       const void* mask_src, int64_t ld_mask, int aux_mode, void* out, int64_t ldc, float* out_f32, float* S1, float* S2,
+                       int max_ctas, int force_v1, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 8)) return -2;
   if (max_ctas <= 0) max_ctas = kNumSMs;
   CUtensorMap ta;
   int rc = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M);
   if (rc) return rc;
-  Epilogue ep{bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, out_f32, ldc, ld_mask, relu};
+  Epilogue ep{bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, out_f32, ldc, ld_mask, relu, aux_mode, S1, S2};
+  const bool v2 = !force_v1 && N > 32 && out_f32 == nullptr;
+  if (v2) {
+    if (N <= 64) return launch_tn_v2<64>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+    if (N <= 128) return launch_tn_v2<128>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+    return launch_tn_v2<256>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+  }
+  if (S1 || S2 || aux_mode == 2) return -4;    // statistics need the v2 epilogue
   if (N <= 16) return launch_tn<16>(ta, B, M, N, K, ldb, ep, max_ctas, s);
   if (N <= 32) return launch_tn<32>(ta, B, M, N, K, ldb, ep, max_ctas, s);
   if (N <= 64) return launch_tn<64>(ta, B, M, N, K, ldb, ep, max_ctas, s);

@@ -63,6 +63,7 @@ class DLRMConfig:
     steps_to_live: int = 0
     seed: int = 1234
     overlap_embedding: bool = True              # fork the embedding branch onto a side stream inside the graph
+    gemm_v1: bool = False                       # A/B switch: direct-store GEMM epilogue + separate statistics passes
 
 
 def _pad8(n: int) -> int:
@@ -151,12 +152,23 @@ class DLRMEngine:
         for L in self.bot + self.top:
             L.w_bf16 = torch.zeros(L.N, L.Kp, dtype=torch.bfloat16, device=dev)
             L.wt_bf16 = torch.zeros(L.Kp, L.Np, dtype=torch.bfloat16, device=dev)
-            L.S1 = torch.zeros(L.N, dtype=torch.float32, device=dev); L.S2 = torch.zeros(L.N, dtype=torch.float32, device=dev)
             if L.has_bn:
                 for nm in ("mean", "rstd", "scale", "shift", "c1", "c2"):
                     setattr(L, nm, torch.zeros(L.N, dtype=torch.float32, device=dev))
                 L.running_mean = torch.zeros(L.N, dtype=torch.float32, device=dev)
                 L.running_var = torch.ones(L.N, dtype=torch.float32, device=dev)
+        # one arena for every per-step column statistic (BatchNorm fwd sums, BatchNorm bwd sums): ONE memset per step
+        tot = sum(4 * ((L.N + 63) // 64 * 64) for L in self.bot)
+        self.stats = torch.zeros(max(tot, 64), dtype=torch.float32, device=dev)
+        o = 0
+        for L in self.bot:
+            n64 = (L.N + 63) // 64 * 64
+            L.S1, L.S2, L.S1b, L.S2b = (self.stats[o + i * n64: o + i * n64 + L.N] for i in range(4))
+            o += 4 * n64
+        # BatchNorm folding: layer l >= 1 consumes the un-normalised activation a_{l-1} with W' = W diag(s), b' = b + W t
+        for L in self.bot[1:]:
+            L.wf_bf16 = torch.zeros(L.N, L.Kp, dtype=torch.bfloat16, device=dev)
+            L.bf = torch.zeros(L.N, dtype=torch.float32, device=dev)
 
     def p(self, name: str) -> torch.Tensor:
         o, n = self.views[name]
@@ -255,9 +267,13 @@ class DLRMEngine:
         _chk(fn(*args, self._s()), fn.__name__)
         self.launches += n
 
-    def _gemm(self, A, lda, Bm, ldb, M, N, K, bias, relu, mask, ldm, out, ldc):
-        self._call(self.lib.dr_cuda_gemm_tn, ptr(A), lda, ptr(Bm), ldb, M, N, K, ptr(bias) if bias is not None else None, int(relu),
-                   ptr(mask) if mask is not None else None, ldm, ptr(out), ldc, None, 0)
+    def _gemm(self, A, lda, Bm, ldb, M, N, K, bias, relu, mask, ldm, out, ldc, aux_mode=None, S1=None, S2=None):
+        """out[M,N] = A[M,K] Bm[N,K]^T (+bias)(relu); aux ``mask`` with aux_mode 1 = ReLU-backward mask, 2 = S2 partner;
+        S1/S2 = column statistics fused into the epilogue (tcgen05 v2 epilogue)."""
+        mode = aux_mode if aux_mode is not None else (1 if mask is not None else 0)
+        self._call(self.lib.dr_cuda_gemm_tn_ex, ptr(A), lda, ptr(Bm), ldb, M, N, K, ptr(bias) if bias is not None else None, int(relu),
+                   ptr(mask) if mask is not None else None, ldm, mode, ptr(out), ldc, None, ptr(S1) if S1 is not None else None,
+                   ptr(S2) if S2 is not None else None, 0, int(self.cfg.gemm_v1))
 
     def _gemm_dw(self, dY, ldy, X, ldx, n_out, k_in, dW, ldw):
         self._call(self.lib.dr_cuda_gemm_dw, ptr(dY), ldy, ptr(X), ldx, self.B, n_out, k_in, ptr(dW), ldw, 0)
@@ -296,6 +312,13 @@ class DLRMEngine:
         self._call(lib.dr_cuda_sparse_apply, ptr(st), ptr(self.ctx.ulist), ptr(self.ctx.nuniq), self.ctx.ulist.numel(), ptr(self.ctx.gsum), D,
                    ptr(self.hp_dev), self.max_unique, 1, n=2)
 
+    def _bn_fold(self, L, Ln, train: bool) -> None:
+        """finalize BatchNorm(L) from the fused epilogue statistics and fold it into the next Linear (Ln)."""
+        cfg = self.cfg
+        self._call(self.lib.dr_cuda_bn_fold, ptr(L.S1), ptr(L.S2), L.N, self.B, ptr(self.p(L.name + "/bn_gamma")), ptr(self.p(L.name + "/bn_beta")),
+                   cfg.bn_eps, cfg.bn_momentum, ptr(L.running_mean), ptr(L.running_var), ptr(L.mean), ptr(L.rstd), ptr(L.scale), ptr(L.shift),
+                   int(train), ptr(self.p(Ln.name + "/kernel")), ptr(self.p(Ln.name + "/bias")), Ln.N, Ln.Kp, ptr(Ln.wf_bf16), ptr(Ln.bf))
+
     def _forward(self, train: bool) -> None:
         lib, B, cfg = self.lib, self.B, self.cfg
         main = torch.cuda.current_stream(self.dev)
@@ -304,18 +327,26 @@ class DLRMEngine:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._embedding_forward(train)
-        # ---- bottom MLP: Dense + ReLU (fused epilogue) -> BatchNorm
+        # ---- bottom MLP.  Layer l: a_l = relu(a_{l-1} W_l'^T + b_l') with BatchNorm_{l-1} folded into (W', b'); the batch
+        #      statistics of a_l come out of the GEMM epilogue, so no activation is read twice and y_l is never written.
         self._call(lib.dr_cuda_cast_pad, ptr(self.dense_in), B, cfg.num_dense, ptr(self.x0), self.x0.shape[1])
         x, ldx = self.x0, self.x0.shape[1]
-        for L in self.bot:
-            self._gemm(x, ldx, L.w_bf16, L.Kp, B, L.N, L.Kp, self.p(L.name + "/bias"), True, None, 0, L.a, L.N)
-            if train:
+        nb = len(self.bot)
+        for i, L in enumerate(self.bot):
+            w, bias = (L.w_bf16, self.p(L.name + "/bias")) if i == 0 else (L.wf_bf16, L.bf)
+            fused = train and L.N > 32 and not cfg.gemm_v1
+            self._gemm(x, ldx, w, L.Kp, B, L.N, L.Kp, bias, True, None, 0, L.a, L.N, S1=L.S1 if fused else None, S2=L.S2 if fused else None)
+            if train and not fused:
                 self._call(lib.dr_cuda_colstats, ptr(L.a), ptr(L.a), B, L.N, L.N, L.N, ptr(L.S1), ptr(L.S2))
-            self._call(lib.dr_cuda_bn_finalize, ptr(L.S1), ptr(L.S2), L.N, B, ptr(self.p(L.name + "/bn_gamma")), ptr(self.p(L.name + "/bn_beta")),
-                       cfg.bn_eps, cfg.bn_momentum, ptr(L.running_mean), ptr(L.running_var), ptr(L.mean), ptr(L.rstd), ptr(L.scale),
-                       ptr(L.shift), int(train))
-            self._call(lib.dr_cuda_bn_apply, ptr(L.a), B, L.N, L.N, ptr(L.scale), ptr(L.shift), ptr(L.y), L.N)
-            x, ldx = L.y, L.N
+            if i + 1 < nb:
+                self._bn_fold(L, self.bot[i + 1], train)
+                x, ldx = L.a, L.N
+            else:   # last bottom layer: its normalised output feeds the interaction, materialise it ([B, 16] only)
+                self._call(lib.dr_cuda_bn_finalize, ptr(L.S1), ptr(L.S2), L.N, B, ptr(self.p(L.name + "/bn_gamma")), ptr(self.p(L.name + "/bn_beta")),
+                           cfg.bn_eps, cfg.bn_momentum, ptr(L.running_mean), ptr(L.running_var), ptr(L.mean), ptr(L.rstd), ptr(L.scale),
+                           ptr(L.shift), int(train))
+                self._call(lib.dr_cuda_bn_apply, ptr(L.a), B, L.N, L.N, ptr(L.scale), ptr(L.shift), ptr(L.y), L.N)
+                x, ldx = L.y, L.N
         if fork:
             main.wait_stream(self._side)
         else:
@@ -335,45 +366,57 @@ class DLRMEngine:
         inv = 1.0 / float(self.B * self.world)
         self._call(self.lib.dr_cuda_head, ptr(h.a), h.N, self.B, self.head_K, ptr(self.p("logits/kernel")), ptr(self.p("logits/bias")),
                    ptr(self.labels), inv, ptr(self.prob), ptr(self.loss), ptr(h.da), ptr(self.g("logits/kernel")),
-                   ptr(self.g("logits/bias")), 1, int(train))
+                   ptr(self.g("logits/bias")), 1, int(train), ptr(self.g(h.name + "/bias")) if train else None)
 
     def _backward(self) -> None:
-        lib, B = self.lib, self.B
-        # ---- top MLP (da already holds grad wrt pre-activation of the last hidden layer)
+        lib, B, cfg = self.lib, self.B, self.cfg
+        v2 = not cfg.gemm_v1
+        # ---- top MLP (da of the last hidden layer and its bias gradient were produced by the head kernel)
         for i in range(len(self.top) - 1, -1, -1):
             L = self.top[i]
             x, ldx = (self.top[i - 1].a, self.top[i - 1].N) if i > 0 else (self.Z, self.Zp)
             self._gemm_dw(L.da, L.N, x, ldx, L.N, L.Kp, self.g(L.name + "/kernel"), L.Kp)
-            self._call(lib.dr_cuda_colstats, ptr(L.da), None, B, L.N, L.N, L.N, ptr(self.g(L.name + "/bias")), None)
             if i > 0:
-                P = self.top[i - 1]
-                self._gemm(L.da, L.N, L.wt_bf16, L.Np, B, P.N, L.N, None, False, P.a, P.N, P.da, P.N)      # * relu'(h_{i-1})
+                P = self.top[i - 1]       # dX epilogue: * relu'(h_{i-1}) and bias gradient of layer i-1 (column sums) fused
+                self._gemm(L.da, L.N, L.wt_bf16, L.Np, B, P.N, L.N, None, False, P.a, P.N, P.da, P.N, aux_mode=1,
+                           S1=self.g(P.name + "/bias") if v2 else None)
+                if not v2:
+                    self._call(lib.dr_cuda_colstats, ptr(P.da), None, B, P.N, P.N, P.N, ptr(self.g(P.name + "/bias")), None)
             else:
                 self._gemm(L.da, L.N, L.wt_bf16, L.Np, B, self.Zp, L.N, None, False, None, 0, self.dZ, self.Zp)
-        # ---- interaction backward -> dx (wrt BN output of last bottom layer), demb (feature-major, peer-readable)
+        # ---- interaction backward -> dy of the last bottom layer, demb (feature-major, peer-readable)
         last = self.bot[-1]
         self._call(lib.dr_cuda_dot_interaction_bwd, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.emb), B * self.D, self.D, self.T, self.D, B,
                    ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
         main = torch.cuda.current_stream(self.dev)
-        fork = self.cfg.overlap_embedding
+        fork = cfg.overlap_embedding
         if fork:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._embedding_backward()
-        # ---- bottom MLP backward: BN backward (+ReLU mask) -> dW / db -> dX
+        # ---- bottom MLP backward
         for i in range(len(self.bot) - 1, -1, -1):
             L = self.bot[i]
-            x, ldx = (self.bot[i - 1].y, self.bot[i - 1].N) if i > 0 else (self.x0, self.x0.shape[1])
-            self._call(lib.dr_cuda_colstats, ptr(L.dy), ptr(L.a), B, L.N, L.N, L.N, ptr(L.S1), ptr(L.S2))
-            self._call(lib.dr_cuda_bn_bwd_finalize, ptr(L.S1), ptr(L.S2), L.N, B, ptr(L.mean), ptr(L.rstd), ptr(self.g(L.name + "/bn_gamma")),
+            if i == len(self.bot) - 1 or not v2:      # statistics of dy not produced by a v2 GEMM epilogue
+                self._call(lib.dr_cuda_colstats, ptr(L.dy), ptr(L.a), B, L.N, L.N, L.N, ptr(L.S1b), ptr(L.S2b))
+            self._call(lib.dr_cuda_bn_bwd_finalize, ptr(L.S1b), ptr(L.S2b), L.N, B, ptr(L.mean), ptr(L.rstd), ptr(self.g(L.name + "/bn_gamma")),
                        ptr(self.g(L.name + "/bn_beta")), ptr(L.c1), ptr(L.c2), 1.0)
-            self._call(lib.dr_cuda_bn_bwd_apply, ptr(L.dy), ptr(L.a), B, L.N, L.N, ptr(L.scale), ptr(L.mean), ptr(L.rstd), ptr(L.c1), ptr(L.c2),
-                       ptr(L.da), 1)
-            self._gemm_dw(L.da, L.N, x, ldx, L.N, L.Kp, self.g(L.name + "/kernel"), L.Kp)
-            self._call(lib.dr_cuda_colstats, ptr(L.da), None, B, L.N, L.N, L.N, ptr(self.g(L.name + "/bias")), None)
+            # da = relu'(a) * BN'(dy)  (+ bias gradient = column sums of da, fused)
+            self._call(lib.dr_cuda_bn_bwd_apply_v2, ptr(L.dy), ptr(L.a), B, L.N, L.N, ptr(L.scale), ptr(L.mean), ptr(L.rstd), ptr(L.c1), ptr(L.c2),
+                       ptr(L.da), 1, ptr(self.g(L.name + "/bias")))
             if i > 0:
                 P = self.bot[i - 1]
-                self._gemm(L.da, L.N, L.wt_bf16, L.Np, B, P.N, L.N, None, False, None, 0, P.dy, P.N)
+                # dW = (da^T a_{l-1}) diag(s_{l-1}) + db t_{l-1}^T  : GEMM on the un-normalised activation + tiny fix-up
+                self._gemm_dw(L.da, L.N, P.a, P.N, L.N, L.Kp, self.g(L.name + "/kernel"), L.Kp)
+                self._call(lib.dr_cuda_dw_fixup, ptr(self.g(L.name + "/kernel")), ptr(self.g(L.name + "/bias")), ptr(P.scale), ptr(P.shift), L.N, L.K, L.Kp)
+                # dy_{l-1} = da W  with BatchNorm-backward statistics (sum dy, sum dy * a_{l-1}) fused into the epilogue
+                fused = v2 and P.N > 32
+                self._gemm(L.da, L.N, L.wt_bf16, L.Np, B, P.N, L.N, None, False, P.a if fused else None, P.N, P.dy, P.N, aux_mode=2 if fused else 0,
+                           S1=P.S1b if fused else None, S2=P.S2b if fused else None)
+                if v2 and not fused:
+                    self._call(lib.dr_cuda_colstats, ptr(P.dy), ptr(P.a), B, P.N, P.N, P.N, ptr(P.S1b), ptr(P.S2b))
+            else:
+                self._gemm_dw(L.da, L.N, self.x0, self.x0.shape[1], L.N, L.Kp, self.g(L.name + "/kernel"), L.Kp)
         if fork:
             main.wait_stream(self._side)
         else:
@@ -391,6 +434,7 @@ class DLRMEngine:
 
     def _step_body(self) -> None:
         self.loss.zero_()
+        self.stats.zero_()
         self._forward(True)
         self._head(True)
         self._backward()

@@ -120,8 +120,8 @@ def test_head():
     b = torch.tensor([0.1, 0, 0, 0], device="cuda")
     y = (torch.rand(B, device="cuda") < 0.3).float()
     prob = torch.empty(B, device="cuda"); loss = torch.zeros(1, device="cuda")
-    dh = torch.empty_like(h); dw = torch.zeros(K, device="cuda"); db = torch.zeros(4, device="cuda")
-    assert lib.dr_cuda_head(_p(h), K, B, K, _p(w), _p(b), _p(y), 1.0 / B, _p(prob), _p(loss), _p(dh), _p(dw), _p(db), 1, 1, _s()) == 0
+    dh = torch.empty_like(h); dw = torch.zeros(K, device="cuda"); db = torch.zeros(4, device="cuda"); dbh = torch.zeros(K, device="cuda")
+    assert lib.dr_cuda_head(_p(h), K, B, K, _p(w), _p(b), _p(y), 1.0 / B, _p(prob), _p(loss), _p(dh), _p(dw), _p(db), 1, 1, _p(dbh), _s()) == 0
     hf = h.float().requires_grad_(True); wf = w.clone().requires_grad_(True); bf = b[:1].clone().requires_grad_(True)
     z = hf @ wf + bf
     ref_loss = torch.nn.functional.binary_cross_entropy_with_logits(z, y)
@@ -133,6 +133,7 @@ def test_head():
     assert abs(db[0].item() - bf.grad.item()) < 1e-4
     ref_dh = hf.grad * (h.float() > 0)
     assert (dh.float() - ref_dh).abs().max().item() < 1e-5 + 2e-2 * ref_dh.abs().max().item()
+    assert (dbh - dh.float().sum(0)).abs().max().item() < 1e-4
 
 
 def test_dot_interaction():
@@ -179,3 +180,75 @@ def test_fm_kernels():
     ref.backward(dfm.float())
     torch.cuda.synchronize()
     assert (demb.float() - ef.grad).abs().max().item() < 3e-2 * (ef.grad.abs().max().item() + 1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 16), (5000, 256, 512), (65536, 512, 368), (3000, 64, 256), (2048, 368, 512), (777, 128, 64)])
+def test_gemm_tn_v2_epilogue_stats_and_aux(M, N, K):
+    """v2 epilogue: TMA-store staging, fused column statistics, aux tile as ReLU mask / statistics partner."""
+    torch.manual_seed(7)
+    lib = _lib()
+    A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda") * 0.1
+    ref0 = A.float() @ B.float().t()
+    # (a) forward: bias + relu + S1 = sum(out), S2 = sum(out^2)
+    out = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    S1 = torch.zeros(N, device="cuda"); S2 = torch.zeros(N, device="cuda")
+    assert lib.dr_cuda_gemm_tn_ex(_p(A), K, _p(B), K, M, N, K, _p(bias), 1, None, 0, 0, _p(out), N, None, _p(S1), _p(S2), 0, 0, _s()) == 0
+    torch.cuda.synchronize()
+    ref = (ref0 + bias).relu()
+    scale = ref.abs().max().item() + 1e-6
+    assert (out.float() - ref).abs().max().item() / scale < 2e-2
+    assert (S1 - ref.sum(0)).abs().max().item() < 2e-3 * M ** 0.5 * scale + 1e-2 * ref.sum(0).abs().max().item()
+    assert (S2 - (ref * ref).sum(0)).abs().max().item() < 2e-2 * (ref * ref).sum(0).abs().max().item() + 1e-3
+    # (b) backward dX with ReLU mask + S1 (bias gradient)
+    act = torch.randn(M, N, device="cuda").relu().bfloat16()
+    S1.zero_()
+    assert lib.dr_cuda_gemm_tn_ex(_p(A), K, _p(B), K, M, N, K, None, 0, _p(act), N, 1, _p(out), N, None, _p(S1), None, 0, 0, _s()) == 0
+    torch.cuda.synchronize()
+    refm = ref0 * (act.float() > 0)
+    assert (out.float() - refm).abs().max().item() < 2e-2 * (refm.abs().max().item() + 1e-6)
+    assert (S1 - refm.sum(0)).abs().max().item() < 1e-2 * refm.abs().sum(0).max().item() + 1e-3
+    # (c) backward dX with BatchNorm-backward statistics: S1 = sum(out), S2 = sum(out * aux), no mask
+    S1.zero_(); S2.zero_()
+    assert lib.dr_cuda_gemm_tn_ex(_p(A), K, _p(B), K, M, N, K, None, 0, _p(act), N, 2, _p(out), N, None, _p(S1), _p(S2), 0, 0, _s()) == 0
+    torch.cuda.synchronize()
+    assert (out.float() - ref0).abs().max().item() < 2e-2 * (ref0.abs().max().item() + 1e-6)
+    assert (S2 - (ref0 * act.float()).sum(0)).abs().max().item() < 1e-2 * (ref0.abs() * act.float()).sum(0).max().item() + 1e-3
+    assert (S1 - ref0.sum(0)).abs().max().item() < 1e-2 * ref0.abs().sum(0).max().item() + 1e-3
+
+
+def test_bn_fold_fixup_and_bwd_apply_v2():
+    torch.manual_seed(8)
+    lib = _lib()
+    B, K, Nn = 4096, 256, 64
+    a = torch.randn(B, K, device="cuda").relu().bfloat16()
+    gamma = torch.rand(K, device="cuda") + 0.5; beta = torch.randn(K, device="cuda") * 0.1
+    Wn = torch.randn(Nn, K, device="cuda") * 0.1; bn = torch.randn(Nn, device="cuda") * 0.1
+    S1 = a.float().sum(0); S2 = (a.float() ** 2).sum(0)
+    mean, rstd, scale, shift = (torch.zeros(K, device="cuda") for _ in range(4))
+    rm, rv = torch.zeros(K, device="cuda"), torch.ones(K, device="cuda")
+    Wf = torch.empty(Nn, K, device="cuda", dtype=torch.bfloat16); bf = torch.empty(Nn, device="cuda")
+    assert lib.dr_cuda_bn_fold(_p(S1), _p(S2), K, B, _p(gamma), _p(beta), 1e-3, 0.99, _p(rm), _p(rv), _p(mean), _p(rstd), _p(scale), _p(shift), 1,
+                               _p(Wn), _p(bn), Nn, K, _p(Wf), _p(bf), _s()) == 0
+    torch.cuda.synchronize()
+    y = torch.nn.functional.batch_norm(a.float(), None, None, gamma, beta, True, 0.0, 1e-3)
+    ref = y @ Wn.t() + bn
+    got = a.float() @ Wf.float().t() + bf
+    assert (got - ref).abs().max().item() < 3e-2 * (ref.abs().max().item() + 1)
+    # dW fix-up: dW = G * s + db t^T
+    da = torch.randn(B, Nn, device="cuda") * 0.1
+    G = (da.t() @ a.float()).contiguous(); db = da.sum(0)
+    dW = G.clone()
+    assert lib.dr_cuda_dw_fixup(_p(dW), _p(db), _p(scale), _p(shift), Nn, K, K, _s()) == 0
+    torch.cuda.synchronize()
+    assert (dW - da.t() @ (a.float() * scale + shift)).abs().max().item() < 1e-2
+    # bn backward apply v2 (+ fused bias gradient)
+    dy = (torch.randn(B, K, device="cuda") * 0.1).bfloat16()
+    c1 = dy.float().mean(0); xhat = (a.float() - mean) * rstd; c2 = (dy.float() * xhat).mean(0)
+    out = torch.empty_like(a); dbias = torch.zeros(K, device="cuda")
+    assert lib.dr_cuda_bn_bwd_apply_v2(_p(dy), _p(a), B, K, K, _p(scale), _p(mean), _p(rstd), _p(c1), _p(c2), _p(out), 1, _p(dbias), _s()) == 0
+    torch.cuda.synchronize()
+    refda = scale * (dy.float() - c1 - xhat * c2) * (a.float() > 0)
+    assert (out.float() - refda).abs().max().item() < 2e-2 * (refda.abs().max().item() + 1e-3)
+    assert (dbias - refda.sum(0)).abs().max().item() < 2e-2 * refda.abs().sum(0).max().item() + 1e-3
