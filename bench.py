@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--alpha", type=float, default=1.05, help="power-law exponent of the synthetic id distribution")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--optimizer", default="adagrad")
+    ap.add_argument("--sparse-blocks", type=int, default=4, help="resident blocks/SM of the side-stream sparse kernels")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--gemm-v1", action="store_true")
     return ap.parse_args()
 
 
@@ -137,7 +140,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from deeprec_b200.models.dlrm_engine import DLRMConfig, DLRMEngine
-    cfg = DLRMConfig(batch_size=args.batch, optimizer=args.optimizer)
+    cfg = DLRMConfig(batch_size=args.batch, optimizer=args.optimizer, sparse_blocks_per_sm=args.sparse_blocks,
+                     overlap_embedding=not args.no_overlap, gemm_v1=args.gemm_v1)
     comm = None
     if world > 1:
         if args.impl == "nccl_baseline":

@@ -139,6 +139,7 @@ def cuda():
                 from . import _cuda_sigs
                 lib = _cuda_sigs.bind(C.CDLL(path))
                 lib.dr_cuda_set_device.argtypes, lib.dr_cuda_set_device.restype = [C.c_int], C.c_int
+                lib.dr_cuda_set_sparse_blocks_per_sm.argtypes, lib.dr_cuda_set_sparse_blocks_per_sm.restype = [C.c_int], C.c_int
                 if torch.cuda.is_available():
                     lib.dr_cuda_set_device(torch.cuda.current_device())
                 _CUDA = lib

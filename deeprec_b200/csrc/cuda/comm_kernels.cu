@@ -197,6 +197,7 @@ extern "C" {
 
 // ---- device / IPC plumbing (this library links its own static cudart: make its current device explicit) ----------
 int dr_cuda_set_device(int dev) { DR_CUDA_CHECK(cudaSetDevice(dev)); return 0; }
+int dr_cuda_set_sparse_blocks_per_sm(int n) { sparse_blocks_per_sm() = n < 1 ? 1 : n; return 0; }
 int dr_cuda_get_device() { int d = -1; cudaGetDevice(&d); return d; }
 
 int dr_comm_alloc(int64_t bytes, void** out) {
@@ -231,7 +232,7 @@ int dr_comm_mp_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map,
                       int32_t* pos_out, int64_t* ulist, int32_t* nunique, int64_t ulist_cap, cudaStream_t s) {
   int64_t n = (int64_t)nl * W * B;
   if (n == 0) return 0;
-  int grid = grid_for(n, 256, kNumSMs * 8);
+  int grid = grid_for(n, 256, kNumSMs * sparse_blocks_per_sm());
   switch (dim / 4) {
     case 2: k_mp_lookup<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
     case 4: k_mp_lookup<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
@@ -249,7 +250,7 @@ int dr_comm_mp_sparse_grad(const DrDeviceTable* tables_dev, const int32_t* table
   int64_t n = (int64_t)nl * W * B;
   if (n == 0) return 0;
   int lpr = dim / 4;
-  int grid = grid_for(n * lpr, 256, kNumSMs * 16);
+  int grid = grid_for(n * lpr, 256, kNumSMs * sparse_blocks_per_sm());
   switch (lpr) {
     case 2: k_mp_sparse_grad<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
     case 4: k_mp_sparse_grad<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;

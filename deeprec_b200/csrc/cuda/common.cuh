@@ -30,6 +30,10 @@
 namespace drc {
 
 constexpr int kNumSMs = 148;
+
+// Resident-block budget (per SM) of the sparse-path kernels.  They run on a side stream next to the tcgen05 GEMMs
+// (1 CTA/SM, ~200 KB smem, 192 threads): capping them leaves thread slots so both streams really overlap.
+inline int& sparse_blocks_per_sm() { static int v = 16; return v; }
 constexpr int64_t kEmptyKey = INT64_MIN;
 constexpr int64_t kTombKey = INT64_MIN + 1;
 

@@ -263,7 +263,8 @@ __global__ void k_fill_i64(int64_t* p, int64_t v, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 16) {
+inline int grid_for(int64_t n, int block, int max_blocks = 0) {
+  if (max_blocks <= 0) max_blocks = kNumSMs * sparse_blocks_per_sm();
   int64_t b = (n + block - 1) / block;
   if (b < 1) b = 1;
   if (b > max_blocks) b = max_blocks;

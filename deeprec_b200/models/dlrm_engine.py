@@ -63,6 +63,7 @@ class DLRMConfig:
     steps_to_live: int = 0
     seed: int = 1234
     overlap_embedding: bool = True              # fork the embedding branch onto a side stream inside the graph
+    sparse_blocks_per_sm: int = 4               # resident-block budget of the side-stream sparse kernels (overlap with the GEMMs)
     gemm_v1: bool = False                       # A/B switch: direct-store GEMM epilogue + separate statistics passes
 
 
@@ -84,6 +85,7 @@ class DLRMEngine:
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.lib = _native.cuda()
         _native.set_device(self.dev.index)
+        self.lib.dr_cuda_set_sparse_blocks_per_sm(int(cfg.sparse_blocks_per_sm if cfg.overlap_embedding else 16))
         self.comm = comm                           # parallel.p2p.P2PComm or parallel.nccl_baseline.NcclComm (world_size > 1)
         self.B, self.T, self.D = cfg.batch_size, len(cfg.cardinalities), cfg.embedding_dim
         self.kind = _OPT_KIND[cfg.optimizer.lower()]

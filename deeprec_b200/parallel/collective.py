@@ -1,0 +1,120 @@
+"""CollectiveStrategy facade + GroupEmbedding strategy switch.
+
+Parity: python/distribute/group_embedding_collective_strategy.py:28-138 (``CollectiveStrategy.{scope, embedding_scope,
+world_size, rank, estimator, export_saved_model}``), python/framework/group_embedding_types.py:24-49 (strategy enum),
+``tf.config.experimental.enable_distributed_strategy`` (framework/config.py:626), env ``COLLECTIVE_STRATEGY`` (sok | hb).
+Here there is one built-in backend: model-parallel embedding shards over NVLink P2P (parallel/p2p.py) with the dense net
+data-parallel; ``localized`` = single-process fused GroupEmbedding.
+"""
+from __future__ import annotations
+
+import contextlib
+import enum
+import os
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import strategy as _strategy
+
+
+class DistStrategy(enum.Enum):
+    SOK = "sok"                 # accepted for API parity: maps onto the built-in P2P model-parallel path
+    HB = "hb"
+    COLLECTIVE = "collective"
+    LOCALIZED = "localized"
+    UNKNOWN = "unknown"
+
+
+_ENABLED = DistStrategy.LOCALIZED
+
+
+def enable_distributed_strategy(strategy: str = "collective") -> None:
+    global _ENABLED
+    _ENABLED = DistStrategy(strategy if strategy in ("sok", "hb", "collective", "localized") else "unknown")
+
+
+class CollectiveStrategy:
+    def __init__(self, backend: Optional[str] = None):
+        name = os.environ.get("COLLECTIVE_STRATEGY", "collective")
+        self.kind = DistStrategy(name) if name in ("sok", "hb", "collective", "localized") else DistStrategy.COLLECTIVE
+        self.in_embedding_scope = False
+        self._in_scope = False
+        if dist.is_available() and not dist.is_initialized() and "RANK" in os.environ:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            be = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+            if be == "nccl":
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            dist.init_process_group(be)
+        self._mp_tables = {}
+        _strategy.set_current(self)
+
+    @property
+    def world_size(self) -> int:
+        return dist.get_world_size() if dist.is_initialized() else 1
+
+    @property
+    def rank(self) -> int:
+        return dist.get_rank() if dist.is_initialized() else 0
+
+    @contextlib.contextmanager
+    def scope(self):
+        """Everything under the scope is data-parallel (dense parameters are kept bitwise in sync by the fused
+        all-reduce + optimizer kernel; the hvd.BroadcastGlobalVariablesHook analogue is ``broadcast_parameters``)."""
+        self._in_scope = True
+        try:
+            yield self
+        finally:
+            self._in_scope = False
+
+    @contextlib.contextmanager
+    def embedding_scope(self):
+        """Lookups issued here are model-parallel: table t lives on rank t % world (table-wise, embedding_ops.py:1671-1676)."""
+        self.in_embedding_scope = True
+        try:
+            yield self
+        finally:
+            self.in_embedding_scope = False
+
+    def broadcast_parameters(self, module: torch.nn.Module, src: int = 0) -> None:
+        if self.world_size > 1:
+            for p in module.parameters():
+                if p.numel():
+                    dist.broadcast(p.data, src)
+
+    def allreduce_gradients(self, params) -> None:
+        """Dense gradient all-reduce for generic modules (the flagship engine fuses this with the optimizer)."""
+        if self.world_size > 1:
+            for p in params:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+
+    # ---- model-parallel GroupEmbedding for generic modules (gloo/nccl all-to-all; the fused engine uses parallel/p2p.py)
+    def owner_of(self, table_index: int) -> int:
+        return table_index % self.world_size
+
+    def distributed_lookup(self, params, sp_ids, combiners, sp_weights=None) -> List[torch.Tensor]:
+        from ..ops.embedding_ops import embedding_lookup_sparse, SparseIds
+        W, r = self.world_size, self.rank
+        outs: List[Optional[torch.Tensor]] = [None] * len(params)
+        # every rank looks up the tables it owns for EVERY rank's ids, then results are exchanged (all-gather of ids,
+        # reduce-scatter-free since one-hot ownership): simple, correct reference path for CPU/gloo tests.
+        for t, (p, s, c) in enumerate(zip(params, sp_ids, combiners)):
+            owner = self.owner_of(t)
+            objs = [None] * W
+            dist.all_gather_object(objs, (s.values.cpu(), s.row_ids.cpu(), s.batch_size, None if s.weights is None else s.weights.cpu()))
+            if owner == r:
+                res = []
+                for (v, rid, B, w) in objs:
+                    res.append(embedding_lookup_sparse(p, SparseIds(v, rid, B, w), None, c))
+            else:
+                res = None
+            recv = [None]
+            dist.scatter_object_list(recv, res if owner == r else None, src=owner)
+            outs[t] = recv[0]
+        return outs
+
+    def export_saved_model(self, *a, **k):
+        from ..serving.export import export_saved_model
+        return export_saved_model(*a, **k)
