@@ -25,6 +25,7 @@ constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;    // 6 warps
+constexpr int kGemmThreadsV2 = 320;  // 10 warps: TMA, MMA, 8 epilogue
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -263,8 +264,8 @@ struct SmemLayoutTN2 {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStoreBytes = 4 * 2 * 4096;      // 4 epilogue warps x double buffer x [32 rows][128 B]
-  static constexpr int kAuxBytes = 4 * 4096;            // 4 epilogue warps x [32 rows][128 B]
+  static constexpr int kStoreBytes = 8 * 4096;          // 8 epilogue warps x [32 rows][128 B] staging
+  static constexpr int kAuxBytes = 8 * 4096;            // 8 epilogue warps x [32 rows][128 B] aux tile
   static constexpr int kTotal = kSt * kStageBytes + kStoreBytes + kAuxBytes + 1024 + 256;
 };
 
@@ -284,7 +285,7 @@ __device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsV2, 1)
 k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
              int M, int N, int K, Epilogue ep) {
   using L = SmemLayoutTN2<BLOCK_N>;
@@ -311,7 +312,7 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
     for (int i = 0; i < kSt; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, kTmemCols); tmem_relinquish(); }
@@ -364,12 +365,15 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ================= epilogue warps =================
+    // 8 epilogue warps: two per TMEM lane quarter (q = warp % 4 is a hardware rule), interleaved over the 64-column
+    // chunks, so every SM sub-partition hosts two independent epilogue instruction streams (latency hiding).
+    const int ew = warp - 2;
     const int q = warp & 3;
-    uint8_t* my_store = store_base + q * 2 * 4096;
-    uint8_t* my_aux = aux_base + q * 4096;
+    const int half = ew >> 2;
+    uint8_t* my_store = store_base + ew * 4096;
+    uint8_t* my_aux = aux_base + ew * 4096;
     const uint32_t swz = (uint32_t)(lane & 7);
     int acc = 0; uint32_t acc_phase = 0;
-    int sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -382,6 +386,7 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
         const int col0 = n_blk * BLOCK_N + c0;
         if (col0 >= N) break;                           // warp-uniform
+        if (((c0 >> 6) & 1) != half) continue;          // the sibling warp of this lane quarter owns this chunk
         // ---- aux tile [32 rows x 64 cols] -> swizzled smem (coalesced: 8 lanes cover one 128 B row segment)
         if (ep.mask_src) {
           __syncwarp();
@@ -394,10 +399,10 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           __syncwarp();
         }
-        // the staging buffer we are about to fill was handed to TMA two chunks ago: wait until it has been read
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // the staging buffer was handed to TMA one chunk ago: wait until it has been read
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-        uint8_t* stg = my_store + sbuf * 4096;
+        uint8_t* stg = my_store;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
@@ -464,7 +469,6 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_store_2d(&tmC, stg, col0, row0);
           tma_store_commit();
         }
-        sbuf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
@@ -637,7 +641,7 @@ int launch_tn_v2(const CUtensorMap& ta, const void* B, int M, int N, int K, int6
   int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;
   if (grid > max_ctas) grid = max_ctas;
-  k_gemm_tn_v2<BN><<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, tc, M, N, K, ep);
+  k_gemm_tn_v2<BN><<<grid, kGemmThreadsV2, L::kTotal, s>>>(ta, tb, tc, M, N, K, ep);
   DR_LAUNCH_CHECK();
   return 0;
 }
