@@ -27,6 +27,7 @@ CUDA_SOURCES = [
     "cuda/interaction_kernels.cu",
     "cuda/comm_kernels.cu",
     "cuda/runtime.cu",
+    "cuda/serving_runtime.cu",
 ]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

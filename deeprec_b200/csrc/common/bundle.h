@@ -1,0 +1,111 @@
+// Checkpoint tensor bundle: <prefix>.data (raw, 64-byte aligned records) + <prefix>.index (text).
+// Header-only so the host engine (training checkpoints) and the serving runtime (model load / delta update)
+// share one implementation.  Streaming 8 MiB writer, CRC32 per tensor, atomic publish (data first, index last).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace dr {
+
+inline uint32_t Crc32(const uint8_t* p, size_t n, uint32_t crc = 0) {
+  static uint32_t table[256]; static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+    init = true;
+  }
+  crc = ~crc;
+  for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Tensor bundle: <prefix>.data (raw, 64-byte aligned records) + <prefix>.index (text).
+// ---------------------------------------------------------------------------------------
+struct BundleEntry { std::string name, dtype; std::vector<int64_t> shape; int64_t offset = 0, nbytes = 0; uint32_t crc = 0; };
+
+class BundleWriter {
+ public:
+  explicit BundleWriter(const std::string& prefix) : prefix_(prefix) {
+    f_ = fopen((prefix + ".data.tmp").c_str(), "wb");
+    buf_.resize(8 << 20);
+    if (f_) setvbuf(f_, buf_.data(), _IOFBF, buf_.size());
+  }
+  bool ok() const { return f_ != nullptr; }
+  int Add(const char* name, const char* dtype, const int64_t* shape, int ndim, const void* data, int64_t nbytes) {
+    if (!f_) return -1;
+    int64_t pad = (64 - (off_ & 63)) & 63;
+    static const char zeros[64] = {0};
+    if (pad) { fwrite(zeros, 1, pad, f_); off_ += pad; }
+    BundleEntry e; e.name = name; e.dtype = dtype; e.shape.assign(shape, shape + ndim); e.offset = off_; e.nbytes = nbytes;
+    e.crc = Crc32(static_cast<const uint8_t*>(data), (size_t)nbytes);
+    if (nbytes && fwrite(data, 1, (size_t)nbytes, f_) != (size_t)nbytes) return -2;
+    off_ += nbytes;
+    entries_.push_back(std::move(e));
+    return 0;
+  }
+  int Close() {
+    if (!f_) return -1;
+    fclose(f_); f_ = nullptr;
+    FILE* fi = fopen((prefix_ + ".index.tmp").c_str(), "w");
+    if (!fi) return -2;
+    fprintf(fi, "DEEPREC_B200_BUNDLE 1 %zu\n", entries_.size());
+    for (auto& e : entries_) {
+      fprintf(fi, "%s\t%s\t%zu", e.name.c_str(), e.dtype.c_str(), e.shape.size());
+      for (auto d : e.shape) fprintf(fi, "\t%lld", (long long)d);
+      fprintf(fi, "\t%lld\t%lld\t%u\n", (long long)e.offset, (long long)e.nbytes, e.crc);
+    }
+    fclose(fi);
+    // atomic publish: data first, index last (a reader that sees the index sees complete data)
+    if (rename((prefix_ + ".data.tmp").c_str(), (prefix_ + ".data").c_str()) != 0) return -3;
+    if (rename((prefix_ + ".index.tmp").c_str(), (prefix_ + ".index").c_str()) != 0) return -4;
+    return 0;
+  }
+  ~BundleWriter() { if (f_) fclose(f_); }
+ private:
+  std::string prefix_; FILE* f_ = nullptr; std::vector<char> buf_; int64_t off_ = 0; std::vector<BundleEntry> entries_;
+};
+
+class BundleReader {
+ public:
+  explicit BundleReader(const std::string& prefix) : prefix_(prefix) {
+    FILE* fi = fopen((prefix + ".index").c_str(), "r");
+    if (!fi) return;
+    char magic[64]; int ver; size_t n;
+    if (fscanf(fi, "%63s %d %zu\n", magic, &ver, &n) != 3 || std::string(magic) != "DEEPREC_B200_BUNDLE") { fclose(fi); return; }
+    std::vector<char> line(1 << 16);
+    for (size_t i = 0; i < n; ++i) {
+      if (!fgets(line.data(), (int)line.size(), fi)) break;
+      std::vector<std::string> tok; char* save = nullptr;
+      for (char* t = strtok_r(line.data(), "\t\n", &save); t; t = strtok_r(nullptr, "\t\n", &save)) tok.emplace_back(t);
+      if (tok.size() < 6) continue;
+      BundleEntry e; e.name = tok[0]; e.dtype = tok[1]; size_t nd = std::stoul(tok[2]);
+      if (tok.size() != 3 + nd + 3) continue;
+      for (size_t d = 0; d < nd; ++d) e.shape.push_back(std::stoll(tok[3 + d]));
+      e.offset = std::stoll(tok[3 + nd]); e.nbytes = std::stoll(tok[4 + nd]); e.crc = (uint32_t)std::stoul(tok[5 + nd]);
+      index_[e.name] = entries_.size(); entries_.push_back(std::move(e));
+    }
+    fclose(fi);
+    f_ = fopen((prefix + ".data").c_str(), "rb");
+  }
+  ~BundleReader() { if (f_) fclose(f_); }
+  bool ok() const { return f_ != nullptr; }
+  const std::vector<BundleEntry>& entries() const { return entries_; }
+  const BundleEntry* Find(const std::string& n) const { auto it = index_.find(n); return it == index_.end() ? nullptr : &entries_[it->second]; }
+  int Read(const BundleEntry& e, void* dst, int verify) {
+    std::lock_guard<std::mutex> l(mu_);
+    if (fseeko(f_, e.offset, SEEK_SET) != 0) return -1;
+    if (e.nbytes && fread(dst, 1, (size_t)e.nbytes, f_) != (size_t)e.nbytes) return -2;
+    if (verify && Crc32(static_cast<const uint8_t*>(dst), (size_t)e.nbytes) != e.crc) return -3;
+    return 0;
+  }
+ private:
+  std::string prefix_; FILE* f_ = nullptr; std::vector<BundleEntry> entries_; std::map<std::string, size_t> index_; std::mutex mu_;
+};
+
+
+}  // namespace dr

@@ -45,7 +45,15 @@ __global__ void __launch_bounds__(256) k_colstats(const __nv_bfloat16* __restric
   extern __shared__ float sh[];                  // [2][N]
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  if (tr < rows_par) {
+  bool leader = tr < rows_par;
+  if (tpr < 32 && (32 % tpr) == 0) {      // narrow matrices: lanes with equal (lane % tpr) own the same columns -> shuffle-reduce first
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      for (int off = 16; off >= tpr; off >>= 1) { a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], off); a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], off); }
+    }
+    leader = (threadIdx.x & 31) < tpr;
+  }
+  if (leader) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { atomicAdd(&sh[tc * 8 + j], a1[j]); if (S2) atomicAdd(&sh[N + tc * 8 + j], a2[j]); }
   }
@@ -318,6 +326,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_v2(const __nv_bfloat16* __
   const int rows_par = blockDim.x / tpr;
   const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
   float sc[8], mu[8], rs[8], k1[8], k2[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (tr < rows_par) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -345,7 +355,14 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_v2(const __nv_bfloat16* __
     extern __shared__ float sh[];
     for (int i = threadIdx.x; i < N; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
-    if (tr < rows_par) {
+    bool leader = tr < rows_par;
+    if (tpr < 32 && (32 % tpr) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        for (int off = 16; off >= tpr; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+      leader = (threadIdx.x & 31) < tpr;
+    }
+    if (leader) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) atomicAdd(&sh[tc * 8 + j], acc[j]);
     }
@@ -424,7 +441,7 @@ int dr_cuda_bn_bwd_apply_v2(const void* dy, const void* a, int64_t B, int N, int
                             const float* rstd, const float* c1, const float* c2, void* da, int relu_mask, float* dbias, cudaStream_t s) {
   if (N % 8 || N / 8 > 256) return -2;
   int tpr = N / 8; int rows_par = 256 / tpr;
-  int grid = grid_for((B + rows_par - 1) / rows_par, 4, kNumSMs * 8);
+  int grid = grid_for((B + rows_par - 1) / rows_par, 2, kNumSMs * 8);
   k_bn_bwd_apply_v2<<<grid, 256, N * sizeof(float), s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a, B, N, ld, scale, mean, rstd, c1, c2,
                                                         (__nv_bfloat16*)da, relu_mask, dbias);
   DR_LAUNCH_CHECK();

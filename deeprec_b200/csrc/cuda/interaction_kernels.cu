@@ -181,6 +181,201 @@ __global__ void __launch_bounds__(256) k_fm_bwd(const __nv_bfloat16* __restrict_
   }
 }
 
+
+// =================================================================================================
+// tcgen05 versions (D = 16, T + 1 <= 32): FOUR samples share one 128-row UMMA tile.
+//   forward :  G = A A^T with A[128 x 16] = 4 samples x 32 (padded) feature rows.  One tcgen05.mma (M=128, N=128, K=16)
+//              per 4 samples; warp w reads the w-th diagonal 32x32 block of the accumulator straight out of TMEM
+//              (tcgen05.ld 32x32b: lane i <- row i of its sample's Gram matrix) and emits the strict lower triangle.
+//   backward:  dF = S F with S the symmetric 32x32 gradient matrix of a sample; A = blockdiag(S_0..S_3) [128 x 128],
+//              B = F^T [16 x 128]; eight tcgen05.mma k-steps (M=128, N=16, K=128); lane i of warp w <- dF_i.
+// Operands are written by the warps into NO-SWIZZLE K-major core-matrix layout (8 rows x 16 B core matrices,
+// LBO = next 8-element K chunk, SBO = next 8-row group), accumulators live in TMEM.  The SIMT kernels above remain
+// as the general-shape fallback.
+// =================================================================================================
+__device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
+  return d;                          // layout_type = 0 (SWIZZLE_NONE)
+}
+
+__global__ void __launch_bounds__(128) k_dot_fwd_tc(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ emb,
+                                                    int64_t emb_stride_t, int64_t emb_stride_b, int T, int64_t B,
+                                                    __nv_bfloat16* __restrict__ Z, int64_t ldz) {
+  constexpr int D = 16;
+  __shared__ __align__(128) uint8_t sA[128 * 32];          // [16 row-groups][2 K-chunks][8 rows][16 B]
+  __shared__ __align__(16) __nv_bfloat16 sZ[4][512];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = T + 1;
+  for (int i = threadIdx.x; i < 128 * 32 / 16; i += 128) reinterpret_cast<int4*>(sA)[i] = make_int4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 128); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t a_addr = smem_u32(sA);
+  const uint64_t desc = umma_desc_noswz(a_addr, 128, 256);
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+  const int R = warp * 32 + lane;                                  // my row in the tile
+  uint8_t* my_row = sA + (R >> 3) * 256 + (R & 7) * 16;
+  const int64_t ngroups = (B + 3) / 4;
+  uint32_t phase = 0;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t b = g * 4 + warp;
+    const bool live = b < B;
+    if (lane < F && live) {
+      const __nv_bfloat16* src = lane == 0 ? x + b * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + b * emb_stride_b;
+      const int4 c0 = ld_nc_v4(src), c1 = ld_nc_v4(src + 8);
+      *reinterpret_cast<int4*>(my_row) = c0;
+      *reinterpret_cast<int4*>(my_row + 128) = c1;
+      if (lane == 0) { *reinterpret_cast<int4*>(&sZ[warp][0]) = c0; *reinterpret_cast<int4*>(&sZ[warp][8]) = c1; }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      umma_bf16(tmem, desc, desc, idesc, 0u);
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    uint32_t r[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + warp * 32, r);
+    tmem_ld_wait();
+    if (live) {
+      const int base = D + lane * (lane - 1) / 2;
+#pragma unroll
+      for (int j = 0; j < 31; ++j)
+        if (j < lane && lane < F) sZ[warp][base + j] = __float2bfloat16(__uint_as_float(r[j]));
+      const int used = D + F * (F - 1) / 2;
+      for (int c = used + lane; c < ldz; c += 32) sZ[warp][c] = __float2bfloat16(0.f);
+      __syncwarp();
+      for (int c = lane * 8; c < ldz; c += 256)
+        *reinterpret_cast<int4*>(Z + b * ldz + c) = *reinterpret_cast<const int4*>(&sZ[warp][c]);
+    }
+    tc_fence_before();
+    __syncthreads();          // all TMEM reads + smem tile reads done before the next group overwrites them
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+__global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restrict__ dZ, int64_t ldz, const __nv_bfloat16* __restrict__ x,
+                                                    int64_t ldx, const __nv_bfloat16* __restrict__ emb, int64_t emb_stride_t,
+                                                    int64_t emb_stride_b, int T, int64_t B, __nv_bfloat16* __restrict__ dx, int64_t lddx,
+                                                    __nv_bfloat16* __restrict__ demb, int64_t demb_stride_t, int64_t demb_stride_b) {
+  constexpr int D = 16;
+  extern __shared__ __align__(128) uint8_t dyn[];
+  uint8_t* sA = dyn;                                   // blockdiag(S): [16 row-groups][16 K-chunks][8 rows][16 B] = 32 KB
+  uint8_t* sB = dyn + 32768;                           // F^T: [2 d-groups][16 K-chunks][8 d][16 B] = 4 KB
+  __nv_bfloat16* sG = reinterpret_cast<__nv_bfloat16*>(dyn + 32768 + 4096);   // [4][512] dZ rows
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = T + 1;
+  for (int i = threadIdx.x; i < (32768 + 4096) / 16; i += 128) reinterpret_cast<int4*>(dyn)[i] = make_int4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 32); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint64_t adesc = umma_desc_noswz(smem_u32(sA), 128, 2048);
+  const uint64_t bdesc = umma_desc_noswz(smem_u32(sB), 128, 2048);
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 16, 0, 0);
+  const int R = warp * 32 + lane;
+  __nv_bfloat16* myG = sG + warp * 512;
+  const int64_t ngroups = (B + 3) / 4;
+  uint32_t phase = 0;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t b = g * 4 + warp;
+    const bool live = b < B;
+    // ---- stage dZ row (coalesced) and F^T
+    if (live) {
+      for (int c = lane * 8; c < ldz; c += 256) *reinterpret_cast<int4*>(myG + c) = ld_nc_v4(dZ + b * ldz + c);
+    } else {
+      for (int c = lane * 8; c < ldz; c += 256) *reinterpret_cast<int4*>(myG + c) = make_int4(0, 0, 0, 0);
+    }
+    if (lane < F) {
+      int4 c0 = make_int4(0, 0, 0, 0), c1 = c0;
+      if (live) {
+        const __nv_bfloat16* src = lane == 0 ? x + b * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + b * emb_stride_b;
+        c0 = ld_nc_v4(src); c1 = ld_nc_v4(src + 8);
+      }
+      const uint32_t w[8] = {(uint32_t)c0.x, (uint32_t)c0.y, (uint32_t)c0.z, (uint32_t)c0.w, (uint32_t)c1.x, (uint32_t)c1.y, (uint32_t)c1.z, (uint32_t)c1.w};
+      // B[n = d][k = R] at (d/8)*2048 + (R/8)*128 + (d%8)*16 + (R%8)*2
+      uint8_t* colbase = sB + (R >> 3) * 128 + (R & 7) * 2;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const uint16_t v = (d & 1) ? (uint16_t)(w[d >> 1] >> 16) : (uint16_t)(w[d >> 1] & 0xFFFF);
+        *reinterpret_cast<uint16_t*>(colbase + (d >> 3) * 2048 + (d & 7) * 16) = v;
+      }
+    }
+    __syncwarp();
+    // ---- my row of S (32 columns of the diagonal block): S[i][j] = dG[max][min], zero on the diagonal / padding
+    {
+      uint32_t packed[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        uint32_t lo = 0, hi = 0;
+        const int j0 = 2 * jj, j1 = 2 * jj + 1;
+        if (lane < F) {
+          if (j0 < F && j0 != lane) { const int hiI = max(lane, j0), loI = min(lane, j0); lo = *reinterpret_cast<const uint16_t*>(myG + D + hiI * (hiI - 1) / 2 + loI); }
+          if (j1 < F && j1 != lane) { const int hiI = max(lane, j1), loI = min(lane, j1); hi = *reinterpret_cast<const uint16_t*>(myG + D + hiI * (hiI - 1) / 2 + loI); }
+        }
+        packed[jj] = lo | (hi << 16);
+      }
+      // A[R][C = 32*warp + j] at (R/8)*2048 + (C/8)*128 + (R%8)*16 + (C%8)*2
+      uint8_t* rowbase = sA + (R >> 3) * 2048 + (warp * 4) * 128 + (R & 7) * 16;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<int4*>(rowbase + c * 128) = make_int4((int)packed[4 * c], (int)packed[4 * c + 1], (int)packed[4 * c + 2], (int)packed[4 * c + 3]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)     // 16 K elements = 2 chunks = 256 B  -> +16 in the (addr >> 4) field
+        umma_bf16(tmem, adesc + (uint64_t)(k * 16), bdesc + (uint64_t)(k * 16), idesc, k != 0);
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    uint32_t r[16];
+    tmem_ld_32x16(tmem + ((uint32_t)(warp * 32) << 16), r);
+    tmem_ld_wait();
+    if (live && lane < F) {
+      float acc[16];
+#pragma unroll
+      for (int d = 0; d < 16; ++d) acc[d] = __uint_as_float(r[d]);
+      if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[d] += __bfloat162float(myG[d]);
+        store_row_bf16<16>(dx + b * lddx, acc);
+      } else {
+        store_row_bf16<16>(demb + (int64_t)(lane - 1) * demb_stride_t + b * demb_stride_b, acc);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
 inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 8) {
   int64_t b = (n + block - 1) / block;
   if (b < 1) b = 1;
@@ -190,11 +385,21 @@ inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 8) {
 
 }  // namespace
 
+static int& dot_force_simt() { static int v = 0; return v; }
+
 extern "C" {
+
+int dr_cuda_dot_set_simt(int v) { dot_force_simt() = v; return 0; }
 
 int dr_cuda_dot_interaction_fwd(const void* x, int64_t ldx, const void* emb, int64_t emb_stride_t, int64_t emb_stride_b, int T, int D,
                                 int64_t B, void* Z, int64_t ldz, cudaStream_t s) {
   if (T + 1 > 32 || ldz > 512 || ldz % 8 || D + (T + 1) * T / 2 > ldz) return -2;
+  if (D == 16 && !dot_force_simt()) {
+    int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
+    k_dot_fwd_tc<<<g, 128, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz);
+    DR_LAUNCH_CHECK();
+    return 0;
+  }
   int grid = grid_for((B + 7) / 8, 1, kNumSMs * 6);
   switch (D) {
     case 8: k_dot_fwd<8><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz); break;
@@ -210,6 +415,16 @@ int dr_cuda_dot_interaction_bwd(const void* dZ, int64_t ldz, const void* x, int6
                                 int64_t emb_stride_b, int T, int D, int64_t B, void* dx, int64_t lddx, void* demb, int64_t demb_stride_t,
                                 int64_t demb_stride_b, cudaStream_t s) {
   if (T + 1 > 32 || ldz > 512 || ldz % 8) return -2;
+  if (D == 16 && !dot_force_simt()) {
+    constexpr int kSmem = 32768 + 4096 + 4 * 1024;
+    static bool attr = false;
+    if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_dot_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
+    int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
+    k_dot_bwd_tc<<<g, 128, kSmem, s>>>((const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B,
+                                       (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b);
+    DR_LAUNCH_CHECK();
+    return 0;
+  }
   int grid = grid_for((B + 7) / 8, 1, kNumSMs * 6);
 #define BWD(DD) k_dot_bwd<DD><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b)
   switch (D) { case 8: BWD(8); break; case 16: BWD(16); break; case 32: BWD(32); break; default: return -3; }

@@ -1,0 +1,504 @@
+// Native serving runtime: Processor C ABI + SessionGroup + model updater (full / delta hot-swap) for the DLRM family.
+//
+// Parity map (behaviour) to the reference's serving/processor (17.6 kLoC):
+//   C ABI  initialize / process / batch_process / get_serving_model_info, return 200 / 500     serving/processor.cc:9-100
+//   ModelConfig JSON (session_num, select_session_policy MOD|RR, gpu id, update threads/interval, warm-up) serving/model_config.cc
+//   SessionGroup: N sessions = N CUDA streams with private activation / pinned IO buffers over ONE shared, read-only set
+//     of tables + weights (direct_session_group.{h,cc}; "sessions share variables, own streams/threads")
+//   ModelUpdater::WorkLoop: poll the version file; new FULL version -> build a fresh model, warm it up, atomically swap,
+//     old one reaped when its last request finishes (shared_ptr refcount); new DELTA -> patch rows of the live tables +
+//     swap the (small) dense parameter block, no warm-up (model_instance.cc:406-446); invalid versions are skipped.
+//   Tracer: per-request stage timings, dumped every N requests (serving/tracer.h).
+// The reference embeds the TF runtime and runs a SavedModel graph; here inference is the sm_100a kernel sequence of the
+// flagship engine (BatchNorm folded at load time, read-only probes), so a request is ~16 kernel launches on the
+// session's stream.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cmath>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../common/bundle.h"
+#include "table.cuh"
+
+// kernel launchers from the other translation units of this library
+extern "C" {
+int dr_cuda_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t s);
+int dr_cuda_table_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map, int T, const int64_t* keys, const int64_t* offsets, int64_t uniform,
+                         int64_t n, int train, const int64_t* step_ptr, int32_t* out_pos, int64_t* ulist, int32_t* group_nunique, int64_t ulist_cap, cudaStream_t s);
+int dr_cuda_table_gather(const DrDeviceTable* tables_dev, const int32_t* table_map, int T, int dim, const int64_t* keys, const int32_t* pos,
+                         const int64_t* offsets, int64_t uniform, int64_t n, void* out, int out_bf16, int64_t stride_b, int64_t stride_t, int flat_out, cudaStream_t s);
+int dr_cuda_table_import(const DrDeviceTable* t_host, const int64_t* keys, const float* rows, int ncols, const int64_t* freqs, const int64_t* versions,
+                         int64_t n, int part_id, int part_num, int reset_version, int32_t* n_kept, cudaStream_t s);
+int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias, int relu, const void* mask_src,
+                       int64_t ld_mask, int aux_mode, void* out, int64_t ldc, float* out_f32, float* S1, float* S2, int max_ctas, int force_v1, cudaStream_t s);
+int dr_cuda_cast_pad(const float* x, int64_t B, int C, void* y, int Cp, cudaStream_t s);
+int dr_cuda_bn_apply(const void* a, int64_t B, int N, int64_t lda, const float* scale, const float* shift, void* y, int64_t ldy, cudaStream_t s);
+int dr_cuda_dot_interaction_fwd(const void* x, int64_t ldx, const void* emb, int64_t emb_stride_t, int64_t emb_stride_b, int T, int D, int64_t B, void* Z,
+                                int64_t ldz, cudaStream_t s);
+int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, const float* bias, const float* labels, float inv_batch, float* prob,
+                 float* loss_sum, void* dh, float* dw, float* db, int relu_mask, int train, float* dbias_h, cudaStream_t s);
+}
+
+namespace serve {
+
+// ---------------------------------------------------------------------------------------------------------------
+// minimal JSON (objects, arrays, strings, numbers, bools) -- enough for ModelConfig / saved_model.json / state files
+// ---------------------------------------------------------------------------------------------------------------
+struct JVal {
+  enum T { NUL, NUM, STR, ARR, OBJ, BOOL } t = NUL;
+  double num = 0; std::string str; std::vector<JVal> arr; std::vector<std::pair<std::string, JVal>> obj;
+  const JVal* get(const std::string& k) const { for (auto& kv : obj) if (kv.first == k) return &kv.second; return nullptr; }
+  double n(const std::string& k, double d) const { auto* v = get(k); return v && (v->t == NUM || v->t == BOOL) ? v->num : d; }
+  std::string s(const std::string& k, const std::string& d) const { auto* v = get(k); return v && v->t == STR ? v->str : d; }
+};
+struct JParser {
+  const char* p; const char* e; bool ok = true;
+  void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+  JVal parse() { ws(); JVal v; if (p >= e) { ok = false; return v; }
+    if (*p == '{') { v.t = JVal::OBJ; ++p; ws(); if (p < e && *p == '}') { ++p; return v; }
+      while (ok) { ws(); JVal k = parse(); if (k.t != JVal::STR) { ok = false; break; } ws(); if (p >= e || *p != ':') { ok = false; break; } ++p;
+        v.obj.emplace_back(k.str, parse()); ws(); if (p < e && *p == ',') { ++p; continue; } if (p < e && *p == '}') { ++p; break; } ok = false; } return v; }
+    if (*p == '[') { v.t = JVal::ARR; ++p; ws(); if (p < e && *p == ']') { ++p; return v; }
+      while (ok) { v.arr.push_back(parse()); ws(); if (p < e && *p == ',') { ++p; continue; } if (p < e && *p == ']') { ++p; break; } ok = false; } return v; }
+    if (*p == '"') { v.t = JVal::STR; ++p; while (p < e && *p != '"') { if (*p == '\\' && p + 1 < e) { ++p; char c = *p; v.str.push_back(c == 'n' ? '\n' : c == 't' ? '\t' : c); } else v.str.push_back(*p); ++p; } if (p < e) ++p; else ok = false; return v; }
+    if (!strncmp(p, "true", 4)) { v.t = JVal::BOOL; v.num = 1; p += 4; return v; }
+    if (!strncmp(p, "false", 5)) { v.t = JVal::BOOL; v.num = 0; p += 5; return v; }
+    if (!strncmp(p, "null", 4)) { p += 4; return v; }
+    char* end = nullptr; v.num = strtod(p, &end); if (end == p) { ok = false; return v; } v.t = JVal::NUM; p = end; return v; }
+};
+static bool ParseJson(const std::string& s, JVal* out) { JParser ps{s.data(), s.data() + s.size()}; *out = ps.parse(); return ps.ok; }
+static bool ReadFile(const std::string& path, std::string* out) {
+  FILE* f = fopen(path.c_str(), "rb"); if (!f) return false;
+  char buf[65536]; size_t n; out->clear();
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) out->append(buf, n);
+  fclose(f); return true;
+}
+
+#define SV_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fprintf(stderr, "[deeprec_serving] %s: %s\n", #expr, cudaGetErrorString(_e)); return false; } } while (0)
+
+static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); uint32_t r = 0x7FFF + ((u >> 16) & 1); return (uint16_t)((u + r) >> 16); }
+static int pad8(int n) { return (n + 7) / 8 * 8; }
+
+struct DevBuf {
+  void* p = nullptr; size_t n = 0;
+  bool alloc(size_t bytes) { n = bytes; return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+template <typename T> static bool Upload(DevBuf& b, const std::vector<T>& h) {
+  if (!b.alloc(h.size() * sizeof(T))) return false;
+  return cudaMemcpy(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+struct Arch { int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0; };
+
+struct LayerW { int N, K, Kp; DevBuf w_bf16, bias; };
+
+// dense parameter block (small; swapped as a whole on full AND delta updates)
+struct DenseParams {
+  std::vector<LayerW> bot, top;
+  DevBuf last_scale, last_shift, head_w, head_b;
+};
+
+struct TableDev {
+  DrDeviceTable t{}; DevBuf keys, freq, version, row_of, tag, dirty, rows, free_list, counters, def;
+  int64_t n_rows = 0;
+};
+
+struct DeviceModel {
+  Arch arch; int64_t version = -1; std::string path;
+  std::shared_ptr<DenseParams> dense;
+  std::vector<std::unique_ptr<TableDev>> tables;
+  DevBuf structs;      // DrDeviceTable[T] on the device
+};
+
+static bool ReadTensor(dr::BundleReader& r, const std::string& name, std::vector<uint8_t>* out, std::vector<int64_t>* shape = nullptr) {
+  auto* e = r.Find(name); if (!e) return false;
+  out->resize((size_t)e->nbytes);
+  if (shape) *shape = e->shape;
+  return r.Read(*e, out->data(), 1) == 0;
+}
+template <typename T> static bool ReadVec(dr::BundleReader& r, const std::string& name, std::vector<T>* out, std::vector<int64_t>* shape = nullptr) {
+  std::vector<uint8_t> raw; if (!ReadTensor(r, name, &raw, shape)) return false;
+  out->resize(raw.size() / sizeof(T)); memcpy(out->data(), raw.data(), raw.size()); return true;
+}
+
+// BatchNorm (moving statistics) of layer l-1 folded into Linear l:  W' = W diag(s), b' = b + W t
+static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<DenseParams>* out) {
+  auto dp = std::make_shared<DenseParams>();
+  std::vector<float> s_prev, t_prev;
+  int k = a.num_dense;
+  for (size_t l = 0; l < a.bot.size(); ++l) {
+    const std::string nm = "mlp_bot_" + std::to_string(l);
+    int N = a.bot[l], Kp = pad8(k);
+    std::vector<float> W, b, gamma, beta, mean, var;
+    if (!ReadVec(r, "dense/" + nm + "/kernel", &W) || !ReadVec(r, "dense/" + nm + "/bias", &b) || !ReadVec(r, "dense/" + nm + "/bn_gamma", &gamma) ||
+        !ReadVec(r, "dense/" + nm + "/bn_beta", &beta) || !ReadVec(r, "bn/" + nm + "/moving_mean", &mean) || !ReadVec(r, "bn/" + nm + "/moving_variance", &var)) return false;
+    if ((int)W.size() != N * Kp) return false;
+    std::vector<uint16_t> wb((size_t)N * Kp); std::vector<float> bias(N);
+    for (int n = 0; n < N; ++n) {
+      double acc = b[n];
+      for (int kk = 0; kk < Kp; ++kk) {
+        float w = W[(size_t)n * Kp + kk];
+        if (l > 0 && kk < k) { acc += (double)w * t_prev[kk]; w *= s_prev[kk]; }
+        wb[(size_t)n * Kp + kk] = f2bf(w);
+      }
+      bias[n] = (float)acc;
+    }
+    LayerW L; L.N = N; L.K = k; L.Kp = Kp;
+    dp->bot.emplace_back(); auto& dst = dp->bot.back(); dst.N = N; dst.K = k; dst.Kp = Kp;
+    if (!Upload(dst.w_bf16, wb) || !Upload(dst.bias, bias)) return false;
+    s_prev.assign(N, 0.f); t_prev.assign(N, 0.f);
+    for (int n = 0; n < N; ++n) { float rs = 1.0f / std::sqrt(var[n] + a.bn_eps); s_prev[n] = gamma[n] * rs; t_prev[n] = beta[n] - mean[n] * s_prev[n]; }
+    k = N;
+  }
+  if (!Upload(dp->last_scale, s_prev) || !Upload(dp->last_shift, t_prev)) return false;
+  k = a.inter;
+  for (size_t l = 0; l < a.top.size(); ++l) {
+    const std::string nm = "mlp_top_" + std::to_string(l);
+    int N = a.top[l], Kp = pad8(k);
+    std::vector<float> W, b;
+    if (!ReadVec(r, "dense/" + nm + "/kernel", &W) || !ReadVec(r, "dense/" + nm + "/bias", &b) || (int)W.size() != N * Kp) return false;
+    std::vector<uint16_t> wb(W.size());
+    for (size_t i = 0; i < W.size(); ++i) wb[i] = f2bf(W[i]);
+    dp->top.emplace_back(); auto& dst = dp->top.back(); dst.N = N; dst.K = k; dst.Kp = Kp;
+    if (!Upload(dst.w_bf16, wb) || !Upload(dst.bias, b)) return false;
+    k = N;
+  }
+  std::vector<float> hw, hb;
+  if (!ReadVec(r, "dense/logits/kernel", &hw) || !ReadVec(r, "dense/logits/bias", &hb)) return false;
+  if (!Upload(dp->head_w, hw) || !Upload(dp->head_b, hb)) return false;
+  *out = dp;
+  return true;
+}
+
+static int64_t NextPow2(int64_t n) { int64_t p = 1; while (p < n) p <<= 1; return p; }
+
+static bool BuildTable(dr::BundleReader& r, int t, int D, TableDev* td, int64_t extra_rows) {
+  const std::string base = "table/" + std::to_string(t);
+  std::vector<int64_t> keys, freqs, vers; std::vector<float> vals, def;
+  if (!ReadVec(r, base + "-keys", &keys) || !ReadVec(r, base + "-values", &vals) || !ReadVec(r, base + "-default", &def)) return false;
+  ReadVec(r, base + "-freqs", &freqs); ReadVec(r, base + "-versions", &vers);
+  const int64_t n = (int64_t)keys.size();
+  const int64_t rows = n + extra_rows, cap = NextPow2(std::max<int64_t>(1024, 2 * rows));
+  auto& T = td->t;
+  if (!td->keys.alloc(cap * 8) || !td->freq.alloc(cap * 4) || !td->version.alloc(cap * 4) || !td->row_of.alloc(cap * 4) || !td->tag.alloc(cap * 4) ||
+      !td->dirty.alloc(cap) || !td->rows.alloc((size_t)rows * D * 4) || !td->free_list.alloc(rows * 4 + 16) || !td->counters.alloc(32) || !Upload(td->def, def)) return false;
+  dr_cuda_fill_i64(td->keys.as<int64_t>(), drc::kEmptyKey, cap, 0);
+  cudaMemset(td->freq.p, 0, cap * 4); cudaMemset(td->version.p, 0xFF, cap * 4); cudaMemset(td->row_of.p, 0xFF, cap * 4);
+  cudaMemset(td->tag.p, 0xFF, cap * 4); cudaMemset(td->dirty.p, 0, cap); cudaMemset(td->counters.p, 0, 32);
+  T.keys = td->keys.as<int64_t>(); T.freq = td->freq.as<int32_t>(); T.version = td->version.as<int32_t>(); T.row_of = td->row_of.as<int32_t>();
+  T.tag = td->tag.as<int32_t>(); T.dirty = td->dirty.as<uint8_t>(); T.rows = td->rows.as<float>(); T.free_list = td->free_list.as<int32_t>();
+  T.counters = td->counters.as<int32_t>(); T.default_matrix = td->def.as<float>(); T.bloom = nullptr;
+  T.capacity = cap; T.row_capacity = rows; T.default_value_dim = (int64_t)def.size() / D; T.bloom_m = 0;
+  T.dim = D; T.stride = D; T.num_slots = 0; T.has_scalars = 0; T.filter_type = 0; T.filter_freq = 0; T.bloom_k = 0; T.is_inference = 1;
+  T.no_permission = 0.f; T.steps_to_live = 0; T.l2_weight_threshold = -1.f;
+  td->n_rows = n;
+  if (n) {
+    DevBuf dk, dv, df, dver, kept;
+    if (!Upload(dk, keys) || !Upload(dv, vals) || !kept.alloc(4)) return false;
+    cudaMemset(kept.p, 0, 4);
+    if (!freqs.empty()) Upload(df, freqs);
+    if (!vers.empty()) Upload(dver, vers);
+    if (dr_cuda_table_import(&T, dk.as<int64_t>(), dv.as<float>(), D, freqs.empty() ? nullptr : df.as<int64_t>(), vers.empty() ? nullptr : dver.as<int64_t>(), n, 0, 1, 0,
+                             kept.as<int32_t>(), 0) != 0) return false;
+    SV_CUDA(cudaDeviceSynchronize());
+  }
+  return true;
+}
+
+static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::string* prefix) {
+  std::string txt; JVal j;
+  if (!ReadFile(dir + "/saved_model.json", &txt) || !ParseJson(txt, &j)) return false;
+  a->num_dense = (int)j.n("num_dense", 13); a->D = (int)j.n("embedding_dim", 16); a->bn_eps = (float)j.n("bn_eps", 1e-3);
+  a->T = (int)j.n("num_tables", 0);
+  if (auto* b = j.get("mlp_bot")) for (auto& v : b->arr) a->bot.push_back((int)v.num);
+  if (auto* b = j.get("mlp_top")) for (auto& v : b->arr) a->top.push_back((int)v.num);
+  int F = a->T + 1; a->inter = a->D + F * (F - 1) / 2; a->Zp = pad8(a->inter);
+  *version = (int64_t)j.n("version", 0);
+  *prefix = dir + "/" + j.s("variables", "variables/variables");
+  return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
+}
+
+static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t extra_rows) {
+  auto m = std::make_shared<DeviceModel>();
+  std::string prefix;
+  if (!LoadArch(dir, &m->arch, &m->version, &prefix)) { fprintf(stderr, "[deeprec_serving] bad saved_model.json in %s\n", dir.c_str()); return nullptr; }
+  dr::BundleReader r(prefix);
+  if (!r.ok()) { fprintf(stderr, "[deeprec_serving] cannot open bundle %s\n", prefix.c_str()); return nullptr; }
+  if (!BuildDense(r, m->arch, &m->dense)) { fprintf(stderr, "[deeprec_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
+  std::vector<DrDeviceTable> structs;
+  for (int t = 0; t < m->arch.T; ++t) {
+    m->tables.emplace_back(new TableDev());
+    if (!BuildTable(r, t, m->arch.D, m->tables.back().get(), extra_rows)) { fprintf(stderr, "[deeprec_serving] table %d incomplete\n", t); return nullptr; }
+    structs.push_back(m->tables.back()->t);
+  }
+  if (!Upload(m->structs, structs)) return nullptr;
+  m->path = dir;
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct Session {
+  cudaStream_t stream = nullptr; int max_batch = 0; std::mutex mu;
+  DevBuf dense_in, ids, x0, emb, pos, Z, prob, loss, labels, y_last;
+  std::vector<DevBuf> a_bot, a_top;
+  float* h_dense = nullptr; int64_t* h_ids = nullptr; float* h_prob = nullptr;    // pinned
+  bool Init(const Arch& a, int maxB) {
+    max_batch = maxB;
+    SV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    bool ok = dense_in.alloc((size_t)maxB * a.num_dense * 4) && ids.alloc((size_t)a.T * maxB * 8) && x0.alloc((size_t)maxB * pad8(a.num_dense) * 2) &&
+              emb.alloc((size_t)a.T * maxB * a.D * 2) && pos.alloc((size_t)a.T * maxB * 4) && Z.alloc((size_t)maxB * a.Zp * 2) && prob.alloc((size_t)maxB * 4) &&
+              loss.alloc(16) && labels.alloc((size_t)maxB * 4) && y_last.alloc((size_t)maxB * a.D * 2);
+    a_bot.resize(a.bot.size()); a_top.resize(a.top.size());
+    for (size_t l = 0; l < a.bot.size(); ++l) ok = ok && a_bot[l].alloc((size_t)maxB * a.bot[l] * 2);
+    for (size_t l = 0; l < a.top.size(); ++l) ok = ok && a_top[l].alloc((size_t)maxB * a.top[l] * 2);
+    if (!ok) return false;
+    cudaMemset(labels.p, 0, (size_t)maxB * 4);
+    SV_CUDA(cudaMallocHost(&h_dense, (size_t)maxB * a.num_dense * 4));
+    SV_CUDA(cudaMallocHost(&h_ids, (size_t)a.T * maxB * 8));
+    SV_CUDA(cudaMallocHost(&h_prob, (size_t)maxB * 4));
+    return true;
+  }
+  ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (stream) cudaStreamDestroy(stream); }
+
+  // inputs already in h_dense / h_ids ([T][B] feature-major); result in h_prob
+  bool Run(const DeviceModel& m, const DenseParams& dp, int B) {
+    const Arch& a = m.arch; cudaStream_t s = stream;
+    SV_CUDA(cudaMemcpyAsync(dense_in.p, h_dense, (size_t)B * a.num_dense * 4, cudaMemcpyHostToDevice, s));
+    SV_CUDA(cudaMemcpyAsync(ids.p, h_ids, (size_t)a.T * B * 8, cudaMemcpyHostToDevice, s));
+    int rc = 0;
+    const int64_t n = (int64_t)a.T * B;
+    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, 0, 0, 1, s);
+    rc |= dr_cuda_cast_pad(dense_in.as<float>(), B, a.num_dense, x0.p, pad8(a.num_dense), s);
+    const void* x = x0.p; int64_t ldx = pad8(a.num_dense);
+    for (size_t l = 0; l < dp.bot.size(); ++l) {
+      const LayerW& L = dp.bot[l];
+      rc |= dr_cuda_gemm_tn_ex(x, ldx, L.w_bf16.p, L.Kp, B, L.N, L.Kp, L.bias.as<float>(), 1, nullptr, 0, 0, a_bot[l].p, L.N, nullptr, nullptr, nullptr, 0, 0, s);
+      x = a_bot[l].p; ldx = L.N;
+    }
+    rc |= dr_cuda_bn_apply(x, B, a.D, a.D, dp.last_scale.as<float>(), dp.last_shift.as<float>(), y_last.p, a.D, s);
+    rc |= dr_cuda_dot_interaction_fwd(y_last.p, a.D, emb.p, (int64_t)B * a.D, a.D, a.T, a.D, B, Z.p, a.Zp, s);
+    x = Z.p; ldx = a.Zp;
+    for (size_t l = 0; l < dp.top.size(); ++l) {
+      const LayerW& L = dp.top[l];
+      rc |= dr_cuda_gemm_tn_ex(x, ldx, L.w_bf16.p, L.Kp, B, L.N, L.Kp, L.bias.as<float>(), 1, nullptr, 0, 0, a_top[l].p, L.N, nullptr, nullptr, nullptr, 0, 0, s);
+      x = a_top[l].p; ldx = L.N;
+    }
+    rc |= dr_cuda_head(x, ldx, B, (int)ldx, dp.head_w.as<float>(), dp.head_b.as<float>(), labels.as<float>(), 1.0f / B, prob.as<float>(), loss.as<float>(),
+                       nullptr, nullptr, nullptr, 0, 0, nullptr, s);
+    if (rc) return false;
+    SV_CUDA(cudaMemcpyAsync(h_prob, prob.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    SV_CUDA(cudaStreamSynchronize(s));
+    return true;
+  }
+};
+
+struct Config {
+  int session_num = 2, select_policy = 0 /*0 RR, 1 MOD*/, gpu_id = 0, max_batch = 4096, update_interval_ms = 1000, extra_rows = 1 << 16;
+  int timeline_start_step = -1, timeline_interval_step = 0, timeline_trace_count = 0;
+  std::string savedmodel_dir, checkpoint_dir, warmup_file_name, timeline_path;
+};
+
+struct ServingModel {
+  Config cfg;
+  std::shared_ptr<DeviceModel> model;      // swapped atomically on full update (std::atomic_load / atomic_store)
+  std::vector<std::unique_ptr<Session>> sessions;
+  std::atomic<uint64_t> rr{0}, requests{0}, failures{0}, full_updates{0}, delta_updates{0};
+  std::atomic<int64_t> delta_version{-1};
+  std::thread updater; std::atomic<bool> stop{false};
+  std::mutex tmu; std::vector<std::string> trace;
+  ~ServingModel() { stop = true; if (updater.joinable()) updater.join(); }
+};
+
+#pragma pack(push, 1)
+struct ReqHeader { uint32_t magic, version, batch, num_dense, num_sparse, reserved; };
+struct RespHeader { uint32_t magic, batch, status, reserved; int64_t model_version; };
+#pragma pack(pop)
+constexpr uint32_t kReqMagic = 0x51525244;   // "DRRQ"
+constexpr uint32_t kRespMagic = 0x53525244;  // "DRRS"
+
+static int Predict(ServingModel* sm, const void* in, int in_size, void** out, int* out_size, int hint) {
+  auto m = std::atomic_load(&sm->model);
+  if (!m || in_size < (int)sizeof(ReqHeader)) return 500;
+  ReqHeader h; memcpy(&h, in, sizeof(h));
+  const Arch& a = m->arch;
+  const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
+  if (h.magic != kReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.T || h.batch == 0 || (size_t)in_size < need) return 500;
+  uint64_t pick = sm->cfg.select_policy == 1 ? (hint >= 0 ? (uint64_t)hint : std::hash<std::thread::id>()(std::this_thread::get_id())) : sm->rr.fetch_add(1);
+  Session& s = *sm->sessions[pick % sm->sessions.size()];
+  std::vector<float> probs(h.batch);
+  auto t0 = std::chrono::steady_clock::now();
+  {
+    std::lock_guard<std::mutex> l(s.mu);
+    cudaSetDevice(sm->cfg.gpu_id);
+    auto dense = std::atomic_load(&m->dense);
+    const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
+    for (uint32_t off = 0; off < h.batch; off += s.max_batch) {          // requests larger than a session's buffers are chunked
+      const int B = (int)std::min<uint32_t>(s.max_batch, h.batch - off);
+      memcpy(s.h_dense, p + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
+      const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
+      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)t * h.batch + off, (size_t)B * 8);
+      if (!s.Run(*m, *dense, B)) { sm->failures++; return 500; }
+      memcpy(probs.data() + off, s.h_prob, (size_t)B * 4);
+    }
+  }
+  const uint64_t rq = ++sm->requests;
+  if (sm->cfg.timeline_interval_step > 0 && (int64_t)rq >= sm->cfg.timeline_start_step && (rq % sm->cfg.timeline_interval_step) == 0 &&
+      (int)sm->trace.size() < sm->cfg.timeline_trace_count) {
+    double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> l(sm->tmu);
+    char line[160]; snprintf(line, sizeof(line), "{\"request\": %llu, \"batch\": %u, \"latency_us\": %.1f, \"model_version\": %lld}", (unsigned long long)rq, h.batch, us, (long long)m->version);
+    sm->trace.emplace_back(line);
+    if (!sm->cfg.timeline_path.empty()) { FILE* f = fopen(sm->cfg.timeline_path.c_str(), "a"); if (f) { fprintf(f, "%s\n", line); fclose(f); } }
+  }
+  RespHeader rh{kRespMagic, h.batch, 200, 0, m->version};
+  *out_size = (int)(sizeof(rh) + probs.size() * 4);
+  *out = malloc(*out_size);
+  memcpy(*out, &rh, sizeof(rh)); memcpy(static_cast<uint8_t*>(*out) + sizeof(rh), probs.data(), probs.size() * 4);
+  return 200;
+}
+
+// delta update: rows of the touched keys are patched into the LIVE tables; the dense block is rebuilt and swapped
+static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t version) {
+  auto m = std::atomic_load(&sm->model);
+  if (!m) return false;
+  dr::BundleReader r(prefix);
+  if (!r.ok()) return false;
+  cudaSetDevice(sm->cfg.gpu_id);
+  for (int t = 0; t < m->arch.T; ++t) {
+    std::vector<int64_t> keys; std::vector<float> vals;
+    const std::string base = "table/" + std::to_string(t);
+    if (!ReadVec(r, base + "-sparse_incr_keys", &keys) || keys.empty()) continue;
+    if (!ReadVec(r, base + "-sparse_incr_values", &vals)) return false;
+    DevBuf dk, dv, kept;
+    if (!Upload(dk, keys) || !Upload(dv, vals) || !kept.alloc(4)) return false;
+    cudaMemset(kept.p, 0, 4);
+    if (dr_cuda_table_import(&m->tables[t]->t, dk.as<int64_t>(), dv.as<float>(), m->arch.D, nullptr, nullptr, (int64_t)keys.size(), 0, 1, 0, kept.as<int32_t>(), 0) != 0) return false;
+    cudaDeviceSynchronize();
+  }
+  std::shared_ptr<DenseParams> dp;
+  if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp)) std::atomic_store(&m->dense, dp);
+  sm->delta_version = version;
+  sm->delta_updates++;
+  return true;
+}
+
+static void WarmUp(ServingModel* sm, const std::shared_ptr<DeviceModel>& m) {
+  for (auto& s : sm->sessions) {
+    std::lock_guard<std::mutex> l(s->mu);
+    const int B = std::min(256, s->max_batch);
+    memset(s->h_dense, 0, (size_t)B * m->arch.num_dense * 4); memset(s->h_ids, 0, (size_t)m->arch.T * B * 8);
+    auto dense = std::atomic_load(&m->dense);
+    s->Run(*m, *dense, B);
+  }
+}
+
+// version file: <dir>/serving_versions.json = {"full": {"version": V, "dir": "..."}, "deltas": [{"version": v, "prefix": "..."}]}
+static void UpdaterLoop(ServingModel* sm) {
+  const std::string vf = (sm->cfg.checkpoint_dir.empty() ? sm->cfg.savedmodel_dir : sm->cfg.checkpoint_dir) + "/serving_versions.json";
+  int bad = 0;
+  while (!sm->stop) {
+    for (int i = 0; i < sm->cfg.update_interval_ms / 20 && !sm->stop; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    std::string txt; JVal j;
+    if (!ReadFile(vf, &txt) || !ParseJson(txt, &j)) continue;
+    auto cur = std::atomic_load(&sm->model);
+    if (auto* f = j.get("full")) {
+      int64_t v = (int64_t)f->n("version", -1); std::string dir = f->s("dir", "");
+      if (cur && v > cur->version && !dir.empty()) {
+        cudaSetDevice(sm->cfg.gpu_id);
+        auto nm = LoadModel(dir, sm->cfg.extra_rows);
+        if (!nm) { if (++bad > 3) fprintf(stderr, "[deeprec_serving] skipping invalid model version %lld\n", (long long)v); continue; }
+        bad = 0;
+        WarmUp(sm, nm);
+        std::atomic_store(&sm->model, nm);          // requests in flight keep the old model alive through their shared_ptr
+        sm->delta_version = -1;
+        sm->full_updates++;
+        continue;
+      }
+    }
+    if (auto* d = j.get("deltas")) {
+      cur = std::atomic_load(&sm->model);
+      for (auto& e : d->arr) {
+        int64_t v = (int64_t)e.n("version", -1), base = (int64_t)e.n("base", -1);
+        if (cur && base == cur->version && v > std::max<int64_t>(cur->version, sm->delta_version.load())) ApplyDelta(sm, e.s("prefix", ""), v);
+      }
+    }
+  }
+}
+
+}  // namespace serve
+
+extern "C" {
+
+// model_entry: saved-model directory (may be empty if the JSON config names it).  Returns an opaque model handle.
+void* initialize(const char* model_entry, const char* model_config, int* state) {
+  using namespace serve;
+  auto* sm = new ServingModel();
+  JVal j;
+  if (model_config && *model_config && !ParseJson(model_config, &j)) { *state = -1; delete sm; return nullptr; }
+  Config& c = sm->cfg;
+  c.session_num = (int)j.n("session_num", 2); c.gpu_id = (int)j.n("gpu_id", 0); c.max_batch = (int)j.n("max_batch", 4096);
+  c.select_policy = j.s("select_session_policy", "RR") == "MOD" ? 1 : 0;
+  c.update_interval_ms = (int)j.n("model_update_interval_ms", 1000); c.extra_rows = (int)j.n("delta_extra_rows", 1 << 16);
+  c.savedmodel_dir = j.s("savedmodel_dir", model_entry ? model_entry : ""); c.checkpoint_dir = j.s("checkpoint_dir", "");
+  c.warmup_file_name = j.s("warmup_file_name", ""); c.timeline_path = j.s("timeline_path", "");
+  c.timeline_start_step = (int)j.n("timeline_start_step", -1); c.timeline_interval_step = (int)j.n("timeline_interval_step", 0);
+  c.timeline_trace_count = (int)j.n("timeline_trace_count", 0);
+  if (cudaSetDevice(c.gpu_id) != cudaSuccess) { *state = -1; delete sm; return nullptr; }
+  auto m = LoadModel(c.savedmodel_dir, c.extra_rows);
+  if (!m) { *state = -1; delete sm; return nullptr; }
+  for (int i = 0; i < std::max(1, c.session_num); ++i) {
+    sm->sessions.emplace_back(new Session());
+    if (!sm->sessions.back()->Init(m->arch, c.max_batch)) { *state = -1; delete sm; return nullptr; }
+  }
+  WarmUp(sm, m);
+  std::atomic_store(&sm->model, m);
+  if (c.update_interval_ms > 0) sm->updater = std::thread(UpdaterLoop, sm);
+  *state = 0;
+  return sm;
+}
+
+int process(void* model_buf, const void* input_data, int input_size, void** output_data, int* output_size) {
+  if (!model_buf) return 500;
+  return serve::Predict(static_cast<serve::ServingModel*>(model_buf), input_data, input_size, output_data, output_size, -1);
+}
+
+int batch_process(void* model_buf, const void* input_data[], int* input_size, void* output_data[], int* output_size) {
+  // input_size[0] = number of requests, followed by their sizes (reference: one call, several PredictRequests)
+  if (!model_buf || !input_size) return 500;
+  int n = input_size[0], rc = 200;
+  for (int i = 0; i < n; ++i) {
+    int r = serve::Predict(static_cast<serve::ServingModel*>(model_buf), input_data[i], input_size[i + 1], &output_data[i], &output_size[i], i);
+    if (r != 200) rc = r;
+  }
+  return rc;
+}
+
+int get_serving_model_info(void* model_buf, void** output_data, int* output_size) {
+  if (!model_buf) return 500;
+  auto* sm = static_cast<serve::ServingModel*>(model_buf);
+  auto m = std::atomic_load(&sm->model);
+  std::ostringstream os;
+  os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
+     << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
+     << ", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
+  std::string s = os.str();
+  *output_size = (int)s.size();
+  *output_data = malloc(s.size() + 1);
+  memcpy(*output_data, s.c_str(), s.size() + 1);
+  return 200;
+}
+
+void dr_serving_release(void* model_buf) { delete static_cast<serve::ServingModel*>(model_buf); }
+void dr_serving_free(void* p) { free(p); }
+
+}  // extern "C"

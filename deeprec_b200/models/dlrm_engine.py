@@ -485,6 +485,10 @@ class DLRMEngine:
     def loss_value(self) -> float:
         return float(self.loss.item())
 
+    def global_step(self) -> int:
+        raw = bytes(self.hp_dev.cpu().numpy().tobytes())
+        return int(OptHyper.from_buffer_copy(raw).global_step)
+
     def l2_flush(self) -> None:
         if self._l2_scratch is None:
             self._l2_scratch = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=self.dev)   # 256 MB > 126 MB L2

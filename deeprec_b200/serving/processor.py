@@ -1,0 +1,103 @@
+"""Python side of the native Processor (C ABI in csrc/cuda/serving_runtime.cu) + the client SDK wire format.
+
+``Processor`` loads the in-tree library with ctypes and calls ``initialize / process / batch_process /
+get_serving_model_info`` exactly as an RPC front-end would (serving/processor/serving/processor.h in the reference;
+the Go/Java/Python SDK demos of serving/sdk map onto ``encode_request`` / ``decode_response``)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import struct
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from .. import build as _build
+
+REQ_MAGIC, RESP_MAGIC = 0x51525244, 0x53525244
+
+
+def encode_request(dense: np.ndarray, ids: np.ndarray) -> bytes:
+    """dense [B, num_dense] float32, ids [num_sparse, B] int64 (feature-major) -> PredictRequest bytes."""
+    dense = np.ascontiguousarray(dense, dtype=np.float32)
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    B, nd = dense.shape
+    ns = ids.shape[0]
+    assert ids.shape[1] == B
+    return struct.pack("<6I", REQ_MAGIC, 1, B, nd, ns, 0) + dense.tobytes() + ids.tobytes()
+
+
+def decode_response(buf: bytes) -> Tuple[np.ndarray, int, int]:
+    magic, batch, status, _r, version = struct.unpack_from("<4Iq", buf, 0)
+    if magic != RESP_MAGIC:
+        raise ValueError("bad PredictResponse")
+    probs = np.frombuffer(buf, dtype=np.float32, count=batch, offset=24).copy()
+    return probs, status, version
+
+
+class Processor:
+    def __init__(self, savedmodel_dir: str, config: dict | None = None):
+        path = os.path.join(_build.LIB, "libdeeprec_cuda.so")
+        if not os.path.exists(path):
+            path = _build.build_cuda()
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.initialize.restype, L.initialize.argtypes = C.c_void_p, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.process.restype, L.process.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.batch_process.restype = C.c_int
+        L.batch_process.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.get_serving_model_info.restype, L.get_serving_model_info.argtypes = C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.dr_serving_release.argtypes, L.dr_serving_free.argtypes = [C.c_void_p], [C.c_void_p]
+        state = C.c_int(0)
+        cfg = dict(config or {})
+        self.model = L.initialize(savedmodel_dir.encode(), json.dumps(cfg).encode(), C.byref(state))
+        if not self.model or state.value != 0:
+            raise RuntimeError(f"Processor.initialize failed for {savedmodel_dir} (state {state.value})")
+
+    def process(self, request: bytes) -> Tuple[int, bytes]:
+        out, n = C.c_void_p(), C.c_int(0)
+        rc = self.lib.process(self.model, request, len(request), C.byref(out), C.byref(n))
+        data = C.string_at(out, n.value) if out else b""
+        if out:
+            self.lib.dr_serving_free(out)
+        return rc, data
+
+    def predict(self, dense: np.ndarray, ids: np.ndarray) -> np.ndarray:
+        rc, data = self.process(encode_request(dense, ids))
+        if rc != 200:
+            raise RuntimeError(f"process returned {rc}")
+        return decode_response(data)[0]
+
+    def batch_process(self, requests: Sequence[bytes]) -> Tuple[int, List[bytes]]:
+        n = len(requests)
+        bufs = [C.create_string_buffer(r, len(r)) for r in requests]
+        ins = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+        sizes = (C.c_int * (n + 1))(n, *[len(r) for r in requests])
+        outs = (C.c_void_p * n)()
+        osz = (C.c_int * n)()
+        rc = self.lib.batch_process(self.model, ins, sizes, outs, osz)
+        res = []
+        for i in range(n):
+            res.append(C.string_at(outs[i], osz[i]) if outs[i] else b"")
+            if outs[i]:
+                self.lib.dr_serving_free(outs[i])
+        return rc, res
+
+    def model_info(self) -> dict:
+        out, n = C.c_void_p(), C.c_int(0)
+        self.lib.get_serving_model_info(self.model, C.byref(out), C.byref(n))
+        s = C.string_at(out, n.value).decode()
+        self.lib.dr_serving_free(out)
+        return json.loads(s)
+
+    def close(self) -> None:
+        if self.model:
+            self.lib.dr_serving_release(self.model)
+            self.model = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
