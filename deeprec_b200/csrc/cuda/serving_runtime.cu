@@ -86,9 +86,14 @@ static bool ReadFile(const std::string& path, std::string* out) {
 static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); uint32_t r = 0x7FFF + ((u >> 16) & 1); return (uint16_t)((u + r) >> 16); }
 static int pad8(int n) { return (n + 7) / 8 * 8; }
 
-struct DevBuf {
+struct DevBuf {      // owning, move-only device allocation
   void* p = nullptr; size_t n = 0;
-  bool alloc(size_t bytes) { n = bytes; return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { if (p) cudaFree(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  bool alloc(size_t bytes) { if (p) { cudaFree(p); p = nullptr; } n = bytes; return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
   ~DevBuf() { if (p) cudaFree(p); }
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
@@ -133,6 +138,7 @@ template <typename T> static bool ReadVec(dr::BundleReader& r, const std::string
 // BatchNorm (moving statistics) of layer l-1 folded into Linear l:  W' = W diag(s), b' = b + W t
 static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<DenseParams>* out) {
   auto dp = std::make_shared<DenseParams>();
+  dp->bot.reserve(a.bot.size()); dp->top.reserve(a.top.size());
   std::vector<float> s_prev, t_prev;
   int k = a.num_dense;
   for (size_t l = 0; l < a.bot.size(); ++l) {
@@ -152,7 +158,6 @@ static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense
       }
       bias[n] = (float)acc;
     }
-    LayerW L; L.N = N; L.K = k; L.Kp = Kp;
     dp->bot.emplace_back(); auto& dst = dp->bot.back(); dst.N = N; dst.K = k; dst.Kp = Kp;
     if (!Upload(dst.w_bf16, wb) || !Upload(dst.bias, bias)) return false;
     s_prev.assign(N, 0.f); t_prev.assign(N, 0.f);

@@ -1,0 +1,103 @@
+"""``python -m deeprec_b200.models.train --model dlrm ...``: the modelzoo train.py flag surface (modelzoo/mlperf/README.md:40-74):
+--ev --ev_filter {counter,cbf} --ev_elimination {l2,gstep} --emb_fusion --op_fusion --smartstaged --optimizer {adam,adamasync,
+adagraddecay,adagrad,gradientdescent,ftrl} --bf16 --incremental_ckpt --workqueue --parquet_dataset --group_embedding
+--adaptive_emb --dynamic_ev --micro_batch --timeline --steps --batch_size --learning_rate --checkpoint.
+Synthetic Criteo / Taobao data (no datasets offline); ``--engine`` runs DLRM through the fused B200 engine."""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+
+import torch
+
+import deeprec_b200 as dr
+from deeprec_b200.data import criteo_batch, smart_stage, taobao_batch
+from deeprec_b200.models.zoo import CRITEO_MODELS, TAOBAO_MODELS, build_model
+from deeprec_b200.optim import make_optimizer
+from deeprec_b200.utils import Trainer
+
+
+def get_arg_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--model", default="dlrm")
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--batch_size", type=int, default=2048)
+    p.add_argument("--learning_rate", type=float, default=0.01)
+    p.add_argument("--optimizer", default="adagrad", choices=["adam", "adamasync", "adagraddecay", "adagrad", "gradientdescent", "ftrl", "adamw"])
+    p.add_argument("--ev", action="store_true", default=True)
+    p.add_argument("--ev_filter", default=None, choices=[None, "counter", "cbf"])
+    p.add_argument("--ev_elimination", default=None, choices=[None, "l2", "gstep"])
+    p.add_argument("--emb_fusion", action="store_true")
+    p.add_argument("--op_fusion", action="store_true")
+    p.add_argument("--group_embedding", action="store_true")
+    p.add_argument("--smartstaged", action="store_true")
+    p.add_argument("--bf16", action="store_true")
+    p.add_argument("--incremental_ckpt", type=float, default=0, help="seconds between incremental checkpoints")
+    p.add_argument("--checkpoint", default=None)
+    p.add_argument("--save_steps", type=int, default=0)
+    p.add_argument("--workqueue", action="store_true")
+    p.add_argument("--micro_batch", type=int, default=1)
+    p.add_argument("--timeline", type=int, default=0)
+    p.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
+    p.add_argument("--engine", action="store_true", help="DLRM through the fused sm_100a engine (models/dlrm_engine.py)")
+    p.add_argument("--log_every", type=int, default=20)
+    return p
+
+
+def ev_option_from_args(a) -> dr.EmbeddingVariableOption:
+    flt = dr.CounterFilter(2) if a.ev_filter == "counter" else dr.CBFFilter(2, 1 << 20, 0.01) if a.ev_filter == "cbf" else None
+    ev = dr.L2WeightEvict(1e-4) if a.ev_elimination == "l2" else dr.GlobalStepEvict(4000) if a.ev_elimination == "gstep" else None
+    st = dr.StorageOption(dr.StorageType.HBM if a.device.startswith("cuda") else dr.StorageType.DRAM)
+    return dr.EmbeddingVariableOption(filter_option=flt, evict_option=ev, storage_option=st)
+
+
+def main(argv=None) -> int:
+    a = get_arg_parser().parse_args(argv)
+    dev = torch.device(a.device)
+    name = a.model.lower()
+    if a.engine and name == "dlrm":
+        from deeprec_b200.models.dlrm_engine import CRITEO_KAGGLE_CARDINALITIES, DLRMConfig, DLRMEngine
+        eng = DLRMEngine(DLRMConfig(batch_size=a.batch_size, cardinalities=CRITEO_KAGGLE_CARDINALITIES, optimizer=a.optimizer, learning_rate=a.learning_rate))
+        t0 = time.time()
+        for s in range(a.steps):
+            d, ids, y = criteo_batch(a.batch_size, 13, CRITEO_KAGGLE_CARDINALITIES, seed=s)
+            eng.load_batch(d.to(dev), ids.to(dev), y.to(dev)); eng.train_step()
+            if s == 2:
+                eng.capture()
+            if a.log_every and s % a.log_every == 0:
+                print(f"global_step {s} loss {eng.loss_value():.5f}")
+        print(f"{a.steps * a.batch_size / (time.time() - t0):.0f} samples/s")
+        return 0
+    cards = [1000] * 26
+    model = build_model(name, ev_option_from_args(a), dev, a.group_embedding or a.emb_fusion, cardinalities=cards)
+    opt = make_optimizer(a.optimizer, model, lr=a.learning_rate)
+    taobao = name in TAOBAO_MODELS
+
+    def gen():
+        s = 0
+        while True:
+            if taobao:
+                b = taobao_batch(a.batch_size, 20, 100000, 200000, 1000, seed=s)
+                yield {k: v.to(dev) for k, v in b.items()}
+            else:
+                d, ids, y = criteo_batch(a.batch_size, 13, cards, seed=s)
+                yield d.to(dev), ids.to(dev), y.to(dev)
+            s += 1
+
+    def loss_fn(m, b):
+        ctx = torch.autocast(dev.type, dtype=torch.bfloat16) if a.bf16 else torch.autocast(dev.type, enabled=False)
+        with ctx:
+            return m.loss(b) if taobao else m.loss(*b)
+
+    src = smart_stage(gen(), device=None) if a.smartstaged else gen()
+    tr = Trainer(model, opt, loss_fn, a.checkpoint, save_checkpoint_steps=a.save_steps, save_incremental_checkpoint_secs=a.incremental_ckpt,
+                 log_every_n_steps=a.log_every, timeline_steps=a.timeline, micro_batch_num=a.micro_batch)
+    t0 = time.time()
+    tr.fit(src, a.steps)
+    print(f"{a.steps * a.batch_size / (time.time() - t0):.0f} samples/s")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
