@@ -43,6 +43,7 @@ def bind(lib):
     _sig(lib, "dr_cuda_table_shrink", [TP, INT, P, S])
     _sig(lib, "dr_cuda_table_remove", [TP, P, i64, P, S])
     _sig(lib, "dr_cuda_table_snapshot", [TP, INT, INT, INT, P, P, P, P, P, P, P, P, S])
+    _sig(lib, "dr_cuda_table_export_keys", [TP, P, i64, P, P, P, P, S])
     _sig(lib, "dr_cuda_table_clear_dirty", [TP, S])
     _sig(lib, "dr_cuda_table_import", [TP, P, P, INT, P, P, i64, INT, INT, INT, P, S])
     _sig(lib, "dr_cuda_sparse_accumulate", [P, P, INT, INT, P, P, i64, i64, P, INT, i64, i64, INT, P, P, P, S])

@@ -78,6 +78,7 @@ def _bind_host(lib):
     _sig(lib, "dr_host_ev_snapshot_end", None, [vp])
     _sig(lib, "dr_host_ev_clear_dirty", None, [vp])
     _sig(lib, "dr_host_ev_import", i64, [vp, P, P, i64, P, P, i64, C.c_int, C.c_int, C.c_int])
+    _sig(lib, "dr_host_ev_export_keys", None, [vp, P, i64, P, P, P, P])
     _sig(lib, "dr_host_bloom_info", i64, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)])
     _sig(lib, "dr_host_bloom_read", None, [vp, P])
     _sig(lib, "dr_host_bloom_write", None, [vp, P])

@@ -28,6 +28,7 @@ CUDA_SOURCES = [
     "cuda/comm_kernels.cu",
     "cuda/runtime.cu",
     "cuda/serving_runtime.cu",
+    "cuda/fused_ops.cu",
 ]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -221,6 +221,19 @@ __global__ void k_snapshot(DrDeviceTable TB, int dirty_only, int part_id, int pa
   }
 }
 
+// rows (full stride) + metadata of specific keys (multi-tier demotion / promotion); found[i] = key owns a row
+__global__ void k_export_keys(DrDeviceTable TB, const int64_t* __restrict__ keys, int64_t n, float* __restrict__ rows, int64_t* __restrict__ freqs,
+                              int64_t* __restrict__ versions, uint8_t* __restrict__ found) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = table_find(TB, keys[i]);
+    int32_t r = p >= 0 ? TB.row_of[p] : -1;
+    found[i] = r >= 0;
+    freqs[i] = p >= 0 ? TB.freq[p] : 0;
+    versions[i] = p >= 0 ? TB.version[p] : -1;
+    if (r >= 0) { const float* src = TB.rows + (int64_t)r * TB.stride; float* dst = rows + i * TB.stride; for (int d = 0; d < TB.stride; ++d) dst[d] = src[d]; }
+  }
+}
+
 __global__ void k_clear_dirty(DrDeviceTable TB) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < TB.capacity; p += (int64_t)gridDim.x * blockDim.x) TB.dirty[p] = 0;
 }
@@ -348,6 +361,14 @@ int dr_cuda_table_snapshot(const DrDeviceTable* t_host, int dirty_only, int part
                            int64_t* fversions, cudaStream_t s) {
   k_snapshot<<<grid_for(t_host->capacity, 256), 256, 0, s>>>(*t_host, dirty_only, part_id, part_num, counts, keys, rows, freqs,
                                                             versions, fkeys, ffreqs, fversions);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_cuda_table_export_keys(const DrDeviceTable* t_host, const int64_t* keys, int64_t n, float* rows, int64_t* freqs, int64_t* versions,
+                               uint8_t* found, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_export_keys<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, n, rows, freqs, versions, found);
   DR_LAUNCH_CHECK();
   return 0;
 }

@@ -587,6 +587,19 @@ class HostEV {
     }
     return kept;
   }
+  // rows (full stride) + metadata of specific keys; found[i] = 1 if the key owns a row (multi-tier promotion path)
+  void ExportKeys(const int64_t* keys, int64_t n, float* rows, int64_t* freqs, int64_t* versions, uint8_t* found) {
+    GlobalPool()->ParallelFor(n, 1024, [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i) {
+        int32_t idx = kv_.Find(keys[i]);
+        int32_t r = idx >= 0 ? *row_.at(idx) : -1;
+        found[i] = r >= 0;
+        freqs[i] = idx >= 0 ? *freq_.at(idx) : 0;
+        versions[i] = idx >= 0 ? *version_.at(idx) : -1;
+        if (r >= 0) memcpy(rows + i * stride_, rows_.at(r), stride_ * sizeof(float));
+      }
+    });
+  }
   CountingBloom* bloom() { return bloom_.get(); }
 
  private:
@@ -671,6 +684,9 @@ void dr_host_ev_clear_dirty(void* h) { static_cast<dr::HostEV*>(h)->ClearDirty()
 int64_t dr_host_ev_import(void* h, const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs,
                           const int64_t* versions, int64_t n, int part_id, int part_num, int reset_version) {
   return static_cast<dr::HostEV*>(h)->Import(keys, rows, ncols, freqs, versions, n, part_id, part_num, reset_version);
+}
+void dr_host_ev_export_keys(void* h, const int64_t* keys, int64_t n, float* rows, int64_t* freqs, int64_t* versions, uint8_t* found) {
+  static_cast<dr::HostEV*>(h)->ExportKeys(keys, n, rows, freqs, versions, found);
 }
 int64_t dr_host_bloom_info(void* h, int64_t* k, int64_t* m, int64_t* bits) {
   auto* b = static_cast<dr::HostEV*>(h)->bloom();

@@ -263,7 +263,10 @@ class EmbeddingVariable(nn.Module):
     def table(self):
         if self._table is None:
             cfg = self._make_config()
-            if self.device.type == "cuda":
+            if self.device.type == "cuda" and int(cfg.storage_type) == int(StorageType.HBM_DRAM):
+                from .ops.multi_tier import MultiTierTable
+                self._table = MultiTierTable(cfg, self.default_matrix, self.device, owner=self._owner)
+            elif self.device.type == "cuda":
                 from .ops.device_table import DeviceTable
                 self._table = DeviceTable(cfg, self.default_matrix, self.device, owner=self._owner)
             else:

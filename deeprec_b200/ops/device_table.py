@@ -348,8 +348,10 @@ class DeviceTable:
         n = torch.zeros(1, dtype=torch.int32, device=self.device)
         _chk(self.lib.dr_cuda_table_remove(C.byref(self.struct), ptr(k), k.numel(), ptr(n), stream_ptr()), "remove")
         removed = int(n.item())
-        if removed:
+        self._tombstones = getattr(self, "_tombstones", 0) + removed
+        if self._tombstones * 4 > self.capacity:      # probes skip tombstones; rebuild only when they pile up
             self._purge_tombstones()
+            self._tombstones = 0
         return removed
 
     def clear_dirty(self) -> None:

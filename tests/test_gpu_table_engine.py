@@ -178,3 +178,35 @@ def test_dlrm_engine_matches_fp32_oracle(graph):
     rows_r = m.tables[t].weight[keys]
     assert (rows_e - rows_r).abs().max().item() < 0.05
     assert eng.tables[0].overflowed() == 0
+
+
+def test_multi_tier_hbm_dram_matches_single_tier():
+    """HBM cache (tiny) over DRAM: training results equal the all-HBM table; cold rows are demoted and promoted back."""
+    import deeprec_b200 as dr
+    torch.manual_seed(0)
+    small = dr.StorageOption(dr.StorageType.HBM_DRAM, storage_size=(2048 * 2 * 16 * 4,), cache_strategy=dr.CacheStrategy.LFU)
+    ev_mt = _mk("mt", 16, "cuda", storage_option=small)
+    ev_ref = _mk("mt", 16, "cuda")
+    gs1, gs2 = dr.optim.GlobalStep(), dr.optim.GlobalStep()
+    o_mt = dr.optim.AdagradOptimizer([], [ev_mt], lr=0.1, global_step=gs1)
+    o_ref = dr.optim.AdagradOptimizer([], [ev_ref], lr=0.1, global_step=gs2)
+    from deeprec_b200.ops.multi_tier import MultiTierTable
+    assert isinstance(ev_mt.table, MultiTierTable) and ev_mt.table.cache_rows == 2048
+    for step in range(12):
+        lo = (step % 4) * 1500                                  # working set rotates: 6000 distinct ids > 2048-row cache
+        ids = torch.randint(lo, lo + 1500, (1200,), device="cuda")
+        if step % 2 == 0:
+            ev_mt.table.prefetch(ids)                              # staged-pipeline style prefetch + pin
+        tgt = torch.randn(1200, 16, device="cuda")
+        for ev, opt in ((ev_mt, o_mt), (ev_ref, o_ref)):
+            ((ev.lookup(ids) - tgt) ** 2).sum().backward(); opt.step()
+    probe = torch.arange(0, 6000, 7, device="cuda")
+    a = ev_mt.table.lookup(probe).cpu(); b = ev_ref.table.lookup(probe).cpu()
+    assert torch.allclose(a, b, atol=1e-4), (a - b).abs().max()
+    st = ev_mt.table.cache_stats()
+    assert st["misses"] > 0 and st["hbm_rows"] <= 2048 + 1024
+    tiers = ev_mt.lookup_tier(torch.tensor([0, 5999, 10 ** 9]))
+    assert tiers[2].item() == -1 and set(tiers[:2].tolist()) <= {0, 1}
+    assert ev_mt.total_count() == ev_ref.total_count()
+    snap = ev_mt.table.snapshot()
+    assert snap["keys"].numel() == ev_ref.total_count()
