@@ -252,6 +252,9 @@ def main():
             "gpu_launches": launches,
         }
         print(json.dumps(out))
+    if comm is not None and getattr(comm, "_timing", False):
+        rep = comm.timing_report()
+        print(f"[rank {rank}] p2p phase ms: " + ", ".join(f"{k}={v:.3f}" for k, v in rep.items()), file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -30,6 +30,9 @@ struct DrPeers {
 namespace {
 
 constexpr int kMaxRanks = 16;
+
+// owner of a key of a ROW-sharded table (decorrelated from the probe hash)
+__device__ __forceinline__ int row_owner(int64_t key, int W) { return (int)((dr_mix64((uint64_t)key ^ 0x5bd1e9955bd1e995ULL) >> 33) % (uint64_t)W); }
 constexpr int kMaxChannels = 16;
 
 // signals layout (per rank, symmetric): uint32 flags[kMaxChannels][kMaxRanks]; epochs[kMaxChannels] lives in LOCAL memory
@@ -54,7 +57,8 @@ __global__ void k_rank_barrier(DrPeers sig, uint32_t* __restrict__ epochs, int c
 template <int LPR>   // lanes per row = dim / 4 (float4 per lane), power of two <= 32
 __global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restrict__ tables, const int32_t* __restrict__ table_map,
                                                    const int32_t* __restrict__ table_global,   // [nl] global table id of local table j
-                                                   int nl, int W, int64_t B, int T, DrPeers ids_peers /* int64 [T][B] */,
+                                                   const uint8_t* __restrict__ row_flag,       // [nl] 1 = row-sharded table (every rank scans it, owns key-hash % W == rank)
+                                                   int rank, int nl, int W, int64_t B, int T, DrPeers ids_peers /* int64 [T][B] */,
                                                    DrPeers emb_peers /* bf16 [T][B][D] */, int train,
                                                    const int64_t* __restrict__ step_ptr, int32_t* __restrict__ pos_out,
                                                    int64_t* __restrict__ ulist, int32_t* __restrict__ nunique, int64_t ulist_cap) {
@@ -73,7 +77,9 @@ __global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restri
       const DrDeviceTable& TB = tables[table_map[j]];
       const int64_t key = reinterpret_cast<const int64_t*>(ids_peers.ptr[s])[(int64_t)tg * B + b];
       int64_t pos;
-      if (!train || TB.is_inference) {
+      if (row_flag && row_flag[j] && row_owner(key, W) != rank) {
+        pos = -2;                                       // another rank's shard serves this key
+      } else if (!train || TB.is_inference) {
         pos = table_find(TB, key);
       } else {
         bool inserted = false, skip = false;
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restri
     for (int it = 0; it < LPR; ++it) {
       const int li = it * ROWS_PER_IT + threadIdx.x / LPR;
       const int64_t ii = base + li;
-      if (ii < n) {
+      if (ii < n && s_pos[li] != -2) {
         const int64_t b = ii % B;
         const int s = (int)((ii / B) % W);
         const int j = (int)(ii / (B * W));
@@ -227,18 +233,18 @@ int dr_comm_barrier(const DrPeers* sig, uint32_t* epochs, int channel, int rank,
   return 0;
 }
 
-int dr_comm_mp_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map, const int32_t* table_global, int nl, int W, int64_t B,
-                      int T, int dim, const DrPeers* ids_peers, const DrPeers* emb_peers, int train, const int64_t* step_ptr,
+int dr_comm_mp_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map, const int32_t* table_global, const uint8_t* row_flag, int rank,
+                      int nl, int W, int64_t B, int T, int dim, const DrPeers* ids_peers, const DrPeers* emb_peers, int train, const int64_t* step_ptr,
                       int32_t* pos_out, int64_t* ulist, int32_t* nunique, int64_t ulist_cap, cudaStream_t s) {
   int64_t n = (int64_t)nl * W * B;
   if (n == 0) return 0;
   int grid = grid_for(n, 256, kNumSMs * sparse_blocks_per_sm());
   switch (dim / 4) {
-    case 2: k_mp_lookup<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 4: k_mp_lookup<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 8: k_mp_lookup<8><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 16: k_mp_lookup<16><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 32: k_mp_lookup<32><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 2: k_mp_lookup<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 4: k_mp_lookup<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 8: k_mp_lookup<8><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 16: k_mp_lookup<16><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 32: k_mp_lookup<32><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
     default: return -3;
   }
   DR_LAUNCH_CHECK();

@@ -63,6 +63,7 @@ class DLRMConfig:
     steps_to_live: int = 0
     seed: int = 1234
     overlap_embedding: bool = True              # fork the embedding branch onto a side stream inside the graph
+    row_shard_threshold: int = 1_000_000        # world > 1: tables with >= this many ids are sharded row-wise (hash(key) % W) over ALL ranks
     sparse_blocks_per_sm: int = 4               # resident-block budget of the side-stream sparse kernels (overlap with the GEMMs)
     gemm_v1: bool = False                       # A/B switch: direct-store GEMM epilogue + separate statistics passes
 
@@ -185,8 +186,18 @@ class DLRMEngine:
     # ------------------------------------------------------------------------------------------------
     def _build_tables(self) -> None:
         cfg = self.cfg
-        self.owner_of = [t % self.world for t in range(self.T)]
-        self.local_tables = [t for t in range(self.T) if self.owner_of[t] == self.rank]
+        W = self.world
+        # hybrid sharding: huge tables row-wise over all ranks (balances the DRAM-bound probe/update work that scales with the
+        # number of distinct keys), small tables table-wise round-robin (their rows stay L2-resident on one owner).
+        rs = getattr(self.comm, "supports_row_sharding", False) and W > 1
+        self.row_tables = [t for t in range(self.T) if rs and cfg.cardinalities[t] >= cfg.row_shard_threshold]
+        small = [t for t in range(self.T) if t not in self.row_tables]
+        self.owner_of = [-1] * self.T
+        for i, t in enumerate(small):
+            self.owner_of[t] = i % W
+        self.local_tables = sorted(self.row_tables + [t for t in small if self.owner_of[t] == self.rank])
+        self.row_flag = (torch.tensor([1 if t in self.row_tables else 0 for t in self.local_tables], dtype=torch.uint8, device=self.dev)
+                         if self.row_tables else None)
         self.ctx = get_context(self.dev, self.D, owner=id(self) & 0x7FFFFFFF)
         self.tables: Dict[int, DeviceTable] = {}
         g = torch.Generator().manual_seed(cfg.seed + 17)
@@ -194,6 +205,8 @@ class DLRMEngine:
         slot_init = [cfg.initial_accumulator_value if self.kind in (OPT_ADAGRAD, OPT_ADAGRAD_DECAY, OPT_FTRL) else 0.0, 0.0, 0.0, 0.0]
         for t in self.local_tables:
             card = int(cfg.cardinalities[t])
+            if t in self.row_tables:
+                card = card // W + 1                      # this rank's shard
             c = EvConfig()
             c.dim, c.num_slots, c.has_scalars = self.D, ns, int(self.kind == OPT_ADAGRAD_DECAY)
             c.init_capacity = card

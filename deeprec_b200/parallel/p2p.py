@@ -45,7 +45,7 @@ def _bind(lib):
         "dr_comm_alloc": [i64, C.POINTER(vp)], "dr_comm_free": [P], "dr_comm_get_handle": [P, P],
         "dr_comm_open_handle": [P, C.POINTER(vp)], "dr_comm_close_handle": [P], "dr_comm_can_access_peer": [INT, INT],
         "dr_comm_barrier": [PP, P, INT, INT, INT, P],
-        "dr_comm_mp_lookup": [P, P, P, INT, INT, i64, INT, INT, PP, PP, INT, P, P, P, P, i64, P],
+        "dr_comm_mp_lookup": [P, P, P, P, INT, INT, INT, i64, INT, INT, PP, PP, INT, P, P, P, P, i64, P],
         "dr_comm_mp_sparse_grad": [P, P, P, INT, INT, i64, INT, PP, P, P, P],
         "dr_comm_allreduce_apply": [PP, INT, P, P, P, i64, P, P, P],
     }
@@ -99,6 +99,8 @@ class SymmetricBuffer:
 
 
 class P2PComm:
+    supports_row_sharding = True
+
     def __init__(self, rank: int, world: int, dev: torch.device, group=None):
         self.rank, self.world, self.dev, self.group = rank, world, dev, group
         self.lib = _native.cuda()
@@ -111,6 +113,25 @@ class P2PComm:
         self.epochs = torch.zeros(16, dtype=torch.int32, device=dev)
         dist.barrier(group=group)
         self.launches = 0
+        import os
+        self._timing = os.environ.get("DEEPREC_P2P_TIMING") == "1"
+        self._events = {}
+
+    def _tick(self, name):
+        if self._timing:
+            e = torch.cuda.Event(enable_timing=True); e.record(torch.cuda.current_stream(self.dev))
+            self._events.setdefault(name, []).append(e)
+
+    def timing_report(self):
+        torch.cuda.synchronize(self.dev)
+        ev, out = self._events, {}
+        names = [("barrier0", "l0", "l1"), ("mp_lookup", "l1", "l2"), ("barrier1", "l2", "l3"), ("barrier2", "s0", "s1"), ("mp_sparse_grad", "s1", "s2"),
+                 ("sparse_apply", "s2", "s3"), ("barrier3", "d0", "d1"), ("allreduce_apply", "d1", "d2")]
+        for nm, a, b in names:
+            if a in ev and b in ev:
+                ts = [x.elapsed_time(y) for x, y in zip(ev[a], ev[b])]
+                out[nm] = sum(ts[2:]) / max(1, len(ts[2:]))
+        return out
 
     def _s(self):
         return vp(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -139,27 +160,39 @@ class P2PComm:
 
     def lookup_forward(self, eng, train: bool) -> None:
         nl, ctx = len(eng.local_tables), eng.ctx
+        self._tick("l0")
         self.barrier(0)
-        _chk(self.lib.dr_comm_mp_lookup(ptr(ctx.structs()), ptr(eng.tmap_local), ptr(self._tg(eng)), nl, self.world, eng.B, eng.T, eng.D,
+        self._tick("l1")
+        _chk(self.lib.dr_comm_mp_lookup(ptr(ctx.structs()), ptr(eng.tmap_local), ptr(self._tg(eng)), ptr(eng.row_flag) if eng.row_flag is not None else None,
+                                        self.rank, nl, self.world, eng.B, eng.T, eng.D,
                                         self.ids_buf.peers_ref(), self.emb_buf.peers_ref(), int(train), eng.step_ptr, ptr(eng.pos),
                                         ptr(ctx.ulist) if train else None, ptr(ctx.nuniq) if train else None,
                                         ctx.ulist.numel() if train else 0, self._s()), "mp_lookup")
+        self._tick("l2")
         self.barrier(1)
+        self._tick("l3")
         eng.launches += 3
 
     def sparse_backward(self, eng) -> None:
         nl, ctx = len(eng.local_tables), eng.ctx
+        self._tick("s0")
         self.barrier(2)
+        self._tick("s1")
         _chk(self.lib.dr_comm_mp_sparse_grad(ptr(ctx.structs()), ptr(eng.tmap_local), ptr(self._tg(eng)), nl, self.world, eng.B, eng.D,
                                              self.demb_buf.peers_ref(), ptr(eng.pos), ptr(ctx.gsum), self._s()), "mp_sparse_grad")
+        self._tick("s2")
         _chk(self.lib.dr_cuda_sparse_apply(ptr(ctx.structs()), ptr(ctx.ulist), ptr(ctx.nuniq), ctx.ulist.numel(), ptr(ctx.gsum), eng.D,
                                            ptr(eng.hp_dev), eng.max_unique, 1, self._s()), "sparse_apply")
+        self._tick("s3")
         eng.launches += 4
 
     def dense_allreduce_update(self, eng) -> None:
+        self._tick("d0")
         self.barrier(3)
+        self._tick("d1")
         _chk(self.lib.dr_comm_allreduce_apply(self.grads_buf.peers_ref(), self.world, ptr(eng.params), ptr(eng.s0) if eng.s0 is not None else None,
                                               ptr(eng.s1) if eng.s1 is not None else None, eng.P, ptr(eng.hp_dev), None, self._s()), "allreduce_apply")
+        self._tick("d2")
         eng.launches += 2
 
     def allreduce(self, out: torch.Tensor) -> None:

@@ -39,13 +39,17 @@ def main():
     cfg = DLRMConfig(batch_size=2048, cardinalities=cards, optimizer="adagrad", learning_rate=0.05)
     batches = [criteo_batch(cfg.batch_size, 13, cards, seed=100 * rank + s) for s in range(4)]
     results = {}
-    for name in ("p2p", "nccl"):
-        comm = P2PComm(rank, world, dev) if name == "p2p" else NcclComm(rank, world, dev)
-        eng = DLRMEngine(cfg, dev, rank, world, comm)
+    import copy
+    for name in ("p2p", "nccl", "p2p_row"):
+        comm = P2PComm(rank, world, dev) if name.startswith("p2p") else NcclComm(rank, world, dev)
+        c = copy.deepcopy(cfg)
+        c.row_shard_threshold = 200 if name == "p2p_row" else 10 ** 12      # p2p_row: tables 1 and 3 are sharded row-wise over all ranks
+        eng = DLRMEngine(c, dev, rank, world, comm)
+        assert (len(eng.row_tables) == 2) == (name == "p2p_row")
         losses = []
         for i, (d, ids, y) in enumerate(batches):
             eng.load_batch(d.to(dev), ids.to(dev), y.to(dev))
-            if name == "p2p" and i == 1:
+            if name.startswith("p2p") and i == 1:
                 eng.capture()                     # captures the P2P step (barriers included) into a CUDA graph
             else:
                 eng.train_step()
@@ -53,9 +57,15 @@ def main():
         torch.cuda.synchronize()
         probe = torch.arange(0, 50, device=dev)
         rows = {t: eng.tables[t].lookup(probe).clone() for t in eng.local_tables}
-        results[name] = (losses, eng.params.clone(), rows, {t: eng.tables[t].size() for t in eng.local_tables})
+        total = torch.tensor([float(sum(eng.tables[t].size() for t in eng.local_tables))], device=dev)
+        dist.all_reduce(total)
+        results[name] = (losses, eng.params.clone(), rows, {t: eng.tables[t].size() for t in eng.local_tables}, int(total.item()))
         dist.barrier()
-    (l1, p1, r1, s1), (l2, p2, r2, s2) = results["p2p"], results["nccl"]
+    (l1, p1, r1, s1, n1), (l2, p2, r2, s2, n2) = results["p2p"], results["nccl"]
+    l3, p3, _, _, n3 = results["p2p_row"]
+    for a, b in zip(l3, l2):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), ("row-sharded", l3, l2)
+    assert (p3 - p2).abs().max().item() < 2e-3 and n3 == n2 == n1, (n1, n2, n3)
     for a, b in zip(l1, l2):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (l1, l2)
     assert (p1 - p2).abs().max().item() < 2e-3, (p1 - p2).abs().max().item()
