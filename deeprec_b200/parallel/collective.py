@@ -19,6 +19,33 @@ import torch.distributed as dist
 from . import strategy as _strategy
 
 
+class _DistLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, strategy, t, table, sp, combiner, weights):
+        from ..ops.embedding_ops import SparseIds, embedding_lookup_sparse
+        W, r, owner = strategy.world_size, strategy.rank, strategy.owner_of(t)
+        objs = [None] * W
+        w = weights if weights is not None else sp.weights
+        dist.all_gather_object(objs, (sp.values.cpu(), sp.row_ids.cpu(), sp.batch_size, None if w is None else w.cpu()))
+        outs = None
+        if owner == r:
+            with torch.enable_grad():
+                outs = [embedding_lookup_sparse(table, SparseIds(v, rid, B, ww), None, combiner) for (v, rid, B, ww) in objs]
+        recv = [None]
+        dist.scatter_object_list(recv, [o.detach().cpu() for o in outs] if owner == r else None, src=owner)
+        ctx.strategy, ctx.owner, ctx.outs = strategy, owner, outs
+        return recv[0].to(sp.values.device if sp.values.is_cuda else "cpu")
+
+    @staticmethod
+    def backward(ctx, g):
+        st = ctx.strategy
+        gl = [None] * st.world_size if st.rank == ctx.owner else None
+        dist.gather_object(g.detach().cpu(), gl, dst=ctx.owner)
+        if st.rank == ctx.owner:
+            torch.autograd.backward(ctx.outs, [x.to(o.device) for x, o in zip(gl, ctx.outs)])
+        return (None,) * 7
+
+
 class DistStrategy(enum.Enum):
     SOK = "sok"                 # accepted for API parity: maps onto the built-in P2P model-parallel path
     HB = "hb"
@@ -95,25 +122,15 @@ class CollectiveStrategy:
         return table_index % self.world_size
 
     def distributed_lookup(self, params, sp_ids, combiners, sp_weights=None) -> List[torch.Tensor]:
-        from ..ops.embedding_ops import embedding_lookup_sparse, SparseIds
-        W, r = self.world_size, self.rank
-        outs: List[Optional[torch.Tensor]] = [None] * len(params)
-        # every rank looks up the tables it owns for EVERY rank's ids, then results are exchanged (all-gather of ids,
-        # reduce-scatter-free since one-hot ownership): simple, correct reference path for CPU/gloo tests.
-        for t, (p, s, c) in enumerate(zip(params, sp_ids, combiners)):
-            owner = self.owner_of(t)
-            objs = [None] * W
-            dist.all_gather_object(objs, (s.values.cpu(), s.row_ids.cpu(), s.batch_size, None if s.weights is None else s.weights.cpu()))
-            if owner == r:
-                res = []
-                for (v, rid, B, w) in objs:
-                    res.append(embedding_lookup_sparse(p, SparseIds(v, rid, B, w), None, c))
-            else:
-                res = None
-            recv = [None]
-            dist.scatter_object_list(recv, res if owner == r else None, src=owner)
-            outs[t] = recv[0]
-        return outs
+        """Model-parallel GroupEmbedding for generic modules over torch.distributed (gloo on CPU, nccl on GPU): table t lives on
+        rank t % world; ids are all-gathered to the owner, the owner looks up + combines for every requester and scatters the
+        results; the backward sends the output gradients back to the owner, whose EmbeddingVariable records the sparse gradient
+        (so only the owner's optimizer ever updates the table).  The flagship engine uses the fused NVLink kernels instead."""
+        if sp_weights is None:
+            sp_weights = [None] * len(params)
+        if not hasattr(self, "_anchor"):
+            self._anchor = torch.zeros(1, requires_grad=True)
+        return [_DistLookup.apply(self._anchor, self, t, p, s, c, w) for t, (p, s, c, w) in enumerate(zip(params, sp_ids, combiners, sp_weights))]
 
     def export_saved_model(self, *a, **k):
         from ..serving.export import export_saved_model
