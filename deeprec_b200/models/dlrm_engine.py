@@ -218,6 +218,7 @@ class DLRMEngine:
             c.storage_type = 1
             for i in range(4):
                 c.slot_init[i] = slot_init[i]
+            g.manual_seed(cfg.seed + 17 + 1000 * t)      # initial values depend on (table, key) only -- never on the sharding
             dm = torch.empty(4096, self.D).normal_(0.0, 1.0 / math.sqrt(self.D), generator=g)
             rows = min(card, cfg.max_rows_per_table)
             # a step can touch at most B*world new keys of this table
