@@ -67,46 +67,44 @@ __global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restri
   const int64_t n = (int64_t)nl * W * B;
   (void)step_ptr;
   for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
-    // ---- phase 1: one thread per key: peer load + probe / insert / admission bookkeeping / dedup claim
+    // ---- phase 1: one thread per key: peer load + probe / insert / admission; bookkeeping aggregated over the warp
     const int64_t i = base + threadIdx.x;
-    if (i < n) {
-      const int64_t b = i % B;
-      const int s = (int)((i / B) % W);
-      const int j = (int)(i / (B * W));
+    {
+      const bool live = i < n;
+      const int64_t ii = live ? i : n - 1;
+      const int64_t b = ii % B;
+      const int s = (int)((ii / B) % W);
+      const int j = (int)(ii / (B * W));
       const int tg = table_global[j];
       const DrDeviceTable& TB = tables[table_map[j]];
-      const int64_t key = reinterpret_cast<const int64_t*>(ids_peers.ptr[s])[(int64_t)tg * B + b];
-      int64_t pos;
-      if (row_flag && row_flag[j] && row_owner(key, W) != rank) {
-        pos = -2;                                       // another rank's shard serves this key
-      } else if (!train || TB.is_inference) {
-        pos = table_find(TB, key);
-      } else {
-        bool inserted = false, skip = false;
-        if (TB.filter_type == DR_FILTER_BLOOM) {
+      int64_t key = 0, pos = -2;
+      bool touch = false;
+      if (live) {
+        key = reinterpret_cast<const int64_t*>(ids_peers.ptr[s])[(int64_t)tg * B + b];
+        if (row_flag && row_flag[j] && row_owner(key, W) != rank) {
+          pos = -2;                                       // another rank's shard serves this key
+        } else if (!train || TB.is_inference) {
           pos = table_find(TB, key);
-          if (pos < 0) {
-            if (bloom_add_min(TB, key, 1u) < (uint32_t)TB.filter_freq) skip = true;
-            else pos = table_find_or_insert(TB, key, &inserted);
-          }
         } else {
-          pos = table_find_or_insert(TB, key, &inserted);
-        }
-        if (!skip && pos < 0) TB.counters[CTR_OVERFLOW] = 1;
-        if (!skip && pos >= 0) {
-          if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
-          atomicAdd(&TB.freq[pos], 1);
-          TB.dirty[pos] = 1;
-          if (atomicCAS(&TB.tag[pos], -1, -2) == -1) {
-            int u = atomicAdd(nunique, 1);
-            if (u < ulist_cap) { ulist[u] = ((int64_t)table_map[j] << 40) | pos; TB.tag[pos] = u; }
-            else { TB.tag[pos] = -1; TB.counters[CTR_OVERFLOW] = 2; }
+          bool inserted = false, skip = false;
+          if (TB.filter_type == DR_FILTER_BLOOM) {
+            pos = table_find(TB, key);
+            if (pos < 0) {
+              if (bloom_add_min(TB, key, 1u) < (uint32_t)TB.filter_freq) skip = true;
+              else pos = table_find_or_insert(TB, key, &inserted);
+            }
+          } else {
+            pos = table_find_or_insert(TB, key, &inserted);
           }
+          if (!skip && pos < 0) TB.counters[CTR_OVERFLOW] = 1;
+          if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
+          touch = !skip && pos >= 0;
         }
+        pos_out[i] = (int32_t)pos;
       }
       s_pos[threadIdx.x] = (int32_t)pos;
       s_key[threadIdx.x] = key;
-      pos_out[i] = (int32_t)pos;
+      if (train) table_touch_aggregated(TB, touch, pos, table_map[j], ulist, nunique, ulist_cap);
     }
     __syncthreads();
     // ---- phase 2: LPR lanes per row copy fp32 row -> bf16 into the requester's buffer over NVLink
@@ -139,8 +137,17 @@ template <int LPR>
 __global__ void __launch_bounds__(256) k_mp_sparse_grad(const DrDeviceTable* __restrict__ tables, const int32_t* __restrict__ table_map,
                                                         const int32_t* __restrict__ table_global, int nl, int W, int64_t B,
                                                         DrPeers demb_peers /* bf16 [T][B][D] */, const int32_t* __restrict__ pos,
-                                                        float* __restrict__ gsum) {
+                                                        float* __restrict__ gsum, int C) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int dim = 4 * LPR;
+  float* s_acc = reinterpret_cast<float*>(smem_raw);
+  int32_t* s_tag = reinterpret_cast<int32_t*>(smem_raw + (size_t)C * dim * 4);
+  for (int e = threadIdx.x; e < C * dim; e += blockDim.x) s_acc[e] = 0.f;
+  for (int e = threadIdx.x; e < C; e += blockDim.x) s_tag[e] = -1;
+  __syncthreads();
   const int lane = threadIdx.x % LPR;
+  const int gleader = (threadIdx.x & 31) / LPR * LPR;
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << gleader);
   const int64_t n = (int64_t)nl * W * B;
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   const int64_t gstride = (int64_t)gridDim.x * blockDim.x / LPR;
@@ -152,11 +159,14 @@ __global__ void __launch_bounds__(256) k_mp_sparse_grad(const DrDeviceTable* __r
     const int j = (int)(i / (B * W));
     const int32_t u = tables[table_map[j]].tag[p];
     if (u < 0) continue;
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(demb_peers.ptr[s]) + ((int64_t)table_global[j] * B + b) * (4 * LPR) + 4 * lane;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(demb_peers.ptr[s]) + ((int64_t)table_global[j] * B + b) * dim + 4 * lane;
     uint2 raw = *reinterpret_cast<const uint2*>(src);
     float2 a = unpack_bf16x2(raw.x), c = unpack_bf16x2(raw.y);
-    red_add_v4_f32(gsum + (int64_t)u * (4 * LPR) + 4 * lane, a.x, a.y, c.x, c.y);
+    const float4 g = make_float4(a.x, a.y, c.x, c.y);
+    combine_add<LPR>(s_tag, s_acc, C, dim, u, lane, gmask, gleader, &g, 1, gsum);
   }
+  __syncthreads();
+  flush_combining_cache(s_tag, s_acc, C, dim, gsum);
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -257,12 +267,14 @@ int dr_comm_mp_sparse_grad(const DrDeviceTable* tables_dev, const int32_t* table
   if (n == 0) return 0;
   int lpr = dim / 4;
   int grid = grid_for(n * lpr, 256, kNumSMs * sparse_blocks_per_sm());
+  const int C = combining_cache_slots(dim);
+  const size_t smem = (size_t)C * dim * 4 + (size_t)C * 4;
   switch (lpr) {
-    case 2: k_mp_sparse_grad<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
-    case 4: k_mp_sparse_grad<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
-    case 8: k_mp_sparse_grad<8><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
-    case 16: k_mp_sparse_grad<16><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
-    case 32: k_mp_sparse_grad<32><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum); break;
+    case 2: k_mp_sparse_grad<2><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 4: k_mp_sparse_grad<4><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 8: k_mp_sparse_grad<8><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 16: k_mp_sparse_grad<16><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 32: k_mp_sparse_grad<32><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
     default: return -3;
   }
   DR_LAUNCH_CHECK();

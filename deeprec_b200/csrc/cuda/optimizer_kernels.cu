@@ -30,8 +30,17 @@ __global__ void __launch_bounds__(256) k_accumulate(const DrDeviceTable* __restr
                                                     int64_t uniform, int64_t n, const void* __restrict__ grad,
                                                     int64_t stride_b, int64_t stride_t, int flat_in,
                                                     const int32_t* __restrict__ row_ids, const float* __restrict__ scale,
-                                                    float* __restrict__ gsum) {
+                                                    float* __restrict__ gsum, int C) {
+  // per-block combining cache (see table.cuh): hot keys are reduced in shared memory and flushed once per block
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* s_acc = reinterpret_cast<float*>(smem_raw);
+  int32_t* s_tag = reinterpret_cast<int32_t*>(smem_raw + (size_t)C * dim * 4);
+  for (int e = threadIdx.x; e < C * dim; e += blockDim.x) s_acc[e] = 0.f;
+  for (int e = threadIdx.x; e < C; e += blockDim.x) s_tag[e] = -1;
+  __syncthreads();
   const int lane = threadIdx.x % LPR;
+  const int gleader = (threadIdx.x & 31) / LPR * LPR;
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << gleader);
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   const int64_t gstride = (int64_t)gridDim.x * blockDim.x / LPR;
   const int nvec = dim >> 2;
@@ -48,8 +57,9 @@ __global__ void __launch_bounds__(256) k_accumulate(const DrDeviceTable* __restr
       o = b * stride_b + (int64_t)t * stride_t;
     }
     const float sc = scale ? scale[i] : 1.0f;
-    float* dst = gsum + (int64_t)u * dim;
-    for (int c = lane; c < nvec; c += LPR) {
+    float4 chunks[4];
+    int k = 0;
+    for (int c = lane; c < nvec && k < 4; c += LPR, ++k) {
       float4 g;
       if (BF16) {
         uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(grad) + o + 4 * c);
@@ -58,9 +68,12 @@ __global__ void __launch_bounds__(256) k_accumulate(const DrDeviceTable* __restr
       } else {
         g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grad) + o + 4 * c);
       }
-      red_add_v4_f32(dst + 4 * c, g.x * sc, g.y * sc, g.z * sc, g.w * sc);
+      chunks[k] = make_float4(g.x * sc, g.y * sc, g.z * sc, g.w * sc);
     }
+    combine_add<LPR>(s_tag, s_acc, C, dim, u, lane, gmask, gleader, chunks, k, gsum);
   }
+  __syncthreads();
+  flush_combining_cache(s_tag, s_acc, C, dim, gsum);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -241,11 +254,14 @@ int dr_cuda_sparse_accumulate(const DrDeviceTable* tables_dev, const int32_t* ta
                               int64_t uniform, int64_t n, const void* grad, int grad_bf16, int64_t stride_b, int64_t stride_t,
                               int flat_in, const int32_t* row_ids, const float* scale, float* gsum, cudaStream_t s) {
   if (n == 0) return 0;
+  if (dim > 512) return -1;
   int lpr = lanes_for(dim);
   int grid = grid_for(n * lpr, 256);
+  const int C = combining_cache_slots(dim);
+  const size_t smem = (size_t)C * dim * 4 + (size_t)C * 4;
 #define LAUNCH(L)                                                                                                  \
-  if (grad_bf16) k_accumulate<L, true><<<grid, 256, 0, s>>>(tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum); \
-  else k_accumulate<L, false><<<grid, 256, 0, s>>>(tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum);
+  if (grad_bf16) k_accumulate<L, true><<<grid, 256, smem, s>>>(tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum, C); \
+  else k_accumulate<L, false><<<grid, 256, smem, s>>>(tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum, C);
   switch (lpr) {
     case 1: LAUNCH(1) break; case 2: LAUNCH(2) break; case 4: LAUNCH(4) break; case 8: LAUNCH(8) break;
     case 16: LAUNCH(16) break; default: LAUNCH(32) break;

@@ -116,4 +116,64 @@ __device__ __forceinline__ const float* table_read_ptr(const DrDeviceTable& T, i
   return T.default_matrix + dr_default_row(key, T.default_value_dim) * T.dim;
 }
 
+
+// ---- training-side bookkeeping of one probe result, aggregated over the warp -------------------------------------
+// All 32 lanes call this (valid = lane has a live key at `pos` of table TB; every valid lane of a warp addresses the
+// SAME table).  Lanes holding the same position elect a leader that performs ONE freq += count, the dirty mark and the
+// per-step dedup claim: hot keys of tiny tables would otherwise serialise tens of thousands of same-address atomics.
+__device__ __forceinline__ void table_touch_aggregated(const DrDeviceTable& TB, bool valid, int64_t pos, int table_index, int64_t* ulist,
+                                                       int32_t* nunique, int64_t ulist_cap) {
+  const unsigned lane = threadIdx.x & 31;
+  // lanes of a warp may straddle two tables when a segment boundary is not 32-aligned: the table is part of the match key
+  const int64_t mkey = valid ? (((int64_t)table_index << 40) | pos) : -(int64_t)(lane + 1);            // invalid lanes match nobody
+  const unsigned same = __match_any_sync(0xffffffffu, mkey);
+  if (!valid) return;
+  if ((unsigned)(__ffs(same) - 1) != lane) return;                    // not the leader of this position
+  atomicAdd(&TB.freq[pos], __popc(same));
+  TB.dirty[pos] = 1;
+  if (ulist != nullptr && atomicCAS(&TB.tag[pos], -1, -2) == -1) {
+    const int u = atomicAdd(nunique, 1);
+    if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; TB.tag[pos] = u; }
+    else { TB.tag[pos] = -1; TB.counters[CTR_OVERFLOW] = 2; }
+  }
+}
+
+// ---- per-block combining cache for gradient accumulation ----------------------------------------------------------------
+// Direct-mapped on the unique index u: s_tag[C] (init -1), s_acc[C * dim] (init 0).  A group of LPR lanes adds its float4
+// chunks either into the cached row (shared-memory atomics) or, on a slot conflict, straight into gsum with red.global.
+// flush_combining_cache() pushes every cached row with ONE vectorised global reduction per chunk.
+template <int LPR>
+__device__ __forceinline__ void combine_add(int32_t* s_tag, float* s_acc, int C, int dim, int32_t u, int lane, unsigned gmask, int gleader,
+                                            const float4* chunks, int nchunks_per_lane, float* __restrict__ gsum) {
+  int hit = 0;
+  const int slot = u & (C - 1);
+  if (lane == 0) { const int32_t old = atomicCAS(&s_tag[slot], -1, u); hit = (old == -1 || old == u); }
+  hit = __shfl_sync(gmask, hit, gleader);
+  const int nvec = dim >> 2;
+#pragma unroll 4
+  for (int k = 0; k < nchunks_per_lane; ++k) {
+    const int c = lane + k * LPR;
+    if (c >= nvec) break;
+    const float4 g = chunks[k];
+    if (hit) {
+      float* d = s_acc + (int64_t)slot * dim + 4 * c;
+      atomicAdd(d, g.x); atomicAdd(d + 1, g.y); atomicAdd(d + 2, g.z); atomicAdd(d + 3, g.w);
+    } else {
+      red_add_v4_f32(gsum + (int64_t)u * dim + 4 * c, g.x, g.y, g.z, g.w);
+    }
+  }
+}
+__device__ __forceinline__ void flush_combining_cache(const int32_t* s_tag, const float* s_acc, int C, int dim, float* __restrict__ gsum) {
+  const int nvec = dim >> 2;
+  for (int e = threadIdx.x; e < C * nvec; e += blockDim.x) {
+    const int slot = e / nvec, c = e % nvec;
+    const int32_t u = s_tag[slot];
+    if (u >= 0) {
+      const float* s = s_acc + (int64_t)slot * dim + 4 * c;
+      red_add_v4_f32(gsum + (int64_t)u * dim + 4 * c, s[0], s[1], s[2], s[3]);
+    }
+  }
+}
+inline int combining_cache_slots(int dim) { int c = 512; while (c > 16 && (int64_t)c * dim * 4 > 32768) c >>= 1; return c; }
+
 }  // namespace drc

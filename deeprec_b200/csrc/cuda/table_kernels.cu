@@ -30,50 +30,38 @@ __global__ void __launch_bounds__(256) k_lookup(const DrDeviceTable* __restrict_
                                                 int32_t* __restrict__ out_pos, int64_t* __restrict__ ulist,
                                                 int32_t* __restrict__ group_nunique, int64_t ulist_cap) {
   (void)step_ptr;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int tl = seg_of(offsets, T, i, uniform);
+  // whole warps iterate together (n rounded up to 32) so the warp-aggregated bookkeeping can use full-mask collectives
+  const int64_t n32 = (n + 31) & ~int64_t(31);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = i < n;
+    const int64_t ii = live ? i : n - 1;
+    const int tl = seg_of(offsets, T, ii, uniform);
     const int t = table_map ? table_map[tl] : tl;      // index into the context-wide table array
     const DrDeviceTable& TB = tables[t];
-    const int64_t key = keys[i];
-    int64_t pos;
-    if (!train || TB.is_inference) {
-      pos = table_find(TB, key);
-      out_pos[i] = (int32_t)pos;
-      continue;
-    }
-    bool inserted = false;
-    if (TB.filter_type == DR_FILTER_BLOOM) {
-      pos = table_find(TB, key);
-      if (pos < 0) {
-        uint32_t c = bloom_add_min(TB, key, 1u);
-        if (c < (uint32_t)TB.filter_freq) { out_pos[i] = -1; continue; }
-        pos = table_find_or_insert(TB, key, &inserted);
-      }
-    } else {
-      pos = table_find_or_insert(TB, key, &inserted);
-    }
-    if (pos < 0) { TB.counters[CTR_OVERFLOW] = 1; out_pos[i] = -1; continue; }
-    if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
-    atomicAdd(&TB.freq[pos], 1);
-    TB.dirty[pos] = 1;          // version is stamped by the apply kernel (UpdateVersion lives in the apply op)
-    out_pos[i] = (int32_t)pos;
-    if (ulist != nullptr) {
-      bool won = atomicCAS(&TB.tag[pos], -1, -2) == -1;
-      if (won) {
-        auto g = cg::coalesced_threads();
-        int base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(group_nunique, (int)g.size());
-        base = g.shfl(base, 0);
-        int u = base + (int)g.thread_rank();
-        if (u < ulist_cap) {
-          ulist[u] = ((int64_t)t << 40) | pos;
-          TB.tag[pos] = u;
+    const int64_t key = keys[ii];
+    int64_t pos = -1;
+    bool touch = false;
+    if (live) {
+      if (!train || TB.is_inference) {
+        pos = table_find(TB, key);
+      } else {
+        bool inserted = false, skip = false;
+        if (TB.filter_type == DR_FILTER_BLOOM) {
+          pos = table_find(TB, key);
+          if (pos < 0) {
+            if (bloom_add_min(TB, key, 1u) < (uint32_t)TB.filter_freq) skip = true;
+            else pos = table_find_or_insert(TB, key, &inserted);
+          }
         } else {
-          TB.tag[pos] = -1;   // unique list overflow: this key's gradient is dropped (flagged)
-          TB.counters[CTR_OVERFLOW] = 2;
+          pos = table_find_or_insert(TB, key, &inserted);
         }
+        if (!skip && pos < 0) TB.counters[CTR_OVERFLOW] = 1;
+        if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
+        touch = !skip && pos >= 0;
       }
+      out_pos[i] = (int32_t)pos;
     }
+    if (train) table_touch_aggregated(TB, touch, pos, t, ulist, group_nunique, ulist_cap);
   }
 }
 
