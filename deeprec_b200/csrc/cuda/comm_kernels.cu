@@ -157,13 +157,15 @@ __global__ void __launch_bounds__(256) k_mp_sparse_grad(const DrDeviceTable* __r
     const int64_t b = i % B;
     const int s = (int)((i / B) % W);
     const int j = (int)(i / (B * W));
-    const int32_t u = tables[table_map[j]].tag[p];
+    const DrDeviceTable& TBa = tables[table_map[j]];
+    const int32_t u = TBa.tag[p];
     if (u < 0) continue;
+    const int Ce = TBa.capacity <= (1 << 17) ? C : 0;
     const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(demb_peers.ptr[s]) + ((int64_t)table_global[j] * B + b) * dim + 4 * lane;
     uint2 raw = *reinterpret_cast<const uint2*>(src);
     float2 a = unpack_bf16x2(raw.x), c = unpack_bf16x2(raw.y);
     const float4 g = make_float4(a.x, a.y, c.x, c.y);
-    combine_add<LPR>(s_tag, s_acc, C, dim, u, lane, gmask, gleader, &g, 1, gsum);
+    combine_add<LPR>(s_tag, s_acc, Ce, dim, u, lane, gmask, gleader, &g, 1, gsum);
   }
   __syncthreads();
   flush_combining_cache(s_tag, s_acc, C, dim, gsum);

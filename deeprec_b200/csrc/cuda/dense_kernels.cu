@@ -334,21 +334,31 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_v2(const __nv_bfloat16* __
       const int n = tc * 8 + j;
       sc[j] = scale[n]; mu[j] = mean[n]; rs[j] = rstd[n]; k1[j] = c1[n]; k2[j] = c2[n]; acc[j] = 0.f;
     }
-    for (int64_t b = (int64_t)blockIdx.x * rows_par + tr; b < B; b += (int64_t)gridDim.x * rows_par) {
-      int4 rdy = ld_nc_v4(dy + b * ld + tc * 8), ra = ld_nc_v4(a + b * ld + tc * 8);
-      const uint32_t wdy[4] = {(uint32_t)rdy.x, (uint32_t)rdy.y, (uint32_t)rdy.z, (uint32_t)rdy.w};
-      const uint32_t wa[4] = {(uint32_t)ra.x, (uint32_t)ra.y, (uint32_t)ra.z, (uint32_t)ra.w};
-      uint32_t o[4];
+    const int64_t rstep = (int64_t)gridDim.x * rows_par;
+    for (int64_t b = (int64_t)blockIdx.x * rows_par + tr; b < B; b += 2 * rstep) {
+      // two rows per iteration: all four 16 B loads are issued before any is consumed (memory-level parallelism)
+      const int64_t b2 = b + rstep;
+      const bool has2 = b2 < B;
+      int4 rdy[2], ra[2];
+      rdy[0] = ld_nc_v4(dy + b * ld + tc * 8); ra[0] = ld_nc_v4(a + b * ld + tc * 8);
+      if (has2) { rdy[1] = ld_nc_v4(dy + b2 * ld + tc * 8); ra[1] = ld_nc_v4(a + b2 * ld + tc * 8); }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 fdy = unpack_bf16x2(wdy[e]), fa = unpack_bf16x2(wa[e]);
-        float g0 = sc[2 * e] * (fdy.x - k1[2 * e] - (fa.x - mu[2 * e]) * rs[2 * e] * k2[2 * e]);
-        float g1 = sc[2 * e + 1] * (fdy.y - k1[2 * e + 1] - (fa.y - mu[2 * e + 1]) * rs[2 * e + 1] * k2[2 * e + 1]);
-        if (relu_mask) { if (!(fa.x > 0.f)) g0 = 0.f; if (!(fa.y > 0.f)) g1 = 0.f; }
-        acc[2 * e] += g0; acc[2 * e + 1] += g1;
-        o[e] = pack_bf16x2(g0, g1);
+      for (int h2 = 0; h2 < 2; ++h2) {
+        if (h2 == 1 && !has2) break;
+        const uint32_t wdy[4] = {(uint32_t)rdy[h2].x, (uint32_t)rdy[h2].y, (uint32_t)rdy[h2].z, (uint32_t)rdy[h2].w};
+        const uint32_t wa[4] = {(uint32_t)ra[h2].x, (uint32_t)ra[h2].y, (uint32_t)ra[h2].z, (uint32_t)ra[h2].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fdy = unpack_bf16x2(wdy[e]), fa = unpack_bf16x2(wa[e]);
+          float g0 = sc[2 * e] * (fdy.x - k1[2 * e] - (fa.x - mu[2 * e]) * rs[2 * e] * k2[2 * e]);
+          float g1 = sc[2 * e + 1] * (fdy.y - k1[2 * e + 1] - (fa.y - mu[2 * e + 1]) * rs[2 * e + 1] * k2[2 * e + 1]);
+          if (relu_mask) { if (!(fa.x > 0.f)) g0 = 0.f; if (!(fa.y > 0.f)) g1 = 0.f; }
+          acc[2 * e] += g0; acc[2 * e + 1] += g1;
+          o[e] = pack_bf16x2(g0, g1);
+        }
+        *reinterpret_cast<int4*>(da + (h2 ? b2 : b) * ld + tc * 8) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
       }
-      *reinterpret_cast<int4*>(da + b * ld + tc * 8) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
     }
   }
   if (dbias) {

@@ -226,16 +226,25 @@ __global__ void __launch_bounds__(128) k_dot_fwd_tc(const __nv_bfloat16* __restr
   uint8_t* my_row = sA + (R >> 3) * 256 + (R & 7) * 16;
   const int64_t ngroups = (B + 3) / 4;
   uint32_t phase = 0;
+  // software pipeline: the rows of group g+1 are fetched into registers while group g is in the tensor core / epilogue
+  int4 c0 = make_int4(0, 0, 0, 0), c1 = c0;
+  auto fetch = [&](int64_t gg, int4& r0, int4& r1) {
+    const int64_t bb = gg * 4 + warp;
+    if (gg < ngroups && lane < F && bb < B) {
+      const __nv_bfloat16* src = lane == 0 ? x + bb * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + bb * emb_stride_b;
+      r0 = ld_nc_v4(src); r1 = ld_nc_v4(src + 8);
+    }
+  };
+  fetch(blockIdx.x, c0, c1);
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t b = g * 4 + warp;
     const bool live = b < B;
     if (lane < F && live) {
-      const __nv_bfloat16* src = lane == 0 ? x + b * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + b * emb_stride_b;
-      const int4 c0 = ld_nc_v4(src), c1 = ld_nc_v4(src + 8);
       *reinterpret_cast<int4*>(my_row) = c0;
       *reinterpret_cast<int4*>(my_row + 128) = c1;
       if (lane == 0) { *reinterpret_cast<int4*>(&sZ[warp][0]) = c0; *reinterpret_cast<int4*>(&sZ[warp][8]) = c1; }
     }
+    fetch(g + gridDim.x, c0, c1);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -296,21 +305,29 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
   __nv_bfloat16* myG = sG + warp * 512;
   const int64_t ngroups = (B + 3) / 4;
   uint32_t phase = 0;
+  // software pipeline: dZ chunks + the feature row of group g+1 are fetched while group g is being processed
+  int4 pz0 = make_int4(0, 0, 0, 0), pz1 = pz0, pf0 = pz0, pf1 = pz0;
+  auto fetch = [&](int64_t gg) {
+    const int64_t bb = gg * 4 + warp;
+    pz0 = pz1 = pf0 = pf1 = make_int4(0, 0, 0, 0);
+    if (gg < ngroups && bb < B) {
+      if (lane * 8 < ldz) pz0 = ld_nc_v4(dZ + bb * ldz + lane * 8);
+      if (lane * 8 + 256 < ldz) pz1 = ld_nc_v4(dZ + bb * ldz + lane * 8 + 256);
+      if (lane < F) {
+        const __nv_bfloat16* src = lane == 0 ? x + bb * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + bb * emb_stride_b;
+        pf0 = ld_nc_v4(src); pf1 = ld_nc_v4(src + 8);
+      }
+    }
+  };
+  fetch(blockIdx.x);
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t b = g * 4 + warp;
     const bool live = b < B;
-    // ---- stage dZ row (coalesced) and F^T
-    if (live) {
-      for (int c = lane * 8; c < ldz; c += 256) *reinterpret_cast<int4*>(myG + c) = ld_nc_v4(dZ + b * ldz + c);
-    } else {
-      for (int c = lane * 8; c < ldz; c += 256) *reinterpret_cast<int4*>(myG + c) = make_int4(0, 0, 0, 0);
-    }
+    // ---- stage dZ row and F^T from the prefetched registers
+    if (lane * 8 < ldz) *reinterpret_cast<int4*>(myG + lane * 8) = pz0;
+    if (lane * 8 + 256 < ldz) *reinterpret_cast<int4*>(myG + lane * 8 + 256) = pz1;
     if (lane < F) {
-      int4 c0 = make_int4(0, 0, 0, 0), c1 = c0;
-      if (live) {
-        const __nv_bfloat16* src = lane == 0 ? x + b * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + b * emb_stride_b;
-        c0 = ld_nc_v4(src); c1 = ld_nc_v4(src + 8);
-      }
+      const int4 c0 = pf0, c1 = pf1;
       const uint32_t w[8] = {(uint32_t)c0.x, (uint32_t)c0.y, (uint32_t)c0.z, (uint32_t)c0.w, (uint32_t)c1.x, (uint32_t)c1.y, (uint32_t)c1.z, (uint32_t)c1.w};
       // B[n = d][k = R] at (d/8)*2048 + (R/8)*128 + (d%8)*16 + (R%8)*2
       uint8_t* colbase = sB + (R >> 3) * 128 + (R & 7) * 2;
@@ -320,6 +337,7 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
         *reinterpret_cast<uint16_t*>(colbase + (d >> 3) * 2048 + (d & 7) * 16) = v;
       }
     }
+    fetch(g + gridDim.x);
     __syncwarp();
     // ---- my row of S (32 columns of the diagonal block): S[i][j] = dG[max][min], zero on the diagonal / padding
     {

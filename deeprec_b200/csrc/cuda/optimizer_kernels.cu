@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(256) k_accumulate(const DrDeviceTable* __restr
     const int32_t p = pos[i];
     if (p < 0) continue;
     const int t = seg_of(offsets, T, i, uniform);
-    const int32_t u = tables[table_map ? table_map[t] : t].tag[p];
+    const DrDeviceTable& TBa = tables[table_map ? table_map[t] : t];
+    const int32_t u = TBa.tag[p];
     if (u < 0) continue;
+    const int Ce = TBa.capacity <= (1 << 17) ? C : 0;      // combining only pays for small (hot-key) tables
     int64_t o;
     if (flat_in) o = i * dim;
     else {
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const DrDeviceTable* __restr
       }
       chunks[k] = make_float4(g.x * sc, g.y * sc, g.z * sc, g.w * sc);
     }
-    combine_add<LPR>(s_tag, s_acc, C, dim, u, lane, gmask, gleader, chunks, k, gsum);
+    combine_add<LPR>(s_tag, s_acc, Ce, dim, u, lane, gmask, gleader, chunks, k, gsum);
   }
   __syncthreads();
   flush_combining_cache(s_tag, s_acc, C, dim, gsum);

@@ -147,8 +147,10 @@ __device__ __forceinline__ void combine_add(int32_t* s_tag, float* s_acc, int C,
                                             const float4* chunks, int nchunks_per_lane, float* __restrict__ gsum) {
   int hit = 0;
   const int slot = u & (C - 1);
-  if (lane == 0) { const int32_t old = atomicCAS(&s_tag[slot], -1, u); hit = (old == -1 || old == u); }
-  hit = __shfl_sync(gmask, hit, gleader);
+  if (C > 0) {      // C == 0: caller decided this table is too large for combining to pay off -> straight to L2 reductions
+    if (lane == 0) { const int32_t old = atomicCAS(&s_tag[slot], -1, u); hit = (old == -1 || old == u); }
+    hit = __shfl_sync(gmask, hit, gleader);
+  }
   const int nvec = dim >> 2;
 #pragma unroll 4
   for (int k = 0; k < nchunks_per_lane; ++k) {
