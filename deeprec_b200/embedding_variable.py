@@ -349,6 +349,15 @@ class EmbeddingVariable(nn.Module):
         s = self.table.snapshot()
         return s["keys"], s["rows"][:, : self.embedding_dim].contiguous(), s["versions"], s["freqs"]
 
+    @torch.no_grad()
+    def scatter_add(self, ids: torch.Tensor, updates: torch.Tensor) -> None:
+        """``KvResourceScatterAdd``: rows[id] += update (creates / admits keys like an SGD apply with lr = -1)."""
+        hp = OptHyper()
+        hp.kind, hp.lr = 0, -1.0
+        from .optim.optimizers import get_or_create_global_step
+        hp.global_step = int(get_or_create_global_step())
+        self.table.apply_raw(ids.reshape(-1), updates.reshape(-1, self.embedding_dim), hp)
+
     def lookup_tier(self, ids: torch.Tensor) -> torch.Tensor:
         """KvResourceLookupTier: 0 = first tier (HBM/DRAM), 1 = second tier, -1 = absent."""
         t = self.table

@@ -29,8 +29,9 @@ class DLRM(nn.Module):
     def __init__(self, num_dense: int = 13, cardinalities: Sequence[int] = (1000,) * 26, embedding_dim: int = 16,
                  mlp_bot: Sequence[int] = (512, 256, 64, 16), mlp_top: Sequence[int] = (512, 256), interaction_op: str = "dot",
                  ev_option: Optional[EmbeddingVariableOption] = None, device=None, use_ev: bool = True,
-                 bn_eps: float = 1e-3, bn_momentum: float = 0.99, name: str = "dlrm"):
+                 bn_eps: float = 1e-3, bn_momentum: float = 0.99, name: str = "dlrm", fused_kernels: bool = False):
         super().__init__()
+        self.fused_kernels = fused_kernels
         import copy
         self.interaction_op = interaction_op
         T = len(cardinalities)
@@ -64,7 +65,14 @@ class DLRM(nn.Module):
         """dense [B, num_dense]; ids [T, B] (feature-major) -> logits [B]."""
         x = self.bot(dense)
         embs = torch.stack([(t.lookup(ids[i]) if isinstance(t, EmbeddingVariable) else t(ids[i])).to(x.device) for i, t in enumerate(self.tables)], dim=1)
-        z = dot_interaction(x, embs) if self.interaction_op == "dot" else torch.cat([x, embs.flatten(1)], dim=1)
+        if self.interaction_op == "dot":
+            if self.fused_kernels:
+                from ..nn import dot_interaction as fused_dot   # tcgen05 kernel on CUDA (bf16), the expression above on CPU
+                z = fused_dot(x, embs)
+            else:
+                z = dot_interaction(x, embs)                    # fp32 oracle path
+        else:
+            z = torch.cat([x, embs.flatten(1)], dim=1)
         return self.logits(self.top(z)).squeeze(-1)
 
     def loss(self, dense, ids, labels) -> torch.Tensor:

@@ -24,8 +24,27 @@ from ..ops.embedding_ops import SparseIds, group_embedding_lookup_sparse
 from .dlrm import DLRM, dot_interaction
 
 
-def mlp(sizes: Sequence[int], in_dim: int, act=nn.ReLU, bn: bool = False, last_act: bool = True, device=None) -> nn.Sequential:
-    layers: List[nn.Module] = []
+def _use_fused(device) -> bool:
+    """CUDA models run their MLPs on the tcgen05 kernels (deeprec_b200.nn) unless DEEPREC_FUSED_NN=0."""
+    import os
+    return device is not None and torch.device(device).type == "cuda" and os.environ.get("DEEPREC_FUSED_NN", "1") != "0"
+
+
+def mlp(sizes: Sequence[int], in_dim: int, act=nn.ReLU, bn: bool = False, last_act: bool = True, device=None) -> nn.Module:
+    if act is nn.ReLU and _use_fused(device):
+        from ..nn import FusedLinear, FusedMLP
+        if not bn:
+            return FusedMLP(in_dim, sizes, last_act=last_act, device=device)       # whole chain = one autograd node
+        layers: List[nn.Module] = []
+        k = in_dim
+        for i, n in enumerate(sizes):
+            has_act = i + 1 < len(sizes) or last_act
+            layers.append(FusedLinear(k, n, relu=has_act, device=device))
+            if has_act:
+                layers.append(nn.BatchNorm1d(n, device=device))
+            k = n
+        return nn.Sequential(*layers)
+    layers = []
     k = in_dim
     for i, n in enumerate(sizes):
         layers.append(nn.Linear(k, n, device=device))
@@ -109,7 +128,8 @@ class DeepFM(CriteoModel):
         self.out = nn.Linear(final_hidden_units[-1], 1, device=dev)
 
     def logits(self, dense, embs):
-        fm = 0.5 * (embs.sum(1) ** 2 - (embs ** 2).sum(1))
+        from ..nn import fm_interaction
+        fm = fm_interaction(embs)
         dnn = self.dnn(torch.cat([dense, embs.flatten(1)], 1))
         return self.out(self.final(torch.cat([self.linear(dense), fm, dnn], 1))).squeeze(-1)
 

@@ -1,0 +1,50 @@
+"""Smaller API pieces: CSV helper ops, scatter_add, sample-aware compression, streaming AUC, tracing."""
+import torch
+
+import deeprec_b200 as dr
+from deeprec_b200.data.csv_ops import sparse_valid_cutoff, string_split_and_pad, string_to_hash_id, trans_csv_id2sparse, trans_csv_kv2dense
+from deeprec_b200.serving.sample_aware import enable_sample_awared_graph_compression
+from deeprec_b200.utils import StreamingAUC, Timeline
+
+
+def test_csv_ops():
+    assert string_split_and_pad(["a,b,c", "d", ""], 2, default_value="<pad>") == [["a", "b"], ["d", "<pad>"], ["<pad>", "<pad>"]]
+    sp = trans_csv_id2sparse(["1,2,99", "", "3"], max_id=10)
+    assert sp.values.tolist() == [1, 2, 3] and sp.row_ids.tolist() == [0, 0, 2] and sp.batch_size == 3
+    d = trans_csv_kv2dense(["0:1.5,2:3", "1:2"], 2)
+    assert d.tolist() == [[1.5, 0.0, 3.0], [0.0, 2.0, 0.0]]
+    sp = dr.SparseIds(torch.arange(7), torch.tensor([0, 0, 0, 0, 1, 1, 2]), 3)
+    assert sparse_valid_cutoff(sp, 2, "left").values.tolist() == [0, 1, 4, 5, 6]
+    assert sparse_valid_cutoff(sp, 2, "right").values.tolist() == [2, 3, 4, 5, 6]
+    assert string_to_hash_id("abc") == string_to_hash_id("abc") != string_to_hash_id("abd")
+
+
+def test_scatter_add_creates_and_accumulates():
+    ev = dr.get_embedding_variable("sa", 4, seed=1)
+    base = ev.lookup(torch.tensor([7])).detach().clone()
+    ev.scatter_add(torch.tensor([7, 7]), torch.ones(2, 4))
+    assert torch.allclose(ev.lookup(torch.tensor([7])).detach(), base + 2.0) and ev.total_count() == 1
+
+
+def test_sample_aware_compression_matches_tiled():
+    torch.manual_seed(0)
+    un, it, hd = torch.nn.Linear(6, 4), torch.nn.Linear(5, 4), torch.nn.Linear(8, 1)
+    sac = enable_sample_awared_graph_compression(un, it, hd)
+    u, items = torch.randn(1, 6), torch.randn(9, 5)
+    ref = hd(torch.cat([un(u.expand(9, -1)), it(items)], -1)).squeeze(-1)
+    assert torch.allclose(sac(u, items), ref, atol=1e-6)
+
+
+def test_auc_and_timeline(tmp_path):
+    auc = StreamingAUC()
+    y = (torch.rand(5000) < 0.3).float()
+    auc.update(torch.where(y > 0, torch.rand(5000) * 0.5 + 0.5, torch.rand(5000) * 0.5), y)
+    assert auc.result() > 0.99
+    auc2 = StreamingAUC(); auc2.update(torch.rand(5000), y)
+    assert 0.45 < auc2.result() < 0.55
+    tl = Timeline()
+    with tl.span("step"):
+        sum(range(1000))
+    tl.save(str(tmp_path / "t.json"))
+    import json
+    assert json.load(open(tmp_path / "t.json"))["traceEvents"][0]["name"] == "step"
