@@ -85,6 +85,18 @@ def _bind_host(lib):
     _sig(lib, "dr_host_unique", i64, [P, i64, P, P, P])
     _sig(lib, "dr_host_segment_sum", None, [P, P, i64, i64, P, i64])
     _sig(lib, "dr_host_num_threads", C.c_int, [])
+    # SSD tier (csrc/host/ssd_store.cc)
+    _sig(lib, "dr_ssd_create", vp, [cp, i64, i64, C.c_int])
+    _sig(lib, "dr_ssd_destroy", None, [vp])
+    for nm in ("dr_ssd_size", "dr_ssd_num_files", "dr_ssd_bytes", "dr_ssd_compactions"):
+        _sig(lib, nm, i64, [vp])
+    _sig(lib, "dr_ssd_put", None, [vp, P, P, P, P, i64])
+    _sig(lib, "dr_ssd_get", None, [vp, P, i64, P, P, P, P])
+    _sig(lib, "dr_ssd_contains", None, [vp, P, i64, P])
+    _sig(lib, "dr_ssd_remove", i64, [vp, P, i64])
+    _sig(lib, "dr_ssd_export_keys", i64, [vp, P, i64])
+    _sig(lib, "dr_ssd_compact", i64, [vp, C.c_double])
+    _sig(lib, "dr_ssd_flush", None, [vp])
     # io runtime
     _sig(lib, "dr_bundle_writer_open", vp, [cp])
     _sig(lib, "dr_bundle_writer_add", C.c_int, [vp, cp, cp, P, C.c_int, P, i64])

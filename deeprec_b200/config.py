@@ -21,6 +21,7 @@ class StorageType(enum.IntEnum):
     HBM = 1
     HBM_DRAM = 2
     DRAM_SSDHASH = 3
+    HBM_DRAM_SSDHASH = 4
 
 
 class CacheStrategy(enum.IntEnum):

@@ -140,6 +140,16 @@ class HostTable:
         v = _i64(versions) if versions is not None else None
         return int(self.lib.dr_host_ev_import(self.h, ptr(k), ptr(r), ncols, ptr(f), ptr(v), k.numel(), part_id, part_num, int(reset_version)))
 
+    def export_keys(self, keys: torch.Tensor):
+        """(rows [n, stride], freqs, versions, found) of specific keys (multi-tier promotion path)."""
+        k = _i64(keys).view(-1)
+        n = k.numel()
+        rows = torch.empty(n, self.stride, dtype=torch.float32)
+        f = torch.empty(n, dtype=torch.int64); v = torch.empty(n, dtype=torch.int64); found = torch.zeros(n, dtype=torch.uint8)
+        if n:
+            self.lib.dr_host_ev_export_keys(self.h, ptr(k), n, ptr(rows), ptr(f), ptr(v), ptr(found))
+        return rows, f, v, found.bool()
+
     def bloom_state(self) -> Optional[torch.Tensor]:
         k, m, b = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         nb = int(self.lib.dr_host_bloom_info(self.h, C.byref(k), C.byref(m), C.byref(b)))
@@ -195,7 +205,8 @@ class EmbeddingVariable(nn.Module):
                                                         self.option.init_option.default_value_no_permission)
         st = self.option.storage_option.storage_type
         if device is None:
-            device = torch.device("cuda", torch.cuda.current_device()) if st in (StorageType.HBM, StorageType.HBM_DRAM) else torch.device("cpu")
+            device = (torch.device("cuda", torch.cuda.current_device()) if st in (StorageType.HBM, StorageType.HBM_DRAM, StorageType.HBM_DRAM_SSDHASH)
+                      else torch.device("cpu"))
         self.device = torch.device(device)
         if self.device.type == "cuda" and st == StorageType.DRAM:
             # kv_variable_ops.cc:225-232: a GPU variable needs an HBM first tier
@@ -263,9 +274,19 @@ class EmbeddingVariable(nn.Module):
     def table(self):
         if self._table is None:
             cfg = self._make_config()
-            if self.device.type == "cuda" and int(cfg.storage_type) == int(StorageType.HBM_DRAM):
+            so = self.option.storage_option
+            row_bytes = 4 * (self.embedding_dim * (1 + self._num_slots) + (4 if self._has_scalars else 0))
+            if self.device.type == "cuda" and int(cfg.storage_type) in (int(StorageType.HBM_DRAM), int(StorageType.HBM_DRAM_SSDHASH)):
                 from .ops.multi_tier import MultiTierTable
-                self._table = MultiTierTable(cfg, self.default_matrix, self.device, owner=self._owner)
+                ssd = None
+                if int(cfg.storage_type) == int(StorageType.HBM_DRAM_SSDHASH):
+                    sz = so.storage_size[1] if len(so.storage_size) > 1 else (1 << 30)
+                    ssd = dict(dram_rows=max(64, int(sz) // row_bytes), path=so.storage_path)
+                self._table = MultiTierTable(cfg, self.default_matrix, self.device, owner=self._owner, ssd=ssd)
+            elif self.device.type == "cpu" and int(cfg.storage_type) == int(StorageType.DRAM_SSDHASH):
+                from .ops.host_tiers import DramSsdTable
+                self._table = DramSsdTable(cfg, self.default_matrix, dram_rows=max(64, int(so.storage_size[0]) // row_bytes), path=so.storage_path,
+                                           strategy=int(so.cache_strategy))
             elif self.device.type == "cuda":
                 from .ops.device_table import DeviceTable
                 self._table = DeviceTable(cfg, self.default_matrix, self.device, owner=self._owner)

@@ -26,7 +26,7 @@ from .device_table import DeviceTable, _chk
 
 
 class MultiTierTable:
-    def __init__(self, cfg: EvConfig, default_matrix: torch.Tensor, device: torch.device, owner: int = 0):
+    def __init__(self, cfg: EvConfig, default_matrix: torch.Tensor, device: torch.device, owner: int = 0, ssd: Optional[dict] = None):
         self.cfg = cfg
         self.device = torch.device(device)
         self.dim = int(cfg.dim)
@@ -37,7 +37,11 @@ class MultiTierTable:
         host_cfg = EvConfig.from_buffer_copy(bytes(cfg))
         host_cfg.filter_type, host_cfg.filter_freq = 0, 0        # admission is decided in tier 0; the host tier stores what it is given
         host_cfg.steps_to_live, host_cfg.l2_weight_threshold = 0, -1.0
-        self.dram = HostTable(host_cfg, default_matrix)
+        if ssd is not None:                                      # HBM_DRAM_SSDHASH: the host tier itself spills to a log-structured SSD store
+            from .host_tiers import DramSsdTable
+            self.dram = DramSsdTable(host_cfg, default_matrix, strategy=int(cfg.cache_strategy), **ssd)
+        else:
+            self.dram = HostTable(host_cfg, default_matrix)
         self.stride = self.hbm.stride
         self.lib = self.hbm.lib
         self.side = torch.cuda.Stream(device=self.device)
@@ -53,13 +57,9 @@ class MultiTierTable:
         n = k.numel()
         if n == 0:
             return
-        rows = torch.empty(n, self.stride, dtype=torch.float32).pin_memory()
-        freqs = torch.empty(n, dtype=torch.int64); vers = torch.empty(n, dtype=torch.int64)
-        found = torch.zeros(n, dtype=torch.uint8)
-        self.dram.lib.dr_host_ev_export_keys(self.dram.h, ptr(k), n, ptr(rows), ptr(freqs), ptr(vers), ptr(found))
-        sel = found.bool()
+        rows, freqs, vers, sel = self.dram.export_keys(k)
         if sel.any():
-            self.hbm.import_(k[sel], rows[sel], freqs[sel], vers[sel])          # pinned H2D + import kernel on the current stream
+            self.hbm.import_(k[sel], rows[sel].pin_memory(), freqs[sel], vers[sel])   # pinned H2D + import kernel on the current stream
 
     def _evict(self, need: int, protect: Optional[torch.Tensor]) -> None:
         """Demote cold rows until ``need`` more rows fit (LFU: lowest freq, LRU: oldest version)."""
@@ -169,12 +169,13 @@ class MultiTierTable:
         _chk(self.lib.dr_cuda_table_get_meta(C.byref(self.hbm.struct), ptr(k), k.numel(), None, None, ptr(row), stream_ptr()), "get_meta")
         in_hbm = (row >= 0).cpu()
         n = k.numel()
-        found = torch.zeros(n, dtype=torch.uint8)
         kc = k.cpu().contiguous()
-        rows = torch.empty(n, self.stride); f = torch.empty(n, dtype=torch.int64); v = torch.empty(n, dtype=torch.int64)
-        self.dram.lib.dr_host_ev_export_keys(self.dram.h, ptr(kc), n, ptr(rows), ptr(f), ptr(v), ptr(found))
         out = torch.full((n,), -1, dtype=torch.int64)
-        out[found.bool()] = 1
+        if hasattr(self.dram, "lookup_tier"):                 # 3 tiers: 1 = DRAM, 2 = SSD
+            lower = self.dram.lookup_tier(kc)
+            out = torch.where(lower >= 0, lower + 1, out)
+        else:
+            out[self.dram.export_keys(kc)[3]] = 1
         out[in_hbm] = 0
         return out.view(keys.shape)
 

@@ -9,6 +9,16 @@ def _rel(a, b):
     return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-6)
 
 
+def _rel_fro(a, b):
+    """relative Frobenius error: robust to the isolated ReLU-mask flips bf16 rounding causes at pre-activations ~ 0"""
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _r(t):
+    """bf16 rounding as a differentiable op (gradient rounded the same way): emulates the kernels' storage precision in fp32 math"""
+    return t.bfloat16().float()
+
+
 @pytest.mark.parametrize("M,in_dim,sizes,last_act", [(4096, 429, (1024, 256, 32), True), (1000, 64, (512, 256), True), (777, 13, (64, 16, 1), False),
                                                       (2048, 96, (80,), False), (513, 40, (200, 80, 2), False)])
 def test_fused_mlp_matches_fp32(M, in_dim, sizes, last_act):
@@ -20,23 +30,24 @@ def test_fused_mlp_matches_fp32(M, in_dim, sizes, last_act):
     x = torch.randn(M, in_dim, device="cuda", requires_grad=True)
     y = m(x)
     assert y.shape == (M, sizes[-1]) and y.dtype == torch.float32
-    # fp32 reference of the same chain (bf16-rounded inputs/weights so only the accumulation differs)
+    # fp32 reference of the same chain with bf16-rounded storage (inputs, weights, activations): only the accumulation differs
     xr = x.detach().clone().requires_grad_(True)
-    h = xr
+    h = _r(xr)
     Ws = [w.detach().clone().requires_grad_(True) for w in m.weights]
     bs = [b.detach().clone().requires_grad_(True) for b in m.biases]
     for i, (w, b) in enumerate(zip(Ws, bs)):
-        h = torch.nn.functional.linear(h, w, b)
+        h = torch.nn.functional.linear(h, _r(w), b)
         if i + 1 < len(Ws) or last_act:
             h = torch.relu(h)
-    assert _rel(y, h) < 3e-2
+        h = _r(h)
+    assert _rel(y, h) < 2e-2
     g = torch.randn_like(h) * 0.1
     y.backward(g); h.backward(g)
-    assert _rel(x.grad, xr.grad) < 6e-2
+    assert _rel_fro(x.grad, xr.grad) < 3e-2, _rel_fro(x.grad, xr.grad)
     for w, wr in zip(m.weights, Ws):
-        assert _rel(w.grad, wr.grad) < 6e-2
+        assert _rel_fro(w.grad, wr.grad) < 3e-2, _rel_fro(w.grad, wr.grad)
     for b, br in zip(m.biases, bs):
-        assert _rel(b.grad, br.grad) < 6e-2
+        assert _rel_fro(b.grad, br.grad) < 3e-2, _rel_fro(b.grad, br.grad)
 
 
 def test_fused_mlp_trains():

@@ -210,3 +210,29 @@ def test_multi_tier_hbm_dram_matches_single_tier():
     assert ev_mt.total_count() == ev_ref.total_count()
     snap = ev_mt.table.snapshot()
     assert snap["keys"].numel() == ev_ref.total_count()
+
+
+def test_three_tier_hbm_dram_ssd(tmp_path):
+    """HBM_DRAM_SSDHASH: tiny HBM cache over a tiny DRAM tier over the log-structured SSD store; results equal all-HBM training."""
+    import deeprec_b200 as dr
+    torch.manual_seed(0)
+    rb = 2 * 16 * 4
+    so = dr.StorageOption(dr.StorageType.HBM_DRAM_SSDHASH, storage_path=str(tmp_path), storage_size=(2048 * rb, 1500 * rb), cache_strategy=dr.CacheStrategy.LFU)
+    ev_mt = _mk("mt3", 16, "cuda", storage_option=so)
+    ev_ref = _mk("mt3", 16, "cuda")
+    o_mt = dr.optim.AdagradOptimizer([], [ev_mt], lr=0.1, global_step=dr.optim.GlobalStep())
+    o_ref = dr.optim.AdagradOptimizer([], [ev_ref], lr=0.1, global_step=dr.optim.GlobalStep())
+    for step in range(12):
+        lo = (step % 4) * 1500
+        ids = torch.randint(lo, lo + 1500, (1200,), device="cuda")
+        tgt = torch.randn(1200, 16, device="cuda")
+        for ev, opt in ((ev_mt, o_mt), (ev_ref, o_ref)):
+            ((ev.lookup(ids) - tgt) ** 2).sum().backward(); opt.step()
+    t = ev_mt.table
+    st = t.dram.tier_stats()
+    assert st["ssd"]["keys"] > 0 and st["demotions"] > 0 and st["promotions"] > 0
+    tiers = ev_mt.lookup_tier(torch.arange(0, 6000, device="cuda"))
+    assert set(tiers.tolist()) >= {0, 1, 2}
+    probe = torch.arange(0, 6000, 7, device="cuda")
+    assert torch.allclose(t.lookup(probe).cpu(), ev_ref.table.lookup(probe).cpu(), atol=1e-4)
+    assert ev_mt.total_count() == ev_ref.total_count()

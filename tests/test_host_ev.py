@@ -168,3 +168,65 @@ def test_partitioned_multihash_dynamic_variants():
     dv = dr.get_dynamic_dimension_embedding_variable("dyn", 4, 3)
     out = dv.lookup(torch.tensor([1, 2]), torch.tensor([1, 3]))
     assert out.shape == (2, 12) and torch.all(out[0, 4:] == 0) and out[1, 8:].abs().sum() > 0
+
+
+def test_dram_ssdhash_tier_matches_dram_only(tmp_path):
+    """DRAM_SSDHASH: a DRAM tier of ~200 rows over the log-structured SSD store trains exactly like an all-DRAM table."""
+    import deeprec_b200 as dr
+    dim = 8
+    row_bytes = 4 * dim * 2                      # emb + adagrad accumulator
+    so = dr.StorageOption(dr.StorageType.DRAM_SSDHASH, storage_path=str(tmp_path), storage_size=(200 * row_bytes,))
+    ev_t = dr.get_embedding_variable("ssd_tiered", dim, ev_option=dr.EmbeddingVariableOption(storage_option=so), seed=11)
+    ev_r = dr.get_embedding_variable("ssd_ref", dim, seed=11)
+    opt_t, opt_r = dr.optim.AdagradOptimizer([], [ev_t], lr=0.1), dr.optim.AdagradOptimizer([], [ev_r], lr=0.1)
+    g = torch.Generator().manual_seed(0)
+    for step in range(12):
+        ids = torch.randint(0, 1500, (256,), generator=g)
+        w = torch.randn(256, dim, generator=g)
+        for ev, opt in ((ev_t, opt_t), (ev_r, opt_r)):
+            opt.zero_grad()
+            (ev.lookup(ids) * w).sum().backward()
+            opt.step()
+    t = ev_t.table
+    st = t.tier_stats()
+    assert st["dram_rows"] <= 200 + 64 and st["ssd"]["keys"] > 0 and st["demotions"] > 0 and st["promotions"] > 0
+    assert ev_t.total_count() == ev_r.total_count()
+    probe = torch.arange(0, 1500)
+    tiers = t.lookup_tier(probe)
+    assert (tiers == 1).any() and (tiers == 0).any()
+    assert torch.equal(ev_t.get_frequency(probe), ev_r.get_frequency(probe))
+    assert torch.allclose(ev_t.lookup(probe).detach(), ev_r.lookup(probe).detach(), atol=1e-6)
+    # checkpoint covers both tiers
+    snap_t, snap_r = t.snapshot(), ev_r.table.snapshot()
+    assert torch.equal(snap_t["keys"], snap_r["keys"]) and torch.allclose(snap_t["rows"], snap_r["rows"], atol=1e-6)
+    # overwrite churn -> dead records -> compaction reclaims files
+    ssd = t.ssd
+    ks = ssd.keys()[:64]
+    rows, f, v, found = ssd.get(ks)
+    assert found.all()
+    before = ssd.stats()
+    for _ in range(40):
+        ssd.put(ks, rows, f, v)
+    ssd.compact(0.0)
+    after = ssd.stats()
+    assert after["keys"] == before["keys"] and after["bytes"] <= before["bytes"] + 64 * (24 + 4 * t.stride) * 2
+    rows2, _, _, found2 = ssd.get(ks)
+    assert found2.all() and torch.equal(rows2, rows)
+
+
+def test_ssd_store_async_compaction(tmp_path):
+    from deeprec_b200.ops.host_tiers import SsdStore
+    s = SsdStore(4, str(tmp_path), file_bytes=40 * 200, async_compaction=True)     # 200 records per file
+    keys = torch.arange(1000)
+    for rep in range(6):
+        s.put(keys, torch.full((1000, 4), float(rep)), torch.full((1000,), rep), torch.full((1000,), rep))
+    import time
+    for _ in range(100):
+        if s.stats()["compactions"] > 0 and s.stats()["files"] <= 12:
+            break
+        time.sleep(0.05)
+    st = s.stats()
+    assert st["keys"] == 1000 and st["compactions"] > 0
+    rows, f, v, found = s.get(keys)
+    assert found.all() and (rows == 5.0).all() and (f == 5).all()
+    assert s.remove(keys[:500]) == 500 and s.size() == 500
