@@ -11,7 +11,7 @@ INT = C.c_int
 class DeviceTableStruct(C.Structure):
     """Mirror of DrDeviceTable (csrc/cuda/table.cuh)."""
     _fields_ = [
-        ("keys", vp), ("freq", vp), ("version", vp), ("row_of", vp), ("tag", vp), ("dirty", vp),
+        ("slots", vp),
         ("rows", vp), ("free_list", vp), ("counters", vp), ("default_matrix", vp), ("bloom", vp),
         ("capacity", i64), ("row_capacity", i64), ("default_value_dim", i64), ("bloom_m", i64),
         ("dim", i32), ("stride", i32), ("num_slots", i32), ("has_scalars", i32),
@@ -37,6 +37,7 @@ def bind(lib):
     _sig(lib, "dr_cuda_fill_i64", [P, i64, i64, S])
     _sig(lib, "dr_cuda_table_lookup", [P, P, INT, P, P, i64, i64, INT, P, P, P, P, i64, S])
     _sig(lib, "dr_cuda_table_gather", [P, P, INT, INT, P, P, P, i64, i64, P, INT, i64, i64, INT, S])
+    _sig(lib, "dr_cuda_table_init_slots", [P, i64, S])
     _sig(lib, "dr_cuda_table_get_meta", [TP, P, i64, P, P, P, S])
     _sig(lib, "dr_cuda_table_gather_slot", [TP, P, i64, INT, P, S])
     _sig(lib, "dr_cuda_table_rehash", [TP, TP, S])

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) k_mp_sparse_grad(const DrDeviceTable* __r
     const int s = (int)((i / B) % W);
     const int j = (int)(i / (B * W));
     const DrDeviceTable& TBa = tables[table_map[j]];
-    const int32_t u = TBa.tag[p];
+    const int32_t u = TBa.slots[p].tag;
     if (u < 0) continue;
     const int Ce = TBa.capacity <= (1 << 17) ? C : 0;
     const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(demb_peers.ptr[s]) + ((int64_t)table_global[j] * B + b) * dim + 4 * lane;

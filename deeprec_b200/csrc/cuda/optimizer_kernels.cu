@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const DrDeviceTable* __restr
     if (p < 0) continue;
     const int t = seg_of(offsets, T, i, uniform);
     const DrDeviceTable& TBa = tables[table_map ? table_map[t] : t];
-    const int32_t u = TBa.tag[p];
+    const int32_t u = TBa.slots[p].tag;
     if (u < 0) continue;
     const int Ce = TBa.capacity <= (1 << 17) ? C : 0;      // combining only pays for small (hot-key) tables
     int64_t o;
@@ -101,18 +101,18 @@ __global__ void __launch_bounds__(256) k_apply(const DrDeviceTable* __restrict__
     float* g = gsum + u * dim;
     int32_t r = 0;
     if (lane == 0) {
-      r = TB.row_of[pos];
+      r = TB.slots[pos].row_of;
       if (r < 0) {
-        bool admit = TB.filter_type == DR_FILTER_COUNTER ? TB.freq[pos] >= TB.filter_freq : true;
+        bool admit = TB.filter_type == DR_FILTER_COUNTER ? TB.slots[pos].freq >= TB.filter_freq : true;
         if (admit) {
           r = table_alloc_row(TB);
-          if (r >= 0) { TB.row_of[pos] = r; atomicAdd(&TB.counters[CTR_NADMITTED], 1); r = -(r + 2); }   // negative => fresh
+          if (r >= 0) { TB.slots[pos].row_of = r; atomicAdd(&TB.counters[CTR_NADMITTED], 1); r = -(r + 2); }   // negative => fresh
         } else {
           r = -1;
         }
       }
-      TB.tag[pos] = -1;   // release the per-step claim
-      TB.version[pos] = (int32_t)hp.global_step;   // UpdateVersion(value_ptr, gs) for every touched key, admitted or not
+      TB.slots[pos].tag = -1;   // release the per-step claim
+      TB.slots[pos].version = (int32_t)hp.global_step;   // UpdateVersion(value_ptr, gs) for every touched key, admitted or not
     }
     r = __shfl_sync(gmask, r, (threadIdx.x & 31) / LPR * LPR);
     bool fresh = r <= -2;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) k_apply(const DrDeviceTable* __restrict__
     }
     float* row = TB.rows + (int64_t)r * TB.stride;
     if (fresh) {
-      const int64_t key = TB.keys[pos];
+      const int64_t key = TB.slots[pos].key;
       const float* def = TB.default_matrix + dr_default_row(key, TB.default_value_dim) * TB.dim;
       for (int c = lane; c < nvec; c += LPR) {
         *reinterpret_cast<float4*>(row + 4 * c) = *reinterpret_cast<const float4*>(def + 4 * c);

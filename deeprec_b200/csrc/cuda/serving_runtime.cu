@@ -30,6 +30,7 @@
 // kernel launchers from the other translation units of this library
 extern "C" {
 int dr_cuda_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t s);
+int dr_cuda_table_init_slots(void* slots, int64_t n, cudaStream_t s);
 int dr_cuda_table_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map, int T, const int64_t* keys, const int64_t* offsets, int64_t uniform,
                          int64_t n, int train, const int64_t* step_ptr, int32_t* out_pos, int64_t* ulist, int32_t* group_nunique, int64_t ulist_cap, cudaStream_t s);
 int dr_cuda_table_gather(const DrDeviceTable* tables_dev, const int32_t* table_map, int T, int dim, const int64_t* keys, const int32_t* pos,
@@ -113,7 +114,7 @@ struct DenseParams {
 };
 
 struct TableDev {
-  DrDeviceTable t{}; DevBuf keys, freq, version, row_of, tag, dirty, rows, free_list, counters, def;
+  DrDeviceTable t{}; DevBuf slots, rows, free_list, counters, def;
   int64_t n_rows = 0;
 };
 
@@ -194,13 +195,12 @@ static bool BuildTable(dr::BundleReader& r, int t, int D, TableDev* td, int64_t 
   const int64_t n = (int64_t)keys.size();
   const int64_t rows = n + extra_rows, cap = NextPow2(std::max<int64_t>(1024, 2 * rows));
   auto& T = td->t;
-  if (!td->keys.alloc(cap * 8) || !td->freq.alloc(cap * 4) || !td->version.alloc(cap * 4) || !td->row_of.alloc(cap * 4) || !td->tag.alloc(cap * 4) ||
-      !td->dirty.alloc(cap) || !td->rows.alloc((size_t)rows * D * 4) || !td->free_list.alloc(rows * 4 + 16) || !td->counters.alloc(32) || !Upload(td->def, def)) return false;
-  dr_cuda_fill_i64(td->keys.as<int64_t>(), drc::kEmptyKey, cap, 0);
-  cudaMemset(td->freq.p, 0, cap * 4); cudaMemset(td->version.p, 0xFF, cap * 4); cudaMemset(td->row_of.p, 0xFF, cap * 4);
-  cudaMemset(td->tag.p, 0xFF, cap * 4); cudaMemset(td->dirty.p, 0, cap); cudaMemset(td->counters.p, 0, 32);
-  T.keys = td->keys.as<int64_t>(); T.freq = td->freq.as<int32_t>(); T.version = td->version.as<int32_t>(); T.row_of = td->row_of.as<int32_t>();
-  T.tag = td->tag.as<int32_t>(); T.dirty = td->dirty.as<uint8_t>(); T.rows = td->rows.as<float>(); T.free_list = td->free_list.as<int32_t>();
+  if (!td->slots.alloc((size_t)cap * sizeof(DrSlot)) ||
+      !td->rows.alloc((size_t)rows * D * 4) || !td->free_list.alloc(rows * 4 + 16) || !td->counters.alloc(32) || !Upload(td->def, def)) return false;
+  dr_cuda_table_init_slots(td->slots.p, cap, 0);
+  cudaMemset(td->counters.p, 0, 32);
+  T.slots = td->slots.as<DrSlot>();
+  T.rows = td->rows.as<float>(); T.free_list = td->free_list.as<int32_t>();
   T.counters = td->counters.as<int32_t>(); T.default_matrix = td->def.as<float>(); T.bloom = nullptr;
   T.capacity = cap; T.row_capacity = rows; T.default_value_dim = (int64_t)def.size() / D; T.bloom_m = 0;
   T.dim = D; T.stride = D; T.num_slots = 0; T.has_scalars = 0; T.filter_type = 0; T.filter_freq = 0; T.bloom_k = 0; T.is_inference = 1;

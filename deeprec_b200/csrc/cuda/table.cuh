@@ -13,14 +13,20 @@
 #include "common.cuh"
 
 extern "C" {
-// Mirrored by ctypes (deeprec_b200/ops/device_table.py::DeviceTableStruct) -- keep in sync.
+// One hash-table slot = ONE 32-byte DRAM sector: the probe that finds the key has also fetched every piece of metadata the
+// lookup / claim / apply kernels need (an SoA layout costs 4-5 random sectors per key; measured in profiles/ncu_summary.md).
+struct __align__(32) DrSlot {
+  int64_t key;             // kEmptyKey / kTombKey / key
+  int32_t freq;
+  int32_t version;         // global step of last update, -1 = never
+  int32_t row_of;          // row index, -1 = not admitted yet
+  int32_t tag;             // per-step unique index (dedup claim), -1 = unclaimed
+  uint32_t dirty;          // touched since last (incremental) checkpoint
+  uint32_t pad;
+};
+// Mirrored by ctypes (deeprec_b200/_cuda_sigs.py::DeviceTableStruct) -- keep in sync.
 struct DrDeviceTable {
-  int64_t* keys;           // [capacity]  kEmptyKey / kTombKey / key
-  int32_t* freq;           // [capacity]
-  int32_t* version;        // [capacity]  global step of last update, -1 = never
-  int32_t* row_of;         // [capacity]  row index, -1 = not admitted yet
-  int32_t* tag;            // [capacity]  per-step unique index (dedup claim), -1 = unclaimed
-  uint8_t* dirty;          // [capacity]  touched since last (incremental) checkpoint
+  DrSlot* slots;           // [capacity]
   float* rows;             // [row_capacity, stride]
   int32_t* free_list;      // [row_capacity]
   int32_t* counters;       // [8]: 0 next_row, 1 free_top, 2 n_keys, 3 n_admitted, 4 overflow, 5 n_unique, 6 n_miss, 7 spare
@@ -53,7 +59,7 @@ __device__ __forceinline__ int64_t table_find(const DrDeviceTable& T, int64_t ke
   const uint64_t mask = (uint64_t)T.capacity - 1;
   uint64_t pos = dr_mix64((uint64_t)key) & mask;
   for (int64_t probes = 0; probes < T.capacity; ++probes, pos = (pos + 1) & mask) {
-    int64_t k = T.keys[pos];
+    int64_t k = T.slots[pos].key;
     if (k == key) return (int64_t)pos;
     if (k == kEmptyKey) return -1;
   }
@@ -66,10 +72,10 @@ __device__ __forceinline__ int64_t table_find_or_insert(const DrDeviceTable& T, 
   uint64_t pos = dr_mix64((uint64_t)key) & mask;
   *inserted = false;
   for (int64_t probes = 0; probes < T.capacity; ++probes) {
-    int64_t k = *(volatile int64_t*)&T.keys[pos];
+    int64_t k = *(volatile int64_t*)&T.slots[pos].key;
     if (k == key) return (int64_t)pos;
     if (k == kEmptyKey) {
-      unsigned long long old = atomicCAS((unsigned long long*)&T.keys[pos], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      unsigned long long old = atomicCAS((unsigned long long*)&T.slots[pos].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
       if ((int64_t)old == kEmptyKey) { *inserted = true; return (int64_t)pos; }
       if ((int64_t)old == key) return (int64_t)pos;
       // another key took the slot: fall through to the next position
@@ -110,7 +116,7 @@ __device__ __forceinline__ int32_t table_alloc_row(const DrDeviceTable& T) {
 // What a forward read returns for position `pos` (or absent key): pointer to a row of `dim` floats,
 // or nullptr meaning "fill with no_permission".
 __device__ __forceinline__ const float* table_read_ptr(const DrDeviceTable& T, int64_t key, int64_t pos) {
-  int32_t r = pos >= 0 ? T.row_of[pos] : -1;
+  int32_t r = pos >= 0 ? T.slots[pos].row_of : -1;
   if (r >= 0) return T.rows + (int64_t)r * T.stride;
   if (T.filter_type != DR_FILTER_NONE && T.filter_freq > 0) return nullptr;
   return T.default_matrix + dr_default_row(key, T.default_value_dim) * T.dim;
@@ -129,12 +135,12 @@ __device__ __forceinline__ void table_touch_aggregated(const DrDeviceTable& TB, 
   const unsigned same = __match_any_sync(0xffffffffu, mkey);
   if (!valid) return;
   if ((unsigned)(__ffs(same) - 1) != lane) return;                    // not the leader of this position
-  atomicAdd(&TB.freq[pos], __popc(same));
-  TB.dirty[pos] = 1;
-  if (ulist != nullptr && atomicCAS(&TB.tag[pos], -1, -2) == -1) {
+  atomicAdd(&TB.slots[pos].freq, __popc(same));
+  TB.slots[pos].dirty = 1;
+  if (ulist != nullptr && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1) {
     const int u = atomicAdd(nunique, 1);
-    if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; TB.tag[pos] = u; }
-    else { TB.tag[pos] = -1; TB.counters[CTR_OVERFLOW] = 2; }
+    if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; TB.slots[pos].tag = u; }
+    else { TB.slots[pos].tag = -1; TB.counters[CTR_OVERFLOW] = 2; }
   }
 }
 

@@ -101,9 +101,9 @@ __global__ void k_get_meta(DrDeviceTable TB, const int64_t* __restrict__ keys, i
                            int64_t* __restrict__ version, int32_t* __restrict__ row) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t pos = table_find(TB, keys[i]);
-    if (freq) freq[i] = pos >= 0 ? TB.freq[pos] : (TB.bloom ? (int64_t)bloom_min(TB, keys[i]) : 0);
-    if (version) version[i] = pos >= 0 ? TB.version[pos] : -1;
-    if (row) row[i] = pos >= 0 ? TB.row_of[pos] : -1;
+    if (freq) freq[i] = pos >= 0 ? TB.slots[pos].freq : (TB.bloom ? (int64_t)bloom_min(TB, keys[i]) : 0);
+    if (version) version[i] = pos >= 0 ? TB.slots[pos].version : -1;
+    if (row) row[i] = pos >= 0 ? TB.slots[pos].row_of : -1;
   }
 }
 
@@ -113,7 +113,7 @@ __global__ void k_gather_slot(DrDeviceTable TB, const int64_t* __restrict__ keys
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t i = e / TB.dim; int d = (int)(e % TB.dim);
     int64_t pos = table_find(TB, keys[i]);
-    int32_t r = pos >= 0 ? TB.row_of[pos] : -1;
+    int32_t r = pos >= 0 ? TB.slots[pos].row_of : -1;
     out[e] = r >= 0 ? TB.rows[(int64_t)r * TB.stride + slot * TB.dim + d] : (slot == 0 ? 0.f : TB.slot_init[slot - 1]);
   }
 }
@@ -123,13 +123,13 @@ __global__ void k_gather_slot(DrDeviceTable TB, const int64_t* __restrict__ keys
 // -----------------------------------------------------------------------------------------------
 __global__ void k_rehash(DrDeviceTable OLD, DrDeviceTable NEW) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < OLD.capacity; p += (int64_t)gridDim.x * blockDim.x) {
-    int64_t key = OLD.keys[p];
+    int64_t key = OLD.slots[p].key;
     if (key == kEmptyKey || key == kTombKey) continue;
     bool ins;
     int64_t q = table_find_or_insert(NEW, key, &ins);
     if (q < 0) { NEW.counters[CTR_OVERFLOW] = 1; continue; }
-    NEW.freq[q] = OLD.freq[p]; NEW.version[q] = OLD.version[p]; NEW.row_of[q] = OLD.row_of[p];
-    NEW.dirty[q] = OLD.dirty[p]; NEW.tag[q] = -1;
+    NEW.slots[q].freq = OLD.slots[p].freq; NEW.slots[q].version = OLD.slots[p].version; NEW.slots[q].row_of = OLD.slots[p].row_of;
+    NEW.slots[q].dirty = OLD.slots[p].dirty; NEW.slots[q].tag = -1;
   }
 }
 
@@ -139,13 +139,13 @@ __global__ void k_rehash(DrDeviceTable OLD, DrDeviceTable NEW) {
 // -----------------------------------------------------------------------------------------------
 __global__ void k_shrink(DrDeviceTable TB, int step, int32_t* __restrict__ n_evicted) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < TB.capacity; p += (int64_t)gridDim.x * blockDim.x) {
-    int64_t key = TB.keys[p];
+    int64_t key = TB.slots[p].key;
     if (key == kEmptyKey || key == kTombKey) continue;
     bool evict = false;
-    int32_t r = TB.row_of[p];
+    int32_t r = TB.slots[p].row_of;
     if (TB.steps_to_live > 0) {
-      int32_t v = TB.version[p];
-      if (v == -1) TB.version[p] = step;
+      int32_t v = TB.slots[p].version;
+      if (v == -1) TB.slots[p].version = step;
       else if (step - v > TB.steps_to_live) evict = true;
     }
     if (!evict && TB.l2_weight_threshold >= 0.f && r >= 0) {
@@ -154,13 +154,13 @@ __global__ void k_shrink(DrDeviceTable TB, int step, int32_t* __restrict__ n_evi
       if (0.5f * s < TB.l2_weight_threshold) evict = true;
     }
     if (evict) {
-      TB.keys[p] = kTombKey;
+      TB.slots[p].key = kTombKey;
       if (r >= 0) {
         int32_t top = atomicAdd(&TB.counters[CTR_FREE_TOP], 1);
         TB.free_list[top] = r;
         atomicSub(&TB.counters[CTR_NADMITTED], 1);
       }
-      TB.row_of[p] = -1; TB.freq[p] = 0; TB.version[p] = -1; TB.dirty[p] = 0; TB.tag[p] = -1;
+      TB.slots[p].row_of = -1; TB.slots[p].freq = 0; TB.slots[p].version = -1; TB.slots[p].dirty = 0; TB.slots[p].tag = -1;
       atomicSub(&TB.counters[CTR_NKEYS], 1);
       atomicAdd(n_evicted, 1);
     }
@@ -171,11 +171,11 @@ __global__ void k_remove(DrDeviceTable TB, const int64_t* __restrict__ keys, int
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = table_find(TB, keys[i]);
     if (p < 0) continue;
-    unsigned long long old = atomicCAS((unsigned long long*)&TB.keys[p], (unsigned long long)keys[i], (unsigned long long)kTombKey);
+    unsigned long long old = atomicCAS((unsigned long long*)&TB.slots[p].key, (unsigned long long)keys[i], (unsigned long long)kTombKey);
     if ((int64_t)old != keys[i]) continue;
-    int32_t r = TB.row_of[p];
+    int32_t r = TB.slots[p].row_of;
     if (r >= 0) { int32_t top = atomicAdd(&TB.counters[CTR_FREE_TOP], 1); TB.free_list[top] = r; atomicSub(&TB.counters[CTR_NADMITTED], 1); }
-    TB.row_of[p] = -1; TB.freq[p] = 0; TB.version[p] = -1; TB.dirty[p] = 0; TB.tag[p] = -1;
+    TB.slots[p].row_of = -1; TB.slots[p].freq = 0; TB.slots[p].version = -1; TB.slots[p].dirty = 0; TB.slots[p].tag = -1;
     atomicSub(&TB.counters[CTR_NKEYS], 1);
     atomicAdd(n_removed, 1);
   }
@@ -190,21 +190,21 @@ __global__ void k_snapshot(DrDeviceTable TB, int dirty_only, int part_id, int pa
                            int64_t* __restrict__ versions, int64_t* __restrict__ fkeys, int64_t* __restrict__ ffreqs,
                            int64_t* __restrict__ fversions) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < TB.capacity; p += (int64_t)gridDim.x * blockDim.x) {
-    int64_t key = TB.keys[p];
+    int64_t key = TB.slots[p].key;
     if (key == kEmptyKey || key == kTombKey) continue;
     if (part_num > 1 && dr_ckpt_bucket(key) % part_num != part_id) continue;
-    if (dirty_only && !TB.dirty[p]) continue;
-    int32_t r = TB.row_of[p];
+    if (dirty_only && !TB.slots[p].dirty) continue;
+    int32_t r = TB.slots[p].row_of;
     if (r >= 0) {
       int32_t o = atomicAdd(&counts[0], 1);
       if (keys) {
-        keys[o] = key; freqs[o] = TB.freq[p]; versions[o] = TB.version[p];
+        keys[o] = key; freqs[o] = TB.slots[p].freq; versions[o] = TB.slots[p].version;
         const float* src = TB.rows + (int64_t)r * TB.stride; float* dst = rows + (int64_t)o * TB.stride;
         for (int d = 0; d < TB.stride; ++d) dst[d] = src[d];
       }
     } else {
       int32_t o = atomicAdd(&counts[1], 1);
-      if (fkeys) { fkeys[o] = key; ffreqs[o] = TB.freq[p]; fversions[o] = TB.version[p]; }
+      if (fkeys) { fkeys[o] = key; ffreqs[o] = TB.slots[p].freq; fversions[o] = TB.slots[p].version; }
     }
   }
 }
@@ -214,16 +214,16 @@ __global__ void k_export_keys(DrDeviceTable TB, const int64_t* __restrict__ keys
                               int64_t* __restrict__ versions, uint8_t* __restrict__ found) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = table_find(TB, keys[i]);
-    int32_t r = p >= 0 ? TB.row_of[p] : -1;
+    int32_t r = p >= 0 ? TB.slots[p].row_of : -1;
     found[i] = r >= 0;
-    freqs[i] = p >= 0 ? TB.freq[p] : 0;
-    versions[i] = p >= 0 ? TB.version[p] : -1;
+    freqs[i] = p >= 0 ? TB.slots[p].freq : 0;
+    versions[i] = p >= 0 ? TB.slots[p].version : -1;
     if (r >= 0) { const float* src = TB.rows + (int64_t)r * TB.stride; float* dst = rows + i * TB.stride; for (int d = 0; d < TB.stride; ++d) dst[d] = src[d]; }
   }
 }
 
 __global__ void k_clear_dirty(DrDeviceTable TB) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < TB.capacity; p += (int64_t)gridDim.x * blockDim.x) TB.dirty[p] = 0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < TB.capacity; p += (int64_t)gridDim.x * blockDim.x) TB.slots[p].dirty = 0;
 }
 
 // Import rows (restore / elastic import / incremental replay).  rows == null imports filtered keys.
@@ -237,14 +237,14 @@ __global__ void k_import(DrDeviceTable TB, const int64_t* __restrict__ keys, con
     int64_t p = table_find_or_insert(TB, key, &ins);
     if (p < 0) { TB.counters[CTR_OVERFLOW] = 1; continue; }
     if (ins) atomicAdd(&TB.counters[CTR_NKEYS], 1);
-    TB.freq[p] = freqs ? (int32_t)min(freqs[i], (int64_t)INT32_MAX) : 0;
-    TB.version[p] = reset_version ? -1 : (versions ? (int32_t)versions[i] : -1);
+    TB.slots[p].freq = freqs ? (int32_t)min(freqs[i], (int64_t)INT32_MAX) : 0;
+    TB.slots[p].version = reset_version ? -1 : (versions ? (int32_t)versions[i] : -1);
     if (rows) {
-      int32_t r = TB.row_of[p];
+      int32_t r = TB.slots[p].row_of;
       if (r < 0) {
         r = table_alloc_row(TB);
         if (r < 0) continue;
-        TB.row_of[p] = r; atomicAdd(&TB.counters[CTR_NADMITTED], 1);
+        TB.slots[p].row_of = r; atomicAdd(&TB.counters[CTR_NADMITTED], 1);
         float* row = TB.rows + (int64_t)r * TB.stride;
         const float* def = TB.default_matrix + dr_default_row(key, TB.default_value_dim) * TB.dim;
         for (int d = 0; d < TB.dim; ++d) row[d] = def[d];
@@ -257,6 +257,16 @@ __global__ void k_import(DrDeviceTable TB, const int64_t* __restrict__ keys, con
       for (int d = 0; d < m; ++d) row[d] = src[d];
     }
     atomicAdd(n_kept, 1);
+  }
+}
+
+// empty slot = {kEmptyKey, freq 0, version -1, row_of -1, tag -1, dirty 0}: two 16 B stores per slot
+__global__ void k_init_slots(DrSlot* slots, int64_t n) {
+  const int4 lo = make_int4((int)(uint32_t)((uint64_t)kEmptyKey & 0xffffffffu), (int)(uint32_t)((uint64_t)kEmptyKey >> 32), 0, -1);
+  const int4 hi = make_int4(-1, -1, 0, 0);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int4* p = reinterpret_cast<int4*>(slots + i);
+    p[0] = lo; p[1] = hi;
   }
 }
 
@@ -275,6 +285,12 @@ inline int grid_for(int64_t n, int block, int max_blocks = 0) {
 }  // namespace
 
 extern "C" {
+
+int dr_cuda_table_init_slots(void* slots, int64_t n, cudaStream_t s) {
+  k_init_slots<<<grid_for(n, 256, kNumSMs * 8), 256, 0, s>>>((DrSlot*)slots, n);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
 
 int dr_cuda_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t s) {
   k_fill_i64<<<grid_for(n, 256), 256, 0, s>>>(p, v, n);

@@ -13,6 +13,8 @@ their default row; creation, admission, frequency and version stamping happen in
 """
 from __future__ import annotations
 
+import zlib
+
 import ctypes as C
 from typing import Dict, List, Optional, Sequence
 
@@ -222,7 +224,7 @@ class EmbeddingVariable(nn.Module):
         self._pending: List = []
         self._seed = seed
         self._inference = inference_mode()
-        g = torch.Generator().manual_seed(seed if seed is not None else (hash(name) & 0x7FFFFFFF))
+        g = torch.Generator().manual_seed(seed if seed is not None else (zlib.crc32(name.encode()) & 0x7FFFFFFF))
         dvd = max(1, int(self.option.init_option.default_value_dim))
         dm = torch.empty(dvd, self.embedding_dim, dtype=torch.float32)
         init = self.option.init_option.initializer

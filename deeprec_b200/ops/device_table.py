@@ -159,12 +159,13 @@ class DeviceTable:
     def _alloc_keys(self, capacity: int) -> None:
         d = self.device
         self.capacity = capacity
-        self.keys = torch.full((capacity,), EMPTY_KEY, dtype=torch.int64, device=d)
-        self.freq = torch.zeros(capacity, dtype=torch.int32, device=d)
-        self.version = torch.full((capacity,), -1, dtype=torch.int32, device=d)
-        self.row_of = torch.full((capacity,), -1, dtype=torch.int32, device=d)
-        self.tag = torch.full((capacity,), -1, dtype=torch.int32, device=d)
-        self.dirty = torch.zeros(capacity, dtype=torch.uint8, device=d)
+        # array-of-structs: one 32-byte DrSlot {key, freq, version, row_of, tag, dirty, pad} per position (csrc/cuda/table.cuh);
+        # the per-field tensors below are strided VIEWS of it (multi-tier victim selection, tests, debugging)
+        self.slots = torch.empty(capacity * 4, dtype=torch.int64, device=d)
+        _chk(self.lib.dr_cuda_table_init_slots(ptr(self.slots), capacity, stream_ptr()), "init_slots")
+        s32 = self.slots.view(torch.int32).view(capacity, 8)
+        self.keys = self.slots.view(capacity, 4)[:, 0]
+        self.freq, self.version, self.row_of, self.tag, self.dirty = s32[:, 2], s32[:, 3], s32[:, 4], s32[:, 5], s32[:, 6]
 
     def _alloc_rows(self, row_capacity: int) -> None:
         self.row_capacity = row_capacity
@@ -174,8 +175,7 @@ class DeviceTable:
     def _refresh_struct(self) -> None:
         s = DeviceTableStruct()
         c = self.cfg
-        s.keys, s.freq, s.version = self.keys.data_ptr(), self.freq.data_ptr(), self.version.data_ptr()
-        s.row_of, s.tag, s.dirty = self.row_of.data_ptr(), self.tag.data_ptr(), self.dirty.data_ptr()
+        s.slots = self.slots.data_ptr()
         s.rows, s.free_list, s.counters = self.rows.data_ptr(), self.free_list.data_ptr(), self.counters.data_ptr()
         s.default_matrix = self.default_matrix.data_ptr()
         s.bloom = self.bloom.data_ptr() if self.bloom is not None else None
@@ -212,7 +212,7 @@ class DeviceTable:
 
     def _grow(self, new_cap: int, new_rows: int) -> None:
         old_struct = self.struct
-        keep = (self.keys, self.freq, self.version, self.row_of, self.tag, self.dirty, self.rows, self.free_list)
+        keep = (self.slots, self.rows, self.free_list)
         if new_rows != self.row_capacity:
             old_rows, old_fl, old_rc = self.rows, self.free_list, self.row_capacity
             self._alloc_rows(new_rows)
@@ -336,7 +336,7 @@ class DeviceTable:
 
     def _purge_tombstones(self) -> None:
         old_struct = self.struct
-        keep = (self.keys, self.freq, self.version, self.row_of, self.tag, self.dirty)
+        keep = (self.slots,)
         self._alloc_keys(self.capacity)
         self._refresh_struct()
         _chk(self.lib.dr_cuda_table_rehash(C.byref(old_struct), C.byref(self.struct), stream_ptr()), "rehash")

@@ -13,6 +13,8 @@ the fused NVLink kernels in csrc/cuda/comm_kernels.cu instead (same dataflow, no
 """
 from __future__ import annotations
 
+import zlib
+
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -116,7 +118,7 @@ class All2AllDenseEmbedding(nn.Module):
         super().__init__()
         rank, _ = _world()
         self.slot_num, self.nnz_per_slot = slot_num, nnz_per_slot
-        self.ev = get_embedding_variable(f"{name}/shard_{rank}", embedding_vec_size, ev_option=ev_option, device=device, seed=hash(name) & 0xFFFF)
+        self.ev = get_embedding_variable(f"{name}/shard_{rank}", embedding_vec_size, ev_option=ev_option, device=device, seed=zlib.crc32(name.encode()) & 0xFFFF)
         self._anchor = nn.Parameter(torch.zeros(0), requires_grad=True)
 
     def forward(self, inputs: torch.Tensor) -> torch.Tensor:
@@ -181,7 +183,7 @@ class DistributedEmbedding(nn.Module):
         assert combiner in ("sum", "mean", "sqrtn")
         rank, _ = _world()
         self.combiner = combiner
-        self.ev = get_embedding_variable(f"{name}/shard_{rank}", embedding_vec_size, ev_option=ev_option, device=device, seed=hash(name) & 0xFFFF)
+        self.ev = get_embedding_variable(f"{name}/shard_{rank}", embedding_vec_size, ev_option=ev_option, device=device, seed=zlib.crc32(name.encode()) & 0xFFFF)
         self._anchor = nn.Parameter(torch.zeros(0), requires_grad=True)
 
     def forward(self, sp: SparseIds) -> torch.Tensor:
