@@ -1,9 +1,11 @@
 #!/bin/bash
 # Serving latency/QPS sweep + one `ncu --set full` capture per hot kernel (single GPU).  Outputs land in gpurun_out/.
 mkdir -p gpurun_out
+for dt in bf16 fp8; do
 for cfg in "1 1 1" "4 8 256" "4 16 2048"; do
   set -- $cfg
-  timeout 200 python benchmarks/serving_bench.py --sessions $1 --threads $2 --batch $3 --requests 2000 2>/dev/null | tail -1 | cut -c1-420
+  timeout 200 python benchmarks/serving_bench.py --sessions $1 --threads $2 --batch $3 --requests 2000 --dtype $dt 2>/dev/null | tail -1 | cut -c1-420
+done
 done > gpurun_out/serving_bench.jsonl
 cat gpurun_out/serving_bench.jsonl
 for k in k_gemm_tn_v2 k_gemm_nt_splitk k_bn_bwd_apply_v2; do

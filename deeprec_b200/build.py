@@ -23,6 +23,7 @@ CUDA_SOURCES = [
     "cuda/embedding_kernels.cu",
     "cuda/optimizer_kernels.cu",
     "cuda/dense_kernels.cu",
+    "cuda/gemm_fp8.cu",
     "cuda/gemm_tcgen05.cu",
     "cuda/interaction_kernels.cu",
     "cuda/comm_kernels.cu",

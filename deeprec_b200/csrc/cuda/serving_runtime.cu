@@ -31,6 +31,11 @@
 extern "C" {
 int dr_cuda_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t s);
 int dr_cuda_table_init_slots(void* slots, int64_t n, cudaStream_t s);
+int dr_cuda_gemm_fp8_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* col_scale, const float* bias,
+                        int relu, void* out, int64_t ldc, int out_fp8, float out_inv_scale, cudaStream_t s);
+int dr_cuda_quantize_e4m3(const void* x, int is_bf16, int64_t M, int C, int64_t ldx, void* y, int Cp, float inv_scale, cudaStream_t s);
+int dr_cuda_quantize_weights_e4m3(const float* w, int N, int K, int64_t ldw, void* q, int Kp, float* scale, cudaStream_t s);
+int dr_cuda_absmax_bf16(const void* x, int64_t n, float* out, cudaStream_t s);
 int dr_cuda_table_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map, int T, const int64_t* keys, const int64_t* offsets, int64_t uniform,
                          int64_t n, int train, const int64_t* step_ptr, int32_t* out_pos, int64_t* ulist, int32_t* group_nunique, int64_t ulist_cap, cudaStream_t s);
 int dr_cuda_table_gather(const DrDeviceTable* tables_dev, const int32_t* table_map, int T, int dim, const int64_t* keys, const int32_t* pos,
@@ -105,17 +110,28 @@ template <typename T> static bool Upload(DevBuf& b, const std::vector<T>& h) {
 
 struct Arch { int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0; };
 
-struct LayerW { int N, K, Kp; DevBuf w_bf16, bias; };
+struct LayerW {
+  int N, K, Kp; DevBuf w_bf16, bias;
+  // fp8 serving path: E4M3 weights [N, Kp16] quantised per output channel; col_scale[n] = w_scale[n] * in_scale
+  int Kp16 = 0; DevBuf w_fp8, w_scale, col_scale;
+};
+static inline int pad16(int n) { return (n + 15) / 16 * 16; }
+
+// static activation scales (amax / 448 with head-room) measured by Calibrate(); index: 0 = x0, 1.. = bottom activations
+struct ActScales { std::vector<float> bot_in, top_in; bool valid = false; };
 
 // dense parameter block (small; swapped as a whole on full AND delta updates)
 struct DenseParams {
   std::vector<LayerW> bot, top;
   DevBuf last_scale, last_shift, head_w, head_b;
+  bool fp8 = false;        // fp8 tensors + scales below are populated
+  ActScales act;
 };
 
 struct TableDev {
   DrDeviceTable t{}; DevBuf slots, rows, free_list, counters, def;
   int64_t n_rows = 0;
+  std::vector<int64_t> sample_keys;     // a few stored keys: calibration / warm-up batches look up rows that exist
 };
 
 struct DeviceModel {
@@ -137,7 +153,29 @@ template <typename T> static bool ReadVec(dr::BundleReader& r, const std::string
 }
 
 // BatchNorm (moving statistics) of layer l-1 folded into Linear l:  W' = W diag(s), b' = b + W t
-static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<DenseParams>* out) {
+static bool QuantizeLayer(LayerW& L, const std::vector<float>& w_folded /*[N, Kp]*/) {
+  L.Kp16 = pad16(L.Kp);
+  DevBuf tmp;
+  if (!Upload(tmp, w_folded) || !L.w_fp8.alloc((size_t)L.N * L.Kp16) || !L.w_scale.alloc((size_t)L.N * 4) || !L.col_scale.alloc((size_t)L.N * 4)) return false;
+  if (dr_cuda_quantize_weights_e4m3(tmp.as<float>(), L.N, L.Kp, L.Kp, L.w_fp8.p, L.Kp16, L.w_scale.as<float>(), 0) != 0) return false;
+  return cudaDeviceSynchronize() == cudaSuccess;
+}
+
+// col_scale[n] = w_scale[n] * in_scale for every layer, from the calibrated activation scales
+static bool ApplyActScales(DenseParams& dp) {
+  auto one = [](LayerW& L, float in_scale) {
+    std::vector<float> ws((size_t)L.N);
+    if (cudaMemcpy(ws.data(), L.w_scale.p, ws.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    for (auto& v : ws) v *= in_scale;
+    return cudaMemcpy(L.col_scale.p, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  for (size_t l = 0; l < dp.bot.size(); ++l) if (!one(dp.bot[l], dp.act.bot_in[l])) return false;
+  for (size_t l = 0; l < dp.top.size(); ++l) if (!one(dp.top[l], dp.act.top_in[l])) return false;
+  dp.fp8 = true;
+  return true;
+}
+
+static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<DenseParams>* out, bool want_fp8 = false) {
   auto dp = std::make_shared<DenseParams>();
   dp->bot.reserve(a.bot.size()); dp->top.reserve(a.top.size());
   std::vector<float> s_prev, t_prev;
@@ -149,18 +187,19 @@ static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense
     if (!ReadVec(r, "dense/" + nm + "/kernel", &W) || !ReadVec(r, "dense/" + nm + "/bias", &b) || !ReadVec(r, "dense/" + nm + "/bn_gamma", &gamma) ||
         !ReadVec(r, "dense/" + nm + "/bn_beta", &beta) || !ReadVec(r, "bn/" + nm + "/moving_mean", &mean) || !ReadVec(r, "bn/" + nm + "/moving_variance", &var)) return false;
     if ((int)W.size() != N * Kp) return false;
-    std::vector<uint16_t> wb((size_t)N * Kp); std::vector<float> bias(N);
+    std::vector<uint16_t> wb((size_t)N * Kp); std::vector<float> bias(N), wf((size_t)N * Kp);
     for (int n = 0; n < N; ++n) {
       double acc = b[n];
       for (int kk = 0; kk < Kp; ++kk) {
         float w = W[(size_t)n * Kp + kk];
         if (l > 0 && kk < k) { acc += (double)w * t_prev[kk]; w *= s_prev[kk]; }
-        wb[(size_t)n * Kp + kk] = f2bf(w);
+        wb[(size_t)n * Kp + kk] = f2bf(w); wf[(size_t)n * Kp + kk] = w;
       }
       bias[n] = (float)acc;
     }
     dp->bot.emplace_back(); auto& dst = dp->bot.back(); dst.N = N; dst.K = k; dst.Kp = Kp;
     if (!Upload(dst.w_bf16, wb) || !Upload(dst.bias, bias)) return false;
+    if (want_fp8 && !QuantizeLayer(dst, wf)) return false;
     s_prev.assign(N, 0.f); t_prev.assign(N, 0.f);
     for (int n = 0; n < N; ++n) { float rs = 1.0f / std::sqrt(var[n] + a.bn_eps); s_prev[n] = gamma[n] * rs; t_prev[n] = beta[n] - mean[n] * s_prev[n]; }
     k = N;
@@ -176,6 +215,7 @@ static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense
     for (size_t i = 0; i < W.size(); ++i) wb[i] = f2bf(W[i]);
     dp->top.emplace_back(); auto& dst = dp->top.back(); dst.N = N; dst.K = k; dst.Kp = Kp;
     if (!Upload(dst.w_bf16, wb) || !Upload(dst.bias, b)) return false;
+    if (want_fp8 && !QuantizeLayer(dst, W)) return false;
     k = N;
   }
   std::vector<float> hw, hb;
@@ -193,6 +233,7 @@ static bool BuildTable(dr::BundleReader& r, int t, int D, TableDev* td, int64_t 
   if (!ReadVec(r, base + "-keys", &keys) || !ReadVec(r, base + "-values", &vals) || !ReadVec(r, base + "-default", &def)) return false;
   ReadVec(r, base + "-freqs", &freqs); ReadVec(r, base + "-versions", &vers);
   const int64_t n = (int64_t)keys.size();
+  td->sample_keys.assign(keys.begin(), keys.begin() + std::min<int64_t>(n, 512));
   const int64_t rows = n + extra_rows, cap = NextPow2(std::max<int64_t>(1024, 2 * rows));
   auto& T = td->t;
   if (!td->slots.alloc((size_t)cap * sizeof(DrSlot)) ||
@@ -232,13 +273,13 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
 }
 
-static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t extra_rows) {
+static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t extra_rows, bool want_fp8 = false) {
   auto m = std::make_shared<DeviceModel>();
   std::string prefix;
   if (!LoadArch(dir, &m->arch, &m->version, &prefix)) { fprintf(stderr, "[deeprec_serving] bad saved_model.json in %s\n", dir.c_str()); return nullptr; }
   dr::BundleReader r(prefix);
   if (!r.ok()) { fprintf(stderr, "[deeprec_serving] cannot open bundle %s\n", prefix.c_str()); return nullptr; }
-  if (!BuildDense(r, m->arch, &m->dense)) { fprintf(stderr, "[deeprec_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
+  if (!BuildDense(r, m->arch, &m->dense, want_fp8)) { fprintf(stderr, "[deeprec_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
   std::vector<DrDeviceTable> structs;
   for (int t = 0; t < m->arch.T; ++t) {
     m->tables.emplace_back(new TableDev());
@@ -255,6 +296,7 @@ struct Session {
   cudaStream_t stream = nullptr; int max_batch = 0; std::mutex mu;
   DevBuf dense_in, ids, x0, emb, pos, Z, prob, loss, labels, y_last;
   std::vector<DevBuf> a_bot, a_top;
+  DevBuf x0_q, Z_q, amax; std::vector<DevBuf> q_bot, q_top;        // fp8 path: E4M3 activations between the GEMMs
   float* h_dense = nullptr; int64_t* h_ids = nullptr; float* h_prob = nullptr;    // pinned
   bool Init(const Arch& a, int maxB) {
     max_batch = maxB;
@@ -265,6 +307,10 @@ struct Session {
     a_bot.resize(a.bot.size()); a_top.resize(a.top.size());
     for (size_t l = 0; l < a.bot.size(); ++l) ok = ok && a_bot[l].alloc((size_t)maxB * a.bot[l] * 2);
     for (size_t l = 0; l < a.top.size(); ++l) ok = ok && a_top[l].alloc((size_t)maxB * a.top[l] * 2);
+    q_bot.resize(a.bot.size()); q_top.resize(a.top.size());
+    ok = ok && x0_q.alloc((size_t)maxB * pad16(a.num_dense)) && Z_q.alloc((size_t)maxB * pad16(a.Zp)) && amax.alloc(64);
+    for (size_t l = 0; l < a.bot.size(); ++l) ok = ok && q_bot[l].alloc((size_t)maxB * pad16(a.bot[l]));
+    for (size_t l = 0; l < a.top.size(); ++l) ok = ok && q_top[l].alloc((size_t)maxB * pad16(a.top[l]));
     if (!ok) return false;
     cudaMemset(labels.p, 0, (size_t)maxB * 4);
     SV_CUDA(cudaMallocHost(&h_dense, (size_t)maxB * a.num_dense * 4));
@@ -275,7 +321,7 @@ struct Session {
   ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (stream) cudaStreamDestroy(stream); }
 
   // inputs already in h_dense / h_ids ([T][B] feature-major); result in h_prob
-  bool Run(const DeviceModel& m, const DenseParams& dp, int B) {
+  bool Run(const DeviceModel& m, const DenseParams& dp, int B, bool force_bf16 = false) {
     const Arch& a = m.arch; cudaStream_t s = stream;
     SV_CUDA(cudaMemcpyAsync(dense_in.p, h_dense, (size_t)B * a.num_dense * 4, cudaMemcpyHostToDevice, s));
     SV_CUDA(cudaMemcpyAsync(ids.p, h_ids, (size_t)a.T * B * 8, cudaMemcpyHostToDevice, s));
@@ -283,8 +329,35 @@ struct Session {
     const int64_t n = (int64_t)a.T * B;
     rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
     rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, 0, 0, 1, s);
+    const void* x; int64_t ldx;
+    if (dp.fp8 && !force_bf16) {
+      // ---- E4M3 path: every hidden activation stays 8-bit; each GEMM epilogue re-quantises with the next layer's static scale
+      const int c0 = pad16(a.num_dense);
+      rc |= dr_cuda_quantize_e4m3(dense_in.p, 0, B, a.num_dense, a.num_dense, x0_q.p, c0, 1.0f / dp.act.bot_in[0], s);
+      x = x0_q.p; ldx = c0;
+      const size_t nb = dp.bot.size();
+      for (size_t l = 0; l < nb; ++l) {
+        const LayerW& L = dp.bot[l];
+        const bool last = l + 1 == nb;        // the last bottom layer feeds BatchNorm + the bf16 interaction kernel
+        rc |= dr_cuda_gemm_fp8_tn(x, ldx, L.w_fp8.p, L.Kp16, B, L.N, L.Kp16, L.col_scale.as<float>(), L.bias.as<float>(), 1,
+                                  last ? a_bot[l].p : q_bot[l].p, last ? L.N : pad16(L.N), last ? 0 : 1, last ? 1.f : 1.0f / dp.act.bot_in[l + 1], s);
+        x = last ? a_bot[l].p : q_bot[l].p; ldx = last ? L.N : pad16(L.N);
+      }
+      rc |= dr_cuda_bn_apply(x, B, a.D, a.D, dp.last_scale.as<float>(), dp.last_shift.as<float>(), y_last.p, a.D, s);
+      rc |= dr_cuda_dot_interaction_fwd(y_last.p, a.D, emb.p, (int64_t)B * a.D, a.D, a.T, a.D, B, Z.p, a.Zp, s);
+      rc |= dr_cuda_quantize_e4m3(Z.p, 1, B, a.Zp, a.Zp, Z_q.p, pad16(a.Zp), 1.0f / dp.act.top_in[0], s);
+      x = Z_q.p; ldx = pad16(a.Zp);
+      const size_t nt = dp.top.size();
+      for (size_t l = 0; l < nt; ++l) {
+        const LayerW& L = dp.top[l];
+        const bool last = l + 1 == nt;        // the head kernel consumes bf16
+        rc |= dr_cuda_gemm_fp8_tn(x, ldx, L.w_fp8.p, L.Kp16, B, L.N, L.Kp16, L.col_scale.as<float>(), L.bias.as<float>(), 1,
+                                  last ? a_top[l].p : q_top[l].p, last ? L.N : pad16(L.N), last ? 0 : 1, last ? 1.f : 1.0f / dp.act.top_in[l + 1], s);
+        x = last ? a_top[l].p : q_top[l].p; ldx = last ? L.N : pad16(L.N);
+      }
+    } else {
     rc |= dr_cuda_cast_pad(dense_in.as<float>(), B, a.num_dense, x0.p, pad8(a.num_dense), s);
-    const void* x = x0.p; int64_t ldx = pad8(a.num_dense);
+    x = x0.p; ldx = pad8(a.num_dense);
     for (size_t l = 0; l < dp.bot.size(); ++l) {
       const LayerW& L = dp.bot[l];
       rc |= dr_cuda_gemm_tn_ex(x, ldx, L.w_bf16.p, L.Kp, B, L.N, L.Kp, L.bias.as<float>(), 1, nullptr, 0, 0, a_bot[l].p, L.N, nullptr, nullptr, nullptr, 0, 0, s);
@@ -298,6 +371,7 @@ struct Session {
       rc |= dr_cuda_gemm_tn_ex(x, ldx, L.w_bf16.p, L.Kp, B, L.N, L.Kp, L.bias.as<float>(), 1, nullptr, 0, 0, a_top[l].p, L.N, nullptr, nullptr, nullptr, 0, 0, s);
       x = a_top[l].p; ldx = L.N;
     }
+    }
     rc |= dr_cuda_head(x, ldx, B, (int)ldx, dp.head_w.as<float>(), dp.head_b.as<float>(), labels.as<float>(), 1.0f / B, prob.as<float>(), loss.as<float>(),
                        nullptr, nullptr, nullptr, 0, 0, nullptr, s);
     if (rc) return false;
@@ -307,7 +381,32 @@ struct Session {
   }
 };
 
+// Static activation scales for the fp8 path: run the bf16 forward on a calibration batch and take amax of every tensor that is
+// stored in E4M3 (network input, hidden activations, interaction output); scale = 2 * amax / 448 (2x head-room: E4M3 keeps 3
+// mantissa bits down to 2^-6 of full scale, so head-room is cheap, saturation is not).
+static bool Calibrate(Session& ss, const DeviceModel& m, DenseParams& dp, int B) {
+  const Arch& a = m.arch;
+  if (!ss.Run(m, dp, B, /*force_bf16=*/true)) return false;
+  auto amax_of = [&](const DevBuf& buf, int64_t n, float* out) {
+    if (dr_cuda_absmax_bf16(buf.p, n, ss.amax.as<float>(), ss.stream) != 0) return false;
+    if (cudaMemcpyAsync(out, ss.amax.p, 4, cudaMemcpyDeviceToHost, ss.stream) != cudaSuccess) return false;
+    return cudaStreamSynchronize(ss.stream) == cudaSuccess;
+  };
+  auto to_scale = [](float amax) { return std::max(amax, 1e-6f) * 2.0f / 448.0f; };
+  dp.act.bot_in.assign(dp.bot.size(), 1.f); dp.act.top_in.assign(dp.top.size(), 1.f);
+  float v = 0.f;
+  if (!amax_of(ss.x0, (int64_t)B * pad8(a.num_dense), &v)) return false;
+  dp.act.bot_in[0] = to_scale(v);
+  for (size_t l = 0; l + 1 < dp.bot.size(); ++l) { if (!amax_of(ss.a_bot[l], (int64_t)B * dp.bot[l].N, &v)) return false; dp.act.bot_in[l + 1] = to_scale(v); }
+  if (!amax_of(ss.Z, (int64_t)B * a.Zp, &v)) return false;
+  dp.act.top_in[0] = to_scale(v);
+  for (size_t l = 0; l + 1 < dp.top.size(); ++l) { if (!amax_of(ss.a_top[l], (int64_t)B * dp.top[l].N, &v)) return false; dp.act.top_in[l + 1] = to_scale(v); }
+  dp.act.valid = true;
+  return ApplyActScales(dp);
+}
+
 struct Config {
+  bool fp8 = false;
   int session_num = 2, select_policy = 0 /*0 RR, 1 MOD*/, gpu_id = 0, max_batch = 4096, update_interval_ms = 1000, extra_rows = 1 << 16;
   int timeline_start_step = -1, timeline_interval_step = 0, timeline_trace_count = 0;
   std::string savedmodel_dir, checkpoint_dir, warmup_file_name, timeline_path;
@@ -391,20 +490,65 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
     cudaDeviceSynchronize();
   }
   std::shared_ptr<DenseParams> dp;
-  if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp)) std::atomic_store(&m->dense, dp);
+  if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp, sm->cfg.fp8)) {
+    if (sm->cfg.fp8) {       // delta updates keep the calibrated activation scales of the serving model (no warm-up on deltas)
+      auto old = std::atomic_load(&m->dense);
+      dp->act = old->act;
+      if (!dp->act.valid || !ApplyActScales(*dp)) return false;
+    }
+    std::atomic_store(&m->dense, dp);
+  }
   sm->delta_version = version;
   sm->delta_updates++;
   return true;
 }
 
-static void WarmUp(ServingModel* sm, const std::shared_ptr<DeviceModel>& m) {
+// Warm-up / calibration batch: the request stored in warmup_file_name (wire format of process()) when present, else a
+// deterministic synthetic batch -- dense features spread over the log-transformed Criteo range, ids cycling over stored keys.
+static int FillWarmupBatch(ServingModel* sm, const DeviceModel& m, Session& s) {
+  const Arch& a = m.arch;
+  int B = std::min(256, s.max_batch);
+  std::string raw;
+  if (!sm->cfg.warmup_file_name.empty() && ReadFile(sm->cfg.warmup_file_name, &raw) && raw.size() >= sizeof(ReqHeader)) {
+    ReqHeader h; memcpy(&h, raw.data(), sizeof(h));
+    const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
+    if (h.magic == kReqMagic && (int)h.num_dense == a.num_dense && (int)h.num_sparse == a.T && h.batch > 0 && raw.size() >= need) {
+      B = std::min<int>(h.batch, s.max_batch);
+      const float* d = reinterpret_cast<const float*>(raw.data() + sizeof(h));
+      const int64_t* ids = reinterpret_cast<const int64_t*>(raw.data() + sizeof(h) + (size_t)h.batch * h.num_dense * 4);
+      memcpy(s.h_dense, d, (size_t)B * a.num_dense * 4);
+      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)t * h.batch, (size_t)B * 8);
+      return B;
+    }
+  }
+  for (int b = 0; b < B; ++b)
+    for (int j = 0; j < a.num_dense; ++j) s.h_dense[(size_t)b * a.num_dense + j] = (float)((b * 31 + j * 17) % 97) / 97.0f * 8.0f;
+  for (int t = 0; t < a.T; ++t) {
+    const auto& sk = m.tables[t]->sample_keys;
+    for (int b = 0; b < B; ++b) s.h_ids[(size_t)t * B + b] = sk.empty() ? 0 : sk[(size_t)(b * 7 + t) % sk.size()];
+  }
+  return B;
+}
+
+static bool WarmUp(ServingModel* sm, const std::shared_ptr<DeviceModel>& m, const ActScales* reuse = nullptr) {
+  bool first = true;
   for (auto& s : sm->sessions) {
     std::lock_guard<std::mutex> l(s->mu);
-    const int B = std::min(256, s->max_batch);
-    memset(s->h_dense, 0, (size_t)B * m->arch.num_dense * 4); memset(s->h_ids, 0, (size_t)m->arch.T * B * 8);
+    const int B = FillWarmupBatch(sm, *m, *s);
     auto dense = std::atomic_load(&m->dense);
-    s->Run(*m, *dense, B);
+    if (sm->cfg.fp8 && first && !dense->fp8) {
+      if (reuse && reuse->valid && reuse->bot_in.size() == dense->bot.size() && reuse->top_in.size() == dense->top.size()) {
+        dense->act = *reuse;
+        if (!ApplyActScales(*dense)) return false;
+      } else if (!Calibrate(*s, *m, *dense, B)) {
+        fprintf(stderr, "[deeprec_serving] fp8 calibration failed\n");
+        return false;
+      }
+    }
+    first = false;
+    if (!s->Run(*m, *dense, B)) return false;
   }
+  return true;
 }
 
 // version file: <dir>/serving_versions.json = {"full": {"version": V, "dir": "..."}, "deltas": [{"version": v, "prefix": "..."}]}
@@ -420,10 +564,10 @@ static void UpdaterLoop(ServingModel* sm) {
       int64_t v = (int64_t)f->n("version", -1); std::string dir = f->s("dir", "");
       if (cur && v > cur->version && !dir.empty()) {
         cudaSetDevice(sm->cfg.gpu_id);
-        auto nm = LoadModel(dir, sm->cfg.extra_rows);
+        auto nm = LoadModel(dir, sm->cfg.extra_rows, sm->cfg.fp8);
         if (!nm) { if (++bad > 3) fprintf(stderr, "[deeprec_serving] skipping invalid model version %lld\n", (long long)v); continue; }
         bad = 0;
-        WarmUp(sm, nm);
+        if (!WarmUp(sm, nm)) continue;
         std::atomic_store(&sm->model, nm);          // requests in flight keep the old model alive through their shared_ptr
         sm->delta_version = -1;
         sm->full_updates++;
@@ -459,13 +603,14 @@ void* initialize(const char* model_entry, const char* model_config, int* state) 
   c.timeline_start_step = (int)j.n("timeline_start_step", -1); c.timeline_interval_step = (int)j.n("timeline_interval_step", 0);
   c.timeline_trace_count = (int)j.n("timeline_trace_count", 0);
   if (cudaSetDevice(c.gpu_id) != cudaSuccess) { *state = -1; delete sm; return nullptr; }
-  auto m = LoadModel(c.savedmodel_dir, c.extra_rows);
+  c.fp8 = j.s("mlp_dtype", "bf16") == "fp8";
+  auto m = LoadModel(c.savedmodel_dir, c.extra_rows, c.fp8);
   if (!m) { *state = -1; delete sm; return nullptr; }
   for (int i = 0; i < std::max(1, c.session_num); ++i) {
     sm->sessions.emplace_back(new Session());
     if (!sm->sessions.back()->Init(m->arch, c.max_batch)) { *state = -1; delete sm; return nullptr; }
   }
-  WarmUp(sm, m);
+  if (!WarmUp(sm, m)) { *state = -1; delete sm; return nullptr; }
   std::atomic_store(&sm->model, m);
   if (c.update_interval_ms > 0) sm->updater = std::thread(UpdaterLoop, sm);
   *state = 0;
@@ -495,7 +640,7 @@ int get_serving_model_info(void* model_buf, void** output_data, int* output_size
   std::ostringstream os;
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
-     << ", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
+     << ", \"mlp_dtype\": \"" << (sm->cfg.fp8 ? "fp8" : "bf16") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
   std::string s = os.str();
   *output_size = (int)s.size();
   *output_data = malloc(s.size() + 1);

@@ -136,8 +136,12 @@ __device__ __forceinline__ void table_touch_aggregated(const DrDeviceTable& TB, 
   if (!valid) return;
   if ((unsigned)(__ffs(same) - 1) != lane) return;                    // not the leader of this position
   atomicAdd(&TB.slots[pos].freq, __popc(same));
-  TB.slots[pos].dirty = 1;
-  if (ulist != nullptr && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1) {
+  // read-before-write: a hot key's slot is hammered by every warp of the batch; once it is dirty / claimed, later warps
+  // must not add a store and a CAS to the same-sector serialisation queue (the probe already pulled the sector in)
+  int4 hi;                                                                             // {row_of, tag, dirty, pad}
+  asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(&TB.slots[pos].row_of));
+  if (hi.z == 0) TB.slots[pos].dirty = 1;
+  if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1) {
     const int u = atomicAdd(nunique, 1);
     if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; TB.slots[pos].tag = u; }
     else { TB.slots[pos].tag = -1; TB.counters[CTR_OVERFLOW] = 2; }

@@ -78,3 +78,31 @@ def test_python_session_group_round_robin():
     m2 = torch.nn.Linear(8, 1).cuda()
     sg.swap_model(m2, warmup_inputs=(x,))
     assert torch.allclose(sg.run(x), m2(x))
+
+
+def test_processor_fp8_mlp_close_to_bf16(tmp_path):
+    """mlp_dtype=fp8: E4M3 tcgen05 GEMMs with calibrated static activation scales; predictions stay close to the bf16 runtime,
+    and a delta update re-quantises the dense block while keeping the calibration."""
+    from deeprec_b200.serving import Processor, export_delta, export_saved_model
+    eng, cards = _engine()
+    d, ids = _train(eng, cards, 6, 0)
+    root = str(tmp_path)
+    export_saved_model(eng, os.path.join(root, "v1"), version=6, root=root)
+    common = {"session_num": 2, "max_batch": 512, "checkpoint_dir": root, "model_update_interval_ms": 100}
+    p16 = Processor(os.path.join(root, "v1"), dict(common, model_update_interval_ms=0))
+    p8 = Processor(os.path.join(root, "v1"), dict(common, mlp_dtype="fp8"))
+    assert p8.model_info()["mlp_dtype"] == "fp8" and p16.model_info()["mlp_dtype"] == "bf16"
+    a, b = p16.predict(d.numpy(), ids.numpy()), p8.predict(d.numpy(), ids.numpy())
+    assert np.isfinite(b).all() and np.abs(a - b).max() < 0.06 and np.abs(a - b).mean() < 0.015, (np.abs(a - b).max(), np.abs(a - b).mean())
+    assert np.corrcoef(a, b)[0, 1] > 0.98
+    _train(eng, cards, 3, 100)
+    export_delta(eng, root, base_version=6, version=9)
+    eng.load_batch(d.cuda(), ids.cuda(), torch.zeros(eng.B, device="cuda"))
+    ref2 = eng.predict().cpu().numpy().copy()
+    for _ in range(100):
+        time.sleep(0.1)
+        if p8.model_info()["delta_updates"] >= 1:
+            break
+    b2 = p8.predict(d.numpy(), ids.numpy())
+    assert p8.model_info()["delta_version"] == 9 and np.abs(b2 - ref2).max() < 0.06
+    p16.close(); p8.close()
