@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restri
                                                    int64_t* __restrict__ ulist, int32_t* __restrict__ nunique, int64_t ulist_cap) {
   __shared__ int32_t s_pos[256];
   __shared__ int64_t s_key[256];
+  __shared__ TouchSmem s_touch;
   const int64_t n = (int64_t)nl * W * B;
   (void)step_ptr;
   for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restri
       }
       s_pos[threadIdx.x] = (int32_t)pos;
       s_key[threadIdx.x] = key;
-      if (train) table_touch_aggregated(TB, touch, pos, table_map[j], ulist, nunique, ulist_cap);
+      if (train) table_touch_block(tables, touch, pos, table_map[j], ulist, nunique, ulist_cap, s_touch);
     }
     __syncthreads();
     // ---- phase 2: LPR lanes per row copy fp32 row -> bf16 into the requester's buffer over NVLink

@@ -374,28 +374,6 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint8_t* my_aux = aux_base + ew * 4096;
     const uint32_t swz = (uint32_t)(lane & 7);
     int acc = 0; uint32_t acc_phase = 0;
-    // ---- aux-tile prefetch: the [32 x 64] aux block of this warp's NEXT chunk is loaded into registers while the current
-    //      chunk is processed, so its DRAM latency (the aux operand streams from HBM exactly once) never sits on the
-    //      epilogue's critical path.  Chunk ownership: c0 = half*64 + 128*j.
-    int4 pre[8];
-    auto first_chunk = [&](int tile) -> int {       // first chunk this warp owns in `tile`, or -1
-      const int c = half * 64;
-      return (c < BLOCK_N && (tile % n_tiles) * BLOCK_N + c < N) ? c : -1;
-    };
-    auto prefetch_aux = [&](int tile, int c0) {
-      const int r0 = (tile / n_tiles) * BLOCK_M + q * 32, cc0 = (tile % n_tiles) * BLOCK_N + c0;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3), ch = lane & 7;
-        pre[it] = make_int4(0, 0, 0, 0);
-        if (r0 + r < M && cc0 + ch * 8 < N) pre[it] = ld_nc_v4(ep.mask_src + (int64_t)(r0 + r) * ep.ld_mask + cc0 + ch * 8);
-      }
-    };
-    if (ep.mask_src) {
-      int t0 = blockIdx.x;
-      while (t0 < num_tiles && first_chunk(t0) < 0) t0 += gridDim.x;
-      if (t0 < num_tiles) prefetch_aux(t0, first_chunk(t0));
-    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -409,23 +387,17 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int col0 = n_blk * BLOCK_N + c0;
         if (col0 >= N) break;                           // warp-uniform
         if (((c0 >> 6) & 1) != half) continue;          // the sibling warp of this lane quarter owns this chunk
-        // ---- aux tile [32 rows x 64 cols]: prefetched registers -> swizzled smem (8 lanes cover one 128 B row segment),
-        //      then immediately issue the loads of the next owned chunk
+        // ---- aux tile [32 rows x 64 cols] -> swizzled smem (coalesced: 8 lanes cover one 128 B row segment)
         if (ep.mask_src) {
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + (lane >> 3), ch = lane & 7;
-            *reinterpret_cast<int4*>(my_aux + r * 128 + ((ch ^ (r & 7)) << 4)) = pre[it];
+            int4 val = make_int4(0, 0, 0, 0);
+            if (row0 + r < M && col0 + ch * 8 < N) val = ld_nc_v4(ep.mask_src + (int64_t)(row0 + r) * ep.ld_mask + col0 + ch * 8);
+            *reinterpret_cast<int4*>(my_aux + r * 128 + ((ch ^ (r & 7)) << 4)) = val;
           }
           __syncwarp();
-          int nt = tile, nc = c0 + 128;
-          if (!(nc < BLOCK_N && n_blk * BLOCK_N + nc < N)) {
-            nt = tile + gridDim.x;
-            while (nt < num_tiles && first_chunk(nt) < 0) nt += gridDim.x;
-            nc = nt < num_tiles ? first_chunk(nt) : -1;
-          }
-          if (nc >= 0) prefetch_aux(nt, nc);
         }
         // the staging buffer was handed to TMA one chunk ago: wait until it has been read
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

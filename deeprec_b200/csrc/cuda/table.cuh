@@ -148,6 +148,50 @@ __device__ __forceinline__ void table_touch_aggregated(const DrDeviceTable& TB, 
   }
 }
 
+// ---- block-aggregated variant ---------------------------------------------------------------------------------------
+// Same bookkeeping, aggregated over the whole 256-thread block through a small shared-memory hash: warp leaders (one per
+// distinct position in the warp) deposit (table, pos) -> count; after a barrier each shared entry performs ONE global
+// freq += count / dirty / claim.  A hot key (power-law ids, tiny tables) costs one global atomic per block iteration instead
+// of one per warp -- same-address L2 atomics serialise at ~14 ns each, which is what bounds the probe kernels on skewed data.
+// Every thread of the block must call it (it synchronises); invalid lanes pass valid = false.
+constexpr int kTouchSlots = 512;
+struct TouchSmem { unsigned long long key[kTouchSlots]; int32_t count[kTouchSlots]; };
+
+__device__ __forceinline__ void table_touch_block(const DrDeviceTable* __restrict__ tables, bool valid, int64_t pos, int table_index, int64_t* ulist,
+                                                  int32_t* nunique, int64_t ulist_cap, TouchSmem& sm) {
+  constexpr unsigned long long kNone = ~0ull;
+  for (int e = threadIdx.x; e < kTouchSlots; e += blockDim.x) { sm.key[e] = kNone; sm.count[e] = 0; }
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31;
+  const int64_t mkey = valid ? (((int64_t)table_index << 40) | pos) : -(int64_t)(lane + 1);
+  const unsigned same = __match_any_sync(0xffffffffu, mkey);
+  if (valid && (unsigned)(__ffs(same) - 1) == lane) {
+    uint32_t h = (uint32_t)(dr_mix64((uint64_t)mkey) >> 40) & (kTouchSlots - 1);
+    for (int probe = 0; probe < kTouchSlots; ++probe, h = (h + 1) & (kTouchSlots - 1)) {
+      const unsigned long long old = atomicCAS(&sm.key[h], kNone, (unsigned long long)mkey);
+      if (old == kNone || old == (unsigned long long)mkey) { atomicAdd(&sm.count[h], __popc(same)); break; }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kTouchSlots; e += blockDim.x) {
+    const unsigned long long k = sm.key[e];
+    if (k == kNone) continue;
+    const int t = (int)(k >> 40);
+    const int64_t p = (int64_t)(k & ((1ull << 40) - 1));
+    const DrDeviceTable& TB = tables[t];
+    atomicAdd(&TB.slots[p].freq, sm.count[e]);
+    int4 hi;                                                                            // {row_of, tag, dirty, pad}
+    asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(&TB.slots[p].row_of));
+    if (hi.z == 0) TB.slots[p].dirty = 1;
+    if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[p].tag, -1, -2) == -1) {
+      const int u = atomicAdd(nunique, 1);
+      if (u < ulist_cap) { ulist[u] = (int64_t)k; TB.slots[p].tag = u; }
+      else { TB.slots[p].tag = -1; TB.counters[CTR_OVERFLOW] = 2; }
+    }
+  }
+  __syncthreads();
+}
+
 // ---- per-block combining cache for gradient accumulation ----------------------------------------------------------------
 // Direct-mapped on the unique index u: s_tag[C] (init -1), s_acc[C * dim] (init 0).  A group of LPR lanes adds its float4
 // chunks either into the cached row (shared-memory atomics) or, on a slot conflict, straight into gsum with red.global.

@@ -30,9 +30,10 @@ __global__ void __launch_bounds__(256) k_lookup(const DrDeviceTable* __restrict_
                                                 int32_t* __restrict__ out_pos, int64_t* __restrict__ ulist,
                                                 int32_t* __restrict__ group_nunique, int64_t ulist_cap) {
   (void)step_ptr;
-  // whole warps iterate together (n rounded up to 32) so the warp-aggregated bookkeeping can use full-mask collectives
-  const int64_t n32 = (n + 31) & ~int64_t(31);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
+  __shared__ TouchSmem s_touch;
+  // whole blocks iterate together (n rounded up to the block size): the training bookkeeping is aggregated over the block
+  const int64_t nb = train ? (n + blockDim.x - 1) / blockDim.x * blockDim.x : n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
     const bool live = i < n;
     const int64_t ii = live ? i : n - 1;
     const int tl = seg_of(offsets, T, ii, uniform);
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) k_lookup(const DrDeviceTable* __restrict_
       }
       out_pos[i] = (int32_t)pos;
     }
-    if (train) table_touch_aggregated(TB, touch, pos, t, ulist, group_nunique, ulist_cap);
+    if (train) table_touch_block(tables, touch, pos, t, ulist, group_nunique, ulist_cap, s_touch);
   }
 }
 
