@@ -37,6 +37,7 @@ constexpr int kMaxChannels = 16;
 
 // signals layout (per rank, symmetric): uint32 flags[kMaxChannels][kMaxRanks]; epochs[kMaxChannels] lives in LOCAL memory
 __global__ void k_rank_barrier(DrPeers sig, uint32_t* __restrict__ epochs, int channel, int rank, int world) {
+  pdl_sync();
   __shared__ uint32_t epoch;
   if (threadIdx.x == 0) { epoch = epochs[channel] + 1; epochs[channel] = epoch; }
   __syncthreads();
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(256) k_mp_lookup(const DrDeviceTable* __restri
                                                    DrPeers emb_peers /* bf16 [T][B][D] */, int train,
                                                    const int64_t* __restrict__ step_ptr, int32_t* __restrict__ pos_out,
                                                    int64_t* __restrict__ ulist, int32_t* __restrict__ nunique, int64_t ulist_cap) {
+  pdl_sync();
   __shared__ int32_t s_pos[256];
   __shared__ int64_t s_key[256];
   __shared__ TouchSmem s_touch;
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(256) k_mp_sparse_grad(const DrDeviceTable* __r
                                                         const int32_t* __restrict__ table_global, int nl, int W, int64_t B,
                                                         DrPeers demb_peers /* bf16 [T][B][D] */, const int32_t* __restrict__ pos,
                                                         float* __restrict__ gsum, int C) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int dim = 4 * LPR;
   float* s_acc = reinterpret_cast<float*>(smem_raw);
@@ -178,6 +181,7 @@ __global__ void __launch_bounds__(256) k_mp_sparse_grad(const DrDeviceTable* __r
 __global__ void __launch_bounds__(256) k_allreduce_apply(DrPeers grad_peers, int W, float* __restrict__ w, float* __restrict__ s0,
                                                          float* __restrict__ s1, int64_t n4 /* n / 4 */, const DrOptHyper* __restrict__ hp_dev,
                                                          float* __restrict__ reduced_out) {
+  pdl_sync();
   DrOptHyper hp = {};
   if (hp_dev) hp = *hp_dev;
   const float alpha = hp_dev ? dr_adam_alpha(hp) : 0.f;
@@ -241,7 +245,7 @@ int dr_comm_close_handle(void* p) { DR_CUDA_CHECK(cudaIpcCloseMemHandle(p)); ret
 int dr_comm_can_access_peer(int dev, int peer) { int ok = 0; cudaDeviceCanAccessPeer(&ok, dev, peer); return ok; }
 
 int dr_comm_barrier(const DrPeers* sig, uint32_t* epochs, int channel, int rank, int world, cudaStream_t s) {
-  k_rank_barrier<<<1, 32, 0, s>>>(*sig, epochs, channel, rank, world);
+  DR_PDL_LAUNCH((k_rank_barrier), 1, 32, 0, s, *sig, epochs, channel, rank, world);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -253,11 +257,11 @@ int dr_comm_mp_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map,
   if (n == 0) return 0;
   int grid = grid_for(n, 256, kNumSMs * sparse_blocks_per_sm());
   switch (dim / 4) {
-    case 2: k_mp_lookup<2><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 4: k_mp_lookup<4><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 8: k_mp_lookup<8><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 16: k_mp_lookup<16><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
-    case 32: k_mp_lookup<32><<<grid, 256, 0, s>>>(tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 2: DR_PDL_LAUNCH((k_mp_lookup<2>), grid, 256, 0, s, tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 4: DR_PDL_LAUNCH((k_mp_lookup<4>), grid, 256, 0, s, tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 8: DR_PDL_LAUNCH((k_mp_lookup<8>), grid, 256, 0, s, tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 16: DR_PDL_LAUNCH((k_mp_lookup<16>), grid, 256, 0, s, tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
+    case 32: DR_PDL_LAUNCH((k_mp_lookup<32>), grid, 256, 0, s, tables_dev, table_map, table_global, row_flag, rank, nl, W, B, T, *ids_peers, *emb_peers, train, step_ptr, pos_out, ulist, nunique, ulist_cap); break;
     default: return -3;
   }
   DR_LAUNCH_CHECK();
@@ -273,11 +277,11 @@ int dr_comm_mp_sparse_grad(const DrDeviceTable* tables_dev, const int32_t* table
   const int C = combining_cache_slots(dim);
   const size_t smem = (size_t)C * dim * 4 + (size_t)C * 4;
   switch (lpr) {
-    case 2: k_mp_sparse_grad<2><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
-    case 4: k_mp_sparse_grad<4><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
-    case 8: k_mp_sparse_grad<8><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
-    case 16: k_mp_sparse_grad<16><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
-    case 32: k_mp_sparse_grad<32><<<grid, 256, smem, s>>>(tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 2: DR_PDL_LAUNCH((k_mp_sparse_grad<2>), grid, 256, smem, s, tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 4: DR_PDL_LAUNCH((k_mp_sparse_grad<4>), grid, 256, smem, s, tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 8: DR_PDL_LAUNCH((k_mp_sparse_grad<8>), grid, 256, smem, s, tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 16: DR_PDL_LAUNCH((k_mp_sparse_grad<16>), grid, 256, smem, s, tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
+    case 32: DR_PDL_LAUNCH((k_mp_sparse_grad<32>), grid, 256, smem, s, tables_dev, table_map, table_global, nl, W, B, *demb_peers, pos, gsum, C); break;
     default: return -3;
   }
   DR_LAUNCH_CHECK();
@@ -288,7 +292,7 @@ int dr_comm_mp_sparse_grad(const DrDeviceTable* tables_dev, const int32_t* table
 int dr_comm_allreduce_apply(const DrPeers* grad_peers, int W, float* w, float* s0, float* s1, int64_t n, const DrOptHyper* hp_dev,
                             float* reduced_out, cudaStream_t s) {
   if (n % 4) return -2;
-  k_allreduce_apply<<<grid_for(n / 4, 256, kNumSMs * 4), 256, 0, s>>>(*grad_peers, W, w, s0, s1, n / 4, hp_dev, reduced_out);
+  DR_PDL_LAUNCH((k_allreduce_apply), grid_for(n / 4, 256, kNumSMs * 4), 256, 0, s, *grad_peers, W, w, s0, s1, n / 4, hp_dev, reduced_out);
   DR_LAUNCH_CHECK();
   return 0;
 }

@@ -1,6 +1,7 @@
 // Common device helpers for the sm_100a kernel library: PTX wrappers (mbarrier, TMA, tcgen05,
 // system-scope acquire/release for NVLink peer signalling), small vector types, error macros.
 #pragma once
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,6 +29,21 @@
   } while (0)
 
 namespace drc {
+
+inline int& pdl_enabled() { static int v = [] { const char* e = getenv("DEEPREC_PDL"); return (e && e[0] == '0') ? 0 : 1; }(); return v; }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t dr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define DR_PDL_LAUNCH(kernel, grid, block, smem, stream, ...) drc::dr_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+
 
 constexpr int kNumSMs = 148;
 
@@ -58,6 +74,23 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   return v;
 }
 // streaming 16-byte accesses that do not pollute L1 (peer data is L2-bypassed anyway)
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// Kernels on the training-step path are launched with cudaLaunchAttributeProgrammaticStreamSerialization (dr_launch_pdl below):
+// the next kernel's CTAs may become resident and run their prologue (barrier init, TMEM alloc, descriptor prefetch, index
+// math) while the previous kernel drains.  griddepcontrol.wait blocks until the predecessor grid has completed and its
+// memory is visible, so NOTHING that touches global memory may precede pdl_sync() in such a kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// An early trigger lets the dependent grid's CTAs become resident while the primary still runs; measured on the DLRM step this
+// steals SM slots from the primary (-4 %), so the trigger is left implicit (at grid completion) unless DEEPREC_PDL_EARLY is built in.
+#ifdef DEEPREC_PDL_EARLY
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+#else
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); }
+#endif
+
+// pull a line into L2 without occupying a register / scoreboard slot (software prefetch for latency-bound streaming kernels)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int4 ld_nc_v4(const void* p) {
   int4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -106,6 +139,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// L2 prefetch of a tensor-map box: no shared memory, no barrier -- lets a producer run further ahead of the smem ring
+__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(desc), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

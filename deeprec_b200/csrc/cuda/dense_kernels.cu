@@ -17,6 +17,7 @@ namespace {
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_colstats(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ v,
                                                   int64_t B, int N, int64_t ldu, int64_t ldv, float* __restrict__ S1, float* __restrict__ S2) {
+  pdl_sync();
   const int tpr = N / 8;                         // threads per row
   const int rows_par = blockDim.x / tpr;         // rows processed in parallel by the block
   const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
@@ -66,6 +67,7 @@ __global__ void k_bn_finalize(float* __restrict__ S1, float* __restrict__ S2, in
                               const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                               float* __restrict__ running_var, float* __restrict__ mean, float* __restrict__ rstd,
                               float* __restrict__ scale, float* __restrict__ shift, int training) {
+  pdl_sync();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float m, var;
@@ -88,6 +90,7 @@ __global__ void k_bn_finalize(float* __restrict__ S1, float* __restrict__ S2, in
 __global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* __restrict__ a, int64_t B, int N, int64_t lda,
                                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                                   __nv_bfloat16* __restrict__ y, int64_t ldy) {
+  pdl_sync();
   const int tpr = N / 8;
   const int64_t total = B * tpr;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* __restric
 __global__ void k_bn_bwd_finalize(float* __restrict__ S1, float* __restrict__ S2, int N, float invB, const float* __restrict__ mean,
                                   const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                   float* __restrict__ c1, float* __restrict__ c2, float grad_accum_scale) {
+  pdl_sync();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float sdy = S1[n], sdya = S2[n];
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(256) k_head(const __nv_bfloat16* __restrict__ 
                                               float* __restrict__ prob, float* __restrict__ loss_sum, __nv_bfloat16* __restrict__ dh,
                                               float* __restrict__ dw, float* __restrict__ db, int relu_mask, int train,
                                               float* __restrict__ dbias_h /* [K]: sum_b dh[b,:] = bias grad of the layer producing h */) {
+  pdl_sync();
   constexpr int K = 256 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(256) k_head(const __nv_bfloat16* __restrict__ 
 // Weight packing: fp32 master W[N, Kp] -> bf16 W[N, Kp] and bf16 W^T[Kp, Np8]   (32x32 smem tile transpose)
 // -------------------------------------------------------------------------------------------------
 __global__ void k_pack_weights(const float* __restrict__ w, int N, int Kp, __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wt, int ldt) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -248,6 +254,7 @@ __global__ void k_pack_weights(const float* __restrict__ w, int N, int Kp, __nv_
 
 // fp32 [B, C] -> bf16 [B, Cp] zero padded
 __global__ void k_cast_pad(const float* __restrict__ x, int64_t B, int C, __nv_bfloat16* __restrict__ y, int Cp) {
+  pdl_sync();
   const int64_t total = B * Cp;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = i / Cp; int c = (int)(i % Cp);
@@ -272,6 +279,7 @@ __global__ void __launch_bounds__(256) k_bn_fold(const float* __restrict__ S1, c
                                                  float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift, int training,
                                                  const float* __restrict__ Wn, const float* __restrict__ bn, int Kp,
                                                  __nv_bfloat16* __restrict__ Wf, float* __restrict__ bf) {
+  pdl_sync();
   const int n = blockIdx.x;
   float part = 0.f;
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
@@ -308,6 +316,7 @@ __global__ void __launch_bounds__(256) k_bn_fold(const float* __restrict__ S1, c
 // dW[n,k] = G[n,k] * s[k] + db[n] * t[k]   (weight gradient of a layer whose input was a folded BatchNorm output)
 __global__ void __launch_bounds__(256) k_dw_fixup(float* __restrict__ dW, const float* __restrict__ db, const float* __restrict__ s,
                                                   const float* __restrict__ t, int N, int K, int Kp) {
+  pdl_sync();
   const int64_t total = (int64_t)N * Kp;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(i / Kp), k = (int)(i % Kp);
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_v2(const __nv_bfloat16* __
                                                          const float* __restrict__ rstd, const float* __restrict__ c1,
                                                          const float* __restrict__ c2, __nv_bfloat16* __restrict__ da, int relu_mask,
                                                          float* __restrict__ dbias) {
+  pdl_sync();
   const int tpr = N / 8;
   const int rows_par = blockDim.x / tpr;
   const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
@@ -396,7 +406,7 @@ int dr_cuda_colstats(const void* u, const void* v, int64_t B, int N, int64_t ldu
   if (N % 8 || N / 8 > 256) return -2;
   int tpr = N / 8; int rows_par = 256 / tpr;
   int grid = grid_for((B + rows_par - 1) / rows_par, 2, kNumSMs * 4);   // >= 2 row-groups per block
-  k_colstats<<<grid, 256, 2 * N * sizeof(float), s>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)v, B, N, ldu, ldv, S1, S2);
+  DR_PDL_LAUNCH((k_colstats), grid, 256, 2 * N * sizeof(float), s, (const __nv_bfloat16*)u, (const __nv_bfloat16*)v, B, N, ldu, ldv, S1, S2);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -404,21 +414,21 @@ int dr_cuda_colstats(const void* u, const void* v, int64_t B, int N, int64_t ldu
 int dr_cuda_bn_finalize(float* S1, float* S2, int N, int64_t B, const float* gamma, const float* beta, float eps, float momentum,
                         float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift, int training,
                         cudaStream_t s) {
-  k_bn_finalize<<<(N + 127) / 128, 128, 0, s>>>(S1, S2, N, 1.0f / (float)B, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, training);
+  DR_PDL_LAUNCH((k_bn_finalize), (N + 127) / 128, 128, 0, s, S1, S2, N, 1.0f / (float)B, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, training);
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_bn_apply(const void* a, int64_t B, int N, int64_t lda, const float* scale, const float* shift, void* y, int64_t ldy, cudaStream_t s) {
   if (N % 8) return -2;
-  k_bn_apply<<<grid_for(B * (N / 8), 256), 256, 0, s>>>((const __nv_bfloat16*)a, B, N, lda, scale, shift, (__nv_bfloat16*)y, ldy);
+  DR_PDL_LAUNCH((k_bn_apply), grid_for(B * (N / 8), 256), 256, 0, s, (const __nv_bfloat16*)a, B, N, lda, scale, shift, (__nv_bfloat16*)y, ldy);
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_bn_bwd_finalize(float* S1, float* S2, int N, int64_t B, const float* mean, const float* rstd, float* dgamma, float* dbeta,
                             float* c1, float* c2, float grad_accum_scale, cudaStream_t s) {
-  k_bn_bwd_finalize<<<(N + 127) / 128, 128, 0, s>>>(S1, S2, N, 1.0f / (float)B, mean, rstd, dgamma, dbeta, c1, c2, grad_accum_scale);
+  DR_PDL_LAUNCH((k_bn_bwd_finalize), (N + 127) / 128, 128, 0, s, S1, S2, N, 1.0f / (float)B, mean, rstd, dgamma, dbeta, c1, c2, grad_accum_scale);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -435,14 +445,14 @@ int dr_cuda_bn_bwd_apply(const void* dy, const void* a, int64_t B, int N, int64_
 int dr_cuda_bn_fold(const float* S1, const float* S2, int K, int64_t B, const float* gamma, const float* beta, float eps, float momentum,
                     float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift, int training,
                     const float* Wn, const float* bn, int Nn, int Kp, void* Wf, float* bf, cudaStream_t s) {
-  k_bn_fold<<<Nn, 256, 0, s>>>(S1, S2, K, 1.0f / (float)B, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift,
+  DR_PDL_LAUNCH((k_bn_fold), Nn, 256, 0, s, S1, S2, K, 1.0f / (float)B, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift,
                               training, Wn, bn, Kp, (__nv_bfloat16*)Wf, bf);
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_dw_fixup(float* dW, const float* db, const float* scale, const float* shift, int N, int K, int Kp, cudaStream_t s) {
-  k_dw_fixup<<<grid_for((int64_t)N * Kp, 256), 256, 0, s>>>(dW, db, scale, shift, N, K, Kp);
+  DR_PDL_LAUNCH((k_dw_fixup), grid_for((int64_t)N * Kp, 256), 256, 0, s, dW, db, scale, shift, N, K, Kp);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -452,7 +462,7 @@ int dr_cuda_bn_bwd_apply_v2(const void* dy, const void* a, int64_t B, int N, int
   if (N % 8 || N / 8 > 256) return -2;
   int tpr = N / 8; int rows_par = 256 / tpr;
   int grid = grid_for((B + rows_par - 1) / rows_par, 2, kNumSMs * 8);
-  k_bn_bwd_apply_v2<<<grid, 256, N * sizeof(float), s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a, B, N, ld, scale, mean, rstd, c1, c2,
+  DR_PDL_LAUNCH((k_bn_bwd_apply_v2), grid, 256, N * sizeof(float), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)a, B, N, ld, scale, mean, rstd, c1, c2,
                                                         (__nv_bfloat16*)da, relu_mask, dbias);
   DR_LAUNCH_CHECK();
   return 0;
@@ -461,7 +471,7 @@ int dr_cuda_bn_bwd_apply_v2(const void* dy, const void* a, int64_t B, int N, int
 int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, const float* bias, const float* labels, float inv_batch,
                  float* prob, float* loss_sum, void* dh, float* dw, float* db, int relu_mask, int train, float* dbias_h, cudaStream_t s) {
   int grid = grid_for((B + 7) / 8, 1, kNumSMs * 4);
-#define HEAD(R) k_head<R><<<grid, 256, 0, s>>>((const __nv_bfloat16*)h, ldh, B, w, bias, labels, inv_batch, prob, loss_sum, (__nv_bfloat16*)dh, dw, db, relu_mask, train, dbias_h)
+#define HEAD(R) DR_PDL_LAUNCH((k_head<R>), grid, 256, 0, s, (const __nv_bfloat16*)h, ldh, B, w, bias, labels, inv_batch, prob, loss_sum, (__nv_bfloat16*)dh, dw, db, relu_mask, train, dbias_h)
   if (K == 256) HEAD(1); else if (K == 512) HEAD(2); else if (K == 1024) HEAD(4); else return -2;
 #undef HEAD
   DR_LAUNCH_CHECK();
@@ -470,13 +480,13 @@ int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, c
 
 int dr_cuda_pack_weights(const float* w, int N, int Kp, void* wb, void* wt, int ldt, cudaStream_t s) {
   dim3 grid((Kp + 31) / 32, ((wt ? max(N, ldt) : N) + 31) / 32), block(32, 8);
-  k_pack_weights<<<grid, block, 0, s>>>(w, N, Kp, (__nv_bfloat16*)wb, (__nv_bfloat16*)wt, ldt);
+  DR_PDL_LAUNCH((k_pack_weights), grid, block, 0, s, w, N, Kp, (__nv_bfloat16*)wb, (__nv_bfloat16*)wt, ldt);
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_cast_pad(const float* x, int64_t B, int C, void* y, int Cp, cudaStream_t s) {
-  k_cast_pad<<<grid_for(B * Cp, 256), 256, 0, s>>>(x, B, C, (__nv_bfloat16*)y, Cp);
+  DR_PDL_LAUNCH((k_cast_pad), grid_for(B * Cp, 256), 256, 0, s, x, B, C, (__nv_bfloat16*)y, Cp);
   DR_LAUNCH_CHECK();
   return 0;
 }

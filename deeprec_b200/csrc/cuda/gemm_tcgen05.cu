@@ -112,6 +112,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_sync();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -266,7 +267,9 @@ struct SmemLayoutTN2 {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStoreBytes = 8 * 4096;          // 8 epilogue warps x [32 rows][128 B] staging
   static constexpr int kAuxBytes = 8 * 4096;            // 8 epilogue warps x [32 rows][128 B] aux tile
-  static constexpr int kTotal = kSt * kStageBytes + kStoreBytes + kAuxBytes + 1024 + 256;
+  static constexpr int kBiasCols = 1024;                // bias vector staged in smem once per CTA (N <= kBiasCols)
+  static constexpr int kBiasBytes = kBiasCols * 4;
+  static constexpr int kTotal = kSt * kStageBytes + kStoreBytes + kAuxBytes + kBiasBytes + 1024 + 256;
 };
 
 // lane c ends with the sum over the warp's 32 rows of column c (v is destroyed)
@@ -295,12 +298,15 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* store_base = smem + kSt * L::kStageBytes;
   uint8_t* aux_base = store_base + L::kStoreBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux_base + L::kAuxBytes);
+  float* s_bias = reinterpret_cast<float*>(aux_base + L::kAuxBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux_base + L::kAuxBytes + L::kBiasBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kSt;
   uint64_t* tfull_bar = bars + 2 * kSt;
   uint64_t* tempty_bar = bars + 2 * kSt + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 4);
+  // the epilogue's bias reads were its largest stall (global loads, long scoreboard, per 32-column half): stage the vector once
+  const bool smem_bias = ep.bias != nullptr && N <= L::kBiasCols;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -320,6 +326,11 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_sync();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel's tail
+  if (smem_bias) {   // (the bias may be produced by the previous kernel: BatchNorm folding)
+    for (int i = threadIdx.x; i < L::kBiasCols; i += blockDim.x) s_bias[i] = i < N ? ep.bias[i] : 0.f;
+    __syncthreads();
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -412,7 +423,13 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias) {
+          if (smem_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {      // broadcast ld.shared.v4 (columns >= N hold 0)
+              const float4 b = *reinterpret_cast<const float4*>(s_bias + colh + j);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          } else if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (colh + j < N) {
@@ -531,6 +548,7 @@ k_gemm_nt_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_sync();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel's tail
   if (num_kb <= 0) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem_base, kTmemCols); return; }
 
   if (warp == 0) {
@@ -616,7 +634,7 @@ int launch_tn(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_t
   int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;
   if (grid > max_ctas) grid = max_ctas;
-  k_gemm_tn<BN><<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, M, N, K, ep);
+  DR_PDL_LAUNCH((k_gemm_tn<BN>), grid, kGemmThreads, L::kTotal, s, ta, tb, M, N, K, ep);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -641,7 +659,7 @@ int launch_tn_v2(const CUtensorMap& ta, const void* B, int M, int N, int K, int6
   int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;
   if (grid > max_ctas) grid = max_ctas;
-  k_gemm_tn_v2<BN><<<grid, kGemmThreadsV2, L::kTotal, s>>>(ta, tb, tc, M, N, K, ep);
+  DR_PDL_LAUNCH((k_gemm_tn_v2<BN>), grid, kGemmThreadsV2, L::kTotal, s, ta, tb, tc, M, N, K, ep);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -657,7 +675,7 @@ int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, int Mo, int No, int 
   int rows_per_split = ((batch + splits - 1) / splits + BLOCK_KB - 1) / BLOCK_KB * BLOCK_KB;
   splits = (batch + rows_per_split - 1) / rows_per_split;
   dim3 grid((Mo + BLOCK_M - 1) / BLOCK_M, (No + BN - 1) / BN, splits);
-  k_gemm_nt_splitk<BN><<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, Mo, No, batch, rows_per_split, dW, ldw);
+  DR_PDL_LAUNCH((k_gemm_nt_splitk<BN>), grid, kGemmThreads, L::kTotal, s, ta, tb, Mo, No, batch, rows_per_split, dW, ldw);
   DR_LAUNCH_CHECK();
   return 0;
 }

@@ -205,6 +205,7 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t
 __global__ void __launch_bounds__(128) k_dot_fwd_tc(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ emb,
                                                     int64_t emb_stride_t, int64_t emb_stride_b, int T, int64_t B,
                                                     __nv_bfloat16* __restrict__ Z, int64_t ldz) {
+  pdl_sync();
   constexpr int D = 16;
   __shared__ __align__(128) uint8_t sA[128 * 32];          // [16 row-groups][2 K-chunks][8 rows][16 B]
   __shared__ __align__(16) __nv_bfloat16 sZ[4][512];
@@ -234,6 +235,9 @@ __global__ void __launch_bounds__(128) k_dot_fwd_tc(const __nv_bfloat16* __restr
       const __nv_bfloat16* src = lane == 0 ? x + bb * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + bb * emb_stride_b;
       r0 = ld_nc_v4(src); r1 = ld_nc_v4(src + 8);
     }
+    // two more groups ahead: L2 prefetch only (one group of register loads per warp cannot cover the DRAM latency)
+    const int64_t pb = (gg + 2 * (int64_t)gridDim.x) * 4 + warp;
+    if (lane < F && pb < B) prefetch_l2(lane == 0 ? x + pb * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + pb * emb_stride_b);
   };
   fetch(blockIdx.x, c0, c1);
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
                                                     int64_t ldx, const __nv_bfloat16* __restrict__ emb, int64_t emb_stride_t,
                                                     int64_t emb_stride_b, int T, int64_t B, __nv_bfloat16* __restrict__ dx, int64_t lddx,
                                                     __nv_bfloat16* __restrict__ demb, int64_t demb_stride_t, int64_t demb_stride_b) {
+  pdl_sync();
   constexpr int D = 16;
   extern __shared__ __align__(128) uint8_t dyn[];
   uint8_t* sA = dyn;                                   // blockdiag(S): [16 row-groups][16 K-chunks][8 rows][16 B] = 32 KB
@@ -317,6 +322,13 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
         const __nv_bfloat16* src = lane == 0 ? x + bb * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + bb * emb_stride_b;
         pf0 = ld_nc_v4(src); pf1 = ld_nc_v4(src + 8);
       }
+    }
+    // two more groups ahead: L2 prefetch only (one group of register loads per warp cannot cover the DRAM latency)
+    const int64_t pb = (gg + 2 * (int64_t)gridDim.x) * 4 + warp;
+    if (pb < B) {
+      if (lane * 8 < ldz) prefetch_l2(dZ + pb * ldz + lane * 8);
+      if (lane * 8 + 256 < ldz) prefetch_l2(dZ + pb * ldz + lane * 8 + 256);
+      if (lane < F) prefetch_l2(lane == 0 ? x + pb * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + pb * emb_stride_b);
     }
   };
   fetch(blockIdx.x);
@@ -414,7 +426,7 @@ int dr_cuda_dot_interaction_fwd(const void* x, int64_t ldx, const void* emb, int
   if (T + 1 > 32 || ldz > 512 || ldz % 8 || D + (T + 1) * T / 2 > ldz) return -2;
   if (D == 16 && !dot_force_simt()) {
     int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
-    k_dot_fwd_tc<<<g, 128, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz);
+    DR_PDL_LAUNCH((k_dot_fwd_tc), g, 128, 0, s, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz);
     DR_LAUNCH_CHECK();
     return 0;
   }
@@ -438,7 +450,7 @@ int dr_cuda_dot_interaction_bwd(const void* dZ, int64_t ldz, const void* x, int6
     static bool attr = false;
     if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_dot_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
     int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
-    k_dot_bwd_tc<<<g, 128, kSmem, s>>>((const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B,
+    DR_PDL_LAUNCH((k_dot_bwd_tc), g, 128, kSmem, s, (const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B,
                                        (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b);
     DR_LAUNCH_CHECK();
     return 0;

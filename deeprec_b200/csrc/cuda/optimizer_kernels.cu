@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const DrDeviceTable* __restr
                                                     int64_t stride_b, int64_t stride_t, int flat_in,
                                                     const int32_t* __restrict__ row_ids, const float* __restrict__ scale,
                                                     float* __restrict__ gsum, int C) {
+  pdl_sync();
   // per-block combining cache (see table.cuh): hot keys are reduced in shared memory and flushed once per block
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* s_acc = reinterpret_cast<float*>(smem_raw);
@@ -85,6 +86,7 @@ template <int LPR>
 __global__ void __launch_bounds__(256) k_apply(const DrDeviceTable* __restrict__ tables, const int64_t* __restrict__ ulist,
                                                const int32_t* __restrict__ n_unique_ptr, int64_t ulist_cap,
                                                float* __restrict__ gsum, int dim, const DrOptHyper* __restrict__ hp_dev) {
+  pdl_sync();
   const DrOptHyper hp = *hp_dev;      // device-resident so a captured CUDA graph sees the live step / beta powers
   const int lane = threadIdx.x % LPR;
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
@@ -194,10 +196,14 @@ __global__ void __launch_bounds__(256) k_apply(const DrDeviceTable* __restrict__
 }
 
 // reset of the per-step unique counter happens in a 1-thread tail so the whole step is graph-capturable
-__global__ void k_reset_counter(int32_t* c) { *c = 0; }
+__global__ void k_reset_counter(int32_t* c) {
+  pdl_sync();
+  *c = 0;
+}
 
 // end-of-step bookkeeping on the device: global_step += 1, Adam-family beta powers advance
 __global__ void k_advance_hyper(DrOptHyper* hp) {
+  pdl_sync();
   hp->global_step += 1;
   if (hp->kind == DR_OPT_ADAM || hp->kind == DR_OPT_ADAMW || hp->kind == DR_OPT_ADAM_ASYNC || hp->kind == DR_OPT_ADAM_ASYNC_RMSPROP) {
     hp->beta1_power *= hp->beta1;
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(256) k_dense_apply(float* __restrict__ w, cons
                                                      float* __restrict__ s0, float* __restrict__ s1, int64_t n,
                                                      const DrOptHyper* __restrict__ hp_dev, float grad_scale, int decay_now,
                                                      __nv_bfloat16* __restrict__ w_bf16) {
+  pdl_sync();
   const DrOptHyper hp = *hp_dev;
   const float alpha = dr_adam_alpha(hp);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -262,8 +269,8 @@ int dr_cuda_sparse_accumulate(const DrDeviceTable* tables_dev, const int32_t* ta
   const int C = combining_cache_slots(dim);
   const size_t smem = (size_t)C * dim * 4 + (size_t)C * 4;
 #define LAUNCH(L)                                                                                                  \
-  if (grad_bf16) k_accumulate<L, true><<<grid, 256, smem, s>>>(tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum, C); \
-  else k_accumulate<L, false><<<grid, 256, smem, s>>>(tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum, C);
+  if (grad_bf16) DR_PDL_LAUNCH((k_accumulate<L, true>), grid, 256, smem, s, tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum, C); \
+  else DR_PDL_LAUNCH((k_accumulate<L, false>), grid, 256, smem, s, tables_dev, table_map, T, dim, pos, offsets, uniform, n, grad, stride_b, stride_t, flat_in, row_ids, scale, gsum, C);
   switch (lpr) {
     case 1: LAUNCH(1) break; case 2: LAUNCH(2) break; case 4: LAUNCH(4) break; case 8: LAUNCH(8) break;
     case 16: LAUNCH(16) break; default: LAUNCH(32) break;
@@ -279,20 +286,20 @@ int dr_cuda_sparse_apply(const DrDeviceTable* tables_dev, const int64_t* ulist, 
   int lpr = lanes_for(dim);
   int grid = grid_for(max_unique * lpr, 256, kNumSMs * (sparse_blocks_per_sm() < 8 ? sparse_blocks_per_sm() : 8));
   switch (lpr) {
-    case 1: k_apply<1><<<grid, 256, 0, s>>>(tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
-    case 2: k_apply<2><<<grid, 256, 0, s>>>(tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
-    case 4: k_apply<4><<<grid, 256, 0, s>>>(tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
-    case 8: k_apply<8><<<grid, 256, 0, s>>>(tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
-    case 16: k_apply<16><<<grid, 256, 0, s>>>(tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
-    default: k_apply<32><<<grid, 256, 0, s>>>(tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
+    case 1: DR_PDL_LAUNCH((k_apply<1>), grid, 256, 0, s, tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
+    case 2: DR_PDL_LAUNCH((k_apply<2>), grid, 256, 0, s, tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
+    case 4: DR_PDL_LAUNCH((k_apply<4>), grid, 256, 0, s, tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
+    case 8: DR_PDL_LAUNCH((k_apply<8>), grid, 256, 0, s, tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
+    case 16: DR_PDL_LAUNCH((k_apply<16>), grid, 256, 0, s, tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
+    default: DR_PDL_LAUNCH((k_apply<32>), grid, 256, 0, s, tables_dev, ulist, n_unique_dev, ulist_cap, gsum, dim, hp_dev); break;
   }
   DR_LAUNCH_CHECK();
-  if (reset_counter) { k_reset_counter<<<1, 1, 0, s>>>(n_unique_dev); DR_LAUNCH_CHECK(); }
+  if (reset_counter) { DR_PDL_LAUNCH((k_reset_counter), 1, 1, 0, s, n_unique_dev); DR_LAUNCH_CHECK(); }
   return 0;
 }
 
 int dr_cuda_advance_hyper(DrOptHyper* hp_dev, cudaStream_t s) {
-  k_advance_hyper<<<1, 1, 0, s>>>(hp_dev);
+  DR_PDL_LAUNCH((k_advance_hyper), 1, 1, 0, s, hp_dev);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -300,7 +307,7 @@ int dr_cuda_advance_hyper(DrOptHyper* hp_dev, cudaStream_t s) {
 int dr_cuda_dense_apply(float* w, const float* grad, float* s0, float* s1, int64_t n, const DrOptHyper* hp_dev, float grad_scale,
                         int decay_now, void* w_bf16, cudaStream_t s) {
   if (n == 0) return 0;
-  k_dense_apply<<<grid_for(n, 256), 256, 0, s>>>(w, grad, s0, s1, n, hp_dev, grad_scale, decay_now, (__nv_bfloat16*)w_bf16);
+  DR_PDL_LAUNCH((k_dense_apply), grid_for(n, 256), 256, 0, s, w, grad, s0, s1, n, hp_dev, grad_scale, decay_now, (__nv_bfloat16*)w_bf16);
   DR_LAUNCH_CHECK();
   return 0;
 }

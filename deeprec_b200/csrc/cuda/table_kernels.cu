@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) k_lookup(const DrDeviceTable* __restrict_
                                                 int64_t uniform, int64_t n, int train, const int64_t* __restrict__ step_ptr,
                                                 int32_t* __restrict__ out_pos, int64_t* __restrict__ ulist,
                                                 int32_t* __restrict__ group_nunique, int64_t ulist_cap) {
+  pdl_sync();
   (void)step_ptr;
   __shared__ TouchSmem s_touch;
   // whole blocks iterate together (n rounded up to the block size): the training bookkeeping is aggregated over the block
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) k_gather(const DrDeviceTable* __restrict_
                                                 const int64_t* __restrict__ keys, const int32_t* __restrict__ pos,
                                                 const int64_t* __restrict__ offsets, int64_t uniform, int64_t n,
                                                 void* __restrict__ out, int64_t stride_b, int64_t stride_t, int flat_out) {
+  pdl_sync();
   const int lane = threadIdx.x % LPR;
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   const int64_t gstride = (int64_t)gridDim.x * blockDim.x / LPR;
@@ -303,7 +305,7 @@ int dr_cuda_table_lookup(const DrDeviceTable* tables_dev, const int32_t* table_m
                          int64_t n, int train, const int64_t* step_ptr, int32_t* out_pos, int64_t* ulist, int32_t* group_nunique,
                          int64_t ulist_cap, cudaStream_t s) {
   if (n == 0) return 0;
-  k_lookup<<<grid_for(n, 256), 256, 0, s>>>(tables_dev, table_map, T, keys, offsets, uniform, n, train, step_ptr, out_pos, ulist, group_nunique, ulist_cap);
+  DR_PDL_LAUNCH((k_lookup), grid_for(n, 256), 256, 0, s, tables_dev, table_map, T, keys, offsets, uniform, n, train, step_ptr, out_pos, ulist, group_nunique, ulist_cap);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -317,8 +319,8 @@ int dr_cuda_table_gather(const DrDeviceTable* tables_dev, const int32_t* table_m
   int lpr = 1; while (lpr < nvec && lpr < 32) lpr <<= 1;
   int grid = grid_for(n * lpr, 256);
 #define LAUNCH(L)                                                                                                      \
-  if (out_bf16) k_gather<L, true><<<grid, 256, 0, s>>>(tables_dev, table_map, T, keys, pos, offsets, uniform, n, out, stride_b, stride_t, flat_out); \
-  else k_gather<L, false><<<grid, 256, 0, s>>>(tables_dev, table_map, T, keys, pos, offsets, uniform, n, out, stride_b, stride_t, flat_out);
+  if (out_bf16) DR_PDL_LAUNCH((k_gather<L, true>), grid, 256, 0, s, tables_dev, table_map, T, keys, pos, offsets, uniform, n, out, stride_b, stride_t, flat_out); \
+  else DR_PDL_LAUNCH((k_gather<L, false>), grid, 256, 0, s, tables_dev, table_map, T, keys, pos, offsets, uniform, n, out, stride_b, stride_t, flat_out);
   switch (lpr) {
     case 1: LAUNCH(1) break; case 2: LAUNCH(2) break; case 4: LAUNCH(4) break; case 8: LAUNCH(8) break;
     case 16: LAUNCH(16) break; default: LAUNCH(32) break;
