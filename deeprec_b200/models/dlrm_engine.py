@@ -195,9 +195,11 @@ class DLRMEngine:
         self.owner_of = [-1] * self.T
         for i, t in enumerate(small):
             self.owner_of[t] = i % W
-        self.local_tables = sorted(self.row_tables + [t for t in small if self.owner_of[t] == self.rank])
-        self.row_flag = (torch.tensor([1 if t in self.row_tables else 0 for t in self.local_tables], dtype=torch.uint8, device=self.dev)
-                         if self.row_tables else None)
+        tw = sorted(t for t in small if self.owner_of[t] == self.rank)
+        self.n_tablewise = len(tw)
+        self.local_tables = tw + sorted(self.row_tables)          # table-wise tables first, then the row-sharded ones (comm_kernels.cu)
+        self.row_flag = None
+        self.row_tg = torch.tensor(sorted(self.row_tables) or [0], dtype=torch.int32, device=self.dev)
         self.ctx = get_context(self.dev, self.D, owner=id(self) & 0x7FFFFFFF)
         self.tables: Dict[int, DeviceTable] = {}
         g = torch.Generator().manual_seed(cfg.seed + 17)

@@ -45,8 +45,9 @@ def _bind(lib):
         "dr_comm_alloc": [i64, C.POINTER(vp)], "dr_comm_free": [P], "dr_comm_get_handle": [P, P],
         "dr_comm_open_handle": [P, C.POINTER(vp)], "dr_comm_close_handle": [P], "dr_comm_can_access_peer": [INT, INT],
         "dr_comm_barrier": [PP, P, INT, INT, INT, P],
-        "dr_comm_mp_lookup": [P, P, P, P, INT, INT, INT, i64, INT, INT, PP, PP, INT, P, P, P, P, i64, P],
-        "dr_comm_mp_sparse_grad": [P, P, P, INT, INT, i64, INT, PP, P, P, P],
+        "dr_comm_mp_partition": [P, P, INT, INT, i64, P, P, P, P],
+        "dr_comm_mp_lookup": [P, P, P, INT, INT, INT, INT, i64, INT, INT, PP, PP, PP, PP, PP, P, P, INT, P, P, P, P, i64, P],
+        "dr_comm_mp_sparse_grad": [P, P, P, INT, INT, INT, i64, INT, PP, P, P, P, P, P],
         "dr_comm_allreduce_apply": [PP, INT, P, P, P, i64, P, P, P],
     }
     for name, args in sigs.items():
@@ -149,6 +150,19 @@ class P2PComm:
         return (self.ids_buf.tensor(torch.int64, (T, B)), self.emb_buf.tensor(torch.bfloat16, (T, B, D)),
                 self.demb_buf.tensor(torch.bfloat16, (T, B, D)))
 
+    def alloc_row_dispatch(self, nr: int, B: int) -> None:
+        """Requester-side buckets for the row-sharded tables (ids grouped by owning rank, read by the owners over NVLink)."""
+        self.nr = nr
+        if nr == 0:
+            return
+        W = self.world
+        self.bkt_key = SymmetricBuffer(self, nr * W * B * 8)
+        self.bkt_b = SymmetricBuffer(self, nr * W * B * 4)
+        self.bkt_cnt = SymmetricBuffer(self, max(256, nr * W) * 4)
+        self.cnt_local = torch.zeros(nr * W, dtype=torch.int32, device=self.dev)
+        self.brow = torch.zeros(nr * W * B, dtype=torch.int32, device=self.dev)
+        dist.barrier(group=self.group)
+
     def barrier(self, channel: int) -> None:
         _chk(self.lib.dr_comm_barrier(self.signals.peers_ref(), ptr(self.epochs), channel, self.rank, self.world, self._s()), "barrier")
 
@@ -159,13 +173,22 @@ class P2PComm:
         return eng._table_global
 
     def lookup_forward(self, eng, train: bool) -> None:
-        nl, ctx = len(eng.local_tables), eng.ctx
+        nl, nr, ctx = eng.n_tablewise, len(eng.row_tables), eng.ctx
+        if not hasattr(self, "nr"):
+            self.alloc_row_dispatch(nr, eng.B)
+        if nr:
+            # dispatch: bucket my ids of the row-sharded tables by owner before everybody meets at barrier 0
+            _chk(self.lib.dr_comm_mp_partition(ptr(eng.ids), ptr(eng.row_tg), nr, self.world, eng.B, vp(self.bkt_key.local), vp(self.bkt_b.local),
+                                               vp(self.bkt_cnt.local), self._s()), "mp_partition")
+            eng.launches += 1
         self._tick("l0")
         self.barrier(0)
         self._tick("l1")
-        _chk(self.lib.dr_comm_mp_lookup(ptr(ctx.structs()), ptr(eng.tmap_local), ptr(self._tg(eng)), ptr(eng.row_flag) if eng.row_flag is not None else None,
-                                        self.rank, nl, self.world, eng.B, eng.T, eng.D,
-                                        self.ids_buf.peers_ref(), self.emb_buf.peers_ref(), int(train), eng.step_ptr, ptr(eng.pos),
+        _chk(self.lib.dr_comm_mp_lookup(ptr(ctx.structs()), ptr(eng.tmap_local), ptr(self._tg(eng)), self.rank, nl, nr, self.world, eng.B, eng.T, eng.D,
+                                        self.ids_buf.peers_ref(), self.emb_buf.peers_ref(),
+                                        self.bkt_key.peers_ref() if nr else None, self.bkt_b.peers_ref() if nr else None,
+                                        self.bkt_cnt.peers_ref() if nr else None, ptr(self.cnt_local) if nr else None, ptr(self.brow) if nr else None,
+                                        int(train), eng.step_ptr, ptr(eng.pos),
                                         ptr(ctx.ulist) if train else None, ptr(ctx.nuniq) if train else None,
                                         ctx.ulist.numel() if train else 0, self._s()), "mp_lookup")
         self._tick("l2")
@@ -174,12 +197,13 @@ class P2PComm:
         eng.launches += 3
 
     def sparse_backward(self, eng) -> None:
-        nl, ctx = len(eng.local_tables), eng.ctx
+        nl, nr, ctx = eng.n_tablewise, len(eng.row_tables), eng.ctx
         self._tick("s0")
         self.barrier(2)
         self._tick("s1")
-        _chk(self.lib.dr_comm_mp_sparse_grad(ptr(ctx.structs()), ptr(eng.tmap_local), ptr(self._tg(eng)), nl, self.world, eng.B, eng.D,
-                                             self.demb_buf.peers_ref(), ptr(eng.pos), ptr(ctx.gsum), self._s()), "mp_sparse_grad")
+        _chk(self.lib.dr_comm_mp_sparse_grad(ptr(ctx.structs()), ptr(eng.tmap_local), ptr(self._tg(eng)), nl, nr, self.world, eng.B, eng.D,
+                                             self.demb_buf.peers_ref(), ptr(eng.pos), ptr(self.cnt_local) if nr else None,
+                                             ptr(self.brow) if nr else None, ptr(ctx.gsum), self._s()), "mp_sparse_grad")
         self._tick("s2")
         _chk(self.lib.dr_cuda_sparse_apply(ptr(ctx.structs()), ptr(ctx.ulist), ptr(ctx.nuniq), ctx.ulist.numel(), ptr(ctx.gsum), eng.D,
                                            ptr(eng.hp_dev), eng.max_unique, 1, self._s()), "sparse_apply")
