@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--sparse-blocks", type=int, default=4, help="resident blocks/SM of the side-stream sparse kernels")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--gemm-v1", action="store_true")
+    ap.add_argument("--row-threshold", type=int, default=None, help="tables with >= this many ids are sharded row-wise over all ranks (default: engine default)")
     return ap.parse_args()
 
 
@@ -142,6 +143,8 @@ def main():
     from deeprec_b200.models.dlrm_engine import DLRMConfig, DLRMEngine
     cfg = DLRMConfig(batch_size=args.batch, optimizer=args.optimizer, sparse_blocks_per_sm=args.sparse_blocks,
                      overlap_embedding=not args.no_overlap, gemm_v1=args.gemm_v1)
+    if args.row_threshold is not None:
+        cfg.row_shard_threshold = args.row_threshold
     comm = None
     if world > 1:
         if args.impl == "nccl_baseline":

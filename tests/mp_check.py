@@ -40,12 +40,13 @@ def main():
     batches = [criteo_batch(cfg.batch_size, 13, cards, seed=100 * rank + s) for s in range(4)]
     results = {}
     import copy
-    for name in ("p2p", "nccl", "p2p_row"):
+    for name in ("p2p", "nccl", "p2p_row", "p2p_allrow"):
         comm = P2PComm(rank, world, dev) if name.startswith("p2p") else NcclComm(rank, world, dev)
         c = copy.deepcopy(cfg)
-        c.row_shard_threshold = 200 if name == "p2p_row" else 10 ** 12      # p2p_row: tables 1 and 3 are sharded row-wise over all ranks
+        # p2p_row: tables 1 and 3 are sharded row-wise over all ranks; p2p_allrow: every table is (requester-side bucketing only)
+        c.row_shard_threshold = {"p2p_row": 200, "p2p_allrow": 0}.get(name, 10 ** 12)
         eng = DLRMEngine(c, dev, rank, world, comm)
-        assert (len(eng.row_tables) == 2) == (name == "p2p_row")
+        assert len(eng.row_tables) == {"p2p_row": 2, "p2p_allrow": 26}.get(name, 0)
         losses = []
         for i, (d, ids, y) in enumerate(batches):
             eng.load_batch(d.to(dev), ids.to(dev), y.to(dev))
@@ -62,10 +63,11 @@ def main():
         results[name] = (losses, eng.params.clone(), rows, {t: eng.tables[t].size() for t in eng.local_tables}, int(total.item()))
         dist.barrier()
     (l1, p1, r1, s1, n1), (l2, p2, r2, s2, n2) = results["p2p"], results["nccl"]
-    l3, p3, _, _, n3 = results["p2p_row"]
-    for a, b in zip(l3, l2):
-        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), ("row-sharded", l3, l2)
-    assert (p3 - p2).abs().max().item() < 2e-3 and n3 == n2 == n1, (n1, n2, n3)
+    for variant in ("p2p_row", "p2p_allrow"):
+        l3, p3, _, _, n3 = results[variant]
+        for a, b in zip(l3, l2):
+            assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (variant, l3, l2)
+        assert (p3 - p2).abs().max().item() < 2e-3 and n3 == n2 == n1, (variant, n1, n2, n3)
     for a, b in zip(l1, l2):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (l1, l2)
     assert (p1 - p2).abs().max().item() < 2e-3, (p1 - p2).abs().max().item()
