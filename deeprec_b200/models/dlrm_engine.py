@@ -64,6 +64,7 @@ class DLRMConfig:
     seed: int = 1234
     overlap_embedding: bool = True              # fork the embedding branch onto a side stream inside the graph
     row_shard_threshold: int = 1_000_000        # world > 1: tables with >= this many ids are sharded row-wise (hash(key) % W) over ALL ranks
+    balance_tablewise: bool = True              # world > 1: also row-shard the largest remaining tables until #table-wise % world == 0
     sparse_blocks_per_sm: int = 4               # resident-block budget of the side-stream sparse kernels (overlap with the GEMMs)
     gemm_v1: bool = False                       # A/B switch: direct-store GEMM epilogue + separate statistics passes
 
@@ -192,6 +193,12 @@ class DLRMEngine:
         rs = getattr(self.comm, "supports_row_sharding", False) and W > 1
         self.row_tables = [t for t in range(self.T) if rs and cfg.cardinalities[t] >= cfg.row_shard_threshold]
         small = [t for t in range(self.T) if t not in self.row_tables]
+        if rs and cfg.balance_tablewise and len(small) % W:
+            # every table-wise table costs its owner W*B probes per step: an uneven count (e.g. 20 tables on 8 ranks = 3/3/3/3/2/2/2/2)
+            # makes the 3-table ranks the step's critical path at every barrier.  Row-shard the largest leftovers instead.
+            extra = sorted(small, key=lambda t: -int(cfg.cardinalities[t]))[: len(small) % W]
+            self.row_tables = sorted(self.row_tables + extra)
+            small = [t for t in small if t not in extra]
         self.owner_of = [-1] * self.T
         for i, t in enumerate(small):
             self.owner_of[t] = i % W

@@ -45,6 +45,7 @@ def main():
         c = copy.deepcopy(cfg)
         # p2p_row: tables 1 and 3 are sharded row-wise over all ranks; p2p_allrow: every table is (requester-side bucketing only)
         c.row_shard_threshold = {"p2p_row": 200, "p2p_allrow": 0}.get(name, 10 ** 12)
+        c.balance_tablewise = False          # exact control of the sharding in this check
         eng = DLRMEngine(c, dev, rank, world, comm)
         assert len(eng.row_tables) == {"p2p_row": 2, "p2p_allrow": 26}.get(name, 0)
         losses = []
