@@ -294,7 +294,52 @@ class EmbeddingVariable(nn.Module):
                 self._table = DeviceTable(cfg, self.default_matrix, self.device, owner=self._owner)
             else:
                 self._table = HostTable(cfg, self.default_matrix)
+            self._warm_start()
         return self._table
+
+    def _warm_start(self) -> None:
+        """``CheckpointOption`` (ops/variables.py:217-227, kv_variable_ops.py:636-705): initialise this variable from a tensor of
+        ANOTHER checkpoint (``ckpt_to_load_from`` + ``tensor_name_in_ckpt``; keys / values / freqs / versions, optimizer slots are
+        not taken over) or from an external ``init_data_source`` (a ``.pt`` / ``.npz`` file or a dict with ``keys`` and ``values``).
+        Runs once, when the table is first materialised, unless ``always_load_from_specific_ckpt`` asks for every re-creation."""
+        co = self.option.ckpt
+        if co is None or (getattr(self, "_warm_started", False) and not co.always_load_from_specific_ckpt):
+            return
+        keys = vals = freqs = vers = None
+        if co.ckpt_to_load_from:
+            from .checkpoint.saver import BundleReader, latest_checkpoint
+            import os
+            prefix = co.ckpt_to_load_from
+            if os.path.isdir(prefix):
+                prefix = latest_checkpoint(prefix) or prefix
+            r = BundleReader(prefix)
+            name = co.tensor_name_in_ckpt or self.name
+            if not r.has(f"{name}-keys"):
+                raise KeyError(f"checkpoint {prefix} has no EmbeddingVariable named {name!r}")
+            keys, vals = r.read(f"{name}-keys"), r.read(f"{name}-values")
+            freqs = r.read(f"{name}-freqs") if r.has(f"{name}-freqs") else None
+            vers = r.read(f"{name}-versions") if r.has(f"{name}-versions") else None
+            r.close()
+        elif co.init_data_source is not None:
+            src = co.init_data_source
+            if isinstance(src, str):
+                if src.endswith(".npz"):
+                    import numpy as np
+                    z = np.load(src)
+                    src = {k: torch.from_numpy(z[k]) for k in z.files}
+                else:
+                    src = torch.load(src)
+            keys, vals = torch.as_tensor(src["keys"]), torch.as_tensor(src["values"])
+            freqs, vers = src.get("freqs"), src.get("versions")
+        if keys is None:
+            return
+        if vals.shape[1] != self.embedding_dim:
+            raise ValueError(f"warm start of {self.name}: source dim {vals.shape[1]} != embedding_dim {self.embedding_dim}")
+        n = keys.numel()
+        self._table.import_(keys.to(torch.int64), vals.to(torch.float32).contiguous(),
+                            freqs if freqs is not None else torch.zeros(n, dtype=torch.int64),
+                            vers if vers is not None else torch.full((n,), -1, dtype=torch.int64))
+        self._warm_started = True
 
     def _set_slots(self, slot_names: Sequence[str], slot_init: Sequence[float], has_scalars: bool, owner: int = 0) -> None:
         """Called by the optimizer: reserve in-row optimizer slots (slot_creator.py:86-134).

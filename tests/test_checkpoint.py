@@ -1,6 +1,7 @@
 """Full / incremental checkpoint round trips, N->M re-shard, filtered keys, eviction-at-save (incr_ckpt_test.py analogue)."""
 import os
 
+import pytest
 import torch
 from torch import nn
 
@@ -103,3 +104,33 @@ def test_incremental_chain_recover(tmp_path):
     assert torch.equal(m.ev.table.lookup(probe), m2.ev.table.lookup(probe))
     assert torch.equal(m.ev.slot_values(probe, "accumulator"), m2.ev.slot_values(probe, "accumulator"))
     assert torch.allclose(m.fc.weight, m2.fc.weight)
+
+
+def test_checkpoint_option_warm_start_and_init_data_source(tmp_path):
+    """CheckpointOption: a new variable (different name, different optimizer) starts from another checkpoint's tensor; init_data_source
+    loads an external key/value table."""
+    import deeprec_b200 as dr
+    from deeprec_b200.checkpoint import Saver
+    from deeprec_b200.optim import GlobalStep
+    src = dr.get_embedding_variable("ws_src", 8, seed=4)
+    opt = dr.optim.AdagradOptimizer([], [src], lr=0.1, global_step=GlobalStep())
+    ids = torch.arange(0, 300, 3)
+    for _ in range(2):
+        opt.zero_grad(); (src.lookup(ids) ** 2).sum().backward(); opt.step()
+    prefix = Saver(embedding_variables=[src], optimizer=opt).save(str(tmp_path / "m.ckpt"), 2)
+    co = dr.CheckpointOption(ckpt_to_load_from=prefix, tensor_name_in_ckpt="ws_src")
+    dst = dr.get_embedding_variable("ws_dst", 8, ev_option=dr.EmbeddingVariableOption(ckpt=co), seed=99)
+    dr.optim.AdamOptimizer([], [dst], lr=0.01, global_step=GlobalStep())       # slots are created fresh, rows come from the checkpoint
+    assert dst.total_count() == src.total_count() == ids.numel()
+    assert torch.allclose(dst.lookup(ids).detach(), src.lookup(ids).detach()) and torch.equal(dst.get_frequency(ids), src.get_frequency(ids))
+    # directory form resolves the latest checkpoint; unknown tensor names fail loudly
+    dst2 = dr.get_embedding_variable("ws_src", 8, ev_option=dr.EmbeddingVariableOption(ckpt=dr.CheckpointOption(ckpt_to_load_from=str(tmp_path))), seed=5)
+    assert torch.allclose(dst2.lookup(ids).detach(), src.lookup(ids).detach())
+    bad = dr.get_embedding_variable("ws_bad", 8, ev_option=dr.EmbeddingVariableOption(ckpt=dr.CheckpointOption(ckpt_to_load_from=prefix, tensor_name_in_ckpt="nope")))
+    with pytest.raises(KeyError):
+        bad.lookup(ids)
+    # external source
+    table = {"keys": torch.tensor([5, 6, 7]), "values": torch.arange(24, dtype=torch.float32).view(3, 8)}
+    torch.save(table, tmp_path / "ext.pt")
+    ext = dr.get_embedding_variable("ws_ext", 8, ev_option=dr.EmbeddingVariableOption(ckpt=dr.CheckpointOption(init_data_source=str(tmp_path / "ext.pt"))))
+    assert torch.equal(ext.lookup(torch.tensor([6])).detach(), table["values"][1:2]) and ext.total_count() == 3
