@@ -378,7 +378,7 @@ class HostEV {
     GlobalPool()->ParallelFor(n, 2048, [&](int64_t b, int64_t e) {
       for (int64_t i = b; i < e; ++i) {
         int32_t idx = kv_.Find(keys[i]);
-        int32_t r = idx >= 0 ? *row_.at(idx) : -1;
+        int32_t r = idx >= 0 ? RowOf(idx) : -1;
         float* o = out + i * dim;
         if (r >= 0) {
           memcpy(o, rows_.at(r), dim * sizeof(float));
@@ -395,7 +395,7 @@ class HostEV {
     const int64_t dim = cfg_.dim;
     for (int64_t i = 0; i < n; ++i) {
       int32_t idx = kv_.Find(keys[i]);
-      int32_t r = idx >= 0 ? *row_.at(idx) : -1;
+      int32_t r = idx >= 0 ? RowOf(idx) : -1;
       float* o = out + i * dim;
       if (r >= 0) memcpy(o, rows_.at(r) + slot * dim, dim * sizeof(float));
       else std::fill(o, o + dim, slot == 0 ? 0.f : cfg_.slot_init[slot - 1]);
@@ -404,12 +404,12 @@ class HostEV {
   void GetFreq(const int64_t* keys, int64_t n, int64_t* out) {
     for (int64_t i = 0; i < n; ++i) {
       int32_t idx = kv_.Find(keys[i]);
-      if (idx >= 0) out[i] = *freq_.at(idx);
+      if (idx >= 0) out[i] = FreqOf(idx);
       else out[i] = bloom_ ? bloom_->Min(keys[i]) : 0;
     }
   }
   void GetVersion(const int64_t* keys, int64_t n, int64_t* out) {
-    for (int64_t i = 0; i < n; ++i) { int32_t idx = kv_.Find(keys[i]); out[i] = idx >= 0 ? *version_.at(idx) : -1; }
+    for (int64_t i = 0; i < n; ++i) { int32_t idx = kv_.Find(keys[i]); out[i] = idx >= 0 ? VersionOf(idx) : -1; }
   }
 
   // ---- LookupOrCreateKey with admission (counter_filter_policy.h:106-139) -------------
@@ -417,7 +417,7 @@ class HostEV {
   int32_t LookupOrCreate(int64_t key, int64_t count, int64_t step) {
     if (cfg_.is_inference) {
       int32_t idx = kv_.Find(key);
-      return idx >= 0 ? *row_.at(idx) : -1;
+      return idx >= 0 ? RowOf(idx) : -1;
     }
     if (bloom_) {
       int32_t idx = kv_.Find(key);
@@ -430,8 +430,8 @@ class HostEV {
     int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
     int64_t* f = freq_.at(idx);
     int64_t nf = __atomic_add_fetch(f, count, __ATOMIC_RELAXED);
-    *version_.at(idx) = step;
-    *dirty_.at(idx) = 1;
+    __atomic_store_n(version_.at(idx), step, __ATOMIC_RELAXED);
+    __atomic_store_n(dirty_.at(idx), (uint8_t)1, __ATOMIC_RELAXED);
     int32_t* rp = row_.at(idx);
     int32_t r = __atomic_load_n(rp, __ATOMIC_ACQUIRE);
     if (r >= 0) return r;
@@ -592,10 +592,10 @@ class HostEV {
     GlobalPool()->ParallelFor(n, 1024, [&](int64_t b, int64_t e) {
       for (int64_t i = b; i < e; ++i) {
         int32_t idx = kv_.Find(keys[i]);
-        int32_t r = idx >= 0 ? *row_.at(idx) : -1;
+        int32_t r = idx >= 0 ? RowOf(idx) : -1;
         found[i] = r >= 0;
-        freqs[i] = idx >= 0 ? *freq_.at(idx) : 0;
-        versions[i] = idx >= 0 ? *version_.at(idx) : -1;
+        freqs[i] = idx >= 0 ? FreqOf(idx) : 0;
+        versions[i] = idx >= 0 ? VersionOf(idx) : -1;
         if (r >= 0) memcpy(rows + i * stride_, rows_.at(r), stride_ * sizeof(float));
       }
     });
@@ -603,6 +603,11 @@ class HostEV {
   CountingBloom* bloom() { return bloom_.get(); }
 
  private:
+  // metadata cells are read by forward lookups while the training thread updates them: all shared accesses are atomic
+  // (acquire on the row index pairs with the release store that publishes an initialised row)
+  int32_t RowOf(int32_t idx) { return __atomic_load_n(row_.at(idx), __ATOMIC_ACQUIRE); }
+  int64_t FreqOf(int32_t idx) { return __atomic_load_n(freq_.at(idx), __ATOMIC_RELAXED); }
+  int64_t VersionOf(int32_t idx) { return __atomic_load_n(version_.at(idx), __ATOMIC_RELAXED); }
   const float* DefaultRow(int64_t key) const {
     return default_.data() + dr_default_row(key, std::max<int64_t>(1, cfg_.default_value_dim)) * cfg_.dim;
   }

@@ -1,0 +1,33 @@
+"""Builds tests/native/host_stress.cc against the host runtime sources with ThreadSanitizer (and AddressSanitizer) and runs it:
+the race-detection tier for the lock-free host structures."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRCS = [os.path.join(ROOT, "deeprec_b200", "csrc", "host", f) for f in ("host_engine.cc", "io_runtime.cc", "ssd_store.cc")]
+
+
+def _build_and_run(tmp_path, sanitizer):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / f"host_stress_{sanitizer}")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", f"-fsanitize={sanitizer}", "-fno-omit-frame-pointer", "-pthread",
+           os.path.join(ROOT, "tests", "native", "host_stress.cc"), *SRCS, "-o", exe]
+    b = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip(f"-fsanitize={sanitizer} unsupported here")
+    assert b.returncode == 0, b.stderr[-3000:]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 second_deadlock_stack=1", ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, str(tmp_path / "ssd")], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "HOST_STRESS_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
+
+
+def test_host_runtime_under_thread_sanitizer(tmp_path):
+    _build_and_run(tmp_path, "thread")
+
+
+def test_host_runtime_under_address_sanitizer(tmp_path):
+    _build_and_run(tmp_path, "address")
