@@ -21,7 +21,15 @@ def _build_and_run(tmp_path, sanitizer):
         pytest.skip(f"-fsanitize={sanitizer} unsupported here")
     assert b.returncode == 0, b.stderr[-3000:]
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 second_deadlock_stack=1", ASAN_OPTIONS="detect_leaks=0")
-    r = subprocess.run([exe, str(tmp_path / "ssd")], capture_output=True, text=True, timeout=900, env=env)
+    run = [exe, str(tmp_path / "ssd")]
+    if sanitizer == "thread" and shutil.which("setarch"):
+        run = ["setarch", "-R"] + run            # TSAN + ASLR: glibc's tpp.c assertion / shadow-memory mapping failures are environment noise
+    for attempt in range(3):
+        r = subprocess.run(run, capture_output=True, text=True, timeout=900, env=env)
+        if r.returncode == 0 or not ("tpp.c" in r.stderr or "unexpected memory mapping" in r.stderr):
+            break
+    else:
+        pytest.skip("ThreadSanitizer runtime is not usable in this environment (glibc / ASLR incompatibility)")
     assert r.returncode == 0 and "HOST_STRESS_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
 
 
