@@ -1,0 +1,294 @@
+"""Asynchronous parameter-server training (the reference's primary distributed mode: SURVEY §2.5 / §2.16 "DP, async (parameter
+server)", tensorflow/core/distributed_runtime/ + contrib/star_server pull/push semantics).
+
+Roles (one process each, ``torch.distributed.rpc`` / TensorPipe as the transport — no graph partitioning, no Send/Recv ops):
+
+  * ``ps{i}``      owns shard *i* of every EmbeddingVariable (``key % 1000 % num_ps``, the fixed_size_partitioner rule also used by the
+                   checkpoint re-sharding) and a slice of the dense parameters, together with the optimizer state.  Updates are
+                   applied the moment a worker pushes them: no barrier, no aggregation across workers (async SGD).
+  * ``worker{j}``  runs the model; embedding lookups are *pulls*, sparse and dense gradients are *pushes*.
+
+Transport optimisations kept from the reference:
+  * FuseRecv (``tensor_fuse``, base_rendezvous_mgr.h:178-185): all tables' lookups of a step travel in ONE RPC per PS
+    (``pull_many``), likewise all sparse gradients (``push_many``);
+  * SliceSend/SliceRecv (kernels/slice_sendrecv_ops.cc): dense tensors larger than ``slice_bytes`` are transferred in slices so a
+    huge parameter never needs one giant message (``pull_dense`` / ``push_dense``).
+
+The synchronous NVLink path (parallel/p2p.py) is the fast path on a B200 box; this module is the functional equivalent of the
+PS mode for CPU clusters / heterogeneous setups and for the reference's async-training semantics (stale reads, lock-free rows).
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed.rpc as rpc
+from torch import nn
+
+from ..config import EmbeddingVariableOption
+from ..embedding_variable import EmbeddingVariable, get_embedding_variable
+
+_SERVER: Optional["ParameterServer"] = None
+
+
+def ps_owner(keys: torch.Tensor, num_ps: int) -> torch.Tensor:
+    return torch.remainder(torch.remainder(keys.to(torch.int64), 1000), num_ps)
+
+
+class ParameterServer:
+    """State of one PS process.  All methods are invoked through RPC (module-level trampolines below)."""
+
+    def __init__(self, index: int, num_ps: int):
+        self.index, self.num_ps = index, num_ps
+        self.evs: Dict[str, EmbeddingVariable] = {}
+        self.opts: Dict[str, object] = {}
+        self.dense: Dict[str, torch.Tensor] = {}
+        self.dense_state: Dict[str, torch.Tensor] = {}
+        self.dense_lr = 0.01
+        self.lock = threading.Lock()            # guards creation / the dense block; rows rely on the engine's own lock-free paths
+        self.pushes = 0
+
+    # ---- variables ----------------------------------------------------------------------------------------------------
+    def create_ev(self, name: str, dim: int, optimizer: str, opt_kw: dict, option: Optional[EmbeddingVariableOption], seed: int) -> bool:
+        from ..optim.optimizers import GlobalStep, make_optimizer
+        with self.lock:
+            if name not in self.evs:
+                ev = get_embedding_variable(f"{name}/part_{self.index}", dim, ev_option=option, seed=seed)
+                self.evs[name] = ev
+                self.opts[name] = make_optimizer(optimizer, [], [ev], global_step=GlobalStep(), **opt_kw)
+        return True
+
+    def create_dense(self, name: str, value: torch.Tensor, lr: float) -> bool:
+        with self.lock:
+            if name not in self.dense:
+                self.dense[name] = value.clone()
+                self.dense_state[name] = torch.full_like(value, 0.1)      # Adagrad accumulator
+            self.dense_lr = lr
+        return True
+
+    # ---- pull / push ------------------------------------------------------------------------------------------------------
+    def pull_many(self, reqs: Sequence[Tuple[str, torch.Tensor]]) -> List[torch.Tensor]:
+        return [self.evs[n].table.lookup(ids) for n, ids in reqs]
+
+    def push_many(self, grads: Sequence[Tuple[str, torch.Tensor, torch.Tensor]]) -> int:
+        for name, ids, g in grads:
+            opt, ev = self.opts[name], self.evs[name]
+            with self.lock:              # one applier at a time per PS keeps the optimizer's step counter / beta powers coherent
+                ev._record_grad(ids, g)
+                opt.step()
+                self.pushes += 1
+        return self.pushes
+
+    def pull_dense(self, name: str, lo: int, hi: int) -> torch.Tensor:
+        return self.dense[name].view(-1)[lo:hi].clone()
+
+    def push_dense(self, name: str, lo: int, grad: torch.Tensor) -> bool:
+        with self.lock:
+            w, a = self.dense[name].view(-1), self.dense_state[name].view(-1)
+            hi = lo + grad.numel()
+            a[lo:hi] += grad * grad
+            w[lo:hi] -= self.dense_lr * grad / a[lo:hi].sqrt()
+        return True
+
+    def stats(self) -> Dict[str, int]:
+        return {n: int(e.total_count()) for n, e in self.evs.items()} | {"pushes": self.pushes}
+
+    def frequency(self, name: str, ids: torch.Tensor) -> torch.Tensor:
+        return self.evs[name].get_frequency(ids)
+
+    def save(self, prefix: str, step: int) -> str:
+        from ..checkpoint.saver import Saver
+        return Saver(embedding_variables=list(self.evs.values())).save(f"{prefix}.ps{self.index}", step)
+
+
+def _srv() -> ParameterServer:
+    if _SERVER is None:
+        raise RuntimeError("this process is not a parameter server (call run_ps first)")
+    return _SERVER
+
+
+# RPC trampolines (TensorPipe pickles functions by reference: they must be importable top-level names)
+def _rpc_create_ev(*a): return _srv().create_ev(*a)
+def _rpc_create_dense(*a): return _srv().create_dense(*a)
+def _rpc_pull_many(reqs): return _srv().pull_many(reqs)
+def _rpc_push_many(grads): return _srv().push_many(grads)
+def _rpc_pull_dense(*a): return _srv().pull_dense(*a)
+def _rpc_push_dense(*a): return _srv().push_dense(*a)
+def _rpc_stats(): return _srv().stats()
+def _rpc_frequency(*a): return _srv().frequency(*a)
+def _rpc_save(*a): return _srv().save(*a)
+
+
+def init_rpc(name: str, rank: int, world_size: int, master_port: int, master_addr: str = "127.0.0.1", threads: int = 8) -> None:
+    os.environ.setdefault("MASTER_ADDR", master_addr)
+    os.environ.setdefault("MASTER_PORT", str(master_port))
+    opts = rpc.TensorPipeRpcBackendOptions(num_worker_threads=threads, init_method=f"tcp://{master_addr}:{master_port}")
+    rpc.init_rpc(name, rank=rank, world_size=world_size, rpc_backend_options=opts)
+
+
+def run_ps(index: int, num_ps: int, num_workers: int, master_port: int, stats_path: Optional[str] = None) -> None:
+    """Body of a PS process: serve until every worker has shut down (optionally dump final statistics as JSON)."""
+    global _SERVER
+    _SERVER = ParameterServer(index, num_ps)
+    init_rpc(f"ps{index}", index, num_ps + num_workers, master_port)
+    rpc.shutdown()          # blocks until all workers called shutdown
+    if stats_path:
+        import json
+        with open(stats_path, "w") as f:
+            json.dump(_SERVER.stats(), f)
+
+
+class PSClient:
+    """Worker-side handle.  ``num_ps`` PS processes occupy RPC ranks [0, num_ps); this worker is rank num_ps + worker_index."""
+
+    def __init__(self, worker_index: int, num_ps: int, num_workers: int, master_port: int, slice_bytes: int = 4 << 20):
+        self.num_ps, self.worker_index, self.slice_elems = num_ps, worker_index, max(1, slice_bytes // 4)
+        init_rpc(f"worker{worker_index}", num_ps + worker_index, num_ps + num_workers, master_port)
+        self._pending: List = []
+
+    def shutdown(self) -> None:
+        self.wait()
+        rpc.shutdown()
+
+    def wait(self) -> None:
+        for f in self._pending:
+            f.wait()
+        self._pending = []
+
+    # ---- variables ------------------------------------------------------------------------------------------------------------
+    def create_embedding(self, name: str, dim: int, optimizer: str = "adagrad", option: Optional[EmbeddingVariableOption] = None,
+                         seed: int = 0, **opt_kw) -> "PSEmbedding":
+        for p in range(self.num_ps):
+            rpc.rpc_sync(f"ps{p}", _rpc_create_ev, args=(name, dim, optimizer, opt_kw, option, seed))
+        return PSEmbedding(self, name, dim)
+
+    def register_dense(self, module: nn.Module, lr: float = 0.01) -> None:
+        """Dense parameters live on PS (hash(name) % num_ps); every worker starts from the PS copy."""
+        self._dense = [(n, p) for n, p in module.named_parameters() if p.numel() > 0]
+        for n, p in self._dense:
+            rpc.rpc_sync(self._dense_owner(n), _rpc_create_dense, args=(n, p.detach().clone(), lr))
+        self.pull_dense()
+
+    def _dense_owner(self, name: str) -> str:
+        import zlib
+        return f"ps{zlib.crc32(name.encode()) % self.num_ps}"
+
+    # ---- FuseRecv-style batched pull / push ----------------------------------------------------------------------------------------
+    def pull_many(self, reqs: Sequence[Tuple[str, torch.Tensor]]) -> List[torch.Tensor]:
+        """One RPC per PS for ALL tables of the step; rows are stitched back into request order."""
+        per_ps: List[List[Tuple[str, torch.Tensor]]] = [[] for _ in range(self.num_ps)]
+        masks = []
+        for name, ids in reqs:
+            flat = ids.reshape(-1)
+            own = ps_owner(flat, self.num_ps)
+            ms = [own == p for p in range(self.num_ps)]
+            masks.append(ms)
+            for p in range(self.num_ps):
+                per_ps[p].append((name, flat[ms[p]]))
+        futs = [rpc.rpc_async(f"ps{p}", _rpc_pull_many, args=(per_ps[p],)) for p in range(self.num_ps)]
+        res = [f.wait() for f in futs]
+        out = []
+        for i, (name, ids) in enumerate(reqs):
+            dim = res[0][i].shape[1]
+            rows = torch.empty(ids.numel(), dim)
+            for p in range(self.num_ps):
+                rows[masks[i][p]] = res[p][i]
+            out.append(rows.view(*ids.shape, dim))
+        return out
+
+    def push_many(self, grads: Sequence[Tuple[str, torch.Tensor, torch.Tensor]], asynchronous: bool = True) -> None:
+        per_ps: List[List] = [[] for _ in range(self.num_ps)]
+        for name, ids, g in grads:
+            flat, g2 = ids.reshape(-1), g.reshape(-1, g.shape[-1])
+            own = ps_owner(flat, self.num_ps)
+            for p in range(self.num_ps):
+                m = own == p
+                if m.any():
+                    per_ps[p].append((name, flat[m], g2[m]))
+        for p in range(self.num_ps):
+            if per_ps[p]:
+                f = rpc.rpc_async(f"ps{p}", _rpc_push_many, args=(per_ps[p],))
+                self._pending.append(f) if asynchronous else f.wait()
+
+    # ---- SliceSend/Recv-style dense transfer --------------------------------------------------------------------------------------
+    def pull_dense(self) -> None:
+        for n, p in self._dense:
+            flat, owner = p.data.view(-1), self._dense_owner(n)
+            futs = [(lo, rpc.rpc_async(owner, _rpc_pull_dense, args=(n, lo, min(lo + self.slice_elems, flat.numel()))))
+                    for lo in range(0, flat.numel(), self.slice_elems)]
+            for lo, f in futs:
+                v = f.wait()
+                flat[lo: lo + v.numel()] = v
+
+    def push_dense(self) -> None:
+        for n, p in self._dense:
+            if p.grad is None:
+                continue
+            g, owner = p.grad.detach().view(-1), self._dense_owner(n)
+            for lo in range(0, g.numel(), self.slice_elems):
+                self._pending.append(rpc.rpc_async(owner, _rpc_push_dense, args=(n, lo, g[lo: lo + self.slice_elems].clone())))
+
+    def stats(self) -> List[Dict[str, int]]:
+        return [rpc.rpc_sync(f"ps{p}", _rpc_stats) for p in range(self.num_ps)]
+
+    def frequency(self, name: str, ids: torch.Tensor) -> torch.Tensor:
+        flat = ids.reshape(-1)
+        own = ps_owner(flat, self.num_ps)
+        out = torch.zeros(flat.numel(), dtype=torch.int64)
+        for p in range(self.num_ps):
+            m = own == p
+            if m.any():
+                out[m] = rpc.rpc_sync(f"ps{p}", _rpc_frequency, args=(name, flat[m]))
+        return out
+
+    def save(self, prefix: str, step: int) -> List[str]:
+        return [rpc.rpc_sync(f"ps{p}", _rpc_save, args=(prefix, step)) for p in range(self.num_ps)]
+
+
+class _PSLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, emb: "PSEmbedding", ids: torch.Tensor, rows: torch.Tensor):
+        ctx.emb, ctx.ids = emb, ids
+        return rows
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.emb._grads.append((ctx.ids, g.detach()))
+        return None, None, None, None
+
+
+class PSEmbedding(nn.Module):
+    """An EmbeddingVariable whose rows live on the parameter servers."""
+
+    def __init__(self, client: PSClient, name: str, dim: int):
+        super().__init__()
+        self.client, self.name, self.embedding_dim = client, name, dim
+        self._anchor = nn.Parameter(torch.zeros(0))
+        self._grads: List[Tuple[torch.Tensor, torch.Tensor]] = []
+
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        return group_pull(self.client, [self], [ids])[0]
+
+    def pop_grads(self) -> List[Tuple[str, torch.Tensor, torch.Tensor]]:
+        out = [(self.name, i, g) for i, g in self._grads]
+        self._grads = []
+        return out
+
+
+def group_pull(client: PSClient, embs: Sequence[PSEmbedding], ids: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Fused pull of several tables (one RPC per PS) returning autograd-tracked rows."""
+    rows = client.pull_many([(e.name, i) for e, i in zip(embs, ids)])
+    if torch.is_grad_enabled():
+        return [_PSLookup.apply(e._anchor, e, i, r) for e, i, r in zip(embs, ids, rows)]
+    return rows
+
+
+def push_gradients(client: PSClient, embs: Sequence[PSEmbedding], asynchronous: bool = True) -> None:
+    """Push every recorded sparse gradient (one fused RPC per PS) and the dense gradients; asynchronous by default."""
+    grads = [g for e in embs for g in e.pop_grads()]
+    if grads:
+        client.push_many(grads, asynchronous)
+    if getattr(client, "_dense", None):
+        client.push_dense()

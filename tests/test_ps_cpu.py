@@ -1,0 +1,85 @@
+"""Asynchronous parameter-server mode on CPU: 2 PS + 2 workers over torch.distributed.rpc."""
+import json
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+NUM_PS, NUM_WORKERS, STEPS = 2, 2, 6
+
+
+def _proc(rank, port, tmp):
+    torch.manual_seed(0)
+    from deeprec_b200.parallel import ps
+    if rank < NUM_PS:
+        ps.run_ps(rank, NUM_PS, NUM_WORKERS, port, stats_path=os.path.join(tmp, f"ps{rank}.json"))
+        return
+    j = rank - NUM_PS
+    client = ps.PSClient(j, NUM_PS, NUM_WORKERS, port, slice_bytes=64)       # tiny slices: the dense transfer is really sliced
+    user = client.create_embedding("user", 8, optimizer="adagrad", lr=0.1, seed=3)
+    item = client.create_embedding("item", 8, optimizer="adagrad", lr=0.1, seed=4)
+    dense = torch.nn.Linear(16, 1)
+    client.register_dense(dense, lr=0.05)
+    w0 = dense.weight.detach().clone()
+    g = torch.Generator().manual_seed(10 + j)
+    losses = []
+    for step in range(STEPS):
+        client.pull_dense()
+        uid = torch.randint(0, 50, (32,), generator=g); iid = torch.randint(0, 80, (32,), generator=g)
+        u, it = ps.group_pull(client, [user, item], [uid, iid])               # ONE rpc per PS for both tables
+        y = ((uid + iid) % 2).float()
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(dense(torch.cat([u, it], 1)).squeeze(-1), y)
+        dense.zero_grad(); loss.backward()
+        ps.push_gradients(client, [user, item])                              # asynchronous pushes, no barrier between workers
+        losses.append(loss.item())
+    client.wait()
+    client.pull_dense()
+    moved = (dense.weight.detach() - w0).abs().max().item()
+    # every id this worker used is now admitted somewhere, with frequency >= its own occurrence count
+    g = torch.Generator().manual_seed(10 + j)
+    mine_u = torch.cat([torch.randint(0, 50, (32,), generator=g) if k % 2 == 0 else torch.randint(0, 80, (32,), generator=g) for k in range(2 * STEPS)][0::2])
+    f = client.frequency("user", torch.unique(mine_u))
+    own_cnt = torch.bincount(mine_u, minlength=50)[torch.unique(mine_u)]
+    assert (f >= own_cnt).all(), (f, own_cnt)
+    if j == 0:
+        client.save(os.path.join(tmp, "ckpt"), STEPS)
+    with open(os.path.join(tmp, f"worker{j}.json"), "w") as fh:
+        json.dump({"losses": losses, "dense_moved": moved}, fh)
+    client.shutdown()
+
+
+def test_async_ps_training(tmp_path):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_proc, args=(r, port, str(tmp_path))) for r in range(NUM_PS + NUM_WORKERS)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0, "a PS/worker process failed"
+    stats = [json.load(open(tmp_path / f"ps{i}.json")) for i in range(NUM_PS)]
+    workers = [json.load(open(tmp_path / f"worker{j}.json")) for j in range(NUM_WORKERS)]
+    # rows are partitioned over the PS processes (key % 1000 % num_ps), both shards non-empty; every push was applied
+    assert all(s["user"] > 0 and s["item"] > 0 for s in stats)
+    assert sum(s["user"] for s in stats) <= 50 and sum(s["item"] for s in stats) <= 80
+    assert sum(s["pushes"] for s in stats) >= NUM_WORKERS * STEPS * 2
+    assert all(w["dense_moved"] > 0 and all(l == l for l in w["losses"]) for w in workers)
+    # the PS-side checkpoint holds exactly the admitted keys of each shard
+    from deeprec_b200.checkpoint.saver import BundleReader
+    import glob
+    n_user = 0
+    for i in range(NUM_PS):
+        prefix = glob.glob(str(tmp_path / f"ckpt.ps{i}-*.index"))[0][:-6]
+        r = BundleReader(prefix)
+        keys = r.read(f"user/part_{i}-keys")
+        assert ((keys % 1000 % NUM_PS) == i).all()
+        n_user += keys.numel()
+    assert n_user == sum(s["user"] for s in stats)
