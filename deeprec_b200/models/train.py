@@ -42,6 +42,7 @@ def get_arg_parser():
     p.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
     p.add_argument("--engine", action="store_true", help="DLRM through the fused sm_100a engine (models/dlrm_engine.py)")
     p.add_argument("--log_every", type=int, default=20)
+    p.add_argument("--watchdog", type=float, default=0, help="seconds without a finished step before the job dumps stacks and exits 86")
     return p
 
 
@@ -92,7 +93,7 @@ def main(argv=None) -> int:
 
     src = smart_stage(gen(), device=None) if a.smartstaged else gen()
     tr = Trainer(model, opt, loss_fn, a.checkpoint, save_checkpoint_steps=a.save_steps, save_incremental_checkpoint_secs=a.incremental_ckpt,
-                 log_every_n_steps=a.log_every, timeline_steps=a.timeline, micro_batch_num=a.micro_batch)
+                 log_every_n_steps=a.log_every, timeline_steps=a.timeline, micro_batch_num=a.micro_batch, watchdog_timeout_s=a.watchdog)
     t0 = time.time()
     tr.fit(src, a.steps)
     print(f"{a.steps * a.batch_size / (time.time() - t0):.0f} samples/s")

@@ -10,6 +10,7 @@ from typing import Callable, Iterable, Optional
 import torch
 
 from ..checkpoint.saver import IncrementalSaver, latest_checkpoint
+from .health import FaultInjector, StepWatchdog
 from .metrics import StreamingAccuracy, StreamingAUC
 from .tracing import Timeline
 
@@ -18,7 +19,7 @@ class Trainer:
     def __init__(self, model: torch.nn.Module, optimizer, loss_fn: Callable, checkpoint_dir: Optional[str] = None,
                  save_checkpoint_steps: int = 0, save_checkpoint_secs: float = 0, save_incremental_checkpoint_secs: float = 0,
                  save_incremental_checkpoint_steps: int = 0, log_every_n_steps: int = 100, timeline_steps: int = 0,
-                 micro_batch_num: int = 1, strategy=None, log: Callable[[str], None] = print):
+                 micro_batch_num: int = 1, strategy=None, log: Callable[[str], None] = print, watchdog_timeout_s: float = 0):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.dir = checkpoint_dir
         self.save_steps, self.save_secs = save_checkpoint_steps, save_checkpoint_secs
@@ -30,6 +31,8 @@ class Trainer:
         self.timeline = Timeline() if timeline_steps else None
         self.auc, self.acc = StreamingAUC(), StreamingAccuracy()
         self._last_save = self._last_incr = time.time()
+        self.watchdog = StepWatchdog(watchdog_timeout_s) if watchdog_timeout_s > 0 else None       # stalled step -> stacks + exit 86
+        self.faults = FaultInjector(rank=strategy.rank if strategy is not None else 0)            # DEEPREC_FAULT=step=..,kind=..
         if self.saver and checkpoint_dir and latest_checkpoint(checkpoint_dir):
             step = self.saver.recover_incr_checkpoints(checkpoint_dir)        # failover: last full + replay deltas
             self.log(f"restored from {checkpoint_dir} at global step {step}")
@@ -62,6 +65,9 @@ class Trainer:
             else:
                 loss = self.train_step(batch)
             step = int(self.opt.global_step)
+            if self.watchdog is not None:
+                self.watchdog.tick()
+            self.faults.maybe_fail(step)
             if self.log_every and step % self.log_every == 0:
                 dt = time.time() - t0
                 self.log(f"global_step {step}  loss {loss:.5f}  {(step - n0) / max(dt, 1e-9):.2f} global_step/sec")
