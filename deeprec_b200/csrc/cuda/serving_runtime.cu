@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../common/bundle.h"
+#include "../common/predict_pb.h"
 #include "table.cuh"
 
 // kernel launchers from the other translation units of this library
@@ -584,6 +585,30 @@ static void UpdaterLoop(ServingModel* sm) {
   }
 }
 
+
+// protobuf PredictRequest (reference predict.proto wire format) -> compact request -> Predict -> PredictResponse
+static int PredictProto(ServingModel* sm, const void* in, int in_size, void** out, int* out_size, int hint) {
+  auto m = std::atomic_load(&sm->model);
+  if (!m) return 500;
+  drpb::Request rq;
+  std::string wire, err, pb;
+  if (!drpb::ParseRequest(in, (size_t)in_size, &rq) || !drpb::RequestToWire(rq, m->arch.num_dense, m->arch.T, &wire, &err)) { sm->failures++; return 500; }
+  void* w_out = nullptr; int w_size = 0;
+  const int rc = Predict(sm, wire.data(), (int)wire.size(), &w_out, &w_size, hint);
+  if (rc != 200) { free(w_out); return rc; }
+  const bool ok = drpb::WireToResponse(w_out, (size_t)w_size, rq.output_filter, &pb);
+  free(w_out);
+  if (!ok) return 500;
+  *out_size = (int)pb.size();
+  *out = malloc(pb.size() ? pb.size() : 1);
+  memcpy(*out, pb.data(), pb.size());
+  return 200;
+}
+
+static int PredictAny(ServingModel* sm, const void* in, int in_size, void** out, int* out_size, int hint) {
+  return drpb::IsWireRequest(in, (size_t)std::max(in_size, 0)) ? Predict(sm, in, in_size, out, out_size, hint) : PredictProto(sm, in, in_size, out, out_size, hint);
+}
+
 }  // namespace serve
 
 extern "C" {
@@ -619,7 +644,7 @@ void* initialize(const char* model_entry, const char* model_config, int* state) 
 
 int process(void* model_buf, const void* input_data, int input_size, void** output_data, int* output_size) {
   if (!model_buf) return 500;
-  return serve::Predict(static_cast<serve::ServingModel*>(model_buf), input_data, input_size, output_data, output_size, -1);
+  return serve::PredictAny(static_cast<serve::ServingModel*>(model_buf), input_data, input_size, output_data, output_size, -1);
 }
 
 int batch_process(void* model_buf, const void* input_data[], int* input_size, void* output_data[], int* output_size) {
@@ -627,7 +652,7 @@ int batch_process(void* model_buf, const void* input_data[], int* input_size, vo
   if (!model_buf || !input_size) return 500;
   int n = input_size[0], rc = 200;
   for (int i = 0; i < n; ++i) {
-    int r = serve::Predict(static_cast<serve::ServingModel*>(model_buf), input_data[i], input_size[i + 1], &output_data[i], &output_size[i], i);
+    int r = serve::PredictAny(static_cast<serve::ServingModel*>(model_buf), input_data[i], input_size[i + 1], &output_data[i], &output_size[i], i);
     if (r != 200) rc = r;
   }
   return rc;

@@ -3,6 +3,7 @@ client SDK demos in serving/sdk/; this is the in-repo equivalent): FastAPI app w
 
   POST /v1/models/{name}:predict     JSON ``{"dense": [[...]], "ids": [[...]]}``  (ids feature-major [T][B], or sample-major with
                                      ``"ids_layout": "BT"``) -> ``{"predictions": [...], "model_version": v}``
+  POST /v1/models/{name}:predict_proto protobuf ``PredictRequest`` -> ``PredictResponse`` (wire format of the reference's predict.proto)
   POST /v1/models/{name}:predict_raw the binary wire format of ``process()`` (``encode_request`` / ``decode_response``) as-is
   GET  /v1/models/{name}             model / version / session information (``get_serving_model_info``)
   GET  /healthz                      liveness
@@ -32,7 +33,7 @@ class ServingBackend:
         return cls(proc.predict, proc.model_info, proc.process)
 
     @classmethod
-    def from_session_group(cls, group, to_inputs: Optional[Callable] = None, version: int = 0) -> "ServingBackend":
+    def from_session_group(cls, group, to_inputs: Optional[Callable] = None, version: int = 0, extra_info: Optional[dict] = None) -> "ServingBackend":
         import torch
 
         def predict(dense: np.ndarray, ids: np.ndarray) -> np.ndarray:
@@ -40,7 +41,7 @@ class ServingBackend:
             args = to_inputs(d, i) if to_inputs else (d, i)
             out = group.run(*args)
             return torch.sigmoid(out).reshape(-1).cpu().numpy()
-        return cls(predict, lambda: {"model_version": version, "sessions": len(group.sessions)})
+        return cls(predict, lambda: {"model_version": version, "sessions": len(group.sessions), **(extra_info or {})})
 
 
 def create_app(backends: Dict[str, ServingBackend]):
@@ -105,23 +106,50 @@ def create_app(backends: Dict[str, ServingBackend]):
         t0 = time.perf_counter()
         if be.process_raw is not None:
             rc, out = be.process_raw(payload)
-        else:                            # emulate the wire format on top of predict()
-            try:
-                import struct
-                magic, ver, b, nd, ns, _ = struct.unpack_from("<6I", payload, 0)
-                dense = np.frombuffer(payload, np.float32, b * nd, 24).reshape(b, nd)
-                ids = np.frombuffer(payload, np.int64, ns * b, 24 + 4 * b * nd).reshape(ns, b)
-                probs = be.predict(dense, ids).astype(np.float32)
-                out = struct.pack("<4Iq", 0x53525244, b, 200, 0, int(be.info().get("model_version", 0))) + probs.tobytes()
-                rc = 200
-            except Exception:
-                rc, out = 500, b""
+        else:
+            rc, out = _emulate_wire(be, payload)
         req_total.labels(name, str(rc)).inc()
         if rc == 200:
             latency.labels(name).observe(time.perf_counter() - t0)
         return Response(out, status_code=rc, media_type="application/octet-stream")
 
+    @app.post("/v1/models/{name}:predict_proto")
+    async def predict_proto(name: str, request: Request):
+        from . import predict_pb
+        be = _backend(name)
+        payload = await request.body()
+        t0 = time.perf_counter()
+        try:
+            if be.process_raw is not None:      # the native runtime parses protobuf itself
+                rc, out = be.process_raw(payload)
+            else:
+                info = be.info()
+                wire = predict_pb.request_to_wire(payload, int(info["num_dense"]), int(info["num_sparse"]))
+                rc, out = _emulate_wire(be, wire)
+                if rc == 200:
+                    out = predict_pb.response_from_wire(out, payload)
+        except (KeyError, ValueError) as e:
+            req_total.labels(name, "400").inc()
+            raise HTTPException(status_code=400, detail=str(e))
+        req_total.labels(name, str(rc)).inc()
+        if rc == 200:
+            latency.labels(name).observe(time.perf_counter() - t0)
+        return Response(out, status_code=rc, media_type="application/x-protobuf")
+
     return app
+
+
+def _emulate_wire(be: "ServingBackend", payload: bytes):
+    """The compact wire format on top of a ``predict()`` callable (backends without a native ``process``)."""
+    import struct
+    try:
+        magic, ver, b, nd, ns, _ = struct.unpack_from("<6I", payload, 0)
+        dense = np.frombuffer(payload, np.float32, b * nd, 24).reshape(b, nd)
+        ids = np.frombuffer(payload, np.int64, ns * b, 24 + 4 * b * nd).reshape(ns, b)
+        probs = np.asarray(be.predict(dense, ids), dtype=np.float32)
+        return 200, struct.pack("<4Iq", 0x53525244, b, 200, 0, int(be.info().get("model_version", 0))) + probs.tobytes()
+    except Exception:
+        return 500, b""
 
 
 def serve(backends: Dict[str, ServingBackend], host: str = "127.0.0.1", port: int = 8500, **uvicorn_kw) -> None:
@@ -140,6 +168,12 @@ class HttpClient:
         r = self.http.post(f"{self.url}/v1/models/{self.model}:predict", json={"dense": np.asarray(dense).tolist(), "ids": np.asarray(ids).tolist()})
         r.raise_for_status()
         return np.asarray(r.json()["predictions"], dtype=np.float32)
+
+    def predict_proto(self, dense: np.ndarray, ids: np.ndarray, per_feature: bool = False) -> np.ndarray:
+        from .predict_pb import decode_predict_response, encode_predict_request
+        r = self.http.post(f"{self.url}/v1/models/{self.model}:predict_proto", data=encode_predict_request(dense, ids, per_feature=per_feature))
+        r.raise_for_status()
+        return decode_predict_response(r.content)[0]
 
     def predict_raw(self, dense: np.ndarray, ids: np.ndarray) -> np.ndarray:
         r = self.http.post(f"{self.url}/v1/models/{self.model}:predict_raw", data=encode_request(dense, ids))

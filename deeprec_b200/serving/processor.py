@@ -69,6 +69,13 @@ class Processor:
             raise RuntimeError(f"process returned {rc}")
         return decode_response(data)[0]
 
+    def predict_proto(self, request_pb: bytes) -> bytes:
+        """PredictRequest protobuf bytes -> PredictResponse protobuf bytes (the runtime's ``process`` accepts both encodings)."""
+        rc, data = self.process(request_pb)
+        if rc != 200:
+            raise RuntimeError(f"process returned {rc}")
+        return data
+
     def batch_process(self, requests: Sequence[bytes]) -> Tuple[int, List[bytes]]:
         n = len(requests)
         bufs = [C.create_string_buffer(r, len(r)) for r in requests]
