@@ -14,6 +14,13 @@ Transport optimisations kept from the reference:
   * SliceSend/SliceRecv (kernels/slice_sendrecv_ops.cc): dense tensors larger than ``slice_bytes`` are transferred in slices so a
     huge parameter never needs one giant message (``pull_dense`` / ``push_dense``).
 
+Elastic scaling (contrib/elastic_grpc_server: ``ElasticTrainingService{IsReadyScaling, ReadyToUpdate, UpdateServerDef,
+FetchParamsMeta}``, elastic_training.proto:71-76): the job starts ``num_ps`` PS processes of which the first ``active_ps`` own
+shards.  ``PSClient.scale(n)`` quiesces the servers, moves every row whose owner changes under ``key % 1000 % n`` directly
+PS -> PS (rows + optimizer slots + freq / version: ``ExportAndRemove`` / ``RestoreFromKeysAndValues``), then publishes the new
+server definition; other workers notice the bumped definition version on their next pull / push (the PS rejects requests made
+under a stale definition) and re-route transparently.
+
 The synchronous NVLink path (parallel/p2p.py) is the fast path on a B200 box; this module is the functional equivalent of the
 PS mode for CPU clusters / heterogeneous setups and for the reference's async-training semantics (stale reads, lock-free rows).
 """
@@ -31,6 +38,11 @@ from ..config import EmbeddingVariableOption
 from ..embedding_variable import EmbeddingVariable, get_embedding_variable
 
 _SERVER: Optional["ParameterServer"] = None
+STALE_DEF = "StaleServerDef"
+
+
+class _StaleServerDef(Exception):
+    pass
 
 
 def ps_owner(keys: torch.Tensor, num_ps: int) -> torch.Tensor:
@@ -40,8 +52,12 @@ def ps_owner(keys: torch.Tensor, num_ps: int) -> torch.Tensor:
 class ParameterServer:
     """State of one PS process.  All methods are invoked through RPC (module-level trampolines below)."""
 
-    def __init__(self, index: int, num_ps: int):
+    def __init__(self, index: int, num_ps: int, active_ps: Optional[int] = None):
         self.index, self.num_ps = index, num_ps
+        self.active = num_ps if active_ps is None else active_ps      # the first ``active`` PS own shards
+        self.def_version = 0                                          # bumped by UpdateServerDef
+        self.frozen = False                                           # rows are moving: every pull / push is turned away
+        self.ev_specs: Dict[str, tuple] = {}
         self.evs: Dict[str, EmbeddingVariable] = {}
         self.opts: Dict[str, object] = {}
         self.dense: Dict[str, torch.Tensor] = {}
@@ -58,6 +74,7 @@ class ParameterServer:
                 ev = get_embedding_variable(f"{name}/part_{self.index}", dim, ev_option=option, seed=seed)
                 self.evs[name] = ev
                 self.opts[name] = make_optimizer(optimizer, [], [ev], global_step=GlobalStep(), **opt_kw)
+                self.ev_specs[name] = (dim, optimizer, dict(opt_kw), option, seed)
         return True
 
     def create_dense(self, name: str, value: torch.Tensor, lr: float) -> bool:
@@ -69,10 +86,19 @@ class ParameterServer:
         return True
 
     # ---- pull / push ------------------------------------------------------------------------------------------------------
-    def pull_many(self, reqs: Sequence[Tuple[str, torch.Tensor]]) -> List[torch.Tensor]:
+    def _stale(self, def_version: Optional[int]) -> bool:
+        """Requests made while rows are moving, or under an outdated server definition, are turned away (the reply is the
+        ``STALE_DEF`` marker, not an exception: it is an expected event during scaling)."""
+        return self.frozen or (def_version is not None and def_version != self.def_version)
+
+    def pull_many(self, reqs: Sequence[Tuple[str, torch.Tensor]], def_version: Optional[int] = None):
+        if self._stale(def_version):
+            return STALE_DEF
         return [self.evs[n].table.lookup(ids) for n, ids in reqs]
 
-    def push_many(self, grads: Sequence[Tuple[str, torch.Tensor, torch.Tensor]]) -> int:
+    def push_many(self, grads: Sequence[Tuple[str, torch.Tensor, torch.Tensor]], def_version: Optional[int] = None):
+        if self._stale(def_version):
+            return STALE_DEF
         for name, ids, g in grads:
             opt, ev = self.opts[name], self.evs[name]
             with self.lock:              # one applier at a time per PS keeps the optimizer's step counter / beta powers coherent
@@ -95,6 +121,46 @@ class ParameterServer:
     def stats(self) -> Dict[str, int]:
         return {n: int(e.total_count()) for n, e in self.evs.items()} | {"pushes": self.pushes}
 
+    # ---- elastic scaling (ElasticTrainingService) ----------------------------------------------------------------------------------
+    def server_def(self) -> Tuple[int, int]:
+        return self.active, self.def_version
+
+    def is_ready_scaling(self) -> bool:
+        """IsReadyScaling: stop admitting pulls / pushes; applies are synchronous under ``lock``, so once it is ours nothing is
+        in flight and rows can move."""
+        with self.lock:
+            self.frozen = True
+            return True
+
+    def fetch_params_meta(self) -> Dict[str, Tuple[int, int]]:
+        """FetchParamsMeta: {variable: (dim, rows held by this PS)}."""
+        return {n: (e.embedding_dim, int(e.total_count())) for n, e in self.evs.items()}
+
+    def scale_export(self, new_active: int) -> int:
+        """ReadyToUpdate on an old owner: ship every row whose owner changes straight to its new PS; returns #rows moved."""
+        from .elastic import export_and_remove
+        moved = 0
+        with self.lock:
+            keep = self.index if self.index < new_active else -1
+            for name, ev in self.evs.items():
+                parts = export_and_remove(ev, keep, new_active, ps_owner)
+                for dst, part in enumerate(parts):
+                    if dst != keep and part["keys"].numel():
+                        moved += rpc.rpc_sync(f"ps{dst}", _rpc_scale_import, args=(name, self.ev_specs[name], part))
+        return moved
+
+    def scale_import(self, name: str, spec: tuple, part: Dict[str, torch.Tensor]) -> int:
+        from .elastic import restore_from_keys_and_values
+        if name not in self.evs:                  # a PS that joins the active set learns the variable from the sender
+            self.create_ev(name, *spec)
+        return restore_from_keys_and_values(self.evs[name], part)      # full-stride rows: embedding + optimizer slots
+
+    def update_server_def(self, new_active: int, def_version: int) -> bool:
+        """UpdateServerDef: from now on requests must be made under ``def_version``."""
+        with self.lock:
+            self.active, self.def_version, self.frozen = new_active, def_version, False
+        return True
+
     def frequency(self, name: str, ids: torch.Tensor) -> torch.Tensor:
         return self.evs[name].get_frequency(ids)
 
@@ -112,8 +178,14 @@ def _srv() -> ParameterServer:
 # RPC trampolines (TensorPipe pickles functions by reference: they must be importable top-level names)
 def _rpc_create_ev(*a): return _srv().create_ev(*a)
 def _rpc_create_dense(*a): return _srv().create_dense(*a)
-def _rpc_pull_many(reqs): return _srv().pull_many(reqs)
-def _rpc_push_many(grads): return _srv().push_many(grads)
+def _rpc_pull_many(*a): return _srv().pull_many(*a)
+def _rpc_push_many(*a): return _srv().push_many(*a)
+def _rpc_server_def(): return _srv().server_def()
+def _rpc_is_ready_scaling(): return _srv().is_ready_scaling()
+def _rpc_fetch_params_meta(): return _srv().fetch_params_meta()
+def _rpc_scale_export(*a): return _srv().scale_export(*a)
+def _rpc_scale_import(*a): return _srv().scale_import(*a)
+def _rpc_update_server_def(*a): return _srv().update_server_def(*a)
 def _rpc_pull_dense(*a): return _srv().pull_dense(*a)
 def _rpc_push_dense(*a): return _srv().push_dense(*a)
 def _rpc_stats(): return _srv().stats()
@@ -128,10 +200,12 @@ def init_rpc(name: str, rank: int, world_size: int, master_port: int, master_add
     rpc.init_rpc(name, rank=rank, world_size=world_size, rpc_backend_options=opts)
 
 
-def run_ps(index: int, num_ps: int, num_workers: int, master_port: int, stats_path: Optional[str] = None) -> None:
-    """Body of a PS process: serve until every worker has shut down (optionally dump final statistics as JSON)."""
+def run_ps(index: int, num_ps: int, num_workers: int, master_port: int, stats_path: Optional[str] = None,
+           active_ps: Optional[int] = None) -> None:
+    """Body of a PS process: serve until every worker has shut down (optionally dump final statistics as JSON).
+    ``active_ps`` < ``num_ps`` starts with spare servers that ``PSClient.scale`` can bring in later."""
     global _SERVER
-    _SERVER = ParameterServer(index, num_ps)
+    _SERVER = ParameterServer(index, num_ps, active_ps)
     init_rpc(f"ps{index}", index, num_ps + num_workers, master_port)
     rpc.shutdown()          # blocks until all workers called shutdown
     if stats_path:
@@ -143,24 +217,64 @@ def run_ps(index: int, num_ps: int, num_workers: int, master_port: int, stats_pa
 class PSClient:
     """Worker-side handle.  ``num_ps`` PS processes occupy RPC ranks [0, num_ps); this worker is rank num_ps + worker_index."""
 
-    def __init__(self, worker_index: int, num_ps: int, num_workers: int, master_port: int, slice_bytes: int = 4 << 20):
-        self.num_ps, self.worker_index, self.slice_elems = num_ps, worker_index, max(1, slice_bytes // 4)
+    def __init__(self, worker_index: int, num_ps: int, num_workers: int, master_port: int, slice_bytes: int = 4 << 20,
+                 active_ps: Optional[int] = None):
+        self.total_ps = num_ps                                  # processes in the job (dense parameters hash over all of them)
+        self.num_ps = num_ps if active_ps is None else active_ps  # servers that currently own embedding shards
+        self.def_version = 0
+        self.worker_index, self.slice_elems = worker_index, max(1, slice_bytes // 4)
         init_rpc(f"worker{worker_index}", num_ps + worker_index, num_ps + num_workers, master_port)
         self._pending: List = []
+
+    # ---- elastic scaling ---------------------------------------------------------------------------------------------------------
+    def refresh_server_def(self) -> None:
+        self.num_ps, self.def_version = rpc.rpc_sync("ps0", _rpc_server_def)
+
+    def fetch_params_meta(self) -> List[Dict[str, Tuple[int, int]]]:
+        return [rpc.rpc_sync(f"ps{p}", _rpc_fetch_params_meta) for p in range(self.total_ps)]
+
+    def scale(self, new_active_ps: int) -> int:
+        """Change the number of PS that own embedding shards (1 <= n <= total).  Returns the number of rows that moved."""
+        if not 1 <= new_active_ps <= self.total_ps:
+            raise ValueError(f"new_active_ps must be in [1, {self.total_ps}]")
+        self.wait()
+        self.refresh_server_def()
+        old = self.num_ps
+        if new_active_ps == old:
+            return 0
+        for p in range(self.total_ps):                                               # IsReadyScaling: fence every server
+            assert rpc.rpc_sync(f"ps{p}", _rpc_is_ready_scaling)
+        moved = sum(rpc.rpc_sync(f"ps{p}", _rpc_scale_export, args=(new_active_ps,)) for p in range(old))   # ReadyToUpdate
+        for p in range(self.total_ps):                                               # UpdateServerDef (lifts the fence)
+            rpc.rpc_sync(f"ps{p}", _rpc_update_server_def, args=(new_active_ps, self.def_version + 1))
+        self.num_ps, self.def_version = new_active_ps, self.def_version + 1
+        return moved
+
+    def _with_current_def(self, fn):
+        """Run ``fn`` (which issues RPCs under self.def_version); on a stale-definition rejection re-read the definition and retry."""
+        import time
+        for _ in range(1200):
+            try:
+                return fn()
+            except _StaleServerDef:
+                time.sleep(0.05)
+                self.refresh_server_def()
+        raise RuntimeError("server definition did not settle")
 
     def shutdown(self) -> None:
         self.wait()
         rpc.shutdown()
 
     def wait(self) -> None:
-        for f in self._pending:
-            f.wait()
-        self._pending = []
+        pending, self._pending = self._pending, []
+        for item in [i for i in pending if not isinstance(i, tuple)]:               # dense slices
+            item.wait()
+        self._settle_pushes([i for i in pending if isinstance(i, tuple)])
 
     # ---- variables ------------------------------------------------------------------------------------------------------------
     def create_embedding(self, name: str, dim: int, optimizer: str = "adagrad", option: Optional[EmbeddingVariableOption] = None,
                          seed: int = 0, **opt_kw) -> "PSEmbedding":
-        for p in range(self.num_ps):
+        for p in range(self.total_ps):
             rpc.rpc_sync(f"ps{p}", _rpc_create_ev, args=(name, dim, optimizer, opt_kw, option, seed))
         return PSEmbedding(self, name, dim)
 
@@ -173,11 +287,14 @@ class PSClient:
 
     def _dense_owner(self, name: str) -> str:
         import zlib
-        return f"ps{zlib.crc32(name.encode()) % self.num_ps}"
+        return f"ps{zlib.crc32(name.encode()) % self.total_ps}"
 
     # ---- FuseRecv-style batched pull / push ----------------------------------------------------------------------------------------
     def pull_many(self, reqs: Sequence[Tuple[str, torch.Tensor]]) -> List[torch.Tensor]:
         """One RPC per PS for ALL tables of the step; rows are stitched back into request order."""
+        return self._with_current_def(lambda: self._pull_many(reqs))
+
+    def _pull_many(self, reqs):
         per_ps: List[List[Tuple[str, torch.Tensor]]] = [[] for _ in range(self.num_ps)]
         masks = []
         for name, ids in reqs:
@@ -187,8 +304,10 @@ class PSClient:
             masks.append(ms)
             for p in range(self.num_ps):
                 per_ps[p].append((name, flat[ms[p]]))
-        futs = [rpc.rpc_async(f"ps{p}", _rpc_pull_many, args=(per_ps[p],)) for p in range(self.num_ps)]
+        futs = [rpc.rpc_async(f"ps{p}", _rpc_pull_many, args=(per_ps[p], self.def_version)) for p in range(self.num_ps)]
         res = [f.wait() for f in futs]
+        if any(isinstance(r, str) for r in res):
+            raise _StaleServerDef()
         out = []
         for i, (name, ids) in enumerate(reqs):
             dim = res[0][i].shape[1]
@@ -199,6 +318,16 @@ class PSClient:
         return out
 
     def push_many(self, grads: Sequence[Tuple[str, torch.Tensor, torch.Tensor]], asynchronous: bool = True) -> None:
+        """Sparse gradients, one fused RPC per PS.  Asynchronous pushes that a PS rejects because the server definition changed
+        in flight are re-sent under the new definition by ``wait()``."""
+        sent = self._send_pushes(grads)
+        if asynchronous:
+            self._pending.extend(sent)
+        else:
+            self._settle_pushes(sent)
+
+    def _send_pushes(self, grads) -> List[Tuple[object, list]]:
+        """Partition by owner under the current definition and fire one RPC per PS; returns (future, payload) pairs."""
         per_ps: List[List] = [[] for _ in range(self.num_ps)]
         for name, ids, g in grads:
             flat, g2 = ids.reshape(-1), g.reshape(-1, g.shape[-1])
@@ -207,10 +336,20 @@ class PSClient:
                 m = own == p
                 if m.any():
                     per_ps[p].append((name, flat[m], g2[m]))
-        for p in range(self.num_ps):
-            if per_ps[p]:
-                f = rpc.rpc_async(f"ps{p}", _rpc_push_many, args=(per_ps[p],))
-                self._pending.append(f) if asynchronous else f.wait()
+        return [(rpc.rpc_async(f"ps{p}", _rpc_push_many, args=(per_ps[p], self.def_version)), per_ps[p])
+                for p in range(self.num_ps) if per_ps[p]]
+
+    def _settle_pushes(self, sent: List[Tuple[object, list]]) -> None:
+        """Wait for pushes; ONLY the payloads a PS turned away are re-partitioned and re-sent (nothing is applied twice)."""
+        import time
+        for _ in range(1200):
+            rejected = [g for f, payload in sent if isinstance(f.wait(), str) for g in payload]
+            if not rejected:
+                return
+            time.sleep(0.05)
+            self.refresh_server_def()
+            sent = self._send_pushes(rejected)
+        raise RuntimeError("server definition did not settle")
 
     # ---- SliceSend/Recv-style dense transfer --------------------------------------------------------------------------------------
     def pull_dense(self) -> None:

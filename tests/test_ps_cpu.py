@@ -16,6 +16,23 @@ def _free_port():
 NUM_PS, NUM_WORKERS, STEPS = 2, 2, 6
 
 
+def _join_all(procs, timeout=240):
+    """Wait for every process; if one fails the rest (blocked in rpc.shutdown) are terminated instead of hanging the test."""
+    import time
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        codes = [p.exitcode for p in procs]
+        if all(c is not None for c in codes) or any(c not in (None, 0) for c in codes):
+            break
+        time.sleep(0.2)
+    codes = [p.exitcode for p in procs]
+    for p in procs:
+        if p.exitcode is None:
+            p.terminate()
+            p.join(10)
+    assert all(c == 0 for c in codes), f"PS/worker exit codes {codes}"
+
+
 def _proc(rank, port, tmp):
     torch.manual_seed(0)
     from deeprec_b200.parallel import ps
@@ -62,9 +79,7 @@ def test_async_ps_training(tmp_path):
     procs = [ctx.Process(target=_proc, args=(r, port, str(tmp_path))) for r in range(NUM_PS + NUM_WORKERS)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout=240)
-        assert p.exitcode == 0, "a PS/worker process failed"
+    _join_all(procs)
     stats = [json.load(open(tmp_path / f"ps{i}.json")) for i in range(NUM_PS)]
     workers = [json.load(open(tmp_path / f"worker{j}.json")) for j in range(NUM_WORKERS)]
     # rows are partitioned over the PS processes (key % 1000 % num_ps), both shards non-empty; every push was applied
@@ -83,3 +98,69 @@ def test_async_ps_training(tmp_path):
         assert ((keys % 1000 % NUM_PS) == i).all()
         n_user += keys.numel()
     assert n_user == sum(s["user"] for s in stats)
+
+
+# ---------------------------------------------------------------------------------------------- elastic PS scaling
+E_TOTAL_PS, E_WORKERS = 3, 2
+
+
+def _elastic_proc(rank, port, tmp):
+    torch.manual_seed(0)
+    from deeprec_b200.parallel import ps
+    if rank < E_TOTAL_PS:
+        ps.run_ps(rank, E_TOTAL_PS, E_WORKERS, port, stats_path=os.path.join(tmp, f"eps{rank}.json"), active_ps=2)
+        return
+    j = rank - E_TOTAL_PS
+    client = ps.PSClient(j, E_TOTAL_PS, E_WORKERS, port, active_ps=2)
+    emb = client.create_embedding("item", 4, optimizer="adagrad", lr=0.1, seed=5)
+    ids = torch.arange(0, 300) * 7 + j            # the two workers touch different keys
+    def step():
+        rows = ps.group_pull(client, [emb], [ids])[0]
+        rows.sum().backward()
+        ps.push_gradients(client, [emb])
+    for _ in range(2):
+        step()
+    client.wait()
+    flag = os.path.join(tmp, "scaled")
+    if j == 0:
+        before = client.pull_many([("item", ids)])[0].clone()
+        acc_meta = client.fetch_params_meta()
+        assert acc_meta[2]["item"][1] == 0 and acc_meta[0]["item"][1] > 0          # the spare server holds nothing yet
+        moved = client.scale(3)                                                     # scale UP 2 -> 3
+        assert moved > 0 and client.num_ps == 3
+        meta = client.fetch_params_meta()
+        assert all(m["item"][1] > 0 for m in meta) and sum(m["item"][1] for m in meta) == sum(m["item"][1] for m in acc_meta)
+        after = client.pull_many([("item", ids)])[0]
+        assert torch.equal(before, after)                                           # rows survive the move bit for bit
+        step(); client.wait()                                                       # optimizer slots moved too: training continues
+        f = client.frequency("item", ids[:5])
+        assert (f == 3).all(), f
+        moved_down = client.scale(1)                                                # scale DOWN 3 -> 1
+        meta = client.fetch_params_meta()
+        assert moved_down > 0 and meta[1]["item"][1] == 0 and meta[2]["item"][1] == 0
+        assert (client.frequency("item", ids[:5]) == 3).all()
+        open(flag, "w").write("1")
+    else:
+        # this worker keeps training while the other one re-shards: stale-definition rejections are retried transparently
+        import time
+        n = 0
+        while not os.path.exists(flag) and n < 400:
+            step(); n += 1
+            time.sleep(0.01)
+        client.wait()
+        client.refresh_server_def()
+        assert client.num_ps == 1
+        f = client.frequency("item", ids[:5])
+        assert (f == 2 + n).all(), (f, n)                                           # no push was lost or applied twice
+    client.shutdown()
+
+
+def test_elastic_ps_scale_up_and_down(tmp_path):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_elastic_proc, args=(r, port, str(tmp_path))) for r in range(E_TOTAL_PS + E_WORKERS)]
+    for p in procs:
+        p.start()
+    _join_all(procs, 300)
+    stats = [json.load(open(tmp_path / f"eps{i}.json")) for i in range(E_TOTAL_PS)]
+    assert stats[0]["item"] == 600 and stats[1]["item"] == 0 and stats[2]["item"] == 0
