@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "csrc")
 LIB = os.path.join(ROOT, "lib")
 OBJ = os.path.join(LIB, "obj")
 
-HOST_SOURCES = ["host/host_engine.cc", "host/io_runtime.cc", "host/ssd_store.cc", "host/predict_codec.cc", "host/redis_store.cc"]
+HOST_SOURCES = ["host/host_engine.cc", "host/io_runtime.cc", "host/ssd_store.cc", "host/predict_codec.cc", "host/redis_store.cc", "host/tensor_pool.cc"]
 CUDA_SOURCES = [
     "cuda/table_kernels.cu",
     "cuda/embedding_kernels.cu",
@@ -30,6 +30,7 @@ CUDA_SOURCES = [
     "cuda/runtime.cu",
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",
+    "cuda/allocator.cu",
 ]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1,0 +1,68 @@
+// GPU TensorPool allocator (reference: TF_GPU_ALLOCATOR=tensorpool, common_runtime/gpu_tensorpool_allocator.*): the planned pool
+// of common/tensor_pool.h over cudaMalloc, exported with the signatures torch.cuda.memory.CUDAPluggableAllocator expects.
+// One pool per device; blocks are tagged with the stream they were last used on, so reuse never crosses streams.
+//
+//   alloc = torch.cuda.memory.CUDAPluggableAllocator(libdeeprec_cuda.so, "dr_tp_cuda_malloc", "dr_tp_cuda_free")
+//   torch.cuda.memory.change_current_allocator(alloc)        # before the first CUDA allocation
+//   ... each step: lib.dr_tp_cuda_step_end(device)
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+
+#include "../common/tensor_pool.h"
+
+namespace {
+constexpr int kMaxDev = 16;
+dr::TensorPool* g_pool[kMaxDev] = {};
+std::mutex g_mu;
+int64_t g_small = 32 << 10;          // reference: allocations below 32 KB bypass the pool
+int g_collect = 3, g_replan = 8;
+
+void* DevAlloc(size_t n, void* ctx) {
+  int prev = 0; cudaGetDevice(&prev);
+  const int dev = (int)(intptr_t)ctx;
+  if (prev != dev) cudaSetDevice(dev);
+  void* p = nullptr;
+  if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+  if (prev != dev) cudaSetDevice(prev);
+  return p;
+}
+void DevFree(void* p, void*) { cudaFree(p); }
+
+dr::TensorPool* Pool(int dev) {
+  if (dev < 0 || dev >= kMaxDev) return nullptr;
+  std::lock_guard<std::mutex> l(g_mu);
+  if (!g_pool[dev]) {
+    if (const char* e = getenv("DEEPREC_TENSORPOOL_SMALL_BYTES")) g_small = atoll(e);
+    if (const char* e = getenv("START_STATISTIC_STEP")) (void)e;          // collection starts at step 0 here
+    if (const char* e = getenv("STABLE_STATISTIC_STEP")) g_collect = atoi(e) > 0 ? atoi(e) : g_collect;
+    g_pool[dev] = new dr::TensorPool(DevAlloc, DevFree, (void*)(intptr_t)dev, (size_t)g_small, g_collect, g_replan);
+  }
+  return g_pool[dev];
+}
+}  // namespace
+
+extern "C" {
+
+void* dr_tp_cuda_malloc(ssize_t size, int device, cudaStream_t stream) {
+  dr::TensorPool* p = Pool(device);
+  return p ? p->Alloc((size_t)size, (uint64_t)(uintptr_t)stream) : nullptr;
+}
+
+void dr_tp_cuda_free(void* ptr, ssize_t /*size*/, int device, cudaStream_t /*stream*/) {
+  if (dr::TensorPool* p = Pool(device)) p->Free(ptr);
+}
+
+void dr_tp_cuda_step_end(int device) { if (dr::TensorPool* p = Pool(device)) p->StepEnd(); }
+
+void dr_tp_cuda_stats(int device, int64_t* out9) {
+  dr::TensorPool* p = Pool(device);
+  if (!p) return;
+  const dr::TensorPoolStats s = p->Stats();
+  const int64_t v[9] = {s.phase, s.steps, s.pool_bytes, s.pool_hits, s.pool_misses, s.small_bypass, s.backend_allocs, s.live_pool_blocks, s.replans};
+  for (int i = 0; i < 9; ++i) out9[i] = v[i];
+}
+
+}  // extern "C"
