@@ -20,5 +20,6 @@ from .ops.embedding_ops import (SparseIds, adaptive_embedding_lookup_sparse, emb
                                 group_embedding_lookup, group_embedding_lookup_sparse,
                                 safe_embedding_lookup_sparse)
 from .optim.optimizers import get_or_create_global_step
+from . import graph_optimizer  # noqa: E402,F401
 
 __version__ = "0.1.0"
