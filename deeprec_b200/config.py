@@ -102,6 +102,8 @@ class EmbeddingVariableOption:
     storage_option: StorageOption = field(default_factory=StorageOption)
     init_option: InitializerOption = field(default_factory=InitializerOption)
     init_capacity: int = 1 << 16                     # initial key capacity (grows)
+    # accepted for API parity (TF_RECORD_FREQ / TF_RECORD_VERSION): both engines keep freq / version in the key's metadata slot
+    # (same cache line / DRAM sector as the key), so they are always maintained and these switches save nothing
     record_freq: bool = True
     record_version: bool = True
 
