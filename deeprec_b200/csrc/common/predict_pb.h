@@ -93,12 +93,12 @@ inline bool ParseArray(Reader r, Array* a) {
       case 1: if (wt == 0) a->dtype = (int)r.Varint(); else r.Skip(wt); break;
       case 2: if (wt == 2) { if (!ParseShape(r.Sub(), &a->shape)) return false; } else r.Skip(wt); break;
       case 3:
-        if (wt == 2) { Reader s = r.Sub(); size_t n = (size_t)(s.end - s.p) / 4, o = a->f32.size(); a->f32.resize(o + n); memcpy(a->f32.data() + o, s.p, n * 4); }
+        if (wt == 2) { Reader s = r.Sub(); size_t n = (size_t)(s.end - s.p) / 4, o = a->f32.size(); a->f32.resize(o + n); if (n) memcpy(a->f32.data() + o, s.p, n * 4); }
         else if (wt == 5) { uint32_t v = r.Fixed32(); float x; memcpy(&x, &v, 4); a->f32.push_back(x); }
         else r.Skip(wt);
         break;
       case 4:
-        if (wt == 2) { Reader s = r.Sub(); size_t n = (size_t)(s.end - s.p) / 8, o = a->f64.size(); a->f64.resize(o + n); memcpy(a->f64.data() + o, s.p, n * 8); }
+        if (wt == 2) { Reader s = r.Sub(); size_t n = (size_t)(s.end - s.p) / 8, o = a->f64.size(); a->f64.resize(o + n); if (n) memcpy(a->f64.data() + o, s.p, n * 8); }
         else if (wt == 1) { uint64_t v = r.Fixed64(); double x; memcpy(&x, &v, 8); a->f64.push_back(x); }
         else r.Skip(wt);
         break;
@@ -279,7 +279,7 @@ inline bool WireToResponse(const void* wire, size_t n, const std::vector<std::st
   Response r;
   if (wanted("probabilities")) {
     Array a; a.dtype = DT_FLOAT; a.shape = {(int64_t)h.batch}; a.f32.resize(h.batch);
-    memcpy(a.f32.data(), static_cast<const uint8_t*>(wire) + sizeof(h), (size_t)h.batch * 4);
+    if (h.batch) memcpy(a.f32.data(), static_cast<const uint8_t*>(wire) + sizeof(h), (size_t)h.batch * 4);
     r.outputs.emplace_back("probabilities", std::move(a));
   }
   if (wanted("model_version")) { Array a; a.dtype = DT_INT64; a.shape = {1}; a.i64 = {h.model_version}; r.outputs.emplace_back("model_version", std::move(a)); }

@@ -39,3 +39,26 @@ def test_host_runtime_under_thread_sanitizer(tmp_path):
 
 def test_host_runtime_under_address_sanitizer(tmp_path):
     _build_and_run(tmp_path, "address")
+
+
+@pytest.mark.parametrize("sanitizer", ["address,undefined", "thread"])
+def test_codec_fuzz_and_tensor_pool_under_sanitizers(tmp_path, sanitizer):
+    """Protobuf request codec under random / truncated / bit-flipped input and the TensorPool under concurrent use."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "codec_pool_fuzz")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", f"-fsanitize={sanitizer}", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer", "-pthread",
+           os.path.join(ROOT, "tests", "native", "codec_pool_fuzz.cc"), "-o", exe]
+    b = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip(f"-fsanitize={sanitizer} unsupported here")
+    assert b.returncode == 0, b.stderr[-3000:]
+    run = ["setarch", "-R", exe] if sanitizer == "thread" and shutil.which("setarch") else [exe]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1", ASAN_OPTIONS="detect_leaks=1")
+    for attempt in range(3):
+        r = subprocess.run(run, capture_output=True, text=True, timeout=900, env=env)
+        if r.returncode == 0 or not ("tpp.c" in r.stderr or "unexpected memory mapping" in r.stderr):
+            break
+    else:
+        pytest.skip("sanitizer runtime is not usable in this environment")
+    assert r.returncode == 0 and "CODEC_POOL_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
