@@ -31,6 +31,7 @@ CUDA_SOURCES = [
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",
     "cuda/allocator.cu",
+    "cuda/attention_kernels.cu",
 ]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -223,12 +223,10 @@ class _SeqBase(nn.Module):
 
 
 def din_attention(q, k, mask, att: nn.Module):
-    """DIN attention unit: concat[q, k, q-k, q*k] -> 80 -> 40 -> 1 (sigmoid acts), masked softmax, weighted sum."""
-    qe = q.unsqueeze(1).expand_as(k)
-    s = att(torch.cat([qe, k, qe - k, qe * k], -1)).squeeze(-1)
-    s = s.masked_fill(~mask, -2 ** 31)
-    w = torch.softmax(s, -1) * mask.any(-1, keepdim=True)
-    return (w.unsqueeze(-1) * k).sum(1)
+    """DIN attention unit: concat[q, k, q-k, q*k] -> 80 -> 40 -> 1 (sigmoid acts), masked softmax, weighted sum
+    (composite autograd path for training, one fused kernel for CUDA inference: ops/attention.py)."""
+    from ..ops.attention import din_attention as _impl
+    return _impl(q, k, mask, att)
 
 
 class DIN(_SeqBase):

@@ -1,0 +1,85 @@
+"""DIN attention unit (modelzoo/din/train.py:143-188): ``concat[q, k, q-k, q*k] -> H1 -> H2 -> 1`` (sigmoid activations), masked
+softmax over the behaviour history, weighted sum of the keys.
+
+* training (autograd needed) -> the composite PyTorch implementation below;
+* inference on CUDA          -> ONE fused kernel (csrc/cuda/attention_kernels.cu): weights resident in shared memory, the
+  ``[B, L, 4D]`` concat never materialised, half the first-layer FLOPs via ``W1 f = (W1q+W1d) q + (W1k-W1d) k + W1p (q*k)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _native
+from .._native import ptr, stream_ptr
+
+_BOUND = False
+
+
+def _lib():
+    global _BOUND
+    L = _native.cuda()
+    if not _BOUND:
+        P, i64, INT = C.c_void_p, C.c_int64, C.c_int
+        L.dr_cuda_din_attention_fwd.restype = INT
+        L.dr_cuda_din_attention_fwd.argtypes = [P, P, P, i64, INT, INT, P, P, INT, P, P, INT, P, C.c_float, P, P]
+        _BOUND = True
+    return L
+
+
+def din_attention_reference(q: torch.Tensor, k: torch.Tensor, mask: torch.Tensor, att: nn.Module) -> torch.Tensor:
+    """Composite implementation (any device, differentiable).  q [B, D], k [B, L, D], mask [B, L] bool -> [B, D]."""
+    qe = q.unsqueeze(1).expand_as(k)
+    s = att(torch.cat([qe, k, qe - k, qe * k], -1)).squeeze(-1)
+    s = s.masked_fill(~mask, -2 ** 31)
+    w = torch.softmax(s, -1) * mask.any(-1, keepdim=True)
+    return (w.unsqueeze(-1) * k).sum(1)
+
+
+def split_first_layer(W1: torch.Tensor, D: int):
+    """The algebra the kernel uses: W1 [H1, 4D] -> (Wq, Wk, Wp) with  W1 @ [q, k, q-k, q*k] = Wq q + Wk k + Wp (q*k)."""
+    Wa, Wb, Wc, Wd = W1[:, :D], W1[:, D:2 * D], W1[:, 2 * D:3 * D], W1[:, 3 * D:]
+    return Wa + Wc, Wb - Wc, Wd
+
+
+def _fusable(att: nn.Module) -> bool:
+    mods = list(att.children()) if isinstance(att, nn.Sequential) else []
+    return (len(mods) == 5 and all(isinstance(mods[i], nn.Linear) for i in (0, 2, 4)) and all(isinstance(mods[i], nn.Sigmoid) for i in (1, 3))
+            and mods[4].out_features == 1 and all(m.bias is not None for m in (mods[0], mods[2], mods[4])))
+
+
+def din_attention(q: torch.Tensor, k: torch.Tensor, mask: torch.Tensor, att: nn.Module) -> torch.Tensor:
+    """Dispatch: fused kernel when on CUDA, no gradient is required and ``att`` is the Linear-Sigmoid-Linear-Sigmoid-Linear(1) unit."""
+    needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or any(p.requires_grad for p in att.parameters()))
+    if not q.is_cuda or needs_grad or not _fusable(att) or att[0].in_features != 4 * q.shape[-1]:
+        return din_attention_reference(q, k, mask, att)
+    B, L, D = k.shape
+    l1, l2, l3 = att[0], att[2], att[4]
+    qf, kf = q.detach().float().contiguous(), k.detach().float().contiguous()
+    mk = mask.to(torch.bool).contiguous()
+    out = torch.empty(B, D, device=q.device, dtype=torch.float32)
+    rc = _lib().dr_cuda_din_attention_fwd(ptr(qf), ptr(kf), ptr(mk), B, L, D, ptr(l1.weight.detach().float().contiguous()),
+                                          ptr(l1.bias.detach().float().contiguous()), l1.out_features,
+                                          ptr(l2.weight.detach().float().contiguous()), ptr(l2.bias.detach().float().contiguous()), l2.out_features,
+                                          ptr(l3.weight.detach().float().contiguous().view(-1)), _b3(l3),
+                                          ptr(out), stream_ptr())
+    if rc == -1:                                   # shape does not fit the kernel's shared-memory budget
+        return din_attention_reference(q, k, mask, att)
+    if rc != 0:
+        raise RuntimeError(f"dr_cuda_din_attention_fwd failed: {rc}")
+    return out.to(q.dtype)
+
+
+_B3_CACHE: dict = {}
+
+
+def _b3(l3: nn.Linear) -> float:
+    """Scalar bias of the last layer as a host float, cached per parameter version (avoids a device sync on every call)."""
+    key = (id(l3.bias), l3.bias._version)
+    v = _B3_CACHE.get(key)
+    if v is None:
+        _B3_CACHE.clear()
+        v = _B3_CACHE[key] = float(l3.bias.detach().float().item())
+    return v
