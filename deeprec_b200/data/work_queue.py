@@ -36,7 +36,12 @@ class WorkQueue:
         if self.store is None or self.h is not None and self.store is None:
             w = self._take_local()
         elif self.rank == 0:
-            w = self._take_local()
+            lock = getattr(self, "_svc_lock", None)
+            if lock is not None:
+                with lock:
+                    w = self._take_local()
+            else:
+                w = self._take_local()
         else:
             # remote take: a monotonically increasing ticket; rank 0 answers through the store (serve_once)
             t = self.store.add(f"{self.name}/ticket", 1)
@@ -50,14 +55,56 @@ class WorkQueue:
     def serve_pending(self) -> int:
         """Rank 0: answer remote tickets issued so far (call from a service thread)."""
         served = 0
-        issued = int(self.store.add(f"{self.name}/ticket", 0))
+        store = getattr(self, "_svc_store", None) or self.store
+        issued = int(store.add(f"{self.name}/ticket", 0))
         done = getattr(self, "_served", 0)
         for t in range(done + 1, issued + 1):
             w = self._take_local()
-            self.store.set(f"{self.name}/ans/{t}", w if w is not None else "\0")
+            store.set(f"{self.name}/ans/{t}", w if w is not None else "\0")
             served += 1
         self._served = issued
         return served
+
+    def start_service(self, poll_s: float = 0.002) -> None:
+        """Rank 0: answer remote ``take()`` calls from a daemon thread until ``stop_service()`` (the reference hosts the queue on
+        the chief / a PS; here the owner is rank 0 and the transport is the torch.distributed store)."""
+        import threading
+        import time
+        if self.store is None or self.rank != 0 or getattr(self, "_svc", None) is not None:
+            return
+        self._svc_stop = threading.Event()
+        self._svc_lock = getattr(self, "_svc_lock", None) or threading.Lock()
+        # a store client is one socket: a blocking wait() on the caller's thread would stall the service, so it gets its own
+        self._svc_store = self._clone_store(self.store)
+
+        def loop():
+            while not self._svc_stop.is_set():
+                with self._svc_lock:
+                    n = self.serve_pending()
+                if n == 0:
+                    time.sleep(poll_s)
+
+        self._svc = threading.Thread(target=loop, name=f"{self.name}-service", daemon=True)
+        self._svc.start()
+
+    @staticmethod
+    def _clone_store(store):
+        try:
+            import torch.distributed as dist
+            if isinstance(store, dist.TCPStore):
+                return dist.TCPStore(store.host, store.port, None, False, timeout=store.timeout)
+        except Exception:
+            pass
+        return store
+
+    def stop_service(self) -> None:
+        svc = getattr(self, "_svc", None)
+        if svc is not None:
+            self._svc_stop.set()
+            svc.join()
+            self._svc = None
+            with self._svc_lock:
+                self.serve_pending()          # tickets issued while stopping still get an answer
 
     def add(self, work: str) -> None:
         self.lib.dr_wq_add(self.h, str(work).encode())

@@ -117,3 +117,44 @@ def test_smart_stage_cpu_passthrough():
     data = [(torch.ones(2) * i,) for i in range(5)]
     out = [b[0][0].item() for b in smart_stage(data, device=None)]
     assert out == [0.0, 1.0, 2.0, 3.0, 4.0]
+
+
+def _wq_proc(rank, port, tmp):
+    import datetime
+    import json
+    import time
+    import torch.distributed as dist
+    from deeprec_b200.data import WorkQueue
+    store = dist.TCPStore("127.0.0.1", port, 2, is_master=(rank == 0), timeout=datetime.timedelta(seconds=60))
+    wq = WorkQueue([f"part-{i:03d}" for i in range(40)], num_epochs=2, shuffle=True, seed=7, store=store, rank=rank, name="wq_test")
+    wq.start_service()
+    got = []
+    while True:
+        w = wq.take()
+        if w is None:
+            break
+        got.append(w)
+        time.sleep(0.001 if rank == 0 else 0.004)          # rank 1 is a straggler: it simply ends up with fewer items
+    with open(f"{tmp}/wq{rank}.json", "w") as f:
+        json.dump(got, f)
+    store.set(f"done{rank}", "1")
+    store.wait(["done0", "done1"])                         # rank 0 keeps serving until everybody is done
+    wq.stop_service()
+
+
+def test_work_queue_shared_between_processes(tmp_path):
+    import json
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_wq_proc, args=(r, port, str(tmp_path))) for r in range(2)]
+    [p.start() for p in procs]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    a, b = json.load(open(tmp_path / "wq0.json")), json.load(open(tmp_path / "wq1.json"))
+    assert len(a) + len(b) == 80 and len(b) > 0 and len(a) > len(b)                    # every item of both epochs exactly once; straggler took fewer
+    from collections import Counter
+    assert set(Counter(a + b).values()) == {2} and len(set(a + b)) == 40
