@@ -45,7 +45,8 @@ class ParquetDataset:
         if a.dtype == object:           # strings -> stable 63-bit hashes (categorical ids)
             import zlib
             a = np.fromiter(((zlib.crc32(str(x).encode()) << 31) ^ zlib.adler32(str(x).encode()) for x in a), dtype=np.int64, count=len(a))
-        return torch.from_numpy(np.ascontiguousarray(a))
+        a = np.ascontiguousarray(a)
+        return torch.from_numpy(a if a.flags.writeable else a.copy())
 
     def __iter__(self) -> Iterator[Dict[str, Union[torch.Tensor, DataFrameValue]]]:
         import pyarrow.parquet as pq

@@ -38,6 +38,13 @@ def get_arg_parser():
     p.add_argument("--save_steps", type=int, default=0)
     p.add_argument("--workqueue", action="store_true")
     p.add_argument("--micro_batch", type=int, default=1)
+    p.add_argument("--parquet_dataset", default=None, help="glob of Criteo-shaped parquet files (label, I1..I13, C1..C26); default: synthetic data")
+    p.add_argument("--multihash", action="store_true", help="Q-R multi-hash embeddings instead of EmbeddingVariables")
+    p.add_argument("--adaptive_emb", action="store_true", help="adaptive embedding: static hashed table for cold ids, EV for hot ids")
+    p.add_argument("--dynamic_ev", action="store_true", help="accepted for parity (the modelzoo marks dynamic-dimension EV as not enabled)")
+    p.add_argument("--protocol", default="local", choices=["local", "grpc", "grpc++", "star_server"],
+                   help="grpc / grpc++ / star_server select the asynchronous parameter-server mode (deeprec_b200.parallel.ps); run the "
+                        "roles with `python -m deeprec_b200.parallel.ps_train`")
     p.add_argument("--timeline", type=int, default=0)
     p.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
     p.add_argument("--engine", action="store_true", help="DLRM through the fused sm_100a engine (models/dlrm_engine.py)")
@@ -70,14 +77,51 @@ def main(argv=None) -> int:
                 print(f"global_step {s} loss {eng.loss_value():.5f}")
         print(f"{a.steps * a.batch_size / (time.time() - t0):.0f} samples/s")
         return 0
+    if a.protocol != "local":
+        print(f"--protocol {a.protocol}: parameter-server roles are started with `python -m deeprec_b200.parallel.ps_train`; training locally here")
     cards = [1000] * 26
-    model = build_model(name, ev_option_from_args(a), dev, a.group_embedding or a.emb_fusion, cardinalities=cards)
+    from deeprec_b200.models import zoo
+    zoo.table_variant("multihash" if a.multihash else "adaptive" if a.adaptive_emb else "ev")
+    try:
+        model = build_model(name, ev_option_from_args(a), dev, a.group_embedding or a.emb_fusion, cardinalities=cards)
+    finally:
+        zoo.table_variant("ev")
+    if a.op_fusion:                       # auto graph fusion (do_op_fusion)
+        from deeprec_b200 import graph_optimizer
+        rep = graph_optimizer.optimize(model)
+        print(f"op_fusion: {rep.count()} rewrites")
     opt = make_optimizer(a.optimizer, model, lr=a.learning_rate)
     taobao = name in TAOBAO_MODELS
 
+    def parquet_batches(files):
+        from deeprec_b200.data import ParquetDataset
+        for rec in ParquetDataset(files, batch_size=a.batch_size, drop_remainder=True):
+            d = torch.stack([rec[f"I{i}"].float() for i in range(1, 14)], 1)
+            ids = torch.stack([rec[f"C{i}"].long() for i in range(1, 27)], 0)
+            yield d.to(dev), ids.to(dev), rec["label"].float().to(dev)
+
     def gen():
         s = 0
+        if a.parquet_dataset and not taobao:
+            import glob
+            files = sorted(glob.glob(a.parquet_dataset))
+            if not files:
+                raise FileNotFoundError(a.parquet_dataset)
+            if a.workqueue:               # files are work items: any number of workers can share the queue, progress is resumable
+                from deeprec_b200.data import WorkQueue
+                wq = WorkQueue(files, num_epochs=1 << 30, shuffle=True)
+                yield from wq.input_dataset(lambda f: parquet_batches([f]))
+            else:
+                while True:
+                    yield from parquet_batches(files)
+            return
+        wq = None
+        if a.workqueue:                   # synthetic shards as work items
+            from deeprec_b200.data import WorkQueue
+            wq = WorkQueue([str(i) for i in range(1 << 16)], num_epochs=1 << 20, shuffle=True)
         while True:
+            if wq is not None:
+                s = int(wq.take())
             if taobao:
                 b = taobao_batch(a.batch_size, 20, 100000, 200000, 1000, seed=s)
                 yield {k: v.to(dev) for k, v in b.items()}

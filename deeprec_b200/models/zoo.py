@@ -62,8 +62,19 @@ class _Tables(nn.Module):
     def __init__(self, names: Sequence[str], dim: int, ev_option: Optional[EmbeddingVariableOption], device, group: bool, prefix: str):
         super().__init__()
         self.group = group
-        self.tables = nn.ModuleList([get_embedding_variable(f"{prefix}/{n}", dim, ev_option=copy.deepcopy(ev_option) if ev_option else None, device=device)
-                                     for n in names])
+        variant = _TABLE_VARIANT["kind"]
+        if variant == "multihash":         # --multihash: Q-R compositional embeddings instead of one row per id (modelzoo/features/multihash_variable)
+            from ..embedding_variable import get_multihash_variable
+            self.group = False
+            self.tables = nn.ModuleList([get_multihash_variable(f"{prefix}/{n}", [[_TABLE_VARIANT["q_rows"], dim], [_TABLE_VARIANT["r_rows"], dim]], device=device)
+                                         for n in names])
+        elif variant == "adaptive":        # --adaptive_emb: hot ids -> EmbeddingVariable, cold ids -> static hashed table (features/adaptive_embedding)
+            self.group = False
+            self.tables = nn.ModuleList([AdaptiveEmbedding(f"{prefix}/{n}", dim, _TABLE_VARIANT["hash_bucket_size"], _TABLE_VARIANT["hot_freq"], ev_option, device)
+                                         for n in names])
+        else:
+            self.tables = nn.ModuleList([get_embedding_variable(f"{prefix}/{n}", dim, ev_option=copy.deepcopy(ev_option) if ev_option else None, device=device)
+                                         for n in names])
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:          # ids [T, B]
         if self.group and self.tables[0].device.type == "cuda":
@@ -73,7 +84,43 @@ class _Tables(nn.Module):
         return torch.stack([t.lookup(ids[i]) for i, t in enumerate(self.tables)], dim=1)
 
     def embedding_variables(self) -> List[EmbeddingVariable]:
-        return list(self.tables)
+        return [t for t in self.modules() if isinstance(t, EmbeddingVariable)]
+
+
+# process-wide switch set by ``table_variant(...)`` (the modelzoo's --multihash / --adaptive_emb flags pick it before build_model)
+_TABLE_VARIANT = {"kind": "ev", "q_rows": 1 << 12, "r_rows": 1 << 12, "hash_bucket_size": 1 << 14, "hot_freq": 3}
+
+
+def table_variant(kind: str = "ev", **kw) -> None:
+    if kind not in ("ev", "multihash", "adaptive"):
+        raise ValueError("table variant must be ev | multihash | adaptive")
+    _TABLE_VARIANT.update(kind=kind, **kw)
+
+
+class AdaptiveEmbedding(nn.Module):
+    """Adaptive embedding (docs/docs_en/Adaptive-Embedding.md; embedding_ops.py:668-836): every id trains a row of a static hashed table
+    until it has been seen ``hot_freq`` times, from then on it owns an EmbeddingVariable row (selected per id by the adaptive mask)."""
+
+    def __init__(self, name: str, dim: int, hash_bucket_size: int, hot_freq: int, ev_option, device):
+        super().__init__()
+        opt = copy.deepcopy(ev_option) if ev_option else EmbeddingVariableOption()
+        self.ev = get_embedding_variable(name, dim, ev_option=opt, device=device)
+        self.hashed = nn.Embedding(hash_bucket_size, dim, device=device)
+        nn.init.normal_(self.hashed.weight, 0.0, 1.0 / dim ** 0.5)
+        self.hot_freq, self.embedding_dim, self.name = hot_freq, dim, name
+
+    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
+        from ..ops.embedding_ops import adaptive_embedding_lookup_sparse
+        flat = ids.reshape(-1)
+        hot = self.ev.get_frequency(flat.to(self.ev.device)) >= self.hot_freq           # adaptive mask
+        sp = SparseIds.from_dense(flat)
+        hashed_ids = SparseIds.from_dense(torch.remainder(flat, self.hashed.num_embeddings))
+        # the EV is looked up for every id (cold ids get a zero gradient through the mask), so occurrences of cold ids are still
+        # counted by the EV's frequency and the id turns hot after ``hot_freq`` sightings
+        out = adaptive_embedding_lookup_sparse(self.hashed, self.ev, sp, hashed_ids, combiner="sum", adaptive_mask_tensor=hot.to(flat.device))
+        return out.view(*ids.shape, self.embedding_dim)
+
+    forward = lookup
 
 
 class CriteoModel(nn.Module):
@@ -423,7 +470,33 @@ class SimpleMultiTask(_MultiTask):
         return {t: self.towers[t](f).squeeze(-1) for t in self.tasks}
 
 
-CRITEO_MODELS = {"wdl": WDL, "wide_and_deep": WDL, "deepfm": DeepFM, "dcn": DCN, "dcnv2": DCNv2, "masknet": MaskNet}
+class DLRMDCN(CriteoModel):
+    """MLPerf DLRM-DCNv2 (modelzoo/mlperf): DLRM bottom MLP on the dense features, low-rank DCNv2 cross layers over
+    [bottom | embeddings] as the interaction, top MLP on the crossed vector."""
+
+    def __init__(self, bot=(512, 256), top=(1024, 1024, 512, 256), cross_layers: int = 3, low_rank: int = 512, **kw):
+        super().__init__(name=kw.pop("name", "dlrm_dcn"), **kw)
+        dev = self.emb.tables[0].device if hasattr(self.emb.tables[0], "device") else None
+        D = self.emb_dim
+        self.bot = mlp(list(bot) + [D], self.num_dense, device=dev)
+        n = D * (self.num_sparse + 1)
+        r = min(low_rank, n)
+        self.U = nn.ParameterList([nn.Parameter(torch.randn(n, r, device=dev) / n ** 0.5) for _ in range(cross_layers)])
+        self.V = nn.ParameterList([nn.Parameter(torch.randn(r, n, device=dev) / r ** 0.5) for _ in range(cross_layers)])
+        self.cb = nn.ParameterList([nn.Parameter(torch.zeros(n, device=dev)) for _ in range(cross_layers)])
+        self.top = mlp(list(top), n, device=dev)
+        self.out = nn.Linear(top[-1], 1, device=dev)
+
+    def logits(self, dense, embs):
+        x0 = torch.cat([self.bot(dense).unsqueeze(1), embs], 1).flatten(1)
+        x = x0
+        for U, V, b in zip(self.U, self.V, self.cb):
+            x = x0 * ((x @ U) @ V + b) + x                     # x_{l+1} = x0 * (U V x_l + b) + x_l
+        return self.out(self.top(x)).squeeze(-1)
+
+
+CRITEO_MODELS = {"wdl": WDL, "wide_and_deep": WDL, "deepfm": DeepFM, "dcn": DCN, "dcnv2": DCNv2, "masknet": MaskNet, "dlrm_dcn": DLRMDCN,
+                 "mlperf": DLRMDCN}
 TAOBAO_MODELS = {"din": DIN, "dien": DIEN, "bst": BST, "dssm": DSSM, "esmm": ESMM, "mmoe": MMoE, "dbmtl": DBMTL, "ple": PLE,
                  "simple_multitask": SimpleMultiTask}
 

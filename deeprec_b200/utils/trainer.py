@@ -51,7 +51,7 @@ class Trainer:
         if self.strategy is not None and self.strategy.world_size > 1:
             self.strategy.allreduce_gradients([p for p in self.model.parameters() if p.numel()])
         self.opt.step()
-        return float(loss)
+        return float(loss.detach()) if torch.is_tensor(loss) else float(loss)
 
     def fit(self, batches: Iterable, max_steps: Optional[int] = None) -> int:
         step = int(self.opt.global_step)

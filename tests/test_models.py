@@ -40,3 +40,41 @@ def test_train_cli_with_filters_ckpt_and_micro_batch(tmp_path):
     assert rc == 0
     from deeprec_b200.checkpoint import latest_checkpoint
     assert latest_checkpoint(str(tmp_path)) is not None
+
+
+def test_mlperf_dlrm_dcn_and_table_variants_train(tmp_path):
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from deeprec_b200.models import train
+    # MLPerf DLRM-DCNv2 variant + auto op fusion + work queue over synthetic shards
+    assert train.main(["--model", "dlrm_dcn", "--steps", "4", "--batch_size", "64", "--device", "cpu", "--op_fusion", "--workqueue", "--log_every", "0"]) == 0
+    # Q-R multi-hash and adaptive embeddings behind the same model code
+    assert train.main(["--model", "deepfm", "--steps", "4", "--batch_size", "64", "--device", "cpu", "--multihash", "--log_every", "0"]) == 0
+    assert train.main(["--model", "wdl", "--steps", "6", "--batch_size", "64", "--device", "cpu", "--adaptive_emb", "--log_every", "0"]) == 0
+    # parquet input (Criteo-shaped) taken through the work queue
+    rng = np.random.default_rng(0)
+    for part in range(2):
+        cols = {"label": rng.integers(0, 2, 256).astype(np.float32)}
+        cols.update({f"I{i}": rng.standard_normal(256).astype(np.float32) for i in range(1, 14)})
+        cols.update({f"C{i}": rng.integers(0, 500, 256).astype(np.int64) for i in range(1, 27)})
+        pq.write_table(pa.table(cols), str(tmp_path / f"part-{part}.parquet"))
+    assert train.main(["--model", "dcnv2", "--steps", "6", "--batch_size", "64", "--device", "cpu", "--parquet_dataset", str(tmp_path / "part-*.parquet"),
+                       "--workqueue", "--log_every", "0"]) == 0
+
+
+def test_adaptive_embedding_switches_cold_ids_to_the_ev():
+    import deeprec_b200 as dr
+    from deeprec_b200.models.zoo import AdaptiveEmbedding
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(0)
+    ae = AdaptiveEmbedding("adp/C1", 8, hash_bucket_size=16, hot_freq=2, ev_option=None, device=None)
+    opt = dr.optim.GradientDescentOptimizer(ae, lr=0.1)
+    ids = torch.tensor([3, 19])                          # both hash to bucket 3
+    e0 = ae(ids)
+    assert torch.equal(e0[0], e0[1]) and torch.equal(e0[0], ae.hashed.weight[3])        # cold: shared static row
+    for _ in range(2):
+        opt.zero_grad(); ae(ids).sum().backward(); opt.step()
+    assert ae.ev.get_frequency(ids).tolist() == [2, 2]
+    e1 = ae(ids)                                          # hot now: each id reads its own EmbeddingVariable row
+    assert not torch.equal(e1[0], e1[1]) and torch.equal(e1.detach(), ae.ev.table.lookup(ids))

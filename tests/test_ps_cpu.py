@@ -164,3 +164,17 @@ def test_elastic_ps_scale_up_and_down(tmp_path):
     _join_all(procs, 300)
     stats = [json.load(open(tmp_path / f"eps{i}.json")) for i in range(E_TOTAL_PS)]
     assert stats[0]["item"] == 600 and stats[1]["item"] == 0 and stats[2]["item"] == 0
+
+
+def test_ps_train_launcher_spawns_roles_and_scales(tmp_path):
+    """`python -m deeprec_b200.parallel.ps_train --spawn`: 1 PS (+1 spare) and 2 workers, elastic re-shard onto 2 servers at step 6."""
+    import subprocess
+    import sys
+    res = str(tmp_path / "res")
+    r = subprocess.run([sys.executable, "-m", "deeprec_b200.parallel.ps_train", "--spawn", "--num_ps", "1", "--spare_ps", "1", "--num_workers", "2",
+                        "--steps", "14", "--batch_size", "128", "--scale_at", "6:2", "--log_every", "0", "--result", res],
+                       capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "re-sharded onto 2 servers" in r.stdout
+    outs = [json.load(open(f"{res}.worker{j}.json")) for j in range(2)]
+    assert all(o["last_loss"] < o["first_loss"] for o in outs) and outs[0]["active_ps"] == 2
