@@ -110,12 +110,53 @@ class CollectiveStrategy:
                 if p.numel():
                     dist.broadcast(p.data, src)
 
-    def allreduce_gradients(self, params) -> None:
-        """Dense gradient all-reduce for generic modules (the flagship engine fuses this with the optimizer)."""
-        if self.world_size > 1:
-            for p in params:
-                if p.grad is not None:
-                    dist.all_reduce(p.grad)
+    def allreduce_gradients(self, params, bucket_bytes: int = 64 << 20, average: bool = False) -> None:
+        """Dense gradient all-reduce for generic modules (the flagship engine fuses this with the optimizer): gradients are packed
+        into flat buckets of <= ``bucket_bytes`` (Horovod's tensor fusion, 64 MB default) so a model with hundreds of small
+        parameters costs a handful of collectives; ``average`` divides by the world size (Horovod's default op is Sum with the
+        learning rate scaled instead -- see ``scale_learning_rate``)."""
+        if self.world_size <= 1:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        by_kind = {}
+        for g in grads:
+            by_kind.setdefault((g.dtype, g.device), []).append(g)
+        for (dtype, device), gs in by_kind.items():
+            cap = max(1, bucket_bytes // max(1, gs[0].element_size()))
+            i = 0
+            while i < len(gs):
+                j, n = i, 0
+                while j < len(gs) and (n == 0 or n + gs[j].numel() <= cap):
+                    n += gs[j].numel(); j += 1
+                flat = torch.cat([g.reshape(-1) for g in gs[i:j]]) if j - i > 1 else gs[i].reshape(-1)
+                dist.all_reduce(flat)
+                if average:
+                    flat /= self.world_size
+                if j - i > 1:
+                    o = 0
+                    for g in gs[i:j]:
+                        g.copy_(flat[o:o + g.numel()].view_as(g)); o += g.numel()
+                elif not gs[i].is_contiguous():
+                    gs[i].copy_(flat.view_as(gs[i]))
+                i = j
+
+    def scale_learning_rate(self, optimizer) -> None:
+        """hvd_strategy.py:378-405: with Sum all-reduce the effective batch grows with the world size; the reference multiplies the
+        learning rate of every wrapped optimizer by ``world_size``."""
+        w = self.world_size
+        if w > 1:
+            for g in optimizer.param_groups:
+                g["lr"] = g["lr"] * w
+            if hasattr(optimizer, "lr"):
+                optimizer.lr = optimizer.lr * w
+
+    def estimator(self, model: torch.nn.Module, optimizer, loss_fn, checkpoint_dir: Optional[str] = None, **trainer_kw):
+        """``CollectiveStrategy.estimator`` (group_embedding_collective_strategy.py:104-121): a training driver wired to this strategy --
+        rank-0 parameter broadcast at start, bucketed gradient all-reduce every step, rank-suffixed checkpoints."""
+        from ..utils.trainer import Trainer
+        self.broadcast_parameters(model)
+        ckpt = None if checkpoint_dir is None else (checkpoint_dir if self.world_size == 1 else os.path.join(checkpoint_dir, f"rank{self.rank}"))
+        return Trainer(model, optimizer, loss_fn, ckpt, strategy=self, **trainer_kw)
 
     # ---- model-parallel GroupEmbedding for generic modules (gloo/nccl all-to-all; the fused engine uses parallel/p2p.py)
     def owner_of(self, table_index: int) -> int:

@@ -80,3 +80,43 @@ def test_gloo_world2_matches_single_process():
         for t, r in rows.items():
             r = torch.tensor(r)
             assert torch.allclose(r, ref_rows[t], atol=1e-5), (t, (r - ref_rows[t]).abs().max())
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import deeprec_b200 as dr
+    from deeprec_b200.parallel import CollectiveStrategy
+    st = CollectiveStrategy(backend="gloo")
+    torch.manual_seed(rank)                                  # different init per rank: the estimator must broadcast rank 0's
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3), torch.nn.ReLU(), torch.nn.Linear(3, 1))
+    opt = dr.optim.GradientDescentOptimizer(model, lr=0.05)
+    st.scale_learning_rate(opt)
+    lr_scaled = opt.param_groups[0]["lr"]
+    # bucketed all-reduce with a bucket so small that the 6 parameters need several collectives, one of them a lone tensor
+    for p in model.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    st.allreduce_gradients(list(model.parameters()), bucket_bytes=64)
+    sums_ok = all(bool((p.grad == 3.0).all()) for p in model.parameters())
+    for p in model.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    st.allreduce_gradients(list(model.parameters()), bucket_bytes=64, average=True)
+    avg_ok = all(bool((p.grad == 1.5).all()) for p in model.parameters())
+    g = torch.Generator().manual_seed(50 + rank)
+    est = st.estimator(model, opt, lambda m, b: (m(b[0]).squeeze(-1) - b[1]).pow(2).mean(), log_every_n_steps=0)
+    batches = [(torch.randn(8, 6, generator=g), torch.randn(8, generator=g)) for _ in range(4)]
+    est.fit(batches, 4)
+    q.put((rank, sums_ok, avg_ok, lr_scaled, [p.detach().flatten().tolist() for p in model.parameters()]))
+
+
+def test_bucketed_allreduce_lr_scaling_and_estimator_keep_replicas_identical():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_dp_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] for r in res) and all(abs(r[3] - 0.1) < 1e-9 for r in res)
+    assert res[0][4] == res[1][4]                            # data-parallel replicas stayed bitwise identical
