@@ -269,8 +269,35 @@ struct SmemLayoutTN2 {
   static constexpr int kAuxBytes = 8 * 4096;            // 8 epilogue warps x [32 rows][128 B] aux tile
   static constexpr int kBiasCols = 1024;                // bias vector staged in smem once per CTA (N <= kBiasCols)
   static constexpr int kBiasBytes = kBiasCols * 4;
+  static constexpr int kBResBytes = 0;                  // (B-resident variant only)
+  static constexpr int kBSliceBytes = kBBytes;
+  static constexpr int kMaxKb = 1 << 30;
   static constexpr int kTotal = kSt * kStageBytes + kStoreBytes + kAuxBytes + kBiasBytes + 1024 + 256;
 };
+
+// B-resident ("weight-stationary") variant of the same kernel.  In the MLP GEMMs the B operand is the layer's weight matrix:
+// every M tile of a CTA multiplies the SAME [BLOCK_N, K] slab, yet the streaming kernel re-fetches it from L2 for every tile
+// (B is 2/3 of the shared-memory ingest at BLOCK_N = 256).  Here a CTA owns one N block for its whole life, loads the slab once
+// (all K blocks, <= kMaxKb x BLOCK_N x 128 B) and then streams only A through the TMA ring; the aux tile and the store staging
+// share one buffer to make room.  Tile order: CTA c -> n_blk = c % n_tiles, m_blk = c / n_tiles, += gridDim / n_tiles.
+template <int BLOCK_N>
+struct SmemLayoutTN3 {
+  static constexpr int kSt = BLOCK_N >= 128 ? 3 : 4;    // A-only stages
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes;
+  static constexpr int kStoreBytes = 8 * 4096;
+  static constexpr int kAuxBytes = 0;                   // aliased onto the store staging (a lane reads its aux chunk before it overwrites it)
+  static constexpr int kBiasCols = 1024;
+  static constexpr int kBiasBytes = kBiasCols * 4;
+  static constexpr int kMaxKb = 8;                      // K <= 512
+  static constexpr int kBSliceBytes = kBBytes;
+  static constexpr int kBResBytes = kMaxKb * kBSliceBytes;
+  static constexpr int kTotal = kBResBytes + kSt * kStageBytes + kStoreBytes + kBiasBytes + 1024 + 256;
+};
+
+template <int BLOCK_N, bool BRES> struct LayoutSel { using type = SmemLayoutTN2<BLOCK_N>; };
+template <int BLOCK_N> struct LayoutSel<BLOCK_N, true> { using type = SmemLayoutTN3<BLOCK_N>; };
 
 // lane c ends with the sum over the warp's 32 rows of column c (v is destroyed)
 __device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
@@ -287,24 +314,27 @@ __device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool BRES = false>
 __global__ void __launch_bounds__(kGemmThreadsV2, 1)
 k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
              int M, int N, int K, Epilogue ep) {
-  using L = SmemLayoutTN2<BLOCK_N>;
+  using L = typename LayoutSel<BLOCK_N, BRES>::type;
   constexpr int kSt = L::kSt;
   constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bres_base = smem_al;                         // [kMaxKb][BLOCK_N x 128 B] resident weight slab (BRES only; 0 bytes otherwise)
+  uint8_t* smem = smem_al + L::kBResBytes;              // TMA ring
   uint8_t* store_base = smem + kSt * L::kStageBytes;
-  uint8_t* aux_base = store_base + L::kStoreBytes;
-  float* s_bias = reinterpret_cast<float*>(aux_base + L::kAuxBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux_base + L::kAuxBytes + L::kBiasBytes);
+  uint8_t* aux_base = store_base + (BRES ? 0 : L::kStoreBytes);
+  float* s_bias = reinterpret_cast<float*>(store_base + L::kStoreBytes + L::kAuxBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + L::kStoreBytes + L::kAuxBytes + L::kBiasBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kSt;
   uint64_t* tfull_bar = bars + 2 * kSt;
   uint64_t* tempty_bar = bars + 2 * kSt + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 4);
+  uint64_t* bfull_bar = bars + 2 * kSt + 5;             // BRES: the weight slab has landed
   // the epilogue's bias reads were its largest stall (global loads, long scoreboard, per 32-column half): stage the vector once
   const bool smem_bias = ep.bias != nullptr && N <= L::kBiasCols;
 
@@ -319,6 +349,7 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
     for (int i = 0; i < kSt; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    if constexpr (BRES) mbar_init(bfull_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, kTmemCols); tmem_relinquish(); }
@@ -331,19 +362,35 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int i = threadIdx.x; i < L::kBiasCols; i += blockDim.x) s_bias[i] = i < N ? ep.bias[i] : 0.f;
     __syncthreads();
   }
+  // tile schedule: streaming kernel = round-robin over all (m, n) tiles; B-resident kernel = fixed n block, strided m blocks.
+  // (Spelled out inside every role branch so that the single-thread producer / MMA loops keep their indices in uniform registers.)
+#define DR_TILE_LOOP(it)                                                                                       \
+  for (int it = BRES ? (int)blockIdx.x / n_tiles : (int)blockIdx.x; it < (BRES ? m_tiles : num_tiles);       \
+       it += BRES ? (int)gridDim.x / n_tiles : (int)gridDim.x)
+#define DR_TILE_M(it) (BRES ? (it) : (it) / n_tiles)
+#define DR_TILE_N(it) (BRES ? (int)blockIdx.x % n_tiles : (it) % n_tiles)
+#define DR_TILE_ANY() ((BRES ? (int)blockIdx.x / n_tiles : (int)blockIdx.x) < (BRES ? m_tiles : num_tiles))
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      if constexpr (BRES) {
+        if (DR_TILE_ANY()) {          // the whole [BLOCK_N, K] weight slab, once
+          mbar_expect_tx(bfull_bar, (uint32_t)(num_kb * L::kBSliceBytes));
+          for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(bres_base + kb * L::kBSliceBytes, &tmB, bfull_bar, kb * BLOCK_K, DR_TILE_N(0) * BLOCK_N);
+        }
+      }
+      DR_TILE_LOOP(it) {
+        const int m_blk = DR_TILE_M(it), n_blk = DR_TILE_N(it);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if constexpr (!BRES) {
+            uint8_t* sb = sa + L::kABytes;
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
           if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
       }
@@ -353,7 +400,10 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if constexpr (BRES) {
+        if (DR_TILE_ANY()) { mbar_wait(bfull_bar, 0); tc_fence_after(); }
+      }
+      DR_TILE_LOOP(it) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -361,7 +411,7 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+          const uint32_t sb = BRES ? smem_u32(bres_base + kb * L::kBSliceBytes) : sa + L::kABytes;
           const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
@@ -385,8 +435,8 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint8_t* my_aux = aux_base + ew * 4096;
     const uint32_t swz = (uint32_t)(lane & 7);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    DR_TILE_LOOP(it) {
+      const int m_blk = DR_TILE_M(it), n_blk = DR_TILE_N(it);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row0 = m_blk * BLOCK_M + q * 32;
@@ -398,6 +448,10 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int col0 = n_blk * BLOCK_N + c0;
         if (col0 >= N) break;                           // warp-uniform
         if (((c0 >> 6) & 1) != half) continue;          // the sibling warp of this lane quarter owns this chunk
+        if constexpr (BRES) {   // aux and store staging share one buffer: the previous chunk's TMA store must have read it first
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         // ---- aux tile [32 rows x 64 cols] -> swizzled smem (coalesced: 8 lanes cover one 128 B row segment)
         if (ep.mask_src) {
           __syncwarp();
@@ -411,8 +465,10 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
         }
         // the staging buffer was handed to TMA one chunk ago: wait until it has been read
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
+        if constexpr (!BRES) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         uint8_t* stg = my_store;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -499,6 +555,11 @@ k_gemm_tn_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
+
+#undef DR_TILE_LOOP
+#undef DR_TILE_M
+#undef DR_TILE_N
+#undef DR_TILE_ANY
 
 // -------------------------------------------------------------------------------------------------
 // dW[N_out, K_in] += sum_b dY[b, N_out] * X[b, K_in]   (split over b; fp32 atomics epilogue)
@@ -643,26 +704,31 @@ int make_tmap_c(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer,
   return make_tmap(m, ptr, inner, outer, pitch_bytes, 64, 32);     // 64 cols (128 B) x 32 rows, 128B swizzle
 }
 
-template <int BN>
+template <int BN, bool BRES = false>
 int launch_tn_v2(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_t ldb, const Epilogue& ep, int max_ctas, cudaStream_t s) {
   CUtensorMap tb, tc;
   int rc = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BLOCK_K, BN);
   if (rc) return rc;
   rc = make_tmap_c(&tc, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldc * 2);
   if (rc) return rc;
-  using L = SmemLayoutTN2<BN>;
+  using L = typename LayoutSel<BN, BRES>::type;
+  static_assert(L::kTotal <= 227 * 1024, "shared-memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn_v2<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn_v2<BN, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;
   if (grid > max_ctas) grid = max_ctas;
-  DR_PDL_LAUNCH((k_gemm_tn_v2<BN>), grid, kGemmThreadsV2, L::kTotal, s, ta, tb, tc, M, N, K, ep);
+  if (BRES) grid = grid / n_tiles * n_tiles;        // every CTA owns one n block: the grid is a whole number of n-block groups
+  DR_PDL_LAUNCH((k_gemm_tn_v2<BN, BRES>), grid, kGemmThreadsV2, L::kTotal, s, ta, tb, tc, M, N, K, ep);
   DR_LAUNCH_CHECK();
   return 0;
 }
+
+// DEEPREC_GEMM_BRES=1 selects the B-resident (weight-stationary) kernel where it applies (K <= 512, enough CTAs for one per n block).
+inline int& gemm_bres_enabled() { static int v = [] { const char* e = getenv("DEEPREC_GEMM_BRES"); return (e && e[0] == '1') ? 1 : 0; }(); return v; }
 
 template <int BN>
 int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, int Mo, int No, int batch, int splits, float* dW, int64_t ldw, cudaStream_t s) {
@@ -709,6 +775,10 @@ int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, i
   if (rc) return rc;
   Epilogue ep{bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, out_f32, ldc, ld_mask, relu, aux_mode, S1, S2};
   const bool v2 = !force_v1 && N > 32 && out_f32 == nullptr;
+  if (v2 && gemm_bres_enabled() && (K + BLOCK_K - 1) / BLOCK_K <= SmemLayoutTN3<128>::kMaxKb) {
+    if (N <= 64) return launch_tn_v2<64, true>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+    if ((N + 127) / 128 <= max_ctas) return launch_tn_v2<128, true>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+  }
   if (v2) {
     if (N <= 64) return launch_tn_v2<64>(ta, B, M, N, K, ldb, ep, max_ctas, s);
     if (N <= 128) return launch_tn_v2<128>(ta, B, M, N, K, ldb, ep, max_ctas, s);
@@ -723,6 +793,9 @@ int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, i
 }
 
 // dW[N_out,K_in](ldw, fp32, accumulated into) += dY[batch,N_out](ldy)^T * X[batch,K_in](ldx)
+// A/B switch for the B-resident GEMM variant (same effect as DEEPREC_GEMM_BRES, settable at run time; returns the previous value).
+int dr_cuda_set_gemm_bres(int on) { int prev = gemm_bres_enabled(); gemm_bres_enabled() = on ? 1 : 0; return prev; }
+
 int dr_cuda_gemm_dw(const void* dY, int64_t ldy, const void* X, int64_t ldx, int batch, int N_out, int K_in, float* dW, int64_t ldw,
                     int splits, cudaStream_t s) {
   if (batch <= 0 || N_out <= 0 || K_in <= 0) return 0;
