@@ -33,7 +33,7 @@ class WorkQueue:
 
     def take(self) -> Optional[str]:
         """Next work item or None when every epoch is consumed."""
-        if self.store is None or self.h is not None and self.store is None:
+        if self.store is None:
             w = self._take_local()
         elif self.rank == 0:
             lock = getattr(self, "_svc_lock", None)

@@ -1,6 +1,7 @@
 """SessionGroup for arbitrary PyTorch models (direct_session_group.{h,cc} analogue): N sessions = N worker contexts, each
-with its own CUDA stream (and optional CUDA graph per input shape), sharing ONE set of read-only parameters / embedding
-tables.  ``run`` picks a session round-robin or by ``hint % n`` (direct_session_group.h:72-89)."""
+with its own CUDA stream and lock, sharing ONE set of read-only parameters / embedding tables.  ``run`` picks a session
+round-robin or by ``hint % n`` (direct_session_group.h:72-89).  (The native ``Processor`` additionally owns per-session pinned
+IO buffers and replays CUDA graphs; this class is the generic-module counterpart used for zoo models and tests.)"""
 from __future__ import annotations
 
 import itertools
