@@ -5,6 +5,8 @@ import sys
 
 import torch
 
+import _path  # noqa: F401  (repository root on sys.path)
+
 
 def worker():
     import deeprec_b200 as dr

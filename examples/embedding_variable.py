@@ -3,6 +3,7 @@ import argparse
 
 import torch
 
+import _path  # noqa: F401  (repository root on sys.path)
 import deeprec_b200 as dr
 
 p = argparse.ArgumentParser(); p.add_argument("--device", default="cpu"); a = p.parse_args()

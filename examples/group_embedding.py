@@ -1,6 +1,7 @@
 """GroupEmbedding: N tables looked up and combined in one fused call; the feature-column scope does it implicitly."""
 import torch
 
+import _path  # noqa: F401  (repository root on sys.path)
 import deeprec_b200 as dr
 from deeprec_b200.feature_column import categorical_column_with_embedding, embedding_column, group_embedding_column_scope, input_layer
 

@@ -3,6 +3,7 @@ import tempfile
 
 import torch
 
+import _path  # noqa: F401  (repository root on sys.path)
 import deeprec_b200 as dr
 from deeprec_b200.checkpoint import IncrementalSaver, Saver
 from deeprec_b200.optim import GlobalStep

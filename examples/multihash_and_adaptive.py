@@ -1,6 +1,7 @@
 """Compositional (Q-R multi-hash) embeddings and adaptive embeddings."""
 import torch
 
+import _path  # noqa: F401  (repository root on sys.path)
 import deeprec_b200 as dr
 from deeprec_b200.models.zoo import AdaptiveEmbedding
 

@@ -3,6 +3,7 @@ import numpy as np
 import torch
 from starlette.testclient import TestClient
 
+import _path  # noqa: F401  (repository root on sys.path)
 import deeprec_b200 as dr
 from deeprec_b200.models.zoo import build_model
 from deeprec_b200.serving import SessionGroup

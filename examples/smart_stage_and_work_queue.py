@@ -6,6 +6,7 @@ import pyarrow as pa
 import pyarrow.parquet as pq
 import torch
 
+import _path  # noqa: F401  (repository root on sys.path)
 import deeprec_b200 as dr
 from deeprec_b200.data import ParquetDataset, SmartStageOptions, WorkQueue, smart_stage
 from deeprec_b200.models.zoo import build_model
