@@ -36,7 +36,6 @@ dr::TensorPool* Pool(int dev) {
   std::lock_guard<std::mutex> l(g_mu);
   if (!g_pool[dev]) {
     if (const char* e = getenv("DEEPREC_TENSORPOOL_SMALL_BYTES")) g_small = atoll(e);
-    if (const char* e = getenv("START_STATISTIC_STEP")) (void)e;          // collection starts at step 0 here
     if (const char* e = getenv("STABLE_STATISTIC_STEP")) g_collect = atoi(e) > 0 ? atoi(e) : g_collect;
     g_pool[dev] = new dr::TensorPool(DevAlloc, DevFree, (void*)(intptr_t)dev, (size_t)g_small, g_collect, g_replan);
   }

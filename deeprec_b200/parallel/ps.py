@@ -121,6 +121,22 @@ class ParameterServer:
     def stats(self) -> Dict[str, int]:
         return {n: int(e.total_count()) for n, e in self.evs.items()} | {"pushes": self.pushes}
 
+    # ---- FileSliceSend / FileSliceRecv (kernels/file_slice_sendrecv_ops.cc): files travel in slices, never as one message ----------
+    def file_write_slice(self, path: str, offset: int, data: bytes, truncate: bool) -> int:
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        with open(path, "wb" if truncate else "r+b") as f:
+            f.seek(offset)
+            f.write(data)
+        return len(data)
+
+    def file_read_slice(self, path: str, offset: int, nbytes: int) -> bytes:
+        with open(path, "rb") as f:
+            f.seek(offset)
+            return f.read(nbytes)
+
+    def file_size(self, path: str) -> int:
+        return os.path.getsize(path) if os.path.exists(path) else -1
+
     # ---- elastic scaling (ElasticTrainingService) ----------------------------------------------------------------------------------
     def server_def(self) -> Tuple[int, int]:
         return self.active, self.def_version
@@ -180,6 +196,9 @@ def _rpc_create_ev(*a): return _srv().create_ev(*a)
 def _rpc_create_dense(*a): return _srv().create_dense(*a)
 def _rpc_pull_many(*a): return _srv().pull_many(*a)
 def _rpc_push_many(*a): return _srv().push_many(*a)
+def _rpc_file_write_slice(*a): return _srv().file_write_slice(*a)
+def _rpc_file_read_slice(*a): return _srv().file_read_slice(*a)
+def _rpc_file_size(*a): return _srv().file_size(*a)
 def _rpc_server_def(): return _srv().server_def()
 def _rpc_is_ready_scaling(): return _srv().is_ready_scaling()
 def _rpc_fetch_params_meta(): return _srv().fetch_params_meta()
@@ -368,6 +387,36 @@ class PSClient:
             g, owner = p.grad.detach().view(-1), self._dense_owner(n)
             for lo in range(0, g.numel(), self.slice_elems):
                 self._pending.append(rpc.rpc_async(owner, _rpc_push_dense, args=(n, lo, g[lo: lo + self.slice_elems].clone())))
+
+    # ---- FileSliceSend / FileSliceRecv: ship a file (checkpoint shard, SSD .emb file, warm-up data) to / from a server in slices --------
+    def send_file(self, ps_index: int, local_path: str, remote_path: str, slice_bytes: int = 4 << 20) -> int:
+        sent, futs = 0, []
+        with open(local_path, "rb") as f:
+            while True:
+                chunk = f.read(slice_bytes)
+                if not chunk and sent > 0:
+                    break
+                futs.append(rpc.rpc_async(f"ps{ps_index}", _rpc_file_write_slice, args=(remote_path, sent, chunk, sent == 0)))
+                if sent == 0:
+                    futs[-1].wait()           # the first slice creates / truncates the file before the others land
+                sent += len(chunk)
+                if not chunk:
+                    break
+        for f_ in futs:
+            f_.wait()
+        return sent
+
+    def recv_file(self, ps_index: int, remote_path: str, local_path: str, slice_bytes: int = 4 << 20) -> int:
+        size = rpc.rpc_sync(f"ps{ps_index}", _rpc_file_size, args=(remote_path,))
+        if size < 0:
+            raise FileNotFoundError(f"ps{ps_index}:{remote_path}")
+        futs = [(o, rpc.rpc_async(f"ps{ps_index}", _rpc_file_read_slice, args=(remote_path, o, min(slice_bytes, size - o)))) for o in range(0, size, slice_bytes)]
+        os.makedirs(os.path.dirname(os.path.abspath(local_path)), exist_ok=True)
+        with open(local_path, "wb") as f:
+            for o, fut in futs:
+                f.seek(o)
+                f.write(fut.wait())
+        return size
 
     def stats(self) -> List[Dict[str, int]]:
         return [rpc.rpc_sync(f"ps{p}", _rpc_stats) for p in range(self.num_ps)]

@@ -68,6 +68,13 @@ def _proc(rank, port, tmp):
     assert (f >= own_cnt).all(), (f, own_cnt)
     if j == 0:
         client.save(os.path.join(tmp, "ckpt"), STEPS)
+        # FileSliceSend / FileSliceRecv: a 1 MB + 3 B file travels in 64 KB slices to a server and back
+        blob = os.urandom((1 << 20) + 3)
+        with open(os.path.join(tmp, "blob.bin"), "wb") as fh:
+            fh.write(blob)
+        assert client.send_file(1, os.path.join(tmp, "blob.bin"), os.path.join(tmp, "remote", "blob.bin"), slice_bytes=64 << 10) == len(blob)
+        assert client.recv_file(1, os.path.join(tmp, "remote", "blob.bin"), os.path.join(tmp, "back.bin"), slice_bytes=100_000) == len(blob)
+        assert open(os.path.join(tmp, "back.bin"), "rb").read() == blob
     with open(os.path.join(tmp, f"worker{j}.json"), "w") as fh:
         json.dump({"losses": losses, "dense_moved": moved}, fh)
     client.shutdown()
