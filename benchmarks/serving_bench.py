@@ -30,10 +30,11 @@ def main():
     ap.add_argument("--requests", type=int, default=2000)
     ap.add_argument("--policy", default="RR")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"], help="MLP compute dtype of the serving runtime")
+    ap.add_argument("--gpus", type=int, default=1, help="serve from this many GPUs (one Processor replica per GPU, ModelConfig gpu_ids_list)")
     a = ap.parse_args()
     from deeprec_b200.data import criteo_batch
     from deeprec_b200.models.dlrm_engine import CRITEO_KAGGLE_CARDINALITIES, DLRMConfig, DLRMEngine
-    from deeprec_b200.serving import Processor, encode_request, export_saved_model
+    from deeprec_b200.serving import Processor, ProcessorGroup, encode_request, export_saved_model
     cards = CRITEO_KAGGLE_CARDINALITIES
     eng = DLRMEngine(DLRMConfig(batch_size=8192, cardinalities=cards))
     for s in range(8):
@@ -43,8 +44,8 @@ def main():
     export_saved_model(eng, os.path.join(root, "v1"), version=8, root=root)
     del eng
     torch.cuda.empty_cache()
-    proc = Processor(os.path.join(root, "v1"), {"session_num": a.sessions, "select_session_policy": a.policy, "max_batch": max(256, a.batch),
-                                                "model_update_interval_ms": 0, "mlp_dtype": a.dtype})
+    cfg = {"session_num": a.sessions, "select_session_policy": a.policy, "max_batch": max(256, a.batch), "model_update_interval_ms": 0, "mlp_dtype": a.dtype}
+    proc = Processor(os.path.join(root, "v1"), cfg) if a.gpus <= 1 else ProcessorGroup(os.path.join(root, "v1"), dict(cfg, gpu_ids_list=list(range(a.gpus))))
     reqs = []
     for s in range(16):
         d, ids, _ = criteo_batch(a.batch, 13, cards, seed=1000 + s)
@@ -71,7 +72,7 @@ def main():
     n = allv.size
     print(json.dumps({"metric": "DLRM serving (Processor C ABI, SessionGroup)", "sessions": a.sessions, "client_threads": a.threads, "batch": a.batch,
                       "requests": int(n), "qps": n / wall, "samples_per_s": n * a.batch / wall, "p50_ms": float(allv[n // 2]),
-                      "p99_ms": float(allv[min(n - 1, int(n * 0.99))]), "mean_ms": float(allv.mean()), "dtype": a.dtype, "model_info": proc.model_info()}))
+                      "p99_ms": float(allv[min(n - 1, int(n * 0.99))]), "mean_ms": float(allv.mean()), "dtype": a.dtype, "n_gpus": a.gpus, "model_info": proc.model_info()}))
     proc.close()
 
 

@@ -108,3 +108,56 @@ class Processor:
             self.close()
         except Exception:
             pass
+
+
+class ProcessorGroup:
+    """One native Processor per GPU behind a single ``process`` entry (ModelConfig ``gpu_ids_list``; SessionGroup.md: total sessions =
+    ``session_num x len(gpu_ids)``).  Every replica polls the same ``checkpoint_dir`` and hot-swaps on its own; requests go to the
+    replicas round-robin (``RR``) or by ``hint % n`` / thread id (``MOD``), each replica then picks one of its sessions."""
+
+    def __init__(self, savedmodel_dir: str, config: dict | None = None):
+        import itertools
+        import threading
+        cfg = dict(config or {})
+        gpus = list(cfg.pop("gpu_ids_list", None) or [cfg.get("gpu_id", 0)])
+        self.policy = str(cfg.get("select_session_policy", "RR")).upper()
+        self.replicas: List[Processor] = [Processor(savedmodel_dir, dict(cfg, gpu_id=int(g))) for g in gpus]
+        self.gpu_ids = [int(g) for g in gpus]
+        self._rr = itertools.count()
+        self._ident = threading.get_ident
+
+    def _pick(self, hint: int | None) -> Processor:
+        n = len(self.replicas)
+        if self.policy == "MOD":
+            return self.replicas[(hint if hint is not None else self._ident()) % n]
+        return self.replicas[next(self._rr) % n]
+
+    def process(self, request: bytes, hint: int | None = None) -> Tuple[int, bytes]:
+        return self._pick(hint).process(request)
+
+    def predict(self, dense: np.ndarray, ids: np.ndarray, hint: int | None = None) -> np.ndarray:
+        return self._pick(hint).predict(dense, ids)
+
+    def batch_process(self, requests: Sequence[bytes]) -> Tuple[int, List[bytes]]:
+        """Requests are spread over the replicas (request i -> replica i % n), each replica runs its share as one batch_process call."""
+        n = len(self.replicas)
+        out: List[bytes] = [b""] * len(requests)
+        rc_all = 200
+        for r, proc in enumerate(self.replicas):
+            idx = list(range(r, len(requests), n))
+            if not idx:
+                continue
+            rc, res = proc.batch_process([requests[i] for i in idx])
+            rc_all = rc if rc != 200 else rc_all
+            for i, b in zip(idx, res):
+                out[i] = b
+        return rc_all, out
+
+    def model_info(self) -> dict:
+        infos = [p.model_info() for p in self.replicas]
+        return {"gpu_ids": self.gpu_ids, "sessions": sum(i["sessions"] for i in infos), "requests": sum(i["requests"] for i in infos),
+                "failures": sum(i["failures"] for i in infos), "model_version": min(i["model_version"] for i in infos), "replicas": infos}
+
+    def close(self) -> None:
+        for p in self.replicas:
+            p.close()
