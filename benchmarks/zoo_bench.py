@@ -7,6 +7,13 @@
                    GlobalStep eviction enabled
 Any other zoo model name works too.  Timing: CUDA events around K steps after W warm-up steps; the input H2D copy of every step
 is inside the timed region.  Prints one JSON line.
+
+Multi-GPU (BASELINE.json config #3, DeepFM on 8 GPUs): launch with torchrun; the Criteo models then run through ``CollectiveStrategy``
+-- tables model-parallel (table t on rank t % world, ids / rows exchanged with NCCL collectives), dense net data-parallel with a
+bucketed gradient all-reduce -- i.e. the generic framework path (the fused NVLink kernels are the DLRM engine's, bench.py).  The value
+is the whole-job samples/s, timed on the device, max over ranks.  ``--device cpu`` (gloo) is a functional dry run.
+
+  torchrun --nnodes 1 --nproc-per-node 8 --master-addr 127.0.0.1 benchmarks/zoo_bench.py --model deepfm
 """
 import argparse
 import json
@@ -33,17 +40,26 @@ def main():
     ap.add_argument("--id_space", type=int, default=1_000_000_000, help="DIN: size of the item id space")
     ap.add_argument("--ssd", action="store_true", help="DIN: add the SSD tier below DRAM (HBM_DRAM_SSDHASH)")
     ap.add_argument("--filter_freq", type=int, default=2)
+    ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"])
     a = ap.parse_args()
-    dev = torch.device("cuda")
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    strategy = None
+    if world > 1:
+        from deeprec_b200.parallel import CollectiveStrategy
+        strategy = CollectiveStrategy(backend="nccl" if a.device == "cuda" else "gloo")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if a.device == "cuda" else torch.device("cpu")
+    cuda = dev.type == "cuda"
     name = a.model.lower()
     criteo = name in CRITEO_MODELS or name == "dlrm"
     if criteo:
-        opt_ev = dr.EmbeddingVariableOption(storage_option=dr.StorageOption(dr.StorageType.HBM))
+        opt_ev = dr.EmbeddingVariableOption(storage_option=dr.StorageOption(dr.StorageType.HBM if cuda else dr.StorageType.DRAM))
         model = build_model(name, ev_option=opt_ev, device=dev, group_embedding=True)
         cards = [1_000_000] * 26
-        gen = lambda s: criteo_batch(a.batch, 13, cards, seed=s)
+        gen = lambda s: criteo_batch(a.batch, 13, cards, seed=s * world + rank)
     else:
         row_bytes = 4 * 16 * 2
+        if not cuda or world > 1:
+            raise SystemExit("the multi-tier DIN configuration is single-GPU (HBM cache over host DRAM)")
         st = dr.StorageType.HBM_DRAM_SSDHASH if a.ssd else dr.StorageType.HBM_DRAM
         opt_ev = dr.EmbeddingVariableOption(storage_option=dr.StorageOption(dr.StorageType.HBM))
         model = build_model(name, ev_option=opt_ev, device=dev)
@@ -54,38 +70,65 @@ def main():
         model.item = dr.get_embedding_variable(f"{name}/item_multitier", 16, ev_option=big, device=dev)
         gen = lambda s: taobao_batch(a.batch, 50, 10_000_000, a.id_space, 10_000, seed=s)
     opt = dr.optim.make_optimizer(a.optimizer, model, lr=0.01)
+    dense_params = [p for g in opt.param_groups for p in g["params"]]
+    if strategy is not None:
+        strategy.broadcast_parameters(model)
 
     def to_dev(b):
+        if not cuda:
+            return b
         if isinstance(b, dict):
             return {k: v.pin_memory().to(dev, non_blocking=True) for k, v in b.items()}
         return tuple(t.pin_memory().to(dev, non_blocking=True) for t in b)
 
     def step(b):
         b = to_dev(b)
-        loss = model.loss(b) if isinstance(b, dict) else model.loss(*b)
-        opt.zero_grad(); loss.backward(); opt.step()
+        if strategy is not None:
+            with strategy.scope(), strategy.embedding_scope():          # group lookups inside are model-parallel
+                loss = model.loss(*b)
+        else:
+            loss = model.loss(b) if isinstance(b, dict) else model.loss(*b)
+        opt.zero_grad(); loss.backward()
+        if strategy is not None:
+            strategy.allreduce_gradients(dense_params, average=True)
+        opt.step()
         return loss
 
+    import torch.distributed as dist
     batches = [gen(s) for s in range(a.warmup + a.steps)]
     for i in range(a.warmup):
         step(batches[i])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if strategy is not None:
+        dist.barrier()
+    if cuda:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     t0 = time.perf_counter()
-    e0.record()
     for i in range(a.steps):
         loss = step(batches[a.warmup + i])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.steps
-    out = {"metric": f"{name} training samples/s (1 GPU, framework API, H2D inside the timed region)", "value": a.batch / ms * 1e3, "unit": "samples/s",
-           "ms_per_step": ms, "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / a.steps, "batch": a.batch, "steps": a.steps, "warmup": a.warmup,
-           "final_loss": float(loss.item()), "dtype": "bf16 GEMMs / fp32 master weights", "data": "synthetic"}
+    if cuda:
+        e1.record()
+        torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    ms = e0.elapsed_time(e1) / a.steps if cuda else wall_ms
+    if strategy is not None:                      # max over ranks
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    out = {"metric": f"{name} training samples/s ({world} GPU{'s' if world > 1 else ''}, framework API, H2D inside the timed region)",
+           "value": a.batch * world / ms * 1e3, "unit": "samples/s", "n_gpus": world, "parallelism": f"mp{world}(emb,table-wise,NCCL)+dp{world}(dense)" if world > 1 else "single",
+           "ms_per_step": ms, "wall_ms_per_step": wall_ms, "batch": a.batch, "global_batch": a.batch * world, "steps": a.steps, "warmup": a.warmup,
+           "final_loss": float(loss.item()), "dtype": "bf16 GEMMs / fp32 master weights" if cuda else "fp32 (cpu dry run)", "data": "synthetic"}
     if not criteo:
         t = model.item.table
         out["multi_tier"] = {k: (float(v) if not isinstance(v, dict) else v) for k, v in t.cache_stats().items()}
         out["item_table"] = {"admitted_rows": int(model.item.total_count()), "id_space": a.id_space, "hbm_rows": a.hbm_rows}
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if strategy is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -77,7 +77,10 @@ class _Tables(nn.Module):
                                          for n in names])
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:          # ids [T, B]
-        if self.group and self.tables[0].device.type == "cuda":
+        from ..parallel import strategy as _strategy
+        st = _strategy.current()
+        model_parallel = st is not None and st.in_embedding_scope and st.world_size > 1 and isinstance(self.tables[0], EmbeddingVariable)
+        if model_parallel or (self.group and self.tables[0].device.type == "cuda"):
             sps = [SparseIds.from_dense(ids[i]) for i in range(len(self.tables))]
             outs = group_embedding_lookup_sparse(list(self.tables), sps, ["sum"] * len(sps))
             return torch.stack(outs, dim=1)

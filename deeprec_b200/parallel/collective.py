@@ -19,31 +19,103 @@ import torch.distributed as dist
 from . import strategy as _strategy
 
 
-class _DistLookup(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, anchor, strategy, t, table, sp, combiner, weights):
-        from ..ops.embedding_ops import SparseIds, embedding_lookup_sparse
-        W, r, owner = strategy.world_size, strategy.rank, strategy.owner_of(t)
-        objs = [None] * W
-        w = weights if weights is not None else sp.weights
-        dist.all_gather_object(objs, (sp.values.cpu(), sp.row_ids.cpu(), sp.batch_size, None if w is None else w.cpu()))
-        outs = None
-        if owner == r:
-            with torch.enable_grad():
-                outs = [embedding_lookup_sparse(table, SparseIds(v, rid, B, ww), None, combiner) for (v, rid, B, ww) in objs]
-        recv = [None]
-        dist.scatter_object_list(recv, [o.detach().cpu() for o in outs] if owner == r else None, src=owner)
-        ctx.strategy, ctx.owner, ctx.outs = strategy, owner, outs
-        return recv[0].to(sp.values.device if sp.values.is_cuda else "cpu")
+def _a2a(send: List[torch.Tensor]) -> List[torch.Tensor]:
+    from .sok import _all_to_all_v
+    return _all_to_all_v(send)
+
+
+class _GroupDistLookup(torch.autograd.Function):
+    """Model-parallel GroupEmbedding for generic modules, ALL tables of the call in one exchange (table t lives on rank t % world):
+
+      forward   all-to-all #1  per-table (nnz, batch) of every requester          -> owners         (tiny)
+                all-to-all #2  ids + row ids of every table, one message per owner                    (C2: id dispatch)
+                owner: ONE lookup + combine per owned table over the concatenated requests of all ranks
+                all-to-all #3  combined rows back, one message per requester                           (C3: embedding combine)
+      backward  all-to-all #4  output gradients to the owners, whose EmbeddingVariables record the sparse gradients  (C4)
+
+    Tensors only (no pickling, no host round trip): nccl on GPUs, gloo on CPU.  The flagship engine replaces these collectives by
+    the fused NVLink kernels (parallel/p2p.py); this is the path every other model uses."""
 
     @staticmethod
-    def backward(ctx, g):
-        st = ctx.strategy
-        gl = [None] * st.world_size if st.rank == ctx.owner else None
-        dist.gather_object(g.detach().cpu(), gl, dst=ctx.owner)
-        if st.rank == ctx.owner:
-            torch.autograd.backward(ctx.outs, [x.to(o.device) for x, o in zip(gl, ctx.outs)])
-        return (None,) * 7
+    def forward(ctx, anchor, strategy, tables, sps, combiners, weights):
+        from ..ops.embedding_ops import SparseIds, embedding_lookup_sparse
+        W, r, T = strategy.world_size, strategy.rank, len(tables)
+        dev = sps[0].values.device
+        owned_by = [[t for t in range(T) if strategy.owner_of(t) == p] for p in range(W)]
+        mine = owned_by[r]
+        ws = [w if w is not None else sp.weights for w, sp in zip(weights, sps)]
+        has_w = [w is not None for w in ws]
+        # ---- #1 meta + #2 ids
+        meta = [torch.tensor([[sps[t].values.numel(), sps[t].batch_size] for t in owned_by[p]], dtype=torch.int64, device=dev).reshape(-1, 2) for p in range(W)]
+        ids = [torch.cat([torch.stack([sps[t].values.to(torch.int64), sps[t].row_ids.to(torch.int64)], 1) for t in owned_by[p]])
+               if owned_by[p] else torch.zeros(0, 2, dtype=torch.int64, device=dev) for p in range(W)]
+        rmeta, rids = _a2a(meta), _a2a(ids)
+        rw = None
+        if any(has_w):
+            wsend = [torch.cat([(ws[t] if has_w[t] else torch.ones(sps[t].values.numel(), device=dev)).to(torch.float32) for t in owned_by[p]])
+                     if owned_by[p] else torch.zeros(0, device=dev) for p in range(W)]
+            rw = _a2a(wsend)
+        # ---- owner: one lookup + combine per owned table over all requesters
+        outs, out_batches, owner_sps = [], [], []
+        cursor = [0] * W
+        for k, t in enumerate(mine):
+            vals, rows, wts, batches, base = [], [], [], [], 0
+            for s_ in range(W):
+                nnz, B = int(rmeta[s_][k, 0]), int(rmeta[s_][k, 1])
+                seg = rids[s_][cursor[s_]: cursor[s_] + nnz]
+                vals.append(seg[:, 0]); rows.append(seg[:, 1] + base)
+                if rw is not None:
+                    wts.append(rw[s_][cursor[s_]: cursor[s_] + nnz])
+                cursor[s_] += nnz
+                batches.append(B); base += B
+            sp = SparseIds(torch.cat(vals), torch.cat(rows), base, torch.cat(wts) if (rw is not None and has_w[t]) else None)
+            owner_sps.append(sp)
+            out_batches.append(batches)
+        from ..embedding_variable import EmbeddingVariable
+        with torch.enable_grad():                                                     # [sum B, D_t] per owned table, autograd graph kept for backward
+            if mine and all(isinstance(tables[t], EmbeddingVariable) and tables[t].device.type == "cuda" for t in mine):
+                from ..ops.device_table import group_lookup_sparse_device             # ONE fused probe + gather + combine launch for all owned tables
+                outs = list(group_lookup_sparse_device([tables[t] for t in mine], owner_sps, [combiners[t] for t in mine], [None] * len(mine)))
+            else:
+                outs = [embedding_lookup_sparse(tables[t], sp, None, combiners[t]) for t, sp in zip(mine, owner_sps)]
+        # ---- #3 rows back to the requesters (flattened: tables may have different dims)
+        back = []
+        for s_ in range(W):
+            parts, off = [], None
+            for k in range(len(mine)):
+                lo = sum(out_batches[k][:s_])
+                parts.append(outs[k].detach()[lo: lo + out_batches[k][s_]].reshape(-1))
+            back.append(torch.cat(parts) if parts else torch.zeros(0, device=dev))
+        recv = _a2a([b.to(torch.float32) for b in back])
+        results: List[Optional[torch.Tensor]] = [None] * T
+        for p in range(W):
+            off = 0
+            for t in owned_by[p]:
+                B, D = sps[t].batch_size, tables[t].embedding_dim
+                results[t] = recv[p][off: off + B * D].view(B, D)
+                off += B * D
+        ctx.strategy, ctx.owned_by, ctx.outs, ctx.out_batches = strategy, owned_by, outs, out_batches
+        ctx.dims = [tb.embedding_dim for tb in tables]
+        ctx.batches = [sp.batch_size for sp in sps]
+        return tuple(results)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        st, W, r = ctx.strategy, ctx.strategy.world_size, ctx.strategy.rank
+        dev = grads[0].device
+        send = [torch.cat([grads[t].reshape(-1).to(torch.float32) for t in ctx.owned_by[p]]) if ctx.owned_by[p] else torch.zeros(0, device=dev) for p in range(W)]
+        recv = _a2a(send)                                                             # C4: gradients travel to the owners
+        mine = ctx.owned_by[r]
+        if mine:
+            gouts, cursor = [], [0] * W
+            for k, t in enumerate(mine):
+                D, parts = ctx.dims[t], []
+                for s_ in range(W):
+                    n = ctx.out_batches[k][s_] * D
+                    parts.append(recv[s_][cursor[s_]: cursor[s_] + n].view(-1, D)); cursor[s_] += n
+                gouts.append(torch.cat(parts).to(ctx.outs[k].device))
+            torch.autograd.backward(ctx.outs, gouts)                                  # the owner's EmbeddingVariables record the sparse gradients
+        return (None,) * 6
 
 
 class DistStrategy(enum.Enum):
@@ -164,14 +236,14 @@ class CollectiveStrategy:
 
     def distributed_lookup(self, params, sp_ids, combiners, sp_weights=None) -> List[torch.Tensor]:
         """Model-parallel GroupEmbedding for generic modules over torch.distributed (gloo on CPU, nccl on GPU): table t lives on
-        rank t % world; ids are all-gathered to the owner, the owner looks up + combines for every requester and scatters the
-        results; the backward sends the output gradients back to the owner, whose EmbeddingVariable records the sparse gradient
-        (so only the owner's optimizer ever updates the table).  The flagship engine uses the fused NVLink kernels instead."""
+        rank t % world; ONE id all-to-all, one lookup + combine per owned table, ONE row all-to-all back; the backward sends the
+        output gradients to the owners, whose EmbeddingVariables record the sparse gradient (only the owner's optimizer ever updates
+        a table).  See ``_GroupDistLookup``.  The flagship engine uses the fused NVLink kernels instead."""
         if sp_weights is None:
             sp_weights = [None] * len(params)
         if not hasattr(self, "_anchor"):
             self._anchor = torch.zeros(1, requires_grad=True)
-        return [_DistLookup.apply(self._anchor, self, t, p, s, c, w) for t, (p, s, c, w) in enumerate(zip(params, sp_ids, combiners, sp_weights))]
+        return list(_GroupDistLookup.apply(self._anchor, self, list(params), list(sp_ids), list(combiners), list(sp_weights)))
 
     def export_saved_model(self, *a, **k):
         from ..serving.export import export_saved_model
