@@ -115,6 +115,12 @@ class DeepRecOptimizer(torch.optim.Optimizer):
     def _dense_update(self, p: torch.Tensor, g: torch.Tensor, state: dict, group: dict, hp: OptHyper) -> None:
         p.add_(g, alpha=-group["lr"])
 
+    def _dense_update_many(self, ps: List[torch.Tensor], gs: List[torch.Tensor], states: List[dict], group: dict, hp: OptHyper) -> None:
+        """All dense parameters of a group at once.  Subclasses with a multi-tensor (``torch._foreach_*``) form override this: a model
+        with dozens of small parameters then costs a handful of launches per step instead of several per parameter."""
+        for p, g, st in zip(ps, gs, states):
+            self._dense_update(p, g, st, group, hp)
+
     def _after_step(self, group) -> None:
         pass
 
@@ -129,10 +135,9 @@ class DeepRecOptimizer(torch.optim.Optimizer):
         hp = self._hyper(group)
         if not self._no_dense:
             for g_ in self.param_groups:
-                for p in g_["params"]:
-                    if p.grad is None:
-                        continue
-                    self._dense_update(p, p.grad, self.state[p], g_, hp)
+                ps = [p for p in g_["params"] if p.grad is not None]
+                if ps:
+                    self._dense_update_many(ps, [p.grad for p in ps], [self.state[p] for p in ps], g_, hp)
         for ev in self.evs:
             if ev.device.type == "cuda":
                 if ev._table is not None:
@@ -156,6 +161,9 @@ class DeepRecOptimizer(torch.optim.Optimizer):
 class GradientDescentOptimizer(DeepRecOptimizer):
     kind = OPT_SGD
 
+    def _dense_update_many(self, ps, gs, states, group, hp):
+        torch._foreach_add_(ps, gs, alpha=-group["lr"])
+
 
 class AdagradOptimizer(DeepRecOptimizer):
     kind = OPT_ADAGRAD
@@ -174,6 +182,14 @@ class AdagradOptimizer(DeepRecOptimizer):
         a = state["acc"]
         a.addcmul_(g, g)
         p.addcdiv_(g, a.sqrt(), value=-group["lr"])
+
+    def _dense_update_many(self, ps, gs, states, group, hp):
+        for p, st in zip(ps, states):
+            if "acc" not in st:
+                st["acc"] = torch.full_like(p, group["initial_accumulator_value"])
+        accs = [st["acc"] for st in states]
+        torch._foreach_addcmul_(accs, gs, gs)
+        torch._foreach_addcdiv_(ps, gs, torch._foreach_sqrt(accs), value=-group["lr"])
 
 
 class AdagradDecayOptimizer(DeepRecOptimizer):
@@ -220,8 +236,22 @@ class AdamOptimizer(DeepRecOptimizer):
         m.add_(g - m, alpha=1 - group["beta1"])
         v.add_(g * g - v, alpha=1 - group["beta2"])
         p.addcdiv_(m, v.sqrt().add_(group["eps"]), value=-alpha)
-        if self.kind == OPT_ADAMW and group.get("weight_decay", 0.0):
-            pass
+
+    def _moments(self, ps, gs, states, group):
+        """m <- m + (1 - b1)(g - m), v <- v + (1 - b2)(g^2 - v) for every parameter; returns (ms, sqrt(v) + eps, step size)."""
+        for p, st in zip(ps, states):
+            if "m" not in st:
+                st["m"] = torch.zeros_like(p); st["v"] = torch.zeros_like(p)
+        ms, vs = [st["m"] for st in states], [st["v"] for st in states]
+        torch._foreach_lerp_(ms, gs, 1 - group["beta1"])
+        torch._foreach_lerp_(vs, torch._foreach_mul(gs, gs), 1 - group["beta2"])
+        denom = torch._foreach_sqrt(vs)
+        torch._foreach_add_(denom, group["eps"])
+        return ms, denom, group["lr"] * (1 - self.beta2_power) ** 0.5 / (1 - self.beta1_power)
+
+    def _dense_update_many(self, ps, gs, states, group, hp):
+        ms, denom, alpha = self._moments(ps, gs, states, group)
+        torch._foreach_addcdiv_(ps, ms, denom, value=-alpha)
 
     def _after_step(self, group):
         self.beta1_power *= group["beta1"]
@@ -243,6 +273,11 @@ class AdamWOptimizer(AdamOptimizer):
         v.add_(g * g - v, alpha=1 - group["beta2"])
         upd = m * alpha / (v.sqrt() + group["eps"]) + group["weight_decay"] * p
         p.sub_(upd)
+
+    def _dense_update_many(self, ps, gs, states, group, hp):
+        ms, denom, alpha = self._moments(ps, gs, states, group)
+        torch._foreach_mul_(ps, 1.0 - group["weight_decay"])             # decoupled decay on the pre-update weights
+        torch._foreach_addcdiv_(ps, ms, denom, value=-alpha)
 
 
 class AdamAsyncOptimizer(DeepRecOptimizer):
@@ -266,6 +301,18 @@ class AdamAsyncOptimizer(DeepRecOptimizer):
         m.mul_(group["beta1"]).add_(g, alpha=1 - group["beta1"])
         v.mul_(group["beta2"]).addcmul_(g, g, value=1 - group["beta2"])
         p.addcdiv_(m, v.sqrt().add_(group["eps"]), value=-alpha)
+
+    def _dense_update_many(self, ps, gs, states, group, hp):
+        for p, st in zip(ps, states):
+            if "m" not in st:
+                st["m"] = torch.zeros_like(p); st["v"] = torch.zeros_like(p)
+        ms, vs = [st["m"] for st in states], [st["v"] for st in states]
+        alpha = group["lr"] * (1 - self.beta2_power) ** 0.5 / (1 - self.beta1_power)
+        torch._foreach_mul_(ms, group["beta1"]); torch._foreach_add_(ms, gs, alpha=1 - group["beta1"])
+        torch._foreach_mul_(vs, group["beta2"]); torch._foreach_addcmul_(vs, gs, gs, value=1 - group["beta2"])
+        denom = torch._foreach_sqrt(vs)
+        torch._foreach_add_(denom, group["eps"])
+        torch._foreach_addcdiv_(ps, ms, denom, value=-alpha)
 
     def _after_step(self, group):
         self.beta1_power *= group["beta1"]

@@ -48,3 +48,35 @@ def test_auc_and_timeline(tmp_path):
     tl.save(str(tmp_path / "t.json"))
     import json
     assert json.load(open(tmp_path / "t.json"))["traceEvents"][0]["name"] == "step"
+
+
+import pytest
+
+
+@pytest.mark.parametrize("name", ["gradientdescent", "adagrad", "adam", "adamw", "adamasync", "adagraddecay", "ftrl"])
+def test_multi_tensor_dense_updates_equal_the_per_parameter_rules(name):
+    """The ``torch._foreach_*`` dense paths must reproduce the scalar rules (which the sparse kernels are tested against)."""
+    import deeprec_b200 as dr
+    from deeprec_b200.optim import GlobalStep, make_optimizer
+    from deeprec_b200.optim.optimizers import DeepRecOptimizer
+    torch.manual_seed(0)
+
+    def net():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3, bias=False), torch.nn.ReLU(), torch.nn.Linear(3, 1))
+
+    a, b = net(), net()
+    kw = dict(lr=0.05)
+    if name == "adagraddecay":
+        kw.update(accumulator_decay_step=2, accumulator_decay_rate=0.5)
+    oa = make_optimizer(name, a, None, global_step=GlobalStep(), **kw)
+    ob = make_optimizer(name, b, None, global_step=GlobalStep(), **kw)
+    ob._dense_update_many = lambda ps, gs, sts, group, hp: DeepRecOptimizer._dense_update_many(ob, ps, gs, sts, group, hp)   # scalar path
+    for step in range(4):
+        x = torch.randn(16, 5)
+        if step == 2:
+            a[4].weight.requires_grad_(False); b[4].weight.requires_grad_(False)      # a parameter without gradient is skipped by both
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad(); m(x).pow(2).mean().backward(); o.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, atol=1e-6, rtol=1e-5), (name, (pa - pb).abs().max())
