@@ -30,6 +30,13 @@ def _use_fused(device) -> bool:
     return device is not None and torch.device(device).type == "cuda" and os.environ.get("DEEPREC_FUSED_NN", "1") != "0"
 
 
+def _fast_onehot() -> bool:
+    """DEEPREC_FAST_ONEHOT=1: one-hot group lookups skip the bag construction (ops/device_table.group_lookup_dense_device).  Off by
+    default until it has been validated and measured on a B200 (written after the round's GPU budget was spent)."""
+    import os
+    return os.environ.get("DEEPREC_FAST_ONEHOT", "0") == "1"
+
+
 def mlp(sizes: Sequence[int], in_dim: int, act=nn.ReLU, bn: bool = False, last_act: bool = True, device=None) -> nn.Module:
     if act is nn.ReLU and _use_fused(device):
         from ..nn import FusedLinear, FusedMLP
@@ -80,6 +87,11 @@ class _Tables(nn.Module):
         from ..parallel import strategy as _strategy
         st = _strategy.current()
         model_parallel = st is not None and st.in_embedding_scope and st.world_size > 1 and isinstance(self.tables[0], EmbeddingVariable)
+        if not model_parallel and self.group and self.tables[0].device.type == "cuda" and _fast_onehot():
+            from ..ops.device_table import group_lookup_dense_device
+            out = group_lookup_dense_device(list(self.tables), ids)          # [B, T, D]; None if the tables cannot share a launch
+            if out is not None:
+                return out
         if model_parallel or (self.group and self.tables[0].device.type == "cuda"):
             sps = [SparseIds.from_dense(ids[i]) for i in range(len(self.tables))]
             outs = group_embedding_lookup_sparse(list(self.tables), sps, ["sum"] * len(sps))

@@ -451,6 +451,28 @@ class _GroupLookupFn(torch.autograd.Function):
         return (None,) * 9
 
 
+_ONEHOT_CACHE: Dict[tuple, tuple] = {}
+
+
+def group_lookup_dense_device(params, ids: torch.Tensor) -> Optional[torch.Tensor]:
+    """One id per (table, sample) -- the Criteo case: ``ids`` [T, B] feature-major -> [B, T, D] through the same two launches as
+    ``group_lookup_sparse_device`` but without building bags (no per-table bincount / cumsum / cat: every bag is one id, the offsets
+    are an iota that is cached per shape).  Returns None when the tables do not share one (dim, step context)."""
+    from ..optim.optimizers import get_or_create_global_step
+    tables = [p.table for p in params]
+    if len({t.dim for t in tables}) != 1 or len({id(t.ctx) for t in tables}) != 1:
+        return None
+    T, B = ids.shape
+    dev = tables[0].device
+    key = (T, B, dev.index)
+    cached = _ONEHOT_CACHE.get(key)
+    if cached is None:
+        cached = _ONEHOT_CACHE[key] = (torch.arange(T * B + 1, dtype=torch.int64, device=dev), torch.zeros(T, dtype=torch.int32, device=dev))   # bags, "sum"
+    keys = ids.to(dev, torch.int64).reshape(-1).contiguous()
+    train = bool(torch.is_grad_enabled() and any(p.trainable and not p._inference for p in params))
+    return _GroupLookupFn.apply(params[0]._anchor, tables, keys, cached[0], None, cached[1], B, int(get_or_create_global_step()), train)
+
+
 def group_lookup_sparse_device(params, sp_ids, combiners, sp_weights) -> List[torch.Tensor]:
     """All device tables of equal dim -> one probe launch + one gather/combine launch."""
     from ..optim.optimizers import get_or_create_global_step
