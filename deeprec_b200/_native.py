@@ -85,6 +85,11 @@ def _bind_host(lib):
     _sig(lib, "dr_host_unique", i64, [P, i64, P, P, P])
     _sig(lib, "dr_host_segment_sum", None, [P, P, i64, i64, P, i64])
     _sig(lib, "dr_host_num_threads", C.c_int, [])
+    _sig(lib, "dr_host_dot_interaction_fwd", None, [P, P, i64, C.c_int, C.c_int, P])
+    _sig(lib, "dr_host_dot_interaction_bwd", None, [P, P, P, i64, C.c_int, C.c_int, P, P])
+    _sig(lib, "dr_host_ev_apply_raw", None, [vp, P, i64, P, i64, C.POINTER(OptHyper)])
+    _sig(lib, "dr_host_group_lookup", None, [P, C.c_int, P, i64, P])
+    _sig(lib, "dr_host_group_apply_raw", None, [P, C.c_int, P, i64, P, C.POINTER(OptHyper)])
     # SSD tier (csrc/host/ssd_store.cc)
     _sig(lib, "dr_ssd_create", vp, [cp, i64, i64, C.c_int])
     _sig(lib, "dr_ssd_destroy", None, [vp])

@@ -84,7 +84,8 @@ def build_host(force: bool = False) -> str:
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libdeeprec_host.so")
     srcs = [os.path.join(CSRC, s) for s in HOST_SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    flags = ["-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-march=x86-64-v3", "-fno-math-errno"]
+    # -fopenmp + DR_USE_OPENMP: the host engine's parallel loops share PyTorch's libgomp pool (see ThreadPool in host_engine.cc)
+    flags = ["-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-march=x86-64-v3", "-fno-math-errno", "-fopenmp", "-DDR_USE_OPENMP"]
     stamp = _stamp(srcs, flags)
     if not force and _up_to_date(out, stamp):
         return out

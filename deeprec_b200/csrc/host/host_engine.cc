@@ -15,6 +15,9 @@
 // partition rehashes or is compacted by eviction.  Key metadata (freq, version, row index,
 // dirty bit) is SoA in chunked arrays so pointers stay stable while the table grows; rows
 // come from a chunked slab with a free list (the EVAllocator analogue: no per-row malloc).
+#ifdef DR_USE_OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -37,6 +40,30 @@ namespace dr {
 // ------------------------------------------------------------------------------------
 // Thread pool (intra-op sharding; the reference uses TF's Shard() over worker threads)
 // ------------------------------------------------------------------------------------
+#ifdef DR_USE_OPENMP
+// Production build: parallel loops run on the process's OpenMP runtime -- the SAME libgomp pool PyTorch's CPU kernels use.  A private
+// std::thread pool next to it is starved by libgomp's spin-waiting workers between torch ops (measured: the native DLRM interaction
+// took 12.8 ms inside a training step vs 3.4 ms stand-alone); sharing the runtime removes the oversubscription.
+class ThreadPool {
+ public:
+  explicit ThreadPool(int n) : n_(n < 1 ? 1 : n) {}
+  int size() const { return n_; }
+  void ParallelFor(int64_t n, int64_t min_grain, const std::function<void(int64_t, int64_t)>& fn) {
+    if (n <= 0) return;
+    const int shards = (int)std::min<int64_t>(n_ + 1, (n + min_grain - 1) / min_grain);
+    if (shards <= 1 || omp_in_parallel()) { fn(0, n); return; }
+    const int64_t per = (n + shards - 1) / shards;
+#pragma omp parallel for schedule(static, 1) num_threads(shards)
+    for (int s = 0; s < shards; ++s) {
+      const int64_t b = s * per, e = std::min(n, b + per);
+      if (b < e) fn(b, e);
+    }
+  }
+ private:
+  int n_;
+};
+#else
+// Sanitizer / stand-alone build: a private pool of std::threads (ThreadSanitizer cannot see into an uninstrumented libgomp).
 class ThreadPool {
  public:
   explicit ThreadPool(int n) : stop_(false) {
@@ -89,10 +116,14 @@ class ThreadPool {
   std::vector<std::function<void()>> q_;
   std::mutex mu_; std::condition_variable cv_; bool stop_;
 };
+#endif
 
 static ThreadPool* GlobalPool() {
   static ThreadPool* p = [] {
     int n = (int)std::thread::hardware_concurrency();
+#ifdef DR_USE_OPENMP
+    n = omp_get_max_threads();                                 // follows OMP_NUM_THREADS / torch.set_num_threads at first use
+#endif
     if (const char* e = getenv("DEEPREC_HOST_THREADS")) n = atoi(e);
     if (n > 64) n = 64;
     return new ThreadPool(std::max(1, n - 1));
@@ -374,21 +405,23 @@ class HostEV {
 
   // ---- forward: read-only gather (embedding_var.h:202-219) ---------------------------
   void Lookup(const int64_t* keys, int64_t n, float* out) {
+    GlobalPool()->ParallelFor(n, 2048, [&](int64_t b, int64_t e) { LookupRange(keys, b, e, out, cfg_.dim); });
+  }
+  // keys[b, e) -> out + i * out_stride (serial; callers parallelise over ranges / tables)
+  void LookupRange(const int64_t* keys, int64_t b, int64_t e, float* out, int64_t out_stride) {
     const int64_t dim = cfg_.dim;
-    GlobalPool()->ParallelFor(n, 2048, [&](int64_t b, int64_t e) {
-      for (int64_t i = b; i < e; ++i) {
-        int32_t idx = kv_.Find(keys[i]);
-        int32_t r = idx >= 0 ? RowOf(idx) : -1;
-        float* o = out + i * dim;
-        if (r >= 0) {
-          memcpy(o, rows_.at(r), dim * sizeof(float));
-        } else if (cfg_.filter_type != DR_FILTER_NONE && cfg_.filter_freq > 0) {
-          std::fill(o, o + dim, cfg_.default_value_no_permission);
-        } else {
-          memcpy(o, DefaultRow(keys[i]), dim * sizeof(float));
-        }
+    for (int64_t i = b; i < e; ++i) {
+      int32_t idx = kv_.Find(keys[i]);
+      int32_t r = idx >= 0 ? RowOf(idx) : -1;
+      float* o = out + i * out_stride;
+      if (r >= 0) {
+        memcpy(o, rows_.at(r), dim * sizeof(float));
+      } else if (cfg_.filter_type != DR_FILTER_NONE && cfg_.filter_freq > 0) {
+        std::fill(o, o + dim, cfg_.default_value_no_permission);
+      } else {
+        memcpy(o, DefaultRow(keys[i]), dim * sizeof(float));
       }
-    });
+    }
   }
   // gather a slot (or the trailing scalars with slot == num_slots+1) for inspection / ckpt
   void LookupSlot(const int64_t* keys, int64_t n, int slot, float* out) {
@@ -452,9 +485,13 @@ class HostEV {
 
   // ---- sparse apply on de-duplicated keys (training_ali_ops.cc) ------------------------
   void Apply(const int64_t* keys, const float* grads, const int64_t* counts, int64_t n, const DrOptHyper& hp) {
+    GlobalPool()->ParallelFor(n, 512, [&](int64_t b, int64_t e) { ApplyRange(keys, grads, counts, b, e, hp); });
+  }
+  // serial body over [b, e): callers parallelise over key ranges (Apply) or over tables (group apply)
+  void ApplyRange(const int64_t* keys, const float* grads, const int64_t* counts, int64_t b, int64_t e, const DrOptHyper& hp) {
     const int64_t dim = cfg_.dim;
     const float alpha = dr_adam_alpha(hp);
-    GlobalPool()->ParallelFor(n, 512, [&](int64_t b, int64_t e) {
+    {
       std::vector<float> newacc(dim);
       for (int64_t i = b; i < e; ++i) {
         int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step);
@@ -482,7 +519,7 @@ class HostEV {
         for (int64_t d = 0; d < dim; ++d)
           dr_apply_elem(hp.kind, hp, alpha, decay_now, g[d], row[d], ns > 0 ? s0[d] : dummy0, ns > 1 ? s1[d] : dummy1);
       }
-    });
+    }
   }
 
   // ---- eviction (only inside save; single_tier_storage.h:235-261) -----------------------
@@ -731,6 +768,195 @@ void dr_host_segment_sum(const float* grads, const int64_t* inverse, int64_t n, 
     float* o = out + inverse[i] * dim; const float* g = grads + i * dim;
     for (int64_t d = 0; d < dim; ++d) o[d] += g[d];
   }
+}
+
+// ---- fused entry points for the framework's CPU path (one native call per step instead of 3-4 per table) ----------------------
+namespace {
+// dedup (first-occurrence order) + per-unique gradient sums of one table; grads row i at grads + i * row_stride
+struct DedupScratch { std::vector<int64_t> uniq, inv, cnt; std::vector<float> gsum; int64_t nu = 0; };
+void DedupAndSum(const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, int64_t dim, DedupScratch* s) {
+  s->uniq.resize(n); s->inv.resize(n); s->cnt.resize(n);
+  s->nu = n ? dr_host_unique(ids, n, s->uniq.data(), s->inv.data(), s->cnt.data()) : 0;
+  s->gsum.assign((size_t)(s->nu * dim), 0.f);
+  for (int64_t i = 0; i < n; ++i) {
+    float* o = s->gsum.data() + s->inv[i] * dim; const float* g = grads + i * row_stride;
+    for (int64_t d = 0; d < dim; ++d) o[d] += g[d];
+  }
+}
+}  // namespace
+
+// unique + segment-sum + apply of ONE table in one call; grads row i at grads + i * row_stride (strided views need no copy)
+void dr_host_ev_apply_raw(void* h, const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, const DrOptHyper* hp) {
+  auto* ev = static_cast<dr::HostEV*>(h);
+  DedupScratch s;
+  DedupAndSum(ids, n, grads, row_stride, ev->cfg().dim, &s);
+  ev->Apply(s.uniq.data(), s.gsum.data(), s.cnt.data(), s.nu, *hp);
+}
+
+// T tables of equal dim, one id per (table, sample): keys feature-major [T][B] -> out sample-major [B][T][dim]
+// (the layout the interaction layers consume: no per-table tensors, no stack).  Parallel over (table, key-chunk) tiles.
+void dr_host_group_lookup(void** hs, int T, const int64_t* keys, int64_t B, float* out) {
+  if (T <= 0 || B <= 0) return;
+  const int64_t dim = static_cast<dr::HostEV*>(hs[0])->cfg().dim;
+  const int64_t chunk = 1024, chunks = (B + chunk - 1) / chunk;
+  dr::GlobalPool()->ParallelFor((int64_t)T * chunks, 1, [&](int64_t b, int64_t e) {
+    for (int64_t w = b; w < e; ++w) {
+      const int64_t t = w / chunks, c = w % chunks, lo = c * chunk, hi = std::min(B, lo + chunk);
+      static_cast<dr::HostEV*>(hs[t])->LookupRange(keys + t * B, lo, hi, out + t * dim, (int64_t)T * dim);
+    }
+  });
+}
+
+// The matching update: ids [T][B], grads [B][T][dim] (as produced by autograd for the lookup above).  Tables are independent, so
+// with many tables each one is processed serially on its own worker (dedup + sums + apply); with few tables they run one after
+// another, each using the whole pool.
+void dr_host_group_apply_raw(void** hs, int T, const int64_t* ids, int64_t B, const float* grads, const DrOptHyper* hp) {
+  if (T <= 0 || B <= 0) return;
+  const int64_t dim = static_cast<dr::HostEV*>(hs[0])->cfg().dim, row_stride = (int64_t)T * dim;
+  if (T >= dr::GlobalPool()->size() + 1) {
+    dr::GlobalPool()->ParallelFor(T, 1, [&](int64_t b, int64_t e) {
+      DedupScratch s;
+      for (int64_t t = b; t < e; ++t) {
+        auto* ev = static_cast<dr::HostEV*>(hs[t]);
+        DedupAndSum(ids + t * B, B, grads + t * dim, row_stride, dim, &s);
+        ev->ApplyRange(s.uniq.data(), s.gsum.data(), s.cnt.data(), 0, s.nu, *hp);
+      }
+    });
+  } else {
+    for (int t = 0; t < T; ++t) dr_host_ev_apply_raw(hs[t], ids + (int64_t)t * B, B, grads + (int64_t)t * dim, row_stride, hp);
+  }
+}
+
+// ---- DLRM dot interaction on the CPU path (modelzoo/dlrm/train.py:121-133) ------------------------------------------------------
+// feats = [dense | embs] ([F = T + 1, D] per sample); out = [dense | strict lower triangle of feats featsT, row-major (i, j < i)].
+// The composite PyTorch form (cat + bmm + advanced-index gather, and an index_put in the backward) moves ~10x the bytes it needs;
+// here each sample is handled in cache by one thread.
+}  // extern "C"  (templates below need C++ linkage)
+
+namespace {
+constexpr int kMaxF = 64;      // features per sample handled by the register-blocked path (T + 1 <= 64)
+
+// fwd: gram rows as small GEMV against the transposed features (vectorised over j, no horizontal sums)
+template <int D>
+void DotFwdRange(const float* __restrict dense, const float* __restrict embs, int64_t b0, int64_t b1, int T, float* __restrict out) {
+  const int F = T + 1, P = F * (F - 1) / 2, Fp = (F + 7) & ~7;
+  alignas(64) float ft[D * kMaxF];
+  alignas(64) float acc[kMaxF];
+  for (int64_t b = b0; b < b1; ++b) {
+    const float* d = dense + b * D; const float* e = embs + b * (int64_t)T * D;
+    float* o = out + b * (int64_t)(D + P);
+    for (int k = 0; k < D; ++k) {                      // ft[k][j] = feat[j][k]
+      float* r = ft + k * Fp;
+      r[0] = d[k];
+      for (int j = 1; j < F; ++j) r[j] = e[(int64_t)(j - 1) * D + k];
+      for (int j = F; j < Fp; ++j) r[j] = 0.f;
+    }
+    for (int k = 0; k < D; ++k) o[k] = d[k];
+    float* z = o + D;
+    for (int i = 1; i < F; ++i) {
+      const float* fi = e + (int64_t)(i - 1) * D;
+      const int n = (i + 7) & ~7;                      // only columns j < i are needed
+      for (int j = 0; j < n; ++j) acc[j] = 0.f;
+      for (int k = 0; k < D; ++k) {
+        const float a = fi[k]; const float* r = ft + k * Fp;
+        for (int j = 0; j < n; ++j) acc[j] += a * r[j];
+      }
+      for (int j = 0; j < i; ++j) *z++ = acc[j];
+    }
+  }
+}
+
+// bwd: dfeat[i] = sum_j S[i][j] feat[j] with S the symmetric zero-diagonal matrix built from dz (vectorised over D)
+template <int D>
+void DotBwdRange(const float* __restrict dense, const float* __restrict embs, const float* __restrict dz, int64_t b0, int64_t b1, int T,
+                 float* __restrict ddense, float* __restrict dembs) {
+  const int F = T + 1, P = F * (F - 1) / 2;
+  alignas(64) float S[kMaxF * kMaxF];
+  alignas(64) float feat[kMaxF * D];
+  alignas(64) float acc[D];
+  for (int64_t b = b0; b < b1; ++b) {
+    const float* d = dense + b * D; const float* e = embs + b * (int64_t)T * D;
+    const float* g = dz + b * (int64_t)(D + P); const float* gz = g + D;
+    for (int k = 0; k < D; ++k) feat[k] = d[k];
+    for (int j = 1; j < F; ++j) for (int k = 0; k < D; ++k) feat[j * D + k] = e[(int64_t)(j - 1) * D + k];
+    for (int i = 0; i < F; ++i) S[i * F + i] = 0.f;
+    for (int i = 1; i < F; ++i) for (int j = 0; j < i; ++j) { const float w = *gz++; S[i * F + j] = w; S[j * F + i] = w; }
+    for (int i = 0; i < F; ++i) {
+      for (int k = 0; k < D; ++k) acc[k] = i == 0 ? g[k] : 0.f;           // feature 0 also receives the pass-through gradient
+      const float* si = S + i * F;
+      for (int j = 0; j < F; ++j) {
+        const float w = si[j]; const float* fj = feat + j * D;
+        for (int k = 0; k < D; ++k) acc[k] += w * fj[k];
+      }
+      float* dst = i == 0 ? ddense + b * D : dembs + b * (int64_t)T * D + (int64_t)(i - 1) * D;
+      for (int k = 0; k < D; ++k) dst[k] = acc[k];
+    }
+  }
+}
+
+// generic (any D, any T) scalar fallbacks
+void DotFwdGeneric(const float* dense, const float* embs, int64_t b0, int64_t b1, int T, int D, float* out) {
+  const int F = T + 1, P = F * (F - 1) / 2;
+  for (int64_t b = b0; b < b1; ++b) {
+    const float* d = dense + b * D; const float* e = embs + b * (int64_t)T * D;
+    float* o = out + b * (int64_t)(D + P);
+    memcpy(o, d, sizeof(float) * D);
+    float* z = o + D;
+    for (int i = 1; i < F; ++i) {
+      const float* fi = e + (int64_t)(i - 1) * D;
+      for (int j = 0; j < i; ++j) {
+        const float* fj = j == 0 ? d : e + (int64_t)(j - 1) * D;
+        float a = 0.f;
+        for (int k = 0; k < D; ++k) a += fi[k] * fj[k];
+        *z++ = a;
+      }
+    }
+  }
+}
+void DotBwdGeneric(const float* dense, const float* embs, const float* dz, int64_t b0, int64_t b1, int T, int D, float* ddense, float* dembs) {
+  const int F = T + 1, P = F * (F - 1) / 2;
+  for (int64_t b = b0; b < b1; ++b) {
+    const float* d = dense + b * D; const float* e = embs + b * (int64_t)T * D;
+    const float* g = dz + b * (int64_t)(D + P);
+    float* dd = ddense + b * D; float* de = dembs + b * (int64_t)T * D;
+    memcpy(dd, g, sizeof(float) * D);
+    memset(de, 0, sizeof(float) * (size_t)T * D);
+    const float* gz = g + D;
+    for (int i = 1; i < F; ++i) {
+      const float* fi = e + (int64_t)(i - 1) * D; float* gi = de + (int64_t)(i - 1) * D;
+      for (int j = 0; j < i; ++j) {
+        const float w = *gz++;
+        const float* fj = j == 0 ? d : e + (int64_t)(j - 1) * D;
+        float* gj = j == 0 ? dd : de + (int64_t)(j - 1) * D;
+        for (int k = 0; k < D; ++k) { gi[k] += w * fj[k]; gj[k] += w * fi[k]; }
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+void dr_host_dot_interaction_fwd(const float* dense, const float* embs, int64_t B, int T, int D, float* out) {
+  const bool blocked = T + 1 <= kMaxF;
+  dr::GlobalPool()->ParallelFor(B, 64, [&](int64_t b0, int64_t b1) {
+    if (blocked && D == 16) DotFwdRange<16>(dense, embs, b0, b1, T, out);
+    else if (blocked && D == 8) DotFwdRange<8>(dense, embs, b0, b1, T, out);
+    else if (blocked && D == 32) DotFwdRange<32>(dense, embs, b0, b1, T, out);
+    else if (blocked && D == 64) DotFwdRange<64>(dense, embs, b0, b1, T, out);
+    else DotFwdGeneric(dense, embs, b0, b1, T, D, out);
+  });
+}
+// dz [B, D + P] -> ddense [B, D], dembs [B, T, D]
+void dr_host_dot_interaction_bwd(const float* dense, const float* embs, const float* dz, int64_t B, int T, int D, float* ddense, float* dembs) {
+  const bool blocked = T + 1 <= kMaxF;
+  dr::GlobalPool()->ParallelFor(B, 64, [&](int64_t b0, int64_t b1) {
+    if (blocked && D == 16) DotBwdRange<16>(dense, embs, dz, b0, b1, T, ddense, dembs);
+    else if (blocked && D == 8) DotBwdRange<8>(dense, embs, dz, b0, b1, T, ddense, dembs);
+    else if (blocked && D == 32) DotBwdRange<32>(dense, embs, dz, b0, b1, T, ddense, dembs);
+    else if (blocked && D == 64) DotBwdRange<64>(dense, embs, dz, b0, b1, T, ddense, dembs);
+    else DotBwdGeneric(dense, embs, dz, b0, b1, T, D, ddense, dembs);
+  });
 }
 
 int dr_host_num_threads() { return dr::GlobalPool()->size() + 1; }

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -102,8 +103,11 @@ class SsdHashStore {
       // verify the key, flush, re-read the index and retry
       bool ok = false;
       for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
-        int fd = FdOf(p.file);
-        ok = fd >= 0 && ::pread(fd, rec.data(), rec_bytes_, p.off) == (ssize_t)rec_bytes_ && memcmp(rec.data(), &keys[i], 8) == 0;
+        {
+          std::shared_lock<std::shared_mutex> rd(fd_mu_);      // compaction may not close this descriptor while it is being read
+          int fd = FdOf(p.file);
+          ok = fd >= 0 && ::pread(fd, rec.data(), rec_bytes_, p.off) == (ssize_t)rec_bytes_ && memcmp(rec.data(), &keys[i], 8) == 0;
+        }
         if (ok) break;
         Flush();
         Shard& S = shard(keys[i]);
@@ -182,6 +186,7 @@ class SsdHashStore {
         it->second = Append(rec.data());
       }
       Flush();
+      std::unique_lock<std::shared_mutex> wr(fd_mu_);          // wait for in-flight readers of this file (found by ThreadSanitizer: close vs pread)
       std::lock_guard<std::mutex> l(wmu_);
       ::close(files_[f].fd); ::unlink(files_[f].path.c_str());
       files_[f].fd = -1; files_[f].total = 0; files_[f].live = 0;
@@ -267,6 +272,7 @@ class SsdHashStore {
   int64_t buf_off_ = 0;
   std::atomic<int64_t> size_{0}, compactions_{0};
   std::mutex compact_mu_;
+  std::shared_mutex fd_mu_;            // readers (Get) shared, descriptor close (Compact) exclusive
   std::mutex cmu_;
   std::condition_variable ccv_;
   bool stop_ = false, wake_ = false;

@@ -93,19 +93,17 @@ class HostTable:
         self.lib.dr_host_ev_apply(self.h, ptr(k), ptr(g), ptr(c), k.numel(), C.byref(hp))
 
     def apply_raw(self, ids: torch.Tensor, grads: torch.Tensor, hp: OptHyper) -> None:
-        """Dedup (unique-with-counts + segment-sum, optimizer.py:91) then apply."""
+        """Dedup (unique-with-counts + segment-sum, optimizer.py:91) then apply -- one native call; a row-strided ``grads`` view
+        (e.g. ``g[:, t, :]`` of a grouped lookup) is consumed in place."""
         k = _i64(ids).view(-1)
         n = k.numel()
         if n == 0:
             return
-        g = grads.to(torch.float32).contiguous().view(n, self.dim)
-        uniq = torch.empty(n, dtype=torch.int64)
-        inv = torch.empty(n, dtype=torch.int64)
-        cnt = torch.empty(n, dtype=torch.int64)
-        nu = int(self.lib.dr_host_unique(ptr(k), n, ptr(uniq), ptr(inv), ptr(cnt)))
-        gs = torch.empty(nu, self.dim, dtype=torch.float32)
-        self.lib.dr_host_segment_sum(ptr(g), ptr(inv), n, self.dim, ptr(gs), nu)
-        self.lib.dr_host_ev_apply(self.h, ptr(uniq), ptr(gs), ptr(cnt), nu, C.byref(hp))
+        g = grads if grads.dtype == torch.float32 else grads.to(torch.float32)
+        g = g.reshape(n, self.dim) if g.is_contiguous() else g
+        if g.dim() != 2 or g.stride(1) != 1:
+            g = g.reshape(n, self.dim).contiguous()
+        self.lib.dr_host_ev_apply_raw(self.h, ptr(k), n, C.c_void_p(g.data_ptr()), int(g.stride(0)), C.byref(hp))
 
     # ---- lifecycle -----------------------------------------------------------------------
     def shrink(self, step: int) -> int:
@@ -222,6 +220,7 @@ class EmbeddingVariable(nn.Module):
         self._table = None
         self._owner = 0
         self._pending: List = []
+        self._group_pending = []          # grouped sparse gradients (ops/host_group.py), drained by the optimizer
         self._seed = seed
         self._inference = inference_mode()
         g = torch.Generator().manual_seed(seed if seed is not None else (zlib.crc32(name.encode()) & 0x7FFFFFFF))
@@ -397,8 +396,11 @@ class EmbeddingVariable(nn.Module):
         """Concatenated (ids, grads) accumulated by backward since the last step."""
         if not self._pending:
             return None
-        ids = torch.cat([p[0] for p in self._pending])
-        grads = torch.cat([p[1] for p in self._pending])
+        if len(self._pending) == 1:                     # the common case: one lookup per step -> no copy
+            ids, grads = self._pending[0]
+        else:
+            ids = torch.cat([p[0] for p in self._pending])
+            grads = torch.cat([p[1] for p in self._pending])
         self._pending.clear()
         return ids, grads
 

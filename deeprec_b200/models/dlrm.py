@@ -15,9 +15,40 @@ from ..config import EmbeddingVariableOption
 from ..embedding_variable import EmbeddingVariable, get_embedding_variable
 
 
+class _HostDotInteraction(torch.autograd.Function):
+    """CPU fp32: the native per-sample kernel of csrc/host/host_engine.cc (no cat / bmm / index gather / index_put)."""
+
+    @staticmethod
+    def forward(ctx, dense, embs):
+        from .. import _native
+        dense, embs = dense.contiguous(), embs.contiguous()
+        B, T, D = embs.shape
+        out = torch.empty(B, D + (T + 1) * T // 2, dtype=torch.float32)
+        _native.host().dr_host_dot_interaction_fwd(_native.ptr(dense), _native.ptr(embs), B, T, D, _native.ptr(out))
+        ctx.save_for_backward(dense, embs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        from .. import _native
+        dense, embs = ctx.saved_tensors
+        B, T, D = embs.shape
+        dz = dz.contiguous()
+        dd, de = torch.empty_like(dense), torch.empty_like(embs)
+        _native.host().dr_host_dot_interaction_bwd(_native.ptr(dense), _native.ptr(embs), _native.ptr(dz), B, T, D, _native.ptr(dd), _native.ptr(de))
+        return dd, de
+
+
 def dot_interaction(dense: torch.Tensor, embs: torch.Tensor) -> torch.Tensor:
     """dense [B, D], embs [B, T, D] -> [B, D + (T+1)T/2]; pair order (i, j<i) row-major
     (tf.boolean_mask of the strict lower triangle, modelzoo/dlrm/train.py:121-133)."""
+    if dense.device.type == "cpu" and dense.dtype == torch.float32 and embs.dtype == torch.float32 and dense.shape[1] == embs.shape[2]:
+        return _HostDotInteraction.apply(dense, embs)
+    return dot_interaction_reference(dense, embs)
+
+
+def dot_interaction_reference(dense: torch.Tensor, embs: torch.Tensor) -> torch.Tensor:
+    """The composite expression (any device / dtype): the numerics oracle of every dot-interaction kernel."""
     feats = torch.cat([dense.unsqueeze(1), embs], dim=1)
     gram = torch.bmm(feats, feats.transpose(1, 2))
     F = feats.shape[1]
@@ -64,7 +95,12 @@ class DLRM(nn.Module):
     def forward(self, dense: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
         """dense [B, num_dense]; ids [T, B] (feature-major) -> logits [B]."""
         x = self.bot(dense)
-        embs = torch.stack([(t.lookup(ids[i]) if isinstance(t, EmbeddingVariable) else t(ids[i])).to(x.device) for i, t in enumerate(self.tables)], dim=1)
+        embs = None
+        if x.device.type == "cpu" and isinstance(self.tables[0], EmbeddingVariable):
+            from ..ops.host_group import group_lookup_dense_host
+            embs = group_lookup_dense_host(list(self.tables), ids)           # one native call -> [B, T, D]
+        if embs is None:
+            embs = torch.stack([(t.lookup(ids[i]) if isinstance(t, EmbeddingVariable) else t(ids[i])).to(x.device) for i, t in enumerate(self.tables)], dim=1)
         if self.interaction_op == "dot":
             if self.fused_kernels:
                 from ..nn import dot_interaction as fused_dot   # tcgen05 kernel on CUDA (bf16), the expression above on CPU

@@ -92,6 +92,11 @@ class _Tables(nn.Module):
             out = group_lookup_dense_device(list(self.tables), ids)          # [B, T, D]; None if the tables cannot share a launch
             if out is not None:
                 return out
+        if not model_parallel and isinstance(self.tables[0], EmbeddingVariable) and self.tables[0].device.type == "cpu":
+            from ..ops.host_group import group_lookup_dense_host
+            out = group_lookup_dense_host(list(self.tables), ids)            # [B, T, D] from one native call; None for tiered tables
+            if out is not None:
+                return out
         if model_parallel or (self.group and self.tables[0].device.type == "cuda"):
             sps = [SparseIds.from_dense(ids[i]) for i in range(len(self.tables))]
             outs = group_embedding_lookup_sparse(list(self.tables), sps, ["sum"] * len(sps))

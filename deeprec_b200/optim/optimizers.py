@@ -138,6 +138,8 @@ class DeepRecOptimizer(torch.optim.Optimizer):
                 ps = [p for p in g_["params"] if p.grad is not None]
                 if ps:
                     self._dense_update_many(ps, [p.grad for p in ps], [self.state[p] for p in ps], g_, hp)
+        from ..ops.host_group import apply_group_pending
+        apply_group_pending(self.evs, hp)          # grouped host lookups: one native dedup + apply call per group
         for ev in self.evs:
             if ev.device.type == "cuda":
                 if ev._table is not None:
@@ -156,6 +158,7 @@ class DeepRecOptimizer(torch.optim.Optimizer):
         super().zero_grad(set_to_none)
         for ev in self.evs:
             ev._pending.clear()
+            ev._group_pending.clear()
 
 
 class GradientDescentOptimizer(DeepRecOptimizer):

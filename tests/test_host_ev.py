@@ -230,3 +230,41 @@ def test_ssd_store_async_compaction(tmp_path):
     rows, f, v, found = s.get(keys)
     assert found.all() and (rows == 5.0).all() and (f == 5).all()
     assert s.remove(keys[:500]) == 500 and s.size() == 500
+
+
+def test_grouped_host_lookup_and_apply_equal_per_table_path():
+    """ops/host_group: one native lookup -> [B, T, D] and one native dedup+apply for T tables == T independent lookups + applies,
+    including admission filters, frequency / version bookkeeping and default rows."""
+    from deeprec_b200.ops.host_group import group_lookup_dense_host
+    T, B, D = 9, 300, 8        # T >= pool size on small boxes exercises the table-parallel branch, see also T=3 below
+
+    def make(tag, T):
+        dr.embedding_variable.clear_registry()
+        evs = [dr.get_embedding_variable(f"{tag}/t{t}", D, seed=20 + t,
+                                         ev_option=dr.EmbeddingVariableOption(filter_option=dr.CounterFilter(2) if t % 2 else None)) for t in range(T)]
+        return evs, dr.optim.AdamOptimizer([], evs, lr=0.01, global_step=GlobalStep())
+
+    for T_ in (T, 3):
+        ga, oa = make("grp", T_)
+        gb, ob = make("ref", T_)
+        g = torch.Generator().manual_seed(5)
+        for step in range(4):
+            ids = (torch.randn(T_, B, generator=g).abs() * 40).long()
+            w = torch.randn(B, T_, D, generator=g)
+            out_a = group_lookup_dense_host(ga, ids)
+            out_b = torch.stack([e.lookup(ids[t]) for t, e in enumerate(gb)], 1)
+            assert out_a.shape == (B, T_, D) and torch.equal(out_a, out_b)
+            (out_a * w).sum().backward(); oa.step(); oa.zero_grad()
+            (out_b * w).sum().backward(); ob.step(); ob.zero_grad()
+        probe = torch.arange(0, 200)
+        for ea, eb in zip(ga, gb):
+            assert ea.total_count() == eb.total_count() and ea.table.total_keys() == eb.table.total_keys()
+            assert torch.allclose(ea.table.lookup(probe), eb.table.lookup(probe), atol=1e-6)
+            assert torch.equal(ea.get_frequency(probe), eb.get_frequency(probe)) and torch.equal(ea.get_version(probe), eb.get_version(probe))
+            assert torch.allclose(ea.slot_values(probe, "v"), eb.slot_values(probe, "v"), atol=1e-7)
+        with torch.no_grad():                                      # inference path: same native call, no autograd node
+            assert torch.equal(group_lookup_dense_host(ga, ids), torch.stack([e.lookup(ids[t]) for t, e in enumerate(ga)], 1))
+    # not eligible -> None (mixed dims)
+    dr.embedding_variable.clear_registry()
+    mixed = [dr.get_embedding_variable("m0", 8), dr.get_embedding_variable("m1", 4)]
+    assert group_lookup_dense_host(mixed, torch.zeros(2, 5, dtype=torch.int64)) is None

@@ -150,10 +150,11 @@ def _elastic_proc(rank, port, tmp):
     else:
         # this worker keeps training while the other one re-shards: stale-definition rejections are retried transparently
         import time
-        n = 0
-        while not os.path.exists(flag) and n < 400:
+        n, t0 = 0, time.time()
+        while not os.path.exists(flag) and time.time() - t0 < 150:
             step(); n += 1
             time.sleep(0.01)
+        assert os.path.exists(flag), "the scaling worker did not finish"
         client.wait()
         client.refresh_server_def()
         assert client.num_ps == 1
