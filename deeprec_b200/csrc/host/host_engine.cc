@@ -208,6 +208,23 @@ class HostKV {
     std::shared_lock<std::shared_mutex> l(P.mu);
     return FindLocked(P, key);
   }
+  // Batch readers: hold every partition's shared lock ONCE for a whole key range instead of once per key (the per-key lock/unlock
+  // is an atomic RMW on a line shared by all reader threads: ~2/3 of the cost of a random lookup), then probe with FindNoLock and
+  // hide the DRAM latency of the probes with PrefetchSlot.
+  class SharedAll {
+   public:
+    explicit SharedAll(HostKV& kv) : kv_(kv) { for (int p = 0; p < kv_.nparts_; ++p) kv_.parts_[p].mu.lock_shared(); }
+    ~SharedAll() { for (int p = kv_.nparts_ - 1; p >= 0; --p) kv_.parts_[p].mu.unlock_shared(); }
+    SharedAll(const SharedAll&) = delete;
+   private:
+    HostKV& kv_;
+  };
+  int32_t FindNoLock(int64_t key) { return FindLocked(parts_[PartOf(key)], key); }
+  void PrefetchSlot(int64_t key) const {
+    const KVPart& P = parts_[PartOf(key)];
+    const uint64_t pos = dr_mix64((uint64_t)key) & (uint64_t)(P.cap - 1);
+    __builtin_prefetch(&P.keys[pos]); __builtin_prefetch(&P.vals[pos]);
+  }
   // find or insert; `alloc` is called exactly once by the inserting thread to get a meta index.
   template <typename Alloc>
   int32_t FindOrInsert(int64_t key, Alloc&& alloc, bool* inserted) {
@@ -410,16 +427,31 @@ class HostEV {
   // keys[b, e) -> out + i * out_stride (serial; callers parallelise over ranges / tables)
   void LookupRange(const int64_t* keys, int64_t b, int64_t e, float* out, int64_t out_stride) {
     const int64_t dim = cfg_.dim;
-    for (int64_t i = b; i < e; ++i) {
-      int32_t idx = kv_.Find(keys[i]);
-      int32_t r = idx >= 0 ? RowOf(idx) : -1;
-      float* o = out + i * out_stride;
-      if (r >= 0) {
-        memcpy(o, rows_.at(r), dim * sizeof(float));
-      } else if (cfg_.filter_type != DR_FILTER_NONE && cfg_.filter_freq > 0) {
-        std::fill(o, o + dim, cfg_.default_value_no_permission);
-      } else {
-        memcpy(o, DefaultRow(keys[i]), dim * sizeof(float));
+    constexpr int W = 16;                                  // software pipeline: slots of W keys, then their metadata, then their rows
+    HostKV::SharedAll guard(kv_);
+    for (int64_t i0 = b; i0 < e; i0 += W) {
+      const int n = (int)std::min<int64_t>(W, e - i0);
+      if (i0 + W < e) for (int j = 0; j < (int)std::min<int64_t>(W, e - i0 - W); ++j) kv_.PrefetchSlot(keys[i0 + W + j]);
+      int32_t row[W];
+      for (int j = 0; j < n; ++j) {
+        const int32_t idx = kv_.FindNoLock(keys[i0 + j]);
+        row[j] = idx;
+        if (idx >= 0) __builtin_prefetch(row_.at(idx));
+      }
+      for (int j = 0; j < n; ++j) {
+        row[j] = row[j] >= 0 ? RowOf(row[j]) : -1;
+        if (row[j] >= 0) __builtin_prefetch(rows_.at(row[j]));
+      }
+      for (int j = 0; j < n; ++j) {
+        const int64_t i = i0 + j;
+        float* o = out + i * out_stride;
+        if (row[j] >= 0) {
+          memcpy(o, rows_.at(row[j]), dim * sizeof(float));
+        } else if (cfg_.filter_type != DR_FILTER_NONE && cfg_.filter_freq > 0) {
+          std::fill(o, o + dim, cfg_.default_value_no_permission);
+        } else {
+          memcpy(o, DefaultRow(keys[i]), dim * sizeof(float));
+        }
       }
     }
   }

@@ -42,8 +42,9 @@ class _HostDotInteraction(torch.autograd.Function):
 def dot_interaction(dense: torch.Tensor, embs: torch.Tensor) -> torch.Tensor:
     """dense [B, D], embs [B, T, D] -> [B, D + (T+1)T/2]; pair order (i, j<i) row-major
     (tf.boolean_mask of the strict lower triangle, modelzoo/dlrm/train.py:121-133)."""
-    if dense.device.type == "cpu" and dense.dtype == torch.float32 and embs.dtype == torch.float32 and dense.shape[1] == embs.shape[2]:
-        return _HostDotInteraction.apply(dense, embs)
+    if dense.device.type == "cpu" and dense.shape[1] == embs.shape[2] and dense.dtype in (torch.float32, torch.bfloat16):
+        # under bf16 autocast the bottom MLP hands over bf16: the interaction itself stays fp32 (it is bandwidth-, not FLOP-bound)
+        return _HostDotInteraction.apply(dense.float(), embs.float())
     return dot_interaction_reference(dense, embs)
 
 
