@@ -479,20 +479,21 @@ class HostEV {
 
   // ---- LookupOrCreateKey with admission (counter_filter_policy.h:106-139) -------------
   // returns row index (>=0) when the key is admitted, -1 otherwise.
-  int32_t LookupOrCreate(int64_t key, int64_t count, int64_t step) {
+  // `known` = meta index already resolved by a batched read-only probe (ApplyRange), or -1
+  int32_t LookupOrCreate(int64_t key, int64_t count, int64_t step, int32_t known = -1) {
     if (cfg_.is_inference) {
-      int32_t idx = kv_.Find(key);
+      int32_t idx = known >= 0 ? known : kv_.Find(key);
       return idx >= 0 ? RowOf(idx) : -1;
     }
     if (bloom_) {
-      int32_t idx = kv_.Find(key);
+      int32_t idx = known >= 0 ? known : kv_.Find(key);
       if (idx < 0) {
         int64_t mn = bloom_->AddAndMin(key, count);
         if (mn < cfg_.filter_freq) return -1;
       }
     }
     bool inserted = false;
-    int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
+    int32_t idx = known >= 0 ? known : kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
     int64_t* f = freq_.at(idx);
     int64_t nf = __atomic_add_fetch(f, count, __ATOMIC_RELAXED);
     __atomic_store_n(version_.at(idx), step, __ATOMIC_RELAXED);
@@ -523,10 +524,28 @@ class HostEV {
   void ApplyRange(const int64_t* keys, const float* grads, const int64_t* counts, int64_t b, int64_t e, const DrOptHyper& hp) {
     const int64_t dim = cfg_.dim;
     const float alpha = dr_adam_alpha(hp);
+    // In steady state almost every key already exists: resolve them with ONE shared-lock acquisition and prefetched probes; only
+    // the misses go through the locking find-or-insert.  (Remove / Shrink never run concurrently with Apply, so an index found
+    // here stays valid.)
+    std::vector<int32_t> known((size_t)(e - b));
+    {
+      HostKV::SharedAll guard(kv_);
+      constexpr int W = 16;
+      for (int64_t i0 = b; i0 < e; i0 += W) {
+        const int n = (int)std::min<int64_t>(W, e - i0);
+        if (i0 + W < e) for (int j = 0; j < (int)std::min<int64_t>(W, e - i0 - W); ++j) kv_.PrefetchSlot(keys[i0 + W + j]);
+        for (int j = 0; j < n; ++j) {
+          const int32_t idx = kv_.FindNoLock(keys[i0 + j]);
+          known[(size_t)(i0 + j - b)] = idx;
+          if (idx >= 0) { __builtin_prefetch(row_.at(idx)); __builtin_prefetch(freq_.at(idx)); }
+        }
+      }
+    }
     {
       std::vector<float> newacc(dim);
       for (int64_t i = b; i < e; ++i) {
-        int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step);
+        if (i + 4 < e && known[(size_t)(i + 4 - b)] >= 0) { const int32_t r4 = RowOf(known[(size_t)(i + 4 - b)]); if (r4 >= 0) __builtin_prefetch(rows_.at(r4)); }
+        int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step, known[(size_t)(i - b)]);
         if (r < 0) continue;
         float* row = rows_.at(r);
         const float* g = grads + i * dim;
@@ -806,13 +825,58 @@ void dr_host_segment_sum(const float* grads, const int64_t* inverse, int64_t n, 
 namespace {
 // dedup (first-occurrence order) + per-unique gradient sums of one table; grads row i at grads + i * row_stride
 struct DedupScratch { std::vector<int64_t> uniq, inv, cnt; std::vector<float> gsum; int64_t nu = 0; };
-void DedupAndSum(const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, int64_t dim, DedupScratch* s) {
+void DedupAndSumSerial(const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, int64_t dim, DedupScratch* s) {
   s->uniq.resize(n); s->inv.resize(n); s->cnt.resize(n);
   s->nu = n ? dr_host_unique(ids, n, s->uniq.data(), s->inv.data(), s->cnt.data()) : 0;
   s->gsum.assign((size_t)(s->nu * dim), 0.f);
   for (int64_t i = 0; i < n; ++i) {
     float* o = s->gsum.data() + s->inv[i] * dim; const float* g = grads + i * row_stride;
     for (int64_t d = 0; d < dim; ++d) o[d] += g[d];
+  }
+}
+
+// Large batches (sequence models push B x L ids into one table): bucket the occurrences by key hash, then every bucket is de-duplicated
+// and summed by its own thread (a key lives in exactly one bucket, so buckets are independent); results are concatenated.
+// The unique order differs from first-occurrence order, which no consumer depends on.
+void DedupAndSum(const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, int64_t dim, DedupScratch* s, bool allow_parallel = true) {
+  const int nb = std::min<int>(64, (dr::GlobalPool()->size() + 1) * 4);
+  if (!allow_parallel || n < 16384 || nb < 4) { DedupAndSumSerial(ids, n, grads, row_stride, dim, s); return; }
+  std::vector<int32_t> bucket_of((size_t)n), order((size_t)n);
+  std::vector<int64_t> start((size_t)nb + 1, 0);
+  dr::GlobalPool()->ParallelFor(n, 8192, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i) bucket_of[(size_t)i] = (int32_t)((dr_mix64((uint64_t)ids[i]) >> 33) % (uint64_t)nb);
+  });
+  for (int64_t i = 0; i < n; ++i) start[(size_t)bucket_of[(size_t)i] + 1]++;
+  for (int k = 0; k < nb; ++k) start[(size_t)k + 1] += start[(size_t)k];
+  { std::vector<int64_t> cur(start.begin(), start.end() - 1); for (int64_t i = 0; i < n; ++i) order[(size_t)cur[(size_t)bucket_of[(size_t)i]]++] = (int32_t)i; }
+  std::vector<DedupScratch> parts((size_t)nb);
+  dr::GlobalPool()->ParallelFor(nb, 1, [&](int64_t b, int64_t e) {
+    std::vector<int64_t> keys;
+    for (int64_t k = b; k < e; ++k) {
+      const int64_t lo = start[(size_t)k], m = start[(size_t)k + 1] - lo;
+      DedupScratch& P = parts[(size_t)k];
+      keys.resize((size_t)m);
+      for (int64_t j = 0; j < m; ++j) keys[(size_t)j] = ids[order[(size_t)(lo + j)]];
+      P.uniq.resize((size_t)m); P.inv.resize((size_t)m); P.cnt.resize((size_t)m);
+      P.nu = m ? dr_host_unique(keys.data(), m, P.uniq.data(), P.inv.data(), P.cnt.data()) : 0;
+      P.gsum.assign((size_t)(P.nu * dim), 0.f);
+      for (int64_t j = 0; j < m; ++j) {
+        float* o = P.gsum.data() + P.inv[(size_t)j] * dim; const float* g = grads + (int64_t)order[(size_t)(lo + j)] * row_stride;
+        for (int64_t d = 0; d < dim; ++d) o[d] += g[d];
+      }
+    }
+  });
+  int64_t nu = 0;
+  for (auto& P : parts) nu += P.nu;
+  s->nu = nu; s->uniq.resize((size_t)nu); s->cnt.resize((size_t)nu); s->gsum.resize((size_t)(nu * dim));
+  int64_t off = 0;
+  for (auto& P : parts) {
+    if (P.nu) {
+      memcpy(s->uniq.data() + off, P.uniq.data(), sizeof(int64_t) * (size_t)P.nu);
+      memcpy(s->cnt.data() + off, P.cnt.data(), sizeof(int64_t) * (size_t)P.nu);
+      memcpy(s->gsum.data() + off * dim, P.gsum.data(), sizeof(float) * (size_t)(P.nu * dim));
+    }
+    off += P.nu;
   }
 }
 }  // namespace
@@ -850,7 +914,7 @@ void dr_host_group_apply_raw(void** hs, int T, const int64_t* ids, int64_t B, co
       DedupScratch s;
       for (int64_t t = b; t < e; ++t) {
         auto* ev = static_cast<dr::HostEV*>(hs[t]);
-        DedupAndSum(ids + t * B, B, grads + t * dim, row_stride, dim, &s);
+        DedupAndSum(ids + t * B, B, grads + t * dim, row_stride, dim, &s, /*allow_parallel=*/false);   // already inside a parallel region
         ev->ApplyRange(s.uniq.data(), s.gsum.data(), s.cnt.data(), 0, s.nu, *hp);
       }
     });
