@@ -38,6 +38,23 @@ def din_attention_reference(q: torch.Tensor, k: torch.Tensor, mask: torch.Tensor
     return (w.unsqueeze(-1) * k).sum(1)
 
 
+def din_attention_composite(q: torch.Tensor, k: torch.Tensor, mask: torch.Tensor, att: nn.Module) -> torch.Tensor:
+    """Differentiable training path: same math as ``din_attention_reference`` with the first layer split
+    (``W1 [q, k, q-k, q*k] = (Wq + Wd) q + (Wk - Wd) k + Wp (q*k)``): the q term is computed once per sample, the ``[B, L, 4D]``
+    concat is never built and the first layer costs half the FLOPs.  Falls back to the reference for other ``att`` shapes."""
+    if not _fusable(att) or att[0].in_features != 4 * q.shape[-1]:
+        return din_attention_reference(q, k, mask, att)
+    import torch.nn.functional as F
+    D = q.shape[-1]
+    Wq, Wk, Wp = split_first_layer(att[0].weight, D)
+    hq = F.linear(q, Wq, att[0].bias)                                        # [B, H1], once per sample
+    h1 = torch.sigmoid(hq.unsqueeze(1) + F.linear(k, Wk) + F.linear(q.unsqueeze(1) * k, Wp))
+    s = att[4](torch.sigmoid(att[2](h1))).squeeze(-1)
+    s = s.masked_fill(~mask, -2 ** 31)
+    w = torch.softmax(s, -1) * mask.any(-1, keepdim=True)
+    return torch.bmm(w.unsqueeze(1), k).squeeze(1)                            # weighted sum of the keys
+
+
 def split_first_layer(W1: torch.Tensor, D: int):
     """The algebra the kernel uses: W1 [H1, 4D] -> (Wq, Wk, Wp) with  W1 @ [q, k, q-k, q*k] = Wq q + Wk k + Wp (q*k)."""
     Wa, Wb, Wc, Wd = W1[:, :D], W1[:, D:2 * D], W1[:, 2 * D:3 * D], W1[:, 3 * D:]
@@ -54,7 +71,7 @@ def din_attention(q: torch.Tensor, k: torch.Tensor, mask: torch.Tensor, att: nn.
     """Dispatch: fused kernel when on CUDA, no gradient is required and ``att`` is the Linear-Sigmoid-Linear-Sigmoid-Linear(1) unit."""
     needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or any(p.requires_grad for p in att.parameters()))
     if not q.is_cuda or needs_grad or not _fusable(att) or att[0].in_features != 4 * q.shape[-1]:
-        return din_attention_reference(q, k, mask, att)
+        return din_attention_composite(q, k, mask, att)
     B, L, D = k.shape
     l1, l2, l3 = att[0], att[2], att[4]
     qf, kf = q.detach().float().contiguous(), k.detach().float().contiguous()

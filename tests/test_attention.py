@@ -46,3 +46,22 @@ def test_dispatch_falls_back_on_cpu_and_under_autograd():
     out.sum().backward()
     assert q.grad is not None and att[0].weight.grad is not None
     assert A._fusable(att) and not A._fusable(nn.Sequential(nn.Linear(8, 1)))
+
+
+def test_composite_training_path_matches_reference_values_and_gradients():
+    att_a, att_b = _unit(), _unit()
+    g = torch.Generator().manual_seed(2)
+    q = torch.randn(12, 32, generator=g); k = torch.randn(12, 9, 32, generator=g)
+    lens = torch.randint(0, 10, (12,), generator=g); lens[0] = 0
+    mask = torch.arange(9).unsqueeze(0) < lens.unsqueeze(1)
+    k = k * mask.unsqueeze(-1)
+    qa, ka = q.clone().requires_grad_(), k.clone().requires_grad_()
+    qb, kb = q.clone().requires_grad_(), k.clone().requires_grad_()
+    oa = A.din_attention_composite(qa, ka, mask, att_a)
+    ob = A.din_attention_reference(qb, kb, mask, att_b)
+    assert torch.allclose(oa, ob, atol=1e-5)
+    w = torch.randn(12, 32, generator=g)
+    (oa * w).sum().backward(); (ob * w).sum().backward()
+    assert torch.allclose(qa.grad, qb.grad, atol=1e-5) and torch.allclose(ka.grad, kb.grad, atol=1e-5)
+    for pa, pb in zip(att_a.parameters(), att_b.parameters()):
+        assert torch.allclose(pa.grad, pb.grad, atol=1e-5)
