@@ -108,6 +108,12 @@ class EmbeddingVariableOption:
     record_version: bool = True
 
 
+# The one int64 value that is never a key (the hash tables' empty-slot marker).  Host tables treat it as PADDING: a lookup returns a zero
+# row, nothing is created / counted / updated for it -- so a dense ``[B, L]`` history tensor can mark its unused positions with it instead
+# of looking up (and polluting the statistics of) a real id.
+PAD_KEY = -(1 << 63)
+
+
 def env_flag(name: str, default: bool = False) -> bool:
     v = os.environ.get(name)
     if v is None:

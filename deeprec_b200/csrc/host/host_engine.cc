@@ -204,6 +204,7 @@ class HostKV {
 
   // wait-free find; returns meta index or -1
   int32_t Find(int64_t key) {
+    if (key == kEmptyKey) return -1;                   // the reserved padding / empty-slot value is never a stored key
     KVPart& P = parts_[PartOf(key)];
     std::shared_lock<std::shared_mutex> l(P.mu);
     return FindLocked(P, key);
@@ -219,7 +220,7 @@ class HostKV {
    private:
     HostKV& kv_;
   };
-  int32_t FindNoLock(int64_t key) { return FindLocked(parts_[PartOf(key)], key); }
+  int32_t FindNoLock(int64_t key) { return key == kEmptyKey ? -1 : FindLocked(parts_[PartOf(key)], key); }
   void PrefetchSlot(int64_t key) const {
     const KVPart& P = parts_[PartOf(key)];
     const uint64_t pos = dr_mix64((uint64_t)key) & (uint64_t)(P.cap - 1);
@@ -434,18 +435,22 @@ class HostEV {
       if (i0 + W < e) for (int j = 0; j < (int)std::min<int64_t>(W, e - i0 - W); ++j) kv_.PrefetchSlot(keys[i0 + W + j]);
       int32_t row[W];
       for (int j = 0; j < n; ++j) {
+        if (keys[i0 + j] == kEmptyKey) { row[j] = -3; continue; }       // DR_PAD_KEY: "no id here" (padding of a dense [B, L] id tensor)
         const int32_t idx = kv_.FindNoLock(keys[i0 + j]);
         row[j] = idx;
         if (idx >= 0) __builtin_prefetch(row_.at(idx));
       }
       for (int j = 0; j < n; ++j) {
+        if (row[j] == -3) continue;
         row[j] = row[j] >= 0 ? RowOf(row[j]) : -1;
         if (row[j] >= 0) __builtin_prefetch(rows_.at(row[j]));
       }
       for (int j = 0; j < n; ++j) {
         const int64_t i = i0 + j;
         float* o = out + i * out_stride;
-        if (row[j] >= 0) {
+        if (row[j] == -3) {
+          std::fill(o, o + dim, 0.f);                                      // padding reads zeros, is never created, counted or updated
+        } else if (row[j] >= 0) {
           memcpy(o, rows_.at(row[j]), dim * sizeof(float));
         } else if (cfg_.filter_type != DR_FILTER_NONE && cfg_.filter_freq > 0) {
           std::fill(o, o + dim, cfg_.default_value_no_permission);
@@ -535,6 +540,7 @@ class HostEV {
         const int n = (int)std::min<int64_t>(W, e - i0);
         if (i0 + W < e) for (int j = 0; j < (int)std::min<int64_t>(W, e - i0 - W); ++j) kv_.PrefetchSlot(keys[i0 + W + j]);
         for (int j = 0; j < n; ++j) {
+          if (keys[i0 + j] == kEmptyKey) { known[(size_t)(i0 + j - b)] = -3; continue; }      // padding id: skipped below
           const int32_t idx = kv_.FindNoLock(keys[i0 + j]);
           known[(size_t)(i0 + j - b)] = idx;
           if (idx >= 0) { __builtin_prefetch(row_.at(idx)); __builtin_prefetch(freq_.at(idx)); }
@@ -545,6 +551,7 @@ class HostEV {
       std::vector<float> newacc(dim);
       for (int64_t i = b; i < e; ++i) {
         if (i + 4 < e && known[(size_t)(i + 4 - b)] >= 0) { const int32_t r4 = RowOf(known[(size_t)(i + 4 - b)]); if (r4 >= 0) __builtin_prefetch(rows_.at(r4)); }
+        if (known[(size_t)(i - b)] == -3) continue;
         int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step, known[(size_t)(i - b)]);
         if (r < 0) continue;
         float* row = rows_.at(r);

@@ -280,7 +280,12 @@ class _SeqBase(nn.Module):
         q = torch.cat([self.item.lookup(b["item"]), self.cat.lookup(b["cat"])], -1)                   # [B, 2D] target
         hi, hc = b["hist_item"], b["hist_cat"]
         mask = (hi >= 0)
-        k = torch.cat([self.item.lookup(hi.clamp_min(0)), self.cat.lookup(hc.clamp_min(0))], -1)      # [B, L, 2D]
+        if hi.device.type == "cpu" and self.item.device.type == "cpu":
+            from ..config import PAD_KEY                     # host tables: padding positions are not looked up at all (zero rows, no statistics)
+            hi_l, hc_l = torch.where(mask, hi, PAD_KEY), torch.where(mask, hc, PAD_KEY)
+        else:
+            hi_l, hc_l = hi.clamp_min(0), hc.clamp_min(0)
+        k = torch.cat([self.item.lookup(hi_l), self.cat.lookup(hc_l)], -1)                            # [B, L, 2D]
         k = k * mask.unsqueeze(-1).to(k.dtype).to(k.device)
         return u, q, k, mask.to(k.device)
 

@@ -268,3 +268,20 @@ def test_grouped_host_lookup_and_apply_equal_per_table_path():
     dr.embedding_variable.clear_registry()
     mixed = [dr.get_embedding_variable("m0", 8), dr.get_embedding_variable("m1", 4)]
     assert group_lookup_dense_host(mixed, torch.zeros(2, 5, dtype=torch.int64)) is None
+
+
+def test_pad_key_reads_zeros_and_is_never_created_or_counted():
+    from deeprec_b200.config import PAD_KEY
+    dr.embedding_variable.clear_registry()
+    ev = _ev("padkey", 4, filter_option=dr.CounterFilter(1))
+    opt = dr.optim.AdagradOptimizer([], [ev], lr=0.5, global_step=GlobalStep())
+    ids = torch.tensor([[5, PAD_KEY, 7], [PAD_KEY, PAD_KEY, 5]])
+    for _ in range(2):
+        out = ev.lookup(ids)
+        assert torch.all(out[0, 1] == 0) and torch.all(out[1, :2] == 0)
+        (out * torch.arange(1.0, 7.0).view(2, 3, 1)).sum().backward(); opt.step(); opt.zero_grad()
+    assert ev.total_count() == 2 and ev.table.total_keys() == 2
+    assert ev.get_frequency(torch.tensor([5, 7, PAD_KEY])).tolist() == [4, 2, 0] and ev.get_version(torch.tensor([PAD_KEY])).tolist() == [-1]
+    assert torch.all(ev.lookup(torch.tensor([PAD_KEY])) == 0) and torch.all(ev.slot_values(torch.tensor([PAD_KEY]), "accumulator") == 0.1)
+    keys = ev.export()[0]
+    assert sorted(keys.tolist()) == [5, 7]
