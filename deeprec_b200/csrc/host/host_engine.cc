@@ -410,7 +410,7 @@ class HostEV {
   explicit HostEV(const DrEvConfig& c)
       : cfg_(c), stride_(dr_row_stride(c.dim, c.num_slots, c.has_scalars)),
         kv_(c.num_partitions > 0 ? c.num_partitions : 16, std::max<int64_t>(1024, c.init_capacity)),
-        freq_(1), version_(1), row_(1), dirty_(1), rows_(stride_) {
+        meta_(1), rows_(stride_) {
     default_.assign((size_t)(std::max<int64_t>(1, c.default_value_dim) * c.dim), 0.0f);
     if (c.filter_type == DR_FILTER_BLOOM)
       bloom_.reset(new CountingBloom(c.bloom_max_elements, c.bloom_fpp, c.bloom_counter_bits > 0 ? c.bloom_counter_bits : 32));
@@ -438,7 +438,7 @@ class HostEV {
         if (keys[i0 + j] == kEmptyKey) { row[j] = -3; continue; }       // DR_PAD_KEY: "no id here" (padding of a dense [B, L] id tensor)
         const int32_t idx = kv_.FindNoLock(keys[i0 + j]);
         row[j] = idx;
-        if (idx >= 0) __builtin_prefetch(row_.at(idx));
+        if (idx >= 0) __builtin_prefetch(meta_.at(idx));
       }
       for (int j = 0; j < n; ++j) {
         if (row[j] == -3) continue;
@@ -499,11 +499,11 @@ class HostEV {
     }
     bool inserted = false;
     int32_t idx = known >= 0 ? known : kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
-    int64_t* f = freq_.at(idx);
+    int64_t* f = (&meta_.at(idx)->freq);
     int64_t nf = __atomic_add_fetch(f, count, __ATOMIC_RELAXED);
-    __atomic_store_n(version_.at(idx), step, __ATOMIC_RELAXED);
-    __atomic_store_n(dirty_.at(idx), (uint8_t)1, __ATOMIC_RELAXED);
-    int32_t* rp = row_.at(idx);
+    __atomic_store_n((&meta_.at(idx)->version), step, __ATOMIC_RELAXED);
+    __atomic_store_n((&meta_.at(idx)->dirty), (uint8_t)1, __ATOMIC_RELAXED);
+    int32_t* rp = (&meta_.at(idx)->row);
     int32_t r = __atomic_load_n(rp, __ATOMIC_ACQUIRE);
     if (r >= 0) return r;
     bool admit = bloom_ ? true : (cfg_.filter_type == DR_FILTER_NONE || nf >= cfg_.filter_freq);
@@ -529,30 +529,35 @@ class HostEV {
   void ApplyRange(const int64_t* keys, const float* grads, const int64_t* counts, int64_t b, int64_t e, const DrOptHyper& hp) {
     const int64_t dim = cfg_.dim;
     const float alpha = dr_adam_alpha(hp);
-    // In steady state almost every key already exists: resolve them with ONE shared-lock acquisition and prefetched probes; only
-    // the misses go through the locking find-or-insert.  (Remove / Shrink never run concurrently with Apply, so an index found
-    // here stays valid.)
-    std::vector<int32_t> known((size_t)(e - b));
-    {
-      HostKV::SharedAll guard(kv_);
-      constexpr int W = 16;
-      for (int64_t i0 = b; i0 < e; i0 += W) {
-        const int n = (int)std::min<int64_t>(W, e - i0);
-        if (i0 + W < e) for (int j = 0; j < (int)std::min<int64_t>(W, e - i0 - W); ++j) kv_.PrefetchSlot(keys[i0 + W + j]);
-        for (int j = 0; j < n; ++j) {
-          if (keys[i0 + j] == kEmptyKey) { known[(size_t)(i0 + j - b)] = -3; continue; }      // padding id: skipped below
-          const int32_t idx = kv_.FindNoLock(keys[i0 + j]);
-          known[(size_t)(i0 + j - b)] = idx;
-          if (idx >= 0) { __builtin_prefetch(row_.at(idx)); __builtin_prefetch(freq_.at(idx)); }
+    // Blocks of kBlock keys: (1) a read-only pass under ONE shared-lock acquisition resolves the keys that already exist (in steady
+    // state almost all of them) with prefetched probes and pulls the slots / metadata of this block into the cache; (2) the update
+    // pass right behind it finds everything it touches still cached, and only the misses go through the locking find-or-insert.
+    // (Remove / Shrink never run concurrently with Apply, so an index found in (1) stays valid.)
+    constexpr int64_t kBlock = 256;
+    int32_t known_blk[kBlock];
+    std::vector<float> newacc(dim);
+    for (int64_t blk = b; blk < e; blk += kBlock) {
+      const int64_t be = std::min(e, blk + kBlock);
+      int32_t* known = known_blk - blk;                       // known[i] for i in [blk, be)
+      {
+        HostKV::SharedAll guard(kv_);
+        constexpr int W = 16;
+        for (int64_t i0 = blk; i0 < be; i0 += W) {
+          const int n = (int)std::min<int64_t>(W, be - i0);
+          if (i0 + W < be) for (int j = 0; j < (int)std::min<int64_t>(W, be - i0 - W); ++j) kv_.PrefetchSlot(keys[i0 + W + j]);
+          for (int j = 0; j < n; ++j) {
+            if (keys[i0 + j] == kEmptyKey) { known[i0 + j] = -3; continue; }      // padding id: skipped below
+            const int32_t idx = kv_.FindNoLock(keys[i0 + j]);
+            known[i0 + j] = idx;
+            if (idx >= 0) __builtin_prefetch(meta_.at(idx), 1);
+          }
         }
+        for (int64_t i = blk; i < be; ++i)
+          if (known[i] >= 0) { const int32_t r = RowOf(known[i]); if (r >= 0) __builtin_prefetch(rows_.at(r), 1); }
       }
-    }
-    {
-      std::vector<float> newacc(dim);
-      for (int64_t i = b; i < e; ++i) {
-        if (i + 4 < e && known[(size_t)(i + 4 - b)] >= 0) { const int32_t r4 = RowOf(known[(size_t)(i + 4 - b)]); if (r4 >= 0) __builtin_prefetch(rows_.at(r4)); }
-        if (known[(size_t)(i - b)] == -3) continue;
-        int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step, known[(size_t)(i - b)]);
+      for (int64_t i = blk; i < be; ++i) {
+        if (known[i] == -3) continue;
+        int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step, known[i]);
         if (r < 0) continue;
         float* row = rows_.at(r);
         const float* g = grads + i * dim;
@@ -588,10 +593,10 @@ class HostEV {
     std::vector<int32_t> freed_meta;
     int64_t removed = kv_.RemoveIf([&](int64_t key, int32_t idx) {
       (void)key;
-      int32_t r = *row_.at(idx);
+      int32_t r = *(&meta_.at(idx)->row);
       bool evict = false;
       if (gs) {
-        int64_t* v = version_.at(idx);
+        int64_t* v = (&meta_.at(idx)->version);
         if (*v == -1) *v = global_step;                       // globalstep_shrink_policy.h:50
         else if (global_step - *v > cfg_.steps_to_live) evict = true;
       }
@@ -614,7 +619,7 @@ class HostEV {
     std::vector<int32_t> freed;
     int64_t removed = kv_.RemoveIf([&](int64_t key, int32_t idx) {
       if (!std::binary_search(ks.begin(), ks.end(), key)) return false;
-      int32_t r = *row_.at(idx);
+      int32_t r = *(&meta_.at(idx)->row);
       if (r >= 0) { FreeRow(r); admitted_.fetch_sub(1); }
       freed.push_back(idx);
       return true;
@@ -631,8 +636,8 @@ class HostEV {
     kv_.ForEach([&](int64_t key, int32_t idx) {
       int bucket = dr_ckpt_bucket(key);
       if (part_num > 1 && bucket % part_num != part_id) return;
-      if (dirty_only && !*dirty_.at(idx)) return;
-      int32_t r = *row_.at(idx);
+      if (dirty_only && !*(&meta_.at(idx)->dirty)) return;
+      int32_t r = *(&meta_.at(idx)->row);
       if (r >= 0) snap_adm_.push_back({bucket, idx, key}); else snap_flt_.push_back({bucket, idx, key});
     });
     auto cmp = [](const SnapItem& a, const SnapItem& b) { return a.bucket != b.bucket ? a.bucket < b.bucket : a.key < b.key; };
@@ -646,9 +651,9 @@ class HostEV {
       if (off) std::fill(off, off + 1001, 0);
       for (size_t i = 0; i < v.size(); ++i) {
         if (k) k[i] = v[i].key;
-        if (f) f[i] = *freq_.at(v[i].idx);
-        if (ver) ver[i] = *version_.at(v[i].idx);
-        if (rw) memcpy(rw + i * stride_, rows_.at(*row_.at(v[i].idx)), stride_ * sizeof(float));
+        if (f) f[i] = *(&meta_.at(v[i].idx)->freq);
+        if (ver) ver[i] = *(&meta_.at(v[i].idx)->version);
+        if (rw) memcpy(rw + i * stride_, rows_.at(*(&meta_.at(v[i].idx)->row)), stride_ * sizeof(float));
         if (off) off[v[i].bucket + 1]++;
       }
       if (off) for (int b = 0; b < 1000; ++b) off[b + 1] += off[b];
@@ -657,7 +662,7 @@ class HostEV {
     fill(snap_flt_, fkeys, nullptr, ffreqs, fversions, fpart_offset);
   }
   void SnapshotEnd() { snap_adm_.clear(); snap_adm_.shrink_to_fit(); snap_flt_.clear(); snap_flt_.shrink_to_fit(); }
-  void ClearDirty() { kv_.ForEach([&](int64_t, int32_t idx) { *dirty_.at(idx) = 0; }); }
+  void ClearDirty() { kv_.ForEach([&](int64_t, int32_t idx) { *(&meta_.at(idx)->dirty) = 0; }); }
 
   // ---- import (restore / elastic import / incremental replay) ---------------------------
   // rows: [n, ncols] (ncols <= stride; missing slot columns take slot_init); rows == nullptr
@@ -670,10 +675,10 @@ class HostEV {
       if (part_num > 1 && dr_ckpt_bucket(key) % part_num != part_id) continue;
       bool inserted = false;
       int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
-      *freq_.at(idx) = freqs ? freqs[i] : 0;
-      *version_.at(idx) = reset_version ? -1 : (versions ? versions[i] : -1);
+      *(&meta_.at(idx)->freq) = freqs ? freqs[i] : 0;
+      *(&meta_.at(idx)->version) = reset_version ? -1 : (versions ? versions[i] : -1);
       if (rows) {
-        int32_t* rp = row_.at(idx);
+        int32_t* rp = (&meta_.at(idx)->row);
         int32_t r = *rp;
         if (r < 0) { r = AllocRow(); InitRow(r, key); *rp = r; admitted_.fetch_add(1); }
         memcpy(rows_.at(r), rows + i * ncols, std::min(ncols, stride_) * sizeof(float));
@@ -700,9 +705,9 @@ class HostEV {
  private:
   // metadata cells are read by forward lookups while the training thread updates them: all shared accesses are atomic
   // (acquire on the row index pairs with the release store that publishes an initialised row)
-  int32_t RowOf(int32_t idx) { return __atomic_load_n(row_.at(idx), __ATOMIC_ACQUIRE); }
-  int64_t FreqOf(int32_t idx) { return __atomic_load_n(freq_.at(idx), __ATOMIC_RELAXED); }
-  int64_t VersionOf(int32_t idx) { return __atomic_load_n(version_.at(idx), __ATOMIC_RELAXED); }
+  int32_t RowOf(int32_t idx) { return __atomic_load_n((&meta_.at(idx)->row), __ATOMIC_ACQUIRE); }
+  int64_t FreqOf(int32_t idx) { return __atomic_load_n((&meta_.at(idx)->freq), __ATOMIC_RELAXED); }
+  int64_t VersionOf(int32_t idx) { return __atomic_load_n((&meta_.at(idx)->version), __ATOMIC_RELAXED); }
   const float* DefaultRow(int64_t key) const {
     return default_.data() + dr_default_row(key, std::max<int64_t>(1, cfg_.default_value_dim)) * cfg_.dim;
   }
@@ -713,40 +718,43 @@ class HostEV {
     for (int64_t d = cfg_.dim * (1 + cfg_.num_slots); d < stride_; ++d) row[d] = 0.f;
   }
   int32_t AllocMeta() {
-    {
+    if (n_free_meta_.load(std::memory_order_relaxed) > 0) {      // the free lists are empty unless something was evicted: no lock on the hot path
       std::lock_guard<std::mutex> l(free_mu_);
-      if (!free_meta_.empty()) { int32_t i = free_meta_.back(); free_meta_.pop_back(); ResetMeta(i); return i; }
+      if (!free_meta_.empty()) { int32_t i = free_meta_.back(); free_meta_.pop_back(); n_free_meta_.fetch_sub(1, std::memory_order_relaxed); ResetMeta(i); return i; }
     }
     int64_t i = next_meta_.fetch_add(1);
-    freq_.EnsureCapacity(i + 1, 0); version_.EnsureCapacity(i + 1, -1); row_.EnsureCapacity(i + 1, -1); dirty_.EnsureCapacity(i + 1, 0);
+    meta_.EnsureCapacity(i + 1, Meta{0, -1, -1, 0, {0}});
     ResetMeta((int32_t)i);
     return (int32_t)i;
   }
-  void ResetMeta(int32_t i) { *freq_.at(i) = 0; *version_.at(i) = -1; *row_.at(i) = -1; *dirty_.at(i) = 0; }
-  void FreeMeta(int32_t i) { std::lock_guard<std::mutex> l(free_mu_); free_meta_.push_back(i); }
+  void ResetMeta(int32_t i) { *(&meta_.at(i)->freq) = 0; *(&meta_.at(i)->version) = -1; *(&meta_.at(i)->row) = -1; *(&meta_.at(i)->dirty) = 0; }
+  void FreeMeta(int32_t i) { std::lock_guard<std::mutex> l(free_mu_); free_meta_.push_back(i); n_free_meta_.fetch_add(1, std::memory_order_relaxed); }
   int32_t AllocRow() {
-    {
+    if (n_free_rows_.load(std::memory_order_relaxed) > 0) {
       std::lock_guard<std::mutex> l(free_mu_);
-      if (!free_rows_.empty()) { int32_t r = free_rows_.back(); free_rows_.pop_back(); return r; }
+      if (!free_rows_.empty()) { int32_t r = free_rows_.back(); free_rows_.pop_back(); n_free_rows_.fetch_sub(1, std::memory_order_relaxed); return r; }
     }
     int64_t r = next_row_.fetch_add(1);
     rows_.EnsureCapacity(r + 1, 0.f);
     return (int32_t)r;
   }
-  void FreeRow(int32_t r) { std::lock_guard<std::mutex> l(free_mu_); free_rows_.push_back(r); }
+  void FreeRow(int32_t r) { std::lock_guard<std::mutex> l(free_mu_); free_rows_.push_back(r); n_free_rows_.fetch_add(1, std::memory_order_relaxed); }
 
   DrEvConfig cfg_;
   int64_t stride_;
   HostKV kv_;
-  ChunkedArray<int64_t> freq_, version_;
-  ChunkedArray<int32_t> row_;
-  ChunkedArray<uint8_t> dirty_;
+  // One 32-byte record per key: a probe that found the key touches ONE cache line for frequency, version, row index and dirty flag
+  // (four parallel arrays cost four DRAM misses per key on tables larger than the caches -- the same AoS lesson as the device table's
+  // 32-byte slot).
+  struct alignas(32) Meta { int64_t freq; int64_t version; int32_t row; uint8_t dirty; uint8_t pad[11]; };
+  ChunkedArray<Meta> meta_;
   ChunkedArray<float, 12> rows_;       // 4096 rows per chunk
   std::vector<float> default_;
   std::unique_ptr<CountingBloom> bloom_;
   std::atomic<int64_t> next_meta_{0}, next_row_{0}, admitted_{0};
   std::mutex free_mu_;
   std::vector<int32_t> free_meta_, free_rows_;
+  std::atomic<int64_t> n_free_meta_{0}, n_free_rows_{0};
   std::vector<SnapItem> snap_adm_, snap_flt_;
 };
 
