@@ -484,8 +484,12 @@ class HostEV {
 
   // ---- LookupOrCreateKey with admission (counter_filter_policy.h:106-139) -------------
   // returns row index (>=0) when the key is admitted, -1 otherwise.
+  // A block of ApplyRange reserves the metadata / row indices of all its new keys with ONE fetch_add each (the per-key global
+  // counters sat on one cache line and made 8 inserting threads slower than one).
+  struct Reserve { int64_t meta_next = 0, meta_end = 0, row_next = 0, row_end = 0, admitted = 0; };
+
   // `known` = meta index already resolved by a batched read-only probe (ApplyRange), or -1
-  int32_t LookupOrCreate(int64_t key, int64_t count, int64_t step, int32_t known = -1) {
+  int32_t LookupOrCreate(int64_t key, int64_t count, int64_t step, int32_t known = -1, Reserve* rs = nullptr) {
     if (cfg_.is_inference) {
       int32_t idx = known >= 0 ? known : kv_.Find(key);
       return idx >= 0 ? RowOf(idx) : -1;
@@ -498,7 +502,7 @@ class HostEV {
       }
     }
     bool inserted = false;
-    int32_t idx = known >= 0 ? known : kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
+    int32_t idx = known >= 0 ? known : kv_.FindOrInsert(key, [this, rs] { return AllocMeta(rs); }, &inserted);
     int64_t* f = (&meta_.at(idx)->freq);
     int64_t nf = __atomic_add_fetch(f, count, __ATOMIC_RELAXED);
     __atomic_store_n((&meta_.at(idx)->version), step, __ATOMIC_RELAXED);
@@ -511,10 +515,10 @@ class HostEV {
     // claim allocation: -1 -> -2 (pending)
     int32_t expect = -1;
     if (__atomic_compare_exchange_n(rp, &expect, -2, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
-      r = AllocRow();
+      r = AllocRow(rs);
       InitRow(r, key);
       __atomic_store_n(rp, r, __ATOMIC_RELEASE);
-      admitted_.fetch_add(1);
+      if (rs) ++rs->admitted; else admitted_.fetch_add(1);
       return r;
     }
     while ((r = __atomic_load_n(rp, __ATOMIC_ACQUIRE)) < 0) std::this_thread::yield();
@@ -555,9 +559,22 @@ class HostEV {
         for (int64_t i = blk; i < be; ++i)
           if (known[i] >= 0) { const int32_t r = RowOf(known[i]); if (r >= 0) __builtin_prefetch(rows_.at(r), 1); }
       }
+      Reserve rs;
+      if (!cfg_.is_inference && !bloom_ && n_free_meta_.load(std::memory_order_relaxed) == 0 && n_free_rows_.load(std::memory_order_relaxed) == 0) {
+        int64_t misses = 0;
+        for (int64_t i = blk; i < be; ++i) misses += known[i] == -1;
+        if (misses) {
+          rs.meta_next = next_meta_.fetch_add(misses); rs.meta_end = rs.meta_next + misses;
+          meta_.EnsureCapacity(rs.meta_end, Meta{0, -1, -1, 0, {0}});
+          if (cfg_.filter_type == DR_FILTER_NONE) {            // every new key is admitted at once: its row can be reserved too
+            rs.row_next = next_row_.fetch_add(misses); rs.row_end = rs.row_next + misses;
+            rows_.EnsureCapacity(rs.row_end, 0.f);
+          }
+        }
+      }
       for (int64_t i = blk; i < be; ++i) {
         if (known[i] == -3) continue;
-        int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step, known[i]);
+        int32_t r = LookupOrCreate(keys[i], counts ? counts[i] : 1, hp.global_step, known[i], &rs);
         if (r < 0) continue;
         float* row = rows_.at(r);
         const float* g = grads + i * dim;
@@ -582,6 +599,7 @@ class HostEV {
         for (int64_t d = 0; d < dim; ++d)
           dr_apply_elem(hp.kind, hp, alpha, decay_now, g[d], row[d], ns > 0 ? s0[d] : dummy0, ns > 1 ? s1[d] : dummy1);
       }
+      if (rs.admitted) admitted_.fetch_add(rs.admitted);
     }
   }
 
@@ -717,7 +735,8 @@ class HostEV {
     for (int s = 0; s < cfg_.num_slots; ++s) std::fill(row + (1 + s) * cfg_.dim, row + (2 + s) * cfg_.dim, cfg_.slot_init[s]);
     for (int64_t d = cfg_.dim * (1 + cfg_.num_slots); d < stride_; ++d) row[d] = 0.f;
   }
-  int32_t AllocMeta() {
+  int32_t AllocMeta(Reserve* rs = nullptr) {
+    if (rs && rs->meta_next < rs->meta_end) { const int64_t i = rs->meta_next++; ResetMeta((int32_t)i); return (int32_t)i; }
     if (n_free_meta_.load(std::memory_order_relaxed) > 0) {      // the free lists are empty unless something was evicted: no lock on the hot path
       std::lock_guard<std::mutex> l(free_mu_);
       if (!free_meta_.empty()) { int32_t i = free_meta_.back(); free_meta_.pop_back(); n_free_meta_.fetch_sub(1, std::memory_order_relaxed); ResetMeta(i); return i; }
@@ -729,7 +748,8 @@ class HostEV {
   }
   void ResetMeta(int32_t i) { *(&meta_.at(i)->freq) = 0; *(&meta_.at(i)->version) = -1; *(&meta_.at(i)->row) = -1; *(&meta_.at(i)->dirty) = 0; }
   void FreeMeta(int32_t i) { std::lock_guard<std::mutex> l(free_mu_); free_meta_.push_back(i); n_free_meta_.fetch_add(1, std::memory_order_relaxed); }
-  int32_t AllocRow() {
+  int32_t AllocRow(Reserve* rs = nullptr) {
+    if (rs && rs->row_next < rs->row_end) return (int32_t)rs->row_next++;
     if (n_free_rows_.load(std::memory_order_relaxed) > 0) {
       std::lock_guard<std::mutex> l(free_mu_);
       if (!free_rows_.empty()) { int32_t r = free_rows_.back(); free_rows_.pop_back(); n_free_rows_.fetch_sub(1, std::memory_order_relaxed); return r; }
@@ -751,7 +771,9 @@ class HostEV {
   ChunkedArray<float, 12> rows_;       // 4096 rows per chunk
   std::vector<float> default_;
   std::unique_ptr<CountingBloom> bloom_;
-  std::atomic<int64_t> next_meta_{0}, next_row_{0}, admitted_{0};
+  alignas(64) std::atomic<int64_t> next_meta_{0};
+  alignas(64) std::atomic<int64_t> next_row_{0};
+  alignas(64) std::atomic<int64_t> admitted_{0};
   std::mutex free_mu_;
   std::vector<int32_t> free_meta_, free_rows_;
   std::atomic<int64_t> n_free_meta_{0}, n_free_rows_{0};
