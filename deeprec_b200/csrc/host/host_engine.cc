@@ -177,18 +177,18 @@ class ChunkedArray {
 // ------------------------------------------------------------------------------------
 static constexpr int64_t kEmptyKey = INT64_MIN;
 
+// One 16-byte slot per entry: key and value index share a cache line, so a probe costs one DRAM access instead of two.
+struct KVSlot { std::atomic<int64_t> key; std::atomic<int32_t> val; int32_t pad; };
 struct KVPart {
-  std::atomic<int64_t>* keys = nullptr;
-  std::atomic<int32_t>* vals = nullptr;
+  KVSlot* slots = nullptr;
   int64_t cap = 0;
   std::atomic<int64_t> size{0};
   std::shared_mutex mu;
-  ~KVPart() { delete[] keys; delete[] vals; }
+  ~KVPart() { delete[] slots; }
   void Alloc(int64_t c) {
     cap = c;
-    keys = new std::atomic<int64_t>[c];
-    vals = new std::atomic<int32_t>[c];
-    for (int64_t i = 0; i < c; ++i) { keys[i].store(kEmptyKey, std::memory_order_relaxed); vals[i].store(-1, std::memory_order_relaxed); }
+    slots = new KVSlot[c];
+    for (int64_t i = 0; i < c; ++i) { slots[i].key.store(kEmptyKey, std::memory_order_relaxed); slots[i].val.store(-1, std::memory_order_relaxed); slots[i].pad = 0; }
   }
 };
 
@@ -224,7 +224,7 @@ class HostKV {
   void PrefetchSlot(int64_t key) const {
     const KVPart& P = parts_[PartOf(key)];
     const uint64_t pos = dr_mix64((uint64_t)key) & (uint64_t)(P.cap - 1);
-    __builtin_prefetch(&P.keys[pos]); __builtin_prefetch(&P.vals[pos]);
+    __builtin_prefetch(&P.slots[pos]);
   }
   // find or insert; `alloc` is called exactly once by the inserting thread to get a meta index.
   template <typename Alloc>
@@ -238,15 +238,15 @@ class HostKV {
         uint64_t mask = P.cap - 1;
         uint64_t pos = dr_mix64((uint64_t)key) & mask;
         for (int64_t probes = 0; probes < P.cap; ++probes, pos = (pos + 1) & mask) {
-          int64_t k = P.keys[pos].load(std::memory_order_acquire);
+          int64_t k = P.slots[pos].key.load(std::memory_order_acquire);
           if (k == key) return WaitVal(P, pos);
           if (k == kEmptyKey) {
             if ((P.size.load(std::memory_order_relaxed) + 1) * 10 > P.cap * 7) { need_grow = true; break; }
             int64_t expected = kEmptyKey;
-            if (P.keys[pos].compare_exchange_strong(expected, key, std::memory_order_acq_rel)) {
+            if (P.slots[pos].key.compare_exchange_strong(expected, key, std::memory_order_acq_rel)) {
               P.size.fetch_add(1, std::memory_order_relaxed);
               int32_t v = alloc();
-              P.vals[pos].store(v, std::memory_order_release);
+              P.slots[pos].val.store(v, std::memory_order_release);
               *inserted = true;
               return v;
             }
@@ -267,8 +267,8 @@ class HostKV {
       KVPart& P = parts_[p];
       std::shared_lock<std::shared_mutex> l(P.mu);
       for (int64_t i = 0; i < P.cap; ++i) {
-        int64_t k = P.keys[i].load(std::memory_order_acquire);
-        if (k != kEmptyKey) f(k, P.vals[i].load(std::memory_order_acquire));
+        int64_t k = P.slots[i].key.load(std::memory_order_acquire);
+        if (k != kEmptyKey) f(k, P.slots[i].val.load(std::memory_order_acquire));
       }
     }
   }
@@ -280,9 +280,9 @@ class HostKV {
       std::unique_lock<std::shared_mutex> l(P.mu);
       std::vector<std::pair<int64_t, int32_t>> keep; keep.reserve(P.size.load());
       for (int64_t i = 0; i < P.cap; ++i) {
-        int64_t k = P.keys[i].load(std::memory_order_relaxed);
+        int64_t k = P.slots[i].key.load(std::memory_order_relaxed);
         if (k == kEmptyKey) continue;
-        int32_t v = P.vals[i].load(std::memory_order_relaxed);
+        int32_t v = P.slots[i].val.load(std::memory_order_relaxed);
         if (pred(k, v)) ++removed; else keep.emplace_back(k, v);
       }
       Rebuild(P, P.cap, keep);
@@ -292,28 +292,28 @@ class HostKV {
  private:
   static int32_t WaitVal(KVPart& P, uint64_t pos) {
     int32_t v;
-    while ((v = P.vals[pos].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+    while ((v = P.slots[pos].val.load(std::memory_order_acquire)) < 0) std::this_thread::yield();
     return v;
   }
   static int32_t FindLocked(KVPart& P, int64_t key) {
     uint64_t mask = P.cap - 1;
     uint64_t pos = dr_mix64((uint64_t)key) & mask;
     for (int64_t probes = 0; probes < P.cap; ++probes, pos = (pos + 1) & mask) {
-      int64_t k = P.keys[pos].load(std::memory_order_acquire);
+      int64_t k = P.slots[pos].key.load(std::memory_order_acquire);
       if (k == key) return WaitVal(P, pos);
       if (k == kEmptyKey) return -1;
     }
     return -1;
   }
   static void Rebuild(KVPart& P, int64_t newcap, const std::vector<std::pair<int64_t, int32_t>>& items) {
-    delete[] P.keys; delete[] P.vals;
+    delete[] P.slots;
     P.Alloc(newcap);
     uint64_t mask = newcap - 1;
     for (auto& kv : items) {
       uint64_t pos = dr_mix64((uint64_t)kv.first) & mask;
-      while (P.keys[pos].load(std::memory_order_relaxed) != kEmptyKey) pos = (pos + 1) & mask;
-      P.keys[pos].store(kv.first, std::memory_order_relaxed);
-      P.vals[pos].store(kv.second, std::memory_order_relaxed);
+      while (P.slots[pos].key.load(std::memory_order_relaxed) != kEmptyKey) pos = (pos + 1) & mask;
+      P.slots[pos].key.store(kv.first, std::memory_order_relaxed);
+      P.slots[pos].val.store(kv.second, std::memory_order_relaxed);
     }
     P.size.store((int64_t)items.size());
   }
@@ -322,8 +322,8 @@ class HostKV {
     if ((P.size.load() + 1) * 10 <= P.cap * 7) return;  // someone else grew it
     std::vector<std::pair<int64_t, int32_t>> items; items.reserve(P.size.load());
     for (int64_t i = 0; i < P.cap; ++i) {
-      int64_t k = P.keys[i].load(std::memory_order_relaxed);
-      if (k != kEmptyKey) items.emplace_back(k, P.vals[i].load(std::memory_order_relaxed));
+      int64_t k = P.slots[i].key.load(std::memory_order_relaxed);
+      if (k != kEmptyKey) items.emplace_back(k, P.slots[i].val.load(std::memory_order_relaxed));
     }
     Rebuild(P, P.cap * 2, items);
   }
