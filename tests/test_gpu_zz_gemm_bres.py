@@ -1,12 +1,16 @@
 """B-resident (weight-stationary) variant of the tcgen05 GEMM (DEEPREC_GEMM_BRES / dr_cuda_set_gemm_bres): same results as the
 streaming kernel and as the fp32 reference, for every epilogue mode.  Opt-in, default off.
 (File name sorts last: written after the round's GPU budget was spent; first validation happens in the next round.)"""
+import os
 import ctypes as C
 
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# Never run on hardware yet (written after the round's GPU budget was spent): opt-in, so that the round-end `pytest -m gpu` stays on
+# validated ground (a wrong mbarrier protocol would hang, not fail).  `benchmarks/ab_validate.sh` runs them under `timeout`.
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("DEEPREC_RUN_UNVALIDATED") != "1",
+                                                   reason="unvalidated GPU path: set DEEPREC_RUN_UNVALIDATED=1 (see benchmarks/ab_validate.sh)")]
 
 
 def _lib():
