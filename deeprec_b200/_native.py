@@ -88,6 +88,8 @@ def _bind_host(lib):
     _sig(lib, "dr_host_dot_interaction_fwd", None, [P, P, i64, C.c_int, C.c_int, P])
     _sig(lib, "dr_host_dot_interaction_bwd", None, [P, P, P, i64, C.c_int, C.c_int, P, P])
     _sig(lib, "dr_host_ev_apply_raw", None, [vp, P, i64, P, i64, C.POINTER(OptHyper)])
+    _sig(lib, "dr_host_ev_apply_multi", None, [vp, C.c_int, P, P, P, P, P, C.POINTER(OptHyper)])
+    _sig(lib, "dr_host_ev_lookup_pooled", None, [vp, P, i64, i64, P, i64])
     _sig(lib, "dr_host_group_lookup", None, [P, C.c_int, P, i64, P])
     _sig(lib, "dr_host_group_apply_raw", None, [P, C.c_int, P, i64, P, C.POINTER(OptHyper)])
     # SSD tier (csrc/host/ssd_store.cc)

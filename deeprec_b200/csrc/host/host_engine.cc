@@ -460,6 +460,31 @@ class HostEV {
       }
     }
   }
+  // samples [b0, b1) of a dense [B, L] id tensor: out[b] = sum of rows (PAD skipped; unseen / un-admitted ids read what Lookup reads)
+  void LookupPooledRange(const int64_t* ids, int64_t b0, int64_t b1, int64_t L, float* out, int64_t out_stride) {
+    const int64_t dim = cfg_.dim;
+    HostKV::SharedAll guard(kv_);
+    std::vector<int32_t> row((size_t)L);
+    for (int64_t b = b0; b < b1; ++b) {
+      const int64_t* k = ids + b * L;
+      if (b + 1 < b1) for (int64_t j = 0; j < L; ++j) kv_.PrefetchSlot(ids[(b + 1) * L + j]);       // next sample's probes in flight
+      for (int64_t j = 0; j < L; ++j) {
+        if (k[j] == kEmptyKey) { row[(size_t)j] = -3; continue; }
+        const int32_t idx = kv_.FindNoLock(k[j]);
+        row[(size_t)j] = idx >= 0 ? RowOf(idx) : -1;
+        if (row[(size_t)j] >= 0) __builtin_prefetch(rows_.at(row[(size_t)j]));
+      }
+      float* o = out + b * out_stride;
+      std::fill(o, o + dim, 0.f);
+      for (int64_t j = 0; j < L; ++j) {
+        const int32_t r = row[(size_t)j];
+        if (r == -3) continue;
+        if (r >= 0) { const float* src = rows_.at(r); for (int64_t d = 0; d < dim; ++d) o[d] += src[d]; }
+        else if (cfg_.filter_type != DR_FILTER_NONE && cfg_.filter_freq > 0) { for (int64_t d = 0; d < dim; ++d) o[d] += cfg_.default_value_no_permission; }
+        else { const float* src = DefaultRow(k[j]); for (int64_t d = 0; d < dim; ++d) o[d] += src[d]; }
+      }
+    }
+  }
   // gather a slot (or the trailing scalars with slot == num_slots+1) for inspection / ckpt
   void LookupSlot(const int64_t* keys, int64_t n, int slot, float* out) {
     const int64_t dim = cfg_.dim;
@@ -859,15 +884,18 @@ void dr_host_segment_sum(const float* grads, const int64_t* inverse, int64_t n, 
 }
 
 // ---- fused entry points for the framework's CPU path (one native call per step instead of 3-4 per table) ----------------------
+}  // extern "C"  (templates below need C++ linkage)
 namespace {
 // dedup (first-occurrence order) + per-unique gradient sums of one table; grads row i at grads + i * row_stride
 struct DedupScratch { std::vector<int64_t> uniq, inv, cnt; std::vector<float> gsum; int64_t nu = 0; };
-void DedupAndSumSerial(const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, int64_t dim, DedupScratch* s) {
+// GradAt(i) -> pointer to the gradient row of occurrence i (strided tensor, or one row shared by a bag of ids)
+template <class GradAt>
+void DedupAndSumSerialT(const int64_t* ids, int64_t n, GradAt grad_at, int64_t dim, DedupScratch* s) {
   s->uniq.resize(n); s->inv.resize(n); s->cnt.resize(n);
   s->nu = n ? dr_host_unique(ids, n, s->uniq.data(), s->inv.data(), s->cnt.data()) : 0;
   s->gsum.assign((size_t)(s->nu * dim), 0.f);
   for (int64_t i = 0; i < n; ++i) {
-    float* o = s->gsum.data() + s->inv[i] * dim; const float* g = grads + i * row_stride;
+    float* o = s->gsum.data() + s->inv[i] * dim; const float* g = grad_at(i);
     for (int64_t d = 0; d < dim; ++d) o[d] += g[d];
   }
 }
@@ -875,9 +903,10 @@ void DedupAndSumSerial(const int64_t* ids, int64_t n, const float* grads, int64_
 // Large batches (sequence models push B x L ids into one table): bucket the occurrences by key hash, then every bucket is de-duplicated
 // and summed by its own thread (a key lives in exactly one bucket, so buckets are independent); results are concatenated.
 // The unique order differs from first-occurrence order, which no consumer depends on.
-void DedupAndSum(const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, int64_t dim, DedupScratch* s, bool allow_parallel = true) {
+template <class GradAt>
+void DedupAndSumT(const int64_t* ids, int64_t n, GradAt grad_at, int64_t dim, DedupScratch* s, bool allow_parallel = true) {
   const int nb = std::min<int>(64, (dr::GlobalPool()->size() + 1) * 4);
-  if (!allow_parallel || n < 16384 || nb < 4) { DedupAndSumSerial(ids, n, grads, row_stride, dim, s); return; }
+  if (!allow_parallel || n < 16384 || nb < 4) { DedupAndSumSerialT(ids, n, grad_at, dim, s); return; }
   std::vector<int32_t> bucket_of((size_t)n), order((size_t)n);
   std::vector<int64_t> start((size_t)nb + 1, 0);
   dr::GlobalPool()->ParallelFor(n, 8192, [&](int64_t b, int64_t e) {
@@ -898,7 +927,7 @@ void DedupAndSum(const int64_t* ids, int64_t n, const float* grads, int64_t row_
       P.nu = m ? dr_host_unique(keys.data(), m, P.uniq.data(), P.inv.data(), P.cnt.data()) : 0;
       P.gsum.assign((size_t)(P.nu * dim), 0.f);
       for (int64_t j = 0; j < m; ++j) {
-        float* o = P.gsum.data() + P.inv[(size_t)j] * dim; const float* g = grads + (int64_t)order[(size_t)(lo + j)] * row_stride;
+        float* o = P.gsum.data() + P.inv[(size_t)j] * dim; const float* g = grad_at((int64_t)order[(size_t)(lo + j)]);
         for (int64_t d = 0; d < dim; ++d) o[d] += g[d];
       }
     }
@@ -916,7 +945,12 @@ void DedupAndSum(const int64_t* ids, int64_t n, const float* grads, int64_t row_
     off += P.nu;
   }
 }
+
+void DedupAndSum(const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, int64_t dim, DedupScratch* s, bool allow_parallel = true) {
+  DedupAndSumT(ids, n, [=](int64_t i) { return grads + i * row_stride; }, dim, s, allow_parallel);
+}
 }  // namespace
+extern "C" {
 
 // unique + segment-sum + apply of ONE table in one call; grads row i at grads + i * row_stride (strided views need no copy)
 void dr_host_ev_apply_raw(void* h, const int64_t* ids, int64_t n, const float* grads, int64_t row_stride, const DrOptHyper* hp) {
@@ -924,6 +958,36 @@ void dr_host_ev_apply_raw(void* h, const int64_t* ids, int64_t n, const float* g
   DedupScratch s;
   DedupAndSum(ids, n, grads, row_stride, ev->cfg().dim, &s);
   ev->Apply(s.uniq.data(), s.gsum.data(), s.cnt.data(), s.nu, *hp);
+}
+
+// ONE de-duplicated apply for everything a table received in a step: `nseg` segments, segment s = n[s] ids whose occurrence i uses the
+// gradient row grads[s] + (i / group[s]) * row_stride[s]  (group 1: one row per occurrence -- a plain lookup; group L: the bag of L ids
+// of sample i / L shares one row -- a sum-pooled lookup, whose [B*L, dim] per-occurrence gradient is therefore never materialised).
+void dr_host_ev_apply_multi(void* h, int nseg, const int64_t* const* ids, const int64_t* n, const float* const* grads, const int64_t* row_stride,
+                            const int64_t* group, const DrOptHyper* hp) {
+  auto* ev = static_cast<dr::HostEV*>(h);
+  int64_t total = 0;
+  for (int s = 0; s < nseg; ++s) total += n[s];
+  if (total == 0) return;
+  std::vector<int64_t> all((size_t)total);
+  std::vector<const float*> gp((size_t)total);
+  int64_t o = 0;
+  for (int s = 0; s < nseg; ++s) {
+    const int64_t g = group[s] > 0 ? group[s] : 1;
+    memcpy(all.data() + o, ids[s], sizeof(int64_t) * (size_t)n[s]);
+    for (int64_t i = 0; i < n[s]; ++i) gp[(size_t)(o + i)] = grads[s] + (i / g) * row_stride[s];
+    o += n[s];
+  }
+  DedupScratch sc;
+  DedupAndSumT(all.data(), total, [&](int64_t i) { return gp[(size_t)i]; }, ev->cfg().dim, &sc);
+  ev->Apply(sc.uniq.data(), sc.gsum.data(), sc.cnt.data(), sc.nu, *hp);
+}
+
+// Sum-pooled lookup of a dense [B, L] id tensor (PAD_KEY = unused position): out[b] = sum of the rows of sample b's ids, written at
+// out + b * out_stride.  The [B, L, dim] intermediate of lookup + mask + sum never exists.
+void dr_host_ev_lookup_pooled(void* h, const int64_t* ids, int64_t B, int64_t L, float* out, int64_t out_stride) {
+  auto* ev = static_cast<dr::HostEV*>(h);
+  dr::GlobalPool()->ParallelFor(B, 64, [&](int64_t b0, int64_t b1) { ev->LookupPooledRange(ids, b0, b1, L, out, out_stride); });
 }
 
 // T tables of equal dim, one id per (table, sample): keys feature-major [T][B] -> out sample-major [B][T][dim]

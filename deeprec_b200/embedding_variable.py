@@ -105,6 +105,33 @@ class HostTable:
             g = g.reshape(n, self.dim).contiguous()
         self.lib.dr_host_ev_apply_raw(self.h, ptr(k), n, C.c_void_p(g.data_ptr()), int(g.stride(0)), C.byref(hp))
 
+    def apply_segments(self, segs, hp: OptHyper) -> None:
+        """ONE de-duplicated apply for everything the table received in a step.  ``segs`` = [(ids, grads, group)]: occurrence i of a segment
+        uses gradient row ``i // group`` (group 1 = plain lookup; group L = sum-pooled bags of L ids sharing one row)."""
+        keep, ids_p, n_p, g_p, st_p, gr_p = [], [], [], [], [], []
+        for ids, grads, group in segs:
+            k = _i64(ids).view(-1)
+            if k.numel() == 0:
+                continue
+            g = grads if grads.dtype == torch.float32 else grads.to(torch.float32)
+            if g.dim() != 2 or g.stride(1) != 1:
+                g = g.reshape(-1, self.dim).contiguous()
+            keep += [k, g]
+            ids_p.append(k.data_ptr()); n_p.append(k.numel()); g_p.append(g.data_ptr()); st_p.append(int(g.stride(0))); gr_p.append(int(group))
+        m = len(ids_p)
+        if m == 0:
+            return
+        vp, i64 = C.c_void_p, C.c_int64
+        self.lib.dr_host_ev_apply_multi(self.h, m, (vp * m)(*ids_p), (i64 * m)(*n_p), (vp * m)(*g_p), (i64 * m)(*st_p), (i64 * m)(*gr_p), C.byref(hp))
+
+    def lookup_pooled(self, ids: torch.Tensor) -> torch.Tensor:
+        """ids [B, L] (PAD_KEY = unused position) -> [B, dim]: per-sample sum of rows, no [B, L, dim] intermediate."""
+        k = _i64(ids)
+        B, L = k.shape
+        out = torch.empty(B, self.dim, dtype=torch.float32)
+        self.lib.dr_host_ev_lookup_pooled(self.h, ptr(k), B, L, ptr(out), self.dim)
+        return out
+
     # ---- lifecycle -----------------------------------------------------------------------
     def shrink(self, step: int) -> int:
         return int(self.lib.dr_host_ev_shrink(self.h, int(step)))
@@ -182,6 +209,21 @@ class _EVLookup(torch.autograd.Function):
             ctx.ev.table.accumulate(ctx.pos, grad_out)
         else:
             ctx.ev._record_grad(ids, grad_out)
+        return None, None, None
+
+
+class _EVLookupPooled(torch.autograd.Function):
+    """Sum-pooled lookup of a dense ``[B, L]`` id tensor on a host table; the backward records ONE gradient row per bag."""
+
+    @staticmethod
+    def forward(ctx, anchor: torch.Tensor, ev: "EmbeddingVariable", ids: torch.Tensor):
+        ctx.ev, ctx.ids = ev, ids
+        return ev.table.lookup_pooled(ids)
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        ids = ctx.ids
+        ctx.ev._pending.append((ids.reshape(-1), grad_out.contiguous(), ids.shape[1]))      # (ids, [B, D] rows, group = L)
         return None, None, None
 
 
@@ -379,7 +421,7 @@ class EmbeddingVariable(nn.Module):
         return self._gather(ids), None
 
     def _record_grad(self, ids: torch.Tensor, grad: torch.Tensor) -> None:
-        self._pending.append((ids.reshape(-1), grad.reshape(-1, self.embedding_dim)))
+        self._pending.append((ids.reshape(-1), grad.reshape(-1, self.embedding_dim), 1))
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
         return self.lookup(ids)
@@ -392,17 +434,39 @@ class EmbeddingVariable(nn.Module):
 
     sparse_read = lookup
 
+    def lookup_pooled(self, ids: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``embedding_lookup_sparse(combiner="sum")`` for a dense ``[B, L]`` id tensor whose valid positions are given by ``mask``
+        (or marked with ``config.PAD_KEY``): -> ``[B, dim]``.  Plain host tables do it in one native pass (no ``[B, L, dim]``
+        intermediate in the forward, one gradient row per bag in the backward); every other table type falls back to
+        lookup + mask + sum."""
+        from .config import PAD_KEY
+        if self.device.type == "cpu" and isinstance(self.table, HostTable) and ids.dim() == 2:
+            k = ids if mask is None else torch.where(mask, ids, PAD_KEY)
+            if self.trainable and torch.is_grad_enabled() and not self._inference:
+                return _EVLookupPooled.apply(self._anchor, self, k.contiguous())
+            return self.table.lookup_pooled(k.contiguous())
+        if mask is None:
+            mask = ids != PAD_KEY
+        rows = self.lookup(torch.where(mask, ids, torch.zeros_like(ids)))
+        return (rows * mask.unsqueeze(-1).to(rows.dtype).to(rows.device)).sum(1)
+
     def pop_sparse_grads(self):
         """Concatenated (ids, grads) accumulated by backward since the last step."""
         if not self._pending:
             return None
-        if len(self._pending) == 1:                     # the common case: one lookup per step -> no copy
-            ids, grads = self._pending[0]
+        segs = [(i, g if grp == 1 else g.repeat_interleave(grp, dim=0)) for i, g, grp in self._pending]   # pooled bags: one row per occurrence
+        if len(segs) == 1:                              # the common case: one lookup per step -> no copy
+            ids, grads = segs[0]
         else:
-            ids = torch.cat([p[0] for p in self._pending])
-            grads = torch.cat([p[1] for p in self._pending])
+            ids = torch.cat([p[0] for p in segs])
+            grads = torch.cat([p[1] for p in segs])
         self._pending.clear()
         return ids, grads
+
+    def pop_sparse_segments(self):
+        """[(ids, grads, group)] recorded since the last step, without concatenating or expanding anything (HostTable.apply_segments)."""
+        segs, self._pending = self._pending, []
+        return segs
 
     # ---- introspection (EVGetFrequency / EVGetVersion / KvVariableShape) ---------------------
     def total_count(self) -> int:

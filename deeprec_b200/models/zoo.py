@@ -289,6 +289,16 @@ class _SeqBase(nn.Module):
         k = k * mask.unsqueeze(-1).to(k.dtype).to(k.device)
         return u, q, k, mask.to(k.device)
 
+    def _embed_pooled(self, b: Dict[str, torch.Tensor]):
+        """(user, target, sum-pooled history [B, 2D]) for models that only consume the pooled behaviour history: the ``[B, L, 2D]``
+        history tensor is never built on host tables (``EmbeddingVariable.lookup_pooled``)."""
+        u = self.user.lookup(b["user"])
+        q = torch.cat([self.item.lookup(b["item"]), self.cat.lookup(b["cat"])], -1)
+        hi, hc = b["hist_item"], b["hist_cat"]
+        mask = hi >= 0
+        pooled = torch.cat([self.item.lookup_pooled(hi, mask), self.cat.lookup_pooled(hc, mask)], -1)
+        return u, q, pooled
+
     def loss(self, b):
         out = self.forward(b)
         return F.binary_cross_entropy_with_logits(out, b["labels"].to(out.device))
@@ -375,8 +385,8 @@ class DSSM(_SeqBase):
         self.scale = nn.Parameter(torch.tensor(5.0, device=dev))
 
     def forward(self, b):
-        u, q, k, mask = self._embed(b)
-        ue = self.user_tower(torch.cat([u, k.sum(1)], -1))
+        u, q, pooled = self._embed_pooled(b)
+        ue = self.user_tower(torch.cat([u, pooled], -1))
         ie = self.item_tower(q)
         return F.cosine_similarity(ue, ie, dim=-1) * self.scale
 
@@ -385,8 +395,8 @@ class _MultiTask(_SeqBase):
     tasks = ("ctr", "cvr")
 
     def _features(self, b):
-        u, q, k, mask = self._embed(b)
-        return torch.cat([u, q, k.sum(1)], -1)
+        u, q, pooled = self._embed_pooled(b)
+        return torch.cat([u, q, pooled], -1)
 
     @property
     def feat_dim(self):

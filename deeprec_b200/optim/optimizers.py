@@ -145,6 +145,11 @@ class DeepRecOptimizer(torch.optim.Optimizer):
                 if ev._table is not None:
                     ev._table.apply_step(hp)      # one fused launch per (device, dim) context; idempotent
                 continue
+            if hasattr(ev.table, "apply_segments"):           # plain host table: one native dedup + apply over all recorded segments
+                segs = ev.pop_sparse_segments()
+                if segs:
+                    ev.table.apply_segments(segs, hp)
+                continue
             sg = ev.pop_sparse_grads()
             if sg is None:
                 continue

@@ -285,3 +285,37 @@ def test_pad_key_reads_zeros_and_is_never_created_or_counted():
     assert torch.all(ev.lookup(torch.tensor([PAD_KEY])) == 0) and torch.all(ev.slot_values(torch.tensor([PAD_KEY]), "accumulator") == 0.1)
     keys = ev.export()[0]
     assert sorted(keys.tolist()) == [5, 7]
+
+
+@pytest.mark.parametrize("n_ids,L", [(300, 7), (2100, 12)])        # the larger case crosses into the parallel bucketed dedup (>= 16384 ids)
+def test_pooled_lookup_and_multi_segment_apply_equal_the_materialised_path(n_ids, L):
+    """lookup_pooled (no [B, L, D] intermediate, one gradient row per bag) mixed with a plain lookup of the SAME table in one step
+    == lookup + mask + sum with every per-occurrence gradient materialised: values, frequencies, versions, optimizer slots."""
+    from deeprec_b200.config import PAD_KEY
+    B, D = n_ids, 8
+    dr.embedding_variable.clear_registry()
+    a = _ev(f"pool_a{L}", D, filter_option=dr.CounterFilter(2)); b = _ev(f"pool_b{L}", D, filter_option=dr.CounterFilter(2))
+    b.default_matrix.copy_(a.default_matrix); b._table = None
+    oa = dr.optim.AdagradOptimizer([], [a], lr=0.1, global_step=GlobalStep()); ob = dr.optim.AdagradOptimizer([], [b], lr=0.1, global_step=GlobalStep())
+    g = torch.Generator().manual_seed(9)
+    for step in range(3):
+        hist = (torch.randn(B, L, generator=g).abs() * 30).long()
+        lens = torch.randint(0, L + 1, (B,), generator=g)
+        mask = torch.arange(L).unsqueeze(0) < lens.unsqueeze(1)
+        tgt = torch.randint(0, 60, (B,), generator=g)
+        w1, w2 = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
+        pa = a.lookup_pooled(hist, mask)
+        ((pa * w1).sum() + (a.lookup(tgt) * w2).sum()).backward(); oa.step(); oa.zero_grad()
+        rows = b.lookup(torch.where(mask, hist, torch.zeros_like(hist)))              # reference: materialise, mask, sum
+        pb = (rows * mask.unsqueeze(-1)).sum(1)
+        assert torch.allclose(pa.detach(), pb.detach(), atol=1e-5)
+        # feed the reference exactly the valid occurrences (the padded positions must not touch key 0)
+        b._pending.clear()
+        ((b.lookup(hist[mask]) * w1.unsqueeze(1).expand(B, L, D)[mask]).sum() + (b.lookup(tgt) * w2).sum()).backward(); ob.step(); ob.zero_grad()
+    probe = torch.arange(0, 150)
+    assert a.total_count() == b.total_count() and a.table.total_keys() == b.table.total_keys()
+    assert torch.allclose(a.table.lookup(probe), b.table.lookup(probe), atol=1e-5)
+    assert torch.equal(a.get_frequency(probe), b.get_frequency(probe)) and torch.equal(a.get_version(probe), b.get_version(probe))
+    assert torch.allclose(a.slot_values(probe, "accumulator"), b.slot_values(probe, "accumulator"), atol=1e-5)
+    with torch.no_grad():
+        assert torch.allclose(a.lookup_pooled(torch.where(mask, hist, PAD_KEY)), pb.detach() * 0 + a.lookup_pooled(hist, mask))
