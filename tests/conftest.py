@@ -18,3 +18,19 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+_MULTIPROCESS_TESTS = ("test_ps_cpu.py", "test_collective_cpu.py", "test_sok_elastic_cpu.py", "test_health.py", "test_examples.py",
+                       "test_work_queue_shared_between_processes")
+
+
+@pytest.fixture(autouse=True)
+def _few_threads_for_multiprocess_tests(request, monkeypatch):
+    """Tests that spawn several worker processes (PS roles, gloo ranks, example scripts): give every child 2 OpenMP threads instead of one
+    per core each -- N processes x all cores of spin-waiting OpenMP workers on a small shared box is what made them time out
+    (torchrun sets OMP_NUM_THREADS=1 for the same reason).  Children inherit the environment at spawn time."""
+    node = request.node.nodeid
+    if any(tag in node for tag in _MULTIPROCESS_TESTS):
+        monkeypatch.setenv("OMP_NUM_THREADS", "2")
+        monkeypatch.setenv("DEEPREC_HOST_THREADS", "2")
+    yield
