@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""CPU Processor benchmark (the reference deploys its processor on CPU hosts): DLRM p50 / p99 latency and samples/s through the native CPU
+runtime's C ABI, for a few (sessions, client threads, batch) operating points.  Prints one JSON line per point.
+
+  python benchmarks/cpu_serving_bench.py [--out profiles/cpu_serving_bench.jsonl]
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import deeprec_b200 as dr  # noqa: E402
+from deeprec_b200.data import criteo_batch  # noqa: E402
+from deeprec_b200.models.dlrm_engine import CRITEO_KAGGLE_CARDINALITIES as CARDS  # noqa: E402
+from deeprec_b200.models.zoo import build_model  # noqa: E402
+from deeprec_b200.serving import Processor, encode_request, export_saved_model_module  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    for s in range(4):
+        d, ids, y = criteo_batch(2048, 13, CARDS, seed=s)
+        loss = model.loss(d, ids, y); opt.zero_grad(); loss.backward(); opt.step()
+    root = tempfile.mkdtemp()
+    export_saved_model_module(model, root + "/v1", version=4)
+    lines = []
+    for sessions, threads, batch, n in ((1, 1, 1, 4000), (4, 4, 1, 8000), (4, 4, 32, 3000), (2, 2, 256, 600), (1, 1, 2048, 60)):
+        proc = Processor(root + "/v1", {"session_num": sessions, "max_batch": max(256, batch), "model_update_interval_ms": 0}, device="cpu")
+        reqs = [encode_request(*[x.numpy() for x in criteo_batch(batch, 13, CARDS, seed=100 + i)[:2]]) for i in range(8)]
+        for r in reqs:
+            assert proc.process(r)[0] == 200
+        lat = [[] for _ in range(threads)]
+
+        def client(i):
+            for k in range(n // threads):
+                t0 = time.perf_counter()
+                rc, _ = proc.process(reqs[(i + k) % 8])
+                lat[i].append((time.perf_counter() - t0) * 1e3)
+                assert rc == 200
+        ts = [threading.Thread(target=client, args=(i,)) for i in range(threads)]
+        t0 = time.perf_counter()
+        [t.start() for t in ts]; [t.join() for t in ts]
+        wall = time.perf_counter() - t0
+        v = np.sort(np.concatenate([np.array(x) for x in lat]))
+        rec = {"metric": "DLRM serving, native CPU Processor (C ABI)", "sessions": sessions, "client_threads": threads, "batch": batch, "requests": int(v.size),
+               "qps": v.size / wall, "samples_per_s": v.size * batch / wall, "p50_ms": float(v[v.size // 2]), "p99_ms": float(v[min(v.size - 1, int(v.size * 0.99))]),
+               "vcpus": os.cpu_count(), "dtype": "fp32"}
+        print(json.dumps(rec), flush=True)
+        lines.append(json.dumps(rec))
+        proc.close()
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    main()

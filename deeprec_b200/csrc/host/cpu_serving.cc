@@ -1,0 +1,450 @@
+// CPU serving runtime: the Processor for hosts without a GPU (the reference's processor is deployed on CPU boxes first of all:
+// serving/processor/, docs/docs_en/Processor.md).  Same saved-model directory, same request encodings (compact "DRRQ" or the
+// reference's protobuf PredictRequest), same ModelConfig JSON, same full / delta hot-swap protocol (serving_versions.json) and the
+// same four entry points as the GPU runtime in csrc/cuda/serving_runtime.cu -- exported here with a `dr_cpu_` prefix because both
+// libraries can live in one process.
+//
+//   tables      read-only HostEV instances (is_inference: lookups never create keys), looked up with ONE grouped call per chunk
+//   dense net   fp32; BatchNorm (moving statistics) of layer l folded into Linear l+1 at load time, weights stored transposed
+//               [K][N] so the GEMM vectorises over the outputs; ReLU fused; DLRM dot interaction via the host kernel
+//   sessions    N scratch-buffer sets behind mutexes, picked round-robin or by hint / thread id (SessionGroup semantics);
+//               the math of one request runs on the process's OpenMP pool
+//   updates     a polling thread: newer full version -> load, warm up, atomic swap (in-flight requests keep the old model alive
+//               through their shared_ptr); delta for the current version -> rows patched into the live tables, dense block swapped
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../common/bundle.h"
+#include "../common/ev_types.h"
+#include "../common/mini_json.h"
+#include "../common/predict_pb.h"
+
+extern "C" {
+void* dr_host_ev_create(const DrEvConfig* cfg);
+void dr_host_ev_destroy(void* h);
+void dr_host_ev_set_default(void* h, const float* m);
+int64_t dr_host_ev_size(void* h);
+int64_t dr_host_ev_import(void* h, const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs, const int64_t* versions, int64_t n,
+                          int part_id, int part_num, int reset_version);
+void dr_host_group_lookup(void** hs, int T, const int64_t* keys, int64_t B, float* out);
+void dr_host_dot_interaction_fwd(const float* dense, const float* embs, int64_t B, int T, int D, float* out);
+}
+
+namespace cpusrv {
+using drjson::JVal;
+
+struct Config {
+  int session_num = 2, max_batch = 4096, select_policy = 0 /*0 RR, 1 MOD*/, update_interval_ms = 1000, intra_threads = 0;
+  std::string savedmodel_dir, checkpoint_dir, warmup_file_name, timeline_path;
+  int64_t timeline_start_step = -1; int timeline_interval_step = 0, timeline_trace_count = 0;
+};
+
+struct Arch { int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0; };
+static int pad8(int n) { return (n + 7) / 8 * 8; }
+
+struct Layer { int N = 0, K = 0; std::vector<float> wt /*[K][N]*/, bias; };
+struct Dense { std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f; };
+
+struct Model {
+  Arch arch; int64_t version = -1; std::string path;
+  std::shared_ptr<Dense> dense;
+  std::vector<void*> tables;                                   // HostEV handles (owned)
+  std::vector<int64_t> sample_keys;                            // a few stored keys per table for the synthetic warm-up batch, [T][<=64]
+  ~Model() { for (void* t : tables) if (t) dr_host_ev_destroy(t); }
+};
+
+template <typename T> static bool ReadVec(dr::BundleReader& r, const std::string& name, std::vector<T>* out) {
+  auto* e = r.Find(name); if (!e) return false;
+  out->resize((size_t)e->nbytes / sizeof(T));
+  return r.Read(*e, out->data(), 1) == 0;
+}
+
+static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::string* prefix) {
+  std::string txt; JVal j;
+  if (!drjson::ReadFile(dir + "/saved_model.json", &txt) || !drjson::ParseJson(txt, &j)) return false;
+  a->num_dense = (int)j.n("num_dense", 13); a->D = (int)j.n("embedding_dim", 16); a->bn_eps = (float)j.n("bn_eps", 1e-3);
+  a->T = (int)j.n("num_tables", 0);
+  if (auto* b = j.get("mlp_bot")) for (auto& v : b->arr) a->bot.push_back((int)v.num);
+  if (auto* b = j.get("mlp_top")) for (auto& v : b->arr) a->top.push_back((int)v.num);
+  const int F = a->T + 1; a->inter = a->D + F * (F - 1) / 2;
+  *version = (int64_t)j.n("version", 0);
+  *prefix = dir + "/" + j.s("variables", "variables/variables");
+  return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
+}
+
+// BatchNorm (moving statistics) of layer l-1 folded into Linear l:  W' = W diag(s), b' = b + W t
+static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense>* out) {
+  auto dp = std::make_shared<Dense>();
+  std::vector<float> s_prev, t_prev;
+  int k = a.num_dense;
+  for (size_t l = 0; l < a.bot.size(); ++l) {
+    const std::string nm = "mlp_bot_" + std::to_string(l);
+    const int N = a.bot[l], Kp = pad8(k);
+    std::vector<float> W, b, gamma, beta, mean, var;
+    if (!ReadVec(r, "dense/" + nm + "/kernel", &W) || !ReadVec(r, "dense/" + nm + "/bias", &b) || !ReadVec(r, "dense/" + nm + "/bn_gamma", &gamma) ||
+        !ReadVec(r, "dense/" + nm + "/bn_beta", &beta) || !ReadVec(r, "bn/" + nm + "/moving_mean", &mean) || !ReadVec(r, "bn/" + nm + "/moving_variance", &var)) return false;
+    if ((int)W.size() != N * Kp || (int)b.size() != N) return false;
+    Layer L; L.N = N; L.K = k; L.wt.assign((size_t)k * N, 0.f); L.bias.resize(N);
+    for (int n = 0; n < N; ++n) {
+      double acc = b[n];
+      for (int kk = 0; kk < k; ++kk) {
+        float w = W[(size_t)n * Kp + kk];
+        if (l > 0) { acc += (double)w * t_prev[kk]; w *= s_prev[kk]; }
+        L.wt[(size_t)kk * N + n] = w;
+      }
+      L.bias[n] = (float)acc;
+    }
+    dp->bot.push_back(std::move(L));
+    s_prev.assign(N, 0.f); t_prev.assign(N, 0.f);
+    for (int n = 0; n < N; ++n) { const float rs = 1.0f / std::sqrt(var[n] + a.bn_eps); s_prev[n] = gamma[n] * rs; t_prev[n] = beta[n] - mean[n] * s_prev[n]; }
+    k = N;
+  }
+  dp->last_scale = s_prev; dp->last_shift = t_prev;
+  k = a.inter;
+  for (size_t l = 0; l < a.top.size(); ++l) {
+    const std::string nm = "mlp_top_" + std::to_string(l);
+    const int N = a.top[l], Kp = pad8(k);
+    std::vector<float> W, b;
+    if (!ReadVec(r, "dense/" + nm + "/kernel", &W) || !ReadVec(r, "dense/" + nm + "/bias", &b) || (int)W.size() != N * Kp || (int)b.size() != N) return false;
+    Layer L; L.N = N; L.K = k; L.wt.resize((size_t)k * N); L.bias = b;
+    for (int n = 0; n < N; ++n) for (int kk = 0; kk < k; ++kk) L.wt[(size_t)kk * N + n] = W[(size_t)n * Kp + kk];
+    dp->top.push_back(std::move(L));
+    k = N;
+  }
+  std::vector<float> hb;
+  if (!ReadVec(r, "dense/logits/kernel", &dp->head_w) || !ReadVec(r, "dense/logits/bias", &hb) || hb.empty() || (int)dp->head_w.size() < k) return false;
+  dp->head_b = hb[0];
+  *out = dp;
+  return true;
+}
+
+static void* BuildTable(dr::BundleReader& r, int t, int D, std::vector<int64_t>* sample) {
+  const std::string base = "table/" + std::to_string(t);
+  std::vector<int64_t> keys, freqs, vers; std::vector<float> vals, def;
+  if (!ReadVec(r, base + "-keys", &keys) || !ReadVec(r, base + "-values", &vals) || !ReadVec(r, base + "-default", &def)) return nullptr;
+  ReadVec(r, base + "-freqs", &freqs); ReadVec(r, base + "-versions", &vers);
+  if (def.empty() || def.size() % (size_t)D || vals.size() != keys.size() * (size_t)D) return nullptr;
+  DrEvConfig c{};
+  c.dim = D; c.num_slots = 0; c.has_scalars = 0; c.init_capacity = std::max<int64_t>(1024, (int64_t)keys.size() * 2);
+  c.default_value_dim = (int64_t)def.size() / D; c.num_partitions = 16; c.record_freq = 1; c.record_version = 1;
+  c.l2_weight_threshold = -1.f;
+  void* h = dr_host_ev_create(&c);                            // created writable for the import below; serving only ever calls Lookup
+  dr_host_ev_set_default(h, def.data());
+  if (!keys.empty())
+    dr_host_ev_import(h, keys.data(), vals.data(), D, freqs.size() == keys.size() ? freqs.data() : nullptr,
+                      vers.size() == keys.size() ? vers.data() : nullptr, (int64_t)keys.size(), 0, 1, 0);
+  sample->assign(keys.begin(), keys.begin() + std::min<size_t>(keys.size(), 64));
+  return h;
+}
+
+static std::shared_ptr<Model> LoadModel(const std::string& dir) {
+  auto m = std::make_shared<Model>();
+  std::string prefix;
+  if (!LoadArch(dir, &m->arch, &m->version, &prefix)) { fprintf(stderr, "[deeprec_cpu_serving] bad saved_model.json in %s\n", dir.c_str()); return nullptr; }
+  dr::BundleReader r(prefix);
+  if (!r.ok()) { fprintf(stderr, "[deeprec_cpu_serving] cannot open bundle %s\n", prefix.c_str()); return nullptr; }
+  if (!BuildDense(r, m->arch, &m->dense)) { fprintf(stderr, "[deeprec_cpu_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
+  m->sample_keys.assign((size_t)m->arch.T * 64, 0);
+  for (int t = 0; t < m->arch.T; ++t) {
+    std::vector<int64_t> sample;
+    void* h = BuildTable(r, t, m->arch.D, &sample);
+    if (!h) { fprintf(stderr, "[deeprec_cpu_serving] table %d incomplete\n", t); return nullptr; }
+    m->tables.push_back(h);
+    for (size_t i = 0; i < 64; ++i) m->sample_keys[(size_t)t * 64 + i] = sample.empty() ? 0 : sample[i % sample.size()];
+  }
+  m->path = dir;
+  return m;
+}
+
+// Y[B, N] = act(X[B, K] (ldx) * Wt[K][N] + bias); rows blocked by 4 so that every weight row read serves four samples
+static void Linear(const float* X, int64_t ldx, int64_t B, const Layer& L, float* Y, bool relu, int threads) {
+  const int N = L.N, K = L.K;
+  const float* __restrict wt = L.wt.data(); const float* __restrict bias = L.bias.data();
+#pragma omp parallel for schedule(static) num_threads(threads) if (B >= 64 && threads > 1)
+  for (int64_t b0 = 0; b0 < B; b0 += 4) {
+    const int nb = (int)std::min<int64_t>(4, B - b0);
+    float* __restrict y0 = Y + (b0 + 0) * N; float* __restrict y1 = Y + (b0 + (nb > 1 ? 1 : 0)) * N;
+    float* __restrict y2 = Y + (b0 + (nb > 2 ? 2 : 0)) * N; float* __restrict y3 = Y + (b0 + (nb > 3 ? 3 : 0)) * N;
+    for (int r = 0; r < nb; ++r) { float* y = Y + (b0 + r) * N; for (int n = 0; n < N; ++n) y[n] = bias[n]; }
+    const float* x0 = X + (b0 + 0) * ldx; const float* x1 = X + (b0 + (nb > 1 ? 1 : 0)) * ldx;
+    const float* x2 = X + (b0 + (nb > 2 ? 2 : 0)) * ldx; const float* x3 = X + (b0 + (nb > 3 ? 3 : 0)) * ldx;
+    if (nb == 4) {
+      for (int k = 0; k < K; ++k) {
+        const float a0 = x0[k], a1 = x1[k], a2 = x2[k], a3 = x3[k]; const float* __restrict w = wt + (size_t)k * N;
+        for (int n = 0; n < N; ++n) { const float wv = w[n]; y0[n] += a0 * wv; y1[n] += a1 * wv; y2[n] += a2 * wv; y3[n] += a3 * wv; }
+      }
+    } else {
+      for (int r = 0; r < nb; ++r) {
+        float* __restrict y = Y + (b0 + r) * N; const float* x = X + (b0 + r) * ldx;
+        for (int k = 0; k < K; ++k) { const float a = x[k]; const float* __restrict w = wt + (size_t)k * N; for (int n = 0; n < N; ++n) y[n] += a * w[n]; }
+      }
+    }
+    if (relu) for (int r = 0; r < nb; ++r) { float* y = Y + (b0 + r) * N; for (int n = 0; n < N; ++n) y[n] = y[n] > 0.f ? y[n] : 0.f; }
+  }
+}
+
+struct Session {
+  std::mutex mu; int max_batch = 0, threads = 1;     // threads: OpenMP team size of this session's GEMMs (cores / sessions)
+  std::vector<float> dense, emb, a, b2, z, prob; std::vector<int64_t> ids;
+  void Init(const Arch& ar, int mb, int nthreads) {
+    max_batch = mb; threads = std::max(1, nthreads);
+    int widest = ar.inter;
+    for (int n : ar.bot) widest = std::max(widest, n);
+    for (int n : ar.top) widest = std::max(widest, n);
+    dense.resize((size_t)mb * ar.num_dense); ids.resize((size_t)mb * ar.T); emb.resize((size_t)mb * ar.T * ar.D);
+    a.resize((size_t)mb * widest); b2.resize((size_t)mb * widest); z.resize((size_t)mb * ar.inter); prob.resize((size_t)mb);
+  }
+  // dense [B, num_dense], ids [T][B] staged in the session buffers -> prob[B]
+  void Run(const Model& m, const Dense& d, int B) {
+    const Arch& ar = m.arch;
+    dr_host_group_lookup(const_cast<void**>(m.tables.data()), ar.T, ids.data(), B, emb.data());              // [B, T, D]
+    const float* x = dense.data(); int64_t ldx = ar.num_dense;
+    float* cur = a.data(); float* nxt = b2.data();
+    for (size_t l = 0; l < d.bot.size(); ++l) { Linear(x, ldx, B, d.bot[l], cur, true, threads); x = cur; ldx = d.bot[l].N; std::swap(cur, nxt); }
+    float* y = const_cast<float*>(x);                                                                          // [B, D]: the last BatchNorm, explicit
+    for (int64_t i = 0; i < (int64_t)B; ++i) for (int k = 0; k < ar.D; ++k) y[i * ar.D + k] = y[i * ar.D + k] * d.last_scale[k] + d.last_shift[k];
+    dr_host_dot_interaction_fwd(y, emb.data(), B, ar.T, ar.D, z.data());                                       // [B, D + F(F-1)/2]
+    x = z.data(); ldx = ar.inter;
+    for (size_t l = 0; l < d.top.size(); ++l) { Linear(x, ldx, B, d.top[l], cur, true, threads); x = cur; ldx = d.top[l].N; std::swap(cur, nxt); }
+    const int K = (int)ldx;
+    for (int64_t i = 0; i < (int64_t)B; ++i) {
+      float acc = d.head_b; const float* xi = x + i * ldx;
+      for (int k = 0; k < K; ++k) acc += xi[k] * d.head_w[k];
+      prob[(size_t)i] = 1.f / (1.f + std::exp(-acc));
+    }
+  }
+};
+
+struct ServingModel {
+  Config cfg;
+  std::shared_ptr<Model> model;                    // atomic_load / atomic_store
+  std::vector<std::unique_ptr<Session>> sessions;
+  std::atomic<uint64_t> rr{0}, requests{0}, failures{0}, full_updates{0}, delta_updates{0};
+  std::atomic<int64_t> delta_version{-1};
+  std::thread updater; std::atomic<bool> stop{false};
+  std::mutex tmu; std::vector<std::string> trace;
+  ~ServingModel() { stop = true; if (updater.joinable()) updater.join(); }
+};
+
+static int Predict(ServingModel* sm, const void* in, int in_size, void** out, int* out_size, int hint) {
+  auto m = std::atomic_load(&sm->model);
+  if (!m || in_size < (int)sizeof(drpb::WireReq)) return 500;
+  drpb::WireReq h; memcpy(&h, in, sizeof(h));
+  const Arch& a = m->arch;
+  const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
+  if (h.magic != drpb::kWireReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.T || h.batch == 0 || (size_t)in_size < need) return 500;
+  const uint64_t pick = sm->cfg.select_policy == 1 ? (hint >= 0 ? (uint64_t)hint : std::hash<std::thread::id>()(std::this_thread::get_id())) : sm->rr.fetch_add(1);
+  Session& s = *sm->sessions[pick % sm->sessions.size()];
+  std::vector<float> probs(h.batch);
+  const auto t0 = std::chrono::steady_clock::now();
+  {
+    std::lock_guard<std::mutex> l(s.mu);
+    auto dense = std::atomic_load(&m->dense);
+    const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
+    const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
+    for (uint32_t off = 0; off < h.batch; off += (uint32_t)s.max_batch) {            // larger requests are chunked
+      const int B = (int)std::min<uint32_t>((uint32_t)s.max_batch, h.batch - off);
+      memcpy(s.dense.data(), p + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
+      for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids + (size_t)t * h.batch + off, (size_t)B * 8);
+      s.Run(*m, *dense, B);
+      memcpy(probs.data() + off, s.prob.data(), (size_t)B * 4);
+    }
+  }
+  const uint64_t rq = ++sm->requests;
+  if (sm->cfg.timeline_interval_step > 0 && (int64_t)rq >= sm->cfg.timeline_start_step && (rq % (uint64_t)sm->cfg.timeline_interval_step) == 0) {
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> l(sm->tmu);
+    if ((int)sm->trace.size() < sm->cfg.timeline_trace_count) {
+      char line[160]; snprintf(line, sizeof(line), "{\"request\": %llu, \"batch\": %u, \"latency_us\": %.1f, \"model_version\": %lld}", (unsigned long long)rq, h.batch, us, (long long)m->version);
+      sm->trace.emplace_back(line);
+      if (!sm->cfg.timeline_path.empty()) { FILE* f = fopen(sm->cfg.timeline_path.c_str(), "a"); if (f) { fprintf(f, "%s\n", line); fclose(f); } }
+    }
+  }
+  drpb::WireResp rh{drpb::kWireRespMagic, h.batch, 200, 0, m->version};
+  *out_size = (int)(sizeof(rh) + probs.size() * 4);
+  *out = malloc((size_t)*out_size);
+  memcpy(*out, &rh, sizeof(rh)); memcpy(static_cast<uint8_t*>(*out) + sizeof(rh), probs.data(), probs.size() * 4);
+  return 200;
+}
+
+static int PredictAny(ServingModel* sm, const void* in, int in_size, void** out, int* out_size, int hint) {
+  if (drpb::IsWireRequest(in, (size_t)std::max(in_size, 0))) return Predict(sm, in, in_size, out, out_size, hint);
+  auto m = std::atomic_load(&sm->model);
+  if (!m) return 500;
+  drpb::Request rq; std::string wire, err, pb;
+  if (!drpb::ParseRequest(in, (size_t)std::max(in_size, 0), &rq) || !drpb::RequestToWire(rq, m->arch.num_dense, m->arch.T, &wire, &err)) { sm->failures++; return 500; }
+  void* w_out = nullptr; int w_size = 0;
+  const int rc = Predict(sm, wire.data(), (int)wire.size(), &w_out, &w_size, hint);
+  if (rc != 200) { free(w_out); return rc; }
+  const bool ok = drpb::WireToResponse(w_out, (size_t)w_size, rq.output_filter, &pb);
+  free(w_out);
+  if (!ok) return 500;
+  *out_size = (int)pb.size(); *out = malloc(pb.size() ? pb.size() : 1); memcpy(*out, pb.data(), pb.size());
+  return 200;
+}
+
+// Warm-up: the request stored in warmup_file_name when present, else a synthetic batch cycling over stored keys -- every session runs once
+static bool WarmUp(ServingModel* sm, const std::shared_ptr<Model>& m) {
+  const Arch& a = m->arch;
+  std::string raw;
+  const bool from_file = !sm->cfg.warmup_file_name.empty() && drjson::ReadFile(sm->cfg.warmup_file_name, &raw) && drpb::IsWireRequest(raw.data(), raw.size());
+  for (auto& sp : sm->sessions) {
+    Session& s = *sp;
+    std::lock_guard<std::mutex> l(s.mu);
+    int B = std::min(64, s.max_batch);
+    bool filled = false;
+    if (from_file) {
+      drpb::WireReq h; memcpy(&h, raw.data(), sizeof(h));
+      const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
+      if ((int)h.num_dense == a.num_dense && (int)h.num_sparse == a.T && h.batch > 0 && raw.size() >= need) {
+        B = (int)std::min<uint32_t>(h.batch, (uint32_t)s.max_batch);
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(raw.data()) + sizeof(h);
+        memcpy(s.dense.data(), p, (size_t)B * a.num_dense * 4);
+        const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
+        for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids + (size_t)t * h.batch, (size_t)B * 8);
+        filled = true;
+      }
+    }
+    if (!filled) {
+      for (int i = 0; i < B * a.num_dense; ++i) s.dense[(size_t)i] = (float)((i * 37) % 100) / 25.f;
+      for (int t = 0; t < a.T; ++t) for (int i = 0; i < B; ++i) s.ids[(size_t)t * B + i] = m->sample_keys[(size_t)t * 64 + (size_t)(i % 64)];
+    }
+    auto dense = std::atomic_load(&m->dense);
+    s.Run(*m, *dense, B);
+    for (int i = 0; i < B; ++i) if (!(s.prob[(size_t)i] >= 0.f && s.prob[(size_t)i] <= 1.f)) return false;       // NaN / garbage -> reject the version
+  }
+  return true;
+}
+
+static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t version) {
+  auto m = std::atomic_load(&sm->model);
+  if (!m) return false;
+  dr::BundleReader r(prefix);
+  if (!r.ok()) return false;
+  for (int t = 0; t < m->arch.T; ++t) {
+    std::vector<int64_t> keys; std::vector<float> vals;
+    const std::string base = "table/" + std::to_string(t);
+    if (!ReadVec(r, base + "-sparse_incr_keys", &keys) || keys.empty()) continue;
+    if (!ReadVec(r, base + "-sparse_incr_values", &vals) || vals.size() != keys.size() * (size_t)m->arch.D) return false;
+    dr_host_ev_import(m->tables[(size_t)t], keys.data(), vals.data(), m->arch.D, nullptr, nullptr, (int64_t)keys.size(), 0, 1, 0);   // rows patched in place
+  }
+  std::shared_ptr<Dense> dp;
+  if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp)) std::atomic_store(&m->dense, dp);
+  sm->delta_version = version;
+  sm->delta_updates++;
+  return true;
+}
+
+// version file: <dir>/serving_versions.json = {"full": {"version": V, "dir": "..."}, "deltas": [{"version": v, "base": V, "prefix": "..."}]}
+static void UpdaterLoop(ServingModel* sm) {
+  const std::string vf = (sm->cfg.checkpoint_dir.empty() ? sm->cfg.savedmodel_dir : sm->cfg.checkpoint_dir) + "/serving_versions.json";
+  int bad = 0;
+  while (!sm->stop) {
+    for (int i = 0; i < std::max(1, sm->cfg.update_interval_ms / 20) && !sm->stop; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    std::string txt; JVal j;
+    if (!drjson::ReadFile(vf, &txt) || !drjson::ParseJson(txt, &j)) continue;
+    auto cur = std::atomic_load(&sm->model);
+    if (auto* f = j.get("full")) {
+      const int64_t v = (int64_t)f->n("version", -1); const std::string dir = f->s("dir", "");
+      if (cur && v > cur->version && !dir.empty()) {
+        auto nm = LoadModel(dir);
+        if (!nm) { if (++bad > 3) fprintf(stderr, "[deeprec_cpu_serving] skipping invalid model version %lld\n", (long long)v); continue; }
+        bad = 0;
+        if (!WarmUp(sm, nm)) continue;
+        std::atomic_store(&sm->model, nm);            // requests in flight keep the old model alive through their shared_ptr
+        sm->delta_version = -1;
+        sm->full_updates++;
+        continue;
+      }
+    }
+    if (auto* d = j.get("deltas")) {
+      cur = std::atomic_load(&sm->model);
+      for (auto& e : d->arr) {
+        const int64_t v = (int64_t)e.n("version", -1), base = (int64_t)e.n("base", -1);
+        if (cur && base == cur->version && v > std::max<int64_t>(cur->version, sm->delta_version.load())) ApplyDelta(sm, e.s("prefix", ""), v);
+      }
+    }
+  }
+}
+
+}  // namespace cpusrv
+
+extern "C" {
+
+// model_entry: saved-model directory (may be empty if the JSON config names it).  Returns an opaque model handle; *state = 0 on success.
+void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* state) {
+  using namespace cpusrv;
+  auto* sm = new ServingModel();
+  JVal j;
+  if (model_config && *model_config && !drjson::ParseJson(model_config, &j)) { *state = -1; delete sm; return nullptr; }
+  Config& c = sm->cfg;
+  c.session_num = (int)j.n("session_num", 2); c.max_batch = (int)j.n("max_batch", 4096);
+  c.select_policy = j.s("select_session_policy", "RR") == "MOD" ? 1 : 0;
+  c.update_interval_ms = (int)j.n("model_update_interval_ms", 1000);
+  c.savedmodel_dir = j.s("savedmodel_dir", model_entry ? model_entry : ""); c.checkpoint_dir = j.s("checkpoint_dir", "");
+  c.warmup_file_name = j.s("warmup_file_name", ""); c.timeline_path = j.s("timeline_path", "");
+  c.timeline_start_step = (int64_t)j.n("timeline_start_step", -1); c.timeline_interval_step = (int)j.n("timeline_interval_step", 0);
+  c.timeline_trace_count = (int)j.n("timeline_trace_count", 0);
+  auto m = LoadModel(c.savedmodel_dir);
+  if (!m || c.max_batch <= 0) { *state = -1; delete sm; return nullptr; }
+  // sessions run concurrently: each gets cores / sessions OpenMP threads for its GEMMs unless intra_op_parallelism_threads says otherwise
+  c.intra_threads = (int)j.n("intra_op_parallelism_threads", 0);
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int per_session = c.intra_threads > 0 ? c.intra_threads : std::max(1, hw / std::max(1, c.session_num));
+  for (int i = 0; i < std::max(1, c.session_num); ++i) { sm->sessions.emplace_back(new Session()); sm->sessions.back()->Init(m->arch, c.max_batch, per_session); }
+  if (!WarmUp(sm, m)) { *state = -1; delete sm; return nullptr; }
+  std::atomic_store(&sm->model, m);
+  if (c.update_interval_ms > 0) sm->updater = std::thread(UpdaterLoop, sm);
+  *state = 0;
+  return sm;
+}
+
+int dr_cpu_process(void* model_buf, const void* input_data, int input_size, void** output_data, int* output_size) {
+  if (!model_buf) return 500;
+  return cpusrv::PredictAny(static_cast<cpusrv::ServingModel*>(model_buf), input_data, input_size, output_data, output_size, -1);
+}
+
+// input_size[0] = number of requests, followed by their sizes (one call, several PredictRequests)
+int dr_cpu_batch_process(void* model_buf, const void* input_data[], int* input_size, void* output_data[], int* output_size) {
+  if (!model_buf || !input_size) return 500;
+  int n = input_size[0], rc = 200;
+  for (int i = 0; i < n; ++i) {
+    const int r = cpusrv::PredictAny(static_cast<cpusrv::ServingModel*>(model_buf), input_data[i], input_size[i + 1], &output_data[i], &output_size[i], i);
+    if (r != 200) rc = r;
+  }
+  return rc;
+}
+
+int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* output_size) {
+  if (!model_buf) return 500;
+  auto* sm = static_cast<cpusrv::ServingModel*>(model_buf);
+  auto m = std::atomic_load(&sm->model);
+  std::ostringstream os;
+  os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
+     << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
+     << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
+     << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.T : 0) << "}";
+  const std::string s = os.str();
+  *output_size = (int)s.size();
+  *output_data = malloc(s.size() + 1);
+  memcpy(*output_data, s.c_str(), s.size() + 1);
+  return 200;
+}
+
+void dr_cpu_serving_release(void* model_buf) { delete static_cast<cpusrv::ServingModel*>(model_buf); }
+void dr_cpu_serving_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -996,6 +996,10 @@ void dr_host_group_lookup(void** hs, int T, const int64_t* keys, int64_t B, floa
   if (T <= 0 || B <= 0) return;
   const int64_t dim = static_cast<dr::HostEV*>(hs[0])->cfg().dim;
   const int64_t chunk = 1024, chunks = (B + chunk - 1) / chunk;
+  if ((int64_t)T * B < 2048) {                     // online-serving sized requests: a parallel region would cost more than the probes
+    for (int t = 0; t < T; ++t) static_cast<dr::HostEV*>(hs[t])->LookupRange(keys + (int64_t)t * B, 0, B, out + (int64_t)t * dim, (int64_t)T * dim);
+    return;
+  }
   dr::GlobalPool()->ParallelFor((int64_t)T * chunks, 1, [&](int64_t b, int64_t e) {
     for (int64_t w = b; w < e; ++w) {
       const int64_t t = w / chunks, c = w % chunks, lo = c * chunk, hi = std::min(B, lo + chunk);

@@ -78,3 +78,80 @@ def export_delta(engine, root: str, base_version: int, version: Optional[int] = 
     w.close()
     _write_versions(root, delta={"version": version, "base": int(base_version), "prefix": os.path.abspath(prefix)})
     return prefix
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# the same saved-model format from the framework-API DLRM module (deeprec_b200.models.dlrm.DLRM) -- CPU training -> CPU / GPU serving
+# ---------------------------------------------------------------------------------------------------------------------------------
+def _pad_k(w: torch.Tensor) -> torch.Tensor:
+    """Linear weight [N, K] -> [N, pad8(K)] (the runtimes read kernels with the K dimension padded to a multiple of 8)."""
+    n, k = w.shape
+    kp = (k + 7) // 8 * 8
+    out = torch.zeros(n, kp, dtype=torch.float32)
+    out[:, :k] = w.detach().float().cpu()
+    return out.contiguous()
+
+
+def _module_dense_tensors(model) -> dict:
+    import torch.nn as nn
+    out = {}
+    bot = [m for m in model.bot if isinstance(m, (nn.Linear, nn.BatchNorm1d))]
+    for l in range(len(bot) // 2):
+        lin, bn = bot[2 * l], bot[2 * l + 1]
+        nm = f"mlp_bot_{l}"
+        out[f"dense/{nm}/kernel"], out[f"dense/{nm}/bias"] = _pad_k(lin.weight), lin.bias.detach().float().cpu().contiguous()
+        out[f"dense/{nm}/bn_gamma"], out[f"dense/{nm}/bn_beta"] = bn.weight.detach().float().cpu().contiguous(), bn.bias.detach().float().cpu().contiguous()
+        out[f"bn/{nm}/moving_mean"], out[f"bn/{nm}/moving_variance"] = bn.running_mean.detach().float().cpu().contiguous(), bn.running_var.detach().float().cpu().contiguous()
+    for l, lin in enumerate(m for m in model.top if isinstance(m, nn.Linear)):
+        out[f"dense/mlp_top_{l}/kernel"], out[f"dense/mlp_top_{l}/bias"] = _pad_k(lin.weight), lin.bias.detach().float().cpu().contiguous()
+    out["dense/logits/kernel"] = model.logits.weight.detach().float().cpu().reshape(-1).contiguous()
+    out["dense/logits/bias"] = model.logits.bias.detach().float().cpu().reshape(-1).contiguous()
+    return out
+
+
+def export_saved_model_module(model, export_dir: str, version: int, root: Optional[str] = None) -> str:
+    """Full export of a ``models.dlrm.DLRM`` module (dot interaction, EmbeddingVariable tables) in the format both serving runtimes load."""
+    import torch.nn as nn
+    if getattr(model, "interaction_op", "dot") != "dot":
+        raise ValueError("the serving runtimes implement the dot interaction")
+    evs = model.embedding_variables()
+    lin_bot = [m for m in model.bot if isinstance(m, nn.Linear)]
+    lin_top = [m for m in model.top if isinstance(m, nn.Linear)]
+    bns = [m for m in model.bot if isinstance(m, nn.BatchNorm1d)]
+    os.makedirs(os.path.join(export_dir, "variables"), exist_ok=True)
+    w = BundleWriter(os.path.join(export_dir, "variables", "variables"))
+    for name, t in _module_dense_tensors(model).items():
+        w.add(name, t)
+    D = evs[0].embedding_dim
+    for t, ev in enumerate(evs):
+        s = ev.table.snapshot()
+        w.add(f"table/{t}-keys", s["keys"].cpu()); w.add(f"table/{t}-values", s["rows"][:, :D].contiguous().cpu())
+        w.add(f"table/{t}-freqs", s["freqs"].cpu()); w.add(f"table/{t}-versions", s["versions"].cpu())
+        w.add(f"table/{t}-default", ev.default_matrix.detach().float().cpu().contiguous())
+        ev.table.clear_dirty()
+    w.close()
+    meta = {"model": "dlrm", "version": int(version), "num_dense": lin_bot[0].in_features, "num_tables": len(evs), "embedding_dim": D,
+            "mlp_bot": [m.out_features for m in lin_bot], "mlp_top": [m.out_features for m in lin_top], "bn_eps": float(bns[0].eps),
+            "variables": "variables/variables",
+            "signature": {"inputs": {"dense": ["B", lin_bot[0].in_features], "ids": [len(evs), "B"]}, "outputs": {"probabilities": ["B"]}}}
+    with open(os.path.join(export_dir, "saved_model.json"), "w") as f:
+        json.dump(meta, f)
+    _write_versions(root or export_dir, full={"version": int(version), "dir": os.path.abspath(export_dir)})
+    return export_dir
+
+
+def export_delta_module(model, root: str, base_version: int, version: int) -> str:
+    """Incremental export of a ``models.dlrm.DLRM`` module: rows touched since the last export + the dense block."""
+    d = os.path.join(root, ".incr")
+    os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, f"delta-{int(version)}")
+    w = BundleWriter(prefix)
+    for name, t in _module_dense_tensors(model).items():
+        w.add(name, t)
+    for t, ev in enumerate(model.embedding_variables()):
+        s = ev.table.snapshot(dirty_only=True)
+        w.add(f"table/{t}-sparse_incr_keys", s["keys"].cpu()); w.add(f"table/{t}-sparse_incr_values", s["rows"][:, : ev.embedding_dim].contiguous().cpu())
+        ev.table.clear_dirty()
+    w.close()
+    _write_versions(root, delta={"version": int(version), "base": int(base_version), "prefix": os.path.abspath(prefix)})
+    return prefix

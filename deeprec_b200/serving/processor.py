@@ -36,22 +36,45 @@ def decode_response(buf: bytes) -> Tuple[np.ndarray, int, int]:
     return probs, status, version
 
 
+class _Abi:
+    """The four entry points (+ release / free) of one runtime, bound with ctypes."""
+
+    def __init__(self, lib, prefix: str):
+        def fn(name, restype, argtypes):
+            f = getattr(lib, prefix + name)
+            f.restype, f.argtypes = restype, argtypes
+            return f
+        self.initialize = fn("initialize", C.c_void_p, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)])
+        self.process = fn("process", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)])
+        self.batch_process = fn("batch_process", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int)])
+        self.get_serving_model_info = fn("get_serving_model_info", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)])
+        rel = "dr_cpu_serving_" if prefix else "dr_serving_"
+        self.dr_serving_release, self.dr_serving_free = getattr(lib, rel + "release"), getattr(lib, rel + "free")
+        self.dr_serving_release.argtypes, self.dr_serving_free.argtypes = [C.c_void_p], [C.c_void_p]
+        self.dr_serving_release.restype = self.dr_serving_free.restype = None
+
+
 class Processor:
-    def __init__(self, savedmodel_dir: str, config: dict | None = None):
-        path = os.path.join(_build.LIB, "libdeeprec_cuda.so")
-        if not os.path.exists(path):
-            path = _build.build_cuda()
-        self.lib = C.CDLL(path)
-        L = self.lib
-        L.initialize.restype, L.initialize.argtypes = C.c_void_p, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
-        L.process.restype, L.process.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
-        L.batch_process.restype = C.c_int
-        L.batch_process.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
-        L.get_serving_model_info.restype, L.get_serving_model_info.argtypes = C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
-        L.dr_serving_release.argtypes, L.dr_serving_free.argtypes = [C.c_void_p], [C.c_void_p]
+    """``device="cuda"``: the GPU runtime (csrc/cuda/serving_runtime.cu: device tables, bf16 / fp8 tcgen05 MLP, CUDA graphs);
+    ``device="cpu"``: the CPU runtime (csrc/host/cpu_serving.cc: host tables, fp32 MLP on the OpenMP pool).  Same saved-model directory,
+    request encodings, ModelConfig keys and hot-swap protocol.  Default: cuda when a GPU is visible, else cpu."""
+
+    def __init__(self, savedmodel_dir: str, config: dict | None = None, device: str | None = None):
+        if device is None:
+            import torch
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = device
+        if device == "cpu":
+            from .. import _native
+            self.lib = _Abi(_native.host(), "dr_cpu_")
+        else:
+            path = os.path.join(_build.LIB, "libdeeprec_cuda.so")
+            if not os.path.exists(path):
+                path = _build.build_cuda()
+            self.lib = _Abi(C.CDLL(path), "")
         state = C.c_int(0)
         cfg = dict(config or {})
-        self.model = L.initialize(savedmodel_dir.encode(), json.dumps(cfg).encode(), C.byref(state))
+        self.model = self.lib.initialize(savedmodel_dir.encode(), json.dumps(cfg).encode(), C.byref(state))
         if not self.model or state.value != 0:
             raise RuntimeError(f"Processor.initialize failed for {savedmodel_dir} (state {state.value})")
 
@@ -121,7 +144,7 @@ class ProcessorGroup:
         cfg = dict(config or {})
         gpus = list(cfg.pop("gpu_ids_list", None) or [cfg.get("gpu_id", 0)])
         self.policy = str(cfg.get("select_session_policy", "RR")).upper()
-        self.replicas: List[Processor] = [Processor(savedmodel_dir, dict(cfg, gpu_id=int(g))) for g in gpus]
+        self.replicas: List[Processor] = [Processor(savedmodel_dir, dict(cfg, gpu_id=int(g)), device="cuda") for g in gpus]
         self.gpu_ids = [int(g) for g in gpus]
         self._rr = itertools.count()
         self._ident = threading.get_ident

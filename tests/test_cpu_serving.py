@@ -1,0 +1,125 @@
+"""Native CPU Processor (csrc/host/cpu_serving.cc) end to end: train the DLRM module on CPU -> export -> initialize -> process /
+batch_process (compact and protobuf encodings) == the module's own predictions; delta update patches the live model; full update swaps
+after warm-up; invalid versions are skipped; HTTP front-end on top."""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+import deeprec_b200 as dr
+from deeprec_b200.data import criteo_batch
+from deeprec_b200.models.zoo import build_model
+from deeprec_b200.serving import (Processor, decode_response, encode_request, export_delta_module, export_saved_model_module, predict_pb)
+
+CARDS = [50, 1000, 7, 300] + [97] * 22
+
+
+def _train(model, opt, steps, seed):
+    for s in range(steps):
+        d, ids, y = criteo_batch(512, 13, CARDS, seed=seed + s)
+        loss = model.loss(d, ids, y); opt.zero_grad(); loss.backward(); opt.step()
+    return d, ids
+
+
+def _ref(model, d, ids):
+    model.eval()
+    with torch.no_grad():
+        p = torch.sigmoid(model(d, ids)).numpy().copy()
+    model.train()
+    return p
+
+
+def _wait(pred, timeout=20.0):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if pred():
+            return True
+        time.sleep(0.05)
+    return False
+
+
+def test_cpu_processor_matches_module_and_hot_swaps(tmp_path):
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(0)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 6, 0)
+    root = str(tmp_path)
+    export_saved_model_module(model, os.path.join(root, "v1"), version=6, root=root)
+    proc = Processor(os.path.join(root, "v1"), {"session_num": 3, "select_session_policy": "RR", "max_batch": 200, "checkpoint_dir": root,
+                                                "model_update_interval_ms": 100, "timeline_interval_step": 1, "timeline_start_step": 0,
+                                                "timeline_trace_count": 3, "timeline_path": os.path.join(root, "trace.jsonl")}, device="cpu")
+    ref = _ref(model, d, ids)
+    got = proc.predict(d.numpy(), ids.numpy())                         # 512 rows > max_batch 200 -> chunked inside the session
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-5, np.abs(got - ref).max()
+    # unseen ids read default rows exactly like the module
+    ids2 = ids.clone(); ids2[:, :50] += 10 ** 9
+    assert np.abs(proc.predict(d.numpy(), ids2.numpy()) - _ref(model, d, ids2)).max() < 1e-5
+    rc, outs = proc.batch_process([encode_request(d.numpy()[:64], ids.numpy()[:, :64]) for _ in range(4)])
+    assert rc == 200 and all(np.abs(decode_response(o)[0] - ref[:64]).max() < 1e-5 for o in outs)
+    # protobuf PredictRequest (both input conventions) straight into process()
+    for per_feature in (False, True):
+        probs, version = predict_pb.decode_predict_response(proc.predict_proto(predict_pb.encode_predict_request(d.numpy(), ids.numpy(), per_feature=per_feature)))
+        assert version == 6 and np.array_equal(probs, got)
+    assert proc.process(b"garbage")[0] == 500 and proc.process(encode_request(d.numpy()[:, :5], ids.numpy()))[0] == 500
+    info = proc.model_info()
+    assert info["model_version"] == 6 and info["sessions"] == 3 and info["device"] == "cpu" and info["requests"] >= 8 and info["failures"] >= 1
+    assert len(open(os.path.join(root, "trace.jsonl")).read().strip().splitlines()) == 3
+    # ---- delta update: only the touched rows + the dense block travel; the live model picks them up without a swap
+    _train(model, opt, 3, 100)
+    export_delta_module(model, root, base_version=6, version=9)
+    ref2 = _ref(model, d, ids)
+    assert _wait(lambda: proc.model_info()["delta_updates"] >= 1)
+    got2 = proc.predict(d.numpy(), ids.numpy())
+    assert proc.model_info()["delta_version"] == 9 and np.abs(got2 - ref2).max() < 1e-5 and np.abs(ref2 - ref).max() > 1e-4
+    # ---- an invalid full version is skipped, the old model keeps serving
+    os.makedirs(os.path.join(root, "bad"))
+    open(os.path.join(root, "bad", "saved_model.json"), "w").write("{not json")
+    from deeprec_b200.serving.export import _write_versions
+    _write_versions(root, full={"version": 10, "dir": os.path.join(root, "bad")})
+    time.sleep(0.5)
+    assert proc.model_info()["model_version"] == 6 and np.abs(proc.predict(d.numpy(), ids.numpy()) - ref2).max() < 1e-5
+    # ---- full update: new version directory, swapped after warm-up
+    _train(model, opt, 2, 200)
+    export_saved_model_module(model, os.path.join(root, "v2"), version=11, root=root)
+    assert _wait(lambda: proc.model_info()["model_version"] == 11)
+    ref3 = _ref(model, d, ids)
+    assert np.abs(proc.predict(d.numpy(), ids.numpy()) - ref3).max() < 1e-5 and proc.model_info()["full_updates"] == 1
+    proc.close()
+
+
+def test_cpu_processor_concurrent_requests_and_http(tmp_path):
+    import threading
+    from starlette.testclient import TestClient
+    from deeprec_b200.serving.http_server import HttpClient, ServingBackend, create_app
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(1)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 3, 7)
+    export_saved_model_module(model, str(tmp_path / "m"), version=3)
+    proc = Processor(str(tmp_path / "m"), {"session_num": 4, "select_session_policy": "MOD", "max_batch": 512, "model_update_interval_ms": 0}, device="cpu")
+    ref = _ref(model, d, ids)
+    errs = []
+
+    def client(i):
+        try:
+            for k in range(10):
+                lo = (i * 17 + k * 31) % 400
+                out = proc.predict(d.numpy()[lo:lo + 64], ids.numpy()[:, lo:lo + 64])
+                assert np.abs(out - ref[lo:lo + 64]).max() < 1e-5
+        except Exception as e:      # pragma: no cover
+            errs.append(e)
+    ts = [threading.Thread(target=client, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errs and proc.model_info()["requests"] == 80
+    with TestClient(create_app({"dlrm": ServingBackend.from_processor(proc)})) as http:
+        cli = HttpClient("http://testserver", "dlrm", session=http)
+        assert np.abs(cli.predict(d.numpy()[:8], ids.numpy()[:, :8]) - ref[:8]).max() < 1e-5
+        assert np.abs(cli.predict_proto(d.numpy()[:8], ids.numpy()[:, :8], per_feature=True) - ref[:8]).max() < 1e-5
+        assert http.get("/v1/models/dlrm").json()["device"] == "cpu"
+    proc.close()
+    with pytest.raises(RuntimeError):
+        Processor(str(tmp_path / "nope"), {}, device="cpu")
