@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../deeprec_b200/csrc/common/mini_json.h"
 #include "../../deeprec_b200/csrc/common/predict_pb.h"
 #include "../../deeprec_b200/csrc/common/tensor_pool.h"
 
@@ -61,6 +62,29 @@ static void FuzzCodec() {
   printf("codec fuzz: %lld mutated requests accepted, %lld rejected\n", (long long)accepted, (long long)rejected);
 }
 
+static void FuzzJson() {
+  std::mt19937_64 rng(77);
+  const std::string valid = "{\"session_num\": 4, \"select_session_policy\": \"MOD\", \"mlp_bot\": [512, 256, 64, 16], \"full\": {\"version\": 12, \"dir\": \"/m/v12\"}, "
+                            "\"deltas\": [{\"version\": 13, \"base\": 12, \"prefix\": \"/m/.incr/delta-13\"}], \"ok\": true, \"none\": null, \"x\": -1.5e3}";
+  drjson::JVal j;
+  CHECK(drjson::ParseJson(valid, &j) && j.n("session_num", 0) == 4 && j.s("select_session_policy", "") == "MOD" && j.get("deltas")->arr.size() == 1);
+  int64_t ok = 0, bad = 0;
+  for (int iter = 0; iter < 4000; ++iter) {
+    std::string m = valid;
+    switch (iter % 4) {
+      case 0: m.resize(rng() % (m.size() + 1)); break;
+      case 1: for (int k = 0; k < 1 + (int)(rng() % 6); ++k) m[rng() % m.size()] ^= (char)(1u << (rng() % 8)); break;
+      case 2: { size_t n = rng() % 120; m.resize(n); for (auto& c : m) c = (char)rng(); break; }
+      case 3: m = std::string(1 + rng() % 200, "[{\""[rng() % 3]); break;                     // deep nesting must be cut off, not overflow the stack
+    }
+    std::string exact(m.data(), m.size());                                                     // exactly-sized heap copy: over-reads are visible to ASAN
+    drjson::JVal v;
+    if (drjson::ParseJson(exact, &v)) ++ok; else ++bad;
+  }
+  CHECK(bad > 1000);
+  printf("json fuzz: %lld parsed, %lld rejected\n", (long long)ok, (long long)bad);
+}
+
 static void* HostAlloc(size_t n, void*) { return malloc(n); }
 static void HostFree(void* p, void*) { free(p); }
 
@@ -103,6 +127,7 @@ static void StressPool() {
 
 int main() {
   FuzzCodec();
+  FuzzJson();
   StressPool();
   printf("CODEC_POOL_OK\n");
   return 0;
