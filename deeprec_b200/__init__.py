@@ -21,5 +21,12 @@ from .ops.embedding_ops import (SparseIds, adaptive_embedding_lookup_sparse, emb
                                 safe_embedding_lookup_sparse)
 from .optim.optimizers import get_or_create_global_step
 from . import graph_optimizer  # noqa: E402,F401
+from . import feature_column  # noqa: E402,F401
+from .config import PAD_KEY  # noqa: E402,F401
+# top-level spellings of the reference's tf.* additions (tf.staged, tf.make_prefetch_hook, tf.SmartStageOptions, tf.stream,
+# tf.train.mark_target_node, tf.config.experimental.enable_distributed_strategy)
+from .data.staged import SmartStageOptions, make_prefetch_hook, smart_stage, staged  # noqa: E402,F401
+from .parallel.collective import CollectiveStrategy, enable_distributed_strategy  # noqa: E402,F401
+from .utils.streams import mark_target_node, stream  # noqa: E402,F401
 
 __version__ = "0.1.0"

@@ -123,6 +123,12 @@ def sequence_categorical_column_with_embedding(key, dtype=torch.int64, partition
     return CategoricalColumn(key, "embedding", 0, dtype, ev_option, partition_num, is_sequence=True)
 
 
+def sparse_column_with_embedding(column_name, dtype=torch.int64, partition_num=None, ev_option=None, **_ignored):
+    """``tf.contrib.layers.sparse_column_with_embedding`` (contrib/layers/python/layers/feature_column.py): the contrib spelling of
+    ``categorical_column_with_embedding`` -- an EmbeddingVariable-backed categorical column."""
+    return categorical_column_with_embedding(column_name, dtype=dtype, partition_num=partition_num, ev_option=ev_option)
+
+
 def weighted_categorical_column(categorical_column, weight_feature_key):
     return WeightedCategoricalColumn(categorical_column, weight_feature_key)
 
