@@ -155,3 +155,43 @@ def export_delta_module(model, root: str, base_version: int, version: int) -> st
     w.close()
     _write_versions(root, delta={"version": int(version), "base": int(base_version), "prefix": os.path.abspath(prefix)})
     return prefix
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# any zoo model -> a servable directory (the reference's SavedModel works for every model; the native Processors are DLRM-shaped, every
+# other model is served by the python SessionGroup / HTTP front-end from this format)
+# ---------------------------------------------------------------------------------------------------------------------------------
+def export_zoo_model(model, name: str, export_dir: str, version: int, build_kwargs: Optional[dict] = None) -> str:
+    """Write ``saved_model.json`` (zoo name + constructor arguments + version) and a full checkpoint (dense parameters, BatchNorm statistics,
+    every EmbeddingVariable with its metadata) of ``model`` -- a model built by ``models.zoo.build_model(name, **build_kwargs)``."""
+    from ..checkpoint.saver import Saver
+    os.makedirs(os.path.join(export_dir, "variables"), exist_ok=True)
+    prefix = Saver(model).save(os.path.join(export_dir, "variables", "variables"), global_step=int(version))
+    meta = {"model": name, "zoo": True, "version": int(version), "build_kwargs": dict(build_kwargs or {}), "variables": os.path.relpath(prefix, export_dir)}
+    tmp = os.path.join(export_dir, "saved_model.json.tmp")
+    with open(tmp, "w") as f:
+        json.dump(meta, f)
+    os.replace(tmp, os.path.join(export_dir, "saved_model.json"))          # the directory becomes visible as a model only when complete
+    return export_dir
+
+
+def load_zoo_model(export_dir: str, device: str = "cpu"):
+    """Rebuild the model of ``export_zoo_model`` for serving: EmbeddingVariables are created in inference mode (lookups never create
+    keys, filters are ignored -- ``INFERENCE_MODE``), state restored, ``eval()`` set.  Returns ``(model, version)``."""
+    from ..checkpoint.saver import Saver
+    from ..models.zoo import build_model
+    with open(os.path.join(export_dir, "saved_model.json")) as f:
+        meta = json.load(f)
+    if not meta.get("zoo"):
+        raise ValueError(f"{export_dir} is an engine / DLRM-module export: load it with serving.Processor")
+    prev = os.environ.get("INFERENCE_MODE")
+    os.environ["INFERENCE_MODE"] = "1"
+    try:
+        model = build_model(meta["model"], device=device, **meta.get("build_kwargs", {}))
+        Saver(model).restore(os.path.join(export_dir, meta["variables"]))
+    finally:
+        if prev is None:
+            os.environ.pop("INFERENCE_MODE", None)
+        else:
+            os.environ["INFERENCE_MODE"] = prev
+    return model.eval(), int(meta["version"])

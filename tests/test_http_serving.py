@@ -41,3 +41,30 @@ def test_http_predict_json_raw_and_metrics():
         cli = HttpClient("http://testserver", "wdl", session=http)
         assert np.allclose(cli.predict(dense.numpy(), ids.numpy()), ref, atol=1e-6)
         assert np.allclose(cli.predict_raw(dense.numpy(), ids.numpy()), ref, atol=1e-6)
+
+
+def test_any_zoo_model_round_trips_through_export_and_serves(tmp_path):
+    """export_zoo_model / load_zoo_model: DIN (sequence features, three EmbeddingVariables) trained, exported, re-loaded in inference mode,
+    served by a SessionGroup -- same predictions, and serving lookups of unseen ids create nothing."""
+    from deeprec_b200.data import taobao_batch
+    from deeprec_b200.serving import export_zoo_model, load_zoo_model
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(0)
+    model = build_model("din", device="cpu")
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    for s in range(3):
+        b = taobao_batch(128, 10, 1000, 2000, 50, seed=s)
+        opt.zero_grad(); model.loss(b).backward(); opt.step()
+    probe = taobao_batch(64, 10, 1000, 2000, 50, seed=99)
+    model.eval()
+    with torch.no_grad():
+        ref = model(probe).clone()
+    export_zoo_model(model, "din", str(tmp_path / "din_v3"), version=3)
+    dr.embedding_variable.clear_registry()
+    served, version = load_zoo_model(str(tmp_path / "din_v3"))
+    assert version == 3
+    group = SessionGroup(served, session_num=2)
+    rows_before = served.item.total_count()
+    got = group.run(probe)
+    assert torch.allclose(got, ref, atol=1e-6)
+    assert served.item.total_count() == rows_before == model.item.total_count()
