@@ -39,6 +39,7 @@ void dr_host_ev_set_default(void* h, const float* m);
 int64_t dr_host_ev_size(void* h);
 int64_t dr_host_ev_import(void* h, const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs, const int64_t* versions, int64_t n,
                           int part_id, int part_num, int reset_version);
+int64_t dr_host_ev_import_cow(void* h, const int64_t* keys, const float* rows, int64_t ncols, int64_t n);
 void dr_host_group_lookup(void** hs, int T, const int64_t* keys, int64_t B, float* out);
 void dr_host_dot_interaction_fwd(const float* dense, const float* embs, int64_t B, int T, int D, float* out);
 }
@@ -339,7 +340,7 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
     const std::string base = "table/" + std::to_string(t);
     if (!ReadVec(r, base + "-sparse_incr_keys", &keys) || keys.empty()) continue;
     if (!ReadVec(r, base + "-sparse_incr_values", &vals) || vals.size() != keys.size() * (size_t)m->arch.D) return false;
-    dr_host_ev_import(m->tables[(size_t)t], keys.data(), vals.data(), m->arch.D, nullptr, nullptr, (int64_t)keys.size(), 0, 1, 0);   // rows patched in place
+    dr_host_ev_import_cow(m->tables[(size_t)t], keys.data(), vals.data(), m->arch.D, (int64_t)keys.size());   // copy-on-write: readers never see a torn row
   }
   std::shared_ptr<Dense> dp;
   if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp)) std::atomic_store(&m->dense, dp);

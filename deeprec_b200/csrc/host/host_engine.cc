@@ -730,6 +730,26 @@ class HostEV {
     }
     return kept;
   }
+  // Import into a table that is being READ concurrently (serving: delta update of a live model).  A new key's row is written first and
+  // its index published with release semantics; an existing key gets a fresh row (copy-on-write) and the index is swapped -- readers see
+  // either the complete old row or the complete new one, never a half-written row.  Replaced rows are not recycled (a reader may still be
+  // copying them): they stay allocated until the table is destroyed, i.e. until the next full model update replaces it.
+  int64_t ImportCow(const int64_t* keys, const float* rows, int64_t ncols, int64_t n) {
+    const int64_t w = std::min(ncols, stride_);
+    for (int64_t i = 0; i < n; ++i) {
+      if (keys[i] == kEmptyKey) continue;
+      bool inserted = false;
+      const int32_t idx = kv_.FindOrInsert(keys[i], [this] { return AllocMeta(); }, &inserted);
+      int32_t* rp = (&meta_.at(idx)->row);
+      const int32_t old = __atomic_load_n(rp, __ATOMIC_ACQUIRE);
+      const int32_t r = AllocRow();
+      InitRow(r, keys[i]);
+      memcpy(rows_.at(r), rows + i * ncols, (size_t)w * sizeof(float));
+      __atomic_store_n(rp, r, __ATOMIC_RELEASE);
+      if (old < 0) admitted_.fetch_add(1);
+    }
+    return n;
+  }
   // rows (full stride) + metadata of specific keys; found[i] = 1 if the key owns a row (multi-tier promotion path)
   void ExportKeys(const int64_t* keys, int64_t n, float* rows, int64_t* freqs, int64_t* versions, uint8_t* found) {
     GlobalPool()->ParallelFor(n, 1024, [&](int64_t b, int64_t e) {
@@ -839,6 +859,9 @@ void dr_host_ev_clear_dirty(void* h) { static_cast<dr::HostEV*>(h)->ClearDirty()
 int64_t dr_host_ev_import(void* h, const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs,
                           const int64_t* versions, int64_t n, int part_id, int part_num, int reset_version) {
   return static_cast<dr::HostEV*>(h)->Import(keys, rows, ncols, freqs, versions, n, part_id, part_num, reset_version);
+}
+int64_t dr_host_ev_import_cow(void* h, const int64_t* keys, const float* rows, int64_t ncols, int64_t n) {
+  return static_cast<dr::HostEV*>(h)->ImportCow(keys, rows, ncols, n);
 }
 void dr_host_ev_export_keys(void* h, const int64_t* keys, int64_t n, float* rows, int64_t* freqs, int64_t* versions, uint8_t* found) {
   static_cast<dr::HostEV*>(h)->ExportKeys(keys, n, rows, freqs, versions, found);

@@ -62,3 +62,28 @@ def test_codec_fuzz_and_tensor_pool_under_sanitizers(tmp_path, sanitizer):
     else:
         pytest.skip("sanitizer runtime is not usable in this environment")
     assert r.returncode == 0 and "CODEC_POOL_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
+
+
+@pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])
+def test_cpu_serving_runtime_under_sanitizers(tmp_path, sanitizer):
+    """The CPU Processor served from 4 client threads while deltas and full versions are published underneath it."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "cpu_serving_stress")
+    host = os.path.join(ROOT, "deeprec_b200", "csrc", "host")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", f"-fsanitize={sanitizer}", "-fno-omit-frame-pointer", "-pthread",
+           os.path.join(ROOT, "tests", "native", "cpu_serving_stress.cc"), os.path.join(host, "cpu_serving.cc"), os.path.join(host, "host_engine.cc"), "-o", exe]
+    b = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip(f"-fsanitize={sanitizer} unsupported here")
+    assert b.returncode == 0, b.stderr[-3000:]
+    run = ["setarch", "-R", exe] if sanitizer == "thread" and shutil.which("setarch") else [exe]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 second_deadlock_stack=1", ASAN_OPTIONS="detect_leaks=1")
+    for attempt in range(3):
+        work = str(tmp_path / f"models{attempt}")
+        r = subprocess.run(run + [work], capture_output=True, text=True, timeout=900, env=env)
+        if r.returncode == 0 or not ("tpp.c" in r.stderr or "unexpected memory mapping" in r.stderr):
+            break
+    else:
+        pytest.skip("sanitizer runtime is not usable in this environment")
+    assert r.returncode == 0 and "CPU_SERVING_STRESS_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
