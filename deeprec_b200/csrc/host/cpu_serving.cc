@@ -42,6 +42,12 @@ int64_t dr_host_ev_import(void* h, const int64_t* keys, const float* rows, int64
 int64_t dr_host_ev_import_cow(void* h, const int64_t* keys, const float* rows, int64_t ncols, int64_t n);
 void dr_host_group_lookup(void** hs, int T, const int64_t* keys, int64_t B, float* out);
 void dr_host_dot_interaction_fwd(const float* dense, const float* embs, int64_t B, int T, int D, float* out);
+void* dr_redis_connect(const char* host, int port, int timeout_ms, const char* password, int db);
+int dr_redis_ok(void* h);
+const char* dr_redis_last_error(void* h);
+void dr_redis_close(void* h);
+int64_t dr_redis_mget_rows(void* h, const char* prefix, const int64_t* keys, int64_t n, float* rows, int dim, uint8_t* found);
+int64_t dr_redis_get(void* h, const char* key, void* out, int64_t cap);
 }
 
 namespace cpusrv {
@@ -51,6 +57,9 @@ struct Config {
   int session_num = 2, max_batch = 4096, select_policy = 0 /*0 RR, 1 MOD*/, update_interval_ms = 1000, intra_threads = 0;
   std::string savedmodel_dir, checkpoint_dir, warmup_file_name, timeline_path;
   int64_t timeline_start_step = -1; int timeline_interval_step = 0, timeline_trace_count = 0;
+  // feature_store_type "redis" (serving/processor/storage/redis_feature_store.*): embedding rows live in a Redis instance shared by all
+  // replicas, key "<redis_prefix>/<model version>/table/<t>:<id>", value = D x fp32; this process keeps only the dense net + default rows
+  bool remote = false; std::string redis_host = "127.0.0.1", redis_password, redis_prefix = "dlrm"; int redis_port = 6379, redis_db = 0, redis_timeout_ms = 2000;
 };
 
 struct Arch { int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0; };
@@ -62,7 +71,8 @@ struct Dense { std::vector<Layer> bot, top; std::vector<float> last_scale, last_
 struct Model {
   Arch arch; int64_t version = -1; std::string path;
   std::shared_ptr<Dense> dense;
-  std::vector<void*> tables;                                   // HostEV handles (owned)
+  std::vector<void*> tables;                                   // HostEV handles (owned); empty in remote (Redis) mode
+  std::vector<std::vector<float>> defaults;                    // remote mode: default-value matrix of every table ([dvd, D])
   std::vector<int64_t> sample_keys;                            // a few stored keys per table for the synthetic warm-up batch, [T][<=64]
   ~Model() { for (void* t : tables) if (t) dr_host_ev_destroy(t); }
 };
@@ -151,7 +161,7 @@ static void* BuildTable(dr::BundleReader& r, int t, int D, std::vector<int64_t>*
   return h;
 }
 
-static std::shared_ptr<Model> LoadModel(const std::string& dir) {
+static std::shared_ptr<Model> LoadModel(const std::string& dir, bool remote = false) {
   auto m = std::make_shared<Model>();
   std::string prefix;
   if (!LoadArch(dir, &m->arch, &m->version, &prefix)) { fprintf(stderr, "[deeprec_cpu_serving] bad saved_model.json in %s\n", dir.c_str()); return nullptr; }
@@ -159,7 +169,12 @@ static std::shared_ptr<Model> LoadModel(const std::string& dir) {
   if (!r.ok()) { fprintf(stderr, "[deeprec_cpu_serving] cannot open bundle %s\n", prefix.c_str()); return nullptr; }
   if (!BuildDense(r, m->arch, &m->dense)) { fprintf(stderr, "[deeprec_cpu_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
   m->sample_keys.assign((size_t)m->arch.T * 64, 0);
-  for (int t = 0; t < m->arch.T; ++t) {
+  for (int t = 0; t < m->arch.T && remote; ++t) {            // rows are in the feature store: only the default rows are needed here
+    std::vector<float> def;
+    if (!ReadVec(r, "table/" + std::to_string(t) + "-default", &def) || def.empty() || def.size() % (size_t)m->arch.D) { fprintf(stderr, "[deeprec_cpu_serving] table %d has no default matrix\n", t); return nullptr; }
+    m->defaults.push_back(std::move(def));
+  }
+  for (int t = 0; t < m->arch.T && !remote; ++t) {
     std::vector<int64_t> sample;
     void* h = BuildTable(r, t, m->arch.D, &sample);
     if (!h) { fprintf(stderr, "[deeprec_cpu_serving] table %d incomplete\n", t); return nullptr; }
@@ -199,7 +214,9 @@ static void Linear(const float* X, int64_t ldx, int64_t B, const Layer& L, float
 
 struct Session {
   std::mutex mu; int max_batch = 0, threads = 1;     // threads: OpenMP team size of this session's GEMMs (cores / sessions)
-  std::vector<float> dense, emb, a, b2, z, prob; std::vector<int64_t> ids;
+  std::vector<float> dense, emb, a, b2, z, prob, rrows; std::vector<int64_t> ids; std::vector<uint8_t> found;
+  void* redis = nullptr;                                       // remote mode: this session's connection to the feature store
+  ~Session() { if (redis) dr_redis_close(redis); }
   void Init(const Arch& ar, int mb, int nthreads) {
     max_batch = mb; threads = std::max(1, nthreads);
     int widest = ar.inter;
@@ -207,11 +224,30 @@ struct Session {
     for (int n : ar.top) widest = std::max(widest, n);
     dense.resize((size_t)mb * ar.num_dense); ids.resize((size_t)mb * ar.T); emb.resize((size_t)mb * ar.T * ar.D);
     a.resize((size_t)mb * widest); b2.resize((size_t)mb * widest); z.resize((size_t)mb * ar.inter); prob.resize((size_t)mb);
+    rrows.resize((size_t)mb * ar.D); found.resize((size_t)mb);
+  }
+  // remote lookup of one chunk: per table ONE pipelined MGET; ids the store does not have read their default row (what a local
+  // inference-mode lookup returns)
+  bool RemoteLookup(const Model& m, const std::string& prefix, int B) {
+    const Arch& ar = m.arch;
+    for (int t = 0; t < ar.T; ++t) {
+      const int64_t* k = ids.data() + (size_t)t * B;
+      const std::string p = prefix + "/" + std::to_string(m.version) + "/table/" + std::to_string(t);
+      if (!dr_redis_ok(redis) || dr_redis_mget_rows(redis, p.c_str(), k, B, rrows.data(), ar.D, found.data()) < 0) return false;
+      const std::vector<float>& def = m.defaults[(size_t)t];
+      const int64_t dvd = (int64_t)def.size() / ar.D;
+      for (int i = 0; i < B; ++i) {
+        const float* src = found[(size_t)i] ? rrows.data() + (size_t)i * ar.D : def.data() + dr_default_row(k[i], dvd) * ar.D;
+        memcpy(emb.data() + ((size_t)i * ar.T + t) * ar.D, src, (size_t)ar.D * sizeof(float));
+      }
+    }
+    return true;
   }
   // dense [B, num_dense], ids [T][B] staged in the session buffers -> prob[B]
-  void Run(const Model& m, const Dense& d, int B) {
+  bool Run(const Model& m, const Dense& d, int B, const std::string& remote_prefix = std::string()) {
     const Arch& ar = m.arch;
-    dr_host_group_lookup(const_cast<void**>(m.tables.data()), ar.T, ids.data(), B, emb.data());              // [B, T, D]
+    if (redis) { if (!RemoteLookup(m, remote_prefix, B)) return false; }
+    else dr_host_group_lookup(const_cast<void**>(m.tables.data()), ar.T, ids.data(), B, emb.data());         // [B, T, D]
     const float* x = dense.data(); int64_t ldx = ar.num_dense;
     float* cur = a.data(); float* nxt = b2.data();
     for (size_t l = 0; l < d.bot.size(); ++l) { Linear(x, ldx, B, d.bot[l], cur, true, threads); x = cur; ldx = d.bot[l].N; std::swap(cur, nxt); }
@@ -226,6 +262,7 @@ struct Session {
       for (int k = 0; k < K; ++k) acc += xi[k] * d.head_w[k];
       prob[(size_t)i] = 1.f / (1.f + std::exp(-acc));
     }
+    return true;
   }
 };
 
@@ -260,7 +297,16 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
       const int B = (int)std::min<uint32_t>((uint32_t)s.max_batch, h.batch - off);
       memcpy(s.dense.data(), p + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
       for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids + (size_t)t * h.batch + off, (size_t)B * 8);
-      s.Run(*m, *dense, B);
+      if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) {
+        // feature store hiccup: one reconnect + retry before the request is failed (the next request tries again)
+        bool ok = false;
+        if (s.redis) {
+          dr_redis_close(s.redis);
+          s.redis = dr_redis_connect(sm->cfg.redis_host.c_str(), sm->cfg.redis_port, sm->cfg.redis_timeout_ms, sm->cfg.redis_password.c_str(), sm->cfg.redis_db);
+          ok = dr_redis_ok(s.redis) && s.Run(*m, *dense, B, sm->cfg.redis_prefix);
+        }
+        if (!ok) { sm->failures++; return 500; }
+      }
       memcpy(probs.data() + off, s.prob.data(), (size_t)B * 4);
     }
   }
@@ -321,10 +367,10 @@ static bool WarmUp(ServingModel* sm, const std::shared_ptr<Model>& m) {
     }
     if (!filled) {
       for (int i = 0; i < B * a.num_dense; ++i) s.dense[(size_t)i] = (float)((i * 37) % 100) / 25.f;
-      for (int t = 0; t < a.T; ++t) for (int i = 0; i < B; ++i) s.ids[(size_t)t * B + i] = m->sample_keys[(size_t)t * 64 + (size_t)(i % 64)];
+      for (int t = 0; t < a.T; ++t) for (int i = 0; i < B; ++i) s.ids[(size_t)t * B + i] = m->tables.empty() ? (int64_t)i : m->sample_keys[(size_t)t * 64 + (size_t)(i % 64)];
     }
     auto dense = std::atomic_load(&m->dense);
-    s.Run(*m, *dense, B);
+    if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) return false;
     for (int i = 0; i < B; ++i) if (!(s.prob[(size_t)i] >= 0.f && s.prob[(size_t)i] <= 1.f)) return false;       // NaN / garbage -> reject the version
   }
   return true;
@@ -335,7 +381,7 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
   if (!m) return false;
   dr::BundleReader r(prefix);
   if (!r.ok()) return false;
-  for (int t = 0; t < m->arch.T; ++t) {
+  for (int t = 0; t < m->arch.T && !m->tables.empty(); ++t) {      // (remote mode: the trainer inserts delta rows into the feature store itself)
     std::vector<int64_t> keys; std::vector<float> vals;
     const std::string base = "table/" + std::to_string(t);
     if (!ReadVec(r, base + "-sparse_incr_keys", &keys) || keys.empty()) continue;
@@ -361,7 +407,7 @@ static void UpdaterLoop(ServingModel* sm) {
     if (auto* f = j.get("full")) {
       const int64_t v = (int64_t)f->n("version", -1); const std::string dir = f->s("dir", "");
       if (cur && v > cur->version && !dir.empty()) {
-        auto nm = LoadModel(dir);
+        auto nm = LoadModel(dir, sm->cfg.remote);
         if (!nm) { if (++bad > 3) fprintf(stderr, "[deeprec_cpu_serving] skipping invalid model version %lld\n", (long long)v); continue; }
         bad = 0;
         if (!WarmUp(sm, nm)) continue;
@@ -399,13 +445,29 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
   c.warmup_file_name = j.s("warmup_file_name", ""); c.timeline_path = j.s("timeline_path", "");
   c.timeline_start_step = (int64_t)j.n("timeline_start_step", -1); c.timeline_interval_step = (int)j.n("timeline_interval_step", 0);
   c.timeline_trace_count = (int)j.n("timeline_trace_count", 0);
-  auto m = LoadModel(c.savedmodel_dir);
+  c.remote = j.s("feature_store_type", "local") == "redis";
+  if (c.remote) {
+    const std::string url = j.s("redis_url", "127.0.0.1:6379");
+    const size_t colon = url.rfind(':');
+    c.redis_host = colon == std::string::npos ? url : url.substr(0, colon);
+    c.redis_port = colon == std::string::npos ? 6379 : atoi(url.c_str() + colon + 1);
+    c.redis_password = j.s("redis_password", ""); c.redis_db = (int)j.n("redis_db_idx", 0);
+    c.redis_prefix = j.s("redis_prefix", "dlrm"); c.redis_timeout_ms = (int)j.n("redis_timeout_ms", 2000);
+  }
+  auto m = LoadModel(c.savedmodel_dir, c.remote);
   if (!m || c.max_batch <= 0) { *state = -1; delete sm; return nullptr; }
   // sessions run concurrently: each gets cores / sessions OpenMP threads for its GEMMs unless intra_op_parallelism_threads says otherwise
   c.intra_threads = (int)j.n("intra_op_parallelism_threads", 0);
   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
   const int per_session = c.intra_threads > 0 ? c.intra_threads : std::max(1, hw / std::max(1, c.session_num));
-  for (int i = 0; i < std::max(1, c.session_num); ++i) { sm->sessions.emplace_back(new Session()); sm->sessions.back()->Init(m->arch, c.max_batch, per_session); }
+  for (int i = 0; i < std::max(1, c.session_num); ++i) {
+    sm->sessions.emplace_back(new Session()); sm->sessions.back()->Init(m->arch, c.max_batch, per_session);
+    if (c.remote) {                                             // one connection per session (sessions run concurrently)
+      void* conn = dr_redis_connect(c.redis_host.c_str(), c.redis_port, c.redis_timeout_ms, c.redis_password.c_str(), c.redis_db);
+      if (!dr_redis_ok(conn)) { fprintf(stderr, "[deeprec_cpu_serving] feature store %s:%d: %s\n", c.redis_host.c_str(), c.redis_port, dr_redis_last_error(conn)); dr_redis_close(conn); *state = -2; delete sm; return nullptr; }
+      sm->sessions.back()->redis = conn;
+    }
+  }
   if (!WarmUp(sm, m)) { *state = -1; delete sm; return nullptr; }
   std::atomic_store(&sm->model, m);
   if (c.update_interval_ms > 0) sm->updater = std::thread(UpdaterLoop, sm);
@@ -436,7 +498,7 @@ int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* outp
   std::ostringstream os;
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
-     << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
+     << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"feature_store_type\": \"" << (sm->cfg.remote ? "redis" : "local") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
      << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.T : 0) << "}";
   const std::string s = os.str();
   *output_size = (int)s.size();

@@ -213,12 +213,21 @@ class _RespHandler(socketserver.StreamRequestHandler):
 
     def handle(self):
         srv: "MiniRedisServer" = self.server.owner       # type: ignore[attr-defined]
+        with srv.mu:
+            srv.conns.add(self.request)
+        try:
+            self._serve(srv)
+        finally:
+            with srv.mu:
+                srv.conns.discard(self.request)
+
+    def _serve(self, srv: "MiniRedisServer"):
         w = self.wfile
         authed = not srv.password
         while True:
             try:
                 args = self._read_command()
-            except (ConnectionError, ValueError):
+            except (ConnectionError, ValueError, OSError):
                 return
             if not args:
                 return
@@ -270,6 +279,7 @@ class MiniRedisServer:
         self.mu = threading.Lock()
         self.password = password
         self.commands = 0
+        self.conns = set()                            # established client sockets (closed by close(): a stopped server drops its clients)
 
         class _Srv(socketserver.ThreadingTCPServer):
             allow_reuse_address = True
@@ -284,6 +294,14 @@ class MiniRedisServer:
     def close(self):
         self._srv.shutdown()
         self._srv.server_close()
+        import socket
+        with self.mu:
+            conns, self.conns = list(self.conns), set()
+        for c in conns:
+            try:
+                c.shutdown(socket.SHUT_RDWR)
+            except OSError:
+                pass
 
     def __enter__(self):
         return self
@@ -321,6 +339,20 @@ def export_delta_to_feature_store(embedding_variables: Iterable, store: FeatureS
         if keys.size:
             store.insert(_table_prefix(model_name, version, ev.name), keys, s["rows"][:, : ev.embedding_dim].contiguous().cpu().numpy())
             total += int(keys.size)
+    return total
+
+
+def export_processor_tables(embedding_variables: Iterable, store: FeatureStore, prefix: str, version: int, dirty_only: bool = False, chunk: int = 65536) -> int:
+    """Rows for the NATIVE CPU Processor in ``feature_store_type: "redis"`` mode (csrc/host/cpu_serving.cc): table t of the exported model
+    lives under ``<prefix>/<version>/table/<t>`` (``prefix`` = the processor's ``redis_prefix``).  Call it BEFORE publishing the
+    saved-model version the rows belong to; ``dirty_only=True`` sends just the rows touched since the last export (delta update)."""
+    total = 0
+    for t, ev in enumerate(embedding_variables):
+        s = ev.table.snapshot(dirty_only=dirty_only)
+        keys, values = s["keys"].cpu().numpy(), s["rows"][:, : ev.embedding_dim].contiguous().cpu().numpy()
+        for o in range(0, keys.size, chunk):
+            store.insert(f"{prefix}/{int(version)}/table/{t}", keys[o:o + chunk], values[o:o + chunk])
+        total += int(keys.size)
     return total
 
 

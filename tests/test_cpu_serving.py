@@ -123,3 +123,47 @@ def test_cpu_processor_concurrent_requests_and_http(tmp_path):
     proc.close()
     with pytest.raises(RuntimeError):
         Processor(str(tmp_path / "nope"), {}, device="cpu")
+
+
+def test_cpu_processor_with_redis_feature_store(tmp_path):
+    """feature_store_type = redis: embedding rows live in the (mini) Redis server, the processor keeps the dense net and default rows;
+    answers equal the local-mode processor and the module, a new full version reads its own key space, an unreachable store is a 500."""
+    from deeprec_b200.serving.feature_store import MiniRedisServer, RedisFeatureStore, export_processor_tables
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(2)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 4, 3)
+    root = str(tmp_path)
+    srv = MiniRedisServer()
+    store = RedisFeatureStore(srv.host, srv.port)
+    evs = model.embedding_variables()
+    n = export_processor_tables(evs, store, "ctr_model", 4)
+    assert n == sum(e.total_count() for e in evs) == store.dbsize()
+    export_saved_model_module(model, os.path.join(root, "v1"), version=4, root=root)
+    cfg = {"session_num": 2, "max_batch": 256, "checkpoint_dir": root, "model_update_interval_ms": 100}
+    remote = Processor(os.path.join(root, "v1"), dict(cfg, feature_store_type="redis", redis_url=f"{srv.host}:{srv.port}", redis_prefix="ctr_model"), device="cpu")
+    local = Processor(os.path.join(root, "v1"), dict(cfg, model_update_interval_ms=0), device="cpu")
+    ids2 = ids.clone(); ids2[:, :40] += 10 ** 9                       # ids the store has never seen -> default rows
+    ref = _ref(model, d, ids2)
+    a, b = remote.predict(d.numpy(), ids2.numpy()), local.predict(d.numpy(), ids2.numpy())
+    assert np.abs(a - ref).max() < 1e-5 and np.array_equal(a, b) and remote.model_info()["feature_store_type"] == "redis"
+    # new full version: rows first (own key space), then the saved model; the processor swaps and reads version 7 rows
+    _train(model, opt, 3, 50)
+    export_processor_tables(evs, store, "ctr_model", 7)
+    export_saved_model_module(model, os.path.join(root, "v2"), version=7, root=root)
+    assert _wait(lambda: remote.model_info()["model_version"] == 7)
+    assert np.abs(remote.predict(d.numpy(), ids2.numpy()) - _ref(model, d, ids2)).max() < 1e-5
+    # store goes away -> requests fail cleanly (500), the process survives
+    srv.close(); store.close()
+    rc, _ = remote.process(encode_request(d.numpy()[:8], ids.numpy()[:, :8]))
+    assert rc == 500 and remote.model_info()["failures"] >= 1
+    # ... and comes back (same port): the session reconnects on the next request
+    srv2 = MiniRedisServer(port=srv.port)
+    store2 = RedisFeatureStore(srv2.host, srv2.port)
+    export_processor_tables(evs, store2, "ctr_model", 7)
+    assert np.abs(remote.predict(d.numpy(), ids2.numpy()) - _ref(model, d, ids2)).max() < 1e-5
+    store2.close(); srv2.close()
+    remote.close(); local.close()
+    with pytest.raises(RuntimeError):
+        Processor(os.path.join(root, "v2"), dict(cfg, feature_store_type="redis", redis_url="127.0.0.1:1"), device="cpu")
