@@ -72,7 +72,7 @@ def test_cpu_serving_runtime_under_sanitizers(tmp_path, sanitizer):
     exe = str(tmp_path / "cpu_serving_stress")
     host = os.path.join(ROOT, "deeprec_b200", "csrc", "host")
     cmd = ["g++", "-O1", "-g", "-std=c++17", f"-fsanitize={sanitizer}", "-fno-omit-frame-pointer", "-pthread",
-           os.path.join(ROOT, "tests", "native", "cpu_serving_stress.cc"), os.path.join(host, "cpu_serving.cc"), os.path.join(host, "host_engine.cc"), "-o", exe]
+           os.path.join(ROOT, "tests", "native", "cpu_serving_stress.cc"), os.path.join(host, "cpu_serving.cc"), os.path.join(host, "host_engine.cc"), os.path.join(host, "redis_store.cc"), "-o", exe]
     b = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     if b.returncode != 0 and "sanitize" in b.stderr:
         pytest.skip(f"-fsanitize={sanitizer} unsupported here")
