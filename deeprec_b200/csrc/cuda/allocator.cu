@@ -25,7 +25,13 @@ void* DevAlloc(size_t n, void* ctx) {
   const int dev = (int)(intptr_t)ctx;
   if (prev != dev) cudaSetDevice(dev);
   void* p = nullptr;
-  if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+  if (cudaMalloc(&p, n) != cudaSuccess) {
+    cudaGetLastError(); p = nullptr;
+    // GPU virtual memory (docs/docs_en/GPU-Virtual-Memory.md, TF_GPU_VMEM): when device memory is exhausted fall back to managed memory,
+    // which the driver pages between host and device -- slower, but the job keeps running instead of failing with OOM
+    static const bool vmem = [] { const char* e = getenv("DEEPREC_GPU_VMEM"); if (!e) e = getenv("TF_GPU_VMEM"); return e && (e[0] == '1' || e[0] == 't' || e[0] == 'T'); }();
+    if (vmem && cudaMallocManaged(&p, n) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+  }
   if (prev != dev) cudaSetDevice(prev);
   return p;
 }
