@@ -38,6 +38,8 @@ def get_arg_parser():
     p.add_argument("--save_steps", type=int, default=0)
     p.add_argument("--workqueue", action="store_true")
     p.add_argument("--micro_batch", type=int, default=1)
+    p.add_argument("--no_eval", action="store_true", help="skip the evaluation pass (ACC / AUC on held-out synthetic batches) after training")
+    p.add_argument("--eval_steps", type=int, default=10)
     p.add_argument("--parquet_dataset", default=None, help="glob of Criteo-shaped parquet files (label, I1..I13, C1..C26); default: synthetic data")
     p.add_argument("--multihash", action="store_true", help="Q-R multi-hash embeddings instead of EmbeddingVariables")
     p.add_argument("--adaptive_emb", action="store_true", help="adaptive embedding: static hashed table for cold ids, EV for hot ids")
@@ -141,6 +143,22 @@ def main(argv=None) -> int:
     t0 = time.time()
     tr.fit(src, a.steps)
     print(f"{a.steps * a.batch_size / (time.time() - t0):.0f} samples/s")
+    if not a.no_eval and a.eval_steps > 0:                  # modelzoo train.py: ACC / AUC after training unless --no_eval
+        def held_out():
+            for s in range(a.eval_steps):
+                if taobao:
+                    yield {k: v.to(dev) for k, v in taobao_batch(a.batch_size, 20, 100000, 200000, 1000, seed=10_000_000 + s).items()}
+                else:
+                    d, ids, y = criteo_batch(a.batch_size, 13, cards, seed=10_000_000 + s)
+                    yield d.to(dev), ids.to(dev), y.to(dev)
+
+        def predict(m, b):
+            out = m(b) if taobao else m(b[0], b[1])
+            if isinstance(out, dict):
+                out = out["ctr"]
+            return torch.sigmoid(out.float()), (b["labels"] if taobao else b[2])
+        res = tr.evaluate(held_out(), predict, max_steps=a.eval_steps)
+        print(f"Evaluation complete: ACC {res['acc']:.4f}  AUC {res['auc']:.4f}")
     return 0
 
 

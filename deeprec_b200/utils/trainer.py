@@ -19,13 +19,17 @@ class Trainer:
     def __init__(self, model: torch.nn.Module, optimizer, loss_fn: Callable, checkpoint_dir: Optional[str] = None,
                  save_checkpoint_steps: int = 0, save_checkpoint_secs: float = 0, save_incremental_checkpoint_secs: float = 0,
                  save_incremental_checkpoint_steps: int = 0, log_every_n_steps: int = 100, timeline_steps: int = 0,
-                 micro_batch_num: int = 1, strategy=None, log: Callable[[str], None] = print, watchdog_timeout_s: float = 0):
+                 micro_batch_num: int = 1, strategy=None, log: Callable[[str], None] = print, watchdog_timeout_s: float = 0,
+                 hooks: Optional[list] = None):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.dir = checkpoint_dir
         self.save_steps, self.save_secs = save_checkpoint_steps, save_checkpoint_secs
         self.incr_secs, self.incr_steps = save_incremental_checkpoint_secs, save_incremental_checkpoint_steps
         self.log_every, self.timeline_steps = log_every_n_steps, timeline_steps
         self.micro = max(1, micro_batch_num)
+        # SessionRunHook analogue: objects with any of begin(trainer) / after_step(trainer, step, loss) / end(trainer, step);
+        # after_step returning True requests a stop (StopAtStepHook, early stopping, NaN guard ...)
+        self.hooks = list(hooks or [])
         self.strategy, self.log = strategy, log
         self.saver = IncrementalSaver(model, optimizer=optimizer) if checkpoint_dir else None
         self.timeline = Timeline() if timeline_steps else None
@@ -56,7 +60,13 @@ class Trainer:
     def fit(self, batches: Iterable, max_steps: Optional[int] = None) -> int:
         step = int(self.opt.global_step)
         t0, n0 = time.time(), step
+        for h in self.hooks:
+            if hasattr(h, "begin"):
+                h.begin(self)
+        stop = False
         for batch in batches:
+            if stop:
+                break
             if max_steps is not None and step - n0 >= max_steps:
                 break
             if self.timeline is not None and step - n0 < self.timeline_steps:
@@ -68,6 +78,9 @@ class Trainer:
             if self.watchdog is not None:
                 self.watchdog.tick()
             self.faults.maybe_fail(step)
+            for h in self.hooks:
+                if hasattr(h, "after_step") and h.after_step(self, step, loss):
+                    stop = True
             if self.log_every and step % self.log_every == 0:
                 dt = time.time() - t0
                 self.log(f"global_step {step}  loss {loss:.5f}  {(step - n0) / max(dt, 1e-9):.2f} global_step/sec")
@@ -80,6 +93,9 @@ class Trainer:
                         self.saver.incremental_save(os.path.join(self.dir, "model.ckpt"), step); self._last_incr = now
         if self.timeline is not None and self.dir:
             self.timeline.save(os.path.join(self.dir, "timeline.json"))
+        for h in self.hooks:
+            if hasattr(h, "end"):
+                h.end(self, step)
         return step
 
     @torch.no_grad()

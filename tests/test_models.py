@@ -78,3 +78,26 @@ def test_adaptive_embedding_switches_cold_ids_to_the_ev():
     assert ae.ev.get_frequency(ids).tolist() == [2, 2]
     e1 = ae(ids)                                          # hot now: each id reads its own EmbeddingVariable row
     assert not torch.equal(e1[0], e1[1]) and torch.equal(e1.detach(), ae.ev.table.lookup(ids))
+
+
+def test_train_cli_evaluates_and_trainer_hooks_can_stop(capsys):
+    from deeprec_b200.models import train
+    assert train.main(["--model", "esmm", "--steps", "3", "--batch_size", "64", "--device", "cpu", "--log_every", "0", "--eval_steps", "2"]) == 0
+    out = capsys.readouterr().out
+    assert "Evaluation complete: ACC" in out and "AUC" in out
+    assert train.main(["--model", "wdl", "--steps", "2", "--batch_size", "64", "--device", "cpu", "--log_every", "0", "--no_eval"]) == 0
+    assert "Evaluation complete" not in capsys.readouterr().out
+    # hooks: begin / after_step (stop request) / end
+    import deeprec_b200 as dr
+    from deeprec_b200.utils import Trainer
+    events = []
+
+    class StopAt:
+        def begin(self, tr): events.append("begin")
+        def after_step(self, tr, step, loss): events.append(step); return step >= 3
+        def end(self, tr, step): events.append(("end", step))
+    model = torch.nn.Linear(4, 1)
+    tr = Trainer(model, dr.optim.GradientDescentOptimizer(model, lr=0.1, global_step=dr.optim.GlobalStep()), lambda m, b: m(b).pow(2).mean(),
+                 log_every_n_steps=0, hooks=[StopAt()])
+    last = tr.fit((torch.randn(8, 4) for _ in range(100)))
+    assert last == 3 and events == ["begin", 1, 2, 3, ("end", 3)]
