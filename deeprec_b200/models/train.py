@@ -38,6 +38,7 @@ def get_arg_parser():
     p.add_argument("--save_steps", type=int, default=0)
     p.add_argument("--workqueue", action="store_true")
     p.add_argument("--micro_batch", type=int, default=1)
+    p.add_argument("--output_dir", default=None, help="TensorBoard event files (loss, global_step/sec, EmbeddingVariable sizes) are written here")
     p.add_argument("--no_eval", action="store_true", help="skip the evaluation pass (ACC / AUC on held-out synthetic batches) after training")
     p.add_argument("--eval_steps", type=int, default=10)
     p.add_argument("--parquet_dataset", default=None, help="glob of Criteo-shaped parquet files (label, I1..I13, C1..C26); default: synthetic data")
@@ -139,7 +140,8 @@ def main(argv=None) -> int:
 
     src = smart_stage(gen(), device=None) if a.smartstaged else gen()
     tr = Trainer(model, opt, loss_fn, a.checkpoint, save_checkpoint_steps=a.save_steps, save_incremental_checkpoint_secs=a.incremental_ckpt,
-                 log_every_n_steps=a.log_every, timeline_steps=a.timeline, micro_batch_num=a.micro_batch, watchdog_timeout_s=a.watchdog)
+                 log_every_n_steps=a.log_every, timeline_steps=a.timeline, micro_batch_num=a.micro_batch, watchdog_timeout_s=a.watchdog,
+                 hooks=[__import__("deeprec_b200.utils.summary", fromlist=["SummaryHook"]).SummaryHook(a.output_dir, max(1, a.log_every or 100))] if a.output_dir else None)
     t0 = time.time()
     tr.fit(src, a.steps)
     print(f"{a.steps * a.batch_size / (time.time() - t0):.0f} samples/s")

@@ -80,3 +80,23 @@ def test_multi_tensor_dense_updates_equal_the_per_parameter_rules(name):
             o.zero_grad(); m(x).pow(2).mean().backward(); o.step()
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, atol=1e-6, rtol=1e-5), (name, (pa - pb).abs().max())
+
+
+def test_summary_hook_writes_tensorboard_events(tmp_path):
+    import glob
+    import deeprec_b200 as dr
+    from deeprec_b200.utils import SummaryHook, Trainer
+    dr.embedding_variable.clear_registry()
+    ev = dr.get_embedding_variable("sum/emb", 4, seed=1)
+    head = torch.nn.Linear(4, 1)
+    model = torch.nn.ModuleList([ev, head])
+    opt = dr.optim.AdagradOptimizer(model, lr=0.1, global_step=dr.optim.GlobalStep())
+    tr = Trainer(model, opt, lambda m, ids: m[1](m[0].lookup(ids)).pow(2).mean(), log_every_n_steps=0, hooks=[SummaryHook(str(tmp_path), every_n_steps=2)])
+    tr.fit((torch.randint(0, 50, (16,)) for _ in range(6)))
+    files = glob.glob(str(tmp_path / "events.out.tfevents.*"))
+    assert files
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(str(tmp_path)); acc.Reload()
+    tags = acc.Tags()["scalars"]
+    assert "loss" in tags and "embedding_variable/sum/emb/rows" in tags and "global_step/sec" in tags
+    assert [e.step for e in acc.Scalars("loss")] == [2, 4, 6] and acc.Scalars("embedding_variable/sum/emb/rows")[-1].value == ev.total_count()
