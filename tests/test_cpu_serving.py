@@ -167,3 +167,25 @@ def test_cpu_processor_with_redis_feature_store(tmp_path):
     remote.close(); local.close()
     with pytest.raises(RuntimeError):
         Processor(os.path.join(root, "v2"), dict(cfg, feature_store_type="redis", redis_url="127.0.0.1:1"), device="cpu")
+
+
+def test_c_client_integrates_the_abi(tmp_path):
+    """examples/c_client.c: a plain C program dlopens the runtime, initializes an exported model and sends protobuf + compact requests."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(3)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    _train(model, opt, 2, 11)
+    export_saved_model_module(model, str(tmp_path / "m"), version=2)
+    exe = str(tmp_path / "c_client")
+    b = subprocess.run(["gcc", "-std=c99", "-Wall", os.path.join(root, "examples", "c_client.c"), "-I" + os.path.join(root, "deeprec_b200", "csrc", "include"), "-ldl", "-o", exe],
+                       capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    from deeprec_b200 import build as _b
+    r = subprocess.run([exe, os.path.join(_b.LIB, "libdeeprec_host.so"), str(tmp_path / "m")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C_CLIENT_OK" in r.stdout and "model version 2" in r.stdout, r.stdout + r.stderr
