@@ -121,6 +121,29 @@ class DeepRecOptimizer(torch.optim.Optimizer):
         for p, g, st in zip(ps, gs, states):
             self._dense_update(p, g, st, group, hp)
 
+    def _sparse_param_update(self, p: torch.Tensor, grad: torch.Tensor, state: dict, group: dict, hp: OptHyper) -> None:
+        """``SparseApply{Adagrad, AdagradDecay, Adam, AdamAsync, Ftrl, ...}`` on a plain (non-EV) variable (training_ali_ops.cc:994,2111):
+        the optimizer's rule applied to the touched rows only (lazy: untouched rows keep their slots -- no decay, no update)."""
+        g = grad.coalesce()
+        idx, vals = g.indices()[0], g.values()
+        if idx.numel() == 0:
+            return
+        if not state:      # slots start from the rule's own initial values (uniform per element): run the rule once on a zero row to get them
+            tmp: dict = {}
+            z = torch.zeros_like(p[:1])
+            self._dense_update(z, torch.zeros_like(z), tmp, group, hp)
+            for k, v in tmp.items():
+                state[k] = v.expand_as(p).clone() if torch.is_tensor(v) and v.dim() == p.dim() else v
+        rows = p.data.index_select(0, idx)
+        sub = {k: (v.index_select(0, idx) if torch.is_tensor(v) and v.dim() == p.dim() and v.shape[0] == p.shape[0] else v) for k, v in state.items()}
+        self._dense_update(rows, vals.to(rows.dtype), sub, group, hp)
+        p.data.index_copy_(0, idx, rows)
+        for k, v in sub.items():
+            if torch.is_tensor(v) and v.dim() == p.dim() and torch.is_tensor(state[k]) and state[k].shape[0] == p.shape[0]:
+                state[k].index_copy_(0, idx, v)
+            else:
+                state[k] = v
+
     def _after_step(self, group) -> None:
         pass
 
@@ -135,9 +158,12 @@ class DeepRecOptimizer(torch.optim.Optimizer):
         hp = self._hyper(group)
         if not self._no_dense:
             for g_ in self.param_groups:
-                ps = [p for p in g_["params"] if p.grad is not None]
+                ps = [p for p in g_["params"] if p.grad is not None and not p.grad.is_sparse]
                 if ps:
                     self._dense_update_many(ps, [p.grad for p in ps], [self.state[p] for p in ps], g_, hp)
+                for p in g_["params"]:
+                    if p.grad is not None and p.grad.is_sparse:          # nn.Embedding(sparse=True): SparseApply* on a plain variable
+                        self._sparse_param_update(p, p.grad, self.state[p], g_, hp)
         from ..ops.host_group import apply_group_pending
         apply_group_pending(self.evs, hp)          # grouped host lookups: one native dedup + apply call per group
         for ev in self.evs:

@@ -100,3 +100,30 @@ def test_summary_hook_writes_tensorboard_events(tmp_path):
     tags = acc.Tags()["scalars"]
     assert "loss" in tags and "embedding_variable/sum/emb/rows" in tags and "global_step/sec" in tags
     assert [e.step for e in acc.Scalars("loss")] == [2, 4, 6] and acc.Scalars("embedding_variable/sum/emb/rows")[-1].value == ev.total_count()
+
+
+@pytest.mark.parametrize("name", ["adagrad", "adam", "adamasync", "adagraddecay", "ftrl", "gradientdescent"])
+def test_sparse_gradients_of_plain_embeddings_are_applied_lazily(name):
+    """nn.Embedding(sparse=True) under the DeepRec optimizers = SparseApply* on a non-EV variable: when every row is touched the result
+    equals the dense update; rows that are not touched keep their values AND their slots (no decay)."""
+    from deeprec_b200.optim import GlobalStep, make_optimizer
+    torch.manual_seed(0)
+    kw = dict(lr=0.05)
+    if name == "adagraddecay":
+        kw.update(accumulator_decay_step=2, accumulator_decay_rate=0.5)
+    es, ed = torch.nn.Embedding(12, 4, sparse=True), torch.nn.Embedding(12, 4)
+    ed.weight.data.copy_(es.weight.data)
+    os_, od = make_optimizer(name, es, None, global_step=GlobalStep(), **kw), make_optimizer(name, ed, None, global_step=GlobalStep(), **kw)
+    allids = torch.arange(12)
+    for step in range(3):                                   # all rows touched: sparse == dense
+        t = torch.randn(12, 4)
+        for e, o in ((es, os_), (ed, od)):
+            o.zero_grad(); ((e(allids) - t) ** 2).sum().backward(); o.step()
+    assert torch.allclose(es.weight, ed.weight, atol=1e-6)
+    before = es.weight.detach().clone()
+    st_before = {k: v.clone() for k, v in os_.state[es.weight].items() if torch.is_tensor(v)}
+    os_.zero_grad(); (es(torch.tensor([2, 2, 5])) ** 2).sum().backward(); os_.step()
+    touched = torch.zeros(12, dtype=torch.bool); touched[[2, 5]] = True
+    assert torch.equal(es.weight.detach()[~touched], before[~touched]) and not torch.allclose(es.weight.detach()[touched], before[touched])
+    for k, v in st_before.items():
+        assert torch.equal(os_.state[es.weight][k][~touched], v[~touched]), k
