@@ -189,3 +189,97 @@ def test_c_client_integrates_the_abi(tmp_path):
     from deeprec_b200 import build as _b
     r = subprocess.run([exe, os.path.join(_b.LIB, "libdeeprec_host.so"), str(tmp_path / "m")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "C_CLIENT_OK" in r.stdout and "model version 2" in r.stdout, r.stdout + r.stderr
+
+
+def test_grpc_front_end_over_the_cpu_processor(tmp_path):
+    """gRPC PredictService (byte-level handlers, no generated stubs): real PredictRequest protobufs in, PredictResponse out; two models on
+    one server selected by metadata; malformed requests map to INVALID_ARGUMENT; a google.protobuf-built request works too."""
+    import grpc
+    from deeprec_b200.serving.grpc_server import PredictClient, create_server
+    procs = {}
+    refs = {}
+    for name, seed in (("ctr", 5), ("cvr", 6)):
+        dr.embedding_variable.clear_registry()
+        torch.manual_seed(seed)
+        model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+        opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+        _train(model, opt, 2, seed)
+        d, ids, _ = criteo_batch(512, 13, CARDS, seed=99)
+        export_saved_model_module(model, str(tmp_path / name), version=seed)
+        procs[name] = Processor(str(tmp_path / name), {"session_num": 2, "model_update_interval_ms": 0}, device="cpu")
+        refs[name] = _ref(model, d, ids)
+    server, port = create_server(procs)
+    try:
+        for name in ("ctr", "cvr"):
+            cli = PredictClient(f"127.0.0.1:{port}", model=name)
+            probs, version = cli.predict(d.numpy(), ids.numpy())
+            assert version == {"ctr": 5, "cvr": 6}[name] and np.abs(probs - refs[name]).max() < 1e-5
+            assert np.array_equal(cli.predict(d.numpy(), ids.numpy(), per_feature=True)[0], probs)
+            assert cli.model_info()["device"] == "cpu"
+            cli.close()
+        cli = PredictClient(f"127.0.0.1:{port}")                      # no metadata -> the first model
+        Req, Resp, _ = predict_pb.message_classes()
+        m = Req(output_filter=["probabilities"])
+        m.inputs["dense"].dtype = 1; m.inputs["dense"].float_val.extend(d.numpy()[:4].reshape(-1).tolist())
+        m.inputs["ids"].dtype = 9; m.inputs["ids"].int64_val.extend(ids.numpy()[:, :4].reshape(-1).tolist())
+        r = Resp.FromString(cli.predict_raw(m.SerializeToString()))
+        assert list(r.outputs) == ["probabilities"] and np.abs(np.asarray(r.outputs["probabilities"].float_val) - refs["ctr"][:4]).max() < 1e-5
+        with pytest.raises(grpc.RpcError) as e:
+            cli.predict_raw(b"\x12\xff\xff\xff\xff\x0f")
+        assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+        bad = PredictClient(f"127.0.0.1:{port}", model="nope")
+        with pytest.raises(grpc.RpcError) as e:
+            bad.model_info()
+        assert e.value.code() == grpc.StatusCode.NOT_FOUND
+        bad.close(); cli.close()
+    finally:
+        server.stop(0)
+        for p in procs.values():
+            p.close()
+
+
+def test_model_server_cli_serves_grpc_and_http(tmp_path):
+    """``python -m deeprec_b200.serving.serve``: a separate process loads the export, listens on gRPC + HTTP, answers both, exits on SIGTERM."""
+    import json
+    import signal
+    import subprocess
+    import sys
+
+    import requests
+
+    from deeprec_b200.serving.grpc_server import PredictClient
+    from deeprec_b200.serving.http_server import HttpClient
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(3)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 2, 3)
+    export_saved_model_module(model, str(tmp_path / "m"), version=9)
+    ref = _ref(model, d, ids)
+    pf = str(tmp_path / "ports.json")
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    p = subprocess.Popen([sys.executable, "-m", "deeprec_b200.serving.serve", "--model", f"ctr={tmp_path / 'm'}", "--device", "cpu", "--config",
+                          '{"session_num": 2, "model_update_interval_ms": 0}', "--grpc_port", "0", "--http_port", "0", "--port_file", pf], env=env)
+    try:
+        assert _wait(lambda: os.path.exists(pf) or p.poll() is not None, 120) and p.poll() is None
+        ports = json.load(open(pf))
+        cli = PredictClient(f"127.0.0.1:{ports['grpc']}", model="ctr")
+        probs, version = cli.predict(d.numpy(), ids.numpy(), timeout=60)
+        assert version == 9 and np.abs(probs - ref).max() < 1e-5
+        cli.close()
+        base = f"http://127.0.0.1:{ports['http']}"
+        assert _wait(lambda: _ok(lambda: requests.get(base + "/healthz", timeout=2).status_code == 200), 30)
+        assert np.abs(HttpClient(base, "ctr").predict_proto(d.numpy(), ids.numpy()) - ref).max() < 1e-5
+    finally:
+        p.send_signal(signal.SIGTERM)
+        try:
+            assert p.wait(30) == 0
+        except subprocess.TimeoutExpired:
+            p.kill(); raise
+
+
+def _ok(fn):
+    try:
+        return fn()
+    except Exception:
+        return False
