@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 import zlib
-from typing import List, Sequence, Tuple
+from typing import List, Sequence
 
 import torch
 

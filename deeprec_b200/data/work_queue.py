@@ -7,7 +7,7 @@ torch.distributed TCP store (the reference places it on the chief / PS); single-
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterable, Iterator, List, Optional
+from typing import Iterable, Iterator, Optional
 
 from .. import _native
 

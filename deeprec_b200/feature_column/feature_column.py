@@ -12,14 +12,14 @@ dense input tensor.  Columns created inside ``group_embedding_column_scope`` are
 from __future__ import annotations
 
 import contextlib
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Union
 
 import torch
 from torch import nn
 
 from ..config import EmbeddingVariableOption
-from ..embedding_variable import EmbeddingVariable, MultiHashVariable, get_embedding_variable, get_multihash_variable
+from ..embedding_variable import EmbeddingVariable, get_embedding_variable, get_multihash_variable
 from ..ops.embedding_ops import (SparseIds, adaptive_embedding_lookup_sparse, embedding_lookup, group_embedding_lookup_sparse,
                                  safe_embedding_lookup_sparse)
 

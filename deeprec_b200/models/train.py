@@ -13,7 +13,7 @@ import torch
 
 import deeprec_b200 as dr
 from deeprec_b200.data import criteo_batch, smart_stage, taobao_batch
-from deeprec_b200.models.zoo import CRITEO_MODELS, TAOBAO_MODELS, build_model
+from deeprec_b200.models.zoo import TAOBAO_MODELS, build_model
 from deeprec_b200.optim import make_optimizer
 from deeprec_b200.utils import Trainer
 

@@ -21,7 +21,7 @@ from torch.nn import functional as F
 from ..config import EmbeddingVariableOption
 from ..embedding_variable import EmbeddingVariable, get_embedding_variable
 from ..ops.embedding_ops import SparseIds, group_embedding_lookup_sparse
-from .dlrm import DLRM, dot_interaction
+from .dlrm import DLRM
 
 
 def _use_fused(device) -> bool:

@@ -13,7 +13,6 @@ The reference runs these through cuBLAS (stream_executor/cuda/cuda_blas.cc) and 
 """
 from __future__ import annotations
 
-import math
 from typing import List, Optional, Sequence
 
 import torch

@@ -19,7 +19,6 @@ from typing import Dict, Optional
 
 import torch
 
-from .. import _native
 from .._native import EvConfig, OptHyper, ptr, stream_ptr
 from ..embedding_variable import HostTable
 from .device_table import DeviceTable, _chk

@@ -11,7 +11,7 @@ from __future__ import annotations
 import contextlib
 import enum
 import os
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist

@@ -9,7 +9,7 @@ tests and by single-process serving) and across ranks (torch.distributed object 
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Sequence
 
 import torch
 import torch.distributed as dist

@@ -5,7 +5,7 @@ from __future__ import annotations
 import contextlib
 import json
 import time
-from typing import List, Optional
+from typing import List
 
 import torch
 
