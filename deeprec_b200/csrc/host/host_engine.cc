@@ -18,8 +18,11 @@
 #ifdef DR_USE_OPENMP
 #include <omp.h>
 #endif
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -81,19 +84,22 @@ class ThreadPool {
     if (n <= 0) return;
     int shards = (int)std::min<int64_t>(size() + 1, (n + min_grain - 1) / min_grain);
     if (shards <= 1) { fn(0, n); return; }
-    std::atomic<int> remaining(shards - 1);
+    // the completion count is only touched under dmu: the waiter can then not observe zero (and destroy dmu / dcv, which live on its
+    // stack) while the last worker is still between its decrement and its notify -- ThreadSanitizer caught exactly that window
+    int remaining = shards - 1;
     std::mutex dmu; std::condition_variable dcv;
     int64_t per = (n + shards - 1) / shards;
     for (int s = 1; s < shards; ++s) {
       int64_t b = s * per, e = std::min(n, b + per);
       Submit([&, b, e] {
         if (b < e) fn(b, e);
-        if (remaining.fetch_sub(1) == 1) { std::lock_guard<std::mutex> l(dmu); dcv.notify_one(); }
+        std::lock_guard<std::mutex> l(dmu);
+        if (--remaining == 0) dcv.notify_one();
       });
     }
     fn(0, std::min(n, per));
     std::unique_lock<std::mutex> l(dmu);
-    dcv.wait(l, [&] { return remaining.load() == 0; });
+    dcv.wait(l, [&] { return remaining == 0; });
   }
   void Submit(std::function<void()> f) {
     { std::lock_guard<std::mutex> l(mu_); q_.push_back(std::move(f)); }
@@ -134,6 +140,20 @@ static ThreadPool* GlobalPool() {
 // ------------------------------------------------------------------------------------
 // Chunked array: stable addresses under growth, lock-free reads.
 // ------------------------------------------------------------------------------------
+// Large blocks (>= 2 MiB) are 2 MiB-aligned and advised as transparent huge pages (the host runs THP in `madvise` mode on most
+// distributions); smaller ones are plain 64-byte aligned allocations.  free() releases either.
+static constexpr int64_t kHugePage = int64_t(2) << 20;
+static inline void* HugeAlloc(size_t bytes) {
+  void* p = nullptr;
+  const bool huge = bytes >= (size_t)kHugePage;
+  if (posix_memalign(&p, huge ? (size_t)kHugePage : 64, bytes) != 0) abort();
+#ifdef MADV_HUGEPAGE
+  static const bool thp = getenv("DEEPREC_HOST_THP") && atoi(getenv("DEEPREC_HOST_THP")) != 0;
+  if (huge && thp) madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+  return p;
+}
+
 template <typename T, int kLog2Chunk = 16>
 class ChunkedArray {
  public:
@@ -144,23 +164,32 @@ class ChunkedArray {
     for (int64_t i = 0; i < kMaxChunks; ++i) chunks_[i].store(nullptr, std::memory_order_relaxed);
   }
   ~ChunkedArray() {
-    for (int64_t i = 0; i < kMaxChunks; ++i) { T* p = chunks_[i].load(); if (p) free(p); }
+    for (T* p : bases_) free(p);
     delete[] chunks_;
   }
   T* at(int64_t idx) {
     T* c = chunks_[idx >> kLog2Chunk].load(std::memory_order_acquire);
     return c + (idx & (kChunk - 1)) * width_;
   }
-  void EnsureCapacity(int64_t n, const T& fill) {
+  // Entries are NOT initialised here: every user resets an entry when it hands it out (ResetMeta / InitRow), and a fill pass would touch
+  // (page-fault) memory long before it is used.  The first kSmallChunks chunks are separate allocations (a 50-row table stays small);
+  // after that chunks come in 2 MiB-aligned slabs advised as transparent huge pages -- creating rows then page-faults once per 2 MiB
+  // instead of once per 4 KiB (the dominant cost of inserting fresh keys), and random row reads of a multi-GB table miss the TLB less.
+  void EnsureCapacity(int64_t n, const T& /*fill*/) {
     int64_t need = (n + kChunk - 1) >> kLog2Chunk;
     if (need <= nchunks_.load(std::memory_order_acquire)) return;
     std::lock_guard<std::mutex> l(mu_);
-    for (int64_t c = nchunks_.load(); c < need; ++c) {
-      T* p = nullptr;
-      if (posix_memalign((void**)&p, 64, sizeof(T) * kChunk * width_) != 0) abort();
-      std::fill(p, p + kChunk * width_, fill);
-      chunks_[c].store(p, std::memory_order_release);
-      nchunks_.store(c + 1, std::memory_order_release);
+    const int64_t chunk_elems = kChunk * width_;
+    const int64_t chunk_bytes = (int64_t)sizeof(T) * chunk_elems;
+    for (int64_t c = nchunks_.load(); c < need;) {
+      int64_t group = 1;
+      if (c >= kSmallChunks) { group = (kHugePage + chunk_bytes - 1) / chunk_bytes; if (group < 1) group = 1; if (c + group > kMaxChunks) group = kMaxChunks - c; }
+      if (group < 1) abort();                              // more than kMaxChunks chunks: index space exhausted
+      T* base = static_cast<T*>(HugeAlloc((size_t)(group * chunk_bytes)));
+      bases_.push_back(base);
+      for (int64_t g = 0; g < group; ++g) chunks_[c + g].store(base + g * chunk_elems, std::memory_order_release);
+      c += group;
+      nchunks_.store(c, std::memory_order_release);
     }
   }
   int64_t capacity() const { return nchunks_.load() << kLog2Chunk; }
@@ -170,6 +199,8 @@ class ChunkedArray {
   std::atomic<T*>* chunks_;
   std::atomic<int64_t> nchunks_{0};
   std::mutex mu_;
+  std::vector<T*> bases_;              // what free() gets: one pointer per chunk (small) or per slab of chunks
+  static constexpr int64_t kSmallChunks = 8;
 };
 
 // ------------------------------------------------------------------------------------
@@ -179,15 +210,16 @@ static constexpr int64_t kEmptyKey = INT64_MIN;
 
 // One 16-byte slot per entry: key and value index share a cache line, so a probe costs one DRAM access instead of two.
 struct KVSlot { std::atomic<int64_t> key; std::atomic<int32_t> val; int32_t pad; };
-struct KVPart {
+// slots / cap are read by every probe, size and the lock word are written by every insert: three separate cache lines
+struct alignas(64) KVPart {
   KVSlot* slots = nullptr;
   int64_t cap = 0;
-  std::atomic<int64_t> size{0};
-  std::shared_mutex mu;
-  ~KVPart() { delete[] slots; }
+  alignas(64) std::atomic<int64_t> size{0};
+  alignas(64) std::shared_mutex mu;
+  ~KVPart() { free(slots); }
   void Alloc(int64_t c) {
     cap = c;
-    slots = new KVSlot[c];
+    slots = static_cast<KVSlot*>(HugeAlloc(sizeof(KVSlot) * (size_t)c));
     for (int64_t i = 0; i < c; ++i) { slots[i].key.store(kEmptyKey, std::memory_order_relaxed); slots[i].val.store(-1, std::memory_order_relaxed); slots[i].pad = 0; }
   }
 };
@@ -261,32 +293,36 @@ class HostKV {
   }
   int64_t Size() const { int64_t s = 0; for (int p = 0; p < nparts_; ++p) s += parts_[p].size.load(); return s; }
 
-  // Iterate all (key, idx) pairs (caller guarantees no concurrent writers, as in Save).
-  template <typename F> void ForEach(F&& f) {
-    for (int p = 0; p < nparts_; ++p) {
-      KVPart& P = parts_[p];
-      std::shared_lock<std::shared_mutex> l(P.mu);
-      for (int64_t i = 0; i < P.cap; ++i) {
-        int64_t k = P.slots[i].key.load(std::memory_order_acquire);
-        if (k != kEmptyKey) f(k, P.slots[i].val.load(std::memory_order_acquire));
-      }
+  int NumParts() const { return nparts_; }
+  // Iterate the (key, idx) pairs of one partition / of all partitions (caller guarantees no concurrent writers, as in Save).  Whole-table
+  // passes (snapshot, eviction, dirty reset) run one partition per worker.
+  template <typename F> void ForEachInPart(int p, F&& f) {
+    KVPart& P = parts_[p];
+    std::shared_lock<std::shared_mutex> l(P.mu);
+    for (int64_t i = 0; i < P.cap; ++i) {
+      int64_t k = P.slots[i].key.load(std::memory_order_acquire);
+      if (k != kEmptyKey) f(k, P.slots[i].val.load(std::memory_order_acquire));
     }
   }
-  // Remove every key for which pred(key, idx) is true (partition rebuilt under exclusive lock).
+  template <typename F> void ForEach(F&& f) { for (int p = 0; p < nparts_; ++p) ForEachInPart(p, f); }
+  // Remove every key for which pred(key, idx) is true (partition rebuilt under exclusive lock; nothing is rebuilt when nothing goes).
+  template <typename Pred> int64_t RemoveIfInPart(int p, Pred&& pred) {
+    int64_t removed = 0;
+    KVPart& P = parts_[p];
+    std::unique_lock<std::shared_mutex> l(P.mu);
+    std::vector<std::pair<int64_t, int32_t>> keep; keep.reserve(P.size.load());
+    for (int64_t i = 0; i < P.cap; ++i) {
+      int64_t k = P.slots[i].key.load(std::memory_order_relaxed);
+      if (k == kEmptyKey) continue;
+      int32_t v = P.slots[i].val.load(std::memory_order_relaxed);
+      if (pred(k, v)) ++removed; else keep.emplace_back(k, v);
+    }
+    if (removed) Rebuild(P, P.cap, keep);
+    return removed;
+  }
   template <typename Pred> int64_t RemoveIf(Pred&& pred) {
     int64_t removed = 0;
-    for (int p = 0; p < nparts_; ++p) {
-      KVPart& P = parts_[p];
-      std::unique_lock<std::shared_mutex> l(P.mu);
-      std::vector<std::pair<int64_t, int32_t>> keep; keep.reserve(P.size.load());
-      for (int64_t i = 0; i < P.cap; ++i) {
-        int64_t k = P.slots[i].key.load(std::memory_order_relaxed);
-        if (k == kEmptyKey) continue;
-        int32_t v = P.slots[i].val.load(std::memory_order_relaxed);
-        if (pred(k, v)) ++removed; else keep.emplace_back(k, v);
-      }
-      Rebuild(P, P.cap, keep);
-    }
+    for (int p = 0; p < nparts_; ++p) removed += RemoveIfInPart(p, pred);
     return removed;
   }
  private:
@@ -306,7 +342,7 @@ class HostKV {
     return -1;
   }
   static void Rebuild(KVPart& P, int64_t newcap, const std::vector<std::pair<int64_t, int32_t>>& items) {
-    delete[] P.slots;
+    free(P.slots);
     P.Alloc(newcap);
     uint64_t mask = newcap - 1;
     for (auto& kv : items) {
@@ -496,15 +532,25 @@ class HostEV {
       else std::fill(o, o + dim, slot == 0 ? 0.f : cfg_.slot_init[slot - 1]);
     }
   }
+  // metadata reads: same probe pipeline as LookupRange (batch lock, slots of W keys in flight, then their metadata lines)
+  template <typename F> void ForEachMetaIndex(const int64_t* keys, int64_t n, F&& f) {
+    GlobalPool()->ParallelFor(n, 4096, [&](int64_t b, int64_t e) {
+      constexpr int W = 16;
+      HostKV::SharedAll guard(kv_);
+      for (int64_t i0 = b; i0 < e; i0 += W) {
+        const int m = (int)std::min<int64_t>(W, e - i0);
+        if (i0 + W < e) for (int j = 0; j < (int)std::min<int64_t>(W, e - i0 - W); ++j) kv_.PrefetchSlot(keys[i0 + W + j]);
+        int32_t idx[W];
+        for (int j = 0; j < m; ++j) { idx[j] = kv_.FindNoLock(keys[i0 + j]); if (idx[j] >= 0) __builtin_prefetch(meta_.at(idx[j])); }
+        for (int j = 0; j < m; ++j) f(i0 + j, idx[j]);
+      }
+    });
+  }
   void GetFreq(const int64_t* keys, int64_t n, int64_t* out) {
-    for (int64_t i = 0; i < n; ++i) {
-      int32_t idx = kv_.Find(keys[i]);
-      if (idx >= 0) out[i] = FreqOf(idx);
-      else out[i] = bloom_ ? bloom_->Min(keys[i]) : 0;
-    }
+    ForEachMetaIndex(keys, n, [&](int64_t i, int32_t idx) { out[i] = idx >= 0 ? FreqOf(idx) : (bloom_ ? bloom_->Min(keys[i]) : 0); });
   }
   void GetVersion(const int64_t* keys, int64_t n, int64_t* out) {
-    for (int64_t i = 0; i < n; ++i) { int32_t idx = kv_.Find(keys[i]); out[i] = idx >= 0 ? VersionOf(idx) : -1; }
+    ForEachMetaIndex(keys, n, [&](int64_t i, int32_t idx) { out[i] = idx >= 0 ? VersionOf(idx) : -1; });
   }
 
   // ---- LookupOrCreateKey with admission (counter_filter_policy.h:106-139) -------------
@@ -633,29 +679,36 @@ class HostEV {
     const bool gs = cfg_.steps_to_live > 0;
     const bool l2 = cfg_.l2_weight_threshold >= 0.f;
     if (!gs && !l2) return 0;
-    std::vector<int32_t> freed_meta;
-    int64_t removed = kv_.RemoveIf([&](int64_t key, int32_t idx) {
-      (void)key;
-      int32_t r = *(&meta_.at(idx)->row);
-      bool evict = false;
-      if (gs) {
-        int64_t* v = (&meta_.at(idx)->version);
-        if (*v == -1) *v = global_step;                       // globalstep_shrink_policy.h:50
-        else if (global_step - *v > cfg_.steps_to_live) evict = true;
+    // one hash partition per worker; each collects what it freed, the free lists are extended once at the end
+    const int np = kv_.NumParts();
+    std::vector<std::vector<int32_t>> freed_meta((size_t)np), freed_rows((size_t)np);
+    std::atomic<int64_t> removed{0};
+    GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
+      for (int64_t p = pb; p < pe; ++p) {
+        removed.fetch_add(kv_.RemoveIfInPart((int)p, [&](int64_t key, int32_t idx) {
+          (void)key;
+          int32_t r = *(&meta_.at(idx)->row);
+          bool evict = false;
+          if (gs) {
+            int64_t* v = (&meta_.at(idx)->version);
+            if (*v == -1) *v = global_step;                       // globalstep_shrink_policy.h:50
+            else if (global_step - *v > cfg_.steps_to_live) evict = true;
+          }
+          if (!evict && l2 && r >= 0) {
+            const float* row = rows_.at(r); float s = 0.f;
+            for (int64_t d = 0; d < cfg_.dim; ++d) s += row[d] * row[d];
+            if (0.5f * s < cfg_.l2_weight_threshold) evict = true;  // l2weight_shrink_policy.h:52
+          }
+          if (evict) {
+            if (r >= 0) freed_rows[(size_t)p].push_back(r);
+            freed_meta[(size_t)p].push_back(idx);
+          }
+          return evict;
+        }));
       }
-      if (!evict && l2 && r >= 0) {
-        const float* row = rows_.at(r); float s = 0.f;
-        for (int64_t d = 0; d < cfg_.dim; ++d) s += row[d] * row[d];
-        if (0.5f * s < cfg_.l2_weight_threshold) evict = true;  // l2weight_shrink_policy.h:52
-      }
-      if (evict) {
-        if (r >= 0) { FreeRow(r); admitted_.fetch_sub(1); }
-        freed_meta.push_back(idx);
-      }
-      return evict;
     });
-    for (int32_t idx : freed_meta) FreeMeta(idx);
-    return removed;
+    FreeBulk(freed_meta, freed_rows);
+    return removed.load();
   }
   int64_t Remove(const int64_t* keys, int64_t n) {
     std::vector<int64_t> ks(keys, keys + n); std::sort(ks.begin(), ks.end());
@@ -675,60 +728,115 @@ class HostEV {
   // dirty_only: incremental checkpoint (keys touched since the last ClearDirty()).
   // part filter: keep key%1000%part_num == part_id (sharded snapshot for elastic scaling).
   void SnapshotBegin(int dirty_only, int part_id, int part_num, int64_t* n_admitted, int64_t* n_filtered) {
-    snap_adm_.clear(); snap_flt_.clear();
-    kv_.ForEach([&](int64_t key, int32_t idx) {
-      int bucket = dr_ckpt_bucket(key);
-      if (part_num > 1 && bucket % part_num != part_id) return;
-      if (dirty_only && !*(&meta_.at(idx)->dirty)) return;
-      int32_t r = *(&meta_.at(idx)->row);
-      if (r >= 0) snap_adm_.push_back({bucket, idx, key}); else snap_flt_.push_back({bucket, idx, key});
+    // pass 1: one hash partition per worker collects its (bucket, idx, key) items
+    const int np = kv_.NumParts();
+    std::vector<std::vector<SnapItem>> adm((size_t)np), flt((size_t)np);
+    GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
+      for (int64_t p = pb; p < pe; ++p)
+        kv_.ForEachInPart((int)p, [&](int64_t key, int32_t idx) {
+          int bucket = dr_ckpt_bucket(key);
+          if (part_num > 1 && bucket % part_num != part_id) return;
+          if (dirty_only && !*(&meta_.at(idx)->dirty)) return;
+          int32_t r = *(&meta_.at(idx)->row);
+          (r >= 0 ? adm : flt)[(size_t)p].push_back({bucket, idx, key});
+        });
     });
-    auto cmp = [](const SnapItem& a, const SnapItem& b) { return a.bucket != b.bucket ? a.bucket < b.bucket : a.key < b.key; };
-    std::sort(snap_adm_.begin(), snap_adm_.end(), cmp);
-    std::sort(snap_flt_.begin(), snap_flt_.end(), cmp);
+    // pass 2: counting sort by checkpoint bucket (per-partition histograms -> disjoint output ranges), then every bucket sorted by key
+    auto gather = [&](std::vector<std::vector<SnapItem>>& src, std::vector<SnapItem>& dst, std::vector<int64_t>& off) {
+      std::vector<int64_t> cnt((size_t)np * 1000, 0);
+      GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
+        for (int64_t p = pb; p < pe; ++p) for (const SnapItem& it : src[(size_t)p]) cnt[(size_t)p * 1000 + it.bucket]++;
+      });
+      off.assign(1001, 0);
+      int64_t run = 0;
+      for (int b = 0; b < 1000; ++b) {
+        off[b] = run;
+        for (int p = 0; p < np; ++p) { const int64_t c = cnt[(size_t)p * 1000 + b]; cnt[(size_t)p * 1000 + b] = run; run += c; }
+      }
+      off[1000] = run;
+      dst.resize((size_t)run);
+      GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
+        for (int64_t p = pb; p < pe; ++p) {
+          for (const SnapItem& it : src[(size_t)p]) dst[(size_t)cnt[(size_t)p * 1000 + it.bucket]++] = it;
+          std::vector<SnapItem>().swap(src[(size_t)p]);
+        }
+      });
+      GlobalPool()->ParallelFor(1000, 8, [&](int64_t bb, int64_t be) {
+        for (int64_t b = bb; b < be; ++b)
+          std::sort(dst.begin() + off[b], dst.begin() + off[b + 1], [](const SnapItem& x, const SnapItem& y) { return x.key < y.key; });
+      });
+    };
+    gather(adm, snap_adm_, snap_adm_off_);
+    gather(flt, snap_flt_, snap_flt_off_);
     *n_admitted = (int64_t)snap_adm_.size(); *n_filtered = (int64_t)snap_flt_.size();
   }
   void SnapshotRead(int64_t* keys, float* rows, int64_t* freqs, int64_t* versions, int64_t* part_offset,
                     int64_t* fkeys, int64_t* ffreqs, int64_t* fversions, int64_t* fpart_offset) {
-    auto fill = [&](std::vector<SnapItem>& v, int64_t* k, float* rw, int64_t* f, int64_t* ver, int64_t* off) {
-      if (off) std::fill(off, off + 1001, 0);
-      for (size_t i = 0; i < v.size(); ++i) {
-        if (k) k[i] = v[i].key;
-        if (f) f[i] = *(&meta_.at(v[i].idx)->freq);
-        if (ver) ver[i] = *(&meta_.at(v[i].idx)->version);
-        if (rw) memcpy(rw + i * stride_, rows_.at(*(&meta_.at(v[i].idx)->row)), stride_ * sizeof(float));
-        if (off) off[v[i].bucket + 1]++;
-      }
-      if (off) for (int b = 0; b < 1000; ++b) off[b + 1] += off[b];
+    auto fill = [&](std::vector<SnapItem>& v, const std::vector<int64_t>& offs, int64_t* k, float* rw, int64_t* f, int64_t* ver, int64_t* off) {
+      if (off) { if (offs.size() == 1001) memcpy(off, offs.data(), 1001 * sizeof(int64_t)); else std::fill(off, off + 1001, 0); }
+      const int64_t n = (int64_t)v.size();
+      GlobalPool()->ParallelFor(n, 4096, [&](int64_t b, int64_t e) {
+        constexpr int64_t W = 8;                                  // metadata lines 2W ahead, row lines W ahead of the copy
+        for (int64_t i = b; i < e; ++i) {
+          if (i + 2 * W < e) __builtin_prefetch(meta_.at(v[(size_t)(i + 2 * W)].idx));
+          if (rw && i + W < e) { const int32_t r = *(&meta_.at(v[(size_t)(i + W)].idx)->row); if (r >= 0) __builtin_prefetch(rows_.at(r)); }
+          const Meta* m = meta_.at(v[(size_t)i].idx);
+          if (k) k[i] = v[(size_t)i].key;
+          if (f) f[i] = m->freq;
+          if (ver) ver[i] = m->version;
+          if (rw) memcpy(rw + i * stride_, rows_.at(m->row), stride_ * sizeof(float));
+        }
+      });
     };
-    fill(snap_adm_, keys, rows, freqs, versions, part_offset);
-    fill(snap_flt_, fkeys, nullptr, ffreqs, fversions, fpart_offset);
+    fill(snap_adm_, snap_adm_off_, keys, rows, freqs, versions, part_offset);
+    fill(snap_flt_, snap_flt_off_, fkeys, nullptr, ffreqs, fversions, fpart_offset);
   }
   void SnapshotEnd() { snap_adm_.clear(); snap_adm_.shrink_to_fit(); snap_flt_.clear(); snap_flt_.shrink_to_fit(); }
-  void ClearDirty() { kv_.ForEach([&](int64_t, int32_t idx) { *(&meta_.at(idx)->dirty) = 0; }); }
+  void ClearDirty() {
+    GlobalPool()->ParallelFor(kv_.NumParts(), 1, [&](int64_t pb, int64_t pe) {
+      for (int64_t p = pb; p < pe; ++p) kv_.ForEachInPart((int)p, [&](int64_t, int32_t idx) { *(&meta_.at(idx)->dirty) = 0; });
+    });
+  }
 
   // ---- import (restore / elastic import / incremental replay) ---------------------------
   // rows: [n, ncols] (ncols <= stride; missing slot columns take slot_init); rows == nullptr
   // imports filtered (un-admitted) keys.  Only keys with key%1000%part_num == part_id are kept.
   int64_t Import(const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs,
                  const int64_t* versions, int64_t n, int part_id, int part_num, int reset_version) {
-    int64_t kept = 0;
-    for (int64_t i = 0; i < n; ++i) {
-      int64_t key = keys[i];
-      if (part_num > 1 && dr_ckpt_bucket(key) % part_num != part_id) continue;
-      bool inserted = false;
-      int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
-      *(&meta_.at(idx)->freq) = freqs ? freqs[i] : 0;
-      *(&meta_.at(idx)->version) = reset_version ? -1 : (versions ? versions[i] : -1);
-      if (rows) {
-        int32_t* rp = (&meta_.at(idx)->row);
-        int32_t r = *rp;
-        if (r < 0) { r = AllocRow(); InitRow(r, key); *rp = r; admitted_.fetch_add(1); }
-        memcpy(rows_.at(r), rows + i * ncols, std::min(ncols, stride_) * sizeof(float));
+    // restore of a large table is insert-bound: key ranges go to the workers (inserts are CAS-based, growth is per partition); a key that
+    // appears twice in one call keeps one row (the claim below) and the later copy wins or loses arbitrarily, as two restores would
+    std::atomic<int64_t> kept{0};
+    GlobalPool()->ParallelFor(n, 4096, [&](int64_t b, int64_t e) {
+      int64_t mine = 0, new_rows = 0;
+      for (int64_t i = b; i < e; ++i) {
+        int64_t key = keys[i];
+        if (key == kEmptyKey) continue;
+        if (part_num > 1 && dr_ckpt_bucket(key) % part_num != part_id) continue;
+        bool inserted = false;
+        int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
+        __atomic_store_n(&meta_.at(idx)->freq, freqs ? freqs[i] : 0, __ATOMIC_RELAXED);
+        __atomic_store_n(&meta_.at(idx)->version, reset_version ? -1 : (versions ? versions[i] : -1), __ATOMIC_RELAXED);
+        if (rows) {
+          int32_t* rp = (&meta_.at(idx)->row);
+          int32_t r = __atomic_load_n(rp, __ATOMIC_ACQUIRE);
+          if (r == -1) {
+            int32_t expect = -1;
+            if (__atomic_compare_exchange_n(rp, &expect, -2, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+              r = AllocRow(); InitRow(r, key);
+              memcpy(rows_.at(r), rows + i * ncols, std::min(ncols, stride_) * sizeof(float));
+              __atomic_store_n(rp, r, __ATOMIC_RELEASE); ++new_rows; ++mine;
+              continue;
+            }
+          }
+          while ((r = __atomic_load_n(rp, __ATOMIC_ACQUIRE)) < 0) std::this_thread::yield();
+          memcpy(rows_.at(r), rows + i * ncols, std::min(ncols, stride_) * sizeof(float));
+        }
+        ++mine;
       }
-      ++kept;
-    }
-    return kept;
+      if (new_rows) admitted_.fetch_add(new_rows);
+      kept.fetch_add(mine);
+    });
+    return kept.load();
   }
   // Import into a table that is being READ concurrently (serving: delta update of a live model).  A new key's row is written first and
   // its index published with release semantics; an existing key gets a fresh row (copy-on-write) and the index is swapped -- readers see
@@ -804,6 +912,14 @@ class HostEV {
     return (int32_t)r;
   }
   void FreeRow(int32_t r) { std::lock_guard<std::mutex> l(free_mu_); free_rows_.push_back(r); n_free_rows_.fetch_add(1, std::memory_order_relaxed); }
+  void FreeBulk(const std::vector<std::vector<int32_t>>& metas, const std::vector<std::vector<int32_t>>& rows) {
+    std::lock_guard<std::mutex> l(free_mu_);
+    int64_t nm = 0, nr = 0;
+    for (auto& v : metas) { free_meta_.insert(free_meta_.end(), v.begin(), v.end()); nm += (int64_t)v.size(); }
+    for (auto& v : rows) { free_rows_.insert(free_rows_.end(), v.begin(), v.end()); nr += (int64_t)v.size(); }
+    n_free_meta_.fetch_add(nm, std::memory_order_relaxed); n_free_rows_.fetch_add(nr, std::memory_order_relaxed);
+    admitted_.fetch_sub(nr);
+  }
 
   DrEvConfig cfg_;
   int64_t stride_;
@@ -823,6 +939,7 @@ class HostEV {
   std::vector<int32_t> free_meta_, free_rows_;
   std::atomic<int64_t> n_free_meta_{0}, n_free_rows_{0};
   std::vector<SnapItem> snap_adm_, snap_flt_;
+  std::vector<int64_t> snap_adm_off_, snap_flt_off_;      // 1001 checkpoint-bucket offsets of the current snapshot
 };
 
 }  // namespace dr

@@ -33,6 +33,10 @@ void dr_host_ev_snapshot_begin(void* h, int dirty_only, int part_id, int part_nu
 void dr_host_ev_snapshot_read(void* h, int64_t* keys, float* rows, int64_t* freqs, int64_t* versions, int64_t* poff, int64_t* fkeys,
                               int64_t* ffreqs, int64_t* fversions, int64_t* fpoff);
 void dr_host_ev_snapshot_end(void* h);
+int64_t dr_host_ev_import(void* h, const int64_t* keys, const float* rows, int64_t ncols, const int64_t* freqs, const int64_t* versions,
+                          int64_t n, int part_id, int part_num, int reset_version);
+void dr_host_ev_clear_dirty(void* h);
+int64_t dr_host_ev_total_keys(void* h);
 void* dr_ssd_create(const char* dir, int64_t stride, int64_t file_bytes, int async_compaction);
 void dr_ssd_destroy(void* h);
 int64_t dr_ssd_size(void* h);
@@ -156,6 +160,86 @@ static void TestFilterRemoveSnapshot() {
   dr_host_ev_destroy(ev);
 }
 
+// 2b. checkpoint-scale passes on the worker pool: snapshot of a 40k-key table (every partition scanned by a different worker, parallel
+// bucket sort), parallel import into a second table -- with every key present twice in the batch and readers probing the table while it
+// grows -- then a parallel eviction pass and a second import that recycles the freed rows.
+static void TestParallelSnapshotImportShrink() {
+  const int dim = 4;
+  const int64_t n = 40000;
+  DrEvConfig cfg = MakeCfg(dim, 0);
+  cfg.steps_to_live = 5;
+  void* src = dr_host_ev_create(&cfg);
+  std::vector<float> def(16 * dim, 0.5f);
+  dr_host_ev_set_default(src, def.data());
+  std::vector<int64_t> keys(n), counts(n, 1);
+  std::vector<float> grads((size_t)n * dim, 0.01f);
+  for (int64_t i = 0; i < n; ++i) keys[i] = i * 7919 + 13;
+  { DrOptHyper hp = Adagrad(1); dr_host_ev_apply(src, keys.data(), grads.data(), counts.data(), n, &hp); }
+  int64_t na = 0, nf = 0;
+  dr_host_ev_snapshot_begin(src, 0, 0, 1, &na, &nf);
+  CHECK(na == n && nf == 0);
+  const int64_t stride = dr_host_ev_stride(src);
+  std::vector<int64_t> sk(na), sf(na), sv(na), poff(1001), fk(1), ff(1), fv(1), fpoff(1001);
+  std::vector<float> rows((size_t)na * stride);
+  dr_host_ev_snapshot_read(src, sk.data(), rows.data(), sf.data(), sv.data(), poff.data(), fk.data(), ff.data(), fv.data(), fpoff.data());
+  dr_host_ev_snapshot_end(src);
+  CHECK(poff[0] == 0 && poff[1000] == n);
+  for (int b = 0; b < 1000; ++b)
+    for (int64_t i = poff[b]; i < poff[b + 1]; ++i) {
+      CHECK(sk[i] % 1000 == b && sf[i] == 1 && sv[i] == 1);
+      if (i > poff[b]) CHECK(sk[i - 1] < sk[i]);                         // bucket-major, key-sorted inside a bucket
+    }
+  // import while readers probe the growing table (new rows are published with release semantics; patching EXISTING rows under readers
+  // is ImportCow's job, not Import's), then the same batch with every key twice into a third table: one row per key
+  void* dst = dr_host_ev_create(&cfg);
+  dr_host_ev_set_default(dst, def.data());
+  std::atomic<bool> stop{false};
+  std::thread reader([&] {
+    std::vector<int64_t> k(512), fr(512);
+    std::vector<float> out(512 * dim);
+    uint64_t x = 1;
+    while (!stop.load()) {
+      for (int i = 0; i < 512; ++i) { x = x * 6364136223846793005ull + 1442695040888963407ull; k[i] = sk[(x >> 33) % (uint64_t)n]; }
+      dr_host_ev_lookup(dst, k.data(), 512, out.data());
+      dr_host_ev_get_freq(dst, k.data(), 512, fr.data());
+      for (int i = 0; i < 512; ++i) CHECK(fr[i] == 0 || fr[i] == 1);
+    }
+  });
+  CHECK(dr_host_ev_import(dst, sk.data(), rows.data(), stride, sf.data(), sv.data(), n, 0, 1, 0) == n);
+  stop = true; reader.join();
+  CHECK(dr_host_ev_size(dst) == n && dr_host_ev_total_keys(dst) == n);
+  std::vector<float> got((size_t)n * dim);
+  dr_host_ev_lookup(dst, sk.data(), n, got.data());
+  for (int64_t i = 0; i < n; ++i) for (int d = 0; d < dim; ++d) CHECK(got[i * dim + d] == rows[i * stride + d]);
+  {
+    void* dup = dr_host_ev_create(&cfg);
+    dr_host_ev_set_default(dup, def.data());
+    std::vector<int64_t> k2(sk); k2.insert(k2.end(), sk.begin(), sk.end());
+    std::vector<int64_t> f2(sf); f2.insert(f2.end(), sf.begin(), sf.end());
+    std::vector<int64_t> v2(sv); v2.insert(v2.end(), sv.begin(), sv.end());
+    std::vector<float> r2(rows); r2.insert(r2.end(), rows.begin(), rows.end());
+    CHECK(dr_host_ev_import(dup, k2.data(), r2.data(), stride, f2.data(), v2.data(), 2 * n, 0, 1, 0) == 2 * n);
+    CHECK(dr_host_ev_size(dup) == n && dr_host_ev_total_keys(dup) == n);     // a duplicated key owns exactly one row
+    dr_host_ev_destroy(dup);
+  }
+  // eviction (every key has version 1, steps_to_live 5): parallel per-partition rebuild, free lists extended once
+  CHECK(dr_host_ev_shrink(dst, 3) == 0 && dr_host_ev_size(dst) == n);
+  CHECK(dr_host_ev_shrink(dst, 100) == n && dr_host_ev_size(dst) == 0 && dr_host_ev_total_keys(dst) == 0);
+  CHECK(dr_host_ev_import(dst, sk.data(), rows.data(), stride, sf.data(), sv.data(), n, 1, 3, 1) > 0);   // partition 1 of 3, versions reset
+  dr_host_ev_snapshot_begin(dst, 0, 0, 1, &na, &nf);
+  std::vector<int64_t> tk(na), tf(na), tv(na);
+  std::vector<float> trow((size_t)na * stride);
+  dr_host_ev_snapshot_read(dst, tk.data(), trow.data(), tf.data(), tv.data(), poff.data(), fk.data(), ff.data(), fv.data(), fpoff.data());
+  dr_host_ev_snapshot_end(dst);
+  CHECK(na == dr_host_ev_size(dst));
+  for (int64_t i = 0; i < na; ++i) CHECK((tk[i] % 1000) % 3 == 1 && tv[i] == -1);
+  dr_host_ev_clear_dirty(dst);
+  dr_host_ev_snapshot_begin(dst, 1, 0, 1, &na, &nf);
+  CHECK(na == 0);
+  dr_host_ev_snapshot_end(dst);
+  dr_host_ev_destroy(src); dr_host_ev_destroy(dst);
+}
+
 // 3. SSD store: writers, readers, removers and compaction all at once
 static void TestSsdStore(const char* dir) {
   const int stride = 8;
@@ -217,6 +301,7 @@ static void TestStagingQueue() {
 int main(int argc, char** argv) {
   TestLookupWhileTraining();
   TestFilterRemoveSnapshot();
+  TestParallelSnapshotImportShrink();
   TestSsdStore(argc > 1 ? argv[1] : "/tmp/deeprec_ssd_stress");
   TestStagingQueue();
   if (g_fail) { fprintf(stderr, "%d checks failed\n", g_fail); return 1; }
