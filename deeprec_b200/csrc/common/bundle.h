@@ -2,6 +2,10 @@
 // Header-only so the host engine (training checkpoints) and the serving runtime (model load / delta update)
 // share one implementation.  Streaming 8 MiB writer, CRC32 per tensor, atomic publish (data first, index last).
 #pragma once
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -12,15 +16,72 @@
 
 namespace dr {
 
-inline uint32_t Crc32(const uint8_t* p, size_t n, uint32_t crc = 0) {
-  static uint32_t table[256]; static bool init = false;
-  if (!init) {
-    for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
-    init = true;
+// CRC-32 (IEEE 802.3, reflected 0xEDB88320), slicing-by-8: eight table lookups per 8 input bytes instead of one per byte -- a multi-GB
+// EmbeddingVariable dump is checksummed at memory-copy-like speed instead of ~0.35 GB/s.  Tables are built once (thread-safe static).
+struct Crc32Tables {
+  uint32_t t[8][256];
+  Crc32Tables() {
+    for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; t[0][i] = c; }
+    for (uint32_t i = 0; i < 256; ++i) for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
   }
+};
+inline uint32_t Crc32(const uint8_t* p, size_t n, uint32_t crc = 0) {
+  static const Crc32Tables tb;
   crc = ~crc;
-  for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { crc = tb.t[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8); --n; }
+  while (n >= 8) {
+    uint64_t v; memcpy(&v, p, 8);                       // little-endian host (x86-64 / aarch64)
+    const uint32_t lo = crc ^ (uint32_t)v, hi = (uint32_t)(v >> 32);
+    crc = tb.t[7][lo & 0xFF] ^ tb.t[6][(lo >> 8) & 0xFF] ^ tb.t[5][(lo >> 16) & 0xFF] ^ tb.t[4][lo >> 24] ^
+          tb.t[3][hi & 0xFF] ^ tb.t[2][(hi >> 8) & 0xFF] ^ tb.t[1][(hi >> 16) & 0xFF] ^ tb.t[0][hi >> 24];
+    p += 8; n -= 8;
+  }
+  while (n--) crc = tb.t[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
   return ~crc;
+}
+
+// crc(A || B) from crc(A), crc(B) and |B|: multiply crc(A) by x^(8|B|) in GF(2)[x] / P(x) by repeated squaring of the "shift one zero
+// bit" operator (the classic combine construction) -- lets large tensors be checksummed in parallel chunks.
+inline uint32_t Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+  if (len2 == 0) return crc1;
+  auto times = [](const uint32_t* mat, uint32_t vec) { uint32_t sum = 0; for (; vec; vec >>= 1, ++mat) if (vec & 1) sum ^= *mat; return sum; };
+  auto square = [&](uint32_t* sq, const uint32_t* mat) { for (int n = 0; n < 32; ++n) sq[n] = times(mat, mat[n]); };
+  uint32_t even[32], odd[32];
+  odd[0] = 0xEDB88320u;                                   // operator for one zero bit
+  for (int n = 1; n < 32; ++n) odd[n] = 1u << (n - 1);
+  square(even, odd);                                      // two zero bits
+  square(odd, even);                                      // four zero bits
+  do {                                                    // first square gives one zero byte, then 2, 4, ... bytes
+    square(even, odd);
+    if (len2 & 1) crc1 = times(even, crc1);
+    len2 >>= 1;
+    if (!len2) break;
+    square(odd, even);
+    if (len2 & 1) crc1 = times(odd, crc1);
+    len2 >>= 1;
+  } while (len2);
+  return crc1 ^ crc2;
+}
+
+// Whole-tensor checksum: chunks in parallel on the OpenMP runtime when the translation unit is built with it (the host library).
+inline uint32_t Crc32Large(const uint8_t* p, size_t n) {
+#ifdef _OPENMP
+  constexpr size_t kMinChunk = size_t(4) << 20;
+  int parts = (int)std::min<size_t>((size_t)omp_get_max_threads(), n / kMinChunk);
+  if (parts > 1 && !omp_in_parallel()) {
+    std::vector<uint32_t> crc((size_t)parts);
+    const size_t per = ((n + parts - 1) / parts + 7) & ~size_t(7);
+#pragma omp parallel for schedule(static, 1) num_threads(parts)
+    for (int i = 0; i < parts; ++i) {
+      const size_t b = std::min(n, (size_t)i * per), e = std::min(n, b + per);
+      crc[(size_t)i] = Crc32(p + b, e - b);
+    }
+    uint32_t c = crc[0];
+    for (int i = 1; i < parts; ++i) { const size_t b = std::min(n, (size_t)i * per), e = std::min(n, b + per); c = Crc32Combine(c, crc[(size_t)i], e - b); }
+    return c;
+  }
+#endif
+  return Crc32(p, n);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -42,7 +103,7 @@ class BundleWriter {
     static const char zeros[64] = {0};
     if (pad) { fwrite(zeros, 1, pad, f_); off_ += pad; }
     BundleEntry e; e.name = name; e.dtype = dtype; e.shape.assign(shape, shape + ndim); e.offset = off_; e.nbytes = nbytes;
-    e.crc = Crc32(static_cast<const uint8_t*>(data), (size_t)nbytes);
+    e.crc = Crc32Large(static_cast<const uint8_t*>(data), (size_t)nbytes);
     if (nbytes && fwrite(data, 1, (size_t)nbytes, f_) != (size_t)nbytes) return -2;
     off_ += nbytes;
     entries_.push_back(std::move(e));
@@ -100,7 +161,7 @@ class BundleReader {
     std::lock_guard<std::mutex> l(mu_);
     if (fseeko(f_, e.offset, SEEK_SET) != 0) return -1;
     if (e.nbytes && fread(dst, 1, (size_t)e.nbytes, f_) != (size_t)e.nbytes) return -2;
-    if (verify && Crc32(static_cast<const uint8_t*>(dst), (size_t)e.nbytes) != e.crc) return -3;
+    if (verify && Crc32Large(static_cast<const uint8_t*>(dst), (size_t)e.nbytes) != e.crc) return -3;
     return 0;
   }
  private:

@@ -134,3 +134,33 @@ def test_checkpoint_option_warm_start_and_init_data_source(tmp_path):
     torch.save(table, tmp_path / "ext.pt")
     ext = dr.get_embedding_variable("ws_ext", 8, ev_option=dr.EmbeddingVariableOption(ckpt=dr.CheckpointOption(init_data_source=str(tmp_path / "ext.pt"))))
     assert torch.equal(ext.lookup(torch.tensor([6])).detach(), table["values"][1:2]) and ext.total_count() == 3
+
+
+def test_bundle_crc_is_ieee_crc32_also_on_the_parallel_path(tmp_path):
+    """The per-tensor checksum is the standard CRC-32 (zlib's): slicing-by-8 for small tensors, parallel chunks + combine for large ones
+    (> 8 MiB) -- both must equal zlib.crc32 of the bytes, and a flipped bit must be detected on read."""
+    import zlib
+    from deeprec_b200.checkpoint.saver import BundleReader, BundleWriter
+    g = torch.Generator().manual_seed(0)
+    tensors = {"tiny": torch.randn(3, generator=g), "odd": torch.randint(0, 255, (12345,), dtype=torch.uint8, generator=g),
+               "large": torch.randn(5_000_011, generator=g)}                     # 20 MB, not a multiple of 8 per chunk
+    prefix = str(tmp_path / "b")
+    w = BundleWriter(prefix)
+    for k, v in tensors.items():
+        w.add(k, v)
+    w.close()
+    crcs = {}
+    for line in open(prefix + ".index").read().splitlines()[1:]:
+        tok = line.split("\t")
+        crcs[tok[0]] = int(tok[-1])
+    for k, v in tensors.items():
+        assert crcs[k] == zlib.crc32(v.numpy().tobytes()), k
+    r = BundleReader(prefix)
+    assert torch.equal(r.read("large"), tensors["large"])
+    r.close()
+    with open(prefix + ".data", "r+b") as f:                                      # corrupt one byte in the middle of the large tensor
+        f.seek(os.path.getsize(prefix + ".data") - 10_000_000); b = f.read(1); f.seek(-1, 1); f.write(bytes([b[0] ^ 0x10]))
+    r = BundleReader(prefix)
+    with pytest.raises(IOError):
+        r.read("large")
+    assert torch.equal(r.read("tiny"), tensors["tiny"])
