@@ -11,8 +11,14 @@
 //               the math of one request runs on the process's OpenMP pool
 //   updates     a polling thread: newer full version -> load, warm up, atomic swap (in-flight requests keep the old model alive
 //               through their shared_ptr); delta for the current version -> rows patched into the live tables, dense block swapped
+#include <sched.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -59,6 +65,9 @@ struct Config {
   int64_t timeline_start_step = -1; int timeline_interval_step = 0, timeline_trace_count = 0;
   // feature_store_type "redis" (serving/processor/storage/redis_feature_store.*): embedding rows live in a Redis instance shared by all
   // replicas, key "<redis_prefix>/<model version>/table/<t>:<id>", value = D x fp32; this process keeps only the dense net + default rows
+  // SessionGroup CPU placement (docs SessionGroup.md "cpusets" / SESSION_GROUP_CPUSET / SET_SESSION_THREAD_POOL_AFFINITY): session i runs on
+  // cpusets[i] -- the caller's thread is moved there for the duration of the request and the session's OpenMP team is pinned core by core
+  std::vector<std::vector<int>> cpusets;
   bool remote = false; std::string redis_host = "127.0.0.1", redis_password, redis_prefix = "dlrm"; int redis_port = 6379, redis_db = 0, redis_timeout_ms = 2000;
 };
 
@@ -232,7 +241,43 @@ static void Linear(const float* X, int64_t ldx, int64_t B, const Layer& L, float
   }
 }
 
+static std::vector<int> ParseCpuList(const std::string& s) {           // "2-4" | "2,3,4" | "0,2-3"
+  std::vector<int> out;
+  size_t i = 0;
+  while (i < s.size()) {
+    while (i < s.size() && !isdigit((unsigned char)s[i])) ++i;
+    if (i >= s.size()) break;
+    int a = 0; while (i < s.size() && isdigit((unsigned char)s[i])) a = a * 10 + (s[i++] - '0');
+    int b = a;
+    if (i < s.size() && s[i] == '-') { ++i; b = 0; while (i < s.size() && isdigit((unsigned char)s[i])) b = b * 10 + (s[i++] - '0'); }
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) out.push_back(c);
+  }
+  return out;
+}
+static std::vector<std::vector<int>> ParseCpusets(const std::string& s) {   // session groups separated by ';'
+  std::vector<std::vector<int>> out;
+  size_t b = 0;
+  while (b <= s.size()) {
+    size_t e = s.find(';', b); if (e == std::string::npos) e = s.size();
+    auto l = ParseCpuList(s.substr(b, e - b));
+    if (!l.empty()) out.push_back(std::move(l));
+    b = e + 1;
+  }
+  return out;
+}
+static std::vector<std::vector<int>> AutoCpusets(int sessions) {           // the CPUs this process may use, split evenly and contiguously
+  cpu_set_t m; CPU_ZERO(&m);
+  std::vector<int> all;
+  if (sched_getaffinity(0, sizeof(m), &m) == 0) for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &m)) all.push_back(c);
+  std::vector<std::vector<int>> out;
+  const int per = (int)all.size() / std::max(1, sessions);
+  if (per < 1) return out;
+  for (int i = 0; i < sessions; ++i) out.emplace_back(all.begin() + (size_t)i * per, all.begin() + (size_t)(i + 1) * per);
+  return out;
+}
+
 struct Session {
+  std::vector<int> cpus; cpu_set_t mask; std::atomic<int> last_cpu{-1};       // empty cpus = no placement
   std::mutex mu; int max_batch = 0, threads = 1;     // threads: OpenMP team size of this session's GEMMs (cores / sessions)
   std::vector<float> dense, emb, a, b2, z, prob, rrows; std::vector<int64_t> ids; std::vector<uint8_t> found;
   void* redis = nullptr;                                       // remote mode: this session's connection to the feature store
@@ -286,6 +331,32 @@ struct Session {
   }
 };
 
+// Runs the enclosed request on the session's CPUs: the calling thread takes the session mask (and gets its own mask back afterwards --
+// it belongs to the application), team member i of a multi-threaded batch is pinned to cpus[i % n] once (it only ever serves this caller).
+struct AffinityScope {
+  bool on = false; cpu_set_t saved;
+  AffinityScope(Session& s, int batch) {
+    if (s.cpus.empty()) return;
+    on = sched_getaffinity(0, sizeof(saved), &saved) == 0 && sched_setaffinity(0, sizeof(s.mask), &s.mask) == 0;
+    if (!on) return;
+#ifdef _OPENMP
+    if (batch >= 64 && s.threads > 1) {
+      const int n = (int)s.cpus.size();
+#pragma omp parallel num_threads(s.threads)
+      {
+        static thread_local int pinned = -1;
+        const int t = omp_get_thread_num(), want = s.cpus[(size_t)(t % n)];
+        if (t != 0 && pinned != want) { cpu_set_t one; CPU_ZERO(&one); CPU_SET(want, &one); if (sched_setaffinity(0, sizeof(one), &one) == 0) pinned = want; }
+      }
+    }
+#else
+    (void)batch;
+#endif
+    s.last_cpu.store(sched_getcpu(), std::memory_order_relaxed);
+  }
+  ~AffinityScope() { if (on) sched_setaffinity(0, sizeof(saved), &saved); }
+};
+
 struct ServingModel {
   Config cfg;
   std::shared_ptr<Model> model;                    // atomic_load / atomic_store
@@ -310,6 +381,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
   const auto t0 = std::chrono::steady_clock::now();
   {
     std::lock_guard<std::mutex> l(s.mu);
+    AffinityScope place(s, (int)std::min<uint32_t>(h.batch, (uint32_t)s.max_batch));
     auto dense = std::atomic_load(&m->dense);
     const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
     const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
@@ -480,8 +552,20 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
   c.intra_threads = (int)j.n("intra_op_parallelism_threads", 0);
   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
   const int per_session = c.intra_threads > 0 ? c.intra_threads : std::max(1, hw / std::max(1, c.session_num));
+  {
+    std::string sets = j.s("cpusets", "");
+    if (sets.empty() && getenv("SESSION_GROUP_CPUSET")) sets = getenv("SESSION_GROUP_CPUSET");
+    if (!sets.empty()) c.cpusets = ParseCpusets(sets);
+    else if (getenv("SET_SESSION_THREAD_POOL_AFFINITY") && atoi(getenv("SET_SESSION_THREAD_POOL_AFFINITY")) != 0) c.cpusets = AutoCpusets(std::max(1, c.session_num));
+  }
   for (int i = 0; i < std::max(1, c.session_num); ++i) {
-    sm->sessions.emplace_back(new Session()); sm->sessions.back()->Init(m->arch, c.max_batch, per_session);
+    sm->sessions.emplace_back(new Session());
+    Session& ns = *sm->sessions.back();
+    if (!c.cpusets.empty()) {                                   // fewer sets than sessions: the sets are reused round-robin
+      ns.cpus = c.cpusets[(size_t)i % c.cpusets.size()];
+      CPU_ZERO(&ns.mask); for (int cpu : ns.cpus) CPU_SET(cpu, &ns.mask);
+    }
+    ns.Init(m->arch, c.max_batch, c.intra_threads > 0 || ns.cpus.empty() ? per_session : (int)ns.cpus.size());
     if (c.remote) {                                             // one connection per session (sessions run concurrently)
       void* conn = dr_redis_connect(c.redis_host.c_str(), c.redis_port, c.redis_timeout_ms, c.redis_password.c_str(), c.redis_db);
       if (!dr_redis_ok(conn)) { fprintf(stderr, "[deeprec_cpu_serving] feature store %s:%d: %s\n", c.redis_host.c_str(), c.redis_port, dr_redis_last_error(conn)); dr_redis_close(conn); *state = -2; delete sm; return nullptr; }
@@ -519,7 +603,12 @@ int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* outp
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
      << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"feature_store_type\": \"" << (sm->cfg.remote ? "redis" : "local") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
-     << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.T : 0) << "}";
+     << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.T : 0);
+  os << ", \"cpusets\": \"";
+  for (size_t i = 0; i < sm->cfg.cpusets.size(); ++i) { if (i) os << ";"; for (size_t k = 0; k < sm->cfg.cpusets[i].size(); ++k) os << (k ? "," : "") << sm->cfg.cpusets[i][k]; }
+  os << "\", \"session_last_cpu\": [";
+  for (size_t i = 0; i < sm->sessions.size(); ++i) os << (i ? ", " : "") << sm->sessions[i]->last_cpu.load();
+  os << "]}";
   const std::string s = os.str();
   *output_size = (int)s.size();
   *output_data = malloc(s.size() + 1);

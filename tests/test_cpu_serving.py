@@ -283,3 +283,32 @@ def _ok(fn):
         return fn()
     except Exception:
         return False
+
+
+def test_session_cpusets_place_sessions_and_leave_the_caller_alone(tmp_path):
+    """``cpusets`` (SessionGroup.md): session i runs on its own CPUs -- observed through sched_getcpu() sampled inside the request -- the
+    per-session thread budget follows the set size, and the calling thread gets its own affinity mask back after every request."""
+    allowed = sorted(os.sched_getaffinity(0))
+    if len(allowed) < 3:
+        pytest.skip("needs 3 CPUs")
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(1)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 2, 1)
+    export_saved_model_module(model, str(tmp_path / "m"), version=1)
+    ref = _ref(model, d, ids)
+    a, b, c = allowed[0], allowed[1], allowed[2]
+    proc = Processor(str(tmp_path / "m"), {"session_num": 2, "select_session_policy": "RR", "model_update_interval_ms": 0,
+                                           "cpusets": f"{a};{b}-{c}" if c == b + 1 else f"{a};{b},{c}"}, device="cpu")
+    try:
+        before = os.sched_getaffinity(0)
+        for _ in range(4):                                              # RR: both sessions serve, small and team-sized batches
+            assert np.abs(proc.predict(d.numpy(), ids.numpy()) - ref).max() < 1e-5
+            assert np.abs(proc.predict(d.numpy()[:8], ids.numpy()[:, :8]) - ref[:8]).max() < 1e-5
+        assert os.sched_getaffinity(0) == before
+        info = proc.model_info()
+        assert info["cpusets"] == f"{a};{b},{c}"
+        assert info["session_last_cpu"][0] == a and info["session_last_cpu"][1] in (b, c)
+    finally:
+        proc.close()
