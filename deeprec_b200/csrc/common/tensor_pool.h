@@ -46,6 +46,10 @@ class TensorPool {
 
   ~TensorPool() { for (void* s : slabs_) free_(s, ctx_); }
 
+  // START_STATISTIC_STEP: the first `s` steps (graph initialisation, warm-up) are passed through and NOT counted into the plan; the
+  // collect phase is steps [s, s + collect_steps).
+  void SetStartStep(int s) { std::lock_guard<std::mutex> l(mu_); start_step_ = std::max(0, s); }
+
   static int ClassOf(size_t bytes) {          // 4 sub-classes per power of two
     if (bytes <= 256) return 3;                                            // ClassBytes(3) == 256
     const size_t b = bytes - 1;
@@ -104,7 +108,8 @@ class TensorPool {
   void StepEnd() {
     std::lock_guard<std::mutex> l(mu_);
     ++st_.steps;
-    if (st_.phase == 0 && st_.steps >= collect_steps_) { Plan(); st_.phase = 1; }
+    if (st_.phase == 0 && start_step_ > 0 && st_.steps == start_step_) for (auto& k : cls_) k.peak = k.live;     // statistics start here
+    if (st_.phase == 0 && st_.steps >= start_step_ + collect_steps_) { Plan(); st_.phase = 1; }
     else if (st_.phase == 1 && misses_since_plan_ >= replan_misses_) { Plan(); ++st_.replans; }
     if (st_.phase == 1) for (auto& k : cls_) k.peak = k.live;      // collect: max over the whole phase; serve: per step window
   }
@@ -138,7 +143,7 @@ class TensorPool {
   }
 
   AllocFn alloc_; FreeFn free_; void* ctx_;
-  size_t small_; int collect_steps_, replan_misses_;
+  size_t small_; int collect_steps_, replan_misses_, start_step_ = 0;
   std::mutex mu_;
   std::vector<Class> cls_;
   std::unordered_map<void*, Owner> owner_;

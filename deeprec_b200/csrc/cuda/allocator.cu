@@ -42,8 +42,14 @@ dr::TensorPool* Pool(int dev) {
   std::lock_guard<std::mutex> l(g_mu);
   if (!g_pool[dev]) {
     if (const char* e = getenv("DEEPREC_TENSORPOOL_SMALL_BYTES")) g_small = atoll(e);
+    // GPU-Memory-Optimization.md: statistics run over steps [START_STATISTIC_STEP, STOP_STATISTIC_STEP); STABLE_STATISTIC_STEP (the CPU
+    // side's name for the length of the collection window) is accepted too
+    int start = 0;
     if (const char* e = getenv("STABLE_STATISTIC_STEP")) g_collect = atoi(e) > 0 ? atoi(e) : g_collect;
+    if (const char* e = getenv("START_STATISTIC_STEP")) start = atoi(e) > 0 ? atoi(e) : 0;
+    if (const char* e = getenv("STOP_STATISTIC_STEP")) { const int stop = atoi(e); if (stop > start) g_collect = stop - start; }
     g_pool[dev] = new dr::TensorPool(DevAlloc, DevFree, (void*)(intptr_t)dev, (size_t)g_small, g_collect, g_replan);
+    g_pool[dev]->SetStartStep(start);
   }
   return g_pool[dev];
 }

@@ -15,6 +15,7 @@ void* dr_tp_create(int64_t small_threshold, int collect_steps, int replan_misses
   return new dr::TensorPool(HostAlloc, HostFree, nullptr, (size_t)small_threshold, collect_steps, replan_misses);
 }
 void dr_tp_destroy(void* h) { delete static_cast<dr::TensorPool*>(h); }
+void dr_tp_set_start_step(void* h, int s) { static_cast<dr::TensorPool*>(h)->SetStartStep(s); }
 void* dr_tp_alloc(void* h, int64_t bytes, uint64_t stream) { return static_cast<dr::TensorPool*>(h)->Alloc((size_t)bytes, stream); }
 void dr_tp_free(void* h, void* p) { static_cast<dr::TensorPool*>(h)->Free(p); }
 void dr_tp_step_end(void* h) { static_cast<dr::TensorPool*>(h)->StepEnd(); }

@@ -34,6 +34,7 @@ def _lib():
         vp, i64 = C.c_void_p, C.c_int64
         L.dr_tp_create.restype, L.dr_tp_create.argtypes = vp, [i64, C.c_int, C.c_int]
         L.dr_tp_destroy.argtypes = [vp]
+        L.dr_tp_set_start_step.argtypes = [vp, C.c_int]
         L.dr_tp_alloc.restype, L.dr_tp_alloc.argtypes = vp, [vp, i64, C.c_uint64]
         L.dr_tp_free.argtypes = [vp, vp]
         L.dr_tp_step_end.argtypes = [vp]
@@ -47,9 +48,26 @@ class HostTensorPool:
     """Planned host allocator.  ``empty(shape, dtype)`` returns a tensor backed by pool memory; the block goes back to the pool when
     the tensor (and every view of it) is garbage collected."""
 
-    def __init__(self, small_threshold: int = 4096, collect_steps: int = 3, replan_misses: int = 8):
+    def __init__(self, small_threshold: int = 4096, collect_steps: int = 3, replan_misses: int = 8, start_step: int = 0):
         self.L = _lib()
         self.h = self.L.dr_tp_create(small_threshold, collect_steps, replan_misses)
+        if start_step > 0:
+            self.L.dr_tp_set_start_step(self.h, start_step)       # steps before it (initialisation) are not part of the plan
+
+    @classmethod
+    def from_env(cls, **kw) -> "HostTensorPool":
+        """The reference's switches (CPU-Memory-Optimization.md): ``START_STATISTIC_STEP`` (first step whose allocations count),
+        ``STABLE_STATISTIC_STEP`` / ``MAX_STATISTIC_STEP`` (length of the collection window; the smaller one wins -- re-planning on
+        misses replaces the reference's stability test), ``ENABLE_MEMORY_OPTIMIZATION=0`` (every request goes to malloc)."""
+        env = os.environ
+        if env.get("ENABLE_MEMORY_OPTIMIZATION", "1").strip() in ("0", "false", "False"):
+            kw.setdefault("small_threshold", 1 << 62)
+        window = [int(env[k]) for k in ("STABLE_STATISTIC_STEP", "MAX_STATISTIC_STEP") if env.get(k, "").isdigit() and int(env[k]) > 0]
+        if window:
+            kw.setdefault("collect_steps", min(window))
+        if env.get("START_STATISTIC_STEP", "").isdigit():
+            kw.setdefault("start_step", int(env["START_STATISTIC_STEP"]))
+        return cls(**kw)
 
     def empty(self, shape: Sequence[int], dtype: torch.dtype = torch.float32) -> torch.Tensor:
         shape = tuple(int(s) for s in shape)

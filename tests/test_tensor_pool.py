@@ -69,3 +69,27 @@ def test_views_keep_the_block_alive():
     del v, u
     gc.collect()
     assert pool.stats()["live_pool_blocks"] == 0
+
+
+def test_statistic_step_env_switches(monkeypatch):
+    """START_STATISTIC_STEP: allocations of the first steps (initialisation) do not enter the plan; STABLE/MAX_STATISTIC_STEP set the
+    collection window; ENABLE_MEMORY_OPTIMIZATION=0 turns the pool into a pass-through."""
+    from deeprec_b200.utils.memory import HostTensorPool
+    monkeypatch.setenv("START_STATISTIC_STEP", "2"); monkeypatch.setenv("STABLE_STATISTIC_STEP", "2"); monkeypatch.setenv("MAX_STATISTIC_STEP", "50")
+    pool = HostTensorPool.from_env()
+    for step in range(6):
+        if step < 2:
+            big = [pool.empty((1 << 20,)) for _ in range(3)]            # 3 x 4 MiB only during initialisation
+            del big
+        a = pool.empty((100_000,)); b = pool.empty((100_000,))
+        del a, b
+        pool.step_end()
+        st = pool.stats()
+        assert st["phase"] == (1 if step >= 3 else 0), (step, st)      # window = steps 2, 3 -> planned at the end of step index 3
+    st = pool.stats()
+    assert st["pool_hits"] >= 4 and 2 * pool.class_bytes(400_000) <= st["pool_bytes"] < (4 << 20)     # the 4 MiB blocks were never planned
+    monkeypatch.setenv("ENABLE_MEMORY_OPTIMIZATION", "0")
+    off = HostTensorPool.from_env()
+    for _ in range(5):
+        x = off.empty((100_000,)); del x; off.step_end()
+    assert off.stats()["pool_hits"] == 0 and off.stats()["pool_bytes"] == 0
