@@ -12,6 +12,9 @@
 //   updates     a polling thread: newer full version -> load, warm up, atomic swap (in-flight requests keep the old model alive
 //               through their shared_ptr); delta for the current version -> rows patched into the live tables, dense block swapped
 #include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -218,25 +221,66 @@ static inline void MicroKernel(const float* const* x, int K, const float* __rest
   for (int r = 0; r < MR; ++r) for (int j = 0; j < nr; ++j) y[r][n0 + j] = relu && acc[r][j] < 0.f ? 0.f : acc[r][j];
 }
 
+#if defined(__x86_64__)
+// AVX-512 tile: 8 rows x 32 outputs = 16 zmm accumulators, per k-step 2 weight loads + 8 broadcasts for 16 FMAs (the 4 x 16 AVX2 tile
+// does 2 loads + 4 broadcasts for 8).  Column tails use lane masks (masked-off lanes are neither read nor written).  Compiled for
+// avx512f regardless of the build flags and selected at run time.
+__attribute__((target("avx512f")))
+static void MicroKernel512(const float* const* x, int K, const float* __restrict wt, int N, int n0, int nr, const float* __restrict bias,
+                           float* const* y, bool relu) {
+  constexpr int R = 8;
+  const __mmask16 m0 = nr >= 16 ? (__mmask16)0xFFFF : (__mmask16)((1u << nr) - 1);
+  const __mmask16 m1 = nr >= 32 ? (__mmask16)0xFFFF : (nr > 16 ? (__mmask16)((1u << (nr - 16)) - 1) : (__mmask16)0);
+  const __m512 bias0 = _mm512_maskz_loadu_ps(m0, bias + n0), bias1 = _mm512_maskz_loadu_ps(m1, bias + n0 + 16);
+  __m512 a0[R], a1[R];
+  for (int r = 0; r < R; ++r) { a0[r] = bias0; a1[r] = bias1; }
+  const float* w = wt + n0;
+  for (int k = 0; k < K; ++k, w += N) {
+    const __m512 w0 = _mm512_maskz_loadu_ps(m0, w), w1 = _mm512_maskz_loadu_ps(m1, w + 16);
+    for (int r = 0; r < R; ++r) {
+      const __m512 v = _mm512_set1_ps(x[r][k]);
+      a0[r] = _mm512_fmadd_ps(v, w0, a0[r]);
+      a1[r] = _mm512_fmadd_ps(v, w1, a1[r]);
+    }
+  }
+  const __m512 zero = _mm512_setzero_ps();
+  for (int r = 0; r < R; ++r) {
+    if (relu) { a0[r] = _mm512_max_ps(a0[r], zero); a1[r] = _mm512_max_ps(a1[r], zero); }
+    _mm512_mask_storeu_ps(y[r] + n0, m0, a0[r]);
+    _mm512_mask_storeu_ps(y[r] + n0 + 16, m1, a1[r]);
+  }
+}
+static const bool kHasAvx512 = __builtin_cpu_supports("avx512f") && !(getenv("DEEPREC_CPU_SERVING_NO_AVX512") && atoi(getenv("DEEPREC_CPU_SERVING_NO_AVX512")));
+#else
+static const bool kHasAvx512 = false;
+#endif
+
 static void Linear(const float* X, int64_t ldx, int64_t B, const Layer& L, float* Y, bool relu, int threads) {
   const int N = L.N, K = L.K;
   const float* wt = L.wt.data(); const float* bias = L.bias.data();
+  const int64_t step = kHasAvx512 ? 8 : kMR;
 #pragma omp parallel for schedule(static) num_threads(threads) if (B >= 64 && threads > 1)
-  for (int64_t b0 = 0; b0 < B; b0 += kMR) {
-    const int mr = (int)std::min<int64_t>(kMR, B - b0);
-    const float* x[kMR]; float* y[kMR];
-    for (int r = 0; r < kMR; ++r) { const int64_t rr = b0 + std::min(r, mr - 1); x[r] = X + rr * ldx; y[r] = Y + rr * N; }   // tail rows alias the last valid row
-    for (int n0 = 0; n0 < N && mr == kMR; n0 += kNR) {
-      const int nr = std::min(kNR, N - n0);
-      MicroKernel<kMR>(x, K, wt, N, n0, nr, bias, y, relu);
+  for (int64_t b0 = 0; b0 < B; b0 += step) {
+    int64_t r0 = b0;
+    const int64_t r1 = std::min<int64_t>(B, b0 + step);
+#if defined(__x86_64__)
+    if (r1 - r0 == 8 && kHasAvx512) {
+      const float* x[8]; float* y[8];
+      for (int r = 0; r < 8; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
+      for (int n0 = 0; n0 < N; n0 += 32) MicroKernel512(x, K, wt, N, n0, std::min(32, N - n0), bias, y, relu);
+      continue;
     }
-    if (mr < kMR) {                // tail rows (and batch-1 requests): stream whole weight rows -- contiguous reads, the matrix-vector case is bandwidth-bound
-      for (int r = 0; r < mr; ++r) {
-        float* __restrict yy = y[r]; const float* xx = x[r];
-        for (int n = 0; n < N; ++n) yy[n] = bias[n];
-        for (int k = 0; k < K; ++k) { const float a = xx[k]; const float* __restrict w = wt + (size_t)k * N; for (int n = 0; n < N; ++n) yy[n] += a * w[n]; }
-        if (relu) for (int n = 0; n < N; ++n) yy[n] = yy[n] > 0.f ? yy[n] : 0.f;
-      }
+#endif
+    for (; r1 - r0 >= kMR; r0 += kMR) {
+      const float* x[kMR]; float* y[kMR];
+      for (int r = 0; r < kMR; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
+      for (int n0 = 0; n0 < N; n0 += kNR) MicroKernel<kMR>(x, K, wt, N, n0, std::min(kNR, N - n0), bias, y, relu);
+    }
+    for (; r0 < r1; ++r0) {          // tail rows (and batch-1 requests): stream whole weight rows -- contiguous reads, the matrix-vector case is bandwidth-bound
+      float* __restrict yy = Y + r0 * N; const float* xx = X + r0 * ldx;
+      for (int n = 0; n < N; ++n) yy[n] = bias[n];
+      for (int k = 0; k < K; ++k) { const float a = xx[k]; const float* __restrict w = wt + (size_t)k * N; for (int n = 0; n < N; ++n) yy[n] += a * w[n]; }
+      if (relu) for (int n = 0; n < N; ++n) yy[n] = yy[n] > 0.f ? yy[n] : 0.f;
     }
   }
 }
