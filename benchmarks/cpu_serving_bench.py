@@ -36,8 +36,13 @@ def main():
     root = tempfile.mkdtemp()
     export_saved_model_module(model, root + "/v1", version=4)
     lines = []
-    for sessions, threads, batch, n in ((1, 1, 1, 4000), (4, 4, 1, 8000), (4, 4, 32, 3000), (2, 2, 256, 600), (1, 1, 2048, 60)):
-        proc = Processor(root + "/v1", {"session_num": sessions, "max_batch": max(256, batch), "model_update_interval_ms": 0}, device="cpu")
+    points = ((1, 1, 1, 4000, 0), (4, 4, 1, 8000, 0), (4, 4, 32, 3000, 0), (2, 2, 256, 600, 0), (1, 1, 2048, 60, 0),
+              (2, 16, 1, 16000, 0), (2, 16, 1, 16000, 32))        # many concurrent single-row callers: without / with request batching
+    for sessions, threads, batch, n, batching in points:
+        cfg = {"session_num": sessions, "max_batch": max(256, batch), "model_update_interval_ms": 0}
+        if batching:
+            cfg.update(enable_batching=True, batching_parameters={"max_batch_size": batching, "batch_timeout_micros": 100})
+        proc = Processor(root + "/v1", cfg, device="cpu")
         reqs = [encode_request(*[x.numpy() for x in criteo_batch(batch, 13, CARDS, seed=100 + i)[:2]]) for i in range(8)]
         for r in reqs:
             assert proc.process(r)[0] == 200
@@ -56,7 +61,9 @@ def main():
         v = np.sort(np.concatenate([np.array(x) for x in lat]))
         rec = {"metric": "DLRM serving, native CPU Processor (C ABI)", "sessions": sessions, "client_threads": threads, "batch": batch, "requests": int(v.size),
                "qps": v.size / wall, "samples_per_s": v.size * batch / wall, "p50_ms": float(v[v.size // 2]), "p99_ms": float(v[min(v.size - 1, int(v.size * 0.99))]),
-               "vcpus": os.cpu_count(), "dtype": "fp32"}
+               "vcpus": os.cpu_count(), "dtype": "fp32", "batching_max_batch_size": batching}
+        if batching:
+            rec["merged"] = proc.model_info()["batching"]
         print(json.dumps(rec), flush=True)
         lines.append(json.dumps(rec))
         proc.close()

@@ -24,6 +24,7 @@
 #include <cctype>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -71,6 +72,10 @@ struct Config {
   // SessionGroup CPU placement (docs SessionGroup.md "cpusets" / SESSION_GROUP_CPUSET / SET_SESSION_THREAD_POOL_AFFINITY): session i runs on
   // cpusets[i] -- the caller's thread is moved there for the duration of the request and the session's OpenMP team is pinned core by core
   std::vector<std::vector<int>> cpusets;
+  // Request batching (TF-Serving's --enable_batching / batching_parameters: max_batch_size, batch_timeout_micros): concurrent small
+  // requests are merged into one forward pass -- the first arrival leads, waits at most batch_timeout_micros for followers, runs the merged
+  // rows on one session and hands every caller its slice.  0 = off.
+  int batching_max_rows = 0, batching_timeout_us = 200; bool batching_adaptive = true;
   bool remote = false; std::string redis_host = "127.0.0.1", redis_password, redis_prefix = "dlrm"; int redis_port = 6379, redis_db = 0, redis_timeout_ms = 2000;
 };
 
@@ -401,8 +406,11 @@ struct AffinityScope {
   ~AffinityScope() { if (on) sched_setaffinity(0, sizeof(saved), &saved); }
 };
 
+struct Batcher;
 struct ServingModel {
   Config cfg;
+  std::shared_ptr<Batcher> batcher;
+  std::atomic<int> busy{0};                        // sessions currently inside a forward pass
   std::shared_ptr<Model> model;                    // atomic_load / atomic_store
   std::vector<std::unique_ptr<Session>> sessions;
   std::atomic<uint64_t> rr{0}, requests{0}, failures{0}, full_updates{0}, delta_updates{0};
@@ -412,6 +420,112 @@ struct ServingModel {
   ~ServingModel() { stop = true; if (updater.joinable()) updater.join(); }
 };
 
+static void SessionReleased(ServingModel* sm);
+
+// rows [0, R) given as dense [R, num_dense] and ids [T][R] (table-major, stride ids_stride) -> probs[R] on one session (chunked by max_batch)
+// (byte pointers: inside a request buffer the id block follows 24 + 4 * R * num_dense bytes and is not 8-byte aligned in general)
+static int RunRows(ServingModel* sm, const std::shared_ptr<Model>& m, const uint8_t* dense_in, const uint8_t* ids_in, size_t ids_stride, uint32_t R,
+                   float* probs, int hint) {
+  const Arch& a = m->arch;
+  const uint64_t pick = sm->cfg.select_policy == 1 ? (hint >= 0 ? (uint64_t)hint : std::hash<std::thread::id>()(std::this_thread::get_id())) : sm->rr.fetch_add(1);
+  const size_t ns = sm->sessions.size();
+  // declared before the session lock: released (and a waiting batch leader woken) only after the session mutex is free again
+  struct Busy { ServingModel* sm; explicit Busy(ServingModel* m) : sm(m) { sm->busy.fetch_add(1); } ~Busy() { SessionReleased(sm); } } busy_mark(sm);
+  Session* sp = sm->sessions[pick % ns].get();
+  std::unique_lock<std::mutex> l(sp->mu, std::defer_lock);
+  if (sm->cfg.select_policy == 1) l.lock();                                       // MOD: the caller / hint owns its session
+  else {                                                                           // RR: start at the round-robin slot, take the first idle session
+    bool got = false;
+    for (size_t i = 0; i < ns && !got; ++i) {
+      Session* c = sm->sessions[(pick + i) % ns].get();
+      std::unique_lock<std::mutex> t(c->mu, std::try_to_lock);
+      if (t.owns_lock()) { l = std::move(t); sp = c; got = true; }
+    }
+    if (!got) l.lock();                                                            // all busy: queue on the round-robin slot
+  }
+  Session& s = *sp;
+  AffinityScope place(s, (int)std::min<uint32_t>(R, (uint32_t)s.max_batch));
+  auto dense = std::atomic_load(&m->dense);
+  for (uint32_t off = 0; off < R; off += (uint32_t)s.max_batch) {                  // larger requests are chunked
+    const int B = (int)std::min<uint32_t>((uint32_t)s.max_batch, R - off);
+    memcpy(s.dense.data(), dense_in + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
+    for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids_in + ((size_t)t * ids_stride + off) * 8, (size_t)B * 8);
+    if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) {
+      // feature store hiccup: one reconnect + retry before the request is failed (the next request tries again)
+      bool ok = false;
+      if (s.redis) {
+        dr_redis_close(s.redis);
+        s.redis = dr_redis_connect(sm->cfg.redis_host.c_str(), sm->cfg.redis_port, sm->cfg.redis_timeout_ms, sm->cfg.redis_password.c_str(), sm->cfg.redis_db);
+        ok = dr_redis_ok(s.redis) && s.Run(*m, *dense, B, sm->cfg.redis_prefix);
+      }
+      if (!ok) { sm->failures++; return 500; }
+    }
+    memcpy(probs + off, s.prob.data(), (size_t)B * 4);
+  }
+  return 200;
+}
+
+// Leader / follower request batcher (see Config::batching_max_rows)
+struct Batcher {
+  struct Item { const uint8_t* dense; const uint8_t* ids; uint32_t rows; float* probs; int rc = 0; int64_t version = -1; bool done = false; };
+  std::mutex mu; std::condition_variable cv_leader, cv_done;
+  std::vector<Item*> pending; uint32_t pending_rows = 0; bool leader_waiting = false;
+  std::atomic<uint64_t> merged_batches{0}, merged_requests{0};
+};
+
+static int PredictBatched(ServingModel* sm, Batcher& bt, const drpb::WireReq& h, const uint8_t* dense_in, const uint8_t* ids_in, float* probs, int64_t* version) {
+  Batcher::Item it{dense_in, ids_in, h.batch, probs};
+  std::unique_lock<std::mutex> l(bt.mu);
+  bt.pending.push_back(&it); bt.pending_rows += h.batch;
+  if (bt.leader_waiting) {                                                        // follower: tell the leader, wait for the slice
+    bt.cv_leader.notify_one();
+    bt.cv_done.wait(l, [&] { return it.done; });
+    *version = it.version;
+    return it.rc;
+  }
+  bt.leader_waiting = true;
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(sm->cfg.batching_timeout_us);
+  // adaptive: an idle session means there is nothing to wait for (latency of a lone request = the unbatched latency); when every
+  // session is busy, requests pile up here until one frees, the row budget is reached or the timeout expires
+  const int nsess = (int)sm->sessions.size();
+  bt.cv_leader.wait_until(l, deadline, [&] { return bt.pending_rows >= (uint32_t)sm->cfg.batching_max_rows || (sm->cfg.batching_adaptive && sm->busy.load() < nsess); });
+  std::vector<Batcher::Item*> mine; mine.swap(bt.pending);                        // everything that arrived: later arrivals elect the next leader
+  const uint32_t R = bt.pending_rows; bt.pending_rows = 0; bt.leader_waiting = false;
+  l.unlock();
+  auto m = std::atomic_load(&sm->model);
+  int rc = 500;
+  if (m) {
+    if (mine.size() == 1) rc = RunRows(sm, m, it.dense, it.ids, it.rows, it.rows, it.probs, -1);
+    else {
+      const Arch& a = m->arch;
+      std::vector<float> dense((size_t)R * a.num_dense), out(R);
+      std::vector<int64_t> ids((size_t)a.T * R);
+      uint32_t off = 0;
+      for (Batcher::Item* q : mine) {
+        memcpy(dense.data() + (size_t)off * a.num_dense, q->dense, (size_t)q->rows * a.num_dense * 4);
+        for (int t = 0; t < a.T; ++t) memcpy(ids.data() + (size_t)t * R + off, q->ids + (size_t)t * q->rows * 8, (size_t)q->rows * 8);
+        off += q->rows;
+      }
+      rc = RunRows(sm, m, reinterpret_cast<const uint8_t*>(dense.data()), reinterpret_cast<const uint8_t*>(ids.data()), R, R, out.data(), -1);
+      off = 0;
+      for (Batcher::Item* q : mine) { if (rc == 200) memcpy(q->probs, out.data() + off, (size_t)q->rows * 4); off += q->rows; }
+    }
+  }
+  bt.merged_batches++; bt.merged_requests += mine.size();
+  l.lock();
+  for (Batcher::Item* q : mine) { q->rc = rc; q->version = m ? m->version : -1; q->done = true; }
+  l.unlock();
+  bt.cv_done.notify_all();
+  *version = it.version;
+  return rc;
+}
+
+static void SessionReleased(ServingModel* sm) {                                    // wakes a batch leader that is waiting for an idle session
+  sm->busy.fetch_sub(1);
+  if (Batcher* bt = sm->batcher.get()) { { std::lock_guard<std::mutex> l(bt->mu); } bt->cv_leader.notify_one(); }
+}
+static Batcher* BatcherOf(ServingModel* sm);
+
 static int Predict(ServingModel* sm, const void* in, int in_size, void** out, int* out_size, int hint) {
   auto m = std::atomic_load(&sm->model);
   if (!m || in_size < (int)sizeof(drpb::WireReq)) return 500;
@@ -419,49 +533,34 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
   const Arch& a = m->arch;
   const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
   if (h.magic != drpb::kWireReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.T || h.batch == 0 || (size_t)in_size < need) return 500;
-  const uint64_t pick = sm->cfg.select_policy == 1 ? (hint >= 0 ? (uint64_t)hint : std::hash<std::thread::id>()(std::this_thread::get_id())) : sm->rr.fetch_add(1);
-  Session& s = *sm->sessions[pick % sm->sessions.size()];
   std::vector<float> probs(h.batch);
   const auto t0 = std::chrono::steady_clock::now();
-  {
-    std::lock_guard<std::mutex> l(s.mu);
-    AffinityScope place(s, (int)std::min<uint32_t>(h.batch, (uint32_t)s.max_batch));
-    auto dense = std::atomic_load(&m->dense);
-    const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
-    const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
-    for (uint32_t off = 0; off < h.batch; off += (uint32_t)s.max_batch) {            // larger requests are chunked
-      const int B = (int)std::min<uint32_t>((uint32_t)s.max_batch, h.batch - off);
-      memcpy(s.dense.data(), p + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
-      for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids + (size_t)t * h.batch + off, (size_t)B * 8);
-      if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) {
-        // feature store hiccup: one reconnect + retry before the request is failed (the next request tries again)
-        bool ok = false;
-        if (s.redis) {
-          dr_redis_close(s.redis);
-          s.redis = dr_redis_connect(sm->cfg.redis_host.c_str(), sm->cfg.redis_port, sm->cfg.redis_timeout_ms, sm->cfg.redis_password.c_str(), sm->cfg.redis_db);
-          ok = dr_redis_ok(s.redis) && s.Run(*m, *dense, B, sm->cfg.redis_prefix);
-        }
-        if (!ok) { sm->failures++; return 500; }
-      }
-      memcpy(probs.data() + off, s.prob.data(), (size_t)B * 4);
-    }
-  }
+  const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
+  const uint8_t* dense_in = p;
+  const uint8_t* ids_in = p + (size_t)h.batch * a.num_dense * 4;
+  int64_t version = m->version;
+  int rc;
+  if (sm->cfg.batching_max_rows > 0 && (int)h.batch * 2 <= sm->cfg.batching_max_rows) rc = PredictBatched(sm, *BatcherOf(sm), h, dense_in, ids_in, probs.data(), &version);
+  else rc = RunRows(sm, m, dense_in, ids_in, h.batch, h.batch, probs.data(), hint);
+  if (rc != 200) return rc;
   const uint64_t rq = ++sm->requests;
   if (sm->cfg.timeline_interval_step > 0 && (int64_t)rq >= sm->cfg.timeline_start_step && (rq % (uint64_t)sm->cfg.timeline_interval_step) == 0) {
     const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     std::lock_guard<std::mutex> l(sm->tmu);
     if ((int)sm->trace.size() < sm->cfg.timeline_trace_count) {
-      char line[160]; snprintf(line, sizeof(line), "{\"request\": %llu, \"batch\": %u, \"latency_us\": %.1f, \"model_version\": %lld}", (unsigned long long)rq, h.batch, us, (long long)m->version);
+      char line[160]; snprintf(line, sizeof(line), "{\"request\": %llu, \"batch\": %u, \"latency_us\": %.1f, \"model_version\": %lld}", (unsigned long long)rq, h.batch, us, (long long)version);
       sm->trace.emplace_back(line);
       if (!sm->cfg.timeline_path.empty()) { FILE* f = fopen(sm->cfg.timeline_path.c_str(), "a"); if (f) { fprintf(f, "%s\n", line); fclose(f); } }
     }
   }
-  drpb::WireResp rh{drpb::kWireRespMagic, h.batch, 200, 0, m->version};
+  drpb::WireResp rh{drpb::kWireRespMagic, h.batch, 200, 0, version};
   *out_size = (int)(sizeof(rh) + probs.size() * 4);
   *out = malloc((size_t)*out_size);
   memcpy(*out, &rh, sizeof(rh)); memcpy(static_cast<uint8_t*>(*out) + sizeof(rh), probs.data(), probs.size() * 4);
   return 200;
 }
+
+static Batcher* BatcherOf(ServingModel* sm) { return sm->batcher.get(); }
 
 static int PredictAny(ServingModel* sm, const void* in, int in_size, void** out, int* out_size, int hint) {
   if (drpb::IsWireRequest(in, (size_t)std::max(in_size, 0))) return Predict(sm, in, in_size, out, out_size, hint);
@@ -577,6 +676,13 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
   c.session_num = (int)j.n("session_num", 2); c.max_batch = (int)j.n("max_batch", 4096);
   c.select_policy = j.s("select_session_policy", "RR") == "MOD" ? 1 : 0;
   c.update_interval_ms = (int)j.n("model_update_interval_ms", 1000);
+  if (j.n("enable_batching", 0) != 0) {
+    const drjson::JVal* bp = j.get("batching_parameters");
+    const drjson::JVal& b = bp && bp->t == drjson::JVal::OBJ ? *bp : j;
+    c.batching_max_rows = std::max(2, (int)b.n("max_batch_size", 64));
+    c.batching_timeout_us = std::max(0, (int)b.n("batch_timeout_micros", 200));
+    c.batching_adaptive = b.n("adaptive", 1) != 0;             // false: always wait for the row budget or the timeout (throughput over latency)
+  }
   c.savedmodel_dir = j.s("savedmodel_dir", model_entry ? model_entry : ""); c.checkpoint_dir = j.s("checkpoint_dir", "");
   c.warmup_file_name = j.s("warmup_file_name", ""); c.timeline_path = j.s("timeline_path", "");
   c.timeline_start_step = (int64_t)j.n("timeline_start_step", -1); c.timeline_interval_step = (int)j.n("timeline_interval_step", 0);
@@ -617,6 +723,7 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
     }
   }
   if (!WarmUp(sm, m)) { *state = -1; delete sm; return nullptr; }
+  sm->batcher = std::make_shared<cpusrv::Batcher>();
   std::atomic_store(&sm->model, m);
   if (c.update_interval_ms > 0) sm->updater = std::thread(UpdaterLoop, sm);
   *state = 0;
@@ -648,6 +755,8 @@ int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* outp
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
      << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"feature_store_type\": \"" << (sm->cfg.remote ? "redis" : "local") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
      << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.T : 0);
+  os << ", \"batching\": {\"max_batch_size\": " << sm->cfg.batching_max_rows << ", \"batch_timeout_micros\": " << sm->cfg.batching_timeout_us
+     << ", \"merged_batches\": " << (sm->batcher ? sm->batcher->merged_batches.load() : 0) << ", \"merged_requests\": " << (sm->batcher ? sm->batcher->merged_requests.load() : 0) << "}";
   os << ", \"cpusets\": \"";
   for (size_t i = 0; i < sm->cfg.cpusets.size(); ++i) { if (i) os << ";"; for (size_t k = 0; k < sm->cfg.cpusets[i].size(); ++k) os << (k ? "," : "") << sm->cfg.cpusets[i][k]; }
   os << "\", \"session_last_cpu\": [";

@@ -126,7 +126,8 @@ int main(int argc, char** argv) {
   WriteFull(root, "v1", 10, rng);
   WriteVersions(root, root + "/v1", 10, {});
   const std::string cfg = "{\"session_num\": 3, \"select_session_policy\": \"MOD\", \"max_batch\": 16, \"checkpoint_dir\": \"" + root +
-                          "\", \"model_update_interval_ms\": 20, \"intra_op_parallelism_threads\": 1}";
+                          "\", \"model_update_interval_ms\": 20, \"intra_op_parallelism_threads\": 1, \"enable_batching\": true, "
+                          "\"max_batch_size\": 24, \"batch_timeout_micros\": 300}";     // requests of <= 12 rows are merged, larger ones bypass the batcher
   int state = -1;
   void* h = dr_cpu_initialize((root + "/v1").c_str(), cfg.c_str(), &state);
   CHECK(h && state == 0);
@@ -188,6 +189,7 @@ int main(int argc, char** argv) {
   printf("%s\nserved %lld requests, newest version seen by a client: %lld\n", s.c_str(), (long long)served.load(), (long long)max_version.load());
   CHECK(s.find("\"model_version\": 30") != std::string::npos && s.find("\"full_updates\": 2") != std::string::npos);
   CHECK(max_version.load() == 30 && served.load() > 50);
+  CHECK(s.find("\"merged_requests\": 0,") == std::string::npos && s.find("\"max_batch_size\": 24") != std::string::npos);
   dr_cpu_serving_release(h);
   printf("CPU_SERVING_STRESS_OK\n");
   return 0;

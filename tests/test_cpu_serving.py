@@ -312,3 +312,47 @@ def test_session_cpusets_place_sessions_and_leave_the_caller_alone(tmp_path):
         assert info["session_last_cpu"][0] == a and info["session_last_cpu"][1] in (b, c)
     finally:
         proc.close()
+
+
+def test_request_batching_merges_concurrent_requests(tmp_path):
+    """enable_batching: concurrent small requests are merged into one forward pass (leader / follower); every caller gets exactly its own
+    rows back, large requests bypass the batcher, and the merge counters show that merging happened."""
+    import threading
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(2)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 2, 2)
+    export_saved_model_module(model, str(tmp_path / "m"), version=4)
+    ref = _ref(model, d, ids)
+    # one session: whoever arrives while it is busy queues up behind a leader and shares the next forward pass (adaptive mode runs a
+    # lone request immediately when a session is idle)
+    proc = Processor(str(tmp_path / "m"), {"session_num": 1, "model_update_interval_ms": 0, "enable_batching": True,
+                                           "batching_parameters": {"max_batch_size": 16, "batch_timeout_micros": 20000}}, device="cpu")
+    try:
+        dn, idn = d.numpy(), ids.numpy()
+        errs, N, T = [], 24, 8
+
+        def client(t):
+            try:
+                for i in range(N):
+                    r0 = (t * N + i) * 2 % 500
+                    rows = 1 + (i % 3)                                   # 1..3 rows per request
+                    got = proc.predict(dn[r0:r0 + rows], idn[:, r0:r0 + rows])
+                    if got.shape != (rows,) or np.abs(got - ref[r0:r0 + rows]).max() > 1e-5:
+                        errs.append((t, i, got, ref[r0:r0 + rows]))
+            except Exception as e:  # noqa: BLE001
+                errs.append(repr(e))
+
+        th = [threading.Thread(target=client, args=(t,)) for t in range(T)]
+        [x.start() for x in th]; [x.join() for x in th]
+        assert not errs, errs[:2]
+        assert np.abs(proc.predict(dn, idn) - ref).max() < 1e-5           # 512 rows: not batched
+        # protobuf requests go through the same batcher
+        rc, out = proc.process(predict_pb.encode_predict_request(dn[:2], idn[:, :2]))
+        assert rc == 200 and np.abs(predict_pb.decode_predict_response(out)[0] - ref[:2]).max() < 1e-5
+        b = proc.model_info()["batching"]
+        assert b["max_batch_size"] == 16 and b["merged_requests"] == T * N + 1
+        assert b["merged_batches"] < b["merged_requests"], b             # at least some requests shared a forward pass
+    finally:
+        proc.close()
