@@ -108,8 +108,17 @@ def main():
         t_read = time.perf_counter() - t0
         table.lib.dr_host_ev_snapshot_end(table.h)
         emit(name, t_begin + t_read, n, begin_ms=t_begin * 1e3, read_ms=t_read * 1e3, read_gb_per_s=rows.numel() * 4 / max(t_read, 1e-9) / 1e9)
+        return keys, rows, fr, ve
 
-    timed_snapshot("snapshot_full", False)
+    def timed_restore(keys, rows, fr, ve):
+        ev2 = dr.get_embedding_variable("bench_restore", a.dim, ev_option=dr.EmbeddingVariableOption(storage_option=dr.StorageOption(dr.StorageType.DRAM)), device="cpu")
+        AdagradOptimizer([], [ev2], lr=0.01)                       # same row layout (one slot)
+        t0 = time.perf_counter(); kept = ev2.table.import_(keys, rows, fr, ve); t = time.perf_counter() - t0
+        emit("restore_import", t, int(kept), rows_after=ev2.total_count())
+
+    snap = timed_snapshot("snapshot_full", False)
+    timed_restore(*snap)
+    del snap
     table.clear_dirty(); table.apply_raw(hit, grads, hp)
     timed_snapshot("snapshot_incremental", True)
     t0 = time.perf_counter(); removed = table.shrink(1000); t = time.perf_counter() - t0      # every key is older than steps_to_live

@@ -294,6 +294,25 @@ class HostKV {
   int64_t Size() const { int64_t s = 0; for (int p = 0; p < nparts_; ++p) s += parts_[p].size.load(); return s; }
 
   int NumParts() const { return nparts_; }
+  // Make room for `extra` more keys up front (restore of a checkpoint: one rebuild per partition instead of one per doubling).
+  template <typename PF> void Reserve(int64_t extra, PF&& parallel_for) {
+    const int64_t per = extra / nparts_ + extra / (nparts_ * 8) + 64;            // uniform hashing: +12.5 % slack per partition
+    parallel_for(nparts_, [&](int64_t pb, int64_t pe) {
+      for (int64_t p = pb; p < pe; ++p) {
+        KVPart& P = parts_[p];
+        std::unique_lock<std::shared_mutex> l(P.mu);
+        int64_t cap = P.cap;
+        while ((P.size.load() + per) * 10 > cap * 7) cap <<= 1;
+        if (cap == P.cap) continue;
+        std::vector<std::pair<int64_t, int32_t>> items; items.reserve((size_t)P.size.load());
+        for (int64_t i = 0; i < P.cap; ++i) {
+          int64_t k = P.slots[i].key.load(std::memory_order_relaxed);
+          if (k != kEmptyKey) items.emplace_back(k, P.slots[i].val.load(std::memory_order_relaxed));
+        }
+        Rebuild(P, cap, items);
+      }
+    });
+  }
   // Iterate the (key, idx) pairs of one partition / of all partitions (caller guarantees no concurrent writers, as in Save).  Whole-table
   // passes (snapshot, eviction, dirty reset) run one partition per worker.
   template <typename F> void ForEachInPart(int p, F&& f) {
@@ -806,14 +825,23 @@ class HostEV {
     // restore of a large table is insert-bound: key ranges go to the workers (inserts are CAS-based, growth is per partition); a key that
     // appears twice in one call keeps one row (the claim below) and the later copy wins or loses arbitrarily, as two restores would
     std::atomic<int64_t> kept{0};
+    if (n >= 4096) kv_.Reserve(part_num > 1 ? n / part_num + n / (part_num * 4) : n, [](int64_t cnt, const std::function<void(int64_t, int64_t)>& fn) { GlobalPool()->ParallelFor(cnt, 1, fn); });
+    // restore into an empty table: every key of a range is new, so its metadata / row indices are reserved with one fetch_add each
+    const bool bulk = kv_.Size() == 0 && part_num <= 1 && n_free_meta_.load(std::memory_order_relaxed) == 0 && n_free_rows_.load(std::memory_order_relaxed) == 0;
     GlobalPool()->ParallelFor(n, 4096, [&](int64_t b, int64_t e) {
       int64_t mine = 0, new_rows = 0;
+      Reserve rs;
+      if (bulk) {
+        rs.meta_next = next_meta_.fetch_add(e - b); rs.meta_end = rs.meta_next + (e - b);
+        meta_.EnsureCapacity(rs.meta_end, Meta{0, -1, -1, 0, {0}});
+        if (rows) { rs.row_next = next_row_.fetch_add(e - b); rs.row_end = rs.row_next + (e - b); rows_.EnsureCapacity(rs.row_end, 0.f); }
+      }
       for (int64_t i = b; i < e; ++i) {
         int64_t key = keys[i];
         if (key == kEmptyKey) continue;
         if (part_num > 1 && dr_ckpt_bucket(key) % part_num != part_id) continue;
         bool inserted = false;
-        int32_t idx = kv_.FindOrInsert(key, [this] { return AllocMeta(); }, &inserted);
+        int32_t idx = kv_.FindOrInsert(key, [this, &rs] { return AllocMeta(&rs); }, &inserted);
         __atomic_store_n(&meta_.at(idx)->freq, freqs ? freqs[i] : 0, __ATOMIC_RELAXED);
         __atomic_store_n(&meta_.at(idx)->version, reset_version ? -1 : (versions ? versions[i] : -1), __ATOMIC_RELAXED);
         if (rows) {
@@ -822,7 +850,8 @@ class HostEV {
           if (r == -1) {
             int32_t expect = -1;
             if (__atomic_compare_exchange_n(rp, &expect, -2, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
-              r = AllocRow(); InitRow(r, key);
+              r = AllocRow(&rs);
+              if (ncols < stride_) InitRow(r, key);                       // missing slot columns take their initial values
               memcpy(rows_.at(r), rows + i * ncols, std::min(ncols, stride_) * sizeof(float));
               __atomic_store_n(rp, r, __ATOMIC_RELEASE); ++new_rows; ++mine;
               continue;
