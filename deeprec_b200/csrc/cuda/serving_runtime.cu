@@ -439,11 +439,25 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
   const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
   if (h.magic != kReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.T || h.batch == 0 || (size_t)in_size < need) return 500;
   uint64_t pick = sm->cfg.select_policy == 1 ? (hint >= 0 ? (uint64_t)hint : std::hash<std::thread::id>()(std::this_thread::get_id())) : sm->rr.fetch_add(1);
-  Session& s = *sm->sessions[pick % sm->sessions.size()];
+  const size_t ns = sm->sessions.size();
+  Session* sp = sm->sessions[pick % ns].get();
   std::vector<float> probs(h.batch);
   auto t0 = std::chrono::steady_clock::now();
   {
-    std::lock_guard<std::mutex> l(s.mu);
+    // MOD: the caller / hint owns its session.  RR: start at the round-robin slot and take the first IDLE session (a serial caller still
+    // rotates through the sessions; concurrent callers no longer queue behind a busy session while another one is free)
+    std::unique_lock<std::mutex> l(sp->mu, std::defer_lock);
+    if (sm->cfg.select_policy == 1) l.lock();
+    else {
+      bool got = false;
+      for (size_t i = 0; i < ns && !got; ++i) {
+        Session* c = sm->sessions[(pick + i) % ns].get();
+        std::unique_lock<std::mutex> t(c->mu, std::try_to_lock);
+        if (t.owns_lock()) { l = std::move(t); sp = c; got = true; }
+      }
+      if (!got) l.lock();
+    }
+    Session& s = *sp;
     cudaSetDevice(sm->cfg.gpu_id);
     auto dense = std::atomic_load(&m->dense);
     const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
