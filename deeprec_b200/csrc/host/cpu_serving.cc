@@ -79,11 +79,22 @@ struct Config {
   bool remote = false; std::string redis_host = "127.0.0.1", redis_password, redis_prefix = "dlrm"; int redis_port = 6379, redis_db = 0, redis_timeout_ms = 2000;
 };
 
-struct Arch { int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0; };
+// Op program (saved_model.json "arch": "program", written by serving/export.py::export_saved_model_program): the inference graph of a
+// Criteo-style model other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].
+enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD };
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; std::string name; };
+struct Arch {
+  int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0;
+  bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1; std::string model_name = "dlrm";
+};
 static int pad8(int n) { return (n + 7) / 8 * 8; }
 
 struct Layer { int N = 0, K = 0; std::vector<float> wt /*[K][N]*/, bias; };
-struct Dense { std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f; };
+struct PData { Layer L; std::vector<float> v0, v1; };                     // weights of one program op (linear | affine scale, shift | cross w, b)
+struct Dense {
+  std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f;
+  std::vector<PData> pdata; std::vector<int> width;                       // program models: per-op weights, per-buffer widths
+};
 
 struct Model {
   Arch arch; int64_t version = -1; std::string path;
@@ -110,11 +121,70 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   const int F = a->T + 1; a->inter = a->D + F * (F - 1) / 2;
   *version = (int64_t)j.n("version", 0);
   *prefix = dir + "/" + j.s("variables", "variables/variables");
+  a->model_name = j.s("model", "dlrm");
+  if (j.s("arch", "") == "program") {
+    a->program = true;
+    std::vector<std::string> names = {"dense", "emb"};
+    auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
+    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add"};
+    const JVal* pr = j.get("program");
+    if (!pr || pr->t != JVal::ARR) return false;
+    for (const JVal& o : pr->arr) {
+      POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.kind = -1;
+      const std::string kind = o.s("op", "");
+      for (int k = 0; k < 7; ++k) if (kind == kNames[k]) op.kind = k;
+      const JVal* in = o.get("in");
+      if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
+      for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
+      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2};
+      if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
+      op.out = (int)names.size(); names.push_back(op.name);
+      a->ops.push_back(std::move(op));
+    }
+    a->nbuf = (int)names.size();
+    a->out_buf = id_of(j.s("output", ""));
+    return a->T > 0 && a->out_buf >= 2;
+  }
   return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
 }
 
+// weights + buffer widths of a program model; every shape is checked against the widths implied by the op list
+static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense>* out) {
+  auto dp = std::make_shared<Dense>();
+  dp->width.assign((size_t)a.nbuf, 0); dp->width[0] = a.num_dense; dp->width[1] = a.T * a.D;
+  dp->pdata.resize(a.ops.size());
+  for (size_t i = 0; i < a.ops.size(); ++i) {
+    const POp& op = a.ops[i]; PData& d = dp->pdata[i];
+    const int w0 = dp->width[(size_t)op.in[0]];
+    int w = w0;
+    const std::string base = "prog/" + op.name + "/";
+    switch (op.kind) {
+      case P_CONCAT: w = 0; for (int b : op.in) w += dp->width[(size_t)b]; break;
+      case P_LINEAR: {
+        std::vector<float> W, b;
+        if (!ReadVec(r, base + "kernel", &W) || !ReadVec(r, base + "bias", &b) || b.empty() || W.size() != b.size() * (size_t)w0) return false;
+        d.L.N = (int)b.size(); d.L.K = w0; d.L.bias = b; d.L.wt.resize(W.size());
+        for (int n = 0; n < d.L.N; ++n) for (int k = 0; k < w0; ++k) d.L.wt[(size_t)k * d.L.N + n] = W[(size_t)n * w0 + k];
+        w = d.L.N; break;
+      }
+      case P_AFFINE: if (!ReadVec(r, base + "scale", &d.v0) || !ReadVec(r, base + "shift", &d.v1) || (int)d.v0.size() != w0 || (int)d.v1.size() != w0) return false; break;
+      case P_FM: if (op.in[0] != 1) return false; w = a.D; break;
+      case P_CROSS: if (!ReadVec(r, base + "w", &d.v0) || !ReadVec(r, base + "b", &d.v1) || (int)d.v0.size() != w0 || (int)d.v1.size() != w0 || dp->width[(size_t)op.in[1]] != w0) return false; break;
+      case P_MUL_ADD: if (dp->width[(size_t)op.in[1]] != w0 || dp->width[(size_t)op.in[2]] != w0) return false; break;
+      case P_ADD: if (dp->width[(size_t)op.in[1]] != w0) return false; break;
+      default: return false;
+    }
+    if (w <= 0) return false;
+    dp->width[(size_t)op.out] = w;
+  }
+  *out = dp;
+  return true;
+}
+
 // BatchNorm (moving statistics) of layer l-1 folded into Linear l:  W' = W diag(s), b' = b + W t
+static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense>* out);
 static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense>* out) {
+  if (a.program) return BuildProgram(r, a, out);
   auto dp = std::make_shared<Dense>();
   std::vector<float> s_prev, t_prev;
   int k = a.num_dense;
@@ -357,11 +427,75 @@ struct Session {
     }
     return true;
   }
+  // ---- op-program models: buffers 0 / 1 alias `dense` / `emb`, the others are sized (max_batch x width) on first use of a program ----
+  std::vector<std::vector<float>> pbuf; std::vector<int> pbuf_width;
+  float* Buf(int id) { return id == 0 ? dense.data() : id == 1 ? emb.data() : pbuf[(size_t)id].data(); }
+  void RunProgram(const Arch& ar, const Dense& d, int B) {
+    if (pbuf_width != d.width) {
+      pbuf.assign(d.width.size(), std::vector<float>());
+      for (size_t i = 2; i < d.width.size(); ++i) pbuf[i].resize((size_t)max_batch * d.width[i]);
+      pbuf_width = d.width;
+    }
+    const bool par = B >= 64 && threads > 1;
+    for (size_t oi = 0; oi < ar.ops.size(); ++oi) {
+      const POp& op = ar.ops[oi]; const PData& pd = d.pdata[oi];
+      float* out = Buf(op.out); const int W = d.width[(size_t)op.out];
+      const float* a0 = Buf(op.in[0]); const int w0 = d.width[(size_t)op.in[0]];
+      switch (op.kind) {
+        case P_LINEAR: Linear(a0, w0, B, pd.L, out, op.relu, threads); break;
+        case P_CONCAT: {
+          int off = 0;
+          for (int src : op.in) {
+            const float* x = Buf(src); const int w = d.width[(size_t)src];
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+            for (int i = 0; i < B; ++i) memcpy(out + (size_t)i * W + off, x + (size_t)i * w, (size_t)w * sizeof(float));
+            off += w;
+          }
+          break;
+        }
+        case P_AFFINE: {
+          const float* sc = pd.v0.data(); const float* sh = pd.v1.data();
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) { const float* x = a0 + (size_t)i * W; float* y = out + (size_t)i * W; for (int k = 0; k < W; ++k) y[k] = x[k] * sc[k] + sh[k]; }
+          break;
+        }
+        case P_FM: {                                             // 0.5 ((sum_t v_t)^2 - sum_t v_t^2) per embedding dimension
+          const int T = ar.T, D = ar.D;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            const float* e = a0 + (size_t)i * T * D; float* y = out + (size_t)i * D;
+            for (int k = 0; k < D; ++k) { float sum = 0.f, sq = 0.f; for (int t = 0; t < T; ++t) { const float v = e[(size_t)t * D + k]; sum += v; sq += v * v; } y[k] = 0.5f * (sum * sum - sq); }
+          }
+          break;
+        }
+        case P_CROSS: {                                          // x_{l+1} = x0 (x_l . w) + b + x_l
+          const float* xl = Buf(op.in[1]); const float* w = pd.v0.data(); const float* bb = pd.v1.data();
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            const float* x0 = a0 + (size_t)i * W; const float* x = xl + (size_t)i * W; float* y = out + (size_t)i * W;
+            float dot = 0.f; for (int k = 0; k < W; ++k) dot += x[k] * w[k];
+            for (int k = 0; k < W; ++k) y[k] = x0[k] * dot + bb[k] + x[k];
+          }
+          break;
+        }
+        case P_MUL_ADD: case P_ADD: {
+          const float* b1 = Buf(op.in[1]); const float* c1 = op.kind == P_MUL_ADD ? Buf(op.in[2]) : nullptr;
+          const size_t n = (size_t)B * W;
+          if (c1) for (size_t k = 0; k < n; ++k) out[k] = a0[k] * b1[k] + c1[k]; else for (size_t k = 0; k < n; ++k) out[k] = a0[k] + b1[k];
+          break;
+        }
+      }
+    }
+    const float* lg = Buf(ar.out_buf); const int W = d.width[(size_t)ar.out_buf];
+    for (int i = 0; i < B; ++i) prob[(size_t)i] = 1.f / (1.f + std::exp(-lg[(size_t)i * W]));
+  }
+
   // dense [B, num_dense], ids [T][B] staged in the session buffers -> prob[B]
   bool Run(const Model& m, const Dense& d, int B, const std::string& remote_prefix = std::string()) {
     const Arch& ar = m.arch;
     if (redis) { if (!RemoteLookup(m, remote_prefix, B)) return false; }
     else dr_host_group_lookup(const_cast<void**>(m.tables.data()), ar.T, ids.data(), B, emb.data());         // [B, T, D]
+    if (ar.program) { RunProgram(ar, d, B); return true; }
     const float* x = dense.data(); int64_t ldx = ar.num_dense;
     float* cur = a.data(); float* nxt = b2.data();
     for (size_t l = 0; l < d.bot.size(); ++l) { Linear(x, ldx, B, d.bot[l], cur, true, threads); x = cur; ldx = d.bot[l].N; std::swap(cur, nxt); }
@@ -624,7 +758,9 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
     dr_host_ev_import_cow(m->tables[(size_t)t], keys.data(), vals.data(), m->arch.D, (int64_t)keys.size());   // copy-on-write: readers never see a torn row
   }
   std::shared_ptr<Dense> dp;
-  if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp)) std::atomic_store(&m->dense, dp);
+  const bool has_dense = m->arch.program ? (!m->arch.ops.empty() && [&] { for (auto& op : m->arch.ops) if (op.kind == P_LINEAR) return r.Find("prog/" + op.name + "/kernel") != nullptr; return false; }())
+                                         : r.Find("dense/logits/kernel") != nullptr;
+  if (has_dense && BuildDense(r, m->arch, &dp)) std::atomic_store(&m->dense, dp);
   sm->delta_version = version;
   sm->delta_updates++;
   return true;
@@ -753,7 +889,7 @@ int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* outp
   std::ostringstream os;
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
-     << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"feature_store_type\": \"" << (sm->cfg.remote ? "redis" : "local") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
+     << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"model\": \"" << (m ? m->arch.model_name : "") << "\", \"feature_store_type\": \"" << (sm->cfg.remote ? "redis" : "local") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
      << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.T : 0);
   os << ", \"batching\": {\"max_batch_size\": " << sm->cfg.batching_max_rows << ", \"batch_timeout_micros\": " << sm->cfg.batching_timeout_us
      << ", \"merged_batches\": " << (sm->batcher ? sm->batcher->merged_batches.load() : 0) << ", \"merged_requests\": " << (sm->batcher ? sm->batcher->merged_requests.load() : 0) << "}";

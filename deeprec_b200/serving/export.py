@@ -195,3 +195,154 @@ def load_zoo_model(export_dir: str, device: str = "cpu"):
         else:
             os.environ["INFERENCE_MODE"] = prev
     return model.eval(), int(meta["version"])
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# Op-program export: Criteo-style zoo models other than DLRM for the native CPU Processor (csrc/host/cpu_serving.cc::Program).
+# The reference's processor executes whatever graph the SavedModel holds; here the inference graph of a model is written as a short
+# list of ops over named [B, width] buffers -- inputs "dense" [B, num_dense] and "emb" [B, T * D] -- with BatchNorm folded into the
+# following Linear at export time (moving statistics), so the runtime only needs concat / linear / affine / fm / cross / mul_add / add.
+# ------------------------------------------------------------------------------------------------------------------------------------
+class _ProgramBuilder:
+    def __init__(self):
+        self.ops, self.tensors, self._n = [], {}, 0
+
+    def _name(self, base):
+        self._n += 1
+        return f"{base}{self._n}"
+
+    def concat(self, srcs):
+        out = self._name("cat"); self.ops.append({"op": "concat", "out": out, "in": list(srcs)}); return out
+
+    def linear(self, src, weight, bias, relu=False):
+        out = self._name("lin")
+        self.tensors[f"prog/{out}/kernel"] = weight.detach().float().cpu().contiguous()                 # [N, K]
+        self.tensors[f"prog/{out}/bias"] = (bias.detach().float().cpu() if bias is not None else torch.zeros(weight.shape[0])).contiguous()
+        self.ops.append({"op": "linear", "out": out, "in": [src], "relu": bool(relu)}); return out
+
+    def affine(self, src, scale, shift):
+        out = self._name("aff")
+        self.tensors[f"prog/{out}/scale"] = scale.detach().float().cpu().contiguous(); self.tensors[f"prog/{out}/shift"] = shift.detach().float().cpu().contiguous()
+        self.ops.append({"op": "affine", "out": out, "in": [src]}); return out
+
+    def fm(self, emb):
+        out = self._name("fm"); self.ops.append({"op": "fm", "out": out, "in": [emb]}); return out
+
+    def cross(self, x0, x, w, b):
+        out = self._name("cross")
+        self.tensors[f"prog/{out}/w"] = w.detach().float().cpu().contiguous(); self.tensors[f"prog/{out}/b"] = b.detach().float().cpu().contiguous()
+        self.ops.append({"op": "cross", "out": out, "in": [x0, x]}); return out
+
+    def mul_add(self, a, b, c):
+        out = self._name("fma"); self.ops.append({"op": "mul_add", "out": out, "in": [a, b, c]}); return out
+
+    def add(self, a, b):
+        out = self._name("add"); self.ops.append({"op": "add", "out": out, "in": [a, b]}); return out
+
+    def sequential(self, src, seq):
+        """nn.Sequential of Linear / ReLU / BatchNorm1d (what ``models.zoo.mlp`` builds on CPU): a BatchNorm folds into the next Linear
+        (W' = W diag(s), b' = b + W t); one left over at the end becomes an explicit affine op."""
+        import torch.nn as nn
+        pending = None
+        mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                W, b = m.weight.detach().float(), (m.bias.detach().float() if m.bias is not None else torch.zeros(m.out_features))
+                if pending is not None:
+                    s, t = pending
+                    b = b + W @ t; W = W * s.unsqueeze(0); pending = None
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                src = self.linear(src, W, b, relu)
+                i += 2 if relu else 1
+            elif isinstance(m, nn.BatchNorm1d):
+                s = m.weight.detach().float() / torch.sqrt(m.running_var.detach().float() + m.eps)
+                pending = (s, m.bias.detach().float() - m.running_mean.detach().float() * s)
+                i += 1
+            else:
+                raise TypeError(f"op-program export: unsupported layer {type(m).__name__} (Linear / ReLU / BatchNorm1d chains only)")
+        if pending is not None:
+            src = self.affine(src, *pending)
+        return src
+
+
+def _build_program(model) -> _ProgramBuilder:
+    from ..models import zoo
+    p = _ProgramBuilder()
+    if isinstance(model, zoo.DeepFM):
+        x0 = p.concat(["dense", "emb"])
+        dnn = p.sequential(x0, model.dnn)
+        lin = p.linear("dense", model.linear.weight, model.linear.bias)
+        h = p.sequential(p.concat([lin, p.fm("emb"), dnn]), model.final)
+        p.out = p.linear(h, model.out.weight, model.out.bias)
+    elif isinstance(model, zoo.DCNv2):                                   # x_{l+1} = x0 * (W x_l + b) + x_l (full-rank or low-rank W)
+        x0 = p.concat(["dense", "emb"])
+        x = x0
+        for W in model.W:
+            x = p.mul_add(x0, p.sequential(x, W), x)
+        p.out = p.linear(p.concat([x, p.sequential(x0, model.deep)]), model.out.weight, model.out.bias)
+    elif isinstance(model, zoo.DCN):
+        x0 = p.concat(["dense", "emb"])
+        x = x0
+        for w, b in zip(model.cw, model.cb):
+            x = p.cross(x0, x, w, b)
+        p.out = p.linear(p.concat([x, p.sequential(x0, model.deep)]), model.out.weight, model.out.bias)
+    else:
+        raise TypeError(f"op-program export: no builder for {type(model).__name__} (DeepFM, DCN, DCNv2; DLRM has export_saved_model_module)")
+    return p
+
+
+def _program_evs(model):
+    from ..optim.optimizers import collect_embedding_variables
+    return collect_embedding_variables(model.emb)
+
+
+def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None) -> str:
+    """Full export of a Criteo-style zoo model (``DeepFM``, ``DCN``, ``DCNv2``) as an op program + EmbeddingVariable tables; loaded by
+    ``Processor(dir, cfg, device="cpu")`` exactly like a DLRM export (same ModelConfig, update protocol, request formats)."""
+    was_training = model.training
+    model.eval()
+    p = _build_program(model)
+    evs = _program_evs(model)
+    D = evs[0].embedding_dim
+    os.makedirs(os.path.join(export_dir, "variables"), exist_ok=True)
+    w = BundleWriter(os.path.join(export_dir, "variables", "variables"))
+    for name, t in p.tensors.items():
+        w.add(name, t)
+    for t, ev in enumerate(evs):
+        s = ev.table.snapshot()
+        w.add(f"table/{t}-keys", s["keys"].cpu()); w.add(f"table/{t}-values", s["rows"][:, :D].contiguous().cpu())
+        w.add(f"table/{t}-freqs", s["freqs"].cpu()); w.add(f"table/{t}-versions", s["versions"].cpu())
+        w.add(f"table/{t}-default", ev.default_matrix.detach().float().cpu().contiguous())
+        ev.table.clear_dirty()
+    w.close()
+    meta = {"model": type(model).__name__.lower(), "arch": "program", "version": int(version), "num_dense": model.num_dense, "num_tables": len(evs),
+            "embedding_dim": D, "program": p.ops, "output": p.out, "variables": "variables/variables",
+            "signature": {"inputs": {"dense": ["B", model.num_dense], "ids": [len(evs), "B"]}, "outputs": {"probabilities": ["B"]}}}
+    with open(os.path.join(export_dir, "saved_model.json"), "w") as f:
+        json.dump(meta, f)
+    _write_versions(root or export_dir, full={"version": int(version), "dir": os.path.abspath(export_dir)})
+    model.train(was_training)
+    return export_dir
+
+
+def export_delta_program(model, root: str, base_version: int, version: int) -> str:
+    """Incremental export for an op-program model: rows touched since the last export + the (re-folded) dense tensors."""
+    was_training = model.training
+    model.eval()
+    p = _build_program(model)
+    d = os.path.join(root, ".incr")
+    os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, f"delta-{int(version)}")
+    w = BundleWriter(prefix)
+    for name, t in p.tensors.items():
+        w.add(name, t)
+    for t, ev in enumerate(_program_evs(model)):
+        s = ev.table.snapshot(dirty_only=True)
+        w.add(f"table/{t}-sparse_incr_keys", s["keys"].cpu()); w.add(f"table/{t}-sparse_incr_values", s["rows"][:, : ev.embedding_dim].contiguous().cpu())
+        ev.table.clear_dirty()
+    w.close()
+    _write_versions(root, delta={"version": int(version), "base": int(base_version), "prefix": os.path.abspath(prefix)})
+    model.train(was_training)
+    return prefix

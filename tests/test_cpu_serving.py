@@ -356,3 +356,43 @@ def test_request_batching_merges_concurrent_requests(tmp_path):
         assert b["merged_batches"] < b["merged_requests"], b             # at least some requests shared a forward pass
     finally:
         proc.close()
+
+
+@pytest.mark.parametrize("name", ["deepfm", "dcn", "dcnv2"])
+def test_op_program_models_on_the_cpu_processor(tmp_path, name):
+    """DeepFM / DCN exported as an op program (BatchNorm folded at export): the native CPU Processor reproduces the module's predictions,
+    takes a delta update (rows + re-folded dense tensors) and serves protobuf requests; a program with a wrong shape is rejected."""
+    import json
+    from deeprec_b200.serving import export_delta_program, export_saved_model_program
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(4)
+    model = build_model(name, device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 4, 4)                                     # BatchNorm statistics move away from (0, 1)
+    root = str(tmp_path)
+    export_saved_model_program(model, os.path.join(root, "v1"), version=4, root=root)
+    meta = json.load(open(os.path.join(root, "v1", "saved_model.json")))
+    assert meta["arch"] == "program" and meta["model"] == name and {o["op"] for o in meta["program"]} >= {"concat", "linear"}
+    proc = Processor(os.path.join(root, "v1"), {"session_num": 2, "max_batch": 200, "checkpoint_dir": root, "model_update_interval_ms": 100}, device="cpu")
+    try:
+        ref = _ref(model, d, ids)
+        got = proc.predict(d.numpy(), ids.numpy())                        # 512 rows > max_batch: chunked, team-sized chunks
+        assert np.abs(got - ref).max() < 2e-5, np.abs(got - ref).max()
+        assert np.abs(proc.predict(d.numpy()[:3], ids.numpy()[:, :3]) - ref[:3]).max() < 2e-5
+        ids2 = ids.clone(); ids2[:, :40] += 10 ** 9                        # unseen ids read default rows like the module
+        assert np.abs(proc.predict(d.numpy(), ids2.numpy()) - _ref(model, d, ids2)).max() < 2e-5
+        rc, out = proc.process(predict_pb.encode_predict_request(d.numpy()[:5], ids.numpy()[:, :5], per_feature=True))
+        assert rc == 200 and np.abs(predict_pb.decode_predict_response(out)[0] - ref[:5]).max() < 2e-5
+        assert proc.model_info()["model"] == name
+        _train(model, opt, 2, 50)
+        export_delta_program(model, root, base_version=4, version=6)
+        assert _wait(lambda: proc.model_info()["delta_version"] == 6)
+        ref2 = _ref(model, d, ids)
+        assert np.abs(ref2 - ref).max() > 1e-4 and np.abs(proc.predict(d.numpy(), ids.numpy()) - ref2).max() < 2e-5
+    finally:
+        proc.close()
+    # a corrupted program (output buffer that does not exist) must fail initialisation, not crash
+    meta["output"] = "nope"
+    json.dump(meta, open(os.path.join(root, "v1", "saved_model.json"), "w"))
+    with pytest.raises(RuntimeError):
+        Processor(os.path.join(root, "v1"), {"session_num": 1, "model_update_interval_ms": 0}, device="cpu")
