@@ -81,8 +81,8 @@ struct Config {
 
 // Op program (saved_model.json "arch": "program", written by serving/export.py::export_saved_model_program): the inference graph of a
 // Criteo-style model other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].
-enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD };
-struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; std::string name; };
+enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL };
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1; std::string model_name = "dlrm";
@@ -126,17 +126,17 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     a->program = true;
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
-    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add"};
+    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul"};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     for (const JVal& o : pr->arr) {
-      POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.kind = -1;
+      POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
       const std::string kind = o.s("op", "");
-      for (int k = 0; k < 7; ++k) if (kind == kNames[k]) op.kind = k;
+      for (int k = 0; k < 9; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
-      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2};
+      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2};
       if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
       op.out = (int)names.size(); names.push_back(op.name);
       a->ops.push_back(std::move(op));
@@ -167,10 +167,12 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
         for (int n = 0; n < d.L.N; ++n) for (int k = 0; k < w0; ++k) d.L.wt[(size_t)k * d.L.N + n] = W[(size_t)n * w0 + k];
         w = d.L.N; break;
       }
+      case P_LAYERNORM:
       case P_AFFINE: if (!ReadVec(r, base + "scale", &d.v0) || !ReadVec(r, base + "shift", &d.v1) || (int)d.v0.size() != w0 || (int)d.v1.size() != w0) return false; break;
       case P_FM: if (op.in[0] != 1) return false; w = a.D; break;
       case P_CROSS: if (!ReadVec(r, base + "w", &d.v0) || !ReadVec(r, base + "b", &d.v1) || (int)d.v0.size() != w0 || (int)d.v1.size() != w0 || dp->width[(size_t)op.in[1]] != w0) return false; break;
       case P_MUL_ADD: if (dp->width[(size_t)op.in[1]] != w0 || dp->width[(size_t)op.in[2]] != w0) return false; break;
+      case P_MUL:
       case P_ADD: if (dp->width[(size_t)op.in[1]] != w0) return false; break;
       default: return false;
     }
@@ -478,10 +480,24 @@ struct Session {
           }
           break;
         }
-        case P_MUL_ADD: case P_ADD: {
+        case P_MUL_ADD: case P_ADD: case P_MUL: {
           const float* b1 = Buf(op.in[1]); const float* c1 = op.kind == P_MUL_ADD ? Buf(op.in[2]) : nullptr;
           const size_t n = (size_t)B * W;
-          if (c1) for (size_t k = 0; k < n; ++k) out[k] = a0[k] * b1[k] + c1[k]; else for (size_t k = 0; k < n; ++k) out[k] = a0[k] + b1[k];
+          if (c1) for (size_t k = 0; k < n; ++k) out[k] = a0[k] * b1[k] + c1[k];
+          else if (op.kind == P_MUL) for (size_t k = 0; k < n; ++k) out[k] = a0[k] * b1[k];
+          else for (size_t k = 0; k < n; ++k) out[k] = a0[k] + b1[k];
+          break;
+        }
+        case P_LAYERNORM: {                                      // (x - mean) / sqrt(var + eps) * gamma + beta, biased variance, optional ReLU
+          const float* g = pd.v0.data(); const float* bt = pd.v1.data(); const float eps = op.eps; const bool relu = op.relu;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            const float* x = a0 + (size_t)i * W; float* y = out + (size_t)i * W;
+            float mean = 0.f; for (int k = 0; k < W; ++k) mean += x[k]; mean /= (float)W;
+            float var = 0.f; for (int k = 0; k < W; ++k) { const float dlt = x[k] - mean; var += dlt * dlt; } var /= (float)W;
+            const float rs = 1.f / std::sqrt(var + eps);
+            for (int k = 0; k < W; ++k) { const float v = (x[k] - mean) * rs * g[k] + bt[k]; y[k] = relu && v < 0.f ? 0.f : v; }
+          }
           break;
         }
       }

@@ -201,7 +201,7 @@ def load_zoo_model(export_dir: str, device: str = "cpu"):
 # Op-program export: Criteo-style zoo models other than DLRM for the native CPU Processor (csrc/host/cpu_serving.cc::Program).
 # The reference's processor executes whatever graph the SavedModel holds; here the inference graph of a model is written as a short
 # list of ops over named [B, width] buffers -- inputs "dense" [B, num_dense] and "emb" [B, T * D] -- with BatchNorm folded into the
-# following Linear at export time (moving statistics), so the runtime only needs concat / linear / affine / fm / cross / mul_add / add.
+# following Linear at export time (moving statistics), so the runtime only needs concat / linear / affine / fm / cross / mul_add / add / mul / layernorm.
 # ------------------------------------------------------------------------------------------------------------------------------------
 class _ProgramBuilder:
     def __init__(self):
@@ -239,6 +239,14 @@ class _ProgramBuilder:
     def add(self, a, b):
         out = self._name("add"); self.ops.append({"op": "add", "out": out, "in": [a, b]}); return out
 
+    def mul(self, a, b):
+        out = self._name("mul"); self.ops.append({"op": "mul", "out": out, "in": [a, b]}); return out
+
+    def layernorm(self, src, ln, relu=False):
+        out = self._name("ln")
+        self.tensors[f"prog/{out}/scale"] = ln.weight.detach().float().cpu().contiguous(); self.tensors[f"prog/{out}/shift"] = ln.bias.detach().float().cpu().contiguous()
+        self.ops.append({"op": "layernorm", "out": out, "in": [src], "eps": float(ln.eps), "relu": bool(relu)}); return out
+
     def sequential(self, src, seq):
         """nn.Sequential of Linear / ReLU / BatchNorm1d (what ``models.zoo.mlp`` builds on CPU): a BatchNorm folds into the next Linear
         (W' = W diag(s), b' = b + W t); one left over at the end becomes an explicit affine op."""
@@ -260,6 +268,12 @@ class _ProgramBuilder:
                 s = m.weight.detach().float() / torch.sqrt(m.running_var.detach().float() + m.eps)
                 pending = (s, m.bias.detach().float() - m.running_mean.detach().float() * s)
                 i += 1
+            elif isinstance(m, nn.LayerNorm):
+                if pending is not None:
+                    src = self.affine(src, *pending); pending = None
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                src = self.layernorm(src, m, relu)
+                i += 2 if relu else 1
             else:
                 raise TypeError(f"op-program export: unsupported layer {type(m).__name__} (Linear / ReLU / BatchNorm1d chains only)")
         if pending is not None:
@@ -276,6 +290,11 @@ def _build_program(model) -> _ProgramBuilder:
         lin = p.linear("dense", model.linear.weight, model.linear.bias)
         h = p.sequential(p.concat([lin, p.fm("emb"), dnn]), model.final)
         p.out = p.linear(h, model.out.weight, model.out.bias)
+    elif isinstance(model, zoo.MaskNet):                                 # serial MaskBlocks: h = ReLU(LN(W (h * mask(v))))
+        h = p.layernorm("emb", model.ln_emb)
+        for m, b in zip(model.masks, model.blocks):
+            h = p.sequential(p.mul(h, p.sequential("emb", m)), b)
+        p.out = p.sequential(p.concat([h, "dense"]), model.out)
     elif isinstance(model, zoo.DCNv2):                                   # x_{l+1} = x0 * (W x_l + b) + x_l (full-rank or low-rank W)
         x0 = p.concat(["dense", "emb"])
         x = x0
@@ -289,7 +308,7 @@ def _build_program(model) -> _ProgramBuilder:
             x = p.cross(x0, x, w, b)
         p.out = p.linear(p.concat([x, p.sequential(x0, model.deep)]), model.out.weight, model.out.bias)
     else:
-        raise TypeError(f"op-program export: no builder for {type(model).__name__} (DeepFM, DCN, DCNv2; DLRM has export_saved_model_module)")
+        raise TypeError(f"op-program export: no builder for {type(model).__name__} (DeepFM, DCN, DCNv2, MaskNet; DLRM has export_saved_model_module)")
     return p
 
 
@@ -299,7 +318,7 @@ def _program_evs(model):
 
 
 def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None) -> str:
-    """Full export of a Criteo-style zoo model (``DeepFM``, ``DCN``, ``DCNv2``) as an op program + EmbeddingVariable tables; loaded by
+    """Full export of a Criteo-style zoo model (``DeepFM``, ``DCN``, ``DCNv2``, ``MaskNet``) as an op program + EmbeddingVariable tables; loaded by
     ``Processor(dir, cfg, device="cpu")`` exactly like a DLRM export (same ModelConfig, update protocol, request formats)."""
     was_training = model.training
     model.eval()

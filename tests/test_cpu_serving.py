@@ -358,7 +358,7 @@ def test_request_batching_merges_concurrent_requests(tmp_path):
         proc.close()
 
 
-@pytest.mark.parametrize("name", ["deepfm", "dcn", "dcnv2"])
+@pytest.mark.parametrize("name", ["deepfm", "dcn", "dcnv2", "masknet"])
 def test_op_program_models_on_the_cpu_processor(tmp_path, name):
     """DeepFM / DCN exported as an op program (BatchNorm folded at export): the native CPU Processor reproduces the module's predictions,
     takes a delta update (rows + re-folded dense tensors) and serves protobuf requests; a program with a wrong shape is rejected."""
