@@ -60,9 +60,18 @@ class Processor:
     request encodings, ModelConfig keys and hot-swap protocol.  Default: cuda when a GPU is visible, else cpu."""
 
     def __init__(self, savedmodel_dir: str, config: dict | None = None, device: str | None = None):
+        program = False
+        try:
+            with open(os.path.join(savedmodel_dir, "saved_model.json")) as f:
+                program = json.load(f).get("arch") == "program"
+        except (OSError, ValueError):
+            pass
         if device is None:
             import torch
-            device = "cuda" if torch.cuda.is_available() else "cpu"
+            # op-program exports (DeepFM, DCN, ... -- export_saved_model_program) are interpreted by the CPU runtime only
+            device = "cuda" if torch.cuda.is_available() and not program else "cpu"
+        if program and device != "cpu":
+            raise ValueError(f"{savedmodel_dir} is an op-program export: served by Processor(..., device='cpu') (the GPU runtime runs the DLRM architecture)")
         self.device = device
         if device == "cpu":
             from .. import _native
