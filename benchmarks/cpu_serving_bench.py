@@ -26,15 +26,20 @@ from deeprec_b200.serving import Processor, encode_request, export_saved_model_m
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--model", default="dlrm", help="dlrm (native architecture) or an op-program model: deepfm, dcn, dcnv2, masknet")
     a = ap.parse_args()
     torch.manual_seed(0)
-    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    model = build_model(a.model, device="cpu", cardinalities=CARDS)
     opt = dr.optim.AdagradOptimizer(model, lr=0.05)
     for s in range(4):
         d, ids, y = criteo_batch(2048, 13, CARDS, seed=s)
         loss = model.loss(d, ids, y); opt.zero_grad(); loss.backward(); opt.step()
     root = tempfile.mkdtemp()
-    export_saved_model_module(model, root + "/v1", version=4)
+    if a.model == "dlrm":
+        export_saved_model_module(model, root + "/v1", version=4)
+    else:
+        from deeprec_b200.serving import export_saved_model_program
+        export_saved_model_program(model, root + "/v1", version=4)
     lines = []
     points = ((1, 1, 1, 4000, 0), (4, 4, 1, 8000, 0), (4, 4, 32, 3000, 0), (2, 2, 256, 600, 0), (1, 1, 2048, 60, 0),
               (2, 16, 1, 16000, 0), (2, 16, 1, 16000, 32))        # many concurrent single-row callers: without / with request batching
@@ -59,7 +64,7 @@ def main():
         [t.start() for t in ts]; [t.join() for t in ts]
         wall = time.perf_counter() - t0
         v = np.sort(np.concatenate([np.array(x) for x in lat]))
-        rec = {"metric": "DLRM serving, native CPU Processor (C ABI)", "sessions": sessions, "client_threads": threads, "batch": batch, "requests": int(v.size),
+        rec = {"metric": f"{a.model} serving, native CPU Processor (C ABI)", "sessions": sessions, "client_threads": threads, "batch": batch, "requests": int(v.size),
                "qps": v.size / wall, "samples_per_s": v.size * batch / wall, "p50_ms": float(v[v.size // 2]), "p99_ms": float(v[min(v.size - 1, int(v.size * 0.99))]),
                "vcpus": os.cpu_count(), "dtype": "fp32", "batching_max_batch_size": batching}
         if batching:

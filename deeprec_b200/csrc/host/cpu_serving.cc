@@ -332,28 +332,49 @@ static const bool kHasAvx512 = __builtin_cpu_supports("avx512f") && !(getenv("DE
 static const bool kHasAvx512 = false;
 #endif
 
+// Loop order: rows are cut into groups (<= 64 rows, what a thread owns at a time), and inside a group the weight PANEL (K x 32 columns,
+// ~50 KB for K = 429) is the outer loop and the group's row tiles the inner one -- a panel is read from L1/L2 by every tile of the group
+// instead of the whole weight matrix (1.7 MB for 429 x 1024) being streamed once per 8-row tile.
 static void Linear(const float* X, int64_t ldx, int64_t B, const Layer& L, float* Y, bool relu, int threads) {
   const int N = L.N, K = L.K;
   const float* wt = L.wt.data(); const float* bias = L.bias.data();
-  const int64_t step = kHasAvx512 ? 8 : kMR;
-#pragma omp parallel for schedule(static) num_threads(threads) if (B >= 64 && threads > 1)
-  for (int64_t b0 = 0; b0 < B; b0 += step) {
-    int64_t r0 = b0;
-    const int64_t r1 = std::min<int64_t>(B, b0 + step);
+  const int64_t tile = kHasAvx512 ? 8 : kMR;
+  const int nr_panel = kHasAvx512 ? 32 : kNR;
+  const bool par = B >= 64 && threads > 1;
+  // a weight matrix that sits comfortably in the per-core L2 is better streamed per row tile (the 8 x K input tile then stays in L1 across
+  // all panels): groups of one tile reproduce that order; larger matrices get the panel-outer order described above (measured: DLRM's
+  // <= 750 KB layers lose ~10 % with 64-row groups, DeepFM's 1.7 MB first layer gains 25-50 %)
+  const bool big_w = (size_t)K * N * sizeof(float) > (size_t(1) << 20);
+  int64_t group = big_w ? 64 : tile;
+  if (par && big_w) { const int64_t per = (B + threads - 1) / threads; group = std::max<int64_t>(tile, std::min<int64_t>(64, (per + tile - 1) / tile * tile)); }
+  const int64_t ngroups = (B + group - 1) / group;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+  for (int64_t g = 0; g < ngroups; ++g) {
+    const int64_t g0 = g * group, g1 = std::min<int64_t>(B, g0 + group);
+    const int64_t full_end = g0 + (g1 - g0) / tile * tile;              // rows [g0, full_end) form complete tiles
+    for (int n0 = 0; n0 < N && full_end > g0; n0 += nr_panel) {
+      const int nr = std::min(nr_panel, N - n0);
+      for (int64_t r0 = g0; r0 < full_end; r0 += tile) {
 #if defined(__x86_64__)
-    if (r1 - r0 == 8 && kHasAvx512) {
-      const float* x[8]; float* y[8];
-      for (int r = 0; r < 8; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
-      for (int n0 = 0; n0 < N; n0 += 32) MicroKernel512(x, K, wt, N, n0, std::min(32, N - n0), bias, y, relu);
-      continue;
-    }
+        if (kHasAvx512) {
+          const float* x[8]; float* y[8];
+          for (int r = 0; r < 8; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
+          MicroKernel512(x, K, wt, N, n0, nr, bias, y, relu);
+          continue;
+        }
 #endif
-    for (; r1 - r0 >= kMR; r0 += kMR) {
+        const float* x[kMR]; float* y[kMR];
+        for (int r = 0; r < kMR; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
+        MicroKernel<kMR>(x, K, wt, N, n0, nr, bias, y, relu);
+      }
+    }
+    int64_t r0 = full_end;
+    for (; g1 - r0 >= kMR; r0 += kMR) {                                   // AVX-512 build: a 4..7-row remainder still gets one 4 x 16 pass
       const float* x[kMR]; float* y[kMR];
       for (int r = 0; r < kMR; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
       for (int n0 = 0; n0 < N; n0 += kNR) MicroKernel<kMR>(x, K, wt, N, n0, std::min(kNR, N - n0), bias, y, relu);
     }
-    for (; r0 < r1; ++r0) {          // tail rows (and batch-1 requests): stream whole weight rows -- contiguous reads, the matrix-vector case is bandwidth-bound
+    for (; r0 < g1; ++r0) {          // tail rows (and batch-1 requests): stream whole weight rows -- contiguous reads, the matrix-vector case is bandwidth-bound
       float* __restrict yy = Y + r0 * N; const float* xx = X + r0 * ldx;
       for (int n = 0; n < N; ++n) yy[n] = bias[n];
       for (int k = 0; k < K; ++k) { const float a = xx[k]; const float* __restrict w = wt + (size_t)k * N; for (int n = 0; n < N; ++n) yy[n] += a * w[n]; }
