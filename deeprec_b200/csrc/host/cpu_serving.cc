@@ -81,11 +81,14 @@ struct Config {
 
 // Op program (saved_model.json "arch": "program", written by serving/export.py::export_saved_model_program): the inference graph of a
 // Criteo-style model other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].
-enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL };
-struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; std::string name; };
+enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE };
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1; std::string model_name = "dlrm";
+  // requests carry R id rows; table t reads request row id_map[t] (identity unless several tables share a feature, e.g. the wide and
+  // the deep table of one Wide&Deep column)
+  int R = 0; std::vector<int> id_map;
 };
 static int pad8(int n) { return (n + 7) / 8 * 8; }
 
@@ -122,21 +125,31 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   *version = (int64_t)j.n("version", 0);
   *prefix = dir + "/" + j.s("variables", "variables/variables");
   a->model_name = j.s("model", "dlrm");
+  a->R = (int)j.n("num_id_rows", a->T);
+  a->id_map.resize((size_t)std::max(0, a->T));
+  for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = t;
+  if (auto* im = j.get("id_map")) {
+    if (im->t != JVal::ARR || (int)im->arr.size() != a->T) return false;
+    for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = (int)im->arr[(size_t)t].num;
+  }
+  for (int v : a->id_map) if (v < 0 || v >= a->R) return false;
+  if (a->R <= 0) return false;
   if (j.s("arch", "") == "program") {
     a->program = true;
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
-    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul"};
+    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice"};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     for (const JVal& o : pr->arr) {
       POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
+      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0);
       const std::string kind = o.s("op", "");
-      for (int k = 0; k < 9; ++k) if (kind == kNames[k]) op.kind = k;
+      for (int k = 0; k < 10; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
-      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2};
+      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1};
       if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
       op.out = (int)names.size(); names.push_back(op.name);
       a->ops.push_back(std::move(op));
@@ -174,6 +187,7 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_MUL_ADD: if (dp->width[(size_t)op.in[1]] != w0 || dp->width[(size_t)op.in[2]] != w0) return false; break;
       case P_MUL:
       case P_ADD: if (dp->width[(size_t)op.in[1]] != w0) return false; break;
+      case P_SLICE: if (op.start < 0 || op.len <= 0 || op.start + op.len > w0) return false; w = op.len; break;
       default: return false;
     }
     if (w <= 0) return false;
@@ -509,6 +523,12 @@ struct Session {
           else for (size_t k = 0; k < n; ++k) out[k] = a0[k] + b1[k];
           break;
         }
+        case P_SLICE: {
+          const int st = op.start;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) memcpy(out + (size_t)i * W, a0 + (size_t)i * w0 + st, (size_t)W * sizeof(float));
+          break;
+        }
         case P_LAYERNORM: {                                      // (x - mean) / sqrt(var + eps) * gamma + beta, biased variance, optional ReLU
           const float* g = pd.v0.data(); const float* bt = pd.v1.data(); const float eps = op.eps; const bool relu = op.relu;
 #pragma omp parallel for schedule(static) num_threads(threads) if (par)
@@ -620,7 +640,7 @@ static int RunRows(ServingModel* sm, const std::shared_ptr<Model>& m, const uint
   for (uint32_t off = 0; off < R; off += (uint32_t)s.max_batch) {                  // larger requests are chunked
     const int B = (int)std::min<uint32_t>((uint32_t)s.max_batch, R - off);
     memcpy(s.dense.data(), dense_in + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
-    for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids_in + ((size_t)t * ids_stride + off) * 8, (size_t)B * 8);
+    for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids_in + ((size_t)a.id_map[(size_t)t] * ids_stride + off) * 8, (size_t)B * 8);
     if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) {
       // feature store hiccup: one reconnect + retry before the request is failed (the next request tries again)
       bool ok = false;
@@ -670,11 +690,11 @@ static int PredictBatched(ServingModel* sm, Batcher& bt, const drpb::WireReq& h,
     else {
       const Arch& a = m->arch;
       std::vector<float> dense((size_t)R * a.num_dense), out(R);
-      std::vector<int64_t> ids((size_t)a.T * R);
+      std::vector<int64_t> ids((size_t)a.R * R);                       // request-shaped: a.R id rows
       uint32_t off = 0;
       for (Batcher::Item* q : mine) {
         memcpy(dense.data() + (size_t)off * a.num_dense, q->dense, (size_t)q->rows * a.num_dense * 4);
-        for (int t = 0; t < a.T; ++t) memcpy(ids.data() + (size_t)t * R + off, q->ids + (size_t)t * q->rows * 8, (size_t)q->rows * 8);
+        for (int t = 0; t < a.R; ++t) memcpy(ids.data() + (size_t)t * R + off, q->ids + (size_t)t * q->rows * 8, (size_t)q->rows * 8);
         off += q->rows;
       }
       rc = RunRows(sm, m, reinterpret_cast<const uint8_t*>(dense.data()), reinterpret_cast<const uint8_t*>(ids.data()), R, R, out.data(), -1);
@@ -703,7 +723,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
   drpb::WireReq h; memcpy(&h, in, sizeof(h));
   const Arch& a = m->arch;
   const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
-  if (h.magic != drpb::kWireReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.T || h.batch == 0 || (size_t)in_size < need) return 500;
+  if (h.magic != drpb::kWireReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.R || h.batch == 0 || (size_t)in_size < need) return 500;
   std::vector<float> probs(h.batch);
   const auto t0 = std::chrono::steady_clock::now();
   const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
@@ -738,7 +758,7 @@ static int PredictAny(ServingModel* sm, const void* in, int in_size, void** out,
   auto m = std::atomic_load(&sm->model);
   if (!m) return 500;
   drpb::Request rq; std::string wire, err, pb;
-  if (!drpb::ParseRequest(in, (size_t)std::max(in_size, 0), &rq) || !drpb::RequestToWire(rq, m->arch.num_dense, m->arch.T, &wire, &err)) { sm->failures++; return 500; }
+  if (!drpb::ParseRequest(in, (size_t)std::max(in_size, 0), &rq) || !drpb::RequestToWire(rq, m->arch.num_dense, m->arch.R, &wire, &err)) { sm->failures++; return 500; }
   void* w_out = nullptr; int w_size = 0;
   const int rc = Predict(sm, wire.data(), (int)wire.size(), &w_out, &w_size, hint);
   if (rc != 200) { free(w_out); return rc; }
@@ -762,12 +782,12 @@ static bool WarmUp(ServingModel* sm, const std::shared_ptr<Model>& m) {
     if (from_file) {
       drpb::WireReq h; memcpy(&h, raw.data(), sizeof(h));
       const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
-      if ((int)h.num_dense == a.num_dense && (int)h.num_sparse == a.T && h.batch > 0 && raw.size() >= need) {
+      if ((int)h.num_dense == a.num_dense && (int)h.num_sparse == a.R && h.batch > 0 && raw.size() >= need) {
         B = (int)std::min<uint32_t>(h.batch, (uint32_t)s.max_batch);
         const uint8_t* p = reinterpret_cast<const uint8_t*>(raw.data()) + sizeof(h);
         memcpy(s.dense.data(), p, (size_t)B * a.num_dense * 4);
         const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
-        for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids + (size_t)t * h.batch, (size_t)B * 8);
+        for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids + (size_t)a.id_map[(size_t)t] * h.batch, (size_t)B * 8);
         filled = true;
       }
     }
@@ -927,7 +947,7 @@ int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* outp
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
      << ", \"mlp_dtype\": \"fp32\", \"device\": \"cpu\", \"model\": \"" << (m ? m->arch.model_name : "") << "\", \"feature_store_type\": \"" << (sm->cfg.remote ? "redis" : "local") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
-     << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.T : 0);
+     << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.R : 0) << ", \"num_tables\": " << (m ? m->arch.T : 0);
   os << ", \"batching\": {\"max_batch_size\": " << sm->cfg.batching_max_rows << ", \"batch_timeout_micros\": " << sm->cfg.batching_timeout_us
      << ", \"merged_batches\": " << (sm->batcher ? sm->batcher->merged_batches.load() : 0) << ", \"merged_requests\": " << (sm->batcher ? sm->batcher->merged_requests.load() : 0) << "}";
   os << ", \"cpusets\": \"";

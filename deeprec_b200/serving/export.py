@@ -239,6 +239,9 @@ class _ProgramBuilder:
     def add(self, a, b):
         out = self._name("add"); self.ops.append({"op": "add", "out": out, "in": [a, b]}); return out
 
+    def slice(self, src, start, length):
+        out = self._name("slice"); self.ops.append({"op": "slice", "out": out, "in": [src], "start": int(start), "len": int(length)}); return out
+
     def mul(self, a, b):
         out = self._name("mul"); self.ops.append({"op": "mul", "out": out, "in": [a, b]}); return out
 
@@ -290,6 +293,15 @@ def _build_program(model) -> _ProgramBuilder:
         lin = p.linear("dense", model.linear.weight, model.linear.bias)
         h = p.sequential(p.concat([lin, p.fm("emb"), dnn]), model.final)
         p.out = p.linear(h, model.out.weight, model.out.bias)
+    elif isinstance(model, zoo.WDL):
+        # tables 0..T-1 = deep (dim D), T..2T-1 = wide (dim 4, stored zero-padded to D); both read the same request id row
+        T, D = model.num_sparse, model.emb_dim
+        deep = p.linear(p.sequential(p.concat(["dense", p.slice("emb", 0, T * D)]), model.deep), model.out.weight, model.out.bias)
+        sel = torch.zeros(1, T * D); sel[0, ::D] = 1.0                     # sum over tables of component 0 of the wide embedding
+        wide = p.add(p.linear(p.slice("emb", T * D, T * D), sel, None), p.linear("dense", model.wide_dense.weight, model.wide_dense.bias))
+        p.out = p.add(wide, deep)
+        p.tables = [(ev, ev.embedding_dim) for ev in _evs_of(model.emb)] + [(ev, ev.embedding_dim) for ev in _evs_of(model.wide)]
+        p.id_map = list(range(T)) + list(range(T))
     elif isinstance(model, zoo.MaskNet):                                 # serial MaskBlocks: h = ReLU(LN(W (h * mask(v))))
         h = p.layernorm("emb", model.ln_emb)
         for m, b in zip(model.masks, model.blocks):
@@ -308,37 +320,53 @@ def _build_program(model) -> _ProgramBuilder:
             x = p.cross(x0, x, w, b)
         p.out = p.linear(p.concat([x, p.sequential(x0, model.deep)]), model.out.weight, model.out.bias)
     else:
-        raise TypeError(f"op-program export: no builder for {type(model).__name__} (DeepFM, DCN, DCNv2, MaskNet; DLRM has export_saved_model_module)")
+        raise TypeError(f"op-program export: no builder for {type(model).__name__} (WDL, DeepFM, DCN, DCNv2, MaskNet; DLRM has export_saved_model_module)")
     return p
 
 
-def _program_evs(model):
+def _evs_of(module):
     from ..optim.optimizers import collect_embedding_variables
-    return collect_embedding_variables(model.emb)
+    return collect_embedding_variables(module)
+
+
+def _program_tables(model, p):
+    """[(EmbeddingVariable, its dim)] in table order, the common row width D (narrower tables are stored zero-padded), id_map or None."""
+    tables = getattr(p, "tables", None) or [(ev, ev.embedding_dim) for ev in _evs_of(model.emb)]
+    return tables, max(d for _, d in tables), getattr(p, "id_map", None)
+
+
+def _padded(rows: torch.Tensor, d: int, D: int) -> torch.Tensor:
+    rows = rows[:, :d].float().cpu()
+    if d == D:
+        return rows.contiguous()
+    out = torch.zeros(rows.shape[0], D); out[:, :d] = rows
+    return out
 
 
 def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None) -> str:
-    """Full export of a Criteo-style zoo model (``DeepFM``, ``DCN``, ``DCNv2``, ``MaskNet``) as an op program + EmbeddingVariable tables; loaded by
+    """Full export of a Criteo-style zoo model (``WDL``, ``DeepFM``, ``DCN``, ``DCNv2``, ``MaskNet``) as an op program + EmbeddingVariable tables; loaded by
     ``Processor(dir, cfg, device="cpu")`` exactly like a DLRM export (same ModelConfig, update protocol, request formats)."""
     was_training = model.training
     model.eval()
     p = _build_program(model)
-    evs = _program_evs(model)
-    D = evs[0].embedding_dim
+    tables, D, id_map = _program_tables(model, p)
     os.makedirs(os.path.join(export_dir, "variables"), exist_ok=True)
     w = BundleWriter(os.path.join(export_dir, "variables", "variables"))
     for name, t in p.tensors.items():
         w.add(name, t)
-    for t, ev in enumerate(evs):
+    for t, (ev, d) in enumerate(tables):
         s = ev.table.snapshot()
-        w.add(f"table/{t}-keys", s["keys"].cpu()); w.add(f"table/{t}-values", s["rows"][:, :D].contiguous().cpu())
+        w.add(f"table/{t}-keys", s["keys"].cpu()); w.add(f"table/{t}-values", _padded(s["rows"], d, D))
         w.add(f"table/{t}-freqs", s["freqs"].cpu()); w.add(f"table/{t}-versions", s["versions"].cpu())
-        w.add(f"table/{t}-default", ev.default_matrix.detach().float().cpu().contiguous())
+        w.add(f"table/{t}-default", _padded(ev.default_matrix.detach(), d, D))
         ev.table.clear_dirty()
     w.close()
-    meta = {"model": type(model).__name__.lower(), "arch": "program", "version": int(version), "num_dense": model.num_dense, "num_tables": len(evs),
-            "embedding_dim": D, "program": p.ops, "output": p.out, "variables": "variables/variables",
-            "signature": {"inputs": {"dense": ["B", model.num_dense], "ids": [len(evs), "B"]}, "outputs": {"probabilities": ["B"]}}}
+    rows = len(tables) if id_map is None else max(id_map) + 1
+    meta = {"model": type(model).__name__.lower(), "arch": "program", "version": int(version), "num_dense": model.num_dense, "num_tables": len(tables),
+            "num_id_rows": rows, "embedding_dim": D, "program": p.ops, "output": p.out, "variables": "variables/variables",
+            "signature": {"inputs": {"dense": ["B", model.num_dense], "ids": [rows, "B"]}, "outputs": {"probabilities": ["B"]}}}
+    if id_map is not None:
+        meta["id_map"] = id_map
     with open(os.path.join(export_dir, "saved_model.json"), "w") as f:
         json.dump(meta, f)
     _write_versions(root or export_dir, full={"version": int(version), "dir": os.path.abspath(export_dir)})
@@ -357,9 +385,10 @@ def export_delta_program(model, root: str, base_version: int, version: int) -> s
     w = BundleWriter(prefix)
     for name, t in p.tensors.items():
         w.add(name, t)
-    for t, ev in enumerate(_program_evs(model)):
+    tables, D, _ = _program_tables(model, p)
+    for t, (ev, dd) in enumerate(tables):
         s = ev.table.snapshot(dirty_only=True)
-        w.add(f"table/{t}-sparse_incr_keys", s["keys"].cpu()); w.add(f"table/{t}-sparse_incr_values", s["rows"][:, : ev.embedding_dim].contiguous().cpu())
+        w.add(f"table/{t}-sparse_incr_keys", s["keys"].cpu()); w.add(f"table/{t}-sparse_incr_values", _padded(s["rows"], dd, D))
         ev.table.clear_dirty()
     w.close()
     _write_versions(root, delta={"version": int(version), "base": int(base_version), "prefix": os.path.abspath(prefix)})

@@ -358,7 +358,7 @@ def test_request_batching_merges_concurrent_requests(tmp_path):
         proc.close()
 
 
-@pytest.mark.parametrize("name", ["deepfm", "dcn", "dcnv2", "masknet"])
+@pytest.mark.parametrize("name", ["wdl", "deepfm", "dcn", "dcnv2", "masknet"])
 def test_op_program_models_on_the_cpu_processor(tmp_path, name):
     """DeepFM / DCN exported as an op program (BatchNorm folded at export): the native CPU Processor reproduces the module's predictions,
     takes a delta update (rows + re-folded dense tensors) and serves protobuf requests; a program with a wrong shape is rejected."""
@@ -391,6 +391,24 @@ def test_op_program_models_on_the_cpu_processor(tmp_path, name):
         assert np.abs(ref2 - ref).max() > 1e-4 and np.abs(proc.predict(d.numpy(), ids.numpy()) - ref2).max() < 2e-5
     finally:
         proc.close()
+    # request batching merges request-shaped id blocks (WDL: 26 id rows feed 52 tables)
+    import threading
+    bp = Processor(os.path.join(root, "v1"), {"session_num": 1, "model_update_interval_ms": 0, "enable_batching": True, "max_batch_size": 16,
+                                              "batch_timeout_micros": 5000}, device="cpu")
+    try:
+        base = bp.predict(d.numpy(), ids.numpy())
+        bad = []
+
+        def cl(t):
+            for i in range(6):
+                r0 = (t * 6 + i) * 3
+                if np.abs(bp.predict(d.numpy()[r0:r0 + 2], ids.numpy()[:, r0:r0 + 2]) - base[r0:r0 + 2]).max() > 1e-5:
+                    bad.append((t, i))
+        th = [threading.Thread(target=cl, args=(t,)) for t in range(4)]
+        [x.start() for x in th]; [x.join() for x in th]
+        assert not bad, bad
+    finally:
+        bp.close()
     # a corrupted program (output buffer that does not exist) must fail initialisation, not crash
     meta["output"] = "nope"
     json.dump(meta, open(os.path.join(root, "v1", "saved_model.json"), "w"))
