@@ -92,7 +92,19 @@ struct Arch {
 };
 static int pad8(int n) { return (n + 7) / 8 * 8; }
 
-struct Layer { int N = 0, K = 0; std::vector<float> wt /*[K][N]*/, bias; };
+// wt: [K][N] row-major (the batch-1 / tail path streams whole rows); wp: the same weights packed panel-major for the tiled kernels --
+// panel p = columns [32p, 32p + 32) stored as K x 32 contiguous floats (zero-padded past N), so a tile's k-loop reads consecutive
+// cache lines instead of one line every N floats (the unpacked layout defeated the hardware prefetchers: 2 KB strides, a page every 2 steps)
+constexpr int kPanel = 32;
+struct Layer {
+  int N = 0, K = 0; std::vector<float> wt, bias, wp;
+  void Pack() {
+    const int np = (N + kPanel - 1) / kPanel;
+    wp.assign((size_t)np * K * kPanel, 0.f);
+    for (int p = 0; p < np; ++p) for (int k = 0; k < K; ++k) for (int j = 0; j < kPanel && p * kPanel + j < N; ++j)
+      wp[((size_t)p * K + k) * kPanel + j] = wt[(size_t)k * N + p * kPanel + j];
+  }
+};
 struct PData { Layer L; std::vector<float> v0, v1; };                     // weights of one program op (linear | affine scale, shift | cross w, b)
 struct Dense {
   std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f;
@@ -178,6 +190,7 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
         if (!ReadVec(r, base + "kernel", &W) || !ReadVec(r, base + "bias", &b) || b.empty() || W.size() != b.size() * (size_t)w0) return false;
         d.L.N = (int)b.size(); d.L.K = w0; d.L.bias = b; d.L.wt.resize(W.size());
         for (int n = 0; n < d.L.N; ++n) for (int k = 0; k < w0; ++k) d.L.wt[(size_t)k * d.L.N + n] = W[(size_t)n * w0 + k];
+        d.L.Pack();
         w = d.L.N; break;
       }
       case P_LAYERNORM:
@@ -221,6 +234,7 @@ static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense
       }
       L.bias[n] = (float)acc;
     }
+    L.Pack();
     dp->bot.push_back(std::move(L));
     s_prev.assign(N, 0.f); t_prev.assign(N, 0.f);
     for (int n = 0; n < N; ++n) { const float rs = 1.0f / std::sqrt(var[n] + a.bn_eps); s_prev[n] = gamma[n] * rs; t_prev[n] = beta[n] - mean[n] * s_prev[n]; }
@@ -235,6 +249,7 @@ static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense
     if (!ReadVec(r, "dense/" + nm + "/kernel", &W) || !ReadVec(r, "dense/" + nm + "/bias", &b) || (int)W.size() != N * Kp || (int)b.size() != N) return false;
     Layer L; L.N = N; L.K = k; L.wt.resize((size_t)k * N); L.bias = b;
     for (int n = 0; n < N; ++n) for (int kk = 0; kk < k; ++kk) L.wt[(size_t)kk * N + n] = W[(size_t)n * Kp + kk];
+    L.Pack();
     dp->top.push_back(std::move(L));
     k = N;
   }
@@ -294,40 +309,33 @@ static std::shared_ptr<Model> LoadModel(const std::string& dir, bool remote = fa
 constexpr int kMR = 4, kNR = 16;
 
 template <int MR>
-static inline void MicroKernel(const float* const* x, int K, const float* __restrict wt, int N, int n0, int nr, const float* __restrict bias,
-                               float* const* y, bool relu) {
+static inline void MicroKernel(const float* const* x, int K, const float* __restrict wp /*packed panel + column offset, row stride kPanel*/, int n0, int nr,
+                               const float* __restrict bias, float* const* y, bool relu) {
   float acc[MR][kNR];
   for (int r = 0; r < MR; ++r) for (int j = 0; j < kNR; ++j) acc[r][j] = j < nr ? bias[n0 + j] : 0.f;
-  if (nr == kNR) {
-    for (int k = 0; k < K; ++k) {
-      const float* __restrict w = wt + (size_t)k * N + n0;
-      for (int r = 0; r < MR; ++r) { const float a = x[r][k]; for (int j = 0; j < kNR; ++j) acc[r][j] += a * w[j]; }
-    }
-  } else {
-    for (int k = 0; k < K; ++k) {
-      const float* __restrict w = wt + (size_t)k * N + n0;
-      for (int r = 0; r < MR; ++r) { const float a = x[r][k]; for (int j = 0; j < nr; ++j) acc[r][j] += a * w[j]; }
-    }
+  for (int k = 0; k < K; ++k) {                                  // columns past N are zero in the packed panel: always the full-width loop
+    const float* __restrict w = wp + (size_t)k * kPanel;
+    for (int r = 0; r < MR; ++r) { const float a = x[r][k]; for (int j = 0; j < kNR; ++j) acc[r][j] += a * w[j]; }
   }
   for (int r = 0; r < MR; ++r) for (int j = 0; j < nr; ++j) y[r][n0 + j] = relu && acc[r][j] < 0.f ? 0.f : acc[r][j];
 }
 
 #if defined(__x86_64__)
 // AVX-512 tile: 8 rows x 32 outputs = 16 zmm accumulators, per k-step 2 weight loads + 8 broadcasts for 16 FMAs (the 4 x 16 AVX2 tile
-// does 2 loads + 4 broadcasts for 8).  Column tails use lane masks (masked-off lanes are neither read nor written).  Compiled for
-// avx512f regardless of the build flags and selected at run time.
+// does 2 loads + 4 broadcasts for 8).  Weights come from the packed panel (zero-padded: no load masks), column tails are masked on
+// the store.  Compiled for avx512f regardless of the build flags and selected at run time.
 __attribute__((target("avx512f")))
-static void MicroKernel512(const float* const* x, int K, const float* __restrict wt, int N, int n0, int nr, const float* __restrict bias,
-                           float* const* y, bool relu) {
+static void MicroKernel512(const float* const* x, int K, const float* __restrict wp /*packed panel: K x 32 contiguous*/, int n0, int nr,
+                           const float* __restrict bias, float* const* y, bool relu) {
   constexpr int R = 8;
   const __mmask16 m0 = nr >= 16 ? (__mmask16)0xFFFF : (__mmask16)((1u << nr) - 1);
   const __mmask16 m1 = nr >= 32 ? (__mmask16)0xFFFF : (nr > 16 ? (__mmask16)((1u << (nr - 16)) - 1) : (__mmask16)0);
   const __m512 bias0 = _mm512_maskz_loadu_ps(m0, bias + n0), bias1 = _mm512_maskz_loadu_ps(m1, bias + n0 + 16);
   __m512 a0[R], a1[R];
   for (int r = 0; r < R; ++r) { a0[r] = bias0; a1[r] = bias1; }
-  const float* w = wt + n0;
-  for (int k = 0; k < K; ++k, w += N) {
-    const __m512 w0 = _mm512_maskz_loadu_ps(m0, w), w1 = _mm512_maskz_loadu_ps(m1, w + 16);
+  const float* w = wp;
+  for (int k = 0; k < K; ++k, w += kPanel) {
+    const __m512 w0 = _mm512_loadu_ps(w), w1 = _mm512_loadu_ps(w + 16);
     for (int r = 0; r < R; ++r) {
       const __m512 v = _mm512_set1_ps(x[r][k]);
       a0[r] = _mm512_fmadd_ps(v, w0, a0[r]);
@@ -373,20 +381,20 @@ static void Linear(const float* X, int64_t ldx, int64_t B, const Layer& L, float
         if (kHasAvx512) {
           const float* x[8]; float* y[8];
           for (int r = 0; r < 8; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
-          MicroKernel512(x, K, wt, N, n0, nr, bias, y, relu);
+          MicroKernel512(x, K, L.wp.data() + (size_t)(n0 / kPanel) * K * kPanel, n0, nr, bias, y, relu);
           continue;
         }
 #endif
         const float* x[kMR]; float* y[kMR];
         for (int r = 0; r < kMR; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
-        MicroKernel<kMR>(x, K, wt, N, n0, nr, bias, y, relu);
+        MicroKernel<kMR>(x, K, L.wp.data() + (size_t)(n0 / kPanel) * K * kPanel + (n0 % kPanel), n0, nr, bias, y, relu);
       }
     }
     int64_t r0 = full_end;
     for (; g1 - r0 >= kMR; r0 += kMR) {                                   // AVX-512 build: a 4..7-row remainder still gets one 4 x 16 pass
       const float* x[kMR]; float* y[kMR];
       for (int r = 0; r < kMR; ++r) { x[r] = X + (r0 + r) * ldx; y[r] = Y + (r0 + r) * N; }
-      for (int n0 = 0; n0 < N; n0 += kNR) MicroKernel<kMR>(x, K, wt, N, n0, std::min(kNR, N - n0), bias, y, relu);
+      for (int n0 = 0; n0 < N; n0 += kNR) MicroKernel<kMR>(x, K, L.wp.data() + (size_t)(n0 / kPanel) * K * kPanel + (n0 % kPanel), n0, std::min(kNR, N - n0), bias, y, relu);
     }
     for (; r0 < g1; ++r0) {          // tail rows (and batch-1 requests): stream whole weight rows -- contiguous reads, the matrix-vector case is bandwidth-bound
       float* __restrict yy = Y + r0 * N; const float* xx = X + r0 * ldx;
