@@ -158,3 +158,47 @@ def test_work_queue_shared_between_processes(tmp_path):
     assert len(a) + len(b) == 80 and len(b) > 0 and len(a) > len(b)                    # every item of both epochs exactly once; straggler took fewer
     from collections import Counter
     assert set(Counter(a + b).values()) == {2} and len(set(a + b)) == 40
+
+
+def test_kafka_dataset_with_an_in_memory_broker():
+    """KafkaDataset (docs/docs_en/KafkaDataset.md): subscriptions "topic:partition:offset:length" are drained in order, eof stops at the
+    end of a partition, message keys on request, and the saved position resumes exactly after the last delivered message."""
+    from deeprec_b200.data import KafkaDataset
+
+    class Broker:
+        def __init__(self):
+            self.logs = {("clicks", 0): [(b"k%d" % i, b"c0-%d" % i) for i in range(25)], ("clicks", 1): [(None, b"c1-%d" % i) for i in range(7)]}
+            self.polls = 0
+
+        def __call__(self, servers, group, config):
+            self.servers, self.group, self.config = servers, group, config
+            return self
+
+        def poll(self, topic, partition, offset, max_records, timeout_ms):
+            self.polls += 1
+            log = self.logs[(topic, partition)]
+            return [(o, log[o][0], log[o][1]) for o in range(offset, min(len(log), offset + max_records))]
+
+    broker = Broker()
+    ds = KafkaDataset(["clicks:0:5:12", "clicks:1"], servers="b1:9092", group="g", eof=True, timeout=10, config_global=["enable.auto.commit=false"],
+                      config_topic=["auto.offset.reset=earliest"], consumer_factory=broker, max_poll_records=4)
+    assert broker.servers == ["b1:9092"] and broker.group == "g" and broker.config == {"enable.auto.commit": "false", "auto.offset.reset": "earliest"}
+    got = list(ds)
+    assert got == [b"c0-%d" % i for i in range(5, 17)] + [b"c1-%d" % i for i in range(7)]            # 12 from partition 0 at offset 5, then all of 1
+    assert ds.positions() == [("clicks", 0, 17), ("clicks", 1, 7)]
+    # batches + keys + resume from a saved position
+    ds2 = KafkaDataset(["clicks:0:0:-1"], eof=True, message_key=True, consumer_factory=Broker(), max_poll_records=10)
+    it = ds2.batch(8, parse_fn=lambda ms: [v.decode() for _, v in ms])
+    first = next(it)
+    assert first == [f"c0-{i}" for i in range(8)]
+    state = ds2.state_dict()
+    ds3 = KafkaDataset(["clicks:0:0:-1"], eof=True, message_key=True, consumer_factory=Broker())
+    ds3.load_state_dict(state)
+    rest = [m for b in ds3.batch(8) for m in b]
+    assert [k for k, _ in rest] == [b"k%d" % i for i in range(8, 25)] and len(rest) == 17
+    # without a client library and without a factory the error says what to do
+    try:
+        import kafka  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="consumer_factory"):
+            KafkaDataset(["t"])
