@@ -1243,7 +1243,6 @@ void DotBwdRange(const float* __restrict dense, const float* __restrict embs, co
   const int F = T + 1, P = F * (F - 1) / 2;
   alignas(64) float S[kMaxF * kMaxF];
   alignas(64) float feat[kMaxF * D];
-  alignas(64) float acc[D];
   for (int64_t b = b0; b < b1; ++b) {
     const float* d = dense + b * D; const float* e = embs + b * (int64_t)T * D;
     const float* g = dz + b * (int64_t)(D + P); const float* gz = g + D;
@@ -1251,15 +1250,24 @@ void DotBwdRange(const float* __restrict dense, const float* __restrict embs, co
     for (int j = 1; j < F; ++j) for (int k = 0; k < D; ++k) feat[j * D + k] = e[(int64_t)(j - 1) * D + k];
     for (int i = 0; i < F; ++i) S[i * F + i] = 0.f;
     for (int i = 1; i < F; ++i) for (int j = 0; j < i; ++j) { const float w = *gz++; S[i * F + j] = w; S[j * F + i] = w; }
-    for (int i = 0; i < F; ++i) {
-      for (int k = 0; k < D; ++k) acc[k] = i == 0 ? g[k] : 0.f;           // feature 0 also receives the pass-through gradient
-      const float* si = S + i * F;
+    // four output rows at a time: one load of feat[j] feeds four independent accumulator rows (a single row is a chain of F dependent FMAs)
+    constexpr int IB = 4;
+    for (int i0 = 0; i0 < F; i0 += IB) {
+      const int ib = std::min(IB, F - i0);
+      float accb[IB][D];
+      for (int r = 0; r < IB; ++r) for (int k = 0; k < D; ++k) accb[r][k] = (i0 + r == 0) ? g[k] : 0.f;   // feature 0 also receives the pass-through gradient
+      const float* s0 = S + (size_t)i0 * F;
+      const float* s1 = S + (size_t)std::min(i0 + 1, F - 1) * F; const float* s2 = S + (size_t)std::min(i0 + 2, F - 1) * F; const float* s3 = S + (size_t)std::min(i0 + 3, F - 1) * F;
       for (int j = 0; j < F; ++j) {
-        const float w = si[j]; const float* fj = feat + j * D;
-        for (int k = 0; k < D; ++k) acc[k] += w * fj[k];
+        const float* fj = feat + j * D;
+        const float w0 = s0[j], w1 = s1[j], w2 = s2[j], w3 = s3[j];
+        for (int k = 0; k < D; ++k) { const float f = fj[k]; accb[0][k] += w0 * f; accb[1][k] += w1 * f; accb[2][k] += w2 * f; accb[3][k] += w3 * f; }
       }
-      float* dst = i == 0 ? ddense + b * D : dembs + b * (int64_t)T * D + (int64_t)(i - 1) * D;
-      for (int k = 0; k < D; ++k) dst[k] = acc[k];
+      for (int r = 0; r < ib; ++r) {
+        const int i = i0 + r;
+        float* dst = i == 0 ? ddense + b * D : dembs + b * (int64_t)T * D + (int64_t)(i - 1) * D;
+        for (int k = 0; k < D; ++k) dst[k] = accb[r][k];
+      }
     }
   }
 }
