@@ -1211,7 +1211,7 @@ template <int D>
 void DotFwdRange(const float* __restrict dense, const float* __restrict embs, int64_t b0, int64_t b1, int T, float* __restrict out) {
   const int F = T + 1, P = F * (F - 1) / 2, Fp = (F + 7) & ~7;
   alignas(64) float ft[D * kMaxF];
-  alignas(64) float acc[kMaxF];
+  alignas(64) float acc[4 * kMaxF];
   for (int64_t b = b0; b < b1; ++b) {
     const float* d = dense + b * D; const float* e = embs + b * (int64_t)T * D;
     float* o = out + b * (int64_t)(D + P);
@@ -1223,15 +1223,18 @@ void DotFwdRange(const float* __restrict dense, const float* __restrict embs, in
     }
     for (int k = 0; k < D; ++k) o[k] = d[k];
     float* z = o + D;
-    for (int i = 1; i < F; ++i) {
-      const float* fi = e + (int64_t)(i - 1) * D;
-      const int n = (i + 7) & ~7;                      // only columns j < i are needed
-      for (int j = 0; j < n; ++j) acc[j] = 0.f;
+    // four gram rows per pass: one load of ft[k] feeds four independent accumulator rows (one row alone is a chain of D dependent FMAs)
+    for (int i0 = 1; i0 < F; i0 += 4) {
+      const int ib = std::min(4, F - i0);
+      const int n = std::min(Fp, (i0 + ib - 1 + 7) & ~7);            // row i needs columns j < i; the block needs j < i0 + ib - 1
+      const float* f0 = e + (int64_t)(i0 - 1) * D;
+      const float* f1 = e + (int64_t)(std::min(i0 + 1, F - 1) - 1) * D; const float* f2 = e + (int64_t)(std::min(i0 + 2, F - 1) - 1) * D; const float* f3 = e + (int64_t)(std::min(i0 + 3, F - 1) - 1) * D;
+      for (int r = 0; r < 4; ++r) for (int j = 0; j < n; ++j) acc[r * kMaxF + j] = 0.f;
       for (int k = 0; k < D; ++k) {
-        const float a = fi[k]; const float* r = ft + k * Fp;
-        for (int j = 0; j < n; ++j) acc[j] += a * r[j];
+        const float a0 = f0[k], a1 = f1[k], a2 = f2[k], a3 = f3[k]; const float* r = ft + k * Fp;
+        for (int j = 0; j < n; ++j) { const float v = r[j]; acc[j] += a0 * v; acc[kMaxF + j] += a1 * v; acc[2 * kMaxF + j] += a2 * v; acc[3 * kMaxF + j] += a3 * v; }
       }
-      for (int j = 0; j < i; ++j) *z++ = acc[j];
+      for (int r = 0; r < ib; ++r) for (int j = 0; j < i0 + r; ++j) *z++ = acc[r * kMaxF + j];
     }
   }
 }
