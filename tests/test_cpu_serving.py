@@ -328,7 +328,7 @@ def test_request_batching_merges_concurrent_requests(tmp_path):
     # one session: whoever arrives while it is busy queues up behind a leader and shares the next forward pass (adaptive mode runs a
     # lone request immediately when a session is idle)
     proc = Processor(str(tmp_path / "m"), {"session_num": 1, "model_update_interval_ms": 0, "enable_batching": True,
-                                           "batching_parameters": {"max_batch_size": 16, "batch_timeout_micros": 20000}}, device="cpu")
+                                           "batching_parameters": {"max_batch_size": 16, "batch_timeout_micros": 2000}}, device="cpu")
     try:
         dn, idn = d.numpy(), ids.numpy()
         errs, N, T = [], 24, 8
