@@ -33,6 +33,8 @@ for fast in 0 1; do
   DEEPREC_FAST_ONEHOT=$fast python benchmarks/zoo_bench.py --model deepfm 2>>"$OUT/log.txt" | tail -1 > "$OUT/zoo_deepfm_fast${fast}.json"
 done
 python benchmarks/zoo_bench.py --model din 2>>"$OUT/log.txt" | tail -1 > "$OUT/zoo_din.json"
+# serving with more callers than sessions: RR now takes the first idle session (compare with profiles/serving_bench_n1.jsonl)
+python benchmarks/serving_bench.py --sessions 4 --threads 16 --batch 256 --requests 8000 --dtype bf16 2>>"$OUT/log.txt" | tail -1 > "$OUT/serving_n1_s4_t16_b256.json"
 # ---- 4. ncu of the two new kernels (one capture each)
 DEEPREC_GEMM_BRES=1 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tn_v2 -c 1 -s 40 -o "$OUT/prof_gemm_bres" -f python bench.py --steps 2 --warmup 1 >>"$OUT/log.txt" 2>&1
 DEEPREC_RUN_UNVALIDATED=1 ncu --set full --clock-control none --import-source on -k regex:k_din_attention_fwd -c 1 -o "$OUT/prof_din_attention" -f python -m pytest tests/test_gpu_zz_attention.py -q -m gpu -k "257" >>"$OUT/log.txt" 2>&1
