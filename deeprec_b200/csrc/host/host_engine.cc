@@ -324,6 +324,21 @@ class HostKV {
     }
   }
   template <typename F> void ForEach(F&& f) { for (int p = 0; p < nparts_; ++p) ForEachInPart(p, f); }
+  template <typename F> void ForEachInPartNoLock(int p, F&& f) {          // caller holds ExclusiveAll
+    KVPart& P = parts_[p];
+    for (int64_t i = 0; i < P.cap; ++i) {
+      int64_t k = P.slots[i].key.load(std::memory_order_acquire);
+      if (k != kEmptyKey) f(k, P.slots[i].val.load(std::memory_order_acquire));
+    }
+  }
+  class ExclusiveAll {                                                     // stops inserts, growth and batch readers on every partition
+   public:
+    explicit ExclusiveAll(HostKV& kv) : kv_(kv) { for (int p = 0; p < kv_.nparts_; ++p) kv_.parts_[p].mu.lock(); }
+    ~ExclusiveAll() { for (int p = kv_.nparts_ - 1; p >= 0; --p) kv_.parts_[p].mu.unlock(); }
+    ExclusiveAll(const ExclusiveAll&) = delete;
+   private:
+    HostKV& kv_;
+  };
   // Remove every key for which pred(key, idx) is true (partition rebuilt under exclusive lock; nothing is rebuilt when nothing goes).
   template <typename Pred> int64_t RemoveIfInPart(int p, Pred&& pred) {
     int64_t removed = 0;
@@ -757,34 +772,51 @@ class HostEV {
       if (dirty_only && !*(&meta_.at(idx)->dirty)) return 0;
       return *(&meta_.at(idx)->row) >= 0 ? 1 : 2;
     };
-    std::vector<int64_t> cnt_a((size_t)np * 1000, 0), cnt_f((size_t)np * 1000, 0);
-    GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
-      for (int64_t p = pb; p < pe; ++p)
-        kv_.ForEachInPart((int)p, [&](int64_t key, int32_t idx) {
-          int b; const int c = classify(key, idx, &b);
-          if (c == 1) cnt_a[(size_t)p * 1000 + b]++; else if (c == 2) cnt_f[(size_t)p * 1000 + b]++;
-        });
-    });
-    auto offsets = [&](std::vector<int64_t>& cnt, std::vector<int64_t>& off, std::vector<SnapItem>& dst) {
-      off.assign(1001, 0);
-      int64_t run = 0;
-      for (int b = 0; b < 1000; ++b) {
-        off[b] = run;
-        for (int p = 0; p < np; ++p) { const int64_t c = cnt[(size_t)p * 1000 + b]; cnt[(size_t)p * 1000 + b] = run; run += c; }
-      }
-      off[1000] = run;
-      dst.resize((size_t)run);
-    };
-    offsets(cnt_a, snap_adm_off_, snap_adm_);
-    offsets(cnt_f, snap_flt_off_, snap_flt_);
-    GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {               // nothing may change between the two scans (Save holds that)
-      for (int64_t p = pb; p < pe; ++p)
-        kv_.ForEachInPart((int)p, [&](int64_t key, int32_t idx) {
-          int b; const int c = classify(key, idx, &b);
-          if (c == 1) snap_adm_[(size_t)cnt_a[(size_t)p * 1000 + b]++] = {b, idx, key};
-          else if (c == 2) snap_flt_[(size_t)cnt_f[(size_t)p * 1000 + b]++] = {b, idx, key};
-        });
-    });
+    // Save runs between steps, so the two scans normally see the same table.  If someone does modify it in between (a parameter server
+    // checkpointing while pushes arrive), the placement pass notices (a range overflows or is left short; overflowing items are dropped,
+    // never written out of range) and the snapshot is retried -- the last attempt under exclusive partition locks.
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      const bool exclusive = attempt == 2;
+      std::unique_ptr<HostKV::ExclusiveAll> guard;
+      if (exclusive) guard.reset(new HostKV::ExclusiveAll(kv_));
+      auto scan = [&](int p, auto&& f) { if (exclusive) kv_.ForEachInPartNoLock(p, f); else kv_.ForEachInPart(p, f); };
+      std::vector<int64_t> cnt_a((size_t)np * 1000, 0), cnt_f((size_t)np * 1000, 0);
+      GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
+        for (int64_t p = pb; p < pe; ++p)
+          scan((int)p, [&](int64_t key, int32_t idx) {
+            int b; const int c = classify(key, idx, &b);
+            if (c == 1) cnt_a[(size_t)p * 1000 + b]++; else if (c == 2) cnt_f[(size_t)p * 1000 + b]++;
+          });
+      });
+      std::vector<int64_t> end_a, end_f;
+      auto offsets = [&](std::vector<int64_t>& cnt, std::vector<int64_t>& end, std::vector<int64_t>& off, std::vector<SnapItem>& dst) {
+        off.assign(1001, 0); end.assign(cnt.size(), 0);
+        int64_t run = 0;
+        for (int b = 0; b < 1000; ++b) {
+          off[b] = run;
+          for (int p = 0; p < np; ++p) { const int64_t c = cnt[(size_t)p * 1000 + b]; cnt[(size_t)p * 1000 + b] = run; run += c; end[(size_t)p * 1000 + b] = run; }
+        }
+        off[1000] = run;
+        dst.resize((size_t)run);
+      };
+      offsets(cnt_a, end_a, snap_adm_off_, snap_adm_);
+      offsets(cnt_f, end_f, snap_flt_off_, snap_flt_);
+      std::atomic<int64_t> dropped{0};
+      GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
+        for (int64_t p = pb; p < pe; ++p)
+          scan((int)p, [&](int64_t key, int32_t idx) {
+            int b; const int c = classify(key, idx, &b);
+            if (c == 0) return;
+            std::vector<int64_t>& cur = c == 1 ? cnt_a : cnt_f; const std::vector<int64_t>& end = c == 1 ? end_a : end_f;
+            const size_t slot = (size_t)p * 1000 + b;
+            if (cur[slot] >= end[slot]) { dropped.fetch_add(1, std::memory_order_relaxed); return; }
+            (c == 1 ? snap_adm_ : snap_flt_)[(size_t)cur[slot]++] = {b, idx, key};
+          });
+      });
+      bool consistent = dropped.load() == 0;
+      for (size_t i = 0; consistent && i < end_a.size(); ++i) consistent = cnt_a[i] == end_a[i] && cnt_f[i] == end_f[i];
+      if (consistent) break;
+    }
     auto sort_buckets = [&](std::vector<SnapItem>& dst, const std::vector<int64_t>& off) {
       GlobalPool()->ParallelFor(1000, 8, [&](int64_t bb, int64_t be) {
         for (int64_t b = bb; b < be; ++b)

@@ -182,7 +182,8 @@ class ParameterServer:
 
     def save(self, prefix: str, step: int) -> str:
         from ..checkpoint.saver import Saver
-        return Saver(embedding_variables=list(self.evs.values())).save(f"{prefix}.ps{self.index}", step)
+        with self.lock:                  # pushes are applied under the same lock: the checkpoint is a consistent cut between two of them
+            return Saver(embedding_variables=list(self.evs.values())).save(f"{prefix}.ps{self.index}", step)
 
 
 def _srv() -> ParameterServer:
