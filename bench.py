@@ -1,16 +1,26 @@
 #!/usr/bin/env python
 """Headline benchmark: DLRM training samples/sec on N B200 GPUs of one node (BASELINE.json).
 
-  python bench.py --gpus 1 --steps 50 --warmup 5
+  python bench.py --gpus 1 --steps 20 --warmup 5
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
-         bench.py --gpus 8 --steps 50 --warmup 5
+         bench.py --gpus 8 --steps 20 --warmup 5
 
 Model/config: modelzoo DLRM (bottom 512-256-64-16 +BN, 26 EmbeddingVariable tables dim 16, dot interaction,
 top 512-256, logits) on synthetic Criteo-Terabyte-shaped data, bf16 MLP compute / fp32 master weights and
 embeddings, Adagrad for dense + sparse, weak scaling (fixed per-GPU batch), 26 tables model-parallel.
 
-Arms:  --impl ours (default) | nccl_baseline (in-repo NCCL + cuBLAS re-creation of the reference dataflow)
-       | reference (the unmodified DeepRec tree: cannot be installed offline -> prints "unavailable").
+Data stream (--stream):
+  fresh (default)  every prefill / warm-up / timed step consumes a batch NEVER SEEN BEFORE, so key inserts, admission
+                   bookkeeping, row allocation and default-row initialisation all run inside the timed region
+                   (reported as new_keys_per_step).  The batches are pre-generated into pinned host memory: the C++
+                   generator needs ~0.13 s per 65536x26 batch, 100x the GPU step, so it cannot run inside the loop.
+  warm             round-1 behaviour (8 rotating batches, tables fully populated before timing) -- labelled secondary.
+
+Arms:  --impl ours (default)  fused unique-first P2P pipeline, one CUDA graph per step
+       | nccl_comm            the SAME engine and dense kernels with the reference (SOK) dataflow over NCCL collectives
+                              (parallel/nccl_baseline.NcclComm: all-to-all ids / vectors / gradients, all-reduce), eager launches
+       | nccl_baseline        NCCL + cuBLAS (torch.nn autocast) + autograd re-creation of the reference step
+       | reference            the unmodified DeepRec tree: cannot be installed offline -> prints "unavailable".
 """
 from __future__ import annotations
 
@@ -33,19 +43,21 @@ BASELINE_SAMPLES_PER_SEC = None   # BASELINE.json "published": {} -- the referen
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=65536, help="per-GPU batch (weak scaling)")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl_baseline"])
-    ap.add_argument("--prefill", type=int, default=8, help="untimed steps that populate the tables before warm-up")
-    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic batches rotated through (pool > L2)")
-    ap.add_argument("--alpha", type=float, default=1.05, help="power-law exponent of the synthetic id distribution")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl_comm", "nccl_baseline"])
+    ap.add_argument("--stream", default="fresh", choices=["fresh", "warm"])
+    ap.add_argument("--prefill", type=int, default=8, help="untimed training steps before warm-up (history of the tables)")
+    ap.add_argument("--pool", type=int, default=0, help="distinct batches of the timed region (0 = one per step; warm stream: 8)")
+    ap.add_argument("--alpha", type=float, default=1.05, help="power-law exponent of the synthetic id distribution (0 = uniform)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--optimizer", default="adagrad")
+    ap.add_argument("--filter-freq", type=int, default=0, help="CounterFilter admission threshold (0 = admit at first sight)")
     ap.add_argument("--sparse-blocks", type=int, default=4, help="resident blocks/SM of the side-stream sparse kernels")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--gemm-v1", action="store_true")
-    ap.add_argument("--row-threshold", type=int, default=None, help="tables with >= this many ids are sharded row-wise over all ranks (default: engine default)")
+    ap.add_argument("--skip-e2e", action="store_true")
     return ap.parse_args()
 
 
@@ -78,20 +90,20 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def reference_arm(args):
@@ -111,14 +123,20 @@ def reference_arm(args):
     return 0
 
 
-def make_host_pool(cfg, pool: int, seed: int, alpha: float, rank: int):
-    """Synthetic Criteo-Terabyte-shaped batches in PINNED host memory (C++ generator, csrc/host/io_runtime.cc)."""
+def make_host_batches(cfg, n: int, seed: int, alpha: float, rank: int):
+    """n distinct synthetic Criteo-Terabyte-shaped batches in PINNED host memory (C++ generator, csrc/host/io_runtime.cc)."""
     from deeprec_b200.data.synthetic import criteo_batch
     out = []
-    for i in range(pool):
-        d, ids, y = criteo_batch(cfg.batch_size, cfg.num_dense, cfg.cardinalities, seed=seed + 1000 * rank + i, alpha=alpha)
+    for i in range(n):
+        d, ids, y = criteo_batch(cfg.batch_size, cfg.num_dense, cfg.cardinalities, seed=seed + 100003 * rank + i, alpha=alpha)
         out.append((d.pin_memory(), ids.pin_memory(), y.pin_memory()))
     return out
+
+
+def unique_ratio(ids: torch.Tensor) -> float:
+    """distinct (table, id) pairs / ids of one batch (host-side, diagnostics only)."""
+    u = sum(int(torch.unique(ids[t]).numel()) for t in range(ids.shape[0]))
+    return u / float(ids.numel())
 
 
 def main():
@@ -128,11 +146,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        if args.gpus == 1 and world == 1:
-            pass
-        else:
-            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if world != args.gpus and not (args.gpus == 1 and world == 1):
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -142,42 +157,62 @@ def main():
 
     from deeprec_b200.models.dlrm_engine import DLRMConfig, DLRMEngine
     cfg = DLRMConfig(batch_size=args.batch, optimizer=args.optimizer, sparse_blocks_per_sm=args.sparse_blocks,
-                     overlap_embedding=not args.no_overlap, gemm_v1=args.gemm_v1)
-    if args.row_threshold is not None:
-        cfg.row_shard_threshold = args.row_threshold
+                     overlap_embedding=not args.no_overlap, gemm_v1=args.gemm_v1, filter_freq=args.filter_freq)
     comm = None
-    if world > 1:
-        if args.impl == "nccl_baseline":
-            from deeprec_b200.parallel.nccl_baseline import NcclComm
-            comm = NcclComm(rank, world, dev)
-        else:
+    graph = not args.no_graph
+    if args.impl in ("nccl_comm", "nccl_baseline"):
+        from deeprec_b200.parallel.nccl_baseline import BaselineDLRM, NcclComm
+        comm = NcclComm(rank, world, dev)
+        graph = False                       # NCCL collectives are launched eagerly between our kernels
+        eng = BaselineDLRM(cfg, dev, rank, world, comm) if args.impl == "nccl_baseline" else DLRMEngine(cfg, dev, rank, world, comm)
+    else:
+        if world > 1:
             from deeprec_b200.parallel.p2p import P2PComm
             comm = P2PComm(rank, world, dev)
-    if args.impl == "nccl_baseline":
-        from deeprec_b200.parallel.nccl_baseline import BaselineDLRM
-        eng = BaselineDLRM(cfg, dev, rank, world, comm)
-    else:
         eng = DLRMEngine(cfg, dev, rank, world, comm)
-
-    pool = make_host_pool(cfg, args.pool, 99, args.alpha, rank)
-    dev_pool = [(d.to(dev), i.to(dev), y.to(dev)) for d, i, y in pool]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def total_keys() -> int:
+        tables = eng.eng.tables if hasattr(eng, "eng") else eng.tables
+        t = torch.tensor([float(sum(tb.size() for tb in tables.values()))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return int(t.item())
+
+    # ---- data: every phase draws from ONE sequence of distinct batches (fresh) or from 8 rotating ones (warm) ---------
+    fresh = args.stream == "fresh"
+    n_timed = args.steps if (fresh and args.pool <= 0) else (min(args.steps, args.pool) if fresh else (args.pool or 8))
+    n_e2e = 0 if args.skip_e2e else n_timed
+    if fresh:
+        host = make_host_batches(cfg, args.prefill + args.warmup + n_timed + n_e2e, 99, args.alpha, rank)
+        pre, warm = host[: args.prefill], host[args.prefill: args.prefill + args.warmup]
+        timed = host[args.prefill + args.warmup: args.prefill + args.warmup + n_timed]
+        e2e_src = host[args.prefill + args.warmup + n_timed:]
+    else:
+        host = make_host_batches(cfg, n_timed, 99, args.alpha, rank)
+        pre = [host[s % len(host)] for s in range(args.prefill)]
+        warm = [host[s % len(host)] for s in range(args.warmup)]
+        timed, e2e_src = host, host
+    uniq = unique_ratio(timed[0][1])
+    dev_timed = [(d.to(dev), i.to(dev), y.to(dev)) for d, i, y in timed]       # device-timed region: inputs resident, > L2 in total
+    in_bytes = sum(t.numel() * t.element_size() for t in timed[0])
+
     # ---- prefill + graph capture + warm-up (all untimed) -------------------------------------------------
-    eng.load_batch(*dev_pool[0])
-    if not args.no_graph and hasattr(eng, "capture"):
-        eng.capture()
-    for s in range(args.prefill):
-        eng.load_batch(*dev_pool[s % len(dev_pool)]); eng.train_step()
-    for s in range(args.warmup):
-        eng.load_batch(*dev_pool[s % len(dev_pool)]); eng.train_step()
+    first = pre[0] if pre else warm[0] if warm else timed[0]
+    eng.load_batch(*[t.to(dev) for t in first])
+    if graph and hasattr(eng, "capture"):
+        eng.capture()                      # one eager step on `first`, then the whole step becomes one CUDA graph
+        pre = pre[1:] if pre else pre
+    for b in pre + warm:
+        eng.load_batch(*[t.to(dev, non_blocking=True) for t in b]); eng.train_step()
     barrier()
 
-    # ---- device-timed region: K steps, inputs already resident (rotating pool > L2) ------------------------
+    # ---- device-timed region: K steps, CUDA events on the launching stream, max over ranks ------------------
+    keys0 = total_keys()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = eng.launches
@@ -185,58 +220,48 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
-        eng.load_batch(*dev_pool[s % len(dev_pool)])
+        eng.load_batch(*dev_timed[s % len(dev_timed)])
         eng.train_step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launches - l0
     clocks = sampler.stop()
+    keys1 = total_keys()
+    final_loss = eng.loss_value()           # mean over the GLOBAL batch of the last timed step (all-reduced)
 
-    # ---- end-to-end region: per step H2D of the inputs from pinned memory + D2H of the loss ----------------
-    copy_stream = torch.cuda.Stream(device=dev)
-    loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
-    stage = [tuple(torch.empty_like(t, device=dev) for t in pool[0]) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    main_stream = torch.cuda.current_stream(dev)
-
-    def h2d(slot, batch):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            for dst, src in zip(stage[slot], batch):
-                dst.copy_(src, non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    for c in consumed:
-        c.record(main_stream)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    h2d(0, pool[0])
-    for s in range(args.steps):
-        slot = s & 1
-        if s + 1 < args.steps:
-            h2d(slot ^ 1, pool[(s + 1) % len(pool)])          # SmartStage-style: next batch streams in under this step
-        main_stream.wait_event(ready[slot])
-        eng.load_batch(*stage[slot])
-        consumed[slot].record(main_stream)
-        eng.train_step()
-        loss_host[s].copy_(eng.loss[0], non_blocking=True)     # D2H of the step result
-    f1.record()
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    h2d_bytes = sum(t.numel() * t.element_size() for t in pool[0])
+    # ---- end-to-end region through the public API: smart_stage (producer thread -> packed pinned H2D on a copy stream, two
+    #      batches ahead) -> load_batch -> train_step -> D2H of the loss, every step ------------------------------
+    e2e_ms = None
+    if not args.skip_e2e:
+        from deeprec_b200.data.staged import SmartStageOptions, smart_stage
+        seq = [e2e_src[s % len(e2e_src)] for s in range(args.steps)]
+        stage = smart_stage(iter(seq), dev, SmartStageOptions(capacity=2, num_threads=1))
+        loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for s in range(args.steps):
+            d, ids, y = next(stage)                                # H2D of THIS step's inputs (17 MB from pinned memory)
+            eng.load_batch(d, ids, y)
+            eng.train_step()
+            loss_host[s].copy_(eng.loss[0], non_blocking=True)     # D2H of the step result
+        f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1)
+        stage.close()
 
     # max over ranks (device-timed)
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_max = float(t[0]), float(t[1])
     gb = cfg.batch_size * world
     value = gb * args.steps / (ms / 1e3)
-    e2e_value = gb * args.steps / (e2e_ms / 1e3)
     if rank == 0:
+        sharding = {"ours": f"mp{world}(emb: every table row-sharded hash(key)%{world}, requester-side dedup)+dp{world}(dense)",
+                    "nccl_comm": f"mp{world}(emb: table t on rank t%{world}, SOK all-to-all dataflow over NCCL)+dp{world}(dense, ncclAllReduce)",
+                    "nccl_baseline": f"mp{world}(emb: table t on rank t%{world}, NCCL)+dp{world}(dense, cuBLAS + autograd + NCCL)"}[args.impl]
         out = {
             "metric": "DLRM samples/sec (whole box, device-timed, max over ranks)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -245,19 +270,22 @@ def main():
             "dtype": "bf16", "data": "synthetic (Criteo-Terabyte-shaped power-law ids, random-init weights)",
             "impl": args.impl,
             "config": {"model": "DLRM modelzoo (bot 512-256-64-16+BN, 26 EV tables dim16, dot, top 512-256)",
-                       "global_batch": gb, "seq_len": 1, "parallelism": f"mp{world}(emb,table-wise)+dp{world}(dense)",
+                       "global_batch": gb, "seq_len": 1, "parallelism": sharding,
                        "optimizer": args.optimizer, "per_gpu_batch": cfg.batch_size,
-                       "l2": f"{len(pool)} rotating batches ({len(pool) * h2d_bytes / 1e6:.0f} MB) + multi-GB embedding tables > 126 MB L2; no flush",
-                       "cuda_graph": not args.no_graph, "final_loss": float(loss_host[-1])},
+                       "stream": ("fresh: every prefill/warm-up/timed step is a never-seen batch (inserts + row init inside the timed region)"
+                                  if fresh else "warm: 8 rotating batches, tables populated before timing (no inserts in the timed region)"),
+                       "prefill_steps": args.prefill, "distinct_timed_batches": len(dev_timed),
+                       "new_keys_per_step": (keys1 - keys0) / float(args.steps), "unique_ratio": uniq, "alpha": args.alpha,
+                       "filter_freq": args.filter_freq,
+                       "l2": f"{len(dev_timed)} distinct resident batches ({len(dev_timed) * in_bytes / 1e6:.0f} MB) + multi-GB embedding tables > 126 MB L2; no flush",
+                       "cuda_graph": bool(graph and hasattr(eng, "capture")), "final_loss": final_loss},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
         }
+        if e2e_ms is not None:
+            out["e2e"] = {"value": gb * args.steps / (e2e_max / 1e3), "unit": "samples/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
+                          "ms_per_step": e2e_max / args.steps, "api": "data.staged.smart_stage -> DLRMEngine.load_batch -> train_step"}
         print(json.dumps(out))
-    if comm is not None and getattr(comm, "_timing", False):
-        rep = comm.timing_report()
-        print(f"[rank {rank}] p2p phase ms: " + ", ".join(f"{k}={v:.3f}" for k, v in rep.items()), file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -27,6 +27,7 @@ CUDA_SOURCES = [
     "cuda/gemm_tcgen05.cu",
     "cuda/interaction_kernels.cu",
     "cuda/comm_kernels.cu",
+    "cuda/sparse_pipeline.cu",
     "cuda/runtime.cu",
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",

@@ -86,10 +86,45 @@ class StagingBuffer:
             pass
 
 
-class PackedHostBatch:
-    """All tensors of a batch packed back-to-back (256 B aligned) in ONE pinned host block."""
+class _PinnedPool:
+    """Recycled pinned host blocks: ``cudaHostAlloc`` costs milliseconds, a training step costs one -- a block is pinned once
+    and handed back by the consumer when the H2D copy that read it has completed (event query, no host sync)."""
 
-    def __init__(self, tensors: List[torch.Tensor], pin: bool = True):
+    def __init__(self):
+        self._free: Dict[int, List[torch.Tensor]] = {}
+        self._pending: List[Tuple[Any, torch.Tensor]] = []
+        self._lock = threading.Lock()
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        cap = 1 << max(12, (max(1, nbytes) - 1).bit_length())
+        with self._lock:
+            self._reap()
+            lst = self._free.get(cap)
+            if lst:
+                return lst.pop()
+        return torch.empty(cap, dtype=torch.uint8).pin_memory()
+
+    def give_back(self, block: torch.Tensor, event) -> None:
+        with self._lock:
+            self._pending.append((event, block))
+            self._reap()
+
+    def _reap(self) -> None:
+        keep = []
+        for ev, blk in self._pending:
+            if ev is None or ev.query():
+                self._free.setdefault(blk.numel(), []).append(blk)
+            else:
+                keep.append((ev, blk))
+        self._pending = keep
+
+
+class PackedHostBatch:
+    """All tensors of a batch packed back-to-back (256 B aligned) in ONE pinned host block (TensorPackTransH2D,
+    gpu_stage_pack_trans_pass.cc).  Tensors that are ALREADY pinned are not repacked: they are copied straight from where
+    they are (zero host copies), into the same packed device layout."""
+
+    def __init__(self, tensors: List[torch.Tensor], pin: bool = True, pool: Optional[_PinnedPool] = None):
         self.meta = []
         off = 0
         for t in tensors:
@@ -97,24 +132,56 @@ class PackedHostBatch:
             self.meta.append((off, nb, t.dtype, tuple(t.shape)))
             off += (nb + 255) // 256 * 256
         self.nbytes = off
-        self.block = torch.empty(max(off, 1), dtype=torch.uint8)
-        if pin and torch.cuda.is_available():
-            self.block = self.block.pin_memory()
+        self.pool = pool
+        self.sources: Optional[List[torch.Tensor]] = None
+        cuda = pin and torch.cuda.is_available()
+        if cuda and all(t.is_pinned() and t.is_contiguous() for t in tensors):
+            self.sources, self.block = list(tensors), None
+            return
+        if cuda and pool is not None:
+            self.block = pool.take(max(off, 1))
+        else:
+            self.block = torch.empty(max(off, 1), dtype=torch.uint8)
+            if cuda:
+                self.block = self.block.pin_memory()
         for (o, nb, _, _), t in zip(self.meta, tensors):
             if nb:
                 self.block[o:o + nb].copy_(t.contiguous().view(-1).view(torch.uint8))
 
-    def to_device(self, device, stream=None) -> List[torch.Tensor]:
-        """ONE H2D copy; returns device views."""
-        if stream is not None:
-            with torch.cuda.stream(stream):
-                d = self.block.to(device, non_blocking=True)
+    def copy_into(self, dev_block: torch.Tensor) -> List[torch.Tensor]:
+        """Async H2D into a caller-owned device block (current stream); returns device views."""
+        if self.sources is not None:
+            for (o, nb, _, _), t in zip(self.meta, self.sources):
+                if nb:
+                    dev_block[o:o + nb].copy_(t.view(-1).view(torch.uint8), non_blocking=True)
         else:
-            d = self.block.to(device, non_blocking=True)
-        return [d[o:o + nb].view(dt).view(shape) for (o, nb, dt, shape) in self.meta]
+            dev_block[: self.nbytes].copy_(self.block[: self.nbytes], non_blocking=True)      # ONE H2D copy
+        return [dev_block[o:o + nb].view(dt).view(shape) for (o, nb, dt, shape) in self.meta]
+
+    def to_device(self, device, stream=None) -> List[torch.Tensor]:
+        """H2D into a fresh device block; returns device views."""
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        with ctx:
+            d = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=device)
+            return self.copy_into(d)
+
+    def release(self, event=None) -> None:
+        if self.pool is not None and self.block is not None:
+            self.pool.give_back(self.block, event)
+            self.block = None
 
     def unpack_host(self) -> List[torch.Tensor]:
+        if self.sources is not None:
+            return list(self.sources)
         return [self.block[o:o + nb].view(dt).view(shape) for (o, nb, dt, shape) in self.meta]
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def _flatten(b: Batch) -> Tuple[List[torch.Tensor], Callable[[List[torch.Tensor]], Batch]]:
@@ -190,10 +257,17 @@ class Staged:
                 with lock:
                     return next(it)
         self._produce_raw = produce_raw
-        self.runner = PrefetchRunner(self.buffer, self._produce, num_threads, name).start()
+        self._pool = _PinnedPool() if self.pin else None
         self.copy_stream = torch.cuda.Stream(device=self.device) if self.pin else None
-        self._ahead: List[Tuple[Any, Any, Any]] = []
+        self._ahead: List[Tuple[Any, Any, Any, int]] = []
         self._depth = max(1, capacity)
+        # device-side ring of packed blocks: slot reuse is ordered by events, never by the caching allocator
+        self._nslots = self._depth + 2
+        self._ring: List[Optional[torch.Tensor]] = [None] * self._nslots
+        self._ring_free: List[Any] = [None] * self._nslots
+        self._next_slot = 0
+        self._last_slot = -1
+        self.runner = PrefetchRunner(self.buffer, self._produce, num_threads, name).start()
 
     def _produce(self):
         b = self._produce_raw()
@@ -201,7 +275,7 @@ class Staged:
             b = self.preprocess(b)             # CPU side of the cut (stage_subgraph_on_cpu)
         ts, rebuild = _flatten(b)
         if self.pin:
-            return PackedHostBatch(ts, True), rebuild
+            return PackedHostBatch(ts, True, self._pool), rebuild
         return ts, rebuild
 
     def _issue(self) -> bool:
@@ -212,13 +286,22 @@ class Staged:
                 raise self.runner.error
             return False
         if self.pin:
-            dts = item.to_device(self.device, self.copy_stream)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-            self._ahead.append((rebuild(dts), ev, item))
+            slot = self._next_slot
+            self._next_slot = (slot + 1) % self._nslots
+            blk = self._ring[slot]
+            if blk is None or blk.numel() < item.nbytes:
+                blk = self._ring[slot] = torch.empty(max(item.nbytes, 1), dtype=torch.uint8, device=self.device)
+            with torch.cuda.stream(self.copy_stream):
+                if self._ring_free[slot] is not None:
+                    self.copy_stream.wait_event(self._ring_free[slot])     # the consumer finished with this slot's previous batch
+                dts = item.copy_into(blk)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            item.release(ev)
+            self._ahead.append((rebuild(dts), ev, item, slot))
         else:
             ts = item if self.device is None else [t.to(self.device) for t in item]
-            self._ahead.append((rebuild(ts), None, item))
+            self._ahead.append((rebuild(ts), None, item, -1))
         return True
 
     def __iter__(self) -> Iterator[Batch]:
@@ -229,9 +312,15 @@ class Staged:
             pass
         if not self._ahead:
             raise StopIteration
-        batch, ev, _keep = self._ahead.pop(0)
+        batch, ev, _keep, slot = self._ahead.pop(0)
         if ev is not None:
-            torch.cuda.current_stream(self.device).wait_event(ev)
+            cur = torch.cuda.current_stream(self.device)
+            if self._last_slot >= 0:         # asking for the next batch == done with the previous one (on the consumer's stream)
+                done = torch.cuda.Event()
+                done.record(cur)
+                self._ring_free[self._last_slot] = done
+            self._last_slot = slot
+            cur.wait_event(ev)
         return batch
 
     get = __next__

@@ -11,10 +11,15 @@ Execution design (B200-first; nothing here is a translation of the TF graph):
   * every GEMM is the hand-written tcgen05/TMEM/TMA kernel (csrc/cuda/gemm_tcgen05.cu) with bias,
     ReLU and ReLU-backward masks fused in the epilogue; weight gradients are split-K tcgen05 GEMMs
     reading both operands MN-major straight from the activations (no transposes);
-  * embeddings are model-parallel (table-wise) and the dense net data-parallel; with world_size > 1
-    the id dispatch + probe + gather, the sparse-gradient return + dedup + Adagrad and the dense
-    all-reduce + optimizer are P2P kernels over NVLink peer memory (parallel/p2p.py), with an
-    NCCL implementation of the same dataflow kept as the measured baseline;
+  * embeddings are model-parallel (every table row-sharded by hash(key) % world) and the dense net
+    data-parallel.  The sparse path is "unique-first" (parallel/sparse_pipeline.py): the requester
+    dedups its ids in an L2-resident scratch hash, owners probe only distinct keys and push bf16
+    rows straight into the requester's unique-row buffer over NVLink, the interaction kernels gather
+    through the inverse index, the backward pre-reduces gradients per distinct key in fp32 and the
+    owners pull one row per key; ranks synchronise with in-kernel release/acquire flags, never with
+    a barrier kernel or an NCCL call.  The same kernels run at world_size 1.  An NCCL
+    implementation of the reference (SOK) dataflow is kept as the measured baseline
+    (parallel/nccl_baseline.py, table-wise sharding, no requester-side dedup);
   * hyper-parameters / global step live in device memory and are advanced by a device kernel, so
     the captured graph needs no per-step host work besides the input H2D copy.
 """
@@ -63,8 +68,6 @@ class DLRMConfig:
     steps_to_live: int = 0
     seed: int = 1234
     overlap_embedding: bool = True              # fork the embedding branch onto a side stream inside the graph
-    row_shard_threshold: int = 1_000_000        # world > 1: tables with >= this many ids are sharded row-wise (hash(key) % W) over ALL ranks
-    balance_tablewise: bool = True              # world > 1: also row-shard the largest remaining tables until #table-wise % world == 0
     sparse_blocks_per_sm: int = 4               # resident-block budget of the side-stream sparse kernels (overlap with the GEMMs)
     gemm_v1: bool = False                       # A/B switch: direct-store GEMM epilogue + separate statistics passes
 
@@ -183,30 +186,19 @@ class DLRMEngine:
         return self.grads[o:o + n]
 
     # ------------------------------------------------------------------------------------------------
-    # embedding tables (model parallel, table-wise: table t lives on rank t % world)
+    # embedding tables.  unique-first mode: every rank owns the hash(key) % world shard of EVERY table;
+    # legacy mode (NCCL baseline arm): table t lives on rank t % world (SOK "localized" placement).
     # ------------------------------------------------------------------------------------------------
     def _build_tables(self) -> None:
         cfg = self.cfg
         W = self.world
-        # hybrid sharding: huge tables row-wise over all ranks (balances the DRAM-bound probe/update work that scales with the
-        # number of distinct keys), small tables table-wise round-robin (their rows stay L2-resident on one owner).
-        rs = getattr(self.comm, "supports_row_sharding", False) and W > 1
-        self.row_tables = [t for t in range(self.T) if rs and cfg.cardinalities[t] >= cfg.row_shard_threshold]
-        small = [t for t in range(self.T) if t not in self.row_tables]
-        if rs and cfg.balance_tablewise and len(small) % W:
-            # every table-wise table costs its owner W*B probes per step: an uneven count (e.g. 20 tables on 8 ranks = 3/3/3/3/2/2/2/2)
-            # makes the 3-table ranks the step's critical path at every barrier.  Row-shard the largest leftovers instead.
-            extra = sorted(small, key=lambda t: -int(cfg.cardinalities[t]))[: len(small) % W]
-            self.row_tables = sorted(self.row_tables + extra)
-            small = [t for t in small if t not in extra]
-        self.owner_of = [-1] * self.T
-        for i, t in enumerate(small):
-            self.owner_of[t] = i % W
-        tw = sorted(t for t in small if self.owner_of[t] == self.rank)
-        self.n_tablewise = len(tw)
-        self.local_tables = tw + sorted(self.row_tables)          # table-wise tables first, then the row-sharded ones (comm_kernels.cu)
-        self.row_flag = None
-        self.row_tg = torch.tensor(sorted(self.row_tables) or [0], dtype=torch.int32, device=self.dev)
+        self.uf = self.comm is None or getattr(self.comm, "unique_first", False)
+        if self.uf:
+            self.owner_of = [-1] * self.T
+            self.local_tables = list(range(self.T))
+        else:
+            self.owner_of = [t % W for t in range(self.T)]
+            self.local_tables = [t for t in range(self.T) if self.owner_of[t] == self.rank]
         self.ctx = get_context(self.dev, self.D, owner=id(self) & 0x7FFFFFFF)
         self.tables: Dict[int, DeviceTable] = {}
         g = torch.Generator().manual_seed(cfg.seed + 17)
@@ -214,8 +206,8 @@ class DLRMEngine:
         slot_init = [cfg.initial_accumulator_value if self.kind in (OPT_ADAGRAD, OPT_ADAGRAD_DECAY, OPT_FTRL) else 0.0, 0.0, 0.0, 0.0]
         for t in self.local_tables:
             card = int(cfg.cardinalities[t])
-            if t in self.row_tables:
-                card = card // W + 1                      # this rank's shard
+            if self.uf and W > 1:
+                card = card // W + card // (8 * W) + 1024        # this rank's shard (+ hash imbalance slack)
             c = EvConfig()
             c.dim, c.num_slots, c.has_scalars = self.D, ns, int(self.kind == OPT_ADAGRAD_DECAY)
             c.init_capacity = card
@@ -230,7 +222,6 @@ class DLRMEngine:
             g.manual_seed(cfg.seed + 17 + 1000 * t)      # initial values depend on (table, key) only -- never on the sharding
             dm = torch.empty(4096, self.D).normal_(0.0, 1.0 / math.sqrt(self.D), generator=g)
             rows = min(card, cfg.max_rows_per_table)
-            # a step can touch at most B*world new keys of this table
             rows = max(rows, 1024)
             cap = _next_pow2(max(2048, 2 * min(card, max(rows, 1))))
             self.tables[t] = DeviceTable(c, dm, self.dev, capacity=cap, row_capacity=rows, owner=id(self) & 0x7FFFFFFF)
@@ -247,13 +238,17 @@ class DLRMEngine:
         self.labels = z(B, dt=f32)
         nl = len(self.local_tables)
         W = self.world
-        if self.comm is None:
-            self.ids = torch.zeros(T, B, dtype=torch.int64, device=dev)          # feature-major
-            self.emb = z(T, B, D)                                               # feature-major receive buffer
-            self.demb = z(T, B, D)
+        if self.uf:
+            from ..parallel.sparse_pipeline import SparsePipeline
+            self.ids = torch.zeros(T, B, dtype=torch.int64, device=dev)          # feature-major id columns (local: never leave the GPU)
+            self.sp = SparsePipeline(dev, self.rank, W, list(range(T)), T, B, D, comm=self.comm)
+            self.emb = self.demb = self.pos = None
+            self.max_unique = max(1, T * B * min(W, 2))          # distinct keys a step can bring to this rank (overflow is flagged, not UB)
         else:
+            self.sp = None
             self.ids, self.emb, self.demb = self.comm.alloc_exchange(T, B, D)
-        self.pos = torch.zeros(max(1, nl * W * B), dtype=torch.int32, device=dev)   # probe results for owned (table, src, sample)
+            self.pos = torch.zeros(max(1, nl * W * B), dtype=torch.int32, device=dev)   # probe results for owned (table, src, sample)
+            self.max_unique = max(1, nl * W * B)
         self.x0 = z(B, _pad8(self.cfg.num_dense))
         for L in self.bot:
             L.a = z(B, L.N); L.y = z(B, L.N); L.dy = z(B, L.N); L.da = z(B, L.N)
@@ -263,7 +258,6 @@ class DLRMEngine:
         self.prob = z(B, dt=f32)
         self.loss = z(1, dt=f32)
         self.dx = z(B, D)
-        self.max_unique = max(1, nl * W * B)
         self.ctx.ensure(self.max_unique)
         self.ctx.claimed_upper = 0
         self._l2_scratch = None
@@ -311,31 +305,24 @@ class DLRMEngine:
     # the step
     # ------------------------------------------------------------------------------------------------
     def _embedding_forward(self, train: bool) -> None:
-        """Owner side of the model-parallel lookup: probe + (train: admit/claim) + gather into the requesters' buffers."""
-        lib, B, D = self.lib, self.B, self.D
-        if self.comm is not None:
+        """Requester: dedup + bucket the local ids.  Owner: probe (+admit/claim) the distinct keys of every source and push rows."""
+        if not self.uf:
             self.comm.lookup_forward(self, train)
             return
-        nl = len(self.local_tables)
-        n = nl * B
-        st = self.ctx.structs()
-        self._call(lib.dr_cuda_table_lookup, ptr(st), ptr(self.tmap_local), nl, ptr(self.ids), None, B, n, int(train), self.step_ptr,
-                   ptr(self.pos), ptr(self.ctx.ulist) if train else None, ptr(self.ctx.nuniq) if train else None,
-                   self.ctx.ulist.numel() if train else 0)
-        self._call(lib.dr_cuda_table_gather, ptr(st), ptr(self.tmap_local), nl, D, ptr(self.ids), ptr(self.pos), None, B, n, ptr(self.emb), 1, 0, 0, 1)
+        self.sp.dedup(self.ids)
+        self.sp.lookup(self.ctx, self.tmap_local, train)
+        self.launches += 2
 
     def _embedding_backward(self) -> None:
-        lib, B, D = self.lib, self.B, self.D
-        if self.comm is not None:
+        """Owner: pull the sources' pre-reduced gradient rows, then the row-wise optimizer over this step's distinct keys."""
+        if not self.uf:
             self.comm.sparse_backward(self)
             return
-        nl = len(self.local_tables)
-        n = nl * B
-        st = self.ctx.structs()
-        self._call(lib.dr_cuda_sparse_accumulate, ptr(st), ptr(self.tmap_local), nl, D, ptr(self.pos), None, B, n, ptr(self.demb), 1, 0, 0, 1,
-                   None, None, ptr(self.ctx.gsum))
-        self._call(lib.dr_cuda_sparse_apply, ptr(st), ptr(self.ctx.ulist), ptr(self.ctx.nuniq), self.ctx.ulist.numel(), ptr(self.ctx.gsum), D,
-                   ptr(self.hp_dev), self.max_unique, 1, n=2)
+        self.sp.reset()                  # every owner has read my bucket lists / counts (ROWS flags seen by the interaction kernel)
+        self.sp.grad(self.ctx, self.tmap_local)
+        self._call(self.lib.dr_cuda_sparse_apply, ptr(self.ctx.structs()), ptr(self.ctx.ulist), ptr(self.ctx.nuniq), self.ctx.ulist.numel(),
+                   ptr(self.ctx.gsum), self.D, ptr(self.hp_dev), self.max_unique, 1, n=2)
+        self.launches += 2
 
     def _bn_fold(self, L, Ln, train: bool) -> None:
         """finalize BatchNorm(L) from the fused epilogue statistics and fold it into the next Linear (Ln)."""
@@ -376,11 +363,15 @@ class DLRMEngine:
             main.wait_stream(self._side)
         else:
             self._embedding_forward(train)
-        if train:
-            # after the step's first rank barrier: every peer has finished reading last step's gradients
-            self.grads.zero_()
         # ---- interaction + top MLP
-        self._call(lib.dr_cuda_dot_interaction_fwd, ptr(x), ldx, ptr(self.emb), B * self.D, self.D, self.T, self.D, B, ptr(self.Z), self.Zp)
+        if self.uf:   # gathers urow[inv[b][t]]; the kernel itself waits for every owner's ROWS flag
+            self._call(lib.dr_cuda_dot_interaction_fwd_u, ptr(x), ldx, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv, self.T, self.D, B, ptr(self.Z),
+                       self.Zp, self.sp.sync_ref())
+        else:
+            self._call(lib.dr_cuda_dot_interaction_fwd, ptr(x), ldx, ptr(self.emb), B * self.D, self.D, self.T, self.D, B, ptr(self.Z), self.Zp)
+        if train:
+            # every owner's ROWS flag of this step has been seen => every peer finished last step's all-reduce reads of this buffer
+            self.grads.zero_()
         x, ldx = self.Z, self.Zp
         for L in self.top:
             self._gemm(x, ldx, L.w_bf16, L.Kp, B, L.N, L.Kp, self.p(L.name + "/bias"), True, None, 0, L.a, L.N)
@@ -411,8 +402,13 @@ class DLRMEngine:
                 self._gemm(L.da, L.N, L.wt_bf16, L.Np, B, self.Zp, L.N, None, False, None, 0, self.dZ, self.Zp)
         # ---- interaction backward -> dy of the last bottom layer, demb (feature-major, peer-readable)
         last = self.bot[-1]
-        self._call(lib.dr_cuda_dot_interaction_bwd, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.emb), B * self.D, self.D, self.T, self.D, B,
-                   ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
+        if self.uf:   # per-sample gradient rows are pre-reduced per distinct key into ugrad (fp32); last block raises the GRAD flags
+            self._call(lib.dr_cuda_dot_interaction_bwd_u, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv,
+                       C.c_void_p(self.sp.scr_buf.local), self.sp.hot_thresh, self.T, self.D, B, ptr(last.dy), last.N, ptr(self.sp.ugrad),
+                       self.sp.sync_ref(), 0)
+        else:
+            self._call(lib.dr_cuda_dot_interaction_bwd, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.emb), B * self.D, self.D, self.T, self.D, B,
+                       ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
         main = torch.cuda.current_stream(self.dev)
         fork = cfg.overlap_embedding
         if fork:
@@ -456,6 +452,9 @@ class DLRMEngine:
                        ptr(self.s1) if self.s1 is not None else None, self.P, ptr(self.hp_dev), 1.0, 0, None)
         self._pack_weights()
         self._call(lib.dr_cuda_advance_hyper, ptr(self.hp_dev))
+        if self.uf:
+            self.sp.step_end()
+            self.launches += 1
 
     def _step_body(self) -> None:
         self.loss.zero_()
@@ -503,10 +502,21 @@ class DLRMEngine:
         self.loss.zero_()
         self._forward(False)
         self._head(False)
+        if self.uf:
+            self.sp.reset()
+            if self.world > 1:       # rendezvous before any rank overwrites its bucket lists again
+                self.sp.signal(3)
+                self.comm.wait_dense(self.sp)
+            self.sp.step_end()
         return self.prob
 
-    def loss_value(self) -> float:
-        return float(self.loss.item())
+    def loss_value(self, global_mean: bool = True) -> float:
+        """Loss of the last step: the mean over the GLOBAL batch (each rank holds its partial sum / (B * world))."""
+        v = self.loss.clone()
+        if global_mean and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(v)
+        return float(v.item())
 
     def global_step(self) -> int:
         raw = bytes(self.hp_dev.cpu().numpy().tobytes())

@@ -28,6 +28,14 @@ def _chk(rc, what):
 
 
 class NcclComm:
+    unique_first = False         # reference (SOK) dataflow: table-wise placement, every id / vector / gradient row crosses the wire
+
+    def _a2a(self, out, inp, recv_counts, send_counts):
+        if self.world == 1:
+            out.copy_(inp)
+        else:
+            dist.all_to_all_single(out, inp, recv_counts, send_counts, group=self.group)
+
     def __init__(self, rank: int, world: int, dev: torch.device, group=None):
         self.rank, self.world, self.dev, self.group = rank, world, dev, group
         self.lib = _native.cuda()
@@ -72,7 +80,7 @@ class NcclComm:
         s = torch.cuda.current_stream(self.dev).cuda_stream
         # 1. pack ids by owner, NCCL all-to-all (C2)
         nb.keys_send.copy_(eng.ids.index_select(0, nb.perm).view(-1))
-        dist.all_to_all_single(nb.keys_recv[: W * nl * B], nb.keys_send, nb.recv_counts_ids, nb.send_counts_ids, group=self.group)
+        self._a2a(nb.keys_recv[: W * nl * B], nb.keys_send, nb.recv_counts_ids, nb.send_counts_ids)
         # 2. probe + gather as separate kernels (K1/K3)
         n = W * nl * B
         if n:
@@ -82,7 +90,7 @@ class NcclComm:
                                           eng.ctx.ulist.numel() if train else 0, s), "lookup")
             _chk(lib.dr_cuda_table_gather(ptr(st), ptr(nb.tmap), W * nl, D, ptr(nb.keys_recv), ptr(eng.pos), None, B, n, ptr(nb.rows_send), 1, 0, 0, 1, s), "gather")
         # 3. NCCL all-to-all of the vectors (C3) + un-permute into feature-major order (S2 reorderKernel)
-        dist.all_to_all_single(nb.rows_recv, nb.rows_send[: W * nl * B], [c for c in nb.send_counts_ids], [c for c in nb.recv_counts_ids], group=self.group)
+        self._a2a(nb.rows_recv, nb.rows_send[: W * nl * B], [c for c in nb.send_counts_ids], [c for c in nb.recv_counts_ids])
         eng.emb.index_copy_(0, nb.perm, nb.rows_recv.view(eng.T, B, D))
         eng.launches += 6
 
@@ -91,7 +99,7 @@ class NcclComm:
         nl = len(nb.owned[self.rank])
         s = torch.cuda.current_stream(self.dev).cuda_stream
         nb.grad_send.copy_(eng.demb.index_select(0, nb.perm).view(-1, D))
-        dist.all_to_all_single(nb.grad_recv[: W * nl * B], nb.grad_send, nb.recv_counts_ids, nb.send_counts_ids, group=self.group)     # C4
+        self._a2a(nb.grad_recv[: W * nl * B], nb.grad_send, nb.recv_counts_ids, nb.send_counts_ids)     # C4
         n = W * nl * B
         if n:
             st = eng.ctx.structs()
@@ -102,7 +110,8 @@ class NcclComm:
         eng.launches += 5
 
     def dense_allreduce_update(self, eng) -> None:
-        dist.all_reduce(eng.grads, group=self.group)                                                                                  # C1
+        if self.world > 1:
+            dist.all_reduce(eng.grads, group=self.group)                                                                              # C1
         s = torch.cuda.current_stream(self.dev).cuda_stream
         _chk(self.lib.dr_cuda_dense_apply(ptr(eng.params), ptr(eng.grads), ptr(eng.s0) if eng.s0 is not None else None,
                                           ptr(eng.s1) if eng.s1 is not None else None, eng.P, ptr(eng.hp_dev), 1.0, 0, None, s), "dense_apply")
@@ -118,7 +127,8 @@ class BaselineDLRM:
         from ..models.dlrm_engine import DLRMEngine
         self.cfg, self.dev, self.rank, self.world = cfg, dev, rank, world
         # reuse the engine for table construction / exchange buffers; its dense kernels are NOT used
-        self.eng = DLRMEngine(cfg, dev, rank, world, comm if comm is not None else None)
+        comm = comm if comm is not None else NcclComm(rank, world, dev)
+        self.eng = DLRMEngine(cfg, dev, rank, world, comm)
         self.comm = comm
         self.net = DLRM(cfg.num_dense, [1] * len(cfg.cardinalities), cfg.embedding_dim, cfg.mlp_bot, cfg.mlp_top, use_ev=False, device=dev,
                         bn_eps=cfg.bn_eps, bn_momentum=cfg.bn_momentum)
@@ -134,10 +144,7 @@ class BaselineDLRM:
     def train_step(self):
         from ..models.dlrm import dot_interaction
         eng, net = self.eng, self.net
-        if self.comm is not None:
-            self.comm.lookup_forward(eng, True)
-        else:
-            eng._embedding_forward(True)
+        self.comm.lookup_forward(eng, True)
         emb = eng.emb.permute(1, 0, 2).float().requires_grad_(True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             x = net.bot(eng.dense_in)
@@ -147,15 +154,13 @@ class BaselineDLRM:
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         eng.demb.copy_(emb.grad.permute(1, 0, 2))
-        if self.comm is not None:
-            self.comm.sparse_backward(eng)
+        self.comm.sparse_backward(eng)
+        if self.world > 1:
             flat = torch.cat([p.grad.view(-1) for p in net.parameters()])
             dist.all_reduce(flat)
             o = 0
             for p in net.parameters():
                 p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
-        else:
-            eng._embedding_backward()
         self.opt.step()
         _chk(eng.lib.dr_cuda_advance_hyper(ptr(eng.hp_dev), torch.cuda.current_stream(self.dev).cuda_stream), "advance")
         self.loss.copy_(loss.detach() * self.world)

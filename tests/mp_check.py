@@ -1,6 +1,7 @@
-"""Multi-GPU correctness script (run under torchrun): the fused P2P paths must agree with the NCCL re-creation of
-the same dataflow, and the P2P all-reduce with ncclAllReduce.  Mirrors the reference's SOK unit tests, which compare
-the multi-GPU embedding against a single-device model (legacy/unit_test/test_scripts/tf1/test_dense_emb_demo.py)."""
+"""Multi-GPU correctness script (run under torchrun): the fused unique-first P2P pipeline must agree with the NCCL
+re-creation of the reference (SOK) dataflow, and the P2P all-reduce with ncclAllReduce.  Mirrors the reference's SOK unit
+tests, which compare the multi-GPU embedding against a single-device model
+(addons/sparse_operation_kit/legacy/unit_test/test_scripts/tf1/test_dense_emb_demo.py)."""
 import os
 import sys
 
@@ -8,6 +9,21 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def gathered_rows(eng, t, probe, dev):
+    """Rows / frequencies of `probe` keys of table t, whichever rank owns them (sum over ranks of the present entries)."""
+    rows = torch.zeros(probe.numel(), eng.D, device=dev)
+    freq = torch.zeros(probe.numel(), device=dev)
+    cnt = torch.zeros(probe.numel(), device=dev)
+    if t in eng.tables:
+        f = eng.tables[t].get_freq(probe).float()
+        present = (f > 0).float()
+        rows = eng.tables[t].lookup(probe) * present[:, None]
+        freq, cnt = f, present
+    for x in (rows, freq, cnt):
+        dist.all_reduce(x)
+    return rows, freq, cnt
 
 
 def main():
@@ -34,53 +50,48 @@ def main():
     assert err < 1e-4, f"p2p allreduce mismatch {err}"
     dist.barrier()
 
-    # ---- 2. DLRM engine: P2P hooks vs NCCL hooks, same seeds / batches
-    cards = [50, 1000, 7, 300] + [97] * 22
+    # ---- 2. DLRM engine: unique-first P2P pipeline vs NCCL (SOK) dataflow, same seeds / batches
+    cards = [50, 1000, 7, 300] + [97] * 21 + [200000]
     cfg = DLRMConfig(batch_size=2048, cardinalities=cards, optimizer="adagrad", learning_rate=0.05)
-    batches = [criteo_batch(cfg.batch_size, 13, cards, seed=100 * rank + s) for s in range(4)]
+    nsteps = 5
+    batches = [criteo_batch(cfg.batch_size, 13, cards, seed=100 * rank + s) for s in range(nsteps)]
     results = {}
-    import copy
-    for name in ("p2p", "nccl", "p2p_row", "p2p_allrow"):
-        comm = P2PComm(rank, world, dev) if name.startswith("p2p") else NcclComm(rank, world, dev)
-        c = copy.deepcopy(cfg)
-        # p2p_row: tables 1 and 3 are sharded row-wise over all ranks; p2p_allrow: every table is (requester-side bucketing only)
-        c.row_shard_threshold = {"p2p_row": 200, "p2p_allrow": 0}.get(name, 10 ** 12)
-        c.balance_tablewise = False          # exact control of the sharding in this check
-        eng = DLRMEngine(c, dev, rank, world, comm)
-        assert len(eng.row_tables) == {"p2p_row": 2, "p2p_allrow": 26}.get(name, 0)
+    probe = torch.arange(0, 300, device=dev)
+    for name in ("p2p", "nccl"):
+        comm = P2PComm(rank, world, dev) if name == "p2p" else NcclComm(rank, world, dev)
+        eng = DLRMEngine(cfg, dev, rank, world, comm)
         losses = []
         for i, (d, ids, y) in enumerate(batches):
             eng.load_batch(d.to(dev), ids.to(dev), y.to(dev))
-            if name.startswith("p2p") and i == 1:
-                eng.capture()                     # captures the P2P step (barriers included) into a CUDA graph
+            if name == "p2p" and i == 1:
+                eng.capture()                     # eager step + capture of the whole P2P step (flag waits included) into a CUDA graph
             else:
                 eng.train_step()
             losses.append(eng.loss_value())
         torch.cuda.synchronize()
-        probe = torch.arange(0, 50, device=dev)
-        rows = {t: eng.tables[t].lookup(probe).clone() for t in eng.local_tables}
-        total = torch.tensor([float(sum(eng.tables[t].size() for t in eng.local_tables))], device=dev)
+        rows = {t: gathered_rows(eng, t, probe, dev) for t in (0, 1, 3, 25)}
+        total = torch.tensor([float(sum(tb.size() for tb in eng.tables.values()))], device=dev)
         dist.all_reduce(total)
-        results[name] = (losses, eng.params.clone(), rows, {t: eng.tables[t].size() for t in eng.local_tables}, int(total.item()))
+        ovf = sum(tb.overflowed() for tb in eng.tables.values())
+        results[name] = (losses, eng.params.clone(), rows, int(total.item()), ovf)
         dist.barrier()
-    (l1, p1, r1, s1, n1), (l2, p2, r2, s2, n2) = results["p2p"], results["nccl"]
-    for variant in ("p2p_row", "p2p_allrow"):
-        l3, p3, _, _, n3 = results[variant]
-        for a, b in zip(l3, l2):
-            assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (variant, l3, l2)
-        assert (p3 - p2).abs().max().item() < 2e-3 and n3 == n2 == n1, (variant, n1, n2, n3)
+    (l1, p1, r1, n1, o1), (l2, p2, r2, n2, o2) = results["p2p"], results["nccl"]
+    assert o1 == 0 and o2 == 0, (o1, o2)
     for a, b in zip(l1, l2):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (l1, l2)
     assert (p1 - p2).abs().max().item() < 2e-3, (p1 - p2).abs().max().item()
-    assert s1 == s2, (s1, s2)
+    assert n1 == n2, ("distinct keys", n1, n2)
     for t in r1:
-        assert (r1[t] - r2[t]).abs().max().item() < 2e-3
+        (ra, fa, ca), (rb, fb, cb) = r1[t], r2[t]
+        assert torch.equal(ca, cb) and float(ca.max()) <= 1.0, f"table {t}: key ownership differs"
+        assert torch.equal(fa, fb), f"table {t}: frequencies differ (occurrence counts must survive the dedup)"
+        assert (ra - rb).abs().max().item() < 2e-3, (t, (ra - rb).abs().max().item())
     # dense replicas stay bitwise identical across ranks (fixed summation order)
     ref = p1.clone()
     dist.broadcast(ref, 0)
     assert torch.equal(ref, p1), "dense parameters diverged across ranks"
     if rank == 0:
-        print(f"MP_CHECK_OK world={world} losses={['%.4f' % x for x in l1]}")
+        print(f"MP_CHECK_OK world={world} losses={['%.4f' % x for x in l1]} distinct_keys={n1}")
     dist.destroy_process_group()
 
 
