@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import threading
 import os
 import time
 from concurrent.futures import ThreadPoolExecutor
@@ -107,15 +108,69 @@ def _read_state(directory: str, name: str = "checkpoint") -> dict:
 
 
 def _write_state(directory: str, st: dict, name: str = "checkpoint") -> None:
-    tmp = _state_file(directory, name) + ".tmp"
+    # unique tmp name: several shards / ranks may publish into the same directory at the same time
+    tmp = f"{_state_file(directory, name)}.tmp.{os.getpid()}.{threading.get_ident()}"
     with open(tmp, "w") as f:
         json.dump(st, f)
     os.replace(tmp, _state_file(directory, name))
 
 
-def latest_checkpoint(directory: str) -> Optional[str]:
-    """``tf.train.latest_checkpoint``."""
-    return _read_state(directory).get("model_checkpoint_path")
+class _DirLock:
+    """Advisory lock serialising the read-modify-write of a directory's state file across processes (sharded savers, PS shards)."""
+
+    def __init__(self, directory: str):
+        self.path = os.path.join(directory, ".checkpoint.lock")
+
+    def __enter__(self):
+        import fcntl
+        self.f = open(self.path, "a+")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+        return False
+
+
+def _register_checkpoint(directory: str, prefix: str, step: int, base: str, max_to_keep: int) -> None:
+    """Retention is per STEP, not per file: a step written as several shards (``<prefix>.ps{i}-<step>``, ``-partXXXXX-of-YYYYY``)
+    is kept or evicted as a whole, so the shards of the step being written are never pruned by its own later shards."""
+    with _DirLock(directory):
+        st = _read_state(directory)
+        ents = st.get("entries")
+        if ents is None:
+            ents = [{"path": q, "step": _step_of(q)} for q in st.get("all_model_checkpoint_paths", [])]
+        ents = [e for e in ents if e["path"] != prefix] + [{"path": prefix, "step": int(step)}]
+        steps = sorted({e["step"] for e in ents})
+        evict = set(steps[:-max_to_keep]) if max_to_keep and len(steps) > max_to_keep else set()
+        for e in ents:
+            if e["step"] in evict:
+                for ext in (".data", ".index"):
+                    if os.path.exists(e["path"] + ext):
+                        os.remove(e["path"] + ext)
+        ents = [e for e in ents if e["step"] not in evict]
+        st["entries"] = ents
+        st["all_model_checkpoint_paths"] = [e["path"] for e in ents]
+        st["model_checkpoint_path"] = prefix
+        st.setdefault("latest_by_base", {})[base] = prefix
+        _write_state(directory, st)
+
+
+def _step_of(prefix: str) -> int:
+    import re
+    m = re.search(r"-(\d+)(?:-part\d+-of-\d+)?$", prefix)
+    return int(m.group(1)) if m else -1
+
+
+def latest_checkpoint(directory: str, base: Optional[str] = None) -> Optional[str]:
+    """``tf.train.latest_checkpoint``.  ``base`` (the ``save_path`` basename a saver writes under, e.g. ``model.ps3``) selects one
+    shard's newest checkpoint when several savers share the directory."""
+    st = _read_state(directory)
+    if base is not None:
+        return st.get("latest_by_base", {}).get(base)
+    return st.get("model_checkpoint_path")
 
 
 class Saver:
@@ -205,15 +260,7 @@ class Saver:
             ev.table.clear_dirty()                        # recorder is cleared on each (full or incremental) save
         d = os.path.dirname(os.path.abspath(save_path))
         if not incremental:
-            st = _read_state(d)
-            st["model_checkpoint_path"] = prefix
-            st["all_model_checkpoint_paths"].append(prefix)
-            while self.max_to_keep and len(st["all_model_checkpoint_paths"]) > self.max_to_keep:
-                old = st["all_model_checkpoint_paths"].pop(0)
-                for ext in (".data", ".index"):
-                    if os.path.exists(old + ext):
-                        os.remove(old + ext)
-            _write_state(d, st)
+            _register_checkpoint(d, prefix, step, os.path.basename(save_path), self.max_to_keep)
         return prefix
 
     # ------------------------------------------------------------------------------------------------

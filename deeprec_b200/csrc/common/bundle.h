@@ -101,17 +101,22 @@ class BundleWriter {
     if (!f_) return -1;
     int64_t pad = (64 - (off_ & 63)) & 63;
     static const char zeros[64] = {0};
-    if (pad) { fwrite(zeros, 1, pad, f_); off_ += pad; }
+    if (pad) { if (fwrite(zeros, 1, (size_t)pad, f_) != (size_t)pad) { failed_ = true; return -2; } off_ += pad; }
     BundleEntry e; e.name = name; e.dtype = dtype; e.shape.assign(shape, shape + ndim); e.offset = off_; e.nbytes = nbytes;
     e.crc = Crc32Large(static_cast<const uint8_t*>(data), (size_t)nbytes);
-    if (nbytes && fwrite(data, 1, (size_t)nbytes, f_) != (size_t)nbytes) return -2;
+    if (nbytes && fwrite(data, 1, (size_t)nbytes, f_) != (size_t)nbytes) { failed_ = true; return -2; }
     off_ += nbytes;
     entries_.push_back(std::move(e));
     return 0;
   }
   int Close() {
     if (!f_) return -1;
-    fclose(f_); f_ = nullptr;
+    // a short write (ENOSPC, quota) surfaces in fwrite, fflush or fclose: NEVER publish the index of a truncated data file --
+    // the caller prunes older checkpoints only after a successful close
+    const bool flush_bad = fflush(f_) != 0 || ferror(f_) != 0;
+    const bool close_bad = fclose(f_) != 0;
+    f_ = nullptr;
+    if (failed_ || flush_bad || close_bad) { remove((prefix_ + ".data.tmp").c_str()); return -5; }
     FILE* fi = fopen((prefix_ + ".index.tmp").c_str(), "w");
     if (!fi) return -2;
     fprintf(fi, "DEEPREC_B200_BUNDLE 1 %zu\n", entries_.size());
@@ -120,7 +125,8 @@ class BundleWriter {
       for (auto d : e.shape) fprintf(fi, "\t%lld", (long long)d);
       fprintf(fi, "\t%lld\t%lld\t%u\n", (long long)e.offset, (long long)e.nbytes, e.crc);
     }
-    fclose(fi);
+    const bool index_bad = ferror(fi) != 0;
+    if (fclose(fi) != 0 || index_bad) { remove((prefix_ + ".index.tmp").c_str()); remove((prefix_ + ".data.tmp").c_str()); return -6; }
     // atomic publish: data first, index last (a reader that sees the index sees complete data)
     if (rename((prefix_ + ".data.tmp").c_str(), (prefix_ + ".data").c_str()) != 0) return -3;
     if (rename((prefix_ + ".index.tmp").c_str(), (prefix_ + ".index").c_str()) != 0) return -4;
@@ -128,7 +134,7 @@ class BundleWriter {
   }
   ~BundleWriter() { if (f_) fclose(f_); }
  private:
-  std::string prefix_; FILE* f_ = nullptr; std::vector<char> buf_; int64_t off_ = 0; std::vector<BundleEntry> entries_;
+  std::string prefix_; FILE* f_ = nullptr; std::vector<char> buf_; int64_t off_ = 0; std::vector<BundleEntry> entries_; bool failed_ = false;
 };
 
 class BundleReader {

@@ -11,10 +11,6 @@
 
 using namespace drc;
 
-extern "C" {
-struct DrSpSlotI { int64_t key; int32_t count; int32_t pad; };   // = DrSpSlot (sparse_pipeline.cu)
-}
-
 namespace {
 
 template <int D>
@@ -307,30 +303,23 @@ __global__ void __launch_bounds__(128) k_dot_fwd_tc(const __nv_bfloat16* __restr
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-// INDIRECT: features come from urow[inv[b][t]] and the per-sample gradient rows are PRE-REDUCED on the requester: ugrad[gs] (fp32)
-// += dF -- the requester-side segment-sum of the unique-first pipeline, so the owners pull one row per distinct key.  Keys that
-// occur >= hot_thresh times in the batch (count in the dedup scratch slot) are combined in a shared-memory cache first: same-address
-// L2 reductions serialise at ~14 ns each, a table with three keys would otherwise put B/3 of them on every row.
-constexpr int kBwdCacheSlots = 1024;
+// INDIRECT: features come from urow[inv[b][t]] (unique-first pipeline); the per-sample gradient rows still go to the feature-major
+// demb buffer, which k_sp_segsum (sparse_pipeline.cu) pre-reduces per distinct key on the side stream.  (A first version reduced
+// them here with shared-memory fp32 atomics: those compile to ATOMS.CAST.SPIN loops and made this kernel 2.6x slower -- see
+// profiles/r2_notes.md.)
 template <bool INDIRECT>
 __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restrict__ dZ, int64_t ldz, const __nv_bfloat16* __restrict__ x,
                                                     int64_t ldx, const __nv_bfloat16* __restrict__ emb, int64_t emb_stride_t,
                                                     int64_t emb_stride_b, int T, int64_t B, __nv_bfloat16* __restrict__ dx, int64_t lddx,
                                                     __nv_bfloat16* __restrict__ demb, int64_t demb_stride_t, int64_t demb_stride_b,
-                                                    const int32_t* __restrict__ inv, int ldinv, const DrSpSlotI* __restrict__ scr, int hot_thresh,
-                                                    float* __restrict__ ugrad, DrSpSync sync) {
+                                                    const int32_t* __restrict__ inv, int ldinv) {
   pdl_sync();
   constexpr int D = 16;
   extern __shared__ __align__(128) uint8_t dyn[];
   uint8_t* sA = dyn;                                   // blockdiag(S): [16 row-groups][16 K-chunks][8 rows][16 B] = 32 KB
   uint8_t* sB = dyn + 32768;                           // F^T: [2 d-groups][16 K-chunks][8 d][16 B] = 4 KB
   __nv_bfloat16* sG = reinterpret_cast<__nv_bfloat16*>(dyn + 32768 + 4096);   // [4][512] dZ rows
-  int32_t* s_ctag = reinterpret_cast<int32_t*>(dyn + 32768 + 4096 + 4096);    // INDIRECT: [kBwdCacheSlots] cached gs (-1 = free)
-  float* s_cacc = reinterpret_cast<float*>(dyn + 32768 + 4096 + 4096 + kBwdCacheSlots * 4);   // [kBwdCacheSlots][16]
-  if (INDIRECT) {
-    for (int i = threadIdx.x; i < kBwdCacheSlots; i += 128) s_ctag[i] = -1;
-    for (int i = threadIdx.x; i < kBwdCacheSlots * D; i += 128) s_cacc[i] = 0.f;
-  }
+
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -351,7 +340,7 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
   uint32_t phase = 0;
   // software pipeline: dZ chunks + the feature row of group g+1 are fetched while group g is being processed
   int4 pz0 = make_int4(0, 0, 0, 0), pz1 = pz0, pf0 = pz0, pf1 = pz0;
-  int32_t gsn = -1, gs_f = -1, cnt_f = 0;            // INDIRECT: index for the next fetch; index / batch count of the rows just fetched
+  int32_t gsn = -1;                                   // INDIRECT: row index of my feature for the NEXT group to fetch
   auto fetch_idx = [&](int64_t gg) {
     const int64_t bb = gg * 4 + warp;
     gsn = (gg < ngroups && lane >= 1 && lane < F && bb < B) ? inv[bb * ldinv + lane - 1] : -1;
@@ -368,7 +357,6 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
           else if (gsn >= 0) {
             const __nv_bfloat16* src = emb + (int64_t)gsn * D;
             pf0 = ld_nc_v4(src); pf1 = ld_nc_v4(src + 8);
-            cnt_f = scr[gsn].count;
           }
         } else {
           const __nv_bfloat16* src = lane == 0 ? x + bb * ldx : emb + (int64_t)(lane - 1) * emb_stride_t + bb * emb_stride_b;
@@ -376,7 +364,7 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
         }
       }
     }
-    if (INDIRECT) { gs_f = gsn; fetch_idx(gg + gridDim.x); }
+    if (INDIRECT) fetch_idx(gg + gridDim.x);
     // two more groups ahead: L2 prefetch only (one group of register loads per warp cannot cover the DRAM latency)
     const int64_t pb = (gg + 2 * (int64_t)gridDim.x) * 4 + warp;
     if (pb < B) {
@@ -390,7 +378,6 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t b = g * 4 + warp;
     const bool live = b < B;
-    const int32_t gs_cur = gs_f, cnt_cur = cnt_f;       // (INDIRECT) of the rows about to be staged
     // ---- stage dZ row and F^T from the prefetched registers
     if (lane * 8 < ldz) *reinterpret_cast<int4*>(myG + lane * 8) = pz0;
     if (lane * 8 + 256 < ldz) *reinterpret_cast<int4*>(myG + lane * 8 + 256) = pz1;
@@ -450,27 +437,8 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
 #pragma unroll
         for (int d = 0; d < 16; ++d) acc[d] += __bfloat162float(myG[d]);
         store_row_bf16<16>(dx + b * lddx, acc);
-      } else if (!INDIRECT) {
+      } else {
         store_row_bf16<16>(demb + (int64_t)(lane - 1) * demb_stride_t + b * demb_stride_b, acc);
-      } else if (gs_cur >= 0) {
-        int slot = -1;
-        if (cnt_cur >= hot_thresh) {                       // hot key: combine in shared memory (4-way linear probing)
-          int h = (int)(((uint32_t)gs_cur * 2654435761u) >> 22) & (kBwdCacheSlots - 1);
-#pragma unroll
-          for (int pr = 0; pr < 4 && slot < 0; ++pr, h = (h + 1) & (kBwdCacheSlots - 1)) {
-            const int32_t old = atomicCAS(&s_ctag[h], -1, gs_cur);
-            if (old == -1 || old == gs_cur) slot = h;
-          }
-        }
-        if (slot >= 0) {
-          float* d16 = s_cacc + slot * D;
-#pragma unroll
-          for (int d = 0; d < 16; ++d) atomicAdd(d16 + d, acc[d]);
-        } else {
-          float* g16 = ugrad + (int64_t)gs_cur * D;
-#pragma unroll
-          for (int d = 0; d < 16; d += 4) red_add_v4_f32(g16 + d, acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
-        }
       }
     }
     tc_fence_before();
@@ -479,17 +447,6 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 32);
-  if (INDIRECT) {
-    for (int e = threadIdx.x; e < kBwdCacheSlots * 4; e += 128) {
-      const int slot = e >> 2, c = e & 3;
-      const int32_t gsv = s_ctag[slot];
-      if (gsv >= 0) {
-        const float* sv = s_cacc + slot * D + 4 * c;
-        red_add_v4_f32(ugrad + (int64_t)gsv * D + 4 * c, sv[0], sv[1], sv[2], sv[3]);
-      }
-    }
-    sp_signal_last_block(sync, SP_CH_GRAD);
-  }
 }
 
 inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 8) {
@@ -518,15 +475,15 @@ int dr_cuda_dot_interaction_fwd_u(const void* x, int64_t ldx, const void* urow, 
 }
 
 int dr_cuda_dot_interaction_bwd_u(const void* dZ, int64_t ldz, const void* x, int64_t ldx, const void* urow, const int32_t* inv, int ldinv,
-                                  const void* scr, int hot_thresh, int T, int D, int64_t B, void* dx, int64_t lddx, float* ugrad,
-                                  const DrSpSync* sync, int max_ctas, cudaStream_t s) {
+                                  int T, int D, int64_t B, void* dx, int64_t lddx, void* demb, int64_t demb_stride_t, int64_t demb_stride_b,
+                                  cudaStream_t s) {
   if (T + 1 > 32 || ldz > 512 || ldz % 8 || D != 16) return -2;
-  constexpr int kSmem = 32768 + 4096 + 4 * 1024 + kBwdCacheSlots * 4 + kBwdCacheSlots * 16 * 4;
+  constexpr int kSmem = 32768 + 4096 + 4 * 1024;
   static bool attr = false;
   if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_dot_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
-  int g = grid_for((B + 3) / 4, 1, max_ctas > 0 ? max_ctas : kNumSMs * 2);
+  int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
   DR_PDL_LAUNCH((k_dot_bwd_tc<true>), g, 128, kSmem, s, (const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)urow, 0, 0, T, B,
-                (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)nullptr, 0, 0, inv, ldinv, (const DrSpSlotI*)scr, hot_thresh, ugrad, *sync);
+                (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b, inv, ldinv);
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -562,8 +519,7 @@ int dr_cuda_dot_interaction_bwd(const void* dZ, int64_t ldz, const void* x, int6
     if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_dot_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
     int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
     DR_PDL_LAUNCH((k_dot_bwd_tc<false>), g, 128, kSmem, s, (const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B,
-                                       (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b,
-                                       (const int32_t*)nullptr, 0, (const DrSpSlotI*)nullptr, 0, (float*)nullptr, DrSpSync{});
+                                       (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b, (const int32_t*)nullptr, 0);
     DR_LAUNCH_CHECK();
     return 0;
   }

@@ -419,6 +419,7 @@ struct ServingModel {
   std::vector<std::unique_ptr<Session>> sessions;
   std::atomic<uint64_t> rr{0}, requests{0}, failures{0}, full_updates{0}, delta_updates{0};
   std::atomic<int64_t> delta_version{-1};
+  int64_t rejected_version = -1;           // updater thread only: last version refused because it changes the architecture
   std::thread updater; std::atomic<bool> stop{false};
   std::mutex tmu; std::vector<std::string> trace;
   ~ServingModel() { stop = true; if (updater.joinable()) updater.join(); }
@@ -582,6 +583,20 @@ static void UpdaterLoop(ServingModel* sm) {
         auto nm = LoadModel(dir, sm->cfg.extra_rows, sm->cfg.fp8);
         if (!nm) { if (++bad > 3) fprintf(stderr, "[deeprec_serving] skipping invalid model version %lld\n", (long long)v); continue; }
         bad = 0;
+        // The sessions' device / pinned buffers were sized from the architecture they were initialised with (Session::Init): a version with
+        // more tables, a larger D, more dense columns or wider layers would overflow them.  Such a version is rejected (logged once) -- the
+        // reference would build a fresh SessionGroup (serving/processor/serving/model_instance.cc:406-427); restart the processor for it.
+        {
+          const Arch& o = cur->arch; const Arch& n = nm->arch;
+          if (n.num_dense != o.num_dense || n.T != o.T || n.D != o.D || n.bot != o.bot || n.top != o.top || n.Zp != o.Zp) {
+            if (sm->rejected_version != v) {
+              fprintf(stderr, "[deeprec_serving] model version %lld changes the architecture (tables %d->%d, D %d->%d, dense %d->%d): rejected, sessions keep serving version %lld\n",
+                      (long long)v, o.T, n.T, o.D, n.D, o.num_dense, n.num_dense, (long long)cur->version);
+              sm->rejected_version = v;
+            }
+            continue;
+          }
+        }
         if (!WarmUp(sm, nm)) continue;
         std::atomic_store(&sm->model, nm);          // requests in flight keep the old model alive through their shared_ptr
         sm->delta_version = -1;

@@ -12,8 +12,9 @@
 //   k_sp_lookup  (owner)      waits per source on its DEDUP flag, reads the source's bucket list + occurrence counts over NVLink,
 //                             probes / inserts / admits in the device EmbeddingVariable, claims the per-step unique index, and
 //                             stores the bf16 row straight into the SOURCE's urow[gs] (P2P stores).  Last block raises ROWS.
-//   (interaction kernels gather urow[inv[b][c]] -- L2-resident, 32 B rows -- and, in the backward, pre-reduce the per-sample
-//    gradient rows into ugrad[gs] in fp32: requester-side segment-sum, so only UNIQUE rows ever cross NVLink)
+//   (interaction kernels gather urow[inv[b][c]] -- L2-resident, 32 B rows)
+//   k_sp_segsum  (requester)  pre-reduces the per-sample gradient rows per distinct key into ugrad[gs] (fp32) with in-warp
+//                             match.any combining, so only UNIQUE rows ever cross NVLink.  Last block raises GRAD.
 //   k_sp_grad    (owner)      waits per source on its GRAD flag, pulls ugrad rows over NVLink and reduces the <= W contributions
 //                             per key into gsum[unique]; the row-wise optimizer (k_apply) follows on the same stream.
 //   k_sp_reset   (requester)  clears the touched scratch slots through the bucket lists (no 50 MB memset per step).
@@ -53,7 +54,8 @@ __device__ __forceinline__ int sp_owner(int64_t key, int W) {
 // k_sp_dedup: a block owns 32 samples; warp w walks columns w, w+8, ...; lane = sample.
 // -----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sp_dedup(const int64_t* __restrict__ ids /* [C][B] */, DrSpGeom g, DrSpSlot* __restrict__ scr,
-                                                  int32_t* __restrict__ inv /* [B][ldinv] */, int64_t* __restrict__ bkt_key,
+                                                  int32_t* __restrict__ inv /* [B][ldinv] */, int32_t* __restrict__ invT /* [C][B] or null */,
+                                                  int64_t* __restrict__ bkt_key,
                                                   int32_t* __restrict__ bkt_gs, int32_t* __restrict__ bcnt /* [T][W] */,
                                                   float* __restrict__ ugrad, DrSpSync sync) {
   pdl_sync();
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) k_sp_dedup(const int64_t* __restrict__ id
         }
       }
       s_inv[lane * lds + c] = gs;
+      if (invT && c < g.C && in_b) invT[(int64_t)c * g.B + b] = gs;
     }
     __syncthreads();
     // coalesced write-out of the tile's 32 x ldinv index block
@@ -264,6 +267,63 @@ __global__ void __launch_bounds__(256) k_sp_lookup(const DrDeviceTable* __restri
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// k_sp_segsum (requester): ugrad[gs] += per-sample gradient rows, pre-reduced per distinct key BEFORE anything crosses NVLink
+// (the reference sums duplicates with unique + unsorted_segment_sum on the OWNER after shipping every row:
+// all2all_output_dispatcher.cu:233-246, kit_cc/framework/compat/kernels/unsorted_segment_sum.cu).
+// One warp = 32 consecutive samples of one id column (coalesced 32 B bf16 rows of the feature-major demb buffer).  Lanes holding
+// the same key are found with match.any; every group's leader sums its members' rows out of a 1 KB shared-memory tile and issues
+// ONE vectorised L2 reduction per 16 B chunk -- no shared-memory atomics (fp32 ATOMS are CAS loops), no sort.
+// -----------------------------------------------------------------------------------------------------------------
+template <int LPR /* dim / 4 */>
+__global__ void __launch_bounds__(256) k_sp_segsum(const __nv_bfloat16* __restrict__ demb /* [C][B][dim] */, const int32_t* __restrict__ invT /* [C][B] */,
+                                                   DrSpGeom g, float* __restrict__ ugrad, DrSpSync sync) {
+  pdl_sync();
+  constexpr int dim = 4 * LPR;
+  constexpr int V = dim / 8;                                   // int4 (8 bf16) chunks per row
+  __shared__ __align__(16) int4 s_row[8][32][V];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tiles = (g.B + 31) / 32;
+  const int64_t units = tiles * g.C;
+  for (int64_t u = (int64_t)blockIdx.x * 8 + warp; u < units; u += (int64_t)gridDim.x * 8) {
+    const int c = (int)(u / tiles);
+    const int64_t b = (u % tiles) * 32 + lane;
+    int32_t gs = -1;
+    if (b < g.B) gs = invT[(int64_t)c * g.B + b];
+    const bool live = gs >= 0;
+    const unsigned lm = __ballot_sync(0xffffffffu, live);
+    if (live) {
+      const int4* src = reinterpret_cast<const int4*>(demb + ((int64_t)c * g.B + b) * dim);
+#pragma unroll
+      for (int v = 0; v < V; ++v) s_row[warp][lane][v] = ld_nc_v4(src + v);
+    }
+    __syncwarp();
+    if (live) {
+      const unsigned same = __match_any_sync(lm, gs);
+      if (lane == __ffs(same) - 1) {                            // leader of this key inside the tile
+        float acc[dim];
+#pragma unroll
+        for (int d = 0; d < dim; ++d) acc[d] = 0.f;
+        for (unsigned m = same; m; m &= m - 1) {
+          const int src_lane = __ffs(m) - 1;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const int4 raw = s_row[warp][src_lane][v];
+            const uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(w[e]); acc[8 * v + 2 * e] += f.x; acc[8 * v + 2 * e + 1] += f.y; }
+          }
+        }
+        float* dst = ugrad + (int64_t)gs * dim;
+#pragma unroll
+        for (int d = 0; d < dim; d += 4) red_add_v4_f32(dst + d, acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
+      }
+    }
+    __syncwarp();
+  }
+  sp_signal_last_block(sync, SP_CH_GRAD);
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // k_sp_grad (owner): gsum[tag(pos)] += ugrad_of_source[gs]      (fp32 rows, pre-reduced per key on the source)
 // -----------------------------------------------------------------------------------------------------------------
 template <int LPR>
@@ -374,12 +434,26 @@ int dr_sp_init_scratch(void* scr, int64_t n, cudaStream_t s) {
   return 0;
 }
 
-int dr_sp_dedup(const int64_t* ids, const DrSpGeom* g, void* scr, int32_t* inv, int64_t* bkt_key, int32_t* bkt_gs, int32_t* bcnt, float* ugrad,
-                const DrSpSync* sync, cudaStream_t s) {
+int dr_sp_dedup(const int64_t* ids, const DrSpGeom* g, void* scr, int32_t* inv, int32_t* invT, int64_t* bkt_key, int32_t* bkt_gs, int32_t* bcnt,
+                float* ugrad, const DrSpSync* sync, cudaStream_t s) {
   if (g->ldinv % 4 || g->ldinv < g->C || g->dim % 4) return -2;
   const size_t smem = (size_t)32 * (g->ldinv + 1) * 4;
   if (smem > 48 * 1024) return -3;
-  DR_PDL_LAUNCH((k_sp_dedup), sp_grid((g->B + 31) / 32), 256, smem, s, ids, *g, (DrSpSlot*)scr, inv, bkt_key, bkt_gs, bcnt, ugrad, *sync);
+  DR_PDL_LAUNCH((k_sp_dedup), sp_grid((g->B + 31) / 32), 256, smem, s, ids, *g, (DrSpSlot*)scr, inv, invT, bkt_key, bkt_gs, bcnt, ugrad, *sync);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+// demb: bf16 [C][B][dim] per-sample gradient rows (feature-major); accumulates into ugrad and raises the GRAD flags
+int dr_sp_segsum(const void* demb, const int32_t* invT, const DrSpGeom* g, float* ugrad, const DrSpSync* sync, cudaStream_t s) {
+  const int64_t units = ((g->B + 31) / 32) * g->C;
+  const int grid = sp_grid((units + 7) / 8);
+#define SPS(L) DR_PDL_LAUNCH((k_sp_segsum<L>), grid, 256, 0, s, (const __nv_bfloat16*)demb, invT, *g, ugrad, *sync)
+  switch (g->dim / 4) {
+    case 2: SPS(2); break; case 4: SPS(4); break; case 8: SPS(8); break; case 16: SPS(16); break;
+    default: return -3;
+  }
+#undef SPS
   DR_LAUNCH_CHECK();
   return 0;
 }

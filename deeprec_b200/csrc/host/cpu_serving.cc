@@ -448,12 +448,21 @@ struct Session {
   ~Session() { if (redis) dr_redis_close(redis); }
   void Init(const Arch& ar, int mb, int nthreads) {
     max_batch = mb; threads = std::max(1, nthreads);
+    Grow(ar);
+  }
+  // Scratch buffers must fit EVERY model version this session may still be asked to run: a full hot update can publish a wider
+  // architecture (more tables, larger D, wider layers) while requests holding the previous model are queued on the mutex.
+  // Grow-only, called with `mu` held (WarmUp of a new version) -- the reference builds fresh sessions per version instead
+  // (serving/processor/serving/model_instance.cc:406-427).
+  void Grow(const Arch& ar) {
+    const size_t mb = (size_t)max_batch;
     int widest = ar.inter;
     for (int n : ar.bot) widest = std::max(widest, n);
     for (int n : ar.top) widest = std::max(widest, n);
-    dense.resize((size_t)mb * ar.num_dense); ids.resize((size_t)mb * ar.T); emb.resize((size_t)mb * ar.T * ar.D);
-    a.resize((size_t)mb * widest); b2.resize((size_t)mb * widest); z.resize((size_t)mb * ar.inter); prob.resize((size_t)mb);
-    rrows.resize((size_t)mb * ar.D); found.resize((size_t)mb);
+    auto grow = [](auto& v, size_t n) { if (v.size() < n) v.resize(n); };
+    grow(dense, mb * ar.num_dense); grow(ids, mb * ar.T); grow(emb, mb * ar.T * ar.D);
+    grow(a, mb * widest); grow(b2, mb * widest); grow(z, mb * ar.inter); grow(prob, mb);
+    grow(rrows, mb * ar.D); grow(found, mb);
   }
   // remote lookup of one chunk: per table ONE pipelined MGET; ids the store does not have read their default row (what a local
   // inference-mode lookup returns)
@@ -785,6 +794,7 @@ static bool WarmUp(ServingModel* sm, const std::shared_ptr<Model>& m) {
   for (auto& sp : sm->sessions) {
     Session& s = *sp;
     std::lock_guard<std::mutex> l(s.mu);
+    s.Grow(a);                                   // the new version may be wider than the one the buffers were sized for
     int B = std::min(64, s.max_batch);
     bool filled = false;
     if (from_file) {

@@ -320,7 +320,11 @@ class HostKV {
     std::shared_lock<std::shared_mutex> l(P.mu);
     for (int64_t i = 0; i < P.cap; ++i) {
       int64_t k = P.slots[i].key.load(std::memory_order_acquire);
-      if (k != kEmptyKey) f(k, P.slots[i].val.load(std::memory_order_acquire));
+      if (k == kEmptyKey) continue;
+      // a CAS insert running under the same shared lock publishes the key first and the value index second: a slot whose value is still
+      // -1 is not part of the table yet (its metadata does not exist) -- skip it, as the point readers' WaitVal would wait for it
+      const int32_t v = P.slots[i].val.load(std::memory_order_acquire);
+      if (v >= 0) f(k, v);
     }
   }
   template <typename F> void ForEach(F&& f) { for (int p = 0; p < nparts_; ++p) ForEachInPart(p, f); }
@@ -328,7 +332,9 @@ class HostKV {
     KVPart& P = parts_[p];
     for (int64_t i = 0; i < P.cap; ++i) {
       int64_t k = P.slots[i].key.load(std::memory_order_acquire);
-      if (k != kEmptyKey) f(k, P.slots[i].val.load(std::memory_order_acquire));
+      if (k == kEmptyKey) continue;
+      const int32_t v = P.slots[i].val.load(std::memory_order_acquire);
+      if (v >= 0) f(k, v);
     }
   }
   class ExclusiveAll {                                                     // stops inserts, growth and batch readers on every partition
@@ -775,12 +781,18 @@ class HostEV {
     // Save runs between steps, so the two scans normally see the same table.  If someone does modify it in between (a parameter server
     // checkpointing while pushes arrive), the placement pass notices (a range overflows or is left short; overflowing items are dropped,
     // never written out of range) and the snapshot is retried -- the last attempt under exclusive partition locks.
+    // NOTE for callers: the exclusive last attempt freezes the hash partitions (inserts, growth, batch readers) but NOT Apply / ImportCow,
+    // which flip meta->row / meta->dirty of already-known indices: whoever checkpoints a live table must quiesce applies (the parameter
+    // server holds its push lock across save()).  If even the last attempt disagrees with its own counting scan, the ranges are compacted
+    // to what was actually placed below -- never a zeroed or stale item in the output.
+    std::vector<int64_t> cnt_a, cnt_f, end_a, end_f, start_a, start_f;
+    bool consistent = false;
     for (int attempt = 0; attempt < 3; ++attempt) {
       const bool exclusive = attempt == 2;
       std::unique_ptr<HostKV::ExclusiveAll> guard;
       if (exclusive) guard.reset(new HostKV::ExclusiveAll(kv_));
       auto scan = [&](int p, auto&& f) { if (exclusive) kv_.ForEachInPartNoLock(p, f); else kv_.ForEachInPart(p, f); };
-      std::vector<int64_t> cnt_a((size_t)np * 1000, 0), cnt_f((size_t)np * 1000, 0);
+      cnt_a.assign((size_t)np * 1000, 0); cnt_f.assign((size_t)np * 1000, 0);
       GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
         for (int64_t p = pb; p < pe; ++p)
           scan((int)p, [&](int64_t key, int32_t idx) {
@@ -788,7 +800,6 @@ class HostEV {
             if (c == 1) cnt_a[(size_t)p * 1000 + b]++; else if (c == 2) cnt_f[(size_t)p * 1000 + b]++;
           });
       });
-      std::vector<int64_t> end_a, end_f;
       auto offsets = [&](std::vector<int64_t>& cnt, std::vector<int64_t>& end, std::vector<int64_t>& off, std::vector<SnapItem>& dst) {
         off.assign(1001, 0); end.assign(cnt.size(), 0);
         int64_t run = 0;
@@ -801,6 +812,7 @@ class HostEV {
       };
       offsets(cnt_a, end_a, snap_adm_off_, snap_adm_);
       offsets(cnt_f, end_f, snap_flt_off_, snap_flt_);
+      start_a = cnt_a; start_f = cnt_f;
       std::atomic<int64_t> dropped{0};
       GlobalPool()->ParallelFor(np, 1, [&](int64_t pb, int64_t pe) {
         for (int64_t p = pb; p < pe; ++p)
@@ -813,9 +825,26 @@ class HostEV {
             (c == 1 ? snap_adm_ : snap_flt_)[(size_t)cur[slot]++] = {b, idx, key};
           });
       });
-      bool consistent = dropped.load() == 0;
+      consistent = dropped.load() == 0;
       for (size_t i = 0; consistent && i < end_a.size(); ++i) consistent = cnt_a[i] == end_a[i] && cnt_f[i] == end_f[i];
       if (consistent) break;
+    }
+    if (!consistent) {
+      // ranges left short (or overflowed): keep exactly the items that were placed, bucket by bucket, and recompute the offsets
+      auto compact = [&](std::vector<SnapItem>& dst, std::vector<int64_t>& off, const std::vector<int64_t>& start, const std::vector<int64_t>& cur) {
+        std::vector<SnapItem> out; out.reserve(dst.size());
+        std::vector<int64_t> noff(1001, 0);
+        for (int b = 0; b < 1000; ++b) {
+          noff[b] = (int64_t)out.size();
+          for (int p = 0; p < np; ++p) { const size_t sl = (size_t)p * 1000 + b; for (int64_t i = start[sl]; i < cur[sl]; ++i) out.push_back(dst[(size_t)i]); }
+        }
+        noff[1000] = (int64_t)out.size();
+        dst.swap(out); off.swap(noff);
+      };
+      compact(snap_adm_, snap_adm_off_, start_a, cnt_a);
+      compact(snap_flt_, snap_flt_off_, start_f, cnt_f);
+      fprintf(stderr, "[deeprec_host] snapshot of a table that kept changing: kept the %zu + %zu items that were placed consistently; "
+                      "quiesce applies while checkpointing\n", snap_adm_.size(), snap_flt_.size());
     }
     auto sort_buckets = [&](std::vector<SnapItem>& dst, const std::vector<int64_t>& off) {
       GlobalPool()->ParallelFor(1000, 8, [&](int64_t bb, int64_t be) {

@@ -1,9 +1,12 @@
 """Streaming input for online learning (reference: docs/docs_en/KafkaDataset.md -- ``KafkaDataset(topics, servers, group, eof, timeout,
 config_global, config_topic, message_key)`` with saveable position).
 
-Subscriptions use the reference's ``"topic:partition:offset:length"`` strings (length -1 = unlimited).  Messages are consumed partition by
-partition in offset order, the position of every subscription is part of ``state_dict()`` so a restored job continues exactly after the last
-message it delivered, and ``batch(n, parse_fn)`` turns the stream into training batches.
+Subscriptions use the reference's ``"topic:partition:offset:length"`` strings where, as in the reference kernel
+(contrib/kafka/kernels/kafka_dataset_ops.cc:121: reading stops when ``offset >= limit``), the 4th field is an ABSOLUTE, EXCLUSIVE end offset
+(-1 = unlimited): ``"t:0:100:200"`` delivers offsets 100..199.  Messages are consumed partition by partition in offset order, the position of
+every subscription is part of ``state_dict()`` so a restored job continues exactly after the last message it delivered -- when the stream is
+consumed through ``batch(n, parse_fn)`` the saved position is the one at the last BATCH boundary, so messages sitting in a partially filled
+batch are read again after a restore instead of being dropped.
 
 The broker client is pluggable: by default ``kafka-python`` (``kafka.KafkaConsumer``) is used when it is installed -- this image has no Kafka
 client library, so the class raises a clear ImportError there -- and ``consumer_factory`` accepts anything with the small interface below
@@ -23,7 +26,7 @@ class _Subscription:
     topic: str
     partition: int
     offset: int           # next offset to read
-    remaining: int        # messages still to deliver, -1 = unlimited
+    limit: int            # exclusive end offset, -1 = unlimited
 
 
 def _parse_subscription(s: str) -> _Subscription:
@@ -75,36 +78,43 @@ class KafkaDataset:
     def __iter__(self) -> Iterator:
         while self._cur < len(self.subs):
             s = self.subs[self._cur]
-            if s.remaining == 0:
+            if s.limit >= 0 and s.offset >= s.limit:
                 self._cur += 1
                 continue
-            want = self.max_poll_records if s.remaining < 0 else min(self.max_poll_records, s.remaining)
+            want = self.max_poll_records if s.limit < 0 else min(self.max_poll_records, s.limit - s.offset)
             msgs = self._consumer.poll(s.topic, s.partition, s.offset, want, self.timeout)
             if not msgs:
                 if self.eof:                            # end of this partition: move on; otherwise keep waiting for new messages
                     self._cur += 1
                 continue
             for off, key, value in msgs:
-                s.offset = off + 1                      # position advances BEFORE the message is handed out: a checkpoint taken by the
-                if s.remaining > 0:                     # consumer of this generator never replays what it already received
-                    s.remaining -= 1
-                yield (key, value) if self.message_key else value
-                if s.remaining == 0:
+                if s.limit >= 0 and off >= s.limit:
+                    s.offset = s.limit
                     break
+                s.offset = off + 1                      # position advances BEFORE the message is handed out: a checkpoint taken by the
+                yield (key, value) if self.message_key else value      # consumer of this generator never replays what it already received
 
     def batch(self, batch_size: int, parse_fn: Optional[Callable] = None, drop_remainder: bool = False) -> Iterator:
         buf = []
+        self._committed = self._snapshot()
         for m in self:
             buf.append(m)
             if len(buf) == batch_size:
+                self._committed = self._snapshot()      # batch boundary: everything up to here has been handed to the trainer
                 yield parse_fn(buf) if parse_fn else buf
                 buf = []
         if buf and not drop_remainder:
+            self._committed = self._snapshot()
             yield parse_fn(buf) if parse_fn else buf
+        self._committed = None
 
     # ---- saveable position (make_saveable_from_iterator in the reference) ---------------------------------------------------------
+    def _snapshot(self) -> dict:
+        return {"current": self._cur, "subscriptions": [f"{s.topic}:{s.partition}:{s.offset}:{s.limit}" for s in self.subs]}
+
     def state_dict(self) -> dict:
-        return {"current": self._cur, "subscriptions": [f"{s.topic}:{s.partition}:{s.offset}:{s.remaining}" for s in self.subs]}
+        committed = getattr(self, "_committed", None)
+        return dict(committed) if committed is not None else self._snapshot()
 
     def load_state_dict(self, state: dict) -> None:
         self.subs = [_parse_subscription(t) for t in state["subscriptions"]]

@@ -96,6 +96,8 @@ class DLRMEngine:
         self.kind = _OPT_KIND[cfg.optimizer.lower()]
         self.launches = 0
         self._graph = None
+        import os as _os
+        self._timing, self._events = _os.environ.get("DEEPREC_STEP_TIMING") == "1", {}
         self._side = torch.cuda.Stream(device=self.dev)
         self._build_params()
         self._build_tables()
@@ -242,7 +244,8 @@ class DLRMEngine:
             from ..parallel.sparse_pipeline import SparsePipeline
             self.ids = torch.zeros(T, B, dtype=torch.int64, device=dev)          # feature-major id columns (local: never leave the GPU)
             self.sp = SparsePipeline(dev, self.rank, W, list(range(T)), T, B, D, comm=self.comm)
-            self.emb = self.demb = self.pos = None
+            self.emb = self.pos = None
+            self.demb = z(T, B, D)                                               # per-sample gradient rows, feature-major (local)
             self.max_unique = max(1, T * B * min(W, 2))          # distinct keys a step can bring to this rank (overflow is flagged, not UB)
         else:
             self.sp = None
@@ -282,6 +285,27 @@ class DLRMEngine:
     def _s(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
+    # ---- optional per-phase CUDA-event timing of EAGER steps (DEEPREC_STEP_TIMING=1; never inside a captured graph) ------------
+    def _tick(self, name: str) -> None:
+        if self._timing and not torch.cuda.is_current_stream_capturing():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.dev))
+            self._events.setdefault(name, []).append(e)
+
+    def timing_report(self, skip: int = 2) -> Dict[str, float]:
+        """Mean milliseconds per phase over the eager steps recorded so far (first `skip` steps dropped)."""
+        torch.cuda.synchronize(self.dev)
+        pairs = [("emb_fwd(side)", "f0", "f_emb"), ("bot_fwd", "f0", "f_bot"), ("dot_fwd", "f_join", "f_dot"), ("top_fwd", "f_dot", "f_top"),
+                 ("head", "f_top", "h1"), ("top_bwd", "h1", "b_top"), ("dot_bwd", "b_top", "b_dot"), ("emb_bwd(side)", "b_dot", "b_emb"),
+                 ("bot_bwd", "b_dot", "b_bot"), ("dense_update", "b_join", "u1"), ("step", "f0", "u1")]
+        out = {}
+        for nm, a, b in pairs:
+            if a in self._events and b in self._events:
+                ts = [x.elapsed_time(y) for x, y in zip(self._events[a], self._events[b])][skip:]
+                if ts:
+                    out[nm] = sum(ts) / len(ts)
+        return out
+
     def _call(self, fn, *args, n=1):
         _chk(fn(*args, self._s()), fn.__name__)
         self.launches += n
@@ -318,11 +342,12 @@ class DLRMEngine:
         if not self.uf:
             self.comm.sparse_backward(self)
             return
+        self.sp.segsum(self.demb)        # requester: per-key pre-reduction of my gradient rows (fp32) -> GRAD flags
         self.sp.reset()                  # every owner has read my bucket lists / counts (ROWS flags seen by the interaction kernel)
         self.sp.grad(self.ctx, self.tmap_local)
         self._call(self.lib.dr_cuda_sparse_apply, ptr(self.ctx.structs()), ptr(self.ctx.ulist), ptr(self.ctx.nuniq), self.ctx.ulist.numel(),
                    ptr(self.ctx.gsum), self.D, ptr(self.hp_dev), self.max_unique, 1, n=2)
-        self.launches += 2
+        self.launches += 3
 
     def _bn_fold(self, L, Ln, train: bool) -> None:
         """finalize BatchNorm(L) from the fused epilogue statistics and fold it into the next Linear (Ln)."""
@@ -335,10 +360,12 @@ class DLRMEngine:
         lib, B, cfg = self.lib, self.B, self.cfg
         main = torch.cuda.current_stream(self.dev)
         fork = cfg.overlap_embedding
+        self._tick("f0")
         if fork:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._embedding_forward(train)
+                self._tick("f_emb")
         # ---- bottom MLP.  Layer l: a_l = relu(a_{l-1} W_l'^T + b_l') with BatchNorm_{l-1} folded into (W', b'); the batch
         #      statistics of a_l come out of the GEMM epilogue, so no activation is read twice and y_l is never written.
         self._call(lib.dr_cuda_cast_pad, ptr(self.dense_in), B, cfg.num_dense, ptr(self.x0), self.x0.shape[1])
@@ -359,16 +386,20 @@ class DLRMEngine:
                            ptr(L.shift), int(train))
                 self._call(lib.dr_cuda_bn_apply, ptr(L.a), B, L.N, L.N, ptr(L.scale), ptr(L.shift), ptr(L.y), L.N)
                 x, ldx = L.y, L.N
+        self._tick("f_bot")
         if fork:
             main.wait_stream(self._side)
         else:
             self._embedding_forward(train)
+            self._tick("f_emb")
+        self._tick("f_join")
         # ---- interaction + top MLP
         if self.uf:   # gathers urow[inv[b][t]]; the kernel itself waits for every owner's ROWS flag
             self._call(lib.dr_cuda_dot_interaction_fwd_u, ptr(x), ldx, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv, self.T, self.D, B, ptr(self.Z),
                        self.Zp, self.sp.sync_ref())
         else:
             self._call(lib.dr_cuda_dot_interaction_fwd, ptr(x), ldx, ptr(self.emb), B * self.D, self.D, self.T, self.D, B, ptr(self.Z), self.Zp)
+        self._tick("f_dot")
         if train:
             # every owner's ROWS flag of this step has been seen => every peer finished last step's all-reduce reads of this buffer
             self.grads.zero_()
@@ -376,6 +407,7 @@ class DLRMEngine:
         for L in self.top:
             self._gemm(x, ldx, L.w_bf16, L.Kp, B, L.N, L.Kp, self.p(L.name + "/bias"), True, None, 0, L.a, L.N)
             x, ldx = L.a, L.N
+        self._tick("f_top")
 
     def _head(self, train: bool) -> None:
         h = self.top[-1]
@@ -387,6 +419,7 @@ class DLRMEngine:
     def _backward(self) -> None:
         lib, B, cfg = self.lib, self.B, self.cfg
         v2 = not cfg.gemm_v1
+        self._tick("h1")
         # ---- top MLP (da of the last hidden layer and its bias gradient were produced by the head kernel)
         for i in range(len(self.top) - 1, -1, -1):
             L = self.top[i]
@@ -400,21 +433,23 @@ class DLRMEngine:
                     self._call(lib.dr_cuda_colstats, ptr(P.da), None, B, P.N, P.N, P.N, ptr(self.g(P.name + "/bias")), None)
             else:
                 self._gemm(L.da, L.N, L.wt_bf16, L.Np, B, self.Zp, L.N, None, False, None, 0, self.dZ, self.Zp)
-        # ---- interaction backward -> dy of the last bottom layer, demb (feature-major, peer-readable)
+        self._tick("b_top")
+        # ---- interaction backward -> dy of the last bottom layer, demb (feature-major)
         last = self.bot[-1]
-        if self.uf:   # per-sample gradient rows are pre-reduced per distinct key into ugrad (fp32); last block raises the GRAD flags
+        if self.uf:   # features gathered through inv; per-sample gradient rows -> demb (pre-reduced per key by k_sp_segsum on the side stream)
             self._call(lib.dr_cuda_dot_interaction_bwd_u, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv,
-                       C.c_void_p(self.sp.scr_buf.local), self.sp.hot_thresh, self.T, self.D, B, ptr(last.dy), last.N, ptr(self.sp.ugrad),
-                       self.sp.sync_ref(), 0)
+                       self.T, self.D, B, ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
         else:
             self._call(lib.dr_cuda_dot_interaction_bwd, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.emb), B * self.D, self.D, self.T, self.D, B,
                        ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
         main = torch.cuda.current_stream(self.dev)
         fork = cfg.overlap_embedding
+        self._tick("b_dot")
         if fork:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._embedding_backward()
+                self._tick("b_emb")
         # ---- bottom MLP backward
         for i in range(len(self.bot) - 1, -1, -1):
             L = self.bot[i]
@@ -438,10 +473,13 @@ class DLRMEngine:
                     self._call(lib.dr_cuda_colstats, ptr(P.dy), ptr(P.a), B, P.N, P.N, P.N, ptr(P.S1b), ptr(P.S2b))
             else:
                 self._gemm_dw(L.da, L.N, self.x0, self.x0.shape[1], L.N, L.Kp, self.g(L.name + "/kernel"), L.Kp)
+        self._tick("b_bot")
         if fork:
             main.wait_stream(self._side)
         else:
             self._embedding_backward()
+            self._tick("b_emb")
+        self._tick("b_join")
 
     def _dense_update(self) -> None:
         lib = self.lib
@@ -455,6 +493,7 @@ class DLRMEngine:
         if self.uf:
             self.sp.step_end()
             self.launches += 1
+        self._tick("u1")
 
     def _step_body(self) -> None:
         self.loss.zero_()

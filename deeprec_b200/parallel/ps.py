@@ -64,6 +64,8 @@ class ParameterServer:
         self.dense_state: Dict[str, torch.Tensor] = {}
         self.dense_lr = 0.01
         self.lock = threading.Lock()            # guards creation / the dense block; rows rely on the engine's own lock-free paths
+        self._gate = threading.Condition()      # admission gate of pulls / pushes (elastic scaling fence)
+        self._inflight = 0
         self.pushes = 0
 
     # ---- variables ----------------------------------------------------------------------------------------------------
@@ -91,21 +93,42 @@ class ParameterServer:
         ``STALE_DEF`` marker, not an exception: it is an expected event during scaling)."""
         return self.frozen or (def_version is not None and def_version != self.def_version)
 
+    def _admit(self, def_version: Optional[int]) -> bool:
+        """Admission of one pull / push: the staleness check and the in-flight count change under ONE lock, so a request is either
+        turned away or counted before ``is_ready_scaling`` can observe a drained server."""
+        with self._gate:
+            if self._stale(def_version):
+                return False
+            self._inflight += 1
+            return True
+
+    def _done(self) -> None:
+        with self._gate:
+            self._inflight -= 1
+            if self._inflight == 0:
+                self._gate.notify_all()
+
     def pull_many(self, reqs: Sequence[Tuple[str, torch.Tensor]], def_version: Optional[int] = None):
-        if self._stale(def_version):
+        if not self._admit(def_version):
             return STALE_DEF
-        return [self.evs[n].table.lookup(ids) for n, ids in reqs]
+        try:
+            return [self.evs[n].table.lookup(ids) for n, ids in reqs]
+        finally:
+            self._done()
 
     def push_many(self, grads: Sequence[Tuple[str, torch.Tensor, torch.Tensor]], def_version: Optional[int] = None):
-        if self._stale(def_version):
+        if not self._admit(def_version):
             return STALE_DEF
-        for name, ids, g in grads:
-            opt, ev = self.opts[name], self.evs[name]
-            with self.lock:              # one applier at a time per PS keeps the optimizer's step counter / beta powers coherent
-                ev._record_grad(ids, g)
-                opt.step()
-                self.pushes += 1
-        return self.pushes
+        try:
+            with self.lock:              # one applier at a time per PS keeps the optimizer's step counter / beta powers coherent; the
+                for name, ids, g in grads:   # whole request is one critical section, so a freeze never lands between two of its tables
+                    opt, ev = self.opts[name], self.evs[name]
+                    ev._record_grad(ids, g)
+                    opt.step()
+                    self.pushes += 1
+            return self.pushes
+        finally:
+            self._done()
 
     def pull_dense(self, name: str, lo: int, hi: int) -> torch.Tensor:
         return self.dense[name].view(-1)[lo:hi].clone()
@@ -141,12 +164,14 @@ class ParameterServer:
     def server_def(self) -> Tuple[int, int]:
         return self.active, self.def_version
 
-    def is_ready_scaling(self) -> bool:
-        """IsReadyScaling: stop admitting pulls / pushes; applies are synchronous under ``lock``, so once it is ours nothing is
-        in flight and rows can move."""
-        with self.lock:
+    def is_ready_scaling(self, timeout: float = 60.0) -> bool:
+        """IsReadyScaling: stop admitting pulls / pushes, then WAIT until every request admitted before the freeze has finished
+        (in-flight count drained) -- only then may rows move.  A push that was admitted earlier completes against the old
+        placement; one that arrives later gets STALE_DEF and is re-routed by the client under the new server definition."""
+        with self._gate:
             self.frozen = True
-            return True
+            ok = self._gate.wait_for(lambda: self._inflight == 0, timeout=timeout)
+        return bool(ok)
 
     def fetch_params_meta(self) -> Dict[str, Tuple[int, int]]:
         """FetchParamsMeta: {variable: (dim, rows held by this PS)}."""

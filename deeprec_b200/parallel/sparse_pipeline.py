@@ -57,7 +57,8 @@ def bind(lib):
     GP, SP, PP = C.POINTER(SpGeom), C.POINTER(SpSync), C.POINTER(Peers)
     sigs = {
         "dr_sp_init_scratch": [P, i64, P],
-        "dr_sp_dedup": [P, GP, P, P, P, P, P, P, SP, P],
+        "dr_sp_dedup": [P, GP, P, P, P, P, P, P, P, SP, P],
+        "dr_sp_segsum": [P, P, GP, P, SP, P],
         "dr_sp_lookup": [P, P, GP, i64, PP, PP, PP, PP, PP, INT, P, P, P, P, P, i64, SP, P],
         "dr_sp_grad": [P, P, GP, i64, PP, P, P, P, P, SP, P],
         "dr_sp_reset": [GP, i64, P, P, P, P, P],
@@ -65,7 +66,7 @@ def bind(lib):
         "dr_sp_step_end": [P, P],
         "dr_sp_stats": [GP, P, P, P],
         "dr_cuda_dot_interaction_fwd_u": [P, i64, P, P, INT, INT, INT, i64, P, i64, SP, P],
-        "dr_cuda_dot_interaction_bwd_u": [P, i64, P, i64, P, P, INT, P, INT, INT, INT, i64, P, i64, P, SP, INT, P],
+        "dr_cuda_dot_interaction_bwd_u": [P, i64, P, i64, P, P, INT, INT, INT, i64, P, i64, P, i64, i64, P],
         "dr_comm_allreduce_apply_sync": [PP, INT, P, P, P, i64, P, P, SP, P],
     }
     for name, args in sigs.items():
@@ -140,7 +141,8 @@ class SparsePipeline:
         self.bcnt = self.bcnt_buf.tensor(i32t, (num_tables, world))
         # ---- local
         self.state = torch.zeros(16, dtype=i32t, device=dev)
-        self.inv = torch.full((batch, self.ldinv), -1, dtype=i32t, device=dev)
+        self.inv = torch.full((batch, self.ldinv), -1, dtype=i32t, device=dev)          # [B][ldinv]: sample-major (interaction gathers)
+        self.invT = torch.full((self.C, batch), -1, dtype=i32t, device=dev) if with_grad else None   # [C][B]: column-major (segment-sum)
         self.own_pos = torch.zeros(self.Btot * world, dtype=i32t, device=dev)
         self.own_gs = torch.zeros(self.Btot * world, dtype=i32t, device=dev)
         self.own_cnt = torch.zeros(num_tables * world, dtype=i32t, device=dev)
@@ -148,7 +150,6 @@ class SparsePipeline:
         s = SpSync()
         s.flags, s.state, s.rank, s.W = self.flags_buf.peers, self.state.data_ptr(), rank, world
         self.sync = s
-        self.hot_thresh = max(8, batch // 256)
         _chk(self.lib.dr_sp_init_scratch(vp(self.scr_buf.local), self.Htot, self._s()), "init_scratch")
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -168,7 +169,7 @@ class SparsePipeline:
     def dedup(self, ids: torch.Tensor) -> None:
         """ids: int64 [C, B] (column-major id columns of the local batch)."""
         assert ids.shape == (self.C, self.B) and ids.dtype == torch.int64
-        _chk(self.lib.dr_sp_dedup(ptr(ids), self.geom_ref(), vp(self.scr_buf.local), ptr(self.inv), vp(self.bkt_key_buf.local), vp(self.bkt_gs_buf.local),
+        _chk(self.lib.dr_sp_dedup(ptr(ids), self.geom_ref(), vp(self.scr_buf.local), ptr(self.inv), ptr(self.invT), vp(self.bkt_key_buf.local), vp(self.bkt_gs_buf.local),
                                   vp(self.bcnt_buf.local), ptr(self.ugrad) if self.ugrad is not None else None, self.sync_ref(), self._s()), "dedup")
         self.launches += 1
 
@@ -179,6 +180,12 @@ class SparsePipeline:
                                    int(train), ptr(self.own_pos), ptr(self.own_gs), ptr(self.own_cnt),
                                    ptr(ctx.ulist) if train else None, ptr(ctx.nuniq) if train else None,
                                    ctx.ulist.numel() if train else 0, self.sync_ref(), self._s()), "lookup")
+        self.launches += 1
+
+    def segsum(self, demb: torch.Tensor) -> None:
+        """Requester side: pre-reduce the per-sample gradient rows (bf16 [C, B, dim]) per distinct key into ugrad; raises GRAD."""
+        assert demb.shape == (self.C, self.B, self.dim) and demb.dtype == torch.bfloat16
+        _chk(self.lib.dr_sp_segsum(ptr(demb), ptr(self.invT), self.geom_ref(), ptr(self.ugrad), self.sync_ref(), self._s()), "segsum")
         self.launches += 1
 
     def grad(self, ctx, table_map: torch.Tensor) -> None:

@@ -164,3 +164,26 @@ def test_bundle_crc_is_ieee_crc32_also_on_the_parallel_path(tmp_path):
     with pytest.raises(IOError):
         r.read("large")
     assert torch.equal(r.read("tiny"), tensors["tiny"])
+
+
+def test_checkpoint_retention_is_per_step_across_shards(tmp_path):
+    """Eight shards writing `<prefix>.ps{i}-<step>` into one directory with max_to_keep=5: every shard of the newest steps survives, whole
+    steps are evicted together, and each shard finds its own latest checkpoint."""
+    import os
+    import torch
+    from deeprec_b200.checkpoint.saver import Saver, latest_checkpoint
+    d = str(tmp_path)
+    savers = [Saver(extra_state={"x": torch.full((4,), float(i))}, max_to_keep=5) for i in range(8)]
+    for step in range(1, 8):
+        for i, sv in enumerate(savers):
+            sv.save(os.path.join(d, f"model.ps{i}"), step)
+    files = sorted(f for f in os.listdir(d) if f.endswith(".index"))
+    assert len(files) == 8 * 5, files                                      # steps 3..7, all 8 shards each
+    for step in range(3, 8):
+        for i in range(8):
+            assert f"model.ps{i}-{step}.index" in files
+    for i in range(8):
+        assert latest_checkpoint(d, base=f"model.ps{i}") == os.path.join(d, f"model.ps{i}-7")
+    sv = Saver(extra_state={"x": torch.zeros(4)})
+    sv.restore(latest_checkpoint(d, base="model.ps5"))
+    assert float(sv.extra["x"][0]) == 5.0

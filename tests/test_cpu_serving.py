@@ -414,3 +414,26 @@ def test_op_program_models_on_the_cpu_processor(tmp_path, name):
     json.dump(meta, open(os.path.join(root, "v1", "saved_model.json"), "w"))
     with pytest.raises(RuntimeError):
         Processor(os.path.join(root, "v1"), {"session_num": 1, "model_update_interval_ms": 0}, device="cpu")
+
+
+def test_full_update_with_a_wider_architecture_resizes_the_sessions(tmp_path):
+    """A hot full update may publish a wider model (more tables, more dense columns, wider layers): the session scratch buffers grow under the
+    session mutex before the version is published (they were sized from the first model only -> heap overflow)."""
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(0)
+    cards_a, cards_b = CARDS[:6], CARDS
+    from deeprec_b200.models.dlrm import DLRM
+    small = DLRM(13, cards_a, 16, mlp_bot=(64, 16), mlp_top=(32,), device="cpu")
+    root = str(tmp_path)
+    export_saved_model_module(small, os.path.join(root, "v1"), version=1, root=root)
+    proc = Processor(os.path.join(root, "v1"), {"session_num": 2, "max_batch": 256, "checkpoint_dir": root, "model_update_interval_ms": 50}, device="cpu")
+    d, ids, _ = criteo_batch(256, 13, cards_a, seed=3)
+    assert np.abs(proc.predict(d.numpy(), ids.numpy()) - _ref(small, d, ids)).max() < 1e-5
+    dr.embedding_variable.clear_registry()
+    big = build_model("dlrm", device="cpu", cardinalities=cards_b)          # 26 tables, 512-256-64-16 / 512-256
+    export_saved_model_module(big, os.path.join(root, "v2"), version=2, root=root)
+    assert _wait(lambda: proc.model_info()["model_version"] == 2)
+    d2, ids2, _ = criteo_batch(256, 13, cards_b, seed=4)
+    for _ in range(3):                                                     # every session runs the wide model at full batch
+        assert np.abs(proc.predict(d2.numpy(), ids2.numpy()) - _ref(big, d2, ids2)).max() < 1e-5
+    proc.close()

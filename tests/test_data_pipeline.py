@@ -180,11 +180,11 @@ def test_kafka_dataset_with_an_in_memory_broker():
             return [(o, log[o][0], log[o][1]) for o in range(offset, min(len(log), offset + max_records))]
 
     broker = Broker()
-    ds = KafkaDataset(["clicks:0:5:12", "clicks:1"], servers="b1:9092", group="g", eof=True, timeout=10, config_global=["enable.auto.commit=false"],
+    ds = KafkaDataset(["clicks:0:5:17", "clicks:1"], servers="b1:9092", group="g", eof=True, timeout=10, config_global=["enable.auto.commit=false"],
                       config_topic=["auto.offset.reset=earliest"], consumer_factory=broker, max_poll_records=4)
     assert broker.servers == ["b1:9092"] and broker.group == "g" and broker.config == {"enable.auto.commit": "false", "auto.offset.reset": "earliest"}
     got = list(ds)
-    assert got == [b"c0-%d" % i for i in range(5, 17)] + [b"c1-%d" % i for i in range(7)]            # 12 from partition 0 at offset 5, then all of 1
+    assert got == [b"c0-%d" % i for i in range(5, 17)] + [b"c1-%d" % i for i in range(7)]            # offsets [5, 17) of partition 0 (4th field = exclusive END offset, as in the reference), then all of 1
     assert ds.positions() == [("clicks", 0, 17), ("clicks", 1, 7)]
     # batches + keys + resume from a saved position
     ds2 = KafkaDataset(["clicks:0:0:-1"], eof=True, message_key=True, consumer_factory=Broker(), max_poll_records=10)
@@ -196,6 +196,15 @@ def test_kafka_dataset_with_an_in_memory_broker():
     ds3.load_state_dict(state)
     rest = [m for b in ds3.batch(8) for m in b]
     assert [k for k, _ in rest] == [b"k%d" % i for i in range(8, 25)] and len(rest) == 17
+    # a position saved while a batch is only partially filled is the last BATCH boundary: nothing is dropped on restore
+    ds4 = KafkaDataset(["clicks:0:0:20"], eof=True, consumer_factory=Broker(), max_poll_records=3)
+    it4 = ds4.batch(8)
+    next(it4)
+    st4 = ds4.state_dict()
+    assert st4["subscriptions"] == ["clicks:0:8:20"]
+    ds5 = KafkaDataset(["clicks:0:0:20"], eof=True, consumer_factory=Broker())
+    ds5.load_state_dict(st4)
+    assert [m for b in ds5.batch(8) for m in b] == [b"c0-%d" % i for i in range(8, 20)]
     # without a client library and without a factory the error says what to do
     try:
         import kafka  # noqa: F401

@@ -91,10 +91,14 @@ def test_lookup_rows_and_gradient_roundtrip():
             rows = sp.urow[inv[t]].float()
             want = tables[t].lookup(ids[t])          # read-only probe of the same table (new keys: default rows)
             assert (rows - want).abs().max().item() < 1e-2, (step, t)
-        # gradients: per-sample rows g[c][b]; the interaction backward's job (pre-reduction into ugrad) done with index_add here
-        g = torch.randn(2, B, D, device=dev)
-        sp.ugrad.index_add_(0, inv.reshape(-1), g.reshape(-1, D))
-        sp.signal(2)                                  # GRAD flag (normally raised by the interaction backward's last block)
+        # gradients: per-sample rows g[c][b] (bf16, feature-major) -> k_sp_segsum pre-reduces them per distinct key (checked vs index_add)
+        g = torch.randn(2, B, D, device=dev).bfloat16()
+        sp.segsum(g)
+        torch.cuda.synchronize()
+        want = torch.zeros_like(sp.ugrad).index_add_(0, inv.reshape(-1), g.float().reshape(-1, D))
+        touched = torch.unique(inv.reshape(-1))
+        assert (sp.ugrad[touched] - want[touched]).abs().max().item() < 1e-4
+        g = g.float()
         sp.reset()
         sp.grad(ctx, tmap)
         rc = lib.dr_cuda_sparse_apply(ptr(ctx.structs()), ptr(ctx.ulist), ptr(ctx.nuniq), ctx.ulist.numel(), ptr(ctx.gsum), D, ptr(ctx.hp_dev), 2 * B, 1,
