@@ -257,6 +257,7 @@ class Staged:
                 with lock:
                     return next(it)
         self._produce_raw = produce_raw
+        self._tls = threading.local()
         self._pool = _PinnedPool() if self.pin else None
         self.copy_stream = torch.cuda.Stream(device=self.device) if self.pin else None
         self._ahead: List[Tuple[Any, Any, Any, int]] = []
@@ -270,6 +271,11 @@ class Staged:
         self.runner = PrefetchRunner(self.buffer, self._produce, num_threads, name).start()
 
     def _produce(self):
+        if self.pin and getattr(self._tls, "dev_set", False) is False:
+            # CUDA's current device is per host thread and starts at 0: without this, the first pinned-memory call of a producer
+            # thread of rank r > 0 creates a context on GPU 0 (hundreds of ms, and memory on the wrong device)
+            torch.cuda.set_device(self.device)
+            self._tls.dev_set = True
         b = self._produce_raw()
         if self.preprocess is not None:
             b = self.preprocess(b)             # CPU side of the cut (stage_subgraph_on_cpu)

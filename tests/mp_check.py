@@ -17,9 +17,9 @@ def gathered_rows(eng, t, probe, dev):
     freq = torch.zeros(probe.numel(), device=dev)
     cnt = torch.zeros(probe.numel(), device=dev)
     if t in eng.tables:
-        f = eng.tables[t].get_freq(probe).float()
+        f = eng.tables[t].get_freq(probe).float().to(dev)
         present = (f > 0).float()
-        rows = eng.tables[t].lookup(probe) * present[:, None]
+        rows = eng.tables[t].lookup(probe).to(dev) * present[:, None]
         freq, cnt = f, present
     for x in (rows, freq, cnt):
         dist.all_reduce(x)
