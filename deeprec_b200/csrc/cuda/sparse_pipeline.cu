@@ -141,6 +141,36 @@ __global__ void __launch_bounds__(256) k_sp_dedup(const int64_t* __restrict__ id
   sp_signal_last_block(sync, SP_CH_DEDUP);
 }
 
+// ---- compact work enumeration -------------------------------------------------------------------------------------------
+// The bucket of (table, peer) is sized for the worst case (every id of the batch distinct and owned by one rank) but holds ~1/W of
+// the distinct keys: enumerating capacity-sized chunk slots made the owner kernels O(T * W * B / chunk) -- at 8 ranks 90 % of a
+// kernel's time was spent skipping empty slots.  Instead every block scans the T counts of the current peer into a chunk prefix
+// (warp 0, shuffle scan) and walks only the chunks that exist; the table of a chunk is found by binary search in shared memory.
+constexpr int kSpMaxTables = 256;
+__device__ __forceinline__ int sp_prefix_chunks(const int32_t* s_cnt, int32_t* s_pre, int T, int unit) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int per = (T + 31) / 32;
+    const int lo = min(T, lane * per), hi = min(T, lo + per);
+    int sum = 0;
+    for (int t = lo; t < hi; ++t) sum += (s_cnt[t] + unit - 1) / unit;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    int run = incl - sum;
+    for (int t = lo; t < hi; ++t) { s_pre[t] = run; run += (s_cnt[t] + unit - 1) / unit; }
+    if (lane == 31) s_pre[T] = incl;
+  }
+  __syncthreads();
+  return s_pre[T];
+}
+__device__ __forceinline__ int sp_chunk_table(const int32_t* s_pre, int T, int k) {      // the t with s_pre[t] <= k < s_pre[t + 1]
+  int lo = 0, hi = T;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= k) lo = mid; else hi = mid; }
+  return lo;
+}
+
 // per-thread training bookkeeping of one (unique-per-source) key: freq += occurrences, dirty mark, per-step dedup claim
 __device__ __forceinline__ void sp_touch(const DrDeviceTable& TB, bool touch, int64_t pos, int32_t occ, int table_index, int64_t* ulist,
                                          int32_t* nunique, int64_t ulist_cap) {
@@ -181,87 +211,83 @@ __global__ void __launch_bounds__(256) k_sp_lookup(const DrDeviceTable* __restri
   __shared__ int32_t s_pos[256];
   __shared__ int64_t s_key[256];
   __shared__ int32_t s_gs[256];
-  __shared__ int32_t s_cnt[256];
+  __shared__ int32_t s_cnt[kSpMaxTables];
+  __shared__ int32_t s_pre[kSpMaxTables + 1];
   const int T = g.T, W = g.W, rank = g.rank;
-  int64_t maxcap = 0;
-  for (int t = 0; t < T; ++t) maxcap = max(maxcap, g.boff[t + 1] - g.boff[t]);
-  const int64_t CB = (maxcap + 255) / 256;
-  const int64_t per_src = (int64_t)T * CB, total = per_src * W;
-  int cur = -1;
-  for (int64_t c = blockIdx.x; c < total; c += gridDim.x) {
-    const int si = (int)(c / per_src);
-    const int s = (rank + si) % W;
-    const int64_t rem = c % per_src;
-    const int t = (int)(rem / CB);
-    const int64_t e0 = (rem % CB) * 256;
-    if (si != cur) {                                          // block-uniform
-      __syncthreads();
-      if (threadIdx.x == 0) sp_wait_one(sync, SP_CH_DEDUP, s);
-      __syncthreads();
-      for (int i = threadIdx.x; i < T; i += blockDim.x)
-        s_cnt[i] = (int32_t)ld_relaxed_sys(reinterpret_cast<const uint32_t*>(P.bcnt.ptr[s]) + i * W + rank);
-      __syncthreads();
-      cur = si;
+  for (int si = 0; si < W; ++si) {
+    const int s = (rank + si) % W;                            // own bucket first, then the peers in ring order
+    __syncthreads();
+    if (threadIdx.x == 0) sp_wait_one(sync, SP_CH_DEDUP, s);
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      const int32_t c = (int32_t)ld_relaxed_sys(reinterpret_cast<const uint32_t*>(P.bcnt.ptr[s]) + i * W + rank);
+      s_cnt[i] = c;
+      if (blockIdx.x == 0) own_cnt[i * W + s] = c;
     }
-    const int64_t cnt = s_cnt[t];
-    if (e0 == 0 && threadIdx.x == 0) own_cnt[t * W + s] = (int32_t)cnt;
-    if (e0 >= cnt) continue;                                  // block-uniform
-    const DrDeviceTable& TB = tables[table_map[t]];
-    const int64_t bcap = g.boff[t + 1] - g.boff[t];
-    const int64_t src_off = g.boff[t] * W + (int64_t)rank * bcap;        // my bucket in the source's lists
-    const int64_t own_off = g.boff[t] * W + (int64_t)s * bcap;           // this (table, source) segment of my own arrays
-    {
-      const int64_t e = e0 + threadIdx.x;
-      const bool live = e < cnt;
-      int64_t key = 0, pos = -2;
-      int32_t gs = -1, occ = 1;
-      bool touch = false;
-      if (live) {
-        key = reinterpret_cast<const int64_t*>(P.bkt_key.ptr[s])[src_off + e];
-        gs = reinterpret_cast<const int32_t*>(P.bkt_gs.ptr[s])[src_off + e];
-        if (!train || TB.is_inference) {
-          pos = table_find(TB, key);
-        } else {
-          occ = reinterpret_cast<const DrSpSlot*>(P.scr.ptr[s])[gs].count;
-          bool inserted = false, skip = false;
-          if (TB.filter_type == DR_FILTER_BLOOM) {
+    const int nchunks = sp_prefix_chunks(s_cnt, s_pre, T, 256);
+    // rotate the starting block per peer so that the few chunks of every peer land on different blocks
+    for (int k = (int)((blockIdx.x + gridDim.x - (unsigned)(si * 67) % gridDim.x) % gridDim.x); k < nchunks; k += gridDim.x) {
+      const int t = sp_chunk_table(s_pre, T, k);
+      const int64_t e0 = (int64_t)(k - s_pre[t]) * 256;
+      const int64_t cnt = s_cnt[t];
+      const DrDeviceTable& TB = tables[table_map[t]];
+      const int64_t bcap = g.boff[t + 1] - g.boff[t];
+      const int64_t src_off = g.boff[t] * W + (int64_t)rank * bcap;        // my bucket in the source's lists
+      const int64_t own_off = g.boff[t] * W + (int64_t)s * bcap;           // this (table, source) segment of my own arrays
+      {
+        const int64_t e = e0 + threadIdx.x;
+        const bool live = e < cnt;
+        int64_t key = 0, pos = -2;
+        int32_t gs = -1, occ = 1;
+        bool touch = false;
+        if (live) {
+          key = reinterpret_cast<const int64_t*>(P.bkt_key.ptr[s])[src_off + e];
+          gs = reinterpret_cast<const int32_t*>(P.bkt_gs.ptr[s])[src_off + e];
+          if (!train || TB.is_inference) {
             pos = table_find(TB, key);
-            if (pos < 0) {
-              if (bloom_add_min(TB, key, (uint32_t)occ) < (uint32_t)TB.filter_freq) skip = true;
-              else pos = table_find_or_insert(TB, key, &inserted);
-            }
           } else {
-            pos = table_find_or_insert(TB, key, &inserted);
+            // the occurrence count is a second (dependent) NVLink round trip: issue it before the probe, consume it after
+            occ = reinterpret_cast<const DrSpSlot*>(P.scr.ptr[s])[gs].count;
+            bool inserted = false, skip = false;
+            if (TB.filter_type == DR_FILTER_BLOOM) {
+              pos = table_find(TB, key);
+              if (pos < 0) {
+                if (bloom_add_min(TB, key, (uint32_t)occ) < (uint32_t)TB.filter_freq) skip = true;
+                else pos = table_find_or_insert(TB, key, &inserted);
+              }
+            } else {
+              pos = table_find_or_insert(TB, key, &inserted);
+            }
+            if (!skip && pos < 0) TB.counters[CTR_OVERFLOW] = 1;
+            if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
+            touch = !skip && pos >= 0;
           }
-          if (!skip && pos < 0) TB.counters[CTR_OVERFLOW] = 1;
-          if (inserted) atomicAdd(&TB.counters[CTR_NKEYS], 1);
-          touch = !skip && pos >= 0;
+          own_pos[own_off + e] = (int32_t)pos;
+          own_gs[own_off + e] = gs;
         }
-        own_pos[own_off + e] = (int32_t)pos;
-        own_gs[own_off + e] = gs;
+        s_pos[threadIdx.x] = live ? (int32_t)pos : -2;
+        s_key[threadIdx.x] = key;
+        s_gs[threadIdx.x] = gs;
+        if (train) sp_touch(TB, touch, pos, occ, table_map[t], ulist, nunique, ulist_cap);
       }
-      s_pos[threadIdx.x] = live ? (int32_t)pos : -2;
-      s_key[threadIdx.x] = key;
-      s_gs[threadIdx.x] = gs;
-      if (train) sp_touch(TB, touch, pos, occ, table_map[t], ulist, nunique, ulist_cap);
-    }
-    __syncthreads();
-    // LPR lanes per row: fp32 row -> bf16 into the SOURCE's unique-row buffer over NVLink
-    constexpr int ROWS_PER_IT = 256 / LPR;
-    const int lane = threadIdx.x % LPR;
-    __nv_bfloat16* dst_base = reinterpret_cast<__nv_bfloat16*>(P.urow.ptr[s]);
+      __syncthreads();
+      // LPR lanes per row: fp32 row -> bf16 into the SOURCE's unique-row buffer over NVLink
+      constexpr int ROWS_PER_IT = 256 / LPR;
+      const int lane = threadIdx.x % LPR;
+      __nv_bfloat16* dst_base = reinterpret_cast<__nv_bfloat16*>(P.urow.ptr[s]);
 #pragma unroll
-    for (int it = 0; it < LPR; ++it) {
-      const int li = it * ROWS_PER_IT + threadIdx.x / LPR;
-      if (s_pos[li] != -2) {
-        const float* src = table_read_ptr(TB, s_key[li], s_pos[li]);
-        const float4 v = src ? *reinterpret_cast<const float4*>(src + 4 * lane)
-                             : make_float4(TB.no_permission, TB.no_permission, TB.no_permission, TB.no_permission);
-        __nv_bfloat16* dst = dst_base + (int64_t)s_gs[li] * (4 * LPR) + 4 * lane;
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      for (int it = 0; it < LPR; ++it) {
+        const int li = it * ROWS_PER_IT + threadIdx.x / LPR;
+        if (s_pos[li] != -2) {
+          const float* src = table_read_ptr(TB, s_key[li], s_pos[li]);
+          const float4 v = src ? *reinterpret_cast<const float4*>(src + 4 * lane)
+                               : make_float4(TB.no_permission, TB.no_permission, TB.no_permission, TB.no_permission);
+          __nv_bfloat16* dst = dst_base + (int64_t)s_gs[li] * (4 * LPR) + 4 * lane;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   sp_signal_last_block(sync, SP_CH_ROWS);
 }
@@ -333,35 +359,32 @@ __global__ void __launch_bounds__(256) k_sp_grad(const DrDeviceTable* __restrict
   pdl_sync();
   constexpr int IPC = 256 / LPR;
   constexpr int dim = 4 * LPR;
+  __shared__ int32_t s_cnt[kSpMaxTables];
+  __shared__ int32_t s_pre[kSpMaxTables + 1];
   const int T = g.T, W = g.W, rank = g.rank;
-  int64_t maxcap = 0;
-  for (int t = 0; t < T; ++t) maxcap = max(maxcap, g.boff[t + 1] - g.boff[t]);
-  const int64_t CB = (maxcap + IPC - 1) / IPC;
-  const int64_t per_src = (int64_t)T * CB, total = per_src * W;
   const int lane = threadIdx.x % LPR;
-  int cur = -1;
-  for (int64_t c = blockIdx.x; c < total; c += gridDim.x) {
-    const int si = (int)(c / per_src);
+  for (int si = 0; si < W; ++si) {
     const int s = (rank + si) % W;
-    const int64_t rem = c % per_src;
-    const int t = (int)(rem / CB);
-    const int64_t e = (rem % CB) * IPC + threadIdx.x / LPR;
-    if (si != cur) {
-      __syncthreads();
-      if (threadIdx.x == 0) sp_wait_one(sync, SP_CH_GRAD, s);
-      __syncthreads();
-      cur = si;
+    __syncthreads();
+    if (threadIdx.x == 0) sp_wait_one(sync, SP_CH_GRAD, s);
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s_cnt[i] = own_cnt[i * W + s];
+    const int nchunks = sp_prefix_chunks(s_cnt, s_pre, T, IPC);
+    for (int k = (int)((blockIdx.x + gridDim.x - (unsigned)(si * 67) % gridDim.x) % gridDim.x); k < nchunks; k += gridDim.x) {
+      const int t = sp_chunk_table(s_pre, T, k);
+      const int64_t e = (int64_t)(k - s_pre[t]) * IPC + threadIdx.x / LPR;
+      if (e >= s_cnt[t]) continue;
+      const int64_t bcap = g.boff[t + 1] - g.boff[t];
+      const int64_t own_off = g.boff[t] * W + (int64_t)s * bcap + e;
+      const int32_t p = own_pos[own_off];
+      if (p < 0) continue;
+      // the peer row does not depend on the tag: both loads are in flight together
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ugrad.ptr[s]) + (int64_t)own_gs[own_off] * dim + 4 * lane);
+      const int32_t u = tables[table_map[t]].slots[p].tag;
+      if (u < 0) continue;
+      if (W == 1) *reinterpret_cast<float4*>(gsum + (int64_t)u * dim + 4 * lane) = v;     // one contribution per key: plain store (gsum is zero)
+      else red_add_v4_f32(gsum + (int64_t)u * dim + 4 * lane, v.x, v.y, v.z, v.w);
     }
-    if (e >= own_cnt[t * W + s]) continue;
-    const int64_t bcap = g.boff[t + 1] - g.boff[t];
-    const int64_t own_off = g.boff[t] * W + (int64_t)s * bcap + e;
-    const int32_t p = own_pos[own_off];
-    if (p < 0) continue;
-    const int32_t u = tables[table_map[t]].slots[p].tag;
-    if (u < 0) continue;
-    const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ugrad.ptr[s]) + (int64_t)own_gs[own_off] * dim + 4 * lane);
-    if (W == 1) *reinterpret_cast<float4*>(gsum + (int64_t)u * dim + 4 * lane) = v;     // one contribution per key: plain store (gsum is zero)
-    else red_add_v4_f32(gsum + (int64_t)u * dim + 4 * lane, v.x, v.y, v.z, v.w);
   }
 }
 
@@ -371,19 +394,22 @@ __global__ void __launch_bounds__(256) k_sp_grad(const DrDeviceTable* __restrict
 __global__ void __launch_bounds__(256) k_sp_reset(DrSpGeom g, DrSpSlot* __restrict__ scr, const int32_t* __restrict__ bkt_gs,
                                                   int32_t* __restrict__ bcnt, int32_t* __restrict__ state) {
   pdl_sync();
+  __shared__ int32_t s_cnt[kSpMaxTables];
+  __shared__ int32_t s_pre[kSpMaxTables + 1];
   const int T = g.T, W = g.W;
-  int64_t maxcap = 0;
-  for (int t = 0; t < T; ++t) maxcap = max(maxcap, g.boff[t + 1] - g.boff[t]);
-  const int64_t CB = (maxcap + 255) / 256;
-  const int64_t total = (int64_t)T * W * CB;
-  for (int64_t c = blockIdx.x; c < total; c += gridDim.x) {
-    const int t = (int)(c / (W * CB)), o = (int)((c / CB) % W);
-    const int64_t e = (c % CB) * 256 + threadIdx.x;
-    if (e >= bcnt[t * W + o]) continue;
-    const int64_t bcap = g.boff[t + 1] - g.boff[t];
-    const int32_t gs = bkt_gs[g.boff[t] * W + (int64_t)o * bcap + e];
-    DrSpSlot z; z.key = kEmptyKey; z.count = 0; z.pad = 0;
-    *reinterpret_cast<int4*>(&scr[gs]) = *reinterpret_cast<int4*>(&z);
+  for (int o = 0; o < W; ++o) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s_cnt[i] = bcnt[i * W + o];
+    const int nchunks = sp_prefix_chunks(s_cnt, s_pre, T, 256);
+    for (int k = (int)((blockIdx.x + gridDim.x - (unsigned)(o * 67) % gridDim.x) % gridDim.x); k < nchunks; k += gridDim.x) {
+      const int t = sp_chunk_table(s_pre, T, k);
+      const int64_t e = (int64_t)(k - s_pre[t]) * 256 + threadIdx.x;
+      if (e >= s_cnt[t]) continue;
+      const int64_t bcap = g.boff[t + 1] - g.boff[t];
+      const int32_t gs = bkt_gs[g.boff[t] * W + (int64_t)o * bcap + e];
+      DrSpSlot z; z.key = kEmptyKey; z.count = 0; z.pad = 0;
+      *reinterpret_cast<int4*>(&scr[gs]) = *reinterpret_cast<int4*>(&z);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -461,7 +487,7 @@ int dr_sp_segsum(const void* demb, const int32_t* invT, const DrSpGeom* g, float
 int dr_sp_lookup(const DrDeviceTable* tables_dev, const int32_t* table_map, const DrSpGeom* g, int64_t max_bcap, const DrPeers* bkt_key,
                  const DrPeers* bkt_gs, const DrPeers* bcnt, const DrPeers* scr, const DrPeers* urow, int train, int32_t* own_pos, int32_t* own_gs,
                  int32_t* own_cnt, int64_t* ulist, int32_t* nunique, int64_t ulist_cap, const DrSpSync* sync, cudaStream_t s) {
-  if (g->T > 256 || g->W > 16) return -2;
+  if (g->T > kSpMaxTables || g->W > 16) return -2;
   SpPeerLists P{*bkt_key, *bkt_gs, *bcnt, *scr, *urow};
   const int64_t chunks = (int64_t)g->T * g->W * ((max_bcap + 255) / 256);
   const int grid = sp_grid(chunks);

@@ -295,7 +295,9 @@ class DLRMEngine:
     def timing_report(self, skip: int = 2) -> Dict[str, float]:
         """Mean milliseconds per phase over the eager steps recorded so far (first `skip` steps dropped)."""
         torch.cuda.synchronize(self.dev)
-        pairs = [("emb_fwd(side)", "f0", "f_emb"), ("bot_fwd", "f0", "f_bot"), ("dot_fwd", "f_join", "f_dot"), ("top_fwd", "f_dot", "f_top"),
+        pairs = [("dedup", "e0", "e_dedup"), ("lookup", "e_dedup", "f_emb"), ("segsum", "g0", "g_segsum"), ("reset", "g_segsum", "g_reset"),
+                 ("grad_pull", "g_reset", "g_grad"), ("apply", "g_grad", "b_emb"),
+                 ("emb_fwd(side)", "f0", "f_emb"), ("bot_fwd", "f0", "f_bot"), ("dot_fwd", "f_join", "f_dot"), ("top_fwd", "f_dot", "f_top"),
                  ("head", "f_top", "h1"), ("top_bwd", "h1", "b_top"), ("dot_bwd", "b_top", "b_dot"), ("emb_bwd(side)", "b_dot", "b_emb"),
                  ("bot_bwd", "b_dot", "b_bot"), ("dense_update", "b_join", "u1"), ("step", "f0", "u1")]
         out = {}
@@ -333,7 +335,9 @@ class DLRMEngine:
         if not self.uf:
             self.comm.lookup_forward(self, train)
             return
+        self._tick("e0")
         self.sp.dedup(self.ids)
+        self._tick("e_dedup")
         self.sp.lookup(self.ctx, self.tmap_local, train)
         self.launches += 2
 
@@ -342,9 +346,13 @@ class DLRMEngine:
         if not self.uf:
             self.comm.sparse_backward(self)
             return
+        self._tick("g0")
         self.sp.segsum(self.demb)        # requester: per-key pre-reduction of my gradient rows (fp32) -> GRAD flags
+        self._tick("g_segsum")
         self.sp.reset()                  # every owner has read my bucket lists / counts (ROWS flags seen by the interaction kernel)
+        self._tick("g_reset")
         self.sp.grad(self.ctx, self.tmap_local)
+        self._tick("g_grad")
         self._call(self.lib.dr_cuda_sparse_apply, ptr(self.ctx.structs()), ptr(self.ctx.ulist), ptr(self.ctx.nuniq), self.ctx.ulist.numel(),
                    ptr(self.ctx.gsum), self.D, ptr(self.hp_dev), self.max_unique, 1, n=2)
         self.launches += 3
