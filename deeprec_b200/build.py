@@ -28,6 +28,7 @@ CUDA_SOURCES = [
     "cuda/interaction_kernels.cu",
     "cuda/comm_kernels.cu",
     "cuda/sparse_pipeline.cu",
+    "cuda/fused_interaction_gemm.cu",
     "cuda/runtime.cu",
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",

@@ -70,6 +70,10 @@ class DLRMConfig:
     overlap_embedding: bool = True              # fork the embedding branch onto a side stream inside the graph
     sparse_blocks_per_sm: int = 4               # resident-block budget of the side-stream sparse kernels (overlap with the GEMMs)
     gemm_v1: bool = False                       # A/B switch: direct-store GEMM epilogue + separate statistics passes
+    # combine + dot interaction + top-MLP layer 0 in ONE tcgen05 kernel (csrc/cuda/fused_interaction_gemm.cu).  Validated against the
+    # unfused path and the fp32 oracle, but measured SLOWER at B = 65536 (215 us vs 64 + 35 us: the per-SM builder phase cannot overlap
+    # the GEMM phase with a single 96 KB Z tile in shared memory -- profiles/r2_notes.md), so the default step keeps the two kernels.
+    fuse_interaction_gemm: bool = False
 
 
 def _pad8(n: int) -> int:
@@ -402,7 +406,12 @@ class DLRMEngine:
             self._tick("f_emb")
         self._tick("f_join")
         # ---- interaction + top MLP
-        if self.uf:   # gathers urow[inv[b][t]]; the kernel itself waits for every owner's ROWS flag
+        fused0 = self.uf and cfg.fuse_interaction_gemm and self.D == 16 and self.top[0].N <= 512 and self.inter_dim <= 384
+        if fused0:    # gather + Gram + lower-triangle pack + Linear(512) + ReLU in one kernel; Z only leaves the SM as a TMA store for the backward
+            L0 = self.top[0]
+            self._call(lib.dr_cuda_dlrm_inter_gemm, ptr(x), ldx, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv, self.T, self.D, B, ptr(L0.w_bf16), L0.Kp,
+                       L0.N, ptr(self.p(L0.name + "/bias")), ptr(L0.a), L0.N, ptr(self.Z) if train else None, self.Zp, self.sp.sync_ref())
+        elif self.uf:   # gathers urow[inv[b][t]]; the kernel itself waits for every owner's ROWS flag
             self._call(lib.dr_cuda_dot_interaction_fwd_u, ptr(x), ldx, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv, self.T, self.D, B, ptr(self.Z),
                        self.Zp, self.sp.sync_ref())
         else:
@@ -412,8 +421,9 @@ class DLRMEngine:
             # every owner's ROWS flag of this step has been seen => every peer finished last step's all-reduce reads of this buffer
             self.grads.zero_()
         x, ldx = self.Z, self.Zp
-        for L in self.top:
-            self._gemm(x, ldx, L.w_bf16, L.Kp, B, L.N, L.Kp, self.p(L.name + "/bias"), True, None, 0, L.a, L.N)
+        for li, L in enumerate(self.top):
+            if not (fused0 and li == 0):
+                self._gemm(x, ldx, L.w_bf16, L.Kp, B, L.N, L.Kp, self.p(L.name + "/bias"), True, None, 0, L.a, L.N)
             x, ldx = L.a, L.N
         self._tick("f_top")
 

@@ -67,6 +67,7 @@ def bind(lib):
         "dr_sp_stats": [GP, P, P, P],
         "dr_cuda_dot_interaction_fwd_u": [P, i64, P, P, INT, INT, INT, i64, P, i64, SP, P],
         "dr_cuda_dot_interaction_bwd_u": [P, i64, P, i64, P, P, INT, INT, INT, i64, P, i64, P, i64, i64, P],
+        "dr_cuda_dlrm_inter_gemm": [P, i64, P, P, INT, INT, INT, i64, P, i64, INT, P, P, i64, P, i64, SP, P],
         "dr_comm_allreduce_apply_sync": [PP, INT, P, P, P, i64, P, P, SP, P],
     }
     for name, args in sigs.items():

@@ -138,3 +138,36 @@ def test_engine_forward_rows_match_tables():
     inv = eng.sp.inv[:, : eng.T].t().long()
     for t in (0, 1, 2, 25):
         assert (eng.sp.urow[inv[t]].float() - eng.tables[t].lookup(ids[t])).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("batch", [512, 1000])
+def test_fused_interaction_gemm_matches_unfused(batch):
+    """k_dlrm_inter_gemm (gather + Gram + pack + Linear + ReLU in one tcgen05 kernel) == k_dot_fwd_tc + tcgen05 GEMM: same Z (bitwise:
+    both round the fp32 Gram to bf16), same first top activation up to accumulation order; and the training losses stay together."""
+    from deeprec_b200.models.dlrm_engine import DLRMConfig, DLRMEngine
+    cards = [50, 1000, 7, 300] + [97] * 22
+    engs = []
+    for fuse in (True, False):
+        torch.manual_seed(3)
+        engs.append(DLRMEngine(DLRMConfig(batch_size=batch, cardinalities=cards, learning_rate=0.05, fuse_interaction_gemm=fuse)))
+    assert engs[0].cfg.fuse_interaction_gemm and not engs[1].cfg.fuse_interaction_gemm
+    torch.manual_seed(4)
+    losses = [[], []]
+    for step in range(3):
+        dense = torch.rand(batch, 13, device="cuda") * 3
+        ids = torch.stack([torch.randint(0, c, (batch,), device="cuda") for c in cards])
+        labels = (torch.rand(batch, device="cuda") < 0.3).float()
+        for i, e in enumerate(engs):
+            e.load_batch(dense, ids, labels)
+            e.train_step()
+            losses[i].append(e.loss_value())
+        torch.cuda.synchronize()
+        if step == 0:        # identical parameters and inputs (later steps drift by bf16 rounding of the differently-ordered accumulations)
+            za, zb = engs[0].Z.float(), engs[1].Z.float()
+            # the bottom-MLP output feeding both paths differs by <= 1 bf16 ulp between two engines (atomic order of the BatchNorm
+            # statistics); a 16-term dot product of zero-mean vectors amplifies that to a few ulps of its largest term
+            assert ((za - zb).abs() - 2e-2 * zb.abs()).max().item() < 0.1, (step, (za - zb).abs().max().item())
+            aa, ab = engs[0].top[0].a.float(), engs[1].top[0].a.float()
+            assert (aa - ab).abs().max().item() < 5e-2 * max(1.0, ab.abs().max().item()), (step, (aa - ab).abs().max().item())
+    for a, b in zip(*losses):
+        assert abs(a - b) < 5e-3, losses
