@@ -350,6 +350,27 @@ __global__ void __launch_bounds__(256) k_sp_segsum(const __nv_bfloat16* __restri
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// k_sp_gather (requester): out[b][c][:] = urow[inv[b][c]]  (padding -> zeros) -- the sample-major [B, C, dim] activation generic dense
+// networks consume (models/rec_engine.py).  Waits in-kernel for every owner's ROWS flag, like the fused interaction kernels do.
+// -----------------------------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256) k_sp_gather(const __nv_bfloat16* __restrict__ urow, const int32_t* __restrict__ inv, int ldinv, int C, int64_t B,
+                                                   __nv_bfloat16* __restrict__ out, DrSpSync sync) {
+  pdl_sync();
+  sp_wait_all(sync, SP_CH_ROWS);
+  constexpr int dim = 4 * LPR;
+  const int lane = threadIdx.x % LPR;
+  const int64_t n = B * C;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR; i < n; i += (int64_t)gridDim.x * blockDim.x / LPR) {
+    const int64_t b = i / C; const int c = (int)(i % C);
+    const int32_t gs = inv[b * ldinv + c];
+    uint2 v = make_uint2(0u, 0u);
+    if (gs >= 0) asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(urow + (int64_t)gs * dim + 4 * lane) : "memory");
+    *reinterpret_cast<uint2*>(out + i * dim + 4 * lane) = v;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // k_sp_grad (owner): gsum[tag(pos)] += ugrad_of_source[gs]      (fp32 rows, pre-reduced per key on the source)
 // -----------------------------------------------------------------------------------------------------------------
 template <int LPR>
@@ -514,6 +535,20 @@ int dr_sp_grad(const DrDeviceTable* tables_dev, const int32_t* table_map, const 
     default: return -3;
   }
 #undef SPG
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_sp_gather(const void* urow, const int32_t* inv, const DrSpGeom* g, void* out, const DrSpSync* sync, cudaStream_t s) {
+  const int lpr = g->dim / 4;
+  const int64_t n = g->B * g->C;
+  const int grid = sp_grid((n * lpr + 255) / 256);
+#define SPGA(L) DR_PDL_LAUNCH((k_sp_gather<L>), grid, 256, 0, s, (const __nv_bfloat16*)urow, inv, g->ldinv, g->C, g->B, (__nv_bfloat16*)out, *sync)
+  switch (lpr) {
+    case 2: SPGA(2); break; case 4: SPGA(4); break; case 8: SPGA(8); break; case 16: SPGA(16); break; case 32: SPGA(32); break;
+    default: return -3;
+  }
+#undef SPGA
   DR_LAUNCH_CHECK();
   return 0;
 }

@@ -320,11 +320,15 @@ class DIN(_SeqBase):
         self.top = nn.Sequential(nn.Linear(self.emb_dim + 3 * D2, 200, device=dev), nn.PReLU(device=dev), nn.Linear(200, 80, device=dev), nn.PReLU(device=dev),
                                  nn.Linear(80, 1, device=dev))
 
-    def forward(self, b):
-        u, q, k, mask = self._embed(b)
+    def head(self, u, q, k, mask):
+        """Dense part on already-looked-up embeddings (user [B, D], target [B, 2D], history [B, L, 2D] zero-padded, mask [B, L]) --
+        what :func:`models.rec_engine.din_engine` runs on top of the unique-first sparse pipeline."""
         pooled = k.sum(1)
         att = din_attention(q, k, mask, self.att)
         return self.top(self.bn(torch.cat([u, q, pooled, att], -1))).squeeze(-1)
+
+    def forward(self, b):
+        return self.head(*self._embed(b))
 
 
 class DIEN(_SeqBase):

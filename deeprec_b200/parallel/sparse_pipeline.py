@@ -59,6 +59,7 @@ def bind(lib):
         "dr_sp_init_scratch": [P, i64, P],
         "dr_sp_dedup": [P, GP, P, P, P, P, P, P, P, SP, P],
         "dr_sp_segsum": [P, P, GP, P, SP, P],
+        "dr_sp_gather": [P, P, GP, P, SP, P],
         "dr_sp_lookup": [P, P, GP, i64, PP, PP, PP, PP, PP, INT, P, P, P, P, P, i64, SP, P],
         "dr_sp_grad": [P, P, GP, i64, PP, P, P, P, P, SP, P],
         "dr_sp_reset": [GP, i64, P, P, P, P, P],
@@ -181,6 +182,12 @@ class SparsePipeline:
                                    int(train), ptr(self.own_pos), ptr(self.own_gs), ptr(self.own_cnt),
                                    ptr(ctx.ulist) if train else None, ptr(ctx.nuniq) if train else None,
                                    ctx.ulist.numel() if train else 0, self.sync_ref(), self._s()), "lookup")
+        self.launches += 1
+
+    def gather(self, out: torch.Tensor) -> None:
+        """Requester side: out[b, c, :] = urow[inv[b, c]] (bf16 [B, C, dim]); the kernel waits for every owner's ROWS flag."""
+        assert out.shape == (self.B, self.C, self.dim) and out.dtype == torch.bfloat16 and out.is_contiguous()
+        _chk(self.lib.dr_sp_gather(ptr(self.urow), ptr(self.inv), self.geom_ref(), ptr(out), self.sync_ref(), self._s()), "gather")
         self.launches += 1
 
     def segsum(self, demb: torch.Tensor) -> None:
