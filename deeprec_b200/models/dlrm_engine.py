@@ -579,6 +579,15 @@ class DLRMEngine:
         raw = bytes(self.hp_dev.cpu().numpy().tobytes())
         return int(OptHyper.from_buffer_copy(raw).global_step)
 
+    # ---- training-state checkpoints (checkpoint/engine_ckpt.py): full / incremental save, restore under any world size ----------
+    def save(self, save_path: str, incremental: bool = False, max_to_keep: int = 5) -> str:
+        from ..checkpoint.engine_ckpt import save_engine
+        return save_engine(self, save_path, incremental=incremental, max_to_keep=max_to_keep)
+
+    def restore(self, save_path: str, step=None, replay_incremental: bool = True) -> int:
+        from ..checkpoint.engine_ckpt import restore_engine
+        return restore_engine(self, save_path, step=step, replay_incremental=replay_incremental)
+
     def l2_flush(self) -> None:
         if self._l2_scratch is None:
             self._l2_scratch = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=self.dev)   # 256 MB > 126 MB L2

@@ -224,6 +224,15 @@ class FusedRecEngine:
         self.net.train(was)
         return out
 
+    # ---- training-state checkpoints (checkpoint/engine_ckpt.py): full / incremental save, restore under any world size ----------
+    def save(self, save_path: str, incremental: bool = False, max_to_keep: int = 5) -> str:
+        from ..checkpoint.engine_ckpt import save_engine
+        return save_engine(self, save_path, incremental=incremental, max_to_keep=max_to_keep)
+
+    def restore(self, save_path: str, step=None, replay_incremental: bool = True) -> int:
+        from ..checkpoint.engine_ckpt import restore_engine
+        return restore_engine(self, save_path, step=step, replay_incremental=replay_incremental)
+
     def loss_value(self, global_mean: bool = True) -> float:
         v = self.loss.clone()
         if global_mean and self.world > 1:

@@ -187,3 +187,22 @@ def test_checkpoint_retention_is_per_step_across_shards(tmp_path):
     sv = Saver(extra_state={"x": torch.zeros(4)})
     sv.restore(latest_checkpoint(d, base="model.ps5"))
     assert float(sv.extra["x"][0]) == 5.0
+
+
+def test_sp_owner_matches_the_device_hash():
+    """checkpoint/engine_ckpt.sp_owner (torch int64 arithmetic) == csrc/cuda/sparse_pipeline.cu::sp_owner (uint64 arithmetic)."""
+    import torch
+    from deeprec_b200.checkpoint.engine_ckpt import sp_owner
+    M = (1 << 64) - 1
+
+    def mix64(x):
+        x ^= x >> 30; x = (x * 0xbf58476d1ce4e5b9) & M
+        x ^= x >> 27; x = (x * 0x94d049bb133111eb) & M
+        x ^= x >> 31
+        return x
+    g = torch.Generator().manual_seed(0)
+    keys = torch.cat([torch.randint(-(1 << 62), 1 << 62, (500,), generator=g), torch.arange(-5, 50), torch.tensor([(1 << 63) - 1, -(1 << 63) + 2])])
+    for W in (2, 3, 8):
+        want = [(mix64(((int(k) & M) ^ 0x5bd1e9955bd1e995)) >> 33) % W for k in keys.tolist()]
+        assert sp_owner(keys, W).tolist() == want
+    assert sp_owner(keys, 1).sum().item() == 0
