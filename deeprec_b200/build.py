@@ -29,6 +29,7 @@ CUDA_SOURCES = [
     "cuda/comm_kernels.cu",
     "cuda/sparse_pipeline.cu",
     "cuda/fused_interaction_gemm.cu",
+    "cuda/tier_kernels.cu",
     "cuda/runtime.cu",
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",

@@ -41,9 +41,12 @@ class FusedRecEngine:
     def __init__(self, net: nn.Module, forward_fn: Callable[..., torch.Tensor], col_table: Sequence[int], table_rows: Sequence[int], batch_size: int,
                  embedding_dim: int = 16, dense_inputs: Optional[Dict[str, tuple]] = None, optimizer: str = "adagrad", learning_rate: float = 0.01,
                  initial_accumulator_value: float = 0.1, filter_freq: int = 0, steps_to_live: int = 0, pad_key: int = -1, seed: int = 1234,
-                 max_rows_per_table: int = 1 << 25, device=None, rank: int = 0, world_size: int = 1, comm=None, loss_fn: Optional[Callable] = None):
+                 max_rows_per_table: int = 1 << 25, device=None, rank: int = 0, world_size: int = 1, comm=None, loss_fn: Optional[Callable] = None,
+                 tiered: Optional[Dict[int, dict]] = None):
         """net: dense module (its parameters are trained); forward_fn(net, dense: dict of static tensors, emb [B, C, D] bf16, ids [C, B]) -> logits [B].
-        col_table[c]: table of id column c; table_rows[t]: expected distinct keys of table t (pre-sizing hint, tables grow)."""
+        col_table[c]: table of id column c; table_rows[t]: expected distinct keys of table t (pre-sizing hint, tables grow).
+        tiered: {table: {"cache_rows": R, "strategy": 0 (LFU) | 1 (LRU)}} -- those tables keep at most ~R rows in HBM over a host DRAM tier
+        (ops/tier_manager.py; world_size 1): call ``prefetch(next_ids)`` one batch ahead."""
         self.net, self.forward_fn = net, forward_fn
         self.rank, self.world, self.comm = rank, world_size, comm
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -79,9 +82,24 @@ class FusedRecEngine:
             g.manual_seed(seed + 17 + 1000 * t)
             dm = torch.empty(4096, self.D).normal_(0.0, 1.0 / math.sqrt(self.D), generator=g)
             rows = max(1024, min(card, max_rows_per_table))
+            if tiered and t in tiered:            # HBM tier = cache: R rows + head-room for the keys two steps can create before an eviction lands
+                ncols_t = sum(1 for ct in col_table if ct == t)
+                rows = int(tiered[t]["cache_rows"]) + 2 * ncols_t * batch_size + 4096
+                card = rows
             cap = _next_pow2(max(2048, 2 * min(card, rows)))
             self.tables[t] = DeviceTable(c, dm, dev, capacity=cap, row_capacity=rows, owner=id(self) & 0x7FFFFFFF)
         self.tmap = torch.tensor([self.tables[t].gid for t in range(self.T)], dtype=torch.int32, device=dev)
+        self.tiers = {}
+        if tiered:
+            if world_size > 1:
+                raise ValueError("tiered tables: the prefetch path is single-rank for now (the owner of a key, not its requester, must promote it)")
+            from ..ops.tier_manager import DeviceTierManager
+            for t, o in tiered.items():
+                cols = torch.tensor([c for c, ct in enumerate(col_table) if ct == t], dtype=torch.int64, device=dev)
+                mgr = DeviceTierManager(self.tables[t], int(o["cache_rows"]), strategy=int(o.get("strategy", 0)), pad_key=pad_key,
+                                        max_batch_keys=max(1 << 16, 2 * int(cols.numel()) * batch_size))
+                self.tiers[t] = (mgr, cols)
+        self._host_step = 0
         # ---- sparse pipeline + static buffers
         self.sp = SparsePipeline(dev, rank, world_size, list(col_table), self.T, batch_size, self.D, comm=comm, pad_key=pad_key)
         self.ids = torch.full((self.C, batch_size), pad_key, dtype=torch.int64, device=dev)
@@ -203,7 +221,15 @@ class FusedRecEngine:
         self.launches_per_step = self.launches - n0
         self._graph = g
 
+    def prefetch(self, next_ids: torch.Tensor) -> None:
+        """Multi-tier tables: hand the id columns of the NEXT batch (device [C, B]) to the tier managers while this step runs."""
+        for mgr, cols in self.tiers.values():
+            mgr.prefetch(next_ids.index_select(0, cols).contiguous())
+
     def train_step(self) -> None:
+        for mgr, _ in self.tiers.values():
+            mgr.commit(self._host_step)          # promoted rows resident / cold rows demoted before the step's kernels are launched
+        self._host_step += 1
         if self._graph is not None:
             self._graph.replay()
         else:

@@ -80,7 +80,11 @@ class StepContext:
         if ptrs != self._ptrs or self.struct_all is None:
             size = C.sizeof(DeviceTableStruct)
             parts = [t.struct_dev if t is not None else torch.zeros(size, dtype=torch.uint8, device=self.device) for t in self.tables]
-            self.struct_all = torch.cat(parts).contiguous()
+            new = torch.cat(parts).contiguous()
+            if self.struct_all is not None and self.struct_all.numel() == new.numel():
+                self.struct_all.copy_(new)        # IN PLACE: a captured CUDA graph holds this buffer's address (tables re-hash / grow at step boundaries)
+            else:
+                self.struct_all = new
             self._ptrs = ptrs
         return self.struct_all
 
