@@ -30,6 +30,7 @@ CUDA_SOURCES = [
     "cuda/sparse_pipeline.cu",
     "cuda/fused_interaction_gemm.cu",
     "cuda/tier_kernels.cu",
+    "cuda/nvls.cu",
     "cuda/runtime.cu",
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",

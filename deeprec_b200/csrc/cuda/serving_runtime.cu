@@ -41,6 +41,9 @@ int dr_cuda_table_lookup(const DrDeviceTable* tables_dev, const int32_t* table_m
                          int64_t n, int train, const int64_t* step_ptr, int32_t* out_pos, int64_t* ulist, int32_t* group_nunique, int64_t ulist_cap, cudaStream_t s);
 int dr_cuda_table_gather(const DrDeviceTable* tables_dev, const int32_t* table_map, int T, int dim, const int64_t* keys, const int32_t* pos,
                          const int64_t* offsets, int64_t uniform, int64_t n, void* out, int out_bf16, int64_t stride_b, int64_t stride_t, int flat_out, cudaStream_t s);
+int dr_cuda_table_import_cow(const DrDeviceTable* t_host, const int64_t* keys, const float* rows, int ncols, int64_t n, int32_t* retired,
+                             int32_t* n_retired, int32_t* n_kept, cudaStream_t s);
+int dr_cuda_table_free_rows(const DrDeviceTable* t_host, const int32_t* rows, const int32_t* n_dev, int64_t max_n, cudaStream_t s);
 int dr_cuda_table_import(const DrDeviceTable* t_host, const int64_t* keys, const float* rows, int ncols, const int64_t* freqs, const int64_t* versions,
                          int64_t n, int part_id, int part_num, int reset_version, int32_t* n_kept, cudaStream_t s);
 int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias, int relu, const void* mask_src,
@@ -420,6 +423,8 @@ struct ServingModel {
   std::atomic<uint64_t> rr{0}, requests{0}, failures{0}, full_updates{0}, delta_updates{0};
   std::atomic<int64_t> delta_version{-1};
   int64_t rejected_version = -1;           // updater thread only: last version refused because it changes the architecture
+  struct Retired { int t; std::shared_ptr<DevBuf> rows; int64_t n; };
+  std::vector<Retired> retired;            // updater thread only: slab rows replaced by the last delta (copy-on-write), freed at the next one
   std::thread updater; std::atomic<bool> stop{false};
   std::mutex tmu; std::vector<std::string> trace;
   ~ServingModel() { stop = true; if (updater.joinable()) updater.join(); }
@@ -494,16 +499,31 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
   dr::BundleReader r(prefix);
   if (!r.ok()) return false;
   cudaSetDevice(sm->cfg.gpu_id);
+  // rows replaced by the PREVIOUS delta: no request that could still read them is in flight once every session has been idle once
+  if (!sm->retired.empty()) {
+    for (auto& sp : sm->sessions) { std::lock_guard<std::mutex> l(sp->mu); cudaStreamSynchronize(sp->stream); }
+    for (auto& rt : sm->retired)
+      if (rt.t < (int)m->tables.size()) dr_cuda_table_free_rows(&m->tables[rt.t]->t, rt.rows->as<int32_t>(), rt.rows->as<int32_t>() + rt.n, rt.n, 0);
+    cudaDeviceSynchronize();
+    sm->retired.clear();
+  }
   for (int t = 0; t < m->arch.T; ++t) {
     std::vector<int64_t> keys; std::vector<float> vals;
     const std::string base = "table/" + std::to_string(t);
     if (!ReadVec(r, base + "-sparse_incr_keys", &keys) || keys.empty()) continue;
     if (!ReadVec(r, base + "-sparse_incr_values", &vals)) return false;
-    DevBuf dk, dv, kept;
-    if (!Upload(dk, keys) || !Upload(dv, vals) || !kept.alloc(4)) return false;
-    cudaMemset(kept.p, 0, 4);
-    if (dr_cuda_table_import(&m->tables[t]->t, dk.as<int64_t>(), dv.as<float>(), m->arch.D, nullptr, nullptr, (int64_t)keys.size(), 0, 1, 0, kept.as<int32_t>(), 0) != 0) return false;
+    // copy-on-write: live sessions keep reading complete rows (old or new) while the delta lands; the replaced rows are recycled at
+    // the NEXT delta, after every session has passed a quiescent point (Quiesce below) -- CPU runtime: dr_host_ev_import_cow
+    DevBuf dk, dv, cnt;
+    auto retired = std::make_shared<DevBuf>();
+    if (!Upload(dk, keys) || !Upload(dv, vals) || !cnt.alloc(16) || !retired->alloc(keys.size() * 4 + 16)) return false;
+    cudaMemset(cnt.p, 0, 16);
+    int32_t* n_retired = retired->as<int32_t>() + keys.size();            // counter lives behind the list
+    cudaMemset(n_retired, 0, 4);
+    if (dr_cuda_table_import_cow(&m->tables[t]->t, dk.as<int64_t>(), dv.as<float>(), m->arch.D, (int64_t)keys.size(), retired->as<int32_t>(), n_retired,
+                                 cnt.as<int32_t>(), 0) != 0) return false;
     cudaDeviceSynchronize();
+    sm->retired.push_back({t, retired, (int64_t)keys.size()});
   }
   std::shared_ptr<DenseParams> dp;
   if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp, sm->cfg.fp8)) {
@@ -599,6 +619,7 @@ static void UpdaterLoop(ServingModel* sm) {
         }
         if (!WarmUp(sm, nm)) continue;
         std::atomic_store(&sm->model, nm);          // requests in flight keep the old model alive through their shared_ptr
+        sm->retired.clear();
         sm->delta_version = -1;
         sm->full_updates++;
         continue;

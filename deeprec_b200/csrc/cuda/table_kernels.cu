@@ -170,6 +170,45 @@ __global__ void k_shrink(DrDeviceTable TB, int step, int32_t* __restrict__ n_evi
   }
 }
 
+// Copy-on-write import (serving delta update under live requests, model_instance.cc:429-446): the new row is written to a FRESH slab
+// row and published with one atomic exchange of slot.row_of -- a concurrent reader (k_lookup + k_gather of a session's stream) sees
+// the old row or the new row, never a torn one.  The replaced rows are returned through `retired` and recycled by the caller once
+// every session has passed a quiescent point.
+__global__ void k_import_cow(DrDeviceTable TB, const int64_t* __restrict__ keys, const float* __restrict__ rows, int ncols, int64_t n,
+                             int32_t* __restrict__ retired, int32_t* __restrict__ n_retired, int32_t* __restrict__ n_kept) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t key = keys[i];
+    bool ins;
+    const int64_t p = table_find_or_insert(TB, key, &ins);
+    if (p < 0) { TB.counters[CTR_OVERFLOW] = 1; continue; }
+    if (ins) atomicAdd(&TB.counters[CTR_NKEYS], 1);
+    const int32_t r_new = table_alloc_row(TB);
+    if (r_new < 0) continue;
+    const int32_t r_old = TB.slots[p].row_of;
+    float* row = TB.rows + (int64_t)r_new * TB.stride;
+    if (r_old >= 0) { const float* o = TB.rows + (int64_t)r_old * TB.stride; for (int d = 0; d < TB.stride; ++d) row[d] = o[d]; }
+    else {
+      const float* def = TB.default_matrix + dr_default_row(key, TB.default_value_dim) * TB.dim;
+      for (int d = 0; d < TB.dim; ++d) row[d] = def[d];
+      for (int d = TB.dim; d < TB.stride; ++d) row[d] = 0.f;
+    }
+    const float* src = rows + (int64_t)i * ncols;
+    const int m = ncols < TB.stride ? ncols : TB.stride;
+    for (int d = 0; d < m; ++d) row[d] = src[d];
+    __threadfence();                                            // the row is complete before it becomes reachable
+    const int32_t prev = atomicExch(&TB.slots[p].row_of, r_new);
+    if (prev >= 0) retired[atomicAdd(n_retired, 1)] = prev; else atomicAdd(&TB.counters[CTR_NADMITTED], 1);
+    atomicAdd(n_kept, 1);
+  }
+}
+__global__ void k_free_rows(DrDeviceTable TB, const int32_t* __restrict__ rows, const int32_t* __restrict__ n_ptr) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t top = atomicAdd(&TB.counters[CTR_FREE_TOP], 1);
+    TB.free_list[top] = rows[i];
+  }
+}
+
 __global__ void k_remove(DrDeviceTable TB, const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ n_removed) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = table_find(TB, keys[i]);
@@ -391,6 +430,21 @@ int dr_cuda_table_import(const DrDeviceTable* t_host, const int64_t* keys, const
                          cudaStream_t s) {
   if (n == 0) return 0;
   k_import<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, rows, ncols, freqs, versions, n, part_id, part_num, reset_version, n_kept);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+// retired: int32 [>= n] device buffer, n_retired / n_kept: device counters (zeroed by the caller)
+int dr_cuda_table_import_cow(const DrDeviceTable* t_host, const int64_t* keys, const float* rows, int ncols, int64_t n, int32_t* retired,
+                             int32_t* n_retired, int32_t* n_kept, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_import_cow<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, rows, ncols, n, retired, n_retired, n_kept);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_cuda_table_free_rows(const DrDeviceTable* t_host, const int32_t* rows, const int32_t* n_dev, int64_t max_n, cudaStream_t s) {
+  if (max_n == 0) return 0;
+  k_free_rows<<<grid_for(max_n, 256), 256, 0, s>>>(*t_host, rows, n_dev);
   DR_LAUNCH_CHECK();
   return 0;
 }

@@ -43,10 +43,17 @@ def _bind(lib):
         "dr_comm_open_handle": [P, C.POINTER(vp)], "dr_comm_close_handle": [P], "dr_comm_can_access_peer": [INT, INT],
         "dr_comm_barrier": [PP, P, INT, INT, INT, P],
         "dr_comm_allreduce_apply": [PP, INT, P, P, P, i64, P, P, P],
+        "dr_nvls_supported": [INT],
+        "dr_nvls_create": [i64, INT, INT, C.POINTER(vp), C.POINTER(C.c_int)],
+        "dr_nvls_import": [INT, i64, INT, INT, C.POINTER(vp)],
+        "dr_nvls_add_device": [P],
+        "dr_nvls_bind": [P, C.POINTER(vp), C.POINTER(vp)],
+        "dr_nvls_allreduce_apply": [P, P, P, P, i64, P, P, P, P],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = args, INT
+    lib.dr_nvls_size.argtypes, lib.dr_nvls_size.restype = [i64, INT], i64
     _bind_sp(lib)
     lib._comm_bound = True
 
@@ -124,8 +131,75 @@ class P2PComm:
         dist.barrier(group=self.group)
 
     def alloc_grads(self, P: int) -> torch.Tensor:
+        """Symmetric dense-gradient buffer.  With NVLS (multicast objects supported on every rank, DEEPREC_NVLS != 0) it is a VMM
+        allocation bound to a multicast object: the backward writes the local unicast mapping, the fused all-reduce + optimizer reads the
+        multicast mapping with multimem.ld_reduce (csrc/cuda/nvls.cu); otherwise a CUDA-IPC buffer read with the one-shot peer pull."""
+        self.nvls = self._try_nvls(P * 4)
+        if self.nvls is not None:
+            return self.nvls["tensor"][:P]
         self.grads_buf = self.symmetric(P * 4)
         return self.grads_buf.tensor(torch.float32, (P,))
+
+    def _all_ok(self, ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
+
+    def _try_nvls(self, nbytes: int):
+        import os
+        import socket
+        lib = self.lib
+        if not self._all_ok(os.environ.get("DEEPREC_NVLS", "1") != "0" and lib.dr_nvls_supported(self.dev.index) == 1):
+            return None
+        size = int(lib.dr_nvls_size(max(nbytes, 1 << 16), self.world))
+        if not self._all_ok(size > 0):
+            return None
+        state, fd = vp(), C.c_int(-1)
+        P2PComm._nvls_seq = getattr(P2PComm, "_nvls_seq", 0) + 1
+        addr = f"\0deeprec_nvls_{os.environ.get('MASTER_PORT', '0')}_{P2PComm._nvls_seq}"
+        ok = True
+        if self.rank == 0:
+            ok = lib.dr_nvls_create(size, self.world, self.dev.index, C.byref(state), C.byref(fd)) == 0
+            srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            try:
+                srv.bind(addr); srv.listen(self.world); srv.settimeout(60)
+            except OSError:
+                ok = False
+            okall = self._all_ok(ok)
+            if okall:
+                try:
+                    for _ in range(self.world - 1):                      # the multicast handle travels as a POSIX fd (SCM_RIGHTS)
+                        c, _a = srv.accept()
+                        socket.send_fds(c, [b"h"], [fd.value]); c.close()
+                except OSError:
+                    ok = False
+            srv.close()
+            if not okall:
+                return None
+        else:
+            if not self._all_ok(True):
+                return None
+            try:
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM); c.settimeout(60)
+                for _ in range(200):
+                    try:
+                        c.connect(addr); break
+                    except OSError:
+                        import time
+                        time.sleep(0.05)
+                _m, fds, _f, _a = socket.recv_fds(c, 16, 1); c.close()
+                ok = len(fds) == 1 and lib.dr_nvls_import(fds[0], size, self.world, self.dev.index, C.byref(state)) == 0
+            except OSError:
+                ok = False
+        if not self._all_ok(ok):
+            return None
+        if not self._all_ok(lib.dr_nvls_add_device(state) == 0):           # every device joins the team BEFORE any memory is bound
+            return None
+        local, mc = vp(), vp()
+        if not self._all_ok(lib.dr_nvls_bind(state, C.byref(local), C.byref(mc)) == 0):
+            return None
+        raw = torch.as_tensor(_RawCuda(local.value, size), device=self.dev)
+        return {"state": state, "mc": mc.value, "local": local.value, "size": size, "tensor": raw.view(torch.float32)}
 
     def barrier(self, channel: int) -> None:
         """Stand-alone device-side rank barrier (tests / utilities; the training step does not use it)."""
@@ -135,6 +209,12 @@ class P2PComm:
         """DENSE flag + one-shot all-reduce fused with the optimizer (the kernel polls the flags itself)."""
         sp = eng.sp
         sp.signal(CH_DENSE)
+        if getattr(self, "nvls", None) is not None:     # in-switch reduction: one multimem.ld_reduce per 16 B instead of W peer loads
+            _chk(self.lib.dr_nvls_allreduce_apply(vp(self.nvls["mc"]), ptr(eng.params), ptr(eng.s0) if eng.s0 is not None else None,
+                                                  ptr(eng.s1) if eng.s1 is not None else None, eng.P, ptr(eng.hp_dev), None, sp.sync_ref(), self._s()),
+                 "nvls_allreduce_apply")
+            eng.launches += 2
+            return
         _chk(self.lib.dr_comm_allreduce_apply_sync(self.grads_buf.peers_ref(), self.world, ptr(eng.params), ptr(eng.s0) if eng.s0 is not None else None,
                                                    ptr(eng.s1) if eng.s1 is not None else None, eng.P, ptr(eng.hp_dev), None, sp.sync_ref(), self._s()),
              "allreduce_apply")
@@ -142,9 +222,16 @@ class P2PComm:
 
     def wait_dense(self, sp) -> None:
         """In-kernel rendezvous on the DENSE flags without any reduction (forward-only passes)."""
+        if getattr(self, "nvls", None) is not None:
+            _chk(self.lib.dr_nvls_allreduce_apply(vp(self.nvls["mc"]), None, None, None, 0, None, None, sp.sync_ref(), self._s()), "wait_dense")
+            return
         _chk(self.lib.dr_comm_allreduce_apply_sync(self.grads_buf.peers_ref(), self.world, None, None, None, 0, None, None, sp.sync_ref(), self._s()), "wait_dense")
 
     def allreduce(self, out: torch.Tensor) -> None:
         """Plain one-shot all-reduce of the symmetric grads buffer into ``out`` (tests / metrics)."""
         self.barrier(3)
-        _chk(self.lib.dr_comm_allreduce_apply(self.grads_buf.peers_ref(), self.world, None, None, None, out.numel(), None, ptr(out), self._s()), "allreduce")
+        if getattr(self, "nvls", None) is not None:
+            _chk(self.lib.dr_nvls_allreduce_apply(vp(self.nvls["mc"]), None, None, None, out.numel(), None, ptr(out), None, self._s()), "nvls_allreduce")
+        else:
+            _chk(self.lib.dr_comm_allreduce_apply(self.grads_buf.peers_ref(), self.world, None, None, None, out.numel(), None, ptr(out), self._s()), "allreduce")
+        self.barrier(4)        # nobody overwrites its contribution before every rank has read it
