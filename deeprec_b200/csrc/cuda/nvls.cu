@@ -75,6 +75,47 @@ __global__ void __launch_bounds__(256) k_nvls_allreduce_apply(const float* __res
   }
 }
 
+// Two-phase variant for large gradients (the one-shot kernel makes every rank pull every element: W * P bytes leave each GPU, no better
+// than the peer pull).  Phase A: rank r owns slice r -- ONE in-switch multimem.ld_reduce per 16 B of its slice, and ONE multimem.st that
+// the switch fans out to every rank's buffer (the reduced value replaces the gradient in place; nobody else touches slice r).  Per GPU:
+// P bytes out + P bytes in, independent of W.  Last block raises REDUCED; phase B (every rank) waits for all REDUCED flags and applies the
+// optimizer from its LOCAL, now fully reduced, buffer.
+constexpr int SP_CH_REDUCED = 5;
+__global__ void __launch_bounds__(256) k_nvls_reduce_bcast(float* __restrict__ mc, int64_t n4, int rank, int W, DrSpSync sync) {
+  pdl_sync();
+  if (sync.state) sp_wait_all(sync, SP_CH_DENSE);
+  const int64_t per = (n4 + W - 1) / W;
+  const int64_t lo = per * rank, hi = min(n4, lo + per);
+  for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 g;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(mc + 4 * i) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + 4 * i), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+  }
+  if (sync.state) sp_signal_last_block(sync, SP_CH_REDUCED);
+}
+__global__ void __launch_bounds__(256) k_nvls_apply_local(const float* __restrict__ g_local, float* __restrict__ w, float* __restrict__ s0,
+                                                          float* __restrict__ s1, int64_t n4, const DrOptHyper* __restrict__ hp_dev, DrSpSync sync) {
+  pdl_sync();
+  if (sync.state) sp_wait_all(sync, SP_CH_REDUCED);      // every slice owner has broadcast its reduced slice into my buffer
+  const DrOptHyper hp = *hp_dev;
+  const float alpha = dr_adam_alpha(hp);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 raw = ld_v4_volatile(reinterpret_cast<const float4*>(g_local) + i);     // written by the switch: bypass L1
+    const float4 g = make_float4(__int_as_float(raw.x), __int_as_float(raw.y), __int_as_float(raw.z), __int_as_float(raw.w));
+    float4 wv = reinterpret_cast<float4*>(w)[i];
+    float4 a = s0 ? reinterpret_cast<float4*>(s0)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 b = s1 ? reinterpret_cast<float4*>(s1)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    dr_apply_elem(hp.kind, hp, alpha, false, g.x, wv.x, a.x, b.x);
+    dr_apply_elem(hp.kind, hp, alpha, false, g.y, wv.y, a.y, b.y);
+    dr_apply_elem(hp.kind, hp, alpha, false, g.z, wv.z, a.z, b.z);
+    dr_apply_elem(hp.kind, hp, alpha, false, g.w, wv.w, a.w, b.w);
+    reinterpret_cast<float4*>(w)[i] = wv;
+    if (s0) reinterpret_cast<float4*>(s0)[i] = a;
+    if (s1) reinterpret_cast<float4*>(s1)[i] = b;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -176,6 +217,29 @@ int dr_nvls_allreduce_apply(const void* mc_ptr, float* w, float* s0, float* s1, 
   DrSpSync sy{}; if (sync) sy = *sync;
   DR_PDL_LAUNCH((k_nvls_allreduce_apply), (int)b, 256, 0, s, (const float*)mc_ptr, w, s0, s1, n / 4, hp_dev, reduced_out, sy);
   DR_LAUNCH_CHECK();
+  return 0;
+}
+
+// Two-phase NVLS all-reduce.  (a) reduce-scatter + multicast broadcast in place over the multicast mapping; with `w` given, (b) the optimizer
+// from the local mapping follows (waits for every rank's REDUCED flag; `sync` required).  Without `w` the caller synchronises the ranks and
+// reads its local buffer.
+int dr_nvls_allreduce_2phase(void* mc_ptr, const float* local_ptr, int rank, int W, float* w, float* s0, float* s1, int64_t n,
+                             const DrOptHyper* hp_dev, const DrSpSync* sync, cudaStream_t s) {
+  if (n % 4) return -2;
+  const int64_t n4 = n / 4, per = (n4 + W - 1) / W;
+  int64_t b = (per + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > kNumSMs * 4) b = kNumSMs * 4;
+  DrSpSync sy{}; if (sync) sy = *sync;
+  DR_PDL_LAUNCH((k_nvls_reduce_bcast), (int)b, 256, 0, s, (float*)mc_ptr, n4, rank, W, sy);
+  DR_LAUNCH_CHECK();
+  if (w) {
+    if (!sync) return -3;
+    int64_t b2 = (n4 + 255) / 256;
+    if (b2 > kNumSMs * 4) b2 = kNumSMs * 4;
+    DR_PDL_LAUNCH((k_nvls_apply_local), (int)b2, 256, 0, s, local_ptr, w, s0, s1, n4, hp_dev, sy);
+    DR_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -15,6 +15,7 @@ Buffer reuse across steps is ordered by the DENSE wait (a full rendezvous) -- se
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List
 
 import torch
@@ -49,6 +50,7 @@ def _bind(lib):
         "dr_nvls_add_device": [P],
         "dr_nvls_bind": [P, C.POINTER(vp), C.POINTER(vp)],
         "dr_nvls_allreduce_apply": [P, P, P, P, i64, P, P, P, P],
+        "dr_nvls_allreduce_2phase": [P, P, INT, INT, P, P, P, i64, P, P, P],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -104,6 +106,7 @@ class SymmetricBuffer:
 
 class P2PComm:
     unique_first = True          # engines build a parallel.sparse_pipeline.SparsePipeline on top of this communicator
+    NVLS_2PHASE_BYTES = int(os.environ.get("DEEPREC_NVLS_2PHASE_BYTES", 8 << 20))  # dense gradients at least this large take the two-phase NVLS all-reduce (one-shot below: fewer launches)
 
     def __init__(self, rank: int, world: int, dev: torch.device, group=None):
         self.rank, self.world, self.dev, self.group = rank, world, dev, group
@@ -209,6 +212,13 @@ class P2PComm:
         """DENSE flag + one-shot all-reduce fused with the optimizer (the kernel polls the flags itself)."""
         sp = eng.sp
         sp.signal(CH_DENSE)
+        if getattr(self, "nvls", None) is not None and eng.P * 4 >= self.NVLS_2PHASE_BYTES:
+            # large dense nets: reduce-scatter (multimem.ld_reduce) + in-switch broadcast (multimem.st), then the optimizer from local memory
+            _chk(self.lib.dr_nvls_allreduce_2phase(vp(self.nvls["mc"]), vp(self.nvls["local"]), self.rank, self.world, ptr(eng.params),
+                                                   ptr(eng.s0) if eng.s0 is not None else None, ptr(eng.s1) if eng.s1 is not None else None, eng.P,
+                                                   ptr(eng.hp_dev), sp.sync_ref(), self._s()), "nvls_allreduce_2phase")
+            eng.launches += 3
+            return
         if getattr(self, "nvls", None) is not None:     # in-switch reduction: one multimem.ld_reduce per 16 B instead of W peer loads
             _chk(self.lib.dr_nvls_allreduce_apply(vp(self.nvls["mc"]), ptr(eng.params), ptr(eng.s0) if eng.s0 is not None else None,
                                                   ptr(eng.s1) if eng.s1 is not None else None, eng.P, ptr(eng.hp_dev), None, sp.sync_ref(), self._s()),
@@ -227,10 +237,16 @@ class P2PComm:
             return
         _chk(self.lib.dr_comm_allreduce_apply_sync(self.grads_buf.peers_ref(), self.world, None, None, None, 0, None, None, sp.sync_ref(), self._s()), "wait_dense")
 
-    def allreduce(self, out: torch.Tensor) -> None:
-        """Plain one-shot all-reduce of the symmetric grads buffer into ``out`` (tests / metrics)."""
+    def allreduce(self, out: torch.Tensor, two_phase: bool = False) -> None:
+        """All-reduce of the symmetric grads buffer into ``out`` (tests / metrics).  ``two_phase`` (NVLS only) reduces IN PLACE: the
+        gradient buffer itself holds the sum afterwards."""
         self.barrier(3)
-        if getattr(self, "nvls", None) is not None:
+        if getattr(self, "nvls", None) is not None and two_phase:
+            _chk(self.lib.dr_nvls_allreduce_2phase(vp(self.nvls["mc"]), vp(self.nvls["local"]), self.rank, self.world, None, None, None, out.numel(), None,
+                                                   None, self._s()), "nvls_allreduce_2phase")
+            self.barrier(5)                         # every slice owner has broadcast its slice: my local buffer now holds the full sum
+            out.copy_(self.nvls["tensor"][: out.numel()])
+        elif getattr(self, "nvls", None) is not None:
             _chk(self.lib.dr_nvls_allreduce_apply(vp(self.nvls["mc"]), None, None, None, out.numel(), None, ptr(out), None, self._s()), "nvls_allreduce")
         else:
             _chk(self.lib.dr_comm_allreduce_apply(self.grads_buf.peers_ref(), self.world, None, None, None, out.numel(), None, ptr(out), self._s()), "allreduce")
