@@ -62,14 +62,52 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  In-process NVML from a sampling thread
+    (a 20-step region lasts ~25 ms: `nvidia-smi -lms` does not even start within it); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"), (0x80, "hw_power_brake"))
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.h, self.stop_flag = None, None, threading.Event()
+        self.sm, self.mx, self.pw, self.mask = [], [], [], 0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.h = pynvml, h
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n, h = self.nvml, self.h
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)))
+            self.pw.append(n.nvmlDeviceGetPowerUsage(h) / 1e3)
+            try:
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            self._sample()
+            time.sleep(0.004)
 
     def start(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True); self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -82,6 +120,11 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set(); self.t.join(timeout=2)
+            reasons = sorted(name for bit, name in self.REASONS if self.mask & bit)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "power_w_max": max(self.pw) if self.pw else None, "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -103,7 +146,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def reference_arm(args):
@@ -186,7 +229,7 @@ def main():
     # ---- data: every phase draws from ONE sequence of distinct batches (fresh) or from 8 rotating ones (warm) ---------
     fresh = args.stream == "fresh"
     n_timed = args.steps if (fresh and args.pool <= 0) else (min(args.steps, args.pool) if fresh else (args.pool or 8))
-    n_e2e = 0 if args.skip_e2e else n_timed
+    n_e2e = 0 if args.skip_e2e else n_timed + args.warmup
     if fresh:
         host = make_host_batches(cfg, args.prefill + args.warmup + n_timed + n_e2e, 99, args.alpha, rank)
         pre, warm = host[: args.prefill], host[args.prefill: args.prefill + args.warmup]
@@ -226,7 +269,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launches - l0
-    clocks = sampler.stop()
     keys1 = total_keys()
     final_loss = eng.loss_value()           # mean over the GLOBAL batch of the last timed step (all-reduced)
 
@@ -235,9 +277,11 @@ def main():
     e2e_ms = None
     if not args.skip_e2e:
         from deeprec_b200.data.staged import SmartStageOptions, smart_stage
-        seq = [e2e_src[s % len(e2e_src)] for s in range(args.steps)]
+        seq = [e2e_src[s % len(e2e_src)] for s in range(args.warmup + args.steps)]
         stage = smart_stage(iter(seq), dev, SmartStageOptions(capacity=2, num_threads=1))
         loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+        for s in range(args.warmup):                               # untimed: producer thread, pinned pool and device ring spin up
+            eng.load_batch(*next(stage)); eng.train_step()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
@@ -250,6 +294,8 @@ def main():
         barrier()
         e2e_ms = f0.elapsed_time(f1)
         stage.close()
+
+    clocks = sampler.stop()                 # sampled across the device-timed AND the end-to-end region (both under load)
 
     # max over ranks (device-timed)
     t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device=dev)

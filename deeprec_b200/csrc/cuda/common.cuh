@@ -47,6 +47,13 @@ inline cudaError_t dr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
 
 constexpr int kNumSMs = 148;
 
+// cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (serving ProcessorGroup: one replica per GPU in one process)
+// must raise the dynamic shared-memory limit on each of them.  One flag per (call site, device).
+struct DrPerDeviceOnce {
+  bool done[64] = {};
+  bool& operator()() { int d = 0; cudaGetDevice(&d); return done[d & 63]; }
+};
+
 // Resident-block budget (per SM) of the sparse-path kernels.  They run on a side stream next to the tcgen05 GEMMs
 // (1 CTA/SM, ~200 KB smem, 192 threads): capping them leaves thread slots so both streams really overlap.
 inline int& sparse_blocks_per_sm() { static int v = 16; return v; }

@@ -373,7 +373,7 @@ int dr_cuda_dlrm_inter_gemm(const void* x, int64_t ldx, const void* urow, const 
   // Z store map: inner extent = ldz so that the zero K-padding columns that exist in memory are written (as zeros) too
   rc = make_tmap(&tz, Z ? Z : out, (uint64_t)(Z ? ldz : ldo), (uint64_t)B, (uint64_t)(Z ? ldz : ldo) * 2, kKB, kTileM);
   if (rc) return rc;
-  static bool attr = false;
+  static DrPerDeviceOnce attr_once; bool& attr = attr_once();
   if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_dlrm_inter_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::kTotal)); attr = true; }
   const int64_t ntiles = (B + kTileM - 1) / kTileM;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);

