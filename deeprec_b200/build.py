@@ -32,6 +32,7 @@ CUDA_SOURCES = [
     "cuda/tier_kernels.cu",
     "cuda/nvls.cu",
     "cuda/runtime.cu",
+    "cuda/program_kernels.cu",
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",
     "cuda/allocator.cu",

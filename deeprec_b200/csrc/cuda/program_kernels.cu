@@ -1,0 +1,167 @@
+// Op-program serving on the GPU: the non-GEMM ops of an exported inference graph (serving/export.py::export_saved_model_program) over
+// bf16 [B, ld] activation buffers.  The LINEAR ops run on the tcgen05 GEMM (gemm_tcgen05.cu, bias + ReLU in its epilogue); everything
+// here is bandwidth-trivial glue between them (a DeepFM forward at batch 2048 moves < 4 MB through these kernels).
+//
+// Reference: the processor runs ANY SavedModel graph per session on the session's device (serving/processor/serving/model_session.cc:377-386,
+// tensorflow/core/common_runtime/direct_session.cc:563-620); the CPU interpreter of the same program is csrc/host/cpu_serving.cc::RunProgram.
+//
+// Buffer convention: bf16, row-major, ld = width rounded up to 8 (TMA / 16-byte rule of the GEMM); pad columns are zero and stay zero
+// (every kernel writes columns [0, width) only; LINEAR writes its zero-padded output channels, which are exact zeros).
+#include "common.cuh"
+
+using namespace drc;
+
+namespace {
+
+__device__ __forceinline__ float ldb(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stb(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// dst[b, off + k] = src[b, start + k], k < w   (CONCAT piece / SLICE)
+__global__ void __launch_bounds__(256) k_prog_copy_cols(const __nv_bfloat16* __restrict__ src, int64_t lds, int start, int w, __nv_bfloat16* __restrict__ dst,
+                                                        int64_t ldd, int off, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / w; const int k = (int)(i - b * w);
+    dst[b * ldd + off + k] = src[b * lds + start + k];
+  }
+}
+
+// y = x * scale[k] + shift[k]   (BatchNorm with moving statistics that could not be folded into a Linear)
+__global__ void __launch_bounds__(256) k_prog_affine(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, const float* __restrict__ sc,
+                                                     const float* __restrict__ sh, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / w; const int k = (int)(i - b * w);
+    stb(y + b * ldy + k, ldb(x + b * ldx + k) * sc[k] + sh[k]);
+  }
+}
+
+// FM second-order term per embedding dimension: 0.5 ((sum_t v_t)^2 - sum_t v_t^2); emb [B, T * D]
+__global__ void __launch_bounds__(256) k_prog_fm(const __nv_bfloat16* __restrict__ e, int64_t lde, int T, int D, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / D; const int k = (int)(i - b * D);
+    const __nv_bfloat16* row = e + b * lde + k;
+    float sum = 0.f, sq = 0.f;
+    for (int t = 0; t < T; ++t) { const float v = ldb(row + (int64_t)t * D); sum += v; sq += v * v; }
+    stb(y + b * ldy + k, 0.5f * (sum * sum - sq));
+  }
+}
+
+// kind 0: a + b, 1: a * b, 2: a * b + c
+__global__ void __launch_bounds__(256) k_prog_binary(int kind, const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_bfloat16* __restrict__ b, int64_t ldb_,
+                                                     const __nv_bfloat16* __restrict__ c, int64_t ldc, int w, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / w; const int k = (int)(i - r * w);
+    const float av = ldb(a + r * lda + k), bv = ldb(b + r * ldb_ + k);
+    float v = kind == 0 ? av + bv : av * bv;
+    if (kind == 2) v += ldb(c + r * ldc + k);
+    stb(y + r * ldy + k, v);
+  }
+}
+
+// DCN cross layer, one warp per row: y = x0 * (xl . w) + bias + xl
+__global__ void __launch_bounds__(256) k_prog_cross(const __nv_bfloat16* __restrict__ x0, int64_t ld0, const __nv_bfloat16* __restrict__ xl, int64_t ldl, int w,
+                                                    const float* __restrict__ wv, const float* __restrict__ bv, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float dot = 0.f;
+    for (int k = lane; k < w; k += 32) dot += ldb(xl + r * ldl + k) * wv[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int k = lane; k < w; k += 32) stb(y + r * ldy + k, ldb(x0 + r * ld0 + k) * dot + bv[k] + ldb(xl + r * ldl + k));
+  }
+}
+
+// LayerNorm (biased variance) + optional ReLU, one warp per row
+__global__ void __launch_bounds__(256) k_prog_layernorm(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, const float* __restrict__ g,
+                                                        const float* __restrict__ bt, float eps, int relu, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float sum = 0.f;
+    for (int k = lane; k < w; k += 32) sum += ldb(x + r * ldx + k);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)w;
+    float var = 0.f;
+    for (int k = lane; k < w; k += 32) { const float d = ldb(x + r * ldx + k) - mean; var += d * d; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rs = rsqrtf(var / (float)w + eps);
+    for (int k = lane; k < w; k += 32) {
+      float v = (ldb(x + r * ldx + k) - mean) * rs * g[k] + bt[k];
+      if (relu && v < 0.f) v = 0.f;
+      stb(y + r * ldy + k, v);
+    }
+  }
+}
+
+// prob[b] = sigmoid(x[b, 0])
+__global__ void __launch_bounds__(256) k_prog_sigmoid0(const __nv_bfloat16* __restrict__ x, int64_t ldx, int64_t B, float* __restrict__ prob) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+    prob[i] = 1.f / (1.f + __expf(-ldb(x + i * ldx)));
+}
+
+inline int grid_el(int64_t n) { const int64_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : b > kNumSMs * 8 ? kNumSMs * 8 : b); }
+inline int grid_rows(int64_t rows) { return grid_el(rows * 32); }
+
+}  // namespace
+
+extern "C" {
+
+int dr_prog_copy_cols(const void* src, int64_t lds, int start, int w, void* dst, int64_t ldd, int off, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_copy_cols<<<grid_el(B * w), 256, 0, s>>>((const __nv_bfloat16*)src, lds, start, w, (__nv_bfloat16*)dst, ldd, off, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_affine(const void* x, int64_t ldx, int w, const float* scale, const float* shift, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_affine<<<grid_el(B * w), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, scale, shift, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_fm(const void* emb, int64_t lde, int T, int D, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || T <= 0 || D <= 0) return 0;
+  k_prog_fm<<<grid_el(B * D), 256, 0, s>>>((const __nv_bfloat16*)emb, lde, T, D, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_binary(int kind, const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc, int w, void* y, int64_t ldy, int64_t B,
+                   cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  if (kind < 0 || kind > 2 || (kind == 2 && !c)) return -2;
+  k_prog_binary<<<grid_el(B * w), 256, 0, s>>>(kind, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, (const __nv_bfloat16*)c, ldc, w, (__nv_bfloat16*)y,
+                                               ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_cross(const void* x0, int64_t ld0, const void* xl, int64_t ldl, int w, const float* wv, const float* bv, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_cross<<<grid_rows(B), 256, 0, s>>>((const __nv_bfloat16*)x0, ld0, (const __nv_bfloat16*)xl, ldl, w, wv, bv, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_layernorm(const void* x, int64_t ldx, int w, const float* gamma, const float* beta, float eps, int relu, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_layernorm<<<grid_rows(B), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, gamma, beta, eps, relu, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_sigmoid0(const void* x, int64_t ldx, int64_t B, float* prob, cudaStream_t s) {
+  if (B <= 0) return 0;
+  k_prog_sigmoid0<<<grid_el(B), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, B, prob);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

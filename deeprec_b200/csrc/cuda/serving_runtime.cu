@@ -52,6 +52,13 @@ int dr_cuda_cast_pad(const float* x, int64_t B, int C, void* y, int Cp, cudaStre
 int dr_cuda_bn_apply(const void* a, int64_t B, int N, int64_t lda, const float* scale, const float* shift, void* y, int64_t ldy, cudaStream_t s);
 int dr_cuda_dot_interaction_fwd(const void* x, int64_t ldx, const void* emb, int64_t emb_stride_t, int64_t emb_stride_b, int T, int D, int64_t B, void* Z,
                                 int64_t ldz, cudaStream_t s);
+int dr_prog_copy_cols(const void* src, int64_t lds, int start, int w, void* dst, int64_t ldd, int off, int64_t B, cudaStream_t s);
+int dr_prog_affine(const void* x, int64_t ldx, int w, const float* scale, const float* shift, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_fm(const void* emb, int64_t lde, int T, int D, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_binary(int kind, const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_cross(const void* x0, int64_t ld0, const void* xl, int64_t ldl, int w, const float* wv, const float* bv, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_layernorm(const void* x, int64_t ldx, int w, const float* gamma, const float* beta, float eps, int relu, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_sigmoid0(const void* x, int64_t ldx, int64_t B, float* prob, cudaStream_t s);
 int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, const float* bias, const float* labels, float inv_batch, float* prob,
                  float* loss_sum, void* dh, float* dw, float* db, int relu_mask, int train, float* dbias_h, cudaStream_t s);
 }
@@ -112,10 +119,21 @@ template <typename T> static bool Upload(DevBuf& b, const std::vector<T>& h) {
   return cudaMemcpy(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
-struct Arch { int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0; };
+// Op program (saved_model.json "arch": "program", serving/export.py::export_saved_model_program): the inference graph of a Criteo-style model
+// other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].  Same format and
+// op set as the CPU runtime (csrc/host/cpu_serving.cc); here LINEAR runs on the tcgen05 GEMM and the rest on program_kernels.cu.
+enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE };
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
+struct Arch {
+  int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0;
+  bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1;
+  // requests carry R id rows; table t reads request row id_map[t] (identity unless several tables share a feature, e.g. Wide&Deep)
+  int R = 0; std::vector<int> id_map;
+};
 
 struct LayerW {
   int N, K, Kp; DevBuf w_bf16, bias;
+  int Np = 0;              // program LINEAR: output channels padded to a tile the GEMM tests cover (16 | 32 | multiple of 8 above)
   // fp8 serving path: E4M3 weights [N, Kp16] quantised per output channel; col_scale[n] = w_scale[n] * in_scale
   int Kp16 = 0; DevBuf w_fp8, w_scale, col_scale;
 };
@@ -130,6 +148,9 @@ struct DenseParams {
   DevBuf last_scale, last_shift, head_w, head_b;
   bool fp8 = false;        // fp8 tensors + scales below are populated
   ActScales act;
+  // program models: per-op weights (LINEAR: bf16 [pad8(N), pad8(K)] + bias[pad8(N)]; affine / layernorm / cross: two fp32 vectors), buffer widths
+  struct PW { LayerW L; DevBuf v0, v1; };
+  std::vector<PW> pdata; std::vector<int> width;
 };
 
 struct TableDev {
@@ -179,7 +200,59 @@ static bool ApplyActScales(DenseParams& dp) {
   return true;
 }
 
+// Row pitch of a program buffer (bf16 elements).  Buffers 0 / 1 are the cast dense inputs and the gathered embeddings; every other buffer
+// is padded like a GEMM output: 16 | 32 for narrow layers (full N tiles of the direct-store kernel), a multiple of 8 above (TMA 16-byte rule).
+static int prog_npad(int w) { return w <= 16 ? 16 : w <= 32 ? 32 : pad8(w); }
+static int prog_ld(const Arch& a, const std::vector<int>& width, int id) { return id == 0 ? pad8(a.num_dense) : id == 1 ? a.T * a.D : prog_npad(width[(size_t)id]); }
+
+// weights + buffer widths of a program model; every shape is checked against the widths implied by the op list
+static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<DenseParams>* out) {
+  auto dp = std::make_shared<DenseParams>();
+  dp->width.assign((size_t)a.nbuf, 0); dp->width[0] = a.num_dense; dp->width[1] = a.T * a.D;
+  dp->pdata.resize(a.ops.size());
+  for (size_t i = 0; i < a.ops.size(); ++i) {
+    const POp& op = a.ops[i]; auto& d = dp->pdata[i];
+    const int w0 = dp->width[(size_t)op.in[0]];
+    int w = w0;
+    const std::string base = "prog/" + op.name + "/";
+    std::vector<float> v0, v1;
+    switch (op.kind) {
+      case P_CONCAT: w = 0; for (int b : op.in) w += dp->width[(size_t)b]; break;
+      case P_LINEAR: {
+        std::vector<float> W, b;
+        if (!ReadVec(r, base + "kernel", &W) || !ReadVec(r, base + "bias", &b) || b.empty() || W.size() != b.size() * (size_t)w0) return false;
+        const int N = (int)b.size(), Np = prog_npad(N), Kp = prog_ld(a, dp->width, op.in[0]);
+        std::vector<uint16_t> wb((size_t)Np * Kp, 0); std::vector<float> bias((size_t)Np, 0.f);     // zero rows / columns: pad outputs are exact zeros
+        for (int n = 0; n < N; ++n) { bias[(size_t)n] = b[(size_t)n]; for (int k = 0; k < w0; ++k) wb[(size_t)n * Kp + k] = f2bf(W[(size_t)n * w0 + k]); }
+        d.L.N = N; d.L.K = w0; d.L.Kp = Kp; d.L.Np = Np;
+        if (!Upload(d.L.w_bf16, wb) || !Upload(d.L.bias, bias)) return false;
+        w = N; break;
+      }
+      case P_LAYERNORM:
+      case P_AFFINE:
+        if (!ReadVec(r, base + "scale", &v0) || !ReadVec(r, base + "shift", &v1) || (int)v0.size() != w0 || (int)v1.size() != w0) return false;
+        if (!Upload(d.v0, v0) || !Upload(d.v1, v1)) return false;
+        break;
+      case P_FM: if (op.in[0] != 1) return false; w = a.D; break;
+      case P_CROSS:
+        if (!ReadVec(r, base + "w", &v0) || !ReadVec(r, base + "b", &v1) || (int)v0.size() != w0 || (int)v1.size() != w0 || dp->width[(size_t)op.in[1]] != w0) return false;
+        if (!Upload(d.v0, v0) || !Upload(d.v1, v1)) return false;
+        break;
+      case P_MUL_ADD: if (dp->width[(size_t)op.in[1]] != w0 || dp->width[(size_t)op.in[2]] != w0) return false; break;
+      case P_MUL:
+      case P_ADD: if (dp->width[(size_t)op.in[1]] != w0) return false; break;
+      case P_SLICE: if (op.start < 0 || op.len <= 0 || op.start + op.len > w0) return false; w = op.len; break;
+      default: return false;
+    }
+    if (w <= 0) return false;
+    dp->width[(size_t)op.out] = w;
+  }
+  *out = dp;
+  return true;
+}
+
 static bool BuildDense(dr::BundleReader& r, const Arch& a, std::shared_ptr<DenseParams>* out, bool want_fp8 = false) {
+  if (a.program) return BuildProgram(r, a, out);
   auto dp = std::make_shared<DenseParams>();
   dp->bot.reserve(a.bot.size()); dp->top.reserve(a.top.size());
   std::vector<float> s_prev, t_prev;
@@ -274,6 +347,40 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   int F = a->T + 1; a->inter = a->D + F * (F - 1) / 2; a->Zp = pad8(a->inter);
   *version = (int64_t)j.n("version", 0);
   *prefix = dir + "/" + j.s("variables", "variables/variables");
+  a->R = (int)j.n("num_id_rows", a->T);
+  a->id_map.resize((size_t)std::max(0, a->T));
+  for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = t;
+  if (auto* im = j.get("id_map")) {
+    if (im->t != JVal::ARR || (int)im->arr.size() != a->T) return false;
+    for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = (int)im->arr[(size_t)t].num;
+  }
+  for (int v : a->id_map) if (v < 0 || v >= a->R) return false;
+  if (a->R <= 0) return false;
+  if (j.s("arch", "") == "program") {
+    a->program = true;
+    std::vector<std::string> names = {"dense", "emb"};
+    auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
+    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice"};
+    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1};
+    const JVal* pr = j.get("program");
+    if (!pr || pr->t != JVal::ARR) return false;
+    for (const JVal& o : pr->arr) {
+      POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
+      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0);
+      const std::string kind = o.s("op", "");
+      for (int k = 0; k < 10; ++k) if (kind == kNames[k]) op.kind = k;
+      const JVal* in = o.get("in");
+      if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
+      for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
+      if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
+      op.out = (int)names.size(); names.push_back(op.name);
+      a->ops.push_back(std::move(op));
+    }
+    a->nbuf = (int)names.size();
+    a->out_buf = id_of(j.s("output", ""));
+    // the embedding buffer doubles as a GEMM operand: its row pitch T * D must obey the 16-byte rule; rows are gathered as float4 groups
+    return a->T > 0 && a->out_buf >= 2 && a->D % 4 == 0 && (a->T * a->D) % 8 == 0;
+  }
   return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
 }
 
@@ -283,7 +390,7 @@ static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t ex
   if (!LoadArch(dir, &m->arch, &m->version, &prefix)) { fprintf(stderr, "[deeprec_serving] bad saved_model.json in %s\n", dir.c_str()); return nullptr; }
   dr::BundleReader r(prefix);
   if (!r.ok()) { fprintf(stderr, "[deeprec_serving] cannot open bundle %s\n", prefix.c_str()); return nullptr; }
-  if (!BuildDense(r, m->arch, &m->dense, want_fp8)) { fprintf(stderr, "[deeprec_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
+  if (!BuildDense(r, m->arch, &m->dense, want_fp8 && !m->arch.program)) { fprintf(stderr, "[deeprec_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
   std::vector<DrDeviceTable> structs;
   for (int t = 0; t < m->arch.T; ++t) {
     m->tables.emplace_back(new TableDev());
@@ -324,11 +431,69 @@ struct Session {
   }
   ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (stream) cudaStreamDestroy(stream); }
 
+  // ---- op-program models: buffers 0 / 1 alias x0 / emb, the others are (max_batch x prog_ld(width)) bf16, zeroed once (pad columns stay zero) ----
+  std::vector<DevBuf> pbuf; std::vector<int> pbuf_width;
+  bool RunProgram(const DeviceModel& m, const DenseParams& dp, int B) {
+    const Arch& a = m.arch; cudaStream_t s = stream;
+    if (pbuf_width != dp.width) {                                     // first program run, or a full update changed the layer widths
+      SV_CUDA(cudaStreamSynchronize(s));
+      pbuf.clear(); pbuf.resize(dp.width.size());
+      for (size_t i = 2; i < dp.width.size(); ++i) {
+        const size_t bytes = (size_t)max_batch * prog_ld(a, dp.width, (int)i) * 2;
+        if (!pbuf[i].alloc(bytes)) return false;
+        SV_CUDA(cudaMemsetAsync(pbuf[i].p, 0, bytes, s));
+      }
+      pbuf_width = dp.width;
+    }
+    auto buf = [&](int id) -> void* { return id == 0 ? x0.p : id == 1 ? emb.p : pbuf[(size_t)id].p; };
+    auto ld = [&](int id) -> int64_t { return prog_ld(a, dp.width, id); };
+    int rc = 0;
+    const int64_t n = (int64_t)a.T * B;
+    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+    // sample-major embeddings [B, T * D]: element (b, t) at b * (T * D) + t * D
+    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, (int64_t)a.T * a.D, a.D, 0, s);
+    rc |= dr_cuda_cast_pad(dense_in.as<float>(), B, a.num_dense, x0.p, pad8(a.num_dense), s);
+    for (size_t oi = 0; oi < a.ops.size() && rc == 0; ++oi) {
+      const POp& op = a.ops[oi]; const auto& pd = dp.pdata[oi];
+      void* out = buf(op.out); const int W = dp.width[(size_t)op.out]; const int64_t ldo = ld(op.out);
+      const void* a0 = buf(op.in[0]); const int w0 = dp.width[(size_t)op.in[0]]; const int64_t ld0 = ld(op.in[0]);
+      switch (op.kind) {
+        case P_LINEAR:                                               // tcgen05 GEMM, bias (+ ReLU) in the epilogue; N padded to 8 with zero rows
+          rc |= dr_cuda_gemm_tn_ex(a0, ld0, pd.L.w_bf16.p, pd.L.Kp, B, pd.L.Np, pd.L.Kp, pd.L.bias.as<float>(), op.relu ? 1 : 0, nullptr, 0, 0, out, ldo,
+                                   nullptr, nullptr, nullptr, 0, 0, s);
+          break;
+        case P_CONCAT: {
+          int off = 0;
+          for (int src : op.in) { const int w = dp.width[(size_t)src]; rc |= dr_prog_copy_cols(buf(src), ld(src), 0, w, out, ldo, off, B, s); off += w; }
+          break;
+        }
+        case P_AFFINE: rc |= dr_prog_affine(a0, ld0, W, pd.v0.as<float>(), pd.v1.as<float>(), out, ldo, B, s); break;
+        case P_FM: rc |= dr_prog_fm(a0, ld0, a.T, a.D, out, ldo, B, s); break;
+        case P_CROSS: rc |= dr_prog_cross(a0, ld0, buf(op.in[1]), ld(op.in[1]), W, pd.v0.as<float>(), pd.v1.as<float>(), out, ldo, B, s); break;
+        case P_ADD: rc |= dr_prog_binary(0, a0, ld0, buf(op.in[1]), ld(op.in[1]), nullptr, 0, W, out, ldo, B, s); break;
+        case P_MUL: rc |= dr_prog_binary(1, a0, ld0, buf(op.in[1]), ld(op.in[1]), nullptr, 0, W, out, ldo, B, s); break;
+        case P_MUL_ADD: rc |= dr_prog_binary(2, a0, ld0, buf(op.in[1]), ld(op.in[1]), buf(op.in[2]), ld(op.in[2]), W, out, ldo, B, s); break;
+        case P_SLICE: rc |= dr_prog_copy_cols(a0, ld0, op.start, W, out, ldo, 0, B, s); break;
+        case P_LAYERNORM: rc |= dr_prog_layernorm(a0, ld0, W, pd.v0.as<float>(), pd.v1.as<float>(), op.eps, op.relu ? 1 : 0, out, ldo, B, s); break;
+        default: rc = -1;
+      }
+      (void)w0;
+    }
+    rc |= dr_prog_sigmoid0(buf(a.out_buf), ld(a.out_buf), B, prob.as<float>(), s);
+    return rc == 0;
+  }
+
   // inputs already in h_dense / h_ids ([T][B] feature-major); result in h_prob
   bool Run(const DeviceModel& m, const DenseParams& dp, int B, bool force_bf16 = false) {
     const Arch& a = m.arch; cudaStream_t s = stream;
     SV_CUDA(cudaMemcpyAsync(dense_in.p, h_dense, (size_t)B * a.num_dense * 4, cudaMemcpyHostToDevice, s));
     SV_CUDA(cudaMemcpyAsync(ids.p, h_ids, (size_t)a.T * B * 8, cudaMemcpyHostToDevice, s));
+    if (a.program) {
+      if (!RunProgram(m, dp, B)) return false;
+      SV_CUDA(cudaMemcpyAsync(h_prob, prob.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+      SV_CUDA(cudaStreamSynchronize(s));
+      return true;
+    }
     int rc = 0;
     const int64_t n = (int64_t)a.T * B;
     rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
@@ -443,7 +608,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
   ReqHeader h; memcpy(&h, in, sizeof(h));
   const Arch& a = m->arch;
   const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
-  if (h.magic != kReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.T || h.batch == 0 || (size_t)in_size < need) return 500;
+  if (h.magic != kReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.R || h.batch == 0 || (size_t)in_size < need) return 500;
   uint64_t pick = sm->cfg.select_policy == 1 ? (hint >= 0 ? (uint64_t)hint : std::hash<std::thread::id>()(std::this_thread::get_id())) : sm->rr.fetch_add(1);
   const size_t ns = sm->sessions.size();
   Session* sp = sm->sessions[pick % ns].get();
@@ -471,7 +636,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
       const int B = (int)std::min<uint32_t>(s.max_batch, h.batch - off);
       memcpy(s.h_dense, p + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
       const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
-      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)t * h.batch + off, (size_t)B * 8);
+      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)a.id_map[(size_t)t] * h.batch + off, (size_t)B * 8);
       if (!s.Run(*m, *dense, B)) { sm->failures++; return 500; }
       memcpy(probs.data() + off, s.h_prob, (size_t)B * 4);
     }
@@ -526,8 +691,10 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
     sm->retired.push_back({t, retired, (int64_t)keys.size()});
   }
   std::shared_ptr<DenseParams> dp;
-  if (r.Find("dense/logits/kernel") && BuildDense(r, m->arch, &dp, sm->cfg.fp8)) {
-    if (sm->cfg.fp8) {       // delta updates keep the calibrated activation scales of the serving model (no warm-up on deltas)
+  const bool has_dense = m->arch.program ? [&] { for (auto& op : m->arch.ops) if (op.kind == P_LINEAR) return r.Find("prog/" + op.name + "/kernel") != nullptr; return false; }()
+                                         : r.Find("dense/logits/kernel") != nullptr;
+  if (has_dense && BuildDense(r, m->arch, &dp, sm->cfg.fp8)) {
+    if (sm->cfg.fp8 && !m->arch.program) {       // delta updates keep the calibrated activation scales of the serving model (no warm-up on deltas)
       auto old = std::atomic_load(&m->dense);
       dp->act = old->act;
       if (!dp->act.valid || !ApplyActScales(*dp)) return false;
@@ -548,12 +715,12 @@ static int FillWarmupBatch(ServingModel* sm, const DeviceModel& m, Session& s) {
   if (!sm->cfg.warmup_file_name.empty() && ReadFile(sm->cfg.warmup_file_name, &raw) && raw.size() >= sizeof(ReqHeader)) {
     ReqHeader h; memcpy(&h, raw.data(), sizeof(h));
     const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
-    if (h.magic == kReqMagic && (int)h.num_dense == a.num_dense && (int)h.num_sparse == a.T && h.batch > 0 && raw.size() >= need) {
+    if (h.magic == kReqMagic && (int)h.num_dense == a.num_dense && (int)h.num_sparse == a.R && h.batch > 0 && raw.size() >= need) {
       B = std::min<int>(h.batch, s.max_batch);
       const float* d = reinterpret_cast<const float*>(raw.data() + sizeof(h));
       const int64_t* ids = reinterpret_cast<const int64_t*>(raw.data() + sizeof(h) + (size_t)h.batch * h.num_dense * 4);
       memcpy(s.h_dense, d, (size_t)B * a.num_dense * 4);
-      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)t * h.batch, (size_t)B * 8);
+      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)a.id_map[(size_t)t] * h.batch, (size_t)B * 8);
       return B;
     }
   }
@@ -572,7 +739,7 @@ static bool WarmUp(ServingModel* sm, const std::shared_ptr<DeviceModel>& m, cons
     std::lock_guard<std::mutex> l(s->mu);
     const int B = FillWarmupBatch(sm, *m, *s);
     auto dense = std::atomic_load(&m->dense);
-    if (sm->cfg.fp8 && first && !dense->fp8) {
+    if (sm->cfg.fp8 && !m->arch.program && first && !dense->fp8) {
       if (reuse && reuse->valid && reuse->bot_in.size() == dense->bot.size() && reuse->top_in.size() == dense->top.size()) {
         dense->act = *reuse;
         if (!ApplyActScales(*dense)) return false;
@@ -608,7 +775,7 @@ static void UpdaterLoop(ServingModel* sm) {
         // reference would build a fresh SessionGroup (serving/processor/serving/model_instance.cc:406-427); restart the processor for it.
         {
           const Arch& o = cur->arch; const Arch& n = nm->arch;
-          if (n.num_dense != o.num_dense || n.T != o.T || n.D != o.D || n.bot != o.bot || n.top != o.top || n.Zp != o.Zp) {
+          if (n.num_dense != o.num_dense || n.T != o.T || n.D != o.D || n.bot != o.bot || n.top != o.top || n.Zp != o.Zp || n.program != o.program || n.R != o.R) {
             if (sm->rejected_version != v) {
               fprintf(stderr, "[deeprec_serving] model version %lld changes the architecture (tables %d->%d, D %d->%d, dense %d->%d): rejected, sessions keep serving version %lld\n",
                       (long long)v, o.T, n.T, o.D, n.D, o.num_dense, n.num_dense, (long long)cur->version);
@@ -642,7 +809,7 @@ static int PredictProto(ServingModel* sm, const void* in, int in_size, void** ou
   if (!m) return 500;
   drpb::Request rq;
   std::string wire, err, pb;
-  if (!drpb::ParseRequest(in, (size_t)in_size, &rq) || !drpb::RequestToWire(rq, m->arch.num_dense, m->arch.T, &wire, &err)) { sm->failures++; return 500; }
+  if (!drpb::ParseRequest(in, (size_t)in_size, &rq) || !drpb::RequestToWire(rq, m->arch.num_dense, m->arch.R, &wire, &err)) { sm->failures++; return 500; }
   void* w_out = nullptr; int w_size = 0;
   const int rc = Predict(sm, wire.data(), (int)wire.size(), &w_out, &w_size, hint);
   if (rc != 200) { free(w_out); return rc; }

@@ -345,7 +345,8 @@ def _padded(rows: torch.Tensor, d: int, D: int) -> torch.Tensor:
 
 def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None) -> str:
     """Full export of a Criteo-style zoo model (``WDL``, ``DeepFM``, ``DCN``, ``DCNv2``, ``MaskNet``) as an op program + EmbeddingVariable tables; loaded by
-    ``Processor(dir, cfg, device="cpu")`` exactly like a DLRM export (same ModelConfig, update protocol, request formats)."""
+    ``Processor(dir, cfg)`` (GPU runtime: tcgen05 GEMMs + csrc/cuda/program_kernels.cu; ``device="cpu"``: the host interpreter) exactly like a DLRM
+    export (same ModelConfig, update protocol, request formats)."""
     was_training = model.training
     model.eval()
     p = _build_program(model)

@@ -55,7 +55,8 @@ class _Abi:
 
 
 class Processor:
-    """``device="cuda"``: the GPU runtime (csrc/cuda/serving_runtime.cu: device tables, bf16 / fp8 tcgen05 MLP, CUDA graphs);
+    """``device="cuda"``: the GPU runtime (csrc/cuda/serving_runtime.cu: device tables, bf16 / fp8 tcgen05 MLP; DLRM exports and op-program
+    exports of the other Criteo-style models);
     ``device="cpu"``: the CPU runtime (csrc/host/cpu_serving.cc: host tables, fp32 MLP on the OpenMP pool).  Same saved-model directory,
     request encodings, ModelConfig keys and hot-swap protocol.  Default: cuda when a GPU is visible, else cpu."""
 
@@ -68,11 +69,10 @@ class Processor:
             pass
         if device is None:
             import torch
-            # op-program exports (DeepFM, DCN, ... -- export_saved_model_program) are interpreted by the CPU runtime only
-            device = "cuda" if torch.cuda.is_available() and not program else "cpu"
-        if program and device != "cpu":
-            raise ValueError(f"{savedmodel_dir} is an op-program export: served by Processor(..., device='cpu') (the GPU runtime runs the DLRM architecture)")
-        self.device = device
+            # both runtimes interpret op-program exports (DeepFM, DCN, WDL, ... -- export_saved_model_program): the GPU one runs the LINEAR ops
+            # on the tcgen05 GEMM and the glue ops on csrc/cuda/program_kernels.cu, the CPU one is csrc/host/cpu_serving.cc::RunProgram
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device, self.program = device, program
         if device == "cpu":
             from .. import _native
             self.lib = _Abi(_native.host(), "dr_cpu_")
