@@ -16,8 +16,9 @@ WANT = {  # object file -> kernel-name substrings to dump in full
     "interaction_kernels.cu.o": ["k_dot_fwd_tcILb1", "k_dot_bwd_tcILb1"],
     "gemm_tcgen05.cu.o": ["k_gemm_tn_v2ILi256ELb0", "k_gemm_nt_splitkILi256"],
     "tier_kernels.cu.o": ["k_tier_miss_list", "k_tier_evict"],
+    "nvls.cu.o": ["k_nvls_allreduce_apply", "k_nvls_reduce_bcast"],
 }
-KEY = ["UTCHMMA", "UTCQMMA", "HMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "ACQBULK", "REDG", "ATOMG", "ATOMS", "MATCH", "LDG", "STG", "MEMBAR", "CCTL", "ERRBAR"]
+KEY = ["UTCHMMA", "UTCQMMA", "HMMA", "LDGMC", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "ACQBULK", "REDG", "ATOMG", "ATOMS", "MATCH", "LDG", "STG", "MEMBAR", "CCTL", "ERRBAR"]
 
 
 def main():
