@@ -19,6 +19,8 @@ from .ops.embedding_ops import (SparseIds, adaptive_embedding_lookup_sparse, emb
                                 fused_embedding_lookup_sparse, fused_safe_embedding_lookup_sparse,
                                 group_embedding_lookup, group_embedding_lookup_sparse,
                                 safe_embedding_lookup_sparse)
+from .ops.sparse_ops import (sparse_fill_empty_rows, sparse_prune_fill, sparse_reshape, sparse_segment_mean,  # noqa: E402,F401
+                             sparse_segment_sqrt_n, sparse_segment_sum, sparse_slice)
 from .optim.optimizers import get_or_create_global_step
 from . import graph_optimizer  # noqa: E402,F401
 from . import feature_column  # noqa: E402,F401

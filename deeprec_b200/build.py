@@ -33,6 +33,7 @@ CUDA_SOURCES = [
     "cuda/nvls.cu",
     "cuda/runtime.cu",
     "cuda/program_kernels.cu",
+    "cuda/sparse_utils.cu",
     "cuda/serving_runtime.cu",
     "cuda/fused_ops.cu",
     "cuda/allocator.cu",

@@ -1,1 +1,2 @@
 from . import embedding_ops  # noqa: F401
+from . import sparse_ops  # noqa: F401,E402
