@@ -8,9 +8,10 @@ every subscription is part of ``state_dict()`` so a restored job continues exact
 consumed through ``batch(n, parse_fn)`` the saved position is the one at the last BATCH boundary, so messages sitting in a partially filled
 batch are read again after a restore instead of being dropped.
 
-The broker client is pluggable: by default ``kafka-python`` (``kafka.KafkaConsumer``) is used when it is installed -- this image has no Kafka
-client library, so the class raises a clear ImportError there -- and ``consumer_factory`` accepts anything with the small interface below
-(the tests drive the dataset with an in-memory broker):
+The broker client is pluggable: ``kafka-python`` (``kafka.KafkaConsumer``) is used when it is installed, otherwise the built-in wire-protocol
+consumer (:mod:`data.kafka_wire`: Metadata / ListOffsets / Fetch over TCP, record-batch v2 + legacy message sets, CRC-32C, gzip) -- and
+``consumer_factory`` accepts anything with the small interface below (the tests drive the dataset with an in-memory broker AND with an
+in-process TCP broker speaking the wire protocol):
 
     consumer = consumer_factory(servers, group, config)      # config: dict from config_global / config_topic "key=value" strings
     consumer.poll(topic, partition, offset, max_records, timeout_ms) -> list[(offset, key: bytes | None, value: bytes)]
@@ -60,6 +61,15 @@ class _KafkaPythonConsumer:
         return [(m.offset, m.key, m.value) for m in got]
 
 
+def _default_consumer():
+    try:
+        import kafka  # type: ignore  # noqa: F401
+        return _KafkaPythonConsumer
+    except ImportError:
+        from .kafka_wire import KafkaWireConsumer
+        return KafkaWireConsumer
+
+
 class KafkaDataset:
     def __init__(self, topics: Sequence[str], servers="localhost", group: str = "", eof: bool = False, timeout: int = 1000,
                  config_global: Optional[Sequence[str]] = None, config_topic: Optional[Sequence[str]] = None, message_key: bool = False,
@@ -71,7 +81,7 @@ class KafkaDataset:
             k, _, v = kv.partition("=")
             config[k.strip()] = v.strip()
         servers = [servers] if isinstance(servers, str) else list(servers)
-        self._consumer = (consumer_factory or _KafkaPythonConsumer)(servers, group, config)
+        self._consumer = (consumer_factory or _default_consumer())(servers, group, config)
         self._cur = 0                                   # subscription being drained (the reference reads them in order)
 
     # ---- iteration ------------------------------------------------------------------------------------------------------------
