@@ -22,6 +22,9 @@ vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
 CH_DEDUP, CH_ROWS, CH_GRAD, CH_DENSE = 0, 1, 2, 3
 
 
+MAX_TABLES = 256          # kSpMaxTables in csrc/cuda/sparse_pipeline.cu
+
+
 class Peers(C.Structure):
     """Mirror of DrPeers (csrc/cuda/sp_sync.cuh)."""
     _fields_ = [("ptr", vp * 16)]
@@ -109,6 +112,16 @@ class SparsePipeline:
         self.ldinv = (self.C + 3) // 4 * 4
         if world > 1 and comm is None:
             raise ValueError("world > 1 needs a P2PComm for the symmetric buffers")
+        # limits of the kernels (csrc/cuda/sparse_pipeline.cu): per-peer pointer tables hold 16 ranks (one NVSwitch domain of 8 today), the per-table
+        # chunk prefix lives in shared memory, rows move as 8-byte bf16 groups
+        if world > 16:
+            raise ValueError(f"SparsePipeline: world size {world} > 16 ranks of one peer-memory domain")
+        if num_tables > MAX_TABLES:
+            raise ValueError(f"SparsePipeline: {num_tables} tables > {MAX_TABLES}; merge small tables (PartitionedEmbeddingVariable / one table with a feature-id prefix)")
+        if dim % 4 or dim <= 0:
+            raise ValueError(f"SparsePipeline: embedding dim {dim} must be a positive multiple of 4")
+        if any(t < 0 or t >= num_tables for t in col_table):
+            raise ValueError("SparsePipeline: col_table entry outside [0, num_tables)")
         ncols = [0] * num_tables
         for t in col_table:
             ncols[t] += 1

@@ -1,4 +1,4 @@
-"""ops/sparse_ops.py on CPU tensors (the torch expressions that are also the oracle of the CUDA kernels, tests/test_gpu_zzz_sparse_utils.py)
+"""ops/sparse_ops.py on CPU tensors (the torch expressions that are also the oracle of the CUDA kernels, tests/test_gpu_zzy_sparse_utils.py)
 against brute-force python loops.  Reference semantics: tf.sparse.retain + fill_empty_rows in safe_embedding_lookup_sparse
 (python/ops/embedding_ops.py:838), tf.sparse.slice / reshape, tf.sparse.segment_{sum,mean,sqrt_n}."""
 import math
