@@ -1,4 +1,4 @@
-from .kafka_dataset import KafkaDataset  # noqa: F401
+from .kafka_dataset import KafkaDataset, KafkaGroupIODataset, merge_group_states  # noqa: F401
 from .parquet_dataset import DataFrameValue, ParquetDataset, read_parquet  # noqa: F401
 from .staged import (AsyncEmbeddingStage, PackedHostBatch, PrefetchRunner, SmartStageOptions, Staged, StagingBuffer,  # noqa: F401
                      make_prefetch_hook, smart_stage, staged)

@@ -132,3 +132,65 @@ class KafkaDataset:
 
     def positions(self) -> List[Tuple[str, int, int]]:
         return [(s.topic, s.partition, s.offset) for s in self.subs]
+
+
+class KafkaGroupIODataset(KafkaDataset):
+    """Group consumption for data-parallel online learning (reference: ``KafkaGroupIODataset`` -- the consumers of one group split the
+    partitions of the subscribed topics among themselves and re-split when the group changes).
+
+    Here the group is the training job: worker ``rank`` of ``world_size`` reads the partitions ``p`` with ``p % world_size == rank`` of every
+    topic, discovered from the broker's metadata (``consumer.partitions(topic)``) -- the assignment a range / round-robin assignor converges
+    to for a static membership, without a coordinator round trip.  ``rebalance(world_size, rank)`` re-splits after an elastic resize;
+    positions travel with the partitions through ``state_dict()`` (merge the workers' states with :func:`merge_group_states` before the resize,
+    load the merged state on every new worker: each keeps the positions of the partitions it now owns)."""
+
+    def __init__(self, topics: Sequence[str], servers="localhost", group: str = "", world_size: int = 1, rank: int = 0, offset: int = 0, **kw):
+        self._topics = [topics] if isinstance(topics, str) else list(topics)
+        self._start = int(offset)
+        super().__init__([], servers=servers, group=group, **kw)
+        self._known: Dict[Tuple[str, int], int] = {}          # (topic, partition) -> next offset, for every partition this worker ever saw or was told about
+        self.rebalance(world_size, rank)
+
+    def _all_partitions(self) -> List[Tuple[str, int]]:
+        if not hasattr(self._consumer, "partitions"):
+            raise TypeError("KafkaGroupIODataset needs a broker client with partitions(topic) (data.kafka_wire.KafkaWireConsumer has it)")
+        return [(t, p) for t in self._topics for p in self._consumer.partitions(t)]
+
+    def rebalance(self, world_size: int, rank: int) -> List[Tuple[str, int]]:
+        """Re-split the partitions for a group of ``world_size`` workers; returns this worker's assignment."""
+        if not 0 <= rank < world_size:
+            raise ValueError(f"rank {rank} outside a group of {world_size}")
+        for s in self.subs:
+            self._known[(s.topic, s.partition)] = s.offset
+        self.world_size, self.rank = int(world_size), int(rank)
+        mine = [(t, p) for i, (t, p) in enumerate(sorted(self._all_partitions())) if i % world_size == rank]
+        self.subs = [_Subscription(t, p, self._known.get((t, p), self._start), -1) for t, p in mine]
+        self._cur = 0
+        return mine
+
+    def state_dict(self) -> dict:
+        st = super().state_dict()
+        known = dict(self._known)
+        for sub in st["subscriptions"]:
+            s = _parse_subscription(sub)
+            known[(s.topic, s.partition)] = s.offset
+        st["group_positions"] = {f"{t}:{p}": o for (t, p), o in sorted(known.items())}
+        return st
+
+    def load_state_dict(self, state: dict) -> None:
+        for k, o in state.get("group_positions", {}).items():
+            t, _, p = k.rpartition(":")
+            self._known[(t, int(p))] = int(o)
+        for s in self.subs:
+            s.offset = self._known.get((s.topic, s.partition), s.offset)
+        self._cur = 0
+
+
+def merge_group_states(states: Sequence[dict]) -> dict:
+    """Union of the per-worker positions of one consumer group (every partition is owned by exactly one worker at a time: the furthest
+    position wins where a partition changed hands)."""
+    pos: Dict[str, int] = {}
+    for st in states:
+        for k, o in st.get("group_positions", {}).items():
+            pos[k] = max(int(o), pos.get(k, -1))
+    return {"current": 0, "subscriptions": [], "group_positions": pos}

@@ -314,6 +314,35 @@ class KafkaWireConsumer:
             raise KafkaProtocolError(f"{topic}:{partition}: UNKNOWN_TOPIC_OR_PARTITION")
         raise ConnectionError(f"no bootstrap server reachable: {self.servers}") from last
 
+    def partitions(self, topic: str) -> List[int]:
+        """Partition ids of ``topic`` (Metadata request to the first reachable bootstrap server)."""
+        last: Optional[Exception] = None
+        for addr in self.servers:
+            try:
+                r = self._call(addr, API_METADATA, 1, struct.pack(">i", 1) + enc_string(topic))
+            except OSError as e:
+                last = e
+                continue
+            for _ in range(r.i32()):
+                r.i32(); r.string(); r.i32(); r.string()
+            r.i32()
+            out: List[int] = []
+            for _ in range(r.i32()):
+                terr, tname = r.i16(), r.string()
+                r.i8()
+                for _ in range(r.i32()):
+                    r.i16(); pid = r.i32(); r.i32()
+                    for _ in range(r.i32()):
+                        r.i32()
+                    for _ in range(r.i32()):
+                        r.i32()
+                    if tname == topic:
+                        out.append(pid)
+                if tname == topic and terr:
+                    raise KafkaProtocolError(f"{topic}: {_ERRORS.get(terr, terr)}")
+            return sorted(out)
+        raise ConnectionError(f"no bootstrap server reachable: {self.servers}") from last
+
     def list_offset(self, topic: str, partition: int, which: int = EARLIEST) -> int:
         """``which``: EARLIEST (-2), LATEST (-1) or a timestamp in ms."""
         body = struct.pack(">ii", -1, 1) + enc_string(topic) + struct.pack(">iiq", 1, partition, which)

@@ -131,10 +131,29 @@ def gpu_tensorpool_stats(device: int | None = None) -> Dict[str, int]:
     return dict(zip(_STAT_NAMES, (int(v) for v in out)))
 
 
+def enable_cuda_malloc_async() -> bool:
+    """Stream-ordered driver allocator (``cudaMallocAsync`` memory pools) as PyTorch's CUDA allocator -- the reference's
+    ``TF_GPU_ALLOCATOR=cuda_malloc_async`` (``common_runtime/gpu/gpu_cudamallocasync_allocator.cc``).  Must run before the first CUDA
+    allocation of the process (PyTorch fixes its allocator backend at that point); returns False when it is too late."""
+    if torch.cuda.is_initialized():
+        return torch.cuda.get_allocator_backend() == "cudaMallocAsync"
+    conf = [c for c in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", "").split(",") if c and not c.startswith("backend:")]
+    os.environ["PYTORCH_CUDA_ALLOC_CONF"] = ",".join(conf + ["backend:cudaMallocAsync"])
+    setter = getattr(torch._C, "_accelerator_setAllocatorSettings", None) or getattr(torch.cuda.memory, "_set_allocator_settings", None)
+    try:
+        if setter is not None:
+            setter(os.environ["PYTORCH_CUDA_ALLOC_CONF"])
+    except Exception:
+        pass                                     # builds that read the variable at first use only
+    return True
+
+
 def maybe_enable_from_env() -> bool:
-    """``TF_GPU_ALLOCATOR=tensorpool`` / ``DEEPREC_GPU_ALLOCATOR=tensorpool`` (the reference's switch)."""
-    v = os.environ.get("DEEPREC_GPU_ALLOCATOR", os.environ.get("TF_GPU_ALLOCATOR", ""))
-    if v.strip().lower() == "tensorpool" and torch.cuda.is_available():
+    """``TF_GPU_ALLOCATOR=tensorpool | cuda_malloc_async`` / ``DEEPREC_GPU_ALLOCATOR=...`` (the reference's switch)."""
+    v = os.environ.get("DEEPREC_GPU_ALLOCATOR", os.environ.get("TF_GPU_ALLOCATOR", "")).strip().lower()
+    if v == "tensorpool" and torch.cuda.is_available():
         enable_gpu_tensorpool()
         return True
+    if v in ("cuda_malloc_async", "cudamallocasync"):
+        return enable_cuda_malloc_async()
     return False

@@ -80,3 +80,29 @@ def test_kafka_dataset_over_the_wire_with_saved_position():
         assert [int(m.split(b",")[0]) for m in ds2] == list(range(7, 17)) + [100, 101]
     finally:
         b.close()
+
+
+def test_group_dataset_splits_partitions_and_survives_a_resize():
+    """Two workers split four partitions; after a resize to three workers every message is still delivered exactly once."""
+    from deeprec_b200.data.kafka_dataset import KafkaGroupIODataset, merge_group_states
+    b = MiniKafkaBroker()
+    try:
+        for p in range(4):
+            b.append("ev", p, [(None, f"{p}-{i}".encode()) for i in range(6)])
+        servers = f"127.0.0.1:{b.port}"
+        ws = [KafkaGroupIODataset(["ev"], servers=servers, world_size=2, rank=r, eof=True, timeout=100, max_poll_records=2) for r in range(2)]
+        assert [sorted(p for _, p in w.rebalance(2, r)) for r, w in enumerate(ws)] == [[0, 2], [1, 3]]
+        seen = []
+        for w in ws:                                                   # every worker consumes 5 messages, then the job is resized
+            it = iter(w)
+            seen += [next(it) for _ in range(5)]
+        merged = merge_group_states([w.state_dict() for w in ws])
+        ws3 = [KafkaGroupIODataset(["ev"], servers=servers, world_size=3, rank=r, eof=True, timeout=100) for r in range(3)]
+        for w in ws3:
+            w.load_state_dict(merged)
+            seen += list(w)
+        assert sorted(seen) == sorted(f"{p}-{i}".encode() for p in range(4) for i in range(6))
+        with pytest.raises(ValueError):
+            ws[0].rebalance(2, 2)
+    finally:
+        b.close()
