@@ -81,14 +81,18 @@ struct Config {
 
 // Op program (saved_model.json "arch": "program", written by serving/export.py::export_saved_model_program): the inference graph of a
 // Criteo-style model other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].
-enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE };
+// Sequence models (DIN): the request's id rows are COLUMNS, several of which may read the same table (`col_table`: target item + L history
+// positions -> the item table); valid_mask / seq_zip / seq_mask / seq_sum / din_attention / prelu are the ops their heads need.
+enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_NUM_OPS };
 struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1; std::string model_name = "dlrm";
-  // requests carry R id rows; table t reads request row id_map[t] (identity unless several tables share a feature, e.g. the wide and
-  // the deep table of one Wide&Deep column)
-  int R = 0; std::vector<int> id_map;
+  // requests carry R id rows; lookup column c reads request row id_map[c] (identity unless several columns share a feature, e.g. the wide
+  // and the deep table of one Wide&Deep column) from table col_table[c] (identity unless several columns share a TABLE, e.g. DIN's target
+  // item and its L history positions).  C == T and col_table == identity for every model exported before col_table existed.
+  int R = 0, C = 0; std::vector<int> id_map, col_table;
 };
 static int pad8(int n) { return (n + 7) / 8 * 8; }
 
@@ -105,7 +109,7 @@ struct Layer {
       wp[((size_t)p * K + k) * kPanel + j] = wt[(size_t)k * N + p * kPanel + j];
   }
 };
-struct PData { Layer L; std::vector<float> v0, v1; };                     // weights of one program op (linear | affine scale, shift | cross w, b)
+struct PData { Layer L; std::vector<float> v0, v1; std::vector<std::vector<float>> att; int H1 = 0, H2 = 0; };   // weights of one program op (linear | affine scale, shift | cross w, b | prelu alpha | din_attention W1 b1 W2 b2 w3 b3)
 struct Dense {
   std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f;
   std::vector<PData> pdata; std::vector<int> width;                       // program models: per-op weights, per-buffer widths
@@ -115,6 +119,7 @@ struct Model {
   Arch arch; int64_t version = -1; std::string path;
   std::shared_ptr<Dense> dense;
   std::vector<void*> tables;                                   // HostEV handles (owned); empty in remote (Redis) mode
+  std::vector<void*> col_handles;                              // tables[col_table[c]] per lookup column (not owned)
   std::vector<std::vector<float>> defaults;                    // remote mode: default-value matrix of every table ([dvd, D])
   std::vector<int64_t> sample_keys;                            // a few stored keys per table for the synthetic warm-up batch, [T][<=64]
   ~Model() { for (void* t : tables) if (t) dr_host_ev_destroy(t); }
@@ -137,12 +142,19 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   *version = (int64_t)j.n("version", 0);
   *prefix = dir + "/" + j.s("variables", "variables/variables");
   a->model_name = j.s("model", "dlrm");
-  a->R = (int)j.n("num_id_rows", a->T);
-  a->id_map.resize((size_t)std::max(0, a->T));
-  for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = t;
+  a->C = a->T;
+  if (auto* ct = j.get("col_table")) {
+    if (ct->t != JVal::ARR || ct->arr.empty()) return false;
+    a->C = (int)ct->arr.size();
+    for (auto& v : ct->arr) a->col_table.push_back((int)v.num);
+  } else for (int t = 0; t < a->T; ++t) a->col_table.push_back(t);
+  for (int v : a->col_table) if (v < 0 || v >= a->T) return false;
+  a->R = (int)j.n("num_id_rows", a->C);
+  a->id_map.resize((size_t)std::max(0, a->C));
+  for (int c = 0; c < a->C; ++c) a->id_map[(size_t)c] = c;
   if (auto* im = j.get("id_map")) {
-    if (im->t != JVal::ARR || (int)im->arr.size() != a->T) return false;
-    for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = (int)im->arr[(size_t)t].num;
+    if (im->t != JVal::ARR || (int)im->arr.size() != a->C) return false;
+    for (int c = 0; c < a->C; ++c) a->id_map[(size_t)c] = (int)im->arr[(size_t)c].num;
   }
   for (int v : a->id_map) if (v < 0 || v >= a->R) return false;
   if (a->R <= 0) return false;
@@ -150,18 +162,19 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     a->program = true;
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
-    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice"};
+    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu"};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     for (const JVal& o : pr->arr) {
       POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
       op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0);
       const std::string kind = o.s("op", "");
-      for (int k = 0; k < 10; ++k) if (kind == kNames[k]) op.kind = k;
+      for (int k = 0; k < P_NUM_OPS; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
-      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1};
+      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1};
       if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
       op.out = (int)names.size(); names.push_back(op.name);
       a->ops.push_back(std::move(op));
@@ -176,7 +189,7 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
 // weights + buffer widths of a program model; every shape is checked against the widths implied by the op list
 static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Dense>* out) {
   auto dp = std::make_shared<Dense>();
-  dp->width.assign((size_t)a.nbuf, 0); dp->width[0] = a.num_dense; dp->width[1] = a.T * a.D;
+  dp->width.assign((size_t)a.nbuf, 0); dp->width[0] = a.num_dense; dp->width[1] = a.C * a.D;
   dp->pdata.resize(a.ops.size());
   for (size_t i = 0; i < a.ops.size(); ++i) {
     const POp& op = a.ops[i]; PData& d = dp->pdata[i];
@@ -201,6 +214,25 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_MUL:
       case P_ADD: if (dp->width[(size_t)op.in[1]] != w0) return false; break;
       case P_SLICE: if (op.start < 0 || op.len <= 0 || op.start + op.len > w0) return false; w = op.len; break;
+      case P_VALID_MASK: if (op.start < 0 || op.len <= 0 || op.start + op.len > a.C) return false; w = op.len; break;      // [B, len]: 1 where the id of column start + l is >= 0
+      case P_SEQ_ZIP: {                                              // a [B, L * Wa], b [B, L * Wb] -> [B, L * (Wa + Wb)], position-wise concat
+        const int wb = dp->width[(size_t)op.in[1]];
+        if (op.len <= 0 || w0 % op.len || wb % op.len) return false;
+        w = w0 + wb; break;
+      }
+      case P_SEQ_MASK: if (op.len <= 0 || w0 % op.len || dp->width[(size_t)op.in[1]] != op.len) return false; break;       // x [B, L * W] * mask [B, L]
+      case P_SEQ_SUM: if (op.len <= 0 || w0 % op.len) return false; w = w0 / op.len; break;                                 // sum over the L positions
+      case P_PRELU: if (!ReadVec(r, base + "alpha", &d.v0) || (int)d.v0.size() != w0) return false; break;
+      case P_DIN_ATT: {                                              // q [B, W], k [B, L * W], mask [B, L] -> [B, W]
+        const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
+        if (L <= 0 || wk != L * w0) return false;
+        d.att.resize(6);
+        static const char* kT[] = {"w1", "b1", "w2", "b2", "w3", "b3"};
+        for (int i2 = 0; i2 < 6; ++i2) if (!ReadVec(r, base + kT[i2], &d.att[(size_t)i2])) return false;
+        d.H1 = (int)d.att[1].size(); d.H2 = (int)d.att[3].size();
+        if (d.H1 <= 0 || d.H2 <= 0 || (int)d.att[0].size() != d.H1 * 4 * w0 || (int)d.att[2].size() != d.H2 * d.H1 || (int)d.att[4].size() != d.H2 || d.att[5].size() != 1) return false;
+        break;
+      }
       default: return false;
     }
     if (w <= 0) return false;
@@ -299,6 +331,7 @@ static std::shared_ptr<Model> LoadModel(const std::string& dir, bool remote = fa
     m->tables.push_back(h);
     for (size_t i = 0; i < 64; ++i) m->sample_keys[(size_t)t * 64 + i] = sample.empty() ? 0 : sample[i % sample.size()];
   }
+  for (int c = 0; c < m->arch.C && !remote; ++c) m->col_handles.push_back(m->tables[(size_t)m->arch.col_table[(size_t)c]]);
   m->path = dir;
   return m;
 }
@@ -460,7 +493,7 @@ struct Session {
     for (int n : ar.bot) widest = std::max(widest, n);
     for (int n : ar.top) widest = std::max(widest, n);
     auto grow = [](auto& v, size_t n) { if (v.size() < n) v.resize(n); };
-    grow(dense, mb * ar.num_dense); grow(ids, mb * ar.T); grow(emb, mb * ar.T * ar.D);
+    grow(dense, mb * ar.num_dense); grow(ids, mb * ar.C); grow(emb, mb * ar.C * ar.D);
     grow(a, mb * widest); grow(b2, mb * widest); grow(z, mb * ar.inter); grow(prob, mb);
     grow(rrows, mb * ar.D); grow(found, mb);
   }
@@ -468,15 +501,16 @@ struct Session {
   // inference-mode lookup returns)
   bool RemoteLookup(const Model& m, const std::string& prefix, int B) {
     const Arch& ar = m.arch;
-    for (int t = 0; t < ar.T; ++t) {
-      const int64_t* k = ids.data() + (size_t)t * B;
+    for (int c = 0; c < ar.C; ++c) {
+      const int t = ar.col_table[(size_t)c];
+      const int64_t* k = ids.data() + (size_t)c * B;
       const std::string p = prefix + "/" + std::to_string(m.version) + "/table/" + std::to_string(t);
       if (!dr_redis_ok(redis) || dr_redis_mget_rows(redis, p.c_str(), k, B, rrows.data(), ar.D, found.data()) < 0) return false;
       const std::vector<float>& def = m.defaults[(size_t)t];
       const int64_t dvd = (int64_t)def.size() / ar.D;
       for (int i = 0; i < B; ++i) {
         const float* src = found[(size_t)i] ? rrows.data() + (size_t)i * ar.D : def.data() + dr_default_row(k[i], dvd) * ar.D;
-        memcpy(emb.data() + ((size_t)i * ar.T + t) * ar.D, src, (size_t)ar.D * sizeof(float));
+        memcpy(emb.data() + ((size_t)i * ar.C + c) * ar.D, src, (size_t)ar.D * sizeof(float));
       }
     }
     return true;
@@ -514,7 +548,7 @@ struct Session {
           break;
         }
         case P_FM: {                                             // 0.5 ((sum_t v_t)^2 - sum_t v_t^2) per embedding dimension
-          const int T = ar.T, D = ar.D;
+          const int T = ar.C, D = ar.D;
 #pragma omp parallel for schedule(static) num_threads(threads) if (par)
           for (int i = 0; i < B; ++i) {
             const float* e = a0 + (size_t)i * T * D; float* y = out + (size_t)i * D;
@@ -546,6 +580,70 @@ struct Session {
           for (int i = 0; i < B; ++i) memcpy(out + (size_t)i * W, a0 + (size_t)i * w0 + st, (size_t)W * sizeof(float));
           break;
         }
+        case P_VALID_MASK: {                                     // out[i, l] = ids[column start + l][i] >= 0
+          for (int l = 0; l < W; ++l) { const int64_t* k = ids.data() + (size_t)(op.start + l) * B; for (int i = 0; i < B; ++i) out[(size_t)i * W + l] = k[i] >= 0 ? 1.f : 0.f; }
+          break;
+        }
+        case P_SEQ_ZIP: {                                        // position-wise concat of two [B, L, *] sequences
+          const float* b1 = Buf(op.in[1]); const int L = op.len, wa = w0 / L, wb = d.width[(size_t)op.in[1]] / L;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i)
+            for (int l = 0; l < L; ++l) {
+              float* y = out + (size_t)i * W + (size_t)l * (wa + wb);
+              memcpy(y, a0 + (size_t)i * w0 + (size_t)l * wa, (size_t)wa * sizeof(float));
+              memcpy(y + wa, b1 + (size_t)i * L * wb + (size_t)l * wb, (size_t)wb * sizeof(float));
+            }
+          break;
+        }
+        case P_SEQ_MASK: {                                       // x [B, L, w] * mask [B, L]
+          const float* mk = Buf(op.in[1]); const int L = op.len, w = W / L;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i)
+            for (int l = 0; l < L; ++l) { const float f = mk[(size_t)i * L + l]; const float* x = a0 + (size_t)i * W + (size_t)l * w; float* y = out + (size_t)i * W + (size_t)l * w; for (int k = 0; k < w; ++k) y[k] = x[k] * f; }
+          break;
+        }
+        case P_SEQ_SUM: {                                        // sum over the L positions of x [B, L, W]
+          const int L = op.len;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            float* y = out + (size_t)i * W; for (int k = 0; k < W; ++k) y[k] = 0.f;
+            for (int l = 0; l < L; ++l) { const float* x = a0 + (size_t)i * w0 + (size_t)l * W; for (int k = 0; k < W; ++k) y[k] += x[k]; }
+          }
+          break;
+        }
+        case P_PRELU: {
+          const float* al = pd.v0.data();
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) { const float* x = a0 + (size_t)i * W; float* y = out + (size_t)i * W; for (int k = 0; k < W; ++k) y[k] = x[k] > 0.f ? x[k] : al[k] * x[k]; }
+          break;
+        }
+        case P_DIN_ATT: {                                        // DIN attention unit: s_l = MLP([q, k_l, q - k_l, q * k_l]), masked softmax, sum_l w_l k_l
+          const float* kk = Buf(op.in[1]); const float* mk = Buf(op.in[2]);
+          const int L = d.width[(size_t)op.in[2]], H1 = pd.H1, H2 = pd.H2, Wq = W;
+          const float *W1 = pd.att[0].data(), *b1 = pd.att[1].data(), *W2 = pd.att[2].data(), *b2 = pd.att[3].data(), *w3 = pd.att[4].data(); const float b3 = pd.att[5][0];
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            const float* q = a0 + (size_t)i * Wq; const float* ks = kk + (size_t)i * L * Wq; const float* m = mk + (size_t)i * L;
+            std::vector<float> f((size_t)4 * Wq), h1((size_t)H1), sc((size_t)L);
+            float mx = -3.4e38f; bool any = false;
+            for (int l = 0; l < L; ++l) {
+              if (m[l] <= 0.f) { sc[(size_t)l] = -3.4e38f; continue; }
+              any = true;
+              const float* k = ks + (size_t)l * Wq;
+              for (int c = 0; c < Wq; ++c) { f[(size_t)c] = q[c]; f[(size_t)Wq + c] = k[c]; f[(size_t)2 * Wq + c] = q[c] - k[c]; f[(size_t)3 * Wq + c] = q[c] * k[c]; }
+              for (int h = 0; h < H1; ++h) { float acc = b1[h]; const float* w = W1 + (size_t)h * 4 * Wq; for (int c = 0; c < 4 * Wq; ++c) acc += w[c] * f[(size_t)c]; h1[(size_t)h] = 1.f / (1.f + std::exp(-acc)); }
+              float s3 = b3;
+              for (int h = 0; h < H2; ++h) { float acc = b2[h]; const float* w = W2 + (size_t)h * H1; for (int c = 0; c < H1; ++c) acc += w[c] * h1[(size_t)c]; s3 += w3[h] / (1.f + std::exp(-acc)); }
+              sc[(size_t)l] = s3; mx = std::max(mx, s3);
+            }
+            float* y = out + (size_t)i * Wq; for (int c = 0; c < Wq; ++c) y[c] = 0.f;
+            if (!any) continue;                                  // no valid history position: zero vector (the module multiplies by mask.any())
+            float den = 0.f;
+            for (int l = 0; l < L; ++l) if (m[l] > 0.f) { sc[(size_t)l] = std::exp(sc[(size_t)l] - mx); den += sc[(size_t)l]; }
+            for (int l = 0; l < L; ++l) if (m[l] > 0.f) { const float wl = sc[(size_t)l] / den; const float* k = ks + (size_t)l * Wq; for (int c = 0; c < Wq; ++c) y[c] += wl * k[c]; }
+          }
+          break;
+        }
         case P_LAYERNORM: {                                      // (x - mean) / sqrt(var + eps) * gamma + beta, biased variance, optional ReLU
           const float* g = pd.v0.data(); const float* bt = pd.v1.data(); const float eps = op.eps; const bool relu = op.relu;
 #pragma omp parallel for schedule(static) num_threads(threads) if (par)
@@ -568,7 +666,7 @@ struct Session {
   bool Run(const Model& m, const Dense& d, int B, const std::string& remote_prefix = std::string()) {
     const Arch& ar = m.arch;
     if (redis) { if (!RemoteLookup(m, remote_prefix, B)) return false; }
-    else dr_host_group_lookup(const_cast<void**>(m.tables.data()), ar.T, ids.data(), B, emb.data());         // [B, T, D]
+    else dr_host_group_lookup(const_cast<void**>(m.col_handles.data()), ar.C, ids.data(), B, emb.data());    // [B, C, D]
     if (ar.program) { RunProgram(ar, d, B); return true; }
     const float* x = dense.data(); int64_t ldx = ar.num_dense;
     float* cur = a.data(); float* nxt = b2.data();
@@ -657,7 +755,7 @@ static int RunRows(ServingModel* sm, const std::shared_ptr<Model>& m, const uint
   for (uint32_t off = 0; off < R; off += (uint32_t)s.max_batch) {                  // larger requests are chunked
     const int B = (int)std::min<uint32_t>((uint32_t)s.max_batch, R - off);
     memcpy(s.dense.data(), dense_in + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
-    for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids_in + ((size_t)a.id_map[(size_t)t] * ids_stride + off) * 8, (size_t)B * 8);
+    for (int c = 0; c < a.C; ++c) memcpy(s.ids.data() + (size_t)c * B, ids_in + ((size_t)a.id_map[(size_t)c] * ids_stride + off) * 8, (size_t)B * 8);
     if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) {
       // feature store hiccup: one reconnect + retry before the request is failed (the next request tries again)
       bool ok = false;
@@ -805,13 +903,14 @@ static bool WarmUp(ServingModel* sm, const std::shared_ptr<Model>& m) {
         const uint8_t* p = reinterpret_cast<const uint8_t*>(raw.data()) + sizeof(h);
         memcpy(s.dense.data(), p, (size_t)B * a.num_dense * 4);
         const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
-        for (int t = 0; t < a.T; ++t) memcpy(s.ids.data() + (size_t)t * B, ids + (size_t)a.id_map[(size_t)t] * h.batch, (size_t)B * 8);
+        for (int c = 0; c < a.C; ++c) memcpy(s.ids.data() + (size_t)c * B, ids + (size_t)a.id_map[(size_t)c] * h.batch, (size_t)B * 8);
         filled = true;
       }
     }
     if (!filled) {
       for (int i = 0; i < B * a.num_dense; ++i) s.dense[(size_t)i] = (float)((i * 37) % 100) / 25.f;
-      for (int t = 0; t < a.T; ++t) for (int i = 0; i < B; ++i) s.ids[(size_t)t * B + i] = m->tables.empty() ? (int64_t)i : m->sample_keys[(size_t)t * 64 + (size_t)(i % 64)];
+      for (int c = 0; c < a.C; ++c) for (int i = 0; i < B; ++i)
+        s.ids[(size_t)c * B + i] = m->tables.empty() ? (int64_t)i : m->sample_keys[(size_t)a.col_table[(size_t)c] * 64 + (size_t)(i % 64)];
     }
     auto dense = std::atomic_load(&m->dense);
     if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) return false;

@@ -250,6 +250,37 @@ class _ProgramBuilder:
         self.tensors[f"prog/{out}/scale"] = ln.weight.detach().float().cpu().contiguous(); self.tensors[f"prog/{out}/shift"] = ln.bias.detach().float().cpu().contiguous()
         self.ops.append({"op": "layernorm", "out": out, "in": [src], "eps": float(ln.eps), "relu": bool(relu)}); return out
 
+    # ---- sequence models (DIN): the id rows of a request are COLUMNS over shared tables (meta "col_table") --------------------------------
+    def valid_mask(self, start, length):
+        """[B, length]: 1.0 where the id of lookup column ``start + l`` is >= 0 (padding of a history is -1)."""
+        out = self._name("valid"); self.ops.append({"op": "valid_mask", "out": out, "in": ["emb"], "start": int(start), "len": int(length)}); return out
+
+    def seq_zip(self, a, b, L):
+        out = self._name("zip"); self.ops.append({"op": "seq_zip", "out": out, "in": [a, b], "len": int(L)}); return out
+
+    def seq_mask(self, x, mask, L):
+        out = self._name("smask"); self.ops.append({"op": "seq_mask", "out": out, "in": [x, mask], "len": int(L)}); return out
+
+    def seq_sum(self, x, L):
+        out = self._name("ssum"); self.ops.append({"op": "seq_sum", "out": out, "in": [x], "len": int(L)}); return out
+
+    def prelu(self, src, alpha, width):
+        out = self._name("prelu")
+        a = alpha.detach().float().cpu().reshape(-1)
+        self.tensors[f"prog/{out}/alpha"] = (a.expand(width) if a.numel() == 1 else a).contiguous()
+        self.ops.append({"op": "prelu", "out": out, "in": [src]}); return out
+
+    def din_attention(self, q, k, mask, att):
+        """Linear(4W, H1)-Sigmoid-Linear(H1, H2)-Sigmoid-Linear(H2, 1) attention unit, masked softmax, weighted sum of the keys."""
+        import torch.nn as nn
+        mods = list(att)
+        if not (len(mods) == 5 and all(isinstance(mods[i], nn.Linear) for i in (0, 2, 4)) and all(isinstance(mods[i], nn.Sigmoid) for i in (1, 3)) and mods[4].out_features == 1):
+            raise TypeError("op-program export: din_attention needs the Linear-Sigmoid-Linear-Sigmoid-Linear(1) unit")
+        out = self._name("att")
+        for nm, t in (("w1", mods[0].weight), ("b1", mods[0].bias), ("w2", mods[2].weight), ("b2", mods[2].bias), ("w3", mods[4].weight), ("b3", mods[4].bias)):
+            self.tensors[f"prog/{out}/{nm}"] = t.detach().float().cpu().reshape(-1).contiguous()
+        self.ops.append({"op": "din_attention", "out": out, "in": [q, k, mask]}); return out
+
     def sequential(self, src, seq):
         """nn.Sequential of Linear / ReLU / BatchNorm1d (what ``models.zoo.mlp`` builds on CPU): a BatchNorm folds into the next Linear
         (W' = W diag(s), b' = b + W t); one left over at the end becomes an explicit affine op."""
@@ -267,6 +298,9 @@ class _ProgramBuilder:
                 relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
                 src = self.linear(src, W, b, relu)
                 i += 2 if relu else 1
+                if i < len(mods) and isinstance(mods[i], nn.PReLU):
+                    src = self.prelu(src, mods[i].weight, m.out_features)
+                    i += 1
             elif isinstance(m, nn.BatchNorm1d):
                 s = m.weight.detach().float() / torch.sqrt(m.running_var.detach().float() + m.eps)
                 pending = (s, m.bias.detach().float() - m.running_mean.detach().float() * s)
@@ -278,13 +312,13 @@ class _ProgramBuilder:
                 src = self.layernorm(src, m, relu)
                 i += 2 if relu else 1
             else:
-                raise TypeError(f"op-program export: unsupported layer {type(m).__name__} (Linear / ReLU / BatchNorm1d chains only)")
+                raise TypeError(f"op-program export: unsupported layer {type(m).__name__} (Linear / ReLU / PReLU / BatchNorm1d / LayerNorm chains only)")
         if pending is not None:
             src = self.affine(src, *pending)
         return src
 
 
-def _build_program(model) -> _ProgramBuilder:
+def _build_program(model, max_len: int = 50) -> _ProgramBuilder:
     from ..models import zoo
     p = _ProgramBuilder()
     if isinstance(model, zoo.DeepFM):
@@ -319,8 +353,21 @@ def _build_program(model) -> _ProgramBuilder:
         for w, b in zip(model.cw, model.cb):
             x = p.cross(x0, x, w, b)
         p.out = p.linear(p.concat([x, p.sequential(x0, model.deep)]), model.out.weight, model.out.bias)
+    elif isinstance(model, zoo.DIN):
+        # lookup columns [user | item | cat | hist_item x L | hist_cat x L] over the three tables (the layout of models.rec_engine.din_ids);
+        # padding ids (-1) give masked (zeroed) history positions
+        import torch.nn as nn
+        L, D = int(max_len), model.emb_dim
+        p.tables = [(model.user, D), (model.item, D), (model.cat, D)]
+        p.col_table = [0, 1, 2] + [1] * L + [2] * L
+        p.num_dense = 1                                                   # a dummy dense column keeps the request format uniform
+        u, q = p.slice("emb", 0, D), p.slice("emb", D, 2 * D)
+        mask = p.valid_mask(3, L)
+        k = p.seq_mask(p.seq_zip(p.slice("emb", 3 * D, L * D), p.slice("emb", (3 + L) * D, L * D), L), mask, L)      # [B, L * 2D]
+        x = p.concat([u, q, p.seq_sum(k, L), p.din_attention(q, k, mask, model.att)])
+        p.out = p.sequential(x, nn.Sequential(model.bn, *list(model.top)))
     else:
-        raise TypeError(f"op-program export: no builder for {type(model).__name__} (WDL, DeepFM, DCN, DCNv2, MaskNet; DLRM has export_saved_model_module)")
+        raise TypeError(f"op-program export: no builder for {type(model).__name__} (WDL, DeepFM, DCN, DCNv2, MaskNet, DIN; DLRM has export_saved_model_module)")
     return p
 
 
@@ -343,14 +390,17 @@ def _padded(rows: torch.Tensor, d: int, D: int) -> torch.Tensor:
     return out
 
 
-def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None) -> str:
-    """Full export of a Criteo-style zoo model (``WDL``, ``DeepFM``, ``DCN``, ``DCNv2``, ``MaskNet``) as an op program + EmbeddingVariable tables; loaded by
+def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None, max_len: int = 50) -> str:
+    """Full export of a zoo model (Criteo-style ``WDL``, ``DeepFM``, ``DCN``, ``DCNv2``, ``MaskNet``; sequence model ``DIN`` with ``max_len`` history
+    positions -- request ids = the ``[3 + 2 L, B]`` block of ``models.rec_engine.din_ids`` and one dummy dense column) as an op program + EmbeddingVariable tables; loaded by
     ``Processor(dir, cfg)`` (GPU runtime: tcgen05 GEMMs + csrc/cuda/program_kernels.cu; ``device="cpu"``: the host interpreter) exactly like a DLRM
     export (same ModelConfig, update protocol, request formats)."""
     was_training = model.training
     model.eval()
-    p = _build_program(model)
+    p = _build_program(model, max_len)
     tables, D, id_map = _program_tables(model, p)
+    col_table = getattr(p, "col_table", None)
+    num_dense = getattr(p, "num_dense", None) or model.num_dense
     os.makedirs(os.path.join(export_dir, "variables"), exist_ok=True)
     w = BundleWriter(os.path.join(export_dir, "variables", "variables"))
     for name, t in p.tensors.items():
@@ -362,12 +412,14 @@ def export_saved_model_program(model, export_dir: str, version: int, root: Optio
         w.add(f"table/{t}-default", _padded(ev.default_matrix.detach(), d, D))
         ev.table.clear_dirty()
     w.close()
-    rows = len(tables) if id_map is None else max(id_map) + 1
-    meta = {"model": type(model).__name__.lower(), "arch": "program", "version": int(version), "num_dense": model.num_dense, "num_tables": len(tables),
+    rows = (len(col_table) if col_table is not None else len(tables)) if id_map is None else max(id_map) + 1
+    meta = {"model": type(model).__name__.lower(), "arch": "program", "version": int(version), "num_dense": num_dense, "num_tables": len(tables),
             "num_id_rows": rows, "embedding_dim": D, "program": p.ops, "output": p.out, "variables": "variables/variables",
-            "signature": {"inputs": {"dense": ["B", model.num_dense], "ids": [rows, "B"]}, "outputs": {"probabilities": ["B"]}}}
+            "signature": {"inputs": {"dense": ["B", num_dense], "ids": [rows, "B"]}, "outputs": {"probabilities": ["B"]}}}
     if id_map is not None:
         meta["id_map"] = id_map
+    if col_table is not None:
+        meta["col_table"] = col_table
     with open(os.path.join(export_dir, "saved_model.json"), "w") as f:
         json.dump(meta, f)
     _write_versions(root or export_dir, full={"version": int(version), "dir": os.path.abspath(export_dir)})
@@ -375,11 +427,11 @@ def export_saved_model_program(model, export_dir: str, version: int, root: Optio
     return export_dir
 
 
-def export_delta_program(model, root: str, base_version: int, version: int) -> str:
+def export_delta_program(model, root: str, base_version: int, version: int, max_len: int = 50) -> str:
     """Incremental export for an op-program model: rows touched since the last export + the (re-folded) dense tensors."""
     was_training = model.training
     model.eval()
-    p = _build_program(model)
+    p = _build_program(model, max_len)
     d = os.path.join(root, ".incr")
     os.makedirs(d, exist_ok=True)
     prefix = os.path.join(d, f"delta-{int(version)}")

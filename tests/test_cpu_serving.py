@@ -437,3 +437,55 @@ def test_full_update_with_a_wider_architecture_resizes_the_sessions(tmp_path):
     for _ in range(3):                                                     # every session runs the wide model at full batch
         assert np.abs(proc.predict(d2.numpy(), ids2.numpy()) - _ref(big, d2, ids2)).max() < 1e-5
     proc.close()
+
+
+def test_din_op_program_on_the_cpu_processor(tmp_path):
+    """DIN as an op program over lookup COLUMNS that share tables (``col_table``: target item + 20 history positions read the item table):
+    valid_mask / seq_zip / seq_mask / seq_sum / din_attention / prelu reproduce the module, padding ids (-1) are masked, a history without
+    any valid position gives the zero attention vector, protobuf requests and a delta update work."""
+    import json
+    from deeprec_b200.data import taobao_batch
+    from deeprec_b200.models.rec_engine import din_ids
+    from deeprec_b200.serving import export_delta_program, export_saved_model_program
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(3)
+    L = 20
+    model = build_model("din", device="cpu")
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+
+    def step(seed):
+        b = taobao_batch(256, L, 500, 3000, 40, seed=seed)
+        loss = model.loss(b); opt.zero_grad(); loss.backward(); opt.step()
+        return b
+    for sd in range(4):
+        b = step(sd)
+    b["hist_item"][:5] = -1; b["hist_cat"][:5] = -1                     # five samples with an empty history
+    root = str(tmp_path)
+    export_saved_model_program(model, os.path.join(root, "v1"), version=2, root=root, max_len=L)
+    meta = json.load(open(os.path.join(root, "v1", "saved_model.json")))
+    assert meta["col_table"] == [0, 1, 2] + [1] * L + [2] * L and meta["num_tables"] == 3 and meta["num_id_rows"] == 3 + 2 * L
+    assert {o["op"] for o in meta["program"]} >= {"valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "linear"}
+
+    def ref():
+        model.eval()
+        with torch.no_grad():
+            p = torch.sigmoid(model(b)).numpy().copy()
+        model.train()
+        return p
+    ids = din_ids(b).numpy(); dense = np.zeros((256, 1), np.float32)
+    proc = Processor(os.path.join(root, "v1"), {"session_num": 2, "max_batch": 100, "checkpoint_dir": root, "model_update_interval_ms": 100}, device="cpu")
+    try:
+        r0 = ref()
+        got = proc.predict(dense, ids)                                   # 256 rows > max_batch: chunked
+        assert np.abs(got - r0).max() < 2e-5, np.abs(got - r0).max()
+        assert np.abs(proc.predict(dense[:3], ids[:, :3]) - r0[:3]).max() < 2e-5
+        rc, out = proc.process(predict_pb.encode_predict_request(dense[:7], ids[:, :7]))
+        assert rc == 200 and np.abs(predict_pb.decode_predict_response(out)[0] - r0[:7]).max() < 2e-5
+        for sd in range(10, 13):
+            step(sd)
+        export_delta_program(model, root, base_version=2, version=3, max_len=L)
+        assert _wait(lambda: proc.model_info()["delta_version"] == 3)
+        r1 = ref()
+        assert np.abs(r1 - r0).max() > 1e-4 and np.abs(proc.predict(dense, ids) - r1).max() < 2e-5
+    finally:
+        proc.close()
