@@ -105,6 +105,66 @@ __global__ void __launch_bounds__(256) k_prog_sigmoid0(const __nv_bfloat16* __re
     prob[i] = 1.f / (1.f + __expf(-ldb(x + i * ldx)));
 }
 
+// ---- sequence models (DIN) -------------------------------------------------------------------------------------------------------------
+// mask[b, l] = ids[(start + l) * B + b] >= 0   (ids: [C][B] lookup columns of the request)
+__global__ void __launch_bounds__(256) k_prog_valid_mask(const int64_t* __restrict__ ids, int64_t B, int start, int L, __nv_bfloat16* __restrict__ y, int64_t ldy) {
+  const int64_t n = B * (int64_t)L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / L; const int l = (int)(i - b * L);
+    stb(y + b * ldy + l, ids[(int64_t)(start + l) * B + b] >= 0 ? 1.f : 0.f);
+  }
+}
+// position-wise concat: y[b, l, :] = [a[b, l, :wa] | c[b, l, :wb]]
+__global__ void __launch_bounds__(256) k_prog_seq_zip(const __nv_bfloat16* __restrict__ a, int64_t lda, int wa, const __nv_bfloat16* __restrict__ c, int64_t ldc, int wb,
+                                                      int L, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int w = wa + wb; const int64_t n = B * (int64_t)L * w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / ((int64_t)L * w); const int r = (int)(i - b * (int64_t)L * w); const int l = r / w, k = r - l * w;
+    y[b * ldy + r] = k < wa ? a[b * lda + l * wa + k] : c[b * ldc + l * wb + (k - wa)];
+  }
+}
+// y[b, l, :] = x[b, l, :] * mask[b, l]
+__global__ void __launch_bounds__(256) k_prog_seq_mask(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ m, int64_t ldm, int L, int w,
+                                                       __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)L * w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / ((int64_t)L * w); const int r = (int)(i - b * (int64_t)L * w);
+    stb(y + b * ldy + r, ldb(x + b * ldx + r) * ldb(m + b * ldm + r / w));
+  }
+}
+// y[b, :] = sum_l x[b, l, :]
+__global__ void __launch_bounds__(256) k_prog_seq_sum(const __nv_bfloat16* __restrict__ x, int64_t ldx, int L, int w, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / w; const int k = (int)(i - b * w);
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) acc += ldb(x + b * ldx + (int64_t)l * w + k);
+    stb(y + b * ldy + k, acc);
+  }
+}
+__global__ void __launch_bounds__(256) k_prog_prelu(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, const float* __restrict__ alpha, __nv_bfloat16* __restrict__ y,
+                                                    int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / w; const int k = (int)(i - b * w);
+    const float v = ldb(x + b * ldx + k);
+    stb(y + b * ldy + k, v > 0.f ? v : alpha[k] * v);
+  }
+}
+// staging for the fp32 attention kernel (attention_kernels.cu): bf16 [B, ld] <-> dense fp32 [B, w]; mask -> uint8
+__global__ void __launch_bounds__(256) k_prog_to_f32(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, float* __restrict__ y, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int64_t b = i / w; y[i] = ldb(x + b * ldx + (i - b * w)); }
+}
+__global__ void __launch_bounds__(256) k_prog_from_f32(const float* __restrict__ x, int w, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int64_t b = i / w; stb(y + b * ldy + (i - b * w), x[i]); }
+}
+__global__ void __launch_bounds__(256) k_prog_to_u8(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, uint8_t* __restrict__ y, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int64_t b = i / w; y[i] = ldb(x + b * ldx + (i - b * w)) > 0.f ? 1 : 0; }
+}
+
 inline int grid_el(int64_t n) { const int64_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : b > kNumSMs * 8 ? kNumSMs * 8 : b); }
 inline int grid_rows(int64_t rows) { return grid_el(rows * 32); }
 
@@ -153,6 +213,55 @@ int dr_prog_cross(const void* x0, int64_t ld0, const void* xl, int64_t ldl, int 
 int dr_prog_layernorm(const void* x, int64_t ldx, int w, const float* gamma, const float* beta, float eps, int relu, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
   if (B <= 0 || w <= 0) return 0;
   k_prog_layernorm<<<grid_rows(B), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, gamma, beta, eps, relu, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_valid_mask(const int64_t* ids, int64_t B, int start, int L, void* y, int64_t ldy, cudaStream_t s) {
+  if (B <= 0 || L <= 0) return 0;
+  k_prog_valid_mask<<<grid_el(B * L), 256, 0, s>>>(ids, B, start, L, (__nv_bfloat16*)y, ldy);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_seq_zip(const void* a, int64_t lda, int wa, const void* c, int64_t ldc, int wb, int L, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || L <= 0) return 0;
+  k_prog_seq_zip<<<grid_el(B * L * (wa + wb)), 256, 0, s>>>((const __nv_bfloat16*)a, lda, wa, (const __nv_bfloat16*)c, ldc, wb, L, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_seq_mask(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || L <= 0 || w <= 0) return 0;
+  k_prog_seq_mask<<<grid_el(B * L * w), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)m, ldm, L, w, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_seq_sum(const void* x, int64_t ldx, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || L <= 0 || w <= 0) return 0;
+  k_prog_seq_sum<<<grid_el(B * w), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, L, w, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_prelu(const void* x, int64_t ldx, int w, const float* alpha, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_prelu<<<grid_el(B * w), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, alpha, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_to_f32(const void* x, int64_t ldx, int w, float* y, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_to_f32<<<grid_el(B * w), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, y, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_from_f32(const float* x, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_from_f32<<<grid_el(B * w), 256, 0, s>>>(x, w, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_to_u8(const void* x, int64_t ldx, int w, uint8_t* y, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_to_u8<<<grid_el(B * w), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, y, B);
   DR_LAUNCH_CHECK();
   return 0;
 }

@@ -59,6 +59,16 @@ int dr_prog_binary(int kind, const void* a, int64_t lda, const void* b, int64_t 
 int dr_prog_cross(const void* x0, int64_t ld0, const void* xl, int64_t ldl, int w, const float* wv, const float* bv, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_layernorm(const void* x, int64_t ldx, int w, const float* gamma, const float* beta, float eps, int relu, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_sigmoid0(const void* x, int64_t ldx, int64_t B, float* prob, cudaStream_t s);
+int dr_prog_valid_mask(const int64_t* ids, int64_t B, int start, int L, void* y, int64_t ldy, cudaStream_t s);
+int dr_prog_seq_zip(const void* a, int64_t lda, int wa, const void* c, int64_t ldc, int wb, int L, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_seq_mask(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_seq_sum(const void* x, int64_t ldx, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_prelu(const void* x, int64_t ldx, int w, const float* alpha, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_to_f32(const void* x, int64_t ldx, int w, float* y, int64_t B, cudaStream_t s);
+int dr_prog_from_f32(const float* x, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_to_u8(const void* x, int64_t ldx, int w, uint8_t* y, int64_t B, cudaStream_t s);
+int dr_cuda_din_attention_fwd(const float* q, const float* k, const uint8_t* mask, int64_t B, int L, int D, const float* W1, const float* b1, int H1,
+                              const float* W2, const float* b2, int H2, const float* w3, float b3, float* out, cudaStream_t s);
 int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, const float* bias, const float* labels, float inv_batch, float* prob,
                  float* loss_sum, void* dh, float* dw, float* db, int relu_mask, int train, float* dbias_h, cudaStream_t s);
 }
@@ -122,13 +132,15 @@ template <typename T> static bool Upload(DevBuf& b, const std::vector<T>& h) {
 // Op program (saved_model.json "arch": "program", serving/export.py::export_saved_model_program): the inference graph of a Criteo-style model
 // other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].  Same format and
 // op set as the CPU runtime (csrc/host/cpu_serving.cc); here LINEAR runs on the tcgen05 GEMM and the rest on program_kernels.cu.
-enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE };
+enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_NUM_OPS };     // the last six: sequence models (DIN), see cpu_serving.cc
 struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1;
-  // requests carry R id rows; table t reads request row id_map[t] (identity unless several tables share a feature, e.g. Wide&Deep)
-  int R = 0; std::vector<int> id_map;
+  // requests carry R id rows; lookup column c reads request row id_map[c] from table col_table[c] (both identity, C == T, unless several
+  // columns share a feature (Wide&Deep) or a table (DIN: target item + L history positions))
+  int R = 0, C = 0; std::vector<int> id_map, col_table;
 };
 
 struct LayerW {
@@ -149,7 +161,7 @@ struct DenseParams {
   bool fp8 = false;        // fp8 tensors + scales below are populated
   ActScales act;
   // program models: per-op weights (LINEAR: bf16 [pad8(N), pad8(K)] + bias[pad8(N)]; affine / layernorm / cross: two fp32 vectors), buffer widths
-  struct PW { LayerW L; DevBuf v0, v1; };
+  struct PW { LayerW L; DevBuf v0, v1; std::vector<DevBuf> att; int H1 = 0, H2 = 0; float b3 = 0.f; };    // att: W1 b1 W2 b2 w3 of a din_attention op
   std::vector<PW> pdata; std::vector<int> width;
 };
 
@@ -164,6 +176,7 @@ struct DeviceModel {
   std::shared_ptr<DenseParams> dense;
   std::vector<std::unique_ptr<TableDev>> tables;
   DevBuf structs;      // DrDeviceTable[T] on the device
+  DevBuf col_table;    // int32 [C]: table of every lookup column (program models; identity otherwise)
 };
 
 static bool ReadTensor(dr::BundleReader& r, const std::string& name, std::vector<uint8_t>* out, std::vector<int64_t>* shape = nullptr) {
@@ -203,12 +216,12 @@ static bool ApplyActScales(DenseParams& dp) {
 // Row pitch of a program buffer (bf16 elements).  Buffers 0 / 1 are the cast dense inputs and the gathered embeddings; every other buffer
 // is padded like a GEMM output: 16 | 32 for narrow layers (full N tiles of the direct-store kernel), a multiple of 8 above (TMA 16-byte rule).
 static int prog_npad(int w) { return w <= 16 ? 16 : w <= 32 ? 32 : pad8(w); }
-static int prog_ld(const Arch& a, const std::vector<int>& width, int id) { return id == 0 ? pad8(a.num_dense) : id == 1 ? a.T * a.D : prog_npad(width[(size_t)id]); }
+static int prog_ld(const Arch& a, const std::vector<int>& width, int id) { return id == 0 ? pad8(a.num_dense) : id == 1 ? a.C * a.D : prog_npad(width[(size_t)id]); }
 
 // weights + buffer widths of a program model; every shape is checked against the widths implied by the op list
 static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<DenseParams>* out) {
   auto dp = std::make_shared<DenseParams>();
-  dp->width.assign((size_t)a.nbuf, 0); dp->width[0] = a.num_dense; dp->width[1] = a.T * a.D;
+  dp->width.assign((size_t)a.nbuf, 0); dp->width[0] = a.num_dense; dp->width[1] = a.C * a.D;
   dp->pdata.resize(a.ops.size());
   for (size_t i = 0; i < a.ops.size(); ++i) {
     const POp& op = a.ops[i]; auto& d = dp->pdata[i];
@@ -242,6 +255,28 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_MUL:
       case P_ADD: if (dp->width[(size_t)op.in[1]] != w0) return false; break;
       case P_SLICE: if (op.start < 0 || op.len <= 0 || op.start + op.len > w0) return false; w = op.len; break;
+      case P_VALID_MASK: if (op.start < 0 || op.len <= 0 || op.start + op.len > a.C) return false; w = op.len; break;
+      case P_SEQ_ZIP: {
+        const int wb = dp->width[(size_t)op.in[1]];
+        if (op.len <= 0 || w0 % op.len || wb % op.len) return false;
+        w = w0 + wb; break;
+      }
+      case P_SEQ_MASK: if (op.len <= 0 || w0 % op.len || dp->width[(size_t)op.in[1]] != op.len) return false; break;
+      case P_SEQ_SUM: if (op.len <= 0 || w0 % op.len) return false; w = w0 / op.len; break;
+      case P_PRELU: if (!ReadVec(r, base + "alpha", &v0) || (int)v0.size() != w0 || !Upload(d.v0, v0)) return false; break;
+      case P_DIN_ATT: {
+        const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
+        if (L <= 0 || wk != L * w0) return false;
+        static const char* kT[] = {"w1", "b1", "w2", "b2", "w3", "b3"};
+        std::vector<std::vector<float>> t(6);
+        for (int i2 = 0; i2 < 6; ++i2) if (!ReadVec(r, base + kT[i2], &t[(size_t)i2])) return false;
+        d.H1 = (int)t[1].size(); d.H2 = (int)t[3].size();
+        if (d.H1 <= 0 || d.H2 <= 0 || (int)t[0].size() != d.H1 * 4 * w0 || (int)t[2].size() != d.H2 * d.H1 || (int)t[4].size() != d.H2 || t[5].size() != 1) return false;
+        d.b3 = t[5][0];
+        d.att.resize(5);
+        for (int i2 = 0; i2 < 5; ++i2) if (!Upload(d.att[(size_t)i2], t[(size_t)i2])) return false;
+        break;
+      }
       default: return false;
     }
     if (w <= 0) return false;
@@ -347,12 +382,19 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   int F = a->T + 1; a->inter = a->D + F * (F - 1) / 2; a->Zp = pad8(a->inter);
   *version = (int64_t)j.n("version", 0);
   *prefix = dir + "/" + j.s("variables", "variables/variables");
-  a->R = (int)j.n("num_id_rows", a->T);
-  a->id_map.resize((size_t)std::max(0, a->T));
-  for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = t;
+  a->C = a->T;
+  if (auto* ct = j.get("col_table")) {
+    if (ct->t != JVal::ARR || ct->arr.empty()) return false;
+    a->C = (int)ct->arr.size();
+    for (auto& v : ct->arr) a->col_table.push_back((int)v.num);
+  } else for (int t = 0; t < a->T; ++t) a->col_table.push_back(t);
+  for (int v : a->col_table) if (v < 0 || v >= a->T) return false;
+  a->R = (int)j.n("num_id_rows", a->C);
+  a->id_map.resize((size_t)std::max(0, a->C));
+  for (int c = 0; c < a->C; ++c) a->id_map[(size_t)c] = c;
   if (auto* im = j.get("id_map")) {
-    if (im->t != JVal::ARR || (int)im->arr.size() != a->T) return false;
-    for (int t = 0; t < a->T; ++t) a->id_map[(size_t)t] = (int)im->arr[(size_t)t].num;
+    if (im->t != JVal::ARR || (int)im->arr.size() != a->C) return false;
+    for (int c = 0; c < a->C; ++c) a->id_map[(size_t)c] = (int)im->arr[(size_t)c].num;
   }
   for (int v : a->id_map) if (v < 0 || v >= a->R) return false;
   if (a->R <= 0) return false;
@@ -360,15 +402,16 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     a->program = true;
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
-    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice"};
-    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1};
+    static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu"};
+    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     for (const JVal& o : pr->arr) {
       POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
       op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0);
       const std::string kind = o.s("op", "");
-      for (int k = 0; k < 10; ++k) if (kind == kNames[k]) op.kind = k;
+      for (int k = 0; k < P_NUM_OPS; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
@@ -379,7 +422,7 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     a->nbuf = (int)names.size();
     a->out_buf = id_of(j.s("output", ""));
     // the embedding buffer doubles as a GEMM operand: its row pitch T * D must obey the 16-byte rule; rows are gathered as float4 groups
-    return a->T > 0 && a->out_buf >= 2 && a->D % 4 == 0 && (a->T * a->D) % 8 == 0;
+    return a->T > 0 && a->out_buf >= 2 && a->D % 4 == 0 && (a->C * a->D) % 8 == 0;
   }
   return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
 }
@@ -398,6 +441,7 @@ static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t ex
     structs.push_back(m->tables.back()->t);
   }
   if (!Upload(m->structs, structs)) return nullptr;
+  { std::vector<int32_t> ct(m->arch.col_table.begin(), m->arch.col_table.end()); if (!Upload(m->col_table, ct)) return nullptr; }
   m->path = dir;
   return m;
 }
@@ -412,8 +456,8 @@ struct Session {
   bool Init(const Arch& a, int maxB) {
     max_batch = maxB;
     SV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    bool ok = dense_in.alloc((size_t)maxB * a.num_dense * 4) && ids.alloc((size_t)a.T * maxB * 8) && x0.alloc((size_t)maxB * pad8(a.num_dense) * 2) &&
-              emb.alloc((size_t)a.T * maxB * a.D * 2) && pos.alloc((size_t)a.T * maxB * 4) && Z.alloc((size_t)maxB * a.Zp * 2) && prob.alloc((size_t)maxB * 4) &&
+    bool ok = dense_in.alloc((size_t)maxB * a.num_dense * 4) && ids.alloc((size_t)a.C * maxB * 8) && x0.alloc((size_t)maxB * pad8(a.num_dense) * 2) &&
+              emb.alloc((size_t)a.C * maxB * a.D * 2) && pos.alloc((size_t)a.C * maxB * 4) && Z.alloc((size_t)maxB * a.Zp * 2) && prob.alloc((size_t)maxB * 4) &&
               loss.alloc(16) && labels.alloc((size_t)maxB * 4) && y_last.alloc((size_t)maxB * a.D * 2);
     a_bot.resize(a.bot.size()); a_top.resize(a.top.size());
     for (size_t l = 0; l < a.bot.size(); ++l) ok = ok && a_bot[l].alloc((size_t)maxB * a.bot[l] * 2);
@@ -425,7 +469,7 @@ struct Session {
     if (!ok) return false;
     cudaMemset(labels.p, 0, (size_t)maxB * 4);
     SV_CUDA(cudaMallocHost(&h_dense, (size_t)maxB * a.num_dense * 4));
-    SV_CUDA(cudaMallocHost(&h_ids, (size_t)a.T * maxB * 8));
+    SV_CUDA(cudaMallocHost(&h_ids, (size_t)a.C * maxB * 8));
     SV_CUDA(cudaMallocHost(&h_prob, (size_t)maxB * 4));
     return true;
   }
@@ -433,6 +477,7 @@ struct Session {
 
   // ---- op-program models: buffers 0 / 1 alias x0 / emb, the others are (max_batch x prog_ld(width)) bf16, zeroed once (pad columns stay zero) ----
   std::vector<DevBuf> pbuf; std::vector<int> pbuf_width;
+  DevBuf att_q, att_k, att_o, att_m;                                 // fp32 / uint8 staging of the din_attention kernel
   bool RunProgram(const DeviceModel& m, const DenseParams& dp, int B) {
     const Arch& a = m.arch; cudaStream_t s = stream;
     if (pbuf_width != dp.width) {                                     // first program run, or a full update changed the layer widths
@@ -443,15 +488,21 @@ struct Session {
         if (!pbuf[i].alloc(bytes)) return false;
         SV_CUDA(cudaMemsetAsync(pbuf[i].p, 0, bytes, s));
       }
+      size_t wq = 0, wk = 0, wl = 0;
+      for (const POp& op : a.ops) if (op.kind == P_DIN_ATT) {
+        wq = std::max(wq, (size_t)dp.width[(size_t)op.in[0]]); wk = std::max(wk, (size_t)dp.width[(size_t)op.in[1]]); wl = std::max(wl, (size_t)dp.width[(size_t)op.in[2]]);
+      }
+      if (wq && (!att_q.alloc((size_t)max_batch * wq * 4) || !att_k.alloc((size_t)max_batch * wk * 4) || !att_o.alloc((size_t)max_batch * wq * 4) || !att_m.alloc((size_t)max_batch * wl))) return false;
       pbuf_width = dp.width;
     }
     auto buf = [&](int id) -> void* { return id == 0 ? x0.p : id == 1 ? emb.p : pbuf[(size_t)id].p; };
     auto ld = [&](int id) -> int64_t { return prog_ld(a, dp.width, id); };
     int rc = 0;
-    const int64_t n = (int64_t)a.T * B;
-    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
-    // sample-major embeddings [B, T * D]: element (b, t) at b * (T * D) + t * D
-    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, (int64_t)a.T * a.D, a.D, 0, s);
+    const int64_t n = (int64_t)a.C * B;
+    const int32_t* ct = m.col_table.as<int32_t>();                   // lookup column -> table
+    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), ct, a.C, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+    // sample-major embeddings [B, C * D]: element (b, c) at b * (C * D) + c * D
+    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), ct, a.C, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, (int64_t)a.C * a.D, a.D, 0, s);
     rc |= dr_cuda_cast_pad(dense_in.as<float>(), B, a.num_dense, x0.p, pad8(a.num_dense), s);
     for (size_t oi = 0; oi < a.ops.size() && rc == 0; ++oi) {
       const POp& op = a.ops[oi]; const auto& pd = dp.pdata[oi];
@@ -468,13 +519,28 @@ struct Session {
           break;
         }
         case P_AFFINE: rc |= dr_prog_affine(a0, ld0, W, pd.v0.as<float>(), pd.v1.as<float>(), out, ldo, B, s); break;
-        case P_FM: rc |= dr_prog_fm(a0, ld0, a.T, a.D, out, ldo, B, s); break;
+        case P_FM: rc |= dr_prog_fm(a0, ld0, a.C, a.D, out, ldo, B, s); break;
         case P_CROSS: rc |= dr_prog_cross(a0, ld0, buf(op.in[1]), ld(op.in[1]), W, pd.v0.as<float>(), pd.v1.as<float>(), out, ldo, B, s); break;
         case P_ADD: rc |= dr_prog_binary(0, a0, ld0, buf(op.in[1]), ld(op.in[1]), nullptr, 0, W, out, ldo, B, s); break;
         case P_MUL: rc |= dr_prog_binary(1, a0, ld0, buf(op.in[1]), ld(op.in[1]), nullptr, 0, W, out, ldo, B, s); break;
         case P_MUL_ADD: rc |= dr_prog_binary(2, a0, ld0, buf(op.in[1]), ld(op.in[1]), buf(op.in[2]), ld(op.in[2]), W, out, ldo, B, s); break;
         case P_SLICE: rc |= dr_prog_copy_cols(a0, ld0, op.start, W, out, ldo, 0, B, s); break;
         case P_LAYERNORM: rc |= dr_prog_layernorm(a0, ld0, W, pd.v0.as<float>(), pd.v1.as<float>(), op.eps, op.relu ? 1 : 0, out, ldo, B, s); break;
+        case P_VALID_MASK: rc |= dr_prog_valid_mask(ids.as<int64_t>(), B, op.start, W, out, ldo, s); break;
+        case P_SEQ_ZIP: { const int L = op.len, wb = dp.width[(size_t)op.in[1]]; rc |= dr_prog_seq_zip(a0, ld0, w0 / L, buf(op.in[1]), ld(op.in[1]), wb / L, L, out, ldo, B, s); break; }
+        case P_SEQ_MASK: rc |= dr_prog_seq_mask(a0, ld0, buf(op.in[1]), ld(op.in[1]), op.len, W / op.len, out, ldo, B, s); break;
+        case P_SEQ_SUM: rc |= dr_prog_seq_sum(a0, ld0, op.len, W, out, ldo, B, s); break;
+        case P_PRELU: rc |= dr_prog_prelu(a0, ld0, W, pd.v0.as<float>(), out, ldo, B, s); break;
+        case P_DIN_ATT: {                                            // fp32 staging -> the fused attention kernel (attention_kernels.cu) -> bf16
+          const int L = dp.width[(size_t)op.in[2]];
+          rc |= dr_prog_to_f32(a0, ld0, W, att_q.as<float>(), B, s);
+          rc |= dr_prog_to_f32(buf(op.in[1]), ld(op.in[1]), L * W, att_k.as<float>(), B, s);
+          rc |= dr_prog_to_u8(buf(op.in[2]), ld(op.in[2]), L, att_m.as<uint8_t>(), B, s);
+          rc |= dr_cuda_din_attention_fwd(att_q.as<float>(), att_k.as<float>(), att_m.as<uint8_t>(), B, L, W, pd.att[0].as<float>(), pd.att[1].as<float>(), pd.H1,
+                                          pd.att[2].as<float>(), pd.att[3].as<float>(), pd.H2, pd.att[4].as<float>(), pd.b3, att_o.as<float>(), s);
+          rc |= dr_prog_from_f32(att_o.as<float>(), W, out, ldo, B, s);
+          break;
+        }
         default: rc = -1;
       }
       (void)w0;
@@ -487,7 +553,7 @@ struct Session {
   bool Run(const DeviceModel& m, const DenseParams& dp, int B, bool force_bf16 = false) {
     const Arch& a = m.arch; cudaStream_t s = stream;
     SV_CUDA(cudaMemcpyAsync(dense_in.p, h_dense, (size_t)B * a.num_dense * 4, cudaMemcpyHostToDevice, s));
-    SV_CUDA(cudaMemcpyAsync(ids.p, h_ids, (size_t)a.T * B * 8, cudaMemcpyHostToDevice, s));
+    SV_CUDA(cudaMemcpyAsync(ids.p, h_ids, (size_t)a.C * B * 8, cudaMemcpyHostToDevice, s));
     if (a.program) {
       if (!RunProgram(m, dp, B)) return false;
       SV_CUDA(cudaMemcpyAsync(h_prob, prob.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
@@ -636,7 +702,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
       const int B = (int)std::min<uint32_t>(s.max_batch, h.batch - off);
       memcpy(s.h_dense, p + (size_t)off * a.num_dense * 4, (size_t)B * a.num_dense * 4);
       const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
-      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)a.id_map[(size_t)t] * h.batch + off, (size_t)B * 8);
+      for (int c = 0; c < a.C; ++c) memcpy(s.h_ids + (size_t)c * B, ids + (size_t)a.id_map[(size_t)c] * h.batch + off, (size_t)B * 8);
       if (!s.Run(*m, *dense, B)) { sm->failures++; return 500; }
       memcpy(probs.data() + off, s.h_prob, (size_t)B * 4);
     }
@@ -720,15 +786,15 @@ static int FillWarmupBatch(ServingModel* sm, const DeviceModel& m, Session& s) {
       const float* d = reinterpret_cast<const float*>(raw.data() + sizeof(h));
       const int64_t* ids = reinterpret_cast<const int64_t*>(raw.data() + sizeof(h) + (size_t)h.batch * h.num_dense * 4);
       memcpy(s.h_dense, d, (size_t)B * a.num_dense * 4);
-      for (int t = 0; t < a.T; ++t) memcpy(s.h_ids + (size_t)t * B, ids + (size_t)a.id_map[(size_t)t] * h.batch, (size_t)B * 8);
+      for (int c = 0; c < a.C; ++c) memcpy(s.h_ids + (size_t)c * B, ids + (size_t)a.id_map[(size_t)c] * h.batch, (size_t)B * 8);
       return B;
     }
   }
   for (int b = 0; b < B; ++b)
     for (int j = 0; j < a.num_dense; ++j) s.h_dense[(size_t)b * a.num_dense + j] = (float)((b * 31 + j * 17) % 97) / 97.0f * 8.0f;
-  for (int t = 0; t < a.T; ++t) {
-    const auto& sk = m.tables[t]->sample_keys;
-    for (int b = 0; b < B; ++b) s.h_ids[(size_t)t * B + b] = sk.empty() ? 0 : sk[(size_t)(b * 7 + t) % sk.size()];
+  for (int c = 0; c < a.C; ++c) {
+    const auto& sk = m.tables[(size_t)a.col_table[(size_t)c]]->sample_keys;
+    for (int b = 0; b < B; ++b) s.h_ids[(size_t)c * B + b] = sk.empty() ? 0 : sk[(size_t)(b * 7 + c) % sk.size()];
   }
   return B;
 }
@@ -775,7 +841,7 @@ static void UpdaterLoop(ServingModel* sm) {
         // reference would build a fresh SessionGroup (serving/processor/serving/model_instance.cc:406-427); restart the processor for it.
         {
           const Arch& o = cur->arch; const Arch& n = nm->arch;
-          if (n.num_dense != o.num_dense || n.T != o.T || n.D != o.D || n.bot != o.bot || n.top != o.top || n.Zp != o.Zp || n.program != o.program || n.R != o.R) {
+          if (n.num_dense != o.num_dense || n.T != o.T || n.D != o.D || n.bot != o.bot || n.top != o.top || n.Zp != o.Zp || n.program != o.program || n.R != o.R || n.C != o.C) {
             if (sm->rejected_version != v) {
               fprintf(stderr, "[deeprec_serving] model version %lld changes the architecture (tables %d->%d, D %d->%d, dense %d->%d): rejected, sessions keep serving version %lld\n",
                       (long long)v, o.T, n.T, o.D, n.D, o.num_dense, n.num_dense, (long long)cur->version);

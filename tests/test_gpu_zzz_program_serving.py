@@ -98,3 +98,36 @@ def test_op_program_processor_group_on_every_visible_gpu(tmp_path):
             assert np.abs(grp.predict(d.numpy()[:128], ids.numpy()[:, :128]) - ref[:128]).max() < TOL
     finally:
         grp.close()
+
+
+def test_din_op_program_on_the_gpu_processor(tmp_path):
+    """DIN (lookup columns over shared tables, valid_mask / seq_zip / seq_mask / seq_sum / prelu glue kernels, the fused attention kernel of
+    attention_kernels.cu behind fp32 staging) on the GPU Processor == the module == the CPU Processor."""
+    from deeprec_b200.data import taobao_batch
+    from deeprec_b200.models.rec_engine import din_ids
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(3)
+    L = 20
+    model = build_model("din", device="cpu")
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    for sd in range(4):
+        b = taobao_batch(256, L, 500, 3000, 40, seed=sd)
+        loss = model.loss(b); opt.zero_grad(); loss.backward(); opt.step()
+    b["hist_item"][:5] = -1; b["hist_cat"][:5] = -1                     # five samples with an empty history
+    root = str(tmp_path)
+    export_saved_model_program(model, os.path.join(root, "v1"), version=2, root=root, max_len=L)
+    model.eval()
+    with torch.no_grad():
+        ref = torch.sigmoid(model(b)).numpy().copy()
+    ids = din_ids(b).numpy(); dense = np.zeros((256, 1), np.float32)
+    cfg = {"session_num": 2, "max_batch": 100, "model_update_interval_ms": 0}
+    gpu = Processor(os.path.join(root, "v1"), cfg, device="cuda")
+    cpu = Processor(os.path.join(root, "v1"), cfg, device="cpu")
+    try:
+        host = cpu.predict(dense, ids)
+        got = gpu.predict(dense, ids)                                     # 256 rows > max_batch: chunked
+        assert np.abs(host - ref).max() < 2e-5
+        assert np.isfinite(got).all() and np.abs(got - ref).max() < TOL, np.abs(got - ref).max()
+        assert np.abs(gpu.predict(dense[:3], ids[:, :3]) - ref[:3]).max() < TOL
+    finally:
+        gpu.close(); cpu.close()
