@@ -191,6 +191,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and not (args.gpus == 1 and world == 1):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    # host threads next to the GPU (pinned staging buffers, producer thread, OpenMP pool): GPUs 4-7 of an HGX box hang off the second socket
+    from deeprec_b200.utils.affinity import bind_to_gpu_numa
+    bound = bind_to_gpu_numa(local_rank)
+    if bound:
+        torch.set_num_threads(max(1, min(torch.get_num_threads(), len(bound))))      # libgomp sized its team before the mask shrank
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -324,7 +329,8 @@ def main():
                        "new_keys_per_step": (keys1 - keys0) / float(args.steps), "unique_ratio": uniq, "alpha": args.alpha,
                        "filter_freq": args.filter_freq,
                        "l2": f"{len(dev_timed)} distinct resident batches ({len(dev_timed) * in_bytes / 1e6:.0f} MB) + multi-GB embedding tables > 126 MB L2; no flush",
-                       "cuda_graph": bool(graph and hasattr(eng, "capture")), "final_loss": final_loss},
+                       "cuda_graph": bool(graph and hasattr(eng, "capture")), "final_loss": final_loss,
+                       "host_cpus": f"{len(bound)} CPUs local to the GPU (NVML ideal set)" if bound else "unpinned"},
             "clocks": clocks,
             "gpu_launches": launches,
         }

@@ -34,6 +34,10 @@ def engine_main(a):
     import torch.distributed as dist
     from deeprec_b200.models.rec_engine import criteo_engine, din_engine, din_ids
     world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    from deeprec_b200.utils.affinity import bind_to_gpu_numa
+    bound = bind_to_gpu_numa(lr)                                    # host threads (pinned buffers, OpenMP pool) next to the GPU
+    if bound:
+        torch.set_num_threads(max(1, min(torch.get_num_threads(), len(bound))))
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
     comm = None
