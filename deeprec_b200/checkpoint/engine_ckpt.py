@@ -11,6 +11,8 @@ hooks ``core/kernels/save_restore_v2_ops.cc:158-360``, ``IncrSave`` / ``IndicesI
   * delta save  = only rows whose dirty bit was set by the apply kernel since the last (full or delta) save + the dense block.
   * restore     = any world size: every rank scans every shard file and imports the keys it owns under the CURRENT world
                   (``hash(key) % world`` -- the sharding function of the sparse pipeline), then replays the delta chain in order.
+  * multi-tier  = tables of ``FusedRecEngine(tiered=...)`` save BOTH tiers (the HBM cache and the DRAM tier; rows demoted since the last save
+                  carry their dirty bit into the DRAM tier, so delta saves stay complete) and restore each into its tier.
 """
 from __future__ import annotations
 
@@ -91,9 +93,18 @@ def save_engine(eng, save_path: str, incremental: bool = False, max_to_keep: int
         for k, v in _dense_state(eng).items():
             w.add(k, v)
     sfx = "sparse_incr_" if incremental else ""
+    tiers = getattr(eng, "tiers", None) or {}
     for t, tbl in eng.tables.items():
         if not incremental and (tbl.cfg.steps_to_live > 0 or tbl.cfg.l2_weight_threshold >= 0):
             tbl.shrink(step)                                      # eviction happens inside a full save (single_tier_storage.h:235-261)
+        if t in tiers:
+            # multi-tier table: the HBM tier is a cache -- rows demoted to the DRAM tier are training state too (hbm_dram_storage.h:
+            # Save() walks both tiers).  In-flight promotions / demotions finish first; the HBM copy of a key wins on restore (imported last).
+            mgr = tiers[t][0]
+            mgr.drain()
+            hs = mgr.host.snapshot(dirty_only=incremental)
+            w.add(f"table/{t}-host-{sfx}keys", hs["keys"]); w.add(f"table/{t}-host-{sfx}values", hs["rows"])
+            w.add(f"table/{t}-host-{sfx}freqs", hs["freqs"]); w.add(f"table/{t}-host-{sfx}versions", hs["versions"])
         s = tbl.snapshot(dirty_only=incremental)
         w.add(f"table/{t}-{sfx}keys", s["keys"]); w.add(f"table/{t}-{sfx}values", s["rows"])
         w.add(f"table/{t}-{sfx}freqs", s["freqs"]); w.add(f"table/{t}-{sfx}versions", s["versions"])
@@ -106,6 +117,8 @@ def save_engine(eng, save_path: str, incremental: bool = False, max_to_keep: int
     w.close()
     for tbl in eng.tables.values():
         tbl.clear_dirty()                                         # the recorder restarts at every (full or delta) save
+    for mgr, _ in tiers.values():
+        mgr.host.clear_dirty()
     if W > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -133,10 +146,22 @@ def latest_engine_step(directory: str, base: str, incremental: bool = False) -> 
 def _load_tables(eng, prefixes: List[str], incremental: bool) -> int:
     W, r = eng.world, eng.rank
     sfx = "sparse_incr_" if incremental else ""
+    tiers = getattr(eng, "tiers", None) or {}
     n = 0
     for p in prefixes:
         rd = BundleReader(p)
         for t, tbl in eng.tables.items():
+            hk = f"table/{t}-host-{sfx}keys"
+            if rd.has(hk):                                        # DRAM-tier rows of a multi-tier table
+                hkeys = rd.read(hk)
+                if hkeys.numel():
+                    mine = sp_owner(hkeys, W) == r
+                    if bool(mine.any()):
+                        rows, fr, ve = rd.read(f"table/{t}-host-{sfx}values")[mine], rd.read(f"table/{t}-host-{sfx}freqs")[mine], rd.read(f"table/{t}-host-{sfx}versions")[mine]
+                        if t in tiers:
+                            n += tiers[t][0].host.import_(hkeys[mine], rows, fr, ve)
+                        else:                                     # restored into an engine without the DRAM tier: everything lives in HBM
+                            n += tbl.import_(hkeys[mine], rows, fr, ve)
             kk = f"table/{t}-{sfx}keys"
             if not rd.has(kk):
                 continue

@@ -153,7 +153,7 @@ struct TierManager {
         cudaEventSynchronize(ev_evict);
         const int64_t n = std::min<int64_t>(h_ctl[2], evict_cap);
         if (n > 0) {
-          fimport(host_ev, h_ev_keys, h_ev_rows, stride, h_ev_freq, h_ev_ver, n, 0, 1, 0);
+          fimport(host_ev, h_ev_keys, h_ev_rows, stride, h_ev_freq, h_ev_ver, n, 0, 1, /*keep versions, mark dirty (incremental checkpoints)*/ 2);
           demoted += n; d2h_bytes += n * ((int64_t)stride * 4 + 24);
         }
         { std::lock_guard<std::mutex> l(mu); evict_inflight = false; }

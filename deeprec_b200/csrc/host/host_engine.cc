@@ -910,7 +910,10 @@ class HostEV {
         bool inserted = false;
         int32_t idx = kv_.FindOrInsert(key, [this, &rs] { return AllocMeta(&rs); }, &inserted);
         __atomic_store_n(&meta_.at(idx)->freq, freqs ? freqs[i] : 0, __ATOMIC_RELAXED);
-        __atomic_store_n(&meta_.at(idx)->version, reset_version ? -1 : (versions ? versions[i] : -1), __ATOMIC_RELAXED);
+        __atomic_store_n(&meta_.at(idx)->version, (reset_version & 1) ? -1 : (versions ? versions[i] : -1), __ATOMIC_RELAXED);
+        // reset_version bit 1: the rows are LIVE training state arriving from another tier (device -> host demotion), not a restore: they
+        // belong in the next incremental checkpoint, so they carry the dirty bit the evicted device row had
+        if (reset_version & 2) __atomic_store_n(&meta_.at(idx)->dirty, (uint8_t)1, __ATOMIC_RELAXED);
         if (rows) {
           int32_t* rp = (&meta_.at(idx)->row);
           int32_t r = __atomic_load_n(rp, __ATOMIC_ACQUIRE);
