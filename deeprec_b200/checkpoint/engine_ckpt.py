@@ -159,6 +159,8 @@ def _load_tables(eng, prefixes: List[str], incremental: bool) -> int:
                     if bool(mine.any()):
                         rows, fr, ve = rd.read(f"table/{t}-host-{sfx}values")[mine], rd.read(f"table/{t}-host-{sfx}freqs")[mine], rd.read(f"table/{t}-host-{sfx}versions")[mine]
                         if t in tiers:
+                            if incremental:                       # demoted since the base checkpoint: the HBM copy an earlier bundle restored is
+                                tbl.remove(hkeys[mine])           # stale, and the HBM tier is authoritative -- drop it before the DRAM-tier import
                             n += tiers[t][0].host.import_(hkeys[mine], rows, fr, ve)
                         else:                                     # restored into an engine without the DRAM tier: everything lives in HBM
                             n += tbl.import_(hkeys[mine], rows, fr, ve)
