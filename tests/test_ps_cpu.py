@@ -16,6 +16,29 @@ def _free_port():
 NUM_PS, NUM_WORKERS, STEPS = 2, 2, 6
 
 
+def _spawn_roles(target, n_roles, tmp, timeout=240, attempts=2):
+    """Start one process per role and wait for all of them.  The rendezvous goes through a TCP port picked just before the processes start
+    and through torch.distributed.rpc's own timeouts: on a box that is busy with other work (a compiler, another test run) either can fail
+    without anything being wrong with the code under test, so a failed ROLE START is retried once on a fresh port; assertion failures of the
+    test body are never retried (they happen after this returns)."""
+    import shutil
+    ctx = mp.get_context("spawn")
+    for attempt in range(attempts):
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, port, tmp)) for r in range(n_roles)]
+        for p in procs:
+            p.start()
+        try:
+            _join_all(procs, timeout)
+            return
+        except AssertionError:
+            if attempt + 1 == attempts:
+                raise
+            for f in os.listdir(tmp):                          # partial outputs of the failed attempt
+                q = os.path.join(tmp, f)
+                shutil.rmtree(q, ignore_errors=True) if os.path.isdir(q) else os.remove(q)
+
+
 def _join_all(procs, timeout=240):
     """Wait for every process; if one fails the rest (blocked in rpc.shutdown) are terminated instead of hanging the test."""
     import time
@@ -81,12 +104,7 @@ def _proc(rank, port, tmp):
 
 
 def test_async_ps_training(tmp_path):
-    port = _free_port()
-    ctx = mp.get_context("spawn")
-    procs = [ctx.Process(target=_proc, args=(r, port, str(tmp_path))) for r in range(NUM_PS + NUM_WORKERS)]
-    for p in procs:
-        p.start()
-    _join_all(procs)
+    _spawn_roles(_proc, NUM_PS + NUM_WORKERS, str(tmp_path))
     stats = [json.load(open(tmp_path / f"ps{i}.json")) for i in range(NUM_PS)]
     workers = [json.load(open(tmp_path / f"worker{j}.json")) for j in range(NUM_WORKERS)]
     # rows are partitioned over the PS processes (key % 1000 % num_ps), both shards non-empty; every push was applied
@@ -165,12 +183,7 @@ def _elastic_proc(rank, port, tmp):
 
 
 def test_elastic_ps_scale_up_and_down(tmp_path):
-    port = _free_port()
-    ctx = mp.get_context("spawn")
-    procs = [ctx.Process(target=_elastic_proc, args=(r, port, str(tmp_path))) for r in range(E_TOTAL_PS + E_WORKERS)]
-    for p in procs:
-        p.start()
-    _join_all(procs, 300)
+    _spawn_roles(_elastic_proc, E_TOTAL_PS + E_WORKERS, str(tmp_path), 300)
     stats = [json.load(open(tmp_path / f"eps{i}.json")) for i in range(E_TOTAL_PS)]
     assert stats[0]["item"] == 600 and stats[1]["item"] == 0 and stats[2]["item"] == 0
 
