@@ -193,6 +193,66 @@ class DistributedEmbedding(nn.Module):
         return [self.ev]
 
 
+class _A2AStatic(torch.autograd.Function):
+    """Dispatch / gather / return over a STATIC table shard (``weight [rows_per_rank, D]``; id k lives on rank k % W at local row k // W)."""
+
+    @staticmethod
+    def forward(ctx, weight: torch.Tensor, ids: torch.Tensor):
+        rank, W = _world()
+        flat = ids.reshape(-1)
+        own = torch.remainder(flat, W)
+        order = torch.argsort(own, stable=True)
+        counts = torch.bincount(own, minlength=W).tolist()
+        recv_ids = _all_to_all_v(list(torch.split(flat[order], counts)))
+        rcounts = [t.numel() for t in recv_ids]
+        local = torch.div(torch.cat(recv_ids) if recv_ids else flat.new_empty(0), W, rounding_mode="floor").clamp_(0, weight.shape[0] - 1)
+        back = _all_to_all_v(list(torch.split(weight.detach()[local], rcounts)))
+        out_sorted = torch.cat(back)
+        out = torch.empty_like(out_sorted)
+        out[order] = out_sorted
+        ctx.save_for_backward(local, order)
+        ctx.counts, ctx.shape = counts, weight.shape
+        return out.view(*ids.shape, weight.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        local, order = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])[order]
+        recv = _all_to_all_v(list(torch.split(g2.contiguous(), ctx.counts)))
+        gw = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
+        gw.index_add_(0, local, torch.cat(recv))
+        return gw, None
+
+
+class TFDistributedEmbedding(nn.Module):
+    """``sok.TFDistributedEmbedding(vocabulary_size, embedding_vec_size, initializer)``: the framework-native twin of the SOK layers -- a
+    plain dense parameter of ``vocabulary_size`` rows, sharded row-wise over the ranks (id ``k`` on rank ``k % world`` at row ``k // world``),
+    trained by the ordinary dense optimizer; no hash table, no admission.  The reference ships it as the correctness oracle of the custom
+    layers (``sparse_operation_kit/embeddings/tf_distributed_embedding.py``); it plays the same role in ``tests/test_sok_elastic_cpu.py``."""
+
+    def __init__(self, vocabulary_size: int, embedding_vec_size: int, initializer="uniform", device=None, dtype=torch.float32):
+        super().__init__()
+        _, W = _world()
+        self.vocabulary_size, self.rows = int(vocabulary_size), (int(vocabulary_size) + W - 1) // W
+        w = torch.empty(self.rows, embedding_vec_size, device=device, dtype=dtype)
+        if callable(initializer):
+            initializer(w)
+        elif initializer in ("uniform", "random_uniform"):
+            nn.init.uniform_(w, -0.05, 0.05)
+        elif initializer == "ones":
+            nn.init.ones_(w)
+        elif initializer == "zeros":
+            nn.init.zeros_(w)
+        else:
+            nn.init.normal_(w, std=0.01)
+        self.weight = nn.Parameter(w)
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        if (inputs < 0).any() or (inputs >= self.vocabulary_size).any():
+            raise IndexError("TFDistributedEmbedding: id outside [0, vocabulary_size)")
+        return _A2AStatic.apply(self.weight, inputs)
+
+
 def split_embedding_variable_from_others(module: nn.Module):
     """``sok.optimizers.utils.split_embedding_variable_from_others``: (embedding variables, other parameters)."""
     from ..optim.optimizers import collect_embedding_variables
@@ -223,3 +283,35 @@ class Saver:
         if W > 1:
             dist.barrier()
         return n
+
+
+class _Utils:
+    split_embedding_variable_from_others = staticmethod(split_embedding_variable_from_others)
+
+
+class _Optimizers:
+    """``sok.optimizers``: ``Adam`` / ``LazyAdam`` update the sharded tables row-wise (only rows that received a gradient move, their moments
+    included -- SOK's ``update_functions.cu`` semantics, which is what this framework's sparse Adam does for every EmbeddingVariable);
+    ``utils.split_embedding_variable_from_others`` separates the tables from the dense parameters of a model."""
+    utils = _Utils
+
+    @staticmethod
+    def Adam(layers_or_evs, lr: float = 0.001, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8):
+        from ..optim.optimizers import AdamOptimizer
+        return AdamOptimizer([], _as_evs(layers_or_evs), lr=lr, beta1=beta1, beta2=beta2, eps=epsilon)
+
+    @staticmethod
+    def LazyAdam(layers_or_evs, lr: float = 0.001, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8):
+        from ..optim.optimizers import AdamAsyncOptimizer
+        return AdamAsyncOptimizer([], _as_evs(layers_or_evs), lr=lr, beta1=beta1, beta2=beta2, eps=epsilon)
+
+
+def _as_evs(x) -> List[EmbeddingVariable]:
+    items = x if isinstance(x, (list, tuple)) else [x]
+    out: List[EmbeddingVariable] = []
+    for it in items:
+        out += it.embedding_variables() if hasattr(it, "embedding_variables") else [it]
+    return out
+
+
+optimizers = _Optimizers

@@ -52,6 +52,18 @@ def _worker(rank, world, port, q, tmp):
     assert n == dense_l.ev.total_count()
     trained = probe[own][dense_l.ev.get_frequency(probe[own]) > 0]
     assert torch.allclose(fresh.ev.table.lookup(trained), dense_l.ev.table.lookup(trained))
+    # sok.TFDistributedEmbedding (static table sharded id % world): forward == the full table, the gradient of a row arrives at its owner only
+    full = torch.arange(50 * 4, dtype=torch.float32).view(50, 4) / 10
+    tfl = sok.TFDistributedEmbedding(50, 4, initializer=lambda w: w.copy_(full[rank::world][: w.shape[0]]))
+    ids_t = torch.randint(0, 50, (7, 2), generator=torch.Generator().manual_seed(7 + rank))
+    e = tfl(ids_t)
+    assert torch.equal(e, full[ids_t])
+    (e * 2.0).sum().backward()
+    all_ids = [torch.randint(0, 50, (7, 2), generator=torch.Generator().manual_seed(7 + r)) for r in range(world)]
+    want = torch.zeros(50, 4); want.index_add_(0, torch.cat(all_ids).reshape(-1), torch.full((7 * 2 * world, 4), 2.0))
+    assert torch.allclose(tfl.weight.grad, want[rank::world][: tfl.weight.shape[0]])
+    # sok.optimizers facade
+    assert type(sok.optimizers.Adam(dense_l)).__name__ == "AdamOptimizer" and type(sok.optimizers.LazyAdam([dense_l, sparse_l])).__name__ == "AdamAsyncOptimizer"
     q.put((rank, out))
 
 
