@@ -124,3 +124,48 @@ def env_flag(name: str, default: bool = False) -> bool:
 def inference_mode() -> bool:
     """``INFERENCE_MODE`` env (kv_variable_ops.cc:200-204): EV lookups never create keys."""
     return env_flag("INFERENCE_MODE")
+
+
+# ---- the reference's environment switches (SURVEY §2.11 "Env-var flags"): what each one does HERE ---------------------------------------
+# status: "honoured" = read by this framework with the reference's meaning; "always" = the behaviour it enables is unconditional here (the
+# switch is accepted and ignored); "n/a" = tied to a component this design does not have (setting it has no effect; env_report() says so).
+REFERENCE_ENV_FLAGS = {
+    "INFERENCE_MODE": ("honoured", "EmbeddingVariable lookups never create keys (config.inference_mode)"),
+    "TF_EV_SAVE_FILTERED_FEATURES": ("honoured", "checkpoints include / omit the un-admitted keys and their counters (checkpoint/saver.py)"),
+    "TF_EV_RESET_VERSION": ("honoured", "restore resets the version (last-update step) of every key (checkpoint/saver.py)"),
+    "TF_SSDHASH_ASYNC_COMPACTION": ("honoured", "SSD tier compaction on a background thread (also DEEPREC_SSDHASH_ASYNC_COMPACTION)"),
+    "COLLECTIVE_STRATEGY": ("honoured", "sok | hb | hvd select the CollectiveStrategy flavour name (parallel/collective.py)"),
+    "TF_GPU_ALLOCATOR": ("honoured", "tensorpool | cuda_malloc_async (utils/memory.maybe_enable_from_env; also DEEPREC_GPU_ALLOCATOR)"),
+    "TF_GPU_VMEM": ("honoured", "managed-memory fallback of the pool allocator on OOM (also DEEPREC_GPU_VMEM)"),
+    "ENABLE_MEMORY_OPTIMIZATION": ("honoured", "host TensorPool planning on / off (utils/memory.HostTensorPool.from_env)"),
+    "START_STATISTIC_STEP": ("honoured", "TensorPool: first step whose allocation sizes are recorded"),
+    "STABLE_STATISTIC_STEP": ("honoured", "TensorPool: steps after which the plan is frozen"),
+    "MAX_STATISTIC_STEP": ("honoured", "TensorPool: re-plan horizon"),
+    "STOP_STATISTIC_STEP": ("honoured", "TensorPool: last recorded step"),
+    "SESSION_GROUP_CPUSET": ("honoured", "per-session CPU sets of the CPU Processor (also ModelConfig cpusets)"),
+    "SET_SESSION_THREAD_POOL_AFFINITY": ("honoured", "automatic even split of the cores over the serving sessions"),
+    "EV_DATA_ALIGNED": ("always", "rows are 16-byte aligned by construction on both engines"),
+    "TF_EMBEDDING_FBJ_OPT": ("always", "lookup and apply share the probed positions by construction (no graph pass to enable)"),
+    "PER_SESSION_HOSTALLOC": ("always", "every serving session owns its pinned staging buffers"),
+    "MERGE_COMPUTE_COPY_STREAM": ("always", "a serving session runs copies and kernels on its ONE stream; training forks explicit side streams inside the CUDA graph"),
+    "USE_INLINE_EXECUTOR": ("always", "sessions execute inline on the caller's thread; there is no op scheduler"),
+    "TF_MULTI_TIER_EV_EVICTION_THREADS": ("n/a", "the device tier manager runs one migration thread per table (ops/tier_manager.py); host tiers demote inline"),
+    "USE_COST_MODEL_EXECUTOR": ("n/a", "no per-op executor: a training step is one CUDA graph"),
+    "START_NODE_STATS_STEP": ("n/a", "cost-model executor tracing"),
+    "STOP_NODE_STATS_STEP": ("n/a", "cost-model executor tracing"),
+    "ENABLE_MPS": ("n/a", "multi-context SessionGroup over MPS: sessions share one context and use one stream each"),
+    "CONTEXTS_COUNT_PER_GPU": ("n/a", "see ENABLE_MPS"),
+    "TARGET_NODES_NAME": ("n/a", "graph-node names: the cut of smart_stage() is the loader boundary; use mark_target_node() for explicit targets"),
+}
+
+
+def env_report(warn: bool = True) -> dict:
+    """The reference switches present in the environment and how this framework treats them; ``warn`` logs the ones without effect."""
+    import logging
+    out = {}
+    for name, (status, note) in REFERENCE_ENV_FLAGS.items():
+        if name in os.environ:
+            out[name] = {"value": os.environ[name], "status": status, "note": note}
+            if warn and status == "n/a":
+                logging.getLogger("deeprec_b200").warning("%s=%s has no effect here: %s", name, os.environ[name], note)
+    return out
