@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import argparse
 import sys
+import os
 import time
 
 import torch
@@ -50,7 +51,7 @@ def get_arg_parser():
                         "roles with `python -m deeprec_b200.parallel.ps_train`")
     p.add_argument("--timeline", type=int, default=0)
     p.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
-    p.add_argument("--engine", action="store_true", help="DLRM through the fused sm_100a engine (models/dlrm_engine.py)")
+    p.add_argument("--engine", action="store_true", help="fused sm_100a engines: DLRM (models/dlrm_engine.py); WDL / DeepFM / DCN / DCNv2 / MaskNet / DIN through FusedRecEngine (models/rec_engine.py)")
     p.add_argument("--log_every", type=int, default=20)
     p.add_argument("--watchdog", type=float, default=0, help="seconds without a finished step before the job dumps stacks and exits 86")
     return p
@@ -79,6 +80,60 @@ def main(argv=None) -> int:
             if a.log_every and s % a.log_every == 0:
                 print(f"global_step {s} loss {eng.loss_value():.5f}")
         print(f"{a.steps * a.batch_size / (time.time() - t0):.0f} samples/s")
+        return 0
+    if a.engine:
+        # every other Criteo-style model (and DIN) through FusedRecEngine: the same unique-first sparse pipeline + one CUDA graph per step
+        # under the model's own dense net (models/rec_engine.py; 1..8 GPUs when launched with torchrun / parallel.launch)
+        from deeprec_b200.models import zoo
+        from deeprec_b200.models.rec_engine import criteo_engine, din_engine, din_ids
+        if name not in zoo.CRITEO_MODELS and name != "din":
+            raise SystemExit(f"--engine: no fused-engine adapter for {name} (dlrm, {', '.join(sorted(zoo.CRITEO_MODELS))}, din)")
+        import torch.distributed as dist
+        world, rank, lrank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(lrank)
+        dev = torch.device("cuda", lrank)
+        comm = None
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+            from deeprec_b200.parallel.p2p import P2PComm
+            comm = P2PComm(rank, world, dev)
+        torch.manual_seed(0)
+        model = build_model(name, device=dev)
+        kw = dict(optimizer=a.optimizer, learning_rate=a.learning_rate, filter_freq=2 if a.ev_filter else 0,
+                  steps_to_live=4000 if a.ev_elimination == "gstep" else 0, device=dev, rank=rank, world_size=world, comm=comm)
+        if name == "din":
+            L = 20
+            eng = din_engine(model, a.batch_size, L, table_rows=(100000, 200000, 1000), **kw)
+
+            def batch(s):
+                b = taobao_batch(a.batch_size, L, 100000, 200000, 1000, seed=s * world + rank)
+                return din_ids(b), b["labels"], None
+        else:
+            cards = [1000] * 26
+            eng = criteo_engine(model, a.batch_size, table_rows=cards, **kw)
+
+            def batch(s):
+                d, ids, y = criteo_batch(a.batch_size, 13, cards, seed=s * world + rank)
+                return ids, y, {"dense": d}
+        t0 = time.time()
+        for s in range(a.steps):
+            ids, y, dense = batch(s)
+            eng.load_batch(ids.to(dev), y.to(dev), {k: v.to(dev) for k, v in dense.items()} if dense else None)
+            if s == 0:
+                eng.capture()                  # one eager step on the loaded batch, then the step is a CUDA graph
+            else:
+                eng.train_step()
+            if a.log_every and s % a.log_every == 0 and rank == 0:
+                print(f"global_step {s} loss {eng.loss_value():.5f}")
+            elif a.log_every and s % a.log_every == 0:
+                eng.loss_value()               # the all-reduce of the loss is collective
+            if a.checkpoint and a.save_steps and s and s % a.save_steps == 0:
+                eng.save(a.checkpoint, incremental=bool(a.incremental_ckpt) and s // a.save_steps > 1)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(f"{a.steps * a.batch_size * world / (time.time() - t0):.0f} samples/s")
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
         return 0
     if a.protocol != "local":
         print(f"--protocol {a.protocol}: parameter-server roles are started with `python -m deeprec_b200.parallel.ps_train`; training locally here")
