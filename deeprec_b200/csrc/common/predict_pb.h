@@ -274,12 +274,14 @@ inline bool WireToResponse(const void* wire, size_t n, const std::vector<std::st
   WireResp h;
   if (n < sizeof(h)) return false;
   memcpy(&h, wire, sizeof(h));
-  if (h.magic != kWireRespMagic || n < sizeof(h) + (size_t)h.batch * 4) return false;
+  const size_t no = h.reserved > 1 ? h.reserved : 1;                 // multi-task models: `reserved` = probabilities per row (sample-major)
+  if (h.magic != kWireRespMagic || n < sizeof(h) + (size_t)h.batch * no * 4) return false;
   auto wanted = [&](const char* name) { return output_filter.empty() || std::find(output_filter.begin(), output_filter.end(), name) != output_filter.end(); };
   Response r;
   if (wanted("probabilities")) {
-    Array a; a.dtype = DT_FLOAT; a.shape = {(int64_t)h.batch}; a.f32.resize(h.batch);
-    if (h.batch) memcpy(a.f32.data(), static_cast<const uint8_t*>(wire) + sizeof(h), (size_t)h.batch * 4);
+    Array a; a.dtype = DT_FLOAT; a.f32.resize((size_t)h.batch * no);
+    if (no > 1) a.shape = {(int64_t)h.batch, (int64_t)no}; else a.shape = {(int64_t)h.batch};
+    if (h.batch) memcpy(a.f32.data(), static_cast<const uint8_t*>(wire) + sizeof(h), (size_t)h.batch * no * 4);
     r.outputs.emplace_back("probabilities", std::move(a));
   }
   if (wanted("model_version")) { Array a; a.dtype = DT_INT64; a.shape = {1}; a.i64 = {h.model_version}; r.outputs.emplace_back("model_version", std::move(a)); }

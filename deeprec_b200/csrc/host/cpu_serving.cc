@@ -84,7 +84,7 @@ struct Config {
 // Sequence models (DIN): the request's id rows are COLUMNS, several of which may read the same table (`col_table`: target item + L history
 // positions -> the item table); valid_mask / seq_zip / seq_mask / seq_sum / din_attention / prelu are the ops their heads need.
 enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
-               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_NUM_OPS };
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_NUM_OPS };
 struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0;
@@ -93,6 +93,8 @@ struct Arch {
   // and the deep table of one Wide&Deep column) from table col_table[c] (identity unless several columns share a TABLE, e.g. DIN's target
   // item and its L history positions).  C == T and col_table == identity for every model exported before col_table existed.
   int R = 0, C = 0; std::vector<int> id_map, col_table;
+  // multi-task programs: the output buffer is [B, n_out] logits, the response carries n_out probabilities per row (sample-major)
+  int n_out = 1; std::vector<std::string> out_names;
 };
 static int pad8(int n) { return (n + 7) / 8 * 8; }
 
@@ -163,7 +165,7 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
     static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
-                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu"};
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine"};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     for (const JVal& o : pr->arr) {
@@ -174,14 +176,16 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
-      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1};
+      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2};
       if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
       op.out = (int)names.size(); names.push_back(op.name);
       a->ops.push_back(std::move(op));
     }
     a->nbuf = (int)names.size();
     a->out_buf = id_of(j.s("output", ""));
-    return a->T > 0 && a->out_buf >= 2;
+    a->n_out = (int)j.n("num_outputs", 1);
+    if (auto* on = j.get("output_names")) for (auto& v : on->arr) a->out_names.push_back(v.str);
+    return a->T > 0 && a->out_buf >= 2 && a->n_out >= 1 && a->n_out <= 16;
   }
   return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
 }
@@ -223,6 +227,8 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_SEQ_MASK: if (op.len <= 0 || w0 % op.len || dp->width[(size_t)op.in[1]] != op.len) return false; break;       // x [B, L * W] * mask [B, L]
       case P_SEQ_SUM: if (op.len <= 0 || w0 % op.len) return false; w = w0 / op.len; break;                                 // sum over the L positions
       case P_PRELU: if (!ReadVec(r, base + "alpha", &d.v0) || (int)d.v0.size() != w0) return false; break;
+      case P_SOFTMAX: break;                                           // row-wise softmax (mixture-of-experts gates)
+      case P_COSINE: if (dp->width[(size_t)op.in[1]] != w0) return false; w = 1; break;     // cosine similarity of two [B, W] towers -> [B, 1]
       case P_DIN_ATT: {                                              // q [B, W], k [B, L * W], mask [B, L] -> [B, W]
         const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
         if (L <= 0 || wk != L * w0) return false;
@@ -238,6 +244,7 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
     if (w <= 0) return false;
     dp->width[(size_t)op.out] = w;
   }
+  if (dp->width[(size_t)a.out_buf] < a.n_out) return false;            // the output buffer holds n_out logits per row
   *out = dp;
   return true;
 }
@@ -494,7 +501,7 @@ struct Session {
     for (int n : ar.top) widest = std::max(widest, n);
     auto grow = [](auto& v, size_t n) { if (v.size() < n) v.resize(n); };
     grow(dense, mb * ar.num_dense); grow(ids, mb * ar.C); grow(emb, mb * ar.C * ar.D);
-    grow(a, mb * widest); grow(b2, mb * widest); grow(z, mb * ar.inter); grow(prob, mb);
+    grow(a, mb * widest); grow(b2, mb * widest); grow(z, mb * ar.inter); grow(prob, mb * (size_t)ar.n_out);
     grow(rrows, mb * ar.D); grow(found, mb);
   }
   // remote lookup of one chunk: per table ONE pipelined MGET; ids the store does not have read their default row (what a local
@@ -617,6 +624,27 @@ struct Session {
           for (int i = 0; i < B; ++i) { const float* x = a0 + (size_t)i * W; float* y = out + (size_t)i * W; for (int k = 0; k < W; ++k) y[k] = x[k] > 0.f ? x[k] : al[k] * x[k]; }
           break;
         }
+        case P_SOFTMAX: {
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            const float* x = a0 + (size_t)i * W; float* y = out + (size_t)i * W;
+            float mx = x[0]; for (int k = 1; k < W; ++k) mx = std::max(mx, x[k]);
+            float den = 0.f; for (int k = 0; k < W; ++k) { y[k] = std::exp(x[k] - mx); den += y[k]; }
+            for (int k = 0; k < W; ++k) y[k] /= den;
+          }
+          break;
+        }
+        case P_COSINE: {                                         // F.cosine_similarity(a, b, eps = 1e-8)
+          const float* b1 = Buf(op.in[1]);
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            const float* x = a0 + (size_t)i * w0; const float* y = b1 + (size_t)i * w0;
+            float xy = 0.f, xx = 0.f, yy = 0.f;
+            for (int k = 0; k < w0; ++k) { xy += x[k] * y[k]; xx += x[k] * x[k]; yy += y[k] * y[k]; }
+            out[(size_t)i] = xy / (std::max(std::sqrt(xx), 1e-8f) * std::max(std::sqrt(yy), 1e-8f));
+          }
+          break;
+        }
         case P_DIN_ATT: {                                        // DIN attention unit: s_l = MLP([q, k_l, q - k_l, q * k_l]), masked softmax, sum_l w_l k_l
           const float* kk = Buf(op.in[1]); const float* mk = Buf(op.in[2]);
           const int L = d.width[(size_t)op.in[2]], H1 = pd.H1, H2 = pd.H2, Wq = W;
@@ -659,7 +687,8 @@ struct Session {
       }
     }
     const float* lg = Buf(ar.out_buf); const int W = d.width[(size_t)ar.out_buf];
-    for (int i = 0; i < B; ++i) prob[(size_t)i] = 1.f / (1.f + std::exp(-lg[(size_t)i * W]));
+    const int no = ar.n_out;
+    for (int i = 0; i < B; ++i) for (int o = 0; o < no; ++o) prob[(size_t)i * no + o] = 1.f / (1.f + std::exp(-lg[(size_t)i * W + o]));
   }
 
   // dense [B, num_dense], ids [T][B] staged in the session buffers -> prob[B]
@@ -766,7 +795,7 @@ static int RunRows(ServingModel* sm, const std::shared_ptr<Model>& m, const uint
       }
       if (!ok) { sm->failures++; return 500; }
     }
-    memcpy(probs + off, s.prob.data(), (size_t)B * 4);
+    memcpy(probs + (size_t)off * a.n_out, s.prob.data(), (size_t)B * a.n_out * 4);
   }
   return 200;
 }
@@ -804,7 +833,7 @@ static int PredictBatched(ServingModel* sm, Batcher& bt, const drpb::WireReq& h,
     if (mine.size() == 1) rc = RunRows(sm, m, it.dense, it.ids, it.rows, it.rows, it.probs, -1);
     else {
       const Arch& a = m->arch;
-      std::vector<float> dense((size_t)R * a.num_dense), out(R);
+      std::vector<float> dense((size_t)R * a.num_dense), out((size_t)R * a.n_out);
       std::vector<int64_t> ids((size_t)a.R * R);                       // request-shaped: a.R id rows
       uint32_t off = 0;
       for (Batcher::Item* q : mine) {
@@ -814,7 +843,7 @@ static int PredictBatched(ServingModel* sm, Batcher& bt, const drpb::WireReq& h,
       }
       rc = RunRows(sm, m, reinterpret_cast<const uint8_t*>(dense.data()), reinterpret_cast<const uint8_t*>(ids.data()), R, R, out.data(), -1);
       off = 0;
-      for (Batcher::Item* q : mine) { if (rc == 200) memcpy(q->probs, out.data() + off, (size_t)q->rows * 4); off += q->rows; }
+      for (Batcher::Item* q : mine) { if (rc == 200) memcpy(q->probs, out.data() + (size_t)off * a.n_out, (size_t)q->rows * a.n_out * 4); off += q->rows; }
     }
   }
   bt.merged_batches++; bt.merged_requests += mine.size();
@@ -839,7 +868,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
   const Arch& a = m->arch;
   const size_t need = sizeof(h) + (size_t)h.batch * h.num_dense * 4 + (size_t)h.num_sparse * h.batch * 8;
   if (h.magic != drpb::kWireReqMagic || (int)h.num_dense != a.num_dense || (int)h.num_sparse != a.R || h.batch == 0 || (size_t)in_size < need) return 500;
-  std::vector<float> probs(h.batch);
+  std::vector<float> probs((size_t)h.batch * a.n_out);
   const auto t0 = std::chrono::steady_clock::now();
   const uint8_t* p = static_cast<const uint8_t*>(in) + sizeof(h);
   const uint8_t* dense_in = p;
@@ -859,7 +888,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
       if (!sm->cfg.timeline_path.empty()) { FILE* f = fopen(sm->cfg.timeline_path.c_str(), "a"); if (f) { fprintf(f, "%s\n", line); fclose(f); } }
     }
   }
-  drpb::WireResp rh{drpb::kWireRespMagic, h.batch, 200, 0, version};
+  drpb::WireResp rh{drpb::kWireRespMagic, h.batch, 200, (uint32_t)(a.n_out > 1 ? a.n_out : 0), version};     // reserved = outputs per row (0: one)
   *out_size = (int)(sizeof(rh) + probs.size() * 4);
   *out = malloc((size_t)*out_size);
   memcpy(*out, &rh, sizeof(rh)); memcpy(static_cast<uint8_t*>(*out) + sizeof(rh), probs.data(), probs.size() * 4);
@@ -914,7 +943,7 @@ static bool WarmUp(ServingModel* sm, const std::shared_ptr<Model>& m) {
     }
     auto dense = std::atomic_load(&m->dense);
     if (!s.Run(*m, *dense, B, sm->cfg.redis_prefix)) return false;
-    for (int i = 0; i < B; ++i) if (!(s.prob[(size_t)i] >= 0.f && s.prob[(size_t)i] <= 1.f)) return false;       // NaN / garbage -> reject the version
+    for (int i = 0; i < B * a.n_out; ++i) if (!(s.prob[(size_t)i] >= 0.f && s.prob[(size_t)i] <= 1.f)) return false;       // NaN / garbage -> reject the version
   }
   return true;
 }

@@ -83,4 +83,13 @@ int64_t dr_pb_decode_response(const void* pb, int64_t n, float* probs, int64_t c
   return count;
 }
 
+// probabilities per row of a PredictResponse (the last dimension of a rank-2 "probabilities" output: multi-task models), 1 otherwise
+int64_t dr_pb_response_cols(const void* pb, int64_t n) {
+  drpb::Response r;
+  if (!drpb::ParseResponse(pb, (size_t)n, &r)) { g_err = "malformed PredictResponse"; return -1; }
+  for (const auto& kv : r.outputs)
+    if (kv.first == "probabilities" && kv.second.shape.size() == 2 && kv.second.shape[1] > 0) return kv.second.shape[1];
+  return 1;
+}
+
 }  // extern "C"

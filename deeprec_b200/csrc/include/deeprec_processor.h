@@ -51,6 +51,7 @@ int dr_pb_encode_request(const float* dense, const int64_t* ids, int64_t B, int 
                          const char* output_filter, void** out, int64_t* out_n);
 /* returns the number of probabilities (copied up to cap), or -1 */
 int64_t dr_pb_decode_response(const void* pb, int64_t n, float* probs, int64_t cap, int64_t* model_version);
+int64_t dr_pb_response_cols(const void* pb, int64_t n);   /* probabilities per row (multi-task models: > 1, sample-major) */
 const char* dr_pb_last_error(void);
 void dr_pb_free(void* p);
 

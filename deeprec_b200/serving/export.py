@@ -281,12 +281,30 @@ class _ProgramBuilder:
             self.tensors[f"prog/{out}/{nm}"] = t.detach().float().cpu().reshape(-1).contiguous()
         self.ops.append({"op": "din_attention", "out": out, "in": [q, k, mask]}); return out
 
+    def softmax(self, src):
+        out = self._name("softmax"); self.ops.append({"op": "softmax", "out": out, "in": [src]}); return out
+
+    def cosine(self, a, b):
+        out = self._name("cos"); self.ops.append({"op": "cosine", "out": out, "in": [a, b]}); return out
+
+    def mixture(self, gate, experts, width):
+        """sum_e gate[:, e] * expert_e: the experts concatenated [B, E * width], weighted position-wise, summed over E."""
+        n = len(experts)
+        return self.seq_sum(self.seq_mask(self.concat(experts), gate, n), n)
+
     def sequential(self, src, seq):
         """nn.Sequential of Linear / ReLU / BatchNorm1d (what ``models.zoo.mlp`` builds on CPU): a BatchNorm folds into the next Linear
         (W' = W diag(s), b' = b + W t); one left over at the end becomes an explicit affine op."""
         import torch.nn as nn
         pending = None
-        mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
+
+        def flat(m):
+            if isinstance(m, nn.Sequential):
+                for c in m:
+                    yield from flat(c)
+            else:
+                yield m
+        mods = list(flat(seq))
         i = 0
         while i < len(mods):
             m = mods[i]
@@ -353,6 +371,48 @@ def _build_program(model, max_len: int = 50) -> _ProgramBuilder:
         for w, b in zip(model.cw, model.cb):
             x = p.cross(x0, x, w, b)
         p.out = p.linear(p.concat([x, p.sequential(x0, model.deep)]), model.out.weight, model.out.bias)
+    elif isinstance(model, (zoo._MultiTask, zoo.DSSM)):
+        # Taobao-shaped models on the pooled behaviour history: lookup columns as for DIN, features = [user | target | sum of the valid history]
+        L, D = int(max_len), model.emb_dim
+        p.tables = [(model.user, D), (model.item, D), (model.cat, D)]
+        p.col_table = [0, 1, 2] + [1] * L + [2] * L
+        p.num_dense = 1
+        u, q = p.slice("emb", 0, D), p.slice("emb", D, 2 * D)
+        mask = p.valid_mask(3, L)
+        pooled = p.seq_sum(p.seq_mask(p.seq_zip(p.slice("emb", 3 * D, L * D), p.slice("emb", (3 + L) * D, L * D), L), mask, L), L)      # [B, 2D]
+        if isinstance(model, zoo.DSSM):
+            ue, ie = p.sequential(p.concat([u, pooled]), model.user_tower), p.sequential(q, model.item_tower)
+            p.out = p.affine(p.cosine(ue, ie), model.scale.detach().reshape(1), torch.zeros(1))
+        else:
+            f = p.concat([u, q, pooled])
+            tasks = list(model.tasks)
+            if isinstance(model, zoo.ESMM):
+                outs = [p.sequential(f, model.ctr), p.sequential(f, model.cvr)]
+            elif isinstance(model, zoo.SimpleMultiTask):
+                outs = [p.sequential(f, model.towers[t]) for t in tasks]
+            elif isinstance(model, zoo.MMoE):
+                ex = [p.sequential(f, e) for e in model.experts]
+                w = model.experts[0][-2].out_features if isinstance(model.experts[0][-1], torch.nn.ReLU) else model.experts[0][-1].out_features
+                outs = [p.sequential(p.mixture(p.softmax(p.linear(f, model.gates[t].weight, model.gates[t].bias)), ex, w), model.towers[t]) for t in tasks]
+            elif isinstance(model, zoo.DBMTL):
+                sh = p.sequential(f, model.bottom)
+                a_, c_ = p.sequential(sh, model.t_ctr), p.sequential(sh, model.t_cvr)
+                outs = [p.linear(a_, model.o_ctr.weight, model.o_ctr.bias), p.linear(p.sequential(p.concat([a_, c_]), model.rel), model.o_cvr.weight, model.o_cvr.bias)]
+            elif isinstance(model, zoo.PLE):
+                xs = {t: f for t in tasks}
+                xs["shared"] = f
+                for Lyr in model.layers:
+                    sh = [p.sequential(xs["shared"], e) for e in Lyr["shared"]]
+                    sp = {t: [p.sequential(xs[t], e) for e in Lyr[f"spec_{t}"]] for t in tasks}
+                    nxt = {t: p.mixture(p.softmax(p.linear(xs[t], Lyr[f"gate_{t}"].weight, Lyr[f"gate_{t}"].bias)), sp[t] + sh, 0) for t in tasks}
+                    allx = [x for t in tasks for x in sp[t]] + sh
+                    nxt["shared"] = p.mixture(p.softmax(p.linear(xs["shared"], Lyr["gate_shared"].weight, Lyr["gate_shared"].bias)), allx, 0)
+                    xs = nxt
+                outs = [p.sequential(xs[t], model.towers[t]) for t in tasks]
+            else:
+                raise TypeError(f"op-program export: no builder for {type(model).__name__}")
+            p.out = p.concat(outs)
+            p.num_outputs, p.output_names = len(outs), tasks
     elif isinstance(model, zoo.DIN):
         # lookup columns [user | item | cat | hist_item x L | hist_cat x L] over the three tables (the layout of models.rec_engine.din_ids);
         # padding ids (-1) give masked (zeroed) history positions
@@ -367,7 +427,7 @@ def _build_program(model, max_len: int = 50) -> _ProgramBuilder:
         x = p.concat([u, q, p.seq_sum(k, L), p.din_attention(q, k, mask, model.att)])
         p.out = p.sequential(x, nn.Sequential(model.bn, *list(model.top)))
     else:
-        raise TypeError(f"op-program export: no builder for {type(model).__name__} (WDL, DeepFM, DCN, DCNv2, MaskNet, DIN; DLRM has export_saved_model_module)")
+        raise TypeError(f"op-program export: no builder for {type(model).__name__} (WDL, DeepFM, DCN, DCNv2, MaskNet, DIN, DSSM, ESMM, MMoE, DBMTL, PLE, SimpleMultiTask; DLRM has export_saved_model_module)")
     return p
 
 
@@ -420,6 +480,9 @@ def export_saved_model_program(model, export_dir: str, version: int, root: Optio
         meta["id_map"] = id_map
     if col_table is not None:
         meta["col_table"] = col_table
+    if getattr(p, "num_outputs", 1) > 1:                                 # multi-task: probabilities [B, num_outputs], one column per task
+        meta["num_outputs"], meta["output_names"] = p.num_outputs, list(p.output_names)
+        meta["signature"]["outputs"] = {"probabilities": ["B", p.num_outputs]}
     with open(os.path.join(export_dir, "saved_model.json"), "w") as f:
         json.dump(meta, f)
     _write_versions(root or export_dir, full={"version": int(version), "dir": os.path.abspath(export_dir)})

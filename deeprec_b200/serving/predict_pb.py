@@ -26,6 +26,7 @@ def _lib():
         L.dr_pb_encode_request.restype = C.c_int
         L.dr_pb_encode_request.argtypes = [vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(i64)]
         L.dr_pb_decode_response.restype, L.dr_pb_decode_response.argtypes = i64, [C.c_char_p, i64, vp, i64, C.POINTER(i64)]
+        L.dr_pb_response_cols.restype, L.dr_pb_response_cols.argtypes = i64, [C.c_char_p, i64]
         _BOUND = True
     return L
 
@@ -54,7 +55,7 @@ def encode_predict_request(dense: np.ndarray, ids: np.ndarray, per_feature: bool
 
 
 def decode_predict_response(pb: bytes) -> Tuple[np.ndarray, int]:
-    """PredictResponse bytes -> (probabilities float32 [B], model_version or -1)."""
+    """PredictResponse bytes -> (probabilities float32 [B] -- [B, num_outputs] for multi-task models --, model_version or -1)."""
     L = _lib()
     ver = C.c_int64(-1)
     cnt = L.dr_pb_decode_response(pb, len(pb), None, 0, C.byref(ver))
@@ -62,7 +63,8 @@ def decode_predict_response(pb: bytes) -> Tuple[np.ndarray, int]:
         raise ValueError(L.dr_pb_last_error().decode())
     probs = np.empty(cnt, dtype=np.float32)
     L.dr_pb_decode_response(pb, len(pb), probs.ctypes.data, cnt, C.byref(ver))
-    return probs, int(ver.value)
+    cols = int(L.dr_pb_response_cols(pb, len(pb)))                  # multi-task models answer [B, num_outputs]
+    return (probs.reshape(-1, cols) if cols > 1 else probs), int(ver.value)
 
 
 def request_to_wire(pb: bytes, num_dense: int, num_sparse: int) -> bytes:

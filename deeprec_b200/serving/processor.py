@@ -32,8 +32,9 @@ def decode_response(buf: bytes) -> Tuple[np.ndarray, int, int]:
     magic, batch, status, _r, version = struct.unpack_from("<4Iq", buf, 0)
     if magic != RESP_MAGIC:
         raise ValueError("bad PredictResponse")
-    probs = np.frombuffer(buf, dtype=np.float32, count=batch, offset=24).copy()
-    return probs, status, version
+    n_out = _r if _r > 1 else 1                          # multi-task models: `reserved` = probabilities per row -> [batch, n_out]
+    probs = np.frombuffer(buf, dtype=np.float32, count=batch * n_out, offset=24).copy()
+    return (probs.reshape(batch, n_out) if n_out > 1 else probs), status, version
 
 
 class _Abi:

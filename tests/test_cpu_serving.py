@@ -489,3 +489,45 @@ def test_din_op_program_on_the_cpu_processor(tmp_path):
         assert np.abs(r1 - r0).max() > 1e-4 and np.abs(proc.predict(dense, ids) - r1).max() < 2e-5
     finally:
         proc.close()
+
+
+@pytest.mark.parametrize("name", ["esmm", "mmoe", "dbmtl", "ple", "simple_multitask", "dssm"])
+def test_multitask_and_dssm_op_programs_on_the_cpu_processor(tmp_path, name):
+    """Taobao-shaped multi-task models (two probabilities per row: ctr, cvr) and the two-tower DSSM as op programs: softmax-gated expert
+    mixtures (seq_mask + seq_sum), cosine similarity, multi-output responses in the compact AND the protobuf encoding."""
+    import json
+    from deeprec_b200.data import taobao_batch
+    from deeprec_b200.models.rec_engine import din_ids
+    from deeprec_b200.serving import export_saved_model_program
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(5)
+    L = 12
+    model = build_model(name, device="cpu")
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    for sd in range(3):
+        b = taobao_batch(128, L, 500, 3000, 40, seed=sd)
+        loss = model.loss(b); opt.zero_grad(); loss.backward(); opt.step()
+    b["hist_item"][:4] = -1; b["hist_cat"][:4] = -1
+    root = str(tmp_path)
+    export_saved_model_program(model, os.path.join(root, "v1"), version=1, root=root, max_len=L)
+    meta = json.load(open(os.path.join(root, "v1", "saved_model.json")))
+    model.eval()
+    with torch.no_grad():
+        out = model(b)
+    if name == "dssm":
+        ref = torch.sigmoid(out).numpy()
+        assert "num_outputs" not in meta and "cosine" in {o["op"] for o in meta["program"]}
+    else:
+        ref = torch.stack([torch.sigmoid(out["ctr"]), torch.sigmoid(out["cvr"])], 1).numpy()
+        assert meta["num_outputs"] == 2 and meta["output_names"] == ["ctr", "cvr"]
+    ids = din_ids(b).numpy(); dense = np.zeros((128, 1), np.float32)
+    proc = Processor(os.path.join(root, "v1"), {"session_num": 2, "max_batch": 50, "model_update_interval_ms": 0}, device="cpu")
+    try:
+        got = proc.predict(dense, ids)                                   # 128 rows > max_batch: chunked
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 3e-5, np.abs(got - ref).max()
+        rc, pb = proc.process(predict_pb.encode_predict_request(dense[:5], ids[:, :5]))
+        assert rc == 200
+        dec = predict_pb.decode_predict_response(pb)[0]
+        assert dec.shape == ref[:5].shape and np.abs(dec - ref[:5]).max() < 3e-5
+    finally:
+        proc.close()
