@@ -165,6 +165,45 @@ __global__ void __launch_bounds__(256) k_prog_to_u8(const __nv_bfloat16* __restr
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int64_t b = i / w; y[i] = ldb(x + b * ldx + (i - b * w)) > 0.f ? 1 : 0; }
 }
 
+// row-wise softmax (mixture-of-experts gates), one warp per row
+__global__ void __launch_bounds__(256) k_prog_softmax(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float mx = -3.4e38f;
+    for (int k = lane; k < w; k += 32) mx = fmaxf(mx, ldb(x + r * ldx + k));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float den = 0.f;
+    for (int k = lane; k < w; k += 32) den += __expf(ldb(x + r * ldx + k) - mx);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+    const float inv = 1.f / den;
+    for (int k = lane; k < w; k += 32) stb(y + r * ldy + k, __expf(ldb(x + r * ldx + k) - mx) * inv);
+  }
+}
+// y[b, 0] = cos(a[b, :], c[b, :]) with each norm clamped at 1e-8, one warp per row
+__global__ void __launch_bounds__(256) k_prog_cosine(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_bfloat16* __restrict__ c, int64_t ldc, int w,
+                                                     __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float xy = 0.f, xx = 0.f, yy = 0.f;
+    for (int k = lane; k < w; k += 32) { const float p = ldb(a + r * lda + k), q = ldb(c + r * ldc + k); xy += p * q; xx += p * p; yy += q * q; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { xy += __shfl_xor_sync(0xffffffffu, xy, o); xx += __shfl_xor_sync(0xffffffffu, xx, o); yy += __shfl_xor_sync(0xffffffffu, yy, o); }
+    if (lane == 0) stb(y + r * ldy, xy / (fmaxf(sqrtf(xx), 1e-8f) * fmaxf(sqrtf(yy), 1e-8f)));
+  }
+}
+// prob[b * no + o] = sigmoid(x[b, o]), o < no   (multi-task programs: no probabilities per row)
+__global__ void __launch_bounds__(256) k_prog_sigmoid_cols(const __nv_bfloat16* __restrict__ x, int64_t ldx, int no, int64_t B, float* __restrict__ prob) {
+  const int64_t n = B * (int64_t)no;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / no;
+    prob[i] = 1.f / (1.f + __expf(-ldb(x + b * ldx + (i - b * no))));
+  }
+}
+
 inline int grid_el(int64_t n) { const int64_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : b > kNumSMs * 8 ? kNumSMs * 8 : b); }
 inline int grid_rows(int64_t rows) { return grid_el(rows * 32); }
 
@@ -262,6 +301,25 @@ int dr_prog_from_f32(const float* x, int w, void* y, int64_t ldy, int64_t B, cud
 int dr_prog_to_u8(const void* x, int64_t ldx, int w, uint8_t* y, int64_t B, cudaStream_t s) {
   if (B <= 0 || w <= 0) return 0;
   k_prog_to_u8<<<grid_el(B * w), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, y, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_softmax(const void* x, int64_t ldx, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_softmax<<<grid_rows(B), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_cosine(const void* a, int64_t lda, const void* c, int64_t ldc, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || w <= 0) return 0;
+  k_prog_cosine<<<grid_rows(B), 256, 0, s>>>((const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)c, ldc, w, (__nv_bfloat16*)y, ldy, B);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_sigmoid_cols(const void* x, int64_t ldx, int no, int64_t B, float* prob, cudaStream_t s) {
+  if (B <= 0 || no <= 0) return 0;
+  k_prog_sigmoid_cols<<<grid_el(B * no), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, no, B, prob);
   DR_LAUNCH_CHECK();
   return 0;
 }

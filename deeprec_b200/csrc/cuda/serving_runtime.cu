@@ -67,6 +67,9 @@ int dr_prog_prelu(const void* x, int64_t ldx, int w, const float* alpha, void* y
 int dr_prog_to_f32(const void* x, int64_t ldx, int w, float* y, int64_t B, cudaStream_t s);
 int dr_prog_from_f32(const float* x, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_to_u8(const void* x, int64_t ldx, int w, uint8_t* y, int64_t B, cudaStream_t s);
+int dr_prog_softmax(const void* x, int64_t ldx, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_cosine(const void* a, int64_t lda, const void* c, int64_t ldc, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_sigmoid_cols(const void* x, int64_t ldx, int no, int64_t B, float* prob, cudaStream_t s);
 int dr_cuda_din_attention_fwd(const float* q, const float* k, const uint8_t* mask, int64_t B, int L, int D, const float* W1, const float* b1, int H1,
                               const float* W2, const float* b2, int H2, const float* w3, float b3, float* out, cudaStream_t s);
 int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, const float* bias, const float* labels, float inv_batch, float* prob,
@@ -133,7 +136,7 @@ template <typename T> static bool Upload(DevBuf& b, const std::vector<T>& h) {
 // other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].  Same format and
 // op set as the CPU runtime (csrc/host/cpu_serving.cc); here LINEAR runs on the tcgen05 GEMM and the rest on program_kernels.cu.
 enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
-               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_NUM_OPS };     // the last six: sequence models (DIN), see cpu_serving.cc
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_NUM_OPS };     // the last six: sequence models (DIN), see cpu_serving.cc
 struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0;
@@ -141,6 +144,7 @@ struct Arch {
   // requests carry R id rows; lookup column c reads request row id_map[c] from table col_table[c] (both identity, C == T, unless several
   // columns share a feature (Wide&Deep) or a table (DIN: target item + L history positions))
   int R = 0, C = 0; std::vector<int> id_map, col_table;
+  int n_out = 1;        // multi-task programs: the output buffer holds n_out logits per row, the response n_out probabilities per row
 };
 
 struct LayerW {
@@ -264,6 +268,8 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_SEQ_MASK: if (op.len <= 0 || w0 % op.len || dp->width[(size_t)op.in[1]] != op.len) return false; break;
       case P_SEQ_SUM: if (op.len <= 0 || w0 % op.len) return false; w = w0 / op.len; break;
       case P_PRELU: if (!ReadVec(r, base + "alpha", &v0) || (int)v0.size() != w0 || !Upload(d.v0, v0)) return false; break;
+      case P_SOFTMAX: break;
+      case P_COSINE: if (dp->width[(size_t)op.in[1]] != w0) return false; w = 1; break;
       case P_DIN_ATT: {
         const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
         if (L <= 0 || wk != L * w0) return false;
@@ -282,6 +288,7 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
     if (w <= 0) return false;
     dp->width[(size_t)op.out] = w;
   }
+  if (dp->width[(size_t)a.out_buf] < a.n_out) return false;
   *out = dp;
   return true;
 }
@@ -403,8 +410,8 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
     static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
-                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu"};
-    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1};
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine"};
+    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     for (const JVal& o : pr->arr) {
@@ -421,6 +428,8 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     }
     a->nbuf = (int)names.size();
     a->out_buf = id_of(j.s("output", ""));
+    a->n_out = (int)j.n("num_outputs", 1);
+    if (a->n_out < 1 || a->n_out > 16) return false;
     // the embedding buffer doubles as a GEMM operand: its row pitch T * D must obey the 16-byte rule; rows are gathered as float4 groups
     return a->T > 0 && a->out_buf >= 2 && a->D % 4 == 0 && (a->C * a->D) % 8 == 0;
   }
@@ -457,7 +466,7 @@ struct Session {
     max_batch = maxB;
     SV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     bool ok = dense_in.alloc((size_t)maxB * a.num_dense * 4) && ids.alloc((size_t)a.C * maxB * 8) && x0.alloc((size_t)maxB * pad8(a.num_dense) * 2) &&
-              emb.alloc((size_t)a.C * maxB * a.D * 2) && pos.alloc((size_t)a.C * maxB * 4) && Z.alloc((size_t)maxB * a.Zp * 2) && prob.alloc((size_t)maxB * 4) &&
+              emb.alloc((size_t)a.C * maxB * a.D * 2) && pos.alloc((size_t)a.C * maxB * 4) && Z.alloc((size_t)maxB * a.Zp * 2) && prob.alloc((size_t)maxB * a.n_out * 4) &&
               loss.alloc(16) && labels.alloc((size_t)maxB * 4) && y_last.alloc((size_t)maxB * a.D * 2);
     a_bot.resize(a.bot.size()); a_top.resize(a.top.size());
     for (size_t l = 0; l < a.bot.size(); ++l) ok = ok && a_bot[l].alloc((size_t)maxB * a.bot[l] * 2);
@@ -470,7 +479,7 @@ struct Session {
     cudaMemset(labels.p, 0, (size_t)maxB * 4);
     SV_CUDA(cudaMallocHost(&h_dense, (size_t)maxB * a.num_dense * 4));
     SV_CUDA(cudaMallocHost(&h_ids, (size_t)a.C * maxB * 8));
-    SV_CUDA(cudaMallocHost(&h_prob, (size_t)maxB * 4));
+    SV_CUDA(cudaMallocHost(&h_prob, (size_t)maxB * a.n_out * 4));
     return true;
   }
   ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (stream) cudaStreamDestroy(stream); }
@@ -531,6 +540,8 @@ struct Session {
         case P_SEQ_MASK: rc |= dr_prog_seq_mask(a0, ld0, buf(op.in[1]), ld(op.in[1]), op.len, W / op.len, out, ldo, B, s); break;
         case P_SEQ_SUM: rc |= dr_prog_seq_sum(a0, ld0, op.len, W, out, ldo, B, s); break;
         case P_PRELU: rc |= dr_prog_prelu(a0, ld0, W, pd.v0.as<float>(), out, ldo, B, s); break;
+        case P_SOFTMAX: rc |= dr_prog_softmax(a0, ld0, W, out, ldo, B, s); break;
+        case P_COSINE: rc |= dr_prog_cosine(a0, ld0, buf(op.in[1]), ld(op.in[1]), w0, out, ldo, B, s); break;
         case P_DIN_ATT: {                                            // fp32 staging -> the fused attention kernel (attention_kernels.cu) -> bf16
           const int L = dp.width[(size_t)op.in[2]];
           rc |= dr_prog_to_f32(a0, ld0, W, att_q.as<float>(), B, s);
@@ -545,7 +556,7 @@ struct Session {
       }
       (void)w0;
     }
-    rc |= dr_prog_sigmoid0(buf(a.out_buf), ld(a.out_buf), B, prob.as<float>(), s);
+    rc |= dr_prog_sigmoid_cols(buf(a.out_buf), ld(a.out_buf), a.n_out, B, prob.as<float>(), s);
     return rc == 0;
   }
 
@@ -556,7 +567,7 @@ struct Session {
     SV_CUDA(cudaMemcpyAsync(ids.p, h_ids, (size_t)a.C * B * 8, cudaMemcpyHostToDevice, s));
     if (a.program) {
       if (!RunProgram(m, dp, B)) return false;
-      SV_CUDA(cudaMemcpyAsync(h_prob, prob.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+      SV_CUDA(cudaMemcpyAsync(h_prob, prob.p, (size_t)B * a.n_out * 4, cudaMemcpyDeviceToHost, s));
       SV_CUDA(cudaStreamSynchronize(s));
       return true;
     }
@@ -678,7 +689,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
   uint64_t pick = sm->cfg.select_policy == 1 ? (hint >= 0 ? (uint64_t)hint : std::hash<std::thread::id>()(std::this_thread::get_id())) : sm->rr.fetch_add(1);
   const size_t ns = sm->sessions.size();
   Session* sp = sm->sessions[pick % ns].get();
-  std::vector<float> probs(h.batch);
+  std::vector<float> probs((size_t)h.batch * a.n_out);
   auto t0 = std::chrono::steady_clock::now();
   {
     // MOD: the caller / hint owns its session.  RR: start at the round-robin slot and take the first IDLE session (a serial caller still
@@ -704,7 +715,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
       const int64_t* ids = reinterpret_cast<const int64_t*>(p + (size_t)h.batch * a.num_dense * 4);
       for (int c = 0; c < a.C; ++c) memcpy(s.h_ids + (size_t)c * B, ids + (size_t)a.id_map[(size_t)c] * h.batch + off, (size_t)B * 8);
       if (!s.Run(*m, *dense, B)) { sm->failures++; return 500; }
-      memcpy(probs.data() + off, s.h_prob, (size_t)B * 4);
+      memcpy(probs.data() + (size_t)off * a.n_out, s.h_prob, (size_t)B * a.n_out * 4);
     }
   }
   const uint64_t rq = ++sm->requests;
@@ -716,7 +727,7 @@ static int Predict(ServingModel* sm, const void* in, int in_size, void** out, in
     sm->trace.emplace_back(line);
     if (!sm->cfg.timeline_path.empty()) { FILE* f = fopen(sm->cfg.timeline_path.c_str(), "a"); if (f) { fprintf(f, "%s\n", line); fclose(f); } }
   }
-  RespHeader rh{kRespMagic, h.batch, 200, 0, m->version};
+  RespHeader rh{kRespMagic, h.batch, 200, (uint32_t)(a.n_out > 1 ? a.n_out : 0), m->version};        // reserved = probabilities per row (0: one)
   *out_size = (int)(sizeof(rh) + probs.size() * 4);
   *out = malloc(*out_size);
   memcpy(*out, &rh, sizeof(rh)); memcpy(static_cast<uint8_t*>(*out) + sizeof(rh), probs.data(), probs.size() * 4);
@@ -841,7 +852,7 @@ static void UpdaterLoop(ServingModel* sm) {
         // reference would build a fresh SessionGroup (serving/processor/serving/model_instance.cc:406-427); restart the processor for it.
         {
           const Arch& o = cur->arch; const Arch& n = nm->arch;
-          if (n.num_dense != o.num_dense || n.T != o.T || n.D != o.D || n.bot != o.bot || n.top != o.top || n.Zp != o.Zp || n.program != o.program || n.R != o.R || n.C != o.C) {
+          if (n.num_dense != o.num_dense || n.T != o.T || n.D != o.D || n.bot != o.bot || n.top != o.top || n.Zp != o.Zp || n.program != o.program || n.R != o.R || n.C != o.C || n.n_out != o.n_out) {
             if (sm->rejected_version != v) {
               fprintf(stderr, "[deeprec_serving] model version %lld changes the architecture (tables %d->%d, D %d->%d, dense %d->%d): rejected, sessions keep serving version %lld\n",
                       (long long)v, o.T, n.T, o.D, n.D, o.num_dense, n.num_dense, (long long)cur->version);

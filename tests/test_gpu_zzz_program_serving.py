@@ -131,3 +131,34 @@ def test_din_op_program_on_the_gpu_processor(tmp_path):
         assert np.abs(gpu.predict(dense[:3], ids[:, :3]) - ref[:3]).max() < TOL
     finally:
         gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("name", ["esmm", "mmoe", "ple", "dssm"])
+def test_multitask_and_dssm_op_programs_on_the_gpu_processor(tmp_path, name):
+    """Two probabilities per row (ctr, cvr) through softmax-gated expert mixtures; DSSM through the cosine kernel."""
+    from deeprec_b200.data import taobao_batch
+    from deeprec_b200.models.rec_engine import din_ids
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(5)
+    L = 12
+    model = build_model(name, device="cpu")
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    for sd in range(3):
+        b = taobao_batch(128, L, 500, 3000, 40, seed=sd)
+        loss = model.loss(b); opt.zero_grad(); loss.backward(); opt.step()
+    b["hist_item"][:4] = -1; b["hist_cat"][:4] = -1
+    root = str(tmp_path)
+    export_saved_model_program(model, os.path.join(root, "v1"), version=1, root=root, max_len=L)
+    model.eval()
+    with torch.no_grad():
+        out = model(b)
+    ref = torch.sigmoid(out).numpy() if name == "dssm" else torch.stack([torch.sigmoid(out["ctr"]), torch.sigmoid(out["cvr"])], 1).numpy()
+    ids = din_ids(b).numpy(); dense = np.zeros((128, 1), np.float32)
+    gpu = Processor(os.path.join(root, "v1"), {"session_num": 1, "max_batch": 50, "model_update_interval_ms": 0}, device="cuda")
+    try:
+        got = gpu.predict(dense, ids)
+        assert got.shape == ref.shape and np.isfinite(got).all() and np.abs(got - ref).max() < TOL, np.abs(got - ref).max()
+        rc, pb = gpu.process(predict_pb.encode_predict_request(dense[:5], ids[:, :5]))
+        assert rc == 200 and np.abs(predict_pb.decode_predict_response(pb)[0] - ref[:5]).max() < TOL
+    finally:
+        gpu.close()
