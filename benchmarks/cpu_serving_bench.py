@@ -26,20 +26,41 @@ from deeprec_b200.serving import Processor, encode_request, export_saved_model_m
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
-    ap.add_argument("--model", default="dlrm", help="dlrm (native architecture) or an op-program model: deepfm, dcn, dcnv2, masknet")
+    ap.add_argument("--model", default="dlrm", help="dlrm (native architecture) or an op-program model: wdl, deepfm, dcn, dcnv2, masknet; din, dssm, esmm, mmoe, dbmtl, ple, simple_multitask (Taobao-shaped, 50-step history)")
     a = ap.parse_args()
     torch.manual_seed(0)
-    model = build_model(a.model, device="cpu", cardinalities=CARDS)
-    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
-    for s in range(4):
-        d, ids, y = criteo_batch(2048, 13, CARDS, seed=s)
-        loss = model.loss(d, ids, y); opt.zero_grad(); loss.backward(); opt.step()
+    from deeprec_b200.models.zoo import TAOBAO_MODELS
+    taobao = a.model in TAOBAO_MODELS                    # din, dssm, esmm, mmoe, dbmtl, ple, simple_multitask: 3 + 2 L id columns, L = 50
+    L = 50
     root = tempfile.mkdtemp()
-    if a.model == "dlrm":
-        export_saved_model_module(model, root + "/v1", version=4)
-    else:
+    if taobao:
+        from deeprec_b200.data import taobao_batch
+        from deeprec_b200.models.rec_engine import din_ids
         from deeprec_b200.serving import export_saved_model_program
-        export_saved_model_program(model, root + "/v1", version=4)
+        model = build_model(a.model, device="cpu")
+        opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+        for s in range(4):
+            b = taobao_batch(2048, L, 100000, 400000, 1000, seed=s)
+            loss = model.loss(b); opt.zero_grad(); loss.backward(); opt.step()
+        export_saved_model_program(model, root + "/v1", version=4, max_len=L)
+
+        def request(batch, seed):
+            b = taobao_batch(batch, L, 100000, 400000, 1000, seed=seed)
+            return encode_request(np.zeros((batch, 1), np.float32), din_ids(b).numpy())
+    else:
+        model = build_model(a.model, device="cpu", cardinalities=CARDS)
+        opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+        for s in range(4):
+            d, ids, y = criteo_batch(2048, 13, CARDS, seed=s)
+            loss = model.loss(d, ids, y); opt.zero_grad(); loss.backward(); opt.step()
+        if a.model == "dlrm":
+            export_saved_model_module(model, root + "/v1", version=4)
+        else:
+            from deeprec_b200.serving import export_saved_model_program
+            export_saved_model_program(model, root + "/v1", version=4)
+
+        def request(batch, seed):
+            return encode_request(*[x.numpy() for x in criteo_batch(batch, 13, CARDS, seed=seed)[:2]])
     lines = []
     points = ((1, 1, 1, 4000, 0), (4, 4, 1, 8000, 0), (4, 4, 32, 3000, 0), (2, 2, 256, 600, 0), (1, 1, 2048, 60, 0),
               (2, 16, 1, 16000, 0), (2, 16, 1, 16000, 32))        # many concurrent single-row callers: without / with request batching
@@ -48,7 +69,7 @@ def main():
         if batching:
             cfg.update(enable_batching=True, batching_parameters={"max_batch_size": batching, "batch_timeout_micros": 100})
         proc = Processor(root + "/v1", cfg, device="cpu")
-        reqs = [encode_request(*[x.numpy() for x in criteo_batch(batch, 13, CARDS, seed=100 + i)[:2]]) for i in range(8)]
+        reqs = [request(batch, 100 + i) for i in range(8)]
         for r in reqs:
             assert proc.process(r)[0] == 200
         lat = [[] for _ in range(threads)]

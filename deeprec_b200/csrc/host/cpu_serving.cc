@@ -111,7 +111,7 @@ struct Layer {
       wp[((size_t)p * K + k) * kPanel + j] = wt[(size_t)k * N + p * kPanel + j];
   }
 };
-struct PData { Layer L; std::vector<float> v0, v1; std::vector<std::vector<float>> att; int H1 = 0, H2 = 0; };   // weights of one program op (linear | affine scale, shift | cross w, b | prelu alpha | din_attention W1 b1 W2 b2 w3 b3)
+struct PData { Layer L; std::vector<float> v0, v1; std::vector<std::vector<float>> att; int H1 = 0, H2 = 0; Layer Lq, L1, L2; };   // weights of one program op (linear | affine scale, shift | cross w, b | prelu alpha | din_attention W1 b1 W2 b2 w3 b3)
 struct Dense {
   std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f;
   std::vector<PData> pdata; std::vector<int> width;                       // program models: per-op weights, per-buffer widths
@@ -237,6 +237,20 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
         for (int i2 = 0; i2 < 6; ++i2) if (!ReadVec(r, base + kT[i2], &d.att[(size_t)i2])) return false;
         d.H1 = (int)d.att[1].size(); d.H2 = (int)d.att[3].size();
         if (d.H1 <= 0 || d.H2 <= 0 || (int)d.att[0].size() != d.H1 * 4 * w0 || (int)d.att[2].size() != d.H2 * d.H1 || (int)d.att[4].size() != d.H2 || d.att[5].size() != 1) return false;
+        {
+          // first layer split (the algebra of csrc/cuda/attention_kernels.cu): W1 [q | k | q - k | q * k] = (Wa + Wc) q + (Wb - Wc) k + Wd (q * k);
+          // the q term is one batched GEMM per request, the per-position work is ONE [rows, 2W] x [2W, H1] GEMM over [k | q * k]
+          const int W = w0, H1 = d.H1, H2 = d.H2; const float* W1 = d.att[0].data(); const float* W2 = d.att[2].data();
+          d.Lq.N = H1; d.Lq.K = W; d.Lq.bias = d.att[1]; d.Lq.wt.assign((size_t)W * H1, 0.f);
+          d.L1.N = H1; d.L1.K = 2 * W; d.L1.bias.assign((size_t)H1, 0.f); d.L1.wt.assign((size_t)2 * W * H1, 0.f);
+          for (int h = 0; h < H1; ++h) for (int c = 0; c < W; ++c) {
+            const float wa = W1[(size_t)h * 4 * W + c], wb = W1[(size_t)h * 4 * W + W + c], wc = W1[(size_t)h * 4 * W + 2 * W + c], wd = W1[(size_t)h * 4 * W + 3 * W + c];
+            d.Lq.wt[(size_t)c * H1 + h] = wa + wc; d.L1.wt[(size_t)c * H1 + h] = wb - wc; d.L1.wt[(size_t)(W + c) * H1 + h] = wd;
+          }
+          d.L2.N = H2; d.L2.K = H1; d.L2.bias = d.att[3]; d.L2.wt.assign((size_t)H1 * H2, 0.f);
+          for (int m2 = 0; m2 < H2; ++m2) for (int h = 0; h < H1; ++h) d.L2.wt[(size_t)h * H2 + m2] = W2[(size_t)m2 * H1 + h];
+          d.Lq.Pack(); d.L1.Pack(); d.L2.Pack();
+        }
         break;
       }
       default: return false;
@@ -397,6 +411,18 @@ static const bool kHasAvx512 = false;
 // Loop order: rows are cut into groups (<= 64 rows, what a thread owns at a time), and inside a group the weight PANEL (K x 32 columns,
 // ~50 KB for K = 429) is the outer loop and the group's row tiles the inner one -- a panel is read from L1/L2 by every tile of the group
 // instead of the whole weight matrix (1.7 MB for 429 x 1024) being streamed once per 8-row tile.
+// exp / sigmoid the compiler can vectorise (no libm call): 2^f by a degree-5 minimax polynomial on [0, 1) (max relative error 9e-8), the integer
+// part through the exponent bits
+static inline float FastExp(float x) {
+  x = std::min(88.f, std::max(-88.f, x));
+  const float t = x * 1.44269504f, fi = std::floor(t), f = t - fi;
+  float p = 1.8775767e-3f; p = p * f + 8.9893397e-3f; p = p * f + 5.5826318e-2f; p = p * f + 2.4015361e-1f; p = p * f + 6.9315308e-1f; p = p * f + 9.9999994e-1f;
+  const int32_t bits = ((int32_t)fi + 127) << 23;
+  float sc; memcpy(&sc, &bits, 4);
+  return p * sc;
+}
+static inline float FastSigmoid(float x) { return 1.f / (1.f + FastExp(-x)); }
+
 static void Linear(const float* X, int64_t ldx, int64_t B, const Layer& L, float* Y, bool relu, int threads) {
   const int N = L.N, K = L.K;
   const float* wt = L.wt.data(); const float* bias = L.bias.data();
@@ -523,7 +549,7 @@ struct Session {
     return true;
   }
   // ---- op-program models: buffers 0 / 1 alias `dense` / `emb`, the others are sized (max_batch x width) on first use of a program ----
-  std::vector<std::vector<float>> pbuf; std::vector<int> pbuf_width;
+  std::vector<std::vector<float>> pbuf; std::vector<int> pbuf_width; std::vector<float> att_hq;
   float* Buf(int id) { return id == 0 ? dense.data() : id == 1 ? emb.data() : pbuf[(size_t)id].data(); }
   void RunProgram(const Arch& ar, const Dense& d, int B) {
     if (pbuf_width != d.width) {
@@ -646,29 +672,60 @@ struct Session {
           break;
         }
         case P_DIN_ATT: {                                        // DIN attention unit: s_l = MLP([q, k_l, q - k_l, q * k_l]), masked softmax, sum_l w_l k_l
+          // blocked: kS samples = kS * L history positions form the rows of two small GEMMs on the packed micro-kernels; sigmoids vectorised
           const float* kk = Buf(op.in[1]); const float* mk = Buf(op.in[2]);
           const int L = d.width[(size_t)op.in[2]], H1 = pd.H1, H2 = pd.H2, Wq = W;
-          const float *W1 = pd.att[0].data(), *b1 = pd.att[1].data(), *W2 = pd.att[2].data(), *b2 = pd.att[3].data(), *w3 = pd.att[4].data(); const float b3 = pd.att[5][0];
-#pragma omp parallel for schedule(static) num_threads(threads) if (par)
-          for (int i = 0; i < B; ++i) {
-            const float* q = a0 + (size_t)i * Wq; const float* ks = kk + (size_t)i * L * Wq; const float* m = mk + (size_t)i * L;
-            std::vector<float> f((size_t)4 * Wq), h1((size_t)H1), sc((size_t)L);
-            float mx = -3.4e38f; bool any = false;
-            for (int l = 0; l < L; ++l) {
-              if (m[l] <= 0.f) { sc[(size_t)l] = -3.4e38f; continue; }
-              any = true;
-              const float* k = ks + (size_t)l * Wq;
-              for (int c = 0; c < Wq; ++c) { f[(size_t)c] = q[c]; f[(size_t)Wq + c] = k[c]; f[(size_t)2 * Wq + c] = q[c] - k[c]; f[(size_t)3 * Wq + c] = q[c] * k[c]; }
-              for (int h = 0; h < H1; ++h) { float acc = b1[h]; const float* w = W1 + (size_t)h * 4 * Wq; for (int c = 0; c < 4 * Wq; ++c) acc += w[c] * f[(size_t)c]; h1[(size_t)h] = 1.f / (1.f + std::exp(-acc)); }
-              float s3 = b3;
-              for (int h = 0; h < H2; ++h) { float acc = b2[h]; const float* w = W2 + (size_t)h * H1; for (int c = 0; c < H1; ++c) acc += w[c] * h1[(size_t)c]; s3 += w3[h] / (1.f + std::exp(-acc)); }
-              sc[(size_t)l] = s3; mx = std::max(mx, s3);
+          const float* w3 = pd.att[4].data(); const float b3 = pd.att[5][0];
+          att_hq.resize((size_t)B * H1);
+          Linear(a0, Wq, B, pd.Lq, att_hq.data(), false, threads);                     // (Wa + Wc) q + b1, once per sample
+          constexpr int kS = 16;
+          const int nblk = (B + kS - 1) / kS;
+#pragma omp parallel num_threads(threads) if (par)
+          {
+            std::vector<float> X((size_t)kS * L * 2 * Wq), h1((size_t)kS * L * H1), h2((size_t)kS * L * H2), sc((size_t)L);
+#pragma omp for schedule(static)
+            for (int blk = 0; blk < nblk; ++blk) {
+              const int s0 = blk * kS, s1 = std::min(B, s0 + kS), rows = (s1 - s0) * L;
+              for (int i = s0; i < s1; ++i) {
+                const float* q = a0 + (size_t)i * Wq; const float* ks = kk + (size_t)i * L * Wq;
+                for (int l = 0; l < L; ++l) {
+                  float* x = X.data() + ((size_t)(i - s0) * L + l) * 2 * Wq; const float* k = ks + (size_t)l * Wq;
+                  for (int c = 0; c < Wq; ++c) { x[c] = k[c]; x[Wq + c] = q[c] * k[c]; }
+                }
+              }
+              Linear(X.data(), 2 * Wq, rows, pd.L1, h1.data(), false, 1);
+              for (int i = s0; i < s1; ++i) {
+                const float* hq = att_hq.data() + (size_t)i * H1;
+                for (int l = 0; l < L; ++l) {
+                  float* h = h1.data() + ((size_t)(i - s0) * L + l) * H1;
+#pragma omp simd
+                  for (int j2 = 0; j2 < H1; ++j2) h[j2] = FastSigmoid(h[j2] + hq[j2]);
+                }
+              }
+              Linear(h1.data(), H1, rows, pd.L2, h2.data(), false, 1);
+              for (int i = s0; i < s1; ++i) {
+                const float* m = mk + (size_t)i * L; const float* ks = kk + (size_t)i * L * Wq;
+                float mx = -3.4e38f; bool any = false;
+                for (int l = 0; l < L; ++l) {
+                  const float* h = h2.data() + ((size_t)(i - s0) * L + l) * H2;
+                  float s3 = 0.f;
+#pragma omp simd reduction(+ : s3)
+                  for (int m2 = 0; m2 < H2; ++m2) s3 += w3[m2] * FastSigmoid(h[m2]);
+                  sc[(size_t)l] = s3 + b3;
+                  if (m[l] > 0.f) { any = true; mx = std::max(mx, sc[(size_t)l]); }
+                }
+                float* y = out + (size_t)i * Wq; for (int c = 0; c < Wq; ++c) y[c] = 0.f;
+                if (!any) continue;                              // no valid history position: zero vector (the module multiplies by mask.any())
+                float den = 0.f;
+                for (int l = 0; l < L; ++l) { sc[(size_t)l] = m[l] > 0.f ? FastExp(sc[(size_t)l] - mx) : 0.f; den += sc[(size_t)l]; }
+                const float inv = 1.f / den;
+                for (int l = 0; l < L; ++l) {
+                  if (sc[(size_t)l] == 0.f) continue;
+                  const float wl = sc[(size_t)l] * inv; const float* k = ks + (size_t)l * Wq;
+                  for (int c = 0; c < Wq; ++c) y[c] += wl * k[c];
+                }
+              }
             }
-            float* y = out + (size_t)i * Wq; for (int c = 0; c < Wq; ++c) y[c] = 0.f;
-            if (!any) continue;                                  // no valid history position: zero vector (the module multiplies by mask.any())
-            float den = 0.f;
-            for (int l = 0; l < L; ++l) if (m[l] > 0.f) { sc[(size_t)l] = std::exp(sc[(size_t)l] - mx); den += sc[(size_t)l]; }
-            for (int l = 0; l < L; ++l) if (m[l] > 0.f) { const float wl = sc[(size_t)l] / den; const float* k = ks + (size_t)l * Wq; for (int c = 0; c < Wq; ++c) y[c] += wl * k[c]; }
           }
           break;
         }
