@@ -31,25 +31,59 @@ def main():
     ap.add_argument("--policy", default="RR")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"], help="MLP compute dtype of the serving runtime")
     ap.add_argument("--gpus", type=int, default=1, help="serve from this many GPUs (one Processor replica per GPU, ModelConfig gpu_ids_list)")
+    ap.add_argument("--model", default="dlrm", help="dlrm (native architecture, trained on the fused engine) or an op-program model served by the same runtime: "
+                    "wdl, deepfm, dcn, dcnv2, masknet (Criteo-shaped); din, dssm, esmm, mmoe, dbmtl, ple, simple_multitask (Taobao-shaped, 50-step history)")
     a = ap.parse_args()
     from deeprec_b200.data import criteo_batch
     from deeprec_b200.models.dlrm_engine import CRITEO_KAGGLE_CARDINALITIES, DLRMConfig, DLRMEngine
     from deeprec_b200.serving import Processor, ProcessorGroup, encode_request, export_saved_model
     cards = CRITEO_KAGGLE_CARDINALITIES
-    eng = DLRMEngine(DLRMConfig(batch_size=8192, cardinalities=cards))
-    for s in range(8):
-        d, ids, y = criteo_batch(8192, 13, cards, seed=s)
-        eng.load_batch(d.cuda(), ids.cuda(), y.cuda()); eng.train_step()
     root = tempfile.mkdtemp()
-    export_saved_model(eng, os.path.join(root, "v1"), version=8, root=root)
-    del eng
-    torch.cuda.empty_cache()
+    if a.model == "dlrm":
+        eng = DLRMEngine(DLRMConfig(batch_size=8192, cardinalities=cards))
+        for s in range(8):
+            d, ids, y = criteo_batch(8192, 13, cards, seed=s)
+            eng.load_batch(d.cuda(), ids.cuda(), y.cuda()); eng.train_step()
+        export_saved_model(eng, os.path.join(root, "v1"), version=8, root=root)
+        del eng
+        torch.cuda.empty_cache()
+
+        def request(seed):
+            d, ids, _ = criteo_batch(a.batch, 13, cards, seed=seed)
+            return encode_request(d.numpy(), ids.numpy())
+    else:                                   # op-program models: trained a few steps through the framework API on the host, exported, served on the GPU
+        import deeprec_b200 as dr
+        from deeprec_b200.models.zoo import TAOBAO_MODELS, build_model
+        from deeprec_b200.serving import export_saved_model_program
+        L = 50
+        if a.model in TAOBAO_MODELS:
+            from deeprec_b200.data import taobao_batch
+            from deeprec_b200.models.rec_engine import din_ids
+            model = build_model(a.model, device="cpu")
+            opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+            for s in range(4):
+                b = taobao_batch(2048, L, 100000, 400000, 1000, seed=s)
+                loss = model.loss(b); opt.zero_grad(); loss.backward(); opt.step()
+            export_saved_model_program(model, os.path.join(root, "v1"), version=8, root=root, max_len=L)
+
+            def request(seed):
+                b = taobao_batch(a.batch, L, 100000, 400000, 1000, seed=seed)
+                return encode_request(np.zeros((a.batch, 1), np.float32), din_ids(b).numpy())
+        else:
+            small = [min(c, 200000) for c in cards]
+            model = build_model(a.model, device="cpu", cardinalities=small)
+            opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+            for s in range(4):
+                d, ids, y = criteo_batch(2048, 13, small, seed=s)
+                loss = model.loss(d, ids, y); opt.zero_grad(); loss.backward(); opt.step()
+            export_saved_model_program(model, os.path.join(root, "v1"), version=8, root=root)
+
+            def request(seed):
+                d, ids, _ = criteo_batch(a.batch, 13, small, seed=seed)
+                return encode_request(d.numpy(), ids.numpy())
     cfg = {"session_num": a.sessions, "select_session_policy": a.policy, "max_batch": max(256, a.batch), "model_update_interval_ms": 0, "mlp_dtype": a.dtype}
-    proc = Processor(os.path.join(root, "v1"), cfg) if a.gpus <= 1 else ProcessorGroup(os.path.join(root, "v1"), dict(cfg, gpu_ids_list=list(range(a.gpus))))
-    reqs = []
-    for s in range(16):
-        d, ids, _ = criteo_batch(a.batch, 13, cards, seed=1000 + s)
-        reqs.append(encode_request(d.numpy(), ids.numpy()))
+    proc = Processor(os.path.join(root, "v1"), cfg, device="cuda") if a.gpus <= 1 else ProcessorGroup(os.path.join(root, "v1"), dict(cfg, gpu_ids_list=list(range(a.gpus))))
+    reqs = [request(1000 + s) for s in range(16)]
     for r in reqs[:4]:
         assert proc.process(r)[0] == 200
     lat = [[] for _ in range(a.threads)]
@@ -70,7 +104,7 @@ def main():
     wall = time.perf_counter() - t0
     allv = np.sort(np.concatenate([np.array(x) for x in lat]))
     n = allv.size
-    print(json.dumps({"metric": "DLRM serving (Processor C ABI, SessionGroup)", "sessions": a.sessions, "client_threads": a.threads, "batch": a.batch,
+    print(json.dumps({"metric": f"{a.model} serving (Processor C ABI, SessionGroup)", "model": a.model, "sessions": a.sessions, "client_threads": a.threads, "batch": a.batch,
                       "requests": int(n), "qps": n / wall, "samples_per_s": n * a.batch / wall, "p50_ms": float(allv[n // 2]),
                       "p99_ms": float(allv[min(n - 1, int(n * 0.99))]), "mean_ms": float(allv.mean()), "dtype": a.dtype, "n_gpus": a.gpus, "model_info": proc.model_info()}))
     proc.close()
