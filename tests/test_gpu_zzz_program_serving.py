@@ -64,7 +64,7 @@ def test_op_program_models_on_the_gpu_processor(tmp_path, name):
         assert got.shape == ref.shape and np.isfinite(got).all()
         assert np.abs(host - ref).max() < 2e-5
         assert np.abs(got - ref).max() < TOL, np.abs(got - ref).max()
-        assert np.corrcoef(got, ref)[0, 1] > 0.999
+        assert np.abs(got - host).max() < TOL                              # and == the fp32 interpreter of the same program
         assert np.abs(gpu.predict(d.numpy()[:3], ids.numpy()[:, :3]) - ref[:3]).max() < TOL      # tiny batch: one partial GEMM tile
         ids2 = ids.clone(); ids2[:, :40] += 10 ** 9                         # unseen ids read the default rows
         assert np.abs(gpu.predict(d.numpy(), ids2.numpy()) - _ref(model, d, ids2)).max() < TOL
