@@ -45,6 +45,46 @@ class _StaleServerDef(Exception):
     pass
 
 
+# ---- native data plane (csrc/host/ps_server.cc): pulls / pushes over TCP served by C++ threads on the HostEV engine -----------------------
+_NATIVE_BOUND = False
+
+
+def _nlib():
+    global _NATIVE_BOUND
+    import ctypes as C
+    from .. import _native
+    lib = _native.host()
+    if not _NATIVE_BOUND:
+        P, INT, i64p = C.c_void_p, C.c_int, C.POINTER(C.c_int64)
+        lib.dr_ps_server_start.restype, lib.dr_ps_server_start.argtypes = P, [C.c_char_p, INT, C.POINTER(INT)]
+        lib.dr_ps_server_add_table.restype, lib.dr_ps_server_add_table.argtypes = INT, [P, P, INT, P]
+        lib.dr_ps_server_set_def.restype, lib.dr_ps_server_set_def.argtypes = None, [P, INT, INT]
+        lib.dr_ps_server_inflight.restype, lib.dr_ps_server_inflight.argtypes = INT, [P]
+        lib.dr_ps_server_stats.restype, lib.dr_ps_server_stats.argtypes = None, [P, C.POINTER(C.c_uint64)]
+        lib.dr_ps_server_stop.restype, lib.dr_ps_server_stop.argtypes = None, [P]
+        lib.dr_ps_client_connect.restype, lib.dr_ps_client_connect.argtypes = P, [C.c_char_p, INT]
+        lib.dr_ps_client_close.restype, lib.dr_ps_client_close.argtypes = None, [P]
+        lib.dr_ps_client_send.restype = INT
+        lib.dr_ps_client_send.argtypes = [P, INT, INT, INT, C.POINTER(INT), i64p, C.POINTER(P), C.POINTER(P), C.POINTER(INT)]
+        lib.dr_ps_partition.restype, lib.dr_ps_partition.argtypes = None, [P, C.c_int64, INT, P, P]
+        lib.dr_ps_client_recv.restype = INT
+        lib.dr_ps_client_recv.argtypes = [P, INT, i64p, C.POINTER(INT), C.POINTER(P), C.POINTER(C.c_uint64)]
+        _NATIVE_BOUND = True
+    return lib
+
+
+def ps_partition(flat: torch.Tensor, num_ps: int):
+    """(order, counts): positions of ``flat`` grouped by owning server (stable), keys per server -- one native pass instead of ``num_ps``
+    boolean masks (``ps_owner`` stays the definition: ``key % 1000 % num_ps``)."""
+    from .._native import ptr
+    k = flat.to(torch.int64).contiguous()
+    order = torch.empty(k.numel(), dtype=torch.int64)
+    counts = torch.zeros(num_ps, dtype=torch.int64)
+    if k.numel():
+        _nlib().dr_ps_partition(ptr(k), k.numel(), int(num_ps), ptr(order), ptr(counts))
+    return order, counts.tolist()
+
+
 def ps_owner(keys: torch.Tensor, num_ps: int) -> torch.Tensor:
     return torch.remainder(torch.remainder(keys.to(torch.int64), 1000), num_ps)
 
@@ -67,6 +107,34 @@ class ParameterServer:
         self._gate = threading.Condition()      # admission gate of pulls / pushes (elastic scaling fence)
         self._inflight = 0
         self.pushes = 0
+        # native data plane: a TCP listener served by C++ threads; tables register as they are created (plain host tables only)
+        self.native, self.native_port, self.native_ids = None, 0, {}
+        if os.environ.get("DEEPREC_PS_NATIVE", "1") != "0":
+            import ctypes as C
+            port = C.c_int(0)
+            h = _nlib().dr_ps_server_start(os.environ.get("DEEPREC_PS_BIND", "").encode(), 0, C.byref(port))
+            if h:
+                self.native, self.native_port = h, int(port.value)
+
+    def _native_def(self) -> None:
+        if self.native:
+            _nlib().dr_ps_server_set_def(self.native, int(self.def_version), int(self.frozen))
+
+    def _native_quiesce(self, timeout: float = 60.0) -> bool:
+        """Native requests admitted before the freeze have finished (the C++ side counts them)."""
+        import time
+        if not self.native:
+            return True
+        t0 = time.time()
+        while _nlib().dr_ps_server_inflight(self.native) > 0:
+            if time.time() - t0 > timeout:
+                return False
+            time.sleep(0.001)
+        return True
+
+    def native_endpoint(self):
+        """(host, port, {variable: (table id, dim)}) of the native data plane; port 0 when it is off."""
+        return _advertise_host(), self.native_port, dict(self.native_ids)
 
     # ---- variables ----------------------------------------------------------------------------------------------------
     def create_ev(self, name: str, dim: int, optimizer: str, opt_kw: dict, option: Optional[EmbeddingVariableOption], seed: int) -> bool:
@@ -77,6 +145,12 @@ class ParameterServer:
                 self.evs[name] = ev
                 self.opts[name] = make_optimizer(optimizer, [], [ev], global_step=GlobalStep(), **opt_kw)
                 self.ev_specs[name] = (dim, optimizer, dict(opt_kw), option, seed)
+                tbl = ev.table
+                if self.native and hasattr(tbl, "h") and type(tbl).__name__ == "HostTable":     # multi-tier tables stay on the RPC path
+                    import ctypes as C
+                    opt = self.opts[name]
+                    hp = opt._hyper(opt.param_groups[0])
+                    self.native_ids[name] = (int(_nlib().dr_ps_server_add_table(self.native, C.c_void_p(tbl.h), dim, C.byref(hp))), dim)
         return True
 
     def create_dense(self, name: str, value: torch.Tensor, lr: float) -> bool:
@@ -142,7 +216,13 @@ class ParameterServer:
         return True
 
     def stats(self) -> Dict[str, int]:
-        return {n: int(e.total_count()) for n, e in self.evs.items()} | {"pushes": self.pushes}
+        npush = 0
+        if self.native:
+            import ctypes as C
+            out = (C.c_uint64 * 6)()
+            _nlib().dr_ps_server_stats(self.native, out)
+            npush = int(out[1])
+        return {n: int(e.total_count()) for n, e in self.evs.items()} | {"pushes": self.pushes + npush}
 
     # ---- FileSliceSend / FileSliceRecv (kernels/file_slice_sendrecv_ops.cc): files travel in slices, never as one message ----------
     def file_write_slice(self, path: str, offset: int, data: bytes, truncate: bool) -> int:
@@ -170,8 +250,9 @@ class ParameterServer:
         placement; one that arrives later gets STALE_DEF and is re-routed by the client under the new server definition."""
         with self._gate:
             self.frozen = True
+            self._native_def()
             ok = self._gate.wait_for(lambda: self._inflight == 0, timeout=timeout)
-        return bool(ok)
+        return bool(ok) and self._native_quiesce(timeout)
 
     def fetch_params_meta(self) -> Dict[str, Tuple[int, int]]:
         """FetchParamsMeta: {variable: (dim, rows held by this PS)}."""
@@ -200,6 +281,7 @@ class ParameterServer:
         """UpdateServerDef: from now on requests must be made under ``def_version``."""
         with self.lock:
             self.active, self.def_version, self.frozen = new_active, def_version, False
+            self._native_def()
         return True
 
     def frequency(self, name: str, ids: torch.Tensor) -> torch.Tensor:
@@ -208,7 +290,14 @@ class ParameterServer:
     def save(self, prefix: str, step: int) -> str:
         from ..checkpoint.saver import Saver
         with self.lock:                  # pushes are applied under the same lock: the checkpoint is a consistent cut between two of them
-            return Saver(embedding_variables=list(self.evs.values())).save(f"{prefix}.ps{self.index}", step)
+            was = self.frozen
+            if self.native and not was:      # native pushes do not take self.lock: fence them for the duration of the snapshot (clients retry)
+                self.frozen = True; self._native_def(); self._native_quiesce()
+            try:
+                return Saver(embedding_variables=list(self.evs.values())).save(f"{prefix}.ps{self.index}", step)
+            finally:
+                if self.native and not was:
+                    self.frozen = False; self._native_def()
 
 
 def _srv() -> ParameterServer:
@@ -236,6 +325,7 @@ def _rpc_push_dense(*a): return _srv().push_dense(*a)
 def _rpc_stats(): return _srv().stats()
 def _rpc_frequency(*a): return _srv().frequency(*a)
 def _rpc_save(*a): return _srv().save(*a)
+def _rpc_native_endpoint(): return _srv().native_endpoint()
 
 
 def init_rpc(name: str, rank: int, world_size: int, master_port: int, master_addr: str = "127.0.0.1", threads: int = 8) -> None:
@@ -259,17 +349,164 @@ def run_ps(index: int, num_ps: int, num_workers: int, master_port: int, stats_pa
             json.dump(_SERVER.stats(), f)
 
 
+class _NativePush:
+    """Future of one asynchronous native push (set by the connection's sender thread)."""
+
+    def __init__(self):
+        self.result, self._ev = None, threading.Event()
+
+    def _set(self, r) -> None:
+        self.result = r
+        self._ev.set()
+
+    def wait(self):
+        self._ev.wait()
+        if isinstance(self.result, Exception):
+            raise self.result
+        return self.result
+
+
+class _NativeConn:
+    """A worker's link to the native data plane of one PS (csrc/host/ps_server.cc): TWO TCP connections -- pulls are synchronous on the first;
+    pushes go through a sender thread on the second (send + acknowledgement per push, in order), so a push being applied on the server never
+    delays the next pull, and the training loop never blocks on a multi-megabyte send.  ctypes releases the GIL around the socket calls."""
+
+    def __init__(self, host: str, port: int, ids: Dict[str, Tuple[int, int]]):
+        import queue
+        self.lib = _nlib()
+        self.h = self.lib.dr_ps_client_connect(host.encode(), int(port))
+        self.hp = self.lib.dr_ps_client_connect(host.encode(), int(port)) if self.h else None
+        if not self.h or not self.hp:
+            self.close()
+            raise ConnectionError(f"native PS data plane {host}:{port} unreachable")
+        self.ids = ids                                          # variable -> (table id, dim)
+        self.q: "queue.Queue" = queue.Queue()
+        self.sender = threading.Thread(target=self._send_loop, daemon=True)
+        self.sender.start()
+
+    def close(self) -> None:
+        if getattr(self, "sender", None) is not None and self.sender.is_alive():
+            self.q.put(None)
+            self.sender.join(timeout=30)
+        for a in ("h", "hp"):
+            if getattr(self, a, None):
+                self.lib.dr_ps_client_close(getattr(self, a)); setattr(self, a, None)
+
+    def _arrays(self, items, with_grads: bool):
+        import ctypes as C
+        nt = len(items)
+        tids, ns, dims = (C.c_int * nt)(), (C.c_int64 * nt)(), (C.c_int * nt)()
+        kp, gp, keep = (C.c_void_p * nt)(), (C.c_void_p * nt)(), []
+        for i, it in enumerate(items):
+            tid, dim = self.ids[it[0]]
+            k = it[1].to(torch.int64).contiguous()
+            keep.append(k)
+            tids[i], ns[i], dims[i], kp[i] = tid, k.numel(), dim, k.data_ptr() if k.numel() else None
+            if with_grads:
+                g = it[2].to(torch.float32).contiguous()
+                keep.append(g)
+                gp[i] = g.data_ptr() if g.numel() else None
+        return nt, tids, ns, dims, kp, gp, keep
+
+    def _send_loop(self) -> None:
+        import ctypes as C
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            fut, (nt, tids, ns, dims, kp, gp, _keep), dv = job
+            try:
+                if self.lib.dr_ps_client_send(self.hp, 2, int(dv), nt, tids, ns, kp, gp, dims) != 0:
+                    raise ConnectionError("native PS connection lost")
+                aux = C.c_uint64(0)
+                rc = self.lib.dr_ps_client_recv(self.hp, 0, None, None, None, C.byref(aux))
+                if rc < 0:
+                    raise ConnectionError("native PS connection lost")
+                if rc == 2:
+                    raise RuntimeError("native PS rejected a malformed push")
+                fut._set(STALE_DEF if rc == 1 else int(aux.value))
+            except Exception as e:  # noqa: BLE001 -- delivered to the waiter
+                fut._set(e)
+
+    def drain_until(self, fut=None) -> None:
+        """Block until every push handed to the sender thread so far has been acknowledged."""
+        done = _NativePush()
+        self.q.put((done, self._arrays([], True), -1))          # an empty push is answered in order after everything before it
+        done.wait()
+
+    def push(self, items, def_version: int) -> _NativePush:
+        f = _NativePush()
+        self.q.put((f, self._arrays(items, True), def_version))
+        return f
+
+    def pull_send(self, items, def_version: int):
+        nt, tids, ns, dims, kp, _gp, _keep = self._arrays(items, False)
+        if self.lib.dr_ps_client_send(self.h, 1, int(def_version), nt, tids, ns, kp, None, dims) != 0:
+            raise ConnectionError("native PS connection lost")
+        return nt, ns, dims
+
+    def pull_recv(self, ticket):
+        import ctypes as C
+        nt, ns, dims = ticket
+        rows = [torch.empty(int(ns[i]), int(dims[i]), dtype=torch.float32) for i in range(nt)]
+        rp = (C.c_void_p * nt)(*[r.data_ptr() if r.numel() else None for r in rows])
+        rc = self.lib.dr_ps_client_recv(self.h, nt, ns, dims, rp, None)
+        if rc < 0:
+            raise ConnectionError("native PS connection lost")
+        if rc == 2:
+            raise RuntimeError("native PS rejected a malformed pull")
+        return STALE_DEF if rc == 1 else rows
+
+
+def _advertise_host() -> str:
+    """Address workers reach this PS at: DEEPREC_PS_ADVERTISE, loopback for single-host jobs, else the interface that routes to the master."""
+    import socket
+    h = os.environ.get("DEEPREC_PS_ADVERTISE")
+    if h:
+        return h
+    master = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    if master in ("127.0.0.1", "localhost"):
+        return "127.0.0.1"
+    try:
+        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s_:
+            s_.connect((master, 9))
+            return s_.getsockname()[0]
+    except OSError:
+        return "127.0.0.1"
+
+
 class PSClient:
-    """Worker-side handle.  ``num_ps`` PS processes occupy RPC ranks [0, num_ps); this worker is rank num_ps + worker_index."""
+    """Worker-side handle.  ``num_ps`` PS processes occupy RPC ranks [0, num_ps); this worker is rank num_ps + worker_index.
+    ``transport``: "native" (default; DEEPREC_PS_TRANSPORT) sends sparse pulls / pushes over the C++ data plane of each PS and falls back to
+    RPC per request for variables a PS did not register there (multi-tier tables); "rpc" keeps everything on torch.distributed.rpc."""
 
     def __init__(self, worker_index: int, num_ps: int, num_workers: int, master_port: int, slice_bytes: int = 4 << 20,
-                 active_ps: Optional[int] = None):
+                 active_ps: Optional[int] = None, transport: Optional[str] = None):
         self.total_ps = num_ps                                  # processes in the job (dense parameters hash over all of them)
         self.num_ps = num_ps if active_ps is None else active_ps  # servers that currently own embedding shards
         self.def_version = 0
         self.worker_index, self.slice_elems = worker_index, max(1, slice_bytes // 4)
         init_rpc(f"worker{worker_index}", num_ps + worker_index, num_ps + num_workers, master_port)
         self._pending: List = []
+        self.transport = (transport or os.environ.get("DEEPREC_PS_TRANSPORT", "native")).lower()
+        self._conns: Dict[int, Optional[_NativeConn]] = {}
+
+    def _conn(self, p: int, names) -> Optional[_NativeConn]:
+        """Native connection to PS ``p`` if every variable in ``names`` is registered on its data plane, else None (-> RPC)."""
+        if self.transport != "native":
+            return None
+        c = self._conns.get(p, False)
+        if c is False or (c is not None and any(n not in c.ids for n in names)):
+            host, port, ids = rpc.rpc_sync(f"ps{p}", _rpc_native_endpoint)
+            if c not in (False, None):
+                c.ids = ids                                     # variables created after the connection was opened
+            else:
+                try:
+                    c = _NativeConn(host, port, ids) if port else None
+                except ConnectionError:
+                    c = None
+                self._conns[p] = c
+        return c if c is not None and all(n in c.ids for n in names) else None
 
     # ---- elastic scaling ---------------------------------------------------------------------------------------------------------
     def refresh_server_def(self) -> None:
@@ -308,6 +545,10 @@ class PSClient:
 
     def shutdown(self) -> None:
         self.wait()
+        for c in self._conns.values():
+            if c:
+                c.drain_until(None); c.close()
+        self._conns.clear()
         rpc.shutdown()
 
     def wait(self) -> None:
@@ -341,24 +582,26 @@ class PSClient:
 
     def _pull_many(self, reqs):
         per_ps: List[List[Tuple[str, torch.Tensor]]] = [[] for _ in range(self.num_ps)]
-        masks = []
+        orders = []
         for name, ids in reqs:
             flat = ids.reshape(-1)
-            own = ps_owner(flat, self.num_ps)
-            ms = [own == p for p in range(self.num_ps)]
-            masks.append(ms)
-            for p in range(self.num_ps):
-                per_ps[p].append((name, flat[ms[p]]))
-        futs = [rpc.rpc_async(f"ps{p}", _rpc_pull_many, args=(per_ps[p], self.def_version)) for p in range(self.num_ps)]
-        res = [f.wait() for f in futs]
+            order, counts = ps_partition(flat, self.num_ps)
+            orders.append(order)
+            for p, part in enumerate(torch.split(flat[order], counts)):
+                per_ps[p].append((name, part))
+        names = [n for n, _ in reqs]
+        conns = [self._conn(p, names) for p in range(self.num_ps)]
+        # every request is on the wire before the first answer is read: the servers work in parallel on either transport
+        tickets = [conns[p].pull_send(per_ps[p], self.def_version) if conns[p] is not None
+                   else rpc.rpc_async(f"ps{p}", _rpc_pull_many, args=(per_ps[p], self.def_version)) for p in range(self.num_ps)]
+        res = [conns[p].pull_recv(tickets[p]) if conns[p] is not None else tickets[p].wait() for p in range(self.num_ps)]
         if any(isinstance(r, str) for r in res):
             raise _StaleServerDef()
         out = []
         for i, (name, ids) in enumerate(reqs):
             dim = res[0][i].shape[1]
             rows = torch.empty(ids.numel(), dim)
-            for p in range(self.num_ps):
-                rows[masks[i][p]] = res[p][i]
+            rows[orders[i]] = torch.cat([res[p][i] for p in range(self.num_ps)])       # un-permute: one scatter per table
             out.append(rows.view(*ids.shape, dim))
         return out
 
@@ -376,13 +619,19 @@ class PSClient:
         per_ps: List[List] = [[] for _ in range(self.num_ps)]
         for name, ids, g in grads:
             flat, g2 = ids.reshape(-1), g.reshape(-1, g.shape[-1])
-            own = ps_owner(flat, self.num_ps)
+            order, counts = ps_partition(flat, self.num_ps)
+            fs, gs = torch.split(flat[order], counts), torch.split(g2[order], counts)
             for p in range(self.num_ps):
-                m = own == p
-                if m.any():
-                    per_ps[p].append((name, flat[m], g2[m]))
-        return [(rpc.rpc_async(f"ps{p}", _rpc_push_many, args=(per_ps[p], self.def_version)), per_ps[p])
-                for p in range(self.num_ps) if per_ps[p]]
+                if counts[p]:
+                    per_ps[p].append((name, fs[p], gs[p]))
+        out = []
+        for p in range(self.num_ps):
+            if not per_ps[p]:
+                continue
+            c = self._conn(p, [n for n, _i, _g in per_ps[p]])
+            fut = c.push(per_ps[p], self.def_version) if c is not None else rpc.rpc_async(f"ps{p}", _rpc_push_many, args=(per_ps[p], self.def_version))
+            out.append((fut, per_ps[p]))
+        return out
 
     def _settle_pushes(self, sent: List[Tuple[object, list]]) -> None:
         """Wait for pushes; ONLY the payloads a PS turned away are re-partitioned and re-sent (nothing is applied twice)."""

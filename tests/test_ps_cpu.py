@@ -98,12 +98,20 @@ def _proc(rank, port, tmp):
         assert client.send_file(1, os.path.join(tmp, "blob.bin"), os.path.join(tmp, "remote", "blob.bin"), slice_bytes=64 << 10) == len(blob)
         assert client.recv_file(1, os.path.join(tmp, "remote", "blob.bin"), os.path.join(tmp, "back.bin"), slice_bytes=100_000) == len(blob)
         assert open(os.path.join(tmp, "back.bin"), "rb").read() == blob
+    native = sorted(p for p, c in client._conns.items() if c is not None)        # PS reached over the C++ data plane
     with open(os.path.join(tmp, f"worker{j}.json"), "w") as fh:
-        json.dump({"losses": losses, "dense_moved": moved}, fh)
+        json.dump({"losses": losses, "dense_moved": moved, "native_ps": native, "transport": client.transport}, fh)
     client.shutdown()
 
 
-def test_async_ps_training(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("transport", ["native", "rpc"])
+def test_async_ps_training(tmp_path, transport, monkeypatch):
+    """``native``: sparse pulls / pushes travel over the C++ data plane (csrc/host/ps_server.cc: TCP, one server thread per worker, applies
+    straight on the HostEV engine); ``rpc``: everything over torch.distributed.rpc.  Same training, same checks."""
+    monkeypatch.setenv("DEEPREC_PS_TRANSPORT", transport)
     _spawn_roles(_proc, NUM_PS + NUM_WORKERS, str(tmp_path))
     stats = [json.load(open(tmp_path / f"ps{i}.json")) for i in range(NUM_PS)]
     workers = [json.load(open(tmp_path / f"worker{j}.json")) for j in range(NUM_WORKERS)]
@@ -112,6 +120,7 @@ def test_async_ps_training(tmp_path):
     assert sum(s["user"] for s in stats) <= 50 and sum(s["item"] for s in stats) <= 80
     assert sum(s["pushes"] for s in stats) >= NUM_WORKERS * STEPS * 2
     assert all(w["dense_moved"] > 0 and all(l == l for l in w["losses"]) for w in workers)
+    assert all(w["transport"] == transport and w["native_ps"] == (list(range(NUM_PS)) if transport == "native" else []) for w in workers), workers
     # the PS-side checkpoint holds exactly the admitted keys of each shard
     from deeprec_b200.checkpoint.saver import BundleReader
     import glob
