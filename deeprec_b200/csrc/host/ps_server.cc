@@ -10,8 +10,8 @@
 //     reads, TCP_NODELAY; every connection owns its receive / send buffers)
 //   * PULL  = FuseRecv: ONE message carries the keys of every table of the step; rows come back in request order
 //   * PUSH  = sparse gradients of every table in ONE message; the server dedups + applies through dr_host_ev_apply_raw; the optimizer
-//     hyper-state (global step, beta powers) advances under a per-table mutex, the row updates themselves run lock-free on the engine
-//     (the reference's "lock-free graph execution on PS": concurrent workers update rows Hogwild-style)
+//     hyper-state (global step, beta powers) advances under a per-table mutex; rows sit behind a per-table reader / writer lock (pulls
+//     shared, a push exclusive for its apply; tables independent) -- DEEPREC_PS_HOGWILD=1 drops it for the reference's lock-free execution
 //   * elastic scaling fence: every request carries the server-definition version it was partitioned under; a frozen server or a version
 //     mismatch answers STALE without touching a row; in-flight requests are counted so IsReadyScaling can wait for a drained server
 //
@@ -26,9 +26,11 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -70,7 +72,12 @@ bool WriteAll(int fd, const void* buf, size_t n) {
 struct PsTable {
   void* ev = nullptr; int dim = 0;
   DrOptHyper hp{}; std::mutex mu;                 // optimizer hyper-state: step counter / beta powers advance once per push
+  // rows: pulls of a table run concurrently (shared), a push excludes them for the duration of its apply (exclusive) -- a row is never
+  // read half-updated and two pushes never interleave on a row; tables are independent.  DEEPREC_PS_HOGWILD=1 drops this lock: the
+  // reference's lock-free PS execution (updates may be lost / torn when two workers hit the same key at once).
+  std::shared_mutex rows;
 };
+const bool kHogwild = [] { const char* e = getenv("DEEPREC_PS_HOGWILD"); return e && e[0] == '1'; }();
 
 struct PsServer {
   int listen_fd = -1, port = 0;
@@ -140,7 +147,11 @@ struct PsServer {
             // keys sit at an arbitrary offset inside the receive buffer: 8-byte alignment is not guaranteed -> aligned copy
             std::vector<int64_t> keys(it.n);
             if (it.n) memcpy(keys.data(), in.data() + it.keys_off, (size_t)it.n * 8);
-            if (it.n) dr_host_ev_lookup(it.t->ev, keys.data(), it.n, reinterpret_cast<float*>(out.data() + o));
+            if (it.n) {
+              std::shared_lock<std::shared_mutex> rl(it.t->rows, std::defer_lock);
+              if (!kHogwild) rl.lock();
+              dr_host_ev_lookup(it.t->ev, keys.data(), it.n, reinterpret_cast<float*>(out.data() + o));
+            }
             o += (size_t)it.n * it.t->dim * 4;
           }
           body = o - 16;
@@ -158,7 +169,11 @@ struct PsServer {
             std::vector<int64_t> keys(it.n); std::vector<float> grads((size_t)it.n * it.t->dim);
             memcpy(keys.data(), in.data() + it.keys_off, (size_t)it.n * 8);
             memcpy(grads.data(), in.data() + it.grads_off, grads.size() * 4);
-            dr_host_ev_apply_raw(it.t->ev, keys.data(), it.n, grads.data(), it.t->dim, &hp);       // dedup + segment-sum + row-wise optimizer
+            {
+              std::unique_lock<std::shared_mutex> wl(it.t->rows, std::defer_lock);
+              if (!kHogwild) wl.lock();
+              dr_host_ev_apply_raw(it.t->ev, keys.data(), it.n, grads.data(), it.t->dim, &hp);     // dedup + segment-sum + row-wise optimizer
+            }
             pushes.fetch_add(1, std::memory_order_relaxed);
           }
         } else {

@@ -87,3 +87,28 @@ def test_cpu_serving_runtime_under_sanitizers(tmp_path, sanitizer):
     else:
         pytest.skip("sanitizer runtime is not usable in this environment")
     assert r.returncode == 0 and "CPU_SERVING_STRESS_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
+
+
+@pytest.mark.parametrize("sanitizer", ["thread", "address"])
+def test_native_ps_data_plane_under_sanitizers(tmp_path, sanitizer):
+    """csrc/host/ps_server.cc: four workers x (pull + push connections) against one server over real TCP while the scaling fence toggles; every
+    accepted push applied exactly once, STALE answers keep the stream in sync, the fence drains, stop() joins with connections open."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / f"ps_stress_{sanitizer}")
+    host = os.path.join(ROOT, "deeprec_b200", "csrc", "host")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", f"-fsanitize={sanitizer}", "-fno-omit-frame-pointer", "-pthread", os.path.join(ROOT, "tests", "native", "ps_stress.cc"),
+           os.path.join(host, "host_engine.cc"), os.path.join(host, "ps_server.cc"), "-o", exe]
+    b = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip(f"-fsanitize={sanitizer} unsupported here")
+    assert b.returncode == 0, b.stderr[-3000:]
+    run = ["setarch", "-R", exe] if sanitizer == "thread" and shutil.which("setarch") else [exe]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 second_deadlock_stack=1", ASAN_OPTIONS="detect_leaks=1")
+    for attempt in range(3):
+        r = subprocess.run(run, capture_output=True, text=True, timeout=900, env=env)
+        if r.returncode == 0 or not ("tpp.c" in r.stderr or "unexpected memory mapping" in r.stderr):
+            break
+    else:
+        pytest.skip("sanitizer runtime is not usable in this environment (glibc / ASLR incompatibility)")
+    assert r.returncode == 0 and "PS_STRESS_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
