@@ -147,9 +147,49 @@ def cuda_available() -> bool:
     return torch.cuda.is_available()
 
 
+_EMU = None          # libdeeprec_cuda_emu.so (csrc/cuda/emu/cuda_emu.h): the SIMT kernels compiled for the host
+_EMU_DEPTH = 0
+
+
+class cuda_emulation:
+    """``with cuda_emulation():`` -- the op wrappers that support it treat CPU tensors as device tensors and call the CUDA-on-CPU emulation
+    build of the same kernels (one host thread per CUDA thread; ``sanitize="address"`` / ``"thread"`` builds need the sanitizer runtime
+    preloaded).  For CPU CI of kernel logic, never a production path: it is 3-4 orders of magnitude slower than the GPU."""
+
+    def __init__(self, sanitize: str | None = None):
+        self.sanitize = sanitize or os.environ.get("DEEPREC_EMU_SANITIZE") or None
+
+    def __enter__(self):
+        global _EMU, _EMU_DEPTH
+        with _LOCK:
+            if _EMU is None or getattr(_EMU, "_sanitize", None) != self.sanitize:
+                lib = C.CDLL(_build.build_cuda_emu(self.sanitize))
+                lib._sanitize = self.sanitize
+                _EMU = lib
+            _EMU_DEPTH += 1
+        return _EMU
+
+    def __exit__(self, *exc):
+        global _EMU_DEPTH
+        with _LOCK:
+            _EMU_DEPTH -= 1
+        return False
+
+
+def emu_active() -> bool:
+    return _EMU_DEPTH > 0
+
+
+def on_device(t: torch.Tensor) -> bool:
+    """Dispatch predicate of the op wrappers: CUDA tensors, or any tensor while the kernel emulation is active."""
+    return t.is_cuda or _EMU_DEPTH > 0
+
+
 def cuda():
     """The sm_100a kernel library.  Raises if it is missing (never falls back silently)."""
     global _CUDA
+    if _EMU_DEPTH > 0:
+        return _EMU
     if _CUDA is None:
         with _LOCK:
             if _CUDA is None:
@@ -182,4 +222,6 @@ def ptr(t: torch.Tensor | None):
 
 
 def stream_ptr():
+    if _EMU_DEPTH > 0:
+        return None
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)

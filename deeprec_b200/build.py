@@ -44,17 +44,6 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
-def _site_cutlass_include() -> list[str]:
-    try:
-        import flashinfer  # noqa: F401  (only for its vendored header tree)
-        p = os.path.join(os.path.dirname(flashinfer.__file__), "data", "cutlass", "include")
-        if os.path.isdir(p):
-            return ["-I" + p]
-    except Exception:
-        pass
-    return []
-
-
 def _stamp(srcs: list[str], flags: list[str]) -> str:
     h = hashlib.sha1()
     for f in flags:
@@ -124,6 +113,112 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     _run([NVCC] + ARCH_FLAGS + ["-shared", "-Xcompiler", "-fPIC", "-cudart", "static"] + objs + ["-o", out])
+    open(out + ".stamp", "w").write(stamp)
+    return out
+
+
+# ---- CUDA-on-CPU emulation build (csrc/cuda/emu/cuda_emu.h): the SIMT kernels compiled by g++, one host thread per CUDA thread -----------------
+# Sources without tcgen05 / TMA / mbarrier code.  The library exports the same dr_* C entry points as libdeeprec_cuda.so, taking host pointers.
+EMU_SOURCES = [
+    "cuda/table_kernels.cu",
+    "cuda/embedding_kernels.cu",
+    "cuda/optimizer_kernels.cu",
+    "cuda/dense_kernels.cu",
+    "cuda/interaction_kernels.cu",      # SIMT variants only (the tcgen05 kernels are compiled out)
+    "cuda/fused_ops.cu",
+    "cuda/program_kernels.cu",
+    "cuda/sparse_utils.cu",
+    "cuda/attention_kernels.cu",
+    "cuda/serving_runtime.cu",
+    "cuda/emu/emu_stubs.cu",            # host-loop stand-ins for the tcgen05 GEMM entry points
+]
+
+
+def _split_top_level(text: str) -> list[str]:
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur.strip())
+    return parts
+
+
+def emu_translate(src: str) -> str:
+    """``kernel<T><<<grid, block, smem, stream>>>(args);`` -> ``emu::launch(grid, block, smem, stream, [&] { kernel<T>(args); });`` and
+    ``extern __shared__ T name[];`` -> a pointer into the block's dynamic shared memory.  Everything else is handled by macros / inline functions."""
+    import re
+    out, pos = [], 0
+    launch = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;(){}]*>)?)\s*<<<")
+    while True:
+        m = launch.search(src, pos)
+        if not m:
+            out.append(src[pos:])
+            break
+        end_cfg = src.index(">>>", m.end())
+        cfg = _split_top_level(src[m.end():end_cfg])
+        cfg += ["0"] * (4 - len(cfg))
+        i = end_cfg + 3
+        while src[i].isspace():
+            i += 1
+        assert src[i] == "(", "kernel launch without an argument list"
+        depth, j = 0, i
+        while True:
+            depth += src[j] == "("
+            depth -= src[j] == ")"
+            if depth == 0:
+                break
+            j += 1
+        out.append(src[pos:m.start()])
+        out.append(f"emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({cfg[2]}), (cudaStream_t)({cfg[3]}), [&] {{ {m.group(1)}{src[i:j + 1]}; }})")
+        pos = j + 1
+    text = "".join(out)
+    text = re.sub(r"extern\s+__shared__\s+((?:__align__\(\d+\)\s+)?)([\w:<> ]+?)\s+(\w+)\[\];",
+                  lambda m: f"{m.group(2)}* {m.group(3)} = ({m.group(2)}*)emu::dyn_smem();", text)
+    return text
+
+
+def build_cuda_emu(sanitize: str | None = None, force: bool = False, sources: list[str] | None = None) -> str:
+    """g++ build of the SIMT kernels (``-DDR_CUDA_EMU``).  ``sanitize`` = ``"address"`` / ``"thread"`` / ``"undefined"`` instruments the kernels
+    themselves: the library then has to be loaded by a process that preloads the sanitizer runtime (tests/native/emu_driver.py does)."""
+    emu_dir = os.path.join(OBJ, "emu" + ("_" + sanitize if sanitize else ""))
+    os.makedirs(os.path.join(emu_dir, "cuda", "emu"), exist_ok=True)
+    out = os.path.join(LIB, "libdeeprec_cuda_emu" + ("_" + sanitize.replace(",", "_") if sanitize else "") + ".so")
+    names = sources or EMU_SOURCES
+    srcs = [os.path.join(CSRC, s) for s in names]
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include")
+    flags = ["-O1" if sanitize else "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DDR_CUDA_EMU", "-x", "c++", "-I" + cuda_inc, "-I" + CSRC,
+             "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-deprecated-declarations"]
+    if sanitize:
+        flags += ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"]
+    stamp = _stamp(srcs + [os.path.join(CSRC, "cuda", "emu", "cuda_emu.h")], flags + names)
+    if not force and _up_to_date(out, stamp):
+        return out
+    # translated copies keep the csrc layout so that "common.cuh" / "../common/ev_types.h" resolve next to them
+    for d in ("common", "cuda", os.path.join("cuda", "emu")):
+        os.makedirs(os.path.join(emu_dir, d), exist_ok=True)
+        for fn in os.listdir(os.path.join(CSRC, d)):
+            if fn.endswith((".h", ".cuh")):
+                with open(os.path.join(CSRC, d, fn)) as fh:
+                    text = fh.read()
+                with open(os.path.join(emu_dir, d, fn), "w") as fh:
+                    fh.write(emu_translate(text) if fn.endswith(".cuh") else text)
+    tus = []
+    for s in srcs:
+        tu = os.path.join(emu_dir, os.path.relpath(s, CSRC) + ".cc")
+        with open(s) as fh:
+            text = fh.read()
+        with open(tu, "w") as fh:
+            fh.write(f'#line 1 "{s}"\n' + emu_translate(text))
+        tus.append(tu)
+    _run(["g++"] + flags + tus + ["-o", out])
     open(out + ".stamp", "w").write(stamp)
     return out
 

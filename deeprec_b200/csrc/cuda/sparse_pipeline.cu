@@ -178,7 +178,7 @@ __device__ __forceinline__ void sp_touch(const DrDeviceTable& TB, bool touch, in
   if (touch) {
     atomicAdd(&TB.slots[pos].freq, occ);
     int4 hi;                                                                             // {row_of, tag, dirty, pad}
-    asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(&TB.slots[pos].row_of));
+    DR_LD_V4_VOLATILE(hi, &TB.slots[pos].row_of);
     if (hi.z == 0) TB.slots[pos].dirty = 1;
     claim = ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1;
   }
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(256) k_sp_gather(const __nv_bfloat16* __restri
     const int64_t b = i / C; const int c = (int)(i % C);
     const int32_t gs = inv[b * ldinv + c];
     uint2 v = make_uint2(0u, 0u);
-    if (gs >= 0) asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(urow + (int64_t)gs * dim + 4 * lane) : "memory");
+    if (gs >= 0) DR_LD_V2_VOLATILE_U32(v, urow + (int64_t)gs * dim + 4 * lane);
     *reinterpret_cast<uint2*>(out + i * dim + 4 * lane) = v;
   }
 }

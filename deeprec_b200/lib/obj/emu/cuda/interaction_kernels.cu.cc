@@ -1,3 +1,4 @@
+#line 1 "/root/repo/deeprec_b200/csrc/cuda/interaction_kernels.cu"
 // Feature-interaction kernels: DLRM pairwise dot (strict lower triangle of F F^T, concatenated with the
 // dense vector), DeepFM second-order FM term, DIN attention pooling.  One warp per sample; lane i owns
 // feature row i in registers, rows are broadcast through shared memory.
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
                                                     const int32_t* __restrict__ inv, int ldinv) {
   pdl_sync();
   constexpr int D = 16;
-  extern __shared__ __align__(128) uint8_t dyn[];
+  uint8_t* dyn = (uint8_t*)emu::dyn_smem();
   uint8_t* sA = dyn;                                   // blockdiag(S): [16 row-groups][16 K-chunks][8 rows][16 B] = 32 KB
   uint8_t* sB = dyn + 32768;                           // F^T: [2 d-groups][16 K-chunks][8 d][16 B] = 4 KB
   __nv_bfloat16* sG = reinterpret_cast<__nv_bfloat16*>(dyn + 32768 + 4096);   // [4][512] dZ rows
@@ -517,9 +518,9 @@ int dr_cuda_dot_interaction_fwd(const void* x, int64_t ldx, const void* emb, int
 #endif
   int grid = grid_for((B + 7) / 8, 1, kNumSMs * 6);
   switch (D) {
-    case 8: k_dot_fwd<8><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz); break;
-    case 16: k_dot_fwd<16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz); break;
-    case 32: k_dot_fwd<32><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz); break;
+    case 8: emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_dot_fwd<8>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz); }); break;
+    case 16: emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_dot_fwd<16>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz); }); break;
+    case 32: emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_dot_fwd<32>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)Z, ldz); }); break;
     default: return -3;
   }
   DR_LAUNCH_CHECK();
@@ -543,7 +544,7 @@ int dr_cuda_dot_interaction_bwd(const void* dZ, int64_t ldz, const void* x, int6
   }
 #endif
   int grid = grid_for((B + 7) / 8, 1, kNumSMs * 6);
-#define BWD(DD) k_dot_bwd<DD><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b)
+#define BWD(DD) emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_dot_bwd<DD>((const __nv_bfloat16*)dZ, ldz, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)emb, emb_stride_t, emb_stride_b, T, B, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)demb, demb_stride_t, demb_stride_b); })
   switch (D) { case 8: BWD(8); break; case 16: BWD(16); break; case 32: BWD(32); break; default: return -3; }
 #undef BWD
   DR_LAUNCH_CHECK();
@@ -553,10 +554,10 @@ int dr_cuda_dot_interaction_bwd(const void* dZ, int64_t ldz, const void* x, int6
 int dr_cuda_fm_fwd(const void* emb, int64_t st, int64_t sb, int T, int D, int64_t B, void* out, int64_t ldo, float* sum_out, cudaStream_t s) {
   int grid = grid_for(B * (D / 8), 256);
   switch (D) {
-    case 8: k_fm_fwd<8><<<grid, 256, 0, s>>>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); break;
-    case 16: k_fm_fwd<16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); break;
-    case 32: k_fm_fwd<32><<<grid, 256, 0, s>>>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); break;
-    case 64: k_fm_fwd<64><<<grid, 256, 0, s>>>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); break;
+    case 8: emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_fm_fwd<8>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); }); break;
+    case 16: emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_fm_fwd<16>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); }); break;
+    case 32: emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_fm_fwd<32>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); }); break;
+    case 64: emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_fm_fwd<64>((const __nv_bfloat16*)emb, st, sb, T, B, (__nv_bfloat16*)out, ldo, sum_out); }); break;
     default: return -3;
   }
   DR_LAUNCH_CHECK();
@@ -566,7 +567,7 @@ int dr_cuda_fm_fwd(const void* emb, int64_t st, int64_t sb, int T, int D, int64_
 int dr_cuda_fm_bwd(const void* dfm, int64_t ldd, const void* emb, int64_t st, int64_t sb, const float* sum_in, int T, int D, int64_t B,
                    void* demb, int64_t dst, int64_t dsb, int accumulate, cudaStream_t s) {
   int grid = grid_for(B * (D / 8), 256);
-#define FMB(DD) k_fm_bwd<DD><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dfm, ldd, (const __nv_bfloat16*)emb, st, sb, sum_in, T, B, (__nv_bfloat16*)demb, dst, dsb, accumulate)
+#define FMB(DD) emu::launch(dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_fm_bwd<DD>((const __nv_bfloat16*)dfm, ldd, (const __nv_bfloat16*)emb, st, sb, sum_in, T, B, (__nv_bfloat16*)demb, dst, dsb, accumulate); })
   switch (D) { case 8: FMB(8); break; case 16: FMB(16); break; case 32: FMB(32); break; case 64: FMB(64); break; default: return -3; }
 #undef FMB
   DR_LAUNCH_CHECK();

@@ -1,3 +1,4 @@
+#line 1 "/root/repo/deeprec_b200/csrc/cuda/table_kernels.cu"
 // sm_100a kernels for the device EmbeddingVariable: fused find-or-insert (+admission, frequency,
 // version, dedup claim), row gather, metadata queries, rehash, eviction scan, snapshot, import.
 //
@@ -327,13 +328,13 @@ inline int grid_for(int64_t n, int block, int max_blocks = 0) {
 extern "C" {
 
 int dr_cuda_table_init_slots(void* slots, int64_t n, cudaStream_t s) {
-  k_init_slots<<<grid_for(n, 256, kNumSMs * 8), 256, 0, s>>>((DrSlot*)slots, n);
+  emu::launch(dim3(grid_for(n, 256, kNumSMs * 8)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_init_slots((DrSlot*)slots, n); });
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t s) {
-  k_fill_i64<<<grid_for(n, 256), 256, 0, s>>>(p, v, n);
+  emu::launch(dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_fill_i64(p, v, n); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -369,33 +370,33 @@ int dr_cuda_table_gather(const DrDeviceTable* tables_dev, const int32_t* table_m
 
 int dr_cuda_table_get_meta(const DrDeviceTable* t_host, const int64_t* keys, int64_t n, int64_t* freq, int64_t* version, int32_t* row, cudaStream_t s) {
   if (n == 0) return 0;
-  k_get_meta<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, n, freq, version, row);
+  emu::launch(dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_get_meta(*t_host, keys, n, freq, version, row); });
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_table_gather_slot(const DrDeviceTable* t_host, const int64_t* keys, int64_t n, int slot, float* out, cudaStream_t s) {
   if (n == 0) return 0;
-  k_gather_slot<<<grid_for(n * t_host->dim, 256), 256, 0, s>>>(*t_host, keys, n, slot, out);
+  emu::launch(dim3(grid_for(n * t_host->dim, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_gather_slot(*t_host, keys, n, slot, out); });
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_table_rehash(const DrDeviceTable* old_host, const DrDeviceTable* new_host, cudaStream_t s) {
-  k_rehash<<<grid_for(old_host->capacity, 256), 256, 0, s>>>(*old_host, *new_host);
+  emu::launch(dim3(grid_for(old_host->capacity, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_rehash(*old_host, *new_host); });
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_table_shrink(const DrDeviceTable* t_host, int step, int32_t* n_evicted, cudaStream_t s) {
-  k_shrink<<<grid_for(t_host->capacity, 256), 256, 0, s>>>(*t_host, step, n_evicted);
+  emu::launch(dim3(grid_for(t_host->capacity, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_shrink(*t_host, step, n_evicted); });
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_table_remove(const DrDeviceTable* t_host, const int64_t* keys, int64_t n, int32_t* n_removed, cudaStream_t s) {
   if (n == 0) return 0;
-  k_remove<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, n, n_removed);
+  emu::launch(dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_remove(*t_host, keys, n, n_removed); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -403,8 +404,8 @@ int dr_cuda_table_remove(const DrDeviceTable* t_host, const int64_t* keys, int64
 int dr_cuda_table_snapshot(const DrDeviceTable* t_host, int dirty_only, int part_id, int part_num, int32_t* counts,
                            int64_t* keys, float* rows, int64_t* freqs, int64_t* versions, int64_t* fkeys, int64_t* ffreqs,
                            int64_t* fversions, cudaStream_t s) {
-  k_snapshot<<<grid_for(t_host->capacity, 256), 256, 0, s>>>(*t_host, dirty_only, part_id, part_num, counts, keys, rows, freqs,
-                                                            versions, fkeys, ffreqs, fversions);
+  emu::launch(dim3(grid_for(t_host->capacity, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_snapshot(*t_host, dirty_only, part_id, part_num, counts, keys, rows, freqs,
+                                                            versions, fkeys, ffreqs, fversions); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -412,13 +413,13 @@ int dr_cuda_table_snapshot(const DrDeviceTable* t_host, int dirty_only, int part
 int dr_cuda_table_export_keys(const DrDeviceTable* t_host, const int64_t* keys, int64_t n, float* rows, int64_t* freqs, int64_t* versions,
                                uint8_t* found, cudaStream_t s) {
   if (n == 0) return 0;
-  k_export_keys<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, n, rows, freqs, versions, found);
+  emu::launch(dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_export_keys(*t_host, keys, n, rows, freqs, versions, found); });
   DR_LAUNCH_CHECK();
   return 0;
 }
 
 int dr_cuda_table_clear_dirty(const DrDeviceTable* t_host, cudaStream_t s) {
-  k_clear_dirty<<<grid_for(t_host->capacity, 256), 256, 0, s>>>(*t_host);
+  emu::launch(dim3(grid_for(t_host->capacity, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_clear_dirty(*t_host); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -427,7 +428,7 @@ int dr_cuda_table_import(const DrDeviceTable* t_host, const int64_t* keys, const
                          const int64_t* versions, int64_t n, int part_id, int part_num, int reset_version, int32_t* n_kept,
                          cudaStream_t s) {
   if (n == 0) return 0;
-  k_import<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, rows, ncols, freqs, versions, n, part_id, part_num, reset_version, n_kept);
+  emu::launch(dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_import(*t_host, keys, rows, ncols, freqs, versions, n, part_id, part_num, reset_version, n_kept); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -436,13 +437,13 @@ int dr_cuda_table_import(const DrDeviceTable* t_host, const int64_t* keys, const
 int dr_cuda_table_import_cow(const DrDeviceTable* t_host, const int64_t* keys, const float* rows, int ncols, int64_t n, int32_t* retired,
                              int32_t* n_retired, int32_t* n_kept, cudaStream_t s) {
   if (n == 0) return 0;
-  k_import_cow<<<grid_for(n, 256), 256, 0, s>>>(*t_host, keys, rows, ncols, n, retired, n_retired, n_kept);
+  emu::launch(dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_import_cow(*t_host, keys, rows, ncols, n, retired, n_retired, n_kept); });
   DR_LAUNCH_CHECK();
   return 0;
 }
 int dr_cuda_table_free_rows(const DrDeviceTable* t_host, const int32_t* rows, const int32_t* n_dev, int64_t max_n, cudaStream_t s) {
   if (max_n == 0) return 0;
-  k_free_rows<<<grid_for(max_n, 256), 256, 0, s>>>(*t_host, rows, n_dev);
+  emu::launch(dim3(grid_for(max_n, 256)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_free_rows(*t_host, rows, n_dev); });
   DR_LAUNCH_CHECK();
   return 0;
 }

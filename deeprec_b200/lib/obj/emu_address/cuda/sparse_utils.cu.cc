@@ -1,3 +1,4 @@
+#line 1 "/root/repo/deeprec_b200/csrc/cuda/sparse_utils.cu"
 // Sparse utility kernels of the input / embedding front-end, sm_100a.  One C entry per op, every data-dependent size stays on the device
 // (the python wrapper reads the count once, where the reference blocks on a D2H copy of the cub select result).
 //
@@ -181,19 +182,19 @@ int dr_cuda_sparse_prune_fill(const int64_t* values, const int64_t* rows, const 
   PfWs w = carve(workspace, nnz, B);
   DR_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, (size_t)B * 4, s));
   if (nnz > 0) {
-    k_spu_flags<<<grid_el(nnz), 256, 0, s>>>(values, rows, weights, nnz, B, prune, w.keep, w.cnt);
+    emu::launch(dim3(grid_el(nnz)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_flags(values, rows, weights, nnz, B, prune, w.keep, w.cnt); });
     DR_LAUNCH_CHECK();
     size_t cb = w.cub_bytes;
     DR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub, cb, w.keep, w.scan_keep, (int)nnz, s));
   }
-  k_spu_rows<<<grid_el(B), 256, 0, s>>>(w.cnt, B, fill, w.row_out_in, empty_indicator);
+  emu::launch(dim3(grid_el(B)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_rows(w.cnt, B, fill, w.row_out_in, empty_indicator); });
   DR_LAUNCH_CHECK();
   size_t cb = w.cub_bytes;
   DR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub, cb, w.cnt, w.row_kept, (int)B, s));
   cb = w.cub_bytes;
   DR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub, cb, w.row_out_in, w.row_out, (int)B, s));
-  k_spu_emit<<<grid_el(nnz > B ? nnz : B), 256, 0, s>>>(values, rows, weights, nnz, B, fill, default_id, w.keep, w.scan_keep, w.cnt, w.row_kept, w.row_out, w.row_out_in,
-                                                      out_values, out_rows, out_weights, out_count);
+  emu::launch(dim3(grid_el(nnz > B ? nnz : B)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_emit(values, rows, weights, nnz, B, fill, default_id, w.keep, w.scan_keep, w.cnt, w.row_kept, w.row_out, w.row_out_in,
+                                                      out_values, out_rows, out_weights, out_count); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -204,14 +205,14 @@ int dr_cuda_sparse_slice(const int64_t* indices, const void* values, int elem_by
   if (nnz <= 0) { DR_CUDA_CHECK(cudaMemsetAsync(out_count, 0, 8, s)); return 0; }
   if (nnz >= (int64_t)1 << 31 || R <= 0 || R > 8 || (elem_bytes != 4 && elem_bytes != 8)) return -2;
   PfWs w = carve(workspace, nnz, 1);
-  k_spu_slice_flags<<<grid_el(nnz), 256, 0, s>>>(indices, nnz, R, start_dev, size_dev, w.keep);
+  emu::launch(dim3(grid_el(nnz)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_slice_flags(indices, nnz, R, start_dev, size_dev, w.keep); });
   DR_LAUNCH_CHECK();
   size_t cb = w.cub_bytes;
   DR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub, cb, w.keep, w.scan_keep, (int)nnz, s));
   if (elem_bytes == 4)
-    k_spu_slice_emit<uint32_t><<<grid_el(nnz), 256, 0, s>>>(indices, (const uint32_t*)values, nnz, R, start_dev, w.keep, w.scan_keep, out_indices, (uint32_t*)out_values, out_count);
+    emu::launch(dim3(grid_el(nnz)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_slice_emit<uint32_t>(indices, (const uint32_t*)values, nnz, R, start_dev, w.keep, w.scan_keep, out_indices, (uint32_t*)out_values, out_count); });
   else
-    k_spu_slice_emit<uint64_t><<<grid_el(nnz), 256, 0, s>>>(indices, (const uint64_t*)values, nnz, R, start_dev, w.keep, w.scan_keep, out_indices, (uint64_t*)out_values, out_count);
+    emu::launch(dim3(grid_el(nnz)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_slice_emit<uint64_t>(indices, (const uint64_t*)values, nnz, R, start_dev, w.keep, w.scan_keep, out_indices, (uint64_t*)out_values, out_count); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -220,7 +221,7 @@ int dr_cuda_sparse_reshape(const int64_t* indices, int64_t nnz, int R0, const in
                            cudaStream_t s) {
   if (nnz <= 0) return 0;
   if (R0 <= 0 || R1 <= 0 || R0 > 8 || R1 > 8) return -2;
-  k_spu_reshape<<<grid_el(nnz), 256, 0, s>>>(indices, nnz, R0, shape0_dev, R1, shape1_dev, out_indices);
+  emu::launch(dim3(grid_el(nnz)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_reshape(indices, nnz, R0, shape0_dev, R1, shape1_dev, out_indices); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -229,7 +230,7 @@ int dr_cuda_sparse_reshape(const int64_t* indices, int64_t nnz, int R0, const in
 int dr_cuda_sparse_segment_fwd(const float* data, int64_t N, int D, const int64_t* indices, const int64_t* segment_ids, int64_t nnz, int64_t S, int mode, float* out,
                                cudaStream_t s) {
   if (S <= 0 || D <= 0) return 0;
-  k_spu_segment_fwd<<<grid_el(S * 32), 256, 0, s>>>(data, N, D, indices, segment_ids, nnz, S, mode, out);
+  emu::launch(dim3(grid_el(S * 32)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_segment_fwd(data, N, D, indices, segment_ids, nnz, S, mode, out); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -238,7 +239,7 @@ int dr_cuda_sparse_segment_fwd(const float* data, int64_t N, int D, const int64_
 int dr_cuda_sparse_segment_bwd(const float* g, int64_t S, int D, const int64_t* indices, const int64_t* segment_ids, int64_t nnz, int64_t N, int mode, float* d_data,
                                cudaStream_t s) {
   if (nnz <= 0 || D <= 0) return 0;
-  k_spu_segment_bwd<<<grid_el(nnz * 32), 256, 0, s>>>(g, S, D, indices, segment_ids, nnz, N, mode, d_data);
+  emu::launch(dim3(grid_el(nnz * 32)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_spu_segment_bwd(g, S, D, indices, segment_ids, nnz, N, mode, d_data); });
   DR_LAUNCH_CHECK();
   return 0;
 }

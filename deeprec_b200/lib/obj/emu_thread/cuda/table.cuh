@@ -139,7 +139,7 @@ __device__ __forceinline__ void table_touch_aggregated(const DrDeviceTable& TB, 
   // read-before-write: a hot key's slot is hammered by every warp of the batch; once it is dirty / claimed, later warps
   // must not add a store and a CAS to the same-sector serialisation queue (the probe already pulled the sector in)
   int4 hi;                                                                             // {row_of, tag, dirty, pad}
-  DR_LD_V4_VOLATILE(hi, &TB.slots[pos].row_of);
+  asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(&TB.slots[pos].row_of));
   if (hi.z == 0) TB.slots[pos].dirty = 1;
   if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1) {
     const int u = atomicAdd(nunique, 1);
@@ -181,7 +181,7 @@ __device__ __forceinline__ void table_touch_block(const DrDeviceTable* __restric
     const DrDeviceTable& TB = tables[t];
     atomicAdd(&TB.slots[p].freq, sm.count[e]);
     int4 hi;                                                                            // {row_of, tag, dirty, pad}
-    DR_LD_V4_VOLATILE(hi, &TB.slots[p].row_of);
+    asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(&TB.slots[p].row_of));
     if (hi.z == 0) TB.slots[p].dirty = 1;
     if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[p].tag, -1, -2) == -1) {
       const int u = atomicAdd(nunique, 1);

@@ -17,19 +17,15 @@ import torch.nn as nn
 from .. import _native
 from .._native import ptr, stream_ptr
 
-_BOUND = False
-
-
 def _lib():
-    global _BOUND
     L = _native.cuda()
-    if not _BOUND:
+    if not getattr(L, "_din_bound", False):
         P, i64, INT = C.c_void_p, C.c_int64, C.c_int
         L.dr_cuda_din_attention_fwd.restype = INT
         L.dr_cuda_din_attention_fwd.argtypes = [P, P, P, i64, INT, INT, P, P, INT, P, P, INT, P, C.c_float, P, P]
         L.dr_cuda_din_attention_bwd.restype = INT
         L.dr_cuda_din_attention_bwd.argtypes = [P, P, P, P, i64, INT, INT, P, P, INT, P, P, INT, P, C.c_float, P, P, P, P, P, P, P, P, P]
-        _BOUND = True
+        L._din_bound = True
     return L
 
 
@@ -121,10 +117,10 @@ def din_attention_fused_train(q: torch.Tensor, k: torch.Tensor, mask: torch.Tens
 def din_attention(q: torch.Tensor, k: torch.Tensor, mask: torch.Tensor, att: nn.Module) -> torch.Tensor:
     """Dispatch: fused kernel when on CUDA, no gradient is required and ``att`` is the Linear-Sigmoid-Linear-Sigmoid-Linear(1) unit."""
     needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or any(p.requires_grad for p in att.parameters()))
-    if needs_grad and q.is_cuda and _fusable(att) and att[0].in_features == 4 * q.shape[-1] and os.environ.get("DEEPREC_DIN_FUSED_TRAIN", "0") == "1" \
+    if needs_grad and _native.on_device(q) and _fusable(att) and att[0].in_features == 4 * q.shape[-1] and os.environ.get("DEEPREC_DIN_FUSED_TRAIN", "0") == "1" \
             and not torch.cuda.is_current_stream_capturing():
         return din_attention_fused_train(q, k, mask, att)
-    if not q.is_cuda or needs_grad or not _fusable(att) or att[0].in_features != 4 * q.shape[-1]:
+    if not _native.on_device(q) or needs_grad or not _fusable(att) or att[0].in_features != 4 * q.shape[-1]:
         return din_attention_composite(q, k, mask, att)
     B, L, D = k.shape
     l1, l2, l3 = att[0], att[2], att[4]

@@ -17,14 +17,12 @@ from .. import _native
 from .._native import ptr, stream_ptr
 from .embedding_ops import SparseIds
 
-_BOUND = False
 _MODES = {"sum": 0, "mean": 1, "sqrtn": 2}
 
 
 def _lib():
-    global _BOUND
     lib = _native.cuda()
-    if not _BOUND:
+    if not getattr(lib, "_spu_bound", False):
         i64, INT, P = C.c_int64, C.c_int, C.c_void_p
         lib.dr_cuda_sparse_utils_workspace.argtypes, lib.dr_cuda_sparse_utils_workspace.restype = [i64, i64], i64
         for name, args in {"dr_cuda_sparse_prune_fill": [P, P, P, i64, i64, INT, INT, i64, P, P, P, P, P, P, P],
@@ -33,7 +31,7 @@ def _lib():
                            "dr_cuda_sparse_segment_fwd": [P, i64, INT, P, P, i64, i64, INT, P, P],
                            "dr_cuda_sparse_segment_bwd": [P, i64, INT, P, P, i64, i64, INT, P, P]}.items():
             fn = getattr(lib, name); fn.argtypes, fn.restype = args, INT
-        _BOUND = True
+        lib._spu_bound = True
     return lib
 
 
@@ -53,7 +51,7 @@ def sparse_prune_fill(sp: SparseIds, default_id: Optional[int] = None, prune: bo
     ``tf.sparse.retain`` + ``tf.sparse.fill_empty_rows`` computes in ``safe_embedding_lookup_sparse`` (embedding_ops.py:838)."""
     v, r, w, B = sp.values, sp.row_ids, sp.weights, sp.batch_size
     fill = default_id is not None
-    if not v.is_cuda:
+    if not _native.on_device(v):
         keep = torch.ones_like(v, dtype=torch.bool)
         if prune:
             keep = v >= 0
@@ -99,7 +97,7 @@ def sparse_slice(indices: torch.Tensor, values: torch.Tensor, shape: Sequence[in
     R = indices.shape[1]
     assert len(shape) == len(start) == len(size) == R
     out_shape = [max(0, min(int(sz), int(sh) - int(st))) for sh, st, sz in zip(shape, start, size)]
-    if not indices.is_cuda:
+    if not _native.on_device(indices):
         st = torch.tensor(list(start), dtype=torch.int64); sz = torch.tensor(list(size), dtype=torch.int64)
         keep = ((indices >= st) & (indices < st + sz)).all(dim=1)
         return indices[keep] - st, values[keep], out_shape
@@ -138,7 +136,7 @@ def sparse_reshape(indices: torch.Tensor, shape: Sequence[int], new_shape: Seque
     if prod != total:
         raise ValueError(f"sparse_reshape: {shape} and {new_shape} hold different numbers of elements")
     R0, R1 = len(shape), len(new_shape)
-    if not indices.is_cuda:
+    if not _native.on_device(indices):
         mul0 = torch.ones(R0, dtype=torch.int64)
         for d in range(R0 - 2, -1, -1):
             mul0[d] = mul0[d + 1] * int(shape[d + 1])
@@ -192,7 +190,7 @@ class _SparseSegment(torch.autograd.Function):
 def _sparse_segment(data, indices, segment_ids, num_segments, mode):
     if num_segments is None:
         num_segments = int(segment_ids.max().item()) + 1 if segment_ids.numel() else 0
-    if data.is_cuda:
+    if _native.on_device(data):
         return _SparseSegment.apply(data, indices.contiguous().long(), segment_ids.contiguous().long(), int(num_segments), _MODES[mode])
     return _segment_ref(data, indices.long(), segment_ids.long(), int(num_segments), mode)
 

@@ -77,6 +77,10 @@ class Processor:
         if device == "cpu":
             from .. import _native
             self.lib = _Abi(_native.host(), "dr_cpu_")
+        elif device == "cuda_emu":
+            # the GPU runtime compiled for the host (csrc/cuda/emu/cuda_emu.h: one host thread per CUDA thread, host-loop GEMM stand-in): CPU CI of
+            # the op-program interpreter and its kernels, optionally under ASAN / TSAN (DEEPREC_EMU_SANITIZE)
+            self.lib = _Abi(C.CDLL(_build.build_cuda_emu(os.environ.get("DEEPREC_EMU_SANITIZE") or None)), "")
         else:
             path = os.path.join(_build.LIB, "libdeeprec_cuda.so")
             if not os.path.exists(path):

@@ -3,6 +3,7 @@
 // fence (frozen flag + definition version).  Checked: every accepted push was applied exactly once (frequency of a key == accepted pushes that
 // carried it ... counted through the row values of an SGD table), pulls never observe a torn message, STALE answers leave the stream in sync,
 // the in-flight count drains to zero under the fence, stop() joins every thread with connections still open.
+#include <chrono>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -83,7 +84,9 @@ int main() {
   for (int round = 0; round < 20 && !failed; ++round) {
     std::this_thread::sleep_for(std::chrono::milliseconds(3));
     dr_ps_server_set_def(sv, def.load(), 1);
-    for (int spin = 0; dr_ps_server_inflight(sv) > 0 && spin < 2000000; ++spin) std::this_thread::yield();
+    // time-bounded (not spin-count-bounded): under TSAN on a loaded box a handler thread can stay descheduled for seconds
+    for (auto t0 = std::chrono::steady_clock::now(); dr_ps_server_inflight(sv) > 0 && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(120);)
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
     CHECK(dr_ps_server_inflight(sv) == 0);
     def.fetch_add(1);
     dr_ps_server_set_def(sv, def.load(), 0);
