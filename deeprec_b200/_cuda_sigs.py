@@ -21,14 +21,28 @@ class DeviceTableStruct(C.Structure):
     ]
 
 
+_MISSING_OK = False
+
+
 def _sig(lib, name, argtypes, restype=INT):
+    if _MISSING_OK and not hasattr(lib, name):
+        return None
     fn = getattr(lib, name)
     fn.argtypes = argtypes
     fn.restype = restype
     return fn
 
 
-def bind(lib):
+def bind(lib, missing_ok: bool = False):
+    global _MISSING_OK
+    _MISSING_OK = missing_ok
+    try:
+        return _bind(lib)
+    finally:
+        _MISSING_OK = False
+
+
+def _bind(lib):
     from ._native import OptHyper
     TP = C.POINTER(DeviceTableStruct)
     HP = C.POINTER(OptHyper)

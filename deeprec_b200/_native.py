@@ -189,6 +189,10 @@ def cuda():
     """The sm_100a kernel library.  Raises if it is missing (never falls back silently)."""
     global _CUDA
     if _EMU_DEPTH > 0:
+        if not getattr(_EMU, "_sigs_bound", False):
+            from . import _cuda_sigs
+            _cuda_sigs.bind(_EMU, missing_ok=True)          # entry points of the tcgen05 / NVLS translation units do not exist in the emulation
+            _EMU._sigs_bound = True
         return _EMU
     if _CUDA is None:
         with _LOCK:
@@ -206,8 +210,17 @@ def cuda():
     return _CUDA
 
 
+def stream_sync(device=None) -> None:
+    """Wait for the current stream (no-op while the kernel emulation is active: emulated launches are synchronous)."""
+    if _EMU_DEPTH > 0:
+        return
+    torch.cuda.current_stream(device).synchronize()
+
+
 def set_device(index: int) -> None:
     """The kernel library links its own static cudart: its current device must follow torch's."""
+    if _EMU_DEPTH > 0:
+        return
     rc = cuda().dr_cuda_set_device(int(index))
     if rc != 0:
         raise RuntimeError(f"dr_cuda_set_device({index}) failed: {rc}")

@@ -130,6 +130,8 @@ EMU_SOURCES = [
     "cuda/sparse_utils.cu",
     "cuda/attention_kernels.cu",
     "cuda/serving_runtime.cu",
+    "cuda/sparse_pipeline.cu",          # unique-first model-parallel pipeline: ranks = host threads, peer memory = the shared address space
+    "cuda/comm_kernels.cu",
     "cuda/emu/emu_stubs.cu",            # host-loop stand-ins for the tcgen05 GEMM entry points
 ]
 
@@ -149,6 +151,25 @@ def _split_top_level(text: str) -> list[str]:
     if cur.strip():
         parts.append(cur.strip())
     return parts
+
+
+def _emu_shared_decls(text: str) -> str:
+    """``__shared__ T name[dims];`` -> a reference into per-BLOCK storage (``emu::shared_var``): function-level statics would be shared by every
+    kernel running in the process (two serving sessions, the rank threads of a multi-rank emulation)."""
+    import re
+    import zlib
+    seed = zlib.crc32(text[:4096].encode()) % 30000
+    counter = [0]
+
+    def repl(m):
+        counter[0] += 1
+        uid = seed * 1000 + counter[0]
+        ty, name, dims = m.group(2), m.group(3), m.group(4) or ""
+        return (f"{m.group(1)}using emu_sh_{uid} = {ty}{dims}; "
+                f"emu_sh_{uid}& {name} = *reinterpret_cast<emu_sh_{uid}*>(emu::shared_var({uid}, sizeof(emu_sh_{uid})));")
+
+    return re.sub(r"(^|[;{}\s])(?<!extern )__shared__\s+(?:__align__\(\d+\)\s+)?([\w:]+(?:<[^<>;]*>)?)\s+(\w+)((?:\[[^\];]*\])*)\s*;",
+                  lambda m: repl(m) if "extern" not in text[max(0, m.start() - 8):m.start() + 1] else m.group(0), text)
 
 
 def emu_translate(src: str) -> str:
@@ -180,6 +201,7 @@ def emu_translate(src: str) -> str:
         out.append(f"emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({cfg[2]}), (cudaStream_t)({cfg[3]}), [&] {{ {m.group(1)}{src[i:j + 1]}; }})")
         pos = j + 1
     text = "".join(out)
+    text = _emu_shared_decls(text)
     text = re.sub(r"extern\s+__shared__\s+((?:__align__\(\d+\)\s+)?)([\w:<> ]+?)\s+(\w+)\[\];",
                   lambda m: f"{m.group(2)}* {m.group(3)} = ({m.group(2)}*)emu::dyn_smem();", text)
     return text
@@ -218,7 +240,16 @@ def build_cuda_emu(sanitize: str | None = None, force: bool = False, sources: li
         with open(tu, "w") as fh:
             fh.write(f'#line 1 "{s}"\n' + emu_translate(text))
         tus.append(tu)
-    _run(["g++"] + flags + tus + ["-o", out])
+    cflags = [f for f in flags if f != "-shared"]
+
+    def compile_one(tu: str) -> str:
+        obj = tu + ".o"
+        _run(["g++"] + cflags + ["-c", tu, "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(tus))) as ex:
+        objs = list(ex.map(compile_one, tus))
+    _run(["g++", "-shared", "-pthread"] + (["-fsanitize=" + sanitize] if sanitize else []) + objs + ["-o", out])
     open(out + ".stamp", "w").write(stamp)
     return out
 

@@ -1,3 +1,4 @@
+#line 1 "/root/repo/deeprec_b200/csrc/cuda/sparse_pipeline.cu"
 // "Unique-first" model-parallel embedding pipeline over NVLink peer memory (sm_100a).
 //
 // The reference dedups ids before every EmbeddingVariable lookup / apply (python/training/optimizer.py:91,
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) k_sp_dedup(const int64_t* __restrict__ id
                                                   int32_t* __restrict__ bkt_gs, int32_t* __restrict__ bcnt /* [T][W] */,
                                                   float* __restrict__ ugrad, DrSpSync sync) {
   pdl_sync();
-  extern __shared__ int32_t s_inv[];                         // [32][ldinv + 1]
+  int32_t* s_inv = (int32_t*)emu::dyn_smem();                         // [32][ldinv + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lds = g.ldinv + 1;
   const int64_t ntiles = (g.B + 31) / 32;
@@ -208,11 +209,11 @@ __global__ void __launch_bounds__(256) k_sp_lookup(const DrDeviceTable* __restri
                                                    int32_t* __restrict__ own_cnt, int64_t* __restrict__ ulist, int32_t* __restrict__ nunique,
                                                    int64_t ulist_cap, DrSpSync sync) {
   pdl_sync();
-  __shared__ int32_t s_pos[256];
-  __shared__ int64_t s_key[256];
-  __shared__ int32_t s_gs[256];
-  __shared__ int32_t s_cnt[kSpMaxTables];
-  __shared__ int32_t s_pre[kSpMaxTables + 1];
+  using emu_sh_11405001 = int32_t[256]; emu_sh_11405001& s_pos = *reinterpret_cast<emu_sh_11405001*>(emu::shared_var(11405001, sizeof(emu_sh_11405001)));
+  using emu_sh_11405002 = int64_t[256]; emu_sh_11405002& s_key = *reinterpret_cast<emu_sh_11405002*>(emu::shared_var(11405002, sizeof(emu_sh_11405002)));
+  using emu_sh_11405003 = int32_t[256]; emu_sh_11405003& s_gs = *reinterpret_cast<emu_sh_11405003*>(emu::shared_var(11405003, sizeof(emu_sh_11405003)));
+  using emu_sh_11405004 = int32_t[kSpMaxTables]; emu_sh_11405004& s_cnt = *reinterpret_cast<emu_sh_11405004*>(emu::shared_var(11405004, sizeof(emu_sh_11405004)));
+  using emu_sh_11405005 = int32_t[kSpMaxTables + 1]; emu_sh_11405005& s_pre = *reinterpret_cast<emu_sh_11405005*>(emu::shared_var(11405005, sizeof(emu_sh_11405005)));
   const int T = g.T, W = g.W, rank = g.rank;
   for (int si = 0; si < W; ++si) {
     const int s = (rank + si) % W;                            // own bucket first, then the peers in ring order
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(256) k_sp_segsum(const __nv_bfloat16* __restri
   pdl_sync();
   constexpr int dim = 4 * LPR;
   constexpr int V = dim / 8;                                   // int4 (8 bf16) chunks per row
-  __shared__ __align__(16) int4 s_row[8][32][V];
+  using emu_sh_11405006 = int4[8][32][V]; emu_sh_11405006& s_row = *reinterpret_cast<emu_sh_11405006*>(emu::shared_var(11405006, sizeof(emu_sh_11405006)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles = (g.B + 31) / 32;
   const int64_t units = tiles * g.C;
@@ -380,8 +381,8 @@ __global__ void __launch_bounds__(256) k_sp_grad(const DrDeviceTable* __restrict
   pdl_sync();
   constexpr int IPC = 256 / LPR;
   constexpr int dim = 4 * LPR;
-  __shared__ int32_t s_cnt[kSpMaxTables];
-  __shared__ int32_t s_pre[kSpMaxTables + 1];
+  using emu_sh_11405007 = int32_t[kSpMaxTables]; emu_sh_11405007& s_cnt = *reinterpret_cast<emu_sh_11405007*>(emu::shared_var(11405007, sizeof(emu_sh_11405007)));
+  using emu_sh_11405008 = int32_t[kSpMaxTables + 1]; emu_sh_11405008& s_pre = *reinterpret_cast<emu_sh_11405008*>(emu::shared_var(11405008, sizeof(emu_sh_11405008)));
   const int T = g.T, W = g.W, rank = g.rank;
   const int lane = threadIdx.x % LPR;
   for (int si = 0; si < W; ++si) {
@@ -415,8 +416,8 @@ __global__ void __launch_bounds__(256) k_sp_grad(const DrDeviceTable* __restrict
 __global__ void __launch_bounds__(256) k_sp_reset(DrSpGeom g, DrSpSlot* __restrict__ scr, const int32_t* __restrict__ bkt_gs,
                                                   int32_t* __restrict__ bcnt, int32_t* __restrict__ state) {
   pdl_sync();
-  __shared__ int32_t s_cnt[kSpMaxTables];
-  __shared__ int32_t s_pre[kSpMaxTables + 1];
+  using emu_sh_11405009 = int32_t[kSpMaxTables]; emu_sh_11405009& s_cnt = *reinterpret_cast<emu_sh_11405009*>(emu::shared_var(11405009, sizeof(emu_sh_11405009)));
+  using emu_sh_11405010 = int32_t[kSpMaxTables + 1]; emu_sh_11405010& s_pre = *reinterpret_cast<emu_sh_11405010*>(emu::shared_var(11405010, sizeof(emu_sh_11405010)));
   const int T = g.T, W = g.W;
   for (int o = 0; o < W; ++o) {
     __syncthreads();
@@ -476,7 +477,7 @@ inline int sp_grid(int64_t blocks) {
 extern "C" {
 
 int dr_sp_init_scratch(void* scr, int64_t n, cudaStream_t s) {
-  k_sp_init_scratch<<<kNumSMs * 4, 256, 0, s>>>((DrSpSlot*)scr, n);
+  emu::launch(dim3(kNumSMs * 4), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_sp_init_scratch((DrSpSlot*)scr, n); });
   DR_LAUNCH_CHECK();
   return 0;
 }
@@ -573,7 +574,7 @@ int dr_sp_step_end(int32_t* state, cudaStream_t s) {
 }
 
 int dr_sp_stats(const DrSpGeom* g, const int32_t* bcnt, int64_t* out, cudaStream_t s) {
-  k_sp_stats<<<1, 1, 0, s>>>(*g, bcnt, out);
+  emu::launch(dim3(1), dim3(1), (size_t)(0), (cudaStream_t)(s), [&] { k_sp_stats(*g, bcnt, out); });
   DR_LAUNCH_CHECK();
   return 0;
 }

@@ -54,7 +54,11 @@ inline cudaError_t dr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
 #endif
 
 
+#ifdef DR_CUDA_EMU
+constexpr int kNumSMs = 2;      // emulated blocks run one after the other: the grid-stride kernels get small grids (any grid size must be correct)
+#else
 constexpr int kNumSMs = 148;
+#endif
 
 // cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (serving ProcessorGroup: one replica per GPU in one process)
 // must raise the dynamic shared-memory limit on each of them.  One flag per (call site, device).
@@ -231,6 +235,36 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 #endif  // DR_CUDA_EMU
+
+// volatile scalar loads of words that other threads update with atomics (probe-then-CAS): plain volatile on the device; relaxed atomic
+// loads in the emulation build, which is what they mean -- ThreadSanitizer then reports only the races that are NOT this idiom
+#ifdef DR_CUDA_EMU
+__device__ __forceinline__ int64_t ld_volatile_i64(const int64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+__device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+#else
+__device__ __forceinline__ int64_t ld_volatile_i64(const int64_t* p) { return *reinterpret_cast<const volatile int64_t*>(p); }
+__device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+#endif
+
+// 16-byte / 8-byte volatile loads of a slot's metadata words (same PTX text as before the emulation build existed: the SASS of the hot
+// probe kernels is unchanged); on the host: relaxed atomic word loads, so ThreadSanitizer sees them as the benign races they are
+#ifdef DR_CUDA_EMU
+#define DR_LD_V4_VOLATILE(hi, p)                                                                   \
+  do {                                                                                             \
+    const int* _q = reinterpret_cast<const int*>(p);                                               \
+    (hi).x = __atomic_load_n(_q, __ATOMIC_RELAXED); (hi).y = __atomic_load_n(_q + 1, __ATOMIC_RELAXED); \
+    (hi).z = __atomic_load_n(_q + 2, __ATOMIC_RELAXED); (hi).w = __atomic_load_n(_q + 3, __ATOMIC_RELAXED); \
+  } while (0)
+#define DR_LD_V2_VOLATILE_U32(v, p)                                                                \
+  do {                                                                                             \
+    const unsigned* _q = reinterpret_cast<const unsigned*>(p);                                     \
+    (v).x = __atomic_load_n(_q, __ATOMIC_RELAXED); (v).y = __atomic_load_n(_q + 1, __ATOMIC_RELAXED); \
+  } while (0)
+#else
+#define DR_LD_V4_VOLATILE(hi, p) \
+  asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"((hi).x), "=r"((hi).y), "=r"((hi).z), "=r"((hi).w) : "l"(p))
+#define DR_LD_V2_VOLATILE_U32(v, p) asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"((v).x), "=r"((v).y) : "l"(p) : "memory")
+#endif
 
 // UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)

@@ -72,7 +72,7 @@ __device__ __forceinline__ int64_t table_find_or_insert(const DrDeviceTable& T, 
   uint64_t pos = dr_mix64((uint64_t)key) & mask;
   *inserted = false;
   for (int64_t probes = 0; probes < T.capacity; ++probes) {
-    int64_t k = *(volatile int64_t*)&T.slots[pos].key;
+    int64_t k = ld_volatile_i64(&T.slots[pos].key);
     if (k == key) return (int64_t)pos;
     if (k == kEmptyKey) {
       unsigned long long old = atomicCAS((unsigned long long*)&T.slots[pos].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
@@ -139,7 +139,7 @@ __device__ __forceinline__ void table_touch_aggregated(const DrDeviceTable& TB, 
   // read-before-write: a hot key's slot is hammered by every warp of the batch; once it is dirty / claimed, later warps
   // must not add a store and a CAS to the same-sector serialisation queue (the probe already pulled the sector in)
   int4 hi;                                                                             // {row_of, tag, dirty, pad}
-  asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(&TB.slots[pos].row_of));
+  DR_LD_V4_VOLATILE(hi, &TB.slots[pos].row_of);
   if (hi.z == 0) TB.slots[pos].dirty = 1;
   if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1) {
     const int u = atomicAdd(nunique, 1);
@@ -181,7 +181,7 @@ __device__ __forceinline__ void table_touch_block(const DrDeviceTable* __restric
     const DrDeviceTable& TB = tables[t];
     atomicAdd(&TB.slots[p].freq, sm.count[e]);
     int4 hi;                                                                            // {row_of, tag, dirty, pad}
-    asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(&TB.slots[p].row_of));
+    DR_LD_V4_VOLATILE(hi, &TB.slots[p].row_of);
     if (hi.z == 0) TB.slots[p].dirty = 1;
     if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[p].tag, -1, -2) == -1) {
       const int u = atomicAdd(nunique, 1);

@@ -128,9 +128,12 @@ class DeviceTable:
         self.lib = _native.cuda()
         self.cfg = cfg
         self.device = torch.device(device)
-        if self.device.index is None:
+        if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        _native.set_device(self.device.index)
+        if self.device.type == "cuda":
+            _native.set_device(self.device.index)
+        elif not _native.emu_active():
+            raise ValueError("DeviceTable lives on a CUDA device (CPU tensors only inside _native.cuda_emulation())")
         self.dim = int(cfg.dim)
         if self.dim % 4:
             raise ValueError("device EmbeddingVariable needs embedding_dim % 4 == 0")
@@ -228,7 +231,7 @@ class DeviceTable:
         self._refresh_struct()
         if rehash:
             _chk(self.lib.dr_cuda_table_rehash(C.byref(old_struct), C.byref(self.struct), stream_ptr()), "rehash")
-        torch.cuda.current_stream().synchronize()
+        _native.stream_sync()
         del keep
 
     # ---- queries ------------------------------------------------------------------------------------
@@ -344,7 +347,7 @@ class DeviceTable:
         self._alloc_keys(self.capacity)
         self._refresh_struct()
         _chk(self.lib.dr_cuda_table_rehash(C.byref(old_struct), C.byref(self.struct), stream_ptr()), "rehash")
-        torch.cuda.current_stream().synchronize()
+        _native.stream_sync()
         del keep
 
     def remove(self, keys: torch.Tensor) -> int:
