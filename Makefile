@@ -15,6 +15,7 @@ test-gpu: build   ## needs a B200
 
 sanitize:         ## TSAN / ASAN / UBSAN builds of the host runtime + fuzzers
 	$(PY) -m pytest tests/test_native_stress.py tests/test_cpu_serving.py -x -q -k "sanitizer or fuzz or stress"
+	DEEPREC_EMU_SANITIZE_FULL=1 $(PY) -m pytest tests/test_cuda_emu_sanitizers.py -x -q      # the CUDA kernels under ASAN / TSAN (CPU emulation)
 
 model-test: build ## smoke-train every zoo model for a few steps (cibuild/model-test.sh)
 	bash cibuild/model-test.sh
