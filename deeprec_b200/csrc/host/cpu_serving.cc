@@ -84,8 +84,11 @@ struct Config {
 // Sequence models (DIN): the request's id rows are COLUMNS, several of which may read the same table (`col_table`: target item + L history
 // positions -> the item table); valid_mask / seq_zip / seq_mask / seq_sum / din_attention / prelu are the ops their heads need.
 enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
-               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_NUM_OPS };
-struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_TILE, P_NUM_OPS };
+// rows1: sample-aware graph compression (serving/export.py::compress_sample_aware) -- the op depends on user-side features only, which are
+// identical for every candidate row of a ranking request: it runs at batch 1 on row 0 of its inputs; a TILE op broadcasts row 0 to the batch
+// where a per-candidate op consumes the result (reference: python/graph_optimizer/sample_awared_graph_compression.py:26).
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false, rows1 = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1; std::string model_name = "dlrm";
@@ -165,24 +168,30 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
     static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
-                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine"};
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine", "tile"};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
+    std::vector<bool> rows1_buf(2, false);
     for (const JVal& o : pr->arr) {
       POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
-      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0);
+      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0); op.rows1 = o.n("rows1", 0) != 0;
       const std::string kind = o.s("op", "");
       for (int k = 0; k < P_NUM_OPS; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
-      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2};
+      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2, 1};
       if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
+      // a buffer computed at batch 1 holds one valid row: only rows1 ops and TILE may read it
+      if (op.kind == P_TILE && op.rows1) return false;
+      if (!op.rows1 && op.kind != P_TILE) for (int id : op.in) if (id < (int)rows1_buf.size() && rows1_buf[(size_t)id]) return false;
       op.out = (int)names.size(); names.push_back(op.name);
+      rows1_buf.resize(names.size(), false); rows1_buf[(size_t)op.out] = op.rows1;
       a->ops.push_back(std::move(op));
     }
     a->nbuf = (int)names.size();
     a->out_buf = id_of(j.s("output", ""));
+    if (a->out_buf >= 0 && a->out_buf < (int)rows1_buf.size() && rows1_buf[(size_t)a->out_buf]) return false;
     a->n_out = (int)j.n("num_outputs", 1);
     if (auto* on = j.get("output_names")) for (auto& v : on->arr) a->out_names.push_back(v.str);
     return a->T > 0 && a->out_buf >= 2 && a->n_out >= 1 && a->n_out <= 16;
@@ -228,6 +237,7 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_SEQ_SUM: if (op.len <= 0 || w0 % op.len) return false; w = w0 / op.len; break;                                 // sum over the L positions
       case P_PRELU: if (!ReadVec(r, base + "alpha", &d.v0) || (int)d.v0.size() != w0) return false; break;
       case P_SOFTMAX: break;                                           // row-wise softmax (mixture-of-experts gates)
+      case P_TILE: break;                                              // row 0 of a once-per-request buffer -> every row of the batch
       case P_COSINE: if (dp->width[(size_t)op.in[1]] != w0) return false; w = 1; break;     // cosine similarity of two [B, W] towers -> [B, 1]
       case P_DIN_ATT: {                                              // q [B, W], k [B, L * W], mask [B, L] -> [B, W]
         const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
@@ -551,15 +561,16 @@ struct Session {
   // ---- op-program models: buffers 0 / 1 alias `dense` / `emb`, the others are sized (max_batch x width) on first use of a program ----
   std::vector<std::vector<float>> pbuf; std::vector<int> pbuf_width; std::vector<float> att_hq;
   float* Buf(int id) { return id == 0 ? dense.data() : id == 1 ? emb.data() : pbuf[(size_t)id].data(); }
-  void RunProgram(const Arch& ar, const Dense& d, int B) {
+  void RunProgram(const Arch& ar, const Dense& d, const int Bfull) {
     if (pbuf_width != d.width) {
       pbuf.assign(d.width.size(), std::vector<float>());
       for (size_t i = 2; i < d.width.size(); ++i) pbuf[i].resize((size_t)max_batch * d.width[i]);
       pbuf_width = d.width;
     }
-    const bool par = B >= 64 && threads > 1;
     for (size_t oi = 0; oi < ar.ops.size(); ++oi) {
       const POp& op = ar.ops[oi]; const PData& pd = d.pdata[oi];
+      const int B = op.rows1 ? 1 : Bfull;                          // sample-aware compression: user-side ops once per request (row 0)
+      const bool par = B >= 64 && threads > 1;
       float* out = Buf(op.out); const int W = d.width[(size_t)op.out];
       const float* a0 = Buf(op.in[0]); const int w0 = d.width[(size_t)op.in[0]];
       switch (op.kind) {
@@ -614,7 +625,12 @@ struct Session {
           break;
         }
         case P_VALID_MASK: {                                     // out[i, l] = ids[column start + l][i] >= 0
-          for (int l = 0; l < W; ++l) { const int64_t* k = ids.data() + (size_t)(op.start + l) * B; for (int i = 0; i < B; ++i) out[(size_t)i * W + l] = k[i] >= 0 ? 1.f : 0.f; }
+          for (int l = 0; l < W; ++l) { const int64_t* k = ids.data() + (size_t)(op.start + l) * Bfull; for (int i = 0; i < B; ++i) out[(size_t)i * W + l] = k[i] >= 0 ? 1.f : 0.f; }
+          break;
+        }
+        case P_TILE: {
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) memcpy(out + (size_t)i * W, a0, (size_t)W * sizeof(float));
           break;
         }
         case P_SEQ_ZIP: {                                        // position-wise concat of two [B, L, *] sequences
@@ -745,7 +761,7 @@ struct Session {
     }
     const float* lg = Buf(ar.out_buf); const int W = d.width[(size_t)ar.out_buf];
     const int no = ar.n_out;
-    for (int i = 0; i < B; ++i) for (int o = 0; o < no; ++o) prob[(size_t)i * no + o] = 1.f / (1.f + std::exp(-lg[(size_t)i * W + o]));
+    for (int i = 0; i < Bfull; ++i) for (int o = 0; o < no; ++o) prob[(size_t)i * no + o] = 1.f / (1.f + std::exp(-lg[(size_t)i * W + o]));
   }
 
   // dense [B, num_dense], ids [T][B] staged in the session buffers -> prob[B]

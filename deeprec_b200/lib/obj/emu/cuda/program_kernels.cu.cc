@@ -107,12 +107,14 @@ __global__ void __launch_bounds__(256) k_prog_sigmoid0(const __nv_bfloat16* __re
 }
 
 // ---- sequence models (DIN) -------------------------------------------------------------------------------------------------------------
-// mask[b, l] = ids[(start + l) * B + b] >= 0   (ids: [C][B] lookup columns of the request)
-__global__ void __launch_bounds__(256) k_prog_valid_mask(const int64_t* __restrict__ ids, int64_t B, int start, int L, __nv_bfloat16* __restrict__ y, int64_t ldy) {
-  const int64_t n = B * (int64_t)L;
+// mask[b, l] = ids[(start + l) * stride + b] >= 0, b < rows   (ids: [C][stride] lookup columns of the request; rows < stride when a
+// sample-aware program evaluates the mask of a user-side history once per request)
+__global__ void __launch_bounds__(256) k_prog_valid_mask(const int64_t* __restrict__ ids, int64_t stride, int64_t rows, int start, int L, __nv_bfloat16* __restrict__ y,
+                                                         int64_t ldy) {
+  const int64_t n = rows * (int64_t)L;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / L; const int l = (int)(i - b * L);
-    stb(y + b * ldy + l, ids[(int64_t)(start + l) * B + b] >= 0 ? 1.f : 0.f);
+    stb(y + b * ldy + l, ids[(int64_t)(start + l) * stride + b] >= 0 ? 1.f : 0.f);
   }
 }
 // position-wise concat: y[b, l, :] = [a[b, l, :wa] | c[b, l, :wb]]
@@ -257,9 +259,10 @@ int dr_prog_layernorm(const void* x, int64_t ldx, int w, const float* gamma, con
   return 0;
 }
 
-int dr_prog_valid_mask(const int64_t* ids, int64_t B, int start, int L, void* y, int64_t ldy, cudaStream_t s) {
-  if (B <= 0 || L <= 0) return 0;
-  emu::launch(dim3(grid_el(B * L)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_prog_valid_mask(ids, B, start, L, (__nv_bfloat16*)y, ldy); });
+int dr_prog_valid_mask(const int64_t* ids, int64_t stride, int64_t rows, int start, int L, void* y, int64_t ldy, cudaStream_t s) {
+  if (rows <= 0 || L <= 0) return 0;
+  if (rows > stride) return -2;
+  emu::launch(dim3(grid_el(rows * L)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_prog_valid_mask(ids, stride, rows, start, L, (__nv_bfloat16*)y, ldy); });
   DR_LAUNCH_CHECK();
   return 0;
 }

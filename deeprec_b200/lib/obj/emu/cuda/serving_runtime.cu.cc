@@ -60,7 +60,7 @@ int dr_prog_binary(int kind, const void* a, int64_t lda, const void* b, int64_t 
 int dr_prog_cross(const void* x0, int64_t ld0, const void* xl, int64_t ldl, int w, const float* wv, const float* bv, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_layernorm(const void* x, int64_t ldx, int w, const float* gamma, const float* beta, float eps, int relu, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_sigmoid0(const void* x, int64_t ldx, int64_t B, float* prob, cudaStream_t s);
-int dr_prog_valid_mask(const int64_t* ids, int64_t B, int start, int L, void* y, int64_t ldy, cudaStream_t s);
+int dr_prog_valid_mask(const int64_t* ids, int64_t stride, int64_t rows, int start, int L, void* y, int64_t ldy, cudaStream_t s);
 int dr_prog_seq_zip(const void* a, int64_t lda, int wa, const void* c, int64_t ldc, int wb, int L, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_seq_mask(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_seq_sum(const void* x, int64_t ldx, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
@@ -137,8 +137,9 @@ template <typename T> static bool Upload(DevBuf& b, const std::vector<T>& h) {
 // other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].  Same format and
 // op set as the CPU runtime (csrc/host/cpu_serving.cc); here LINEAR runs on the tcgen05 GEMM and the rest on program_kernels.cu.
 enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
-               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_NUM_OPS };     // the last six: sequence models (DIN), see cpu_serving.cc
-struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_TILE, P_NUM_OPS };     // sequence-model ops: see cpu_serving.cc
+// rows1 / P_TILE: sample-aware graph compression (serving/export.py::compress_sample_aware): user-side ops run once per request on row 0
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false, rows1 = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1;
@@ -270,6 +271,7 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_SEQ_SUM: if (op.len <= 0 || w0 % op.len) return false; w = w0 / op.len; break;
       case P_PRELU: if (!ReadVec(r, base + "alpha", &v0) || (int)v0.size() != w0 || !Upload(d.v0, v0)) return false; break;
       case P_SOFTMAX: break;
+      case P_TILE: break;
       case P_COSINE: if (dp->width[(size_t)op.in[1]] != w0) return false; w = 1; break;
       case P_DIN_ATT: {
         const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
@@ -411,24 +413,30 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
     static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
-                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine"};
-    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2};
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine", "tile"};
+    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2, 1};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
+    std::vector<bool> rows1_buf(2, false);
     for (const JVal& o : pr->arr) {
       POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
-      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0);
+      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0); op.rows1 = o.n("rows1", 0) != 0;
       const std::string kind = o.s("op", "");
       for (int k = 0; k < P_NUM_OPS; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
       if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
+      // a buffer computed at batch 1 holds one valid row: only rows1 ops and TILE may read it
+      if (op.kind == P_TILE && op.rows1) return false;
+      if (!op.rows1 && op.kind != P_TILE) for (int id : op.in) if (id < (int)rows1_buf.size() && rows1_buf[(size_t)id]) return false;
       op.out = (int)names.size(); names.push_back(op.name);
+      rows1_buf.resize(names.size(), false); rows1_buf[(size_t)op.out] = op.rows1;
       a->ops.push_back(std::move(op));
     }
     a->nbuf = (int)names.size();
     a->out_buf = id_of(j.s("output", ""));
+    if (a->out_buf >= 0 && a->out_buf < (int)rows1_buf.size() && rows1_buf[(size_t)a->out_buf]) return false;
     a->n_out = (int)j.n("num_outputs", 1);
     if (a->n_out < 1 || a->n_out > 16) return false;
     // the embedding buffer doubles as a GEMM operand: its row pitch T * D must obey the 16-byte rule; rows are gathered as float4 groups
@@ -488,7 +496,7 @@ struct Session {
   // ---- op-program models: buffers 0 / 1 alias x0 / emb, the others are (max_batch x prog_ld(width)) bf16, zeroed once (pad columns stay zero) ----
   std::vector<DevBuf> pbuf; std::vector<int> pbuf_width;
   DevBuf att_q, att_k, att_o, att_m;                                 // fp32 / uint8 staging of the din_attention kernel
-  bool RunProgram(const DeviceModel& m, const DenseParams& dp, int B) {
+  bool RunProgram(const DeviceModel& m, const DenseParams& dp, const int Bfull) {
     const Arch& a = m.arch; cudaStream_t s = stream;
     if (pbuf_width != dp.width) {                                     // first program run, or a full update changed the layer widths
       SV_CUDA(cudaStreamSynchronize(s));
@@ -508,14 +516,15 @@ struct Session {
     auto buf = [&](int id) -> void* { return id == 0 ? x0.p : id == 1 ? emb.p : pbuf[(size_t)id].p; };
     auto ld = [&](int id) -> int64_t { return prog_ld(a, dp.width, id); };
     int rc = 0;
-    const int64_t n = (int64_t)a.C * B;
+    const int64_t n = (int64_t)a.C * Bfull;
     const int32_t* ct = m.col_table.as<int32_t>();                   // lookup column -> table
-    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), ct, a.C, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), ct, a.C, ids.as<int64_t>(), nullptr, Bfull, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
     // sample-major embeddings [B, C * D]: element (b, c) at b * (C * D) + c * D
-    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), ct, a.C, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, (int64_t)a.C * a.D, a.D, 0, s);
-    rc |= dr_cuda_cast_pad(dense_in.as<float>(), B, a.num_dense, x0.p, pad8(a.num_dense), s);
+    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), ct, a.C, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, Bfull, n, emb.p, 1, (int64_t)a.C * a.D, a.D, 0, s);
+    rc |= dr_cuda_cast_pad(dense_in.as<float>(), Bfull, a.num_dense, x0.p, pad8(a.num_dense), s);
     for (size_t oi = 0; oi < a.ops.size() && rc == 0; ++oi) {
       const POp& op = a.ops[oi]; const auto& pd = dp.pdata[oi];
+      const int B = op.rows1 ? 1 : Bfull;                            // sample-aware compression: user-side ops once per request (row 0 of their inputs)
       void* out = buf(op.out); const int W = dp.width[(size_t)op.out]; const int64_t ldo = ld(op.out);
       const void* a0 = buf(op.in[0]); const int w0 = dp.width[(size_t)op.in[0]]; const int64_t ld0 = ld(op.in[0]);
       switch (op.kind) {
@@ -536,7 +545,8 @@ struct Session {
         case P_MUL_ADD: rc |= dr_prog_binary(2, a0, ld0, buf(op.in[1]), ld(op.in[1]), buf(op.in[2]), ld(op.in[2]), W, out, ldo, B, s); break;
         case P_SLICE: rc |= dr_prog_copy_cols(a0, ld0, op.start, W, out, ldo, 0, B, s); break;
         case P_LAYERNORM: rc |= dr_prog_layernorm(a0, ld0, W, pd.v0.as<float>(), pd.v1.as<float>(), op.eps, op.relu ? 1 : 0, out, ldo, B, s); break;
-        case P_VALID_MASK: rc |= dr_prog_valid_mask(ids.as<int64_t>(), B, op.start, W, out, ldo, s); break;
+        case P_VALID_MASK: rc |= dr_prog_valid_mask(ids.as<int64_t>(), Bfull, B, op.start, W, out, ldo, s); break;
+        case P_TILE: rc |= dr_prog_copy_cols(a0, /*row pitch 0: broadcast row 0*/ 0, 0, W, out, ldo, 0, B, s); break;
         case P_SEQ_ZIP: { const int L = op.len, wb = dp.width[(size_t)op.in[1]]; rc |= dr_prog_seq_zip(a0, ld0, w0 / L, buf(op.in[1]), ld(op.in[1]), wb / L, L, out, ldo, B, s); break; }
         case P_SEQ_MASK: rc |= dr_prog_seq_mask(a0, ld0, buf(op.in[1]), ld(op.in[1]), op.len, W / op.len, out, ldo, B, s); break;
         case P_SEQ_SUM: rc |= dr_prog_seq_sum(a0, ld0, op.len, W, out, ldo, B, s); break;
@@ -557,7 +567,7 @@ struct Session {
       }
       (void)w0;
     }
-    rc |= dr_prog_sigmoid_cols(buf(a.out_buf), ld(a.out_buf), a.n_out, B, prob.as<float>(), s);
+    rc |= dr_prog_sigmoid_cols(buf(a.out_buf), ld(a.out_buf), a.n_out, Bfull, prob.as<float>(), s);
     return rc == 0;
   }
 

@@ -236,6 +236,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 #endif  // DR_CUDA_EMU
 
+// volatile scalar loads of words that other threads update with atomics (probe-then-CAS): plain volatile on the device; relaxed atomic
+// loads in the emulation build, which is what they mean -- ThreadSanitizer then reports only the races that are NOT this idiom
+#ifdef DR_CUDA_EMU
+__device__ __forceinline__ int64_t ld_volatile_i64(const int64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+__device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+#else
+__device__ __forceinline__ int64_t ld_volatile_i64(const int64_t* p) { return *reinterpret_cast<const volatile int64_t*>(p); }
+__device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+#endif
+
 // 16-byte / 8-byte volatile loads of a slot's metadata words (same PTX text as before the emulation build existed: the SASS of the hot
 // probe kernels is unchanged); on the host: relaxed atomic word loads, so ThreadSanitizer sees them as the benign races they are
 #ifdef DR_CUDA_EMU

@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(256) k_head(const __nv_bfloat16* __restrict__ 
       }
     }
   }
-  __shared__ float sdw[K];
-  __shared__ float sdh[K];
-  __shared__ float sred[2];
+  using emu_sh_8773001 = float[K]; emu_sh_8773001& sdw = *reinterpret_cast<emu_sh_8773001*>(emu::shared_var(8773001, sizeof(emu_sh_8773001)));
+  using emu_sh_8773002 = float[K]; emu_sh_8773002& sdh = *reinterpret_cast<emu_sh_8773002*>(emu::shared_var(8773002, sizeof(emu_sh_8773002)));
+  using emu_sh_8773003 = float[2]; emu_sh_8773003& sred = *reinterpret_cast<emu_sh_8773003*>(emu::shared_var(8773003, sizeof(emu_sh_8773003)));
   for (int i = threadIdx.x; i < K; i += blockDim.x) { sdw[i] = 0.f; sdh[i] = 0.f; }
   if (threadIdx.x < 2) sred[threadIdx.x] = 0.f;
   __syncthreads();
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_head(const __nv_bfloat16* __restrict__ 
 // -------------------------------------------------------------------------------------------------
 __global__ void k_pack_weights(const float* __restrict__ w, int N, int Kp, __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wt, int ldt) {
   pdl_sync();
-  __shared__ float tile[32][33];
+  using emu_sh_8773004 = float[32][33]; emu_sh_8773004& tile = *reinterpret_cast<emu_sh_8773004*>(emu::shared_var(8773004, sizeof(emu_sh_8773004)));
   const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     int n = n0 + r, k = k0 + threadIdx.x;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) k_bn_fold(const float* __restrict__ S1, c
     Wf[(int64_t)n * Kp + k] = __float2bfloat16(w * s);
     part += w * t;
   }
-  __shared__ float red[8];
+  using emu_sh_8773005 = float[8]; emu_sh_8773005& red = *reinterpret_cast<emu_sh_8773005*>(emu::shared_var(8773005, sizeof(emu_sh_8773005)));
   part = warp_sum(part);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
   __syncthreads();

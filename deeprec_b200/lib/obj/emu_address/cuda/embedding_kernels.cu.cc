@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_unique_insert(const int64_t* __restrict
     const int64_t key = vals[i];
     uint64_t p = dr_mix64((uint64_t)key) & mask;
     for (;;) {
-      int64_t k = *(volatile int64_t*)&tkeys[p];
+      int64_t k = ld_volatile_i64(&tkeys[p]);
       if (k == key) break;
       if (k == kEmptyKey) {
         unsigned long long old = atomicCAS((unsigned long long*)&tkeys[p], (unsigned long long)kEmptyKey, (unsigned long long)key);

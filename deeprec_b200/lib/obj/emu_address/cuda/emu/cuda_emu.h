@@ -22,6 +22,7 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <map>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -78,21 +79,28 @@ struct Warp {
   std::mutex m;
   std::condition_variable cv;
   uint32_t live = 0;            // lanes still inside the kernel
-  int waiting = 0;
-  uint64_t gen = 0;
+  // one rendezvous per mask value: disjoint sub-masks of a warp (the match_any groups of a dedup, lanes that skipped a branch and already sit in
+  // the next full-mask collective) synchronise independently -- every participant of one collective passes the same mask
+  struct Group { int waiting = 0; uint64_t gen = 0; };
+  std::map<uint32_t, Group> grp;
   uint64_t slot[32];
-  void reset(uint32_t lanes) { live = lanes; waiting = 0; }
+  void reset(uint32_t lanes) { live = lanes; grp.clear(); }
   void sync(uint32_t mask) {
     std::unique_lock<std::mutex> l(m);
-    const uint64_t g = gen;
-    if (++waiting >= __builtin_popcount(mask & live)) { waiting = 0; ++gen; cv.notify_all(); return; }
-    cv.wait(l, [&] { return gen != g; });
+    if (!(mask & live)) return;
+    Group& g = grp[mask];
+    const uint64_t gen = g.gen;
+    if (++g.waiting >= __builtin_popcount(mask & live)) { g.waiting = 0; ++g.gen; cv.notify_all(); return; }
+    cv.wait(l, [&] { return g.gen != gen; });
   }
   void drop(int lane) {
     std::unique_lock<std::mutex> l(m);
     live &= ~(1u << lane);
     // lanes parked in a collective whose mask named this lane are released by the lanes that remain (mask & live shrank)
-    if (waiting > 0 && waiting >= __builtin_popcount(live)) { waiting = 0; ++gen; cv.notify_all(); }
+    bool any = false;
+    for (auto& kv : grp)
+      if (kv.second.waiting > 0 && kv.second.waiting >= __builtin_popcount(kv.first & live)) { kv.second.waiting = 0; ++kv.second.gen; any = true; }
+    if (any) cv.notify_all();
   }
 };
 
@@ -101,6 +109,8 @@ struct Block {
   Barrier full;                     // block boundaries of the emulation itself (never dropped)
   std::vector<Warp> warps;
   std::vector<char> dyn;            // dynamic shared memory
+  std::mutex sh_mu;                 // static shared memory: one allocation per (declaration, size), living as long as the launch
+  std::map<std::pair<int, size_t>, std::unique_ptr<char[]>> sh;
 };
 
 struct Ctx {
@@ -111,7 +121,16 @@ struct Ctx {
 };
 inline thread_local Ctx ctx;
 
+inline void* shared_var(int id, size_t bytes);
 inline void* dyn_smem() { return (void*)(((uintptr_t)ctx.blk->dyn.data() + 127) & ~(uintptr_t)127); }
+
+inline void* shared_var(int id, size_t bytes) {
+  Block& b = *ctx.blk;
+  std::lock_guard<std::mutex> l(b.sh_mu);
+  auto& slot = b.sh[{id, bytes}];
+  if (!slot) { slot.reset(new char[bytes + 128]); memset(slot.get(), 0, bytes + 128); }
+  return (void*)(((uintptr_t)slot.get() + 127) & ~(uintptr_t)127);
+}
 
 inline std::atomic<int64_t>& launch_count() { static std::atomic<int64_t> c{0}; return c; }
 
@@ -436,3 +455,11 @@ inline const char* emu_cudaGetErrorString(cudaError_t e) { return e == cudaSucce
 #define cudaEventSynchronize(e) emu::rt_ok()
 #define cudaEventDestroy(e) emu::rt_ok()
 #define cudaStreamWaitEvent(s, e, f) emu::rt_ok()
+// CUDA IPC: "another process's allocation" is just the pointer (emulated ranks are threads of one process)
+inline cudaError_t emu_cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t emu_cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t emu_cudaDeviceCanAccessPeer(int* ok, int, int) { *ok = 1; return cudaSuccess; }
+#define cudaIpcGetMemHandle emu_cudaIpcGetMemHandle
+#define cudaIpcOpenMemHandle emu_cudaIpcOpenMemHandle
+#define cudaIpcCloseMemHandle(p) emu::rt_ok()
+#define cudaDeviceCanAccessPeer emu_cudaDeviceCanAccessPeer

@@ -52,7 +52,6 @@ int dr_cuda_quantize_e4m3(const void*, int, int64_t, int, int64_t, void*, int, f
 int dr_cuda_quantize_weights_e4m3(const float*, int, int, int64_t, void*, int, float*, cudaStream_t) { return -100; }
 int dr_cuda_absmax_bf16(const void*, int64_t, float*, cudaStream_t) { return -100; }
 
-int dr_cuda_set_device(int) { return 0; }
 int64_t dr_cuda_emu_launch_count() { return emu::launch_count().load(); }
 
 }  // extern "C"

@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(256) k_dot_fwd(const __nv_bfloat16* __restrict
                                                  int64_t emb_stride_t, int64_t emb_stride_b, int T, int64_t B,
                                                  __nv_bfloat16* __restrict__ Z, int64_t ldz) {
   constexpr int WPB = 8;
-  __shared__ __align__(16) float sF[WPB][32][D];
-  __shared__ __align__(16) __nv_bfloat16 sZ[WPB][512];
+  using emu_sh_4613001 = float[WPB][32][D]; emu_sh_4613001& sF = *reinterpret_cast<emu_sh_4613001*>(emu::shared_var(4613001, sizeof(emu_sh_4613001)));
+  using emu_sh_4613002 = __nv_bfloat16[WPB][512]; emu_sh_4613002& sZ = *reinterpret_cast<emu_sh_4613002*>(emu::shared_var(4613002, sizeof(emu_sh_4613002)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int F = T + 1;
   for (int64_t b = (int64_t)blockIdx.x * WPB + warp; b < B; b += (int64_t)gridDim.x * WPB) {
@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(256) k_dot_bwd(const __nv_bfloat16* __restrict
                                                  int64_t emb_stride_b, int T, int64_t B, __nv_bfloat16* __restrict__ dx, int64_t lddx,
                                                  __nv_bfloat16* __restrict__ demb, int64_t demb_stride_t, int64_t demb_stride_b) {
   constexpr int WPB = 8;
-  __shared__ __align__(16) float sF[WPB][32][D];
-  __shared__ __align__(16) float sG[WPB][512];
+  using emu_sh_4613003 = float[WPB][32][D]; emu_sh_4613003& sF = *reinterpret_cast<emu_sh_4613003*>(emu::shared_var(4613003, sizeof(emu_sh_4613003)));
+  using emu_sh_4613004 = float[WPB][512]; emu_sh_4613004& sG = *reinterpret_cast<emu_sh_4613004*>(emu::shared_var(4613004, sizeof(emu_sh_4613004)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int F = T + 1;
   const int used = D + F * (F - 1) / 2;
@@ -214,10 +214,10 @@ __global__ void __launch_bounds__(128) k_dot_fwd_tc(const __nv_bfloat16* __restr
   pdl_sync();
   if (INDIRECT) sp_wait_all(sync, SP_CH_ROWS);
   constexpr int D = 16;
-  __shared__ __align__(128) uint8_t sA[128 * 32];          // [16 row-groups][2 K-chunks][8 rows][16 B]
-  __shared__ __align__(16) __nv_bfloat16 sZ[4][512];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
+  using emu_sh_4613005 = uint8_t[128 * 32]; emu_sh_4613005& sA = *reinterpret_cast<emu_sh_4613005*>(emu::shared_var(4613005, sizeof(emu_sh_4613005)));          // [16 row-groups][2 K-chunks][8 rows][16 B]
+  using emu_sh_4613006 = __nv_bfloat16[4][512]; emu_sh_4613006& sZ = *reinterpret_cast<emu_sh_4613006*>(emu::shared_var(4613006, sizeof(emu_sh_4613006)));
+  using emu_sh_4613007 = uint64_t; emu_sh_4613007& bar = *reinterpret_cast<emu_sh_4613007*>(emu::shared_var(4613007, sizeof(emu_sh_4613007)));
+  using emu_sh_4613008 = uint32_t; emu_sh_4613008& tmem_slot = *reinterpret_cast<emu_sh_4613008*>(emu::shared_var(4613008, sizeof(emu_sh_4613008)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int F = T + 1;
   for (int i = threadIdx.x; i < 128 * 32 / 16; i += 128) reinterpret_cast<int4*>(sA)[i] = make_int4(0, 0, 0, 0);
@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(128) k_dot_bwd_tc(const __nv_bfloat16* __restr
   uint8_t* sB = dyn + 32768;                           // F^T: [2 d-groups][16 K-chunks][8 d][16 B] = 4 KB
   __nv_bfloat16* sG = reinterpret_cast<__nv_bfloat16*>(dyn + 32768 + 4096);   // [4][512] dZ rows
 
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
+  using emu_sh_4613009 = uint64_t; emu_sh_4613009& bar = *reinterpret_cast<emu_sh_4613009*>(emu::shared_var(4613009, sizeof(emu_sh_4613009)));
+  using emu_sh_4613010 = uint32_t; emu_sh_4613010& tmem_slot = *reinterpret_cast<emu_sh_4613010*>(emu::shared_var(4613010, sizeof(emu_sh_4613010)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int F = T + 1;
   for (int i = threadIdx.x; i < (32768 + 4096) / 16; i += 128) reinterpret_cast<int4*>(dyn)[i] = make_int4(0, 0, 0, 0);

@@ -28,7 +28,7 @@ namespace drc {
 constexpr int kSpChannels = 8;
 enum { SP_CH_DEDUP = 0, SP_CH_ROWS = 1, SP_CH_GRAD = 2, SP_CH_DENSE = 3, SP_CH_AUX = 4 };
 
-__device__ __forceinline__ uint32_t sp_epoch(const DrSpSync& s) { return (uint32_t)(*(volatile int32_t*)&s.state[0]) + 1u; }
+__device__ __forceinline__ uint32_t sp_epoch(const DrSpSync& s) { return (uint32_t)ld_volatile_i32(&s.state[0]) + 1u; }
 
 // Called by ALL threads of EVERY block as the last thing the kernel does with the data being published.
 __device__ __forceinline__ void sp_signal_last_block(const DrSpSync& s, int ch) {

@@ -72,7 +72,7 @@ __device__ __forceinline__ int64_t table_find_or_insert(const DrDeviceTable& T, 
   uint64_t pos = dr_mix64((uint64_t)key) & mask;
   *inserted = false;
   for (int64_t probes = 0; probes < T.capacity; ++probes) {
-    int64_t k = *(volatile int64_t*)&T.slots[pos].key;
+    int64_t k = ld_volatile_i64(&T.slots[pos].key);
     if (k == key) return (int64_t)pos;
     if (k == kEmptyKey) {
       unsigned long long old = atomicCAS((unsigned long long*)&T.slots[pos].key, (unsigned long long)kEmptyKey, (unsigned long long)key);

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_lookup(const DrDeviceTable* __restrict_
                                                 int32_t* __restrict__ group_nunique, int64_t ulist_cap) {
   pdl_sync();
   (void)step_ptr;
-  __shared__ TouchSmem s_touch;
+  using emu_sh_4939001 = TouchSmem; emu_sh_4939001& s_touch = *reinterpret_cast<emu_sh_4939001*>(emu::shared_var(4939001, sizeof(emu_sh_4939001)));
   // whole blocks iterate together (n rounded up to the block size): the training bookkeeping is aggregated over the block
   const int64_t nb = train ? (n + blockDim.x - 1) / blockDim.x * blockDim.x : n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {

@@ -281,6 +281,10 @@ class _ProgramBuilder:
             self.tensors[f"prog/{out}/{nm}"] = t.detach().float().cpu().reshape(-1).contiguous()
         self.ops.append({"op": "din_attention", "out": out, "in": [q, k, mask]}); return out
 
+    def tile(self, src):
+        """Broadcast row 0 of a buffer computed once per request (``rows1`` ops, sample-aware compression) to every row of the batch."""
+        out = self._name("tile"); self.ops.append({"op": "tile", "out": out, "in": [src]}); return out
+
     def softmax(self, src):
         out = self._name("softmax"); self.ops.append({"op": "softmax", "out": out, "in": [src]}); return out
 
@@ -431,6 +435,68 @@ def _build_program(model, max_len: int = 50) -> _ProgramBuilder:
     return p
 
 
+# ---- sample-aware graph compression as a pass over the op program ---------------------------------------------------------------------------
+_ROW_WISE = {"concat", "linear", "affine", "cross", "mul_add", "add", "mul", "layernorm", "slice", "seq_zip", "seq_mask", "seq_sum", "prelu", "softmax",
+             "cosine", "din_attention", "valid_mask"}
+
+
+def compress_sample_aware(ops: list, output: str, user_columns, emb_dim: int, user_dense: bool = False):
+    """Sample-aware graph compression (reference: ``python/graph_optimizer/sample_awared_graph_compression.py:26`` -- a ranking request scores N
+    candidate items for ONE user, so everything that depends on user-side features only is computed once and tiled to N as late as possible).
+
+    ``user_columns``: lookup columns (indices into the request's id rows) that carry user-side features -- identical for every row of a request;
+    ``user_dense``: the dense block is user-side too.  The pass marks every op whose inputs are all user-side ``rows1`` (both native interpreters run
+    it at batch 1, reading row 0 of its inputs) and inserts a ``tile`` op where a per-candidate op consumes such a buffer.  Returns
+    ``(ops, output, n_compressed)``; requests stay ``[rows, B]`` -- only row 0 of the user columns is read by the compressed part (clients may
+    pad the rest with -1)."""
+    user_cols = set(int(c) for c in user_columns)
+    D = int(emb_dim)
+    user_only = {"dense": bool(user_dense), "emb": False}
+    tiled, new_ops, n = {}, [], 0
+
+    def emb_range_user(start, length):
+        if start % D or length % D:
+            return False
+        return all(c in user_cols for c in range(start // D, (start + length) // D))
+
+    for op in ops:
+        op = dict(op)
+        kind, ins = op["op"], list(op["in"])
+        if kind == "slice" and ins[0] == "emb":
+            u = emb_range_user(op["start"], op["len"])
+        elif kind == "valid_mask":
+            u = all(c in user_cols for c in range(op["start"], op["start"] + op["len"]))
+        elif kind in _ROW_WISE:
+            u = all(user_only.get(i, False) for i in ins)
+        else:                                       # fm reads the whole embedding block; unknown ops stay per-candidate
+            u = False
+        if u:
+            op["rows1"] = 1
+            n += 1
+        else:                                       # a per-candidate op: user-side inputs are tiled first (once per buffer)
+            for k, i in enumerate(ins):
+                if user_only.get(i, False):
+                    if i not in tiled:
+                        tiled[i] = f"{i}_tile"
+                        new_ops.append({"op": "tile", "out": tiled[i], "in": [i]})
+                        user_only[tiled[i]] = False
+                    ins[k] = tiled[i]
+            op["in"] = ins
+        user_only[op["out"]] = u
+        new_ops.append(op)
+    if user_only.get(output, False):                # degenerate: the whole model is user-side
+        new_ops.append({"op": "tile", "out": f"{output}_tile", "in": [output]})
+        output = f"{output}_tile"
+    return new_ops, output, n
+
+
+def taobao_user_columns(max_len: int):
+    """User-side lookup columns of the Taobao-shaped programs (``[user | item | cat | hist_item x L | hist_cat x L]``): the user id and the whole
+    behaviour history; the target item / category are per candidate."""
+    L = int(max_len)
+    return [0] + list(range(3, 3 + 2 * L))
+
+
 def _evs_of(module):
     from ..optim.optimizers import collect_embedding_variables
     return collect_embedding_variables(module)
@@ -450,7 +516,8 @@ def _padded(rows: torch.Tensor, d: int, D: int) -> torch.Tensor:
     return out
 
 
-def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None, max_len: int = 50) -> str:
+def export_saved_model_program(model, export_dir: str, version: int, root: Optional[str] = None, max_len: int = 50,
+                               sample_aware: Optional[dict] = None) -> str:
     """Full export of a zoo model (Criteo-style ``WDL``, ``DeepFM``, ``DCN``, ``DCNv2``, ``MaskNet``; sequence model ``DIN`` with ``max_len`` history
     positions -- request ids = the ``[3 + 2 L, B]`` block of ``models.rec_engine.din_ids`` and one dummy dense column) as an op program + EmbeddingVariable tables; loaded by
     ``Processor(dir, cfg)`` (GPU runtime: tcgen05 GEMMs + csrc/cuda/program_kernels.cu; ``device="cpu"``: the host interpreter) exactly like a DLRM
@@ -461,6 +528,9 @@ def export_saved_model_program(model, export_dir: str, version: int, root: Optio
     tables, D, id_map = _program_tables(model, p)
     col_table = getattr(p, "col_table", None)
     num_dense = getattr(p, "num_dense", None) or model.num_dense
+    n_compressed = 0
+    if sample_aware:                               # {"user_columns": [...], "user_dense": bool}: user-side sub-graph once per request
+        p.ops, p.out, n_compressed = compress_sample_aware(p.ops, p.out, sample_aware["user_columns"], D, bool(sample_aware.get("user_dense", False)))
     os.makedirs(os.path.join(export_dir, "variables"), exist_ok=True)
     w = BundleWriter(os.path.join(export_dir, "variables", "variables"))
     for name, t in p.tensors.items():
@@ -480,6 +550,9 @@ def export_saved_model_program(model, export_dir: str, version: int, root: Optio
         meta["id_map"] = id_map
     if col_table is not None:
         meta["col_table"] = col_table
+    if sample_aware:
+        meta["sample_aware"] = {"user_columns": [int(c) for c in sample_aware["user_columns"]], "user_dense": bool(sample_aware.get("user_dense", False)),
+                                "ops_at_batch_1": int(n_compressed)}
     if getattr(p, "num_outputs", 1) > 1:                                 # multi-task: probabilities [B, num_outputs], one column per task
         meta["num_outputs"], meta["output_names"] = p.num_outputs, list(p.output_names)
         meta["signature"]["outputs"] = {"probabilities": ["B", p.num_outputs]}
