@@ -65,6 +65,13 @@ using drjson::JVal;
 
 struct Config {
   int session_num = 2, max_batch = 4096, select_policy = 0 /*0 RR, 1 MOD*/, update_interval_ms = 1000, intra_threads = 0;
+  // Executor policy of op-program models (the reference's ExecutorPolicy {NORMAL, COST_MODEL, INLINE}: core/protobuf/config.proto:19-26,
+  // common_runtime/executor.cc:414-478 inline, costmodel*.{h,cc} + kernel_stat.h cost model; env USE_INLINE_EXECUTOR / USE_COST_MODEL_EXECUTOR,
+  // START_NODE_STATS_STEP / STOP_NODE_STATS_STEP).  0 = ops in program order, each one spread over the session's threads when the batch is
+  // large; 1 = COST_MODEL: per-op times are traced over the requests [stats_start, stats_stop), then small-batch requests run the op DAG
+  // critical-path-first on the session's threads (independent towers / experts in parallel, chains of ready ops stay on one thread);
+  // 2 = INLINE: the whole request on the caller's thread, no team.
+  int executor_policy = 0, stats_start = 2, stats_stop = 34;
   std::string savedmodel_dir, checkpoint_dir, warmup_file_name, timeline_path;
   int64_t timeline_start_step = -1; int timeline_interval_step = 0, timeline_trace_count = 0;
   // feature_store_type "redis" (serving/processor/storage/redis_feature_store.*): embedding rows live in a Redis instance shared by all
@@ -118,6 +125,50 @@ struct PData { Layer L; std::vector<float> v0, v1; std::vector<std::vector<float
 struct Dense {
   std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f;
   std::vector<PData> pdata; std::vector<int> width;                       // program models: per-op weights, per-buffer widths
+  std::shared_ptr<struct ProgPlan> plan;                                  // op DAG + traced cost model (COST_MODEL executor)
+};
+
+// Dependency graph of an op program and its cost model.  Built at load (edges from the producer of every input buffer), filled by tracing.
+struct ProgPlan {
+  std::vector<std::vector<int>> succ; std::vector<int> indeg;
+  std::unique_ptr<std::atomic<int64_t>[]> cost_ns;                       // accumulated over the traced runs
+  std::atomic<int> traced{0}, seen{0}; std::atomic<bool> ready{false};
+  std::vector<double> cost_us, rank_us;                                  // per-op mean cost; rank = cost + longest path below (critical-path priority)
+  double total_us = 0, critical_us = 0; int width = 1, team = 1; bool parallel = false;
+  std::mutex mu;
+  explicit ProgPlan(const std::vector<POp>& ops, int nbuf) {
+    const size_t n = ops.size();
+    succ.assign(n, {}); indeg.assign(n, 0); cost_ns.reset(new std::atomic<int64_t>[n]);
+    for (size_t i = 0; i < n; ++i) cost_ns[i].store(0);
+    std::vector<int> producer((size_t)nbuf, -1);
+    for (size_t i = 0; i < n; ++i) {
+      std::vector<int> deps;
+      for (int b : ops[i].in) { const int pr = producer[(size_t)b]; if (pr >= 0 && std::find(deps.begin(), deps.end(), pr) == deps.end()) deps.push_back(pr); }
+      for (int pr : deps) { succ[(size_t)pr].push_back((int)i); ++indeg[i]; }
+      producer[(size_t)ops[i].out] = (int)i;
+    }
+  }
+  // mean costs -> ranks; parallel execution only when the DAG has real slack (total work well above the critical path) and the critical
+  // path is long enough to amortise a team start
+  void Finalize() {
+    std::lock_guard<std::mutex> l(mu);
+    if (ready.load()) return;
+    const size_t n = succ.size(); const int runs = std::max(1, traced.load());
+    cost_us.assign(n, 0.0); rank_us.assign(n, 0.0); total_us = 0; critical_us = 0;
+    for (size_t i = 0; i < n; ++i) { cost_us[i] = (double)cost_ns[i].load() / 1e3 / runs; total_us += cost_us[i]; }
+    for (size_t k = n; k-- > 0;) { double below = 0; for (int s2 : succ[k]) below = std::max(below, rank_us[(size_t)s2]); rank_us[k] = cost_us[k] + below; critical_us = std::max(critical_us, rank_us[k]); }
+    // width: the largest antichain reachable by level scheduling (how many threads can ever be busy)
+    std::vector<int> level(n, 0); std::vector<int> per_level; 
+    for (size_t i = 0; i < n; ++i) { for (int s2 : succ[i]) level[(size_t)s2] = std::max(level[(size_t)s2], level[i] + 1); if ((size_t)level[i] >= per_level.size()) per_level.resize((size_t)level[i] + 1, 0); ++per_level[(size_t)level[i]]; }
+    width = 1; for (int c : per_level) width = std::max(width, c);
+    // decision from the model itself: a scheduled run costs about max(critical path, total / team) stretched by the cores sharing caches,
+    // plus the team start and ~0.5 us of list handling per op; it must beat the sequential total by a clear margin (measured on 8 vCPUs:
+    // two-tower programs -- ESMM, DSSM: total / critical = 1.5 -- lose to the overheads, expert mixtures -- MMoE 2.3, PLE 3.4 -- win 1.4-1.8x)
+    team = std::max(1, std::min(width, (int)std::ceil(total_us / std::max(1e-3, critical_us))));
+    const double est = std::max(critical_us, total_us / team) * 1.15 + 12.0 + 0.5 * (double)n / team;
+    parallel = team > 1 && est < 0.8 * total_us;
+    ready.store(true);
+  }
 };
 
 struct Model {
@@ -269,6 +320,7 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
     dp->width[(size_t)op.out] = w;
   }
   if (dp->width[(size_t)a.out_buf] < a.n_out) return false;            // the output buffer holds n_out logits per row
+  dp->plan = std::make_shared<ProgPlan>(a.ops, a.nbuf);
   *out = dp;
   return true;
 }
@@ -561,15 +613,11 @@ struct Session {
   // ---- op-program models: buffers 0 / 1 alias `dense` / `emb`, the others are sized (max_batch x width) on first use of a program ----
   std::vector<std::vector<float>> pbuf; std::vector<int> pbuf_width; std::vector<float> att_hq;
   float* Buf(int id) { return id == 0 ? dense.data() : id == 1 ? emb.data() : pbuf[(size_t)id].data(); }
-  void RunProgram(const Arch& ar, const Dense& d, const int Bfull) {
-    if (pbuf_width != d.width) {
-      pbuf.assign(d.width.size(), std::vector<float>());
-      for (size_t i = 2; i < d.width.size(); ++i) pbuf[i].resize((size_t)max_batch * d.width[i]);
-      pbuf_width = d.width;
-    }
-    for (size_t oi = 0; oi < ar.ops.size(); ++oi) {
+  // one op of the program on `op_threads` threads (its OpenMP team when the batch is large; 1 under the DAG scheduler)
+  void ExecOp(const Arch& ar, const Dense& d, const size_t oi, const int Bfull, const int op_threads) {
       const POp& op = ar.ops[oi]; const PData& pd = d.pdata[oi];
       const int B = op.rows1 ? 1 : Bfull;                          // sample-aware compression: user-side ops once per request (row 0)
+      const int threads = op_threads;                              // team size of THIS op (1 when the scheduler runs ops side by side)
       const bool par = B >= 64 && threads > 1;
       float* out = Buf(op.out); const int W = d.width[(size_t)op.out];
       const float* a0 = Buf(op.in[0]); const int w0 = d.width[(size_t)op.in[0]];
@@ -692,6 +740,7 @@ struct Session {
           const float* kk = Buf(op.in[1]); const float* mk = Buf(op.in[2]);
           const int L = d.width[(size_t)op.in[2]], H1 = pd.H1, H2 = pd.H2, Wq = W;
           const float* w3 = pd.att[4].data(); const float b3 = pd.att[5][0];
+          std::lock_guard<std::mutex> att_lock(att_mu);              // one scratch per session: two attention ops never run side by side
           att_hq.resize((size_t)B * H1);
           Linear(a0, Wq, B, pd.Lq, att_hq.data(), false, threads);                     // (Wa + Wc) q + b1, once per sample
           constexpr int kS = 16;
@@ -758,6 +807,83 @@ struct Session {
           break;
         }
       }
+  }
+
+  // COST_MODEL executor, small batches: the op DAG on `team` threads.  Ready ops sit in a rank-ordered list (rank = traced cost + longest
+  // path below: critical path first); a thread that finishes an op keeps the best newly-ready successor for itself (chains never leave their
+  // thread, cheap glue ops are never queued) and publishes the others.
+  void RunScheduled(const Arch& ar, const Dense& d, const ProgPlan& pl, const int Bfull, const int team) {
+    const int n = (int)ar.ops.size();
+    if ((int)sched_indeg.size() < n) { sched_indeg = std::vector<std::atomic<int>>((size_t)n); }
+    for (int i = 0; i < n; ++i) sched_indeg[(size_t)i].store(pl.indeg[(size_t)i], std::memory_order_relaxed);
+    sched_ready.clear();
+    for (int i = 0; i < n; ++i) if (pl.indeg[(size_t)i] == 0) sched_ready.push_back(i);
+    std::atomic<int> remaining{n};
+    std::atomic_flag lock = ATOMIC_FLAG_INIT;
+    auto pop_best = [&]() -> int {
+      while (lock.test_and_set(std::memory_order_acquire)) _mm_pause();
+      int best = -1; size_t at = 0;
+      for (size_t k = 0; k < sched_ready.size(); ++k) if (best < 0 || pl.rank_us[(size_t)sched_ready[k]] > pl.rank_us[(size_t)best]) { best = sched_ready[k]; at = k; }
+      if (best >= 0) { sched_ready[at] = sched_ready.back(); sched_ready.pop_back(); }
+      lock.clear(std::memory_order_release);
+      return best;
+    };
+#pragma omp parallel num_threads(team)
+    {
+      while (remaining.load(std::memory_order_acquire) > 0) {
+        int oi = pop_best();
+        if (oi < 0) { _mm_pause(); continue; }
+        while (oi >= 0) {
+          ExecOp(ar, d, (size_t)oi, Bfull, 1);
+          int keep = -1;
+          for (int s2 : pl.succ[(size_t)oi]) {
+            if (sched_indeg[(size_t)s2].fetch_sub(1, std::memory_order_acq_rel) != 1) continue;
+            if (keep < 0) { keep = s2; continue; }
+            const int other = pl.rank_us[(size_t)s2] > pl.rank_us[(size_t)keep] ? keep : s2;      // the lower-rank one goes to the list
+            if (other == keep) keep = s2;
+            while (lock.test_and_set(std::memory_order_acquire)) _mm_pause();
+            sched_ready.push_back(other);
+            lock.clear(std::memory_order_release);
+          }
+          remaining.fetch_sub(1, std::memory_order_acq_rel);
+          oi = keep;
+        }
+      }
+    }
+  }
+
+  int exec_policy = 0, stats_start = 2, stats_stop = 34;           // Config::executor_policy & tracing window, copied at Init
+  std::mutex att_mu; std::vector<std::atomic<int>> sched_indeg; std::vector<int> sched_ready;
+  void RunProgram(const Arch& ar, const Dense& d, const int Bfull) {
+    if (pbuf_width != d.width) {
+      pbuf.assign(d.width.size(), std::vector<float>());
+      for (size_t i = 2; i < d.width.size(); ++i) pbuf[i].resize((size_t)max_batch * d.width[i]);
+      pbuf_width = d.width;
+    }
+    const int nops = (int)ar.ops.size();
+    ProgPlan* pl = d.plan.get();
+    // the regime of the DAG scheduler: latency-bound requests.  Up to ~16 rows an op streams its weights once and waits on memory -- side-by-side
+    // branches overlap those waits (MMoE 1.3-1.4x, PLE 1.7-1.9x at 1-8 rows on 8 vCPUs); at 32 rows the GEMMs are FMA-bound, sibling hyper-threads
+    // add nothing and the team start is pure cost (measured: MMoE 0.85x), so those run in program order; from 64 rows every op uses its own team
+    const bool small = Bfull <= 16;
+    if (exec_policy == 2) {                                          // INLINE: everything on the caller's thread
+      for (int oi = 0; oi < nops; ++oi) ExecOp(ar, d, (size_t)oi, Bfull, 1);
+    } else if (exec_policy == 1 && pl && small && pl->ready.load(std::memory_order_acquire) && pl->parallel && threads > 1) {
+      RunScheduled(ar, d, *pl, Bfull, std::min(threads, pl->team));
+    } else if (exec_policy == 1 && pl && small && !pl->ready.load(std::memory_order_acquire)) {
+      // tracing window (START / STOP_NODE_STATS_STEP): single-thread op times of the small-batch regime the scheduler will run in
+      const int seen = pl->seen.fetch_add(1);
+      const bool trace = seen >= stats_start && seen < stats_stop;
+      for (int oi = 0; oi < nops; ++oi) {
+        if (!trace) { ExecOp(ar, d, (size_t)oi, Bfull, threads); continue; }
+        const auto t0 = std::chrono::steady_clock::now();
+        ExecOp(ar, d, (size_t)oi, Bfull, 1);
+        pl->cost_ns[(size_t)oi].fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+      }
+      if (trace) pl->traced.fetch_add(1);
+      if (seen + 1 >= stats_stop) pl->Finalize();
+    } else {
+      for (int oi = 0; oi < nops; ++oi) ExecOp(ar, d, (size_t)oi, Bfull, threads);
     }
     const float* lg = Buf(ar.out_buf); const int W = d.width[(size_t)ar.out_buf];
     const int no = ar.n_out;
@@ -1112,6 +1238,20 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
   if (!m || c.max_batch <= 0) { *state = -1; delete sm; return nullptr; }
   // sessions run concurrently: each gets cores / sessions OpenMP threads for its GEMMs unless intra_op_parallelism_threads says otherwise
   c.intra_threads = (int)j.n("intra_op_parallelism_threads", 0);
+  {                                                                  // executor policy: ModelConfig first, then the reference's environment switches
+    const std::string ep = j.s("executor_policy", "");
+    if (ep == "cost_model") c.executor_policy = 1; else if (ep == "inline") c.executor_policy = 2; else if (ep == "normal") c.executor_policy = 0;
+    else {
+      if (j.n("enable_inline_execute", 0) != 0) c.executor_policy = 2;
+      const char* e1 = getenv("USE_COST_MODEL_EXECUTOR"); const char* e2 = getenv("USE_INLINE_EXECUTOR");
+      if (e1 && e1[0] == '1') c.executor_policy = 1;
+      if (e2 && e2[0] == '1') c.executor_policy = 2;
+    }
+    const char* s0 = getenv("START_NODE_STATS_STEP"); const char* s1 = getenv("STOP_NODE_STATS_STEP");
+    c.stats_start = (int)j.n("start_node_stats_step", s0 ? atoi(s0) : c.stats_start);
+    c.stats_stop = (int)j.n("stop_node_stats_step", s1 ? atoi(s1) : c.stats_stop);
+    if (c.stats_stop <= c.stats_start) c.stats_stop = c.stats_start + 1;
+  }
   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
   const int per_session = c.intra_threads > 0 ? c.intra_threads : std::max(1, hw / std::max(1, c.session_num));
   {
@@ -1128,6 +1268,7 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
       CPU_ZERO(&ns.mask); for (int cpu : ns.cpus) CPU_SET(cpu, &ns.mask);
     }
     ns.Init(m->arch, c.max_batch, c.intra_threads > 0 || ns.cpus.empty() ? per_session : (int)ns.cpus.size());
+    ns.exec_policy = c.executor_policy; ns.stats_start = c.stats_start; ns.stats_stop = c.stats_stop;
     if (c.remote) {                                             // one connection per session (sessions run concurrently)
       void* conn = dr_redis_connect(c.redis_host.c_str(), c.redis_port, c.redis_timeout_ms, c.redis_password.c_str(), c.redis_db);
       if (!dr_redis_ok(conn)) { fprintf(stderr, "[deeprec_cpu_serving] feature store %s:%d: %s\n", c.redis_host.c_str(), c.redis_port, dr_redis_last_error(conn)); dr_redis_close(conn); *state = -2; delete sm; return nullptr; }
@@ -1169,6 +1310,17 @@ int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* outp
      << ", \"num_dense\": " << (m ? m->arch.num_dense : 0) << ", \"num_sparse\": " << (m ? m->arch.R : 0) << ", \"num_tables\": " << (m ? m->arch.T : 0);
   os << ", \"batching\": {\"max_batch_size\": " << sm->cfg.batching_max_rows << ", \"batch_timeout_micros\": " << sm->cfg.batching_timeout_us
      << ", \"merged_batches\": " << (sm->batcher ? sm->batcher->merged_batches.load() : 0) << ", \"merged_requests\": " << (sm->batcher ? sm->batcher->merged_requests.load() : 0) << "}";
+  {
+    static const char* kPol[] = {"normal", "cost_model", "inline"};
+    os << ", \"executor\": {\"policy\": \"" << kPol[std::min(2, std::max(0, sm->cfg.executor_policy))] << "\"";
+    const cpusrv::ProgPlan* pl = (m && m->dense) ? m->dense->plan.get() : nullptr;
+    if (pl) {
+      os << ", \"ops\": " << pl->succ.size() << ", \"traced_runs\": " << pl->traced.load() << ", \"cost_model_ready\": " << (pl->ready.load() ? "true" : "false");
+      if (pl->ready.load()) os << ", \"total_us\": " << pl->total_us << ", \"critical_path_us\": " << pl->critical_us << ", \"dag_width\": " << pl->width
+                               << ", \"team\": " << pl->team << ", \"parallel\": " << (pl->parallel ? "true" : "false");
+    }
+    os << "}";
+  }
   os << ", \"cpusets\": \"";
   for (size_t i = 0; i < sm->cfg.cpusets.size(); ++i) { if (i) os << ";"; for (size_t k = 0; k < sm->cfg.cpusets[i].size(); ++k) os << (k ? "," : "") << sm->cfg.cpusets[i][k]; }
   os << "\", \"session_last_cpu\": [";
