@@ -13,8 +13,8 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(ROOT, "csrc")
-LIB = os.path.join(ROOT, "lib")
+CSRC = os.environ.get("DEEPREC_CSRC") or os.path.join(ROOT, "csrc")           # overridable: build a scratch copy of the sources next to a running test suite
+LIB = os.environ.get("DEEPREC_LIB") or os.path.join(ROOT, "lib")
 OBJ = os.path.join(LIB, "obj")
 
 HOST_SOURCES = ["host/host_engine.cc", "host/io_runtime.cc", "host/ssd_store.cc", "host/predict_codec.cc", "host/redis_store.cc", "host/tensor_pool.cc", "host/cpu_serving.cc", "host/ps_server.cc"]

@@ -91,11 +91,13 @@ struct Config {
 // Sequence models (DIN): the request's id rows are COLUMNS, several of which may read the same table (`col_table`: target item + L history
 // positions -> the item table); valid_mask / seq_zip / seq_mask / seq_sum / din_attention / prelu are the ops their heads need.
 enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
-               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_TILE, P_NUM_OPS };
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_TILE, P_GRU, P_SEQ_LAST, P_MHA, P_SEQ_MEAN, P_NUM_OPS };
 // rows1: sample-aware graph compression (serving/export.py::compress_sample_aware) -- the op depends on user-side features only, which are
 // identical for every candidate row of a ranking request: it runs at batch 1 on row 0 of its inputs; a TILE op broadcasts row 0 to the batch
 // where a per-candidate op consumes the result (reference: python/graph_optimizer/sample_awared_graph_compression.py:26).
-struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false, rows1 = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
+// len on LINEAR / LAYERNORM: the op is applied at each of `len` positions of a [B, len * w] sequence buffer (DIEN / BST); mode: din_attention output
+// (0 = weighted sum of the keys, 1 = the softmax weights); heads: mha
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false, rows1 = false; float eps = 1e-5f; int start = 0, len = 0, mode = 0, heads = 1; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1; std::string model_name = "dlrm";
@@ -121,7 +123,7 @@ struct Layer {
       wp[((size_t)p * K + k) * kPanel + j] = wt[(size_t)k * N + p * kPanel + j];
   }
 };
-struct PData { Layer L; std::vector<float> v0, v1; std::vector<std::vector<float>> att; int H1 = 0, H2 = 0; Layer Lq, L1, L2; };   // weights of one program op (linear | affine scale, shift | cross w, b | prelu alpha | din_attention W1 b1 W2 b2 w3 b3)
+struct PData { Layer L; std::vector<float> v0, v1; std::vector<std::vector<float>> att; int H1 = 0, H2 = 0; Layer Lq, L1, L2; Layer Gih, Ghh; };   // weights of one program op (linear | affine scale, shift | cross w, b | prelu alpha | din_attention W1 b1 W2 b2 w3 b3)
 struct Dense {
   std::vector<Layer> bot, top; std::vector<float> last_scale, last_shift, head_w; float head_b = 0.f;
   std::vector<PData> pdata; std::vector<int> width;                       // program models: per-op weights, per-buffer widths
@@ -219,19 +221,19 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
     static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
-                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine", "tile"};
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine", "tile", "gru", "seq_last", "mha", "seq_mean"};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     std::vector<bool> rows1_buf(2, false);
     for (const JVal& o : pr->arr) {
       POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
-      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0); op.rows1 = o.n("rows1", 0) != 0;
+      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0); op.rows1 = o.n("rows1", 0) != 0; op.mode = (int)o.n("mode", 0); op.heads = (int)o.n("heads", 1);
       const std::string kind = o.s("op", "");
       for (int k = 0; k < P_NUM_OPS; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
       if (op.kind < 0 || op.name.empty() || !in || id_of(op.name) >= 0) return false;
       for (const JVal& v : in->arr) { const int id = id_of(v.str); if (id < 0) return false; op.in.push_back(id); }    // inputs must already exist
-      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2, 1};
+      static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2, 1, 1, 2, 2, 2};
       if ((kArity[op.kind] >= 0 && (int)op.in.size() != kArity[op.kind]) || op.in.empty()) return false;
       // a buffer computed at batch 1 holds one valid row: only rows1 ops and TILE may read it
       if (op.kind == P_TILE && op.rows1) return false;
@@ -262,15 +264,22 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
     const std::string base = "prog/" + op.name + "/";
     switch (op.kind) {
       case P_CONCAT: w = 0; for (int b : op.in) w += dp->width[(size_t)b]; break;
-      case P_LINEAR: {
+      case P_LINEAR: {                                               // len > 0: the same Linear at each of len positions of a [B, len * K] sequence
         std::vector<float> W, b;
-        if (!ReadVec(r, base + "kernel", &W) || !ReadVec(r, base + "bias", &b) || b.empty() || W.size() != b.size() * (size_t)w0) return false;
-        d.L.N = (int)b.size(); d.L.K = w0; d.L.bias = b; d.L.wt.resize(W.size());
-        for (int n = 0; n < d.L.N; ++n) for (int k = 0; k < w0; ++k) d.L.wt[(size_t)k * d.L.N + n] = W[(size_t)n * w0 + k];
+        const int S = op.len > 0 ? op.len : 1;
+        if (w0 % S) return false;
+        const int K = w0 / S;
+        if (!ReadVec(r, base + "kernel", &W) || !ReadVec(r, base + "bias", &b) || b.empty() || W.size() != b.size() * (size_t)K) return false;
+        d.L.N = (int)b.size(); d.L.K = K; d.L.bias = b; d.L.wt.resize(W.size());
+        for (int n = 0; n < d.L.N; ++n) for (int k = 0; k < K; ++k) d.L.wt[(size_t)k * d.L.N + n] = W[(size_t)n * K + k];
         d.L.Pack();
-        w = d.L.N; break;
+        w = d.L.N * S; break;
       }
-      case P_LAYERNORM:
+      case P_LAYERNORM: {                                            // len > 0: per position of a [B, len * w] sequence
+        const int S = op.len > 0 ? op.len : 1;
+        if (w0 % S || !ReadVec(r, base + "scale", &d.v0) || !ReadVec(r, base + "shift", &d.v1) || (int)d.v0.size() != w0 / S || (int)d.v1.size() != w0 / S) return false;
+        break;
+      }
       case P_AFFINE: if (!ReadVec(r, base + "scale", &d.v0) || !ReadVec(r, base + "shift", &d.v1) || (int)d.v0.size() != w0 || (int)d.v1.size() != w0) return false; break;
       case P_FM: if (op.in[0] != 1) return false; w = a.D; break;
       case P_CROSS: if (!ReadVec(r, base + "w", &d.v0) || !ReadVec(r, base + "b", &d.v1) || (int)d.v0.size() != w0 || (int)d.v1.size() != w0 || dp->width[(size_t)op.in[1]] != w0) return false; break;
@@ -289,10 +298,31 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_PRELU: if (!ReadVec(r, base + "alpha", &d.v0) || (int)d.v0.size() != w0) return false; break;
       case P_SOFTMAX: break;                                           // row-wise softmax (mixture-of-experts gates)
       case P_TILE: break;                                              // row 0 of a once-per-request buffer -> every row of the batch
+      case P_GRU: {                                                    // x [B, L * I] -> every hidden state [B, L * H] (PyTorch gate order r, z, n; h0 = 0)
+        std::vector<float> wih, whh, bih, bhh;
+        if (op.len <= 0 || w0 % op.len || !ReadVec(r, base + "w_ih", &wih) || !ReadVec(r, base + "w_hh", &whh) || !ReadVec(r, base + "b_ih", &bih) || !ReadVec(r, base + "b_hh", &bhh)) return false;
+        const int I = w0 / op.len, H3 = (int)bih.size(), H = H3 / 3;
+        if (H <= 0 || H3 != 3 * H || (int)bhh.size() != H3 || (int)wih.size() != H3 * I || (int)whh.size() != H3 * H) return false;
+        d.Gih.N = H3; d.Gih.K = I; d.Gih.bias = bih; d.Gih.wt.resize(wih.size());
+        for (int n = 0; n < H3; ++n) for (int k = 0; k < I; ++k) d.Gih.wt[(size_t)k * H3 + n] = wih[(size_t)n * I + k];
+        d.Ghh.N = H3; d.Ghh.K = H; d.Ghh.bias = bhh; d.Ghh.wt.resize(whh.size());
+        for (int n = 0; n < H3; ++n) for (int k = 0; k < H; ++k) d.Ghh.wt[(size_t)k * H3 + n] = whh[(size_t)n * H + k];
+        d.Gih.Pack(); d.Ghh.Pack(); d.H1 = H;
+        w = op.len * H; break;
+      }
+      case P_SEQ_LAST: if (op.len <= 0 || w0 % op.len || dp->width[(size_t)op.in[1]] != op.len) return false; w = w0 / op.len; break;
+      case P_SEQ_MEAN: if (op.len <= 0 || w0 % op.len || dp->width[(size_t)op.in[1]] != op.len) return false; w = w0 / op.len; break;
+      case P_MHA: {                                                    // qkv [B, S * 3E] (per position [q | k | v]), valid [B, S] -> [B, S * E]
+        if (op.len <= 0 || w0 % (3 * op.len) || dp->width[(size_t)op.in[1]] != op.len) return false;
+        const int E = w0 / (3 * op.len);
+        if (op.heads <= 0 || E % op.heads) return false;
+        w = op.len * E; break;
+      }
       case P_COSINE: if (dp->width[(size_t)op.in[1]] != w0) return false; w = 1; break;     // cosine similarity of two [B, W] towers -> [B, 1]
       case P_DIN_ATT: {                                              // q [B, W], k [B, L * W], mask [B, L] -> [B, W]
         const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
-        if (L <= 0 || wk != L * w0) return false;
+        if (L <= 0 || wk != L * w0 || op.mode < 0 || op.mode > 1) return false;
+        if (op.mode == 1) w = L;                                       // the softmax weights themselves (DIEN)
         d.att.resize(6);
         static const char* kT[] = {"w1", "b1", "w2", "b2", "w3", "b3"};
         for (int i2 = 0; i2 < 6; ++i2) if (!ReadVec(r, base + kT[i2], &d.att[(size_t)i2])) return false;
@@ -622,7 +652,10 @@ struct Session {
       float* out = Buf(op.out); const int W = d.width[(size_t)op.out];
       const float* a0 = Buf(op.in[0]); const int w0 = d.width[(size_t)op.in[0]];
       switch (op.kind) {
-        case P_LINEAR: Linear(a0, w0, B, pd.L, out, op.relu, threads); break;
+        case P_LINEAR: {
+          const int S = op.len > 0 ? op.len : 1;                     // a sequence buffer [B, S * K] is [B * S, K] in memory
+          Linear(a0, w0 / S, (int64_t)B * S, pd.L, out, op.relu, threads); break;
+        }
         case P_CONCAT: {
           int off = 0;
           for (int src : op.in) {
@@ -674,6 +707,70 @@ struct Session {
         }
         case P_VALID_MASK: {                                     // out[i, l] = ids[column start + l][i] >= 0
           for (int l = 0; l < W; ++l) { const int64_t* k = ids.data() + (size_t)(op.start + l) * Bfull; for (int i = 0; i < B; ++i) out[(size_t)i * W + l] = k[i] >= 0 ? 1.f : 0.f; }
+          break;
+        }
+        case P_GRU: {                                            // r, z, n gates; h' = (1 - z) n + z h; input projection as ONE GEMM over B * L rows
+          const int L = op.len, I = w0 / L, H = pd.H1, H3 = 3 * H;
+          std::vector<float> gi((size_t)B * L * H3), gh((size_t)B * H3), h((size_t)B * H, 0.f);
+          Linear(a0, I, (int64_t)B * L, pd.Gih, gi.data(), false, threads);
+          for (int t = 0; t < L; ++t) {
+            Linear(h.data(), H, B, pd.Ghh, gh.data(), false, threads);
+            for (int i = 0; i < B; ++i) {
+              const float* a = gi.data() + ((size_t)i * L + t) * H3; const float* b = gh.data() + (size_t)i * H3;
+              float* hh = h.data() + (size_t)i * H; float* y = out + ((size_t)i * L + t) * H;
+              for (int j = 0; j < H; ++j) {
+                const float rg = 1.f / (1.f + std::exp(-(a[j] + b[j]))), zg = 1.f / (1.f + std::exp(-(a[H + j] + b[H + j])));
+                const float ng = std::tanh(a[2 * H + j] + rg * b[2 * H + j]);
+                hh[j] = (1.f - zg) * ng + zg * hh[j]; y[j] = hh[j];
+              }
+            }
+          }
+          break;
+        }
+        case P_SEQ_LAST: {                                       // the state at the last valid position: max(sum(mask), 1) - 1
+          const float* mk = Buf(op.in[1]); const int L = op.len;
+          for (int i = 0; i < B; ++i) {
+            int cnt = 0; for (int l = 0; l < L; ++l) cnt += mk[(size_t)i * L + l] > 0.f ? 1 : 0;
+            memcpy(out + (size_t)i * W, a0 + (size_t)i * w0 + (size_t)(std::max(cnt, 1) - 1) * W, (size_t)W * sizeof(float));
+          }
+          break;
+        }
+        case P_SEQ_MEAN: {                                       // mean over the valid positions
+          const float* mk = Buf(op.in[1]); const int L = op.len;
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            float* y = out + (size_t)i * W; for (int k = 0; k < W; ++k) y[k] = 0.f;
+            int cnt = 0;
+            for (int l = 0; l < L; ++l) if (mk[(size_t)i * L + l] > 0.f) { ++cnt; const float* x = a0 + (size_t)i * w0 + (size_t)l * W; for (int k = 0; k < W; ++k) y[k] += x[k]; }
+            const float inv = 1.f / (float)std::max(cnt, 1);
+            for (int k = 0; k < W; ++k) y[k] *= inv;
+          }
+          break;
+        }
+        case P_MHA: {                                            // softmax(q k^T / sqrt(dh)) v per head, keys of invalid positions masked
+          const float* mk = Buf(op.in[1]); const int S = op.len, E = w0 / (3 * S), nh = op.heads, dh = E / nh; const float scale = 1.f / std::sqrt((float)dh);
+#pragma omp parallel for schedule(static) num_threads(threads) if (par)
+          for (int i = 0; i < B; ++i) {
+            std::vector<float> p((size_t)S);
+            const float* x = a0 + (size_t)i * w0; const float* m = mk + (size_t)i * S; float* y = out + (size_t)i * S * E;
+            for (int hd = 0; hd < nh; ++hd)
+              for (int s1 = 0; s1 < S; ++s1) {
+                const float* q = x + (size_t)s1 * 3 * E + hd * dh;
+                float mx = -3.4e38f;
+                for (int s2 = 0; s2 < S; ++s2) {
+                  if (!(m[s2] > 0.f)) { p[(size_t)s2] = -3.4e38f; continue; }
+                  const float* k = x + (size_t)s2 * 3 * E + E + hd * dh;
+                  float dot = 0.f; for (int c = 0; c < dh; ++c) dot += q[c] * k[c];
+                  p[(size_t)s2] = dot * scale; mx = std::max(mx, p[(size_t)s2]);
+                }
+                float den = 0.f;
+                for (int s2 = 0; s2 < S; ++s2) { p[(size_t)s2] = m[s2] > 0.f ? std::exp(p[(size_t)s2] - mx) : 0.f; den += p[(size_t)s2]; }
+                float* o = y + (size_t)s1 * E + hd * dh; for (int c = 0; c < dh; ++c) o[c] = 0.f;
+                if (den <= 0.f) continue;
+                const float inv = 1.f / den;
+                for (int s2 = 0; s2 < S; ++s2) { if (p[(size_t)s2] == 0.f) continue; const float wgt = p[(size_t)s2] * inv; const float* v = x + (size_t)s2 * 3 * E + 2 * E + hd * dh; for (int c = 0; c < dh; ++c) o[c] += wgt * v[c]; }
+              }
+          }
           break;
         }
         case P_TILE: {
@@ -738,7 +835,7 @@ struct Session {
         case P_DIN_ATT: {                                        // DIN attention unit: s_l = MLP([q, k_l, q - k_l, q * k_l]), masked softmax, sum_l w_l k_l
           // blocked: kS samples = kS * L history positions form the rows of two small GEMMs on the packed micro-kernels; sigmoids vectorised
           const float* kk = Buf(op.in[1]); const float* mk = Buf(op.in[2]);
-          const int L = d.width[(size_t)op.in[2]], H1 = pd.H1, H2 = pd.H2, Wq = W;
+          const int L = d.width[(size_t)op.in[2]], H1 = pd.H1, H2 = pd.H2, Wq = w0; const bool weights_out = op.mode == 1;
           const float* w3 = pd.att[4].data(); const float b3 = pd.att[5][0];
           std::lock_guard<std::mutex> att_lock(att_mu);              // one scratch per session: two attention ops never run side by side
           att_hq.resize((size_t)B * H1);
@@ -779,6 +876,15 @@ struct Session {
                   sc[(size_t)l] = s3 + b3;
                   if (m[l] > 0.f) { any = true; mx = std::max(mx, sc[(size_t)l]); }
                 }
+                if (weights_out) {                               // DIEN: softmax(masked_fill(s, -2^31)) -- uniform when nothing is valid
+                  float* y = out + (size_t)i * L;
+                  if (!any) { for (int l = 0; l < L; ++l) y[l] = 1.f / (float)L; continue; }
+                  float den = 0.f;
+                  for (int l = 0; l < L; ++l) { y[l] = m[l] > 0.f ? FastExp(sc[(size_t)l] - mx) : 0.f; den += y[l]; }
+                  const float inv = 1.f / den;
+                  for (int l = 0; l < L; ++l) y[l] *= inv;
+                  continue;
+                }
                 float* y = out + (size_t)i * Wq; for (int c = 0; c < Wq; ++c) y[c] = 0.f;
                 if (!any) continue;                              // no valid history position: zero vector (the module multiplies by mask.any())
                 float den = 0.f;
@@ -796,6 +902,7 @@ struct Session {
         }
         case P_LAYERNORM: {                                      // (x - mean) / sqrt(var + eps) * gamma + beta, biased variance, optional ReLU
           const float* g = pd.v0.data(); const float* bt = pd.v1.data(); const float eps = op.eps; const bool relu = op.relu;
+          const int S = op.len > 0 ? op.len : 1, W = d.width[(size_t)op.out] / S, B = (op.rows1 ? 1 : Bfull) * S;      // per position of a sequence buffer
 #pragma omp parallel for schedule(static) num_threads(threads) if (par)
           for (int i = 0; i < B; ++i) {
             const float* x = a0 + (size_t)i * W; float* y = out + (size_t)i * W;

@@ -270,8 +270,43 @@ class _ProgramBuilder:
         self.tensors[f"prog/{out}/alpha"] = (a.expand(width) if a.numel() == 1 else a).contiguous()
         self.ops.append({"op": "prelu", "out": out, "in": [src]}); return out
 
-    def din_attention(self, q, k, mask, att):
-        """Linear(4W, H1)-Sigmoid-Linear(H1, H2)-Sigmoid-Linear(H2, 1) attention unit, masked softmax, weighted sum of the keys."""
+    # ---- recurrent / transformer sequence models (DIEN, BST) -------------------------------------------------------------------------------
+    def gru(self, x, L, gru):
+        """Single-layer batch-first ``nn.GRU`` over ``x [B, L * I]`` -> every hidden state ``[B, L * H]`` (h0 = 0, PyTorch gate order r, z, n)."""
+        if gru.num_layers != 1 or gru.bidirectional or not gru.batch_first:
+            raise TypeError("op-program export: single-layer, unidirectional, batch_first GRU only")
+        out = self._name("gru")
+        for nm, t in (("w_ih", gru.weight_ih_l0), ("w_hh", gru.weight_hh_l0), ("b_ih", gru.bias_ih_l0), ("b_hh", gru.bias_hh_l0)):
+            self.tensors[f"prog/{out}/{nm}"] = t.detach().float().cpu().contiguous()
+        self.ops.append({"op": "gru", "out": out, "in": [x], "len": int(L)}); return out
+
+    def seq_last(self, x, mask, L):
+        """``x [B, L * W]`` at the last valid position of every row (``max(sum(mask), 1) - 1``) -> ``[B, W]``."""
+        out = self._name("last"); self.ops.append({"op": "seq_last", "out": out, "in": [x, mask], "len": int(L)}); return out
+
+    def seq_linear(self, src, weight, bias, L, relu=False):
+        """The same Linear at every one of the L positions of ``src [B, L * K]`` -> ``[B, L * N]`` (one GEMM over B * L rows)."""
+        out = self._name("slin")
+        self.tensors[f"prog/{out}/kernel"] = weight.detach().float().cpu().contiguous()
+        self.tensors[f"prog/{out}/bias"] = (bias.detach().float().cpu() if bias is not None else torch.zeros(weight.shape[0])).contiguous()
+        self.ops.append({"op": "linear", "out": out, "in": [src], "relu": bool(relu), "len": int(L)}); return out
+
+    def seq_layernorm(self, src, ln, L):
+        out = self._name("sln")
+        self.tensors[f"prog/{out}/scale"] = ln.weight.detach().float().cpu().contiguous(); self.tensors[f"prog/{out}/shift"] = ln.bias.detach().float().cpu().contiguous()
+        self.ops.append({"op": "layernorm", "out": out, "in": [src], "eps": float(ln.eps), "relu": False, "len": int(L)}); return out
+
+    def mha(self, qkv, valid, S, heads):
+        """Multi-head self-attention core over ``qkv [B, S * 3E]`` (per position ``[q | k | v]``), keys with ``valid [B, S] == 0`` masked -> ``[B, S * E]``."""
+        out = self._name("mha"); self.ops.append({"op": "mha", "out": out, "in": [qkv, valid], "len": int(S), "heads": int(heads)}); return out
+
+    def seq_mean(self, x, valid, S):
+        """Mean of ``x [B, S * W]`` over the valid positions -> ``[B, W]``."""
+        out = self._name("smean"); self.ops.append({"op": "seq_mean", "out": out, "in": [x, valid], "len": int(S)}); return out
+
+    def din_attention(self, q, k, mask, att, weights=False):
+        """Linear(4W, H1)-Sigmoid-Linear(H1, H2)-Sigmoid-Linear(H2, 1) attention unit, masked softmax, weighted sum of the keys
+        (``weights=True``: the softmax weights ``[B, L]`` themselves -- DIEN scales its hidden states with them)."""
         import torch.nn as nn
         mods = list(att)
         if not (len(mods) == 5 and all(isinstance(mods[i], nn.Linear) for i in (0, 2, 4)) and all(isinstance(mods[i], nn.Sigmoid) for i in (1, 3)) and mods[4].out_features == 1):
@@ -279,7 +314,7 @@ class _ProgramBuilder:
         out = self._name("att")
         for nm, t in (("w1", mods[0].weight), ("b1", mods[0].bias), ("w2", mods[2].weight), ("b2", mods[2].bias), ("w3", mods[4].weight), ("b3", mods[4].bias)):
             self.tensors[f"prog/{out}/{nm}"] = t.detach().float().cpu().reshape(-1).contiguous()
-        self.ops.append({"op": "din_attention", "out": out, "in": [q, k, mask]}); return out
+        self.ops.append({"op": "din_attention", "out": out, "in": [q, k, mask], "mode": 1 if weights else 0}); return out
 
     def tile(self, src):
         """Broadcast row 0 of a buffer computed once per request (``rows1`` ops, sample-aware compression) to every row of the batch."""
@@ -430,14 +465,47 @@ def _build_program(model, max_len: int = 50) -> _ProgramBuilder:
         k = p.seq_mask(p.seq_zip(p.slice("emb", 3 * D, L * D), p.slice("emb", (3 + L) * D, L * D), L), mask, L)      # [B, L * 2D]
         x = p.concat([u, q, p.seq_sum(k, L), p.din_attention(q, k, mask, model.att)])
         p.out = p.sequential(x, nn.Sequential(model.bn, *list(model.top)))
+    elif isinstance(model, (zoo.DIEN, zoo.BST)):
+        L, D = int(max_len), model.emb_dim
+        E = 2 * D
+        p.tables = [(model.user, D), (model.item, D), (model.cat, D)]
+        p.col_table = [0, 1, 2] + [1] * L + [2] * L
+        p.num_dense = 1
+        u, q = p.slice("emb", 0, D), p.slice("emb", D, 2 * D)
+        mask = p.valid_mask(3, L)
+        k = p.seq_mask(p.seq_zip(p.slice("emb", 3 * D, L * D), p.slice("emb", (3 + L) * D, L * D), L), mask, L)      # [B, L * E], padding zeroed
+        if isinstance(model, zoo.DIEN):
+            # interest extractor GRU -> attention weights of the target against every hidden state -> evolution GRU over the weighted states
+            h1 = p.gru(k, L, model.gru1)
+            qh = p.linear(q, model.qproj.weight, model.qproj.bias)
+            w = p.din_attention(qh, h1, mask, model.att, weights=True)
+            h2 = p.gru(p.seq_mask(h1, w, L), L, model.gru2)
+            x = p.concat([u, q, p.seq_last(h2, mask, L), p.seq_sum(k, L)])
+            p.out = p.sequential(x, model.top)
+        else:
+            # one post-norm encoder block over [history ; target] with key-padding mask, masked mean pooling
+            enc = model.enc
+            if enc.norm_first or enc.self_attn.batch_first is not True or not getattr(enc, "activation_relu_or_gelu", 1) == 1:
+                raise TypeError("op-program export: BST needs the post-norm, batch_first, ReLU TransformerEncoderLayer")
+            S = L + 1
+            if S > model.pos.shape[0]:
+                raise ValueError(f"op-program export: max_len {L} exceeds the model's positional table ({model.pos.shape[0] - 1})")
+            x = p.affine(p.concat([k, q]), torch.ones(S * E), model.pos[:S].detach().reshape(-1))
+            valid = p.concat([mask, p.affine(p.slice("dense", 0, 1), torch.zeros(1), torch.ones(1))])              # the target position is always valid
+            at = enc.self_attn
+            a_ = p.seq_linear(p.mha(p.seq_linear(x, at.in_proj_weight, at.in_proj_bias, S), valid, S, at.num_heads), at.out_proj.weight, at.out_proj.bias, S)
+            x1 = p.seq_layernorm(p.add(x, a_), enc.norm1, S)
+            f_ = p.seq_linear(p.seq_linear(x1, enc.linear1.weight, enc.linear1.bias, S, relu=True), enc.linear2.weight, enc.linear2.bias, S)
+            x2 = p.seq_layernorm(p.add(x1, f_), enc.norm2, S)
+            p.out = p.linear(p.sequential(p.concat([u, q, p.seq_mean(x2, valid, S)]), model.final), model.out.weight, model.out.bias)
     else:
-        raise TypeError(f"op-program export: no builder for {type(model).__name__} (WDL, DeepFM, DCN, DCNv2, MaskNet, DIN, DSSM, ESMM, MMoE, DBMTL, PLE, SimpleMultiTask; DLRM has export_saved_model_module)")
+        raise TypeError(f"op-program export: no builder for {type(model).__name__} (WDL, DeepFM, DCN, DCNv2, MaskNet, DIN, DIEN, BST, DSSM, ESMM, MMoE, DBMTL, PLE, SimpleMultiTask; DLRM has export_saved_model_module)")
     return p
 
 
 # ---- sample-aware graph compression as a pass over the op program ---------------------------------------------------------------------------
 _ROW_WISE = {"concat", "linear", "affine", "cross", "mul_add", "add", "mul", "layernorm", "slice", "seq_zip", "seq_mask", "seq_sum", "prelu", "softmax",
-             "cosine", "din_attention", "valid_mask"}
+             "cosine", "din_attention", "valid_mask", "gru", "seq_last", "mha", "seq_mean"}
 
 
 def compress_sample_aware(ops: list, output: str, user_columns, emb_dim: int, user_dense: bool = False):
