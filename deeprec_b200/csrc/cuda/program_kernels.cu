@@ -167,6 +167,16 @@ __global__ void __launch_bounds__(256) k_prog_to_u8(const __nv_bfloat16* __restr
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int64_t b = i / w; y[i] = ldb(x + b * ldx + (i - b * w)) > 0.f ? 1 : 0; }
 }
 
+// host-resident tables (device placement optimisation): rows looked up on the CPU arrive sample-major fp32 [B, T * D]; the DLRM path wants them
+// feature-major bf16 [T][B][D]
+__global__ void __launch_bounds__(256) k_prog_emb_feature_major(const float* __restrict__ x, int T, int D, int64_t B, __nv_bfloat16* __restrict__ y) {
+  const int64_t n = B * (int64_t)T * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / ((int64_t)T * D); const int r = (int)(i - b * (int64_t)T * D); const int t = r / D, d = r - t * D;
+    stb(y + ((int64_t)t * B + b) * D + d, x[i]);
+  }
+}
+
 // row-wise softmax (mixture-of-experts gates), one warp per row
 __global__ void __launch_bounds__(256) k_prog_softmax(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
   const int lane = threadIdx.x & 31;
@@ -440,6 +450,12 @@ int dr_prog_mha(const void* qkv, int64_t ldq, const void* valid, int64_t ldv, in
   return 0;
 }
 
+int dr_prog_emb_feature_major(const float* x, int T, int D, int64_t B, void* y, cudaStream_t s) {
+  if (B <= 0 || T <= 0 || D <= 0) return 0;
+  k_prog_emb_feature_major<<<grid_el(B * T * D), 256, 0, s>>>(x, T, D, B, (__nv_bfloat16*)y);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
 int dr_prog_softmax(const void* x, int64_t ldx, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
   if (B <= 0 || w <= 0) return 0;
   k_prog_softmax<<<grid_rows(B), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)y, ldy, B);

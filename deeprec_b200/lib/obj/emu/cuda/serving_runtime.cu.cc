@@ -13,6 +13,8 @@
 // The reference embeds the TF runtime and runs a SavedModel graph; here inference is the sm_100a kernel sequence of the
 // flagship engine (BatchNorm folded at load time, read-only probes), so a request is ~16 kernel launches on the
 // session's stream.
+#include <dlfcn.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -71,6 +73,7 @@ int dr_prog_to_u8(const void* x, int64_t ldx, int w, uint8_t* y, int64_t B, cuda
 int dr_prog_softmax(const void* x, int64_t ldx, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_cosine(const void* a, int64_t lda, const void* c, int64_t ldc, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_sigmoid_cols(const void* x, int64_t ldx, int no, int64_t B, float* prob, cudaStream_t s);
+int dr_prog_emb_feature_major(const float* x, int T, int D, int64_t B, void* y, cudaStream_t s);
 int dr_prog_gru(const void* gi, int64_t ldg, const float* whh, const float* bhh, int L, int H, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_seq_last(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_seq_mean(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
@@ -84,6 +87,34 @@ int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, c
 }
 
 namespace serve {
+
+// ---- device placement optimisation (ModelConfig "enable_device_placement_optimization", the reference's gpu_device_placement_pass.cc: the embedding
+// layer stays on the CPU for GPU inference) -- the tables live in the HOST engine (libdeeprec_host.so next to this library, bound at run time so
+// that the GPU library keeps no link-time dependency on it): tables larger than HBM, or one copy shared by the replicas of every GPU of a box.
+// A request looks its rows up on the caller's thread, ships them as one H2D copy and runs the dense part on the GPU as usual.
+struct HostApi {
+  void* (*create)(const DrEvConfig*) = nullptr; void (*destroy)(void*) = nullptr; void (*set_default)(void*, const float*) = nullptr;
+  int64_t (*import)(void*, const int64_t*, const float*, int64_t, const int64_t*, const int64_t*, int64_t, int, int, int) = nullptr;
+  int64_t (*import_cow)(void*, const int64_t*, const float*, int64_t, int64_t) = nullptr;
+  void (*group_lookup)(void**, int, const int64_t*, int64_t, float*) = nullptr;
+  bool ok = false;
+  static HostApi& Get() {
+    static HostApi api = [] {
+      HostApi a;
+      Dl_info info{};
+      std::string dir = ".";
+      if (dladdr((void*)&HostApi::Get, &info) && info.dli_fname) { dir = info.dli_fname; const size_t p = dir.find_last_of('/'); dir = p == std::string::npos ? "." : dir.substr(0, p); }
+      void* h = dlopen((dir + "/libdeeprec_host.so").c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (!h) { fprintf(stderr, "[deeprec_serving] device placement optimisation needs %s/libdeeprec_host.so: %s\n", dir.c_str(), dlerror()); return a; }
+      a.create = (decltype(a.create))dlsym(h, "dr_host_ev_create"); a.destroy = (decltype(a.destroy))dlsym(h, "dr_host_ev_destroy");
+      a.set_default = (decltype(a.set_default))dlsym(h, "dr_host_ev_set_default"); a.import = (decltype(a.import))dlsym(h, "dr_host_ev_import");
+      a.import_cow = (decltype(a.import_cow))dlsym(h, "dr_host_ev_import_cow"); a.group_lookup = (decltype(a.group_lookup))dlsym(h, "dr_host_group_lookup");
+      a.ok = a.create && a.destroy && a.set_default && a.import && a.import_cow && a.group_lookup;
+      return a;
+    }();
+    return api;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // minimal JSON (objects, arrays, strings, numbers, bools) -- enough for ModelConfig / saved_model.json / state files
@@ -191,6 +222,9 @@ struct DeviceModel {
   std::vector<std::unique_ptr<TableDev>> tables;
   DevBuf structs;      // DrDeviceTable[T] on the device
   DevBuf col_table;    // int32 [C]: table of every lookup column (program models; identity otherwise)
+  // device placement optimisation: the tables live in the host engine instead (HostEV handles, owned), col_handles[c] = table of lookup column c
+  bool host_resident = false; std::vector<void*> host_tables, col_handles; std::vector<int64_t> host_sample_keys;
+  ~DeviceModel() { if (host_resident) for (void* h : host_tables) if (h) HostApi::Get().destroy(h); }
 };
 
 static bool ReadTensor(dr::BundleReader& r, const std::string& name, std::vector<uint8_t>* out, std::vector<int64_t>* shape = nullptr) {
@@ -423,6 +457,28 @@ static bool BuildTable(dr::BundleReader& r, int t, int D, TableDev* td, int64_t 
   return true;
 }
 
+// host-resident twin of BuildTable (device placement optimisation): the rows go into a HostEV of the host engine
+static void* BuildHostTable(dr::BundleReader& r, int t, int D, std::vector<int64_t>* sample) {
+  HostApi& api = HostApi::Get();
+  if (!api.ok) return nullptr;
+  const std::string base = "table/" + std::to_string(t);
+  std::vector<int64_t> keys, freqs, vers; std::vector<float> vals, def;
+  if (!ReadVec(r, base + "-keys", &keys) || !ReadVec(r, base + "-values", &vals) || !ReadVec(r, base + "-default", &def)) return nullptr;
+  ReadVec(r, base + "-freqs", &freqs); ReadVec(r, base + "-versions", &vers);
+  if (def.empty() || def.size() % (size_t)D || vals.size() != keys.size() * (size_t)D) return nullptr;
+  DrEvConfig c{};
+  c.dim = D; c.num_slots = 0; c.has_scalars = 0; c.init_capacity = std::max<int64_t>(1024, (int64_t)keys.size() * 2);
+  c.default_value_dim = (int64_t)def.size() / D; c.num_partitions = 16; c.record_freq = 1; c.record_version = 1; c.l2_weight_threshold = -1.f;
+  void* h = api.create(&c);
+  if (!h) return nullptr;
+  api.set_default(h, def.data());
+  if (!keys.empty())
+    api.import(h, keys.data(), vals.data(), D, freqs.size() == keys.size() ? freqs.data() : nullptr, vers.size() == keys.size() ? vers.data() : nullptr,
+               (int64_t)keys.size(), 0, 1, 0);
+  sample->assign(keys.begin(), keys.begin() + std::min<size_t>(keys.size(), 512));
+  return h;
+}
+
 static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::string* prefix) {
   std::string txt; JVal j;
   if (!ReadFile(dir + "/saved_model.json", &txt) || !ParseJson(txt, &j)) return false;
@@ -486,13 +542,28 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
 }
 
-static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t extra_rows, bool want_fp8 = false) {
+static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t extra_rows, bool want_fp8 = false, bool host_tables = false) {
   auto m = std::make_shared<DeviceModel>();
   std::string prefix;
   if (!LoadArch(dir, &m->arch, &m->version, &prefix)) { fprintf(stderr, "[deeprec_serving] bad saved_model.json in %s\n", dir.c_str()); return nullptr; }
   dr::BundleReader r(prefix);
   if (!r.ok()) { fprintf(stderr, "[deeprec_serving] cannot open bundle %s\n", prefix.c_str()); return nullptr; }
   if (!BuildDense(r, m->arch, &m->dense, want_fp8 && !m->arch.program)) { fprintf(stderr, "[deeprec_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
+  if (host_tables) {                                                 // device placement optimisation: embedding layer on the CPU
+    m->host_resident = true;
+    for (int t = 0; t < m->arch.T; ++t) {
+      std::vector<int64_t> sample;
+      void* h = BuildHostTable(r, t, m->arch.D, &sample);
+      if (!h) { fprintf(stderr, "[deeprec_serving] host table %d incomplete (or libdeeprec_host.so missing)\n", t); return nullptr; }
+      m->host_tables.push_back(h);
+      m->host_sample_keys.insert(m->host_sample_keys.end(), sample.begin(), sample.end());
+      m->tables.emplace_back(new TableDev());
+      m->tables.back()->sample_keys = sample;
+    }
+    for (int c = 0; c < m->arch.C; ++c) m->col_handles.push_back(m->host_tables[(size_t)m->arch.col_table[(size_t)c]]);
+    m->path = dir;
+    return m;
+  }
   std::vector<DrDeviceTable> structs;
   for (int t = 0; t < m->arch.T; ++t) {
     m->tables.emplace_back(new TableDev());
@@ -512,6 +583,18 @@ struct Session {
   std::vector<DevBuf> a_bot, a_top;
   DevBuf x0_q, Z_q, amax; std::vector<DevBuf> q_bot, q_top;        // fp8 path: E4M3 activations between the GEMMs
   float* h_dense = nullptr; int64_t* h_ids = nullptr; float* h_prob = nullptr;    // pinned
+  float* h_emb = nullptr; DevBuf emb_f32;                            // host-resident tables: looked-up rows [B, C, D] fp32 (pinned) and their device copy
+  // rows of this chunk from the host engine -> one H2D copy -> bf16 in the layout the dense part expects (program: [B, C * D]; DLRM: [T][B][D])
+  bool HostLookup(const DeviceModel& m, int B) {
+    const Arch& a = m.arch; cudaStream_t s = stream;
+    const size_t n = (size_t)B * a.C * a.D;
+    if (!h_emb) { SV_CUDA(cudaMallocHost(&h_emb, (size_t)max_batch * a.C * a.D * 4)); if (!emb_f32.alloc((size_t)max_batch * a.C * a.D * 4)) return false; }
+    HostApi::Get().group_lookup(const_cast<void**>(m.col_handles.data()), a.C, h_ids, B, h_emb);
+    SV_CUDA(cudaMemcpyAsync(emb_f32.p, h_emb, n * 4, cudaMemcpyHostToDevice, s));
+    const int rc = a.program ? dr_prog_from_f32(emb_f32.as<float>(), a.C * a.D, emb.p, (int64_t)a.C * a.D, B, s)
+                             : dr_prog_emb_feature_major(emb_f32.as<float>(), a.C, a.D, B, emb.p, s);
+    return rc == 0;
+  }
   bool Init(const Arch& a, int maxB) {
     max_batch = maxB;
     SV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -532,7 +615,7 @@ struct Session {
     SV_CUDA(cudaMallocHost(&h_prob, (size_t)maxB * a.n_out * 4));
     return true;
   }
-  ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (stream) cudaStreamDestroy(stream); }
+  ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (h_emb) cudaFreeHost(h_emb); if (stream) cudaStreamDestroy(stream); }
 
   // ---- op-program models: buffers 0 / 1 alias x0 / emb, the others are (max_batch x prog_ld(width)) bf16, zeroed once (pad columns stay zero) ----
   std::vector<DevBuf> pbuf; std::vector<int> pbuf_width;
@@ -564,9 +647,12 @@ struct Session {
     int rc = 0;
     const int64_t n = (int64_t)a.C * Bfull;
     const int32_t* ct = m.col_table.as<int32_t>();                   // lookup column -> table
-    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), ct, a.C, ids.as<int64_t>(), nullptr, Bfull, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
-    // sample-major embeddings [B, C * D]: element (b, c) at b * (C * D) + c * D
-    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), ct, a.C, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, Bfull, n, emb.p, 1, (int64_t)a.C * a.D, a.D, 0, s);
+    if (m.host_resident) { if (!HostLookup(m, Bfull)) return false; }
+    else {
+      rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), ct, a.C, ids.as<int64_t>(), nullptr, Bfull, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+      // sample-major embeddings [B, C * D]: element (b, c) at b * (C * D) + c * D
+      rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), ct, a.C, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, Bfull, n, emb.p, 1, (int64_t)a.C * a.D, a.D, 0, s);
+    }
     rc |= dr_cuda_cast_pad(dense_in.as<float>(), Bfull, a.num_dense, x0.p, pad8(a.num_dense), s);
     for (size_t oi = 0; oi < a.ops.size() && rc == 0; ++oi) {
       const POp& op = a.ops[oi]; const auto& pd = dp.pdata[oi];
@@ -648,8 +734,11 @@ struct Session {
     }
     int rc = 0;
     const int64_t n = (int64_t)a.T * B;
-    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
-    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, 0, 0, 1, s);
+    if (m.host_resident) { if (!HostLookup(m, B)) return false; }
+    else {
+      rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+      rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, 0, 0, 1, s);
+    }
     const void* x; int64_t ldx;
     if (dp.fp8 && !force_bf16) {
       // ---- E4M3 path: every hidden activation stays 8-bit; each GEMM epilogue re-quantises with the next layer's static scale
@@ -727,7 +816,7 @@ static bool Calibrate(Session& ss, const DeviceModel& m, DenseParams& dp, int B)
 }
 
 struct Config {
-  bool fp8 = false;
+  bool fp8 = false, host_tables = false;                 // host_tables: "enable_device_placement_optimization" -- embedding lookups on the CPU
   int session_num = 2, select_policy = 0 /*0 RR, 1 MOD*/, gpu_id = 0, max_batch = 4096, update_interval_ms = 1000, extra_rows = 1 << 16;
   int timeline_start_step = -1, timeline_interval_step = 0, timeline_trace_count = 0;
   std::string savedmodel_dir, checkpoint_dir, warmup_file_name, timeline_path;
@@ -829,6 +918,11 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
     const std::string base = "table/" + std::to_string(t);
     if (!ReadVec(r, base + "-sparse_incr_keys", &keys) || keys.empty()) continue;
     if (!ReadVec(r, base + "-sparse_incr_values", &vals)) return false;
+    if (m->host_resident) {                                          // host engine: copy-on-write import, readers never see a torn row
+      if (vals.size() != keys.size() * (size_t)m->arch.D) return false;
+      HostApi::Get().import_cow(m->host_tables[(size_t)t], keys.data(), vals.data(), m->arch.D, (int64_t)keys.size());
+      continue;
+    }
     // copy-on-write: live sessions keep reading complete rows (old or new) while the delta lands; the replaced rows are recycled at
     // the NEXT delta, after every session has passed a quiescent point (Quiesce below) -- CPU runtime: dr_host_ev_import_cow
     DevBuf dk, dv, cnt;
@@ -919,7 +1013,7 @@ static void UpdaterLoop(ServingModel* sm) {
       int64_t v = (int64_t)f->n("version", -1); std::string dir = f->s("dir", "");
       if (cur && v > cur->version && !dir.empty()) {
         cudaSetDevice(sm->cfg.gpu_id);
-        auto nm = LoadModel(dir, sm->cfg.extra_rows, sm->cfg.fp8);
+        auto nm = LoadModel(dir, sm->cfg.extra_rows, sm->cfg.fp8, sm->cfg.host_tables);
         if (!nm) { if (++bad > 3) fprintf(stderr, "[deeprec_serving] skipping invalid model version %lld\n", (long long)v); continue; }
         bad = 0;
         // The sessions' device / pinned buffers were sized from the architecture they were initialised with (Session::Init): a version with
@@ -998,7 +1092,8 @@ void* initialize(const char* model_entry, const char* model_config, int* state) 
   c.timeline_trace_count = (int)j.n("timeline_trace_count", 0);
   if (cudaSetDevice(c.gpu_id) != cudaSuccess) { *state = -1; delete sm; return nullptr; }
   c.fp8 = j.s("mlp_dtype", "bf16") == "fp8";
-  auto m = LoadModel(c.savedmodel_dir, c.extra_rows, c.fp8);
+  c.host_tables = j.n("enable_device_placement_optimization", 0) != 0 || j.s("embedding_placement", "device") == "host";
+  auto m = LoadModel(c.savedmodel_dir, c.extra_rows, c.fp8, c.host_tables);
   if (!m) { *state = -1; delete sm; return nullptr; }
   for (int i = 0; i < std::max(1, c.session_num); ++i) {
     sm->sessions.emplace_back(new Session());
@@ -1034,7 +1129,7 @@ int get_serving_model_info(void* model_buf, void** output_data, int* output_size
   std::ostringstream os;
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
-     << ", \"mlp_dtype\": \"" << (sm->cfg.fp8 ? "fp8" : "bf16") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
+     << ", \"mlp_dtype\": \"" << (sm->cfg.fp8 ? "fp8" : "bf16") << "\", \"embedding_placement\": \"" << (sm->cfg.host_tables ? "host" : "device") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
   std::string s = os.str();
   *output_size = (int)s.size();
   *output_data = malloc(s.size() + 1);
