@@ -217,6 +217,13 @@ def stream_sync(device=None) -> None:
     torch.cuda.current_stream(device).synchronize()
 
 
+def device_sync(device=None) -> None:
+    """torch.cuda.synchronize(device), or nothing while the kernel emulation is active."""
+    if _EMU_DEPTH > 0:
+        return
+    torch.cuda.synchronize(device)
+
+
 def set_device(index: int) -> None:
     """The kernel library links its own static cudart: its current device must follow torch's."""
     if _EMU_DEPTH > 0:

@@ -132,6 +132,7 @@ EMU_SOURCES = [
     "cuda/serving_runtime.cu",
     "cuda/sparse_pipeline.cu",          # unique-first model-parallel pipeline: ranks = host threads, peer memory = the shared address space
     "cuda/comm_kernels.cu",
+    "cuda/tier_kernels.cu",             # multi-tier: miss list / histogram eviction kernels + the manager's background thread
     "cuda/emu/emu_stubs.cu",            # host-loop stand-ins for the tcgen05 GEMM entry points
 ]
 

@@ -58,19 +58,24 @@ class DeviceTierManager:
         fimp = C.cast(hl.dr_host_ev_import, vp)
         self.evict_chunk = int(evict_chunk or max(4096, self.cache_rows // 8))
         self.low = int(self.cache_rows * low_watermark)
-        _native.set_device(self.dev.index)
-        self.h = self.lib.dr_tier_create(vp(host.h), fexp, fimp, table.stride, int(max_batch_keys), self.evict_chunk, self.dev.index)
+        self.emu = _native.emu_active()                                  # CPU CI: the kernels and the manager thread on the CUDA-on-CPU emulation
+        if not self.emu:
+            _native.set_device(self.dev.index)
+        self.h = self.lib.dr_tier_create(vp(host.h), fexp, fimp, table.stride, int(max_batch_keys), self.evict_chunk, self.dev.index or 0)
         if not self.h:
             raise RuntimeError("dr_tier_create failed")
-        self.side = torch.cuda.Stream(device=self.dev)
-        self._count = torch.zeros(1, dtype=torch.int32).pin_memory()      # admitted-row count of the HBM tier, refreshed asynchronously
+        self.side = None if self.emu else torch.cuda.Stream(device=self.dev)
+        self._count = torch.zeros(1, dtype=torch.int32)                   # admitted-row count of the HBM tier, refreshed asynchronously
+        if not self.emu:
+            self._count = self._count.pin_memory()
         self._epoch = 0
         self._keep = None
         self._purged_at = 0
 
     def close(self) -> None:
         if self.h:
-            torch.cuda.synchronize(self.dev)
+            if not self.emu:
+                torch.cuda.synchronize(self.dev)
             self.lib.dr_tier_destroy(self.h)
             self.h = None
 
@@ -85,17 +90,19 @@ class DeviceTierManager:
         """Called with the ids of the NEXT batch (device tensor, duplicates / padding allowed) while the current step runs: probes on a
         side stream, pins the hits, hands the misses to the background thread."""
         k = keys.reshape(-1)
-        assert k.is_cuda and k.dtype == torch.int64 and k.is_contiguous()
+        assert (k.is_cuda or self.emu) and k.dtype == torch.int64 and k.is_contiguous()
         self._keep = k                                                   # alive until the probe kernel has run (commit)
-        self.side.wait_stream(torch.cuda.current_stream(self.dev))       # the ids were produced on the caller's stream
-        rc = self.lib.dr_tier_prefetch(self.h, C.byref(self.table.struct), ptr(k), k.numel(), self.pad_key, self._epoch + 1, vp(self.side.cuda_stream))
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream(self.dev))   # the ids were produced on the caller's stream
+        rc = self.lib.dr_tier_prefetch(self.h, C.byref(self.table.struct), ptr(k), k.numel(), self.pad_key, self._epoch + 1,
+                                       vp(self.side.cuda_stream) if self.side is not None else None)
         if rc != 0:
             raise RuntimeError(f"dr_tier_prefetch failed ({rc}): commit() the previous batch first")
 
     def commit(self, step: int) -> int:
         """Step boundary (before the step that consumes the prefetched batch is launched): promoted rows are imported on the current
         stream; cold rows are demoted when the slab passed its high watermark.  Returns the number of promoted rows."""
-        s = vp(torch.cuda.current_stream(self.dev).cuda_stream)
+        s = None if self.emu else vp(torch.cuda.current_stream(self.dev).cuda_stream)
         self._epoch += 1
         n = int(self.lib.dr_tier_commit(self.h, C.byref(self.table.struct), self._epoch, s))
         if n < 0:
@@ -134,7 +141,8 @@ class DeviceTierManager:
         return out
 
     def drain(self) -> None:
-        torch.cuda.synchronize(self.dev)
+        if not self.emu:
+            torch.cuda.synchronize(self.dev)
         self.lib.dr_tier_drain(self.h)
 
     def stats(self) -> Dict[str, float]:

@@ -53,11 +53,12 @@ def test_emulated_kernels_under_address_sanitizer():
 def test_emulated_kernels_under_thread_sanitizer():
     """Shared-memory protocols of the fused attention kernels (forward + backward), warp collectives, atomics of the sparse utilities, and the
     cross-rank flag protocol of the unique-first pipeline (sp_sync.cuh) with 2 and 3 ranks running as threads -- the racecheck of the NVLink
-    signalling: a missing release / acquire or a buffer reused before its consumer finished shows up as a data race between rank threads."""
+    signalling: a missing release / acquire or a buffer reused before its consumer finished shows up as a data race between rank threads;
+    plus the multi-tier manager: emulated kernels vs its background (EvictionManager) thread over mapped pinned memory, events and the job queue."""
     prefix = ("setarch", "-R") if shutil.which("setarch") else ()           # TSAN's shadow mapping wants ASLR off on recent kernels
     supp = os.path.join(ROOT, "tests", "native", "tsan_emu.supp")
     r = _run({"LD_PRELOAD": _runtime("libtsan.so"), "TSAN_OPTIONS": f"halt_on_error=0 report_signal_unsafe=0 exitcode=0 suppressions={supp}",
-              "DEEPREC_EMU_SANITIZE": "thread"}, ["test_cuda_emu_attention.py", "test_cuda_emu_sparse_utils.py", "test_cuda_emu_sparse_pipeline.py"], prefix=prefix)
+              "DEEPREC_EMU_SANITIZE": "thread"}, ["test_cuda_emu_attention.py", "test_cuda_emu_sparse_utils.py", "test_cuda_emu_sparse_pipeline.py", "test_cuda_emu_tier.py"], prefix=prefix)
     if r.returncode != 0 and ("unexpected memory mapping" in r.stderr or "tpp.c" in r.stderr or "cannot allocate memory in static TLS" in r.stderr):
         pytest.skip("TSAN runtime is not usable in this environment")
     # exitcode=0: the python process also hosts PyTorch, whose uninstrumented runtime produces reports of its own (e.g. at interpreter teardown);
