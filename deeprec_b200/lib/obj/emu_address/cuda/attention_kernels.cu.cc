@@ -52,7 +52,7 @@ struct DinSmem {
 __global__ void __launch_bounds__(kThreads) k_din_attention_fwd(const float* __restrict__ q, const float* __restrict__ k, const uint8_t* __restrict__ mask, int64_t B,
                                                                 DinShape p, const float* __restrict__ W1, const float* __restrict__ b1,
                                                                 const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ w3, float b3,
-                                                                float* __restrict__ out) {
+                                                                float* __restrict__ out, float* __restrict__ weights_out) {
   float* sm = (float*)emu::dyn_smem();
   const DinSmem o(p);
   const int L = p.L, D = p.D, H1 = p.H1, H2 = p.H2, tid = threadIdx.x;
@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(kThreads) k_din_attention_fwd(const float* __r
       sum = warp_sum(sum);
       const float inv = sum > 0.f ? 1.f / sum : 0.f;        // no valid position -> zero output (softmax * mask.any())
       for (int t = tid; t < L; t += 32) sS[t] *= inv;
+      // DIEN reads the weights themselves: softmax(masked_fill(s, -2^31)) is UNIFORM when no position is valid
+      if (weights_out) for (int t = tid; t < L; t += 32) weights_out[b * L + t] = sum > 0.f ? sS[t] : 1.f / (float)L;
     }
     __syncthreads();
     // ---- weighted sum of the keys
@@ -362,8 +364,8 @@ extern "C" {
 
 // q [B, D], k [B, L, D], mask [B, L] (uint8), W1 [H1, 4D], W2 [H2, H1], w3 [H2] (PyTorch Linear layouts) -> out [B, D].
 // Returns 0, a CUDA error code, or -1 when the shape does not fit in shared memory.
-int dr_cuda_din_attention_fwd(const float* q, const float* k, const uint8_t* mask, int64_t B, int L, int D, const float* W1, const float* b1, int H1,
-                              const float* W2, const float* b2, int H2, const float* w3, float b3, float* out, cudaStream_t s) {
+int dr_cuda_din_attention_fwd_w(const float* q, const float* k, const uint8_t* mask, int64_t B, int L, int D, const float* W1, const float* b1, int H1,
+                                const float* W2, const float* b2, int H2, const float* w3, float b3, float* out, float* weights_out, cudaStream_t s) {
   if (B <= 0) return 0;
   const DinShape p{L, D, H1, H2};
   const size_t bytes = (size_t)DinSmem(p).total * sizeof(float);
@@ -371,9 +373,14 @@ int dr_cuda_din_attention_fwd(const float* q, const float* k, const uint8_t* mas
   DR_CUDA_CHECK(cudaFuncSetAttribute(k_din_attention_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const int per_sm = bytes <= 100 * 1024 ? 2 : 1;
   const int grid = (int)(B < (int64_t)kNumSMs * per_sm ? B : (int64_t)kNumSMs * per_sm);
-  emu::launch(dim3(grid), dim3(kThreads), (size_t)(bytes), (cudaStream_t)(s), [&] { k_din_attention_fwd(q, k, mask, B, p, W1, b1, W2, b2, w3, b3, out); });
+  emu::launch(dim3(grid), dim3(kThreads), (size_t)(bytes), (cudaStream_t)(s), [&] { k_din_attention_fwd(q, k, mask, B, p, W1, b1, W2, b2, w3, b3, out, weights_out); });
   DR_LAUNCH_CHECK();
   return 0;
+}
+// weights_out [B, L] (optional): the softmax weights themselves (uniform for a row without a valid position) -- the DIEN op program
+int dr_cuda_din_attention_fwd(const float* q, const float* k, const uint8_t* mask, int64_t B, int L, int D, const float* W1, const float* b1, int H1,
+                              const float* W2, const float* b2, int H2, const float* w3, float b3, float* out, cudaStream_t s) {
+  return dr_cuda_din_attention_fwd_w(q, k, mask, B, L, D, W1, b1, H1, W2, b2, H2, w3, b3, out, nullptr, s);
 }
 
 // Gradients of dr_cuda_din_attention_fwd.  dq [B, D] and dk [B, L, D] are written; dW1 [H1, 4D], db1 [H1], dW2 [H2, H1], db2 [H2], dw3 [H2],

@@ -168,6 +168,16 @@ __global__ void __launch_bounds__(256) k_prog_to_u8(const __nv_bfloat16* __restr
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int64_t b = i / w; y[i] = ldb(x + b * ldx + (i - b * w)) > 0.f ? 1 : 0; }
 }
 
+// host-resident tables (device placement optimisation): rows looked up on the CPU arrive sample-major fp32 [B, T * D]; the DLRM path wants them
+// feature-major bf16 [T][B][D]
+__global__ void __launch_bounds__(256) k_prog_emb_feature_major(const float* __restrict__ x, int T, int D, int64_t B, __nv_bfloat16* __restrict__ y) {
+  const int64_t n = B * (int64_t)T * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / ((int64_t)T * D); const int r = (int)(i - b * (int64_t)T * D); const int t = r / D, d = r - t * D;
+    stb(y + ((int64_t)t * B + b) * D + d, x[i]);
+  }
+}
+
 // row-wise softmax (mixture-of-experts gates), one warp per row
 __global__ void __launch_bounds__(256) k_prog_softmax(const __nv_bfloat16* __restrict__ x, int64_t ldx, int w, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
   const int lane = threadIdx.x & 31;
@@ -204,6 +214,104 @@ __global__ void __launch_bounds__(256) k_prog_sigmoid_cols(const __nv_bfloat16* 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / no;
     prob[i] = 1.f / (1.f + __expf(-ldb(x + b * ldx + (i - b * no))));
+  }
+}
+
+// ---- recurrent / transformer sequence models (DIEN, BST) -------------------------------------------------------------------------------------
+// GRU recurrence over the pre-computed input projection gi [B * L, 3H] (the tcgen05 GEMM x W_ih^T + b_ih): one block per sample, W_hh^T in
+// shared memory ([k][j]: consecutive threads read consecutive gate columns), two barriers per time step.  PyTorch gate order r, z, n:
+//   r = s(gi_r + W_hr h + b_hr), z = s(gi_z + W_hz h + b_hz), n = tanh(gi_n + r (W_hn h + b_hn)), h' = (1 - z) n + z h
+__global__ void __launch_bounds__(256) k_prog_gru(const __nv_bfloat16* __restrict__ gi, int64_t ldg, const float* __restrict__ whh /* [3H][H] */,
+                                                  const float* __restrict__ bhh, int L, int H, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  float* sm_gru = (float*)emu::dyn_smem();
+  float* sW = sm_gru;                       // [H][3H]
+  float* sh = sW + 3 * H * H;               // [H] hidden state
+  float* sg = sh + H;                       // [3H] W_hh h + b_hh
+  const int H3 = 3 * H;
+  for (int i = threadIdx.x; i < H3 * H; i += blockDim.x) { const int j = i / H, k = i - j * H; sW[k * H3 + j] = whh[i]; }
+  __syncthreads();
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int j = threadIdx.x; j < H; j += blockDim.x) sh[j] = 0.f;
+    __syncthreads();
+    for (int t = 0; t < L; ++t) {
+      for (int j = threadIdx.x; j < H3; j += blockDim.x) {
+        float a = bhh[j];
+        for (int k = 0; k < H; ++k) a = fmaf(sW[k * H3 + j], sh[k], a);
+        sg[j] = a;
+      }
+      __syncthreads();
+      const __nv_bfloat16* g = gi + (b * L + t) * ldg;
+      for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        const float r = 1.f / (1.f + __expf(-(ldb(g + j) + sg[j])));
+        const float z = 1.f / (1.f + __expf(-(ldb(g + H + j) + sg[H + j])));
+        const float n = tanhf(ldb(g + 2 * H + j) + r * sg[2 * H + j]);
+        const float h = (1.f - z) * n + z * sh[j];
+        sh[j] = h;
+        stb(y + b * ldy + (int64_t)t * H + j, h);
+      }
+      __syncthreads();
+    }
+  }
+}
+// y[b, :] = x[b, last(b), :], last = max(sum_l mask[b, l], 1) - 1   (one warp per row)
+__global__ void __launch_bounds__(256) k_prog_seq_last(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ m, int64_t ldm, int L, int w,
+                                                       __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    int cnt = 0;
+    for (int l = lane; l < L; l += 32) cnt += ldb(m + r * ldm + l) > 0.f ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int last = (cnt > 1 ? cnt : 1) - 1;
+    for (int k = lane; k < w; k += 32) y[r * ldy + k] = x[r * ldx + (int64_t)last * w + k];
+  }
+}
+// y[b, :] = mean over the valid positions of x[b, l, :]
+__global__ void __launch_bounds__(256) k_prog_seq_mean(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ m, int64_t ldm, int L, int w,
+                                                       __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  const int64_t n = B * (int64_t)w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / w; const int k = (int)(i - b * w);
+    float acc = 0.f; int cnt = 0;
+    for (int l = 0; l < L; ++l) if (ldb(m + b * ldm + l) > 0.f) { acc += ldb(x + b * ldx + (int64_t)l * w + k); ++cnt; }
+    stb(y + b * ldy + k, acc / (float)(cnt > 1 ? cnt : 1));
+  }
+}
+// multi-head self-attention core: qkv [B, S * 3E] (per position [q | k | v]), valid [B, S] -> [B, S * E].  One block per sample, the sample's qkv
+// staged in shared memory as fp32; one thread per (head, query position) runs an online softmax over the valid keys (dh <= 64).
+constexpr int kMhaMaxDh = 64;
+__global__ void __launch_bounds__(256) k_prog_mha(const __nv_bfloat16* __restrict__ qkv, int64_t ldq, const __nv_bfloat16* __restrict__ valid, int64_t ldv, int S, int E,
+                                                  int heads, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t B) {
+  float* sm_mha = (float*)emu::dyn_smem();
+  float* sx = sm_mha;                       // [S][3E]
+  float* sv = sx + (size_t)S * 3 * E;       // [S] validity
+  const int dh = E / heads; const float scale = rsqrtf((float)dh);
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int i = threadIdx.x; i < S * 3 * E; i += blockDim.x) sx[i] = ldb(qkv + b * ldq + i);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sv[i] = ldb(valid + b * ldv + i);
+    __syncthreads();
+    for (int it = threadIdx.x; it < heads * S; it += blockDim.x) {
+      const int hd = it / S, s1 = it - hd * S;
+      const float* q = sx + (size_t)s1 * 3 * E + hd * dh;
+      float acc[kMhaMaxDh];
+      for (int c = 0; c < dh; ++c) acc[c] = 0.f;
+      float mx = -3.4e38f, den = 0.f;
+      for (int s2 = 0; s2 < S; ++s2) {
+        if (!(sv[s2] > 0.f)) continue;
+        const float* kk = sx + (size_t)s2 * 3 * E + E + hd * dh;
+        float dot = 0.f;
+        for (int c = 0; c < dh; ++c) dot = fmaf(q[c], kk[c], dot);
+        dot *= scale;
+        const float nm = fmaxf(mx, dot), corr = __expf(mx - nm), pe = __expf(dot - nm);
+        const float* vv = kk + E;
+        for (int c = 0; c < dh; ++c) acc[c] = acc[c] * corr + pe * vv[c];
+        den = den * corr + pe; mx = nm;
+      }
+      const float inv = den > 0.f ? 1.f / den : 0.f;
+      for (int c = 0; c < dh; ++c) stb(y + b * ldy + (int64_t)s1 * E + hd * dh + c, acc[c] * inv);
+    }
+    __syncthreads();
   }
 }
 
@@ -309,6 +417,46 @@ int dr_prog_to_u8(const void* x, int64_t ldx, int w, uint8_t* y, int64_t B, cuda
   return 0;
 }
 
+int dr_prog_gru(const void* gi, int64_t ldg, const float* whh, const float* bhh, int L, int H, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || L <= 0 || H <= 0) return 0;
+  const size_t bytes = ((size_t)3 * H * H + 4 * (size_t)H) * sizeof(float);
+  if (bytes > 200 * 1024) return -1;                                // W_hh must fit in shared memory (H <= 126)
+  static DrPerDeviceOnce attr_once; bool& attr = attr_once();
+  if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_prog_gru, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  emu::launch(dim3((int)(B < kNumSMs * 4 ? B : kNumSMs * 4)), dim3(256), (size_t)(bytes), (cudaStream_t)(s), [&] { k_prog_gru((const __nv_bfloat16*)gi, ldg, whh, bhh, L, H, (__nv_bfloat16*)y, ldy, B); });
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_seq_last(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || L <= 0 || w <= 0) return 0;
+  emu::launch(dim3(grid_rows(B)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_prog_seq_last((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)m, ldm, L, w, (__nv_bfloat16*)y, ldy, B); });
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_seq_mean(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || L <= 0 || w <= 0) return 0;
+  emu::launch(dim3(grid_el(B * w)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_prog_seq_mean((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)m, ldm, L, w, (__nv_bfloat16*)y, ldy, B); });
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+int dr_prog_mha(const void* qkv, int64_t ldq, const void* valid, int64_t ldv, int S, int E, int heads, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
+  if (B <= 0 || S <= 0 || E <= 0) return 0;
+  if (heads <= 0 || E % heads || E / heads > kMhaMaxDh) return -2;
+  const size_t bytes = ((size_t)S * 3 * E + (size_t)S) * sizeof(float);
+  if (bytes > 200 * 1024) return -1;
+  static DrPerDeviceOnce attr_once; bool& attr = attr_once();
+  if (!attr) { DR_CUDA_CHECK(cudaFuncSetAttribute(k_prog_mha, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  emu::launch(dim3((int)(B < kNumSMs * 4 ? B : kNumSMs * 4)), dim3(256), (size_t)(bytes), (cudaStream_t)(s), [&] { k_prog_mha((const __nv_bfloat16*)qkv, ldq, (const __nv_bfloat16*)valid, ldv, S, E, heads, (__nv_bfloat16*)y, ldy, B); });
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+int dr_prog_emb_feature_major(const float* x, int T, int D, int64_t B, void* y, cudaStream_t s) {
+  if (B <= 0 || T <= 0 || D <= 0) return 0;
+  emu::launch(dim3(grid_el(B * T * D)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_prog_emb_feature_major(x, T, D, B, (__nv_bfloat16*)y); });
+  DR_LAUNCH_CHECK();
+  return 0;
+}
 int dr_prog_softmax(const void* x, int64_t ldx, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s) {
   if (B <= 0 || w <= 0) return 0;
   emu::launch(dim3(grid_rows(B)), dim3(256), (size_t)(0), (cudaStream_t)(s), [&] { k_prog_softmax((const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)y, ldy, B); });

@@ -13,6 +13,8 @@
 // The reference embeds the TF runtime and runs a SavedModel graph; here inference is the sm_100a kernel sequence of the
 // flagship engine (BatchNorm folded at load time, read-only probes), so a request is ~16 kernel launches on the
 // session's stream.
+#include <dlfcn.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -71,6 +73,13 @@ int dr_prog_to_u8(const void* x, int64_t ldx, int w, uint8_t* y, int64_t B, cuda
 int dr_prog_softmax(const void* x, int64_t ldx, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_cosine(const void* a, int64_t lda, const void* c, int64_t ldc, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
 int dr_prog_sigmoid_cols(const void* x, int64_t ldx, int no, int64_t B, float* prob, cudaStream_t s);
+int dr_prog_emb_feature_major(const float* x, int T, int D, int64_t B, void* y, cudaStream_t s);
+int dr_prog_gru(const void* gi, int64_t ldg, const float* whh, const float* bhh, int L, int H, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_seq_last(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_seq_mean(const void* x, int64_t ldx, const void* m, int64_t ldm, int L, int w, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_prog_mha(const void* qkv, int64_t ldq, const void* valid, int64_t ldv, int S, int E, int heads, void* y, int64_t ldy, int64_t B, cudaStream_t s);
+int dr_cuda_din_attention_fwd_w(const float* q, const float* k, const uint8_t* mask, int64_t B, int L, int D, const float* W1, const float* b1, int H1,
+                                const float* W2, const float* b2, int H2, const float* w3, float b3, float* out, float* weights_out, cudaStream_t s);
 int dr_cuda_din_attention_fwd(const float* q, const float* k, const uint8_t* mask, int64_t B, int L, int D, const float* W1, const float* b1, int H1,
                               const float* W2, const float* b2, int H2, const float* w3, float b3, float* out, cudaStream_t s);
 int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, const float* bias, const float* labels, float inv_batch, float* prob,
@@ -78,6 +87,34 @@ int dr_cuda_head(const void* h, int64_t ldh, int64_t B, int K, const float* w, c
 }
 
 namespace serve {
+
+// ---- device placement optimisation (ModelConfig "enable_device_placement_optimization", the reference's gpu_device_placement_pass.cc: the embedding
+// layer stays on the CPU for GPU inference) -- the tables live in the HOST engine (libdeeprec_host.so next to this library, bound at run time so
+// that the GPU library keeps no link-time dependency on it): tables larger than HBM, or one copy shared by the replicas of every GPU of a box.
+// A request looks its rows up on the caller's thread, ships them as one H2D copy and runs the dense part on the GPU as usual.
+struct HostApi {
+  void* (*create)(const DrEvConfig*) = nullptr; void (*destroy)(void*) = nullptr; void (*set_default)(void*, const float*) = nullptr;
+  int64_t (*import)(void*, const int64_t*, const float*, int64_t, const int64_t*, const int64_t*, int64_t, int, int, int) = nullptr;
+  int64_t (*import_cow)(void*, const int64_t*, const float*, int64_t, int64_t) = nullptr;
+  void (*group_lookup)(void**, int, const int64_t*, int64_t, float*) = nullptr;
+  bool ok = false;
+  static HostApi& Get() {
+    static HostApi api = [] {
+      HostApi a;
+      Dl_info info{};
+      std::string dir = ".";
+      if (dladdr((void*)&HostApi::Get, &info) && info.dli_fname) { dir = info.dli_fname; const size_t p = dir.find_last_of('/'); dir = p == std::string::npos ? "." : dir.substr(0, p); }
+      void* h = dlopen((dir + "/libdeeprec_host.so").c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (!h) { fprintf(stderr, "[deeprec_serving] device placement optimisation needs %s/libdeeprec_host.so: %s\n", dir.c_str(), dlerror()); return a; }
+      a.create = (decltype(a.create))dlsym(h, "dr_host_ev_create"); a.destroy = (decltype(a.destroy))dlsym(h, "dr_host_ev_destroy");
+      a.set_default = (decltype(a.set_default))dlsym(h, "dr_host_ev_set_default"); a.import = (decltype(a.import))dlsym(h, "dr_host_ev_import");
+      a.import_cow = (decltype(a.import_cow))dlsym(h, "dr_host_ev_import_cow"); a.group_lookup = (decltype(a.group_lookup))dlsym(h, "dr_host_group_lookup");
+      a.ok = a.create && a.destroy && a.set_default && a.import && a.import_cow && a.group_lookup;
+      return a;
+    }();
+    return api;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // minimal JSON (objects, arrays, strings, numbers, bools) -- enough for ModelConfig / saved_model.json / state files
@@ -137,9 +174,11 @@ template <typename T> static bool Upload(DevBuf& b, const std::vector<T>& h) {
 // other than DLRM as a list of ops over [B, width] buffers; buffer 0 = dense inputs, buffer 1 = embeddings [B, T * D].  Same format and
 // op set as the CPU runtime (csrc/host/cpu_serving.cc); here LINEAR runs on the tcgen05 GEMM and the rest on program_kernels.cu.
 enum POpKind { P_CONCAT, P_LINEAR, P_AFFINE, P_FM, P_CROSS, P_MUL_ADD, P_ADD, P_LAYERNORM, P_MUL, P_SLICE,
-               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_TILE, P_NUM_OPS };     // sequence-model ops: see cpu_serving.cc
+               P_VALID_MASK, P_SEQ_ZIP, P_SEQ_MASK, P_SEQ_SUM, P_DIN_ATT, P_PRELU, P_SOFTMAX, P_COSINE, P_TILE, P_GRU, P_SEQ_LAST, P_MHA, P_SEQ_MEAN, P_NUM_OPS };     // sequence-model ops: see cpu_serving.cc
 // rows1 / P_TILE: sample-aware graph compression (serving/export.py::compress_sample_aware): user-side ops run once per request on row 0
-struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false, rows1 = false; float eps = 1e-5f; int start = 0, len = 0; std::string name; };
+// len on LINEAR / LAYERNORM: applied at each of `len` positions of a [B, len * w] sequence buffer (DIEN / BST; the buffer must be un-padded so that it
+// IS a [B * len, w] matrix); mode: din_attention output (0 weighted sum, 1 softmax weights); heads: mha
+struct POp { int kind = 0, out = 0; std::vector<int> in; bool relu = false, rows1 = false; float eps = 1e-5f; int start = 0, len = 0, mode = 0, heads = 1; std::string name; };
 struct Arch {
   int num_dense = 13, T = 0, D = 16; std::vector<int> bot, top; float bn_eps = 1e-3f; int Zp = 0, inter = 0;
   bool program = false; std::vector<POp> ops; int nbuf = 2, out_buf = -1;
@@ -167,7 +206,7 @@ struct DenseParams {
   bool fp8 = false;        // fp8 tensors + scales below are populated
   ActScales act;
   // program models: per-op weights (LINEAR: bf16 [pad8(N), pad8(K)] + bias[pad8(N)]; affine / layernorm / cross: two fp32 vectors), buffer widths
-  struct PW { LayerW L; DevBuf v0, v1; std::vector<DevBuf> att; int H1 = 0, H2 = 0; float b3 = 0.f; };    // att: W1 b1 W2 b2 w3 of a din_attention op
+  struct PW { LayerW L; DevBuf v0, v1; std::vector<DevBuf> att; int H1 = 0, H2 = 0; float b3 = 0.f; };    // gru: L = input projection [3H, I], v0 = W_hh, v1 = b_hh, H1 = H    // att: W1 b1 W2 b2 w3 of a din_attention op
   std::vector<PW> pdata; std::vector<int> width;
 };
 
@@ -183,6 +222,9 @@ struct DeviceModel {
   std::vector<std::unique_ptr<TableDev>> tables;
   DevBuf structs;      // DrDeviceTable[T] on the device
   DevBuf col_table;    // int32 [C]: table of every lookup column (program models; identity otherwise)
+  // device placement optimisation: the tables live in the host engine instead (HostEV handles, owned), col_handles[c] = table of lookup column c
+  bool host_resident = false; std::vector<void*> host_tables, col_handles; std::vector<int64_t> host_sample_keys;
+  ~DeviceModel() { if (host_resident) for (void* h : host_tables) if (h) HostApi::Get().destroy(h); }
 };
 
 static bool ReadTensor(dr::BundleReader& r, const std::string& name, std::vector<uint8_t>* out, std::vector<int64_t>* shape = nullptr) {
@@ -237,17 +279,29 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
     std::vector<float> v0, v1;
     switch (op.kind) {
       case P_CONCAT: w = 0; for (int b : op.in) w += dp->width[(size_t)b]; break;
-      case P_LINEAR: {
+      case P_LINEAR: {                                               // len > 0: the same Linear at each of len positions ([B, len * K] == [B * len, K])
         std::vector<float> W, b;
-        if (!ReadVec(r, base + "kernel", &W) || !ReadVec(r, base + "bias", &b) || b.empty() || W.size() != b.size() * (size_t)w0) return false;
-        const int N = (int)b.size(), Np = prog_npad(N), Kp = prog_ld(a, dp->width, op.in[0]);
+        const int S = op.len > 0 ? op.len : 1;
+        if (w0 % S) return false;
+        const int K = w0 / S;
+        if (!ReadVec(r, base + "kernel", &W) || !ReadVec(r, base + "bias", &b) || b.empty() || W.size() != b.size() * (size_t)K) return false;
+        const int N = (int)b.size();
+        // a sequence GEMM needs both buffers un-padded (row pitch == width) and K, N on the GEMM's 8-element rule with no output padding
+        if (S > 1 && (prog_ld(a, dp->width, op.in[0]) != w0 || K % 8 || prog_npad(N) != N || prog_npad(S * N) != S * N)) return false;
+        const int Np = prog_npad(N), Kp = S > 1 ? K : prog_ld(a, dp->width, op.in[0]);
         std::vector<uint16_t> wb((size_t)Np * Kp, 0); std::vector<float> bias((size_t)Np, 0.f);     // zero rows / columns: pad outputs are exact zeros
-        for (int n = 0; n < N; ++n) { bias[(size_t)n] = b[(size_t)n]; for (int k = 0; k < w0; ++k) wb[(size_t)n * Kp + k] = f2bf(W[(size_t)n * w0 + k]); }
-        d.L.N = N; d.L.K = w0; d.L.Kp = Kp; d.L.Np = Np;
+        for (int n = 0; n < N; ++n) { bias[(size_t)n] = b[(size_t)n]; for (int k = 0; k < K; ++k) wb[(size_t)n * Kp + k] = f2bf(W[(size_t)n * K + k]); }
+        d.L.N = N; d.L.K = K; d.L.Kp = Kp; d.L.Np = Np;
         if (!Upload(d.L.w_bf16, wb) || !Upload(d.L.bias, bias)) return false;
-        w = N; break;
+        w = N * S; break;
       }
-      case P_LAYERNORM:
+      case P_LAYERNORM: {                                            // len > 0: per position of an un-padded sequence buffer
+        const int S = op.len > 0 ? op.len : 1;
+        if (w0 % S || (S > 1 && prog_ld(a, dp->width, op.in[0]) != w0)) return false;
+        if (!ReadVec(r, base + "scale", &v0) || !ReadVec(r, base + "shift", &v1) || (int)v0.size() != w0 / S || (int)v1.size() != w0 / S) return false;
+        if (!Upload(d.v0, v0) || !Upload(d.v1, v1)) return false;
+        break;
+      }
       case P_AFFINE:
         if (!ReadVec(r, base + "scale", &v0) || !ReadVec(r, base + "shift", &v1) || (int)v0.size() != w0 || (int)v1.size() != w0) return false;
         if (!Upload(d.v0, v0) || !Upload(d.v1, v1)) return false;
@@ -272,10 +326,31 @@ static bool BuildProgram(dr::BundleReader& r, const Arch& a, std::shared_ptr<Den
       case P_PRELU: if (!ReadVec(r, base + "alpha", &v0) || (int)v0.size() != w0 || !Upload(d.v0, v0)) return false; break;
       case P_SOFTMAX: break;
       case P_TILE: break;
+      case P_GRU: {                                                  // input projection on the GEMM ([B * L, I] x W_ih^T + b_ih -> [B * L, 3H]), recurrence kernel
+        std::vector<float> wih, whh, bih, bhh;
+        if (op.len <= 0 || w0 % op.len || !ReadVec(r, base + "w_ih", &wih) || !ReadVec(r, base + "w_hh", &whh) || !ReadVec(r, base + "b_ih", &bih) || !ReadVec(r, base + "b_hh", &bhh)) return false;
+        const int I = w0 / op.len, H3 = (int)bih.size(), H = H3 / 3;
+        if (H <= 0 || H3 != 3 * H || (int)bhh.size() != H3 || (int)wih.size() != H3 * I || (int)whh.size() != H3 * H) return false;
+        if (prog_ld(a, dp->width, op.in[0]) != w0 || I % 8 || H3 % 8 || H > 126) return false;       // un-padded input sequence, GEMM 8-element rule
+        std::vector<uint16_t> wb((size_t)H3 * I);
+        for (size_t i2 = 0; i2 < wb.size(); ++i2) wb[i2] = f2bf(wih[i2]);
+        d.L.N = H3; d.L.K = I; d.L.Kp = I; d.L.Np = H3; d.H1 = H;
+        if (!Upload(d.L.w_bf16, wb) || !Upload(d.L.bias, bih) || !Upload(d.v0, whh) || !Upload(d.v1, bhh)) return false;
+        w = op.len * H; break;
+      }
+      case P_SEQ_LAST:
+      case P_SEQ_MEAN: if (op.len <= 0 || w0 % op.len || dp->width[(size_t)op.in[1]] != op.len) return false; w = w0 / op.len; break;
+      case P_MHA: {
+        if (op.len <= 0 || w0 % (3 * op.len) || dp->width[(size_t)op.in[1]] != op.len) return false;
+        const int E = w0 / (3 * op.len);
+        if (op.heads <= 0 || E % op.heads || E / op.heads > 64) return false;
+        w = op.len * E; break;
+      }
       case P_COSINE: if (dp->width[(size_t)op.in[1]] != w0) return false; w = 1; break;
       case P_DIN_ATT: {
         const int wk = dp->width[(size_t)op.in[1]], L = dp->width[(size_t)op.in[2]];
-        if (L <= 0 || wk != L * w0) return false;
+        if (L <= 0 || wk != L * w0 || op.mode < 0 || op.mode > 1) return false;
+        if (op.mode == 1) w = L;                                     // the softmax weights themselves (DIEN)
         static const char* kT[] = {"w1", "b1", "w2", "b2", "w3", "b3"};
         std::vector<std::vector<float>> t(6);
         for (int i2 = 0; i2 < 6; ++i2) if (!ReadVec(r, base + kT[i2], &t[(size_t)i2])) return false;
@@ -382,6 +457,28 @@ static bool BuildTable(dr::BundleReader& r, int t, int D, TableDev* td, int64_t 
   return true;
 }
 
+// host-resident twin of BuildTable (device placement optimisation): the rows go into a HostEV of the host engine
+static void* BuildHostTable(dr::BundleReader& r, int t, int D, std::vector<int64_t>* sample) {
+  HostApi& api = HostApi::Get();
+  if (!api.ok) return nullptr;
+  const std::string base = "table/" + std::to_string(t);
+  std::vector<int64_t> keys, freqs, vers; std::vector<float> vals, def;
+  if (!ReadVec(r, base + "-keys", &keys) || !ReadVec(r, base + "-values", &vals) || !ReadVec(r, base + "-default", &def)) return nullptr;
+  ReadVec(r, base + "-freqs", &freqs); ReadVec(r, base + "-versions", &vers);
+  if (def.empty() || def.size() % (size_t)D || vals.size() != keys.size() * (size_t)D) return nullptr;
+  DrEvConfig c{};
+  c.dim = D; c.num_slots = 0; c.has_scalars = 0; c.init_capacity = std::max<int64_t>(1024, (int64_t)keys.size() * 2);
+  c.default_value_dim = (int64_t)def.size() / D; c.num_partitions = 16; c.record_freq = 1; c.record_version = 1; c.l2_weight_threshold = -1.f;
+  void* h = api.create(&c);
+  if (!h) return nullptr;
+  api.set_default(h, def.data());
+  if (!keys.empty())
+    api.import(h, keys.data(), vals.data(), D, freqs.size() == keys.size() ? freqs.data() : nullptr, vers.size() == keys.size() ? vers.data() : nullptr,
+               (int64_t)keys.size(), 0, 1, 0);
+  sample->assign(keys.begin(), keys.begin() + std::min<size_t>(keys.size(), 512));
+  return h;
+}
+
 static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::string* prefix) {
   std::string txt; JVal j;
   if (!ReadFile(dir + "/saved_model.json", &txt) || !ParseJson(txt, &j)) return false;
@@ -413,14 +510,14 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
     std::vector<std::string> names = {"dense", "emb"};
     auto id_of = [&](const std::string& n) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i; return -1; };
     static const char* kNames[] = {"concat", "linear", "affine", "fm", "cross", "mul_add", "add", "layernorm", "mul", "slice",
-                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine", "tile"};
-    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2, 1};
+                                   "valid_mask", "seq_zip", "seq_mask", "seq_sum", "din_attention", "prelu", "softmax", "cosine", "tile", "gru", "seq_last", "mha", "seq_mean"};
+    static const int kArity[] = {-1, 1, 1, 1, 2, 3, 2, 1, 2, 1, 1, 2, 2, 1, 3, 1, 1, 2, 1, 1, 2, 2, 2};
     const JVal* pr = j.get("program");
     if (!pr || pr->t != JVal::ARR) return false;
     std::vector<bool> rows1_buf(2, false);
     for (const JVal& o : pr->arr) {
       POp op; op.name = o.s("out", ""); op.relu = o.n("relu", 0) != 0; op.eps = (float)o.n("eps", 1e-5); op.kind = -1;
-      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0); op.rows1 = o.n("rows1", 0) != 0;
+      op.start = (int)o.n("start", 0); op.len = (int)o.n("len", 0); op.rows1 = o.n("rows1", 0) != 0; op.mode = (int)o.n("mode", 0); op.heads = (int)o.n("heads", 1);
       const std::string kind = o.s("op", "");
       for (int k = 0; k < P_NUM_OPS; ++k) if (kind == kNames[k]) op.kind = k;
       const JVal* in = o.get("in");
@@ -445,13 +542,28 @@ static bool LoadArch(const std::string& dir, Arch* a, int64_t* version, std::str
   return a->T > 0 && !a->bot.empty() && !a->top.empty() && a->bot.back() == a->D;
 }
 
-static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t extra_rows, bool want_fp8 = false) {
+static std::shared_ptr<DeviceModel> LoadModel(const std::string& dir, int64_t extra_rows, bool want_fp8 = false, bool host_tables = false) {
   auto m = std::make_shared<DeviceModel>();
   std::string prefix;
   if (!LoadArch(dir, &m->arch, &m->version, &prefix)) { fprintf(stderr, "[deeprec_serving] bad saved_model.json in %s\n", dir.c_str()); return nullptr; }
   dr::BundleReader r(prefix);
   if (!r.ok()) { fprintf(stderr, "[deeprec_serving] cannot open bundle %s\n", prefix.c_str()); return nullptr; }
   if (!BuildDense(r, m->arch, &m->dense, want_fp8 && !m->arch.program)) { fprintf(stderr, "[deeprec_serving] dense parameters incomplete in %s\n", prefix.c_str()); return nullptr; }
+  if (host_tables) {                                                 // device placement optimisation: embedding layer on the CPU
+    m->host_resident = true;
+    for (int t = 0; t < m->arch.T; ++t) {
+      std::vector<int64_t> sample;
+      void* h = BuildHostTable(r, t, m->arch.D, &sample);
+      if (!h) { fprintf(stderr, "[deeprec_serving] host table %d incomplete (or libdeeprec_host.so missing)\n", t); return nullptr; }
+      m->host_tables.push_back(h);
+      m->host_sample_keys.insert(m->host_sample_keys.end(), sample.begin(), sample.end());
+      m->tables.emplace_back(new TableDev());
+      m->tables.back()->sample_keys = sample;
+    }
+    for (int c = 0; c < m->arch.C; ++c) m->col_handles.push_back(m->host_tables[(size_t)m->arch.col_table[(size_t)c]]);
+    m->path = dir;
+    return m;
+  }
   std::vector<DrDeviceTable> structs;
   for (int t = 0; t < m->arch.T; ++t) {
     m->tables.emplace_back(new TableDev());
@@ -471,6 +583,18 @@ struct Session {
   std::vector<DevBuf> a_bot, a_top;
   DevBuf x0_q, Z_q, amax; std::vector<DevBuf> q_bot, q_top;        // fp8 path: E4M3 activations between the GEMMs
   float* h_dense = nullptr; int64_t* h_ids = nullptr; float* h_prob = nullptr;    // pinned
+  float* h_emb = nullptr; DevBuf emb_f32;                            // host-resident tables: looked-up rows [B, C, D] fp32 (pinned) and their device copy
+  // rows of this chunk from the host engine -> one H2D copy -> bf16 in the layout the dense part expects (program: [B, C * D]; DLRM: [T][B][D])
+  bool HostLookup(const DeviceModel& m, int B) {
+    const Arch& a = m.arch; cudaStream_t s = stream;
+    const size_t n = (size_t)B * a.C * a.D;
+    if (!h_emb) { SV_CUDA(cudaMallocHost(&h_emb, (size_t)max_batch * a.C * a.D * 4)); if (!emb_f32.alloc((size_t)max_batch * a.C * a.D * 4)) return false; }
+    HostApi::Get().group_lookup(const_cast<void**>(m.col_handles.data()), a.C, h_ids, B, h_emb);
+    SV_CUDA(cudaMemcpyAsync(emb_f32.p, h_emb, n * 4, cudaMemcpyHostToDevice, s));
+    const int rc = a.program ? dr_prog_from_f32(emb_f32.as<float>(), a.C * a.D, emb.p, (int64_t)a.C * a.D, B, s)
+                             : dr_prog_emb_feature_major(emb_f32.as<float>(), a.C, a.D, B, emb.p, s);
+    return rc == 0;
+  }
   bool Init(const Arch& a, int maxB) {
     max_batch = maxB;
     SV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -491,11 +615,12 @@ struct Session {
     SV_CUDA(cudaMallocHost(&h_prob, (size_t)maxB * a.n_out * 4));
     return true;
   }
-  ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (stream) cudaStreamDestroy(stream); }
+  ~Session() { if (h_dense) cudaFreeHost(h_dense); if (h_ids) cudaFreeHost(h_ids); if (h_prob) cudaFreeHost(h_prob); if (h_emb) cudaFreeHost(h_emb); if (stream) cudaStreamDestroy(stream); }
 
   // ---- op-program models: buffers 0 / 1 alias x0 / emb, the others are (max_batch x prog_ld(width)) bf16, zeroed once (pad columns stay zero) ----
   std::vector<DevBuf> pbuf; std::vector<int> pbuf_width;
-  DevBuf att_q, att_k, att_o, att_m;                                 // fp32 / uint8 staging of the din_attention kernel
+  DevBuf att_q, att_k, att_o, att_m, att_w;                          // fp32 / uint8 staging of the din_attention kernel (att_w: its softmax weights)
+  DevBuf gru_gi;                                                     // bf16 [max_batch * L, 3H]: input projection of a gru op
   bool RunProgram(const DeviceModel& m, const DenseParams& dp, const int Bfull) {
     const Arch& a = m.arch; cudaStream_t s = stream;
     if (pbuf_width != dp.width) {                                     // first program run, or a full update changed the layer widths
@@ -506,11 +631,15 @@ struct Session {
         if (!pbuf[i].alloc(bytes)) return false;
         SV_CUDA(cudaMemsetAsync(pbuf[i].p, 0, bytes, s));
       }
-      size_t wq = 0, wk = 0, wl = 0;
-      for (const POp& op : a.ops) if (op.kind == P_DIN_ATT) {
-        wq = std::max(wq, (size_t)dp.width[(size_t)op.in[0]]); wk = std::max(wk, (size_t)dp.width[(size_t)op.in[1]]); wl = std::max(wl, (size_t)dp.width[(size_t)op.in[2]]);
+      size_t wq = 0, wk = 0, wl = 0, wg = 0;
+      for (size_t oi = 0; oi < a.ops.size(); ++oi) {
+        const POp& op = a.ops[oi];
+        if (op.kind == P_DIN_ATT) { wq = std::max(wq, (size_t)dp.width[(size_t)op.in[0]]); wk = std::max(wk, (size_t)dp.width[(size_t)op.in[1]]); wl = std::max(wl, (size_t)dp.width[(size_t)op.in[2]]); }
+        if (op.kind == P_GRU) wg = std::max(wg, (size_t)op.len * 3 * (size_t)dp.pdata[oi].H1);
       }
-      if (wq && (!att_q.alloc((size_t)max_batch * wq * 4) || !att_k.alloc((size_t)max_batch * wk * 4) || !att_o.alloc((size_t)max_batch * wq * 4) || !att_m.alloc((size_t)max_batch * wl))) return false;
+      if (wq && (!att_q.alloc((size_t)max_batch * wq * 4) || !att_k.alloc((size_t)max_batch * wk * 4) || !att_o.alloc((size_t)max_batch * wq * 4) || !att_m.alloc((size_t)max_batch * wl) ||
+                 !att_w.alloc((size_t)max_batch * wl * 4))) return false;
+      if (wg && !gru_gi.alloc((size_t)max_batch * wg * 2)) return false;
       pbuf_width = dp.width;
     }
     auto buf = [&](int id) -> void* { return id == 0 ? x0.p : id == 1 ? emb.p : pbuf[(size_t)id].p; };
@@ -518,9 +647,12 @@ struct Session {
     int rc = 0;
     const int64_t n = (int64_t)a.C * Bfull;
     const int32_t* ct = m.col_table.as<int32_t>();                   // lookup column -> table
-    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), ct, a.C, ids.as<int64_t>(), nullptr, Bfull, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
-    // sample-major embeddings [B, C * D]: element (b, c) at b * (C * D) + c * D
-    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), ct, a.C, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, Bfull, n, emb.p, 1, (int64_t)a.C * a.D, a.D, 0, s);
+    if (m.host_resident) { if (!HostLookup(m, Bfull)) return false; }
+    else {
+      rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), ct, a.C, ids.as<int64_t>(), nullptr, Bfull, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+      // sample-major embeddings [B, C * D]: element (b, c) at b * (C * D) + c * D
+      rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), ct, a.C, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, Bfull, n, emb.p, 1, (int64_t)a.C * a.D, a.D, 0, s);
+    }
     rc |= dr_cuda_cast_pad(dense_in.as<float>(), Bfull, a.num_dense, x0.p, pad8(a.num_dense), s);
     for (size_t oi = 0; oi < a.ops.size() && rc == 0; ++oi) {
       const POp& op = a.ops[oi]; const auto& pd = dp.pdata[oi];
@@ -529,9 +661,22 @@ struct Session {
       const void* a0 = buf(op.in[0]); const int w0 = dp.width[(size_t)op.in[0]]; const int64_t ld0 = ld(op.in[0]);
       switch (op.kind) {
         case P_LINEAR:                                               // tcgen05 GEMM, bias (+ ReLU) in the epilogue; N padded to 8 with zero rows
-          rc |= dr_cuda_gemm_tn_ex(a0, ld0, pd.L.w_bf16.p, pd.L.Kp, B, pd.L.Np, pd.L.Kp, pd.L.bias.as<float>(), op.relu ? 1 : 0, nullptr, 0, 0, out, ldo,
-                                   nullptr, nullptr, nullptr, 0, 0, s);
+          if (op.len > 1)                                            // sequence form: [B, S * K] is a [B * S, K] matrix (un-padded buffers, checked at load)
+            rc |= dr_cuda_gemm_tn_ex(a0, pd.L.K, pd.L.w_bf16.p, pd.L.Kp, B * op.len, pd.L.Np, pd.L.Kp, pd.L.bias.as<float>(), op.relu ? 1 : 0, nullptr, 0, 0, out, pd.L.N,
+                                     nullptr, nullptr, nullptr, 0, 0, s);
+          else
+            rc |= dr_cuda_gemm_tn_ex(a0, ld0, pd.L.w_bf16.p, pd.L.Kp, B, pd.L.Np, pd.L.Kp, pd.L.bias.as<float>(), op.relu ? 1 : 0, nullptr, 0, 0, out, ldo,
+                                     nullptr, nullptr, nullptr, 0, 0, s);
           break;
+        case P_GRU: {
+          const int L = op.len, I = w0 / L, H = pd.H1;
+          rc |= dr_cuda_gemm_tn_ex(a0, I, pd.L.w_bf16.p, I, B * L, 3 * H, I, pd.L.bias.as<float>(), 0, nullptr, 0, 0, gru_gi.p, 3 * H, nullptr, nullptr, nullptr, 0, 0, s);
+          rc |= dr_prog_gru(gru_gi.p, 3 * H, pd.v0.as<float>(), pd.v1.as<float>(), L, H, out, ldo, B, s);
+          break;
+        }
+        case P_SEQ_LAST: rc |= dr_prog_seq_last(a0, ld0, buf(op.in[1]), ld(op.in[1]), op.len, W, out, ldo, B, s); break;
+        case P_SEQ_MEAN: rc |= dr_prog_seq_mean(a0, ld0, buf(op.in[1]), ld(op.in[1]), op.len, W, out, ldo, B, s); break;
+        case P_MHA: rc |= dr_prog_mha(a0, ld0, buf(op.in[1]), ld(op.in[1]), op.len, W / op.len, op.heads, out, ldo, B, s); break;
         case P_CONCAT: {
           int off = 0;
           for (int src : op.in) { const int w = dp.width[(size_t)src]; rc |= dr_prog_copy_cols(buf(src), ld(src), 0, w, out, ldo, off, B, s); off += w; }
@@ -544,7 +689,10 @@ struct Session {
         case P_MUL: rc |= dr_prog_binary(1, a0, ld0, buf(op.in[1]), ld(op.in[1]), nullptr, 0, W, out, ldo, B, s); break;
         case P_MUL_ADD: rc |= dr_prog_binary(2, a0, ld0, buf(op.in[1]), ld(op.in[1]), buf(op.in[2]), ld(op.in[2]), W, out, ldo, B, s); break;
         case P_SLICE: rc |= dr_prog_copy_cols(a0, ld0, op.start, W, out, ldo, 0, B, s); break;
-        case P_LAYERNORM: rc |= dr_prog_layernorm(a0, ld0, W, pd.v0.as<float>(), pd.v1.as<float>(), op.eps, op.relu ? 1 : 0, out, ldo, B, s); break;
+        case P_LAYERNORM:
+          if (op.len > 1) rc |= dr_prog_layernorm(a0, W / op.len, W / op.len, pd.v0.as<float>(), pd.v1.as<float>(), op.eps, op.relu ? 1 : 0, out, W / op.len, (int64_t)B * op.len, s);
+          else rc |= dr_prog_layernorm(a0, ld0, W, pd.v0.as<float>(), pd.v1.as<float>(), op.eps, op.relu ? 1 : 0, out, ldo, B, s);
+          break;
         case P_VALID_MASK: rc |= dr_prog_valid_mask(ids.as<int64_t>(), Bfull, B, op.start, W, out, ldo, s); break;
         case P_TILE: rc |= dr_prog_copy_cols(a0, /*row pitch 0: broadcast row 0*/ 0, 0, W, out, ldo, 0, B, s); break;
         case P_SEQ_ZIP: { const int L = op.len, wb = dp.width[(size_t)op.in[1]]; rc |= dr_prog_seq_zip(a0, ld0, w0 / L, buf(op.in[1]), ld(op.in[1]), wb / L, L, out, ldo, B, s); break; }
@@ -554,13 +702,15 @@ struct Session {
         case P_SOFTMAX: rc |= dr_prog_softmax(a0, ld0, W, out, ldo, B, s); break;
         case P_COSINE: rc |= dr_prog_cosine(a0, ld0, buf(op.in[1]), ld(op.in[1]), w0, out, ldo, B, s); break;
         case P_DIN_ATT: {                                            // fp32 staging -> the fused attention kernel (attention_kernels.cu) -> bf16
-          const int L = dp.width[(size_t)op.in[2]];
-          rc |= dr_prog_to_f32(a0, ld0, W, att_q.as<float>(), B, s);
-          rc |= dr_prog_to_f32(buf(op.in[1]), ld(op.in[1]), L * W, att_k.as<float>(), B, s);
+          const int L = dp.width[(size_t)op.in[2]], Wq = w0;         // mode 1 (DIEN): the output is the softmax weights [B, L], not the weighted sum [B, Wq]
+          rc |= dr_prog_to_f32(a0, ld0, Wq, att_q.as<float>(), B, s);
+          rc |= dr_prog_to_f32(buf(op.in[1]), ld(op.in[1]), L * Wq, att_k.as<float>(), B, s);
           rc |= dr_prog_to_u8(buf(op.in[2]), ld(op.in[2]), L, att_m.as<uint8_t>(), B, s);
-          rc |= dr_cuda_din_attention_fwd(att_q.as<float>(), att_k.as<float>(), att_m.as<uint8_t>(), B, L, W, pd.att[0].as<float>(), pd.att[1].as<float>(), pd.H1,
-                                          pd.att[2].as<float>(), pd.att[3].as<float>(), pd.H2, pd.att[4].as<float>(), pd.b3, att_o.as<float>(), s);
-          rc |= dr_prog_from_f32(att_o.as<float>(), W, out, ldo, B, s);
+          rc |= dr_cuda_din_attention_fwd_w(att_q.as<float>(), att_k.as<float>(), att_m.as<uint8_t>(), B, L, Wq, pd.att[0].as<float>(), pd.att[1].as<float>(), pd.H1,
+                                            pd.att[2].as<float>(), pd.att[3].as<float>(), pd.H2, pd.att[4].as<float>(), pd.b3, att_o.as<float>(),
+                                            op.mode == 1 ? att_w.as<float>() : nullptr, s);
+          if (op.mode == 1) rc |= dr_prog_from_f32(att_w.as<float>(), L, out, ldo, B, s);
+          else rc |= dr_prog_from_f32(att_o.as<float>(), Wq, out, ldo, B, s);
           break;
         }
         default: rc = -1;
@@ -584,8 +734,11 @@ struct Session {
     }
     int rc = 0;
     const int64_t n = (int64_t)a.T * B;
-    rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
-    rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, 0, 0, 1, s);
+    if (m.host_resident) { if (!HostLookup(m, B)) return false; }
+    else {
+      rc |= dr_cuda_table_lookup(m.structs.as<DrDeviceTable>(), nullptr, a.T, ids.as<int64_t>(), nullptr, B, n, 0, nullptr, pos.as<int32_t>(), nullptr, nullptr, 0, s);
+      rc |= dr_cuda_table_gather(m.structs.as<DrDeviceTable>(), nullptr, a.T, a.D, ids.as<int64_t>(), pos.as<int32_t>(), nullptr, B, n, emb.p, 1, 0, 0, 1, s);
+    }
     const void* x; int64_t ldx;
     if (dp.fp8 && !force_bf16) {
       // ---- E4M3 path: every hidden activation stays 8-bit; each GEMM epilogue re-quantises with the next layer's static scale
@@ -663,7 +816,7 @@ static bool Calibrate(Session& ss, const DeviceModel& m, DenseParams& dp, int B)
 }
 
 struct Config {
-  bool fp8 = false;
+  bool fp8 = false, host_tables = false;                 // host_tables: "enable_device_placement_optimization" -- embedding lookups on the CPU
   int session_num = 2, select_policy = 0 /*0 RR, 1 MOD*/, gpu_id = 0, max_batch = 4096, update_interval_ms = 1000, extra_rows = 1 << 16;
   int timeline_start_step = -1, timeline_interval_step = 0, timeline_trace_count = 0;
   std::string savedmodel_dir, checkpoint_dir, warmup_file_name, timeline_path;
@@ -765,6 +918,11 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
     const std::string base = "table/" + std::to_string(t);
     if (!ReadVec(r, base + "-sparse_incr_keys", &keys) || keys.empty()) continue;
     if (!ReadVec(r, base + "-sparse_incr_values", &vals)) return false;
+    if (m->host_resident) {                                          // host engine: copy-on-write import, readers never see a torn row
+      if (vals.size() != keys.size() * (size_t)m->arch.D) return false;
+      HostApi::Get().import_cow(m->host_tables[(size_t)t], keys.data(), vals.data(), m->arch.D, (int64_t)keys.size());
+      continue;
+    }
     // copy-on-write: live sessions keep reading complete rows (old or new) while the delta lands; the replaced rows are recycled at
     // the NEXT delta, after every session has passed a quiescent point (Quiesce below) -- CPU runtime: dr_host_ev_import_cow
     DevBuf dk, dv, cnt;
@@ -855,7 +1013,7 @@ static void UpdaterLoop(ServingModel* sm) {
       int64_t v = (int64_t)f->n("version", -1); std::string dir = f->s("dir", "");
       if (cur && v > cur->version && !dir.empty()) {
         cudaSetDevice(sm->cfg.gpu_id);
-        auto nm = LoadModel(dir, sm->cfg.extra_rows, sm->cfg.fp8);
+        auto nm = LoadModel(dir, sm->cfg.extra_rows, sm->cfg.fp8, sm->cfg.host_tables);
         if (!nm) { if (++bad > 3) fprintf(stderr, "[deeprec_serving] skipping invalid model version %lld\n", (long long)v); continue; }
         bad = 0;
         // The sessions' device / pinned buffers were sized from the architecture they were initialised with (Session::Init): a version with
@@ -934,7 +1092,8 @@ void* initialize(const char* model_entry, const char* model_config, int* state) 
   c.timeline_trace_count = (int)j.n("timeline_trace_count", 0);
   if (cudaSetDevice(c.gpu_id) != cudaSuccess) { *state = -1; delete sm; return nullptr; }
   c.fp8 = j.s("mlp_dtype", "bf16") == "fp8";
-  auto m = LoadModel(c.savedmodel_dir, c.extra_rows, c.fp8);
+  c.host_tables = j.n("enable_device_placement_optimization", 0) != 0 || j.s("embedding_placement", "device") == "host";
+  auto m = LoadModel(c.savedmodel_dir, c.extra_rows, c.fp8, c.host_tables);
   if (!m) { *state = -1; delete sm; return nullptr; }
   for (int i = 0; i < std::max(1, c.session_num); ++i) {
     sm->sessions.emplace_back(new Session());
@@ -970,7 +1129,7 @@ int get_serving_model_info(void* model_buf, void** output_data, int* output_size
   std::ostringstream os;
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
-     << ", \"mlp_dtype\": \"" << (sm->cfg.fp8 ? "fp8" : "bf16") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
+     << ", \"mlp_dtype\": \"" << (sm->cfg.fp8 ? "fp8" : "bf16") << "\", \"embedding_placement\": \"" << (sm->cfg.host_tables ? "host" : "device") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
   std::string s = os.str();
   *output_size = (int)s.size();
   *output_data = malloc(s.size() + 1);

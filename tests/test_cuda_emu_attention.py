@@ -1,5 +1,7 @@
 """csrc/cuda/attention_kernels.cu (fused DIN attention forward and backward) on the CUDA-on-CPU emulation against autograd through the
 composite fp32 reference -- the CPU twin of tests/test_gpu_zz_attention*.py / test_gpu_zzzz_din_attention_bwd.py."""
+import os
+
 import pytest
 import torch
 import torch.nn as nn
@@ -9,7 +11,10 @@ from deeprec_b200 import _native
 pytestmark = [pytest.mark.timeout(900)]
 
 
-@pytest.mark.parametrize("B,L,D,H1,H2", [(5, 50, 32, 80, 40), (9, 20, 32, 80, 40), (7, 9, 16, 24, 12)])
+QUICK = os.environ.get("DEEPREC_EMU_QUICK") == "1"          # the sanitizer re-runs (tests/test_cuda_emu_sanitizers.py) use the small case only
+
+
+@pytest.mark.parametrize("B,L,D,H1,H2", [(7, 9, 16, 24, 12)] if QUICK else [(5, 50, 32, 80, 40), (9, 20, 32, 80, 40), (7, 9, 16, 24, 12)])
 def test_fused_din_attention_forward_and_gradients_on_the_emulation(B, L, D, H1, H2):
     from deeprec_b200.ops.attention import din_attention, din_attention_fused_train, din_attention_reference
     torch.manual_seed(B + L)
