@@ -28,6 +28,7 @@ CUDA_SOURCES = [
     "cuda/interaction_kernels.cu",
     "cuda/comm_kernels.cu",
     "cuda/sparse_pipeline.cu",
+    "cuda/ag_embedding.cu",
     "cuda/fused_interaction_gemm.cu",
     "cuda/tier_kernels.cu",
     "cuda/nvls.cu",
@@ -132,6 +133,7 @@ EMU_SOURCES = [
     "cuda/serving_runtime.cu",
     "cuda/sparse_pipeline.cu",          # unique-first model-parallel pipeline: ranks = host threads, peer memory = the shared address space
     "cuda/comm_kernels.cu",
+    "cuda/ag_embedding.cu",             # all-gather -> lookup -> reduce-scatter embedding (SOK DistributedEmbedding dataflow) over peer memory
     "cuda/tier_kernels.cu",             # multi-tier: miss list / histogram eviction kernels + the manager's background thread
     "cuda/emu/emu_stubs.cu",            # host-loop stand-ins for the tcgen05 GEMM entry points
 ]

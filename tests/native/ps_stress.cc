@@ -84,10 +84,15 @@ int main() {
   for (int round = 0; round < 20 && !failed; ++round) {
     std::this_thread::sleep_for(std::chrono::milliseconds(3));
     dr_ps_server_set_def(sv, def.load(), 1);
-    // time-bounded (not spin-count-bounded): under TSAN on a loaded box a handler thread can stay descheduled for seconds
-    for (auto t0 = std::chrono::steady_clock::now(); dr_ps_server_inflight(sv) > 0 && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(120);)
+    // time-bounded (not spin-count-bounded): under TSAN on a loaded box a handler thread can stay descheduled for seconds.  ONE observation of
+    // zero after the freeze means drained (nothing can be admitted any more); later reads may see the transient +1 of a request that Admit() is
+    // in the middle of rejecting, so the verdict is the observation itself, not a second read
+    bool drained = false;
+    for (auto t0 = std::chrono::steady_clock::now(); std::chrono::steady_clock::now() - t0 < std::chrono::seconds(120);) {
+      if (dr_ps_server_inflight(sv) == 0) { drained = true; break; }
       std::this_thread::sleep_for(std::chrono::microseconds(50));
-    CHECK(dr_ps_server_inflight(sv) == 0);
+    }
+    CHECK(drained);
     def.fetch_add(1);
     dr_ps_server_set_def(sv, def.load(), 0);
   }

@@ -60,7 +60,7 @@ def test_emulated_kernels_under_thread_sanitizer():
     prefix = ("setarch", "-R") if shutil.which("setarch") else ()           # TSAN's shadow mapping wants ASLR off on recent kernels
     supp = os.path.join(ROOT, "tests", "native", "tsan_emu.supp")
     r = _run({"LD_PRELOAD": _runtime("libtsan.so"), "TSAN_OPTIONS": f"halt_on_error=0 report_signal_unsafe=0 exitcode=0 suppressions={supp}",
-              "DEEPREC_EMU_SANITIZE": "thread"}, ["test_cuda_emu_attention.py", "test_cuda_emu_sparse_utils.py", "test_cuda_emu_sparse_pipeline.py", "test_cuda_emu_tier.py"], prefix=prefix)
+              "DEEPREC_EMU_SANITIZE": "thread"}, ["test_cuda_emu_attention.py", "test_cuda_emu_sparse_utils.py", "test_cuda_emu_sparse_pipeline.py", "test_cuda_emu_tier.py", "test_cuda_emu_ag_embedding.py"], prefix=prefix)
     if r.returncode != 0 and ("unexpected memory mapping" in r.stderr or "tpp.c" in r.stderr or "cannot allocate memory in static TLS" in r.stderr):
         pytest.skip("TSAN runtime is not usable in this environment")
     # exitcode=0: the python process also hosts PyTorch, whose uninstrumented runtime produces reports of its own (e.g. at interpreter teardown);
