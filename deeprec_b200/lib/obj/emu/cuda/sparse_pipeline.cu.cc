@@ -180,7 +180,7 @@ __device__ __forceinline__ void sp_touch(const DrDeviceTable& TB, bool touch, in
     atomicAdd(&TB.slots[pos].freq, occ);
     int4 hi;                                                                             // {row_of, tag, dirty, pad}
     DR_LD_V4_VOLATILE(hi, &TB.slots[pos].row_of);
-    if (hi.z == 0) TB.slots[pos].dirty = 1;
+    if (hi.z == 0) DR_ST_RACY(TB.slots[pos].dirty, 1u);
     claim = ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1;
   }
   // one counter atomic per warp for the claims
@@ -192,8 +192,8 @@ __device__ __forceinline__ void sp_touch(const DrDeviceTable& TB, bool touch, in
   base = __shfl_sync(0xffffffffu, base, lead);
   if (claim) {
     const int u = base + __popc(cm & ((1u << (threadIdx.x & 31)) - 1u));
-    if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; TB.slots[pos].tag = u; }
-    else { TB.slots[pos].tag = -1; TB.counters[CTR_OVERFLOW] = 2; }
+    if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; DR_ST_RACY(TB.slots[pos].tag, u); }
+    else { DR_ST_RACY(TB.slots[pos].tag, -1); DR_ST_RACY(TB.counters[CTR_OVERFLOW], 2); }
   }
 }
 
