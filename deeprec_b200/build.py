@@ -17,7 +17,7 @@ CSRC = os.environ.get("DEEPREC_CSRC") or os.path.join(ROOT, "csrc")           # 
 LIB = os.environ.get("DEEPREC_LIB") or os.path.join(ROOT, "lib")
 OBJ = os.path.join(LIB, "obj")
 
-HOST_SOURCES = ["host/host_engine.cc", "host/io_runtime.cc", "host/ssd_store.cc", "host/predict_codec.cc", "host/redis_store.cc", "host/tensor_pool.cc", "host/cpu_serving.cc", "host/ps_server.cc"]
+HOST_SOURCES = ["host/host_engine.cc", "host/io_runtime.cc", "host/ssd_store.cc", "host/predict_codec.cc", "host/redis_store.cc", "host/tensor_pool.cc", "host/cpu_serving.cc", "host/ps_server.cc", "host/csv_ops.cc"]
 CUDA_SOURCES = [
     "cuda/table_kernels.cu",
     "cuda/embedding_kernels.cu",

@@ -2,17 +2,37 @@
 import torch
 
 import deeprec_b200 as dr
-from deeprec_b200.data.csv_ops import sparse_valid_cutoff, string_split_and_pad, string_to_hash_id, trans_csv_id2sparse, trans_csv_kv2dense
+from deeprec_b200.data.csv_ops import (sparse_valid_cutoff, string_split_and_pad, string_split_and_pad_ids, string_to_hash_id, trans_csv_id2dense,
+                                        trans_csv_id2sparse, trans_csv_kv2dense, trans_csv_kv2sparse, trans_csv_to_dense)
 from deeprec_b200.serving.sample_aware import enable_sample_awared_graph_compression
 from deeprec_b200.utils import StreamingAUC, Timeline
 
 
 def test_csv_ops():
     assert string_split_and_pad(["a,b,c", "d", ""], 2, default_value="<pad>") == [["a", "b"], ["d", "<pad>"], ["<pad>", "<pad>"]]
-    sp = trans_csv_id2sparse(["1,2,99", "", "3"], max_id=10)
-    assert sp.values.tolist() == [1, 2, 3] and sp.row_ids.tolist() == [0, 0, 2] and sp.batch_size == 3
-    d = trans_csv_kv2dense(["0:1.5,2:3", "1:2"], 2)
-    assert d.tolist() == [[1.5, 0.0, 3.0], [0.0, 2.0, 0.0]]
+    # the examples of kernels/trans_csv_ali_ops.cc:8-55 (the second dimension of every result is max_id; ids / keys live in [0, max_id))
+    sp = trans_csv_id2sparse(["2,10", "7", "0,8"], max_id=12)
+    assert sp.values.tolist() == [2, 10, 7, 0, 8] and sp.row_ids.tolist() == [0, 0, 1, 2, 2] and sp.batch_size == 3 and sp.dense_shape == (3, 12)
+    sp = trans_csv_id2sparse(["1, 2,,9", "", "3"], max_id=None)                      # empty tokens / records skipped, max_id detected
+    assert sp.values.tolist() == [1, 2, 9, 3] and sp.row_ids.tolist() == [0, 0, 0, 2] and sp.dense_shape == (3, 10)
+    assert trans_csv_id2sparse(["4"], max_id=5, id_as_value=False, default_value=2.0).weights.tolist() == [2.0]
+    assert trans_csv_id2dense(["2,1", "3", "0,2"], max_id=4, default_value=1).tolist() == [[0, 1, 1, 0], [0, 0, 0, 1], [1, 0, 1, 0]]
+    kv = trans_csv_kv2sparse(["2:2.0,10:0.1", "7:-0.7", "8:0.8"], max_id=12)
+    assert kv.values.tolist() == [2, 10, 7, 8] and kv.row_ids.tolist() == [0, 0, 1, 2] and torch.allclose(kv.weights, torch.tensor([2.0, 0.1, -0.7, 0.8]))
+    d = trans_csv_kv2dense(["2:0.2,1:0.1", "3:-0.3", "0:0.4,2:0.2"], max_id=4)
+    assert torch.allclose(d, torch.tensor([[0.0, 0.1, 0.2, 0.0], [0.0, 0.0, 0.0, -0.3], [0.4, 0.0, 0.2, 0.0]]))
+    assert torch.allclose(trans_csv_to_dense(["0.2,0.1", "-0.3", "0.4,0.2"], max_id=4), torch.tensor([[0.2, 0.1, 0, 0], [-0.3, 0, 0, 0], [0.4, 0.2, 0, 0]]))
+    assert trans_csv_to_dense(["1;2;3", "4"], field_delim=";").shape == (2, 3)
+    assert string_split_and_pad_ids(["5,6,7,8", "", "9"], 3).tolist() == [[5, 6, 7], [-1, -1, -1], [9, -1, -1]]
+    for bad in (lambda: trans_csv_id2sparse(["1,99"], max_id=10), lambda: trans_csv_id2sparse(["1,x"]), lambda: trans_csv_kv2dense(["1=2"], 4),
+                lambda: trans_csv_to_dense(["1,abc"])):
+        try:
+            bad(); raise AssertionError("malformed / out-of-range input must raise")
+        except ValueError:
+            pass
+    big = [",".join(str((i * 7 + j) % 1000) for j in range(i % 9)) for i in range(5000)]         # a real batch: parallel count + fill passes
+    sp = trans_csv_id2sparse(big, max_id=1000)
+    assert sp.values.numel() == sum(i % 9 for i in range(5000)) and torch.equal(torch.bincount(sp.row_ids, minlength=5000), torch.tensor([i % 9 for i in range(5000)]))
     sp = dr.SparseIds(torch.arange(7), torch.tensor([0, 0, 0, 0, 1, 1, 2]), 3)
     assert sparse_valid_cutoff(sp, 2, "left").values.tolist() == [0, 1, 4, 5, 6]
     assert sparse_valid_cutoff(sp, 2, "right").values.tolist() == [2, 3, 4, 5, 6]
