@@ -184,6 +184,7 @@ struct Model {
 };
 
 template <typename T> static bool ReadVec(dr::BundleReader& r, const std::string& name, std::vector<T>* out) {
+  if constexpr (std::is_same<T, float>::value) return dr::ReadAsFloat(r, name, out);       // bf16 / f16 / int8(+scale) tensors of a converted model
   auto* e = r.Find(name); if (!e) return false;
   out->resize((size_t)e->nbytes / sizeof(T));
   return r.Read(*e, out->data(), 1) == 0;
