@@ -59,7 +59,8 @@ def engine_main(a):
         extra = {}
     else:
         eng = din_engine(model, a.batch, 50, table_rows=(10_000_000, min(a.id_space, 200_000_000), 10_000), optimizer=a.optimizer,
-                         filter_freq=a.filter_freq, steps_to_live=100000, device=dev, rank=rank, world_size=world, comm=comm)
+                         filter_freq=a.filter_freq, steps_to_live=100000, device=dev, rank=rank, world_size=world, comm=comm,
+                         tiered={1: {"cache_rows": a.tier_rows, "strategy": 0}} if a.tier_rows > 0 else None)      # table 1 = the 1B-id behaviour (item) table
         host = []
         for s in range(n):
             b = taobao_batch(a.batch, 50, 10_000_000, a.id_space, 10_000, seed=s * world + rank)
@@ -67,9 +68,12 @@ def engine_main(a):
         extra = {"item_id_space": a.id_space, "filter_freq": a.filter_freq}
     put = lambda b: eng.load_batch(b[0].to(dev, non_blocking=True), b[1].to(dev, non_blocking=True),
                                    {k: v.to(dev, non_blocking=True) for k, v in b[2].items()} if b[2] else None)
+    tiered = bool(getattr(eng, "tiers", None))
+    ahead = (lambda j: eng.prefetch(host[j][0].to(dev, non_blocking=True))) if tiered else (lambda j: None)   # multi-tier: the NEXT batch's ids, one step ahead
     put(host[0]); eng.capture()
+    ahead(3)
     for i in range(a.warmup):
-        put(host[3 + i]); eng.train_step()
+        put(host[3 + i]); eng.train_step(); ahead(3 + i + 1)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -78,6 +82,8 @@ def engine_main(a):
     for i in range(a.steps):
         put(host[3 + a.warmup + i])                     # H2D of every step's inputs inside the timed region (pinned -> device)
         eng.train_step()
+        if i + 1 < a.steps:
+            ahead(3 + a.warmup + i + 1)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
@@ -89,6 +95,9 @@ def engine_main(a):
     if world > 1:
         dist.all_reduce(keys)
     loss = eng.loss_value()
+    if tiered:
+        st = eng.tiers[1][0].stats()
+        extra["multi_tier"] = {"hbm_cache_rows_per_rank": a.tier_rows, **{k: st[k] for k in ("hit_rate", "promoted_rows", "demoted_rows", "h2d_bytes", "d2h_bytes", "hbm_rows", "dram_rows")}}
     if rank == 0:
         print(json.dumps({"metric": f"{name} training samples/s ({world} GPU, FusedRecEngine: unique-first sparse pipeline + CUDA graph, H2D inside the timed region)",
                           "value": a.batch * world / ms * 1e3, "unit": "samples/s", "n_gpus": world, "ms_per_step": ms, "batch": a.batch,
@@ -111,6 +120,7 @@ def main():
     ap.add_argument("--ssd", action="store_true", help="DIN: add the SSD tier below DRAM (HBM_DRAM_SSDHASH)")
     ap.add_argument("--filter_freq", type=int, default=2)
     ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"])
+    ap.add_argument("--tier_rows", type=int, default=0, help="--engine, DIN: HBM cache rows PER RANK of the behaviour table over a host DRAM tier (0 = single tier); works at 1-8 GPUs")
     ap.add_argument("--engine", action="store_true", help="FusedRecEngine: unique-first sparse pipeline + one CUDA graph per step (1-8 GPUs, NVLink P2P)")
     a = ap.parse_args()
     if a.engine:

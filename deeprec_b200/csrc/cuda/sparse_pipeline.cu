@@ -46,9 +46,7 @@ struct DrSpGeom {
 
 namespace {
 
-__device__ __forceinline__ int sp_owner(int64_t key, int W) {
-  return W == 1 ? 0 : (int)((dr_mix64((uint64_t)key ^ 0x5bd1e9955bd1e995ULL) >> 33) % (uint64_t)W);
-}
+__device__ __forceinline__ int sp_owner(int64_t key, int W) { return dr_sp_owner(key, W); }      // csrc/common/ev_types.h
 
 // -----------------------------------------------------------------------------------------------------------------
 // k_sp_dedup: a block owns 32 samples; warp w walks columns w, w+8, ...; lane = sample.

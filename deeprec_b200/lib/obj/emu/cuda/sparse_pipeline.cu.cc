@@ -47,9 +47,7 @@ struct DrSpGeom {
 
 namespace {
 
-__device__ __forceinline__ int sp_owner(int64_t key, int W) {
-  return W == 1 ? 0 : (int)((dr_mix64((uint64_t)key ^ 0x5bd1e9955bd1e995ULL) >> 33) % (uint64_t)W);
-}
+__device__ __forceinline__ int sp_owner(int64_t key, int W) { return dr_sp_owner(key, W); }      // csrc/common/ev_types.h
 
 // -----------------------------------------------------------------------------------------------------------------
 // k_sp_dedup: a block owns 32 samples; warp w walks columns w, w+8, ...; lane = sample.
@@ -209,11 +207,11 @@ __global__ void __launch_bounds__(256) k_sp_lookup(const DrDeviceTable* __restri
                                                    int32_t* __restrict__ own_cnt, int64_t* __restrict__ ulist, int32_t* __restrict__ nunique,
                                                    int64_t ulist_cap, DrSpSync sync) {
   pdl_sync();
-  using emu_sh_11405001 = int32_t[256]; emu_sh_11405001& s_pos = *reinterpret_cast<emu_sh_11405001*>(emu::shared_var(11405001, sizeof(emu_sh_11405001)));
-  using emu_sh_11405002 = int64_t[256]; emu_sh_11405002& s_key = *reinterpret_cast<emu_sh_11405002*>(emu::shared_var(11405002, sizeof(emu_sh_11405002)));
-  using emu_sh_11405003 = int32_t[256]; emu_sh_11405003& s_gs = *reinterpret_cast<emu_sh_11405003*>(emu::shared_var(11405003, sizeof(emu_sh_11405003)));
-  using emu_sh_11405004 = int32_t[kSpMaxTables]; emu_sh_11405004& s_cnt = *reinterpret_cast<emu_sh_11405004*>(emu::shared_var(11405004, sizeof(emu_sh_11405004)));
-  using emu_sh_11405005 = int32_t[kSpMaxTables + 1]; emu_sh_11405005& s_pre = *reinterpret_cast<emu_sh_11405005*>(emu::shared_var(11405005, sizeof(emu_sh_11405005)));
+  using emu_sh_4979001 = int32_t[256]; emu_sh_4979001& s_pos = *reinterpret_cast<emu_sh_4979001*>(emu::shared_var(4979001, sizeof(emu_sh_4979001)));
+  using emu_sh_4979002 = int64_t[256]; emu_sh_4979002& s_key = *reinterpret_cast<emu_sh_4979002*>(emu::shared_var(4979002, sizeof(emu_sh_4979002)));
+  using emu_sh_4979003 = int32_t[256]; emu_sh_4979003& s_gs = *reinterpret_cast<emu_sh_4979003*>(emu::shared_var(4979003, sizeof(emu_sh_4979003)));
+  using emu_sh_4979004 = int32_t[kSpMaxTables]; emu_sh_4979004& s_cnt = *reinterpret_cast<emu_sh_4979004*>(emu::shared_var(4979004, sizeof(emu_sh_4979004)));
+  using emu_sh_4979005 = int32_t[kSpMaxTables + 1]; emu_sh_4979005& s_pre = *reinterpret_cast<emu_sh_4979005*>(emu::shared_var(4979005, sizeof(emu_sh_4979005)));
   const int T = g.T, W = g.W, rank = g.rank;
   for (int si = 0; si < W; ++si) {
     const int s = (rank + si) % W;                            // own bucket first, then the peers in ring order
@@ -307,7 +305,7 @@ __global__ void __launch_bounds__(256) k_sp_segsum(const __nv_bfloat16* __restri
   pdl_sync();
   constexpr int dim = 4 * LPR;
   constexpr int V = dim / 8;                                   // int4 (8 bf16) chunks per row
-  using emu_sh_11405006 = int4[8][32][V]; emu_sh_11405006& s_row = *reinterpret_cast<emu_sh_11405006*>(emu::shared_var(11405006, sizeof(emu_sh_11405006)));
+  using emu_sh_4979006 = int4[8][32][V]; emu_sh_4979006& s_row = *reinterpret_cast<emu_sh_4979006*>(emu::shared_var(4979006, sizeof(emu_sh_4979006)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles = (g.B + 31) / 32;
   const int64_t units = tiles * g.C;
@@ -381,8 +379,8 @@ __global__ void __launch_bounds__(256) k_sp_grad(const DrDeviceTable* __restrict
   pdl_sync();
   constexpr int IPC = 256 / LPR;
   constexpr int dim = 4 * LPR;
-  using emu_sh_11405007 = int32_t[kSpMaxTables]; emu_sh_11405007& s_cnt = *reinterpret_cast<emu_sh_11405007*>(emu::shared_var(11405007, sizeof(emu_sh_11405007)));
-  using emu_sh_11405008 = int32_t[kSpMaxTables + 1]; emu_sh_11405008& s_pre = *reinterpret_cast<emu_sh_11405008*>(emu::shared_var(11405008, sizeof(emu_sh_11405008)));
+  using emu_sh_4979007 = int32_t[kSpMaxTables]; emu_sh_4979007& s_cnt = *reinterpret_cast<emu_sh_4979007*>(emu::shared_var(4979007, sizeof(emu_sh_4979007)));
+  using emu_sh_4979008 = int32_t[kSpMaxTables + 1]; emu_sh_4979008& s_pre = *reinterpret_cast<emu_sh_4979008*>(emu::shared_var(4979008, sizeof(emu_sh_4979008)));
   const int T = g.T, W = g.W, rank = g.rank;
   const int lane = threadIdx.x % LPR;
   for (int si = 0; si < W; ++si) {
@@ -416,8 +414,8 @@ __global__ void __launch_bounds__(256) k_sp_grad(const DrDeviceTable* __restrict
 __global__ void __launch_bounds__(256) k_sp_reset(DrSpGeom g, DrSpSlot* __restrict__ scr, const int32_t* __restrict__ bkt_gs,
                                                   int32_t* __restrict__ bcnt, int32_t* __restrict__ state) {
   pdl_sync();
-  using emu_sh_11405009 = int32_t[kSpMaxTables]; emu_sh_11405009& s_cnt = *reinterpret_cast<emu_sh_11405009*>(emu::shared_var(11405009, sizeof(emu_sh_11405009)));
-  using emu_sh_11405010 = int32_t[kSpMaxTables + 1]; emu_sh_11405010& s_pre = *reinterpret_cast<emu_sh_11405010*>(emu::shared_var(11405010, sizeof(emu_sh_11405010)));
+  using emu_sh_4979009 = int32_t[kSpMaxTables]; emu_sh_4979009& s_cnt = *reinterpret_cast<emu_sh_4979009*>(emu::shared_var(4979009, sizeof(emu_sh_4979009)));
+  using emu_sh_4979010 = int32_t[kSpMaxTables + 1]; emu_sh_4979010& s_pre = *reinterpret_cast<emu_sh_4979010*>(emu::shared_var(4979010, sizeof(emu_sh_4979010)));
   const int T = g.T, W = g.W;
   for (int o = 0; o < W; ++o) {
     __syncthreads();

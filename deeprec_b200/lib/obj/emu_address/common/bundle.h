@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace dr {
@@ -174,5 +175,50 @@ class BundleReader {
   std::string prefix_; FILE* f_ = nullptr; std::vector<BundleEntry> entries_; std::map<std::string, size_t> index_; std::mutex mu_;
 };
 
+
+
+// fp32 view of a tensor that a low-precision conversion may have stored as bf16 / f16 / int8 (tools/low_precision_optimize.py: int8 tensors carry a
+// sibling `<name>/scale`, one fp32 per leading-dimension row or one for the whole tensor).  The serving runtimes read every float tensor through
+// this, so a converted saved model (2-4x smaller to ship, deltas included) loads like the original.
+inline bool ReadAsFloat(BundleReader& r, const std::string& name, std::vector<float>* out, std::vector<int64_t>* shape = nullptr) {
+  const BundleEntry* e = r.Find(name);
+  if (!e) return false;
+  if (shape) *shape = e->shape;
+  if (e->dtype == "f32") { out->resize((size_t)e->nbytes / 4); return r.Read(*e, out->data(), 1) == 0; }
+  std::vector<uint8_t> raw((size_t)e->nbytes);
+  if (r.Read(*e, raw.data(), 1) != 0) return false;
+  if (e->dtype == "bf16") {
+    const size_t n = raw.size() / 2; out->resize(n);
+    for (size_t i = 0; i < n; ++i) { uint16_t h; memcpy(&h, raw.data() + 2 * i, 2); const uint32_t u = (uint32_t)h << 16; memcpy(&(*out)[i], &u, 4); }
+    return true;
+  }
+  if (e->dtype == "f16") {
+    const size_t n = raw.size() / 2; out->resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      uint16_t h; memcpy(&h, raw.data() + 2 * i, 2);
+      const uint32_t sign = (uint32_t)(h & 0x8000) << 16; uint32_t ex = (h >> 10) & 0x1F, man = h & 0x3FF, u;
+      if (ex == 0) {
+        if (man == 0) u = sign;
+        else { int sh = 0; while (!(man & 0x400)) { man <<= 1; ++sh; } man &= 0x3FF; u = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | (man << 13); }
+      } else if (ex == 31) u = sign | 0x7F800000u | (man << 13);
+      else u = sign | ((ex - 15 + 127) << 23) | (man << 13);
+      memcpy(&(*out)[i], &u, 4);
+    }
+    return true;
+  }
+  if (e->dtype == "i8") {
+    std::vector<float> sc;
+    const BundleEntry* se = r.Find(name + "/scale");
+    if (!se || se->dtype != "f32") return false;
+    sc.resize((size_t)se->nbytes / 4);
+    if (r.Read(*se, sc.data(), 1) != 0 || sc.empty()) return false;
+    const size_t n = raw.size(); out->resize(n);
+    const size_t rows = sc.size(), per = rows ? n / rows : n;
+    if (rows > 1 && per * rows != n) return false;
+    for (size_t i = 0; i < n; ++i) (*out)[i] = (float)(int8_t)raw[i] * sc[rows > 1 ? i / per : 0];
+    return true;
+  }
+  return false;
+}
 
 }  // namespace dr

@@ -219,6 +219,12 @@ DR_HD uint64_t dr_hash_seed(uint64_t key, uint64_t seed) {
   return dr_mix64(key + 0x9e3779b97f4a7c15ULL * (seed + 1));
 }
 
+// Rank that owns `key` under row-wise model parallelism (every table sharded hash(key) % W): the ONE definition shared by the sparse pipeline's
+// requester-side bucketing (sparse_pipeline.cu), the multi-tier prefetch of an owner (tier_kernels.cu) and host-side tools (checkpoint re-sharding).
+DR_HD int dr_sp_owner(int64_t key, int W) {
+  return W == 1 ? 0 : (int)((dr_mix64((uint64_t)key ^ 0x5bd1e9955bd1e995ULL) >> 33) % (uint64_t)W);
+}
+
 // Row of the default-value matrix a fresh key is initialised from (embedding_var.h:207-209).
 DR_HD int64_t dr_default_row(int64_t key, int64_t default_value_dim) {
   int64_t r = key % default_value_dim;

@@ -246,6 +246,14 @@ __device__ __forceinline__ int64_t ld_volatile_i64(const int64_t* p) { return *r
 __device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
 #endif
 
+// idempotent metadata stores that race BY DESIGN with the volatile reads above (every writer stores the same "dirty" mark; the claim winner publishes
+// its list index to readers that accept either value): plain stores on the device, relaxed atomic stores in the emulation build
+#ifdef DR_CUDA_EMU
+#define DR_ST_RACY(lhs, v) __atomic_store_n(&(lhs), (v), __ATOMIC_RELAXED)
+#else
+#define DR_ST_RACY(lhs, v) (lhs) = (v)
+#endif
+
 // 16-byte / 8-byte volatile loads of a slot's metadata words (same PTX text as before the emulation build existed: the SASS of the hot
 // probe kernels is unchanged); on the host: relaxed atomic word loads, so ThreadSanitizer sees them as the benign races they are
 #ifdef DR_CUDA_EMU

@@ -234,6 +234,7 @@ static bool ReadTensor(dr::BundleReader& r, const std::string& name, std::vector
   return r.Read(*e, out->data(), 1) == 0;
 }
 template <typename T> static bool ReadVec(dr::BundleReader& r, const std::string& name, std::vector<T>* out, std::vector<int64_t>* shape = nullptr) {
+  if constexpr (std::is_same<T, float>::value) return dr::ReadAsFloat(r, name, out, shape);    // bf16 / f16 / int8(+scale) tensors of a converted model
   std::vector<uint8_t> raw; if (!ReadTensor(r, name, &raw, shape)) return false;
   out->resize(raw.size() / sizeof(T)); memcpy(out->data(), raw.data(), raw.size()); return true;
 }

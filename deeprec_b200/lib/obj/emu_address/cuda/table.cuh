@@ -140,11 +140,11 @@ __device__ __forceinline__ void table_touch_aggregated(const DrDeviceTable& TB, 
   // must not add a store and a CAS to the same-sector serialisation queue (the probe already pulled the sector in)
   int4 hi;                                                                             // {row_of, tag, dirty, pad}
   DR_LD_V4_VOLATILE(hi, &TB.slots[pos].row_of);
-  if (hi.z == 0) TB.slots[pos].dirty = 1;
+  if (hi.z == 0) DR_ST_RACY(TB.slots[pos].dirty, 1u);
   if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[pos].tag, -1, -2) == -1) {
     const int u = atomicAdd(nunique, 1);
-    if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; TB.slots[pos].tag = u; }
-    else { TB.slots[pos].tag = -1; TB.counters[CTR_OVERFLOW] = 2; }
+    if (u < ulist_cap) { ulist[u] = ((int64_t)table_index << 40) | pos; DR_ST_RACY(TB.slots[pos].tag, u); }
+    else { DR_ST_RACY(TB.slots[pos].tag, -1); DR_ST_RACY(TB.counters[CTR_OVERFLOW], 2); }
   }
 }
 
@@ -182,11 +182,11 @@ __device__ __forceinline__ void table_touch_block(const DrDeviceTable* __restric
     atomicAdd(&TB.slots[p].freq, sm.count[e]);
     int4 hi;                                                                            // {row_of, tag, dirty, pad}
     DR_LD_V4_VOLATILE(hi, &TB.slots[p].row_of);
-    if (hi.z == 0) TB.slots[p].dirty = 1;
+    if (hi.z == 0) DR_ST_RACY(TB.slots[p].dirty, 1u);
     if (ulist != nullptr && hi.y == -1 && atomicCAS(&TB.slots[p].tag, -1, -2) == -1) {
       const int u = atomicAdd(nunique, 1);
-      if (u < ulist_cap) { ulist[u] = (int64_t)k; TB.slots[p].tag = u; }
-      else { TB.slots[p].tag = -1; TB.counters[CTR_OVERFLOW] = 2; }
+      if (u < ulist_cap) { ulist[u] = (int64_t)k; DR_ST_RACY(TB.slots[p].tag, u); }
+      else { DR_ST_RACY(TB.slots[p].tag, -1); DR_ST_RACY(TB.counters[CTR_OVERFLOW], 2); }
     }
   }
   __syncthreads();

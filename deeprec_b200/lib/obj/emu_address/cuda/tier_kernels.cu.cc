@@ -19,6 +19,15 @@
 //       to the free list and tombstones their keys; D2H on the same stream; the background thread commits them to the DRAM tier
 //       (HostEV::Import) when the copy's event fires -- strictly BEFORE it serves the next prefetch, so a key can never be looked for
 //       in the host tier while it is still in flight.
+//
+// World > 1 (row-wise model parallelism: rank r holds the keys with dr_sp_owner(key, W) == r of every table, and with them BOTH tiers of those
+// keys).  A key must be promoted by its OWNER, whichever ranks' batches it appears in, so the prefetch is a fused id all-gather + probe over
+// peer memory -- no gathered copy of the ids, no NCCL call: k_tier_publish copies the rank's next-batch ids into its symmetric buffer (double
+// buffered by epoch parity) and its last block raises the rank's epoch flag on every peer (st.release.sys); k_tier_wait (ONE block, so the spin can
+// never starve the training step's kernels of SMs) polls the W flags; k_tier_miss_list_mp walks every rank's id buffer in place over NVLink and
+// keeps the keys this rank owns.  Everything after the miss list (staging, import, pin, eviction) is rank-local.  Reuse of a parity buffer two
+// prefetches later is safe because a step of the sparse pipeline cannot complete on any rank before every rank has launched it, which a rank
+// does only after commit() saw its own probe kernel of the previous epoch finish.
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -28,6 +37,7 @@
 #include <algorithm>
 
 #include "table.cuh"
+#include "sp_sync.cuh"
 
 using namespace drc;
 
@@ -43,6 +53,48 @@ __global__ void __launch_bounds__(256) k_tier_miss_list(DrDeviceTable TB, const 
     const int64_t pos = table_find(TB, key);
     if (pos >= 0 && TB.slots[pos].row_of >= 0) {
       TB.slots[pos].pad = epoch;                      // pinned until the step that consumes this batch has run
+      atomicAdd(&counters[1], 1);
+    } else {
+      const int m = atomicAdd(&counters[0], 1);
+      if (m < miss_cap) miss_keys[m] = key;
+    }
+  }
+}
+
+// ---- world > 1: publish my ids / wait for every rank's / probe the keys I own out of all of them ------------------------------------------------
+__global__ void __launch_bounds__(256) k_tier_publish(const int64_t* __restrict__ keys, int64_t n, int64_t* __restrict__ mine /* my symmetric slot of this parity */,
+                                                      DrPeers flags, int32_t* __restrict__ done /* device counter */, uint32_t epoch, int W, int rank) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mine[i] = keys[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                      // this block's ids before the count
+    const int prev = atomicAdd(done, 1);
+    if (prev == (int)gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();                                    // every block's ids before the flag
+      for (int r = 0; r < W; ++r) st_release_sys(reinterpret_cast<uint32_t*>(flags.ptr[r]) + rank, epoch);
+    }
+  }
+}
+
+__global__ void k_tier_wait(DrPeers flags, uint32_t epoch, int W, int rank) {
+  if ((int)threadIdx.x < W) {
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(flags.ptr[rank]) + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) __nanosleep(200);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tier_miss_list_mp(DrDeviceTable TB, DrPeers ids /* int64 [2][n] per rank */, int64_t n, int parity, int64_t pad_key,
+                                                           uint32_t epoch, int W, int rank, int64_t* __restrict__ miss_keys, int32_t* __restrict__ counters,
+                                                           int64_t miss_cap) {
+  const int64_t total = n * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i / n);
+    const int64_t key = reinterpret_cast<const int64_t*>(ids.ptr[(rank + s) % W])[(int64_t)parity * n + (i - (int64_t)s * n)];     // own list first, peers in ring order
+    if (key == pad_key || key == kEmptyKey || key == kTombKey || dr_sp_owner(key, W) != rank) continue;
+    const int64_t pos = table_find(TB, key);
+    if (pos >= 0 && TB.slots[pos].row_of >= 0) {
+      TB.slots[pos].pad = epoch;
       atomicAdd(&counters[1], 1);
     } else {
       const int m = atomicAdd(&counters[0], 1);
@@ -69,7 +121,7 @@ __device__ __forceinline__ bool tier_evictable(const DrSlot& s, uint32_t epoch_m
 }
 
 __global__ void __launch_bounds__(256) k_tier_hist(DrDeviceTable TB, int strategy, int64_t step, uint32_t epoch_min, int32_t* __restrict__ hist /* [64] */) {
-  using emu_sh_5025001 = int32_t[64]; emu_sh_5025001& sh = *reinterpret_cast<emu_sh_5025001*>(emu::shared_var(5025001, sizeof(emu_sh_5025001)));
+  using emu_sh_10145001 = int32_t[64]; emu_sh_10145001& sh = *reinterpret_cast<emu_sh_10145001*>(emu::shared_var(10145001, sizeof(emu_sh_10145001)));
   if (threadIdx.x < 64) sh[threadIdx.x] = 0;
   __syncthreads();
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < TB.capacity; p += (int64_t)gridDim.x * blockDim.x) {
@@ -164,6 +216,7 @@ struct TierManager {
       // ---- prefetch: miss keys are in mapped pinned memory once the probe kernel's event fires
       cudaEventSynchronize(ev_miss);
       const int64_t nm = std::min<int64_t>(h_counters[0], miss_cap);
+      const bool overflow = h_counters[0] > miss_cap;               // a dropped miss would be re-created from the default row: refuse (commit returns -20)
       hits += h_counters[1]; misses += h_counters[0];
       uniq.assign(h_miss, h_miss + nm);
       std::sort(uniq.begin(), uniq.end());
@@ -185,7 +238,7 @@ struct TierManager {
           ++ni;
         }
       }
-      { std::lock_guard<std::mutex> l(mu); n_import = ni; prefetch_ready = true; prefetch_inflight = false; }
+      { std::lock_guard<std::mutex> l(mu); n_import = overflow ? -20 : ni; prefetch_ready = true; prefetch_inflight = false; }
       cv.notify_all();
     }
   }
@@ -259,6 +312,30 @@ int dr_tier_prefetch(void* h, const DrDeviceTable* tb, const int64_t* keys, int6
   return 0;
 }
 
+// World > 1: `keys` are THIS rank's next-batch ids (n entries, the same n on every rank); `ids` is a symmetric int64 [2][n] buffer and `flags` a
+// symmetric zero-initialised uint32 [16] buffer (parallel.p2p.P2PComm.symmetric).  Every rank calls this once per epoch.
+int dr_tier_prefetch_mp(void* h, const DrDeviceTable* tb, const int64_t* keys, int64_t n, int64_t pad_key, uint32_t epoch, const DrPeers* ids,
+                        const DrPeers* flags, int W, int rank, cudaStream_t side) {
+  auto* m = static_cast<TierManager*>(h);
+  if (W < 1 || W > 16 || rank < 0 || rank >= W || n < 0) return -11;
+  {
+    std::unique_lock<std::mutex> l(m->mu);
+    if (m->prefetch_inflight || m->prefetch_ready) return -10;
+    m->prefetch_inflight = true;
+  }
+  const int parity = (int)(epoch & 1u);
+  DR_CUDA_CHECK(cudaMemsetAsync(m->d_counters, 0, 16, side));
+  emu::launch(dim3(grid_of(n)), dim3(256), (size_t)(0), (cudaStream_t)(side), [&] { k_tier_publish(keys, n, reinterpret_cast<int64_t*>(ids->ptr[rank]) + (int64_t)parity * n, *flags, m->d_counters + 2, epoch, W, rank); });
+  emu::launch(dim3(1), dim3(32), (size_t)(0), (cudaStream_t)(side), [&] { k_tier_wait(*flags, epoch, W, rank); });
+  if (n > 0) emu::launch(dim3(grid_of(n * W)), dim3(256), (size_t)(0), (cudaStream_t)(side), [&] { k_tier_miss_list_mp(*tb, *ids, n, parity, pad_key, epoch, W, rank, m->d_miss_alias, m->d_counters, m->miss_cap); });
+  DR_LAUNCH_CHECK();
+  DR_CUDA_CHECK(cudaMemcpyAsync(m->h_counters, m->d_counters, 16, cudaMemcpyDeviceToHost, side));
+  DR_CUDA_CHECK(cudaEventRecord(m->ev_miss, side));
+  { std::lock_guard<std::mutex> l(m->mu); m->q.push_back(0); }
+  m->cv.notify_all();
+  return 0;
+}
+
 // Step boundary: make the prefetched batch resident (waits for the background thread's staging, then enqueues H2D + import + pin on
 // `main`).  Returns the number of rows promoted, or < 0 on error.
 int64_t dr_tier_commit(void* h, const DrDeviceTable* tb, uint32_t epoch, cudaStream_t main) {
@@ -270,6 +347,7 @@ int64_t dr_tier_commit(void* h, const DrDeviceTable* tb, uint32_t epoch, cudaStr
     m->cv.wait(l, [&] { return m->prefetch_ready; });
     n = m->n_import; m->prefetch_ready = false;
   }
+  if (n < 0) { fprintf(stderr, "[deeprec_cuda] dr_tier_commit: the miss list of the prefetched batch overflowed (max_batch_keys = %lld): raise it\n", (long long)m->miss_cap); return n; }
   if (n > 0) {
     if (cudaMemcpyAsync(m->d_imp_keys, m->h_imp_keys, (size_t)n * 8, cudaMemcpyHostToDevice, main) != cudaSuccess) return -1;
     cudaMemcpyAsync(m->d_imp_freq, m->h_imp_freq, (size_t)n * 8, cudaMemcpyHostToDevice, main);

@@ -45,8 +45,10 @@ class FusedRecEngine:
                  tiered: Optional[Dict[int, dict]] = None):
         """net: dense module (its parameters are trained); forward_fn(net, dense: dict of static tensors, emb [B, C, D] bf16, ids [C, B]) -> logits [B].
         col_table[c]: table of id column c; table_rows[t]: expected distinct keys of table t (pre-sizing hint, tables grow).
-        tiered: {table: {"cache_rows": R, "strategy": 0 (LFU) | 1 (LRU)}} -- those tables keep at most ~R rows in HBM over a host DRAM tier
-        (ops/tier_manager.py; world_size 1): call ``prefetch(next_ids)`` one batch ahead."""
+        tiered: {table: {"cache_rows": R, "strategy": 0 (LFU) | 1 (LRU)}} -- those tables keep at most ~R rows PER RANK in HBM over a host DRAM tier
+        (ops/tier_manager.py): call ``prefetch(next_ids)`` one batch ahead with this rank's next id columns.  With world_size > 1 every rank holds
+        both tiers of the keys it owns and the owners find their keys in every rank's next batch over peer memory (tier_kernels.cu:
+        k_tier_publish / k_tier_wait / k_tier_miss_list_mp) -- ``prefetch`` is then a collective, like ``train_step``."""
         self.net, self.forward_fn = net, forward_fn
         self.rank, self.world, self.comm = rank, world_size, comm
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -84,20 +86,23 @@ class FusedRecEngine:
             rows = max(1024, min(card, max_rows_per_table))
             if tiered and t in tiered:            # HBM tier = cache: R rows + head-room for the keys two steps can create before an eviction lands
                 ncols_t = sum(1 for ct in col_table if ct == t)
-                rows = int(tiered[t]["cache_rows"]) + 2 * ncols_t * batch_size + 4096
+                # (world > 1: a rank owns ~1/W of the W batches' keys -- the same expectation, plus slack for the imbalance of hash(key) % W)
+                rows = int(tiered[t]["cache_rows"]) + (2 if world_size == 1 else 3) * ncols_t * batch_size + 4096
                 card = rows
             cap = _next_pow2(max(2048, 2 * min(card, rows)))
             self.tables[t] = DeviceTable(c, dm, dev, capacity=cap, row_capacity=rows, owner=id(self) & 0x7FFFFFFF)
         self.tmap = torch.tensor([self.tables[t].gid for t in range(self.T)], dtype=torch.int32, device=dev)
         self.tiers = {}
         if tiered:
-            if world_size > 1:
-                raise ValueError("tiered tables: the prefetch path is single-rank for now (the owner of a key, not its requester, must promote it)")
+            if world_size > 1 and (comm is None or not hasattr(comm, "symmetric")):
+                raise ValueError("tiered tables with world_size > 1 need a peer-memory communicator (parallel.p2p.P2PComm)")
             from ..ops.tier_manager import DeviceTierManager
-            for t, o in tiered.items():
+            for t, o in sorted(tiered.items()):            # sorted: the symmetric allocations inside are collective calls
                 cols = torch.tensor([c for c, ct in enumerate(col_table) if ct == t], dtype=torch.int64, device=dev)
+                n_ids = int(cols.numel()) * batch_size
                 mgr = DeviceTierManager(self.tables[t], int(o["cache_rows"]), strategy=int(o.get("strategy", 0)), pad_key=pad_key,
-                                        max_batch_keys=max(1 << 16, 2 * int(cols.numel()) * batch_size))
+                                        max_batch_keys=max(1 << 16, (2 if world_size == 1 else 4) * n_ids),
+                                        comm=comm if world_size > 1 else None, ids_per_prefetch=n_ids)
                 self.tiers[t] = (mgr, cols)
         self._host_step = 0
         # ---- sparse pipeline + static buffers

@@ -27,6 +27,7 @@ def _bind(lib):
     lib.dr_tier_create.argtypes, lib.dr_tier_create.restype = [vp, vp, vp, C.c_int, i64, i64, C.c_int], vp
     lib.dr_tier_destroy.argtypes, lib.dr_tier_destroy.restype = [vp], None
     lib.dr_tier_prefetch.argtypes, lib.dr_tier_prefetch.restype = [vp, vp, vp, i64, i64, C.c_uint32, vp], C.c_int
+    lib.dr_tier_prefetch_mp.argtypes, lib.dr_tier_prefetch_mp.restype = [vp, vp, vp, i64, i64, C.c_uint32, vp, vp, C.c_int, C.c_int, vp], C.c_int
     lib.dr_tier_commit.argtypes, lib.dr_tier_commit.restype = [vp, vp, C.c_uint32, vp], i64
     lib.dr_tier_evict.argtypes, lib.dr_tier_evict.restype = [vp, vp, i32, C.c_uint32, i64, C.c_int, vp], C.c_int
     lib.dr_tier_drain.argtypes, lib.dr_tier_drain.restype = [vp], None
@@ -37,11 +38,17 @@ def _bind(lib):
 
 class DeviceTierManager:
     """``table``: the HBM tier (its row slab is the cache: ``cache_rows`` rows + head-room for one step's new keys).
-    ``host``: the DRAM tier (created here when omitted; admission / eviction policies stay with tier 0)."""
+    ``host``: the DRAM tier (created here when omitted; admission / eviction policies stay with tier 0).
+    ``comm`` (world > 1, row-wise model parallelism): ``table`` is this rank's shard -- the keys with ``dr_sp_owner(key, W) == rank`` -- and so is
+    the DRAM tier; ``prefetch`` takes the rank's OWN next-batch ids (``ids_per_prefetch`` of them on every rank) and the kernels find the keys
+    this rank owns in every rank's list over peer memory (collective: every rank calls ``prefetch`` / ``commit`` once per step)."""
 
     def __init__(self, table: DeviceTable, cache_rows: int, host: Optional[HostTable] = None, strategy: int = 0, max_batch_keys: int = 1 << 20,
-                 evict_chunk: Optional[int] = None, pad_key: int = -1, low_watermark: float = 0.85):
+                 evict_chunk: Optional[int] = None, pad_key: int = -1, low_watermark: float = 0.85, comm=None, ids_per_prefetch: int = 0):
         self.table, self.cache_rows, self.strategy, self.pad_key = table, int(cache_rows), int(strategy), int(pad_key)
+        self.comm = comm if (comm is not None and getattr(comm, "world", 1) > 1) else None
+        self.world, self.rank = (self.comm.world, self.comm.rank) if self.comm is not None else (1, 0)
+        self.n_sym = int(ids_per_prefetch)
         self.dev = table.device
         if host is None:
             hc = EvConfig.from_buffer_copy(bytes(table.cfg))
@@ -71,6 +78,14 @@ class DeviceTierManager:
         self._epoch = 0
         self._keep = None
         self._purged_at = 0
+        if self.comm is not None:
+            if self.n_sym <= 0:
+                raise ValueError("world > 1: ids_per_prefetch (ids handed to prefetch() per rank per step) is required")
+            self.ids_sym = self.comm.symmetric(2 * self.n_sym * 8)       # [parity][n] int64, read in place by every peer's probe kernel
+            self.flags_sym = self.comm.symmetric(64)                      # uint32 [16]: flags[r] = last epoch rank r published
+            self.ids_sym.tensor(torch.int64, (2 * self.n_sym,)).fill_(self.pad_key)
+            self.flags_sym.tensor(torch.int32, (16,)).zero_()
+            self.comm.host_barrier()
 
     def close(self) -> None:
         if self.h:
@@ -94,8 +109,14 @@ class DeviceTierManager:
         self._keep = k                                                   # alive until the probe kernel has run (commit)
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream(self.dev))   # the ids were produced on the caller's stream
-        rc = self.lib.dr_tier_prefetch(self.h, C.byref(self.table.struct), ptr(k), k.numel(), self.pad_key, self._epoch + 1,
-                                       vp(self.side.cuda_stream) if self.side is not None else None)
+        side = vp(self.side.cuda_stream) if self.side is not None else None
+        if self.comm is not None:
+            if k.numel() != self.n_sym:
+                raise ValueError(f"world > 1: prefetch() takes exactly ids_per_prefetch = {self.n_sym} ids per rank (got {k.numel()}; pad with pad_key)")
+            rc = self.lib.dr_tier_prefetch_mp(self.h, C.byref(self.table.struct), ptr(k), k.numel(), self.pad_key, self._epoch + 1,
+                                              self.ids_sym.peers_ref(), self.flags_sym.peers_ref(), self.world, self.rank, side)
+        else:
+            rc = self.lib.dr_tier_prefetch(self.h, C.byref(self.table.struct), ptr(k), k.numel(), self.pad_key, self._epoch + 1, side)
         if rc != 0:
             raise RuntimeError(f"dr_tier_prefetch failed ({rc}): commit() the previous batch first")
 

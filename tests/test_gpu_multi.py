@@ -47,3 +47,14 @@ def test_sharded_checkpoint_restores_under_another_world_size(tmp_path):
         assert torch.equal(f, freq), t
         got = eng.tables[t].lookup(probe).cpu() * (f > 0).float()[:, None]
         assert torch.allclose(got, rows, atol=1e-6), t
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_tiered_tables_under_model_parallelism_2gpu():
+    """FusedRecEngine(tiered=...) at world 2: every rank keeps a 1024-row HBM cache over its own DRAM tier for the keys it owns; the owners find
+    their keys in both ranks' next batches over peer memory (tier_kernels.cu: k_tier_miss_list_mp).  Same losses / rows as single-tier tables.
+    CPU twin with ranks as threads: tests/test_cuda_emu_tier.py::test_owner_side_promotion_with_ranks_as_threads."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29535",
+           os.path.join(ROOT, "tests", "mp_tier.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "MP_TIER_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
