@@ -56,5 +56,6 @@ setup(
         "deeprec-train=deeprec_b200.models.train:main",
         "deeprec-serve=deeprec_b200.serving.serve:main",
         "deeprec-inspect-checkpoint=deeprec_b200.tools.inspect_checkpoint:main",
+        "deeprec-ckpt-transform=deeprec_b200.tools.ckpt_format_transform:main",
     ]},
 )
