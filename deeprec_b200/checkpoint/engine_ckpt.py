@@ -30,6 +30,11 @@ from .saver import BundleReader, BundleWriter, _register_checkpoint
 _M64 = (1 << 64) - 1
 
 
+
+def _native_device_sync(dev) -> None:
+    from .. import _native
+    _native.device_sync(dev)                        # torch.cuda.synchronize on a GPU; a no-op on the CUDA-on-CPU emulation
+
 def _lsr(x: torch.Tensor, n: int) -> torch.Tensor:
     """logical shift right of int64 bit patterns"""
     return (x >> n) & ((1 << (64 - n)) - 1)
@@ -78,7 +83,7 @@ def _step_of(eng) -> int:
 
 def save_engine(eng, save_path: str, incremental: bool = False, max_to_keep: int = 5) -> str:
     """Write this rank's shard; returns the bundle prefix.  Call on every rank (collectively: a barrier follows when world > 1)."""
-    torch.cuda.synchronize(eng.dev)
+    _native_device_sync(eng.dev)
     step, W, r = _step_of(eng), eng.world, eng.rank
     d = os.path.dirname(os.path.abspath(save_path))
     base = os.path.basename(save_path)
@@ -220,5 +225,5 @@ def restore_engine(eng, save_path: str, step: Optional[int] = None, replay_incre
             last = s
     for tbl in eng.tables.values():
         tbl.clear_dirty()
-    torch.cuda.synchronize(eng.dev)
+    _native_device_sync(eng.dev)
     return last

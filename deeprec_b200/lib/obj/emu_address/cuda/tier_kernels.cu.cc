@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_tier_miss_list(DrDeviceTable TB, const 
     if (key == pad_key || key == kEmptyKey || key == kTombKey) continue;
     const int64_t pos = table_find(TB, key);
     if (pos >= 0 && TB.slots[pos].row_of >= 0) {
-      TB.slots[pos].pad = epoch;                      // pinned until the step that consumes this batch has run
+      DR_ST_RACY(TB.slots[pos].pad, epoch);           // pinned until the step that consumes this batch has run (duplicates store the same value)
       atomicAdd(&counters[1], 1);
     } else {
       const int m = atomicAdd(&counters[0], 1);
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_tier_miss_list_mp(DrDeviceTable TB, DrP
     if (key == pad_key || key == kEmptyKey || key == kTombKey || dr_sp_owner(key, W) != rank) continue;
     const int64_t pos = table_find(TB, key);
     if (pos >= 0 && TB.slots[pos].row_of >= 0) {
-      TB.slots[pos].pad = epoch;
+      DR_ST_RACY(TB.slots[pos].pad, epoch);
       atomicAdd(&counters[1], 1);
     } else {
       const int m = atomicAdd(&counters[0], 1);

@@ -51,9 +51,11 @@ class FusedRecEngine:
         k_tier_publish / k_tier_wait / k_tier_miss_list_mp) -- ``prefetch`` is then a collective, like ``train_step``."""
         self.net, self.forward_fn = net, forward_fn
         self.rank, self.world, self.comm = rank, world_size, comm
-        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.emu = _native.emu_active()              # CPU CI: the same step on the CUDA-on-CPU emulation of the kernels (eager, no CUDA graph)
+        self.dev = torch.device("cpu") if self.emu else (torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()))
         self.lib = _native.cuda()
-        _native.set_device(self.dev.index)
+        if not self.emu:
+            _native.set_device(self.dev.index)
         self.B, self.D, self.C, self.T = batch_size, embedding_dim, len(col_table), len(table_rows)
         self.kind = _OPT_KIND[optimizer.lower()]
         self.lr, self.init_acc = learning_rate, initial_accumulator_value
@@ -135,10 +137,13 @@ class FusedRecEngine:
         # them into the flat (symmetric, with world > 1) buffer the fused optimizer / all-reduce kernel reads
         self._plist, self._gviews = plist, views
         if world_size > 1:      # identical replicas: rank 0's initial values everywhere
-            import torch.distributed as dist
-            dist.broadcast(self.params, 0)
-            for b in self.net.buffers():
-                dist.broadcast(b, 0)
+            if hasattr(comm, "host_broadcast"):              # emulation: ranks are threads of this process (parallel/emu_comm.py)
+                comm.host_broadcast([self.params] + list(self.net.buffers()))
+            else:
+                import torch.distributed as dist
+                dist.broadcast(self.params, 0)
+                for b in self.net.buffers():
+                    dist.broadcast(b, 0)
         self.s0 = torch.full((self.P,), initial_accumulator_value if self.kind in (OPT_ADAGRAD, OPT_ADAGRAD_DECAY, OPT_FTRL) else 0.0,
                              dtype=torch.float32, device=dev) if ns > 0 else None
         self.s1 = torch.zeros(self.P, dtype=torch.float32, device=dev) if ns > 1 else None
@@ -151,11 +156,11 @@ class FusedRecEngine:
         hp.decay_step, hp.global_step = 100000, 0
         self.ctx.set_hyper(hp)
         self.hp_dev = self.ctx.hp_dev
-        torch.cuda.synchronize(dev)
+        _native.device_sync(dev)
 
     # ------------------------------------------------------------------------------------------------------------------
     def _s(self):
-        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        return None if self.emu else C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _sparse_forward(self, train: bool) -> None:
         self.sp.dedup(self.ids)
@@ -211,6 +216,11 @@ class FusedRecEngine:
     def capture(self, warmup: int = 3) -> None:
         """Three eager steps on a side stream (autograd / allocator warm-up; they DO train on the loaded batch), then the whole step
         is captured into one CUDA graph."""
+        if self.emu:                                  # kernels run synchronously on the host: the eager step IS the step
+            for _ in range(warmup):
+                self._step_body()
+            self.launches_per_step = 0
+            return
         cur = torch.cuda.current_stream(self.dev)
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(cur)
@@ -267,8 +277,11 @@ class FusedRecEngine:
     def loss_value(self, global_mean: bool = True) -> float:
         v = self.loss.clone()
         if global_mean and self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(v)
+            if hasattr(self.comm, "host_all_reduce"):
+                self.comm.host_all_reduce(v)
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(v)
         return float(v.item())
 
 
@@ -281,7 +294,7 @@ def criteo_engine(model, batch_size: int, table_rows: Optional[Sequence[int]] = 
 
     def fwd(net, dense, emb, ids):
         # bf16 activations end to end (tcgen05 FusedMLP in / out, BatchNorm, FM kernel); fp32 master weights; the loss is taken in fp32
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast(emb.device.type, dtype=torch.bfloat16):
             return net.inner.logits(dense["dense"].to(torch.bfloat16), emb)
     return FusedRecEngine(dense_net, fwd, list(range(T)), rows, batch_size, embedding_dim=model.emb_dim,
                           dense_inputs={"dense": ((batch_size, model.num_dense), torch.float32)}, **kw)
@@ -299,7 +312,7 @@ def din_engine(model, batch_size: int, max_len: int = 50, table_rows: Sequence[i
         q = torch.cat([emb[:, 1], emb[:, 2]], -1)
         k = torch.cat([emb[:, 3:3 + L], emb[:, 3 + L:3 + 2 * L]], -1)             # [B, L, 2D] bf16 (padding rows are already zero)
         mask = (ids[3:3 + L] >= 0).t()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast(emb.device.type, dtype=torch.bfloat16):
             return net.inner.head(u, q, k, mask)
     return FusedRecEngine(dense_net, fwd, col_table, list(table_rows), batch_size, embedding_dim=model.emb_dim, **kw)
 

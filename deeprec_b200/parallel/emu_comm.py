@@ -68,3 +68,50 @@ class EmuComm:
 
     def host_barrier(self) -> None:
         self.shared.barrier.wait()
+
+    # ---- what the engines ask of a communicator beyond symmetric buffers (parallel.p2p.P2PComm's surface) ---------------------------------------
+    def alloc_grads(self, P: int) -> torch.Tensor:
+        self.grads_buf = self.symmetric(P * 4)
+        return self.grads_buf.tensor(torch.float32, (P,))
+
+    def dense_allreduce_update(self, eng) -> None:
+        """DENSE flag + the one-shot peer-pull all-reduce fused with the optimizer (comm_kernels.cu: k_allreduce_apply polls the flags itself)."""
+        from .. import _native
+        from .._native import ptr
+        sp = eng.sp
+        sp.signal(3)
+        rc = _native.cuda().dr_comm_allreduce_apply_sync(self.grads_buf.peers_ref(), self.world, ptr(eng.params), ptr(eng.s0) if eng.s0 is not None else None,
+                                                         ptr(eng.s1) if eng.s1 is not None else None, eng.P, ptr(eng.hp_dev), None, sp.sync_ref(), None)
+        if rc != 0:
+            raise RuntimeError(f"allreduce_apply failed ({rc})")
+        eng.launches += 2
+
+    def wait_dense(self, sp) -> None:
+        from .. import _native
+        rc = _native.cuda().dr_comm_allreduce_apply_sync(self.grads_buf.peers_ref(), self.world, None, None, None, 0, None, None, sp.sync_ref(), None)
+        if rc != 0:
+            raise RuntimeError(f"wait_dense failed ({rc})")
+
+    def host_broadcast(self, tensors, src: int = 0) -> None:
+        """Rank ``src``'s values into every rank's tensors (engine construction)."""
+        w = self.shared
+        if self.rank == src:
+            with w.lock:
+                w.published["bcast"] = [t.detach().clone() for t in tensors]
+        w.barrier.wait()
+        if self.rank != src:
+            with torch.no_grad():
+                for t, v in zip(tensors, w.published["bcast"]):
+                    t.copy_(v)
+        w.barrier.wait()
+
+    def host_all_reduce(self, t: torch.Tensor) -> None:
+        """Sum over the ranks, in place (metrics)."""
+        w = self.shared
+        with w.lock:
+            w.published.setdefault("allred", {})[self.rank] = t.detach().clone()
+        w.barrier.wait()
+        total = sum(w.published["allred"][r] for r in range(self.world))
+        w.barrier.wait()
+        t.copy_(total)
+        w.barrier.wait()
