@@ -42,13 +42,16 @@ class FusedRecEngine:
                  embedding_dim: int = 16, dense_inputs: Optional[Dict[str, tuple]] = None, optimizer: str = "adagrad", learning_rate: float = 0.01,
                  initial_accumulator_value: float = 0.1, filter_freq: int = 0, steps_to_live: int = 0, pad_key: int = -1, seed: int = 1234,
                  max_rows_per_table: int = 1 << 25, device=None, rank: int = 0, world_size: int = 1, comm=None, loss_fn: Optional[Callable] = None,
-                 tiered: Optional[Dict[int, dict]] = None):
+                 tiered: Optional[Dict[int, dict]] = None, micro_batch_num: int = 1):
         """net: dense module (its parameters are trained); forward_fn(net, dense: dict of static tensors, emb [B, C, D] bf16, ids [C, B]) -> logits [B].
         col_table[c]: table of id column c; table_rows[t]: expected distinct keys of table t (pre-sizing hint, tables grow).
         tiered: {table: {"cache_rows": R, "strategy": 0 (LFU) | 1 (LRU)}} -- those tables keep at most ~R rows PER RANK in HBM over a host DRAM tier
         (ops/tier_manager.py): call ``prefetch(next_ids)`` one batch ahead with this rank's next id columns.  With world_size > 1 every rank holds
         both tiers of the keys it owns and the owners find their keys in every rank's next batch over peer memory (tier_kernels.cu:
-        k_tier_publish / k_tier_wait / k_tier_miss_list_mp) -- ``prefetch`` is then a collective, like ``train_step``."""
+        k_tier_publish / k_tier_wait / k_tier_miss_list_mp) -- ``prefetch`` is then a collective, like ``train_step``.
+        micro_batch_num: auto micro-batch (graph_execution_state.cc:635-729, ConfigProto.micro_batch_num): the DENSE net's forward + backward run
+        over M slices of the batch inside the same step (same CUDA graph), parameter gradients accumulate, one optimizer step -- peak activation
+        memory / M.  The sparse pipeline still runs ONCE per step on the whole batch: dedup gets better with batch size, and its buffers are static."""
         self.net, self.forward_fn = net, forward_fn
         self.rank, self.world, self.comm = rank, world_size, comm
         self.emu = _native.emu_active()              # CPU CI: the same step on the CUDA-on-CPU emulation of the kernels (eager, no CUDA graph)
@@ -61,6 +64,9 @@ class FusedRecEngine:
         self.lr, self.init_acc = learning_rate, initial_accumulator_value
         self.loss_fn = loss_fn or (lambda logits, labels: nn.functional.binary_cross_entropy_with_logits(logits.float(), labels))
         self.launches, self._graph = 0, None
+        self.micro = max(1, int(micro_batch_num))
+        if batch_size % self.micro:
+            raise ValueError(f"micro_batch_num {self.micro} must divide the batch size {batch_size}")
         dev = self.dev
         # ---- tables: this rank's hash(key) % world shard of every table
         self.ctx = get_context(dev, self.D, owner=id(self) & 0x7FFFFFFF)
@@ -182,12 +188,24 @@ class FusedRecEngine:
         # sparse forward outside autograd; the gathered [B, C, D] activation enters the dense net's graph as a leaf whose .grad is what
         # the sparse backward consumes (no custom autograd.Function inside the captured backward)
         self._sparse_forward(True)
-        emb = self.emb_out.detach().requires_grad_(True)
-        logits = self.forward_fn(self.net, self.dense, emb, self.ids)
-        loss = self.loss_fn(logits, self.labels) / self.world
-        self.loss.copy_(loss.detach().reshape(1))
-        loss.backward()
-        self.demb.copy_(emb.grad.permute(1, 0, 2))      # [B, C, D] -> feature-major bf16 [C, B, D] (what k_sp_segsum reads coalesced)
+        if self.micro == 1:
+            emb = self.emb_out.detach().requires_grad_(True)
+            logits = self.forward_fn(self.net, self.dense, emb, self.ids)
+            loss = self.loss_fn(logits, self.labels) / self.world
+            self.loss.copy_(loss.detach().reshape(1))
+            loss.backward()
+            self.demb.copy_(emb.grad.permute(1, 0, 2))      # [B, C, D] -> feature-major bf16 [C, B, D] (what k_sp_segsum reads coalesced)
+        else:                                               # auto micro-batch: slices of the gathered activation, gradients accumulate in .grad
+            mb = self.B // self.micro
+            self.loss.zero_()
+            for m in range(self.micro):
+                lo, hi = m * mb, (m + 1) * mb
+                emb = self.emb_out[lo:hi].detach().requires_grad_(True)
+                logits = self.forward_fn(self.net, {k: v[lo:hi] for k, v in self.dense.items()}, emb, self.ids[:, lo:hi])
+                loss = self.loss_fn(logits, self.labels[lo:hi]) / (self.world * self.micro)       # mean over the whole batch = mean of the slice means
+                self.loss.add_(loss.detach().reshape(1))
+                loss.backward()
+                self.demb[:, lo:hi].copy_(emb.grad.permute(1, 0, 2))
         self._sparse_backward()
         # (the gather kernel of this step waited for every owner's ROWS flag, so every peer has finished last step's all-reduce reads
         #  of the flat gradient buffer: it may be overwritten now)

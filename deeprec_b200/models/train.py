@@ -100,7 +100,8 @@ def main(argv=None) -> int:
         torch.manual_seed(0)
         model = build_model(name, device=dev)
         kw = dict(optimizer=a.optimizer, learning_rate=a.learning_rate, filter_freq=2 if a.ev_filter else 0,
-                  steps_to_live=4000 if a.ev_elimination == "gstep" else 0, device=dev, rank=rank, world_size=world, comm=comm)
+                  steps_to_live=4000 if a.ev_elimination == "gstep" else 0, device=dev, rank=rank, world_size=world, comm=comm,
+                  micro_batch_num=a.micro_batch)
         if name == "din":
             L = 20
             eng = din_engine(model, a.batch_size, L, table_rows=(100000, 200000, 1000), **kw)

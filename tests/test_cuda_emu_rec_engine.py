@@ -165,3 +165,31 @@ def test_model_parallel_engine_ranks_as_threads():
     for r in range(W):
         mine = owner == r
         assert torch.allclose(plain[r][2][mine], tier[r][2][mine], atol=1e-4), r
+
+
+def test_micro_batches_through_the_dense_net_equal_one_big_batch():
+    """FusedRecEngine(micro_batch_num=4) (auto micro-batch, graph_execution_state.cc:635-729): a net without batch statistics must train exactly as
+    with the whole batch at once -- slice losses average to the batch loss, parameter gradients accumulate, embedding gradients land in their slices."""
+    from deeprec_b200.models.rec_engine import FusedRecEngine
+    B, C, D = 128, 4, 16
+    res = []
+    with _native.cuda_emulation():
+        for M in (1, 4):
+            torch.manual_seed(3)
+            net = torch.nn.Sequential(torch.nn.Linear(C * D + 5, 32), torch.nn.ReLU(), torch.nn.Linear(32, 1))
+            fwd = lambda net, dense, emb, ids: net(torch.cat([emb.float().flatten(1), dense["x"]], 1)).squeeze(1)
+            eng = FusedRecEngine(net, fwd, [0, 1, 1, 2], [50, 300, 20], B, embedding_dim=D, dense_inputs={"x": ((B, 5), torch.float32)}, learning_rate=0.05,
+                                 micro_batch_num=M)
+            losses = []
+            for s in range(5):
+                g = torch.Generator().manual_seed(50 + s)
+                ids = torch.stack([torch.randint(0, 50, (B,), generator=g), torch.randint(0, 300, (B,), generator=g), torch.randint(0, 300, (B,), generator=g),
+                                   torch.randint(0, 20, (B,), generator=g)])
+                eng.load_batch(ids, (torch.rand(B, generator=g) < 0.4).float(), {"x": torch.rand(B, 5, generator=g)})
+                eng.train_step(); losses.append(eng.loss_value())
+            res.append((losses, eng.params.clone(), eng.tables[1].lookup(torch.arange(300)).clone()))
+    assert max(abs(a - b) for a, b in zip(res[0][0], res[1][0])) < 1e-5, (res[0][0], res[1][0])
+    assert torch.allclose(res[0][1], res[1][1], atol=1e-5) and torch.allclose(res[0][2], res[1][2], atol=1e-4)
+    with pytest.raises(ValueError):
+        with _native.cuda_emulation():
+            FusedRecEngine(torch.nn.Linear(16, 1), lambda *a: None, [0], [10], 10, micro_batch_num=3)
