@@ -40,6 +40,7 @@
 #include "../common/bundle.h"
 #include "../common/ev_types.h"
 #include "../common/mini_json.h"
+#include "../common/model_config.h"
 #include "../common/predict_pb.h"
 
 extern "C" {
@@ -1051,6 +1052,7 @@ struct AffinityScope {
 struct Batcher;
 struct ServingModel {
   Config cfg;
+  drcfg::Compat compat;                            // reference ModelConfig keys without a 1:1 field (csrc/common/model_config.h)
   std::shared_ptr<Batcher> batcher;
   std::atomic<int> busy{0};                        // sessions currently inside a forward pass
   std::shared_ptr<Model> model;                    // atomic_load / atomic_store
@@ -1280,6 +1282,7 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
 static void UpdaterLoop(ServingModel* sm) {
   const std::string vf = (sm->cfg.checkpoint_dir.empty() ? sm->cfg.savedmodel_dir : sm->cfg.checkpoint_dir) + "/serving_versions.json";
   int bad = 0;
+  if (sm->compat.update_intra_threads > 0) omp_set_num_threads(sm->compat.update_intra_threads);    // model_update_intra_threads: the hot update's imports / packing run on this thread's team
   while (!sm->stop) {
     for (int i = 0; i < std::max(1, sm->cfg.update_interval_ms / 20) && !sm->stop; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(20));
     std::string txt; JVal j;
@@ -1319,6 +1322,8 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
   JVal j;
   if (model_config && *model_config && !drjson::ParseJson(model_config, &j)) { *state = -1; delete sm; return nullptr; }
   Config& c = sm->cfg;
+  sm->compat = drcfg::ParseCompat(j, "deeprec_cpu_serving");
+  if (!sm->compat.error.empty()) { *state = -1; delete sm; return nullptr; }
   c.session_num = (int)j.n("session_num", 2); c.max_batch = (int)j.n("max_batch", 4096);
   c.select_policy = j.s("select_session_policy", "RR") == "MOD" ? 1 : 0;
   c.update_interval_ms = (int)j.n("model_update_interval_ms", 1000);
@@ -1345,7 +1350,7 @@ void* dr_cpu_initialize(const char* model_entry, const char* model_config, int* 
   auto m = LoadModel(c.savedmodel_dir, c.remote);
   if (!m || c.max_batch <= 0) { *state = -1; delete sm; return nullptr; }
   // sessions run concurrently: each gets cores / sessions OpenMP threads for its GEMMs unless intra_op_parallelism_threads says otherwise
-  c.intra_threads = (int)j.n("intra_op_parallelism_threads", 0);
+  c.intra_threads = (int)j.n("intra_op_parallelism_threads", sm->compat.omp_num_threads);      // omp_num_threads: the reference's MKL team = a session's OpenMP team here
   {                                                                  // executor policy: ModelConfig first, then the reference's environment switches
     const std::string ep = j.s("executor_policy", "");
     if (ep == "cost_model") c.executor_policy = 1; else if (ep == "inline") c.executor_policy = 2; else if (ep == "normal") c.executor_policy = 0;
@@ -1429,6 +1434,7 @@ int dr_cpu_get_serving_model_info(void* model_buf, void** output_data, int* outp
     }
     os << "}";
   }
+  os << ", \"threads_per_session\": " << (sm->sessions.empty() ? 0 : sm->sessions[0]->threads) << ", \"model_config\": " << drcfg::ToJson(sm->compat);
   os << ", \"cpusets\": \"";
   for (size_t i = 0; i < sm->cfg.cpusets.size(); ++i) { if (i) os << ";"; for (size_t k = 0; k < sm->cfg.cpusets[i].size(); ++k) os << (k ? "," : "") << sm->cfg.cpusets[i][k]; }
   os << "\", \"session_last_cpu\": [";

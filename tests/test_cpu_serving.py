@@ -531,3 +531,53 @@ def test_multitask_and_dssm_op_programs_on_the_cpu_processor(tmp_path, name):
         assert dec.shape == ref[:5].shape and np.abs(dec - ref[:5]).max() < 3e-5
     finally:
         proc.close()
+
+
+def test_the_reference_model_config_is_accepted_key_by_key(tmp_path):
+    """The JSON a DeepRec Processor deployment already has (docs/docs_en/Processor.md "Configure file", serving/model_config.cc) initialises both native
+    runtimes unchanged: implemented keys act, mapped keys map (omp_num_threads -> session team, model_update_intra_threads, gpu_ids_list), structural keys
+    are reported, what this build cannot honour (oss / hdfs stores, another serialize_protocol) fails initialisation with the reason, typos are reported."""
+    dr.embedding_variable.clear_registry()
+    torch.manual_seed(2)
+    model = build_model("dlrm", device="cpu", cardinalities=CARDS)
+    opt = dr.optim.AdagradOptimizer(model, lr=0.05)
+    d, ids = _train(model, opt, 2, 2)
+    root = str(tmp_path)
+    export_saved_model_module(model, os.path.join(root, "v1"), version=2, root=root)
+    ref = _ref(model, d, ids)
+    reference_config = {
+        "session_num": 2, "select_session_policy": "MOD", "use_per_session_threads": False, "gpu_ids_list": "0,2", "use_multi_stream": False,
+        "enable_device_placement_optimization": False, "enable_inline_execute": False, "omp_num_threads": 2, "kmp_blocktime": 0, "feature_store_type": "local",
+        "read_thread_num": 4, "update_thread_num": 1, "serialize_protocol": "protobuf", "inter_op_parallelism_threads": 10, "model_update_inter_threads": 4,
+        "model_update_intra_threads": 2, "init_timeout_minutes": 1, "signature_name": "serving_default", "model_store_type": "local",
+        "checkpoint_dir": root, "savedmodel_dir": os.path.join(root, "v1"), "timeline_start_step": 1, "timeline_interval_step": 2, "timeline_trace_count": 3,
+        "model_update_interval_ms": 100, "sesion_num": 7}                                  # <- a typo: must be reported, not silently defaulted
+    for device in ("cpu", "cuda_emu"):
+        proc = Processor(os.path.join(root, "v1"), dict(reference_config, max_batch=64 if device != "cpu" else 4096), device=device)
+        try:
+            n = 64 if device != "cpu" else 512
+            assert np.abs(proc.predict(d.numpy()[:n], ids.numpy()[:, :n]) - ref[:n]).max() < (1e-5 if device == "cpu" else 3e-2)
+            info = proc.model_info()
+            mc = info["model_config"]
+            assert mc["unknown"] == ["sesion_num"] and mc["signature_name"] == "serving_default"
+            assert {"use_per_session_threads", "use_multi_stream", "inter_op_parallelism_threads", "model_update_inter_threads", "kmp_blocktime"} <= set(mc["structural"])
+            assert info["sessions"] == 2
+            if device == "cpu":
+                assert info["threads_per_session"] == 2 and mc["model_update_intra_threads"] == 2           # omp_num_threads -> the session's OpenMP team
+            else:
+                assert info["gpu_id"] == 0                                                                  # first entry of gpu_ids_list
+        finally:
+            proc.close()
+    # a hot update still lands with model_update_intra_threads bounding the updater's team
+    proc = Processor(os.path.join(root, "v1"), reference_config, device="cpu")
+    try:
+        _train(model, opt, 2, 9)
+        export_delta_module(model, root, base_version=2, version=4)
+        assert _wait(lambda: proc.model_info()["delta_version"] == 4)
+        assert np.abs(proc.predict(d.numpy(), ids.numpy()) - _ref(model, d, ids)).max() < 1e-5
+    finally:
+        proc.close()
+    for bad in ({"model_store_type": "oss"}, {"checkpoint_dir": "oss://bucket/ckpt/"}, {"serialize_protocol": "flatbuffers"}):
+        for device in ("cpu", "cuda_emu"):
+            with pytest.raises(Exception):
+                Processor(os.path.join(root, "v1"), dict(reference_config, **bad), device=device)
