@@ -91,9 +91,11 @@ class DLRMEngine:
     def __init__(self, cfg: DLRMConfig, device: Optional[torch.device] = None, rank: int = 0, world_size: int = 1, comm=None):
         self.cfg = cfg
         self.rank, self.world = rank, world_size
-        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.emu = _native.emu_active()          # CPU CI: the same launch sequence on the CUDA-on-CPU emulation (eager, one stream, no CUDA graph)
+        self.dev = torch.device("cpu") if self.emu else (torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()))
         self.lib = _native.cuda()
-        _native.set_device(self.dev.index)
+        if not self.emu:
+            _native.set_device(self.dev.index)
         self.lib.dr_cuda_set_sparse_blocks_per_sm(int(cfg.sparse_blocks_per_sm if cfg.overlap_embedding else 16))
         self.comm = comm                           # parallel.p2p.P2PComm or parallel.nccl_baseline.NcclComm (world_size > 1)
         self.B, self.T, self.D = cfg.batch_size, len(cfg.cardinalities), cfg.embedding_dim
@@ -102,13 +104,13 @@ class DLRMEngine:
         self._graph = None
         import os as _os
         self._timing, self._events = _os.environ.get("DEEPREC_STEP_TIMING") == "1", {}
-        self._side = torch.cuda.Stream(device=self.dev)
+        self._side = None if self.emu else torch.cuda.Stream(device=self.dev)
         self._build_params()
         self._build_tables()
         self._build_buffers()
         self._init_hyper()
         self._pack_weights()
-        torch.cuda.synchronize(self.dev)
+        _native.device_sync(self.dev)
 
     # ------------------------------------------------------------------------------------------------
     # parameters
@@ -287,11 +289,11 @@ class DLRMEngine:
     # kernel-call helpers (every call is one launch of one of OUR kernels; counted for gpu_launches)
     # ------------------------------------------------------------------------------------------------
     def _s(self):
-        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        return None if self.emu else C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     # ---- optional per-phase CUDA-event timing of EAGER steps (DEEPREC_STEP_TIMING=1; never inside a captured graph) ------------
     def _tick(self, name: str) -> None:
-        if self._timing and not torch.cuda.is_current_stream_capturing():
+        if self._timing and not self.emu and not torch.cuda.is_current_stream_capturing():
             e = torch.cuda.Event(enable_timing=True)
             e.record(torch.cuda.current_stream(self.dev))
             self._events.setdefault(name, []).append(e)
@@ -370,8 +372,8 @@ class DLRMEngine:
 
     def _forward(self, train: bool) -> None:
         lib, B, cfg = self.lib, self.B, self.cfg
-        main = torch.cuda.current_stream(self.dev)
-        fork = cfg.overlap_embedding
+        main = None if self.emu else torch.cuda.current_stream(self.dev)
+        fork = cfg.overlap_embedding and not self.emu
         self._tick("f0")
         if fork:
             self._side.wait_stream(main)
@@ -406,11 +408,16 @@ class DLRMEngine:
             self._tick("f_emb")
         self._tick("f_join")
         # ---- interaction + top MLP
-        fused0 = self.uf and cfg.fuse_interaction_gemm and self.D == 16 and self.top[0].N <= 512 and self.inter_dim <= 384
+        fused0 = self.uf and cfg.fuse_interaction_gemm and self.D == 16 and self.top[0].N <= 512 and self.inter_dim <= 384 and not self.emu
         if fused0:    # gather + Gram + lower-triangle pack + Linear(512) + ReLU in one kernel; Z only leaves the SM as a TMA store for the backward
             L0 = self.top[0]
             self._call(lib.dr_cuda_dlrm_inter_gemm, ptr(x), ldx, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv, self.T, self.D, B, ptr(L0.w_bf16), L0.Kp,
                        L0.N, ptr(self.p(L0.name + "/bias")), ptr(L0.a), L0.N, ptr(self.Z) if train else None, self.Zp, self.sp.sync_ref())
+        elif self.uf and self.emu:   # emulation: the indirect kernels are mma code -> k_sp_gather (waits for the ROWS flags) + the SIMT interaction kernel
+            if getattr(self, "_emb_g", None) is None:
+                self._emb_g = torch.zeros(B, self.T, self.D, dtype=torch.bfloat16, device=self.dev)
+            self.sp.gather(self._emb_g)
+            self._call(lib.dr_cuda_dot_interaction_fwd, ptr(x), ldx, ptr(self._emb_g), self.D, self.T * self.D, self.T, self.D, B, ptr(self.Z), self.Zp)
         elif self.uf:   # gathers urow[inv[b][t]]; the kernel itself waits for every owner's ROWS flag
             self._call(lib.dr_cuda_dot_interaction_fwd_u, ptr(x), ldx, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv, self.T, self.D, B, ptr(self.Z),
                        self.Zp, self.sp.sync_ref())
@@ -454,14 +461,17 @@ class DLRMEngine:
         self._tick("b_top")
         # ---- interaction backward -> dy of the last bottom layer, demb (feature-major)
         last = self.bot[-1]
-        if self.uf:   # features gathered through inv; per-sample gradient rows -> demb (pre-reduced per key by k_sp_segsum on the side stream)
+        if self.uf and self.emu:
+            self._call(lib.dr_cuda_dot_interaction_bwd, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self._emb_g), self.D, self.T * self.D, self.T, self.D, B,
+                       ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
+        elif self.uf:   # features gathered through inv; per-sample gradient rows -> demb (pre-reduced per key by k_sp_segsum on the side stream)
             self._call(lib.dr_cuda_dot_interaction_bwd_u, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.sp.urow), ptr(self.sp.inv), self.sp.ldinv,
                        self.T, self.D, B, ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
         else:
             self._call(lib.dr_cuda_dot_interaction_bwd, ptr(self.dZ), self.Zp, ptr(last.y), last.N, ptr(self.emb), B * self.D, self.D, self.T, self.D, B,
                        ptr(last.dy), last.N, ptr(self.demb), B * self.D, self.D)
-        main = torch.cuda.current_stream(self.dev)
-        fork = cfg.overlap_embedding
+        main = None if self.emu else torch.cuda.current_stream(self.dev)
+        fork = cfg.overlap_embedding and not self.emu
         self._tick("b_dot")
         if fork:
             self._side.wait_stream(main)
@@ -533,6 +543,8 @@ class DLRMEngine:
     def capture(self) -> None:
         """Warm up eagerly (loads modules, sizes everything) then capture the whole step into one CUDA graph."""
         self.train_step_eager()
+        if self.emu:                                # kernels run synchronously on the host: the eager step IS the step
+            return
         torch.cuda.synchronize(self.dev)
         n0 = self.launches
         g = torch.cuda.CUDAGraph()
@@ -571,8 +583,11 @@ class DLRMEngine:
         """Loss of the last step: the mean over the GLOBAL batch (each rank holds its partial sum / (B * world))."""
         v = self.loss.clone()
         if global_mean and self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(v)
+            if hasattr(self.comm, "host_all_reduce"):          # emulation: ranks are threads (parallel/emu_comm.py)
+                self.comm.host_all_reduce(v)
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(v)
         return float(v.item())
 
     def global_step(self) -> int:
