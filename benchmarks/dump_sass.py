@@ -14,7 +14,7 @@ WANT = {  # object file -> kernel-name substrings to dump in full
     "comm_kernels.cu.o": ["k_allreduce_apply", "k_rank_barrier"],
     "fused_interaction_gemm.cu.o": ["k_dlrm_inter_gemm"],
     "interaction_kernels.cu.o": ["k_dot_fwd_tcILb1", "k_dot_bwd_tcILb1"],
-    "gemm_tcgen05.cu.o": ["k_gemm_tn_v2ILi256ELb0", "k_gemm_nt_splitkILi256"],
+    "gemm_tcgen05.cu.o": ["k_gemm_tn_v2ILi256ELb0", "k_gemm_nt_splitkILi256", "k_gemm_tn_2ctaILi256"],
     "tier_kernels.cu.o": ["k_tier_miss_list", "k_tier_evict"],
     "nvls.cu.o": ["k_nvls_allreduce_apply", "k_nvls_reduce_bcast"],
 }
@@ -26,6 +26,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     summary = ["# SASS mnemonic counts per kernel (cuobjdump -sass of deeprec_b200/lib/obj/*.o, sm_100a); full listings of the starred kernels in profiles/sass/",
                "# UTCHMMA = tcgen05.mma (bf16), LDTM = tcgen05.ld, UTMALDG/UTMASTG = TMA load/store, SYNCS = mbarrier, REDG = red.global, MATCH = match.any,",
+               "# *.2CTA = cta_group::2 forms (UTCHMMA.2CTA, UTMALDG.2D.2CTA, UTCBAR.2CTA.MULTICAST), UCGABAR_ARV = barrier.cluster.arrive,",
                "# LDG/STG with .SYS or on peer-mapped pointers + MEMBAR.SC.SYS / ld.acquire.sys (LDG.E.STRONG.SYS) = in-kernel NVLink signalling", ""]
     for obj in sorted(os.listdir(OBJ)):
         if not obj.endswith(".o"):
@@ -42,10 +43,12 @@ def main():
                     ops[m.group(1).split(".")[0]] += 1
                     if ".SYS" in m.group(1):
                         ops["*.SYS"] += 1
+                    if ".2CTA" in m.group(1):                      # cta_group::2 forms: UTCHMMA.2CTA, UTMALDG.2D.2CTA, UTCBAR.2CTA.MULTICAST
+                        ops["*.2CTA"] += 1
             short = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip() or name
             short = re.sub(r"\(anonymous namespace\)::", "", short).split("(")[0]
             star = any(w in name for w in WANT.get(obj, []))
-            keyc = ", ".join(f"{k}={ops[k]}" for k in KEY + ["*.SYS"] if ops.get(k))
+            keyc = ", ".join(f"{k}={ops[k]}" for k in KEY + ["*.SYS", "*.2CTA", "UCGABAR_ARV"] if ops.get(k))
             summary.append(f"{'*' if star else ' '} {obj[:-5]:28s} {short[:70]:70s} instrs={sum(ops.values()):6d}  {keyc}")
             if star:
                 fn = re.sub(r"[^A-Za-z0-9_]+", "_", short)[:80] + ".sass"

@@ -248,6 +248,240 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // -------------------------------------------------------------------------------------------------
+// k_gemm_tn_2cta: the same GEMM on a CTA PAIR (thread-block cluster of 2 = the two SMs of one TPC, `cta_group::2`).
+//   * one 256 x BLOCK_N output tile per pair: CTA r owns rows [r*128, r*128+128) of it (its TMEM holds 128 lanes x BLOCK_N fp32
+//     columns, double-buffered), loads ITS 128 rows of A and ITS HALF (BLOCK_N / 2 rows) of B per k block -- every B byte is
+//     fetched once per 256 output rows instead of once per 128: the per-SM L2 -> smem traffic that bounds k_gemm_tn_v2 at these
+//     shapes (34-40 % of copy bandwidth, profiles/ncu_summary.md) drops by BLOCK_N / (128 + BLOCK_N) of the B share;
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (`cp.async.bulk.tensor...cta_group::2`, barrier address with
+//     the peer bit cleared); the leader's elected thread issues ONE `tcgen05.mma.cta_group::2` (M = 256) per 16-wide k step that
+//     reads both CTAs' shared memory and writes both CTAs' TMEM; `tcgen05.commit.cta_group::2 ... multicast::cluster` frees the
+//     smem stage in both CTAs / hands the accumulator to both epilogues;
+//   * the epilogue warps of both CTAs release the accumulator with a remote `mbarrier.arrive` on the leader's barrier (`mapa`).
+// Direct-store epilogue (bias / ReLU / ReLU-backward mask / optional fp32 copy), i.e. the k_gemm_tn feature set.
+// Opt-in (DEEPREC_GEMM_2CTA=1 / dr_cuda_set_gemm_2cta): written after the round's GPU budget was spent -- first hardware run is
+// tests/test_gpu_zzzzzz_gemm_2cta.py.  Reference: none (cuBLAS call, stream_executor/cuda/cuda_blas.cc:431-455).
+// -------------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the pair's even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes land on the pair LEADER's mbarrier (executed by both CTAs; destination = the executing CTA's smem)
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once every MMA issued so far has retired
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this offset in cluster CTA `rank`
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+
+template <int BLOCK_N>
+struct SmemLayoutTN2CTA {
+  static constexpr int kStages2 = BLOCK_N >= 256 ? 5 : 6;
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;             // my 128 rows of A
+  static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;       // my half of B (multiple of 1024 for BLOCK_N >= 16)
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kStages2 * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+k_gemm_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, Epilogue ep) {
+  using L = SmemLayoutTN2CTA<BLOCK_N>;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "M = 256 pair MMA: N multiple of 16 in [16, 256]; halves of 32+");
+  constexpr int S = L::kStages2;
+  constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * L::kStageBytes);
+  uint64_t* full_bar = bars;                  // [S]  used in the leader only (both CTAs' TMA bytes land there)
+  uint64_t* empty_bar = bars + S;             // [S]  per CTA: multicast commit from the leader's MMA thread
+  uint64_t* tfull_bar = bars + 2 * S;         // [2]  per CTA: multicast commit
+  uint64_t* tempty_bar = bars + 2 * S + 2;    // [2]  leader only: 4 epilogue warps x 2 CTAs
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_pairs * n_tiles;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int first_tile = (int)cluster_id_x(), tile_step = (int)cluster_nid_x();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {      // the same warp index in both CTAs performs the pair allocation
+    tmem_alloc_2cta(tmem_ptr, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits of BOTH CTAs are visible before any remote arrive / multicast commit / peer TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer (one per CTA: my A rows, my half of B) =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
+        const int row0 = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M;
+        const int col0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (L::kABytes + L::kBBytes));   // both CTAs' bytes
+          tma_load_2d_2cta(sa, &tmA, &full_bar[stage], kb * BLOCK_K, row0);
+          tma_load_2d_2cta(sb, &tmB, &full_bar[stage], kb * BLOCK_K, col0);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: ONE thread of the LEADER CTA drives both SMs' tensor cores =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit_2cta(&tfull_bar[acc]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= Epilogue warps of both CTAs: my 128 rows of the pair tile =================
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c0, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c0;
+        if (row < M && col0 < N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < N) {
+                float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (ep.mask_src) {
+            const __nv_bfloat16* ms = ep.mask_src + (int64_t)row * ep.ld_mask + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < N) {
+                int4 raw = *reinterpret_cast<const int4*>(ms + j);
+                const uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = unpack_bf16x2(w[e]);
+                  if (!(f.x > 0.f)) v[j + 2 * e] = 0.f;
+                  if (!(f.y > 0.f)) v[j + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+          }
+          __nv_bfloat16* dst = ep.out + (int64_t)row * ep.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < N) {   // N is a multiple of 8 (checked on the host)
+              int4 pk;
+              pk.x = (int)pack_bf16x2(v[j], v[j + 1]); pk.y = (int)pack_bf16x2(v[j + 2], v[j + 3]);
+              pk.z = (int)pack_bf16x2(v[j + 4], v[j + 5]); pk.w = (int)pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<int4*>(dst + j) = pk;
+            }
+          }
+          if (ep.out_f32) {
+            float* d32 = ep.out_f32 + (int64_t)row * ep.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (col0 + j < N) *reinterpret_cast<float4*>(d32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);     // the leader's MMA thread owns the accumulator hand-back
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  __syncwarp();         // re-converge the single-lane role branches before the aligned cluster barrier
+  tc_fence_before();
+  cluster_sync_all();   // the peer's smem / TMEM / barriers stay alive until both CTAs are done
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, kTmemCols);
+}
+
+// -------------------------------------------------------------------------------------------------
 // k_gemm_tn_v2: same mainloop, production epilogue.
 //   * accumulator -> registers (tcgen05.ld) -> fused math -> bf16 -> 128B-swizzled smem staging -> TMA store
 //     (cp.async.bulk.tensor, full 128 B lines; M/N tails clipped by the tensor map), double-buffered per warp;
@@ -730,6 +964,30 @@ int launch_tn_v2(const CUtensorMap& ta, const void* B, int M, int N, int K, int6
 // DEEPREC_GEMM_BRES=1 selects the B-resident (weight-stationary) kernel where it applies (K <= 512, enough CTAs for one per n block).
 inline int& gemm_bres_enabled() { static int v = [] { const char* e = getenv("DEEPREC_GEMM_BRES"); return (e && e[0] == '1') ? 1 : 0; }(); return v; }
 
+// CTA-pair launcher: grid = 2 x min(pair tiles, max_ctas / 2); the cluster shape is a kernel attribute (__cluster_dims__).
+template <int BN>
+int launch_tn_2cta(const CUtensorMap& ta, const void* B, int M, int N, int K, int64_t ldb, const Epilogue& ep, int max_ctas, cudaStream_t s) {
+  CUtensorMap tb;
+  int rc = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BLOCK_K, BN / 2);
+  if (rc) return rc;
+  using L = SmemLayoutTN2CTA<BN>;
+  static_assert(L::kTotal <= 227 * 1024, "shared-memory budget");
+  static DrPerDeviceOnce attr_once; bool& attr_set = attr_once();
+  if (!attr_set) {
+    DR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn_2cta<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + BN - 1) / BN;
+  int pairs = m_pairs * n_tiles;
+  if (pairs > max_ctas / 2) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+  k_gemm_tn_2cta<BN><<<2 * pairs, kGemmThreads, L::kTotal, s>>>(ta, tb, M, N, K, ep);
+  DR_LAUNCH_CHECK();
+  return 0;
+}
+
+// DEEPREC_GEMM_2CTA=1 routes the direct-store-epilogue shapes (no fused statistics) with N >= 64 to the CTA-pair kernel.
+inline int& gemm_2cta_enabled() { static int v = [] { const char* e = getenv("DEEPREC_GEMM_2CTA"); return (e && e[0] == '1') ? 1 : 0; }(); return v; }
+
 template <int BN>
 int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, int Mo, int No, int batch, int splits, float* dW, int64_t ldw, cudaStream_t s) {
   using L = SmemLayoutNT<BN>;
@@ -774,6 +1032,10 @@ int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, i
   int rc = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M);
   if (rc) return rc;
   Epilogue ep{bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, out_f32, ldc, ld_mask, relu, aux_mode, S1, S2};
+  if (gemm_2cta_enabled() && !force_v1 && N >= 64 && !S1 && !S2 && aux_mode != 2) {
+    if (N <= 128) return launch_tn_2cta<128>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+    return launch_tn_2cta<256>(ta, B, M, N, K, ldb, ep, max_ctas, s);
+  }
   const bool v2 = !force_v1 && N > 32 && out_f32 == nullptr;
   if (v2 && gemm_bres_enabled() && (K + BLOCK_K - 1) / BLOCK_K <= SmemLayoutTN3<128>::kMaxKb) {
     if (N <= 64) return launch_tn_v2<64, true>(ta, B, M, N, K, ldb, ep, max_ctas, s);
@@ -794,6 +1056,7 @@ int dr_cuda_gemm_tn_ex(const void* A, int64_t lda, const void* B, int64_t ldb, i
 
 // dW[N_out,K_in](ldw, fp32, accumulated into) += dY[batch,N_out](ldy)^T * X[batch,K_in](ldx)
 // A/B switch for the B-resident GEMM variant (same effect as DEEPREC_GEMM_BRES, settable at run time; returns the previous value).
+int dr_cuda_set_gemm_2cta(int on) { int prev = gemm_2cta_enabled(); gemm_2cta_enabled() = on ? 1 : 0; return prev; }
 int dr_cuda_set_gemm_bres(int on) { int prev = gemm_bres_enabled(); gemm_bres_enabled() = on ? 1 : 0; return prev; }
 
 int dr_cuda_gemm_dw(const void* dY, int64_t ldy, const void* X, int64_t ldx, int batch, int N_out, int K_in, float* dW, int64_t ldw,
