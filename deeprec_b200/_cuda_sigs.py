@@ -74,6 +74,8 @@ def _bind(lib):
     _sig(lib, "dr_cuda_quantize_e4m3", [P, INT, i64, INT, i64, P, INT, f32, S])
     _sig(lib, "dr_cuda_quantize_weights_e4m3", [P, INT, INT, i64, P, INT, P, S])
     _sig(lib, "dr_cuda_absmax_bf16", [P, i64, P, S])
+    _sig(lib, "dr_cuda_quantize_mxfp8", [P, INT, i64, INT, i64, P, INT, P, S])
+    _sig(lib, "dr_cuda_gemm_mxfp8_tn", [P, P, P, P, INT, INT, INT, P, INT, P, i64, INT, S])
     _sig(lib, "dr_cuda_bn_fold", [P, P, INT, i64, P, P, f32, f32, P, P, P, P, P, P, INT, P, P, INT, INT, P, P, S])
     _sig(lib, "dr_cuda_dw_fixup", [P, P, P, P, INT, INT, INT, S])
     _sig(lib, "dr_cuda_bn_bwd_apply_v2", [P, P, i64, INT, i64, P, P, P, P, P, P, INT, P, S])

@@ -24,6 +24,7 @@ CUDA_SOURCES = [
     "cuda/optimizer_kernels.cu",
     "cuda/dense_kernels.cu",
     "cuda/gemm_fp8.cu",
+    "cuda/gemm_mxfp8.cu",
     "cuda/gemm_tcgen05.cu",
     "cuda/interaction_kernels.cu",
     "cuda/comm_kernels.cu",
