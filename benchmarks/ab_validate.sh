@@ -24,6 +24,15 @@ fi
 for t in tests/test_gpu_zz_*.py; do
   DEEPREC_RUN_UNVALIDATED=1 timeout 600 python -m pytest "$t" -q -m gpu -x > "$OUT/$(basename "$t" .py).txt" 2>&1; echo "$t rc=$?" | tee -a "$OUT/log.txt"
 done
+# ---- 1b. kernels written in the last session of round 2 (CTA-pair GEMM, block-scaled fp8): tests, then the GEMM A/B table, then the step A/B
+for t in tests/test_gpu_zzzzzz_gemm_2cta.py tests/test_gpu_zzzzzzz_mxfp8.py; do
+  timeout 900 python -m pytest "$t" -q -m gpu > "$OUT/$(basename "$t" .py).txt" 2>&1; echo "$t rc=$?" | tee -a "$OUT/log.txt"
+done
+timeout 600 python benchmarks/gemm_ab.py > "$OUT/gemm_ab.jsonl" 2>>"$OUT/log.txt"
+for c in 0 1; do
+  DEEPREC_GEMM_2CTA=$c timeout 600 python bench.py --steps 30 --warmup 5 2>>"$OUT/log.txt" | tail -1 > "$OUT/bench_n1_2cta${c}.json"
+done
+DEEPREC_GEMM_2CTA=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tn_2cta -c 1 -s 10 -o "$OUT/prof_gemm_2cta" -f python bench.py --steps 2 --warmup 1 >>"$OUT/log.txt" 2>&1
 # ---- 2. A/B: B-resident GEMM
 for bres in 0 1; do
   DEEPREC_GEMM_BRES=$bres timeout 600 python bench.py --steps 30 --warmup 5 2>>"$OUT/log.txt" | tail -1 > "$OUT/bench_n1_bres${bres}.json"

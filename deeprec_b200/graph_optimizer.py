@@ -39,6 +39,7 @@ class OptimizerOptions:
     fold_batchnorm: bool = True          # only applied to modules in eval mode
     min_chain: int = 1                   # Linear layers a chain needs before it is rewritten
     min_width: int = 8                   # narrower layers (e.g. the final logit) stay plain Linear: no GEMM tile to fill
+    mxfp8_inference: bool = False        # eval-mode Linear(+ReLU) -> block-scaled fp8 layer (ops/mxfp8.py: tcgen05 kind::mxf8f6f4.block_scale)
 
 
 @dataclass
@@ -142,6 +143,23 @@ class LinearReluChain(FusionTemplate):
         return j - i, [fused]
 
 
+class LinearToMXFP8(FusionTemplate):
+    """Inference-only: Linear (+ReLU) in eval mode -> MXFP8Linear (weights quantised once with one power-of-two scale per 32 inputs,
+    activations per call; the tensor core applies both scales).  The low-precision rewrite of tools/low_precision_optimize, B200 form."""
+    name = "LinearToMXFP8"
+
+    def enabled(self, opts):
+        return opts.mxfp8_inference
+
+    def match(self, mods, i, opts):
+        m = mods[i]
+        if type(m) is not nn.Linear or m.training or m.out_features < opts.min_width or m.in_features < 32:
+            return None
+        from .ops.mxfp8 import MXFP8Linear
+        relu = i + 1 < len(mods) and type(mods[i + 1]) is nn.ReLU
+        return (2 if relu else 1), [MXFP8Linear(m, relu=relu)]
+
+
 class LinearBatchNormFold(FusionTemplate):
     name = "LinearBatchNormFold"
 
@@ -216,7 +234,7 @@ class DiceTemplate(_Single):
         return FusedDice(m)
 
 
-_TEMPLATES: List[FusionTemplate] = [LinearBatchNormFold(), LinearReluChain(), LayerNormTemplate(), GeluTemplate(), DiceTemplate()]
+_TEMPLATES: List[FusionTemplate] = [LinearBatchNormFold(), LinearToMXFP8(), LinearReluChain(), LayerNormTemplate(), GeluTemplate(), DiceTemplate()]
 
 
 def register_template(t: FusionTemplate, first: bool = False) -> None:

@@ -184,7 +184,9 @@ inline bool ReadAsFloat(BundleReader& r, const std::string& name, std::vector<fl
   const BundleEntry* e = r.Find(name);
   if (!e) return false;
   if (shape) *shape = e->shape;
-  if (e->dtype == "f32") { out->resize((size_t)e->nbytes / 4); return r.Read(*e, out->data(), 1) == 0; }
+  if (e->dtype != "bf16" && e->dtype != "f16" && e->dtype != "i8") {           // fp32 under any spelling ("f32", writers of other tools: "float32"): raw bytes
+    out->resize((size_t)e->nbytes / 4); return r.Read(*e, out->data(), 1) == 0;
+  }
   std::vector<uint8_t> raw((size_t)e->nbytes);
   if (r.Read(*e, raw.data(), 1) != 0) return false;
   if (e->dtype == "bf16") {

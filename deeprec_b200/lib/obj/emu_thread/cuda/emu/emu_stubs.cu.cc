@@ -46,6 +46,22 @@ int dr_cuda_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int 
   return dr_cuda_gemm_tn_ex(A, lda, B, ldb, M, N, K, bias, relu, mask_src, ld_mask, mask_src ? 1 : 0, out, ldc, out_f32, nullptr, nullptr, max_ctas, 0, s);
 }
 
+// gemm_tcgen05.cu::dr_cuda_gemm_dw: dW[N_out,K_in](ldw, fp32, accumulated into) += dY[batch,N_out](ldy)^T * X[batch,K_in](ldx)
+int dr_cuda_gemm_dw(const void* dY, int64_t ldy, const void* X, int64_t ldx, int batch, int N_out, int K_in, float* dW, int64_t ldw, int splits, cudaStream_t) {
+  (void)splits;
+  if (batch <= 0 || N_out <= 0 || K_in <= 0) return 0;
+  if ((ldy % 8) || (ldx % 8)) return -2;
+  if (((uintptr_t)dY | (uintptr_t)X) & 15) return -3;
+  const __nv_bfloat16* y = (const __nv_bfloat16*)dY; const __nv_bfloat16* x = (const __nv_bfloat16*)X;
+  for (int n = 0; n < N_out; ++n)
+    for (int k = 0; k < K_in; ++k) {
+      float acc = 0.f;
+      for (int b = 0; b < batch; ++b) acc += bf(y + (int64_t)b * ldy + n) * bf(x + (int64_t)b * ldx + k);
+      dW[(int64_t)n * ldw + k] += acc;
+    }
+  return 0;
+}
+
 // gemm_fp8.cu: the fp8 serving path is not emulated (ModelConfig {"fp8": true} fails to initialise on the emulation, loudly)
 int dr_cuda_gemm_fp8_tn(const void*, int64_t, const void*, int64_t, int, int, int, const float*, const float*, int, void*, int64_t, int, float, cudaStream_t) { return -100; }
 int dr_cuda_quantize_e4m3(const void*, int, int64_t, int, int64_t, void*, int, float, cudaStream_t) { return -100; }

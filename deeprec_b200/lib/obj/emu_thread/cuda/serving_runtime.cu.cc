@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../common/bundle.h"
+#include "../common/model_config.h"
 #include "../common/predict_pb.h"
 #include "table.cuh"
 
@@ -825,6 +826,7 @@ struct Config {
 
 struct ServingModel {
   Config cfg;
+  drcfg::Compat compat;                    // reference ModelConfig keys without a 1:1 field (csrc/common/model_config.h)
   std::shared_ptr<DeviceModel> model;      // swapped atomically on full update (std::atomic_load / atomic_store)
   std::vector<std::unique_ptr<Session>> sessions;
   std::atomic<uint64_t> rr{0}, requests{0}, failures{0}, full_updates{0}, delta_updates{0};
@@ -1084,7 +1086,9 @@ void* initialize(const char* model_entry, const char* model_config, int* state) 
   JVal j;
   if (model_config && *model_config && !ParseJson(model_config, &j)) { *state = -1; delete sm; return nullptr; }
   Config& c = sm->cfg;
-  c.session_num = (int)j.n("session_num", 2); c.gpu_id = (int)j.n("gpu_id", 0); c.max_batch = (int)j.n("max_batch", 4096);
+  sm->compat = drcfg::ParseCompat(j, "deeprec_cuda_serving");                 // every reference ModelConfig key classified (csrc/common/model_config.h)
+  if (!sm->compat.error.empty()) { *state = -1; delete sm; return nullptr; }
+  c.session_num = (int)j.n("session_num", 2); c.gpu_id = (int)j.n("gpu_id", sm->compat.first_gpu >= 0 ? sm->compat.first_gpu : 0); c.max_batch = (int)j.n("max_batch", 4096);
   c.select_policy = j.s("select_session_policy", "RR") == "MOD" ? 1 : 0;
   c.update_interval_ms = (int)j.n("model_update_interval_ms", 1000); c.extra_rows = (int)j.n("delta_extra_rows", 1 << 16);
   c.savedmodel_dir = j.s("savedmodel_dir", model_entry ? model_entry : ""); c.checkpoint_dir = j.s("checkpoint_dir", "");
@@ -1130,7 +1134,8 @@ int get_serving_model_info(void* model_buf, void** output_data, int* output_size
   std::ostringstream os;
   os << "{\"model_version\": " << (m ? m->version : -1) << ", \"delta_version\": " << sm->delta_version.load() << ", \"model_path\": \"" << (m ? m->path : "")
      << "\", \"sessions\": " << sm->sessions.size() << ", \"requests\": " << sm->requests.load() << ", \"failures\": " << sm->failures.load()
-     << ", \"mlp_dtype\": \"" << (sm->cfg.fp8 ? "fp8" : "bf16") << "\", \"embedding_placement\": \"" << (sm->cfg.host_tables ? "host" : "device") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load() << "}";
+     << ", \"mlp_dtype\": \"" << (sm->cfg.fp8 ? "fp8" : "bf16") << "\", \"embedding_placement\": \"" << (sm->cfg.host_tables ? "host" : "device") << "\", \"full_updates\": " << sm->full_updates.load() << ", \"delta_updates\": " << sm->delta_updates.load()
+     << ", \"gpu_id\": " << sm->cfg.gpu_id << ", \"model_config\": " << drcfg::ToJson(sm->compat) << "}";
   std::string s = os.str();
   *output_size = (int)s.size();
   *output_data = malloc(s.size() + 1);

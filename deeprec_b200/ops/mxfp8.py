@@ -110,7 +110,7 @@ def mxfp8_gemm(aq, sfa, bq, sfb, n: int, bias=None, relu: bool = False, max_ctas
 
 
 class MXFP8Linear(torch.nn.Module):
-    """Inference Linear (+ReLU) with MXFP8 weights: the weight is quantised once, activations per call; output bf16 (N padded to 8)."""
+    """Inference Linear (+ReLU) with MXFP8 weights: the weight is quantised once, activations per call; the kernel stores bf16 (N padded to 8), returned in the input's dtype."""
 
     def __init__(self, linear: torch.nn.Linear, relu: bool = False):
         super().__init__()
@@ -132,6 +132,6 @@ class MXFP8Linear(torch.nn.Module):
         if not x.is_cuda:                 # host fallback for tests / export checks: the same arithmetic in fp32
             xq, sfa = quantize_mxfp8_reference(x.float())
             y = dequantize_mxfp8(xq, sfa) @ dequantize_mxfp8(self.wq, self.sfb)[: self.out_features].t() + self.bias[: self.out_features]
-            return (y.relu() if self.relu else y).bfloat16()
+            return (y.relu() if self.relu else y).bfloat16().to(x.dtype)      # same rounding point as the kernel's bf16 store
         xq, sfa = quantize_mxfp8(x.contiguous() if x.dtype in (torch.float32, torch.bfloat16) else x.float().contiguous())
-        return mxfp8_gemm(xq, sfa, self.wq, self.sfb, self.np, self.bias, self.relu)[:, : self.out_features]
+        return mxfp8_gemm(xq, sfa, self.wq, self.sfb, self.np, self.bias, self.relu)[:, : self.out_features].to(x.dtype)

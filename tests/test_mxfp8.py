@@ -49,3 +49,20 @@ def test_mxfp8_linear_host_path_tracks_fp32():
     y = layer(x).float()
     ref = lin(x).relu()
     assert y.shape == ref.shape and (y - ref).abs().max() / ref.abs().max() < 4e-2
+
+
+def test_graph_optimizer_rewrites_eval_mlp_to_mxfp8():
+    from deeprec_b200 import graph_optimizer as go
+    torch.manual_seed(2)
+    net = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 32), torch.nn.ReLU(), torch.nn.Linear(32, 1)).eval()
+    x = torch.randn(50, 64)
+    ref, ref_h = net(x), net[:4](x)
+    rep = go.optimize(net, go.OptimizerOptions(mxfp8_inference=True))
+    assert rep.count("LinearToMXFP8") == 2 and type(net[-1]) is torch.nn.Linear           # the 1-wide logit layer stays a plain Linear
+    assert [type(m).__name__ for m in net] == ["MXFP8Linear", "MXFP8Linear", "Linear"]
+    out = net(x)
+    h = net[:2](x)
+    assert (h - ref_h).abs().max() / ref_h.abs().max() < 6e-2                              # two fp8 layers
+    assert (out - ref).abs().max() / ref.abs().max() < 0.2                                # the logit is a cancelling sum of those activations
+    net2 = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU())                 # training mode: untouched by the inference rewrite
+    assert go.optimize(net2, go.OptimizerOptions(mxfp8_inference=True)).count("LinearToMXFP8") == 0
