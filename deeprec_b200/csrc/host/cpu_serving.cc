@@ -1282,7 +1282,9 @@ static bool ApplyDelta(ServingModel* sm, const std::string& prefix, int64_t vers
 static void UpdaterLoop(ServingModel* sm) {
   const std::string vf = (sm->cfg.checkpoint_dir.empty() ? sm->cfg.savedmodel_dir : sm->cfg.checkpoint_dir) + "/serving_versions.json";
   int bad = 0;
+#ifdef _OPENMP
   if (sm->compat.update_intra_threads > 0) omp_set_num_threads(sm->compat.update_intra_threads);    // model_update_intra_threads: the hot update's imports / packing run on this thread's team
+#endif
   while (!sm->stop) {
     for (int i = 0; i < std::max(1, sm->cfg.update_interval_ms / 20) && !sm->stop; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(20));
     std::string txt; JVal j;
